@@ -1,0 +1,136 @@
+"""ctypes bindings of oracle/_build/liboracle.so (the CPU restatement of the reference's
+ORB / LSD / LBD / matcher hot path).  TEST INFRASTRUCTURE ONLY — see oracle/__init__.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "_build", "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cc", ".inc", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "_build", "liboracle.so")
+        if not os.path.exists(so):
+            so = build()
+        _LIB = C.CDLL(so)
+        L = _LIB
+        L.oracle_fast_atan2.restype = C.c_float
+        L.oracle_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.oracle_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.oracle_orb_create.restype = C.c_void_p
+        L.oracle_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.oracle_orb_destroy.argtypes = [C.c_void_p]
+        L.oracle_orb_pattern.restype = C.POINTER(C.c_int)
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().oracle_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def blur7(src, k=(18, 34, 48, 56, 48, 34, 18)):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    kk = np.asarray(k, np.int32)
+    lib().oracle_blur7_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0], _p(kk))
+    return dst
+
+
+def fast9(img, th):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size
+    out = np.empty((cap, 3), np.int32)
+    n = lib().oracle_fast9(_p(img), img.shape[1], img.shape[0], img.strides[0], int(th), _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    return float(lib().oracle_fast_atan2(float(y), float(x)))
+
+
+def sincos(x):
+    s, c = C.c_float(), C.c_float()
+    lib().oracle_sincos(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def orb_pattern():
+    return np.ctypeslib.as_array(lib().oracle_orb_pattern(), shape=(1024,)).copy()
+
+
+class OrbOracle:
+    """Restatement of ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-111)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = C.c_void_p(lib().oracle_orb_create(nfeatures, scale_factor, nlevels, ini_th, min_th))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_orb_destroy(self.h)
+            self.h = None
+
+    def set_blur_kernel(self, k):
+        kk = np.asarray(k, np.int32)
+        lib().oracle_orb_set_blur_kernel(self.h, _p(kk))
+
+    def tables(self):
+        n = self.nlevels
+        f = [np.empty(n, np.float32) for _ in range(4)]
+        quota = np.empty(n, np.int32)
+        umax = np.empty(16, np.int32)
+        lib().oracle_orb_tables(self.h, _p(f[0]), _p(f[1]), _p(f[2]), _p(f[3]), _p(quota), _p(umax))
+        return dict(scale=f[0], inv_scale=f[1], sigma2=f[2], inv_sigma2=f[3], quota=quota, umax=umax)
+
+    def extract(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures * 2 + 64
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = lib().oracle_orb_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+        assert n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l, blurred=False):
+        w, h = C.c_int(), C.c_int()
+        assert lib().oracle_orb_level_size(self.h, l, C.byref(w), C.byref(h)) == 0
+        out = np.empty((h.value, w.value), np.uint8)
+        n = lib().oracle_orb_level_copy(self.h, l, int(blurred), _p(out))
+        return out if n else None
+
+    def candidates(self, l):
+        cap = 1 << 18
+        out = np.empty((cap, 3), np.int32)
+        n = lib().oracle_orb_candidates(self.h, l, _p(out), cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def distribute(self, xyr, minX, maxX, minY, maxY, N):
+        xyr = np.ascontiguousarray(xyr, np.int32)
+        out = np.empty(len(xyr) + 8, np.int32)
+        n = lib().oracle_orb_distribute(self.h, _p(xyr), len(xyr), minX, maxX, minY, maxY, N, _p(out), len(out))
+        return out[:n].copy()
