@@ -1,0 +1,115 @@
+/* plslam_b200.h — C-ABI of the B200-native RGBD-PL-SLAM front-end (ORB + LSD/LBD + matchers).
+ *
+ * This is the drop-in boundary: plain pointers, sizes, int status codes, opaque handles and an
+ * explicit cudaStream_t (passed as void*).  No torch / OpenCV types appear here.  The C++ classes
+ * in rgbd-pl-slam_b200/host/ (ORB_SLAM2::ORBextractor, LineSegment, ORBmatcher, LSDmatcher) are
+ * thin veneers over these entry points with the reference's exact signatures.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference
+ * repo maxee1900/RGBD-PL-SLAM; "@0x…" = address in its prebuilt lib/libORB_SLAM2.so, the only
+ * form in which the reference ships ORBextractor / ORBmatcher).
+ *
+ * There is NO CPU fallback: every compute entry point returns PLSLAM_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef PLSLAM_B200_H
+#define PLSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLSLAM_OK 0
+#define PLSLAM_ERR_INVALID 1   /* bad argument */
+#define PLSLAM_ERR_CUDA 2      /* CUDA runtime failure (see plslam_last_error) */
+#define PLSLAM_ERR_CAPACITY 3  /* caller-provided output capacity too small */
+#define PLSLAM_ERR_OVERFLOW 4  /* an internal fixed-capacity buffer overflowed (reported, never truncated silently) */
+
+/* cv::KeyPoint layout (28 B; stores @0x7656d-0x7659d): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct plslam_keypoint {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} plslam_keypoint_t;
+
+/* cv::line_descriptor::KeyLine layout (OpenCV-contrib, used by include/ExtractLineSegment.h:38) */
+typedef struct plslam_keyline {
+  float angle;
+  int32_t class_id;
+  int32_t octave;
+  float pt_x, pt_y;
+  float response;
+  float size;
+  float startPointX, startPointY, endPointX, endPointY;
+  float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+  float lineLength;
+  int32_t numOfPixels;
+} plslam_keyline_t;
+
+const char* plslam_last_error(void);      /* thread-local message of the last failing call */
+const char* plslam_version(void);
+int plslam_device_count(void);            /* number of usable CUDA devices (0 => every compute call fails) */
+
+/* ------------------------------------------------------------------------------------------
+ * ORB extractor  — replaces ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-111)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plslam_orb plslam_orb_t;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (ORBextractor.h:51-52, @0x73050).  Binds to the current CUDA device. */
+int plslam_orb_create(plslam_orb_t** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                      int minThFAST);
+void plslam_orb_destroy(plslam_orb_t* h);
+
+/* 7-tap integer Gaussian table (sum 256) used for the 7x7 sigma=2 blur (@0x77487).  Default is
+ * OpenCV 4.13's {18,34,48,56,48,34,18}; OpenCV 3.3 builds may want {18,34,49,55,49,34,18}. */
+int plslam_orb_set_blur_kernel(plslam_orb_t* h, const int32_t k[7]);
+
+/* GetLevels / GetScaleFactor(s) / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (ORBextractor.h:63-83) plus the per-level quotas and umax table.
+ * Any output pointer may be NULL.  Arrays hold nlevels entries (umax: 16). */
+int plslam_orb_levels(const plslam_orb_t* h);
+int plslam_orb_tables(const plslam_orb_t* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                      int32_t* features_per_level, int32_t* umax16);
+/* Upper bound of keypoints per frame: sum over levels of (quota + 3) (DistributeOctTree may overshoot by 3). */
+int plslam_orb_max_keypoints(const plslam_orb_t* h);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors) (ORBextractor.h:59-61, @0x76da0)
+ * on ONE host image (CV_8UC1, `pitch` bytes per row).  Keypoints are written level-major, in
+ * the reference's order, coordinates rescaled to level 0; descriptors are n x 32 bytes row-major.
+ * An empty image (NULL / zero size) returns PLSLAM_OK with *n_out = 0 (@0x76dda). */
+int plslam_orb_extract(plslam_orb_t* h, const uint8_t* image, int width, int height, int pitch,
+                       plslam_keypoint_t* keypoints, uint8_t* descriptors, int capacity, int* n_out);
+
+/* Batched extension (additive; the reference is single-frame): `batch` frames of identical size in
+ * host memory, `frame_stride` bytes apart.  Output for frame f starts at keypoints + f*capacity
+ * and descriptors + f*capacity*32; counts[f] receives its keypoint count.  Host<->device copies
+ * happen inside the call. */
+int plslam_orb_extract_batch_host(plslam_orb_t* h, const uint8_t* images, int batch, int width, int height,
+                                  int pitch, size_t frame_stride, plslam_keypoint_t* keypoints,
+                                  uint8_t* descriptors, int capacity, int32_t* counts);
+
+/* Same with device-resident inputs and outputs; asynchronous on `stream` (a cudaStream_t).
+ * capacity must be >= plslam_orb_max_keypoints().  d_status (device int32, may be NULL) receives
+ * PLSLAM_OK or PLSLAM_ERR_OVERFLOW. */
+int plslam_orb_extract_batch_device(plslam_orb_t* h, const uint8_t* d_images, int batch, int width, int height,
+                                    int pitch, size_t frame_stride, plslam_keypoint_t* d_keypoints,
+                                    uint8_t* d_descriptors, int capacity, int32_t* d_counts, void* stream);
+
+/* ORBextractor::mvImagePyramid (public member, ORBextractor.h:85): copy level `level` of frame `frame`
+ * of the last batch into `out` (dense rows, width*height bytes).  which: 0 = pyramid level,
+ * 1 = 7x7-blurred level (the reference's workingMat, @0x773ff-0x77487). */
+int plslam_orb_level_size(const plslam_orb_t* h, int level, int* width, int* height);
+int plslam_orb_copy_level(plslam_orb_t* h, int frame, int level, int which, uint8_t* out, size_t out_bytes);
+
+/* Parity/debug: FAST candidates of (frame, level) of the last batch before DistributeOctTree, as
+ * (x, y, response) int32 triples in border-local coordinates, sorted in the reference's list order
+ * (cell row, cell col, y, x) (@0x765b8-0x765e3).  Returns the count in *n_out. */
+int plslam_orb_copy_candidates(plslam_orb_t* h, int frame, int level, int32_t* xyr, int capacity, int* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLSLAM_B200_H */

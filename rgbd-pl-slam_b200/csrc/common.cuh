@@ -1,0 +1,102 @@
+// common.cuh — shared helpers for the sm_100a kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/plslam_b200.h"
+
+namespace plslam {
+
+// thread-local error text returned by plslam_last_error()
+void set_error(const char* fmt, ...);
+
+#define PL_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::plslam::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PLSLAM_ERR_CUDA;                                                                 \
+    }                                                                                         \
+  } while (0)
+
+#define PL_CHECK_ARG(cond)                                                    \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      ::plslam::set_error("invalid argument: %s (%s:%d)", #cond, __FILE__, __LINE__); \
+      return PLSLAM_ERR_INVALID;                                              \
+    }                                                                         \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// Simple owning device buffer that only grows.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return PLSLAM_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    PL_CUDA(cudaMalloc(&p, need));
+    bytes = need;
+    return PLSLAM_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+#ifdef __CUDACC__
+// cvRound on float: round-half-even (x86 vcvtss2si in the reference binary)
+__device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
+
+// block-wide exclusive scan of a shared-memory int array, in place; returns the total.
+// All threads of the block must call it; n may be any size. `warp_tmp` needs 33 ints of smem.
+__device__ inline int block_scan_excl(int* a, int n, int* warp_tmp) {
+  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = (T + 31) >> 5;
+  const int per = (n + T - 1) / T;
+  const int b = min(t * per, n), e = min(b + per, n);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += a[i];
+  int incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_tmp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int v = lane < nw ? warp_tmp[lane] : 0, iv = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, iv, d);
+      if (lane >= d) iv += u;
+    }
+    if (lane < nw) warp_tmp[lane] = iv - v;
+    if (lane == 31) warp_tmp[32] = iv;
+  }
+  __syncthreads();
+  int run = warp_tmp[w] + incl - sum;
+  for (int i = b; i < e; ++i) {
+    int v = a[i];
+    a[i] = run;
+    run += v;
+  }
+  int total = warp_tmp[32];
+  __syncthreads();
+  return total;
+}
+#endif
+
+}  // namespace plslam

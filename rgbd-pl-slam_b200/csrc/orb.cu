@@ -1,0 +1,1062 @@
+// orb.cu — B200-native ORB extractor: batched pyramid, per-cell FAST-9 + NMS, quad-tree keypoint
+// distribution, intensity-centroid orientation, 7x7 integer blur and 256-bit rBRIEF.
+//
+// Replaces ORB_SLAM2::ORBextractor (reference include/ORBextractor.h:45-111; implementation only
+// as machine code in lib/libORB_SLAM2.so, addresses cited per kernel).  All kernels are integer /
+// byte work bounded by HBM traffic; none uses tensor cores.  One launch per stage covers the
+// whole batch (grid.y = frame), so a 256-frame batch is ~16 launches.
+#include "orb.cuh"
+#include "fast_score.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace plslam {
+
+namespace {
+
+// bit_pattern_31_ (256 x 4 coordinates in [-13, 12]), see tools/extract_pattern.py.  Kept in global
+// memory (not __constant__): every lane reads its own 32 bytes, which the constant cache would serialise.
+__device__ __align__(16) int8_t g_pattern[1024];
+const int h_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+__device__ __forceinline__ const uint8_t* level_ptr(const OrbParams& P, const OrbImages& I, int f, int l, int& pitch) {
+  if (l == 0) {
+    pitch = I.pitch0;
+    return I.img0 + (size_t)f * I.stride0;
+  }
+  pitch = P.lv[l].pitch;
+  return I.pyr + (size_t)f * P.pyrFrameStride + P.lv[l].off;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1  pyramid level l from level l-1: cv::resize INTER_LINEAR, 11-bit fixed point
+// (ComputePyramid @0x70430, resize call @0x70b07; arithmetic SURVEY B.1).
+// One thread = 4 horizontally adjacent output pixels (one uchar4 store).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ OrbParams P, OrbImages I, int l,
+                                                const int* __restrict__ coef) {
+  const OrbLevel& D = P.lv[l];
+  const int f = blockIdx.z;
+  const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x4 >= D.w || y >= D.h) return;
+  int sp;
+  const uint8_t* S = level_ptr(P, I, f, l - 1, sp);
+  const int sh = P.lv[l - 1].h;
+  // tables: xofs[dw], xa[dw] (c0 | c1<<16), yofs[dh], ya[dh]
+  const int* xofs = coef + D.coefOff;
+  const int* xa = xofs + D.w;
+  const int* yofs = xa + D.w;
+  const int* ya = yofs + D.h;
+  const int sy = __ldg(yofs + y);
+  const int yab = __ldg(ya + y);
+  const int b0 = (short)(yab & 0xffff), b1 = yab >> 16;
+  const uint8_t* S0 = S + (size_t)sy * sp;
+  const uint8_t* S1 = S + (size_t)min(sy + 1, sh - 1) * sp;
+  uint32_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = min(x4 + i, D.w - 1);
+    const int sx = __ldg(xofs + x);
+    const int xab = __ldg(xa + x);
+    const int a0 = (short)(xab & 0xffff), a1 = xab >> 16;
+    int t0 = S0[sx] * a0, t1 = S1[sx] * a0;
+    if (a1) {
+      t0 += S0[sx + 1] * a1;
+      t1 += S1[sx + 1] * a1;
+    }
+    const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+    out |= (uint32_t)(v & 0xff) << (8 * i);
+  }
+  uint8_t* Dp = I.pyr + (size_t)f * P.pyrFrameStride + D.off + (size_t)y * D.pitch + x4;
+  *reinterpret_cast<uint32_t*>(Dp) = out;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2  per-cell FAST-9 + 3x3 NMS + empty-cell retry (ComputeKeyPointsOctTree FAST stage
+// @0x75fa0-0x76890; cv::FAST call sites @0x763d4 / @0x76753; arithmetic SURVEY B.3).
+// One warp = one 30-px cell (with its 3-px dead border).  The cell tile is staged in shared
+// memory; pixels that pass the 4-point quick test at minThFAST are warp-compacted into a queue
+// so the full 16-arc score is evaluated with all lanes busy.
+//
+// Arc score s = max over the 16 arcs of 9 contiguous circle pixels of min|v-p| (better polarity).
+// corner(th) <=> s > th, response = s-1.  NMS(th) = strict 3x3 local maxima of the raw s map
+// with s > th (neighbours below th count as 0 in OpenCV, which is < s either way), so the local
+// maxima are found once and the threshold only selects among them.
+//
+// Candidate record (64 bit): [63:56] response+1 (=s), [55:28] list-order key, [27:14] Y, [13:0] X
+// (X, Y border-local).  key = ((cellRow*256 + cellCol)*64 + yLocal)*64 + xLocal reproduces the
+// reference list order (cell-major, then FAST's row-major) without ordered writes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams P, OrbImages I,
+                                              unsigned long long* __restrict__ cand, int* __restrict__ candCount,
+                                              int* __restrict__ status) {
+  extern __shared__ uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cell = blockIdx.x * 8 + warp;
+  const int f = blockIdx.y;
+  if (cell >= P.totalCells) return;
+  int l = 0;
+  while (l + 1 < P.nlevels && cell >= P.lv[l + 1].cellBase) ++l;
+  const OrbLevel& L = P.lv[l];
+  const int ci = (cell - L.cellBase) / L.nCols, cj = (cell - L.cellBase) % L.nCols;
+  const int iniY = ORB_MINB + ci * L.hCell, iniX = ORB_MINB + cj * L.wCell;
+  if (iniY >= L.maxBorderY - 3 || iniX >= L.maxBorderX - 6) return;
+  const int pw = min(iniX + L.wCell + 6, L.maxBorderX) - iniX;
+  const int ph = min(iniY + L.hCell + 6, L.maxBorderY) - iniY;
+  if (pw < 7 || ph < 7) return;
+
+  const int pp = P.patchPitch;
+  const int tileBytes = pp * P.patchRows;
+  uint8_t* patch = smem + (size_t)warp * (2 * tileBytes + 128);
+  uint8_t* score = patch + tileBytes;
+  unsigned short* queue = reinterpret_cast<unsigned short*>(score + tileBytes);  // 64 entries
+
+  int sp;
+  const uint8_t* S = level_ptr(P, I, f, l, sp);
+  S += (size_t)iniY * sp + iniX;
+  for (int i = lane; i < pw * ph; i += 32) {
+    const int y = i / pw, x = i - y * pw;
+    patch[y * pp + x] = S[(size_t)y * sp + x];
+  }
+  for (int i = lane; i < tileBytes / 4; i += 32) reinterpret_cast<uint32_t*>(score)[i] = 0;
+  __syncwarp();
+
+  const int dw = pw - 6, dh = ph - 6, npx = dw * dh;
+  const int th0 = P.minTh;
+  int qn = 0;
+  for (int base = 0; base < npx; base += 32) {
+    const int i = base + lane;
+    bool pass = false;
+    int pos = 0;
+    if (i < npx) {
+      const int y = i / dw + 3, x = i - (y - 3) * dw + 3;
+      pos = y * pp + x;
+      const uint8_t* p = patch + pos;
+      const int v = p[0];
+      const bool a = abs(v - p[3 * pp]) > th0 || abs(v - p[-3 * pp]) > th0;
+      const bool b = abs(v - p[3]) > th0 || abs(v - p[-3]) > th0;
+      pass = a && b;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (pass) queue[qn + __popc(m & ((1u << lane) - 1))] = (unsigned short)pos;
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32) {
+      const int q = queue[qn - 32 + lane];
+      const int s = fast_arc_score(patch + q, pp);
+      score[q] = (uint8_t)s;
+      qn -= 32;
+    }
+    __syncwarp();
+  }
+  if (lane < qn) {
+    const int q = queue[lane];
+    score[q] = (uint8_t)fast_arc_score(patch + q, pp);
+  }
+  __syncwarp();
+
+  // local maxima of the raw score map; flags (score of maxima, else 0) overwrite the patch tile
+  int nHi = 0, nLo = 0;
+  for (int base = 0; base < npx; base += 32) {
+    const int i = base + lane;
+    int keep = 0;
+    int pos = 0;
+    if (i < npx) {
+      const int y = i / dw + 3, x = i - (y - 3) * dw + 3;
+      pos = y * pp + x;
+      const uint8_t* s = score + pos;
+      const int c = s[0];
+      if (c > th0) {
+        const int m = max(max(max(s[-pp - 1], s[-pp]), max(s[-pp + 1], s[-1])),
+                          max(max(s[1], s[pp - 1]), max(s[pp], s[pp + 1])));
+        if (c > m) keep = c;
+      }
+    }
+    if (i < npx) patch[pos] = (uint8_t)keep;  // safe: the patch tile is no longer read as pixels
+    nHi += __popc(__ballot_sync(0xffffffffu, keep > P.iniTh));
+    nLo += __popc(__ballot_sync(0xffffffffu, keep > 0));
+  }
+  __syncwarp();
+  const int thSel = nHi > 0 ? P.iniTh : th0;
+  const int nOut = nHi > 0 ? nHi : nLo;
+  if (nOut == 0) return;
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(candCount + f * ORB_MAXL + l, nOut);
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  if (slot + nOut > L.candCap) {
+    if (lane == 0) atomicMax(status, PLSLAM_ERR_OVERFLOW);
+    return;
+  }
+  unsigned long long* out = cand + (size_t)f * P.candFrameStride + L.candOff + slot;
+  int wr = 0;
+  for (int base = 0; base < npx; base += 32) {
+    const int i = base + lane;
+    int keep = 0, x = 0, y = 0;
+    if (i < npx) {
+      y = i / dw + 3;
+      x = i - (y - 3) * dw + 3;
+      keep = patch[y * pp + x];
+    }
+    const bool emit = keep > thSel;
+    const unsigned m = __ballot_sync(0xffffffffu, emit);
+    if (emit) {
+      const unsigned key = (((unsigned)(ci * 256 + cj) * 64u + (unsigned)y) * 64u + (unsigned)x);
+      const unsigned X = x + cj * L.wCell, Y = y + ci * L.hCell;
+      out[wr + __popc(m & ((1u << lane) - 1))] =
+          ((unsigned long long)keep << 56) | ((unsigned long long)key << 28) | ((unsigned long long)Y << 14) | X;
+    }
+    wr += __popc(m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3  DistributeOctTree (@0x73c60) + DivideNode (@0x70c60): one CTA per (frame, level).
+// The std::list of nodes is kept as an array in list order (index == position); every pass
+// rebuilds it: children of the divided nodes are "push_front"ed in division order (so they end
+// reversed at the head) and untouched nodes follow in their old order.  A full pass divides all
+// expandable nodes in list order; the finishing phase divides them in (size, creation seq)
+// descending order and stops at the first prefix that reaches N nodes — all divisions are
+// independent, only the cut depends on the running count, so it is a prefix sum.
+// Tie-break pinned to creation sequence (the reference compares heap addresses, @0x74d74).
+// ------------------------------------------------------------------------------------------
+struct QtNode {
+  short x0, y0, x1, y1;
+};
+
+__global__ void __launch_bounds__(256) k_quadtree(const __grid_constant__ OrbParams P,
+                                                  const unsigned long long* __restrict__ cand,
+                                                  const int* __restrict__ candCount, unsigned short* __restrict__ knodeAll,
+                                                  uint2* __restrict__ lvlKp, int* __restrict__ lvlCnt) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int l = blockIdx.x, f = blockIdx.y, t = threadIdx.x, T = blockDim.x;
+  const OrbLevel& L = P.lv[l];
+  const int NC = P.nodeCap;
+  // shared layout
+  QtNode* box[2];
+  int* cnt[2];
+  box[0] = reinterpret_cast<QtNode*>(smem);
+  box[1] = box[0] + NC;
+  cnt[0] = reinterpret_cast<int*>(box[1] + NC);
+  cnt[1] = cnt[0] + NC;
+  int* seq[2];
+  seq[0] = cnt[1] + NC;
+  seq[1] = seq[0] + NC;
+  int* childCnt = seq[1] + NC;      // [NC][4]; later reused as child new position
+  int* newPos = childCnt + 4 * NC;  // new index of a non-divided node / scan scratch
+  int* ord = newPos + NC;           // division order (node indices)
+  int* pushOff = ord + NC;          // per order slot: exclusive count of pushed children
+  int* expOff = pushOff + NC;       // per order slot: exclusive count of pushed children with cnt>1
+  int* divRank = expOff + NC;       // per node: rank in division order or -1
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(divRank + NC + (NC & 1));
+  __shared__ int warpTmp[33];
+  __shared__ int sh_n, sh_D, sh_mode, sh_done, sh_E;
+
+  const int nk = min(candCount[f * ORB_MAXL + l], L.candCap);
+  const unsigned long long* K = cand + (size_t)f * P.candFrameStride + L.candOff;
+  unsigned short* knode = knodeAll + (size_t)f * P.candFrameStride + L.candOff;
+  const int N = L.quota;
+  int* outCnt = lvlCnt + f * ORB_MAXL + l;
+  if (nk == 0) {
+    if (t == 0) *outCnt = 0;
+    return;
+  }
+
+  // roots
+  const int nIni = L.nIni;
+  const int H = L.maxBorderY - ORB_MINB;
+  for (int i = t; i < NC; i += T) { cnt[0][i] = 0; cnt[1][i] = 0; }
+  __syncthreads();
+  for (int k = t; k < nk; k += T) {
+    const int X = (int)(K[k] & 0x3fff);
+    int r = (int)__fdiv_rn((float)X, L.hX);
+    r = min(r, nIni - 1);
+    knode[k] = (unsigned short)r;
+    atomicAdd(&cnt[0][r], 1);
+  }
+  __syncthreads();
+  if (t == 0) {
+    // erase empty roots (list order preserved); nIni is 1..few
+    int n = 0;
+    for (int i = 0; i < nIni; ++i) {
+      const int c = cnt[0][i];
+      newPos[i] = c ? n : -1;
+      if (c) {
+        QtNode b;
+        b.x0 = (short)(int)(L.hX * (float)i);
+        b.x1 = (short)(int)(L.hX * (float)(i + 1));
+        b.y0 = 0;
+        b.y1 = (short)H;
+        box[1][n] = b;
+        cnt[1][n] = c;
+        ++n;
+      }
+    }
+    sh_n = n;
+    sh_mode = 0;
+    sh_done = 0;
+  }
+  __syncthreads();
+  if (nIni > 1) {
+    for (int k = t; k < nk; k += T) knode[k] = (unsigned short)newPos[knode[k]];
+  }
+  int cur = 1;  // buffer holding the current list
+  __syncthreads();
+
+  while (true) {
+    const int n = sh_n, mode = sh_mode;
+    QtNode* B = box[cur];
+    int* C = cnt[cur];
+    int* SQ = seq[cur];
+    // A. division order
+    if (mode == 0) {
+      for (int i = t; i < n; i += T) newPos[i] = C[i] > 1 ? 1 : 0;
+      __syncthreads();
+      const int E = block_scan_excl(newPos, n, warpTmp);
+      for (int i = t; i < n; i += T) {
+        if (C[i] > 1) { ord[newPos[i]] = i; divRank[i] = newPos[i]; } else divRank[i] = -1;
+      }
+      if (t == 0) sh_E = E;
+    } else {
+      // rank by (size desc, seq desc) among expandable nodes
+      for (int i = t; i < n; i += T) {
+        int r = -1;
+        const int ci = C[i];
+        if (ci > 1) {
+          const int si = SQ[i];
+          r = 0;
+          for (int j = 0; j < n; ++j) {
+            const int cj = C[j];
+            if (cj > 1 && (cj > ci || (cj == ci && SQ[j] > si))) ++r;
+          }
+          ord[r] = i;
+        }
+        divRank[i] = r;
+      }
+      if (t == 0) {
+        int E = 0;
+        for (int i = 0; i < n; ++i) E += C[i] > 1;
+        sh_E = E;
+      }
+    }
+    for (int i = t; i < 4 * n; i += T) childCnt[i] = 0;
+    __syncthreads();
+    const int E = sh_E;
+    // B. quadrant of every key of an expandable node
+    for (int k = t; k < nk; k += T) {
+      const int nd = knode[k];
+      if (C[nd] > 1) {
+        const unsigned long long r = K[k];
+        const int X = (int)(r & 0x3fff), Y = (int)((r >> 14) & 0x3fff);
+        const QtNode b = B[nd];
+        const int mx = b.x0 + (b.x1 - b.x0 + 1) / 2, my = b.y0 + (b.y1 - b.y0 + 1) / 2;
+        const int q = (X < mx ? 0 : 1) + (Y < my ? 0 : 2);
+        atomicAdd(&childCnt[4 * nd + q], 1);
+      }
+    }
+    __syncthreads();
+    // C. pushes per division slot, cut for the finishing phase
+    for (int e = t; e < E; e += T) {
+      const int nd = ord[e];
+      int ne = 0, nx = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = childCnt[4 * nd + q];
+        ne += c > 0;
+        nx += c > 1;
+      }
+      pushOff[e] = ne;
+      expOff[e] = nx;
+    }
+    __syncthreads();
+    block_scan_excl(pushOff, E, warpTmp);
+    if (t == 0) {
+      int D = E;
+      if (mode == 1) {
+        // smallest prefix with n + sum(pushed - 1) >= N
+        for (int e = 0; e < E; ++e) {
+          const int nd = ord[e];
+          int ne = 0;
+          for (int q = 0; q < 4; ++q) ne += childCnt[4 * nd + q] > 0;
+          const int after = n + (pushOff[e] + ne) - (e + 1);
+          if (after >= N) { D = e + 1; break; }
+        }
+      }
+      sh_D = D;
+    }
+    __syncthreads();
+    const int D = sh_D;
+    block_scan_excl(expOff, D, warpTmp);
+    // total pushes / expandable children among the first D slots
+    int Ctot, Etot;
+    {
+      const int nd = ord[D - 1 < 0 ? 0 : D - 1];
+      int ne = 0, nx = 0;
+      for (int q = 0; q < 4; ++q) {
+        const int c = childCnt[4 * nd + q];
+        ne += c > 0;
+        nx += c > 1;
+      }
+      Ctot = D > 0 ? pushOff[D - 1] + ne : 0;
+      Etot = D > 0 ? expOff[D - 1] + nx : 0;
+    }
+    // D. positions of untouched nodes
+    for (int i = t; i < n; i += T) newPos[i] = (divRank[i] < 0 || divRank[i] >= D) ? 1 : 0;
+    __syncthreads();
+    const int keepTot = block_scan_excl(newPos, n, warpTmp);
+    QtNode* B2 = box[cur ^ 1];
+    int* C2 = cnt[cur ^ 1];
+    int* SQ2 = seq[cur ^ 1];
+    for (int i = t; i < n; i += T) {
+      const int r = divRank[i];
+      if (r < 0 || r >= D) {
+        const int np = Ctot + newPos[i];
+        newPos[i] = np;
+        B2[np] = B[i];
+        C2[np] = C[i];
+        SQ2[np] = SQ[i];
+      } else {
+        const QtNode b = B[i];
+        const int mx = b.x0 + (b.x1 - b.x0 + 1) / 2, my = b.y0 + (b.y1 - b.y0 + 1) / 2;
+        int p = pushOff[r], x = expOff[r];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = childCnt[4 * i + q];
+          if (c > 0) {
+            const int np = Ctot - 1 - p;
+            QtNode cb;
+            cb.x0 = (q & 1) ? (short)mx : b.x0;
+            cb.x1 = (q & 1) ? b.x1 : (short)mx;
+            cb.y0 = (q & 2) ? (short)my : b.y0;
+            cb.y1 = (q & 2) ? b.y1 : (short)my;
+            B2[np] = cb;
+            C2[np] = c;
+            SQ2[np] = c > 1 ? x : -1;
+            childCnt[4 * i + q] = np;  // reuse as new position
+            ++p;
+            x += c > 1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // E. relabel keys
+    for (int k = t; k < nk; k += T) {
+      const int nd = knode[k];
+      const int r = divRank[nd];
+      if (r < 0 || r >= D) {
+        knode[k] = (unsigned short)newPos[nd];
+      } else {
+        const unsigned long long rec = K[k];
+        const int X = (int)(rec & 0x3fff), Y = (int)((rec >> 14) & 0x3fff);
+        const QtNode b = B[nd];
+        const int mx = b.x0 + (b.x1 - b.x0 + 1) / 2, my = b.y0 + (b.y1 - b.y0 + 1) / 2;
+        const int q = (X < mx ? 0 : 1) + (Y < my ? 0 : 2);
+        knode[k] = (unsigned short)childCnt[4 * nd + q];
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      const int n2 = Ctot + keepTot;
+      sh_n = n2;
+      if (n2 >= N || n2 == n) sh_done = 1;
+      else if (mode == 0 && n2 + 3 * Etot > N) sh_mode = 1;
+    }
+    cur ^= 1;
+    __syncthreads();
+    if (sh_done) break;
+  }
+
+  // best key per node: max response, first in list order on ties (cmova @0x75a77-0x75a7f)
+  const int n = sh_n;
+  for (int i = t; i < n; i += T) best[i] = 0ull;
+  __syncthreads();
+  for (int k = t; k < nk; k += T) {
+    const unsigned long long r = K[k];
+    const unsigned long long v = ((r >> 56) << 28) | (0x0fffffffull - ((r >> 28) & 0x0fffffffull));
+    atomicMax(&best[knode[k]], v);
+  }
+  __syncthreads();
+  uint2* out = lvlKp + (size_t)f * P.maxKp + L.kpOff;
+  for (int i = t; i < n; i += T) {
+    const unsigned long long v = best[i];
+    const unsigned key = 0x0fffffffu - (unsigned)(v & 0x0fffffffull);
+    const int s = (int)(v >> 28);
+    const int xl = key & 63, yl = (key >> 6) & 63, cj = (key >> 12) & 255, ci = key >> 20;
+    const int X = xl + cj * L.wCell + ORB_MINB, Y = yl + ci * L.hCell + ORB_MINB;
+    out[i] = make_uint2((unsigned)X | ((unsigned)Y << 16), (unsigned)(s - 1));
+  }
+  if (t == 0) *outCnt = n;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4  7x7 Gaussian blur, sigma 2, BORDER_REFLECT_101, on the borderless level (GaussianBlur call
+// @0x77487; arithmetic SURVEY B.2): dst = (sum_y sum_x k[y]k[x]p + 32768) >> 16.
+// Tile 128x16 per CTA; the horizontal pass result (<= 255*256, fits u16) is kept in shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int BT_W = 128, BT_H = 16;
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams P, OrbImages I,
+                                              const int* __restrict__ lvlCnt) {
+  __shared__ uint8_t raw[BT_H + 6][BT_W + 8];
+  __shared__ unsigned short hs[BT_H + 6][BT_W];
+  const int f = blockIdx.y;
+  int tile = blockIdx.x;
+  int l = 0;
+  while (l + 1 < P.nlevels && tile >= P.lv[l + 1].tileBase) ++l;
+  if (lvlCnt[f * ORB_MAXL + l] == 0) return;  // the reference blurs only levels with keypoints
+  const OrbLevel& L = P.lv[l];
+  tile -= L.tileBase;
+  const int tx = (tile % L.tilesX) * BT_W, ty = (tile / L.tilesX) * BT_H;
+  int sp;
+  const uint8_t* S = level_ptr(P, I, f, l, sp);
+  const int w = L.w, h = L.h;
+  for (int i = threadIdx.x; i < (BT_H + 6) * (BT_W + 6); i += 256) {
+    const int yy = i / (BT_W + 6), xx = i - yy * (BT_W + 6);
+    int gx = tx + xx - 3, gy = ty + yy - 3;
+    gx = gx < 0 ? -gx : (gx >= w ? 2 * (w - 1) - gx : gx);
+    gy = gy < 0 ? -gy : (gy >= h ? 2 * (h - 1) - gy : gy);
+    gx = max(0, min(gx, w - 1));
+    gy = max(0, min(gy, h - 1));
+    raw[yy][xx] = S[(size_t)gy * sp + gx];
+  }
+  __syncthreads();
+  const int k0 = P.blurk[0], k1 = P.blurk[1], k2 = P.blurk[2], k3 = P.blurk[3], k4 = P.blurk[4], k5 = P.blurk[5],
+            k6 = P.blurk[6];
+  for (int i = threadIdx.x; i < (BT_H + 6) * BT_W; i += 256) {
+    const int yy = i / BT_W, xx = i - yy * BT_W;
+    const uint8_t* r = &raw[yy][xx];
+    hs[yy][xx] = (unsigned short)(k0 * r[0] + k1 * r[1] + k2 * r[2] + k3 * r[3] + k4 * r[4] + k5 * r[5] + k6 * r[6]);
+  }
+  __syncthreads();
+  uint8_t* Dst = I.blurred + (size_t)f * P.pyrFrameStride + L.off;
+  for (int i = threadIdx.x; i < BT_H * BT_W / 4; i += 256) {
+    const int yy = i / (BT_W / 4), x4 = (i - yy * (BT_W / 4)) * 4;
+    const int gy = ty + yy, gx = tx + x4;
+    if (gy >= h || gx >= w) continue;
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x4 + j;
+      const int a = 32768 + k0 * hs[yy][x] + k1 * hs[yy + 1][x] + k2 * hs[yy + 2][x] + k3 * hs[yy + 3][x] +
+                    k4 * hs[yy + 4][x] + k5 * hs[yy + 5][x] + k6 * hs[yy + 6][x];
+      out |= (uint32_t)((a >> 16) & 0xff) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t*>(Dst + (size_t)gy * L.pitch + gx) = out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5  IC_Angle (@0x6fb10) + computeOrbDescriptor (@0x777a8-0x77c72) + keypoint rescale
+// (@0x77cb1-0x77d10): one warp per keypoint.  Orientation: lane = column u in [-15,15], loop
+// over rows (coalesced 31-byte row reads), integer moments reduced by shuffles, then
+// cv::fastAtan2's float polynomial evaluated without FMA contraction.  Descriptor: lane = output
+// byte; its 16 pattern points are rotated with the pinned sin/cos (double Cody-Waite + fdlibm
+// kernels, every op individually rounded) and the FMA form of the shipped binary (@0x77888-0x778a7).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_dev(float y, float x) {
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
+              p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+  const float eps = (float)2.2204460492503131e-16;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+__device__ __forceinline__ void orb_sincos_dev(float x, float* s_out, float* c_out) {
+  const double xd = (double)x;
+  const double kf = rint(__dmul_rn(xd, 0.63661977236758134308));
+  const int k = (int)kf;
+  double r = __dsub_rn(xd, __dmul_rn(kf, 1.57079632673412561417e+00));
+  r = __dsub_rn(r, __dmul_rn(kf, 6.07710050650619224932e-11));
+  const double z = __dmul_rn(r, r);
+  double ps = __dadd_rn(-2.50507602534068634195e-08, __dmul_rn(z, 1.58969099521155010221e-10));
+  ps = __dadd_rn(2.75573137070700676789e-06, __dmul_rn(z, ps));
+  ps = __dadd_rn(-1.98412698298579493134e-04, __dmul_rn(z, ps));
+  ps = __dadd_rn(8.33333333332248946124e-03, __dmul_rn(z, ps));
+  ps = __dadd_rn(-1.66666666666666324348e-01, __dmul_rn(z, ps));
+  const double sn = __dadd_rn(r, __dmul_rn(__dmul_rn(r, z), ps));
+  double pc = __dadd_rn(2.08757232129817482790e-09, __dmul_rn(z, -1.13596475577881948265e-11));
+  pc = __dadd_rn(-2.75573143513906633035e-07, __dmul_rn(z, pc));
+  pc = __dadd_rn(2.48015872894767294178e-05, __dmul_rn(z, pc));
+  pc = __dadd_rn(-1.38888888888741095749e-03, __dmul_rn(z, pc));
+  pc = __dadd_rn(4.16666666666666019037e-02, __dmul_rn(z, pc));
+  const double cs = __dadd_rn(__dsub_rn(1.0, __dmul_rn(0.5, z)), __dmul_rn(__dmul_rn(z, z), pc));
+  double s, c;
+  switch (k & 3) {
+    case 0: s = sn; c = cs; break;
+    case 1: s = cs; c = -sn; break;
+    case 2: s = -sn; c = -cs; break;
+    default: s = -cs; c = sn; break;
+  }
+  *s_out = (float)s;
+  *c_out = (float)c;
+}
+
+__global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ OrbParams P, OrbImages I,
+                                                     const uint2* __restrict__ lvlKp, const int* __restrict__ lvlCnt,
+                                                     plslam_keypoint_t* __restrict__ kps, uint8_t* __restrict__ desc,
+                                                     int capacity, int* __restrict__ counts) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.y;
+  const int g = blockIdx.x * 8 + warp;
+  // level of keypoint g (level-major output order)
+  int l = 0, base = 0, total = 0;
+  {
+    int acc = 0;
+    bool found = false;
+    for (int i = 0; i < P.nlevels; ++i) {
+      const int c = lvlCnt[f * ORB_MAXL + i];
+      if (!found && g < acc + c) { l = i; base = acc; found = true; }
+      acc += c;
+    }
+    total = acc;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[f] = total;
+    if (!found) return;
+  }
+  const OrbLevel& L = P.lv[l];
+  const uint2 rec = lvlKp[(size_t)f * P.maxKp + L.kpOff + (g - base)];
+  const int X = rec.x & 0xffff, Y = rec.x >> 16;
+
+  // --- orientation on the unblurred level ---
+  int sp;
+  const uint8_t* S = level_ptr(P, I, f, l, sp);
+  const uint8_t* center = S + (size_t)Y * sp + X;
+  int m10 = 0, m01 = 0;
+  {
+    const int u = lane - ORB_HALF_PATCH;  // lanes 0..30
+    const int au = abs(u);
+    if (lane < 31) {
+#pragma unroll 1
+      for (int v = -ORB_HALF_PATCH; v <= ORB_HALF_PATCH; ++v) {
+        if (au <= P.umax[abs(v)]) {
+          const int p = center[v * sp + u];
+          m10 += u * p;
+          m01 += v * p;
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, d);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+    }
+  }
+  const float angle = fast_atan2_dev((float)m01, (float)m10);
+
+  // --- descriptor on the blurred level ---
+  float sn, cs;
+  orb_sincos_dev(__fmul_rn(angle, 0.017453292f), &sn, &cs);
+  const uint8_t* Bc = I.blurred + (size_t)f * P.pyrFrameStride + L.off + (size_t)Y * L.pitch + X;
+  const int bp = L.pitch;
+  int val = 0;
+  // lane's 16 pattern points = 32 signed bytes
+  uint32_t pw[8];
+  {
+    const uint4 a = reinterpret_cast<const uint4*>(g_pattern)[lane * 2];
+    const uint4 b = reinterpret_cast<const uint4*>(g_pattern)[lane * 2 + 1];
+    pw[0] = a.x; pw[1] = a.y; pw[2] = a.z; pw[3] = a.w;
+    pw[4] = b.x; pw[5] = b.y; pw[6] = b.z; pw[7] = b.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int tv[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t h = pw[k] >> (16 * j);
+      const float px = (float)(int)(int8_t)(h & 0xff), py = (float)(int)(int8_t)((h >> 8) & 0xff);
+      const int r = cv_round(__fmaf_rn(px, sn, __fmul_rn(py, cs)));
+      const int c = cv_round(__fmaf_rn(px, cs, -__fmul_rn(py, sn)));
+      tv[j] = Bc[r * bp + c];
+    }
+    val |= (tv[0] < tv[1]) << k;
+  }
+  if (g < capacity) {
+    desc[((size_t)f * capacity + g) * 32 + lane] = (uint8_t)val;
+    if (lane < 7) {
+      float fx = (float)X, fy = (float)Y;
+      if (l != 0) { fx = __fmul_rn(fx, L.scale); fy = __fmul_rn(fy, L.scale); }
+      uint32_t w;
+      switch (lane) {
+        case 0: w = __float_as_uint(fx); break;
+        case 1: w = __float_as_uint(fy); break;
+        case 2: w = __float_as_uint(L.patchSize); break;
+        case 3: w = __float_as_uint(angle); break;
+        case 4: w = __float_as_uint((float)rec.y); break;
+        case 5: w = (uint32_t)l; break;
+        default: w = 0xffffffffu; break;
+      }
+      reinterpret_cast<uint32_t*>(kps + (size_t)f * capacity + g)[lane] = w;
+    }
+  }
+}
+
+inline int cvRoundf_host(float v) { return (int)lrintf(v); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+
+// ORBextractor::ORBextractor (ORBextractor.h:51-52, @0x73050)
+OrbExtractor::OrbExtractor(int nf, float sf, int nl, int ini, int mn)
+    : nfeatures(nf), nlevels(nl), iniThFAST(ini), minThFAST(mn), scaleFactor((double)sf) {
+  mvScaleFactor.resize(nl);
+  mvLevelSigma2.resize(nl);
+  mvInvScaleFactor.resize(nl);
+  mvInvLevelSigma2.resize(nl);
+  mvScaleFactor[0] = 1.f;
+  mvLevelSigma2[0] = 1.f;
+  for (int i = 1; i < nl; ++i) {
+    mvScaleFactor[i] = (float)((double)mvScaleFactor[i - 1] * scaleFactor);
+    mvLevelSigma2[i] = mvScaleFactor[i] * mvScaleFactor[i];
+  }
+  for (int i = 0; i < nl; ++i) {
+    mvInvScaleFactor[i] = 1.f / mvScaleFactor[i];
+    mvInvLevelSigma2[i] = 1.f / mvLevelSigma2[i];
+  }
+  mnFeaturesPerLevel.resize(nl);
+  const float factor = (float)(1.0 / scaleFactor);
+  float nDesired = (float)nf * (1.f - factor) / (1.f - (float)std::pow((double)factor, (double)nl));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; ++l) {
+    mnFeaturesPerLevel[l] = cvRoundf_host(nDesired);
+    sum += mnFeaturesPerLevel[l];
+    nDesired *= factor;
+  }
+  mnFeaturesPerLevel[nl - 1] = std::max(nf - sum, 0);
+  umax.assign(ORB_HALF_PATCH + 1, 0);
+  const int vmax = (int)std::floor(ORB_HALF_PATCH * std::sqrt(2.f) / 2 + 1);
+  const int vmin = (int)std::ceil(ORB_HALF_PATCH * std::sqrt(2.f) / 2);
+  const double hp2 = ORB_HALF_PATCH * ORB_HALF_PATCH;
+  for (int v = 0; v <= vmax; ++v) umax[v] = (int)lrint(std::sqrt(hp2 - v * v));
+  for (int v = ORB_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+    while (umax[v0] == umax[v0 + 1]) ++v0;
+    umax[v] = v0;
+    ++v0;
+  }
+}
+
+OrbExtractor::~OrbExtractor() {
+  DevBuf* all[] = {&pyr, &blurred, &coef, &cand, &candCount, &knode, &lvlKp, &lvlCnt, &status,
+                   &stageIn, &stageKps, &stageDesc, &stageCnt};
+  for (DevBuf* b : all) b->release();
+  if (ownStream) cudaStreamDestroy(ownStream);
+  if (pinnedStatus) cudaFreeHost(pinnedStatus);
+}
+
+int OrbExtractor::set_blur_kernel(const int32_t k[7]) {
+  int s = 0;
+  for (int i = 0; i < 7; ++i) s += k[i];
+  PL_CHECK_ARG(s == 256);
+  for (int i = 0; i < 7; ++i) { blurk[i] = k[i]; P.blurk[i] = k[i]; }
+  return PLSLAM_OK;
+}
+
+int OrbExtractor::max_keypoints() const {
+  int s = 0;
+  for (int q : mnFeaturesPerLevel) s += q + 3;
+  return s;
+}
+
+int OrbExtractor::level_size(int level, int* w, int* h) const {
+  PL_CHECK_ARG(level >= 0 && level < nlevels && cfgW > 0);
+  *w = P.lv[level].w;
+  *h = P.lv[level].h;
+  return PLSLAM_OK;
+}
+
+// Level geometry, FAST cell grid, quad-tree roots, resize tables, workspace (per image size / batch).
+int OrbExtractor::configure(int W, int H, int batch) {
+  if (W == cfgW && H == cfgH && batch <= cfgB) return PLSLAM_OK;
+  PL_CHECK_ARG(nlevels >= 1 && nlevels <= ORB_MAXL);
+  PL_CHECK_ARG(W <= 16000 && H <= 16000);
+  if (device < 0) {
+    PL_CUDA(cudaGetDevice(&device));
+    int8_t pat[1024];
+    for (int i = 0; i < 1024; ++i) pat[i] = (int8_t)h_pattern[i];
+    PL_CUDA(cudaMemcpyToSymbol(g_pattern, pat, sizeof(pat)));
+    PL_CUDA(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
+    PL_CUDA(cudaMallocHost(&pinnedStatus, 64));
+  }
+  std::memset(&P, 0, sizeof(P));
+  P.nlevels = nlevels;
+  P.iniTh = iniThFAST;
+  P.minTh = minThFAST;
+  for (int i = 0; i < 16; ++i) P.umax[i] = umax[i];
+  for (int i = 0; i < 7; ++i) P.blurk[i] = blurk[i];
+  size_t off = 0, candOff = 0, coefOff = 0;
+  int cellBase = 0, tileBase = 0, kpOff = 0, maxQuota = 0, maxPw = 7, maxPh = 7;
+  std::vector<int> coefHost;
+  for (int l = 0; l < nlevels; ++l) {
+    OrbLevel& L = P.lv[l];
+    // ComputePyramid sizes (@0x7051e-0x705ba)
+    L.w = cvRoundf_host((float)W * mvInvScaleFactor[l]);
+    L.h = cvRoundf_host((float)H * mvInvScaleFactor[l]);
+    PL_CHECK_ARG(L.w >= 2 * ORB_EDGE + 1 && L.h >= 2 * ORB_EDGE + 1);
+    L.pitch = (int)align_up(L.w, 32);
+    L.off = off;
+    off += align_up((size_t)L.pitch * L.h, 256);
+    // FAST grid (@0x760c6-0x76196)
+    L.maxBorderX = L.w - ORB_EDGE + 3;
+    L.maxBorderY = L.h - ORB_EDGE + 3;
+    const float width = (float)(L.maxBorderX - ORB_MINB), height = (float)(L.maxBorderY - ORB_MINB);
+    L.nCols = (int)(width / 30.f);
+    L.nRows = (int)(height / 30.f);
+    if (L.nCols > 0 && L.nRows > 0) {
+      L.wCell = (int)std::ceil(width / L.nCols);
+      L.hCell = (int)std::ceil(height / L.nRows);
+    } else {
+      L.nCols = L.nRows = 0;
+      L.wCell = L.hCell = 1;
+    }
+    PL_CHECK_ARG(L.nCols < 256 && L.nRows < 256 && L.wCell + 6 <= 64 && L.hCell + 6 <= 64);
+    maxPw = std::max(maxPw, L.wCell + 6);
+    maxPh = std::max(maxPh, L.hCell + 6);
+    L.cellBase = cellBase;
+    cellBase += L.nCols * L.nRows;
+    // DistributeOctTree roots (@0x73cca-0x73d49)
+    L.quota = mnFeaturesPerLevel[l];
+    maxQuota = std::max(maxQuota, L.quota);
+    L.nIni = (int)std::round((float)(L.maxBorderX - ORB_MINB) / (L.maxBorderY - ORB_MINB));
+    PL_CHECK_ARG(L.nIni >= 1);  // the reference divides by zero for portrait images narrower than h/2
+    L.hX = (float)(L.maxBorderX - ORB_MINB) / L.nIni;
+    // strict 3x3 local maxima cannot be 8-adjacent: at most one per 2x2 block
+    L.candCap = ((L.w + 1) / 2) * ((L.h + 1) / 2);
+    L.candOff = candOff;
+    candOff += align_up((size_t)L.candCap, 32);
+    L.kpOff = kpOff;
+    kpOff += L.quota + 3;
+    L.tilesX = div_up(L.w, BT_W);
+    L.tileBase = tileBase;
+    tileBase += L.tilesX * div_up(L.h, BT_H);
+    L.scale = mvScaleFactor[l];
+    L.patchSize = (float)(int)(31.f * mvScaleFactor[l]);
+    if (l > 0) {
+      // resize tables: xofs, xa, yofs, ya
+      L.coefOff = coefOff;
+      const OrbLevel& S = P.lv[l - 1];
+      auto emit = [&](int ssize, int dsize) {
+        std::vector<int> ofs(dsize), ab(dsize);
+        const double scale = 1.0 / ((double)dsize / ssize);
+        for (int d = 0; d < dsize; ++d) {
+          float fx = (float)((d + 0.5) * scale - 0.5);
+          int s = (int)std::floor(fx);
+          fx -= s;
+          if (s < 0) { s = 0; fx = 0.f; }
+          if (s >= ssize - 1) { s = ssize - 1; fx = 0.f; }
+          const int c0 = cvRoundf_host((1.f - fx) * 2048.f), c1 = cvRoundf_host(fx * 2048.f);
+          ofs[d] = s;
+          ab[d] = (c0 & 0xffff) | (c1 << 16);
+        }
+        coefHost.insert(coefHost.end(), ofs.begin(), ofs.end());
+        coefHost.insert(coefHost.end(), ab.begin(), ab.end());
+      };
+      emit(S.w, L.w);
+      emit(S.h, L.h);
+      coefOff = coefHost.size();
+    }
+  }
+  P.totalCells = cellBase;
+  P.totalTiles = tileBase;
+  P.maxKp = kpOff;
+  P.nodeCap = std::max(maxQuota + 8, 16);
+  P.patchPitch = (int)align_up(maxPw, 4);
+  P.patchRows = maxPh;
+  P.pyrFrameStride = off;
+  P.candFrameStride = candOff;
+  PL_CHECK_ARG(P.nodeCap < 65535);
+
+  int rc;
+  const int B = std::max(batch, cfgB);
+  if ((rc = pyr.ensure(off * B))) return rc;
+  if ((rc = blurred.ensure(off * B))) return rc;
+  if ((rc = coef.ensure(std::max<size_t>(coefHost.size(), 1) * sizeof(int)))) return rc;
+  if (!coefHost.empty())
+    PL_CUDA(cudaMemcpy(coef.p, coefHost.data(), coefHost.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if ((rc = cand.ensure(candOff * B * sizeof(unsigned long long)))) return rc;
+  if ((rc = knode.ensure(candOff * B * sizeof(unsigned short)))) return rc;
+  if ((rc = candCount.ensure((size_t)B * ORB_MAXL * sizeof(int)))) return rc;
+  if ((rc = lvlCnt.ensure((size_t)B * ORB_MAXL * sizeof(int)))) return rc;
+  if ((rc = lvlKp.ensure((size_t)B * P.maxKp * sizeof(uint2)))) return rc;
+  if ((rc = status.ensure(sizeof(int)))) return rc;
+  cfgW = W;
+  cfgH = H;
+  cfgB = B;
+  return PLSLAM_OK;
+}
+
+static size_t quadtree_smem(int NC) {
+  // box[2], cnt[2], seq[2], childCnt[4], newPos, ord, pushOff, expOff, divRank, pad, best(u64)
+  return (size_t)NC * (2 * sizeof(QtNode) + 2 * 4 + 2 * 4 + 16 + 5 * 4) + 8 + (size_t)NC * 8;
+}
+
+int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int H, int pitch, size_t frame_stride,
+                                 plslam_keypoint_t* d_kps, uint8_t* d_desc, int capacity, int32_t* d_counts,
+                                 cudaStream_t st) {
+  PL_CHECK_ARG(d_images && d_kps && d_desc && d_counts);
+  PL_CHECK_ARG(batch >= 1 && batch <= 65535 && W > 0 && H > 0 && pitch >= W);
+  PL_CHECK_ARG(frame_stride >= (size_t)pitch * (H - 1) + W);
+  int rc = configure(W, H, batch);
+  if (rc) return rc;
+  if (capacity < P.maxKp) {
+    set_error("capacity %d < plslam_orb_max_keypoints() = %d", capacity, P.maxKp);
+    return PLSLAM_ERR_CAPACITY;
+  }
+  OrbImages I;
+  I.img0 = d_images;
+  I.pitch0 = pitch;
+  I.stride0 = frame_stride;
+  I.pyr = pyr.as<uint8_t>();
+  I.blurred = blurred.as<uint8_t>();
+  last_img0 = d_images;
+  last_pitch0 = pitch;
+  last_stride0 = frame_stride;
+  last_batch = batch;
+
+  PL_CUDA(cudaMemsetAsync(candCount.p, 0, (size_t)batch * ORB_MAXL * sizeof(int), st));
+  PL_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), st));
+  for (int l = 1; l < nlevels; ++l) {
+    dim3 grid(div_up(P.lv[l].w, 128), div_up(P.lv[l].h, 8), batch);
+    k_resize<<<grid, dim3(32, 8), 0, st>>>(P, I, l, coef.as<int>());
+  }
+  {
+    const size_t smem = 8 * (2 * (size_t)P.patchPitch * P.patchRows + 128);
+    static bool attr = false;
+    if (!attr) {
+      PL_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      PL_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    k_fast<<<dim3(div_up(P.totalCells, 8), batch), 256, smem, st>>>(P, I, cand.as<unsigned long long>(),
+                                                                    candCount.as<int>(), status.as<int>());
+  }
+  {
+    const size_t smem = quadtree_smem(P.nodeCap);
+    if (smem > 200 * 1024) {
+      set_error("nfeatures too large for the shared-memory quad-tree (%zu B)", smem);
+      return PLSLAM_ERR_INVALID;
+    }
+    k_quadtree<<<dim3(nlevels, batch), 256, smem, st>>>(P, cand.as<unsigned long long>(), candCount.as<int>(),
+                                                        knode.as<unsigned short>(), lvlKp.as<uint2>(), lvlCnt.as<int>());
+  }
+  k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, I, lvlCnt.as<int>());
+  k_orient_desc<<<dim3(div_up(P.maxKp, 8), batch), 256, 0, st>>>(P, I, lvlKp.as<uint2>(), lvlCnt.as<int>(), d_kps,
+                                                                 d_desc, capacity, d_counts);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int OrbExtractor::check_status(cudaStream_t st) {
+  PL_CUDA(cudaMemcpyAsync(pinnedStatus, status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaStreamSynchronize(st));
+  const int s = *reinterpret_cast<int*>(pinnedStatus);
+  if (s != PLSLAM_OK) set_error("device status %d (internal candidate buffer overflow)", s);
+  return s;
+}
+
+int OrbExtractor::extract_host(const uint8_t* images, int batch, int W, int H, int pitch, size_t frame_stride,
+                               plslam_keypoint_t* kps, uint8_t* desc, int capacity, int32_t* counts) {
+  PL_CHECK_ARG(images && kps && desc && counts && batch >= 1 && W > 0 && H > 0 && pitch >= W);
+  int rc = configure(W, H, batch);
+  if (rc) return rc;
+  const int cap = P.maxKp;
+  const size_t dpitch = align_up(W, 32), dstride = dpitch * H;
+  if ((rc = stageIn.ensure(dstride * batch))) return rc;
+  if ((rc = stageKps.ensure((size_t)batch * cap * sizeof(plslam_keypoint_t)))) return rc;
+  if ((rc = stageDesc.ensure((size_t)batch * cap * 32))) return rc;
+  if ((rc = stageCnt.ensure((size_t)batch * sizeof(int)))) return rc;
+  cudaStream_t st = ownStream;
+  if (frame_stride == (size_t)pitch * H) {
+    PL_CUDA(cudaMemcpy2DAsync(stageIn.p, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int f = 0; f < batch; ++f)
+      PL_CUDA(cudaMemcpy2DAsync(stageIn.as<uint8_t>() + f * dstride, dpitch, images + f * frame_stride, pitch, W, H,
+                                cudaMemcpyHostToDevice, st));
+  }
+  rc = extract_device(stageIn.as<uint8_t>(), batch, W, H, (int)dpitch, dstride, stageKps.as<plslam_keypoint_t>(),
+                      stageDesc.as<uint8_t>(), cap, stageCnt.as<int>(), st);
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpyAsync(counts, stageCnt.p, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if ((rc = check_status(st))) return rc;
+  for (int f = 0; f < batch; ++f) {
+    const int n = counts[f];
+    if (n > capacity) {
+      set_error("frame %d has %d keypoints, capacity %d", f, n, capacity);
+      return PLSLAM_ERR_CAPACITY;
+    }
+  }
+  if (capacity == cap) {
+    PL_CUDA(cudaMemcpyAsync(kps, stageKps.p, (size_t)batch * cap * sizeof(plslam_keypoint_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(desc, stageDesc.p, (size_t)batch * cap * 32, cudaMemcpyDeviceToHost, st));
+  } else {
+    for (int f = 0; f < batch; ++f) {
+      const int n = counts[f];
+      if (!n) continue;
+      PL_CUDA(cudaMemcpyAsync(kps + (size_t)f * capacity, stageKps.as<plslam_keypoint_t>() + (size_t)f * cap,
+                              (size_t)n * sizeof(plslam_keypoint_t), cudaMemcpyDeviceToHost, st));
+      PL_CUDA(cudaMemcpyAsync(desc + (size_t)f * capacity * 32, stageDesc.as<uint8_t>() + (size_t)f * cap * 32,
+                              (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  PL_CUDA(cudaStreamSynchronize(st));
+  return PLSLAM_OK;
+}
+
+int OrbExtractor::copy_level(int frame, int level, int which, uint8_t* out, size_t out_bytes) {
+  PL_CHECK_ARG(cfgW > 0 && frame >= 0 && frame < last_batch && level >= 0 && level < nlevels && out);
+  const OrbLevel& L = P.lv[level];
+  PL_CHECK_ARG(out_bytes >= (size_t)L.w * L.h);
+  const uint8_t* src;
+  size_t sp;
+  if (which == 0 && level == 0) {
+    src = last_img0 + (size_t)frame * last_stride0;
+    sp = last_pitch0;
+  } else {
+    src = (which ? blurred.as<uint8_t>() : pyr.as<uint8_t>()) + (size_t)frame * P.pyrFrameStride + L.off;
+    sp = L.pitch;
+  }
+  PL_CUDA(cudaDeviceSynchronize());
+  PL_CUDA(cudaMemcpy2D(out, L.w, src, sp, L.w, L.h, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int OrbExtractor::copy_candidates(int frame, int level, int32_t* xyr, int capacity, int* n_out) {
+  PL_CHECK_ARG(cfgW > 0 && frame >= 0 && frame < last_batch && level >= 0 && level < nlevels && n_out);
+  PL_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  PL_CUDA(cudaMemcpy(&n, candCount.as<int>() + frame * ORB_MAXL + level, sizeof(int), cudaMemcpyDeviceToHost));
+  *n_out = n;
+  if (n > capacity) return PLSLAM_ERR_CAPACITY;
+  if (n == 0) return PLSLAM_OK;
+  PL_CHECK_ARG(xyr);
+  std::vector<unsigned long long> rec(n);
+  PL_CUDA(cudaMemcpy(rec.data(), cand.as<unsigned long long>() + (size_t)frame * P.candFrameStride + P.lv[level].candOff,
+                     (size_t)n * 8, cudaMemcpyDeviceToHost));
+  std::sort(rec.begin(), rec.end(), [](unsigned long long a, unsigned long long b) {
+    return ((a >> 28) & 0x0fffffffull) < ((b >> 28) & 0x0fffffffull);
+  });
+  for (int i = 0; i < n; ++i) {
+    xyr[3 * i] = (int)(rec[i] & 0x3fff);
+    xyr[3 * i + 1] = (int)((rec[i] >> 14) & 0x3fff);
+    xyr[3 * i + 2] = (int)(rec[i] >> 56) - 1;
+  }
+  return PLSLAM_OK;
+}
+
+}  // namespace plslam

@@ -1,0 +1,179 @@
+"""Python harness over libplslam_b200.so (the C-ABI in include/plslam_b200.h).
+
+The product is the CUDA library + the C++ classes in rgbd-pl-slam_b200/host/; this module only
+binds the C-ABI with ctypes so tests and bench.py can drive it, and uses torch for device memory,
+streams and torch.distributed.  There is no CPU fallback: importing works anywhere, but every
+compute call raises PlslamError when the library or a CUDA device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_ROOT, "libplslam_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"),
+                          ("pt_y", "<f4"), ("response", "<f4"), ("size", "<f4"),
+                          ("startPointX", "<f4"), ("startPointY", "<f4"), ("endPointX", "<f4"),
+                          ("endPointY", "<f4"), ("sPointInOctaveX", "<f4"), ("sPointInOctaveY", "<f4"),
+                          ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"), ("lineLength", "<f4"),
+                          ("numOfPixels", "<i4")])
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW = 0, 1, 2, 3, 4
+
+
+class PlslamError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("plslam_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libplslam_b200.so (built in-tree by `make -C rgbd-pl-slam_b200` / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PlslamError(ERR_CUDA, "CUDA extension %s is missing — run __graft_entry__.build()" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.plslam_last_error.restype = C.c_char_p
+        L.plslam_version.restype = C.c_char_p
+        L.plslam_orb_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.plslam_orb_destroy.argtypes = [C.c_void_p]
+        L.plslam_orb_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise PlslamError(rc, lib().plslam_last_error().decode())
+
+
+def _vp(x):
+    """void* of a numpy array, a torch tensor or an int."""
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+def _stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM2::ORBextractor (reference include/ORBextractor.h:45-111) over the C-ABI."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7):
+        self._h = C.c_void_p()
+        _check(lib().plslam_orb_create(C.byref(self._h), nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST))
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.max_keypoints = lib().plslam_orb_max_keypoints(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().plslam_orb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    # getters (ORBextractor.h:63-83)
+    def GetLevels(self):
+        return self.nlevels
+
+    def tables(self):
+        n = self.nlevels
+        f = [np.empty(n, np.float32) for _ in range(4)]
+        quota = np.empty(n, np.int32)
+        umax = np.empty(16, np.int32)
+        _check(lib().plslam_orb_tables(self._h, _vp(f[0]), _vp(f[1]), _vp(f[2]), _vp(f[3]), _vp(quota), _vp(umax)))
+        return dict(scale=f[0], inv_scale=f[1], sigma2=f[2], inv_sigma2=f[3], quota=quota, umax=umax)
+
+    def GetScaleFactors(self):
+        return self.tables()["scale"]
+
+    def set_blur_kernel(self, k):
+        kk = np.asarray(k, np.int32)
+        _check(lib().plslam_orb_set_blur_kernel(self._h, _vp(kk)))
+
+    def __call__(self, image, mask=None):
+        """operator()(image, mask, keypoints, descriptors): one host image -> (keypoints, descriptors)."""
+        if image is None or image.size == 0:
+            return np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        image = np.ascontiguousarray(image, np.uint8)
+        cap = self.max_keypoints
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        _check(lib().plslam_orb_extract(self._h, _vp(image), image.shape[1], image.shape[0], image.strides[0],
+                                        _vp(kps), _vp(desc), cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch_host(self, images):
+        """images: (B, H, W) uint8 numpy (pinned or pageable).  Returns (kps[B, cap], desc[B, cap, 32], counts[B])."""
+        images = np.ascontiguousarray(images, np.uint8)
+        B, H, W = images.shape
+        cap = self.max_keypoints
+        kps = np.empty((B, cap), KP_DTYPE)
+        desc = np.empty((B, cap, 32), np.uint8)
+        counts = np.empty(B, np.int32)
+        _check(lib().plslam_orb_extract_batch_host(self._h, _vp(images), B, W, H, images.strides[1],
+                                                   C.c_size_t(images.strides[0]), _vp(kps), _vp(desc), cap, _vp(counts)))
+        return kps, desc, counts
+
+    def extract_batch_device(self, d_images, out=None, stream=None):
+        """d_images: (B, H, W) uint8 CUDA tensor.  Asynchronous on the current torch stream.
+        Returns CUDA tensors (kps[B, cap, 7] int32 view, desc[B, cap, 32] uint8, counts[B] int32)."""
+        import torch
+        assert d_images.is_cuda and d_images.dtype == torch.uint8 and d_images.dim() == 3
+        B, H, W = d_images.shape
+        assert d_images.stride(2) == 1
+        cap = self.max_keypoints
+        if out is None:
+            out = (torch.empty((B, cap, 7), dtype=torch.int32, device=d_images.device),
+                   torch.empty((B, cap, 32), dtype=torch.uint8, device=d_images.device),
+                   torch.empty((B,), dtype=torch.int32, device=d_images.device))
+        kps, desc, counts = out
+        _check(lib().plslam_orb_extract_batch_device(self._h, _vp(d_images), B, W, H, d_images.stride(1),
+                                                     C.c_size_t(d_images.stride(0)), _vp(kps), _vp(desc), cap,
+                                                     _vp(counts), _stream_ptr(stream)))
+        return out
+
+    def check_status(self, stream=None):
+        _check(lib().plslam_orb_check_status(self._h, _stream_ptr(stream)))
+
+    # parity / mvImagePyramid accessors
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        _check(lib().plslam_orb_level_size(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level(self, frame, level, blurred=False):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        _check(lib().plslam_orb_copy_level(self._h, frame, level, int(blurred), _vp(out), C.c_size_t(out.size)))
+        return out
+
+    def candidates(self, frame, level):
+        w, h = self.level_size(level)
+        cap = ((w + 1) // 2) * ((h + 1) // 2)
+        out = np.empty((cap, 3), np.int32)
+        n = C.c_int()
+        _check(lib().plslam_orb_copy_candidates(self._h, frame, level, _vp(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+def kps_from_tensor(t):
+    """(.., 7) int32 torch tensor (device layout of plslam_keypoint_t) -> numpy structured array."""
+    a = t.detach().cpu().numpy()
+    return a.view(KP_DTYPE).reshape(a.shape[:-1])

@@ -1,0 +1,95 @@
+"""GPU parity: the CUDA ORB extractor (through the C-ABI) against the CPU oracle, stage by stage
+and end to end.  Bit-exact for pyramid / blur pixels, FAST candidates (position, response, list
+order), keypoint order/positions/octave/response and descriptor bytes; angles must match bit for
+bit as well (same float sequence), the north-star tolerance of 1e-4 is asserted as the bound."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ext(**kw):
+    import plslam_b200 as pl
+    return pl.ORBextractor(**kw)
+
+
+def _compare_frame(o_kps, o_desc, g_kps, g_desc, tag=""):
+    assert len(o_kps) == len(g_kps), "%s keypoint count %d vs %d" % (tag, len(o_kps), len(g_kps))
+    for fld in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(o_kps[fld], g_kps[fld]), "%s field %s differs" % (tag, fld)
+    assert np.max(np.abs(o_kps["angle"] - g_kps["angle"]), initial=0) <= 1e-4, tag + " angle tolerance"
+    assert np.array_equal(o_kps["angle"], g_kps["angle"]), tag + " angle bits"
+    assert np.array_equal(o_desc, g_desc), tag + " descriptor bytes"
+
+
+def test_stages_and_end_to_end_640x480(oracle):
+    from plslam_b200.synth import synth_frame
+    img = synth_frame(0)
+    ex = _ext()
+    orc = oracle.OrbOracle()
+    o_kps, o_desc = orc.extract(img)
+    g_kps, g_desc = ex(img)
+    t_o, t_g = orc.tables(), ex.tables()
+    for k in t_o:
+        assert np.array_equal(t_o[k], t_g[k]), k
+    for l in range(8):
+        assert np.array_equal(orc.level(l), ex.level(0, l)), "pyramid level %d" % l
+        assert np.array_equal(orc.candidates(l), ex.candidates(0, l)), "FAST candidates level %d" % l
+        ob = orc.level(l, blurred=True)
+        if ob is not None:
+            assert np.array_equal(ob, ex.level(0, l, blurred=True)), "blurred level %d" % l
+    _compare_frame(o_kps, o_desc, g_kps, g_desc)
+    assert len(g_kps) >= 1000
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (720, 1280), (250, 333)])
+def test_batch_parity(oracle, shape):
+    from plslam_b200.synth import synth_frame
+    H, W = shape
+    B = 6
+    imgs = np.stack([synth_frame(100 + i, W, H) for i in range(B)])
+    nf = 2000 if W > 1000 else 1000
+    ex = _ext(nfeatures=nf)
+    orc = oracle.OrbOracle(nfeatures=nf)
+    kps, desc, counts = ex.extract_batch_host(imgs)
+    for f in range(B):
+        o_kps, o_desc = orc.extract(imgs[f])
+        n = counts[f]
+        _compare_frame(o_kps, o_desc, kps[f, :n], desc[f, :n], "frame %d" % f)
+
+
+def test_noise_and_flat_frames(oracle):
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, (480, 640)).astype(np.uint8)
+    flat = np.full((480, 640), 77, np.uint8)
+    ex = _ext()
+    orc = oracle.OrbOracle()
+    for name, img in (("noise", noise), ("flat", flat)):
+        o_kps, o_desc = orc.extract(img)
+        g_kps, g_desc = ex(img)
+        _compare_frame(o_kps, o_desc, g_kps, g_desc, name)
+    assert len(ex(flat)[0]) == 0
+
+
+def test_device_resident_batch(oracle):
+    import torch
+    import plslam_b200 as pl
+    from plslam_b200.synth import synth_frame
+    imgs = np.stack([synth_frame(300 + i) for i in range(4)])
+    ex = _ext()
+    d = torch.from_numpy(imgs).cuda()
+    kps, desc, counts = ex.extract_batch_device(d)
+    ex.check_status()
+    torch.cuda.synchronize()
+    k = pl.kps_from_tensor(kps)
+    orc = oracle.OrbOracle()
+    for f in range(4):
+        o_kps, o_desc = orc.extract(imgs[f])
+        n = int(counts[f])
+        _compare_frame(o_kps, o_desc, k[f, :n], desc[f, :n].cpu().numpy(), "frame %d" % f)
+
+
+def test_empty_image_is_silent():
+    ex = _ext()
+    k, d = ex(np.empty((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
