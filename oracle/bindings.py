@@ -134,3 +134,99 @@ class OrbOracle:
         out = np.empty(len(xyr) + 8, np.int32)
         n = lib().oracle_orb_distribute(self.h, _p(xyr), len(xyr), minX, maxX, minY, maxY, N, _p(out), len(out))
         return out[:n].copy()
+
+
+# ---------------------------------------------------------------------------
+# line side (oracle/lsd_oracle.cc)
+# ---------------------------------------------------------------------------
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"),
+                          ("pt_y", "<f4"), ("response", "<f4"), ("size", "<f4"),
+                          ("startPointX", "<f4"), ("startPointY", "<f4"), ("endPointX", "<f4"),
+                          ("endPointY", "<f4"), ("sPointInOctaveX", "<f4"), ("sPointInOctaveY", "<f4"),
+                          ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"), ("lineLength", "<f4"),
+                          ("numOfPixels", "<i4")])
+assert KEYLINE_DTYPE.itemsize == 68
+
+
+def gauss_table_u8(sigma, ksize):
+    k = np.zeros(ksize, np.int32)
+    lib().oracle_gauss_table_u8(C.c_double(sigma), ksize, _p(k))
+    return k
+
+
+def gauss_blur_u8(img, k):
+    img = np.ascontiguousarray(img, np.uint8)
+    k = np.asarray(k, np.int32)
+    out = np.empty_like(img)
+    lib().oracle_gauss_blur_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), out.strides[0], _p(k), len(k))
+    return out
+
+
+def resize_linear_exact(img, dw, dh, inv_scale=0.0):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty((dh, dw), np.uint8)
+    lib().oracle_resize_linear_exact_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), dw, dh, dw,
+                                        C.c_double(inv_scale))
+    return out
+
+
+def lsd_detect(img, compat=0):
+    """LSD_REFINE_ADV segments: (n, 7) doubles x1, y1, x2, y2 (float32 values), width, prec, log-NFA; plus stats."""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = 1 << 15
+    out = np.empty((cap, 7))
+    st = (C.c_long * 4)()
+    n = lib().oracle_lsd_detect(_p(img), img.shape[1], img.shape[0], img.strides[0], int(compat), _p(out), cap, st)
+    assert n <= cap
+    return out[:n].copy(), dict(regions=st[0], region_points=st[1], rects=st[2], defined=st[3])
+
+
+def lsd_stage(img):
+    """scaled image, level-line angles (rad, -1024 = NOTDEF) and gradient norms of the LSD front half."""
+    img = np.ascontiguousarray(img, np.uint8)
+    H, W = img.shape
+    dw, dh = int(np.rint(W * 0.8)), int(np.rint(H * 0.8))
+    sc = np.empty((dh, dw), np.uint8)
+    ang = np.empty((dh, dw))
+    mg = np.empty((dh, dw))
+    wh = (C.c_int * 2)()
+    lib().oracle_lsd_stage(_p(img), W, H, img.strides[0], _p(sc), _p(ang), _p(mg), wh)
+    assert (wh[0], wh[1]) == (dw, dh)
+    return sc, ang, mg
+
+
+def extract_lines(img, max_lines=40, compat=0):
+    """LineSegment::ExtractLineSegment restatement -> (keylines, desc[n,32], funcs[n,3], n_detected)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = 1 << 14
+    kl = np.empty(cap, KEYLINE_DTYPE)
+    desc = np.empty((cap, 32), np.uint8)
+    funcs = np.empty((cap, 3))
+    nd = C.c_int()
+    n = lib().oracle_extract_lines(_p(img), img.shape[1], img.shape[0], img.strides[0], int(compat), int(max_lines),
+                                   _p(kl), _p(desc), _p(funcs), cap, C.byref(nd))
+    assert n >= 0
+    return kl[:n].copy(), desc[:n].copy(), funcs[:n].copy(), nd.value
+
+
+def lbd(img, keylines, compat=0):
+    img = np.ascontiguousarray(img, np.uint8)
+    kl = np.ascontiguousarray(keylines)
+    n = len(kl)
+    d32 = np.empty((n, 32), np.uint8)
+    d72 = np.empty((n, 72), np.float32)
+    lib().oracle_lbd(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(kl), n, int(compat), _p(d32), _p(d72))
+    return d32, d72
+
+
+def pl_sincos(x):
+    s, c = C.c_double(), C.c_double()
+    lib().oracle_pl_sincos(C.c_double(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def pl_atan2f(y, x):
+    f = lib().oracle_pl_atan2f
+    f.restype = C.c_float
+    f.argtypes = [C.c_float, C.c_float]
+    return float(f(float(y), float(x)))
