@@ -109,6 +109,49 @@ int plslam_orb_copy_level(plslam_orb_t* h, int frame, int level, int which, uint
  * (cell row, cell col, y, x) (@0x765b8-0x765e3).  Returns the count in *n_out. */
 int plslam_orb_copy_candidates(plslam_orb_t* h, int frame, int level, int32_t* xyr, int capacity, int* n_out);
 
+/* ------------------------------------------------------------------------------------------
+ * Line extractor — replaces ORB_SLAM2::LineSegment (include/ExtractLineSegment.h:30-55)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plslam_lines plslam_lines_t;
+
+/* LineSegment::LineSegment() (ExtractLineSegment.h:33).  Binds to the current CUDA device. */
+int plslam_lines_create(plslam_lines_t** out);
+void plslam_lines_destroy(plslam_lines_t* h);
+
+/* Number of strongest lines (by KeyLine::response, comparator include/auxiliar.h:67-72) kept per
+ * frame before LBD; the PL-SLAM fork family hard-codes 40.  0 keeps every detected line. */
+int plslam_lines_set_max_lines(plslam_lines_t* h, int max_lines);
+/* Per-frame output capacity the batched device entry point requires. */
+int plslam_lines_capacity(const plslam_lines_t* h);
+
+/* LineSegment::ExtractLineSegment(img, keylines, ldesc, keylineFunctions, scale=1, numOctaves=1)
+ * (ExtractLineSegment.h:38; scale/numOctaves are the header defaults: one full-resolution octave) on
+ * ONE host image.  keylines: n x 68 B (cv::line_descriptor::KeyLine layout), descriptors: n x 32 B
+ * LBD rows (CV_8U), line_functions: n x 3 doubles (Eigen::Vector3d, l = sp x ep / |(l0,l1)|). */
+int plslam_lines_extract(plslam_lines_t* h, const uint8_t* image, int width, int height, int pitch,
+                         plslam_keyline_t* keylines, uint8_t* descriptors, double* line_functions, int capacity,
+                         int* n_out);
+
+/* Batched extensions (additive), same conventions as the ORB batch entry points. */
+int plslam_lines_extract_batch_host(plslam_lines_t* h, const uint8_t* images, int batch, int width, int height,
+                                    int pitch, size_t frame_stride, plslam_keyline_t* keylines, uint8_t* descriptors,
+                                    double* line_functions, int capacity, int32_t* counts);
+int plslam_lines_extract_batch_device(plslam_lines_t* h, const uint8_t* d_images, int batch, int width, int height,
+                                      int pitch, size_t frame_stride, plslam_keyline_t* d_keylines,
+                                      uint8_t* d_descriptors, double* d_line_functions, int capacity,
+                                      int32_t* d_counts, void* stream);
+/* Synchronises `stream` and returns PLSLAM_ERR_OVERFLOW if an internal list overflowed in the last batch. */
+int plslam_lines_check_status(plslam_lines_t* h, void* stream);
+int plslam_orb_check_status(plslam_orb_t* h, void* stream);
+
+/* Parity/debug accessors on the last batch: the x0.8 scaled image LSD works on, the level-line
+ * field (degrees, -1024 = undefined; gx^2+gy^2), and every accepted LSD segment in detection order
+ * as 5 doubles x1,y1,x2,y2 (float32 values),width + prec + log-NFA = 7 doubles per segment. */
+int plslam_lines_scaled_size(const plslam_lines_t* h, int* width, int* height);
+int plslam_lines_copy_scaled(plslam_lines_t* h, int frame, uint8_t* out, size_t out_bytes);
+int plslam_lines_copy_level_lines(plslam_lines_t* h, int frame, float* degrees, int32_t* grad2, size_t count);
+int plslam_lines_copy_segments(plslam_lines_t* h, int frame, double* seg7, int capacity, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

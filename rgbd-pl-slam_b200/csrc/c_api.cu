@@ -2,6 +2,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "lines.cuh"
 #include "orb.cuh"
 
 namespace plslam {
@@ -19,6 +20,10 @@ using namespace plslam;
 struct plslam_orb {
   OrbExtractor impl;
   plslam_orb(int nf, float sf, int nl, int ini, int mn) : impl(nf, sf, nl, ini, mn) {}
+};
+
+struct plslam_lines {
+  LineExtractor impl;
 };
 
 extern "C" {
@@ -123,6 +128,79 @@ int plslam_orb_copy_level(plslam_orb_t* h, int frame, int level, int which, uint
 int plslam_orb_copy_candidates(plslam_orb_t* h, int frame, int level, int32_t* xyr, int capacity, int* n_out) {
   PL_CHECK_ARG(h);
   return h->impl.copy_candidates(frame, level, xyr, capacity, n_out);
+}
+
+// ---- lines ----
+int plslam_lines_create(plslam_lines_t** out) {
+  PL_CHECK_ARG(out != nullptr);
+  *out = new (std::nothrow) plslam_lines();
+  if (!*out) {
+    set_error("out of host memory");
+    return PLSLAM_ERR_INVALID;
+  }
+  return PLSLAM_OK;
+}
+void plslam_lines_destroy(plslam_lines_t* h) { delete h; }
+int plslam_lines_set_max_lines(plslam_lines_t* h, int max_lines) {
+  PL_CHECK_ARG(h && max_lines >= 0 && max_lines <= h->impl.rect_cap);
+  h->impl.set_max_lines(max_lines);
+  return PLSLAM_OK;
+}
+int plslam_lines_capacity(const plslam_lines_t* h) { return h ? h->impl.out_capacity() : 0; }
+int plslam_lines_extract(plslam_lines_t* h, const uint8_t* image, int width, int height, int pitch,
+                         plslam_keyline_t* keylines, uint8_t* descriptors, double* line_functions, int capacity,
+                         int* n_out) {
+  PL_CHECK_ARG(h && n_out);
+  *n_out = 0;
+  if (!image || width <= 0 || height <= 0) return PLSLAM_OK;
+  int32_t cnt = 0;
+  int rc = h->impl.extract_host(image, 1, width, height, pitch, (size_t)pitch * height, keylines, descriptors,
+                                line_functions, capacity, &cnt);
+  *n_out = cnt;
+  return rc;
+}
+int plslam_lines_extract_batch_host(plslam_lines_t* h, const uint8_t* images, int batch, int width, int height,
+                                    int pitch, size_t frame_stride, plslam_keyline_t* keylines, uint8_t* descriptors,
+                                    double* line_functions, int capacity, int32_t* counts) {
+  PL_CHECK_ARG(h);
+  return h->impl.extract_host(images, batch, width, height, pitch, frame_stride, keylines, descriptors, line_functions,
+                              capacity, counts);
+}
+int plslam_lines_extract_batch_device(plslam_lines_t* h, const uint8_t* d_images, int batch, int width, int height,
+                                      int pitch, size_t frame_stride, plslam_keyline_t* d_keylines,
+                                      uint8_t* d_descriptors, double* d_line_functions, int capacity,
+                                      int32_t* d_counts, void* stream) {
+  PL_CHECK_ARG(h);
+  return h->impl.extract_device(d_images, batch, width, height, pitch, frame_stride, d_keylines, d_descriptors,
+                                d_line_functions, capacity, d_counts, (cudaStream_t)stream);
+}
+int plslam_lines_check_status(plslam_lines_t* h, void* stream) {
+  PL_CHECK_ARG(h);
+  return h->impl.check_status((cudaStream_t)stream);
+}
+int plslam_lines_scaled_size(const plslam_lines_t* h, int* width, int* height) {
+  PL_CHECK_ARG(h && width && height);
+  return h->impl.scaled_size(width, height);
+}
+int plslam_lines_copy_scaled(plslam_lines_t* h, int frame, uint8_t* out, size_t out_bytes) {
+  PL_CHECK_ARG(h);
+  return h->impl.copy_scaled(frame, out, out_bytes);
+}
+int plslam_lines_copy_level_lines(plslam_lines_t* h, int frame, float* degrees, int32_t* grad2, size_t count) {
+  PL_CHECK_ARG(h);
+  return h->impl.copy_angles(frame, degrees, grad2, count);
+}
+int plslam_lines_copy_segments(plslam_lines_t* h, int frame, double* seg7, int capacity, int* n_out) {
+  PL_CHECK_ARG(h && n_out);
+  std::vector<LsdSegment> v(capacity > 0 ? capacity : 1);
+  int rc = h->impl.copy_segments(frame, v.data(), capacity, n_out);
+  if (rc) return rc;
+  for (int i = 0; i < *n_out; ++i) {
+    double* o = seg7 + 7 * i;
+    o[0] = v[i].x1; o[1] = v[i].y1; o[2] = v[i].x2; o[3] = v[i].y2;
+    o[4] = v[i].width; o[5] = v[i].prec; o[6] = v[i].nfa;
+  }
+  return PLSLAM_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,1223 @@
+// lines.cu — B200-native line front-end: LSD (LSD_REFINE_ADV) + KeyLine filling + LBD descriptors.
+//
+// Replaces ORB_SLAM2::LineSegment::ExtractLineSegment (reference include/ExtractLineSegment.h:38),
+// whose arithmetic lives in OpenCV-contrib line_descriptor (LSDDetector::detect ->
+// imgproc LineSegmentDetector, BinaryDescriptor::compute).  The algorithm restated here is the one
+// pinned by oracle/lsd_oracle.cc (bit-identical to cv2 4.13 for LSD in its libm mode); this file
+// reproduces the oracle's PINNED mode bit for bit.
+//
+// Stage map (one launch per stage for the whole batch):
+//   k_lsd_scale    7x7 sigma-0.75 Gaussian + x0.8 INTER_LINEAR_EXACT, fused through shared memory
+//   k_lsd_grad     2x2 gradient, level-line angle (fastAtan2), per-pixel record {deg, cos, sin, g2}
+//   k_lsd_rowhist / k_lsd_colscan / k_lsd_scatter   stable counting sort of the seeds (bin desc, raster)
+//   k_lsd_grow     region growing + rectangle fit + density refinement: one warp per frame, because
+//                  the greedy growth is sequential inside a frame (running region angle, shared
+//                  `used` map); lanes cooperate on neighbour tests and the `used` map lives in shared memory
+//   k_lsd_nfa      rect_improve / rect_nfa: one warp per rectangle (independent of `used`)
+//   k_lsd_finish   ordered compaction, KeyLine fields, strongest-N selection, LBD, line equations
+#include "lines.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+#include "pl_math.cuh"
+
+namespace plslam {
+
+namespace {
+
+constexpr float NOTDEF_F = -1024.f;
+constexpr double M_3_2_PI_D = (3 * PL_PI) / 2;
+constexpr double M_2__PI_D = 2 * PL_PI;
+
+// ------------------------------------------------------------------------------------------
+// k_lsd_scale: GaussianBlur(7x7, sigma 0.75) then resize(x0.8, INTER_LINEAR_EXACT) (lsd.cpp flsd()).
+// Both are OpenCV's 8-bit fixed-point paths: blur = (sum k k p + 32768) >> 16 with the table
+// {0,4,56,136,56,4,0}; resize uses 8.8 coefficients, exact products and one final rounding.
+// Tile = 64x16 scaled pixels; the 82x22 blurred source patch never leaves shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int ST_W = 64, ST_H = 16, SB_W = 84, SB_H = 24;
+
+__global__ void __launch_bounds__(256) k_lsd_scale(const __grid_constant__ LineParams L, const uint8_t* __restrict__ img,
+                                                   int pitch, size_t frame_stride, const int* __restrict__ coef,
+                                                   uint8_t* __restrict__ scaled) {
+  __shared__ uint8_t raw[SB_H + 6][SB_W + 8];
+  __shared__ unsigned short hs[SB_H + 6][SB_W];
+  __shared__ uint8_t bl[SB_H][SB_W];
+  const int f = blockIdx.z;
+  const int ox0 = blockIdx.x * ST_W, oy0 = blockIdx.y * ST_H;
+  const int* xofs = coef;
+  const int* xc1 = coef + L.sw;
+  const int* yofs = xc1 + L.sw;
+  const int* yc1 = yofs + L.sh;
+  const int oxl = min(ox0 + ST_W, L.sw) - 1, oyl = min(oy0 + ST_H, L.sh) - 1;
+  const int bx0 = xofs[ox0], bx1 = min(xofs[oxl] + 1, L.W - 1);
+  const int by0 = yofs[oy0], by1 = min(yofs[oyl] + 1, L.H - 1);
+  const int nbx = bx1 - bx0 + 1, nby = by1 - by0 + 1;
+  const uint8_t* S = img + (size_t)f * frame_stride;
+  for (int i = threadIdx.x; i < (nby + 6) * (nbx + 6); i += 256) {
+    const int r = i / (nbx + 6), c = i - r * (nbx + 6);
+    const int gx = reflect101_dev(bx0 - 3 + c, L.W), gy = reflect101_dev(by0 - 3 + r, L.H);
+    raw[r][c] = S[(size_t)gy * pitch + gx];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (nby + 6) * nbx; i += 256) {
+    const int r = i / nbx, c = i - r * nbx;
+    int a = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) a += L.blurk[k] * raw[r][c + k];
+    hs[r][c] = (unsigned short)a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nby * nbx; i += 256) {
+    const int r = i / nbx, c = i - r * nbx;
+    int a = 32768;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) a += L.blurk[k] * hs[r + k][c];
+    bl[r][c] = (uint8_t)(a >> 16);
+  }
+  __syncthreads();
+  uint8_t* D = scaled + (size_t)f * L.spitch * L.sh;
+  for (int i = threadIdx.x; i < ST_W * ST_H; i += 256) {
+    const int ty = i / ST_W, tx = i - ty * ST_W;
+    const int ox = ox0 + tx, oy = oy0 + ty;
+    if (ox >= L.sw || oy >= L.sh) continue;
+    const int sx = xofs[ox], sy = yofs[oy];
+    const int sx1 = min(sx + 1, L.W - 1), sy1 = min(sy + 1, L.H - 1);
+    const int a1 = xc1[ox], a0 = 256 - a1, b1 = yc1[oy], b0 = 256 - b1;
+    const int t0 = bl[sy - by0][sx - bx0] * a0 + bl[sy - by0][sx1 - bx0] * a1;
+    const int t1 = bl[sy1 - by0][sx - bx0] * a0 + bl[sy1 - by0][sx1 - bx0] * a1;
+    D[(size_t)oy * L.spitch + ox] = (uint8_t)((t0 * b0 + t1 * b1 + 32768) >> 16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_lsd_grad: ll_angle() of lsd.cpp.  Per scaled pixel a 16-byte record:
+//   .x level-line angle in degrees (fastAtan2(gx, -gy)) or NOTDEF, .y/.z cos/sin of float(angle in rad)
+//   (what region_grow adds to its running direction), .w gx^2 + gy^2 (modgrad = sqrt(.w / 4)).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double modgrad_of(int g2) { return sqrt(__dmul_rn((double)g2, 0.25)); }
+
+__global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LineParams L, const uint8_t* __restrict__ scaled,
+                                                  uint4* __restrict__ pix, int* __restrict__ maxg2) {
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  int g2 = 0;
+  bool defined = false;
+  if (x < L.sw && y < L.sh) {
+    float deg = NOTDEF_F, cs = 0.f, sn = 0.f;
+    if (x < L.sw - 1 && y < L.sh - 1) {
+      const uint8_t* r0 = scaled + (size_t)f * L.spitch * L.sh + (size_t)y * L.spitch + x;
+      const uint8_t* r1 = r0 + L.spitch;
+      const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
+      const int gx = DA + BC, gy = DA - BC;
+      g2 = gx * gx + gy * gy;
+      if (modgrad_of(g2) > L.rho) {
+        defined = true;
+        deg = fast_atan2_dev((float)gx, (float)(-gy));
+        const float af = (float)__dmul_rn((double)deg, PL_DEG_TO_RADS);
+        pl_sincosf_dev(af, &sn, &cs);
+      }
+    }
+    pix[(size_t)f * L.P + (size_t)y * L.sw + x] =
+        make_uint4(__float_as_uint(deg), __float_as_uint(cs), __float_as_uint(sn), (unsigned)g2);
+  }
+  int m = defined ? g2 : 0;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxg2 + f, m);
+}
+
+// ------------------------------------------------------------------------------------------
+// Seed ordering: cv2 4.13 stable-sorts all pixels by bin = int(modgrad * 1023 / max_grad) descending
+// (stable => raster order inside a bin).  Only pixels with a defined angle can seed a region, so
+// only those are sorted.  Counting sort: per-row bin histograms, a column scan over rows, a scan
+// over bins (descending), and a per-row stable scatter.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lsd_bin(int g2, int mg2) {
+  const double max_grad = modgrad_of(mg2);
+  const double bin_coef = __ddiv_rn((double)(LSD_BINS - 1), max_grad);
+  return (int)__dmul_rn(modgrad_of(g2), bin_coef);
+}
+
+__global__ void __launch_bounds__(256) k_lsd_rowhist(const __grid_constant__ LineParams L, const uint4* __restrict__ pix,
+                                                     const int* __restrict__ maxg2, unsigned* __restrict__ rowhist) {
+  __shared__ unsigned hist[8][LSD_BINS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.y, y = blockIdx.x * 8 + warp;
+  if (y >= L.sh) return;
+  for (int i = lane; i < LSD_BINS; i += 32) hist[warp][i] = 0;
+  __syncwarp();
+  const int mg2 = maxg2[f];
+  const uint4* row = pix + (size_t)f * L.P + (size_t)y * L.sw;
+  if (mg2 > 0)
+    for (int x = lane; x < L.sw; x += 32) {
+      const uint4 r = row[x];
+      if (__uint_as_float(r.x) != NOTDEF_F) atomicAdd(&hist[warp][lsd_bin((int)r.w, mg2)], 1u);
+    }
+  __syncwarp();
+  unsigned* out = rowhist + ((size_t)f * L.sh + y) * LSD_BINS;
+  for (int i = lane; i < LSD_BINS; i += 32) out[i] = hist[warp][i];
+}
+
+__global__ void __launch_bounds__(LSD_BINS) k_lsd_colscan(const __grid_constant__ LineParams L, unsigned* __restrict__ rowhist,
+                                                          unsigned* __restrict__ binstart, int* __restrict__ nseeds) {
+  __shared__ int tot[LSD_BINS];
+  __shared__ int warpTmp[33];
+  const int f = blockIdx.x, b = threadIdx.x;
+  unsigned* col = rowhist + (size_t)f * L.sh * LSD_BINS + b;
+  unsigned run = 0;
+  for (int y = 0; y < L.sh; ++y) {
+    const unsigned v = col[(size_t)y * LSD_BINS];
+    col[(size_t)y * LSD_BINS] = run;
+    run += v;
+  }
+  tot[LSD_BINS - 1 - b] = (int)run;  // descending bin order
+  __syncthreads();
+  const int total = block_scan_excl(tot, LSD_BINS, warpTmp);
+  binstart[(size_t)f * LSD_BINS + b] = (unsigned)tot[LSD_BINS - 1 - b];
+  if (b == 0) nseeds[f] = total;
+}
+
+__global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ LineParams L, const uint4* __restrict__ pix,
+                                                     const int* __restrict__ maxg2, const unsigned* __restrict__ rowhist,
+                                                     const unsigned* __restrict__ binstart, unsigned* __restrict__ seeds) {
+  __shared__ unsigned cnt[8][LSD_BINS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.y, y = blockIdx.x * 8 + warp;
+  if (y >= L.sh) return;
+  const int mg2 = maxg2[f];
+  if (mg2 <= 0) return;
+  for (int i = lane; i < LSD_BINS; i += 32) cnt[warp][i] = 0;
+  __syncwarp();
+  const uint4* row = pix + (size_t)f * L.P + (size_t)y * L.sw;
+  const unsigned* roff = rowhist + ((size_t)f * L.sh + y) * LSD_BINS;
+  const unsigned* bs = binstart + (size_t)f * LSD_BINS;
+  unsigned* out = seeds + (size_t)f * L.P;
+  for (int x0 = 0; x0 < L.sw; x0 += 32) {
+    const int x = x0 + lane;
+    bool def = false;
+    int bin = -1 - lane;  // unique non-matching key for undefined lanes
+    if (x < L.sw) {
+      const uint4 r = row[x];
+      if (__uint_as_float(r.x) != NOTDEF_F) {
+        def = true;
+        bin = lsd_bin((int)r.w, mg2);
+      }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (def) {
+      const int rank = __popc(peers & ((1u << lane) - 1));
+      const unsigned base = cnt[warp][bin];
+      out[bs[bin] + roff[bin] + base + rank] = (unsigned)(y * L.sw + x);
+    }
+    __syncwarp();
+    if (def && (peers >> lane) == 1u) cnt[warp][bin] += __popc(peers);  // highest lane of each peer group
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_lsd_grow: the sequential heart of LSD, one warp per frame.
+// ------------------------------------------------------------------------------------------
+struct GrowCtx {
+  const uint4* pix;   // per-pixel records of this frame
+  unsigned* used;     // shared-memory bitmap
+  unsigned* reg;      // region list (pixel indices) of this frame
+  double* stage;      // 3 x 32 doubles of shared staging
+  int sw, sh;
+  int lane;
+};
+
+__device__ __forceinline__ bool used_get(const unsigned* used, int idx) { return (used[idx >> 5] >> (idx & 31)) & 1u; }
+
+__device__ __forceinline__ bool lsd_aligned(double theta, float deg, double prec) {
+  const double a = __dmul_rn((double)deg, PL_DEG_TO_RADS);
+  double n_theta = __dsub_rn(theta, a);
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > M_3_2_PI_D) {
+    n_theta = __dsub_rn(n_theta, M_2__PI_D);
+    if (n_theta < 0) n_theta = -n_theta;
+  }
+  return n_theta <= prec;
+}
+
+// region_grow(): returns the region size; reg[0] must already hold the seed pixel index.
+__device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_out) {
+  const int lane = C.lane;
+  const int seed = (int)C.reg[0];
+  const uint4 srec = C.pix[seed];
+  double reg_angle = __dmul_rn((double)__uint_as_float(srec.x), PL_DEG_TO_RADS);
+  float sumdx, sumdy;
+  {
+    double s, c;
+    pl_sincos_dev(reg_angle, &s, &c);  // the seed uses the double-precision angle (sincos() in lsd.cpp)
+    sumdx = (float)c;
+    sumdy = (float)s;
+  }
+  if (lane == 0) C.used[seed >> 5] |= 1u << (seed & 31);
+  __syncwarp();
+  int n = 1;
+  for (int i = 0; i < n;) {
+    const int m = min(3, n - i);
+    // 27 lanes: lane = 9 * point + neighbour (row-major 3x3, yy outer / xx inner as in lsd.cpp)
+    const int pt = lane / 9, nb = lane - pt * 9;
+    int nidx = -1;
+    float deg = NOTDEF_F, cs = 0.f, sn = 0.f;
+    if (lane < 27 && pt < m) {
+      const int p = (int)C.reg[i + pt];
+      const int py = p / C.sw, px = p - py * C.sw;
+      const int nx = px + (nb % 3) - 1, ny = py + (nb / 3) - 1;
+      if (nx >= 0 && ny >= 0 && nx < C.sw && ny < C.sh) {
+        nidx = ny * C.sw + nx;
+        const uint4 r = __ldg(C.pix + nidx);
+        deg = __uint_as_float(r.x);
+        cs = __uint_as_float(r.y);
+        sn = __uint_as_float(r.z);
+      }
+    }
+    unsigned todo = 0xffffffffu;  // lanes not yet passed by the sequential scan
+    while (true) {
+      const bool cand = nidx >= 0 && deg != NOTDEF_F && !used_get(C.used, nidx) && lsd_aligned(reg_angle, deg, prec);
+      const unsigned mask = __ballot_sync(0xffffffffu, cand) & todo;
+      if (!mask) break;
+      const int j = __ffs(mask) - 1;
+      const int aidx = __shfl_sync(0xffffffffu, nidx, j);
+      if (lane == 0) {
+        C.used[aidx >> 5] |= 1u << (aidx & 31);
+        C.reg[n] = (unsigned)aidx;
+      }
+      ++n;
+      sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, cs, j));
+      sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, sn, j));
+      reg_angle = __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), PL_DEG_TO_RADS);
+      todo = j == 31 ? 0u : (0xffffffffu << (j + 1));
+      __syncwarp();
+    }
+    i += m;
+    __syncwarp();
+  }
+  *reg_angle_out = reg_angle;
+  return n;
+}
+
+__device__ __forceinline__ double angle_diff_signed_dev(double a, double b) {
+  double diff = __dsub_rn(a, b);
+  while (diff <= -PL_PI) diff = __dadd_rn(diff, M_2__PI_D);
+  while (diff > PL_PI) diff = __dsub_rn(diff, M_2__PI_D);
+  return diff;
+}
+
+// region2rect() + get_theta(); sums run in region order (staged through shared memory, accumulated
+// redundantly by every lane so the results are warp-uniform).
+__device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, double prec, double p, LsdRect* rec) {
+  const int lane = C.lane;
+  double* sA = C.stage;
+  double* sB = C.stage + 32;
+  double* sC = C.stage + 64;
+  double x = 0, y = 0, sum = 0;
+  for (int c = 0; c < n; c += 32) {
+    const int i = c + lane;
+    if (i < n) {
+      const int idx = (int)C.reg[i];
+      const int py = idx / C.sw, px = idx - py * C.sw;
+      const double w = modgrad_of((int)__ldg(C.pix + idx).w);
+      sA[lane] = __dmul_rn((double)px, w);
+      sB[lane] = __dmul_rn((double)py, w);
+      sC[lane] = w;
+    }
+    __syncwarp();
+    const int cnt = min(32, n - c);
+    for (int j = 0; j < cnt; ++j) {
+      x = __dadd_rn(x, sA[j]);
+      y = __dadd_rn(y, sB[j]);
+      sum = __dadd_rn(sum, sC[j]);
+    }
+    __syncwarp();
+  }
+  x = __ddiv_rn(x, sum);
+  y = __ddiv_rn(y, sum);
+  double Ixx = 0, Iyy = 0, Ixy = 0;
+  for (int c = 0; c < n; c += 32) {
+    const int i = c + lane;
+    if (i < n) {
+      const int idx = (int)C.reg[i];
+      const int py = idx / C.sw, px = idx - py * C.sw;
+      const double w = modgrad_of((int)__ldg(C.pix + idx).w);
+      const double dx = __dsub_rn((double)px, x), dy = __dsub_rn((double)py, y);
+      sA[lane] = __dmul_rn(__dmul_rn(dy, dy), w);
+      sB[lane] = __dmul_rn(__dmul_rn(dx, dx), w);
+      sC[lane] = __dmul_rn(__dmul_rn(dx, dy), w);
+    }
+    __syncwarp();
+    const int cnt = min(32, n - c);
+    for (int j = 0; j < cnt; ++j) {
+      Ixx = __dadd_rn(Ixx, sA[j]);
+      Iyy = __dadd_rn(Iyy, sB[j]);
+      Ixy = __dsub_rn(Ixy, sC[j]);
+    }
+    __syncwarp();
+  }
+  const double dI = __dsub_rn(Ixx, Iyy);
+  const double disc = __dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy));
+  const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy), sqrt(disc)));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_dev((float)__dsub_rn(lambda, Ixx), (float)Ixy)
+                                         : (double)fast_atan2_dev((float)Ixy, (float)__dsub_rn(lambda, Iyy));
+  theta = __dmul_rn(theta, PL_DEG_TO_RADS);
+  if (fabs(angle_diff_signed_dev(theta, reg_angle)) > prec) theta = __dadd_rn(theta, PL_PI);
+  double dx, dy;
+  pl_sincos_dev(theta, &dy, &dx);
+  double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+  for (int i = lane; i < n; i += 32) {
+    const int idx = (int)C.reg[i];
+    const int py = idx / C.sw, px = idx - py * C.sw;
+    const double rdx = __dsub_rn((double)px, x), rdy = __dsub_rn((double)py, y);
+    const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
+    const double w = __dadd_rn(__dmul_rn(-rdx, dy), __dmul_rn(rdy, dx));
+    l_max = fmax(l_max, l);
+    l_min = fmin(l_min, l);
+    w_max = fmax(w_max, w);
+    w_min = fmin(w_min, w);
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    l_max = fmax(l_max, __shfl_xor_sync(0xffffffffu, l_max, d));
+    l_min = fmin(l_min, __shfl_xor_sync(0xffffffffu, l_min, d));
+    w_max = fmax(w_max, __shfl_xor_sync(0xffffffffu, w_max, d));
+    w_min = fmin(w_min, __shfl_xor_sync(0xffffffffu, w_min, d));
+  }
+  rec->x1 = __dadd_rn(x, __dmul_rn(l_min, dx));
+  rec->y1 = __dadd_rn(y, __dmul_rn(l_min, dy));
+  rec->x2 = __dadd_rn(x, __dmul_rn(l_max, dx));
+  rec->y2 = __dadd_rn(y, __dmul_rn(l_max, dy));
+  rec->width = __dsub_rn(w_max, w_min);
+  rec->x = x;
+  rec->y = y;
+  rec->theta = theta;
+  rec->dx = dx;
+  rec->dy = dy;
+  rec->prec = prec;
+  rec->p = p;
+  if (rec->width < 1.0) rec->width = 1.0;
+}
+
+__device__ __forceinline__ double dist_sq_dev(double x1, double y1, double x2, double y2) {
+  const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1);
+  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+__device__ __forceinline__ double rect_density(int n, const LsdRect& r) {
+  return __ddiv_rn((double)n, __dmul_rn(sqrt(dist_sq_dev(r.x1, r.y1, r.x2, r.y2)), r.width));
+}
+
+// refine() + reduce_region_radius(); returns false when the region must be dropped. *n_io = region size.
+__device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double prec, double p, LsdRect* rec,
+                           double density_th) {
+  const int lane = C.lane;
+  int n = *n_io;
+  double density = rect_density(n, *rec);
+  if (density >= density_th) return true;
+  const int seed = (int)C.reg[0];
+  const int sy = seed / C.sw, sx = seed - sy * C.sw;
+  const double xc = (double)sx, yc = (double)sy;
+  const double ang_c = __dmul_rn((double)__uint_as_float(__ldg(C.pix + seed).x), PL_DEG_TO_RADS);
+  double* sA = C.stage;
+  double* sF = C.stage + 32;
+  double sum = 0, s_sum = 0;
+  int cntN = 0;
+  for (int c = 0; c < n; c += 32) {
+    const int i = c + lane;
+    if (i < n) {
+      const int idx = (int)C.reg[i];
+      atomicAnd(&C.used[idx >> 5], ~(1u << (idx & 31)));
+      const int py = idx / C.sw, px = idx - py * C.sw;
+      double flag = 0.0, v = 0.0;
+      if (sqrt(dist_sq_dev(xc, yc, (double)px, (double)py)) < rec->width) {
+        const double ang = __dmul_rn((double)__uint_as_float(__ldg(C.pix + idx).x), PL_DEG_TO_RADS);
+        v = angle_diff_signed_dev(ang, ang_c);
+        flag = 1.0;
+      }
+      sA[lane] = v;
+      sF[lane] = flag;
+    }
+    __syncwarp();
+    const int cnt = min(32, n - c);
+    for (int j = 0; j < cnt; ++j)
+      if (sF[j] != 0.0) {
+        const double v = sA[j];
+        sum = __dadd_rn(sum, v);
+        s_sum = __dadd_rn(s_sum, __dmul_rn(v, v));
+        ++cntN;
+      }
+    __syncwarp();
+  }
+  const double mean_angle = __ddiv_rn(sum, (double)cntN);
+  const double tau = __dmul_rn(
+      2.0, sqrt(__dadd_rn(__ddiv_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)), (double)cntN),
+                          __dmul_rn(mean_angle, mean_angle))));
+  n = lsd_region_grow(C, tau, &reg_angle);
+  *n_io = n;
+  if (n < 2) return false;
+  lsd_region2rect(C, n, reg_angle, prec, p, rec);
+  density = rect_density(n, *rec);
+  if (density >= density_th) return true;
+  // reduce_region_radius()
+  const double radSq1 = dist_sq_dev(xc, yc, rec->x1, rec->y1), radSq2 = dist_sq_dev(xc, yc, rec->x2, rec->y2);
+  double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
+  while (density < density_th) {
+    radSq = __dmul_rn(radSq, 0.75 * 0.75);
+    if (lane == 0) {
+      // swap-with-last removal exactly as the reference (it defines the order of the later sums)
+      for (int i = 0; i < n; ++i) {
+        const int idx = (int)C.reg[i];
+        const int py = idx / C.sw, px = idx - py * C.sw;
+        if (dist_sq_dev(xc, yc, (double)px, (double)py) > radSq) {
+          C.used[idx >> 5] &= ~(1u << (idx & 31));
+          C.reg[i] = C.reg[n - 1];
+          C.reg[n - 1] = (unsigned)idx;
+          --n;
+          --i;
+        }
+      }
+    }
+    n = __shfl_sync(0xffffffffu, n, 0);
+    __syncwarp();
+    *n_io = n;
+    if (n < 2) return false;
+    lsd_region2rect(C, n, reg_angle, prec, p, rec);
+    density = rect_density(n, *rec);
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
+                                                 const unsigned* __restrict__ seedsAll, const int* __restrict__ nseeds,
+                                                 unsigned* __restrict__ regAll, LsdRect* __restrict__ rectsAll,
+                                                 int* __restrict__ nrects, int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int f = blockIdx.x, lane = threadIdx.x;
+  GrowCtx C;
+  C.stage = reinterpret_cast<double*>(smem_raw);
+  C.used = reinterpret_cast<unsigned*>(smem_raw + 96 * sizeof(double));
+  C.pix = pixAll + (size_t)f * L.P;
+  C.reg = regAll + (size_t)f * L.P;
+  C.sw = L.sw;
+  C.sh = L.sh;
+  C.lane = lane;
+  const int words = (L.P + 31) >> 5;
+  for (int i = lane; i < words; i += 32) C.used[i] = 0;
+  __syncwarp();
+  const unsigned* seeds = seedsAll + (size_t)f * L.P;
+  const int ns = nseeds[f];
+  LsdRect* rects = rectsAll + (size_t)f * L.rect_cap;
+  int nrect = 0;
+  for (int base = 0; base < ns; base += 32) {
+    int s = base + lane < ns ? (int)seeds[base + lane] : -1;
+    while (true) {
+      const bool unused = s >= 0 && !used_get(C.used, s);
+      const unsigned m = __ballot_sync(0xffffffffu, unused);
+      if (!m) break;
+      const int j = __ffs(m) - 1;
+      const int seed = __shfl_sync(0xffffffffu, s, j);
+      if (lane <= j) s = -1;
+      if (lane == 0) C.reg[0] = (unsigned)seed;
+      __syncwarp();
+      double reg_angle;
+      int n = lsd_region_grow(C, L.prec, &reg_angle);
+      if (n < L.min_reg_size) continue;
+      LsdRect rec;
+      lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
+      if (!lsd_refine(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th)) continue;
+      if (nrect < L.rect_cap) {
+        if (lane == 0) rects[nrect] = rec;
+      } else if (lane == 0) {
+        atomicMax(status, PLSLAM_ERR_OVERFLOW);
+      }
+      ++nrect;
+    }
+  }
+  if (lane == 0) nrects[f] = min(nrect, L.rect_cap);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_lsd_nfa: rect_improve() / rect_nfa() / nfa(), one warp per rectangle.  The row scan is the one
+// compiled into cv2 4.13 (see oracle/lsd_oracle.cc rect_nfa_rows); lanes split the rows or the
+// columns of the scan, counts are integer so the reduction order is irrelevant.  nfa() uses the CUDA
+// double-precision log/exp/pow/sinh: its value only feeds comparisons.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool double_equal_dev(double a, double b) {
+  if (a == b) return true;
+  const double abs_diff = fabs(a - b), aa = fabs(a), bb = fabs(b);
+  double abs_max = aa > bb ? aa : bb;
+  if (abs_max < 2.2250738585072014e-308) abs_max = 2.2250738585072014e-308;
+  return (abs_diff / abs_max) <= (100.0 * 2.2204460492503131e-16);
+}
+__device__ double log_gamma_dev(double x) {
+  if (x > 15.0)
+    return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+  const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+  double a = (x + 0.5) * log(x + 5.5) - (x + 5.5);
+  double b = 0;
+  for (int n = 0; n < 7; ++n) {
+    a -= log(x + (double)n);
+    b += q[n] * pow(x, (double)n);
+  }
+  return a + log(b);
+}
+__device__ double nfa_dev(int n, int k, double p, double LOG_NT) {
+  if (n == 0 || k == 0) return -LOG_NT;
+  if (n == k) return -LOG_NT - (double)n * log10(p);
+  const double p_term = p / (1 - p);
+  const double log1term = log_gamma_dev((double)n + 1) - log_gamma_dev((double)k + 1) - log_gamma_dev((double)(n - k) + 1) +
+                          (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+  double term = exp(log1term);
+  if (double_equal_dev(term, 0)) {
+    if (k > n * p) return -log1term / 2.30258509299404568402 - LOG_NT;
+    return -LOG_NT;
+  }
+  double bin_tail = term;
+  const double tolerance = 0.1;
+  for (int i = k + 1; i <= n; ++i) {
+    const double bin_term = (double)(n - i + 1) / (double)i;
+    const double mult_term = bin_term * p_term;
+    term *= mult_term;
+    bin_tail += term;
+    if (bin_term < 1) {
+      const double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+      if (err < tolerance * fabs(-log10(bin_tail) - LOG_NT) * bin_tail) break;
+    }
+  }
+  return -log10(bin_tail) - LOG_NT;
+}
+
+__device__ double rect_nfa_dev(const LsdRect& r, const uint4* __restrict__ pix, int sw, int sh, double LOG_NT, int lane) {
+  const double hw = __dmul_rn(0.5, r.width);
+  const double dyhw = __dmul_rn(r.dy, hw), dxhw = __dmul_rn(r.dx, hw);
+  const double ux[4] = {__dsub_rn(r.x1, dyhw), __dsub_rn(r.x2, dyhw), __dadd_rn(r.x2, dyhw), __dadd_rn(r.x1, dyhw)};
+  const double uy[4] = {__dadd_rn(r.y1, dxhw), __dadd_rn(r.y2, dxhw), __dsub_rn(r.y2, dxhw), __dsub_rn(r.y1, dxhw)};
+  int off = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (uy[i] < uy[off] || (uy[i] == uy[off] && ux[i] < ux[off])) off = i;
+  double vx[4], vy[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    vx[n] = ux[(off + n) & 3];
+    vy[n] = uy[(off + n) & 3];
+  }
+  const int iy0 = (int)ceil(vy[0]), iy1 = (int)ceil(vy[1]), iy2 = (int)ceil(vy[2]), iy3 = (int)ceil(vy[3]);
+  const double s01 = (iy1 == iy0) ? 0.0 : __ddiv_rn(__dsub_rn(vx[1], vx[0]), __dsub_rn(vy[1], vy[0]));
+  const double s12 = (iy2 == iy1) ? 0.0 : __ddiv_rn(__dsub_rn(vx[2], vx[1]), __dsub_rn(vy[2], vy[1]));
+  const double s03 = (iy3 == iy0) ? 0.0 : __ddiv_rn(__dsub_rn(vx[3], vx[0]), __dsub_rn(vy[3], vy[0]));
+  const double s32 = (iy3 == iy2) ? 0.0 : __ddiv_rn(__dsub_rn(vx[2], vx[3]), __dsub_rn(vy[2], vy[3]));
+  int total = 0, alg = 0;
+  const int nrows = iy2 - iy0 + 1;
+  const bool byRows = nrows >= 12;
+  for (int yy = byRows ? iy0 + lane : iy0; yy <= iy2; yy += byRows ? 32 : 1) {
+    if (yy < 0 || yy >= sh) continue;
+    const double yd = (double)yy;
+    const double xa = (iy1 < yy) ? __dadd_rn(__dmul_rn(__dsub_rn(yd, vy[1]), s12), vx[1])
+                                 : __dadd_rn(__dmul_rn(__dsub_rn(yd, vy[0]), s01), vx[0]);
+    const double xb = (iy3 <= yy) ? __dadd_rn(__dmul_rn(__dsub_rn(yd, vy[3]), s32), vx[3])
+                                  : __dadd_rn(__dmul_rn(__dsub_rn(yd, vy[0]), s03), vx[0]);
+    int xs = (int)ceil(xa);
+    int xe = (int)xb;
+    if (xs < 0) xs = 0;
+    if (xe > sw - 1) xe = sw - 1;
+    const uint4* row = pix + (size_t)yy * sw;
+    for (int x = byRows ? xs : xs + lane; x <= xe; x += byRows ? 1 : 32) {
+      ++total;
+      const float deg = __uint_as_float(__ldg(row + x).x);
+      if (deg != NOTDEF_F && lsd_aligned(r.theta, deg, r.prec)) ++alg;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    total += __shfl_xor_sync(0xffffffffu, total, d);
+    alg += __shfl_xor_sync(0xffffffffu, alg, d);
+  }
+  return nfa_dev(total, alg, r.p, LOG_NT);
+}
+
+__global__ void __launch_bounds__(256) k_lsd_nfa(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
+                                                 const LsdRect* __restrict__ rectsAll, const int* __restrict__ nrects,
+                                                 LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.y, ri = blockIdx.x * 8 + warp;
+  if (ri >= nrects[f]) return;
+  const uint4* pix = pixAll + (size_t)f * L.P;
+  LsdRect rec = rectsAll[(size_t)f * L.rect_cap + ri];
+  const double LOG_EPS = L.log_eps, LOG_NT = L.log_nt;
+  const int sw = L.sw, sh = L.sh;
+  // rect_improve()
+  const double delta = 0.5, delta_2 = delta / 2.0;
+  double log_nfa = rect_nfa_dev(rec, pix, sw, sh, LOG_NT, lane);
+  if (!(log_nfa > LOG_EPS)) {
+    LsdRect r = rec;
+    for (int n = 0; n < 5; ++n) {
+      r.p = __ddiv_rn(r.p, 2.0);
+      r.prec = __dmul_rn(r.p, PL_PI);
+      const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
+      if (v > log_nfa) { log_nfa = v; rec = r; }
+    }
+    if (!(log_nfa > LOG_EPS)) {
+      r = rec;
+      for (int n = 0; n < 5; ++n) {
+        if (__dsub_rn(r.width, delta) >= 0.5) {
+          r.width = __dsub_rn(r.width, delta);
+          const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
+          if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+      }
+    }
+    if (!(log_nfa > LOG_EPS)) {
+      r = rec;
+      for (int n = 0; n < 5; ++n) {
+        if (__dsub_rn(r.width, delta) >= 0.5) {
+          r.x1 = __dadd_rn(r.x1, __dmul_rn(-r.dy, delta_2));
+          r.y1 = __dadd_rn(r.y1, __dmul_rn(r.dx, delta_2));
+          r.x2 = __dadd_rn(r.x2, __dmul_rn(-r.dy, delta_2));
+          r.y2 = __dadd_rn(r.y2, __dmul_rn(r.dx, delta_2));
+          r.width = __dsub_rn(r.width, delta);
+          const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
+          if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+      }
+    }
+    if (!(log_nfa > LOG_EPS)) {
+      r = rec;
+      for (int n = 0; n < 5; ++n) {
+        if (__dsub_rn(r.width, delta) >= 0.5) {
+          r.x1 = __dsub_rn(r.x1, __dmul_rn(-r.dy, delta_2));
+          r.y1 = __dsub_rn(r.y1, __dmul_rn(r.dx, delta_2));
+          r.x2 = __dsub_rn(r.x2, __dmul_rn(-r.dy, delta_2));
+          r.y2 = __dsub_rn(r.y2, __dmul_rn(r.dx, delta_2));
+          r.width = __dsub_rn(r.width, delta);
+          const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
+          if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+      }
+    }
+    if (!(log_nfa > LOG_EPS)) {
+      r = rec;
+      for (int n = 0; n < 5; ++n) {
+        if (__dsub_rn(r.width, delta) >= 0.5) {
+          r.p = __ddiv_rn(r.p, 2.0);
+          r.prec = __dmul_rn(r.p, PL_PI);
+          const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
+          if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    const size_t o = (size_t)f * L.rect_cap + ri;
+    rectValid[o] = log_nfa > LOG_EPS ? 1 : 0;
+    LsdSegment s;
+    // "+0.5" offset then "/ SCALE" (flsd())
+    s.x1 = (float)__ddiv_rn(__dadd_rn(rec.x1, 0.5), L.scale);
+    s.y1 = (float)__ddiv_rn(__dadd_rn(rec.y1, 0.5), L.scale);
+    s.x2 = (float)__ddiv_rn(__dadd_rn(rec.x2, 0.5), L.scale);
+    s.y2 = (float)__ddiv_rn(__dadd_rn(rec.y2, 0.5), L.scale);
+    s.width = __ddiv_rn(rec.width, L.scale);
+    s.prec = rec.p;
+    s.nfa = log_nfa;
+    rectOut[o] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_lsd_finish: per frame — ordered compaction of the accepted rectangles, KeyLine fields
+// (LSDDetector::detectImpl), keep the `max_lines` strongest by response (auxiliar.h:67-72; ties in
+// detection order), LBD (BinaryDescriptor::computeLBD + binaryConversion) and the line equations
+// sp x ep / |(l0, l1)| of ExtractLineSegment.
+// ------------------------------------------------------------------------------------------
+__constant__ int c_lbd_comb[32][2] = {{0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6},
+                                      {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7}, {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8},
+                                      {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
+
+__device__ __forceinline__ plslam_keyline_t make_keyline(const LsdSegment& s, int W, int H, int class_id) {
+  float e0 = s.x1, e1 = s.y1, e2 = s.x2, e3 = s.y2;
+  if (e0 < 0) e0 = 0;
+  if (e0 >= W) e0 = (float)W - 1.0f;
+  if (e2 < 0) e2 = 0;
+  if (e2 >= W) e2 = (float)W - 1.0f;
+  if (e1 < 0) e1 = 0;
+  if (e1 >= H) e1 = (float)H - 1.0f;
+  if (e3 < 0) e3 = 0;
+  if (e3 >= H) e3 = (float)H - 1.0f;
+  plslam_keyline_t kl;
+  kl.startPointX = e0; kl.startPointY = e1; kl.endPointX = e2; kl.endPointY = e3;
+  kl.sPointInOctaveX = e0; kl.sPointInOctaveY = e1; kl.ePointInOctaveX = e2; kl.ePointInOctaveY = e3;
+  const double dx = (double)__fsub_rn(e0, e2), dy = (double)__fsub_rn(e1, e3);
+  kl.lineLength = (float)sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  const int x0 = __float2int_rn(e0), y0 = __float2int_rn(e1), x1 = __float2int_rn(e2), y1 = __float2int_rn(e3);
+  kl.numOfPixels = max(abs(x1 - x0), abs(y1 - y0)) + 1;
+  kl.angle = pl_atan2f_dev(__fsub_rn(e3, e1), __fsub_rn(e2, e0));
+  kl.class_id = class_id;
+  kl.octave = 0;
+  kl.size = __fmul_rn(__fsub_rn(e2, e0), __fsub_rn(e3, e1));
+  kl.response = __fdiv_rn(kl.lineLength, (float)max(W, H));
+  kl.pt_x = __fdiv_rn(__fadd_rn(e2, e0), 2.f);
+  kl.pt_y = __fdiv_rn(__fadd_rn(e3, e1), 2.f);
+  return kl;
+}
+
+__device__ __forceinline__ void sobel_at_dev(const uint8_t* img, int W, int H, int pitch, int x, int y, int& dx, int& dy) {
+  const int xm = reflect101_dev(x - 1, W), xp = reflect101_dev(x + 1, W);
+  const int ym = reflect101_dev(y - 1, H), yp = reflect101_dev(y + 1, H);
+  const uint8_t* r0 = img + (size_t)ym * pitch;
+  const uint8_t* r1 = img + (size_t)y * pitch;
+  const uint8_t* r2 = img + (size_t)yp * pitch;
+  dx = ((int)r0[xp] - (int)r0[xm]) + 2 * ((int)r1[xp] - (int)r1[xm]) + ((int)r2[xp] - (int)r2[xm]);
+  dy = ((int)r2[xm] - (int)r0[xm]) + 2 * ((int)r2[x] - (int)r0[x]) + ((int)r2[xp] - (int)r0[xp]);
+}
+
+__global__ void __launch_bounds__(256) k_lsd_finish(const __grid_constant__ LineParams L, const uint8_t* __restrict__ img,
+                                                    int pitch, size_t frame_stride, const int* __restrict__ nrects,
+                                                    const LsdSegment* __restrict__ rectOut,
+                                                    const uint8_t* __restrict__ rectValid, LsdSegment* __restrict__ segsAll,
+                                                    int* __restrict__ nsegs, float* __restrict__ rowsumAll,
+                                                    plslam_keyline_t* __restrict__ keylines, uint8_t* __restrict__ desc,
+                                                    double* __restrict__ funcs, int capacity, int* __restrict__ counts) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ int warpTmp[33];
+  __shared__ int sh_nseg, sh_nkeep;
+  const int f = blockIdx.x, t = threadIdx.x, T = blockDim.x;
+  int* flag = reinterpret_cast<int*>(smem_raw);                 // [rect_cap]
+  float* resp = reinterpret_cast<float*>(flag + L.rect_cap);    // [rect_cap] response of segment i
+  int* keepIdx = reinterpret_cast<int*>(resp + L.rect_cap);     // [out_cap] segment index of kept line r
+  const int nr = nrects[f];
+  const LsdSegment* rin = rectOut + (size_t)f * L.rect_cap;
+  const uint8_t* valid = rectValid + (size_t)f * L.rect_cap;
+  LsdSegment* segs = segsAll + (size_t)f * L.rect_cap;
+  for (int i = t; i < nr; i += T) flag[i] = valid[i];
+  __syncthreads();
+  const int nseg = block_scan_excl(flag, nr, warpTmp);
+  for (int i = t; i < nr; i += T)
+    if (valid[i]) segs[flag[i]] = rin[i];
+  if (t == 0) { sh_nseg = nseg; nsegs[f] = nseg; }
+  __syncthreads();
+  // responses
+  const uint8_t* I = img + (size_t)f * frame_stride;
+  for (int i = t; i < nseg; i += T) resp[i] = make_keyline(segs[i], L.W, L.H, i).response;
+  __syncthreads();
+  int nkeep = nseg;
+  if (L.max_lines > 0 && nseg > L.max_lines) {
+    nkeep = L.max_lines;
+    for (int i = t; i < nseg; i += T) {
+      const float ri = resp[i];
+      int rank = 0;
+      for (int j = 0; j < nseg; ++j) {
+        const float rj = resp[j];
+        rank += (rj > ri) || (rj == ri && j < i);
+      }
+      if (rank < nkeep) keepIdx[rank] = i;
+    }
+  } else {
+    for (int i = t; i < nseg; i += T) keepIdx[i] = i;
+  }
+  if (nkeep > capacity) nkeep = capacity;  // host checks counts against capacity and reports
+  if (t == 0) { sh_nkeep = nkeep; counts[f] = (L.max_lines > 0 && nseg > L.max_lines) ? L.max_lines : nseg; }
+  __syncthreads();
+  plslam_keyline_t* KL = keylines + (size_t)f * capacity;
+  for (int r = t; r < nkeep; r += T) {
+    const plslam_keyline_t kl = make_keyline(segs[keepIdx[r]], L.W, L.H, r);
+    KL[r] = kl;
+    // lineF = sp x ep / sqrt(l0^2 + l1^2) in double
+    const double x1 = kl.startPointX, y1 = kl.startPointY, x2 = kl.endPointX, y2 = kl.endPointY;
+    const double l0 = __dsub_rn(y1, y2), l1 = __dsub_rn(x2, x1), l2 = __dsub_rn(__dmul_rn(x1, y2), __dmul_rn(y1, x2));
+    const double nrm = sqrt(__dadd_rn(__dmul_rn(l0, l0), __dmul_rn(l1, l1)));
+    double* F = funcs + ((size_t)f * capacity + r) * 3;
+    F[0] = __ddiv_rn(l0, nrm);
+    F[1] = __ddiv_rn(l1, nrm);
+    F[2] = __ddiv_rn(l2, nrm);
+  }
+  __syncthreads();
+  // LBD row sums: one thread per (line, support-region row), sequential along the line
+  float* rowsum = rowsumAll + (size_t)f * L.out_cap * LBD_ROWS * 4;
+  for (int task = t; task < nkeep * LBD_ROWS; task += T) {
+    const int r = task / LBD_ROWS, hID = task - r * LBD_ROWS;
+    const plslam_keyline_t kl = KL[r];
+    const short lengthOfLSP = (short)kl.numOfPixels;
+    const short halfWidth = (lengthOfLSP - 1) / 2, halfHeight = (LBD_ROWS - 1) / 2;
+    const float midX = (float)__dmul_rn(0.5, (double)__fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
+    const float midY = (float)__dmul_rn(0.5, (double)__fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
+    float dL0, dL1;
+    {
+      double s, c;
+      pl_sincos_dev((double)kl.angle, &s, &c);
+      dL0 = (float)c;
+      dL1 = (float)s;
+    }
+    const float dO0 = -dL1, dO1 = dL0;
+    // sCor0 after hID row steps (each step: sCorX0 -= dL[1]; sCorY0 += dL[0])
+    float sx0 = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, (float)halfHeight)), midX);
+    float sy0 = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, (float)halfHeight)), midY);
+    for (int k = 0; k < hID; ++k) {
+      sx0 = __fsub_rn(sx0, dL1);
+      sy0 = __fadd_rn(sy0, dL0);
+    }
+    float sCorX = sx0, sCorY = sy0;
+    float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
+    const short imageWidth = (short)(L.W - 1), imageHeight = (short)(L.H - 1);
+    for (short wID = 0; wID < lengthOfLSP; ++wID) {
+      short tc = (short)roundf(sCorX);
+      const short xCor = (tc < 0) ? 0 : (tc > imageWidth) ? imageWidth : tc;
+      tc = (short)roundf(sCorY);
+      const short yCor = (tc < 0) ? 0 : (tc > imageHeight) ? imageHeight : tc;
+      int dx, dy;
+      sobel_at_dev(I, L.W, L.H, pitch, xCor, yCor, dx, dy);
+      const float gDL = __fadd_rn(__fmul_rn((float)dx, dL0), __fmul_rn((float)dy, dL1));
+      const float gDO = __fadd_rn(__fmul_rn((float)dx, dO0), __fmul_rn((float)dy, dO1));
+      if (gDL > 0) pgdL = __fadd_rn(pgdL, gDL); else ngdL = __fsub_rn(ngdL, gDL);
+      if (gDO > 0) pgdO = __fadd_rn(pgdO, gDO); else ngdO = __fsub_rn(ngdO, gDO);
+      sCorX = __fadd_rn(sCorX, dL0);
+      sCorY = __fadd_rn(sCorY, dL1);
+    }
+    const float cg = L.gaussG[hID];
+    float* o = rowsum + (size_t)task * 4;
+    o[0] = __fmul_rn(cg, pgdL);
+    o[1] = __fmul_rn(cg, ngdL);
+    o[2] = __fmul_rn(cg, pgdO);
+    o[3] = __fmul_rn(cg, ngdO);
+  }
+  __syncthreads();
+  // band accumulation, normalisation and binarisation: one thread per line
+  for (int r = t; r < nkeep; r += T) {
+    float band[LBD_BANDS][8];
+#pragma unroll
+    for (int b = 0; b < LBD_BANDS; ++b)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) band[b][q] = 0.f;
+    const float* rs = rowsum + (size_t)r * LBD_ROWS * 4;
+    for (int hID = 0; hID < LBD_ROWS; ++hID) {
+      const float pL = rs[hID * 4], nL = rs[hID * 4 + 1], pO = rs[hID * 4 + 2], nO = rs[hID * 4 + 3];
+      const float pL2 = __fmul_rn(pL, pL), nL2 = __fmul_rn(nL, nL), pO2 = __fmul_rn(pO, pO), nO2 = __fmul_rn(nO, nO);
+      const int b0 = hID / LBD_W, m = hID % LBD_W;
+      // current band, band above (b0-1), band below (b0+1) — in that order, as computeLBD
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int b = k == 0 ? b0 : (k == 1 ? b0 - 1 : b0 + 1);
+        if (b < 0 || b >= LBD_BANDS) continue;
+        const float coef = k == 0 ? L.gaussL[m + LBD_W] : (k == 1 ? L.gaussL[m + 2 * LBD_W] : L.gaussL[m]);
+        const float cc = __fmul_rn(coef, coef);
+        band[b][0] = __fadd_rn(band[b][0], __fmul_rn(coef, pL));
+        band[b][1] = __fadd_rn(band[b][1], __fmul_rn(coef, nL));
+        band[b][2] = __fadd_rn(band[b][2], __fmul_rn(cc, pL2));
+        band[b][3] = __fadd_rn(band[b][3], __fmul_rn(cc, nL2));
+        band[b][4] = __fadd_rn(band[b][4], __fmul_rn(coef, pO));
+        band[b][5] = __fadd_rn(band[b][5], __fmul_rn(coef, nO));
+        band[b][6] = __fadd_rn(band[b][6], __fmul_rn(cc, pO2));
+        band[b][7] = __fadd_rn(band[b][7], __fmul_rn(cc, nO2));
+      }
+    }
+    float des[LBD_BANDS * 8];
+    const float invN2 = (float)(1.0 / (LBD_W * 2.0)), invN3 = (float)(1.0 / (LBD_W * 3.0));
+#pragma unroll
+    for (int b = 0; b < LBD_BANDS; ++b) {
+      const float invN = (b == 0 || b == LBD_BANDS - 1) ? invN2 : invN3;
+      float tmp = __fmul_rn(band[b][0], invN);
+      des[b * 8] = tmp;
+      des[b * 8 + 4] = sqrtf(__fsub_rn(__fmul_rn(band[b][2], invN), __fmul_rn(tmp, tmp)));
+      tmp = __fmul_rn(band[b][1], invN);
+      des[b * 8 + 1] = tmp;
+      des[b * 8 + 5] = sqrtf(__fsub_rn(__fmul_rn(band[b][3], invN), __fmul_rn(tmp, tmp)));
+      tmp = __fmul_rn(band[b][4], invN);
+      des[b * 8 + 2] = tmp;
+      des[b * 8 + 6] = sqrtf(__fsub_rn(__fmul_rn(band[b][6], invN), __fmul_rn(tmp, tmp)));
+      tmp = __fmul_rn(band[b][5], invN);
+      des[b * 8 + 3] = tmp;
+      des[b * 8 + 7] = sqrtf(__fsub_rn(__fmul_rn(band[b][7], invN), __fmul_rn(tmp, tmp)));
+    }
+    float tempM = 0, tempS = 0;
+#pragma unroll
+    for (int b = 0; b < LBD_BANDS; ++b) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tempM = __fadd_rn(tempM, __fmul_rn(des[b * 8 + q], des[b * 8 + q]));
+#pragma unroll
+      for (int q = 4; q < 8; ++q) tempS = __fadd_rn(tempS, __fmul_rn(des[b * 8 + q], des[b * 8 + q]));
+    }
+    tempM = __fdiv_rn(1.f, sqrtf(tempM));
+    tempS = __fdiv_rn(1.f, sqrtf(tempS));
+#pragma unroll
+    for (int b = 0; b < LBD_BANDS; ++b) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) des[b * 8 + q] = __fmul_rn(des[b * 8 + q], tempM);
+#pragma unroll
+      for (int q = 4; q < 8; ++q) des[b * 8 + q] = __fmul_rn(des[b * 8 + q], tempS);
+    }
+#pragma unroll
+    for (int i = 0; i < LBD_BANDS * 8; ++i)
+      if ((double)des[i] > 0.4) des[i] = (float)0.4;
+    float tmp = 0;
+#pragma unroll
+    for (int i = 0; i < LBD_BANDS * 8; ++i) tmp = __fadd_rn(tmp, __fmul_rn(des[i], des[i]));
+    tmp = __fdiv_rn(1.f, sqrtf(tmp));
+#pragma unroll
+    for (int i = 0; i < LBD_BANDS * 8; ++i) des[i] = __fmul_rn(des[i], tmp);
+    uint8_t* D = desc + ((size_t)f * capacity + r) * 32;
+    for (int comb = 0; comb < 32; ++comb) {
+      const int a = c_lbd_comb[comb][0] * 8, b = c_lbd_comb[comb][1] * 8;
+      unsigned res = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (des[a + i] > des[b + i]) res += 1u << i;
+      D[comb] = (uint8_t)res;
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+LineExtractor::LineExtractor() {}
+
+LineExtractor::~LineExtractor() {
+  DevBuf* all[] = {&scaled, &pix, &coef, &rowhist, &binstart, &maxg2, &seeds, &nseeds, &regbuf, &rects, &nrects,
+                   &rectout, &segs, &nsegs, &rowsum, &status, &stageIn, &stageKl, &stageDesc, &stageFuncs, &stageCnt};
+  for (DevBuf* b : all) b->release();
+  if (ownStream) cudaStreamDestroy(ownStream);
+  if (pinnedStatus) cudaFreeHost(pinnedStatus);
+}
+
+// OpenCV's 8-bit fixed-point Gaussian table (error diffusion from the borders, centre = 256 - 2*side)
+static void gauss_table_u8(double sigma, int ksize, int* out) {
+  std::vector<double> k(ksize);
+  double sum = 0;
+  const double scale2X = -0.5 / (sigma * sigma);
+  for (int i = 0; i < ksize; ++i) {
+    const double x = i - (ksize - 1) * 0.5;
+    k[i] = std::exp(scale2X * x * x);
+    sum += k[i];
+  }
+  double err = 0;
+  int side = 0;
+  for (int i = 0; i < ksize / 2; ++i) {
+    const double v = k[i] / sum * 256.0 + err;
+    const int r = (int)std::lrint(v);
+    err = v - r;
+    out[i] = out[ksize - 1 - i] = r;
+    side += r;
+  }
+  out[ksize / 2] = 256 - 2 * side;
+}
+
+int LineExtractor::configure(int W, int H, int batch) {
+  if (W == cfgW && H == cfgH && batch <= cfgB) return PLSLAM_OK;
+  PL_CHECK_ARG(W >= 16 && H >= 16 && W <= 16000 && H <= 16000);
+  if (device < 0) {
+    PL_CUDA(cudaGetDevice(&device));
+    PL_CUDA(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
+    PL_CUDA(cudaMallocHost(&pinnedStatus, 64));
+  }
+  std::memset(&P, 0, sizeof(P));
+  // createLineSegmentDetector(LSD_REFINE_ADV) defaults: scale 0.8, sigma_scale 0.6, quant 2, ang_th 22.5,
+  // log_eps 0, density_th 0.7, n_bins 1024
+  const double SCALE = 0.8, SIGMA_SCALE = 0.6, QUANT = 2.0, ANG_TH = 22.5;
+  P.W = W;
+  P.H = H;
+  P.scale = SCALE;
+  P.sw = (int)std::lrint(W * SCALE);
+  P.sh = (int)std::lrint(H * SCALE);
+  P.spitch = (int)align_up(P.sw, 32);
+  P.P = P.sw * P.sh;
+  const double sigma = SIGMA_SCALE / SCALE;
+  const unsigned h = (unsigned)std::ceil(sigma * std::sqrt(2 * 3.0 * std::log(10.0)));
+  P.ksize = 1 + 2 * (int)h;
+  PL_CHECK_ARG(P.ksize == 7);
+  gauss_table_u8(sigma, P.ksize, P.blurk);
+  P.prec = PL_PI * ANG_TH / 180;
+  P.p = ANG_TH / 180;
+  P.rho = QUANT / std::sin(P.prec);
+  P.log_nt = 5 * (std::log10((double)P.sw) + std::log10((double)P.sh)) / 2 + std::log10(11.0);
+  P.min_reg_size = (int)(size_t)(-P.log_nt / std::log10(P.p));
+  P.density_th = 0.7;
+  P.log_eps = 0.0;
+  P.max_lines = max_lines;
+  P.rect_cap = rect_cap;
+  P.out_cap = out_capacity();
+  {  // LBD weights (BinaryDescriptor constructor)
+    double u = (LBD_W * 3 - 1) / 2;
+    double sg = (LBD_W * 2 + 1) / 2;
+    double inv = -1 / (2 * sg * sg);
+    for (int i = 0; i < LBD_W * 3; ++i) { const double d = i - u; P.gaussL[i] = (float)std::exp(d * d * inv); }
+    u = (LBD_BANDS * LBD_W - 1) / 2;
+    sg = u;
+    inv = -1 / (2 * sg * sg);
+    for (int i = 0; i < LBD_ROWS; ++i) { const double d = i - u; P.gaussG[i] = (float)std::exp(d * d * inv); }
+  }
+  // INTER_LINEAR_EXACT tables (step exactly 1/SCALE)
+  std::vector<int> tab;
+  auto emit = [&](int ssize, int dsize) {
+    std::vector<int> ofs(dsize), c1(dsize);
+    const double sc = 1.0 / SCALE;
+    for (int d = 0; d < dsize; ++d) {
+      const double fv = sc * (d + 0.5) - 0.5;
+      const int i = (int)std::floor(fv);
+      if (i >= 0 && ssize > 1) {
+        if (i < ssize - 1) { ofs[d] = i; c1[d] = (int)std::lrint((fv - i) * 256.0); }
+        else { ofs[d] = ssize - 1; c1[d] = 0; }
+      } else { ofs[d] = 0; c1[d] = 0; }
+    }
+    tab.insert(tab.end(), ofs.begin(), ofs.end());
+    tab.insert(tab.end(), c1.begin(), c1.end());
+  };
+  emit(W, P.sw);
+  emit(H, P.sh);
+  int rc;
+  const size_t B = std::max(batch, cfgB);
+  if ((rc = coef.ensure(tab.size() * sizeof(int)))) return rc;
+  PL_CUDA(cudaMemcpy(coef.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if ((rc = scaled.ensure(B * P.spitch * P.sh))) return rc;
+  if ((rc = pix.ensure(B * P.P * sizeof(uint4)))) return rc;
+  if ((rc = rowhist.ensure(B * P.sh * LSD_BINS * sizeof(unsigned)))) return rc;
+  if ((rc = binstart.ensure(B * LSD_BINS * sizeof(unsigned)))) return rc;
+  if ((rc = maxg2.ensure(B * sizeof(int)))) return rc;
+  if ((rc = seeds.ensure(B * P.P * sizeof(unsigned)))) return rc;
+  if ((rc = nseeds.ensure(B * sizeof(int)))) return rc;
+  if ((rc = regbuf.ensure(B * P.P * sizeof(unsigned)))) return rc;
+  if ((rc = rects.ensure(B * P.rect_cap * sizeof(LsdRect)))) return rc;
+  if ((rc = nrects.ensure(B * sizeof(int)))) return rc;
+  if ((rc = rectout.ensure(B * P.rect_cap * (sizeof(LsdSegment) + 1)))) return rc;
+  if ((rc = segs.ensure(B * P.rect_cap * sizeof(LsdSegment)))) return rc;
+  if ((rc = nsegs.ensure(B * sizeof(int)))) return rc;
+  if ((rc = rowsum.ensure(B * P.out_cap * LBD_ROWS * 4 * sizeof(float)))) return rc;
+  if ((rc = status.ensure(sizeof(int)))) return rc;
+  const size_t growSmem = 96 * sizeof(double) + (size_t)((P.P + 31) / 32) * 4;
+  if (growSmem > 200 * 1024) {
+    set_error("frame too large for the shared-memory `used` map of k_lsd_grow (%zu B)", growSmem);
+    return PLSLAM_ERR_INVALID;
+  }
+  PL_CUDA(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PL_CUDA(cudaFuncSetAttribute(k_lsd_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  cfgW = W;
+  cfgH = H;
+  cfgB = (int)B;
+  return PLSLAM_OK;
+}
+
+int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int H, int pitch, size_t frame_stride,
+                                  plslam_keyline_t* d_keylines, uint8_t* d_desc, double* d_funcs, int capacity,
+                                  int32_t* d_counts, cudaStream_t st) {
+  PL_CHECK_ARG(d_images && d_keylines && d_desc && d_funcs && d_counts);
+  PL_CHECK_ARG(batch >= 1 && batch <= 65535 && pitch >= W);
+  int rc = configure(W, H, batch);
+  if (rc) return rc;
+  if (capacity < P.out_cap) {
+    set_error("capacity %d < line output capacity %d", capacity, P.out_cap);
+    return PLSLAM_ERR_CAPACITY;
+  }
+  last_batch = batch;
+  PL_CUDA(cudaMemsetAsync(maxg2.p, 0, (size_t)batch * sizeof(int), st));
+  PL_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), st));
+  k_lsd_scale<<<dim3(div_up(P.sw, ST_W), div_up(P.sh, ST_H), batch), 256, 0, st>>>(P, d_images, pitch, frame_stride,
+                                                                                     coef.as<int>(), scaled.as<uint8_t>());
+  k_lsd_grad<<<dim3(div_up(P.sw, 32), div_up(P.sh, 8), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(),
+                                                                             maxg2.as<int>());
+  k_lsd_rowhist<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>());
+  k_lsd_colscan<<<batch, LSD_BINS, 0, st>>>(P, rowhist.as<unsigned>(), binstart.as<unsigned>(), nseeds.as<int>());
+  k_lsd_scatter<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>(),
+                                                              binstart.as<unsigned>(), seeds.as<unsigned>());
+  const size_t growSmem = 96 * sizeof(double) + (size_t)((P.P + 31) / 32) * 4;
+  k_lsd_grow<<<batch, 32, growSmem, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
+                                          rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());
+  LsdSegment* rout = rectout.as<LsdSegment>();
+  uint8_t* rvalid = reinterpret_cast<uint8_t*>(rout + (size_t)cfgB * P.rect_cap);
+  k_lsd_nfa<<<dim3(div_up(P.rect_cap, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), rects.as<LsdRect>(), nrects.as<int>(),
+                                                                rout, rvalid);
+  const size_t finSmem = (size_t)P.rect_cap * 8 + (size_t)P.out_cap * 4;
+  k_lsd_finish<<<batch, 256, finSmem, st>>>(P, d_images, pitch, frame_stride, nrects.as<int>(), rout, rvalid,
+                                            segs.as<LsdSegment>(), nsegs.as<int>(), rowsum.as<float>(), d_keylines, d_desc,
+                                            d_funcs, capacity, d_counts);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int LineExtractor::check_status(cudaStream_t st) {
+  PL_CUDA(cudaMemcpyAsync(pinnedStatus, status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaStreamSynchronize(st));
+  const int s = *reinterpret_cast<int*>(pinnedStatus);
+  if (s != PLSLAM_OK) set_error("device status %d (rectangle list overflow: raise rect_cap)", s);
+  return s;
+}
+
+int LineExtractor::extract_host(const uint8_t* images, int batch, int W, int H, int pitch, size_t frame_stride,
+                                plslam_keyline_t* keylines, uint8_t* desc, double* funcs, int capacity, int32_t* counts) {
+  PL_CHECK_ARG(images && keylines && desc && funcs && counts && batch >= 1 && pitch >= W);
+  int rc = configure(W, H, batch);
+  if (rc) return rc;
+  const int cap = P.out_cap;
+  const size_t dpitch = align_up(W, 32), dstride = dpitch * H;
+  if ((rc = stageIn.ensure(dstride * batch))) return rc;
+  if ((rc = stageKl.ensure((size_t)batch * cap * sizeof(plslam_keyline_t)))) return rc;
+  if ((rc = stageDesc.ensure((size_t)batch * cap * 32))) return rc;
+  if ((rc = stageFuncs.ensure((size_t)batch * cap * 3 * sizeof(double)))) return rc;
+  if ((rc = stageCnt.ensure((size_t)batch * sizeof(int)))) return rc;
+  cudaStream_t st = ownStream;
+  for (int f = 0; f < batch; ++f)
+    PL_CUDA(cudaMemcpy2DAsync(stageIn.as<uint8_t>() + f * dstride, dpitch, images + f * frame_stride, pitch, W, H,
+                              cudaMemcpyHostToDevice, st));
+  rc = extract_device(stageIn.as<uint8_t>(), batch, W, H, (int)dpitch, dstride, stageKl.as<plslam_keyline_t>(),
+                      stageDesc.as<uint8_t>(), stageFuncs.as<double>(), cap, stageCnt.as<int>(), st);
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpyAsync(counts, stageCnt.p, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if ((rc = check_status(st))) return rc;
+  for (int f = 0; f < batch; ++f) {
+    const int n = counts[f];
+    if (n > capacity || n > cap) {
+      set_error("frame %d has %d lines, capacity %d", f, n, std::min(capacity, cap));
+      return PLSLAM_ERR_CAPACITY;
+    }
+    if (!n) continue;
+    PL_CUDA(cudaMemcpyAsync(keylines + (size_t)f * capacity, stageKl.as<plslam_keyline_t>() + (size_t)f * cap,
+                            (size_t)n * sizeof(plslam_keyline_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(desc + (size_t)f * capacity * 32, stageDesc.as<uint8_t>() + (size_t)f * cap * 32, (size_t)n * 32,
+                            cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(funcs + (size_t)f * capacity * 3, stageFuncs.as<double>() + (size_t)f * cap * 3,
+                            (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  PL_CUDA(cudaStreamSynchronize(st));
+  return PLSLAM_OK;
+}
+
+int LineExtractor::scaled_size(int* w, int* h) const {
+  PL_CHECK_ARG(cfgW > 0);
+  *w = P.sw;
+  *h = P.sh;
+  return PLSLAM_OK;
+}
+
+int LineExtractor::copy_scaled(int frame, uint8_t* out, size_t bytes) {
+  PL_CHECK_ARG(cfgW > 0 && frame >= 0 && frame < last_batch && out && bytes >= (size_t)P.P);
+  PL_CUDA(cudaDeviceSynchronize());
+  PL_CUDA(cudaMemcpy2D(out, P.sw, scaled.as<uint8_t>() + (size_t)frame * P.spitch * P.sh, P.spitch, P.sw, P.sh,
+                       cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int LineExtractor::copy_angles(int frame, float* deg_out, int32_t* g2_out, size_t n) {
+  PL_CHECK_ARG(cfgW > 0 && frame >= 0 && frame < last_batch && n >= (size_t)P.P);
+  PL_CUDA(cudaDeviceSynchronize());
+  std::vector<uint4> h(P.P);
+  PL_CUDA(cudaMemcpy(h.data(), pix.as<uint4>() + (size_t)frame * P.P, (size_t)P.P * sizeof(uint4), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < P.P; ++i) {
+    if (deg_out) std::memcpy(&deg_out[i], &h[i].x, 4);
+    if (g2_out) g2_out[i] = (int32_t)h[i].w;
+  }
+  return PLSLAM_OK;
+}
+
+int LineExtractor::copy_segments(int frame, LsdSegment* out, int capacity, int* n_out) {
+  PL_CHECK_ARG(cfgW > 0 && frame >= 0 && frame < last_batch && n_out);
+  PL_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  PL_CUDA(cudaMemcpy(&n, nsegs.as<int>() + frame, sizeof(int), cudaMemcpyDeviceToHost));
+  *n_out = n;
+  if (n > capacity) return PLSLAM_ERR_CAPACITY;
+  if (n) PL_CUDA(cudaMemcpy(out, segs.as<LsdSegment>() + (size_t)frame * P.rect_cap, (size_t)n * sizeof(LsdSegment), cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+}  // namespace plslam

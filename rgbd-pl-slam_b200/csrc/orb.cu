@@ -7,6 +7,7 @@
 // whole batch (grid.y = frame), so a 256-frame batch is ~16 launches.
 #include "orb.cuh"
 #include "fast_score.cuh"
+#include "pl_math.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -556,57 +557,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams 
 // byte; its 16 pattern points are rotated with the pinned sin/cos (double Cody-Waite + fdlibm
 // kernels, every op individually rounded) and the FMA form of the shipped binary (@0x77888-0x778a7).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_atan2_dev(float y, float x) {
-  const float scale = (float)(180.0 / 3.14159265358979323846);
-  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
-              p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
-  const float eps = (float)2.2204460492503131e-16;
-  const float ax = fabsf(x), ay = fabsf(y);
-  float a, c, c2;
-  if (ax >= ay) {
-    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-  } else {
-    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-  }
-  if (x < 0) a = __fsub_rn(180.f, a);
-  if (y < 0) a = __fsub_rn(360.f, a);
-  return a;
-}
-
-__device__ __forceinline__ void orb_sincos_dev(float x, float* s_out, float* c_out) {
-  const double xd = (double)x;
-  const double kf = rint(__dmul_rn(xd, 0.63661977236758134308));
-  const int k = (int)kf;
-  double r = __dsub_rn(xd, __dmul_rn(kf, 1.57079632673412561417e+00));
-  r = __dsub_rn(r, __dmul_rn(kf, 6.07710050650619224932e-11));
-  const double z = __dmul_rn(r, r);
-  double ps = __dadd_rn(-2.50507602534068634195e-08, __dmul_rn(z, 1.58969099521155010221e-10));
-  ps = __dadd_rn(2.75573137070700676789e-06, __dmul_rn(z, ps));
-  ps = __dadd_rn(-1.98412698298579493134e-04, __dmul_rn(z, ps));
-  ps = __dadd_rn(8.33333333332248946124e-03, __dmul_rn(z, ps));
-  ps = __dadd_rn(-1.66666666666666324348e-01, __dmul_rn(z, ps));
-  const double sn = __dadd_rn(r, __dmul_rn(__dmul_rn(r, z), ps));
-  double pc = __dadd_rn(2.08757232129817482790e-09, __dmul_rn(z, -1.13596475577881948265e-11));
-  pc = __dadd_rn(-2.75573143513906633035e-07, __dmul_rn(z, pc));
-  pc = __dadd_rn(2.48015872894767294178e-05, __dmul_rn(z, pc));
-  pc = __dadd_rn(-1.38888888888741095749e-03, __dmul_rn(z, pc));
-  pc = __dadd_rn(4.16666666666666019037e-02, __dmul_rn(z, pc));
-  const double cs = __dadd_rn(__dsub_rn(1.0, __dmul_rn(0.5, z)), __dmul_rn(__dmul_rn(z, z), pc));
-  double s, c;
-  switch (k & 3) {
-    case 0: s = sn; c = cs; break;
-    case 1: s = cs; c = -sn; break;
-    case 2: s = -sn; c = -cs; break;
-    default: s = -cs; c = sn; break;
-  }
-  *s_out = (float)s;
-  *c_out = (float)c;
-}
-
 __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ OrbParams P, OrbImages I,
                                                      const uint2* __restrict__ lvlKp, const int* __restrict__ lvlCnt,
                                                      plslam_keypoint_t* __restrict__ kps, uint8_t* __restrict__ desc,
@@ -660,7 +610,7 @@ __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Orb
 
   // --- descriptor on the blurred level ---
   float sn, cs;
-  orb_sincos_dev(__fmul_rn(angle, 0.017453292f), &sn, &cs);
+  pl_sincosf_dev(__fmul_rn(angle, 0.017453292f), &sn, &cs);
   const uint8_t* Bc = I.blurred + (size_t)f * P.pyrFrameStride + L.off + (size_t)Y * L.pitch + X;
   const int bp = L.pitch;
   int val = 0;

@@ -83,9 +83,12 @@ class ORBextractor:
         self.max_keypoints = lib().plslam_orb_max_keypoints(self._h)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().plslam_orb_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().plslam_orb_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
 
     # getters (ORBextractor.h:63-83)
     def GetLevels(self):
@@ -177,3 +180,101 @@ def kps_from_tensor(t):
     """(.., 7) int32 torch tensor (device layout of plslam_keypoint_t) -> numpy structured array."""
     a = t.detach().cpu().numpy()
     return a.view(KP_DTYPE).reshape(a.shape[:-1])
+
+
+class LineSegment:
+    """Mirror of ORB_SLAM2::LineSegment (reference include/ExtractLineSegment.h:30-55) over the C-ABI."""
+
+    def __init__(self, max_lines=40):
+        self._h = C.c_void_p()
+        L = lib()
+        L.plslam_lines_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.plslam_lines_destroy.argtypes = [C.c_void_p]
+        L.plslam_lines_destroy.restype = None
+        _check(L.plslam_lines_create(C.byref(self._h)))
+        _check(L.plslam_lines_set_max_lines(self._h, int(max_lines)))
+        self.capacity = L.plslam_lines_capacity(self._h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().plslam_lines_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def ExtractLineSegment(self, img):
+        """-> (keylines[n], ldesc[n, 32], keylineFunctions[n, 3])"""
+        if img is None or img.size == 0:
+            return np.empty(0, KEYLINE_DTYPE), np.empty((0, 32), np.uint8), np.empty((0, 3))
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.capacity
+        kl = np.empty(cap, KEYLINE_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        funcs = np.empty((cap, 3), np.float64)
+        n = C.c_int(0)
+        _check(lib().plslam_lines_extract(self._h, _vp(img), img.shape[1], img.shape[0], img.strides[0], _vp(kl),
+                                          _vp(desc), _vp(funcs), cap, C.byref(n)))
+        n = n.value
+        return kl[:n].copy(), desc[:n].copy(), funcs[:n].copy()
+
+    def extract_batch_host(self, images):
+        images = np.ascontiguousarray(images, np.uint8)
+        B, H, W = images.shape
+        cap = self.capacity
+        kl = np.empty((B, cap), KEYLINE_DTYPE)
+        desc = np.empty((B, cap, 32), np.uint8)
+        funcs = np.empty((B, cap, 3), np.float64)
+        counts = np.empty(B, np.int32)
+        _check(lib().plslam_lines_extract_batch_host(self._h, _vp(images), B, W, H, images.strides[1],
+                                                     C.c_size_t(images.strides[0]), _vp(kl), _vp(desc), _vp(funcs), cap,
+                                                     _vp(counts)))
+        return kl, desc, funcs, counts
+
+    def extract_batch_device(self, d_images, out=None, stream=None):
+        import torch
+        assert d_images.is_cuda and d_images.dtype == torch.uint8 and d_images.dim() == 3 and d_images.stride(2) == 1
+        B, H, W = d_images.shape
+        cap = self.capacity
+        if out is None:
+            dev = d_images.device
+            out = (torch.empty((B, cap, 17), dtype=torch.int32, device=dev),
+                   torch.empty((B, cap, 32), dtype=torch.uint8, device=dev),
+                   torch.empty((B, cap, 3), dtype=torch.float64, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+        kl, desc, funcs, counts = out
+        _check(lib().plslam_lines_extract_batch_device(self._h, _vp(d_images), B, W, H, d_images.stride(1),
+                                                       C.c_size_t(d_images.stride(0)), _vp(kl), _vp(desc), _vp(funcs),
+                                                       cap, _vp(counts), _stream_ptr(stream)))
+        return out
+
+    def check_status(self, stream=None):
+        _check(lib().plslam_lines_check_status(self._h, _stream_ptr(stream)))
+
+    # parity accessors
+    def scaled(self, frame):
+        w, h = C.c_int(), C.c_int()
+        _check(lib().plslam_lines_scaled_size(self._h, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        _check(lib().plslam_lines_copy_scaled(self._h, frame, _vp(out), C.c_size_t(out.size)))
+        return out
+
+    def level_lines(self, frame):
+        w, h = C.c_int(), C.c_int()
+        _check(lib().plslam_lines_scaled_size(self._h, C.byref(w), C.byref(h)))
+        deg = np.empty((h.value, w.value), np.float32)
+        g2 = np.empty((h.value, w.value), np.int32)
+        _check(lib().plslam_lines_copy_level_lines(self._h, frame, _vp(deg), _vp(g2), C.c_size_t(deg.size)))
+        return deg, g2
+
+    def segments(self, frame):
+        cap = 4096
+        out = np.empty((cap, 7), np.float64)
+        n = C.c_int()
+        _check(lib().plslam_lines_copy_segments(self._h, frame, _vp(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+def keylines_from_tensor(t):
+    a = t.detach().cpu().numpy()
+    return a.view(KEYLINE_DTYPE).reshape(a.shape[:-1])
