@@ -152,6 +152,86 @@ int plslam_lines_copy_scaled(plslam_lines_t* h, int frame, uint8_t* out, size_t 
 int plslam_lines_copy_level_lines(plslam_lines_t* h, int frame, float* degrees, int32_t* grad2, size_t count);
 int plslam_lines_copy_segments(plslam_lines_t* h, int frame, double* seg7, int capacity, int* n_out);
 
+/* ------------------------------------------------------------------------------------------
+ * Matchers — Hamming cores of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-141) and
+ * ORB_SLAM2::LSDmatcher / LineSegment::LineSegmentMathch (include/LSDmatcher.h:25-78,
+ * include/ExtractLineSegment.h:41).  Pointer-based containers (MapPoint*, DBoW2::FeatureVector,
+ * Frame::mGrid) are passed flattened; all pointers inside a job are DEVICE pointers.
+ * ---------------------------------------------------------------------------------------- */
+#define PLSLAM_TH_LOW 50        /* ORBmatcher::TH_LOW       (@0x1269e4) */
+#define PLSLAM_TH_HIGH 100      /* ORBmatcher::TH_HIGH      (@0x1269e8) */
+#define PLSLAM_HISTO_LENGTH 30  /* ORBmatcher::HISTO_LENGTH (@0x1269e0) */
+#define PLSLAM_GRID_COLS 64     /* FRAME_GRID_COLS (include/Frame.h:42) */
+#define PLSLAM_GRID_ROWS 48     /* FRAME_GRID_ROWS (include/Frame.h:41) */
+
+/* ORBmatcher::DescriptorDistance(a, b) (ORBmatcher.h:44, @0x79d20; FORB.cpp:82-102) on two 32-byte
+ * host rows.  Scalar, host-side: one pair is 8 popcounts; the batched forms below are the GPU path. */
+int plslam_descriptor_distance(const uint8_t* a, const uint8_t* b);
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) — what LineSegmentMathch / LSDmatcher run on
+ * LBD rows (include/auxiliar.h:30-51) and the all-pairs ORB case.  out: nq x 4 int32
+ * (trainIdx1, dist1, trainIdx2, dist2), -1 where fewer than 2 train rows exist; ties -> lower index. */
+typedef struct plslam_knn_job {
+  const uint8_t* query; /* nq x 32 */
+  const uint8_t* train; /* nt x 32 */
+  int32_t* out;         /* nq x 4 */
+  int32_t nq, nt;
+} plslam_knn_job_t;
+int plslam_match_knn2_batch_device(const plslam_knn_job_t* d_jobs, int njobs, int max_nq, void* stream);
+int plslam_match_knn2_host(const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* out);
+
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& matches) (ORBmatcher.h:104, @0x80150).
+ * FeatureVectors (std::map<NodeId, vector<unsigned>>) as CSR sorted by node id. */
+typedef struct plslam_bow_job {
+  const uint8_t* kf_desc;   /* N1 x 32 : pKF->mDescriptors */
+  const float* kf_angle;    /* N1      : pKF->mvKeysUn[i].angle */
+  const uint8_t* kf_valid;  /* N1      : pMP && !pMP->isBad() */
+  const int32_t* kf_nodes;  /* n_kf_nodes   : FeatureVector keys, ascending */
+  const int32_t* kf_start;  /* n_kf_nodes+1 : offsets into kf_idx */
+  const int32_t* kf_idx;    /* feature indices per node */
+  const uint8_t* f_desc;    /* N2 x 32 : F.mDescriptors */
+  const float* f_angle;     /* N2      : F.mvKeys[i].angle */
+  const int32_t* f_nodes;
+  const int32_t* f_start;
+  const int32_t* f_idx;
+  int32_t* match_f;         /* N2 : KF feature index matched to each F feature, -1 = none (vpMapPointMatches) */
+  int32_t* nmatches;        /* 1  : return value */
+  int32_t n1, n2, n_kf_nodes, n_f_nodes;
+  float nnratio;            /* mfNNratio */
+  int32_t check_orientation;/* mbCheckOrientation */
+} plslam_bow_job_t;
+int plslam_match_bow_batch_device(const plslam_bow_job_t* d_jobs, int njobs, int max_n, void* stream); /* max_n >= every job's n1 and n2 */
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono)
+ * (ORBmatcher.h:78, @0x80d00) including Frame::GetFeaturesInArea (Frame.h:113). */
+typedef struct plslam_proj_job {
+  /* LastFrame */
+  const uint8_t* last_valid;   /* N1 : mvpMapPoints[i] && !mvbOutlier[i] */
+  const float* last_xyz;       /* N1 x 3 : pMP->GetWorldPos() */
+  const uint8_t* last_desc;    /* N1 x 32 : pMP->GetDescriptor() */
+  const int32_t* last_octave;  /* N1 : mvKeys[i].octave */
+  const float* last_angle;     /* N1 : mvKeysUn[i].angle */
+  const uint8_t* last_obs;     /* N1 : pMP->Observations() > 0 */
+  /* CurrentFrame */
+  const float* cur_xy;         /* N2 x 2 : mvKeysUn[i].pt */
+  const int32_t* cur_octave;   /* N2 */
+  const float* cur_angle;      /* N2 */
+  const uint8_t* cur_desc;     /* N2 x 32 */
+  const float* cur_uright;     /* N2 : mvuRight */
+  const uint8_t* cur_taken;    /* N2 : mvpMapPoints[i] && Observations() > 0 on entry */
+  const int32_t* grid_start;   /* 64*48+1 : CSR of mGrid in [ix][iy] order */
+  const int32_t* grid_items;
+  const float* scale_factors;  /* mvScaleFactors */
+  int32_t* match_cur;          /* N2 : LastFrame index assigned to each current keypoint, -1 = none */
+  int32_t* nmatches;           /* 1 */
+  float cam[12];               /* fx, fy, cx, cy, mbf, mb, mnMinX, mnMaxX, mnMinY, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv */
+  float tcw_cur[12];           /* CurrentFrame.mTcw rows 0..2 (3x4 row-major) */
+  float tcw_last[12];          /* LastFrame.mTcw */
+  float th;
+  int32_t n1, n2, mono, check_orientation;
+} plslam_proj_job_t;
+int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

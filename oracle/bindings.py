@@ -230,3 +230,48 @@ def pl_atan2f(y, x):
     f.restype = C.c_float
     f.argtypes = [C.c_float, C.c_float]
     return float(f(float(y), float(x)))
+
+
+# ---------------------------------------------------------------------------
+# matchers (oracle/match_oracle.cc)
+# ---------------------------------------------------------------------------
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().oracle_descriptor_distance(_p(a), _p(b))
+
+
+def knn2(query, train):
+    query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+    train = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    out = np.empty((len(query), 4), np.int32)
+    lib().oracle_knn2(_p(query), len(query), _p(train), len(train), _p(out))
+    return out
+
+
+def search_by_bow(kf, f, nnratio=0.7, check_ori=True):
+    """kf / f: dicts with desc, angle, (kf: valid), nodes, start, idx.  -> (matchF, nmatches)"""
+    n2 = len(f["desc"])
+    match = np.empty(n2, np.int32)
+    L = lib()
+    L.oracle_search_by_bow.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int] + \
+        [C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_void_p]
+    n = L.oracle_search_by_bow(_p(kf["desc"]), _p(kf["angle"]), _p(kf["valid"]), len(kf["nodes"]), _p(kf["nodes"]),
+                               _p(kf["start"]), _p(kf["idx"]), _p(f["desc"]), _p(f["angle"]), n2, len(f["nodes"]),
+                               _p(f["nodes"]), _p(f["start"]), _p(f["idx"]), nnratio, int(check_ori), _p(match))
+    return match, n
+
+
+def search_by_projection(last, cur, cam, scale_factors, tcw_cur, tcw_last, th, mono=False, check_ori=True):
+    n1, n2 = len(last["desc"]), len(cur["desc"])
+    match = np.empty(n2, np.int32)
+    L = lib()
+    L.oracle_search_by_projection.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 12 + \
+        [C.c_float, C.c_int, C.c_int, C.c_void_p]
+    cam = np.ascontiguousarray(cam, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    tc = np.ascontiguousarray(tcw_cur, np.float32); tl = np.ascontiguousarray(tcw_last, np.float32)
+    n = L.oracle_search_by_projection(n1, _p(last["valid"]), _p(last["xyz"]), _p(last["desc"]), _p(last["octave"]),
+                                      _p(last["angle"]), _p(last["obs"]), n2, _p(cur["xy"]), _p(cur["octave"]),
+                                      _p(cur["angle"]), _p(cur["desc"]), _p(cur["uright"]), _p(cur["taken"]),
+                                      _p(cur["grid_start"]), _p(cur["grid_items"]), _p(cam), _p(sf), _p(tc), _p(tl),
+                                      th, int(mono), int(check_ori), _p(match))
+    return match, n

@@ -1,0 +1,240 @@
+// oracle/match_oracle.cc — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+//
+// Array-form restatement of the Hamming matching cores of the reference:
+//   ORBmatcher::DescriptorDistance            include/ORBmatcher.h:44, lib/libORB_SLAM2.so@0x79d20;
+//                                             same source as Thirdparty/DBoW2/DBoW2/FORB.cpp:82-102 (golden)
+//   ORBmatcher::SearchByBoW(KeyFrame*,Frame&) include/ORBmatcher.h:104, @0x80150
+//   ORBmatcher::SearchByProjection(Frame&,const Frame&,th,bMono)   include/ORBmatcher.h:78, @0x80d00
+//   Frame::GetFeaturesInArea                  include/Frame.h:113
+//   ORBmatcher::ComputeThreeMaxima            @0x79c40
+//   LSDmatcher / LineSegment::LineSegmentMathch: cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) semantics
+//                                             (header evidence include/auxiliar.h:30-51; UNPINNED beyond that)
+// Constants from the binary: TH_LOW=50, TH_HIGH=100, HISTO_LENGTH=30 (@0x1269e0-e8), histogram factor
+// HISTO_LENGTH/360 (@0x1269f8), secondary-bin cut 0.1 (@0x1269f0).
+// The pointer-based containers (MapPoint*, std::map FeatureVector, mGrid vectors) are flattened to
+// arrays/CSR; iteration orders are preserved.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30;
+constexpr int FRAME_GRID_ROWS = 48, FRAME_GRID_COLS = 64;  // include/Frame.h:41-42
+
+// FORB::distance / ORBmatcher::DescriptorDistance: SWAR popcount over 8 x uint32
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  const int32_t* pa = (const int32_t*)a;
+  const int32_t* pb = (const int32_t*)b;
+  int dist = 0;
+  for (int i = 0; i < 8; i++, pa++, pb++) {
+    unsigned int v = *pa ^ *pb;
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+void compute_three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = (int)histo[i].size();
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+inline int rot_bin(float a1, float a2) {
+  const float factor = (float)HISTO_LENGTH / 360.0f;  // 0.0833333 @0x1269f8
+  float rot = a1 - a2;
+  if (rot < 0.0) rot += 360.0f;
+  int bin = (int)roundf(rot * factor);
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+// BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2): per query the two nearest train rows, ties by lower
+// train index.  out: nq x 4 ints (idx1, dist1, idx2, dist2); missing entries are -1.
+void oracle_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* out) {
+  for (int i = 0; i < nq; ++i) {
+    int b1 = -1, d1 = 1 << 30, b2 = -1, d2 = 1 << 30;
+    for (int j = 0; j < nt; ++j) {
+      const int d = descriptor_distance(q + 32 * i, t + 32 * j);
+      if (d < d1) { b2 = b1; d2 = d1; b1 = j; d1 = d; }
+      else if (d < d2) { b2 = j; d2 = d; }
+    }
+    out[4 * i] = b1; out[4 * i + 1] = b1 < 0 ? -1 : d1; out[4 * i + 2] = b2; out[4 * i + 3] = b2 < 0 ? -1 : d2;
+  }
+}
+
+// SearchByBoW(KeyFrame*, Frame&, matches).  FeatureVectors as CSR sorted by node id:
+//   nodes[k], start[k]..start[k+1] into idx[].  kfValid[i] = (pMP && !pMP->isBad()).
+// matchF[N2] receives the KF feature index matched to each F feature (-1 = none).  Returns nmatches.
+int oracle_search_by_bow(const uint8_t* dKF, const float* angKF, const uint8_t* kfValid, int nNodesKF, const int* nodesKF,
+                         const int* startKF, const int* idxKF, const uint8_t* dF, const float* angF, int N2, int nNodesF,
+                         const int* nodesF, const int* startF, const int* idxF, float nnratio, int checkOri, int* matchF) {
+  for (int i = 0; i < N2; ++i) matchF[i] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int a = 0, b = 0;
+  while (a < nNodesKF && b < nNodesF) {
+    if (nodesKF[a] == nodesF[b]) {
+      for (int iKF = startKF[a]; iKF < startKF[a + 1]; ++iKF) {
+        const int realIdxKF = idxKF[iKF];
+        if (!kfValid[realIdxKF]) continue;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int iF = startF[b]; iF < startF[b + 1]; ++iF) {
+          const int realIdxF = idxF[iF];
+          if (matchF[realIdxF] >= 0) continue;
+          const int dist = descriptor_distance(dKF + 32 * realIdxKF, dF + 32 * realIdxF);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+          else if (dist < bestDist2) { bestDist2 = dist; }
+        }
+        if (bestDist1 <= TH_LOW) {
+          if ((float)bestDist1 < nnratio * (float)bestDist2) {
+            matchF[bestIdxF] = realIdxKF;
+            if (checkOri) rotHist[rot_bin(angKF[realIdxKF], angF[bestIdxF])].push_back(bestIdxF);
+            nmatches++;
+          }
+        }
+      }
+      ++a; ++b;
+    } else if (nodesKF[a] < nodesF[b]) {
+      a = (int)(std::lower_bound(nodesKF, nodesKF + nNodesKF, nodesF[b]) - nodesKF);
+    } else {
+      b = (int)(std::lower_bound(nodesF, nodesF + nNodesF, nodesKF[a]) - nodesF);
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int j : rotHist[i]) { matchF[j] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono).
+// Last frame: N1 points with lastValid[i] = (pMP && !outlier), world position (x,y,z), representative
+// descriptor, mvKeys[i].octave, mvKeysUn[i].angle, lastObs[i] = (pMP->Observations() > 0).
+// Current frame: N2 undistorted keypoints (x, y, octave, angle), descriptors, mvuRight, curTaken[i] =
+// (mvpMapPoints[i] && Observations() > 0) on entry, the 64x48 grid as CSR in [ix][iy] order, bounds,
+// intrinsics and pose.  cam = {fx, fy, cx, cy, mbf, mb, mnMinX, mnMaxX, mnMinY, mnMaxY, gridWInv, gridHInv}.
+// matchCur[N2] receives the last-frame index assigned to each current keypoint (-1 = none). Returns nmatches.
+int oracle_search_by_projection(int N1, const uint8_t* lastValid, const float* lastXYZ, const uint8_t* lastDesc,
+                                const int* lastOctave, const float* lastAngle, const uint8_t* lastObs, int N2,
+                                const float* curXY, const int* curOctave, const float* curAngle, const uint8_t* curDesc,
+                                const float* curURight, const uint8_t* curTaken, const int* gridStart,
+                                const int* gridItems, const float* cam, const float* scaleFactors, const float* TcwCur,
+                                const float* TcwLast, float th, int bMono, int checkOri, int* matchCur) {
+  const float fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3], mbf = cam[4], mb = cam[5];
+  const float mnMinX = cam[6], mnMaxX = cam[7], mnMinY = cam[8], mnMaxY = cam[9], gwi = cam[10], ghi = cam[11];
+  std::vector<uint8_t> taken(curTaken, curTaken + N2);
+  for (int i = 0; i < N2; ++i) matchCur[i] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  // Rcw, tcw (row-major 3x4); twc = -Rcw^T tcw; tlc = Rlw twc + tlw.  cv::Mat products of CV_32F matrices go
+  // through cv::gemm, which accumulates in double and rounds once (alpha * sum + beta * C) to float.
+  const float* Rc = TcwCur;  // Rc[r*4+c], t = Rc[r*4+3]
+  float twc[3];
+  for (int r = 0; r < 3; ++r) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += (double)Rc[k * 4 + r] * (double)Rc[k * 4 + 3];
+    twc[r] = (float)(-1.0 * s);
+  }
+  float tlc2;
+  {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += (double)TcwLast[2 * 4 + k] * (double)twc[k];
+    tlc2 = (float)(s + (double)TcwLast[2 * 4 + 3]);
+  }
+  const bool bForward = tlc2 > mb && !bMono;
+  const bool bBackward = -tlc2 > mb && !bMono;
+  for (int i = 0; i < N1; i++) {
+    if (!lastValid[i]) continue;
+    const float* X = lastXYZ + 3 * i;
+    float pc[3];
+    for (int r = 0; r < 3; ++r) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += (double)Rc[r * 4 + k] * (double)X[k];
+      pc[r] = (float)(s + (double)Rc[r * 4 + 3]);
+    }
+    const float xc = pc[0], yc = pc[1];
+    const float invzc = (float)(1.0 / pc[2]);
+    if (invzc < 0) continue;
+    float u = fx * xc * invzc + cx;
+    float v = fy * yc * invzc + cy;
+    if (u < mnMinX || u > mnMaxX) continue;
+    if (v < mnMinY || v > mnMaxY) continue;
+    const int nLastOctave = lastOctave[i];
+    const float radius = th * scaleFactors[nLastOctave];
+    int minLevel, maxLevel;
+    if (bForward) { minLevel = nLastOctave; maxLevel = -1; }
+    else if (bBackward) { minLevel = 0; maxLevel = nLastOctave; }
+    else { minLevel = nLastOctave - 1; maxLevel = nLastOctave + 1; }
+    // Frame::GetFeaturesInArea(u, v, radius, minLevel, maxLevel)
+    const int nMinCellX = std::max(0, (int)floorf((u - mnMinX - radius) * gwi));
+    if (nMinCellX >= FRAME_GRID_COLS) continue;
+    const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceilf((u - mnMinX + radius) * gwi));
+    if (nMaxCellX < 0) continue;
+    const int nMinCellY = std::max(0, (int)floorf((v - mnMinY - radius) * ghi));
+    if (nMinCellY >= FRAME_GRID_ROWS) continue;
+    const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceilf((v - mnMinY + radius) * ghi));
+    if (nMaxCellY < 0) continue;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    int bestDist = 256, bestIdx2 = -1;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+      for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+        const int c = ix * FRAME_GRID_ROWS + iy;
+        for (int j = gridStart[c]; j < gridStart[c + 1]; ++j) {
+          const int i2 = gridItems[j];
+          if (bCheckLevels) {
+            if (curOctave[i2] < minLevel) continue;
+            if (maxLevel >= 0 && curOctave[i2] > maxLevel) continue;
+          }
+          const float distx = curXY[2 * i2] - u, disty = curXY[2 * i2 + 1] - v;
+          if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
+          // candidate i2
+          if (taken[i2]) continue;
+          if (curURight[i2] > 0) {
+            const float ur = u - mbf * invzc;
+            const float er = fabsf(ur - curURight[i2]);
+            if (er > radius) continue;
+          }
+          const int dist = descriptor_distance(lastDesc + 32 * i, curDesc + 32 * i2);
+          if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+      }
+    if (bestDist <= TH_HIGH) {
+      matchCur[bestIdx2] = i;
+      if (lastObs[i]) taken[bestIdx2] = 1;
+      nmatches++;
+      if (checkOri) rotHist[rot_bin(lastAngle[i], curAngle[bestIdx2])].push_back(bestIdx2);
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int j : rotHist[i]) { matchCur[j] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
+}  // extern "C"

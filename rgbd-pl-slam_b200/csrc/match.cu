@@ -1,0 +1,411 @@
+// match.cu — Hamming matching cores: brute-force kNN(k=2), SearchByBoW, SearchByProjection.
+//
+// Replaces the inner loops of ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:37-141, machine
+// code lib/libORB_SLAM2.so@0x79b50-0x8a086) and the kNN matching LSDmatcher / LineSegmentMathch run
+// on LBD rows (include/LSDmatcher.h, include/auxiliar.h:30-51).  All-pairs Hamming moves ~64 B per
+// descriptor and does 8 popc per pair: it is integer-ALU (popc issue) bound, not HBM bound.
+#include <vector>
+
+#include "common.cuh"
+
+namespace plslam {
+namespace {
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ------------------------------------------------------------------------------------------
+// kNN (k = 2): one CTA per (job, 256-query slab); the train set streams through shared memory in
+// chunks, every thread keeps its query in registers and reads train rows as broadcast LDS.128.
+// ------------------------------------------------------------------------------------------
+constexpr int KNN_CHUNK = 1024;
+
+__global__ void __launch_bounds__(256) k_knn2(const plslam_knn_job_t* __restrict__ jobs) {
+  __shared__ uint4 tr[KNN_CHUNK * 2];
+  const plslam_knn_job_t J = jobs[blockIdx.y];
+  const int q0 = blockIdx.x * 256;
+  if (q0 >= J.nq) return;
+  const int q = q0 + threadIdx.x;
+  const bool active = q < J.nq;
+  uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+  if (active) {
+    const uint4* Q = reinterpret_cast<const uint4*>(J.query) + (size_t)q * 2;
+    a0 = Q[0];
+    a1 = Q[1];
+  }
+  int b1 = -1, d1 = 1 << 30, b2 = -1, d2 = 1 << 30;
+  const uint4* T = reinterpret_cast<const uint4*>(J.train);
+  for (int c0 = 0; c0 < J.nt; c0 += KNN_CHUNK) {
+    const int cn = min(KNN_CHUNK, J.nt - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cn * 2; i += 256) tr[i] = T[(size_t)c0 * 2 + i];
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int j = 0; j < cn; ++j) {
+        const int d = hamming256(a0, a1, tr[2 * j], tr[2 * j + 1]);
+        if (d < d1) { b2 = b1; d2 = d1; b1 = c0 + j; d1 = d; }
+        else if (d < d2) { b2 = c0 + j; d2 = d; }
+      }
+    }
+  }
+  if (active) {
+    int4 o = make_int4(b1, b1 < 0 ? -1 : d1, b2, b2 < 0 ? -1 : d2);
+    reinterpret_cast<int4*>(J.out)[q] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// rotation-consistency helpers (ComputeThreeMaxima @0x79c40; factor HISTO_LENGTH/360 @0x1269f8)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rot_bin_dev(float a1, float a2) {
+  const float factor = (float)PLSLAM_HISTO_LENGTH / 360.0f;
+  float rot = __fsub_rn(a1, a2);
+  if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+  int bin = (int)roundf(__fmul_rn(rot, factor));
+  if (bin == PLSLAM_HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+__device__ void three_maxima_dev(const int* hist, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  ind1 = ind2 = ind3 = -1;
+  for (int i = 0; i < PLSLAM_HISTO_LENGTH; i++) {
+    const int s = hist[i];
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// warp-wide (dist, order) minimum: returns the lane holding the smallest key; key = dist << 20 | order
+__device__ __forceinline__ unsigned warp_min_u32(unsigned v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// SearchByBoW: greedy and order dependent (an F feature claimed by an earlier KF feature is skipped
+// by later ones), so one warp walks the KF features of a job in FeatureVector order and the lanes
+// split the F candidates of the shared vocabulary node.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_bow(const plslam_bow_job_t* __restrict__ jobs) {
+  extern __shared__ int smem_i[];
+  const plslam_bow_job_t J = jobs[blockIdx.x];
+  const int lane = threadIdx.x;
+  int* matchF = smem_i;                   // [n2]
+  int* entryIdx = smem_i + J.n2;          // [n1] matched F index per accepted KF feature, in order
+  int* entryBin = entryIdx + J.n1;        // [n1]
+  __shared__ int hist[PLSLAM_HISTO_LENGTH];
+  for (int i = lane; i < J.n2; i += 32) matchF[i] = -1;
+  if (lane < PLSLAM_HISTO_LENGTH) hist[lane] = 0;
+  __syncwarp();
+  int nmatches = 0, nentries = 0;
+  int a = 0, b = 0;
+  const uint4* DK = reinterpret_cast<const uint4*>(J.kf_desc);
+  const uint4* DF = reinterpret_cast<const uint4*>(J.f_desc);
+  while (a < J.n_kf_nodes && b < J.n_f_nodes) {
+    const int na = J.kf_nodes[a], nb = J.f_nodes[b];
+    if (na == nb) {
+      const int fs = J.f_start[b], fe = J.f_start[b + 1];
+      for (int iKF = J.kf_start[a]; iKF < J.kf_start[a + 1]; ++iKF) {
+        const int realIdxKF = J.kf_idx[iKF];
+        if (!J.kf_valid[realIdxKF]) continue;
+        const uint4 a0 = DK[2 * realIdxKF], a1 = DK[2 * realIdxKF + 1];
+        // per lane: best and second best over its candidates; order = position in the node list
+        unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;  // keys dist << 20 | order (order < 2^20)
+        for (int iF = fs + lane; iF < fe; iF += 32) {
+          const int realIdxF = J.f_idx[iF];
+          if (matchF[realIdxF] >= 0) continue;
+          const int dist = hamming256(a0, a1, DF[2 * realIdxF], DF[2 * realIdxF + 1]);
+          const unsigned key = ((unsigned)dist << 20) | (unsigned)(iF - fs);
+          if (key < k1) { k2 = k1; k1 = key; }
+          else if (key < k2) { k2 = key; }
+        }
+        // global best = min key; second best distance = min over the remaining keys
+        const unsigned g1 = warp_min_u32(k1);
+        const unsigned mine2 = (k1 == g1) ? k2 : k1;
+        const unsigned g2 = warp_min_u32(mine2);
+        if (g1 == 0xffffffffu) continue;
+        const int bestDist1 = (int)(g1 >> 20);
+        const int bestDist2 = g2 == 0xffffffffu ? 256 : (int)(g2 >> 20);
+        if (bestDist1 <= PLSLAM_TH_LOW && (float)bestDist1 < __fmul_rn(J.nnratio, (float)bestDist2)) {
+          const int bestIdxF = J.f_idx[fs + (int)(g1 & 0xfffffu)];
+          if (lane == 0) {
+            matchF[bestIdxF] = realIdxKF;
+            if (J.check_orientation) {
+              const int bin = rot_bin_dev(J.kf_angle[realIdxKF], J.f_angle[bestIdxF]);
+              hist[bin]++;
+              entryIdx[nentries] = bestIdxF;
+              entryBin[nentries] = bin;
+            }
+          }
+          ++nentries;
+          ++nmatches;
+          __syncwarp();
+        }
+      }
+      ++a;
+      ++b;
+    } else if (na < nb) {
+      while (a < J.n_kf_nodes && J.kf_nodes[a] < nb) ++a;  // lower_bound
+    } else {
+      while (b < J.n_f_nodes && J.f_nodes[b] < na) ++b;
+    }
+  }
+  __syncwarp();
+  if (J.check_orientation) {
+    int i1, i2, i3;
+    three_maxima_dev(hist, i1, i2, i3);
+    int removed = 0;
+    for (int e = lane; e < nentries; e += 32) {
+      const int bin = entryBin[e];
+      if (bin != i1 && bin != i2 && bin != i3) {
+        matchF[entryIdx[e]] = -1;
+        ++removed;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, d);
+    nmatches -= removed;
+  }
+  __syncwarp();
+  for (int i = lane; i < J.n2; i += 32) J.match_f[i] = matchF[i];
+  if (lane == 0) *J.nmatches = nmatches;
+}
+
+// ------------------------------------------------------------------------------------------
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono): one warp per frame pair walks the last
+// frame's map points in order (a current keypoint claimed by an earlier point is skipped later);
+// lanes split the grid cells of the search window, candidate order = [ix][iy][position in cell].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __restrict__ jobs) {
+  extern __shared__ int smem_i[];
+  const plslam_proj_job_t& J = jobs[blockIdx.x];
+  const int lane = threadIdx.x;
+  const int N1 = J.n1, N2 = J.n2;
+  int* matchCur = smem_i;            // [N2]
+  int* entryIdx = matchCur + N2;     // [N1]
+  int* entryBin = entryIdx + N1;     // [N1]
+  uint8_t* taken = reinterpret_cast<uint8_t*>(entryBin + N1);  // [N2]
+  __shared__ int hist[PLSLAM_HISTO_LENGTH];
+  for (int i = lane; i < N2; i += 32) { matchCur[i] = -1; taken[i] = J.cur_taken[i]; }
+  if (lane < PLSLAM_HISTO_LENGTH) hist[lane] = 0;
+  __syncwarp();
+  const float fx = J.cam[0], fy = J.cam[1], cx = J.cam[2], cy = J.cam[3], mbf = J.cam[4], mb = J.cam[5];
+  const float mnMinX = J.cam[6], mnMaxX = J.cam[7], mnMinY = J.cam[8], mnMaxY = J.cam[9], gwi = J.cam[10], ghi = J.cam[11];
+  const float* Rc = J.tcw_cur;
+  float twc[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)Rc[k * 4 + r], (double)Rc[k * 4 + 3]));
+    twc[r] = (float)__dmul_rn(-1.0, s);
+  }
+  float tlc2;
+  {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)J.tcw_last[8 + k], (double)twc[k]));
+    tlc2 = (float)__dadd_rn(s, (double)J.tcw_last[11]);
+  }
+  const bool bForward = tlc2 > mb && !J.mono;
+  const bool bBackward = -tlc2 > mb && !J.mono;
+  int nmatches = 0, nentries = 0;
+  const uint4* DL = reinterpret_cast<const uint4*>(J.last_desc);
+  const uint4* DC = reinterpret_cast<const uint4*>(J.cur_desc);
+  for (int i = 0; i < N1; ++i) {
+    if (!J.last_valid[i]) continue;
+    const float* X = J.last_xyz + 3 * i;
+    float pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)Rc[r * 4 + k], (double)X[k]));
+      pc[r] = (float)__dadd_rn(s, (double)Rc[r * 4 + 3]);
+    }
+    const float invzc = (float)__ddiv_rn(1.0, (double)pc[2]);
+    if (invzc < 0) continue;
+    const float u = __fadd_rn(__fmul_rn(__fmul_rn(fx, pc[0]), invzc), cx);
+    const float v = __fadd_rn(__fmul_rn(__fmul_rn(fy, pc[1]), invzc), cy);
+    if (u < mnMinX || u > mnMaxX) continue;
+    if (v < mnMinY || v > mnMaxY) continue;
+    const int oct = J.last_octave[i];
+    const float radius = __fmul_rn(J.th, J.scale_factors[oct]);
+    int minLevel, maxLevel;
+    if (bForward) { minLevel = oct; maxLevel = -1; }
+    else if (bBackward) { minLevel = 0; maxLevel = oct; }
+    else { minLevel = oct - 1; maxLevel = oct + 1; }
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, mnMinX), radius), gwi)));
+    if (nMinCellX >= PLSLAM_GRID_COLS) continue;
+    const int nMaxCellX = min(PLSLAM_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, mnMinX), radius), gwi)));
+    if (nMaxCellX < 0) continue;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, mnMinY), radius), ghi)));
+    if (nMinCellY >= PLSLAM_GRID_ROWS) continue;
+    const int nMaxCellY = min(PLSLAM_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, mnMinY), radius), ghi)));
+    if (nMaxCellY < 0) continue;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    const int ncy = nMaxCellY - nMinCellY + 1, ncells = (nMaxCellX - nMinCellX + 1) * ncy;
+    const uint4 a0 = DL[2 * i], a1 = DL[2 * i + 1];
+    const float ur = __fsub_rn(u, __fmul_rn(mbf, invzc));
+    unsigned best = 0xffffffffu;  // dist << 22 | cellRank << 8 | pos  (cellRank < 2^14, pos < 2^8)
+    int bestI2 = -1;
+    for (int c = lane; c < ncells; c += 32) {
+      const int ix = nMinCellX + c / ncy, iy = nMinCellY + c % ncy;
+      const int cell = ix * PLSLAM_GRID_ROWS + iy;
+      const int s0 = J.grid_start[cell], s1 = J.grid_start[cell + 1];
+      for (int j = s0; j < s1; ++j) {
+        const int i2 = J.grid_items[j];
+        if (bCheckLevels) {
+          const int o2 = J.cur_octave[i2];
+          if (o2 < minLevel) continue;
+          if (maxLevel >= 0 && o2 > maxLevel) continue;
+        }
+        const float distx = __fsub_rn(J.cur_xy[2 * i2], u), disty = __fsub_rn(J.cur_xy[2 * i2 + 1], v);
+        if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
+        if (taken[i2]) continue;
+        const float ur2 = J.cur_uright[i2];
+        if (ur2 > 0) {
+          if (fabsf(__fsub_rn(ur, ur2)) > radius) continue;
+        }
+        const int dist = hamming256(a0, a1, DC[2 * i2], DC[2 * i2 + 1]);
+        const unsigned key = ((unsigned)dist << 22) | ((unsigned)c << 8) | (unsigned)min(j - s0, 255);
+        if (key < best) { best = key; bestI2 = i2; }
+      }
+    }
+    const unsigned g = warp_min_u32(best);
+    if (g == 0xffffffffu) continue;
+    const int bestDist = (int)(g >> 22);
+    if (bestDist <= PLSLAM_TH_HIGH) {
+      const unsigned src = __ballot_sync(0xffffffffu, best == g);
+      const int bestIdx2 = __shfl_sync(0xffffffffu, bestI2, __ffs(src) - 1);
+      if (lane == 0) {
+        matchCur[bestIdx2] = i;
+        if (J.last_obs[i]) taken[bestIdx2] = 1;
+        if (J.check_orientation) {
+          const int bin = rot_bin_dev(J.last_angle[i], J.cur_angle[bestIdx2]);
+          hist[bin]++;
+          entryIdx[nentries] = bestIdx2;
+          entryBin[nentries] = bin;
+        }
+      }
+      ++nentries;
+      ++nmatches;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  if (J.check_orientation) {
+    int i1, i2, i3;
+    three_maxima_dev(hist, i1, i2, i3);
+    int removed = 0;
+    for (int e = lane; e < nentries; e += 32) {
+      const int bin = entryBin[e];
+      if (bin != i1 && bin != i2 && bin != i3) {
+        matchCur[entryIdx[e]] = -1;
+        ++removed;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, d);
+    nmatches -= removed;
+  }
+  __syncwarp();
+  for (int i = lane; i < N2; i += 32) J.match_cur[i] = matchCur[i];
+  if (lane == 0) *J.nmatches = nmatches;
+}
+
+}  // namespace
+}  // namespace plslam
+
+using namespace plslam;
+
+extern "C" {
+
+int plslam_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  // Bit-count of a XOR b over 8 x 32-bit words, as FORB::distance (reference Thirdparty/DBoW2/DBoW2/FORB.cpp:82-102)
+  int dist = 0;
+  for (int i = 0; i < 8; ++i) {
+    uint32_t x, y;
+    std::memcpy(&x, a + 4 * i, 4);
+    std::memcpy(&y, b + 4 * i, 4);
+    dist += __builtin_popcount(x ^ y);
+  }
+  return dist;
+}
+
+int plslam_match_knn2_batch_device(const plslam_knn_job_t* d_jobs, int njobs, int max_nq, void* stream) {
+  PL_CHECK_ARG(d_jobs && njobs >= 1 && njobs <= 65535 && max_nq >= 1);
+  k_knn2<<<dim3(div_up(max_nq, 256), njobs), 256, 0, (cudaStream_t)stream>>>(d_jobs);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_match_knn2_host(const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* out) {
+  PL_CHECK_ARG(nq >= 0 && nt >= 0 && (nq == 0 || (query && out)) && (nt == 0 || train));
+  if (nq == 0) return PLSLAM_OK;
+  DevBuf dq, dt, dout, djob;
+  int rc;
+  if ((rc = dq.ensure((size_t)nq * 32)) || (rc = dt.ensure((size_t)std::max(nt, 1) * 32)) ||
+      (rc = dout.ensure((size_t)nq * 16)) || (rc = djob.ensure(sizeof(plslam_knn_job_t)))) {
+    dq.release(); dt.release(); dout.release(); djob.release();
+    return rc;
+  }
+  auto cleanup = [&]() { dq.release(); dt.release(); dout.release(); djob.release(); };
+  cudaError_t e = cudaMemcpy(dq.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nt) e = cudaMemcpy(dt.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice);
+  plslam_knn_job_t job{dq.as<uint8_t>(), dt.as<uint8_t>(), dout.as<int32_t>(), nq, nt};
+  if (e == cudaSuccess) e = cudaMemcpy(djob.p, &job, sizeof(job), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = plslam_match_knn2_batch_device(djob.as<plslam_knn_job_t>(), 1, nq, nullptr);
+    if (rc) { cleanup(); return rc; }
+    e = cudaMemcpy(out, dout.p, (size_t)nq * 16, cudaMemcpyDeviceToHost);
+  }
+  cleanup();
+  if (e != cudaSuccess) {
+    set_error("knn2 host path: %s", cudaGetErrorString(e));
+    return PLSLAM_ERR_CUDA;
+  }
+  return PLSLAM_OK;
+}
+
+int plslam_match_bow_batch_device(const plslam_bow_job_t* d_jobs, int njobs, int max_n, void* stream) {
+  const int max_n2 = max_n;
+  PL_CHECK_ARG(d_jobs && njobs >= 1 && max_n2 >= 0);
+  // shared: matchF[n2] + entryIdx[n1] + entryBin[n1]; n1 is bounded by the caller's max_n2-style capacity
+  const size_t smem = (size_t)max_n2 * 4 * 3;
+  PL_CHECK_ARG(smem <= 200 * 1024);
+  static bool attr = false;
+  if (!attr) {
+    PL_CUDA(cudaFuncSetAttribute(k_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PL_CUDA(cudaFuncSetAttribute(k_projection, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  k_bow<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream) {
+  PL_CHECK_ARG(d_jobs && njobs >= 1 && max_n1 >= 0 && max_n2 >= 0);
+  const size_t smem = (size_t)max_n2 * 4 + (size_t)max_n1 * 8 + (size_t)max_n2 + 16;
+  PL_CHECK_ARG(smem <= 200 * 1024);
+  static bool attr = false;
+  if (!attr) {
+    PL_CUDA(cudaFuncSetAttribute(k_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PL_CUDA(cudaFuncSetAttribute(k_projection, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  k_projection<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+}  // extern "C"

@@ -278,3 +278,80 @@ class LineSegment:
 def keylines_from_tensor(t):
     a = t.detach().cpu().numpy()
     return a.view(KEYLINE_DTYPE).reshape(a.shape[:-1])
+
+
+# ---------------------------------------------------------------------------
+# matchers (ORBmatcher / LSDmatcher Hamming cores)
+# ---------------------------------------------------------------------------
+TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
+
+
+class KnnJob(C.Structure):
+    _fields_ = [("query", C.c_void_p), ("train", C.c_void_p), ("out", C.c_void_p), ("nq", C.c_int32), ("nt", C.c_int32)]
+
+
+class BowJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("kf_desc", "kf_angle", "kf_valid", "kf_nodes", "kf_start", "kf_idx", "f_desc",
+                                          "f_angle", "f_nodes", "f_start", "f_idx", "match_f", "nmatches")] + \
+               [("n1", C.c_int32), ("n2", C.c_int32), ("n_kf_nodes", C.c_int32), ("n_f_nodes", C.c_int32),
+                ("nnratio", C.c_float), ("check_orientation", C.c_int32)]
+
+
+class ProjJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("last_valid", "last_xyz", "last_desc", "last_octave", "last_angle", "last_obs",
+                                          "cur_xy", "cur_octave", "cur_angle", "cur_desc", "cur_uright", "cur_taken",
+                                          "grid_start", "grid_items", "scale_factors", "match_cur", "nmatches")] + \
+               [("cam", C.c_float * 12), ("tcw_cur", C.c_float * 12), ("tcw_last", C.c_float * 12), ("th", C.c_float),
+                ("n1", C.c_int32), ("n2", C.c_int32), ("mono", C.c_int32), ("check_orientation", C.c_int32)]
+
+
+assert C.sizeof(KnnJob) == 32 and C.sizeof(BowJob) == 128 and C.sizeof(ProjJob) == 304
+
+
+def _jobs_to_device(jobs, device):
+    import torch
+    arr = (type(jobs[0]) * len(jobs))(*jobs)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device)
+
+
+def DescriptorDistance(a, b):
+    """ORBmatcher::DescriptorDistance (static, host scalar)."""
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().plslam_descriptor_distance(_vp(a), _vp(b))
+
+
+def knn2_host(query, train):
+    """BFMatcher(NORM_HAMMING).knnMatch(k=2) on host arrays -> (nq, 4) int32 idx1, dist1, idx2, dist2."""
+    query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+    train = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    out = np.empty((len(query), 4), np.int32)
+    _check(lib().plslam_match_knn2_host(_vp(query), len(query), _vp(train), len(train), _vp(out)))
+    return out
+
+
+def knn2_batch_device(pairs, stream=None, jobs_dev=None):
+    """pairs: list of (query CUDA uint8 [nq,32], train CUDA uint8 [nt,32], out CUDA int32 [nq,4]).  Async."""
+    if jobs_dev is None:
+        jobs = [KnnJob(q.data_ptr(), t.data_ptr(), o.data_ptr(), q.shape[0], t.shape[0]) for q, t, o in pairs]
+        jobs_dev = _jobs_to_device(jobs, pairs[0][0].device)
+    max_nq = max(int(q.shape[0]) for q, _, _ in pairs)
+    _check(lib().plslam_match_knn2_batch_device(_vp(jobs_dev), len(pairs), max_nq, _stream_ptr(stream)))
+    return jobs_dev
+
+
+def knn2_jobs_device(jobs_dev, njobs, max_nq, stream=None):
+    _check(lib().plslam_match_knn2_batch_device(_vp(jobs_dev), njobs, max_nq, _stream_ptr(stream)))
+
+
+def bow_batch_device(jobs, max_n, device, stream=None):
+    jd = _jobs_to_device(jobs, device)
+    _check(lib().plslam_match_bow_batch_device(_vp(jd), len(jobs), int(max_n), _stream_ptr(stream)))
+    return jd
+
+
+def projection_batch_device(jobs, max_n1, max_n2, device, stream=None):
+    jd = _jobs_to_device(jobs, device)
+    _check(lib().plslam_match_projection_batch_device(_vp(jd), len(jobs), int(max_n1), int(max_n2), _stream_ptr(stream)))
+    return jd
