@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""bench.py — frames/s of the ORB + LSD/LBD extract + match hot path on N B200s (BASELINE.json metric).
+
+A "step" is one pass of the front-end over one batch of synthetic 640x480 frames (config C2 of
+BASELINE.md: batch = 256 frames = 128 frame pairs per GPU): ORB extraction (8-level pyramid, FAST,
+quad-tree, orientation, rBRIEF), LSD + LBD line extraction and brute-force Hamming kNN(k=2) matching of
+both descriptor sets inside every frame pair.  Frames shard over ranks (weak scaling, no data-path
+collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our CUDA path (rank 0 prints one JSON line)
+  python bench.py --impl reference ...                         the reference algorithm on the host cores
+                                                               (oracle restatement: the reference ships no
+                                                               buildable source for this path)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "rgbd-pl-slam_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+METRIC = "frames/sec ORB+LSD extract+match 640x480 RGB-D"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step (even: frame pairs)")
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--nfeatures", type=int, default=1000)
+    ap.add_argument("--max-lines", type=int, default=40)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "C2: %dx%d synthetic RGB-D, batch=%d frames (%d pairs)/GPU, ORB nFeatures=%d 8 levels + LSD/LBD top-%d, kNN2 ORB+LBD per pair" % (
+        a.width, a.height, a.batch, a.batch // 2, a.nfeatures, a.max_lines)
+
+
+def make_frames(a, rank):
+    from plslam_b200.synth import synth_pair
+    frames = np.empty((a.batch, a.height, a.width), np.uint8)
+    for p in range(a.batch // 2):
+        x, y = synth_pair(rank * 100000 + p, a.width, a.height)
+        frames[2 * p], frames[2 * p + 1] = x, y
+    return frames
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes per frame and stage (every stage reads its input once and
+# writes its output once)
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(a, kp_avg, cand_avg):
+    W, H = a.width, a.height
+    inv = [1.0]
+    for _ in range(7):
+        inv.append(inv[-1] / 1.2)
+    areas = [int(round(W * s)) * int(round(H * s)) for s in inv]
+    S = sum(areas)
+    P = int(round(W * 0.8)) * int(round(H * 0.8))
+    K = kp_avg
+    stages = {
+        "orb_pyramid(7 launches)": sum(areas[l - 1] + areas[l] for l in range(1, 8)),
+        "orb_fast": S + 8 * cand_avg,
+        "orb_quadtree": 8 * cand_avg + 8 * K,
+        "orb_blur": 2 * S,
+        "orb_orient_desc": K * (709 + 4) + K * (512 + 32) + K * 28,
+        "match_orb_knn2": (2 * K * 32 + K * 16) // 2,  # per frame (a pair reads 2K rows, writes K results)
+        "lsd_scale": 2 * W * H + W * H + P,
+        "lsd_grad": P + 16 * P,
+        "lsd_rowhist": 8 * P,
+        "lsd_colscan": 8 * P,
+        "lsd_scatter": 8 * P,
+        "lsd_grow": 9 * P,
+        "lsd_nfa": 4 * P,
+        "lsd_finish_lbd": W * H + a.max_lines * (60 * 63 * 4 + 32),
+        "match_lbd_knn2": (2 * a.max_lines * 32 + a.max_lines * 16) // 2,
+    }
+    return stages
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML during the timed region."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_pairs_per_second(a, frames, threads):
+    """ORB + LSD/LBD extraction of both frames of each pair + kNN2 matching, frame-pair tasks over `threads` threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import bindings as ob
+    ob.build()
+    tl = threading.local()
+
+    def task(p):
+        if not hasattr(tl, "orb"):
+            tl.orb = ob.OrbOracle(a.nfeatures, 1.2, 8, 20, 7)
+        r = []
+        for f in (2 * p, 2 * p + 1):
+            k, d = tl.orb.extract(frames[f])
+            kl, ld, lf, _ = ob.extract_lines(frames[f], a.max_lines)
+            r.append((d, ld))
+        ob.knn2(r[0][0], r[1][0])
+        ob.knn2(r[0][1], r[1][1])
+        return len(r[0][0])
+
+    npairs = len(frames) // 2
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(task, range(npairs)))
+    return time.perf_counter() - t0
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = a.cpu_sample or max(2 * threads, 16)
+    sample -= sample % 2
+    a_s = argparse.Namespace(**vars(a))
+    a_s.batch = sample
+    frames = make_frames(a_s, 0)
+    for _ in range(a.warmup):
+        cpu_pairs_per_second(a, frames, threads)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_pairs_per_second(a, frames, threads)
+    dt = time.perf_counter() - t0
+    fps = sample * a.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(a), "frames_per_step_sample": sample,
+                       "note": "reference CPU algorithm = oracle restatement (the reference ships no source for this path; "
+                               "its prebuilt .so cannot load here: SURVEY.md 8c), all host threads, one frame pair per task"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d frames (%d pairs) per step x %d steps" % (sample, sample // 2, a.steps)},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import plslam_b200 as pl
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    frames = make_frames(a, rank)
+    fe = pl.Frontend(a.nfeatures, 1.2, 8, 20, 7, a.max_lines)
+    d_images = torch.from_numpy(frames).cuda()
+    out = fe.alloc(a.batch, device="cuda")
+    h_images = torch.from_numpy(frames).pin_memory()
+    h_out = fe.alloc(a.batch, pinned=True)
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(max(a.warmup, 3)):
+        fe.process_device(d_images, out, True)
+    fe.check_status()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0.record()
+    for _ in range(a.steps):
+        fe.process_device(d_images, out, True)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.result()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    fe.check_status()
+    value = world * a.batch * a.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the C-ABI with host buffers (`e2e`) ----
+    for _ in range(2):
+        fe.process_host(h_images, h_out, True)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fe.process_host(h_images, h_out, True)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = world * a.batch * a.steps / e2e_s
+    h2d = int(h_images.numel())
+    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()))
+
+    line = None
+    if rank == 0:
+        kp_avg = float(out["kp_counts"].float().mean())
+        # ---- per-stage device times (CUDA events on the launching streams) for the roofline ----
+        fe.enable_timing(True)
+        acc = {}
+        reps = 3
+        for _ in range(reps):
+            fe.process_device(d_images, out, True)
+            torch.cuda.synchronize()
+            for n, ms in fe.stage_times():
+                acc[n] = acc.get(n, 0.0) + ms / reps
+        fe.enable_timing(False)
+        stages = algorithmic_bytes(a, kp_avg, 5.0 * kp_avg)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+        dom = max(acc, key=acc.get)
+        dom_bytes = stages.get(dom, 0) * a.batch
+        achieved = dom_bytes / (acc[dom] * 1e-3) / 1e9
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+            traffic = prof.get(dom)
+        except Exception:
+            pass
+        total_bytes = sum(stages.values()) * a.batch
+        step_ms = dev_ms / a.steps
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": acc[dom],
+                    "note": "k_lsd_grow is latency bound (sequential greedy region growing, one warp per frame), not HBM bound; "
+                            "see DESIGN.md",
+                    "pipeline": {"algorithmic_bytes_per_step": total_bytes, "achieved": total_bytes / (step_ms * 1e-3) / 1e9,
+                                 "frac": total_bytes / (step_ms * 1e-3) / 1e9 / peak},
+                    "stages_ms": {k: round(v, 4) for k, v in sorted(acc.items(), key=lambda kv: -kv[1])}}
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = a.cpu_sample or min(a.batch, max(4 * threads, 32))
+            sample -= sample % 2
+            dt = cpu_pairs_per_second(a, frames[:sample], threads)
+            cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "first %d frames (%d pairs) of the same batch, one frame pair per task, %d threads" % (sample, sample // 2, threads)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": workload_name(a), "frames_per_gpu_per_step": a.batch,
+                           "cache": "inputs + intermediates (~7 MB/frame, ~1.8 GB/step) exceed the 126 MB L2; no flush needed",
+                           "parallelism": "frames sharded over %d rank(s), no data-path collective" % world},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "plslam_frontend_process_host (pinned host buffers, H2D + kernels + D2H inside the call)"},
+                "gpu_launches": world * a.steps * fe.launches_per_call(True),
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "counts": {"keypoints_per_frame": kp_avg, "lines_per_frame": float(out["line_counts"].float().mean())}}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    a = parse()
+    if a.batch % 2:
+        a.batch += 1
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

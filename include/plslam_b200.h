@@ -232,6 +232,52 @@ typedef struct plslam_proj_job {
 } plslam_proj_job_t;
 int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream);
 
+/* Pair matching on the batched extractor outputs without a host round trip: for p in [0, npairs)
+ * query = frame (2p), train = frame (2p+1) of a [frames][capacity][32] descriptor block whose valid
+ * row counts live in the device array d_counts.  d_out: [npairs][capacity][4] int32 as knn2.
+ * d_jobs_scratch: npairs job descriptors of device scratch. */
+int plslam_match_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int capacity, int npairs,
+                                   int32_t* d_out, plslam_knn_job_t* d_jobs_scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Front-end = what Frame::Frame (include/Frame.h:60) runs per RGB-D frame on the hot path:
+ * ExtractORB (Frame.h:67) + ExtractLSD (Frame.h:70), batched, plus optional frame-pair kNN matching
+ * of both descriptor sets (ORB all-pairs and LineSegmentMathch).  ORB and line stages run on two
+ * internal streams forked from / joined to the caller's stream.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plslam_frontend plslam_frontend_t;
+typedef struct plslam_frontend_io {
+  plslam_keypoint_t* keypoints;   /* [batch][kp_capacity] */
+  uint8_t* descriptors;           /* [batch][kp_capacity][32] */
+  int32_t* kp_counts;             /* [batch] */
+  plslam_keyline_t* keylines;     /* [batch][line_capacity] */
+  uint8_t* line_descriptors;      /* [batch][line_capacity][32] */
+  double* line_functions;         /* [batch][line_capacity][3] */
+  int32_t* line_counts;           /* [batch] */
+  int32_t* orb_matches;           /* [batch/2][kp_capacity][4] or NULL */
+  int32_t* line_matches;          /* [batch/2][line_capacity][4] or NULL */
+} plslam_frontend_io_t;
+
+int plslam_frontend_create(plslam_frontend_t** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                           int minThFAST, int max_lines);
+void plslam_frontend_destroy(plslam_frontend_t* h);
+int plslam_frontend_capacities(const plslam_frontend_t* h, int* kp_capacity, int* line_capacity);
+/* All pointers in `io` are device pointers; asynchronous on `stream`. match_pairs != 0 also fills the match blocks. */
+int plslam_frontend_process_device(plslam_frontend_t* h, const uint8_t* d_images, int batch, int width, int height,
+                                   int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs,
+                                   void* stream);
+/* All pointers are HOST pointers (pinned memory makes the copies asynchronous); returns after the results landed. */
+int plslam_frontend_process_host(plslam_frontend_t* h, const uint8_t* images, int batch, int width, int height,
+                                 int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs);
+/* Per-stage device times (ms, CUDA events on the launching streams) of the last process call made after
+ * plslam_frontend_enable_timing(h, 1).  names/ms hold up to `capacity` entries; returns the number of stages. */
+int plslam_frontend_enable_timing(plslam_frontend_t* h, int enable);
+int plslam_frontend_stage_times(plslam_frontend_t* h, const char** names, float* ms, int capacity);
+/* Number of kernel launches one process call issues for `batch` frames (for launch accounting). */
+int plslam_frontend_launches_per_call(const plslam_frontend_t* h, int match_pairs);
+/* Synchronises `stream` and reports PLSLAM_ERR_OVERFLOW if an internal list overflowed in the last call. */
+int plslam_frontend_check_status(plslam_frontend_t* h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "../../include/plslam_b200.h"
 
@@ -55,6 +56,53 @@ struct DevBuf {
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// Optional per-stage device timing: CUDA events recorded on the launching stream around each kernel.
+struct StageTimer {
+  struct Rec {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  bool enabled = false;
+  std::vector<Rec> recs;
+  size_t used = 0;
+  void reset() { used = 0; }
+  void begin(const char* name, cudaStream_t st) {
+    if (!enabled) return;
+    if (used == recs.size()) {
+      Rec r{name, nullptr, nullptr};
+      cudaEventCreate(&r.a);
+      cudaEventCreate(&r.b);
+      recs.push_back(r);
+    }
+    recs[used].name = name;
+    cudaEventRecord(recs[used].a, st);
+  }
+  void end(cudaStream_t st) {
+    if (!enabled) return;
+    cudaEventRecord(recs[used].b, st);
+    ++used;
+  }
+  int collect(const char** names, float* ms, int cap) {
+    int n = 0;
+    for (size_t i = 0; i < used && n < cap; ++i, ++n) {
+      cudaEventSynchronize(recs[i].b);
+      float t = 0;
+      cudaEventElapsedTime(&t, recs[i].a, recs[i].b);
+      names[n] = recs[i].name;
+      ms[n] = t;
+    }
+    return n;
+  }
+  ~StageTimer() {
+    for (auto& r : recs) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+  }
+};
+#define PL_STAGE_BEGIN(tm, name, st) do { if (tm) (tm)->begin(name, st); } while (0)
+#define PL_STAGE_END(tm, st) do { if (tm) (tm)->end(st); } while (0)
 
 #ifdef __CUDACC__
 // cvRound on float: round-half-even (x86 vcvtss2si in the reference binary)

@@ -1,0 +1,245 @@
+// frontend.cu — batched front-end: ORB + LSD/LBD extraction (+ frame-pair kNN matching) for a batch of
+// frames, i.e. the hot path Frame::Frame runs per RGB-D frame (reference include/Frame.h:60,67,70).
+// ORB and line stages are independent, so they run on two internal streams forked from the caller's
+// stream: the latency-bound line kernels (one warp per frame) overlap the throughput-bound ORB kernels.
+#include <new>
+
+#include "common.cuh"
+#include "lines.cuh"
+#include "orb.cuh"
+
+namespace plslam {
+namespace {
+
+__global__ void k_make_pair_jobs(const uint8_t* desc, const int32_t* counts, int capacity, int npairs, int32_t* out,
+                                 plslam_knn_job_t* jobs) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  plslam_knn_job_t j;
+  j.query = desc + (size_t)(2 * p) * capacity * 32;
+  j.train = desc + (size_t)(2 * p + 1) * capacity * 32;
+  j.out = out + (size_t)p * capacity * 4;
+  j.nq = min(counts[2 * p], capacity);
+  j.nt = min(counts[2 * p + 1], capacity);
+  jobs[p] = j;
+}
+
+}  // namespace
+
+struct Frontend {
+  OrbExtractor orb;
+  LineExtractor lines;
+  StageTimer tOrb, tLines;
+  cudaStream_t sOrb = nullptr, sLines = nullptr, sHost = nullptr;
+  cudaEvent_t evFork = nullptr, evOrb = nullptr, evLines = nullptr;
+  DevBuf jobsOrb, jobsLines;
+  DevBuf dIn, dKps, dDesc, dKpCnt, dKl, dLdesc, dFuncs, dLCnt, dOrbM, dLineM;
+  int* pinnedStatus = nullptr;
+  bool timing = false;
+  Frontend(int nf, float sf, int nl, int ini, int mn, int max_lines) : orb(nf, sf, nl, ini, mn) {
+    lines.set_max_lines(max_lines);
+  }
+  ~Frontend() {
+    DevBuf* all[] = {&jobsOrb, &jobsLines, &dIn, &dKps, &dDesc, &dKpCnt, &dKl, &dLdesc, &dFuncs, &dLCnt, &dOrbM, &dLineM};
+    for (DevBuf* b : all) b->release();
+    if (sOrb) cudaStreamDestroy(sOrb);
+    if (sLines) cudaStreamDestroy(sLines);
+    if (sHost) cudaStreamDestroy(sHost);
+    if (evFork) cudaEventDestroy(evFork);
+    if (evOrb) cudaEventDestroy(evOrb);
+    if (evLines) cudaEventDestroy(evLines);
+    if (pinnedStatus) cudaFreeHost(pinnedStatus);
+  }
+  int init() {
+    if (sOrb) return PLSLAM_OK;
+    PL_CUDA(cudaStreamCreateWithFlags(&sOrb, cudaStreamNonBlocking));
+    PL_CUDA(cudaStreamCreateWithFlags(&sLines, cudaStreamNonBlocking));
+    PL_CUDA(cudaStreamCreateWithFlags(&sHost, cudaStreamNonBlocking));
+    PL_CUDA(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
+    PL_CUDA(cudaEventCreateWithFlags(&evOrb, cudaEventDisableTiming));
+    PL_CUDA(cudaEventCreateWithFlags(&evLines, cudaEventDisableTiming));
+    PL_CUDA(cudaMallocHost((void**)&pinnedStatus, 64));
+    return PLSLAM_OK;
+  }
+  int process_device(const uint8_t* d_images, int batch, int W, int H, int pitch, size_t stride,
+                     const plslam_frontend_io_t& io, int match_pairs, cudaStream_t st) {
+    int rc = init();
+    if (rc) return rc;
+    PL_CHECK_ARG(io.keypoints && io.descriptors && io.kp_counts && io.keylines && io.line_descriptors &&
+                 io.line_functions && io.line_counts);
+    const int kpCap = orb.max_keypoints(), lnCap = lines.out_capacity();
+    const int npairs = batch / 2;
+    if (match_pairs) {
+      PL_CHECK_ARG(io.orb_matches && io.line_matches && npairs >= 1);
+      if ((rc = jobsOrb.ensure((size_t)npairs * sizeof(plslam_knn_job_t)))) return rc;
+      if ((rc = jobsLines.ensure((size_t)npairs * sizeof(plslam_knn_job_t)))) return rc;
+    }
+    tOrb.enabled = tLines.enabled = timing;
+    tOrb.reset();
+    tLines.reset();
+    orb.timer = timing ? &tOrb : nullptr;
+    lines.timer = timing ? &tLines : nullptr;
+    PL_CUDA(cudaEventRecord(evFork, st));
+    PL_CUDA(cudaStreamWaitEvent(sOrb, evFork, 0));
+    PL_CUDA(cudaStreamWaitEvent(sLines, evFork, 0));
+    // line branch first: its long sequential kernel should start as early as possible
+    rc = lines.extract_device(d_images, batch, W, H, pitch, stride, io.keylines, io.line_descriptors, io.line_functions,
+                              lnCap, io.line_counts, sLines);
+    if (rc) return rc;
+    rc = orb.extract_device(d_images, batch, W, H, pitch, stride, io.keypoints, io.descriptors, kpCap, io.kp_counts, sOrb);
+    if (rc) return rc;
+    if (match_pairs) {
+      PL_STAGE_BEGIN(orb.timer, "match_orb_knn2", sOrb);
+      rc = plslam_match_knn2_pairs_device(io.descriptors, io.kp_counts, kpCap, npairs, io.orb_matches,
+                                          jobsOrb.as<plslam_knn_job_t>(), sOrb);
+      PL_STAGE_END(orb.timer, sOrb);
+      if (rc) return rc;
+      PL_STAGE_BEGIN(lines.timer, "match_lbd_knn2", sLines);
+      rc = plslam_match_knn2_pairs_device(io.line_descriptors, io.line_counts, lnCap, npairs, io.line_matches,
+                                          jobsLines.as<plslam_knn_job_t>(), sLines);
+      PL_STAGE_END(lines.timer, sLines);
+      if (rc) return rc;
+    }
+    PL_CUDA(cudaEventRecord(evOrb, sOrb));
+    PL_CUDA(cudaEventRecord(evLines, sLines));
+    PL_CUDA(cudaStreamWaitEvent(st, evOrb, 0));
+    PL_CUDA(cudaStreamWaitEvent(st, evLines, 0));
+    return PLSLAM_OK;
+  }
+  int check_status(cudaStream_t st) {
+    PL_CUDA(cudaMemcpyAsync(pinnedStatus, orb.device_status(), sizeof(int), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(pinnedStatus + 1, lines.device_status(), sizeof(int), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaStreamSynchronize(st));
+    if (pinnedStatus[0] != PLSLAM_OK || pinnedStatus[1] != PLSLAM_OK) {
+      set_error("device status orb=%d lines=%d (internal fixed-capacity buffer overflow)", pinnedStatus[0], pinnedStatus[1]);
+      return PLSLAM_ERR_OVERFLOW;
+    }
+    return PLSLAM_OK;
+  }
+  int process_host(const uint8_t* images, int batch, int W, int H, int pitch, size_t stride, const plslam_frontend_io_t& io,
+                   int match_pairs) {
+    int rc = init();
+    if (rc) return rc;
+    PL_CHECK_ARG(images && batch >= 1 && pitch >= W);
+    const int kpCap = orb.max_keypoints(), lnCap = lines.out_capacity();
+    const int npairs = batch / 2;
+    const size_t dpitch = align_up(W, 32), dstride = dpitch * H;
+    if ((rc = dIn.ensure(dstride * batch)) || (rc = dKps.ensure((size_t)batch * kpCap * sizeof(plslam_keypoint_t))) ||
+        (rc = dDesc.ensure((size_t)batch * kpCap * 32)) || (rc = dKpCnt.ensure((size_t)batch * 4)) ||
+        (rc = dKl.ensure((size_t)batch * lnCap * sizeof(plslam_keyline_t))) || (rc = dLdesc.ensure((size_t)batch * lnCap * 32)) ||
+        (rc = dFuncs.ensure((size_t)batch * lnCap * 24)) || (rc = dLCnt.ensure((size_t)batch * 4)))
+      return rc;
+    if (match_pairs) {
+      if ((rc = dOrbM.ensure((size_t)std::max(npairs, 1) * kpCap * 16)) || (rc = dLineM.ensure((size_t)std::max(npairs, 1) * lnCap * 16)))
+        return rc;
+    }
+    cudaStream_t st = sHost;
+    if (stride == (size_t)pitch * H) {
+      PL_CUDA(cudaMemcpy2DAsync(dIn.p, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, st));
+    } else {
+      for (int f = 0; f < batch; ++f)
+        PL_CUDA(cudaMemcpy2DAsync(dIn.as<uint8_t>() + f * dstride, dpitch, images + f * stride, pitch, W, H,
+                                  cudaMemcpyHostToDevice, st));
+    }
+    plslam_frontend_io_t d{};
+    d.keypoints = dKps.as<plslam_keypoint_t>();
+    d.descriptors = dDesc.as<uint8_t>();
+    d.kp_counts = dKpCnt.as<int32_t>();
+    d.keylines = dKl.as<plslam_keyline_t>();
+    d.line_descriptors = dLdesc.as<uint8_t>();
+    d.line_functions = dFuncs.as<double>();
+    d.line_counts = dLCnt.as<int32_t>();
+    d.orb_matches = match_pairs ? dOrbM.as<int32_t>() : nullptr;
+    d.line_matches = match_pairs ? dLineM.as<int32_t>() : nullptr;
+    rc = process_device(dIn.as<uint8_t>(), batch, W, H, (int)dpitch, dstride, d, match_pairs, st);
+    if (rc) return rc;
+    PL_CUDA(cudaMemcpyAsync(io.keypoints, d.keypoints, (size_t)batch * kpCap * sizeof(plslam_keypoint_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(io.descriptors, d.descriptors, (size_t)batch * kpCap * 32, cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(io.kp_counts, d.kp_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(io.keylines, d.keylines, (size_t)batch * lnCap * sizeof(plslam_keyline_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(io.line_descriptors, d.line_descriptors, (size_t)batch * lnCap * 32, cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(io.line_functions, d.line_functions, (size_t)batch * lnCap * 24, cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(io.line_counts, d.line_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    if (match_pairs) {
+      PL_CUDA(cudaMemcpyAsync(io.orb_matches, d.orb_matches, (size_t)npairs * kpCap * 16, cudaMemcpyDeviceToHost, st));
+      PL_CUDA(cudaMemcpyAsync(io.line_matches, d.line_matches, (size_t)npairs * lnCap * 16, cudaMemcpyDeviceToHost, st));
+    }
+    return check_status(st);
+  }
+};
+
+}  // namespace plslam
+
+using namespace plslam;
+
+struct plslam_frontend {
+  Frontend impl;
+  plslam_frontend(int nf, float sf, int nl, int ini, int mn, int ml) : impl(nf, sf, nl, ini, mn, ml) {}
+};
+
+extern "C" {
+
+int plslam_match_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int capacity, int npairs,
+                                   int32_t* d_out, plslam_knn_job_t* d_jobs_scratch, void* stream) {
+  PL_CHECK_ARG(d_desc && d_counts && d_out && d_jobs_scratch && capacity >= 1 && npairs >= 1);
+  k_make_pair_jobs<<<div_up(npairs, 128), 128, 0, (cudaStream_t)stream>>>(d_desc, d_counts, capacity, npairs, d_out,
+                                                                          d_jobs_scratch);
+  PL_CUDA(cudaGetLastError());
+  return plslam_match_knn2_batch_device(d_jobs_scratch, npairs, capacity, stream);
+}
+
+int plslam_frontend_create(plslam_frontend_t** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                           int minThFAST, int max_lines) {
+  PL_CHECK_ARG(out != nullptr);
+  *out = nullptr;
+  PL_CHECK_ARG(nfeatures > 0 && nlevels >= 1 && nlevels <= ORB_MAXL && scaleFactor > 1.0f && max_lines >= 0);
+  PL_CHECK_ARG(iniThFAST >= minThFAST && minThFAST >= 1 && iniThFAST < 255);
+  *out = new (std::nothrow) plslam_frontend(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_lines);
+  if (!*out) {
+    set_error("out of host memory");
+    return PLSLAM_ERR_INVALID;
+  }
+  return PLSLAM_OK;
+}
+void plslam_frontend_destroy(plslam_frontend_t* h) { delete h; }
+int plslam_frontend_capacities(const plslam_frontend_t* h, int* kp_capacity, int* line_capacity) {
+  PL_CHECK_ARG(h);
+  if (kp_capacity) *kp_capacity = h->impl.orb.max_keypoints();
+  if (line_capacity) *line_capacity = h->impl.lines.out_capacity();
+  return PLSLAM_OK;
+}
+int plslam_frontend_process_device(plslam_frontend_t* h, const uint8_t* d_images, int batch, int width, int height,
+                                   int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs,
+                                   void* stream) {
+  PL_CHECK_ARG(h && io && d_images);
+  return h->impl.process_device(d_images, batch, width, height, pitch, frame_stride, *io, match_pairs, (cudaStream_t)stream);
+}
+int plslam_frontend_process_host(plslam_frontend_t* h, const uint8_t* images, int batch, int width, int height,
+                                 int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs) {
+  PL_CHECK_ARG(h && io);
+  return h->impl.process_host(images, batch, width, height, pitch, frame_stride, *io, match_pairs);
+}
+int plslam_frontend_check_status(plslam_frontend_t* h, void* stream) {
+  PL_CHECK_ARG(h);
+  int rc = h->impl.init();
+  if (rc) return rc;
+  return h->impl.check_status((cudaStream_t)stream);
+}
+int plslam_frontend_enable_timing(plslam_frontend_t* h, int enable) {
+  PL_CHECK_ARG(h);
+  h->impl.timing = enable != 0;
+  return PLSLAM_OK;
+}
+int plslam_frontend_stage_times(plslam_frontend_t* h, const char** names, float* ms, int capacity) {
+  if (!h || !names || !ms) return 0;
+  int n = h->impl.tLines.collect(names, ms, capacity);
+  n += h->impl.tOrb.collect(names + n, ms + n, capacity - n);
+  return n;
+}
+int plslam_frontend_launches_per_call(const plslam_frontend_t* h, int match_pairs) {
+  if (!h) return 0;
+  // ORB: (nlevels-1) resize + fast + quadtree + blur + orient_desc; lines: 8 kernels; matching: 2 x (jobs + knn2)
+  return (h->impl.orb.nlevels - 1) + 4 + 8 + (match_pairs ? 4 : 0);
+}
+
+}  // extern "C"

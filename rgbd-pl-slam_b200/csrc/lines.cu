@@ -1112,25 +1112,41 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   last_batch = batch;
   PL_CUDA(cudaMemsetAsync(maxg2.p, 0, (size_t)batch * sizeof(int), st));
   PL_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), st));
+  PL_STAGE_BEGIN(timer, "lsd_scale", st);
   k_lsd_scale<<<dim3(div_up(P.sw, ST_W), div_up(P.sh, ST_H), batch), 256, 0, st>>>(P, d_images, pitch, frame_stride,
                                                                                      coef.as<int>(), scaled.as<uint8_t>());
+  PL_STAGE_END(timer, st);
+  PL_STAGE_BEGIN(timer, "lsd_grad", st);
   k_lsd_grad<<<dim3(div_up(P.sw, 32), div_up(P.sh, 8), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(),
                                                                              maxg2.as<int>());
+  PL_STAGE_END(timer, st);
+  PL_STAGE_BEGIN(timer, "lsd_rowhist", st);
   k_lsd_rowhist<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>());
+  PL_STAGE_END(timer, st);
+  PL_STAGE_BEGIN(timer, "lsd_colscan", st);
   k_lsd_colscan<<<batch, LSD_BINS, 0, st>>>(P, rowhist.as<unsigned>(), binstart.as<unsigned>(), nseeds.as<int>());
+  PL_STAGE_END(timer, st);
+  PL_STAGE_BEGIN(timer, "lsd_scatter", st);
   k_lsd_scatter<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>(),
                                                               binstart.as<unsigned>(), seeds.as<unsigned>());
+  PL_STAGE_END(timer, st);
   const size_t growSmem = 96 * sizeof(double) + (size_t)((P.P + 31) / 32) * 4;
+  PL_STAGE_BEGIN(timer, "lsd_grow", st);
   k_lsd_grow<<<batch, 32, growSmem, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
                                           rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());
+  PL_STAGE_END(timer, st);
   LsdSegment* rout = rectout.as<LsdSegment>();
   uint8_t* rvalid = reinterpret_cast<uint8_t*>(rout + (size_t)cfgB * P.rect_cap);
+  PL_STAGE_BEGIN(timer, "lsd_nfa", st);
   k_lsd_nfa<<<dim3(div_up(P.rect_cap, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), rects.as<LsdRect>(), nrects.as<int>(),
                                                                 rout, rvalid);
+  PL_STAGE_END(timer, st);
   const size_t finSmem = (size_t)P.rect_cap * 8 + (size_t)P.out_cap * 4;
+  PL_STAGE_BEGIN(timer, "lsd_finish_lbd", st);
   k_lsd_finish<<<batch, 256, finSmem, st>>>(P, d_images, pitch, frame_stride, nrects.as<int>(), rout, rvalid,
                                             segs.as<LsdSegment>(), nsegs.as<int>(), rowsum.as<float>(), d_keylines, d_desc,
                                             d_funcs, capacity, d_counts);
+  PL_STAGE_END(timer, st);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;
 }

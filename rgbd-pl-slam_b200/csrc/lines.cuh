@@ -52,6 +52,8 @@ class LineExtractor {
   int copy_angles(int frame, float* deg_out, int32_t* g2_out, size_t n);
   int copy_segments(int frame, LsdSegment* out, int capacity, int* n_out);
 
+  StageTimer* timer = nullptr;
+  const int* device_status() const { return status.as<int>(); }
   int max_lines = 40;  // lsdNFeatures of the PL-SLAM fork family
   int rect_cap = 4096;
 

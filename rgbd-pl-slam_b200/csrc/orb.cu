@@ -881,10 +881,12 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
 
   PL_CUDA(cudaMemsetAsync(candCount.p, 0, (size_t)batch * ORB_MAXL * sizeof(int), st));
   PL_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), st));
+  PL_STAGE_BEGIN(timer, "orb_pyramid(7 launches)", st);
   for (int l = 1; l < nlevels; ++l) {
     dim3 grid(div_up(P.lv[l].w, 128), div_up(P.lv[l].h, 8), batch);
     k_resize<<<grid, dim3(32, 8), 0, st>>>(P, I, l, coef.as<int>());
   }
+  PL_STAGE_END(timer, st);
   {
     const size_t smem = 8 * (2 * (size_t)P.patchPitch * P.patchRows + 128);
     static bool attr = false;
@@ -893,8 +895,10 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
       PL_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr = true;
     }
+    PL_STAGE_BEGIN(timer, "orb_fast", st);
     k_fast<<<dim3(div_up(P.totalCells, 8), batch), 256, smem, st>>>(P, I, cand.as<unsigned long long>(),
                                                                     candCount.as<int>(), status.as<int>());
+    PL_STAGE_END(timer, st);
   }
   {
     const size_t smem = quadtree_smem(P.nodeCap);
@@ -902,12 +906,18 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
       set_error("nfeatures too large for the shared-memory quad-tree (%zu B)", smem);
       return PLSLAM_ERR_INVALID;
     }
+    PL_STAGE_BEGIN(timer, "orb_quadtree", st);
     k_quadtree<<<dim3(nlevels, batch), 256, smem, st>>>(P, cand.as<unsigned long long>(), candCount.as<int>(),
                                                         knode.as<unsigned short>(), lvlKp.as<uint2>(), lvlCnt.as<int>());
+    PL_STAGE_END(timer, st);
   }
+  PL_STAGE_BEGIN(timer, "orb_blur", st);
   k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, I, lvlCnt.as<int>());
+  PL_STAGE_END(timer, st);
+  PL_STAGE_BEGIN(timer, "orb_orient_desc", st);
   k_orient_desc<<<dim3(div_up(P.maxKp, 8), batch), 256, 0, st>>>(P, I, lvlKp.as<uint2>(), lvlCnt.as<int>(), d_kps,
                                                                  d_desc, capacity, d_counts);
+  PL_STAGE_END(timer, st);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;
 }

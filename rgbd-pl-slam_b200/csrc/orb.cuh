@@ -64,6 +64,8 @@ class OrbExtractor {
   int level_size(int level, int* w, int* h) const;
   int max_keypoints() const;
   int check_status(cudaStream_t st);  // synchronises st and maps the device status word to a return code
+  StageTimer* timer = nullptr;        // optional per-stage event timing (owned by the caller)
+  const int* device_status() const { return status.as<int>(); }
 
   // constructor tables (ORBextractor.h:102-110)
   int nfeatures, nlevels, iniThFAST, minThFAST;

@@ -355,3 +355,90 @@ def projection_batch_device(jobs, max_n1, max_n2, device, stream=None):
     jd = _jobs_to_device(jobs, device)
     _check(lib().plslam_match_projection_batch_device(_vp(jd), len(jobs), int(max_n1), int(max_n2), _stream_ptr(stream)))
     return jd
+
+
+# ---------------------------------------------------------------------------
+# batched front-end (Frame::ExtractORB + Frame::ExtractLSD + pair matching)
+# ---------------------------------------------------------------------------
+class FrontendIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("keypoints", "descriptors", "kp_counts", "keylines", "line_descriptors",
+                                          "line_functions", "line_counts", "orb_matches", "line_matches")]
+
+
+class Frontend:
+    """plslam_frontend_*: ORB + LSD/LBD (+ frame-pair kNN) for a batch of frames in one call."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, max_lines=40):
+        L = lib()
+        self._h = C.c_void_p()
+        L.plslam_frontend_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.plslam_frontend_destroy.argtypes = [C.c_void_p]
+        L.plslam_frontend_destroy.restype = None
+        _check(L.plslam_frontend_create(C.byref(self._h), nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_lines))
+        a, b = C.c_int(), C.c_int()
+        _check(L.plslam_frontend_capacities(self._h, C.byref(a), C.byref(b)))
+        self.kp_capacity, self.line_capacity = a.value, b.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().plslam_frontend_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def alloc(self, batch, device=None, pinned=False):
+        """Output block for `batch` frames: torch tensors on `device`, or pinned/pageable host tensors."""
+        import torch
+        kw = dict(device=device) if device is not None else dict(pin_memory=pinned)
+        kc, lc, npairs = self.kp_capacity, self.line_capacity, max(batch // 2, 1)
+        return dict(keypoints=torch.empty((batch, kc, 7), dtype=torch.int32, **kw),
+                    descriptors=torch.empty((batch, kc, 32), dtype=torch.uint8, **kw),
+                    kp_counts=torch.empty((batch,), dtype=torch.int32, **kw),
+                    keylines=torch.empty((batch, lc, 17), dtype=torch.int32, **kw),
+                    line_descriptors=torch.empty((batch, lc, 32), dtype=torch.uint8, **kw),
+                    line_functions=torch.empty((batch, lc, 3), dtype=torch.float64, **kw),
+                    line_counts=torch.empty((batch,), dtype=torch.int32, **kw),
+                    orb_matches=torch.empty((npairs, kc, 4), dtype=torch.int32, **kw),
+                    line_matches=torch.empty((npairs, lc, 4), dtype=torch.int32, **kw))
+
+    @staticmethod
+    def _io(out):
+        io = FrontendIO()
+        for k, _ in FrontendIO._fields_:
+            setattr(io, k, out[k].data_ptr())
+        return io
+
+    def process_device(self, d_images, out, match_pairs=True, stream=None):
+        B, H, W = d_images.shape
+        io = self._io(out)
+        _check(lib().plslam_frontend_process_device(self._h, _vp(d_images), B, W, H, d_images.stride(1),
+                                                    C.c_size_t(d_images.stride(0)), C.byref(io), int(match_pairs),
+                                                    _stream_ptr(stream)))
+        return out
+
+    def process_host(self, images, out, match_pairs=True):
+        """images: (B, H, W) uint8 host tensor/array (pinned => asynchronous copies); out: host block from alloc()."""
+        B, H, W = images.shape
+        io = self._io(out)
+        ptr = images.data_ptr() if hasattr(images, "data_ptr") else images.ctypes.data
+        st0 = images.stride(0) if hasattr(images, "stride") else images.strides[0]
+        st1 = images.stride(1) if hasattr(images, "stride") else images.strides[1]
+        _check(lib().plslam_frontend_process_host(self._h, C.c_void_p(ptr), B, W, H, st1, C.c_size_t(st0), C.byref(io),
+                                                  int(match_pairs)))
+        return out
+
+    def check_status(self, stream=None):
+        _check(lib().plslam_frontend_check_status(self._h, _stream_ptr(stream)))
+
+    def enable_timing(self, on=True):
+        _check(lib().plslam_frontend_enable_timing(self._h, int(on)))
+
+    def stage_times(self):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = lib().plslam_frontend_stage_times(self._h, names, ms, 64)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    def launches_per_call(self, match_pairs=True):
+        return lib().plslam_frontend_launches_per_call(self._h, int(match_pairs))
