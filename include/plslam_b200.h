@@ -260,6 +260,13 @@ typedef struct plslam_frontend_io {
 
 int plslam_frontend_create(plslam_frontend_t** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
                            int minThFAST, int max_lines);
+/* Same with `depth` independent pipeline slots (each a full workspace): successive process/submit calls rotate
+ * over the slots, so up to `depth` batches are in flight on the GPU when the caller uses separate streams (device
+ * path) or the asynchronous host path below.  The line detector's region growing is sequential per frame (one warp
+ * per frame), so batches in flight are what fills the machine. */
+int plslam_frontend_create_pipelined(plslam_frontend_t** out, int nfeatures, float scaleFactor, int nlevels,
+                                     int iniThFAST, int minThFAST, int max_lines, int depth);
+int plslam_frontend_depth(const plslam_frontend_t* h);
 void plslam_frontend_destroy(plslam_frontend_t* h);
 int plslam_frontend_capacities(const plslam_frontend_t* h, int* kp_capacity, int* line_capacity);
 /* All pointers in `io` are device pointers; asynchronous on `stream`. match_pairs != 0 also fills the match blocks. */
@@ -269,6 +276,12 @@ int plslam_frontend_process_device(plslam_frontend_t* h, const uint8_t* d_images
 /* All pointers are HOST pointers (pinned memory makes the copies asynchronous); returns after the results landed. */
 int plslam_frontend_process_host(plslam_frontend_t* h, const uint8_t* images, int batch, int width, int height,
                                  int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs);
+/* Asynchronous host path: submit enqueues H2D + kernels + D2H on the next slot and returns; the host output
+ * buffers of a submit are valid after plslam_frontend_wait_host(), which waits for every pending slot and reports
+ * PLSLAM_ERR_OVERFLOW if any batch overflowed an internal list. */
+int plslam_frontend_submit_host(plslam_frontend_t* h, const uint8_t* images, int batch, int width, int height, int pitch,
+                                size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs);
+int plslam_frontend_wait_host(plslam_frontend_t* h);
 /* Per-stage device times (ms, CUDA events on the launching streams) of the last process call made after
  * plslam_frontend_enable_timing(h, 1).  names/ms hold up to `capacity` entries; returns the number of stages. */
 int plslam_frontend_enable_timing(plslam_frontend_t* h, int enable);

@@ -26,28 +26,29 @@ __global__ void k_make_pair_jobs(const uint8_t* desc, const int32_t* counts, int
 
 }  // namespace
 
-struct Frontend {
+// One pipeline slot = one complete workspace (ORB + line extractors, streams, staging).  Independent
+// batches submitted on different slots overlap on the GPU: k_lsd_grow keeps one warp per frame busy for
+// tens of milliseconds at ~0.13 IPC, so several batches in flight are needed to fill the issue slots.
+struct Slot {
   OrbExtractor orb;
   LineExtractor lines;
   StageTimer tOrb, tLines;
   cudaStream_t sOrb = nullptr, sLines = nullptr, sHost = nullptr;
-  cudaEvent_t evFork = nullptr, evOrb = nullptr, evLines = nullptr;
+  cudaEvent_t evFork = nullptr, evOrb = nullptr, evLines = nullptr, evDone = nullptr;
   DevBuf jobsOrb, jobsLines;
   DevBuf dIn, dKps, dDesc, dKpCnt, dKl, dLdesc, dFuncs, dLCnt, dOrbM, dLineM;
   int* pinnedStatus = nullptr;
-  bool timing = false;
-  Frontend(int nf, float sf, int nl, int ini, int mn, int max_lines) : orb(nf, sf, nl, ini, mn) {
-    lines.set_max_lines(max_lines);
-  }
-  ~Frontend() {
+  bool used = false, hostPending = false;
+  Slot(int nf, float sf, int nl, int ini, int mn, int max_lines) : orb(nf, sf, nl, ini, mn) { lines.set_max_lines(max_lines); }
+  ~Slot() {
     DevBuf* all[] = {&jobsOrb, &jobsLines, &dIn, &dKps, &dDesc, &dKpCnt, &dKl, &dLdesc, &dFuncs, &dLCnt, &dOrbM, &dLineM};
     for (DevBuf* b : all) b->release();
     if (sOrb) cudaStreamDestroy(sOrb);
     if (sLines) cudaStreamDestroy(sLines);
     if (sHost) cudaStreamDestroy(sHost);
-    if (evFork) cudaEventDestroy(evFork);
-    if (evOrb) cudaEventDestroy(evOrb);
-    if (evLines) cudaEventDestroy(evLines);
+    cudaEvent_t evs[] = {evFork, evOrb, evLines, evDone};
+    for (cudaEvent_t e : evs)
+      if (e) cudaEventDestroy(e);
     if (pinnedStatus) cudaFreeHost(pinnedStatus);
   }
   int init() {
@@ -58,11 +59,12 @@ struct Frontend {
     PL_CUDA(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
     PL_CUDA(cudaEventCreateWithFlags(&evOrb, cudaEventDisableTiming));
     PL_CUDA(cudaEventCreateWithFlags(&evLines, cudaEventDisableTiming));
+    PL_CUDA(cudaEventCreateWithFlags(&evDone, cudaEventDisableTiming));
     PL_CUDA(cudaMallocHost((void**)&pinnedStatus, 64));
     return PLSLAM_OK;
   }
   int process_device(const uint8_t* d_images, int batch, int W, int H, int pitch, size_t stride,
-                     const plslam_frontend_io_t& io, int match_pairs, cudaStream_t st) {
+                     const plslam_frontend_io_t& io, int match_pairs, cudaStream_t st, bool timing) {
     int rc = init();
     if (rc) return rc;
     PL_CHECK_ARG(io.keypoints && io.descriptors && io.kp_counts && io.keylines && io.line_descriptors &&
@@ -79,6 +81,8 @@ struct Frontend {
     tLines.reset();
     orb.timer = timing ? &tOrb : nullptr;
     lines.timer = timing ? &tLines : nullptr;
+    // the slot's previous batch (possibly submitted from another stream) must have drained: its workspace is reused
+    if (used) PL_CUDA(cudaStreamWaitEvent(st, evDone, 0));
     PL_CUDA(cudaEventRecord(evFork, st));
     PL_CUDA(cudaStreamWaitEvent(sOrb, evFork, 0));
     PL_CUDA(cudaStreamWaitEvent(sLines, evFork, 0));
@@ -104,9 +108,14 @@ struct Frontend {
     PL_CUDA(cudaEventRecord(evLines, sLines));
     PL_CUDA(cudaStreamWaitEvent(st, evOrb, 0));
     PL_CUDA(cudaStreamWaitEvent(st, evLines, 0));
+    PL_CUDA(cudaEventRecord(evDone, st));
+    used = true;
     return PLSLAM_OK;
   }
   int check_status(cudaStream_t st) {
+    int rc = init();
+    if (rc) return rc;
+    if (!used) return PLSLAM_OK;
     PL_CUDA(cudaMemcpyAsync(pinnedStatus, orb.device_status(), sizeof(int), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaMemcpyAsync(pinnedStatus + 1, lines.device_status(), sizeof(int), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaStreamSynchronize(st));
@@ -116,8 +125,9 @@ struct Frontend {
     }
     return PLSLAM_OK;
   }
-  int process_host(const uint8_t* images, int batch, int W, int H, int pitch, size_t stride, const plslam_frontend_io_t& io,
-                   int match_pairs) {
+  // enqueue H2D + kernels + D2H on the slot's host stream; returns without waiting
+  int submit_host(const uint8_t* images, int batch, int W, int H, int pitch, size_t stride, const plslam_frontend_io_t& io,
+                  int match_pairs, bool timing) {
     int rc = init();
     if (rc) return rc;
     PL_CHECK_ARG(images && batch >= 1 && pitch >= W);
@@ -151,7 +161,7 @@ struct Frontend {
     d.line_counts = dLCnt.as<int32_t>();
     d.orb_matches = match_pairs ? dOrbM.as<int32_t>() : nullptr;
     d.line_matches = match_pairs ? dLineM.as<int32_t>() : nullptr;
-    rc = process_device(dIn.as<uint8_t>(), batch, W, H, (int)dpitch, dstride, d, match_pairs, st);
+    rc = process_device(dIn.as<uint8_t>(), batch, W, H, (int)dpitch, dstride, d, match_pairs, st, timing);
     if (rc) return rc;
     PL_CUDA(cudaMemcpyAsync(io.keypoints, d.keypoints, (size_t)batch * kpCap * sizeof(plslam_keypoint_t), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaMemcpyAsync(io.descriptors, d.descriptors, (size_t)batch * kpCap * 32, cudaMemcpyDeviceToHost, st));
@@ -164,7 +174,31 @@ struct Frontend {
       PL_CUDA(cudaMemcpyAsync(io.orb_matches, d.orb_matches, (size_t)npairs * kpCap * 16, cudaMemcpyDeviceToHost, st));
       PL_CUDA(cudaMemcpyAsync(io.line_matches, d.line_matches, (size_t)npairs * lnCap * 16, cudaMemcpyDeviceToHost, st));
     }
-    return check_status(st);
+    PL_CUDA(cudaEventRecord(evDone, st));
+    hostPending = true;
+    return PLSLAM_OK;
+  }
+  int wait_host() {
+    if (!hostPending) return PLSLAM_OK;
+    hostPending = false;
+    return check_status(sHost);
+  }
+};
+
+struct Frontend {
+  std::vector<Slot*> slots;
+  int next = 0, lastSlot = 0;
+  bool timing = false;
+  Frontend(int nf, float sf, int nl, int ini, int mn, int max_lines, int depth) {
+    for (int i = 0; i < depth; ++i) slots.push_back(new Slot(nf, sf, nl, ini, mn, max_lines));
+  }
+  ~Frontend() {
+    for (Slot* s : slots) delete s;
+  }
+  Slot& take() {
+    lastSlot = next;
+    next = (next + 1) % (int)slots.size();
+    return *slots[lastSlot];
   }
 };
 
@@ -174,7 +208,7 @@ using namespace plslam;
 
 struct plslam_frontend {
   Frontend impl;
-  plslam_frontend(int nf, float sf, int nl, int ini, int mn, int ml) : impl(nf, sf, nl, ini, mn, ml) {}
+  plslam_frontend(int nf, float sf, int nl, int ini, int mn, int ml, int depth) : impl(nf, sf, nl, ini, mn, ml, depth) {}
 };
 
 extern "C" {
@@ -188,42 +222,69 @@ int plslam_match_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_count
   return plslam_match_knn2_batch_device(d_jobs_scratch, npairs, capacity, stream);
 }
 
-int plslam_frontend_create(plslam_frontend_t** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
-                           int minThFAST, int max_lines) {
+int plslam_frontend_create_pipelined(plslam_frontend_t** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                                     int minThFAST, int max_lines, int depth) {
   PL_CHECK_ARG(out != nullptr);
   *out = nullptr;
   PL_CHECK_ARG(nfeatures > 0 && nlevels >= 1 && nlevels <= ORB_MAXL && scaleFactor > 1.0f && max_lines >= 0);
-  PL_CHECK_ARG(iniThFAST >= minThFAST && minThFAST >= 1 && iniThFAST < 255);
-  *out = new (std::nothrow) plslam_frontend(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_lines);
+  PL_CHECK_ARG(iniThFAST >= minThFAST && minThFAST >= 1 && iniThFAST < 255 && depth >= 1 && depth <= 64);
+  *out = new (std::nothrow) plslam_frontend(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_lines, depth);
   if (!*out) {
     set_error("out of host memory");
     return PLSLAM_ERR_INVALID;
   }
   return PLSLAM_OK;
 }
+int plslam_frontend_create(plslam_frontend_t** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                           int minThFAST, int max_lines) {
+  return plslam_frontend_create_pipelined(out, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_lines, 1);
+}
 void plslam_frontend_destroy(plslam_frontend_t* h) { delete h; }
+int plslam_frontend_depth(const plslam_frontend_t* h) { return h ? (int)h->impl.slots.size() : 0; }
 int plslam_frontend_capacities(const plslam_frontend_t* h, int* kp_capacity, int* line_capacity) {
   PL_CHECK_ARG(h);
-  if (kp_capacity) *kp_capacity = h->impl.orb.max_keypoints();
-  if (line_capacity) *line_capacity = h->impl.lines.out_capacity();
+  if (kp_capacity) *kp_capacity = h->impl.slots[0]->orb.max_keypoints();
+  if (line_capacity) *line_capacity = h->impl.slots[0]->lines.out_capacity();
   return PLSLAM_OK;
 }
 int plslam_frontend_process_device(plslam_frontend_t* h, const uint8_t* d_images, int batch, int width, int height,
                                    int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs,
                                    void* stream) {
   PL_CHECK_ARG(h && io && d_images);
-  return h->impl.process_device(d_images, batch, width, height, pitch, frame_stride, *io, match_pairs, (cudaStream_t)stream);
+  return h->impl.take().process_device(d_images, batch, width, height, pitch, frame_stride, *io, match_pairs,
+                                       (cudaStream_t)stream, h->impl.timing);
+}
+int plslam_frontend_submit_host(plslam_frontend_t* h, const uint8_t* images, int batch, int width, int height, int pitch,
+                                size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs) {
+  PL_CHECK_ARG(h && io);
+  Slot& s = h->impl.take();
+  int rc = s.wait_host();  // the slot's previous host batch must have landed before its staging is reused
+  if (rc) return rc;
+  return s.submit_host(images, batch, width, height, pitch, frame_stride, *io, match_pairs, h->impl.timing);
+}
+int plslam_frontend_wait_host(plslam_frontend_t* h) {
+  PL_CHECK_ARG(h);
+  int rc = PLSLAM_OK;
+  for (Slot* s : h->impl.slots) {
+    const int r = s->wait_host();
+    if (r && !rc) rc = r;
+  }
+  return rc;
 }
 int plslam_frontend_process_host(plslam_frontend_t* h, const uint8_t* images, int batch, int width, int height,
                                  int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs) {
-  PL_CHECK_ARG(h && io);
-  return h->impl.process_host(images, batch, width, height, pitch, frame_stride, *io, match_pairs);
+  int rc = plslam_frontend_submit_host(h, images, batch, width, height, pitch, frame_stride, io, match_pairs);
+  if (rc) return rc;
+  return h->impl.slots[h->impl.lastSlot]->wait_host();
 }
 int plslam_frontend_check_status(plslam_frontend_t* h, void* stream) {
   PL_CHECK_ARG(h);
-  int rc = h->impl.init();
-  if (rc) return rc;
-  return h->impl.check_status((cudaStream_t)stream);
+  int rc = PLSLAM_OK;
+  for (Slot* s : h->impl.slots) {
+    const int r = s->check_status((cudaStream_t)stream);
+    if (r && !rc) rc = r;
+  }
+  return rc;
 }
 int plslam_frontend_enable_timing(plslam_frontend_t* h, int enable) {
   PL_CHECK_ARG(h);
@@ -232,14 +293,15 @@ int plslam_frontend_enable_timing(plslam_frontend_t* h, int enable) {
 }
 int plslam_frontend_stage_times(plslam_frontend_t* h, const char** names, float* ms, int capacity) {
   if (!h || !names || !ms) return 0;
-  int n = h->impl.tLines.collect(names, ms, capacity);
-  n += h->impl.tOrb.collect(names + n, ms + n, capacity - n);
+  Slot& s = *h->impl.slots[h->impl.lastSlot];
+  int n = s.tLines.collect(names, ms, capacity);
+  n += s.tOrb.collect(names + n, ms + n, capacity - n);
   return n;
 }
 int plslam_frontend_launches_per_call(const plslam_frontend_t* h, int match_pairs) {
   if (!h) return 0;
   // ORB: (nlevels-1) resize + fast + quadtree + blur + orient_desc; lines: 8 kernels; matching: 2 x (jobs + knn2)
-  return (h->impl.orb.nlevels - 1) + 4 + 8 + (match_pairs ? 4 : 0);
+  return (h->impl.slots[0]->orb.nlevels - 1) + 4 + 8 + (match_pairs ? 4 : 0);
 }
 
 }  // extern "C"

@@ -220,13 +220,20 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ Lin
 // ------------------------------------------------------------------------------------------
 // k_lsd_grow: the sequential heart of LSD, one warp per frame.
 // ------------------------------------------------------------------------------------------
+constexpr int REG_SMEM = 1024;  // region-list entries kept in shared memory (larger regions spill to global)
+
 struct GrowCtx {
   const uint4* pix;   // per-pixel records of this frame
   unsigned* used;     // shared-memory bitmap
-  unsigned* reg;      // region list (pixel indices) of this frame
+  unsigned* regS;     // region list (pixel indices): first REG_SMEM entries in shared memory ...
+  unsigned* regG;     // ... the rest in this frame's global scratch
   double* stage;      // 3 x 32 doubles of shared staging
   int sw, sh;
   int lane;
+  __device__ __forceinline__ unsigned reg_get(int i) const { return i < REG_SMEM ? regS[i] : regG[i]; }
+  __device__ __forceinline__ void reg_set(int i, unsigned v) const {
+    if (i < REG_SMEM) regS[i] = v; else regG[i] = v;
+  }
 };
 
 __device__ __forceinline__ bool used_get(const unsigned* used, int idx) { return (used[idx >> 5] >> (idx & 31)) & 1u; }
@@ -245,7 +252,7 @@ __device__ __forceinline__ bool lsd_aligned(double theta, float deg, double prec
 // region_grow(): returns the region size; reg[0] must already hold the seed pixel index.
 __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_out) {
   const int lane = C.lane;
-  const int seed = (int)C.reg[0];
+  const int seed = (int)C.reg_get(0);
   const uint4 srec = C.pix[seed];
   double reg_angle = __dmul_rn((double)__uint_as_float(srec.x), PL_DEG_TO_RADS);
   float sumdx, sumdy;
@@ -259,33 +266,36 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
   __syncwarp();
   int n = 1;
   for (int i = 0; i < n;) {
-    const int m = min(3, n - i);
-    // 27 lanes: lane = 9 * point + neighbour (row-major 3x3, yy outer / xx inner as in lsd.cpp)
-    const int pt = lane / 9, nb = lane - pt * 9;
+    const int m = min(4, n - i);
+    // 32 lanes: lane = 8 * point + neighbour; neighbours in the 3x3 row-major order of lsd.cpp (yy outer, xx
+    // inner) without the centre, which is always already used
+    const int pt = lane >> 3, nb8 = lane & 7, nb = nb8 < 4 ? nb8 : nb8 + 1;
     int nidx = -1;
     float deg = NOTDEF_F, cs = 0.f, sn = 0.f;
-    if (lane < 27 && pt < m) {
-      const int p = (int)C.reg[i + pt];
+    if (pt < m) {
+      const int p = (int)C.reg_get(i + pt);
       const int py = p / C.sw, px = p - py * C.sw;
       const int nx = px + (nb % 3) - 1, ny = py + (nb / 3) - 1;
       if (nx >= 0 && ny >= 0 && nx < C.sw && ny < C.sh) {
         nidx = ny * C.sw + nx;
-        const uint4 r = __ldg(C.pix + nidx);
-        deg = __uint_as_float(r.x);
-        cs = __uint_as_float(r.y);
-        sn = __uint_as_float(r.z);
+        if (!used_get(C.used, nidx)) {
+          const uint4 r = __ldg(C.pix + nidx);
+          deg = __uint_as_float(r.x);
+          cs = __uint_as_float(r.y);
+          sn = __uint_as_float(r.z);
+        }
       }
     }
     unsigned todo = 0xffffffffu;  // lanes not yet passed by the sequential scan
     while (true) {
-      const bool cand = nidx >= 0 && deg != NOTDEF_F && !used_get(C.used, nidx) && lsd_aligned(reg_angle, deg, prec);
+      const bool cand = deg != NOTDEF_F && !used_get(C.used, nidx) && lsd_aligned(reg_angle, deg, prec);
       const unsigned mask = __ballot_sync(0xffffffffu, cand) & todo;
       if (!mask) break;
       const int j = __ffs(mask) - 1;
       const int aidx = __shfl_sync(0xffffffffu, nidx, j);
       if (lane == 0) {
         C.used[aidx >> 5] |= 1u << (aidx & 31);
-        C.reg[n] = (unsigned)aidx;
+        C.reg_set(n, (unsigned)aidx);
       }
       ++n;
       sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, cs, j));
@@ -319,7 +329,7 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
     if (i < n) {
-      const int idx = (int)C.reg[i];
+      const int idx = (int)C.reg_get(i);
       const int py = idx / C.sw, px = idx - py * C.sw;
       const double w = modgrad_of((int)__ldg(C.pix + idx).w);
       sA[lane] = __dmul_rn((double)px, w);
@@ -341,7 +351,7 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
     if (i < n) {
-      const int idx = (int)C.reg[i];
+      const int idx = (int)C.reg_get(i);
       const int py = idx / C.sw, px = idx - py * C.sw;
       const double w = modgrad_of((int)__ldg(C.pix + idx).w);
       const double dx = __dsub_rn((double)px, x), dy = __dsub_rn((double)py, y);
@@ -369,7 +379,7 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
   pl_sincos_dev(theta, &dy, &dx);
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int i = lane; i < n; i += 32) {
-    const int idx = (int)C.reg[i];
+    const int idx = (int)C.reg_get(i);
     const int py = idx / C.sw, px = idx - py * C.sw;
     const double rdx = __dsub_rn((double)px, x), rdy = __dsub_rn((double)py, y);
     const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
@@ -416,7 +426,7 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   int n = *n_io;
   double density = rect_density(n, *rec);
   if (density >= density_th) return true;
-  const int seed = (int)C.reg[0];
+  const int seed = (int)C.reg_get(0);
   const int sy = seed / C.sw, sx = seed - sy * C.sw;
   const double xc = (double)sx, yc = (double)sy;
   const double ang_c = __dmul_rn((double)__uint_as_float(__ldg(C.pix + seed).x), PL_DEG_TO_RADS);
@@ -427,7 +437,7 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
     if (i < n) {
-      const int idx = (int)C.reg[i];
+      const int idx = (int)C.reg_get(i);
       atomicAnd(&C.used[idx >> 5], ~(1u << (idx & 31)));
       const int py = idx / C.sw, px = idx - py * C.sw;
       double flag = 0.0, v = 0.0;
@@ -468,12 +478,12 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
     if (lane == 0) {
       // swap-with-last removal exactly as the reference (it defines the order of the later sums)
       for (int i = 0; i < n; ++i) {
-        const int idx = (int)C.reg[i];
+        const int idx = (int)C.reg_get(i);
         const int py = idx / C.sw, px = idx - py * C.sw;
         if (dist_sq_dev(xc, yc, (double)px, (double)py) > radSq) {
           C.used[idx >> 5] &= ~(1u << (idx & 31));
-          C.reg[i] = C.reg[n - 1];
-          C.reg[n - 1] = (unsigned)idx;
+          C.reg_set(i, C.reg_get(n - 1));
+          C.reg_set(n - 1, (unsigned)idx);
           --n;
           --i;
         }
@@ -497,9 +507,10 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LinePar
   const int f = blockIdx.x, lane = threadIdx.x;
   GrowCtx C;
   C.stage = reinterpret_cast<double*>(smem_raw);
-  C.used = reinterpret_cast<unsigned*>(smem_raw + 96 * sizeof(double));
+  C.regS = reinterpret_cast<unsigned*>(smem_raw + 96 * sizeof(double));
+  C.used = C.regS + REG_SMEM;
   C.pix = pixAll + (size_t)f * L.P;
-  C.reg = regAll + (size_t)f * L.P;
+  C.regG = regAll + (size_t)f * L.P;
   C.sw = L.sw;
   C.sh = L.sh;
   C.lane = lane;
@@ -510,8 +521,10 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LinePar
   const int ns = nseeds[f];
   LsdRect* rects = rectsAll + (size_t)f * L.rect_cap;
   int nrect = 0;
+  int snext = lane < ns ? (int)seeds[lane] : -1;
   for (int base = 0; base < ns; base += 32) {
-    int s = base + lane < ns ? (int)seeds[base + lane] : -1;
+    int s = snext;
+    snext = base + 32 + lane < ns ? (int)seeds[base + 32 + lane] : -1;  // prefetch the next chunk of seeds
     while (true) {
       const bool unused = s >= 0 && !used_get(C.used, s);
       const unsigned m = __ballot_sync(0xffffffffu, unused);
@@ -519,7 +532,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LinePar
       const int j = __ffs(m) - 1;
       const int seed = __shfl_sync(0xffffffffu, s, j);
       if (lane <= j) s = -1;
-      if (lane == 0) C.reg[0] = (unsigned)seed;
+      if (lane == 0) C.reg_set(0, (unsigned)seed);
       __syncwarp();
       double reg_angle;
       int n = lsd_region_grow(C, L.prec, &reg_angle);
@@ -551,15 +564,20 @@ __device__ __forceinline__ bool double_equal_dev(double a, double b) {
   if (abs_max < 2.2250738585072014e-308) abs_max = 2.2250738585072014e-308;
   return (abs_diff / abs_max) <= (100.0 * 2.2204460492503131e-16);
 }
+// log_gamma / nfa of lsd.cpp.  Integer powers are formed by repeated multiplication (pow() differs from
+// it by ulps only, and the NFA value feeds comparisons, never an output).
 __device__ double log_gamma_dev(double x) {
-  if (x > 15.0)
-    return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+  if (x > 15.0) {
+    const double x2 = x * x;
+    return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * (x2 * x2 * x2)));
+  }
   const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
   double a = (x + 0.5) * log(x + 5.5) - (x + 5.5);
-  double b = 0;
+  double b = 0, xn = 1.0;
   for (int n = 0; n < 7; ++n) {
     a -= log(x + (double)n);
-    b += q[n] * pow(x, (double)n);
+    b += q[n] * xn;
+    xn *= x;
   }
   return a + log(b);
 }
@@ -589,7 +607,23 @@ __device__ double nfa_dev(int n, int k, double p, double LOG_NT) {
   return -log10(bin_tail) - LOG_NT;
 }
 
-__device__ double rect_nfa_dev(const LsdRect& r, const uint4* __restrict__ pix, int sw, int sh, double LOG_NT, int lane) {
+// angular distance used by isAligned(); +inf for undefined pixels
+__device__ __forceinline__ double lsd_ntheta(double theta, float deg) {
+  if (deg == NOTDEF_F) return 1e300;
+  const double a = __dmul_rn((double)deg, PL_DEG_TO_RADS);
+  double n_theta = __dsub_rn(theta, a);
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > M_3_2_PI_D) {
+    n_theta = __dsub_rn(n_theta, M_2__PI_D);
+    if (n_theta < 0) n_theta = -n_theta;
+  }
+  return n_theta;
+}
+
+// Row scan of rect_nfa(): counts the pixels of the rectangle (total) and, for up to 5 angular
+// tolerances at once, the aligned ones.  Warp-cooperative; results are warp-uniform.
+__device__ void rect_count_dev(const LsdRect& r, const double* precs, int nprec, const uint4* __restrict__ pix, int sw,
+                               int sh, int lane, int* total_out, int* alg_out) {
   const double hw = __dmul_rn(0.5, r.width);
   const double dyhw = __dmul_rn(r.dy, hw), dxhw = __dmul_rn(r.dx, hw);
   const double ux[4] = {__dsub_rn(r.x1, dyhw), __dsub_rn(r.x2, dyhw), __dadd_rn(r.x2, dyhw), __dadd_rn(r.x1, dyhw)};
@@ -609,7 +643,7 @@ __device__ double rect_nfa_dev(const LsdRect& r, const uint4* __restrict__ pix, 
   const double s12 = (iy2 == iy1) ? 0.0 : __ddiv_rn(__dsub_rn(vx[2], vx[1]), __dsub_rn(vy[2], vy[1]));
   const double s03 = (iy3 == iy0) ? 0.0 : __ddiv_rn(__dsub_rn(vx[3], vx[0]), __dsub_rn(vy[3], vy[0]));
   const double s32 = (iy3 == iy2) ? 0.0 : __ddiv_rn(__dsub_rn(vx[2], vx[3]), __dsub_rn(vy[2], vy[3]));
-  int total = 0, alg = 0;
+  int total = 0, alg[5] = {0, 0, 0, 0, 0};
   const int nrows = iy2 - iy0 + 1;
   const bool byRows = nrows >= 12;
   for (int yy = byRows ? iy0 + lane : iy0; yy <= iy2; yy += byRows ? 32 : 1) {
@@ -626,18 +660,26 @@ __device__ double rect_nfa_dev(const LsdRect& r, const uint4* __restrict__ pix, 
     const uint4* row = pix + (size_t)yy * sw;
     for (int x = byRows ? xs : xs + lane; x <= xe; x += byRows ? 1 : 32) {
       ++total;
-      const float deg = __uint_as_float(__ldg(row + x).x);
-      if (deg != NOTDEF_F && lsd_aligned(r.theta, deg, r.prec)) ++alg;
+      const double nt = lsd_ntheta(r.theta, __uint_as_float(__ldg(row + x).x));
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        if (j < nprec && nt <= precs[j]) ++alg[j];
     }
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
     total += __shfl_xor_sync(0xffffffffu, total, d);
-    alg += __shfl_xor_sync(0xffffffffu, alg, d);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) alg[j] += __shfl_xor_sync(0xffffffffu, alg[j], d);
   }
-  return nfa_dev(total, alg, r.p, LOG_NT);
+  *total_out = total;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) alg_out[j] = alg[j];
 }
 
+// rect_improve(): within a stage the five candidate rectangles do not depend on which of them is
+// accepted, so their pixel counts are gathered first and the five nfa() evaluations (the expensive
+// part: log-gamma, a binomial tail) run on five lanes at once; the accept chain is then replayed in order.
 __global__ void __launch_bounds__(256) k_lsd_nfa(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
                                                  const LsdRect* __restrict__ rectsAll, const int* __restrict__ nrects,
                                                  LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid) {
@@ -648,64 +690,80 @@ __global__ void __launch_bounds__(256) k_lsd_nfa(const __grid_constant__ LinePar
   LsdRect rec = rectsAll[(size_t)f * L.rect_cap + ri];
   const double LOG_EPS = L.log_eps, LOG_NT = L.log_nt;
   const int sw = L.sw, sh = L.sh;
-  // rect_improve()
   const double delta = 0.5, delta_2 = delta / 2.0;
-  double log_nfa = rect_nfa_dev(rec, pix, sw, sh, LOG_NT, lane);
-  if (!(log_nfa > LOG_EPS)) {
+  int total, alg[5];
+  double precs[5];
+  precs[0] = rec.prec;
+  rect_count_dev(rec, precs, 1, pix, sw, sh, lane, &total, alg);
+  double log_nfa = nfa_dev(total, alg[0], rec.p, LOG_NT);
+  for (int stage = 1; stage <= 5 && !(log_nfa > LOG_EPS); ++stage) {
+    LsdRect rv[5];
+    bool ok[5];
     LsdRect r = rec;
+#pragma unroll
     for (int n = 0; n < 5; ++n) {
-      r.p = __ddiv_rn(r.p, 2.0);
-      r.prec = __dmul_rn(r.p, PL_PI);
-      const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
-      if (v > log_nfa) { log_nfa = v; rec = r; }
-    }
-    if (!(log_nfa > LOG_EPS)) {
-      r = rec;
-      for (int n = 0; n < 5; ++n) {
-        if (__dsub_rn(r.width, delta) >= 0.5) {
+      ok[n] = (stage == 1) || (__dsub_rn(r.width, delta) >= 0.5);
+      if (ok[n]) {
+        if (stage == 1 || stage == 5) {
+          r.p = __ddiv_rn(r.p, 2.0);
+          r.prec = __dmul_rn(r.p, PL_PI);
+        } else if (stage == 2) {
           r.width = __dsub_rn(r.width, delta);
-          const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
-          if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
-      }
-    }
-    if (!(log_nfa > LOG_EPS)) {
-      r = rec;
-      for (int n = 0; n < 5; ++n) {
-        if (__dsub_rn(r.width, delta) >= 0.5) {
+        } else if (stage == 3) {
           r.x1 = __dadd_rn(r.x1, __dmul_rn(-r.dy, delta_2));
           r.y1 = __dadd_rn(r.y1, __dmul_rn(r.dx, delta_2));
           r.x2 = __dadd_rn(r.x2, __dmul_rn(-r.dy, delta_2));
           r.y2 = __dadd_rn(r.y2, __dmul_rn(r.dx, delta_2));
           r.width = __dsub_rn(r.width, delta);
-          const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
-          if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
-      }
-    }
-    if (!(log_nfa > LOG_EPS)) {
-      r = rec;
-      for (int n = 0; n < 5; ++n) {
-        if (__dsub_rn(r.width, delta) >= 0.5) {
+        } else {
           r.x1 = __dsub_rn(r.x1, __dmul_rn(-r.dy, delta_2));
           r.y1 = __dsub_rn(r.y1, __dmul_rn(r.dx, delta_2));
           r.x2 = __dsub_rn(r.x2, __dmul_rn(-r.dy, delta_2));
           r.y2 = __dsub_rn(r.y2, __dmul_rn(r.dx, delta_2));
           r.width = __dsub_rn(r.width, delta);
-          const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
-          if (v > log_nfa) { rec = r; log_nfa = v; }
         }
       }
+      rv[n] = r;
     }
-    if (!(log_nfa > LOG_EPS)) {
-      r = rec;
+    // pixel counts of the variants: lane n keeps (myTotal, myAlg) of variant n
+    int myTotal = 0, myAlg = 0;
+    if (stage == 1 || stage == 5) {
+      if (ok[0]) {
+#pragma unroll
+        for (int n = 0; n < 5; ++n) precs[n] = rv[n].prec;
+        rect_count_dev(rec, precs, 5, pix, sw, sh, lane, &total, alg);
+        myTotal = total;
+#pragma unroll
+        for (int n = 0; n < 5; ++n)
+          if (lane == n) myAlg = alg[n];
+      }
+    } else {
+#pragma unroll
       for (int n = 0; n < 5; ++n) {
-        if (__dsub_rn(r.width, delta) >= 0.5) {
-          r.p = __ddiv_rn(r.p, 2.0);
-          r.prec = __dmul_rn(r.p, PL_PI);
-          const double v = rect_nfa_dev(r, pix, sw, sh, LOG_NT, lane);
-          if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
+        if (!ok[n]) continue;
+        precs[0] = rv[n].prec;
+        rect_count_dev(rv[n], precs, 1, pix, sw, sh, lane, &total, alg);
+        if (lane == n) { myTotal = total; myAlg = alg[0]; }
+      }
+    }
+    double myNfa = 0.0;
+    {
+      double myP = rec.p;
+#pragma unroll
+      for (int n = 0; n < 5; ++n)
+        if (lane == n) myP = rv[n].p;
+      bool mine = false;
+#pragma unroll
+      for (int n = 0; n < 5; ++n)
+        if (lane == n) mine = ok[n];
+      if (lane < 5 && mine) myNfa = nfa_dev(myTotal, myAlg, myP, LOG_NT);
+    }
+#pragma unroll
+    for (int n = 0; n < 5; ++n) {
+      const double v = __shfl_sync(0xffffffffu, myNfa, n);
+      if (ok[n] && v > log_nfa) {
+        log_nfa = v;
+        rec = rv[n];
       }
     }
   }
@@ -1085,7 +1143,7 @@ int LineExtractor::configure(int W, int H, int batch) {
   if ((rc = nsegs.ensure(B * sizeof(int)))) return rc;
   if ((rc = rowsum.ensure(B * P.out_cap * LBD_ROWS * 4 * sizeof(float)))) return rc;
   if ((rc = status.ensure(sizeof(int)))) return rc;
-  const size_t growSmem = 96 * sizeof(double) + (size_t)((P.P + 31) / 32) * 4;
+  const size_t growSmem = 96 * sizeof(double) + (size_t)REG_SMEM * 4 + (size_t)((P.P + 31) / 32) * 4;
   if (growSmem > 200 * 1024) {
     set_error("frame too large for the shared-memory `used` map of k_lsd_grow (%zu B)", growSmem);
     return PLSLAM_ERR_INVALID;
@@ -1130,7 +1188,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   k_lsd_scatter<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>(),
                                                               binstart.as<unsigned>(), seeds.as<unsigned>());
   PL_STAGE_END(timer, st);
-  const size_t growSmem = 96 * sizeof(double) + (size_t)((P.P + 31) / 32) * 4;
+  const size_t growSmem = 96 * sizeof(double) + (size_t)REG_SMEM * 4 + (size_t)((P.P + 31) / 32) * 4;
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
   k_lsd_grow<<<batch, 32, growSmem, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
                                           rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());

@@ -368,13 +368,16 @@ class FrontendIO(C.Structure):
 class Frontend:
     """plslam_frontend_*: ORB + LSD/LBD (+ frame-pair kNN) for a batch of frames in one call."""
 
-    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, max_lines=40):
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, max_lines=40, depth=1):
         L = lib()
         self._h = C.c_void_p()
-        L.plslam_frontend_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.plslam_frontend_create_pipelined.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_int, C.c_int,
+                                                       C.c_int, C.c_int, C.c_int]
         L.plslam_frontend_destroy.argtypes = [C.c_void_p]
         L.plslam_frontend_destroy.restype = None
-        _check(L.plslam_frontend_create(C.byref(self._h), nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_lines))
+        _check(L.plslam_frontend_create_pipelined(C.byref(self._h), nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST,
+                                                  max_lines, depth))
+        self.depth = depth
         a, b = C.c_int(), C.c_int()
         _check(L.plslam_frontend_capacities(self._h, C.byref(a), C.byref(b)))
         self.kp_capacity, self.line_capacity = a.value, b.value
@@ -417,16 +420,25 @@ class Frontend:
                                                     _stream_ptr(stream)))
         return out
 
-    def process_host(self, images, out, match_pairs=True):
-        """images: (B, H, W) uint8 host tensor/array (pinned => asynchronous copies); out: host block from alloc()."""
+    def _host_call(self, fn, images, out, match_pairs):
         B, H, W = images.shape
         io = self._io(out)
         ptr = images.data_ptr() if hasattr(images, "data_ptr") else images.ctypes.data
         st0 = images.stride(0) if hasattr(images, "stride") else images.strides[0]
         st1 = images.stride(1) if hasattr(images, "stride") else images.strides[1]
-        _check(lib().plslam_frontend_process_host(self._h, C.c_void_p(ptr), B, W, H, st1, C.c_size_t(st0), C.byref(io),
-                                                  int(match_pairs)))
+        _check(fn(self._h, C.c_void_p(ptr), B, W, H, st1, C.c_size_t(st0), C.byref(io), int(match_pairs)))
         return out
+
+    def process_host(self, images, out, match_pairs=True):
+        """images: (B, H, W) uint8 host tensor/array (pinned => asynchronous copies); out: host block from alloc()."""
+        return self._host_call(lib().plslam_frontend_process_host, images, out, match_pairs)
+
+    def submit_host(self, images, out, match_pairs=True):
+        """Asynchronous process_host on the next pipeline slot; `out` is valid after wait_host()."""
+        return self._host_call(lib().plslam_frontend_submit_host, images, out, match_pairs)
+
+    def wait_host(self):
+        _check(lib().plslam_frontend_wait_host(self._h))
 
     def check_status(self, stream=None):
         _check(lib().plslam_frontend_check_status(self._h, _stream_ptr(stream)))
