@@ -232,6 +232,11 @@ typedef struct plslam_proj_job {
 } plslam_proj_job_t;
 int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream);
 
+/* Single-job convenience forms for the class veneers: every pointer inside *job is a HOST pointer; the call
+ * uploads the arrays, runs the kernel and writes match_* / nmatches back.  n_grid_items = grid_start[64*48]. */
+int plslam_match_bow_host(const plslam_bow_job_t* job);
+int plslam_match_projection_host(const plslam_proj_job_t* job, int n_scale_levels);
+
 /* Pair matching on the batched extractor outputs without a host round trip: for p in [0, npairs)
  * query = frame (2p), train = frame (2p+1) of a [frames][capacity][32] descriptor block whose valid
  * row counts live in the device array d_counts.  d_out: [npairs][capacity][4] int32 as knn2.

@@ -4,6 +4,7 @@
 // code lib/libORB_SLAM2.so@0x79b50-0x8a086) and the kNN matching LSDmatcher / LineSegmentMathch run
 // on LBD rows (include/LSDmatcher.h, include/auxiliar.h:30-51).  All-pairs Hamming moves ~64 B per
 // descriptor and does 8 popc per pair: it is integer-ALU (popc issue) bound, not HBM bound.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -405,6 +406,94 @@ int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int nj
   }
   k_projection<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
   PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// tiny RAII helper for the single-job host paths
+struct Uploader {
+  std::vector<void*> bufs;
+  cudaError_t err = cudaSuccess;
+  ~Uploader() { for (void* p : bufs) cudaFree(p); }
+  template <typename T>
+  const T* up(const T* host, size_t n) {
+    void* d = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d, std::max<size_t>(n * sizeof(T), 16));
+    if (err == cudaSuccess) bufs.push_back(d);
+    if (err == cudaSuccess && n) err = cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    return static_cast<const T*>(d);
+  }
+  template <typename T>
+  T* out(size_t n) {
+    void* d = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d, std::max<size_t>(n * sizeof(T), 16));
+    if (err == cudaSuccess) bufs.push_back(d);
+    return static_cast<T*>(d);
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int plslam_match_bow_host(const plslam_bow_job_t* job) {
+  PL_CHECK_ARG(job && job->match_f && job->nmatches && job->n1 >= 0 && job->n2 >= 0);
+  Uploader U;
+  plslam_bow_job_t d = *job;
+  const int nk = job->n_kf_nodes, nf = job->n_f_nodes;
+  const int lenK = nk ? job->kf_start[nk] : 0, lenF = nf ? job->f_start[nf] : 0;
+  d.kf_desc = U.up(job->kf_desc, (size_t)job->n1 * 32);
+  d.kf_angle = U.up(job->kf_angle, job->n1);
+  d.kf_valid = U.up(job->kf_valid, job->n1);
+  d.kf_nodes = U.up(job->kf_nodes, nk);
+  d.kf_start = U.up(job->kf_start, nk + 1);
+  d.kf_idx = U.up(job->kf_idx, lenK);
+  d.f_desc = U.up(job->f_desc, (size_t)job->n2 * 32);
+  d.f_angle = U.up(job->f_angle, job->n2);
+  d.f_nodes = U.up(job->f_nodes, nf);
+  d.f_start = U.up(job->f_start, nf + 1);
+  d.f_idx = U.up(job->f_idx, lenF);
+  d.match_f = U.out<int32_t>(job->n2);
+  d.nmatches = U.out<int32_t>(1);
+  const plslam_bow_job_t* dj = U.up(&d, 1);
+  if (U.err != cudaSuccess) { set_error("bow host path: %s", cudaGetErrorString(U.err)); return PLSLAM_ERR_CUDA; }
+  int rc = plslam_match_bow_batch_device(dj, 1, std::max(job->n1, job->n2), nullptr);
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpy(job->match_f, d.match_f, (size_t)job->n2 * 4, cudaMemcpyDeviceToHost));
+  PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int plslam_match_projection_host(const plslam_proj_job_t* job, int n_scale_levels) {
+  PL_CHECK_ARG(job && job->match_cur && job->nmatches && job->n1 >= 0 && job->n2 >= 0 && n_scale_levels >= 1);
+  Uploader U;
+  plslam_proj_job_t d = *job;
+  const int n1 = job->n1, n2 = job->n2, ncell = PLSLAM_GRID_COLS * PLSLAM_GRID_ROWS;
+  const int nitems = job->grid_start[ncell];
+  d.last_valid = U.up(job->last_valid, n1);
+  d.last_xyz = U.up(job->last_xyz, (size_t)n1 * 3);
+  d.last_desc = U.up(job->last_desc, (size_t)n1 * 32);
+  d.last_octave = U.up(job->last_octave, n1);
+  d.last_angle = U.up(job->last_angle, n1);
+  d.last_obs = U.up(job->last_obs, n1);
+  d.cur_xy = U.up(job->cur_xy, (size_t)n2 * 2);
+  d.cur_octave = U.up(job->cur_octave, n2);
+  d.cur_angle = U.up(job->cur_angle, n2);
+  d.cur_desc = U.up(job->cur_desc, (size_t)n2 * 32);
+  d.cur_uright = U.up(job->cur_uright, n2);
+  d.cur_taken = U.up(job->cur_taken, n2);
+  d.grid_start = U.up(job->grid_start, ncell + 1);
+  d.grid_items = U.up(job->grid_items, nitems);
+  d.scale_factors = U.up(job->scale_factors, n_scale_levels);
+  d.match_cur = U.out<int32_t>(n2);
+  d.nmatches = U.out<int32_t>(1);
+  const plslam_proj_job_t* dj = U.up(&d, 1);
+  if (U.err != cudaSuccess) { set_error("projection host path: %s", cudaGetErrorString(U.err)); return PLSLAM_ERR_CUDA; }
+  int rc = plslam_match_projection_batch_device(dj, 1, n1, n2, nullptr);
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpy(job->match_cur, d.match_cur, (size_t)n2 * 4, cudaMemcpyDeviceToHost));
+  PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
   return PLSLAM_OK;
 }
 

@@ -1,0 +1,39 @@
+// FrameView.h — the slice of ORB_SLAM2::Frame / KeyFrame state the Hamming matchers read, as plain arrays.
+// Frame, KeyFrame and MapPoint themselves (pointer graphs guarded by mutexes) are outside the hot path
+// (SURVEY.md section 2, rows 6/11); INTEGRATION.md shows the ~20 lines that fill these views from the real classes.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "cv_compat.h"
+
+namespace ORB_SLAM2 {
+
+struct FeatureVectorView {         // DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>> flattened
+  std::vector<int32_t> nodes;      // keys, ascending
+  std::vector<int32_t> start;      // nodes.size() + 1 offsets into idx
+  std::vector<int32_t> idx;        // feature indices, in the vectors' order
+};
+
+struct FrameView {
+  // features
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+  cv::Mat mDescriptors;                        // N x 32
+  std::vector<float> mvuRight;
+  std::vector<float> mvScaleFactors;
+  FeatureVectorView mFeatVec;
+  // per-feature map point state
+  std::vector<uint8_t> hasMapPoint;            // mvpMapPoints[i] != NULL (KeyFrame: && !isBad())
+  std::vector<uint8_t> mapPointObserved;       // mvpMapPoints[i] && Observations() > 0
+  std::vector<uint8_t> mvbOutlier;
+  std::vector<float> mapPointWorldPos;         // N x 3, GetWorldPos()
+  cv::Mat mapPointDescriptor;                  // N x 32, pMP->GetDescriptor()
+  // grid (Frame::mGrid[64][48]) as CSR in [ix][iy] order, and bounds
+  std::vector<int32_t> gridStart, gridItems;
+  float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0, mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+  // camera
+  float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
+  float mTcw[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};  // rows 0..2 of the 4x4 pose
+};
+
+}  // namespace ORB_SLAM2
