@@ -581,11 +581,21 @@ __device__ double log_gamma_dev(double x) {
   }
   return a + log(b);
 }
+// nfa() only ever asks log_gamma for integer arguments (n+1, k+1, n-k+1 with n = pixels of a rectangle), so the
+// values are tabulated once per process by k_lsd_lgamma_table with the very same device function.
+constexpr int LGAMMA_TABLE = 1 << 15;
+__device__ double g_lgamma[LGAMMA_TABLE];
+__global__ void k_lsd_lgamma_table() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < LGAMMA_TABLE) g_lgamma[i] = i > 0 ? log_gamma_dev((double)i) : 0.0;
+}
+__device__ __forceinline__ double log_gamma_int(int x) { return x < LGAMMA_TABLE ? g_lgamma[x] : log_gamma_dev((double)x); }
+
 __device__ double nfa_dev(int n, int k, double p, double LOG_NT) {
   if (n == 0 || k == 0) return -LOG_NT;
   if (n == k) return -LOG_NT - (double)n * log10(p);
   const double p_term = p / (1 - p);
-  const double log1term = log_gamma_dev((double)n + 1) - log_gamma_dev((double)k + 1) - log_gamma_dev((double)(n - k) + 1) +
+  const double log1term = log_gamma_int(n + 1) - log_gamma_int(k + 1) - log_gamma_int(n - k + 1) +
                           (double)k * log(p) + (double)(n - k) * log(1.0 - p);
   double term = exp(log1term);
   if (double_equal_dev(term, 0)) {
@@ -1149,6 +1159,8 @@ int LineExtractor::configure(int W, int H, int batch) {
     return PLSLAM_ERR_INVALID;
   }
   PL_CUDA(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  k_lsd_lgamma_table<<<div_up(LGAMMA_TABLE, 256), 256>>>();
+  PL_CUDA(cudaDeviceSynchronize());
   PL_CUDA(cudaFuncSetAttribute(k_lsd_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   cfgW = W;
   cfgH = H;
