@@ -221,11 +221,14 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ Lin
 // k_lsd_grow: the sequential heart of LSD, one warp per frame.
 // ------------------------------------------------------------------------------------------
 constexpr int REG_SMEM = 1024;  // region-list entries kept in shared memory (larger regions spill to global)
+constexpr unsigned USED_BIT = 0x80000000u;  // `used` flag of a pixel: bit 31 of its record's .w (gx^2+gy^2 < 2^20)
 
+// The `used` map lives in the pixel records themselves (global memory, L1-resident around the growing region),
+// so a frame's CTA needs ~5 KB of shared memory and 32 frames fit on one SM.  Only this warp touches the frame's
+// records while the kernel runs; __syncwarp() orders its stores and loads.
 struct GrowCtx {
-  const uint4* pix;   // per-pixel records of this frame
-  unsigned* used;     // shared-memory bitmap
-  unsigned* regS;     // region list (pixel indices): first REG_SMEM entries in shared memory ...
+  uint4* pix;         // per-pixel records of this frame (read-write: used flags)
+  unsigned* regS;     // region list ((y << 16) | x): first REG_SMEM entries in shared memory ...
   unsigned* regG;     // ... the rest in this frame's global scratch
   double* stage;      // 3 x 32 doubles of shared staging
   int sw, sh;
@@ -234,9 +237,8 @@ struct GrowCtx {
   __device__ __forceinline__ void reg_set(int i, unsigned v) const {
     if (i < REG_SMEM) regS[i] = v; else regG[i] = v;
   }
+  __device__ __forceinline__ unsigned* wptr(int idx) const { return reinterpret_cast<unsigned*>(pix + idx) + 3; }
 };
-
-__device__ __forceinline__ bool used_get(const unsigned* used, int idx) { return (used[idx >> 5] >> (idx & 31)) & 1u; }
 
 __device__ __forceinline__ bool lsd_aligned(double theta, float deg, double prec) {
   const double a = __dmul_rn((double)deg, PL_DEG_TO_RADS);
@@ -249,10 +251,11 @@ __device__ __forceinline__ bool lsd_aligned(double theta, float deg, double prec
   return n_theta <= prec;
 }
 
-// region_grow(): returns the region size; reg[0] must already hold the seed pixel index.
+// region_grow(): returns the region size; reg[0] must already hold the seed pixel.
 __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_out) {
   const int lane = C.lane;
-  const int seed = (int)C.reg_get(0);
+  const unsigned seedxy = C.reg_get(0);
+  const int seed = (int)(seedxy >> 16) * C.sw + (int)(seedxy & 0xffff);
   const uint4 srec = C.pix[seed];
   double reg_angle = __dmul_rn((double)__uint_as_float(srec.x), PL_DEG_TO_RADS);
   float sumdx, sumdy;
@@ -262,7 +265,7 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
     sumdx = (float)c;
     sumdy = (float)s;
   }
-  if (lane == 0) C.used[seed >> 5] |= 1u << (seed & 31);
+  if (lane == 0) *C.wptr(seed) = srec.w | USED_BIT;
   __syncwarp();
   int n = 1;
   for (int i = 0; i < n;) {
@@ -271,15 +274,17 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
     // inner) without the centre, which is always already used
     const int pt = lane >> 3, nb8 = lane & 7, nb = nb8 < 4 ? nb8 : nb8 + 1;
     int nidx = -1;
+    unsigned nxy = 0, w = 0;
     float deg = NOTDEF_F, cs = 0.f, sn = 0.f;
     if (pt < m) {
-      const int p = (int)C.reg_get(i + pt);
-      const int py = p / C.sw, px = p - py * C.sw;
-      const int nx = px + (nb % 3) - 1, ny = py + (nb / 3) - 1;
+      const unsigned p = C.reg_get(i + pt);
+      const int nx = (int)(p & 0xffff) + (nb % 3) - 1, ny = (int)(p >> 16) + (nb / 3) - 1;
       if (nx >= 0 && ny >= 0 && nx < C.sw && ny < C.sh) {
         nidx = ny * C.sw + nx;
-        if (!used_get(C.used, nidx)) {
-          const uint4 r = __ldg(C.pix + nidx);
+        nxy = ((unsigned)ny << 16) | (unsigned)nx;
+        const uint4 r = C.pix[nidx];
+        w = r.w;
+        if (!(w & USED_BIT)) {
           deg = __uint_as_float(r.x);
           cs = __uint_as_float(r.y);
           sn = __uint_as_float(r.z);
@@ -288,21 +293,21 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
     }
     unsigned todo = 0xffffffffu;  // lanes not yet passed by the sequential scan
     while (true) {
-      const bool cand = deg != NOTDEF_F && !used_get(C.used, nidx) && lsd_aligned(reg_angle, deg, prec);
+      const bool cand = deg != NOTDEF_F && lsd_aligned(reg_angle, deg, prec);
       const unsigned mask = __ballot_sync(0xffffffffu, cand) & todo;
       if (!mask) break;
       const int j = __ffs(mask) - 1;
       const int aidx = __shfl_sync(0xffffffffu, nidx, j);
-      if (lane == 0) {
-        C.used[aidx >> 5] |= 1u << (aidx & 31);
-        C.reg_set(n, (unsigned)aidx);
+      if (lane == j) {
+        *C.wptr(nidx) = w | USED_BIT;
+        C.reg_set(n, nxy);
       }
       ++n;
       sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, cs, j));
       sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, sn, j));
       reg_angle = __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), PL_DEG_TO_RADS);
+      if (nidx == aidx) deg = NOTDEF_F;  // the same pixel seen from another frontier point is now used
       todo = j == 31 ? 0u : (0xffffffffu << (j + 1));
-      __syncwarp();
     }
     i += m;
     __syncwarp();
@@ -329,9 +334,9 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
     if (i < n) {
-      const int idx = (int)C.reg_get(i);
-      const int py = idx / C.sw, px = idx - py * C.sw;
-      const double w = modgrad_of((int)__ldg(C.pix + idx).w);
+      const unsigned pxy = C.reg_get(i);
+      const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+      const double w = modgrad_of((int)(*C.wptr(py * C.sw + px) & ~USED_BIT));
       sA[lane] = __dmul_rn((double)px, w);
       sB[lane] = __dmul_rn((double)py, w);
       sC[lane] = w;
@@ -351,9 +356,9 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
     if (i < n) {
-      const int idx = (int)C.reg_get(i);
-      const int py = idx / C.sw, px = idx - py * C.sw;
-      const double w = modgrad_of((int)__ldg(C.pix + idx).w);
+      const unsigned pxy = C.reg_get(i);
+      const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+      const double w = modgrad_of((int)(*C.wptr(py * C.sw + px) & ~USED_BIT));
       const double dx = __dsub_rn((double)px, x), dy = __dsub_rn((double)py, y);
       sA[lane] = __dmul_rn(__dmul_rn(dy, dy), w);
       sB[lane] = __dmul_rn(__dmul_rn(dx, dx), w);
@@ -379,8 +384,8 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
   pl_sincos_dev(theta, &dy, &dx);
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int i = lane; i < n; i += 32) {
-    const int idx = (int)C.reg_get(i);
-    const int py = idx / C.sw, px = idx - py * C.sw;
+    const unsigned pxy = C.reg_get(i);
+    const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
     const double rdx = __dsub_rn((double)px, x), rdy = __dsub_rn((double)py, y);
     const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
     const double w = __dadd_rn(__dmul_rn(-rdx, dy), __dmul_rn(rdy, dx));
@@ -426,10 +431,10 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   int n = *n_io;
   double density = rect_density(n, *rec);
   if (density >= density_th) return true;
-  const int seed = (int)C.reg_get(0);
-  const int sy = seed / C.sw, sx = seed - sy * C.sw;
+  const unsigned seedxy = C.reg_get(0);
+  const int sy = (int)(seedxy >> 16), sx = (int)(seedxy & 0xffff);
   const double xc = (double)sx, yc = (double)sy;
-  const double ang_c = __dmul_rn((double)__uint_as_float(__ldg(C.pix + seed).x), PL_DEG_TO_RADS);
+  const double ang_c = __dmul_rn((double)__uint_as_float(C.pix[sy * C.sw + sx].x), PL_DEG_TO_RADS);
   double* sA = C.stage;
   double* sF = C.stage + 32;
   double sum = 0, s_sum = 0;
@@ -437,12 +442,14 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
     if (i < n) {
-      const int idx = (int)C.reg_get(i);
-      atomicAnd(&C.used[idx >> 5], ~(1u << (idx & 31)));
-      const int py = idx / C.sw, px = idx - py * C.sw;
+      const unsigned pxy = C.reg_get(i);
+      const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+      const int idx = py * C.sw + px;
+      const uint4 r = C.pix[idx];
+      *C.wptr(idx) = r.w & ~USED_BIT;
       double flag = 0.0, v = 0.0;
       if (sqrt(dist_sq_dev(xc, yc, (double)px, (double)py)) < rec->width) {
-        const double ang = __dmul_rn((double)__uint_as_float(__ldg(C.pix + idx).x), PL_DEG_TO_RADS);
+        const double ang = __dmul_rn((double)__uint_as_float(r.x), PL_DEG_TO_RADS);
         v = angle_diff_signed_dev(ang, ang_c);
         flag = 1.0;
       }
@@ -478,12 +485,13 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
     if (lane == 0) {
       // swap-with-last removal exactly as the reference (it defines the order of the later sums)
       for (int i = 0; i < n; ++i) {
-        const int idx = (int)C.reg_get(i);
-        const int py = idx / C.sw, px = idx - py * C.sw;
+        const unsigned pxy = C.reg_get(i);
+        const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
         if (dist_sq_dev(xc, yc, (double)px, (double)py) > radSq) {
-          C.used[idx >> 5] &= ~(1u << (idx & 31));
+          unsigned* wp = C.wptr(py * C.sw + px);
+          *wp = *wp & ~USED_BIT;
           C.reg_set(i, C.reg_get(n - 1));
-          C.reg_set(n - 1, (unsigned)idx);
+          C.reg_set(n - 1, pxy);
           --n;
           --i;
         }
@@ -499,24 +507,21 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   return true;
 }
 
-__global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
+__global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineParams L, uint4* pixAll,
                                                  const unsigned* __restrict__ seedsAll, const int* __restrict__ nseeds,
-                                                 unsigned* __restrict__ regAll, LsdRect* __restrict__ rectsAll,
+                                                 unsigned* regAll, LsdRect* __restrict__ rectsAll,
                                                  int* __restrict__ nrects, int* __restrict__ status) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ double stage[96];
+  __shared__ unsigned regS[REG_SMEM];
   const int f = blockIdx.x, lane = threadIdx.x;
   GrowCtx C;
-  C.stage = reinterpret_cast<double*>(smem_raw);
-  C.regS = reinterpret_cast<unsigned*>(smem_raw + 96 * sizeof(double));
-  C.used = C.regS + REG_SMEM;
+  C.stage = stage;
+  C.regS = regS;
   C.pix = pixAll + (size_t)f * L.P;
   C.regG = regAll + (size_t)f * L.P;
   C.sw = L.sw;
   C.sh = L.sh;
   C.lane = lane;
-  const int words = (L.P + 31) >> 5;
-  for (int i = lane; i < words; i += 32) C.used[i] = 0;
-  __syncwarp();
   const unsigned* seeds = seedsAll + (size_t)f * L.P;
   const int ns = nseeds[f];
   LsdRect* rects = rectsAll + (size_t)f * L.rect_cap;
@@ -526,13 +531,13 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LinePar
     int s = snext;
     snext = base + 32 + lane < ns ? (int)seeds[base + 32 + lane] : -1;  // prefetch the next chunk of seeds
     while (true) {
-      const bool unused = s >= 0 && !used_get(C.used, s);
+      const bool unused = s >= 0 && !(*C.wptr(s) & USED_BIT);
       const unsigned m = __ballot_sync(0xffffffffu, unused);
       if (!m) break;
       const int j = __ffs(m) - 1;
       const int seed = __shfl_sync(0xffffffffu, s, j);
       if (lane <= j) s = -1;
-      if (lane == 0) C.reg_set(0, (unsigned)seed);
+      if (lane == 0) C.reg_set(0, ((unsigned)(seed / L.sw) << 16) | (unsigned)(seed % L.sw));
       __syncwarp();
       double reg_angle;
       int n = lsd_region_grow(C, L.prec, &reg_angle);
@@ -1153,12 +1158,7 @@ int LineExtractor::configure(int W, int H, int batch) {
   if ((rc = nsegs.ensure(B * sizeof(int)))) return rc;
   if ((rc = rowsum.ensure(B * P.out_cap * LBD_ROWS * 4 * sizeof(float)))) return rc;
   if ((rc = status.ensure(sizeof(int)))) return rc;
-  const size_t growSmem = 96 * sizeof(double) + (size_t)REG_SMEM * 4 + (size_t)((P.P + 31) / 32) * 4;
-  if (growSmem > 200 * 1024) {
-    set_error("frame too large for the shared-memory `used` map of k_lsd_grow (%zu B)", growSmem);
-    return PLSLAM_ERR_INVALID;
-  }
-  PL_CUDA(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PL_CHECK_ARG(P.sw < 65536 && P.sh < 32768);
   k_lsd_lgamma_table<<<div_up(LGAMMA_TABLE, 256), 256>>>();
   PL_CUDA(cudaDeviceSynchronize());
   PL_CUDA(cudaFuncSetAttribute(k_lsd_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1200,9 +1200,8 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   k_lsd_scatter<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>(),
                                                               binstart.as<unsigned>(), seeds.as<unsigned>());
   PL_STAGE_END(timer, st);
-  const size_t growSmem = 96 * sizeof(double) + (size_t)REG_SMEM * 4 + (size_t)((P.P + 31) / 32) * 4;
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
-  k_lsd_grow<<<batch, 32, growSmem, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
+  k_lsd_grow<<<batch, 32, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
                                           rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());
   PL_STAGE_END(timer, st);
   LsdSegment* rout = rectout.as<LsdSegment>();
@@ -1290,7 +1289,7 @@ int LineExtractor::copy_angles(int frame, float* deg_out, int32_t* g2_out, size_
   PL_CUDA(cudaMemcpy(h.data(), pix.as<uint4>() + (size_t)frame * P.P, (size_t)P.P * sizeof(uint4), cudaMemcpyDeviceToHost));
   for (int i = 0; i < P.P; ++i) {
     if (deg_out) std::memcpy(&deg_out[i], &h[i].x, 4);
-    if (g2_out) g2_out[i] = (int32_t)h[i].w;
+    if (g2_out) g2_out[i] = (int32_t)(h[i].w & 0x7fffffffu);  // bit 31 = LSD `used` flag
   }
   return PLSLAM_OK;
 }
