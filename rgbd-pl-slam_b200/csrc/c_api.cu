@@ -142,7 +142,7 @@ int plslam_lines_create(plslam_lines_t** out) {
 }
 void plslam_lines_destroy(plslam_lines_t* h) { delete h; }
 int plslam_lines_set_max_lines(plslam_lines_t* h, int max_lines) {
-  PL_CHECK_ARG(h && max_lines >= 0 && max_lines <= h->impl.rect_cap);
+  PL_CHECK_ARG(h && max_lines >= 0 && max_lines <= 256);
   h->impl.set_max_lines(max_lines);
   return PLSLAM_OK;
 }

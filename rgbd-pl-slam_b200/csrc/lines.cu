@@ -849,52 +849,90 @@ __global__ void __launch_bounds__(256) k_lsd_finish(const __grid_constant__ Line
                                                     int pitch, size_t frame_stride, const int* __restrict__ nrects,
                                                     const LsdSegment* __restrict__ rectOut,
                                                     const uint8_t* __restrict__ rectValid, LsdSegment* __restrict__ segsAll,
-                                                    int* __restrict__ nsegs, float* __restrict__ rowsumAll,
+                                                    int* __restrict__ nsegs, float* __restrict__ respAll,
+                                                    float* __restrict__ rowsumAll,
                                                     plslam_keyline_t* __restrict__ keylines, uint8_t* __restrict__ desc,
-                                                    double* __restrict__ funcs, int capacity, int* __restrict__ counts) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+                                                    double* __restrict__ funcs, int capacity, int* __restrict__ counts,
+                                                    int* __restrict__ status) {
   __shared__ int warpTmp[33];
-  __shared__ int sh_nseg, sh_nkeep;
+  __shared__ int sh_nkeep, sh_run;
+  __shared__ unsigned long long sh_best[8];
+  __shared__ int keepIdxS[256];  // segment index of kept line r when a strongest-N selection is active (N <= 256)
   const int f = blockIdx.x, t = threadIdx.x, T = blockDim.x;
-  int* flag = reinterpret_cast<int*>(smem_raw);                 // [rect_cap]
-  float* resp = reinterpret_cast<float*>(flag + L.rect_cap);    // [rect_cap] response of segment i
-  int* keepIdx = reinterpret_cast<int*>(resp + L.rect_cap);     // [out_cap] segment index of kept line r
   const int nr = nrects[f];
   const LsdSegment* rin = rectOut + (size_t)f * L.rect_cap;
   const uint8_t* valid = rectValid + (size_t)f * L.rect_cap;
   LsdSegment* segs = segsAll + (size_t)f * L.rect_cap;
-  for (int i = t; i < nr; i += T) flag[i] = valid[i];
+  float* resp = respAll + (size_t)f * L.rect_cap;
+  // ordered compaction of the accepted rectangles, one 256-wide chunk at a time
+  if (t == 0) sh_run = 0;
   __syncthreads();
-  const int nseg = block_scan_excl(flag, nr, warpTmp);
-  for (int i = t; i < nr; i += T)
-    if (valid[i]) segs[flag[i]] = rin[i];
-  if (t == 0) { sh_nseg = nseg; nsegs[f] = nseg; }
-  __syncthreads();
-  // responses
-  const uint8_t* I = img + (size_t)f * frame_stride;
-  for (int i = t; i < nseg; i += T) resp[i] = make_keyline(segs[i], L.W, L.H, i).response;
-  __syncthreads();
-  int nkeep = nseg;
-  if (L.max_lines > 0 && nseg > L.max_lines) {
-    nkeep = L.max_lines;
-    for (int i = t; i < nseg; i += T) {
-      const float ri = resp[i];
-      int rank = 0;
-      for (int j = 0; j < nseg; ++j) {
-        const float rj = resp[j];
-        rank += (rj > ri) || (rj == ri && j < i);
-      }
-      if (rank < nkeep) keepIdx[rank] = i;
+  for (int base = 0; base < nr; base += T) {
+    const int i = base + t;
+    const int v = (i < nr) ? valid[i] : 0;
+    // block-exclusive scan of one flag per thread
+    const int lane = t & 31, w = t >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    const int inWarp = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warpTmp[w] = __popc(bal);
+    __syncthreads();
+    int off = sh_run;
+    for (int k = 0; k < w; ++k) off += warpTmp[k];
+    if (v) segs[off + inWarp] = rin[i];
+    __syncthreads();
+    if (t == 0) {
+      int tot = 0;
+      for (int k = 0; k < (T + 31) / 32; ++k) tot += warpTmp[k];
+      sh_run += tot;
     }
-  } else {
-    for (int i = t; i < nseg; i += T) keepIdx[i] = i;
+    __syncthreads();
   }
-  if (nkeep > capacity) nkeep = capacity;  // host checks counts against capacity and reports
-  if (t == 0) { sh_nkeep = nkeep; counts[f] = (L.max_lines > 0 && nseg > L.max_lines) ? L.max_lines : nseg; }
+  const int nseg = sh_run;
+  if (t == 0) nsegs[f] = nseg;
+  const uint8_t* I = img + (size_t)f * frame_stride;
+  const bool select = L.max_lines > 0 && nseg > L.max_lines;
+  int nkeep = nseg;
+  if (select) {
+    // keep the max_lines strongest by response (ties: detection order): repeated block-wide arg-max
+    nkeep = L.max_lines;
+    for (int i = t; i < nseg; i += T) resp[i] = make_keyline(segs[i], L.W, L.H, i).response;
+    __syncthreads();
+    for (int r = 0; r < nkeep; ++r) {
+      unsigned long long best = 0ull;
+      for (int i = t; i < nseg; i += T) {
+        const float v = resp[i];
+        if (v >= 0.f) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(0x7fffffff - i);
+          best = key > best ? key : best;
+        }
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o > best ? o : best;
+      }
+      if ((t & 31) == 0) sh_best[t >> 5] = best;
+      __syncthreads();
+      if (t == 0) {
+        unsigned long long b2 = 0ull;
+        for (int k = 0; k < (T + 31) / 32; ++k) b2 = sh_best[k] > b2 ? sh_best[k] : b2;
+        const int idx = 0x7fffffff - (int)(b2 & 0xffffffffull);
+        keepIdxS[r] = idx;
+        resp[idx] = -1.f;
+      }
+      __syncthreads();
+    }
+  }
+  if (nkeep > L.out_cap) {  // keep-all mode on a frame with more lines than the fixed output capacity: reported, not hidden
+    nkeep = L.out_cap;
+    if (t == 0) atomicMax(status, PLSLAM_ERR_OVERFLOW);
+  }
+  if (t == 0) { sh_nkeep = nkeep; counts[f] = nkeep; }
   __syncthreads();
+#define KEEP_IDX(r) (select ? keepIdxS[r] : (r))
   plslam_keyline_t* KL = keylines + (size_t)f * capacity;
   for (int r = t; r < nkeep; r += T) {
-    const plslam_keyline_t kl = make_keyline(segs[keepIdx[r]], L.W, L.H, r);
+    const plslam_keyline_t kl = make_keyline(segs[KEEP_IDX(r)], L.W, L.H, r);
     KL[r] = kl;
     // lineF = sp x ep / sqrt(l0^2 + l1^2) in double
     const double x1 = kl.startPointX, y1 = kl.startPointY, x2 = kl.endPointX, y2 = kl.endPointY;
@@ -1049,7 +1087,7 @@ LineExtractor::LineExtractor() {}
 
 LineExtractor::~LineExtractor() {
   DevBuf* all[] = {&scaled, &pix, &coef, &rowhist, &binstart, &maxg2, &seeds, &nseeds, &regbuf, &rects, &nrects,
-                   &rectout, &segs, &nsegs, &rowsum, &status, &stageIn, &stageKl, &stageDesc, &stageFuncs, &stageCnt};
+                   &rectout, &segs, &nsegs, &resp, &rowsum, &status, &stageIn, &stageKl, &stageDesc, &stageFuncs, &stageCnt};
   for (DevBuf* b : all) b->release();
   if (ownStream) cudaStreamDestroy(ownStream);
   if (pinnedStatus) cudaFreeHost(pinnedStatus);
@@ -1109,7 +1147,10 @@ int LineExtractor::configure(int W, int H, int batch) {
   P.density_th = 0.7;
   P.log_eps = 0.0;
   P.max_lines = max_lines;
+  // accepted rectangles per frame: ~1 per 300 scaled pixels on the synthetic frames; capacity 1 per 32, overflow is reported
+  rect_cap = std::min(std::max(4096, P.P / 32), 1 << 17);
   P.rect_cap = rect_cap;
+  PL_CHECK_ARG(max_lines <= 256);
   P.out_cap = out_capacity();
   {  // LBD weights (BinaryDescriptor constructor)
     double u = (LBD_W * 3 - 1) / 2;
@@ -1156,12 +1197,12 @@ int LineExtractor::configure(int W, int H, int batch) {
   if ((rc = rectout.ensure(B * P.rect_cap * (sizeof(LsdSegment) + 1)))) return rc;
   if ((rc = segs.ensure(B * P.rect_cap * sizeof(LsdSegment)))) return rc;
   if ((rc = nsegs.ensure(B * sizeof(int)))) return rc;
+  if ((rc = resp.ensure(B * P.rect_cap * sizeof(float)))) return rc;
   if ((rc = rowsum.ensure(B * P.out_cap * LBD_ROWS * 4 * sizeof(float)))) return rc;
   if ((rc = status.ensure(sizeof(int)))) return rc;
   PL_CHECK_ARG(P.sw < 65536 && P.sh < 32768);
   k_lsd_lgamma_table<<<div_up(LGAMMA_TABLE, 256), 256>>>();
   PL_CUDA(cudaDeviceSynchronize());
-  PL_CUDA(cudaFuncSetAttribute(k_lsd_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   cfgW = W;
   cfgH = H;
   cfgB = (int)B;
@@ -1210,11 +1251,10 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   k_lsd_nfa<<<dim3(div_up(P.rect_cap, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), rects.as<LsdRect>(), nrects.as<int>(),
                                                                 rout, rvalid);
   PL_STAGE_END(timer, st);
-  const size_t finSmem = (size_t)P.rect_cap * 8 + (size_t)P.out_cap * 4;
   PL_STAGE_BEGIN(timer, "lsd_finish_lbd", st);
-  k_lsd_finish<<<batch, 256, finSmem, st>>>(P, d_images, pitch, frame_stride, nrects.as<int>(), rout, rvalid,
-                                            segs.as<LsdSegment>(), nsegs.as<int>(), rowsum.as<float>(), d_keylines, d_desc,
-                                            d_funcs, capacity, d_counts);
+  k_lsd_finish<<<batch, 256, 0, st>>>(P, d_images, pitch, frame_stride, nrects.as<int>(), rout, rvalid,
+                                            segs.as<LsdSegment>(), nsegs.as<int>(), resp.as<float>(), rowsum.as<float>(), d_keylines, d_desc,
+                                            d_funcs, capacity, d_counts, status.as<int>());
   PL_STAGE_END(timer, st);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;

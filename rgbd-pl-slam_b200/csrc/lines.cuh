@@ -38,7 +38,7 @@ class LineExtractor {
   LineExtractor();
   ~LineExtractor();
   void set_max_lines(int n) { max_lines = n; cfgW = 0; }
-  int out_capacity() const { return max_lines > 0 ? max_lines : rect_cap; }
+  int out_capacity() const { return max_lines > 0 ? max_lines : 8192; }  // keep-all mode: fixed bound, overflow reported
 
   int extract_device(const uint8_t* d_images, int batch, int W, int H, int pitch, size_t frame_stride,
                      plslam_keyline_t* d_keylines, uint8_t* d_desc, double* d_funcs, int capacity, int32_t* d_counts,
@@ -61,7 +61,7 @@ class LineExtractor {
   int configure(int W, int H, int batch);
   int device = -1, cfgW = 0, cfgH = 0, cfgB = 0, last_batch = 0;
   LineParams P{};
-  DevBuf scaled, pix, coef, rowhist, binstart, maxg2, seeds, nseeds, regbuf, rects, nrects, rectout, segs, nsegs,
+  DevBuf scaled, pix, coef, rowhist, binstart, maxg2, seeds, nseeds, regbuf, rects, nrects, rectout, segs, nsegs, resp,
       rowsum, status;
   DevBuf stageIn, stageKl, stageDesc, stageFuncs, stageCnt;
   cudaStream_t ownStream = nullptr;

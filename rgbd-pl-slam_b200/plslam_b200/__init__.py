@@ -268,7 +268,7 @@ class LineSegment:
         return deg, g2
 
     def segments(self, frame):
-        cap = 4096
+        cap = 1 << 17
         out = np.empty((cap, 7), np.float64)
         n = C.c_int()
         _check(lib().plslam_lines_copy_segments(self._h, frame, _vp(out), cap, C.byref(n)))
