@@ -6,6 +6,8 @@
 // byte work bounded by HBM traffic; none uses tensor cores.  One launch per stage covers the
 // whole batch (grid.y = frame), so a 256-frame batch is ~16 launches.
 #include "orb.cuh"
+
+#include <cuda.h>
 #include "fast_score.cuh"
 #include "pl_math.cuh"
 
@@ -496,13 +498,29 @@ __global__ void __launch_bounds__(256) k_quadtree(const __grid_constant__ OrbPar
 // ------------------------------------------------------------------------------------------
 // K4  7x7 Gaussian blur, sigma 2, BORDER_REFLECT_101, on the borderless level (GaussianBlur call
 // @0x77487; arithmetic SURVEY B.2): dst = (sum_y sum_x k[y]k[x]p + 32768) >> 16.
-// Tile 128x16 per CTA; the horizontal pass result (<= 255*256, fits u16) is kept in shared memory.
+// Tile = 128x16 outputs per CTA.  The (128+16)x22 source box is fetched by one TMA bulk-tensor copy
+// (cp.async.bulk.tensor.3d, tensor = [frame][row][byte] of the level) into shared memory and signalled
+// through an mbarrier; TMA zero-fills outside the level, so only CTAs on the level's rim patch the
+// 3-px reflected halo by hand.  Levels whose base/pitch are not 16-byte aligned (a caller's level-0
+// image) fall back to plain loads inside the same kernel.  Horizontal pass: 4 outputs per item with
+// funnel-shifted byte windows and dp4a; vertical pass: one thread per column half with a register window.
 // ------------------------------------------------------------------------------------------
-constexpr int BT_W = 128, BT_H = 16;
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams P, OrbImages I,
-                                              const int* __restrict__ lvlCnt) {
-  __shared__ uint8_t raw[BT_H + 6][BT_W + 8];
-  __shared__ unsigned short hs[BT_H + 6][BT_W];
+// TMA needs the innermost start coordinate 16-byte aligned, so the box starts 16 px left of the tile
+// (BOX_XOFF = 13 columns before the 3-px halo) and is 160 bytes wide.
+constexpr int BT_W = 128, BT_H = 16, BOX_W = 160, BOX_H = BT_H + 6, BOX_XOFF = 13;
+
+struct BlurMaps {
+  CUtensorMap m[ORB_MAXL];
+  unsigned tmaMask;  // bit l set: level l is read through its tensor map
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams P, const BlurMaps* __restrict__ Mp,
+                                              OrbImages I, const int* __restrict__ lvlCnt) {
+  __shared__ __align__(128) uint8_t raw[BOX_H][BOX_W];
+  __shared__ __align__(16) unsigned short hs[BOX_H][BT_W];
+  __shared__ __align__(8) unsigned long long mbar;
   const int f = blockIdx.y;
   int tile = blockIdx.x;
   int l = 0;
@@ -511,41 +529,103 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams 
   const OrbLevel& L = P.lv[l];
   tile -= L.tileBase;
   const int tx = (tile % L.tilesX) * BT_W, ty = (tile / L.tilesX) * BT_H;
+  const int w = L.w, h = L.h;
   int sp;
   const uint8_t* S = level_ptr(P, I, f, l, sp);
-  const int w = L.w, h = L.h;
-  for (int i = threadIdx.x; i < (BT_H + 6) * (BT_W + 6); i += 256) {
-    const int yy = i / (BT_W + 6), xx = i - yy * (BT_W + 6);
-    int gx = tx + xx - 3, gy = ty + yy - 3;
-    gx = gx < 0 ? -gx : (gx >= w ? 2 * (w - 1) - gx : gx);
-    gy = gy < 0 ? -gy : (gy >= h ? 2 * (h - 1) - gy : gy);
-    gx = max(0, min(gx, w - 1));
-    gy = max(0, min(gy, h - 1));
-    raw[yy][xx] = S[(size_t)gy * sp + gx];
-  }
-  __syncthreads();
-  const int k0 = P.blurk[0], k1 = P.blurk[1], k2 = P.blurk[2], k3 = P.blurk[3], k4 = P.blurk[4], k5 = P.blurk[5],
-            k6 = P.blurk[6];
-  for (int i = threadIdx.x; i < (BT_H + 6) * BT_W; i += 256) {
-    const int yy = i / BT_W, xx = i - yy * BT_W;
-    const uint8_t* r = &raw[yy][xx];
-    hs[yy][xx] = (unsigned short)(k0 * r[0] + k1 * r[1] + k2 * r[2] + k3 * r[3] + k4 * r[4] + k5 * r[5] + k6 * r[6]);
-  }
-  __syncthreads();
-  uint8_t* Dst = I.blurred + (size_t)f * P.pyrFrameStride + L.off;
-  for (int i = threadIdx.x; i < BT_H * BT_W / 4; i += 256) {
-    const int yy = i / (BT_W / 4), x4 = (i - yy * (BT_W / 4)) * 4;
-    const int gy = ty + yy, gx = tx + x4;
-    if (gy >= h || gx >= w) continue;
-    uint32_t out = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int x = x4 + j;
-      const int a = 32768 + k0 * hs[yy][x] + k1 * hs[yy + 1][x] + k2 * hs[yy + 2][x] + k3 * hs[yy + 3][x] +
-                    k4 * hs[yy + 4][x] + k5 * hs[yy + 5][x] + k6 * hs[yy + 6][x];
-      out |= (uint32_t)((a >> 16) & 0xff) << (8 * j);
+  const bool useTma = (Mp->tmaMask >> l) & 1u;
+  const bool rim = tx < 3 || ty < 3 || tx + BT_W + 3 > w || ty + BT_H + 3 > h;
+  if (useTma) {
+    if (threadIdx.x == 0) {
+      const unsigned bar = smem_u32(&mbar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BOX_W * BOX_H) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(smem_u32(&raw[0][0])), "l"(reinterpret_cast<unsigned long long>(&Mp->m[l])), "r"(tx - 16), "r"(ty - 3), "r"(f),
+            "r"(bar)
+          : "memory");
     }
-    *reinterpret_cast<uint32_t*>(Dst + (size_t)gy * L.pitch + gx) = out;
+    __syncthreads();  // makes the initialised barrier visible to the waiting threads
+    {
+      const unsigned bar = smem_u32(&mbar);
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+      }
+    }
+    if (rim) {
+      // reflect-101 halo outside the level (TMA wrote zeros there)
+      for (int i = threadIdx.x; i < BOX_H * (BT_W + 6); i += 256) {
+        const int yy = i / (BT_W + 6), xx = i - yy * (BT_W + 6);
+        int gx = tx + xx - 3, gy = ty + yy - 3;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) continue;
+        gx = gx < 0 ? -gx : (gx >= w ? 2 * (w - 1) - gx : gx);
+        gy = gy < 0 ? -gy : (gy >= h ? 2 * (h - 1) - gy : gy);
+        gx = max(0, min(gx, w - 1));
+        gy = max(0, min(gy, h - 1));
+        raw[yy][BOX_XOFF + xx] = S[(size_t)gy * sp + gx];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < BOX_H * (BT_W + 6); i += 256) {
+      const int yy = i / (BT_W + 6), xx = i - yy * (BT_W + 6);
+      int gx = tx + xx - 3, gy = ty + yy - 3;
+      gx = gx < 0 ? -gx : (gx >= w ? 2 * (w - 1) - gx : gx);
+      gy = gy < 0 ? -gy : (gy >= h ? 2 * (h - 1) - gy : gy);
+      gx = max(0, min(gx, w - 1));
+      gy = max(0, min(gy, h - 1));
+      raw[yy][BOX_XOFF + xx] = S[(size_t)gy * sp + gx];
+    }
+  }
+  __syncthreads();
+  // horizontal pass: item = (row, 4 consecutive outputs); byte windows by funnel shift, taps by dp4a
+  const unsigned k0123 = (unsigned)P.blurk[0] | ((unsigned)P.blurk[1] << 8) | ((unsigned)P.blurk[2] << 16) | ((unsigned)P.blurk[3] << 24);
+  const unsigned k456 = (unsigned)P.blurk[4] | ((unsigned)P.blurk[5] << 8) | ((unsigned)P.blurk[6] << 16);
+  for (int i = threadIdx.x; i < BOX_H * (BT_W / 4); i += 256) {
+    const int r = i / (BT_W / 4), x4 = (i - r * (BT_W / 4)) * 4;
+    // output x4+j reads raw bytes [BOX_XOFF + x4 + j, +7): BOX_XOFF = 12 + 1, so word 3 + x4/4 shifted by 1 + j bytes
+    const unsigned* wp = reinterpret_cast<const unsigned*>(&raw[r][x4 + BOX_XOFF - 1]);
+    const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    unsigned o[4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const unsigned lo = __funnelshift_r(w0, w1, 8 * (j + 1));
+      const unsigned hi = __funnelshift_r(w1, w2, 8 * (j + 1));
+      o[j] = __dp4a(hi, k456, __dp4a(lo, k0123, 0u));
+    }
+    o[3] = __dp4a(w2, k456, __dp4a(w1, k0123, 0u));
+    uint2 pk;
+    pk.x = o[0] | (o[1] << 16);
+    pk.y = o[2] | (o[3] << 16);
+    *reinterpret_cast<uint2*>(&hs[r][x4]) = pk;
+  }
+  __syncthreads();
+  // vertical pass: thread = (column, 8-row half), 14-value register window
+  {
+    const int c = threadIdx.x & (BT_W - 1), half = threadIdx.x >> 7;
+    const int gx = tx + c;
+    if (gx < w) {
+      int win[14];
+#pragma unroll
+      for (int i = 0; i < 14; ++i) win[i] = hs[half * 8 + i][c];
+      const int k0 = P.blurk[0], k1 = P.blurk[1], k2 = P.blurk[2], k3 = P.blurk[3], k4 = P.blurk[4], k5 = P.blurk[5],
+                k6 = P.blurk[6];
+      uint8_t* Dst = I.blurred + (size_t)f * P.pyrFrameStride + L.off + gx;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        const int gy = ty + half * 8 + y;
+        if (gy < h) {
+          const int a = 32768 + k0 * win[y] + k1 * win[y + 1] + k2 * win[y + 2] + k3 * win[y + 3] + k4 * win[y + 4] +
+                        k5 * win[y + 5] + k6 * win[y + 6];
+          Dst[(size_t)gy * L.pitch] = (uint8_t)(a >> 16);
+        }
+      }
+    }
   }
 }
 
@@ -657,6 +737,39 @@ __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Orb
 
 inline int cvRoundf_host(float v) { return (int)lrintf(v); }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// [frame][row][byte] view of one level of `batch` frames; false if the layout is not TMA-legal
+bool encode_level_map(CUtensorMap* m, const void* base, int w, int h, size_t pitch, size_t frameStride, int batch) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (frameStride & 15)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
+  const cuuint32_t box[3] = {BOX_W, BOX_H, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -703,7 +816,7 @@ OrbExtractor::OrbExtractor(int nf, float sf, int nl, int ini, int mn)
 }
 
 OrbExtractor::~OrbExtractor() {
-  DevBuf* all[] = {&pyr, &blurred, &coef, &cand, &candCount, &knode, &lvlKp, &lvlCnt, &status,
+  DevBuf* all[] = {&pyr, &blurred, &coef, &cand, &candCount, &knode, &lvlKp, &lvlCnt, &status, &blurMaps,
                    &stageIn, &stageKps, &stageDesc, &stageCnt};
   for (DevBuf* b : all) b->release();
   if (ownStream) cudaStreamDestroy(ownStream);
@@ -912,7 +1025,24 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
     PL_STAGE_END(timer, st);
   }
   PL_STAGE_BEGIN(timer, "orb_blur", st);
-  k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, I, lvlCnt.as<int>());
+  {
+    BlurMaps M;
+    std::memset(&M, 0, sizeof(M));
+    bool k8 = true;
+    for (int i = 0; i < 7; ++i) k8 = k8 && blurk[i] >= 0 && blurk[i] <= 255;
+    PL_CHECK_ARG(k8);
+    for (int l = 0; l < nlevels; ++l) {
+      const void* base = l ? (const void*)(pyr.as<uint8_t>() + P.lv[l].off) : (const void*)d_images;
+      const size_t lp = l ? (size_t)P.lv[l].pitch : (size_t)pitch, ls = l ? (size_t)P.pyrFrameStride : frame_stride;
+      if (encode_level_map(&M.m[l], base, P.lv[l].w, P.lv[l].h, lp, ls, batch)) M.tmaMask |= 1u << l;
+    }
+    // the descriptors live in global memory (TMA needs them in global/const/param space); pageable source: the
+    // runtime stages the 1.5 KB before cudaMemcpyAsync returns
+    int rcm = blurMaps.ensure(sizeof(BlurMaps));
+    if (rcm) return rcm;
+    PL_CUDA(cudaMemcpyAsync(blurMaps.p, &M, sizeof(M), cudaMemcpyHostToDevice, st));
+    k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, blurMaps.as<BlurMaps>(), I, lvlCnt.as<int>());
+  }
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "orb_orient_desc", st);
   k_orient_desc<<<dim3(div_up(P.maxKp, 8), batch), 256, 0, st>>>(P, I, lvlKp.as<uint2>(), lvlCnt.as<int>(), d_kps,
