@@ -571,7 +571,7 @@ __device__ __forceinline__ bool double_equal_dev(double a, double b) {
 }
 // log_gamma / nfa of lsd.cpp.  Integer powers are formed by repeated multiplication (pow() differs from
 // it by ulps only, and the NFA value feeds comparisons, never an output).
-__device__ double log_gamma_dev(double x) {
+__device__ __noinline__ double log_gamma_dev(double x) {
   if (x > 15.0) {
     const double x2 = x * x;
     return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * (x2 * x2 * x2)));
@@ -596,7 +596,7 @@ __global__ void k_lsd_lgamma_table() {
 }
 __device__ __forceinline__ double log_gamma_int(int x) { return x < LGAMMA_TABLE ? g_lgamma[x] : log_gamma_dev((double)x); }
 
-__device__ double nfa_dev(int n, int k, double p, double LOG_NT) {
+__device__ __noinline__ double nfa_dev(int n, int k, double p, double LOG_NT) {
   if (n == 0 || k == 0) return -LOG_NT;
   if (n == k) return -LOG_NT - (double)n * log10(p);
   const double p_term = p / (1 - p);
@@ -637,7 +637,7 @@ __device__ __forceinline__ double lsd_ntheta(double theta, float deg) {
 
 // Row scan of rect_nfa(): counts the pixels of the rectangle (total) and, for up to 5 angular
 // tolerances at once, the aligned ones.  Warp-cooperative; results are warp-uniform.
-__device__ void rect_count_dev(const LsdRect& r, const double* precs, int nprec, const uint4* __restrict__ pix, int sw,
+__device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* precs, int nprec, const uint4* __restrict__ pix, int sw,
                                int sh, int lane, int* total_out, int* alg_out) {
   const double hw = __dmul_rn(0.5, r.width);
   const double dyhw = __dmul_rn(r.dy, hw), dxhw = __dmul_rn(r.dx, hw);
@@ -695,7 +695,7 @@ __device__ void rect_count_dev(const LsdRect& r, const double* precs, int nprec,
 // rect_improve(): within a stage the five candidate rectangles do not depend on which of them is
 // accepted, so their pixel counts are gathered first and the five nfa() evaluations (the expensive
 // part: log-gamma, a binomial tail) run on five lanes at once; the accept chain is then replayed in order.
-__global__ void __launch_bounds__(256) k_lsd_nfa(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
+__global__ void __launch_bounds__(256, 3) k_lsd_nfa(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
                                                  const LsdRect* __restrict__ rectsAll, const int* __restrict__ nrects,
                                                  LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -712,73 +712,75 @@ __global__ void __launch_bounds__(256) k_lsd_nfa(const __grid_constant__ LinePar
   rect_count_dev(rec, precs, 1, pix, sw, sh, lane, &total, alg);
   double log_nfa = nfa_dev(total, alg[0], rec.p, LOG_NT);
   for (int stage = 1; stage <= 5 && !(log_nfa > LOG_EPS); ++stage) {
-    LsdRect rv[5];
-    bool ok[5];
-    LsdRect r = rec;
-#pragma unroll
-    for (int n = 0; n < 5; ++n) {
-      ok[n] = (stage == 1) || (__dsub_rn(r.width, delta) >= 0.5);
-      if (ok[n]) {
+    const LsdRect rec0 = rec;  // the stage's variants derive from the rectangle it starts with
+    // variant n = the stage's step applied n+1 times (each step only if its width test holds, as in rect_improve)
+    auto variant = [&](int n, bool* ok) {
+      LsdRect r = rec0;
+      bool o = true;
+      for (int k = 0; k <= n; ++k) {
+        o = (stage == 1) || (__dsub_rn(r.width, delta) >= 0.5);
+        if (!o) break;
         if (stage == 1 || stage == 5) {
           r.p = __ddiv_rn(r.p, 2.0);
           r.prec = __dmul_rn(r.p, PL_PI);
         } else if (stage == 2) {
           r.width = __dsub_rn(r.width, delta);
-        } else if (stage == 3) {
-          r.x1 = __dadd_rn(r.x1, __dmul_rn(-r.dy, delta_2));
-          r.y1 = __dadd_rn(r.y1, __dmul_rn(r.dx, delta_2));
-          r.x2 = __dadd_rn(r.x2, __dmul_rn(-r.dy, delta_2));
-          r.y2 = __dadd_rn(r.y2, __dmul_rn(r.dx, delta_2));
-          r.width = __dsub_rn(r.width, delta);
         } else {
-          r.x1 = __dsub_rn(r.x1, __dmul_rn(-r.dy, delta_2));
-          r.y1 = __dsub_rn(r.y1, __dmul_rn(r.dx, delta_2));
-          r.x2 = __dsub_rn(r.x2, __dmul_rn(-r.dy, delta_2));
-          r.y2 = __dsub_rn(r.y2, __dmul_rn(r.dx, delta_2));
+          const double sx = __dmul_rn(-r.dy, delta_2), sy = __dmul_rn(r.dx, delta_2);
+          if (stage == 3) {
+            r.x1 = __dadd_rn(r.x1, sx); r.y1 = __dadd_rn(r.y1, sy);
+            r.x2 = __dadd_rn(r.x2, sx); r.y2 = __dadd_rn(r.y2, sy);
+          } else {
+            r.x1 = __dsub_rn(r.x1, sx); r.y1 = __dsub_rn(r.y1, sy);
+            r.x2 = __dsub_rn(r.x2, sx); r.y2 = __dsub_rn(r.y2, sy);
+          }
           r.width = __dsub_rn(r.width, delta);
         }
       }
-      rv[n] = r;
-    }
-    // pixel counts of the variants: lane n keeps (myTotal, myAlg) of variant n
+      *ok = o;
+      return r;
+    };
+    // pixel counts of the variants: lane n keeps (myTotal, myAlg, myP, myOk) of variant n
     int myTotal = 0, myAlg = 0;
+    double myP = rec0.p;
+    bool myOk = false;
+    unsigned okMask = 0;
     if (stage == 1 || stage == 5) {
-      if (ok[0]) {
-#pragma unroll
-        for (int n = 0; n < 5; ++n) precs[n] = rv[n].prec;
-        rect_count_dev(rec, precs, 5, pix, sw, sh, lane, &total, alg);
+      bool ok0;
+      variant(0, &ok0);
+      if (ok0) {
+        okMask = 0x1fu;
+        for (int n = 0; n < 5; ++n) {
+          bool o;
+          const LsdRect r = variant(n, &o);
+          precs[n] = r.prec;
+          if (lane == n) { myP = r.p; myOk = true; }
+        }
+        rect_count_dev(rec0, precs, 5, pix, sw, sh, lane, &total, alg);
         myTotal = total;
 #pragma unroll
         for (int n = 0; n < 5; ++n)
           if (lane == n) myAlg = alg[n];
       }
     } else {
-#pragma unroll
       for (int n = 0; n < 5; ++n) {
-        if (!ok[n]) continue;
-        precs[0] = rv[n].prec;
-        rect_count_dev(rv[n], precs, 1, pix, sw, sh, lane, &total, alg);
-        if (lane == n) { myTotal = total; myAlg = alg[0]; }
+        bool o;
+        const LsdRect r = variant(n, &o);
+        if (!o) break;
+        okMask |= 1u << n;
+        precs[0] = r.prec;
+        rect_count_dev(r, precs, 1, pix, sw, sh, lane, &total, alg);
+        if (lane == n) { myTotal = total; myAlg = alg[0]; myP = r.p; myOk = true; }
       }
     }
     double myNfa = 0.0;
-    {
-      double myP = rec.p;
-#pragma unroll
-      for (int n = 0; n < 5; ++n)
-        if (lane == n) myP = rv[n].p;
-      bool mine = false;
-#pragma unroll
-      for (int n = 0; n < 5; ++n)
-        if (lane == n) mine = ok[n];
-      if (lane < 5 && mine) myNfa = nfa_dev(myTotal, myAlg, myP, LOG_NT);
-    }
-#pragma unroll
+    if (myOk) myNfa = nfa_dev(myTotal, myAlg, myP, LOG_NT);
     for (int n = 0; n < 5; ++n) {
       const double v = __shfl_sync(0xffffffffu, myNfa, n);
-      if (ok[n] && v > log_nfa) {
+      if (((okMask >> n) & 1u) && v > log_nfa) {
         log_nfa = v;
-        rec = rv[n];
+        bool o;
+        rec = variant(n, &o);
       }
     }
   }
