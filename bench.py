@@ -88,7 +88,8 @@ def algorithmic_bytes(a, kp_avg, cand_avg):
         "lsd_scatter": 8 * P,
         "lsd_grow": 9 * P,
         "lsd_nfa": 4 * P,
-        "lsd_finish_lbd": W * H + a.max_lines * (60 * 63 * 4 + 32),
+        "lsd_finish": 40 * 650 + a.max_lines * (68 + 24),
+        "lbd": W * H + a.max_lines * (60 * 63 * 4 + 32),
         "match_lbd_knn2": (2 * a.max_lines * 32 + a.max_lines * 16) // 2,
     }
     return stages

@@ -891,7 +891,6 @@ __global__ void __launch_bounds__(256) k_lsd_finish(const __grid_constant__ Line
   }
   const int nseg = sh_run;
   if (t == 0) nsegs[f] = nseg;
-  const uint8_t* I = img + (size_t)f * frame_stride;
   const bool select = L.max_lines > 0 && nseg > L.max_lines;
   int nkeep = nseg;
   if (select) {
@@ -945,12 +944,25 @@ __global__ void __launch_bounds__(256) k_lsd_finish(const __grid_constant__ Line
     F[1] = __ddiv_rn(l1, nrm);
     F[2] = __ddiv_rn(l2, nrm);
   }
-  __syncthreads();
-  // LBD row sums: one thread per (line, support-region row), sequential along the line
-  float* rowsum = rowsumAll + (size_t)f * L.out_cap * LBD_ROWS * 4;
-  for (int task = t; task < nkeep * LBD_ROWS; task += T) {
-    const int r = task / LBD_ROWS, hID = task - r * LBD_ROWS;
-    const plslam_keyline_t kl = KL[r];
+}
+
+// ------------------------------------------------------------------------------------------
+// k_lbd: BinaryDescriptor::computeLBD + binaryConversion, one CTA per (frame, kept line).
+// Thread = one of the 63 rows of the line support region (sequential float sums along the line, as the
+// reference); then thread = one of the 72 (band, statistic) accumulators, each summing its <= 21 row
+// contributions in row order; thread 0 normalises, clamps and binarises.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(96) k_lbd(const __grid_constant__ LineParams L, const uint8_t* __restrict__ img, int pitch,
+                                            size_t frame_stride, const plslam_keyline_t* __restrict__ keylines,
+                                            const int* __restrict__ counts, uint8_t* __restrict__ desc, int capacity) {
+  __shared__ float rowsum[LBD_ROWS][4];
+  __shared__ float band[LBD_BANDS][8];
+  const int f = blockIdx.y, r = blockIdx.x, t = threadIdx.x;
+  if (r >= counts[f]) return;
+  const uint8_t* I = img + (size_t)f * frame_stride;
+  const plslam_keyline_t kl = keylines[(size_t)f * capacity + r];
+  if (t < LBD_ROWS) {
+    const int hID = t;
     const short lengthOfLSP = (short)kl.numOfPixels;
     const short halfWidth = (lengthOfLSP - 1) / 2, halfHeight = (LBD_ROWS - 1) / 2;
     const float midX = (float)__dmul_rn(0.5, (double)__fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
@@ -972,14 +984,23 @@ __global__ void __launch_bounds__(256) k_lsd_finish(const __grid_constant__ Line
     }
     float sCorX = sx0, sCorY = sy0;
     float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
-    const short imageWidth = (short)(L.W - 1), imageHeight = (short)(L.H - 1);
+    const int W = L.W, H = L.H;
     for (short wID = 0; wID < lengthOfLSP; ++wID) {
       short tc = (short)roundf(sCorX);
-      const short xCor = (tc < 0) ? 0 : (tc > imageWidth) ? imageWidth : tc;
+      const int x = (tc < 0) ? 0 : (tc > W - 1) ? W - 1 : tc;
       tc = (short)roundf(sCorY);
-      const short yCor = (tc < 0) ? 0 : (tc > imageHeight) ? imageHeight : tc;
+      const int y = (tc < 0) ? 0 : (tc > H - 1) ? H - 1 : tc;
       int dx, dy;
-      sobel_at_dev(I, L.W, L.H, pitch, xCor, yCor, dx, dy);
+      if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {  // interior: no border reflection
+        const uint8_t* r1 = I + (size_t)y * pitch + x;
+        const uint8_t* r0 = r1 - pitch;
+        const uint8_t* r2 = r1 + pitch;
+        const int a = r0[-1], b = r0[0], c = r0[1], d = r1[-1], e = r1[1], g = r2[-1], h = r2[0], i = r2[1];
+        dx = (c - a) + 2 * (e - d) + (i - g);
+        dy = (g - a) + 2 * (h - b) + (i - c);
+      } else {
+        sobel_at_dev(I, W, H, pitch, x, y, dx, dy);
+      }
       const float gDL = __fadd_rn(__fmul_rn((float)dx, dL0), __fmul_rn((float)dy, dL1));
       const float gDO = __fadd_rn(__fmul_rn((float)dx, dO0), __fmul_rn((float)dy, dO1));
       if (gDL > 0) pgdL = __fadd_rn(pgdL, gDL); else ngdL = __fsub_rn(ngdL, gDL);
@@ -988,45 +1009,32 @@ __global__ void __launch_bounds__(256) k_lsd_finish(const __grid_constant__ Line
       sCorY = __fadd_rn(sCorY, dL1);
     }
     const float cg = L.gaussG[hID];
-    float* o = rowsum + (size_t)task * 4;
-    o[0] = __fmul_rn(cg, pgdL);
-    o[1] = __fmul_rn(cg, ngdL);
-    o[2] = __fmul_rn(cg, pgdO);
-    o[3] = __fmul_rn(cg, ngdO);
+    rowsum[hID][0] = __fmul_rn(cg, pgdL);
+    rowsum[hID][1] = __fmul_rn(cg, ngdL);
+    rowsum[hID][2] = __fmul_rn(cg, pgdO);
+    rowsum[hID][3] = __fmul_rn(cg, ngdO);
   }
   __syncthreads();
-  // band accumulation, normalisation and binarisation: one thread per line
-  for (int r = t; r < nkeep; r += T) {
-    float band[LBD_BANDS][8];
-#pragma unroll
-    for (int b = 0; b < LBD_BANDS; ++b)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) band[b][q] = 0.f;
-    const float* rs = rowsum + (size_t)r * LBD_ROWS * 4;
-    for (int hID = 0; hID < LBD_ROWS; ++hID) {
-      const float pL = rs[hID * 4], nL = rs[hID * 4 + 1], pO = rs[hID * 4 + 2], nO = rs[hID * 4 + 3];
-      const float pL2 = __fmul_rn(pL, pL), nL2 = __fmul_rn(nL, nL), pO2 = __fmul_rn(pO, pO), nO2 = __fmul_rn(nO, nO);
+  if (t < LBD_BANDS * 8) {
+    // accumulator (band b, statistic q): q = 0 pgdL, 1 ngdL, 2 pgdL^2, 3 ngdL^2, 4 pgdO, 5 ngdO, 6 pgdO^2, 7 ngdO^2
+    const int b = t >> 3, q = t & 7;
+    const int src = (q & 1) + ((q & 4) ? 2 : 0);  // which of the 4 row sums
+    const bool sq = (q & 2) != 0;
+    float acc = 0.f;
+    const int h0 = max(0, (b - 1) * LBD_W), h1 = min(LBD_ROWS, (b + 2) * LBD_W);
+    for (int hID = h0; hID < h1; ++hID) {
       const int b0 = hID / LBD_W, m = hID % LBD_W;
-      // current band, band above (b0-1), band below (b0+1) — in that order, as computeLBD
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int b = k == 0 ? b0 : (k == 1 ? b0 - 1 : b0 + 1);
-        if (b < 0 || b >= LBD_BANDS) continue;
-        const float coef = k == 0 ? L.gaussL[m + LBD_W] : (k == 1 ? L.gaussL[m + 2 * LBD_W] : L.gaussL[m]);
-        const float cc = __fmul_rn(coef, coef);
-        band[b][0] = __fadd_rn(band[b][0], __fmul_rn(coef, pL));
-        band[b][1] = __fadd_rn(band[b][1], __fmul_rn(coef, nL));
-        band[b][2] = __fadd_rn(band[b][2], __fmul_rn(cc, pL2));
-        band[b][3] = __fadd_rn(band[b][3], __fmul_rn(cc, nL2));
-        band[b][4] = __fadd_rn(band[b][4], __fmul_rn(coef, pO));
-        band[b][5] = __fadd_rn(band[b][5], __fmul_rn(coef, nO));
-        band[b][6] = __fadd_rn(band[b][6], __fmul_rn(cc, pO2));
-        band[b][7] = __fadd_rn(band[b][7], __fmul_rn(cc, nO2));
-      }
+      // row hID adds to its own band with gaussL[m+7], to the band above (b0-1) with gaussL[m+14], below (b0+1) with gaussL[m]
+      const float coef = (b == b0) ? L.gaussL[m + LBD_W] : (b == b0 - 1 ? L.gaussL[m + 2 * LBD_W] : L.gaussL[m]);
+      const float v = rowsum[hID][src];
+      acc = sq ? __fadd_rn(acc, __fmul_rn(__fmul_rn(coef, coef), __fmul_rn(v, v))) : __fadd_rn(acc, __fmul_rn(coef, v));
     }
+    band[b][q] = acc;
+  }
+  __syncthreads();
+  if (t == 0) {
     float des[LBD_BANDS * 8];
     const float invN2 = (float)(1.0 / (LBD_W * 2.0)), invN3 = (float)(1.0 / (LBD_W * 3.0));
-#pragma unroll
     for (int b = 0; b < LBD_BANDS; ++b) {
       const float invN = (b == 0 || b == LBD_BANDS - 1) ? invN2 : invN3;
       float tmp = __fmul_rn(band[b][0], invN);
@@ -1043,36 +1051,26 @@ __global__ void __launch_bounds__(256) k_lsd_finish(const __grid_constant__ Line
       des[b * 8 + 7] = sqrtf(__fsub_rn(__fmul_rn(band[b][7], invN), __fmul_rn(tmp, tmp)));
     }
     float tempM = 0, tempS = 0;
-#pragma unroll
     for (int b = 0; b < LBD_BANDS; ++b) {
-#pragma unroll
       for (int q = 0; q < 4; ++q) tempM = __fadd_rn(tempM, __fmul_rn(des[b * 8 + q], des[b * 8 + q]));
-#pragma unroll
       for (int q = 4; q < 8; ++q) tempS = __fadd_rn(tempS, __fmul_rn(des[b * 8 + q], des[b * 8 + q]));
     }
     tempM = __fdiv_rn(1.f, sqrtf(tempM));
     tempS = __fdiv_rn(1.f, sqrtf(tempS));
-#pragma unroll
     for (int b = 0; b < LBD_BANDS; ++b) {
-#pragma unroll
       for (int q = 0; q < 4; ++q) des[b * 8 + q] = __fmul_rn(des[b * 8 + q], tempM);
-#pragma unroll
       for (int q = 4; q < 8; ++q) des[b * 8 + q] = __fmul_rn(des[b * 8 + q], tempS);
     }
-#pragma unroll
     for (int i = 0; i < LBD_BANDS * 8; ++i)
       if ((double)des[i] > 0.4) des[i] = (float)0.4;
     float tmp = 0;
-#pragma unroll
     for (int i = 0; i < LBD_BANDS * 8; ++i) tmp = __fadd_rn(tmp, __fmul_rn(des[i], des[i]));
     tmp = __fdiv_rn(1.f, sqrtf(tmp));
-#pragma unroll
     for (int i = 0; i < LBD_BANDS * 8; ++i) des[i] = __fmul_rn(des[i], tmp);
     uint8_t* D = desc + ((size_t)f * capacity + r) * 32;
     for (int comb = 0; comb < 32; ++comb) {
       const int a = c_lbd_comb[comb][0] * 8, b = c_lbd_comb[comb][1] * 8;
       unsigned res = 0;
-#pragma unroll
       for (int i = 0; i < 8; ++i)
         if (des[a + i] > des[b + i]) res += 1u << i;
       D[comb] = (uint8_t)res;
@@ -1253,10 +1251,13 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   k_lsd_nfa<<<dim3(div_up(P.rect_cap, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), rects.as<LsdRect>(), nrects.as<int>(),
                                                                 rout, rvalid);
   PL_STAGE_END(timer, st);
-  PL_STAGE_BEGIN(timer, "lsd_finish_lbd", st);
+  PL_STAGE_BEGIN(timer, "lsd_finish", st);
   k_lsd_finish<<<batch, 256, 0, st>>>(P, d_images, pitch, frame_stride, nrects.as<int>(), rout, rvalid,
                                             segs.as<LsdSegment>(), nsegs.as<int>(), resp.as<float>(), rowsum.as<float>(), d_keylines, d_desc,
                                             d_funcs, capacity, d_counts, status.as<int>());
+  PL_STAGE_END(timer, st);
+  PL_STAGE_BEGIN(timer, "lbd", st);
+  k_lbd<<<dim3(P.out_cap, batch), 96, 0, st>>>(P, d_images, pitch, frame_stride, d_keylines, d_counts, d_desc, capacity);
   PL_STAGE_END(timer, st);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;
