@@ -275,3 +275,122 @@ def search_by_projection(last, cur, cam, scale_factors, tcw_cur, tcw_last, th, m
                                       _p(cur["grid_start"]), _p(cur["grid_items"]), _p(cam), _p(sf), _p(tc), _p(tl),
                                       th, int(mono), int(check_ori), _p(match))
     return match, n
+
+
+# ---------------------------------------------------------------------------
+# bag of words (oracle/bow_oracle.cc) and the reference's own DBoW2 build (oracle/_ref/libdbow2_ref.so)
+# ---------------------------------------------------------------------------
+def write_vocabulary_text(path, k, L, seed=0, leaf_fraction_early=0.0):
+    """Synthetic vocabulary in the ORBvoc.txt format (TemplatedVocabulary.h:1362-1448): first line 'k L 0 0',
+    then one line per node 'parent isLeaf d0..d31 weight' in breadth-first order; no trailing newline."""
+    rng = np.random.default_rng(seed)
+    lines = ["%d %d 0 0" % (k, L)]
+    frontier = [0]
+    next_id = 1
+    for level in range(1, L + 1):
+        new_frontier = []
+        for parent in frontier:
+            base = rng.integers(0, 256, 32)
+            for _ in range(k):
+                d = base ^ (rng.integers(0, 256, 32) & rng.integers(0, 256, 32) & rng.integers(0, 256, 32))
+                leaf = level == L or (leaf_fraction_early > 0 and level > 1 and rng.random() < leaf_fraction_early)
+                w = float(np.round(rng.random() * 10, 5)) if leaf else 0.0
+                lines.append("%d %d %s %g" % (parent, int(leaf), " ".join(str(int(x)) for x in d), w))
+                if not leaf:
+                    new_frontier.append(next_id)
+                next_id += 1
+        frontier = new_frontier
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+    return next_id
+
+
+class VocOracle:
+    def __init__(self, path):
+        L = lib()
+        L.oracle_voc_load_text.restype = C.c_void_p
+        L.oracle_voc_load_text.argtypes = [C.c_char_p]
+        for fn in (L.oracle_voc_free, L.oracle_voc_nodes, L.oracle_voc_words):
+            fn.argtypes = [C.c_void_p]
+        L.oracle_voc_export.argtypes = [C.c_void_p] * 8
+        L.oracle_voc_transform_features.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        self.h = L.oracle_voc_load_text(path.encode())
+        assert self.h, "cannot load vocabulary " + path
+        self.n_nodes = L.oracle_voc_nodes(self.h)
+        self.n_words = L.oracle_voc_words(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_voc_free(self.h)
+            self.h = None
+
+    def export(self):
+        n = self.n_nodes
+        out = dict(parent=np.empty(n, np.int32), first_child=np.empty(n, np.int32), n_children=np.empty(n, np.int32),
+                   desc=np.empty((n, 32), np.uint8), weight=np.empty(n, np.float64), word_id=np.empty(n, np.int32))
+        kL = np.empty(2, np.int32)
+        lib().oracle_voc_export(self.h, _p(out["parent"]), _p(out["first_child"]), _p(out["n_children"]), _p(out["desc"]),
+                                _p(out["weight"]), _p(out["word_id"]), _p(kL))
+        out["k"], out["L"] = int(kL[0]), int(kL[1])
+        return out
+
+    def transform_features(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word = np.empty(n, np.int32); weight = np.empty(n, np.float64); node = np.empty(n, np.int32)
+        lib().oracle_voc_transform_features(self.h, _p(desc), n, levelsup, _p(word), _p(weight), _p(node))
+        return word, weight, node
+
+    def transform(self, desc, levelsup=4):
+        return _voc_transform(lib().oracle_voc_transform, self.h, desc, levelsup)
+
+
+def _voc_transform(fn, h, desc, levelsup):
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(desc)
+    ids = np.empty(n, np.uint32); vals = np.empty(n, np.float64); nb = C.c_int()
+    nodes = np.empty(n, np.uint32); start = np.empty(n + 1, np.int32); idx = np.empty(n, np.uint32); nf = C.c_int()
+    fn(C.c_void_p(h), _p(desc), n, levelsup, _p(ids), _p(vals), C.byref(nb), _p(nodes), _p(start), _p(idx), C.byref(nf))
+    return dict(bow_ids=ids[:nb.value].copy(), bow_vals=vals[:nb.value].copy(), fv_nodes=nodes[:nf.value].copy(),
+                fv_start=start[:nf.value + 1].copy(), fv_idx=idx[:start[nf.value]].copy())
+
+
+_REF = None
+
+
+def dbow2_ref():
+    """The reference's own DBoW2 sources compiled into oracle/_ref/libdbow2_ref.so (None if never built)."""
+    global _REF
+    if _REF is None:
+        so = os.path.join(_HERE, "_ref", "libdbow2_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF = C.CDLL(so)
+        _REF.dbow2_ref_load_text.restype = C.c_void_p
+        _REF.dbow2_ref_load_text.argtypes = [C.c_char_p]
+        _REF.dbow2_ref_free.argtypes = [C.c_void_p]
+        _REF.dbow2_ref_size.argtypes = [C.c_void_p]
+        _REF.dbow2_ref_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+    return _REF
+
+
+class VocReference:
+    def __init__(self, path):
+        R = dbow2_ref()
+        self.h = R.dbow2_ref_load_text(path.encode())
+        assert self.h
+        self.n_words = R.dbow2_ref_size(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            dbow2_ref().dbow2_ref_free(self.h)
+            self.h = None
+
+    def transform(self, desc, levelsup=4):
+        return _voc_transform(dbow2_ref().dbow2_ref_transform, self.h, desc, levelsup)
+
+    @staticmethod
+    def forb_distance(a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return dbow2_ref().dbow2_ref_forb_distance(_p(a), _p(b))
