@@ -296,6 +296,38 @@ int plslam_frontend_launches_per_call(const plslam_frontend_t* h, int match_pair
 /* Synchronises `stream` and reports PLSLAM_ERR_OVERFLOW if an internal list overflowed in the last call. */
 int plslam_frontend_check_status(plslam_frontend_t* h, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * ORB vocabulary — the part of DBoW2 (reference Thirdparty/DBoW2) that Frame::ComputeBoW
+ * (include/Frame.h:80, @0xf84f0) uses: ORBVocabulary::loadFromTextFile (TemplatedVocabulary.h:1362-1448)
+ * and the per-feature tree descent of transform() (TemplatedVocabulary.h:1242-1284).  The descent
+ * (k Hamming distances per level) runs on the GPU; BowVector / FeatureVector assembly (std::map
+ * accumulation and L1 normalisation, TemplatedVocabulary.h:1151-1217) is host work on the results.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plslam_voc plslam_voc_t;
+
+/* loadFromTextFile(path) for ORBvoc.txt-style files ("k L scoring weighting" then "parent isLeaf d0..d31 weight"
+ * per node; only L1_NORM/TF_IDF = "0 0" is supported). */
+int plslam_voc_load_text(plslam_voc_t** out, const char* path);
+/* Same from arrays in node order 1..n_nodes-1 (entry 0 = root, ignored): parent id, leaf flag, 32-byte descriptor,
+ * weight.  Children lists are built in node order, as loadFromTextFile does. */
+int plslam_voc_create(plslam_voc_t** out, int k, int L, int n_nodes, const int32_t* parent, const uint8_t* is_leaf,
+                      const uint8_t* descriptors, const double* weights);
+void plslam_voc_destroy(plslam_voc_t* h);
+int plslam_voc_info(const plslam_voc_t* h, int* k, int* L, int* n_nodes, int* n_words);
+
+/* Flat device image of the vocabulary, for the one-off broadcast at start-up (NCCL over NVLink in bench/tests:
+ * rank 0 loads, exports, every rank imports).  export copies blob_bytes to d_out (device memory of the caller). */
+size_t plslam_voc_blob_bytes(const plslam_voc_t* h);
+int plslam_voc_export_blob(const plslam_voc_t* h, void* d_out, void* stream);
+int plslam_voc_import_blob(plslam_voc_t** out, const void* d_blob, size_t bytes);
+
+/* transform(feature, word_id, weight, nid, levelsup) for n descriptors (n x 32 bytes).  d_node receives the node
+ * at level L - levelsup (0 when that level is not reached).  Features with weight 0 are "stopped" words. */
+int plslam_voc_transform_device(const plslam_voc_t* h, const uint8_t* d_descriptors, int n, int levelsup,
+                                int32_t* d_word, double* d_weight, int32_t* d_node, void* stream);
+int plslam_voc_transform_host(const plslam_voc_t* h, const uint8_t* descriptors, int n, int levelsup, int32_t* word,
+                              double* weight, int32_t* node);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,14 +63,18 @@ void* oracle_voc_load_text(const char* path) {
     // the reference appends a node for every line it reads, including a trailing empty one (TemplatedVocabulary.h:1401-1443)
     int nid = (int)v->nodes.size();
     v->nodes.resize(nid + 1);
-    int pid = 0, leaf = 0;
-    ss >> pid;
+    // on a trailing empty line the stream sentry fails, so no extraction stores anything: `pid` and the leaf flag
+    // (unassigned locals in the reference) keep the previous line's values, the descriptor and weight are never
+    // written => a phantom, weightless extra child of the LAST parent (observed with the reference's sources
+    // compiled here; its descriptor is uninitialised memory there, zeros here)
+    static thread_local int leaf = 0, pid = 0;
+    { int v2; if (ss >> v2) pid = v2; }
     v->nodes[nid].parent = pid;
     v->nodes[pid].children.push_back(nid);
-    ss >> leaf;
+    { int lf; if (ss >> lf) leaf = lf; }
     for (int i = 0; i < 32; ++i) {
       int e = 0;
-      ss >> e;
+      if (!(ss >> e)) e = 0;
       v->nodes[nid].desc[i] = (uint8_t)e;
     }
     ss >> v->nodes[nid].weight;

@@ -34,7 +34,9 @@ class Mat {
   void create(int r, int c, int type) {
     const size_t es = type == CV_32F ? 4 : 1;
     rows = r; cols = c; step = (size_t)c * es;
-    own_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * c * es > 0 ? (size_t)r * c * es : 1], std::default_delete<uint8_t[]>());
+    // zero-initialised (value-init): the reference reads a never-written descriptor for the phantom node a trailing
+    // empty line of the vocabulary file creates (TemplatedVocabulary.h:1401-1443); zeros make that defined here
+    own_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * c * es > 0 ? (size_t)r * c * es : 1](), std::default_delete<uint8_t[]>());
     data = own_.get();
   }
   static Mat zeros(int r, int c, int t) { Mat m(r, c, t); std::memset(m.data, 0, (size_t)r * c); return m; }

@@ -1,0 +1,277 @@
+// bow.cu — ORB vocabulary on the device: per-feature tree descent of DBoW2's transform()
+// (reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1242-1284, FORB::distance FORB.cpp:82-102), as
+// Frame::ComputeBoW (include/Frame.h:80, lib/libORB_SLAM2.so@0xf84f0) needs it.  One thread per feature walks
+// L levels of k children; the node table (~35 MB for ORBvoc) lives in L2.
+#include <cstdlib>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace plslam {
+
+struct VocHeader {  // first bytes of the device blob
+  int32_t magic, k, L, n_nodes, n_words, n_child;
+  int32_t pad[2];
+  uint64_t off_desc, off_child_start, off_child_idx, off_weight, off_word;
+  uint64_t bytes;
+};
+
+struct VocDev {
+  const uint4* desc;
+  const int32_t* child_start;
+  const int32_t* child_idx;
+  const double* weight;
+  const int32_t* word;
+  int L;
+};
+
+namespace {
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(128) k_bow_transform(VocDev V, const uint8_t* __restrict__ desc, int n, int levelsup,
+                                                       int32_t* __restrict__ word, double* __restrict__ weight,
+                                                       int32_t* __restrict__ node) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* F = reinterpret_cast<const uint4*>(desc) + 2 * (size_t)i;
+  const uint4 f0 = F[0], f1 = F[1];
+  const int nid_level = V.L - levelsup;
+  int nid = 0, final_id = 0, level = 0;
+  int c0 = V.child_start[0], c1 = V.child_start[1];
+  do {
+    ++level;
+    int best_id = __ldg(V.child_idx + c0);
+    int best = hamming256(f0, f1, __ldg(V.desc + 2 * (size_t)best_id), __ldg(V.desc + 2 * (size_t)best_id + 1));
+    for (int c = c0 + 1; c < c1; ++c) {
+      const int id = __ldg(V.child_idx + c);
+      const int d = hamming256(f0, f1, __ldg(V.desc + 2 * (size_t)id), __ldg(V.desc + 2 * (size_t)id + 1));
+      if (d < best) { best = d; best_id = id; }
+    }
+    final_id = best_id;
+    if (level == nid_level) nid = final_id;
+    c0 = __ldg(V.child_start + final_id);
+    c1 = __ldg(V.child_start + final_id + 1);
+  } while (c1 > c0);
+  word[i] = V.word[final_id];
+  weight[i] = V.weight[final_id];
+  node[i] = nid;
+}
+
+}  // namespace
+
+struct Vocabulary {
+  VocHeader H{};
+  void* blob = nullptr;
+  VocDev dev{};
+  ~Vocabulary() { if (blob) cudaFree(blob); }
+  void bind() {
+    const char* b = static_cast<const char*>(blob);
+    dev.desc = reinterpret_cast<const uint4*>(b + H.off_desc);
+    dev.child_start = reinterpret_cast<const int32_t*>(b + H.off_child_start);
+    dev.child_idx = reinterpret_cast<const int32_t*>(b + H.off_child_idx);
+    dev.weight = reinterpret_cast<const double*>(b + H.off_weight);
+    dev.word = reinterpret_cast<const int32_t*>(b + H.off_word);
+    dev.L = H.L;
+  }
+  // host arrays in node order -> device blob
+  int build(int k, int L, int n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc, const double* weights) {
+    PL_CHECK_ARG(k >= 1 && k <= 20 && L >= 1 && L <= 10 && n_nodes >= 2);
+    std::vector<std::vector<int32_t>> children(n_nodes);
+    std::vector<int32_t> word(n_nodes, -1);
+    int n_words = 0;
+    for (int i = 1; i < n_nodes; ++i) {
+      PL_CHECK_ARG(parent[i] >= 0 && parent[i] < i);
+      children[parent[i]].push_back(i);
+      if (is_leaf[i]) word[i] = n_words++;
+    }
+    PL_CHECK_ARG(!children[0].empty());
+    std::vector<int32_t> cstart(n_nodes + 1, 0), cidx;
+    cidx.reserve(n_nodes);
+    for (int i = 0; i < n_nodes; ++i) {
+      cstart[i] = (int32_t)cidx.size();
+      cidx.insert(cidx.end(), children[i].begin(), children[i].end());
+    }
+    cstart[n_nodes] = (int32_t)cidx.size();
+    H.magic = 0x564f4332;
+    H.k = k; H.L = L; H.n_nodes = n_nodes; H.n_words = n_words; H.n_child = (int32_t)cidx.size();
+    size_t off = align_up(sizeof(VocHeader), 256);
+    H.off_desc = off; off = align_up(off + (size_t)n_nodes * 32, 256);
+    H.off_child_start = off; off = align_up(off + (size_t)(n_nodes + 1) * 4, 256);
+    H.off_child_idx = off; off = align_up(off + std::max<size_t>(cidx.size(), 1) * 4, 256);
+    H.off_weight = off; off = align_up(off + (size_t)n_nodes * 8, 256);
+    H.off_word = off; off = align_up(off + (size_t)n_nodes * 4, 256);
+    H.bytes = off;
+    std::vector<char> host(off, 0);
+    std::memcpy(host.data(), &H, sizeof(H));
+    std::memcpy(host.data() + H.off_desc, desc, (size_t)n_nodes * 32);
+    std::memset(host.data() + H.off_desc, 0, 32);  // root has no descriptor
+    std::memcpy(host.data() + H.off_child_start, cstart.data(), cstart.size() * 4);
+    if (!cidx.empty()) std::memcpy(host.data() + H.off_child_idx, cidx.data(), cidx.size() * 4);
+    std::memcpy(host.data() + H.off_weight, weights, (size_t)n_nodes * 8);
+    std::memcpy(host.data() + H.off_word, word.data(), (size_t)n_nodes * 4);
+    PL_CUDA(cudaMalloc(&blob, off));
+    PL_CUDA(cudaMemcpy(blob, host.data(), off, cudaMemcpyHostToDevice));
+    bind();
+    return PLSLAM_OK;
+  }
+};
+
+}  // namespace plslam
+
+using namespace plslam;
+
+struct plslam_voc {
+  Vocabulary v;
+};
+
+extern "C" {
+
+int plslam_voc_create(plslam_voc_t** out, int k, int L, int n_nodes, const int32_t* parent, const uint8_t* is_leaf,
+                      const uint8_t* descriptors, const double* weights) {
+  PL_CHECK_ARG(out && parent && is_leaf && descriptors && weights);
+  *out = nullptr;
+  plslam_voc* h = new (std::nothrow) plslam_voc();
+  PL_CHECK_ARG(h != nullptr);
+  int rc = h->v.build(k, L, n_nodes, parent, is_leaf, descriptors, weights);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return PLSLAM_OK;
+}
+
+int plslam_voc_load_text(plslam_voc_t** out, const char* path) {
+  PL_CHECK_ARG(out && path);
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("cannot open vocabulary %s", path); return PLSLAM_ERR_INVALID; }
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::string buf((size_t)sz, '\0');
+  const size_t rd = fread(&buf[0], 1, (size_t)sz, f);
+  fclose(f);
+  if (rd != (size_t)sz) { set_error("short read on %s", path); return PLSLAM_ERR_INVALID; }
+  const char* p = buf.c_str();
+  char* e = nullptr;
+  const long k = strtol(p, &e, 10); p = e;
+  const long L = strtol(p, &e, 10); p = e;
+  const long n1 = strtol(p, &e, 10); p = e;
+  const long n2 = strtol(p, &e, 10); p = e;
+  if (k < 1 || k > 20 || L < 1 || L > 10 || n1 != 0 || n2 != 0) {
+    set_error("%s: not an L1_NORM/TF_IDF vocabulary text file (header %ld %ld %ld %ld)", path, k, L, n1, n2);
+    return PLSLAM_ERR_INVALID;
+  }
+  while (*p && *p != '\n') ++p;
+  if (*p == '\n') ++p;
+  std::vector<int32_t> parent(1, 0);
+  std::vector<uint8_t> leaf(1, 0), desc(32, 0);
+  std::vector<double> weight(1, 0.0);
+  // one node per remaining line; the reference also appends a node for a trailing empty line: the stream sentry
+  // fails there and nothing is stored, so the node becomes a phantom extra child of the PREVIOUS line's parent with
+  // that line's leaf flag (both unassigned locals), weight 0 and a descriptor that is never written
+  // (TemplatedVocabulary.h:1401-1443; behaviour observed with the reference's sources compiled in oracle/_ref) — kept, with zeros
+  long prevLeaf = 0, prevPid = 0;
+  while (true) {
+    const char* eol = p;
+    while (*eol && *eol != '\n') ++eol;
+    const char* q = p;
+    const bool emptyLine = (q == eol);
+    const long pid = emptyLine ? prevPid : strtol(q, &e, 10);
+    if (!emptyLine) { q = e; prevPid = pid; }
+    long lf = prevLeaf;
+    if (!emptyLine) { lf = strtol(q, &e, 10); q = e; prevLeaf = lf; }
+    uint8_t d[32] = {0};
+    for (int i = 0; i < 32 && !emptyLine; ++i) { const long v = strtol(q, &e, 10); if (e == q || e > eol) break; d[i] = (uint8_t)v; q = e; }
+    double w = emptyLine ? 0.0 : strtod(q, &e);
+    if (!emptyLine && (e == q || e > eol)) w = 0.0;
+    if (pid < 0 || pid >= (long)parent.size()) { set_error("%s: bad parent id %ld at node %zu", path, pid, parent.size()); return PLSLAM_ERR_INVALID; }
+    parent.push_back((int32_t)pid);
+    leaf.push_back(lf > 0);
+    desc.insert(desc.end(), d, d + 32);
+    weight.push_back(w);
+    if (!*eol) break;
+    p = eol + 1;
+  }
+  return plslam_voc_create(out, (int)k, (int)L, (int)parent.size(), parent.data(), leaf.data(), desc.data(), weight.data());
+}
+
+void plslam_voc_destroy(plslam_voc_t* h) { delete h; }
+
+int plslam_voc_info(const plslam_voc_t* h, int* k, int* L, int* n_nodes, int* n_words) {
+  PL_CHECK_ARG(h);
+  if (k) *k = h->v.H.k;
+  if (L) *L = h->v.H.L;
+  if (n_nodes) *n_nodes = h->v.H.n_nodes;
+  if (n_words) *n_words = h->v.H.n_words;
+  return PLSLAM_OK;
+}
+
+size_t plslam_voc_blob_bytes(const plslam_voc_t* h) { return h ? (size_t)h->v.H.bytes : 0; }
+
+int plslam_voc_export_blob(const plslam_voc_t* h, void* d_out, void* stream) {
+  PL_CHECK_ARG(h && d_out);
+  PL_CUDA(cudaMemcpyAsync(d_out, h->v.blob, h->v.H.bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return PLSLAM_OK;
+}
+
+int plslam_voc_import_blob(plslam_voc_t** out, const void* d_blob, size_t bytes) {
+  PL_CHECK_ARG(out && d_blob && bytes >= sizeof(VocHeader));
+  *out = nullptr;
+  VocHeader H;
+  PL_CUDA(cudaMemcpy(&H, d_blob, sizeof(H), cudaMemcpyDeviceToHost));
+  PL_CHECK_ARG(H.magic == 0x564f4332 && H.bytes == bytes);
+  plslam_voc* h = new (std::nothrow) plslam_voc();
+  PL_CHECK_ARG(h != nullptr);
+  h->v.H = H;
+  if (cudaMalloc(&h->v.blob, bytes) != cudaSuccess || cudaMemcpy(h->v.blob, d_blob, bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+    set_error("vocabulary import: %s", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return PLSLAM_ERR_CUDA;
+  }
+  h->v.bind();
+  *out = h;
+  return PLSLAM_OK;
+}
+
+int plslam_voc_transform_device(const plslam_voc_t* h, const uint8_t* d_descriptors, int n, int levelsup,
+                                int32_t* d_word, double* d_weight, int32_t* d_node, void* stream) {
+  PL_CHECK_ARG(h && n >= 0);
+  if (n == 0) return PLSLAM_OK;
+  PL_CHECK_ARG(d_descriptors && d_word && d_weight && d_node);
+  k_bow_transform<<<div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(h->v.dev, d_descriptors, n, levelsup, d_word, d_weight, d_node);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_voc_transform_host(const plslam_voc_t* h, const uint8_t* descriptors, int n, int levelsup, int32_t* word,
+                              double* weight, int32_t* node) {
+  PL_CHECK_ARG(h && n >= 0);
+  if (n == 0) return PLSLAM_OK;
+  PL_CHECK_ARG(descriptors && word && weight && node);
+  DevBuf d, w, wt, nd;
+  int rc;
+  if ((rc = d.ensure((size_t)n * 32)) || (rc = w.ensure((size_t)n * 4)) || (rc = wt.ensure((size_t)n * 8)) || (rc = nd.ensure((size_t)n * 4))) {
+    d.release(); w.release(); wt.release(); nd.release();
+    return rc;
+  }
+  cudaError_t e = cudaMemcpy(d.p, descriptors, (size_t)n * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = plslam_voc_transform_device(h, d.as<uint8_t>(), n, levelsup, w.as<int32_t>(), wt.as<double>(), nd.as<int32_t>(), nullptr);
+    if (!rc) {
+      e = cudaMemcpy(word, w.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(weight, wt.p, (size_t)n * 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(node, nd.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    }
+  }
+  d.release(); w.release(); wt.release(); nd.release();
+  if (rc) return rc;
+  if (e != cudaSuccess) { set_error("voc transform host path: %s", cudaGetErrorString(e)); return PLSLAM_ERR_CUDA; }
+  return PLSLAM_OK;
+}
+
+}  // extern "C"

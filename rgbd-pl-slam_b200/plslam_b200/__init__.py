@@ -454,3 +454,96 @@ class Frontend:
 
     def launches_per_call(self, match_pairs=True):
         return lib().plslam_frontend_launches_per_call(self._h, int(match_pairs))
+
+
+# ---------------------------------------------------------------------------
+# ORB vocabulary (DBoW2 transform as used by Frame::ComputeBoW)
+# ---------------------------------------------------------------------------
+class ORBVocabulary:
+    """plslam_voc_*: loadFromTextFile + per-feature tree descent on the GPU; BowVector / FeatureVector assembly
+    (std::map accumulation in feature order, L1 normalisation) on the host, as DBoW2's transform()."""
+
+    def __init__(self, path=None, handle=None):
+        L = lib()
+        L.plslam_voc_load_text.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
+        L.plslam_voc_destroy.argtypes = [C.c_void_p]
+        L.plslam_voc_destroy.restype = None
+        L.plslam_voc_blob_bytes.restype = C.c_size_t
+        L.plslam_voc_blob_bytes.argtypes = [C.c_void_p]
+        self._h = C.c_void_p()
+        if handle is not None:
+            self._h = handle
+        else:
+            _check(L.plslam_voc_load_text(C.byref(self._h), path.encode()))
+        k, Lv, nn, nw = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(L.plslam_voc_info(self._h, C.byref(k), C.byref(Lv), C.byref(nn), C.byref(nw)))
+        self.k, self.L, self.n_nodes, self.n_words = k.value, Lv.value, nn.value, nw.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().plslam_voc_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def export_blob(self):
+        import torch
+        n = lib().plslam_voc_blob_bytes(self._h)
+        t = torch.empty(n, dtype=torch.uint8, device="cuda")
+        _check(lib().plslam_voc_export_blob(self._h, _vp(t), _stream_ptr()))
+        torch.cuda.synchronize()
+        return t
+
+    @classmethod
+    def from_blob(cls, blob):
+        h = C.c_void_p()
+        _check(lib().plslam_voc_import_blob(C.byref(h), _vp(blob), C.c_size_t(blob.numel())))
+        return cls(handle=h)
+
+    def transform_features_device(self, d_desc, levelsup=4, stream=None):
+        import torch
+        n = d_desc.shape[0]
+        word = torch.empty(n, dtype=torch.int32, device=d_desc.device)
+        weight = torch.empty(n, dtype=torch.float64, device=d_desc.device)
+        node = torch.empty(n, dtype=torch.int32, device=d_desc.device)
+        _check(lib().plslam_voc_transform_device(self._h, _vp(d_desc), n, levelsup, _vp(word), _vp(weight), _vp(node),
+                                                 _stream_ptr(stream)))
+        return word, weight, node
+
+    def transform_features(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word = np.empty(n, np.int32); weight = np.empty(n, np.float64); node = np.empty(n, np.int32)
+        _check(lib().plslam_voc_transform_host(self._h, _vp(desc), n, levelsup, _vp(word), _vp(weight), _vp(node)))
+        return word, weight, node
+
+    def transform(self, desc, levelsup=4):
+        """-> dict(bow_ids, bow_vals, fv_nodes, fv_start, fv_idx): BowVector and FeatureVector in std::map order."""
+        word, weight, node = self.transform_features(desc, levelsup)
+        return assemble_bow(word, weight, node)
+
+
+def assemble_bow(word, weight, node):
+    """BowVector::addWeight in feature order + normalize(L1); FeatureVector::addFeature (TemplatedVocabulary.h:1151-1217)."""
+    bow, fv = {}, {}
+    for i in range(len(word)):
+        w = float(weight[i])
+        if w > 0:
+            bow[int(word[i])] = bow.get(int(word[i]), 0.0) + w if int(word[i]) in bow else w
+            fv.setdefault(int(node[i]), []).append(i)
+    ids = sorted(bow)
+    vals = [bow[i] for i in ids]
+    norm = 0.0
+    for v in vals:
+        norm += abs(v)
+    if norm > 0.0:
+        vals = [v / norm for v in vals]
+    nodes = sorted(fv)
+    start = [0]
+    idx = []
+    for nd in nodes:
+        idx.extend(fv[nd])
+        start.append(len(idx))
+    return dict(bow_ids=np.array(ids, np.uint32), bow_vals=np.array(vals, np.float64), fv_nodes=np.array(nodes, np.uint32),
+                fv_start=np.array(start, np.int32), fv_idx=np.array(idx, np.uint32))

@@ -48,3 +48,42 @@ def test_transform_on_real_orb_features(ref, tmp_path):
     for key in a:
         assert np.array_equal(a[key], b[key]), key
     assert len(a["fv_idx"]) == len(d)
+
+
+def test_trailing_empty_line_creates_the_same_phantom_node(ref, tmp_path):
+    """ORBvoc.txt ends with '\\n'; the reference's loader then appends one more node whose parent / leaf flag are the
+    previous line's (unassigned locals) and whose weight is 0 (TemplatedVocabulary.h:1401-1443)."""
+    path = str(tmp_path / "voc.txt")
+    ref.write_vocabulary_text(path, 5, 3, seed=9)
+    with open(path, "a") as f:
+        f.write("\n")
+    mine, theirs = ref.VocOracle(path), ref.VocReference(path)
+    assert mine.n_words == theirs.n_words
+    rng = np.random.default_rng(4)
+    desc = rng.integers(0, 256, (3000, 32)).astype(np.uint8)
+    desc[:200] &= rng.integers(0, 256, (200, 32)).astype(np.uint8) & rng.integers(0, 256, (200, 32)).astype(np.uint8)  # near-zero rows
+    a, b = mine.transform(desc, 1), theirs.transform(desc, 1)
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+
+
+REAL_VOC = "/root/reference/Vocabulary/ORBvoc.txt.tar.gz"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REAL_VOC), reason="the reference's ORBvoc archive is not on this machine")
+def test_real_orbvoc_equals_reference_dbow2(ref, tmp_path):
+    """The shipped vocabulary (k=10, L=6, 1,082,073 nodes + the phantom), levelsup=4 as Frame::ComputeBoW uses (Frame.cc:354-362)."""
+    import tarfile
+    with tarfile.open(REAL_VOC) as t:
+        t.extract("ORBvoc.txt", tmp_path)
+    path = str(tmp_path / "ORBvoc.txt")
+    mine, theirs = ref.VocOracle(path), ref.VocReference(path)
+    assert mine.n_words == theirs.n_words == 971815
+    from plslam_b200.synth import synth_frame
+    o = ref.OrbOracle()
+    rng = np.random.default_rng(0)
+    sets = [o.extract(synth_frame(s))[1] for s in range(3)] + [rng.integers(0, 256, (5000, 32)).astype(np.uint8)]
+    for d in sets:
+        a, b = mine.transform(d, 4), theirs.transform(d, 4)
+        for key in a:
+            assert np.array_equal(a[key], b[key]), key
