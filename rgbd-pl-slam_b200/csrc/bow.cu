@@ -243,6 +243,7 @@ int plslam_voc_transform_device(const plslam_voc_t* h, const uint8_t* d_descript
   PL_CHECK_ARG(h && n >= 0);
   if (n == 0) return PLSLAM_OK;
   PL_CHECK_ARG(d_descriptors && d_word && d_weight && d_node);
+  PL_CARVEOUT(k_bow_transform);
   k_bow_transform<<<div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(h->v.dev, d_descriptors, n, levelsup, d_word, d_weight, d_node);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // c_api.cu — extern "C" entry points declared in include/plslam_b200.h (the drop-in boundary).
 #include <new>
 
@@ -25,6 +26,16 @@ struct plslam_orb {
 struct plslam_lines {
   LineExtractor impl;
 };
+
+namespace plslam {
+int carveout_pct() {
+  static const int v = [] {
+    const char* e = std::getenv("PLSLAM_CARVEOUT");
+    return e ? std::atoi(e) : 50;
+  }();
+  return v;
+}
+}  // namespace plslam
 
 extern "C" {
 

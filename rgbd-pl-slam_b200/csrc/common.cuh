@@ -32,6 +32,21 @@ void set_error(const char* fmt, ...);
     }                                                                         \
   } while (0)
 
+// Every kernel of the library asks for the same L1/shared-memory split.  Kernels whose carve-outs differ cannot be
+// resident on one SM at the same time, and the front-end relies on short streaming kernels of one batch running
+// beside the long region-growing kernels of other batches.  PLSLAM_CARVEOUT (percent of shared memory, -1 = leave
+// the driver's per-kernel choice) overrides the default.
+int carveout_pct();
+#define PL_CARVEOUT(kernel)                                                                                   \
+  do {                                                                                                        \
+    static bool _pl_done = false;                                                                             \
+    if (!_pl_done) {                                                                                          \
+      if (::plslam::carveout_pct() >= 0)                                                                      \
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ::plslam::carveout_pct()); \
+      _pl_done = true;                                                                                        \
+    }                                                                                                         \
+  } while (0)
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 

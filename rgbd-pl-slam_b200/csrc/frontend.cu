@@ -216,6 +216,7 @@ extern "C" {
 int plslam_match_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int capacity, int npairs,
                                    int32_t* d_out, plslam_knn_job_t* d_jobs_scratch, void* stream) {
   PL_CHECK_ARG(d_desc && d_counts && d_out && d_jobs_scratch && capacity >= 1 && npairs >= 1);
+  PL_CARVEOUT(k_make_pair_jobs);
   k_make_pair_jobs<<<div_up(npairs, 128), 128, 0, (cudaStream_t)stream>>>(d_desc, d_counts, capacity, npairs, d_out,
                                                                           d_jobs_scratch);
   PL_CUDA(cudaGetLastError());

@@ -226,13 +226,30 @@ constexpr unsigned USED_BIT = 0x80000000u;  // `used` flag of a pixel: bit 31 of
 // The `used` map lives in the pixel records themselves (global memory, L1-resident around the growing region),
 // so a frame's CTA needs ~5 KB of shared memory and 32 frames fit on one SM.  Only this warp touches the frame's
 // records while the kernel runs; __syncwarp() orders its stores and loads.
+#ifdef PLSLAM_GROW_PROF
+// debug build only (make PROF=1): cycle counters of k_lsd_grow, lane 0 of every frame adds its totals
+__device__ unsigned long long g_grow_prof[16];
+#define GP_DECL long long gp_t0 = 0
+#define GP_START() gp_t0 = clock64()
+#define GP_ADD(slot) C.prof[slot] += clock64() - gp_t0
+#define GP_CNT(slot, v) C.prof[slot] += (v)
+#else
+#define GP_DECL
+#define GP_START()
+#define GP_ADD(slot)
+#define GP_CNT(slot, v)
+#endif
 struct GrowCtx {
+#ifdef PLSLAM_GROW_PROF
+  long long* prof;
+#endif
   uint4* pix;         // per-pixel records of this frame (read-write: used flags)
   unsigned* regS;     // region list ((y << 16) | x): first REG_SMEM entries in shared memory ...
   unsigned* regG;     // ... the rest in this frame's global scratch
   double* stage;      // 3 x 32 doubles of shared staging
   int sw, sh;
   int lane;
+  bool prefetch;
   __device__ __forceinline__ unsigned reg_get(int i) const { return i < REG_SMEM ? regS[i] : regG[i]; }
   __device__ __forceinline__ void reg_set(int i, unsigned v) const {
     if (i < REG_SMEM) regS[i] = v; else regG[i] = v;
@@ -312,6 +329,144 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
     i += m;
     __syncwarp();
   }
+  *reg_angle_out = reg_angle;
+  return n;
+}
+
+// region_grow() with in-batch speculation.  The reference examines the 8 neighbours of each region point in
+// order and updates the region angle after every accepted pixel, so later tests see the new angle.  Here the
+// 32 neighbour slots of 4 frontier points are first tested against the angle at batch entry (set m); every lane
+// then rebuilds, with the same float additions in the same order, the sums it would have seen had all earlier
+// lanes of m been accepted, re-tests itself against that exact pre-state and the warp commits the longest prefix
+// on which the two tests agree (plus the corrected decision of the first disagreeing lane).  A batch whose
+// decisions do not depend on the drift of the angle costs one round instead of one round per accepted pixel;
+// the result is identical to the sequential scan by construction.
+__device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_angle_out) {
+  const int lane = C.lane;
+  const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+  const unsigned seedxy = C.reg_get(0);
+  const int seed = (int)(seedxy >> 16) * C.sw + (int)(seedxy & 0xffff);
+  const uint4 srec = C.pix[seed];
+  double reg_angle = __dmul_rn((double)__uint_as_float(srec.x), PL_DEG_TO_RADS);
+  float sumdx, sumdy;
+  {
+    double s, c;
+    pl_sincos_dev(reg_angle, &s, &c);
+    sumdx = (float)c;
+    sumdy = (float)s;
+  }
+  if (lane == 0) *C.wptr(seed) = srec.w | USED_BIT;
+  __syncwarp();
+  int n = 1;
+  GP_DECL;
+  GP_CNT(8, 1);
+  const int pt = lane >> 3, nb8 = lane & 7, nb = nb8 < 4 ? nb8 : nb8 + 1;
+  const int ox = (nb % 3) - 1, oy = (nb / 3) - 1;
+  for (int i = 0; i < n;) {
+    const int m4 = min(4, n - i);
+    GP_START();
+    GP_CNT(9, 1);
+    int nidx = -1;
+    unsigned nxy = 0, w = 0;
+    float deg = NOTDEF_F, cs = 0.f, sn = 0.f;
+    if (pt < m4) {
+      const unsigned p = C.reg_get(i + pt);
+      const int nx = (int)(p & 0xffff) + ox, ny = (int)(p >> 16) + oy;
+      if (nx >= 0 && ny >= 0 && nx < C.sw && ny < C.sh) {
+        const int id = ny * C.sw + nx;
+        const uint4 r = C.pix[id];
+        if (!(r.w & USED_BIT) && __uint_as_float(r.x) != NOTDEF_F) {
+          nidx = id;
+          nxy = ((unsigned)ny << 16) | (unsigned)nx;
+          w = r.w;
+          deg = __uint_as_float(r.x);
+          cs = __uint_as_float(r.y);
+          sn = __uint_as_float(r.z);
+        }
+      }
+    }
+    const bool anyc = __any_sync(FULL, deg != NOTDEF_F);
+    GP_ADD(0);
+    GP_START();
+    if (anyc) {
+      // lanes looking at the same pixel (MATCH.ANY costs a step per distinct value: only the candidate lanes take part)
+      const unsigned candm = __ballot_sync(FULL, deg != NOTDEF_F);
+      const unsigned peers = deg != NOTDEF_F ? __match_any_sync(candm, nidx) : (1u << lane);
+      unsigned todo = FULL;                                 // lanes the sequential scan has not passed yet
+      while (true) {
+        const bool in = (todo >> lane) & 1u;
+        const bool a0 = in && deg != NOTDEF_F && lsd_aligned(reg_angle, deg, prec) && !(peers & todo & lt);
+        const unsigned m = __ballot_sync(FULL, a0);
+        if (!m) break;
+        GP_CNT(10, 1);
+        // sums before this lane, assuming every earlier lane of m is accepted (additions in scan order)
+        float sx = sumdx, sy = sumdy;
+        for (unsigned r = m; r; r &= r - 1u) {
+          const int j = __ffs(r) - 1;
+          const float cj = __shfl_sync(FULL, cs, j), sj = __shfl_sync(FULL, sn, j);
+          if (lane > j) {
+            sx = __fadd_rn(sx, cj);
+            sy = __fadd_rn(sy, sj);
+          }
+        }
+        const float px = a0 ? __fadd_rn(sx, cs) : sx, py = a0 ? __fadd_rn(sy, sn) : sy;  // sums after this lane
+        const double ra_post = __dmul_rn((double)fast_atan2_dev(py, px), PL_DEG_TO_RADS);
+        const double ra_up = __shfl_up_sync(FULL, ra_post, 1);
+        const double ra = (m & lt) ? ra_up : reg_angle;  // exact region angle this lane is tested against
+        const bool a1 = in && deg != NOTDEF_F && lsd_aligned(ra, deg, prec) && !(peers & m & lt);
+        const unsigned m1 = __ballot_sync(FULL, a1);
+        const unsigned bad = (m ^ m1) & todo;
+        unsigned commit;
+        if (!bad) {
+          commit = m;
+        } else {
+          const int b = __ffs(bad) - 1;
+          commit = (m & ((1u << b) - 1u)) | (m1 & (1u << b));
+        }
+        if ((commit >> lane) & 1u) {
+          *C.wptr(nidx) = w | USED_BIT;
+          C.reg_set(n + __popc(commit & lt), nxy);
+          if (C.prefetch) {
+            // the 3x3 neighbourhood of the new region point is examined when the point reaches the scan front, a
+            // few batches from now: pull its three record rows (48 B each, possibly straddling two lines) towards L1
+            const int up = (nxy >> 16) > 0 ? nidx - C.sw : nidx, dn = (int)(nxy >> 16) < C.sh - 1 ? nidx + C.sw : nidx;
+            const int l = (nxy & 0xffff) > 0 ? -1 : 0, r = (int)(nxy & 0xffff) < C.sw - 1 ? 1 : 0;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + up + l));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + up + r));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + nidx + l));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + nidx + r));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + dn + l));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + dn + r));
+          }
+        }
+        n += __popc(commit);
+        if (!bad) {
+          sumdx = __shfl_sync(FULL, px, 31);
+          sumdy = __shfl_sync(FULL, py, 31);
+          reg_angle = __shfl_sync(FULL, ra_post, 31);
+          break;
+        }
+        GP_CNT(11, 1);
+        const int b = __ffs(bad) - 1;
+        const float bx = __shfl_sync(FULL, sx, b), by = __shfl_sync(FULL, sy, b);
+        if ((m1 >> b) & 1u) {  // lane b is accepted after all: its own contribution enters the sums
+          sumdx = __fadd_rn(bx, __shfl_sync(FULL, cs, b));
+          sumdy = __fadd_rn(by, __shfl_sync(FULL, sn, b));
+          reg_angle = __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), PL_DEG_TO_RADS);
+        } else {  // lane b is rejected under its exact pre-state: the state stays that pre-state
+          sumdx = bx;
+          sumdy = by;
+          reg_angle = __shfl_sync(FULL, ra, b);
+        }
+        if (peers & commit) deg = NOTDEF_F;  // the pixel is used now, whichever frontier point looks at it
+        todo = b == 31 ? 0u : (FULL << (b + 1));
+      }
+    }
+    i += m4;
+    __syncwarp();
+    GP_ADD(1);
+  }
+  GP_CNT(12, n);
   *reg_angle_out = reg_angle;
   return n;
 }
@@ -426,7 +581,7 @@ __device__ __forceinline__ double rect_density(int n, const LsdRect& r) {
 
 // refine() + reduce_region_radius(); returns false when the region must be dropped. *n_io = region size.
 __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double prec, double p, LsdRect* rec,
-                           double density_th) {
+                           double density_th, int variant) {
   const int lane = C.lane;
   int n = *n_io;
   double density = rect_density(n, *rec);
@@ -471,7 +626,7 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   const double tau = __dmul_rn(
       2.0, sqrt(__dadd_rn(__ddiv_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)), (double)cntN),
                           __dmul_rn(mean_angle, mean_angle))));
-  n = lsd_region_grow(C, tau, &reg_angle);
+  n = (variant & 1) ? lsd_region_grow_spec(C, tau, &reg_angle) : lsd_region_grow(C, tau, &reg_angle);
   *n_io = n;
   if (n < 2) return false;
   lsd_region2rect(C, n, reg_angle, prec, p, rec);
@@ -507,21 +662,32 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   return true;
 }
 
-__global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineParams L, uint4* pixAll,
+constexpr int GROW_WARPS = 4;  // frames per CTA (one warp each): keeps the long-running kernel from holding every CTA slot of an SM
+__global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_constant__ LineParams L, uint4* pixAll,
                                                  const unsigned* __restrict__ seedsAll, const int* __restrict__ nseeds,
                                                  unsigned* regAll, LsdRect* __restrict__ rectsAll,
                                                  int* __restrict__ nrects, int* __restrict__ status) {
-  __shared__ double stage[96];
-  __shared__ unsigned regS[REG_SMEM];
-  const int f = blockIdx.x, lane = threadIdx.x;
+  __shared__ double stage[GROW_WARPS][96];
+  __shared__ unsigned regS[GROW_WARPS][REG_SMEM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * GROW_WARPS + warp;
+  if (f >= L.batch) return;
   GrowCtx C;
-  C.stage = stage;
-  C.regS = regS;
+  C.stage = stage[warp];
+  C.regS = regS[warp];
+  C.prefetch = (L.grow_variant & 2) != 0;
   C.pix = pixAll + (size_t)f * L.P;
   C.regG = regAll + (size_t)f * L.P;
   C.sw = L.sw;
   C.sh = L.sh;
   C.lane = lane;
+#ifdef PLSLAM_GROW_PROF
+  long long prof[16];
+  for (int k = 0; k < 16; ++k) prof[k] = 0;
+  C.prof = prof;
+  const long long gp_k0 = clock64();
+  long long gp_t0 = 0;
+#endif
   const unsigned* seeds = seedsAll + (size_t)f * L.P;
   const int ns = nseeds[f];
   LsdRect* rects = rectsAll + (size_t)f * L.rect_cap;
@@ -540,11 +706,16 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LinePar
       if (lane == 0) C.reg_set(0, ((unsigned)(seed / L.sw) << 16) | (unsigned)(seed % L.sw));
       __syncwarp();
       double reg_angle;
-      int n = lsd_region_grow(C, L.prec, &reg_angle);
+      int n = (L.grow_variant & 1) ? lsd_region_grow_spec(C, L.prec, &reg_angle) : lsd_region_grow(C, L.prec, &reg_angle);
       if (n < L.min_reg_size) continue;
       LsdRect rec;
+      GP_START();
       lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
-      if (!lsd_refine(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th)) continue;
+      GP_ADD(2);
+      GP_START();
+      const bool keep = lsd_refine(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, L.grow_variant);
+      GP_ADD(3);
+      if (!keep) continue;
       if (nrect < L.rect_cap) {
         if (lane == 0) rects[nrect] = rec;
       } else if (lane == 0) {
@@ -554,7 +725,13 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LinePar
     }
   }
   if (lane == 0) nrects[f] = min(nrect, L.rect_cap);
+#ifdef PLSLAM_GROW_PROF
+  prof[4] = clock64() - gp_k0;
+  if (lane == 0)
+    for (int k = 0; k < 16; ++k) atomicAdd(&g_grow_prof[k], (unsigned long long)prof[k]);
+#endif
 }
+
 
 // ------------------------------------------------------------------------------------------
 // k_lsd_nfa: rect_improve() / rect_nfa() / nfa(), one warp per rectangle.  The row scan is the one
@@ -1079,6 +1256,15 @@ __global__ void __launch_bounds__(96) k_lbd(const __grid_constant__ LineParams L
 }
 
 }  // namespace
+#ifdef PLSLAM_GROW_PROF
+int debug_grow_prof(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_grow_prof, sizeof(g_grow_prof));
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_grow_prof, z, sizeof(z));
+  return 0;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -1147,6 +1333,10 @@ int LineExtractor::configure(int W, int H, int batch) {
   P.density_th = 0.7;
   P.log_eps = 0.0;
   P.max_lines = max_lines;
+  {  // experiment switch (default 3): bit 0 = in-batch speculation, bit 1 = L1 prefetch
+    const char* gv = std::getenv("PLSLAM_GROW_VARIANT");
+    P.grow_variant = gv ? std::atoi(gv) : 3;  // bit 0: in-batch speculation, bit 1: L1 prefetch of new region points' neighbourhoods
+  }
   // accepted rectangles per frame: ~1 per 300 scaled pixels on the synthetic frames; capacity 1 per 32, overflow is reported
   rect_cap = std::min(std::max(4096, P.P / 32), 1 << 17);
   P.rect_cap = rect_cap;
@@ -1201,6 +1391,7 @@ int LineExtractor::configure(int W, int H, int batch) {
   if ((rc = rowsum.ensure(B * P.out_cap * LBD_ROWS * 4 * sizeof(float)))) return rc;
   if ((rc = status.ensure(sizeof(int)))) return rc;
   PL_CHECK_ARG(P.sw < 65536 && P.sh < 32768);
+  PL_CARVEOUT(k_lsd_lgamma_table);
   k_lsd_lgamma_table<<<div_up(LGAMMA_TABLE, 256), 256>>>();
   PL_CUDA(cudaDeviceSynchronize());
   cfgW = W;
@@ -1224,39 +1415,51 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_CUDA(cudaMemsetAsync(maxg2.p, 0, (size_t)batch * sizeof(int), st));
   PL_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), st));
   PL_STAGE_BEGIN(timer, "lsd_scale", st);
+  PL_CARVEOUT(k_lsd_scale);
   k_lsd_scale<<<dim3(div_up(P.sw, ST_W), div_up(P.sh, ST_H), batch), 256, 0, st>>>(P, d_images, pitch, frame_stride,
                                                                                      coef.as<int>(), scaled.as<uint8_t>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_grad", st);
+  PL_CARVEOUT(k_lsd_grad);
   k_lsd_grad<<<dim3(div_up(P.sw, 32), div_up(P.sh, 8), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(),
                                                                              maxg2.as<int>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_rowhist", st);
+  PL_CARVEOUT(k_lsd_rowhist);
   k_lsd_rowhist<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_colscan", st);
+  PL_CARVEOUT(k_lsd_colscan);
   k_lsd_colscan<<<batch, LSD_BINS, 0, st>>>(P, rowhist.as<unsigned>(), binstart.as<unsigned>(), nseeds.as<int>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_scatter", st);
+  PL_CARVEOUT(k_lsd_scatter);
   k_lsd_scatter<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>(),
                                                               binstart.as<unsigned>(), seeds.as<unsigned>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
-  k_lsd_grow<<<batch, 32, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
+  P.batch = batch;
+  PL_CARVEOUT(k_lsd_grow);
+  k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
                                           rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());
   PL_STAGE_END(timer, st);
+  static const bool grow_only = std::getenv("PLSLAM_DEBUG_STOP_AFTER_GROW") != nullptr;  // profiling aid (tools/)
+  if (grow_only) return PLSLAM_OK;
   LsdSegment* rout = rectout.as<LsdSegment>();
   uint8_t* rvalid = reinterpret_cast<uint8_t*>(rout + (size_t)cfgB * P.rect_cap);
   PL_STAGE_BEGIN(timer, "lsd_nfa", st);
+  PL_CARVEOUT(k_lsd_nfa);
   k_lsd_nfa<<<dim3(div_up(P.rect_cap, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), rects.as<LsdRect>(), nrects.as<int>(),
                                                                 rout, rvalid);
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_finish", st);
+  PL_CARVEOUT(k_lsd_finish);
   k_lsd_finish<<<batch, 256, 0, st>>>(P, d_images, pitch, frame_stride, nrects.as<int>(), rout, rvalid,
                                             segs.as<LsdSegment>(), nsegs.as<int>(), resp.as<float>(), rowsum.as<float>(), d_keylines, d_desc,
                                             d_funcs, capacity, d_counts, status.as<int>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lbd", st);
+  PL_CARVEOUT(k_lbd);
   k_lbd<<<dim3(P.out_cap, batch), 96, 0, st>>>(P, d_images, pitch, frame_stride, d_keylines, d_counts, d_desc, capacity);
   PL_STAGE_END(timer, st);
   PL_CUDA(cudaGetLastError());
@@ -1349,3 +1552,6 @@ int LineExtractor::copy_segments(int frame, LsdSegment* out, int capacity, int* 
 }
 
 }  // namespace plslam
+#ifdef PLSLAM_GROW_PROF
+extern "C" int plslam_debug_grow_prof(unsigned long long* out16) { return plslam::debug_grow_prof(out16); }
+#endif

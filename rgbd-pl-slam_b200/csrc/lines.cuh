@@ -30,6 +30,8 @@ struct LineParams {
   int max_lines;       // keep the strongest max_lines by response (0 = keep all)
   int rect_cap;        // capacity of the per-frame rectangle / segment lists
   int out_cap;         // capacity of the per-frame output (keylines kept)
+  int batch;           // frames of the current launch
+  int grow_variant;    // k_lsd_grow neighbour scan: 0 = one accept per round, 1 = in-batch speculation
   float gaussL[LBD_W * 3], gaussG[LBD_ROWS];
 };
 

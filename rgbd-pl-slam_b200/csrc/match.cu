@@ -344,6 +344,7 @@ int plslam_descriptor_distance(const uint8_t* a, const uint8_t* b) {
 
 int plslam_match_knn2_batch_device(const plslam_knn_job_t* d_jobs, int njobs, int max_nq, void* stream) {
   PL_CHECK_ARG(d_jobs && njobs >= 1 && njobs <= 65535 && max_nq >= 1);
+  PL_CARVEOUT(k_knn2);
   k_knn2<<<dim3(div_up(max_nq, 256), njobs), 256, 0, (cudaStream_t)stream>>>(d_jobs);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;
@@ -389,6 +390,7 @@ int plslam_match_bow_batch_device(const plslam_bow_job_t* d_jobs, int njobs, int
     PL_CUDA(cudaFuncSetAttribute(k_projection, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
+  PL_CARVEOUT(k_bow);
   k_bow<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;
@@ -404,6 +406,7 @@ int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int nj
     PL_CUDA(cudaFuncSetAttribute(k_projection, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
+  PL_CARVEOUT(k_projection);
   k_projection<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;

@@ -997,6 +997,7 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
   PL_STAGE_BEGIN(timer, "orb_pyramid(7 launches)", st);
   for (int l = 1; l < nlevels; ++l) {
     dim3 grid(div_up(P.lv[l].w, 128), div_up(P.lv[l].h, 8), batch);
+    PL_CARVEOUT(k_resize);
     k_resize<<<grid, dim3(32, 8), 0, st>>>(P, I, l, coef.as<int>());
   }
   PL_STAGE_END(timer, st);
@@ -1009,6 +1010,7 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
       attr = true;
     }
     PL_STAGE_BEGIN(timer, "orb_fast", st);
+    PL_CARVEOUT(k_fast);
     k_fast<<<dim3(div_up(P.totalCells, 8), batch), 256, smem, st>>>(P, I, cand.as<unsigned long long>(),
                                                                     candCount.as<int>(), status.as<int>());
     PL_STAGE_END(timer, st);
@@ -1020,6 +1022,7 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
       return PLSLAM_ERR_INVALID;
     }
     PL_STAGE_BEGIN(timer, "orb_quadtree", st);
+    PL_CARVEOUT(k_quadtree);
     k_quadtree<<<dim3(nlevels, batch), 256, smem, st>>>(P, cand.as<unsigned long long>(), candCount.as<int>(),
                                                         knode.as<unsigned short>(), lvlKp.as<uint2>(), lvlCnt.as<int>());
     PL_STAGE_END(timer, st);
@@ -1041,10 +1044,12 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
     int rcm = blurMaps.ensure(sizeof(BlurMaps));
     if (rcm) return rcm;
     PL_CUDA(cudaMemcpyAsync(blurMaps.p, &M, sizeof(M), cudaMemcpyHostToDevice, st));
+    PL_CARVEOUT(k_blur);
     k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, blurMaps.as<BlurMaps>(), I, lvlCnt.as<int>());
   }
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "orb_orient_desc", st);
+  PL_CARVEOUT(k_orient_desc);
   k_orient_desc<<<dim3(div_up(P.maxKp, 8), batch), 256, 0, st>>>(P, I, lvlKp.as<uint2>(), lvlCnt.as<int>(), d_kps,
                                                                  d_desc, capacity, d_counts);
   PL_STAGE_END(timer, st);
