@@ -328,6 +328,41 @@ int plslam_voc_transform_device(const plslam_voc_t* h, const uint8_t* d_descript
 int plslam_voc_transform_host(const plslam_voc_t* h, const uint8_t* descriptors, int n, int levelsup, int32_t* word,
                               double* weight, int32_t* node);
 
+/* ------------------------------------------------------------------------------------------
+ * Frame post-extraction steps — what ORB_SLAM2::Frame::Frame (include/Frame.h:60, @0xf9370) runs on the
+ * extractor's output before any matcher can use it: UndistortKeyPoints (Frame.h:266, @0xfa0db),
+ * ComputeStereoFromRGBD (Frame.h:120, @0xfa0ea), AssignFeaturesToGrid / PosInGrid (Frame.h:273,110, @0xfa382)
+ * and, once per run, ComputeImageBounds (Frame.h:270, @0xfa27e).  Batched on the device so keypoints stay in HBM
+ * between extraction and plslam_match_projection_* (whose grid_start / grid_items layout this produces).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plslam_frame_calib {
+  float fx, fy, cx, cy;     /* mK (Camera.fx ... of the settings file, Examples/RGB-D/TUM1.yaml:8-11) */
+  float k1, k2, p1, p2, k3; /* mDistCoef (TUM1.yaml:13-17); k1 == 0 means "not distorted" as in UndistortKeyPoints */
+  float bf;                 /* mbf (Camera.bf, TUM1.yaml:26) */
+} plslam_frame_calib_t;
+
+/* ComputeImageBounds: bounds4 = mnMinX, mnMaxX, mnMinY, mnMaxY (undistorted image corners; the image itself if
+ * k1 == 0).  Four points once per run: host scalar arithmetic, the same double sequence as the device code. */
+int plslam_frame_image_bounds(const plslam_frame_calib_t* calib, int cols, int rows, float bounds4[4]);
+
+/* Per frame f of the batch, for its d_counts[f] keypoints (block layout [batch][kp_capacity] as produced by
+ * plslam_orb_extract_batch_device / plslam_frontend_process_device):
+ *   d_un_xy      [batch][kp_capacity][2]  mvKeysUn[i].pt
+ *   d_uright     [batch][kp_capacity]     mvuRight (-1 without depth)
+ *   d_depth_out  [batch][kp_capacity]     mvDepth  (-1 without depth)
+ *   d_grid_start [batch][64*48+1], d_grid_items [batch][kp_capacity]  CSR of mGrid in [ix][iy] order
+ * d_depth: float depth maps (imDepth after convertTo(CV_32F, mDepthMapFactor)), rows x depth_pitch floats per
+ * frame, frames depth_frame_stride floats apart (0 = one map shared by all frames). */
+int plslam_frame_post_batch_device(const plslam_frame_calib_t* calib, const float bounds4[4],
+                                   const plslam_keypoint_t* d_keypoints, const int32_t* d_counts, int batch,
+                                   int kp_capacity, const float* d_depth, int cols, int rows, int depth_pitch,
+                                   size_t depth_frame_stride, float* d_un_xy, float* d_uright, float* d_depth_out,
+                                   int32_t* d_grid_start, int32_t* d_grid_items, void* stream);
+/* One frame, HOST pointers (uploads, runs the kernel, copies the results back). */
+int plslam_frame_post_host(const plslam_frame_calib_t* calib, const float bounds4[4], const plslam_keypoint_t* keypoints,
+                           int n, const float* depth, int cols, int rows, int depth_pitch, float* un_xy, float* uright,
+                           float* depth_out, int32_t* grid_start, int32_t* grid_items);
+
 #ifdef __cplusplus
 }
 #endif

@@ -394,3 +394,37 @@ class VocReference:
     def forb_distance(a, b):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return dbow2_ref().dbow2_ref_forb_distance(_p(a), _p(b))
+
+
+# ---- Frame post-extraction steps (frame_oracle.cc) ----
+def _calib10(calib):
+    """calib: dict fx fy cx cy k1 k2 p1 p2 k3 bf -> 10 float32"""
+    return np.array([calib[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3", "bf")], np.float32)
+
+
+def undistort_points(calib, xy):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.empty_like(xy)
+    c = _calib10(calib)
+    lib().oracle_undistort_points(_p(c), _p(xy), len(xy), _p(out))
+    return out
+
+
+def image_bounds(calib, cols, rows):
+    b = np.empty(4, np.float32)
+    c = _calib10(calib)
+    lib().oracle_image_bounds(_p(c), cols, rows, _p(b))
+    return b
+
+
+def frame_post(calib, bounds, xy, depth):
+    """-> dict un_xy (n,2) f32, uright (n,), depth (n,), grid_start (64*48+1,), grid_items (inside-grid count,)"""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    depth = np.ascontiguousarray(depth, np.float32)
+    n = len(xy)
+    un, ur, z = np.empty((n, 2), np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+    gs, gi = np.empty(64 * 48 + 1, np.int32), np.empty(max(n, 1), np.int32)
+    c, b = _calib10(calib), np.ascontiguousarray(bounds, np.float32)
+    lib().oracle_frame_post(_p(c), _p(b), _p(xy), n, _p(depth), depth.shape[1], depth.shape[0], depth.strides[0] // 4,
+                            _p(un), _p(ur), _p(z), _p(gs), _p(gi))
+    return {"un_xy": un, "uright": ur, "depth": z, "grid_start": gs, "grid_items": gi[:gs[-1]]}

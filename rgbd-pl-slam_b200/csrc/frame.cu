@@ -1,0 +1,246 @@
+// frame.cu — the per-frame steps that follow extraction in ORB_SLAM2::Frame::Frame (reference include/Frame.h:60,
+// lib/libORB_SLAM2.so@0xf9370), batched on the device so the extractor's keypoints never leave HBM before matching:
+//   UndistortKeyPoints        Frame.h:266, call @0xfa0db   cv::undistortPoints(mat, mat, mK, mDistCoef, Mat(), mK)
+//   ComputeStereoFromRGBD     Frame.h:120, call @0xfa0ea   d = imDepth.at<float>((int)kp.y, (int)kp.x) on the DISTORTED
+//                                                           keypoint (@0xf6cd0-0xf6cd6); d > 0 => mvDepth = d,
+//                                                           mvuRight = kpUn.x - mbf / d (@0xf6ceb-0xf6d14)
+//   AssignFeaturesToGrid      Frame.h:273, call @0xfa382   PosInGrid: roundf((pt - min) * inv), 64 x 48 cells (@0xf5fa0)
+//   ComputeImageBounds        Frame.h:270, call @0xfa27e   (once per run: host scalar code on 4 corner points)
+// The grid is produced as the CSR ([ix][iy] order, keypoint indices ascending inside a cell, i.e. push_back order) that
+// plslam_match_projection_* consumes.  One CTA per frame; undistortion in double with individually rounded operations
+// (twin of oracle/frame_oracle.cc, which is pinned bit for bit against cv2 4.13's undistortPoints).
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace plslam {
+namespace {
+
+constexpr int GC = PLSLAM_GRID_COLS, GR = PLSLAM_GRID_ROWS, NCELL = GC * GR;
+
+struct FrameParams {
+  plslam_frame_calib_t c;
+  float minX, maxX, minY, maxY, wInv, hInv;
+  int cols, rows, dpitch;
+  size_t dstride;
+  int cap;
+};
+
+// one point of cv::undistortPoints(src, dst, K, D, noArray(), K): float in, float out, double inside
+__host__ __device__ inline void undistort_point(const plslam_frame_calib_t& c, float xf, float yf, float* ox, float* oy) {
+#ifdef __CUDA_ARCH__
+#define DM(a, b) __dmul_rn(a, b)
+#define DA(a, b) __dadd_rn(a, b)
+#define DS(a, b) __dsub_rn(a, b)
+#define DD(a, b) __ddiv_rn(a, b)
+#else
+#define DM(a, b) ((a) * (b))
+#define DA(a, b) ((a) + (b))
+#define DS(a, b) ((a) - (b))
+#define DD(a, b) ((a) / (b))
+#endif
+  const double fx = c.fx, fy = c.fy, cx = c.cx, cy = c.cy;
+  const double ifx = DD(1., fx), ify = DD(1., fy);
+  const double k0 = c.k1, k1 = c.k2, k2 = c.p1, k3 = c.p2, k4 = c.k3;
+  double x = xf, y = yf;
+  const double u = x, v = y;
+  x = DM(DS(x, cx), ifx);
+  y = DM(DS(y, cy), ify);
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = DA(DM(x, x), DM(y, y));
+    // k[5..11] are zero for the 4/5-coefficient model: the numerator is 1 + 0 and the thin-prism terms add +0.0
+    const double den = DA(1., DM(DA(DM(DA(DM(k4, r2), k1), r2), k0), r2));
+    const double icdist = DD(1., den);
+    if (icdist < 0) {
+      x = DM(DS(u, cx), ifx);
+      y = DM(DS(v, cy), ify);
+      break;
+    }
+    const double deltaX = DA(DM(DM(DM(2., k2), x), y), DM(k3, DA(r2, DM(DM(2., x), x))));
+    const double deltaY = DA(DM(k2, DA(r2, DM(DM(2., y), y))), DM(DM(DM(2., k3), x), y));
+    x = DM(DS(x0, deltaX), icdist);
+    y = DM(DS(y0, deltaY), icdist);
+  }
+  *ox = (float)DA(DM(fx, x), cx);
+  *oy = (float)DA(DM(fy, y), cy);
+#undef DM
+#undef DA
+#undef DS
+#undef DD
+}
+
+__device__ __forceinline__ int cell_of(const FrameParams& P, float x, float y) {
+  const int px = (int)roundf(__fmul_rn(__fsub_rn(x, P.minX), P.wInv));
+  const int py = (int)roundf(__fmul_rn(__fsub_rn(y, P.minY), P.hInv));
+  if (px < 0 || px >= GC || py < 0 || py >= GR) return -1;
+  return px * GR + py;
+}
+
+__global__ void __launch_bounds__(256) k_frame_post(const __grid_constant__ FrameParams P,
+                                                    const plslam_keypoint_t* __restrict__ kps,
+                                                    const int32_t* __restrict__ counts, const float* __restrict__ depth,
+                                                    float2* __restrict__ un_xy, float* __restrict__ uright,
+                                                    float* __restrict__ zdepth, int32_t* __restrict__ grid_start,
+                                                    int32_t* __restrict__ grid_items) {
+  __shared__ int cnt[NCELL];
+  __shared__ int fill[NCELL];
+  __shared__ int warp_tmp[33];
+  const int f = blockIdx.x, t = threadIdx.x;
+  const int n = min(counts[f], P.cap);
+  const plslam_keypoint_t* K = kps + (size_t)f * P.cap;
+  float2* U = un_xy + (size_t)f * P.cap;
+  float* R = uright + (size_t)f * P.cap;
+  float* Z = zdepth + (size_t)f * P.cap;
+  const float* D = depth + (size_t)f * P.dstride;
+  int32_t* GS = grid_start + (size_t)f * (NCELL + 1);
+  int32_t* GI = grid_items + (size_t)f * P.cap;
+  for (int c = t; c < NCELL; c += 256) {
+    cnt[c] = 0;
+    fill[c] = 0;
+  }
+  __syncthreads();
+  const bool distorted = P.c.k1 != 0.0f;  // mDistCoef.at<float>(0) == 0.0 -> mvKeysUn = mvKeys
+  for (int i = t; i < n; i += 256) {
+    const float x = K[i].x, y = K[i].y;
+    float ux = x, uy = y;
+    if (distorted) undistort_point(P.c, x, y, &ux, &uy);
+    U[i] = make_float2(ux, uy);
+    const int v = (int)y, u = (int)x;
+    float d = 0.f;
+    if (u >= 0 && v >= 0 && u < P.cols && v < P.rows) d = __ldg(D + (size_t)v * P.dpitch + u);
+    float z = -1.f, r = -1.f;
+    if (d > 0) {
+      z = d;
+      r = __fsub_rn(ux, __fdiv_rn(P.c.bf, d));
+    }
+    Z[i] = z;
+    R[i] = r;
+    const int c = cell_of(P, ux, uy);
+    if (c >= 0) atomicAdd(&cnt[c], 1);
+  }
+  __syncthreads();
+  const int total = block_scan_excl(cnt, NCELL, warp_tmp);  // cnt[c] = start of cell c
+  for (int c = t; c < NCELL; c += 256) GS[c] = cnt[c];
+  if (t == 0) GS[NCELL] = total;
+  __syncthreads();
+  for (int i = t; i < n; i += 256) {
+    const float2 p = U[i];
+    const int c = cell_of(P, p.x, p.y);
+    if (c >= 0) GI[cnt[c] + atomicAdd(&fill[c], 1)] = i;
+  }
+  __syncthreads();
+  // push_back order inside a cell = ascending keypoint index
+  for (int c = t; c < NCELL; c += 256) {
+    const int b = cnt[c], e = b + fill[c];
+    for (int i = b + 1; i < e; ++i) {
+      const int v = GI[i];
+      int j = i - 1;
+      while (j >= b && GI[j] > v) {
+        GI[j + 1] = GI[j];
+        --j;
+      }
+      GI[j + 1] = v;
+    }
+  }
+}
+
+int make_params(const plslam_frame_calib_t* calib, const float* bounds4, int cols, int rows, int dpitch, size_t dstride,
+                int cap, FrameParams* P) {
+  PL_CHECK_ARG(calib && bounds4 && cols > 0 && rows > 0 && dpitch >= cols && cap > 0);
+  PL_CHECK_ARG(bounds4[1] > bounds4[0] && bounds4[3] > bounds4[2]);
+  P->c = *calib;
+  P->minX = bounds4[0];
+  P->maxX = bounds4[1];
+  P->minY = bounds4[2];
+  P->maxY = bounds4[3];
+  // Frame::Frame: mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (mnMaxX - mnMinX)
+  P->wInv = (float)GC / (bounds4[1] - bounds4[0]);
+  P->hInv = (float)GR / (bounds4[3] - bounds4[2]);
+  P->cols = cols;
+  P->rows = rows;
+  P->dpitch = dpitch;
+  P->dstride = dstride;
+  P->cap = cap;
+  return PLSLAM_OK;
+}
+
+}  // namespace
+}  // namespace plslam
+
+using namespace plslam;
+
+extern "C" {
+
+int plslam_frame_image_bounds(const plslam_frame_calib_t* calib, int cols, int rows, float bounds4[4]) {
+  PL_CHECK_ARG(calib && bounds4 && cols > 0 && rows > 0);
+  if (calib->k1 != 0.0f) {
+    const float corners[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+    float m[8];
+    for (int i = 0; i < 4; ++i) undistort_point(*calib, corners[2 * i], corners[2 * i + 1], &m[2 * i], &m[2 * i + 1]);
+    bounds4[0] = std::min(m[0], m[4]);
+    bounds4[1] = std::max(m[2], m[6]);
+    bounds4[2] = std::min(m[1], m[3]);
+    bounds4[3] = std::max(m[5], m[7]);
+  } else {
+    bounds4[0] = 0.f;
+    bounds4[1] = (float)cols;
+    bounds4[2] = 0.f;
+    bounds4[3] = (float)rows;
+  }
+  return PLSLAM_OK;
+}
+
+int plslam_frame_post_batch_device(const plslam_frame_calib_t* calib, const float bounds4[4],
+                                   const plslam_keypoint_t* d_keypoints, const int32_t* d_counts, int batch,
+                                   int kp_capacity, const float* d_depth, int cols, int rows, int depth_pitch,
+                                   size_t depth_frame_stride, float* d_un_xy, float* d_uright, float* d_depth_out,
+                                   int32_t* d_grid_start, int32_t* d_grid_items, void* stream) {
+  PL_CHECK_ARG(d_keypoints && d_counts && d_depth && d_un_xy && d_uright && d_depth_out && d_grid_start && d_grid_items);
+  PL_CHECK_ARG(batch >= 1 && batch <= 65535);
+  FrameParams P;
+  int rc = make_params(calib, bounds4, cols, rows, depth_pitch, depth_frame_stride, kp_capacity, &P);
+  if (rc) return rc;
+  PL_CARVEOUT(k_frame_post);
+  k_frame_post<<<batch, 256, 0, (cudaStream_t)stream>>>(P, d_keypoints, d_counts, d_depth,
+                                                        reinterpret_cast<float2*>(d_un_xy), d_uright, d_depth_out,
+                                                        d_grid_start, d_grid_items);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_frame_post_host(const plslam_frame_calib_t* calib, const float bounds4[4], const plslam_keypoint_t* keypoints,
+                           int n, const float* depth, int cols, int rows, int depth_pitch, float* un_xy, float* uright,
+                           float* depth_out, int32_t* grid_start, int32_t* grid_items) {
+  PL_CHECK_ARG(keypoints && depth && un_xy && uright && depth_out && grid_start && grid_items && n >= 0);
+  const int cap = std::max(n, 1);
+  struct Scoped : DevBuf {
+    ~Scoped() { release(); }
+  } dk, dc, dd, du, dr, dz, gs, gi;
+  int rc;
+  if ((rc = dk.ensure((size_t)cap * sizeof(plslam_keypoint_t))) || (rc = dc.ensure(4)) ||
+      (rc = dd.ensure((size_t)rows * depth_pitch * 4)) || (rc = du.ensure((size_t)cap * 8)) ||
+      (rc = dr.ensure((size_t)cap * 4)) || (rc = dz.ensure((size_t)cap * 4)) ||
+      (rc = gs.ensure((size_t)(NCELL + 1) * 4)) || (rc = gi.ensure((size_t)cap * 4)))
+    return rc;
+  const int32_t cnt = n;
+  if (n) PL_CUDA(cudaMemcpy(dk.p, keypoints, (size_t)n * sizeof(plslam_keypoint_t), cudaMemcpyHostToDevice));
+  PL_CUDA(cudaMemcpy(dc.p, &cnt, 4, cudaMemcpyHostToDevice));
+  PL_CUDA(cudaMemcpy(dd.p, depth, (size_t)rows * depth_pitch * 4, cudaMemcpyHostToDevice));
+  rc = plslam_frame_post_batch_device(calib, bounds4, dk.as<plslam_keypoint_t>(), dc.as<int32_t>(), 1, cap, dd.as<float>(),
+                                      cols, rows, depth_pitch, 0, du.as<float>(), dr.as<float>(), dz.as<float>(),
+                                      gs.as<int32_t>(), gi.as<int32_t>(), nullptr);
+  if (rc) return rc;
+  PL_CUDA(cudaDeviceSynchronize());
+  if (n) {
+    PL_CUDA(cudaMemcpy(un_xy, du.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    PL_CUDA(cudaMemcpy(uright, dr.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    PL_CUDA(cudaMemcpy(depth_out, dz.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  PL_CUDA(cudaMemcpy(grid_start, gs.p, (size_t)(NCELL + 1) * 4, cudaMemcpyDeviceToHost));
+  if (n) PL_CUDA(cudaMemcpy(grid_items, gi.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+}  // extern "C"

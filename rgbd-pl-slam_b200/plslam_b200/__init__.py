@@ -547,3 +547,84 @@ def assemble_bow(word, weight, node):
         start.append(len(idx))
     return dict(bow_ids=np.array(ids, np.uint32), bow_vals=np.array(vals, np.float64), fv_nodes=np.array(nodes, np.uint32),
                 fv_start=np.array(start, np.int32), fv_idx=np.array(idx, np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------
+# Frame post-extraction steps (reference include/Frame.h:110-120,266-273): undistortion, RGB-D stereo
+# coordinates, grid assignment
+# ------------------------------------------------------------------------------------------------
+class FrameCalib(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3", "bf")]
+
+    @classmethod
+    def from_dict(cls, d):
+        return cls(*[float(d.get(n, 0.0)) for n, _ in cls._fields_])
+
+
+TUM1_CALIB = dict(fx=517.306408, fy=516.469215, cx=318.643040, cy=255.313989, k1=0.262383, k2=-0.953104,
+                  p1=-0.005358, p2=0.002628, k3=1.163314, bf=40.0)  # reference Examples/RGB-D/TUM1.yaml:8-26
+
+
+def frame_image_bounds(calib, cols, rows):
+    """Frame::ComputeImageBounds -> float32[4] mnMinX, mnMaxX, mnMinY, mnMaxY."""
+    c = calib if isinstance(calib, FrameCalib) else FrameCalib.from_dict(calib)
+    b = np.empty(4, np.float32)
+    _check(lib().plslam_frame_image_bounds(C.byref(c), int(cols), int(rows), _vp(b)))
+    return b
+
+
+def frame_post_device(calib, bounds, d_keypoints, d_counts, d_depth, out=None, stream=None):
+    """Batched UndistortKeyPoints + ComputeStereoFromRGBD + AssignFeaturesToGrid on device tensors.
+    d_keypoints [B][cap][7] int32 view of cv::KeyPoint, d_counts [B] int32, d_depth [B or 1][H][W] float32."""
+    import torch
+    c = calib if isinstance(calib, FrameCalib) else FrameCalib.from_dict(calib)
+    B, cap = d_keypoints.shape[0], d_keypoints.shape[1]
+    assert d_depth.dtype == torch.float32 and d_depth.dim() == 3 and d_depth.stride(2) == 1
+    H, W = d_depth.shape[1], d_depth.shape[2]
+    dev = d_keypoints.device
+    if out is None:
+        out = dict(un_xy=torch.empty((B, cap, 2), dtype=torch.float32, device=dev),
+                   uright=torch.empty((B, cap), dtype=torch.float32, device=dev),
+                   depth=torch.empty((B, cap), dtype=torch.float32, device=dev),
+                   grid_start=torch.empty((B, 64 * 48 + 1), dtype=torch.int32, device=dev),
+                   grid_items=torch.empty((B, cap), dtype=torch.int32, device=dev))
+    b = np.ascontiguousarray(bounds, np.float32)
+    stride = d_depth.stride(0) if d_depth.shape[0] > 1 else 0
+    _check(lib().plslam_frame_post_batch_device(C.byref(c), _vp(b), _vp(d_keypoints), _vp(d_counts), B, cap, _vp(d_depth),
+                                                W, H, d_depth.stride(1), C.c_size_t(stride), _vp(out["un_xy"]),
+                                                _vp(out["uright"]), _vp(out["depth"]), _vp(out["grid_start"]),
+                                                _vp(out["grid_items"]), _stream_ptr(stream)))
+    return out
+
+
+def frame_post_host(calib, bounds, keypoints, depth):
+    """One frame, numpy in / numpy out (KP_DTYPE keypoints, float32 depth map)."""
+    c = calib if isinstance(calib, FrameCalib) else FrameCalib.from_dict(calib)
+    kps = np.ascontiguousarray(keypoints, KP_DTYPE)
+    depth = np.ascontiguousarray(depth, np.float32)
+    n = len(kps)
+    un, ur, z = np.empty((n, 2), np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+    gs, gi = np.empty(64 * 48 + 1, np.int32), np.empty(max(n, 1), np.int32)
+    b = np.ascontiguousarray(bounds, np.float32)
+    _check(lib().plslam_frame_post_host(C.byref(c), _vp(b), _vp(kps), n, _vp(depth), depth.shape[1], depth.shape[0],
+                                        depth.strides[0] // 4, _vp(un), _vp(ur), _vp(z), _vp(gs), _vp(gi)))
+    return dict(un_xy=un, uright=ur, depth=z, grid_start=gs, grid_items=gi[:gs[-1]])
+
+
+def search_by_projection_host(last, cur, cam, scale_factors, tcw_cur, tcw_last, th, mono=False, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on host arrays (dict layout of tests/matchdata.py)
+    through plslam_match_projection_host -> (match_cur, nmatches)."""
+    keep = {k: np.ascontiguousarray(v) for k, v in list(last.items()) + [("c_" + k, v) for k, v in cur.items()]}
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    n1, n2 = len(last["desc"]), len(cur["desc"])
+    m, n = np.empty(max(n2, 1), np.int32), np.zeros(1, np.int32)
+    p = lambda a: a.ctypes.data
+    j = ProjJob(p(keep["valid"]), p(keep["xyz"]), p(keep["desc"]), p(keep["octave"]), p(keep["angle"]), p(keep["obs"]),
+                p(keep["c_xy"]), p(keep["c_octave"]), p(keep["c_angle"]), p(keep["c_desc"]), p(keep["c_uright"]),
+                p(keep["c_taken"]), p(keep["c_grid_start"]), p(keep["c_grid_items"]), p(sf), p(m), p(n))
+    j.cam[:] = np.asarray(cam, np.float32).tolist()
+    j.tcw_cur[:] = np.asarray(tcw_cur, np.float32).ravel().tolist()
+    j.tcw_last[:] = np.asarray(tcw_last, np.float32).ravel().tolist()
+    j.th = float(th); j.n1 = n1; j.n2 = n2; j.mono = int(mono); j.check_orientation = int(check_ori)
+    _check(lib().plslam_match_projection_host(C.byref(j), len(sf)))
+    return m[:n2], int(n[0])
