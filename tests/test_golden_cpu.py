@@ -1,0 +1,90 @@
+"""The oracle against the COMMITTED golden vectors of tests/golden/ (made by tests/golden/make_golden.py from cv2 4.13,
+from the reference's own DBoW2 sources and from constants of the reference binary).  Nothing here imports cv2 or reads
+/root/reference: this is the pin that travels to the GPU box."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def prim():
+    return np.load(os.path.join(G, "cv2_primitives.npz"))
+
+
+def test_reference_binary_constants(oracle):
+    import plslam_b200 as pl
+    c = json.load(open(os.path.join(G, "reference_binary.json")))
+    p = oracle.orb_pattern().astype("<i4")
+    assert hashlib.sha256(p.tobytes()).hexdigest() == c["bit_pattern_31_sha256"]
+    assert p[:16].tolist() == c["bit_pattern_31_first16"]
+    assert (pl.TH_LOW, pl.TH_HIGH, pl.HISTO_LENGTH) == (c["TH_LOW"], c["TH_HIGH"], c["HISTO_LENGTH"]) == (50, 100, 30)
+
+
+def test_resize_blur_fast_atan2(oracle, prim):
+    assert np.array_equal(oracle.resize_linear(prim["img"], 133, 107), prim["resize_img_133x107"])
+    assert np.array_equal(oracle.resize_linear(prim["noise"], 69, 51), prim["resize_noise_69x51"])
+    assert np.array_equal(oracle.blur7(prim["img"]), prim["blur_img"])
+    assert np.array_equal(oracle.blur7(prim["noise"]), prim["blur_noise"])
+    cell = np.ascontiguousarray(prim["img"][16:54, 100:137])
+    for th in (20, 7):
+        assert np.array_equal(oracle.fast9(prim["img"], th), prim["fast%d_img" % th])
+        assert np.array_equal(oracle.fast9(cell, th), prim["fast%d_cell" % th])
+    assert len(prim["fast20_img"]) > 20 and len(prim["fast7_img"]) > len(prim["fast20_img"])
+    mine = np.array([oracle.fast_atan2(y, x) for y, x in prim["atan2_yx"]], np.float32)
+    assert np.array_equal(mine, prim["atan2_deg"])
+
+
+def test_undistort_points(oracle, prim):
+    c = prim["undist_calib"]
+    cal = dict(zip(("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3"), [float(v) for v in c]), bf=40.0)
+    assert np.array_equal(oracle.undistort_points(cal, prim["undist_in"]), prim["undist_out"])
+
+
+def test_lsd_front_half(oracle, prim):
+    k = oracle.gauss_table_u8(0.75, 7)
+    assert np.array_equal(oracle.gauss_blur_u8(prim["noise"], k), prim["lsd_blur_noise"])
+    b = oracle.gauss_blur_u8(prim["img"], k)
+    ref = prim["lsd_scaled_img"]
+    assert np.array_equal(oracle.resize_linear_exact(b, ref.shape[1], ref.shape[0], 0.8), ref)
+
+
+def test_lsd_segments_identical_to_cv2(oracle):
+    g = np.load(os.path.join(G, "cv2_lsd.npz"))
+    for i in range(2):
+        mine, _ = oracle.lsd_detect(g["img%d" % i], compat=1)  # libm trig mode = what cv2 computes
+        assert len(mine) == len(g["lines%d" % i]) > 20
+        assert np.array_equal(mine[:, :4].astype(np.float32), g["lines%d" % i])
+        assert np.array_equal(mine[:, 4], g["width%d" % i])
+        assert np.array_equal(mine[:, 5], g["prec%d" % i])
+        assert np.allclose(mine[:, 6], g["nfa%d" % i], rtol=0, atol=1e-9)
+        # the pinned-trig mode (the one the CUDA path reproduces) agrees on (nearly) every segment
+        pinned, _ = oracle.lsd_detect(g["img%d" % i], compat=0)
+        s = {tuple(np.float32(r[:4])) for r in pinned}
+        assert sum(tuple(r) in s for r in g["lines%d" % i]) >= len(g["lines%d" % i]) - 2
+
+
+def test_bow_transform_equals_reference_dbow2(oracle):
+    g = np.load(os.path.join(G, "dbow2_ref.npz"))
+    voc = oracle.VocOracle(os.path.join(G, "voc_k6_L3.txt"))
+    desc = g["desc"]
+    for lu in (0, 1, 2):
+        t = voc.transform(desc, lu)
+        for k, v in t.items():
+            assert np.array_equal(v, g["lu%d_%s" % (lu, k)]), (lu, k)
+    d = np.array([oracle.descriptor_distance(a, b) for a, b in zip(desc[:200], desc[200:])], np.int32)
+    assert np.array_equal(d, g["forb_distance"])
+
+
+def test_product_host_pieces_against_golden():
+    """Host-side scalar pieces of the product (no GPU needed): DescriptorDistance, vocabulary loader + BoW assembly use the
+    same golden data through the C-ABI where no device is required."""
+    import plslam_b200 as pl
+    g = np.load(os.path.join(G, "dbow2_ref.npz"))
+    desc = g["desc"]
+    d = np.array([pl.DescriptorDistance(a, b) for a, b in zip(desc[:200], desc[200:])], np.int32)
+    assert np.array_equal(d, g["forb_distance"])
