@@ -328,6 +328,26 @@ int plslam_voc_transform_device(const plslam_voc_t* h, const uint8_t* d_descript
 int plslam_voc_transform_host(const plslam_voc_t* h, const uint8_t* descriptors, int n, int levelsup, int32_t* word,
                               double* weight, int32_t* node);
 
+/* Frame::ComputeBoW for a whole batch on the extractor's block layout ([frames][capacity][32] descriptors with
+ * d_counts[f] valid rows): the descent of every descriptor plus the assembly of each frame's FeatureVector
+ * (`if (w > 0) fv.addFeature(nid, i)`, TemplatedVocabulary.h:1196-1213) as a CSR — d_fv_nodes [frames][capacity]
+ * ascending node ids, d_fv_start [frames][capacity+1], d_fv_idx [frames][capacity] feature indices ascending inside
+ * a node, d_fv_count [frames] number of nodes — i.e. exactly the arrays plslam_bow_job_t takes.  d_word / d_weight /
+ * d_node are [frames][capacity] (BowVector accumulation stays with the caller: plslam_voc_transform_* semantics). */
+int plslam_voc_featvec_batch_device(const plslam_voc_t* h, const uint8_t* d_descriptors, const int32_t* d_counts, int frames,
+                                    int capacity, int levelsup, int32_t* d_word, double* d_weight, int32_t* d_node,
+                                    int32_t* d_fv_nodes, int32_t* d_fv_start, int32_t* d_fv_idx, int32_t* d_fv_count,
+                                    void* stream);
+/* ORBmatcher::SearchByBoW on the frame pairs of a batch without a host round trip (config C4): pair p matches
+ * "keyframe" = frame 2p against frame 2p+1.  d_kf_valid [frames][capacity] = pMP && !pMP->isBad() per keyframe
+ * feature.  d_match [npairs][capacity] (index into frame 2p per feature of frame 2p+1, -1 = none), d_nmatches [npairs].
+ * Scratch: d_angle_scratch 2*npairs*capacity floats, d_jobs_scratch npairs jobs. */
+int plslam_match_bow_pairs_device(const plslam_keypoint_t* d_keypoints, const uint8_t* d_descriptors, const int32_t* d_counts,
+                                  int capacity, int npairs, const int32_t* d_fv_nodes, const int32_t* d_fv_start,
+                                  const int32_t* d_fv_idx, const int32_t* d_fv_count, const uint8_t* d_kf_valid,
+                                  float nnratio, int check_orientation, float* d_angle_scratch, plslam_bow_job_t* d_jobs_scratch,
+                                  int32_t* d_match, int32_t* d_nmatches, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Frame post-extraction steps — what ORB_SLAM2::Frame::Frame (include/Frame.h:60, @0xf9370) runs on the
  * extractor's output before any matcher can use it: UndistortKeyPoints (Frame.h:266, @0xfa0db),

@@ -63,6 +63,139 @@ __global__ void __launch_bounds__(128) k_bow_transform(VocDev V, const uint8_t* 
   node[i] = nid;
 }
 
+
+// Batched form on the extractor's block layout [frames][capacity][32]: one launch for every descriptor of a batch.
+__global__ void __launch_bounds__(128) k_bow_transform_batch(VocDev V, const uint8_t* __restrict__ desc,
+                                                             const int32_t* __restrict__ counts, int capacity, int levelsup,
+                                                             int32_t* __restrict__ word, double* __restrict__ weight,
+                                                             int32_t* __restrict__ node) {
+  const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= min(counts[f], capacity)) return;
+  const size_t o = (size_t)f * capacity + i;
+  const uint4* F = reinterpret_cast<const uint4*>(desc) + 2 * o;
+  const uint4 f0 = F[0], f1 = F[1];
+  const int nid_level = V.L - levelsup;
+  int nid = 0, final_id = 0, level = 0;
+  int c0 = V.child_start[0], c1 = V.child_start[1];
+  do {
+    ++level;
+    int best_id = __ldg(V.child_idx + c0);
+    int best = hamming256(f0, f1, __ldg(V.desc + 2 * (size_t)best_id), __ldg(V.desc + 2 * (size_t)best_id + 1));
+    for (int c = c0 + 1; c < c1; ++c) {
+      const int id = __ldg(V.child_idx + c);
+      const int d = hamming256(f0, f1, __ldg(V.desc + 2 * (size_t)id), __ldg(V.desc + 2 * (size_t)id + 1));
+      if (d < best) { best = d; best_id = id; }
+    }
+    final_id = best_id;
+    if (level == nid_level) nid = final_id;
+    c0 = __ldg(V.child_start + final_id);
+    c1 = __ldg(V.child_start + final_id + 1);
+  } while (c1 > c0);
+  word[o] = V.word[final_id];
+  weight[o] = V.weight[final_id];
+  node[o] = nid;
+}
+
+// FeatureVector assembly (TemplatedVocabulary.h:1196-1213: `if(w > 0) fv.addFeature(nid, i)` in feature order into a
+// std::map<NodeId, vector<unsigned>>) as a CSR per frame: nodes ascending, feature indices ascending inside a node.
+// One CTA per frame: bitonic sort of (node << 32 | i) keys in shared memory, heads by comparison with the left
+// neighbour, ranks by a block scan.
+__global__ void __launch_bounds__(256) k_featvec_csr(const int32_t* __restrict__ node, const double* __restrict__ weight,
+                                                     const int32_t* __restrict__ counts, int capacity, int npow2,
+                                                     int32_t* __restrict__ fv_nodes, int32_t* __restrict__ fv_start,
+                                                     int32_t* __restrict__ fv_idx, int32_t* __restrict__ fv_count) {
+  extern __shared__ unsigned long long fv_smem[];
+  unsigned long long* key = fv_smem;
+  int* head = reinterpret_cast<int*>(key + npow2);
+  int* warp_tmp = head + npow2;
+  const int f = blockIdx.x, t = threadIdx.x;
+  const int n = min(counts[f], capacity);
+  const size_t o = (size_t)f * capacity;
+  for (int i = t; i < npow2; i += 256) {
+    unsigned long long k = ~0ull;
+    if (i < n && weight[o + i] > 0) k = ((unsigned long long)(unsigned)node[o + i] << 32) | (unsigned)i;
+    key[i] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < npow2; i += 256) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = key[i], b = key[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            key[i] = b;
+            key[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = t; i < npow2; i += 256) {
+    const unsigned long long k = key[i];
+    head[i] = (k != ~0ull && (i == 0 || (unsigned)(key[i - 1] >> 32) != (unsigned)(k >> 32))) ? 1 : 0;
+  }
+  __syncthreads();
+  const int nuniq = block_scan_excl(head, npow2, warp_tmp);  // head[i] = rank of the node of entry i (at head entries)
+  int32_t* N = fv_nodes + o;
+  int32_t* S = fv_start + (size_t)f * (capacity + 1);
+  int32_t* I = fv_idx + o;
+  int m = 0;
+  for (int i = t; i < npow2; i += 256) {
+    const unsigned long long k = key[i];
+    if (k == ~0ull) continue;
+    I[i] = (int32_t)(unsigned)k;
+    const bool isHead = i == 0 || (unsigned)(key[i - 1] >> 32) != (unsigned)(k >> 32);
+    if (isHead) {
+      N[head[i]] = (int32_t)(unsigned)(k >> 32);
+      S[head[i]] = i;
+    }
+    if (i + 1 == npow2 || key[i + 1] == ~0ull) m = i + 1;  // last valid entry
+  }
+  if (m) S[nuniq] = m;
+  if (t == 0) {
+    fv_count[f] = nuniq;
+    if (nuniq == 0) S[0] = 0;
+  }
+}
+
+__global__ void k_kp_angles(const plslam_keypoint_t* __restrict__ kps, size_t n, float* __restrict__ angle) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) angle[i] = kps[i].angle;
+}
+
+// SearchByBoW jobs of the frame pairs (2p = "keyframe", 2p+1 = current frame) of a batch, built on the device
+__global__ void k_make_bow_jobs(int npairs, int capacity, const uint8_t* desc, const float* angle, const uint8_t* valid,
+                                const int32_t* counts, const int32_t* fv_nodes, const int32_t* fv_start, const int32_t* fv_idx,
+                                const int32_t* fv_count, int32_t* match, int32_t* nmatches, float nnratio, int check_ori,
+                                plslam_bow_job_t* jobs) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const size_t a = (size_t)(2 * p) * capacity, b = (size_t)(2 * p + 1) * capacity;
+  plslam_bow_job_t j;
+  j.kf_desc = desc + a * 32;
+  j.kf_angle = angle + a;
+  j.kf_valid = valid + a;
+  j.kf_nodes = fv_nodes + a;
+  j.kf_start = fv_start + (size_t)(2 * p) * (capacity + 1);
+  j.kf_idx = fv_idx + a;
+  j.f_desc = desc + b * 32;
+  j.f_angle = angle + b;
+  j.f_nodes = fv_nodes + b;
+  j.f_start = fv_start + (size_t)(2 * p + 1) * (capacity + 1);
+  j.f_idx = fv_idx + b;
+  j.match_f = match + (size_t)p * capacity;
+  j.nmatches = nmatches + p;
+  j.n1 = min(counts[2 * p], capacity);
+  j.n2 = min(counts[2 * p + 1], capacity);
+  j.n_kf_nodes = fv_count[2 * p];
+  j.n_f_nodes = fv_count[2 * p + 1];
+  j.nnratio = nnratio;
+  j.check_orientation = check_ori;
+  jobs[p] = j;
+}
+
 }  // namespace
 
 struct Vocabulary {
@@ -273,6 +406,50 @@ int plslam_voc_transform_host(const plslam_voc_t* h, const uint8_t* descriptors,
   if (rc) return rc;
   if (e != cudaSuccess) { set_error("voc transform host path: %s", cudaGetErrorString(e)); return PLSLAM_ERR_CUDA; }
   return PLSLAM_OK;
+}
+
+int plslam_voc_featvec_batch_device(const plslam_voc_t* h, const uint8_t* d_descriptors, const int32_t* d_counts, int frames,
+                                    int capacity, int levelsup, int32_t* d_word, double* d_weight, int32_t* d_node,
+                                    int32_t* d_fv_nodes, int32_t* d_fv_start, int32_t* d_fv_idx, int32_t* d_fv_count,
+                                    void* stream) {
+  PL_CHECK_ARG(h && d_descriptors && d_counts && d_word && d_weight && d_node && d_fv_nodes && d_fv_start && d_fv_idx && d_fv_count);
+  PL_CHECK_ARG(frames >= 1 && frames <= 65535 && capacity >= 1 && capacity <= 16384);
+  cudaStream_t st = (cudaStream_t)stream;
+  PL_CARVEOUT(k_bow_transform_batch);
+  k_bow_transform_batch<<<dim3(div_up(capacity, 128), frames), 128, 0, st>>>(h->v.dev, d_descriptors, d_counts, capacity,
+                                                                              levelsup, d_word, d_weight, d_node);
+  int npow2 = 32;
+  while (npow2 < capacity) npow2 <<= 1;
+  const size_t smem = (size_t)npow2 * 12 + 33 * 4;
+  static bool attr = false;
+  if (!attr) {
+    PL_CUDA(cudaFuncSetAttribute(k_featvec_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  PL_CARVEOUT(k_featvec_csr);
+  k_featvec_csr<<<frames, 256, smem, st>>>(d_node, d_weight, d_counts, capacity, npow2, d_fv_nodes, d_fv_start, d_fv_idx,
+                                           d_fv_count);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_match_bow_pairs_device(const plslam_keypoint_t* d_keypoints, const uint8_t* d_descriptors, const int32_t* d_counts,
+                                  int capacity, int npairs, const int32_t* d_fv_nodes, const int32_t* d_fv_start,
+                                  const int32_t* d_fv_idx, const int32_t* d_fv_count, const uint8_t* d_kf_valid,
+                                  float nnratio, int check_orientation, float* d_angle_scratch, plslam_bow_job_t* d_jobs_scratch,
+                                  int32_t* d_match, int32_t* d_nmatches, void* stream) {
+  PL_CHECK_ARG(d_keypoints && d_descriptors && d_counts && d_fv_nodes && d_fv_start && d_fv_idx && d_fv_count && d_kf_valid);
+  PL_CHECK_ARG(d_angle_scratch && d_jobs_scratch && d_match && d_nmatches && capacity >= 1 && npairs >= 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)2 * npairs * capacity;
+  PL_CARVEOUT(k_kp_angles);
+  k_kp_angles<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_keypoints, n, d_angle_scratch);
+  PL_CARVEOUT(k_make_bow_jobs);
+  k_make_bow_jobs<<<div_up(npairs, 128), 128, 0, st>>>(npairs, capacity, d_descriptors, d_angle_scratch, d_kf_valid, d_counts,
+                                                       d_fv_nodes, d_fv_start, d_fv_idx, d_fv_count, d_match, d_nmatches,
+                                                       nnratio, check_orientation, d_jobs_scratch);
+  PL_CUDA(cudaGetLastError());
+  return plslam_match_bow_batch_device(d_jobs_scratch, npairs, capacity, stream);
 }
 
 }  // extern "C"

@@ -511,6 +511,22 @@ class ORBVocabulary:
                                                  _stream_ptr(stream)))
         return word, weight, node
 
+    def featvec_batch_device(self, d_desc, d_counts, levelsup=4, out=None, stream=None):
+        """Frame::ComputeBoW for a batch: d_desc [B][cap][32] uint8, d_counts [B] -> dict of device tensors word, weight,
+        node [B][cap], fv_nodes [B][cap], fv_start [B][cap+1], fv_idx [B][cap], fv_count [B]."""
+        import torch
+        B, cap = d_desc.shape[0], d_desc.shape[1]
+        dev = d_desc.device
+        if out is None:
+            i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+            out = dict(word=i32(B, cap), weight=torch.empty((B, cap), dtype=torch.float64, device=dev), node=i32(B, cap),
+                       fv_nodes=i32(B, cap), fv_start=i32(B, cap + 1), fv_idx=i32(B, cap), fv_count=i32(B))
+        _check(lib().plslam_voc_featvec_batch_device(self._h, _vp(d_desc), _vp(d_counts), B, cap, int(levelsup), _vp(out["word"]),
+                                                     _vp(out["weight"]), _vp(out["node"]), _vp(out["fv_nodes"]),
+                                                     _vp(out["fv_start"]), _vp(out["fv_idx"]), _vp(out["fv_count"]),
+                                                     _stream_ptr(stream)))
+        return out
+
     def transform_features(self, desc, levelsup=4):
         desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
         n = len(desc)
@@ -628,3 +644,24 @@ def search_by_projection_host(last, cur, cam, scale_factors, tcw_cur, tcw_last, 
     j.th = float(th); j.n1 = n1; j.n2 = n2; j.mono = int(mono); j.check_orientation = int(check_ori)
     _check(lib().plslam_match_projection_host(C.byref(j), len(sf)))
     return m[:n2], int(n[0])
+
+
+def bow_pairs_device(d_kps, d_desc, d_counts, fv, d_kf_valid=None, nnratio=0.7, check_ori=True, out=None, stream=None):
+    """ORBmatcher::SearchByBoW on the frame pairs (2p, 2p+1) of a batch, everything device-resident.
+    fv = ORBVocabulary.featvec_batch_device(...) -> dict(match [B/2][cap] int32, nmatches [B/2] int32)."""
+    import torch
+    B, cap = d_desc.shape[0], d_desc.shape[1]
+    npairs = B // 2
+    dev = d_desc.device
+    if d_kf_valid is None:
+        d_kf_valid = torch.ones((B, cap), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = dict(match=torch.empty((npairs, cap), dtype=torch.int32, device=dev),
+                   nmatches=torch.empty((npairs,), dtype=torch.int32, device=dev),
+                   _angle=torch.empty((B, cap), dtype=torch.float32, device=dev),
+                   _jobs=torch.empty((npairs, C.sizeof(BowJob)), dtype=torch.uint8, device=dev), _valid=d_kf_valid)
+    _check(lib().plslam_match_bow_pairs_device(_vp(d_kps), _vp(d_desc), _vp(d_counts), cap, npairs, _vp(fv["fv_nodes"]),
+                                               _vp(fv["fv_start"]), _vp(fv["fv_idx"]), _vp(fv["fv_count"]), _vp(d_kf_valid),
+                                               C.c_float(nnratio), int(check_ori), _vp(out["_angle"]), _vp(out["_jobs"]),
+                                               _vp(out["match"]), _vp(out["nmatches"]), _stream_ptr(stream)))
+    return out

@@ -85,3 +85,52 @@ def test_search_by_bow_with_real_feature_vectors(oracle, voc):
     pl.bow_batch_device([job], max(len(da), len(db)), "cuda")
     torch.cuda.synchronize()
     assert int(n) == en and np.array_equal(m.cpu().numpy(), em) and en > 30
+
+
+def test_c4_device_chain_extract_bow_search(oracle, voc):
+    """Config C4 without host round trips: batched extraction -> ComputeBoW (descent + FeatureVector CSR on the device) ->
+    SearchByBoW on the frame pairs of the batch, against the oracle chain (ORB oracle -> vocabulary oracle -> SearchByBoW
+    oracle) pair by pair."""
+    import torch
+    import plslam_b200 as pl
+    from plslam_b200.synth import synth_pair
+    V = pl.ORBVocabulary(voc)
+    O = oracle.VocOracle(voc)
+    orc = oracle.OrbOracle()
+    pairs = [synth_pair(20 + s) for s in range(3)]
+    imgs = np.stack([im for pr in pairs for im in pr])
+    imgs[5] = 128  # a pair whose second frame has no features
+    ex = pl.ORBextractor()
+    d_kps, d_desc, d_cnt = ex.extract_batch_device(torch.from_numpy(imgs).cuda())
+    fv = V.featvec_batch_device(d_desc, d_cnt, levelsup=2)
+    res = pl.bow_pairs_device(d_kps, d_desc, d_cnt, fv, nnratio=0.7, check_ori=True)
+    torch.cuda.synchronize()
+    cnt = d_cnt.cpu().numpy()
+    feats = []
+    for f in range(6):
+        k, d = orc.extract(imgs[f])
+        n = int(cnt[f])
+        assert n == len(k)
+        t = O.transform(d, 2)
+        nn = int(fv["fv_count"][f])
+        assert nn == len(t["fv_nodes"])
+        assert np.array_equal(fv["fv_nodes"][f, :nn].cpu().numpy(), t["fv_nodes"].astype(np.int32))
+        assert np.array_equal(fv["fv_start"][f, :nn + 1].cpu().numpy(), t["fv_start"])
+        m = int(t["fv_start"][-1])
+        assert np.array_equal(fv["fv_idx"][f, :m].cpu().numpy(), t["fv_idx"].astype(np.int32))
+        feats.append((k, d, t))
+    total = 0
+    for p in range(3):
+        (ka, da, ta), (kb, db, tb) = feats[2 * p], feats[2 * p + 1]
+        kf = dict(desc=da, angle=np.ascontiguousarray(ka["angle"]), valid=np.ones(len(da), np.uint8),
+                  nodes=ta["fv_nodes"].astype(np.int32), start=ta["fv_start"], idx=ta["fv_idx"].astype(np.int32))
+        f = dict(desc=db, angle=np.ascontiguousarray(kb["angle"]), nodes=tb["fv_nodes"].astype(np.int32), start=tb["fv_start"],
+                 idx=tb["fv_idx"].astype(np.int32))
+        if len(db) == 0:
+            assert int(res["nmatches"][p]) == 0
+            continue
+        em, en = oracle.search_by_bow(kf, f, 0.7, True)
+        assert int(res["nmatches"][p]) == en
+        assert np.array_equal(res["match"][p, :len(db)].cpu().numpy(), em)
+        total += en
+    assert total > 60
