@@ -24,6 +24,9 @@ for p in (ROOT, os.path.join(ROOT, "rgbd-pl-slam_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# one hardware queue per stream of the pipelined front-end (read when the CUDA context is created; see c_api.cu)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 METRIC = "frames/sec ORB+LSD extract+match 640x480 RGB-D"
@@ -33,7 +36,7 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step (even: frame pairs)")
@@ -41,15 +44,52 @@ def parse():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--nfeatures", type=int, default=1000)
     ap.add_argument("--max-lines", type=int, default=40)
-    ap.add_argument("--depth", type=int, default=8, help="batches (steps) in flight per GPU: pipeline slots of the front-end")
+    ap.add_argument("--depth", type=int, default=16, help="batches (steps) in flight per GPU: pipeline slots of the front-end")
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2: extract + kNN matching (headline); c4: the same step plus ComputeBoW + SearchByBoW on every pair")
+    ap.add_argument("--voc-levels", type=int, default=6, help="depth L of the synthetic k=10 vocabulary (ORBvoc.txt: 6)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return "C2: %dx%d synthetic RGB-D, batch=%d frames (%d pairs)/GPU, ORB nFeatures=%d 8 levels + LSD/LBD top-%d, kNN2 ORB+LBD per pair" % (
+    base = "%dx%d synthetic RGB-D, batch=%d frames (%d pairs)/GPU, ORB nFeatures=%d 8 levels + LSD/LBD top-%d, kNN2 ORB+LBD per pair" % (
         a.width, a.height, a.batch, a.batch // 2, a.nfeatures, a.max_lines)
+    if getattr(a, "workload", "c2") == "c4":
+        return "C4: " + base + " + ComputeBoW (k=10 L=%d synthetic vocabulary) + SearchByBoW per pair" % a.voc_levels
+    return "C2: " + base
+
+
+def broadcast_vocabulary(a, pl, dist, rank, world):
+    """Rank 0 builds the vocabulary and exports its flat device image; one NCCL broadcast puts it on every GPU
+    (the only collective besides the timing barrier; nothing NCCL on the per-frame path)."""
+    import torch
+    from plslam_b200.synth import synth_vocabulary_arrays
+    info = {}
+    voc = None
+    nbytes = torch.zeros(1, dtype=torch.int64, device="cuda")
+    blob = None
+    if rank == 0:
+        voc = pl.ORBVocabulary.from_arrays(10, a.voc_levels, *synth_vocabulary_arrays(10, a.voc_levels, seed=0))
+        blob = voc.export_blob()
+        nbytes[0] = blob.numel()
+    if world > 1:
+        dist.broadcast(nbytes, 0)
+        if rank != 0:
+            blob = torch.empty(int(nbytes.item()), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(blob, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        info = {"voc_broadcast_bytes": int(nbytes.item()), "voc_broadcast_ms": e0.elapsed_time(e1)}
+        if rank != 0:
+            voc = pl.ORBVocabulary.from_blob(blob)
+    info["voc_nodes"] = voc.n_nodes
+    return voc, info
 
 
 def make_frames(a, rank):
@@ -220,6 +260,15 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    voc, voc_info = None, {}
+    if a.workload == "c4" or world > 1:
+        try:
+            voc, voc_info = broadcast_vocabulary(a, pl, dist, rank, world)
+        except Exception as e:  # the vocabulary only matters for C4; never lose a C2 scaling run over it
+            if a.workload == "c4":
+                raise
+            voc_info = {"voc_broadcast": "failed: %s" % e}
+
     frames = make_frames(a, rank)
     depth = max(1, min(a.depth, a.steps))
     fe = pl.Frontend(a.nfeatures, 1.2, 8, 20, 7, a.max_lines, depth=depth)
@@ -230,13 +279,24 @@ def run_ours(a):
     h_images = torch.from_numpy(frames).pin_memory()
     h_outs = [fe.alloc(a.batch, pinned=True) for _ in range(depth)]
 
+    c4 = a.workload == "c4"
+    fvs = bows = None
+    if c4:
+        fvs = [voc.featvec_batch_device(o["descriptors"], o["kp_counts"], 4) for o in outs]
+        bows = [pl.bow_pairs_device(o["keypoints"], o["descriptors"], o["kp_counts"], fv) for o, fv in zip(outs, fvs)]
+
     def device_steps(n):
         """n steps, step k on stream/slot k % depth (up to `depth` batches in flight)."""
         main = torch.cuda.current_stream()
         for s in streams:
             s.wait_stream(main)
         for k in range(n):
-            fe.process_device(d_images, outs[k % depth], True, stream=streams[k % depth])
+            i = k % depth
+            fe.process_device(d_images, outs[i], True, stream=streams[i])
+            if c4:  # Frame::ComputeBoW + ORBmatcher::SearchByBoW on the pairs of the batch, same stream, no host round trip
+                voc.featvec_batch_device(outs[i]["descriptors"], outs[i]["kp_counts"], 4, out=fvs[i], stream=streams[i])
+                pl.bow_pairs_device(outs[i]["keypoints"], outs[i]["descriptors"], outs[i]["kp_counts"], fvs[i], out=bows[i],
+                                    stream=streams[i])
         for s in streams:
             main.wait_stream(s)
 
@@ -328,12 +388,13 @@ def run_ours(a):
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": workload_name(a), "frames_per_gpu_per_step": a.batch,
                            "cache": "inputs + intermediates (~7 MB/frame, ~1.8 GB/step) exceed the 126 MB L2; no flush needed",
-                           "steps_in_flight": depth,
+                           "steps_in_flight": depth, **voc_info,
                            "parallelism": "frames sharded over %d rank(s), no data-path collective" % world},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "plslam_frontend_submit_host x K + plslam_frontend_wait_host (pinned host buffers; H2D, kernels and D2H of "
-                               "every step inside the timed region, up to `steps_in_flight` steps overlapped)"},
-                "gpu_launches": world * a.steps * fe.launches_per_call(True),
+                               "every step inside the timed region, up to `steps_in_flight` steps overlapped)" +
+                               ("; the C4 extras (ComputeBoW + SearchByBoW) are device-path only and not part of this e2e figure" if c4 else "")},
+                "gpu_launches": world * a.steps * (fe.launches_per_call(True) + (5 if c4 else 0)),
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "counts": {"keypoints_per_frame": kp_avg, "lines_per_frame": float(out["line_counts"].float().mean())}}
     if dist is not None:

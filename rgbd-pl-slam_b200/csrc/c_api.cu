@@ -27,6 +27,12 @@ struct plslam_lines {
   LineExtractor impl;
 };
 
+// The pipelined front-end keeps two streams per batch in flight.  CUDA maps streams onto CUDA_DEVICE_MAX_CONNECTIONS
+// hardware queues (default 8); streams that share a queue serialise behind each other's 50 ms region-growing kernels.
+// Ask for the maximum (32) when the library is loaded, unless the host application already chose a value.  This only
+// takes effect if the CUDA context is created after the library is loaded.
+__attribute__((constructor)) static void plslam_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 namespace plslam {
 int carveout_pct() {
   static const int v = [] {

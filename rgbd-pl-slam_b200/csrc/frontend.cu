@@ -33,7 +33,7 @@ struct Slot {
   OrbExtractor orb;
   LineExtractor lines;
   StageTimer tOrb, tLines;
-  cudaStream_t sOrb = nullptr, sLines = nullptr, sHost = nullptr;
+  cudaStream_t sOrb = nullptr, sHost = nullptr;  // the line branch runs on the caller's stream, the ORB branch beside it
   cudaEvent_t evFork = nullptr, evOrb = nullptr, evLines = nullptr, evDone = nullptr;
   DevBuf jobsOrb, jobsLines;
   DevBuf dIn, dKps, dDesc, dKpCnt, dKl, dLdesc, dFuncs, dLCnt, dOrbM, dLineM;
@@ -44,7 +44,6 @@ struct Slot {
     DevBuf* all[] = {&jobsOrb, &jobsLines, &dIn, &dKps, &dDesc, &dKpCnt, &dKl, &dLdesc, &dFuncs, &dLCnt, &dOrbM, &dLineM};
     for (DevBuf* b : all) b->release();
     if (sOrb) cudaStreamDestroy(sOrb);
-    if (sLines) cudaStreamDestroy(sLines);
     if (sHost) cudaStreamDestroy(sHost);
     cudaEvent_t evs[] = {evFork, evOrb, evLines, evDone};
     for (cudaEvent_t e : evs)
@@ -54,7 +53,6 @@ struct Slot {
   int init() {
     if (sOrb) return PLSLAM_OK;
     PL_CUDA(cudaStreamCreateWithFlags(&sOrb, cudaStreamNonBlocking));
-    PL_CUDA(cudaStreamCreateWithFlags(&sLines, cudaStreamNonBlocking));
     PL_CUDA(cudaStreamCreateWithFlags(&sHost, cudaStreamNonBlocking));
     PL_CUDA(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
     PL_CUDA(cudaEventCreateWithFlags(&evOrb, cudaEventDisableTiming));
@@ -85,7 +83,7 @@ struct Slot {
     if (used) PL_CUDA(cudaStreamWaitEvent(st, evDone, 0));
     PL_CUDA(cudaEventRecord(evFork, st));
     PL_CUDA(cudaStreamWaitEvent(sOrb, evFork, 0));
-    PL_CUDA(cudaStreamWaitEvent(sLines, evFork, 0));
+    cudaStream_t sLines = st;  // every stream is a hardware connection: two per slot keep deep pipelines from aliasing queues
     // line branch first: its long sequential kernel should start as early as possible
     rc = lines.extract_device(d_images, batch, W, H, pitch, stride, io.keylines, io.line_descriptors, io.line_functions,
                               lnCap, io.line_counts, sLines);
@@ -105,9 +103,7 @@ struct Slot {
       if (rc) return rc;
     }
     PL_CUDA(cudaEventRecord(evOrb, sOrb));
-    PL_CUDA(cudaEventRecord(evLines, sLines));
     PL_CUDA(cudaStreamWaitEvent(st, evOrb, 0));
-    PL_CUDA(cudaStreamWaitEvent(st, evLines, 0));
     PL_CUDA(cudaEventRecord(evDone, st));
     used = true;
     return PLSLAM_OK;

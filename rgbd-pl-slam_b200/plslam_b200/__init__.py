@@ -487,6 +487,16 @@ class ORBVocabulary:
         except Exception:
             pass
 
+    @classmethod
+    def from_arrays(cls, k, L, parent, is_leaf, descriptors, weights):
+        """plslam_voc_create: nodes in loadFromTextFile order (entry 0 = root)."""
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        descriptors = np.ascontiguousarray(descriptors, np.uint8); weights = np.ascontiguousarray(weights, np.float64)
+        h = C.c_void_p()
+        _check(lib().plslam_voc_create(C.byref(h), int(k), int(L), len(parent), _vp(parent), _vp(is_leaf), _vp(descriptors),
+                                       _vp(weights)))
+        return cls(handle=h)
+
     def export_blob(self):
         import torch
         n = lib().plslam_voc_blob_bytes(self._h)
@@ -653,8 +663,8 @@ def bow_pairs_device(d_kps, d_desc, d_counts, fv, d_kf_valid=None, nnratio=0.7, 
     B, cap = d_desc.shape[0], d_desc.shape[1]
     npairs = B // 2
     dev = d_desc.device
-    if d_kf_valid is None:
-        d_kf_valid = torch.ones((B, cap), dtype=torch.uint8, device=dev)
+    if d_kf_valid is None:  # every keyframe feature has a good map point; reuse the buffer of a previous call
+        d_kf_valid = out["_valid"] if out is not None else torch.ones((B, cap), dtype=torch.uint8, device=dev)
     if out is None:
         out = dict(match=torch.empty((npairs, cap), dtype=torch.int32, device=dev),
                    nmatches=torch.empty((npairs,), dtype=torch.int32, device=dev),

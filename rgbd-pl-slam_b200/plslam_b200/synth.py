@@ -49,3 +49,30 @@ def synth_pair(seed, W=640, H=480):
 
 def synth_batch(seed0, B, W=640, H=480):
     return np.stack([synth_frame(seed0 + i, W, H) for i in range(B)])
+
+
+def synth_vocabulary_arrays(k=10, L=6, seed=0):
+    """A complete k-ary vocabulary tree of depth L in node (breadth-first) order, the arrays plslam_voc_create takes:
+    parent [n], is_leaf [n], descriptors [n][32], weights [n].  ORBvoc.txt has k=10, L=6 (1 111 111 nodes when complete).
+    Children are noisy copies of their parent's descriptor so that descents discriminate like a trained tree."""
+    rng = np.random.default_rng(seed)
+    n = (k ** (L + 1) - 1) // (k - 1)
+    parent = np.zeros(n, np.int32)
+    parent[1:] = (np.arange(1, n, dtype=np.int64) - 1) // k
+    first_leaf = (k ** L - 1) // (k - 1)
+    is_leaf = np.zeros(n, np.uint8)
+    is_leaf[first_leaf:] = 1
+    desc = np.zeros((n, 32), np.uint8)
+    desc[1:k + 1] = rng.integers(0, 256, (k, 32), dtype=np.uint8)
+    lo = 1
+    for level in range(1, L):
+        cnt = k ** level
+        hi = lo + cnt
+        ch_lo = hi
+        noise = rng.integers(0, 256, (cnt * k, 32), dtype=np.uint8) & rng.integers(0, 256, (cnt * k, 32), dtype=np.uint8) \
+            & rng.integers(0, 256, (cnt * k, 32), dtype=np.uint8)
+        desc[ch_lo:ch_lo + cnt * k] = np.repeat(desc[lo:hi], k, axis=0) ^ noise
+        lo = hi
+    weights = np.zeros(n, np.float64)
+    weights[first_leaf:] = np.round(rng.random(n - first_leaf) * 10, 5) + 0.01
+    return parent, is_leaf, desc, weights
