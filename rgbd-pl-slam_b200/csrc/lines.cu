@@ -872,12 +872,8 @@ __device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* prec
 // rect_improve(): within a stage the five candidate rectangles do not depend on which of them is
 // accepted, so their pixel counts are gathered first and the five nfa() evaluations (the expensive
 // part: log-gamma, a binomial tail) run on five lanes at once; the accept chain is then replayed in order.
-__global__ void __launch_bounds__(256, 3) k_lsd_nfa(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
-                                                 const LsdRect* __restrict__ rectsAll, const int* __restrict__ nrects,
-                                                 LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.y, ri = blockIdx.x * 8 + warp;
-  if (ri >= nrects[f]) return;
+__device__ void lsd_nfa_rect(const LineParams& L, const uint4* __restrict__ pixAll, const LsdRect* __restrict__ rectsAll,
+                             LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid, int f, int ri, int lane) {
   const uint4* pix = pixAll + (size_t)f * L.P;
   LsdRect rec = rectsAll[(size_t)f * L.rect_cap + ri];
   const double LOG_EPS = L.log_eps, LOG_NT = L.log_nt;
@@ -974,6 +970,25 @@ __global__ void __launch_bounds__(256, 3) k_lsd_nfa(const __grid_constant__ Line
     s.prec = rec.p;
     s.nfa = log_nfa;
     rectOut[o] = s;
+  }
+}
+
+// Persistent launch: a fixed grid of warps strides over (frame, group of NFA_GROUP rectangles) items.  The rectangle
+// counts are only known on the device and vary from ~50 to several hundred per frame; a grid sized for the capacity
+// would be 97 % empty CTAs, and rectangles that enter rect_improve cost ~25x the others, so small items matter.
+constexpr int NFA_GROUP = 4;
+__global__ void __launch_bounds__(256, 3) k_lsd_nfa(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
+                                                 const LsdRect* __restrict__ rectsAll, const int* __restrict__ nrects,
+                                                 LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * 8, wid = blockIdx.x * 8 + warp;
+  const int groups = (L.rect_cap + NFA_GROUP - 1) / NFA_GROUP;
+  const long long nitems = (long long)L.batch * groups;
+  for (long long item = wid; item < nitems; item += nwarps) {
+    const int f = (int)(item / groups), g = (int)(item % groups);
+    const int n = __ldg(nrects + f);
+    for (int ri = g * NFA_GROUP; ri < min(n, (g + 1) * NFA_GROUP); ++ri)
+      lsd_nfa_rect(L, pixAll, rectsAll, rectOut, rectValid, f, ri, lane);
   }
 }
 
@@ -1306,6 +1321,7 @@ int LineExtractor::configure(int W, int H, int batch) {
   PL_CHECK_ARG(W >= 16 && H >= 16 && W <= 16000 && H <= 16000);
   if (device < 0) {
     PL_CUDA(cudaGetDevice(&device));
+    PL_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, device));
     PL_CUDA(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
     PL_CUDA(cudaMallocHost(&pinnedStatus, 64));
   }
@@ -1449,7 +1465,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   uint8_t* rvalid = reinterpret_cast<uint8_t*>(rout + (size_t)cfgB * P.rect_cap);
   PL_STAGE_BEGIN(timer, "lsd_nfa", st);
   PL_CARVEOUT(k_lsd_nfa);
-  k_lsd_nfa<<<dim3(div_up(P.rect_cap, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), rects.as<LsdRect>(), nrects.as<int>(),
+  k_lsd_nfa<<<numSMs * 3, 256, 0, st>>>(P, pix.as<uint4>(), rects.as<LsdRect>(), nrects.as<int>(),
                                                                 rout, rvalid);
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_finish", st);

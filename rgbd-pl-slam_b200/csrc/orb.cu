@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ OrbParam
 // (X, Y border-local).  key = ((cellRow*256 + cellCol)*64 + yLocal)*64 + xLocal reproduces the
 // reference list order (cell-major, then FAST's row-major) without ordered writes.
 // ------------------------------------------------------------------------------------------
+constexpr int FAST_QUEUE_BYTES = 320;  // 160 queue entries: < 32 left over + up to 128 new per iteration
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams P, OrbImages I,
                                               unsigned long long* __restrict__ cand, int* __restrict__ candCount,
                                               int* __restrict__ status) {
@@ -112,77 +113,129 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams 
   const int ph = min(iniY + L.hCell + 6, L.maxBorderY) - iniY;
   if (pw < 7 || ph < 7) return;
 
-  const int pp = P.patchPitch;
+  const int pp = P.patchPitch;  // multiple of 4
   const int tileBytes = pp * P.patchRows;
-  uint8_t* patch = smem + (size_t)warp * (2 * tileBytes + 128);
+  uint8_t* patch = smem + (size_t)warp * (2 * tileBytes + FAST_QUEUE_BYTES);
   uint8_t* score = patch + tileBytes;
-  unsigned short* queue = reinterpret_cast<unsigned short*>(score + tileBytes);  // 64 entries
+  unsigned short* queue = reinterpret_cast<unsigned short*>(score + tileBytes);  // FAST_QUEUE_BYTES / 2 entries
+  uint32_t* PW = reinterpret_cast<uint32_t*>(patch);
+  uint32_t* SW = reinterpret_cast<uint32_t*>(score);
+  const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
 
   int sp;
   const uint8_t* S = level_ptr(P, I, f, l, sp);
   S += (size_t)iniY * sp + iniX;
-  for (int i = lane; i < pw * ph; i += 32) {
-    const int y = i / pw, x = i - y * pw;
-    patch[y * pp + x] = S[(size_t)y * sp + x];
+  // Stage the cell with aligned 32-bit loads (lane = (row, word) of a group of rows): pixel x of the cell then lives
+  // in byte column shift + x of the shared tile.  Byte loads when the level's pitch is not a multiple of 4.
+  for (int i = lane; i < tileBytes / 4; i += 32) SW[i] = 0;
+  const int nwd = pp >> 2;                           // words per tile row
+  const int rpi = nwd <= 32 ? 32 / nwd : 1;          // tile rows handled per warp iteration
+  const int r = nwd <= 32 ? lane / nwd : 0;          // this lane's row within the group ...
+  const int wl = nwd <= 32 ? lane - r * nwd : lane;  // ... and word within the row
+  const bool rowLane = r < rpi;
+  int shift = (int)(reinterpret_cast<uintptr_t>(S) & 3);
+  if ((sp & 3) == 0 && shift + pw <= pp) {
+    const uint32_t* Sw = reinterpret_cast<const uint32_t*>(S - shift);
+    const int nw = (shift + pw + 3) >> 2;
+    for (int yb = 0; yb < ph; yb += rpi)
+      for (int wb = 0; wb < nw; wb += 32) {
+        const int y = yb + r, w = wb + wl;
+        if (rowLane && y < ph && w < nw) PW[y * nwd + w] = __ldg(Sw + (size_t)y * (sp >> 2) + w);
+      }
+  } else {
+    shift = 0;
+    for (int y = 0; y < ph; ++y)
+      for (int x = lane; x < pw; x += 32) patch[y * pp + x] = S[(size_t)y * sp + x];
   }
-  for (int i = lane; i < tileBytes / 4; i += 32) reinterpret_cast<uint32_t*>(score)[i] = 0;
   __syncwarp();
 
-  const int dw = pw - 6, dh = ph - 6, npx = dw * dh;
+  // All passes below work on 4 pixels per lane with the byte-SIMD instructions.  Detection area: rows [3, yEnd),
+  // byte columns [cLo, cHi).
+  const int yEnd = ph - 3, cLo = shift + 3, cHi = shift + pw - 3;
+  auto valid_mask_of = [&](int w) -> unsigned {  // bytes of word w inside [cLo, cHi)
+    const int lo = max(cLo - 4 * w, 0), hi = min(cHi - 4 * w, 4);
+    return hi > lo ? ((FULL >> (32 - 8 * hi)) & (FULL << (8 * lo))) : 0u;
+  };
+  // the usual case (a tile row fits one warp iteration): the lane's word, hence its mask, never changes
+  const unsigned vmLane = (rowLane && wl < nwd) ? valid_mask_of(wl) : 0u;
+  auto valid_mask = [&](int w) -> unsigned { return nwd <= 32 ? vmLane : valid_mask_of(w); };
+  // exclusive prefix over the lanes of a per-lane count in [0, 4]; *total = warp sum
+  auto lane_prefix = [&](int cnt, int* total) -> int {
+    const unsigned b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
+    *total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    return __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+  };
   const int th0 = P.minTh;
+  const unsigned th4 = (unsigned)th0 * 0x01010101u;
+
+  // pass 1: 4-point quick test at minThFAST (N/S and E/W compass pixels), survivors queued for the 16-arc score
   int qn = 0;
-  for (int base = 0; base < npx; base += 32) {
-    const int i = base + lane;
-    bool pass = false;
-    int pos = 0;
-    if (i < npx) {
-      const int y = i / dw + 3, x = i - (y - 3) * dw + 3;
-      pos = y * pp + x;
-      const uint8_t* p = patch + pos;
-      const int v = p[0];
-      const bool a = abs(v - p[3 * pp]) > th0 || abs(v - p[-3 * pp]) > th0;
-      const bool b = abs(v - p[3]) > th0 || abs(v - p[-3]) > th0;
-      pass = a && b;
+  for (int yb = 3; yb < yEnd; yb += rpi)
+    for (int wb = 0; wb < nwd; wb += 32) {
+      const int y = yb + r, w = wb + wl;
+      unsigned pass = 0;
+      if (rowLane && y < yEnd && w < nwd) {
+        const unsigned vm = valid_mask(w);
+        if (vm) {
+          const uint32_t* R = PW + y * nwd;
+          const unsigned C = R[w], N = R[w - 3 * nwd], So = R[w + 3 * nwd];
+          const unsigned E = __funnelshift_r(C, R[w + 1], 24), We = __funnelshift_r(R[w - 1], C, 8);
+          const unsigned a = __vcmpgtu4(__vabsdiffu4(C, N), th4) | __vcmpgtu4(__vabsdiffu4(C, So), th4);
+          const unsigned b = __vcmpgtu4(__vabsdiffu4(C, E), th4) | __vcmpgtu4(__vabsdiffu4(C, We), th4);
+          pass = a & b & vm & 0x01010101u;
+        }
+      }
+      int tot;
+      int at = qn + lane_prefix(__popc(pass), &tot);
+      const int base = y * pp + 4 * w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((pass >> (8 * k)) & 1u) queue[at++] = (unsigned short)(base + k);
+      qn += tot;
+      __syncwarp();
+      while (qn >= 32) {
+        const int q = queue[qn - 32 + lane];
+        score[q] = (uint8_t)fast_arc_score(patch + q, pp);
+        qn -= 32;
+      }
+      __syncwarp();
     }
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (pass) queue[qn + __popc(m & ((1u << lane) - 1))] = (unsigned short)pos;
-    qn += __popc(m);
-    __syncwarp();
-    if (qn >= 32) {
-      const int q = queue[qn - 32 + lane];
-      const int s = fast_arc_score(patch + q, pp);
-      score[q] = (uint8_t)s;
-      qn -= 32;
-    }
-    __syncwarp();
-  }
   if (lane < qn) {
     const int q = queue[lane];
     score[q] = (uint8_t)fast_arc_score(patch + q, pp);
   }
   __syncwarp();
 
-  // local maxima of the raw score map; flags (score of maxima, else 0) overwrite the patch tile
+  // pass 2: strict 3x3 local maxima of the raw score map (scores outside the detection area are 0); the maxima
+  // (score, else 0) overwrite the pixel tile, which is no longer read as pixels
+  const unsigned ini4 = (unsigned)P.iniTh * 0x01010101u;
   int nHi = 0, nLo = 0;
-  for (int base = 0; base < npx; base += 32) {
-    const int i = base + lane;
-    int keep = 0;
-    int pos = 0;
-    if (i < npx) {
-      const int y = i / dw + 3, x = i - (y - 3) * dw + 3;
-      pos = y * pp + x;
-      const uint8_t* s = score + pos;
-      const int c = s[0];
-      if (c > th0) {
-        const int m = max(max(max(s[-pp - 1], s[-pp]), max(s[-pp + 1], s[-1])),
-                          max(max(s[1], s[pp - 1]), max(s[pp], s[pp + 1])));
-        if (c > m) keep = c;
+  for (int yb = 3; yb < yEnd; yb += rpi)
+    for (int wb = 0; wb < nwd; wb += 32) {
+      const int y = yb + r, w = wb + wl;
+      if (rowLane && y < yEnd && w < nwd) {
+        const unsigned vm = valid_mask(w);
+        unsigned keep4 = 0;
+        const uint32_t* R = SW + y * nwd;
+        const unsigned C = R[w];
+        if (C & vm) {
+          const uint32_t* U = R - nwd;
+          const uint32_t* D = R + nwd;
+          const unsigned u0 = U[w], d0 = D[w];
+          const unsigned m =
+              __vmaxu4(__vmaxu4(__vmaxu4(__funnelshift_r(U[w - 1], u0, 24), u0),
+                                __vmaxu4(__funnelshift_r(u0, U[w + 1], 8), __funnelshift_r(R[w - 1], C, 24))),
+                       __vmaxu4(__vmaxu4(__funnelshift_r(C, R[w + 1], 8), __funnelshift_r(D[w - 1], d0, 24)),
+                                __vmaxu4(d0, __funnelshift_r(d0, D[w + 1], 8))));
+          keep4 = C & __vcmpgtu4(C, m) & __vcmpgtu4(C, th4) & vm;
+        }
+        PW[y * nwd + w] = keep4;
+        nHi += __popc(__vcmpgtu4(keep4, ini4) & 0x01010101u);
+        nLo += __popc(__vcmpgtu4(keep4, 0u) & 0x01010101u);
       }
     }
-    if (i < npx) patch[pos] = (uint8_t)keep;  // safe: the patch tile is no longer read as pixels
-    nHi += __popc(__ballot_sync(0xffffffffu, keep > P.iniTh));
-    nLo += __popc(__ballot_sync(0xffffffffu, keep > 0));
-  }
+  nHi = __reduce_add_sync(FULL, nHi);
+  nLo = __reduce_add_sync(FULL, nLo);
   __syncwarp();
   const int thSel = nHi > 0 ? P.iniTh : th0;
   const int nOut = nHi > 0 ? nHi : nLo;
@@ -195,25 +248,30 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams 
     return;
   }
   unsigned long long* out = cand + (size_t)f * P.candFrameStride + L.candOff + slot;
+  // pass 3: emit the maxima above the selected threshold in FAST's row-major order
+  const unsigned sel4 = (unsigned)thSel * 0x01010101u;
   int wr = 0;
-  for (int base = 0; base < npx; base += 32) {
-    const int i = base + lane;
-    int keep = 0, x = 0, y = 0;
-    if (i < npx) {
-      y = i / dw + 3;
-      x = i - (y - 3) * dw + 3;
-      keep = patch[y * pp + x];
+  for (int yb = 3; yb < yEnd; yb += rpi)
+    for (int wb = 0; wb < nwd; wb += 32) {
+      const int y = yb + r, w = wb + wl;
+      unsigned kw = 0, e = 0;
+      if (rowLane && y < yEnd && w < nwd) {
+        kw = PW[y * nwd + w];
+        e = __vcmpgtu4(kw, sel4) & 0x01010101u;
+      }
+      int tot;
+      int at = wr + lane_prefix(__popc(e), &tot);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((e >> (8 * k)) & 1u) {
+          const int x = 4 * w + k - shift;
+          const unsigned keep = (kw >> (8 * k)) & 0xffu;
+          const unsigned key = (((unsigned)(ci * 256 + cj) * 64u + (unsigned)y) * 64u + (unsigned)x);
+          const unsigned X = x + cj * L.wCell, Y = y + ci * L.hCell;
+          out[at++] = ((unsigned long long)keep << 56) | ((unsigned long long)key << 28) | ((unsigned long long)Y << 14) | X;
+        }
+      wr += tot;
     }
-    const bool emit = keep > thSel;
-    const unsigned m = __ballot_sync(0xffffffffu, emit);
-    if (emit) {
-      const unsigned key = (((unsigned)(ci * 256 + cj) * 64u + (unsigned)y) * 64u + (unsigned)x);
-      const unsigned X = x + cj * L.wCell, Y = y + ci * L.hCell;
-      out[wr + __popc(m & ((1u << lane) - 1))] =
-          ((unsigned long long)keep << 56) | ((unsigned long long)key << 28) | ((unsigned long long)Y << 14) | X;
-    }
-    wr += __popc(m);
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -939,7 +997,7 @@ int OrbExtractor::configure(int W, int H, int batch) {
   P.totalTiles = tileBase;
   P.maxKp = kpOff;
   P.nodeCap = std::max(maxQuota + 8, 16);
-  P.patchPitch = (int)align_up(maxPw, 4);
+  P.patchPitch = (int)align_up(maxPw + 3, 4);  // + 3: room for the alignment shift of the staged tile
   P.patchRows = maxPh;
   P.pyrFrameStride = off;
   P.candFrameStride = candOff;
@@ -1002,7 +1060,7 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
   }
   PL_STAGE_END(timer, st);
   {
-    const size_t smem = 8 * (2 * (size_t)P.patchPitch * P.patchRows + 128);
+    const size_t smem = 8 * (2 * (size_t)P.patchPitch * P.patchRows + FAST_QUEUE_BYTES);
     static bool attr = false;
     if (!attr) {
       PL_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
