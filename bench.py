@@ -26,6 +26,8 @@ for p in (ROOT, os.path.join(ROOT, "rgbd-pl-slam_b200")):
 
 # one hardware queue per stream of the pipelined front-end (read when the CUDA context is created; see c_api.cu)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# keep stdout to the one JSON line: NCCL's version banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np
 

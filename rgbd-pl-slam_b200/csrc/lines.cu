@@ -1456,7 +1456,16 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
   P.batch = batch;
   PL_CARVEOUT(k_lsd_grow);
-  k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
+  // Residency cap: region growing is a long, register-heavy, latency-bound kernel (72 registers x 128 threads per CTA).
+  // Left alone, the CTAs of many batches in flight fill the register files and starve the streaming kernels of the
+  // other batches; dynamic shared memory that is never touched bounds the CTAs per SM (PLSLAM_GROW_SMEM_KB to tune).
+  static const int growPadKB = [] { const char* e = std::getenv("PLSLAM_GROW_SMEM_KB"); return e ? std::atoi(e) : 0; }();
+  static bool growAttr = false;
+  if (!growAttr && growPadKB > 0) {
+    PL_CUDA(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, growPadKB * 1024));
+    growAttr = true;
+  }
+  k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, (size_t)growPadKB * 1024, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
                                           rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());
   PL_STAGE_END(timer, st);
   static const bool grow_only = std::getenv("PLSLAM_DEBUG_STOP_AFTER_GROW") != nullptr;  // profiling aid (tools/)
