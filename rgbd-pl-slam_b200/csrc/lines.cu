@@ -37,12 +37,14 @@ constexpr double M_2__PI_D = 2 * PL_PI;
 // Tile = 64x16 scaled pixels; the 82x22 blurred source patch never leaves shared memory.
 // ------------------------------------------------------------------------------------------
 constexpr int ST_W = 64, ST_H = 16, SB_W = 84, SB_H = 24;
+constexpr int RAW_P = 96;  // bytes per row of the raw patch (word aligned; >= SB_W + 6 + 3 bytes of over-read)
+constexpr int HS_P = 88;   // u16 per row of the horizontally filtered patch
 
 __global__ void __launch_bounds__(256) k_lsd_scale(const __grid_constant__ LineParams L, const uint8_t* __restrict__ img,
                                                    int pitch, size_t frame_stride, const int* __restrict__ coef,
                                                    uint8_t* __restrict__ scaled) {
-  __shared__ uint8_t raw[SB_H + 6][SB_W + 8];
-  __shared__ unsigned short hs[SB_H + 6][SB_W];
+  __shared__ __align__(16) uint8_t raw[SB_H + 6][RAW_P];
+  __shared__ __align__(16) unsigned short hs[SB_H + 6][HS_P];
   __shared__ uint8_t bl[SB_H][SB_W];
   const int f = blockIdx.z;
   const int ox0 = blockIdx.x * ST_W, oy0 = blockIdx.y * ST_H;
@@ -55,26 +57,49 @@ __global__ void __launch_bounds__(256) k_lsd_scale(const __grid_constant__ LineP
   const int by0 = yofs[oy0], by1 = min(yofs[oyl] + 1, L.H - 1);
   const int nbx = bx1 - bx0 + 1, nby = by1 - by0 + 1;
   const uint8_t* S = img + (size_t)f * frame_stride;
-  for (int i = threadIdx.x; i < (nby + 6) * (nbx + 6); i += 256) {
-    const int r = i / (nbx + 6), c = i - r * (nbx + 6);
-    const int gx = reflect101_dev(bx0 - 3 + c, L.W), gy = reflect101_dev(by0 - 3 + r, L.H);
-    raw[r][c] = S[(size_t)gy * pitch + gx];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // raw patch (3-px halo, BORDER_REFLECT_101 at the image edges): warp = row, lanes along x
+  for (int r = warp; r < nby + 6; r += 8) {
+    const uint8_t* row = S + (size_t)reflect101_dev(by0 - 3 + r, L.H) * pitch;
+    for (int c = lane; c < RAW_P; c += 32)
+      raw[r][c] = c < nbx + 6 ? row[reflect101_dev(bx0 - 3 + c, L.W)] : (uint8_t)0;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < (nby + 6) * nbx; i += 256) {
-    const int r = i / nbx, c = i - r * nbx;
-    int a = 0;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) a += L.blurk[k] * raw[r][c + k];
-    hs[r][c] = (unsigned short)a;
-  }
+  // horizontal 7-tap pass, 4 outputs per thread: aligned words, funnel shifts for the byte windows, dp4a for the taps
+  const unsigned K0 = (unsigned)L.blurk[0] | ((unsigned)L.blurk[1] << 8) | ((unsigned)L.blurk[2] << 16) | ((unsigned)L.blurk[3] << 24);
+  const unsigned K1 = (unsigned)L.blurk[4] | ((unsigned)L.blurk[5] << 8) | ((unsigned)L.blurk[6] << 16);
+  const int nwq = (nbx + 3) >> 2;
+  for (int r = warp; r < nby + 6; r += 8)
+    for (int wq = lane; wq < nwq; wq += 32) {
+      const uint32_t* R = reinterpret_cast<const uint32_t*>(raw[r]) + wq;
+      const unsigned w0 = R[0], w1 = R[1], w2 = R[2];
+      const unsigned h0 = __dp4a(w0, K0, __dp4a(w1, K1, 0u));
+      const unsigned h1 = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
+      const unsigned h2 = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
+      const unsigned h3 = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
+      uint2 o;
+      o.x = h0 | (h1 << 16);
+      o.y = h2 | (h3 << 16);
+      *reinterpret_cast<uint2*>(&hs[r][4 * wq]) = o;
+    }
   __syncthreads();
-  for (int i = threadIdx.x; i < nby * nbx; i += 256) {
-    const int r = i / nbx, c = i - r * nbx;
-    int a = 32768;
+  // vertical pass: thread = (column, segment of 8 rows), 14-value register window
+  {
+    const int k0 = L.blurk[0], k1 = L.blurk[1], k2 = L.blurk[2], k3 = L.blurk[3], k4 = L.blurk[4], k5 = L.blurk[5], k6 = L.blurk[6];
+    for (int it = threadIdx.x; it < 3 * SB_W; it += 256) {
+      const int seg = it / SB_W, c = it - seg * SB_W;
+      const int r0 = seg * 8;
+      if (c >= nbx || r0 >= nby) continue;
+      int v[14];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) a += L.blurk[k] * hs[r + k][c];
-    bl[r][c] = (uint8_t)(a >> 16);
+      for (int j = 0; j < 14; ++j) v[j] = r0 + j < nby + 6 ? hs[r0 + j][c] : 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (r0 + j < nby) {
+          const int a = 32768 + k0 * v[j] + k1 * v[j + 1] + k2 * v[j + 2] + k3 * v[j + 3] + k4 * v[j + 4] + k5 * v[j + 5] + k6 * v[j + 6];
+          bl[r0 + j][c] = (uint8_t)(a >> 16);
+        }
+    }
   }
   __syncthreads();
   uint8_t* D = scaled + (size_t)f * L.spitch * L.sh;
@@ -82,9 +107,9 @@ __global__ void __launch_bounds__(256) k_lsd_scale(const __grid_constant__ LineP
     const int ty = i / ST_W, tx = i - ty * ST_W;
     const int ox = ox0 + tx, oy = oy0 + ty;
     if (ox >= L.sw || oy >= L.sh) continue;
-    const int sx = xofs[ox], sy = yofs[oy];
+    const int sx = __ldg(xofs + ox), sy = __ldg(yofs + oy);
     const int sx1 = min(sx + 1, L.W - 1), sy1 = min(sy + 1, L.H - 1);
-    const int a1 = xc1[ox], a0 = 256 - a1, b1 = yc1[oy], b0 = 256 - b1;
+    const int a1 = __ldg(xc1 + ox), a0 = 256 - a1, b1 = __ldg(yc1 + oy), b0 = 256 - b1;
     const int t0 = bl[sy - by0][sx - bx0] * a0 + bl[sy - by0][sx1 - bx0] * a1;
     const int t1 = bl[sy1 - by0][sx - bx0] * a0 + bl[sy1 - by0][sx1 - bx0] * a1;
     D[(size_t)oy * L.spitch + ox] = (uint8_t)((t0 * b0 + t1 * b1 + 32768) >> 16);
