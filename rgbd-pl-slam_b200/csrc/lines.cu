@@ -839,7 +839,8 @@ __device__ __forceinline__ double lsd_ntheta(double theta, float deg) {
 
 // Row scan of rect_nfa(): counts the pixels of the rectangle (total) and, for up to 5 angular
 // tolerances at once, the aligned ones.  Warp-cooperative; results are warp-uniform.
-__device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* precs, int nprec, const uint4* __restrict__ pix, int sw,
+template <int NPREC>
+__device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* precs, const uint4* __restrict__ pix, int sw,
                                int sh, int lane, int* total_out, int* alg_out) {
   const double hw = __dmul_rn(0.5, r.width);
   const double dyhw = __dmul_rn(r.dy, hw), dxhw = __dmul_rn(r.dx, hw);
@@ -879,19 +880,19 @@ __device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* prec
       ++total;
       const double nt = lsd_ntheta(r.theta, __uint_as_float(__ldg(row + x).x));
 #pragma unroll
-      for (int j = 0; j < 5; ++j)
-        if (j < nprec && nt <= precs[j]) ++alg[j];
+      for (int j = 0; j < NPREC; ++j)
+        if (nt <= precs[j]) ++alg[j];
     }
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
     total += __shfl_xor_sync(0xffffffffu, total, d);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) alg[j] += __shfl_xor_sync(0xffffffffu, alg[j], d);
+    for (int j = 0; j < NPREC; ++j) alg[j] += __shfl_xor_sync(0xffffffffu, alg[j], d);
   }
   *total_out = total;
 #pragma unroll
-  for (int j = 0; j < 5; ++j) alg_out[j] = alg[j];
+  for (int j = 0; j < NPREC; ++j) alg_out[j] = alg[j];
 }
 
 // rect_improve(): within a stage the five candidate rectangles do not depend on which of them is
@@ -907,7 +908,7 @@ __device__ void lsd_nfa_rect(const LineParams& L, const uint4* __restrict__ pixA
   int total, alg[5];
   double precs[5];
   precs[0] = rec.prec;
-  rect_count_dev(rec, precs, 1, pix, sw, sh, lane, &total, alg);
+  rect_count_dev<1>(rec, precs, pix, sw, sh, lane, &total, alg);
   double log_nfa = nfa_dev(total, alg[0], rec.p, LOG_NT);
   for (int stage = 1; stage <= 5 && !(log_nfa > LOG_EPS); ++stage) {
     const LsdRect rec0 = rec;  // the stage's variants derive from the rectangle it starts with
@@ -954,7 +955,7 @@ __device__ void lsd_nfa_rect(const LineParams& L, const uint4* __restrict__ pixA
           precs[n] = r.prec;
           if (lane == n) { myP = r.p; myOk = true; }
         }
-        rect_count_dev(rec0, precs, 5, pix, sw, sh, lane, &total, alg);
+        rect_count_dev<5>(rec0, precs, pix, sw, sh, lane, &total, alg);
         myTotal = total;
 #pragma unroll
         for (int n = 0; n < 5; ++n)
@@ -967,7 +968,7 @@ __device__ void lsd_nfa_rect(const LineParams& L, const uint4* __restrict__ pixA
         if (!o) break;
         okMask |= 1u << n;
         precs[0] = r.prec;
-        rect_count_dev(r, precs, 1, pix, sw, sh, lane, &total, alg);
+        rect_count_dev<1>(r, precs, pix, sw, sh, lane, &total, alg);
         if (lane == n) { myTotal = total; myAlg = alg[0]; myP = r.p; myOk = true; }
       }
     }

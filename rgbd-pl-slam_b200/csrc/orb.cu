@@ -604,8 +604,9 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams 
             "r"(bar)
           : "memory");
     }
-    __syncthreads();  // makes the initialised barrier visible to the waiting threads
-    {
+    // one thread polls the mbarrier, the other 255 park at the CTA barrier: a polling loop in every warp burns issue
+    // slots that the kernels of the other batches in flight could use
+    if (threadIdx.x == 0) {
       const unsigned bar = smem_u32(&mbar);
       unsigned done = 0;
       while (!done) {
@@ -616,6 +617,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams 
             : "memory");
       }
     }
+    __syncthreads();
     if (rim) {
       // reflect-101 halo outside the level (TMA wrote zeros there)
       for (int i = threadIdx.x; i < BOX_H * (BT_W + 6); i += 256) {
