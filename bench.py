@@ -376,7 +376,11 @@ def run_ours(a):
                             "see DESIGN.md",
                     "pipeline": {"algorithmic_bytes_per_step": total_bytes, "achieved": total_bytes / (step_ms * 1e-3) / 1e9,
                                  "frac": total_bytes / (step_ms * 1e-3) / 1e9 / peak},
-                    "stages_ms": {k: round(v, 4) for k, v in sorted(acc.items(), key=lambda kv: -kv[1])}}
+                    "stages_ms": {k: round(v, 4) for k, v in sorted(acc.items(), key=lambda kv: -kv[1])},
+                    # algorithmic GB/s of every stage (same definition as `achieved`), one batch in flight, the ORB and
+                    # line branches running side by side on two streams
+                    "stages_gbs": {k: round(stages.get(k, 0) * a.batch / (v * 1e-3) / 1e9, 1)
+                                   for k, v in sorted(acc.items(), key=lambda kv: -kv[1]) if v > 0}}
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -232,6 +232,34 @@ typedef struct plslam_proj_job {
 } plslam_proj_job_t;
 int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream);
 
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (ORBmatcher.h:61,
+ * @0x79f10) — the local-map search of Tracking::SearchLocalPoints, including Frame::GetFeaturesInArea and
+ * RadiusByViewingCos (@0x79b60).  The map-point fields it reads (filled by Frame::isInFrustum in the reference) are
+ * passed flattened. */
+typedef struct plslam_local_job {
+  const uint8_t* mp_valid;     /* M : pMP->mbTrackInView && !pMP->isBad() */
+  const float* mp_proj;        /* M x 3 : mTrackProjX, mTrackProjY, mTrackProjXR */
+  const int32_t* mp_level;     /* M : mnTrackScaleLevel */
+  const float* mp_viewcos;     /* M : mTrackViewCos */
+  const uint8_t* mp_desc;      /* M x 32 : pMP->GetDescriptor() */
+  const uint8_t* mp_obs;       /* M : pMP->Observations() > 0 */
+  const float* f_xy;           /* N x 2 : F.mvKeysUn[i].pt */
+  const int32_t* f_octave;     /* N */
+  const uint8_t* f_desc;       /* N x 32 */
+  const float* f_uright;       /* N : F.mvuRight */
+  const uint8_t* f_taken;      /* N : F.mvpMapPoints[i] && Observations() > 0 on entry */
+  const int32_t* grid_start;   /* 64*48+1 : CSR of F.mGrid in [ix][iy] order */
+  const int32_t* grid_items;
+  const float* scale_factors;  /* F.mvScaleFactors */
+  int32_t* match_f;            /* N : map-point index assigned to each keypoint, -1 = none */
+  int32_t* nmatches;           /* 1 */
+  float cam[4];                /* mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv */
+  float th, nnratio;           /* th; mfNNratio */
+  int32_t m, n;
+} plslam_local_job_t;
+int plslam_match_local_points_batch_device(const plslam_local_job_t* d_jobs, int njobs, int max_n, void* stream); /* max_n >= every job's n */
+int plslam_match_local_points_host(const plslam_local_job_t* job, int n_scale_levels);
+
 /* Single-job convenience forms for the class veneers: every pointer inside *job is a HOST pointer; the call
  * uploads the arrays, runs the kernel and writes match_* / nmatches back.  n_grid_items = grid_start[64*48]. */
 int plslam_match_bow_host(const plslam_bow_job_t* job);

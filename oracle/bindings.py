@@ -428,3 +428,18 @@ def frame_post(calib, bounds, xy, depth):
     lib().oracle_frame_post(_p(c), _p(b), _p(xy), n, _p(depth), depth.shape[1], depth.shape[0], depth.strides[0] // 4,
                             _p(un), _p(ur), _p(z), _p(gs), _p(gi))
     return {"un_xy": un, "uright": ur, "depth": z, "grid_start": gs, "grid_items": gi[:gs[-1]]}
+
+
+def search_local_points(mp, fr, cam4, scale_factors, th, nnratio=0.8):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th): mp / fr dicts as tests/matchdata.local_points_case."""
+    m, n = len(mp["desc"]), len(fr["desc"])
+    match = np.empty(max(n, 1), np.int32)
+    L = lib()
+    L.oracle_search_local_points.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 9 + [C.c_float, C.c_float, C.c_void_p]
+    k = {a: np.ascontiguousarray(b) for a, b in mp.items()}
+    f = {a: np.ascontiguousarray(b) for a, b in fr.items()}
+    cam = np.ascontiguousarray(cam4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    cnt = L.oracle_search_local_points(m, _p(k["valid"]), _p(k["proj"]), _p(k["level"]), _p(k["viewcos"]), _p(k["desc"]), _p(k["obs"]),
+                                       n, _p(f["xy"]), _p(f["octave"]), _p(f["desc"]), _p(f["uright"]), _p(f["taken"]),
+                                       _p(f["grid_start"]), _p(f["grid_items"]), _p(cam), _p(sf), th, nnratio, _p(match))
+    return match[:n], cnt

@@ -237,4 +237,81 @@ int oracle_search_by_projection(int N1, const uint8_t* lastValid, const float* l
   return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (reference
+// include/ORBmatcher.h:61; lib/libORB_SLAM2.so@0x79f10, called by Tracking::SearchLocalPoints).  Read from the binary:
+// mbTrackInView (+0x30) / isBad() gate @0x79fab-0x79fbc; RadiusByViewingCos(&mTrackViewCos) @0x79fd9 (2.5 / 4.0, @0x79b60);
+// `th != 1.0 => r *= th` @0x79fe4-0x7a002; GetFeaturesInArea(mTrackProjX, mTrackProjY, r * mvScaleFactors[level],
+// level - 1, level) @0x7a051; bestDist = bestDist2 = 256 @0x7a09a; Observations() > 0 skip @0x7a0d8; mvuRight > 0 =>
+// |mTrackProjXR - uR| > r * sf skips @0x7a113-0x7a146; dist < bestDist / else dist < bestDist2 @0x7a192,0x7a368;
+// bestDist <= TH_HIGH (100) @0x7a27b; same level && bestDist > mfNNratio * bestDist2 rejects @0x7a286,0x7a39c.
+// Map points flattened: mpValid = mbTrackInView && !isBad(), mpProj = (mTrackProjX, mTrackProjY, mTrackProjXR),
+// mpLevel = mnTrackScaleLevel, mpViewCos = mTrackViewCos, mpDesc = GetDescriptor(), mpObs = Observations() > 0.
+// cam4 = {mnMinX, mnMinY, gridWInv, gridHInv}.  matchF[N] = map point index assigned to each frame keypoint (-1 = none).
+int oracle_search_local_points(int M, const uint8_t* mpValid, const float* mpProj, const int* mpLevel, const float* mpViewCos,
+                               const uint8_t* mpDesc, const uint8_t* mpObs, int N, const float* fXY, const int* fOctave,
+                               const uint8_t* fDesc, const float* fURight, const uint8_t* fTaken, const int* gridStart,
+                               const int* gridItems, const float* cam4, const float* scaleFactors, float th, float nnratio,
+                               int* matchF) {
+  const float mnMinX = cam4[0], mnMinY = cam4[1], gwi = cam4[2], ghi = cam4[3];
+  std::vector<uint8_t> taken(fTaken, fTaken + N);
+  for (int i = 0; i < N; ++i) matchF[i] = -1;
+  int nmatches = 0;
+  const bool bFactor = th != 1.0f;
+  for (int iMP = 0; iMP < M; ++iMP) {
+    if (!mpValid[iMP]) continue;
+    const int nPredictedLevel = mpLevel[iMP];
+    float r = mpViewCos[iMP] > 0.998f ? 2.5f : 4.0f;  // RadiusByViewingCos
+    if (bFactor) r *= th;
+    const float x = mpProj[3 * iMP], y = mpProj[3 * iMP + 1], xr = mpProj[3 * iMP + 2];
+    const float radius = r * scaleFactors[nPredictedLevel];
+    const int minLevel = nPredictedLevel - 1, maxLevel = nPredictedLevel;
+    const int nMinCellX = std::max(0, (int)floorf((x - mnMinX - radius) * gwi));
+    if (nMinCellX >= FRAME_GRID_COLS) continue;
+    const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceilf((x - mnMinX + radius) * gwi));
+    if (nMaxCellX < 0) continue;
+    const int nMinCellY = std::max(0, (int)floorf((y - mnMinY - radius) * ghi));
+    if (nMinCellY >= FRAME_GRID_ROWS) continue;
+    const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceilf((y - mnMinY + radius) * ghi));
+    if (nMaxCellY < 0) continue;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+      for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+        const int c = ix * FRAME_GRID_ROWS + iy;
+        for (int j = gridStart[c]; j < gridStart[c + 1]; ++j) {
+          const int idx = gridItems[j];
+          if (bCheckLevels) {
+            if (fOctave[idx] < minLevel) continue;
+            if (maxLevel >= 0 && fOctave[idx] > maxLevel) continue;
+          }
+          const float distx = fXY[2 * idx] - x, disty = fXY[2 * idx + 1] - y;
+          if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
+          if (taken[idx]) continue;
+          if (fURight[idx] > 0) {
+            const float er = fabsf(xr - fURight[idx]);
+            if (er > radius) continue;
+          }
+          const int dist = descriptor_distance(mpDesc + 32 * iMP, fDesc + 32 * idx);
+          if (dist < bestDist) {
+            bestDist2 = bestDist;
+            bestDist = dist;
+            bestLevel2 = bestLevel;
+            bestLevel = fOctave[idx];
+            bestIdx = idx;
+          } else if (dist < bestDist2) {
+            bestLevel2 = fOctave[idx];
+            bestDist2 = dist;
+          }
+        }
+      }
+    if (bestDist <= TH_HIGH) {
+      if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+      matchF[bestIdx] = iMP;
+      if (mpObs[iMP]) taken[bestIdx] = 1;
+      nmatches++;
+    }
+  }
+  return nmatches;
+}
+
 }  // extern "C"

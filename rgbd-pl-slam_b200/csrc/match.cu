@@ -323,6 +323,98 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
   if (lane == 0) *J.nmatches = nmatches;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// SearchByProjection(Frame &F, const vector<MapPoint*>&, th) (@0x79f10, Tracking::SearchLocalPoints): one warp per
+// frame walks the local map points in order (a keypoint assigned to an observed map point is skipped later); lanes
+// split the grid cells of the search window.  The reference's best / second-best update over the candidates in
+// [ix][iy][position] order ends with the two smallest (distance, order) keys: the best is the first occurrence of
+// the minimum, the second-best slot holds the first occurrence of the smallest remaining value (see
+// oracle/match_oracle.cc for the sequential form the result is compared with).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_local_points(const plslam_local_job_t* __restrict__ jobs) {
+  extern __shared__ int smem_i[];
+  const plslam_local_job_t& J = jobs[blockIdx.x];
+  const int lane = threadIdx.x;
+  const int M = J.m, N = J.n;
+  int* matchF = smem_i;                                       // [N]
+  uint8_t* taken = reinterpret_cast<uint8_t*>(matchF + N);    // [N]
+  for (int i = lane; i < N; i += 32) { matchF[i] = -1; taken[i] = J.f_taken[i]; }
+  __syncwarp();
+  const float mnMinX = J.cam[0], mnMinY = J.cam[1], gwi = J.cam[2], ghi = J.cam[3];
+  const bool bFactor = J.th != 1.0f;
+  const uint4* DM = reinterpret_cast<const uint4*>(J.mp_desc);
+  const uint4* DF = reinterpret_cast<const uint4*>(J.f_desc);
+  int nmatches = 0;
+  for (int i = 0; i < M; ++i) {
+    if (!J.mp_valid[i]) continue;
+    const int level = J.mp_level[i];
+    float r = J.mp_viewcos[i] > 0.998f ? 2.5f : 4.0f;
+    if (bFactor) r = __fmul_rn(r, J.th);
+    const float x = J.mp_proj[3 * i], y = J.mp_proj[3 * i + 1], xr = J.mp_proj[3 * i + 2];
+    const float radius = __fmul_rn(r, J.scale_factors[level]);
+    const int minLevel = level - 1, maxLevel = level;
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, mnMinX), radius), gwi)));
+    if (nMinCellX >= PLSLAM_GRID_COLS) continue;
+    const int nMaxCellX = min(PLSLAM_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, mnMinX), radius), gwi)));
+    if (nMaxCellX < 0) continue;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, mnMinY), radius), ghi)));
+    if (nMinCellY >= PLSLAM_GRID_ROWS) continue;
+    const int nMaxCellY = min(PLSLAM_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, mnMinY), radius), ghi)));
+    if (nMaxCellY < 0) continue;
+    const int ncy = nMaxCellY - nMinCellY + 1, ncells = (nMaxCellX - nMinCellX + 1) * ncy;
+    const uint4 a0 = DM[2 * i], a1 = DM[2 * i + 1];
+    // per lane: the two smallest keys dist << 22 | cellRank << 8 | pos, with keypoint index and octave
+    unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;
+    int i1 = -1, o1 = -1, o2 = -1;
+    for (int c = lane; c < ncells; c += 32) {
+      const int ix = nMinCellX + c / ncy, iy = nMinCellY + c % ncy;
+      const int cell = ix * PLSLAM_GRID_ROWS + iy;
+      const int s0 = J.grid_start[cell], s1 = J.grid_start[cell + 1];
+      for (int j = s0; j < s1; ++j) {
+        const int idx = J.grid_items[j];
+        const int oc = J.f_octave[idx];
+        if (oc < minLevel || oc > maxLevel) continue;  // bCheckLevels is always true here (maxLevel = level >= 0)
+        const float distx = __fsub_rn(J.f_xy[2 * idx], x), disty = __fsub_rn(J.f_xy[2 * idx + 1], y);
+        if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
+        if (taken[idx]) continue;
+        const float ur = J.f_uright[idx];
+        if (ur > 0 && fabsf(__fsub_rn(xr, ur)) > radius) continue;
+        const int dist = hamming256(a0, a1, DF[2 * idx], DF[2 * idx + 1]);
+        const unsigned key = ((unsigned)dist << 22) | ((unsigned)c << 8) | (unsigned)min(j - s0, 255);
+        if (key < k1) { k2 = k1; o2 = o1; k1 = key; i1 = idx; o1 = oc; }
+        else if (key < k2) { k2 = key; o2 = oc; }
+      }
+    }
+    const unsigned g1 = warp_min_u32(k1);
+    if (g1 == 0xffffffffu) continue;
+    const int bestDist = (int)(g1 >> 22);
+    if (bestDist > PLSLAM_TH_HIGH) continue;
+    const int src1 = __ffs(__ballot_sync(0xffffffffu, k1 == g1)) - 1;
+    const int bestIdx = __shfl_sync(0xffffffffu, i1, src1), bestLevel = __shfl_sync(0xffffffffu, o1, src1);
+    // runner-up over all lanes: the owner of the best contributes its own second key
+    const unsigned mine2 = lane == src1 ? k2 : k1;
+    const int mine2o = lane == src1 ? o2 : o1;
+    const unsigned g2 = warp_min_u32(mine2);
+    int bestDist2 = 256, bestLevel2 = -1;
+    if (g2 != 0xffffffffu) {
+      const int src2 = __ffs(__ballot_sync(0xffffffffu, mine2 == g2)) - 1;
+      bestDist2 = (int)(g2 >> 22);
+      bestLevel2 = __shfl_sync(0xffffffffu, mine2o, src2);
+    }
+    if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2)) continue;
+    if (lane == 0) {
+      matchF[bestIdx] = i;
+      if (J.mp_obs[i]) taken[bestIdx] = 1;
+    }
+    ++nmatches;
+    __syncwarp();
+  }
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) J.match_f[i] = matchF[i];
+  if (lane == 0) *J.nmatches = nmatches;
+}
+
 }  // namespace
 }  // namespace plslam
 
@@ -496,6 +588,52 @@ int plslam_match_projection_host(const plslam_proj_job_t* job, int n_scale_level
   int rc = plslam_match_projection_batch_device(dj, 1, n1, n2, nullptr);
   if (rc) return rc;
   PL_CUDA(cudaMemcpy(job->match_cur, d.match_cur, (size_t)n2 * 4, cudaMemcpyDeviceToHost));
+  PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int plslam_match_local_points_batch_device(const plslam_local_job_t* d_jobs, int njobs, int max_n, void* stream) {
+  PL_CHECK_ARG(d_jobs && njobs >= 1 && max_n >= 0);
+  const size_t smem = (size_t)max_n * 5 + 16;  // matchF[n] ints + taken[n] bytes
+  PL_CHECK_ARG(smem <= 200 * 1024);
+  static bool attr = false;
+  if (!attr) {
+    PL_CUDA(cudaFuncSetAttribute(k_local_points, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  PL_CARVEOUT(k_local_points);
+  k_local_points<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_match_local_points_host(const plslam_local_job_t* job, int n_scale_levels) {
+  PL_CHECK_ARG(job && job->match_f && job->nmatches && job->m >= 0 && job->n >= 0 && n_scale_levels >= 1);
+  Uploader U;
+  plslam_local_job_t d = *job;
+  const int m = job->m, n = job->n, ncell = PLSLAM_GRID_COLS * PLSLAM_GRID_ROWS;
+  const int nitems = job->grid_start[ncell];
+  d.mp_valid = U.up(job->mp_valid, m);
+  d.mp_proj = U.up(job->mp_proj, (size_t)m * 3);
+  d.mp_level = U.up(job->mp_level, m);
+  d.mp_viewcos = U.up(job->mp_viewcos, m);
+  d.mp_desc = U.up(job->mp_desc, (size_t)m * 32);
+  d.mp_obs = U.up(job->mp_obs, m);
+  d.f_xy = U.up(job->f_xy, (size_t)n * 2);
+  d.f_octave = U.up(job->f_octave, n);
+  d.f_desc = U.up(job->f_desc, (size_t)n * 32);
+  d.f_uright = U.up(job->f_uright, n);
+  d.f_taken = U.up(job->f_taken, n);
+  d.grid_start = U.up(job->grid_start, ncell + 1);
+  d.grid_items = U.up(job->grid_items, nitems);
+  d.scale_factors = U.up(job->scale_factors, n_scale_levels);
+  d.match_f = U.out<int32_t>(n);
+  d.nmatches = U.out<int32_t>(1);
+  const plslam_local_job_t* dj = U.up(&d, 1);
+  if (U.err != cudaSuccess) { set_error("local points host path: %s", cudaGetErrorString(U.err)); return PLSLAM_ERR_CUDA; }
+  int rc = plslam_match_local_points_batch_device(dj, 1, n, nullptr);
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpy(job->match_f, d.match_f, (size_t)n * 4, cudaMemcpyDeviceToHost));
   PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
   return PLSLAM_OK;
 }

@@ -675,3 +675,36 @@ def bow_pairs_device(d_kps, d_desc, d_counts, fv, d_kf_valid=None, nnratio=0.7, 
                                                C.c_float(nnratio), int(check_ori), _vp(out["_angle"]), _vp(out["_jobs"]),
                                                _vp(out["match"]), _vp(out["nmatches"]), _stream_ptr(stream)))
     return out
+
+
+class LocalJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("mp_valid", "mp_proj", "mp_level", "mp_viewcos", "mp_desc", "mp_obs", "f_xy", "f_octave",
+                                          "f_desc", "f_uright", "f_taken", "grid_start", "grid_items", "scale_factors", "match_f",
+                                          "nmatches")] + \
+               [("cam", C.c_float * 4), ("th", C.c_float), ("nnratio", C.c_float), ("m", C.c_int32), ("n", C.c_int32)]
+
+
+assert C.sizeof(LocalJob) == 160
+
+
+def local_points_batch_device(jobs, max_n, device, stream=None):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) for a list of LocalJob (device pointers)."""
+    jd = _jobs_to_device(jobs, device)
+    _check(lib().plslam_match_local_points_batch_device(_vp(jd), len(jobs), int(max_n), _stream_ptr(stream)))
+    return jd
+
+
+def search_local_points_host(mp, fr, cam4, scale_factors, th, nnratio=0.8):
+    """Host-array form (dict layout of tests/matchdata.local_points_case) -> (match_f, nmatches)."""
+    keep = {k: np.ascontiguousarray(v) for k, v in list(mp.items()) + [("f_" + k, v) for k, v in fr.items()]}
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    m, n = len(mp["desc"]), len(fr["desc"])
+    out, cnt = np.empty(max(n, 1), np.int32), np.zeros(1, np.int32)
+    p = lambda a: a.ctypes.data
+    j = LocalJob(p(keep["valid"]), p(keep["proj"]), p(keep["level"]), p(keep["viewcos"]), p(keep["desc"]), p(keep["obs"]),
+                 p(keep["f_xy"]), p(keep["f_octave"]), p(keep["f_desc"]), p(keep["f_uright"]), p(keep["f_taken"]),
+                 p(keep["f_grid_start"]), p(keep["f_grid_items"]), p(sf), p(out), p(cnt))
+    j.cam[:] = np.asarray(cam4, np.float32).tolist()
+    j.th = float(th); j.nnratio = float(nnratio); j.m = m; j.n = n
+    _check(lib().plslam_match_local_points_host(C.byref(j), len(sf)))
+    return out[:n], int(cnt[0])

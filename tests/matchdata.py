@@ -62,3 +62,29 @@ def projection_case(kps_last, desc_last, kps_cur, desc_cur, scale_factors, W=640
                uright=uright, taken=(rng.random(n2) < 0.05).astype(np.uint8), grid_start=gs, grid_items=gi)
     cam = np.array([fx, fy, cx, cy, bf, mb, mnx, mxx, mny, mxy, gwi, ghi], np.float32)
     return last, cur, cam, np.ascontiguousarray(scale_factors, np.float32), tcw_cur, tcw_last
+
+
+def local_points_case(kps_map, desc_map, kps_cur, desc_cur, W=640, H=480, seed=0, jitter=3.0):
+    """Tracking::SearchLocalPoints-like inputs: "map points" = the other frame's features projected near their true
+    position in the current frame (what Frame::isInFrustum would have stored in mTrackProjX/Y/XR, mnTrackScaleLevel,
+    mTrackViewCos), current frame = keypoints + grid."""
+    rng = np.random.default_rng(seed)
+    m, n = len(kps_map), len(kps_cur)
+    bf = np.float32(40.0)
+    z = (1.5 + rng.random(m) * 2.0).astype(np.float32)
+    px = (kps_map["x"] + 3.0 + rng.normal(0, jitter, m)).astype(np.float32)
+    py = (kps_map["y"] + 3.0 + rng.normal(0, jitter, m)).astype(np.float32)
+    proj = np.stack([px, py, px - bf / z], 1).astype(np.float32)
+    level = np.clip(kps_map["octave"] + rng.integers(-1, 2, m), 0, 7).astype(np.int32)
+    mp = dict(valid=(rng.random(m) < 0.85).astype(np.uint8), proj=np.ascontiguousarray(proj), level=level,
+              viewcos=(0.99 + 0.01 * rng.random(m)).astype(np.float32), desc=np.ascontiguousarray(desc_map),
+              obs=(rng.random(m) < 0.9).astype(np.uint8))
+    xy = np.stack([kps_cur["x"], kps_cur["y"]], 1).astype(np.float32)
+    gs, gi, (mnx, mxx, mny, mxy, gwi, ghi) = frame_grid(xy, W, H)
+    zc = (1.5 + rng.random(n) * 2.0).astype(np.float32)
+    fr = dict(xy=np.ascontiguousarray(xy), octave=np.ascontiguousarray(kps_cur["octave"], np.int32),
+              desc=np.ascontiguousarray(desc_cur),
+              uright=np.where(rng.random(n) < 0.7, kps_cur["x"] - bf / zc, -1).astype(np.float32),
+              taken=(rng.random(n) < 0.05).astype(np.uint8), grid_start=gs, grid_items=gi)
+    cam4 = np.array([mnx, mny, gwi, ghi], np.float32)
+    return mp, fr, cam4

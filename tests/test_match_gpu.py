@@ -106,3 +106,39 @@ def test_search_by_projection_matches_oracle(oracle, feats):
         assert np.array_equal(em, m.cpu().numpy())
         total += en
     assert total > 200
+
+
+def test_search_local_points_matches_oracle(oracle, feats):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (Tracking::SearchLocalPoints): batched device form and the
+    host form against the sequential oracle, th = 1 (no factor) and th = 3 (after relocalisation), two nnratio values."""
+    import torch
+    import plslam_b200 as pl
+    from matchdata import local_points_case
+    fs, scale = feats
+    jobs, keep, expect = [], [], []
+    for s, ((ka, da), (kb, db)) in enumerate(fs):
+        for th, nnr, jitter in ((1.0, 0.8, 2.0), (3.0, 0.8, 6.0), (1.0, 0.6, 1.0), (5.0, 0.9, 10.0)):
+            mp, fr, cam4 = local_points_case(ka, da, kb, db, seed=10 * s + int(th), jitter=jitter)
+            expect.append(oracle.search_local_points(mp, fr, cam4, scale, th, nnr))
+            Mp = {k: _dev(v) for k, v in mp.items()}
+            Fr = {k: _dev(v) for k, v in fr.items()}
+            sfd = _dev(scale)
+            m = torch.empty(len(db), dtype=torch.int32, device="cuda"); n = torch.zeros(1, dtype=torch.int32, device="cuda")
+            keep.append((Mp, Fr, sfd, m, n))
+            j = pl.LocalJob(Mp["valid"].data_ptr(), Mp["proj"].data_ptr(), Mp["level"].data_ptr(), Mp["viewcos"].data_ptr(),
+                            Mp["desc"].data_ptr(), Mp["obs"].data_ptr(), Fr["xy"].data_ptr(), Fr["octave"].data_ptr(),
+                            Fr["desc"].data_ptr(), Fr["uright"].data_ptr(), Fr["taken"].data_ptr(), Fr["grid_start"].data_ptr(),
+                            Fr["grid_items"].data_ptr(), sfd.data_ptr(), m.data_ptr(), n.data_ptr())
+            j.cam[:] = cam4.tolist(); j.th = th; j.nnratio = nnr; j.m = len(da); j.n = len(db)
+            jobs.append(j)
+            if s == 0:
+                hm, hn = pl.search_local_points_host(mp, fr, cam4, scale, th, nnr)
+                assert hn == expect[-1][1] and np.array_equal(hm, expect[-1][0])
+    pl.local_points_batch_device(jobs, max(j.n for j in jobs), "cuda")
+    torch.cuda.synchronize()
+    total = 0
+    for (em, en), (_, _, _, m, n) in zip(expect, keep):
+        assert int(n) == en
+        assert np.array_equal(em, m.cpu().numpy())
+        total += en
+    assert total > 300
