@@ -12,7 +12,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_ROOT, "libplslam_b200.so")
+LIB_PATH = os.environ.get("PLSLAM_LIB") or os.path.join(_ROOT, "libplslam_b200.so")  # PLSLAM_LIB: experiment builds (tools/)
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
