@@ -453,15 +453,12 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
           C.reg_set(n + __popc(commit & lt), nxy);
           if (C.prefetch) {
             // the 3x3 neighbourhood of the new region point is examined when the point reaches the scan front, a
-            // few batches from now: pull its three record rows (48 B each, possibly straddling two lines) towards L1
+            // few batches from now: pull the lines holding its three record rows towards L1
             const int up = (nxy >> 16) > 0 ? nidx - C.sw : nidx, dn = (int)(nxy >> 16) < C.sh - 1 ? nidx + C.sw : nidx;
-            const int l = (nxy & 0xffff) > 0 ? -1 : 0, r = (int)(nxy & 0xffff) < C.sw - 1 ? 1 : 0;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + up + l));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + up + r));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + nidx + l));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + nidx + r));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + dn + l));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.pix + dn + r));
+            const uint4* q = C.pix + nidx;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (up - nidx)));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (dn - nidx)));
           }
         }
         n += __popc(commit);
@@ -510,7 +507,10 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
   double* sA = C.stage;
   double* sB = C.stage + 32;
   double* sC = C.stage + 64;
-  double x = 0, y = 0, sum = 0;
+  // The three running sums are independent chains that must add in region order: lanes 0..2 own one chain each (lane k
+  // reads its own staging row), so a chunk costs one load + one add per point instead of three of each.
+  const double* myRow = C.stage + 32 * min(lane, 2);
+  double acc = 0;
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
     if (i < n) {
@@ -523,16 +523,14 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
     }
     __syncwarp();
     const int cnt = min(32, n - c);
-    for (int j = 0; j < cnt; ++j) {
-      x = __dadd_rn(x, sA[j]);
-      y = __dadd_rn(y, sB[j]);
-      sum = __dadd_rn(sum, sC[j]);
-    }
+    if (lane < 3)
+      for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, myRow[j]);
     __syncwarp();
   }
-  x = __ddiv_rn(x, sum);
-  y = __ddiv_rn(y, sum);
-  double Ixx = 0, Iyy = 0, Ixy = 0;
+  const double sum = __shfl_sync(0xffffffffu, acc, 2);
+  const double x = __ddiv_rn(__shfl_sync(0xffffffffu, acc, 0), sum);
+  const double y = __ddiv_rn(__shfl_sync(0xffffffffu, acc, 1), sum);
+  acc = 0;
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
     if (i < n) {
@@ -542,17 +540,16 @@ __device__ void lsd_region2rect(const GrowCtx& C, int n, double reg_angle, doubl
       const double dx = __dsub_rn((double)px, x), dy = __dsub_rn((double)py, y);
       sA[lane] = __dmul_rn(__dmul_rn(dy, dy), w);
       sB[lane] = __dmul_rn(__dmul_rn(dx, dx), w);
-      sC[lane] = __dmul_rn(__dmul_rn(dx, dy), w);
+      sC[lane] = -__dmul_rn(__dmul_rn(dx, dy), w);  // Ixy -= v  ==  Ixy += -v exactly
     }
     __syncwarp();
     const int cnt = min(32, n - c);
-    for (int j = 0; j < cnt; ++j) {
-      Ixx = __dadd_rn(Ixx, sA[j]);
-      Iyy = __dadd_rn(Iyy, sB[j]);
-      Ixy = __dsub_rn(Ixy, sC[j]);
-    }
+    if (lane < 3)
+      for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, myRow[j]);
     __syncwarp();
   }
+  const double Ixx = __shfl_sync(0xffffffffu, acc, 0), Iyy = __shfl_sync(0xffffffffu, acc, 1),
+               Ixy = __shfl_sync(0xffffffffu, acc, 2);
   const double dI = __dsub_rn(Ixx, Iyy);
   const double disc = __dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy));
   const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy), sqrt(disc)));
@@ -617,10 +614,12 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   const double ang_c = __dmul_rn((double)__uint_as_float(C.pix[sy * C.sw + sx].x), PL_DEG_TO_RADS);
   double* sA = C.stage;
   double* sF = C.stage + 32;
-  double sum = 0, s_sum = 0;
+  double* sV2 = C.stage + 64;
+  double acc = 0;
   int cntN = 0;
   for (int c = 0; c < n; c += 32) {
     const int i = c + lane;
+    bool inside = false;
     if (i < n) {
       const unsigned pxy = C.reg_get(i);
       const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
@@ -635,18 +634,21 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
       }
       sA[lane] = v;
       sF[lane] = flag;
+      sV2[lane] = __dmul_rn(v, v);
+      inside = flag != 0.0;
     }
+    cntN += __popc(__ballot_sync(0xffffffffu, inside));
     __syncwarp();
     const int cnt = min(32, n - c);
-    for (int j = 0; j < cnt; ++j)
-      if (sF[j] != 0.0) {
-        const double v = sA[j];
-        sum = __dadd_rn(sum, v);
-        s_sum = __dadd_rn(s_sum, __dmul_rn(v, v));
-        ++cntN;
-      }
+    // two ordered chains (sum of v, sum of v*v over the flagged points): lane 0 and lane 1 own one each
+    if (lane < 2) {
+      const double* row = lane == 0 ? sA : sV2;
+      for (int j = 0; j < cnt; ++j)
+        if (sF[j] != 0.0) acc = __dadd_rn(acc, row[j]);
+    }
     __syncwarp();
   }
+  const double sum = __shfl_sync(0xffffffffu, acc, 0), s_sum = __shfl_sync(0xffffffffu, acc, 1);
   const double mean_angle = __ddiv_rn(sum, (double)cntN);
   const double tau = __dmul_rn(
       2.0, sqrt(__dadd_rn(__ddiv_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)), (double)cntN),
