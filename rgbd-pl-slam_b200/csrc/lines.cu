@@ -395,7 +395,7 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
     unsigned nxy = 0, w = 0;
     float deg = NOTDEF_F, cs = 0.f, sn = 0.f;
     if (pt < m4) {
-      const unsigned p = C.reg_get(i + pt);
+      const unsigned p = i + 4 <= REG_SMEM ? C.regS[i + pt] : C.reg_get(i + pt);  // warp-uniform fast path
       const int nx = (int)(p & 0xffff) + ox, ny = (int)(p >> 16) + oy;
       if (nx >= 0 && ny >= 0 && nx < C.sw && ny < C.sh) {
         const int id = ny * C.sw + nx;
@@ -424,6 +424,30 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
         const unsigned m = __ballot_sync(FULL, a0);
         if (!m) break;
         GP_CNT(10, 1);
+        {
+          // common case of thin regions: the accepted lane is the last lane that holds a candidate pixel at all, so no
+          // later decision can depend on the new angle and the earlier lanes were tested against the exact state
+          const unsigned defm = __ballot_sync(FULL, in && deg != NOTDEF_F);
+          const int j0 = __ffs(m) - 1;
+          if ((defm >> j0) == 1u) {
+            if (lane == j0) {
+              *C.wptr(nidx) = w | USED_BIT;
+              C.reg_set(n, nxy);
+              if (C.prefetch) {
+                const int up = (nxy >> 16) > 0 ? nidx - C.sw : nidx, dn = (int)(nxy >> 16) < C.sh - 1 ? nidx + C.sw : nidx;
+                const uint4* q = C.pix + nidx;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (up - nidx)));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (dn - nidx)));
+              }
+            }
+            ++n;
+            sumdx = __fadd_rn(sumdx, __shfl_sync(FULL, cs, j0));
+            sumdy = __fadd_rn(sumdy, __shfl_sync(FULL, sn, j0));
+            reg_angle = __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), PL_DEG_TO_RADS);
+            break;
+          }
+        }
         // sums before this lane, assuming every earlier lane of m is accepted (additions in scan order)
         float sx = sumdx, sy = sumdy;
         for (unsigned r = m; r; r &= r - 1u) {
