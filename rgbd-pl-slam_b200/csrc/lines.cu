@@ -272,7 +272,7 @@ struct GrowCtx {
   unsigned* regS;     // region list ((y << 16) | x): first REG_SMEM entries in shared memory ...
   unsigned* regG;     // ... the rest in this frame's global scratch
   double* stage;      // 3 x 32 doubles of shared staging
-  int sw, sh;
+  int sw, sh, P;
   int lane;
   bool prefetch;
   __device__ __forceinline__ unsigned reg_get(int i) const { return i < REG_SMEM ? regS[i] : regG[i]; }
@@ -284,6 +284,16 @@ struct GrowCtx {
 
 __device__ __forceinline__ bool lsd_aligned(double theta, float deg, double prec) {
   const double a = __dmul_rn((double)deg, PL_DEG_TO_RADS);
+  double n_theta = __dsub_rn(theta, a);
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > M_3_2_PI_D) {
+    n_theta = __dsub_rn(n_theta, M_2__PI_D);
+    if (n_theta < 0) n_theta = -n_theta;
+  }
+  return n_theta <= prec;
+}
+
+__device__ __forceinline__ bool lsd_aligned_rad(double theta, double a, double prec) {
   double n_theta = __dsub_rn(theta, a);
   if (n_theta < 0) n_theta = -n_theta;
   if (n_theta > M_3_2_PI_D) {
@@ -410,6 +420,8 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
         }
       }
     }
+    // the candidate's level-line angle in radians, once per batch (both alignment tests of every round use it)
+    const double arad = __dmul_rn((double)deg, PL_DEG_TO_RADS);
     const bool anyc = __any_sync(FULL, deg != NOTDEF_F);
     GP_ADD(0);
     GP_START();
@@ -420,7 +432,7 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
       unsigned todo = FULL;                                 // lanes the sequential scan has not passed yet
       while (true) {
         const bool in = (todo >> lane) & 1u;
-        const bool a0 = in && deg != NOTDEF_F && lsd_aligned(reg_angle, deg, prec) && !(peers & todo & lt);
+        const bool a0 = in && deg != NOTDEF_F && lsd_aligned_rad(reg_angle, arad, prec) && !(peers & todo & lt);
         const unsigned m = __ballot_sync(FULL, a0);
         if (!m) break;
         GP_CNT(10, 1);
@@ -462,7 +474,7 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
         const double ra_post = __dmul_rn((double)fast_atan2_dev(py, px), PL_DEG_TO_RADS);
         const double ra_up = __shfl_up_sync(FULL, ra_post, 1);
         const double ra = (m & lt) ? ra_up : reg_angle;  // exact region angle this lane is tested against
-        const bool a1 = in && deg != NOTDEF_F && lsd_aligned(ra, deg, prec) && !(peers & m & lt);
+        const bool a1 = in && deg != NOTDEF_F && lsd_aligned_rad(ra, arad, prec) && !(peers & m & lt);
         const unsigned m1 = __ballot_sync(FULL, a1);
         const unsigned bad = (m ^ m1) & todo;
         unsigned commit;
@@ -688,22 +700,68 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
   while (density < density_th) {
     radSq = __dmul_rn(radSq, 0.75 * 0.75);
-    if (lane == 0) {
-      // swap-with-last removal exactly as the reference (it defines the order of the later sums)
-      for (int i = 0; i < n; ++i) {
-        const unsigned pxy = C.reg_get(i);
-        const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
-        if (dist_sq_dev(xc, yc, (double)px, (double)py) > radSq) {
-          unsigned* wp = C.wptr(py * C.sw + px);
-          *wp = *wp & ~USED_BIT;
-          C.reg_set(i, C.reg_get(n - 1));
-          C.reg_set(n - 1, pxy);
-          --n;
-          --i;
+    // The reference removes far points by swapping each with the current last element (that order defines the later
+    // sums).  Equivalent closed form (checked exhaustively against the sequential loop): with n' points kept, the far
+    // positions below n' in increasing order receive the kept points at or above n' in decreasing order.
+    if (n + (n >> 1) + 32 > C.P) {  // no room for the scratch list behind the region (never seen; kept for safety)
+      if (lane == 0) {
+        for (int i = 0; i < n; ++i) {
+          const unsigned pxy = C.reg_get(i);
+          const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+          if (dist_sq_dev(xc, yc, (double)px, (double)py) > radSq) {
+            unsigned* wp = C.wptr(py * C.sw + px);
+            *wp = *wp & ~USED_BIT;
+            C.reg_set(i, C.reg_get(n - 1));
+            C.reg_set(n - 1, pxy);
+            --n;
+            --i;
+          }
         }
       }
+      n = __shfl_sync(0xffffffffu, n, 0);
+    } else {
+      const unsigned FAR = 0x80000000u, FULL = 0xffffffffu, lt = (1u << lane) - 1u;  // row index < 2^15: bit 31 is free
+      int nfar = 0;
+      for (int c = 0; c < n; c += 32) {
+        const int i = c + lane;
+        bool far = false;
+        if (i < n) {
+          const unsigned pxy = C.reg_get(i);
+          const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+          far = dist_sq_dev(xc, yc, (double)px, (double)py) > radSq;
+          if (far) {
+            unsigned* wp = C.wptr(py * C.sw + px);
+            *wp = *wp & ~USED_BIT;
+            C.reg_set(i, pxy | FAR);
+          }
+        }
+        nfar += __popc(__ballot_sync(FULL, far));
+      }
+      __syncwarp();
+      const int nk = n - nfar;
+      // holes (far positions below nk, ascending) into scratch: the global list beyond n is free
+      unsigned* holes = C.regG + n;
+      int nh = 0;
+      for (int c = 0; c < nk; c += 32) {
+        const int i = c + lane;
+        const bool hole = i < nk && (C.reg_get(i) & FAR);
+        const unsigned b = __ballot_sync(FULL, hole);
+        if (hole) holes[nh + __popc(b & lt)] = (unsigned)i;
+        nh += __popc(b);
+      }
+      __syncwarp();
+      // fillers (kept positions at or above nk, descending): the k-th goes to the k-th hole
+      int nf = 0;
+      for (int c = n - 1; c >= nk; c -= 32) {
+        const int i = c - lane;
+        unsigned v = 0;
+        const bool fill = i >= nk && !((v = C.reg_get(i)) & FAR);
+        const unsigned b = __ballot_sync(FULL, fill);
+        if (fill) C.reg_set((int)holes[nf + __popc(b & lt)], v);
+        nf += __popc(b);
+      }
+      n = nk;
     }
-    n = __shfl_sync(0xffffffffu, n, 0);
     __syncwarp();
     *n_io = n;
     if (n < 2) return false;
@@ -731,6 +789,7 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
   C.regG = regAll + (size_t)f * L.P;
   C.sw = L.sw;
   C.sh = L.sh;
+  C.P = L.P;
   C.lane = lane;
 #ifdef PLSLAM_GROW_PROF
   long long prof[16];
