@@ -15,6 +15,18 @@ struct FeatureVectorView {         // DBoW2::FeatureVector = std::map<NodeId, st
   std::vector<int32_t> idx;        // feature indices, in the vectors' order
 };
 
+// The fields of the local map points that ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) reads
+// (reference include/MapPoint.h: mTrackProjX/Y/XR, mbTrackInView, mnTrackScaleLevel, mTrackViewCos, set by
+// Frame::isInFrustum for Tracking::SearchLocalPoints), flattened in the order of vpMapPoints.
+struct MapPointsView {
+  std::vector<uint8_t> inViewAndGood;   // pMP->mbTrackInView && !pMP->isBad()
+  std::vector<float> trackProj;         // M x 3: mTrackProjX, mTrackProjY, mTrackProjXR
+  std::vector<int32_t> trackScaleLevel; // mnTrackScaleLevel
+  std::vector<float> trackViewCos;      // mTrackViewCos
+  cv::Mat descriptors;                  // M x 32: GetDescriptor()
+  std::vector<uint8_t> observed;        // Observations() > 0
+};
+
 struct FrameView {
   // features
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn;

@@ -59,6 +59,30 @@ int ORBmatcher::SearchByProjection(FrameView& Cur, const FrameView& Last, const 
   return nm;
 }
 
+int ORBmatcher::SearchByProjection(FrameView& F, const MapPointsView& MP, const float th, std::vector<int>& vnMatches) {
+  const int m = (int)MP.inViewAndGood.size(), n = (int)F.mvKeysUn.size();
+  vnMatches.assign(n, -1);
+  if (m == 0 || n == 0) return 0;
+  std::vector<int32_t> oct(n);
+  std::vector<float> xy((size_t)n * 2);
+  for (int i = 0; i < n; ++i) {
+    oct[i] = F.mvKeysUn[i].octave;
+    xy[2 * i] = F.mvKeysUn[i].pt.x;
+    xy[2 * i + 1] = F.mvKeysUn[i].pt.y;
+  }
+  int32_t nm = 0;
+  plslam_local_job_t j{};
+  j.mp_valid = MP.inViewAndGood.data(); j.mp_proj = MP.trackProj.data(); j.mp_level = MP.trackScaleLevel.data();
+  j.mp_viewcos = MP.trackViewCos.data(); j.mp_desc = MP.descriptors.data; j.mp_obs = MP.observed.data();
+  j.f_xy = xy.data(); j.f_octave = oct.data(); j.f_desc = F.mDescriptors.data; j.f_uright = F.mvuRight.data();
+  j.f_taken = F.mapPointObserved.data(); j.grid_start = F.gridStart.data(); j.grid_items = F.gridItems.data();
+  j.scale_factors = F.mvScaleFactors.data(); j.match_f = vnMatches.data(); j.nmatches = &nm;
+  j.cam[0] = F.mnMinX; j.cam[1] = F.mnMinY; j.cam[2] = F.mfGridElementWidthInv; j.cam[3] = F.mfGridElementHeightInv;
+  j.th = th; j.nnratio = mfNNratio; j.m = m; j.n = n;
+  check(plslam_match_local_points_host(&j, (int)F.mvScaleFactors.size()), "SearchByProjection(local map)");
+  return nm;
+}
+
 int ORBmatcher::SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>& vnMatches) {
   const int n1 = (int)KF.mvKeysUn.size(), n2 = (int)F.mvKeys.size();
   vnMatches.assign(n2, -1);
