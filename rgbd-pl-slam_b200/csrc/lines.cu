@@ -125,32 +125,47 @@ __device__ __forceinline__ double modgrad_of(int g2) { return sqrt(__dmul_rn((do
 
 __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LineParams L, const uint8_t* __restrict__ scaled,
                                                   uint4* __restrict__ pix, int* __restrict__ maxg2) {
+  // Only ~1 pixel in 4 has a gradient above rho and needs the angle and its double-precision sin/cos.  The CTA's 32x8
+  // tile first writes the records of the undefined pixels and queues the defined ones in shared memory; the queue is
+  // then processed by full warps, so the double-precision pipe is not spent on mostly idle lanes.
+  __shared__ uint2 q[256];  // (pixel index in frame, gx & 0xffff | gy << 16)
+  __shared__ int qn;
   const int f = blockIdx.z;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (threadIdx.x == 0) qn = 0;
+  __syncthreads();
+  uint4* P = pix + (size_t)f * L.P;
   int g2 = 0;
   bool defined = false;
   if (x < L.sw && y < L.sh) {
-    float deg = NOTDEF_F, cs = 0.f, sn = 0.f;
+    int gx = 0, gy = 0;
     if (x < L.sw - 1 && y < L.sh - 1) {
       const uint8_t* r0 = scaled + (size_t)f * L.spitch * L.sh + (size_t)y * L.spitch + x;
       const uint8_t* r1 = r0 + L.spitch;
       const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
-      const int gx = DA + BC, gy = DA - BC;
+      gx = DA + BC;
+      gy = DA - BC;
       g2 = gx * gx + gy * gy;
-      if (modgrad_of(g2) > L.rho) {
-        defined = true;
-        deg = fast_atan2_dev((float)gx, (float)(-gy));
-        const float af = (float)__dmul_rn((double)deg, PL_DEG_TO_RADS);
-        pl_sincosf_dev(af, &sn, &cs);
-      }
+      defined = g2 >= L.g2_min;  // <=> sqrt(g2 / 4) > rho, threshold found on the host with the same double operations
     }
-    pix[(size_t)f * L.P + (size_t)y * L.sw + x] =
-        make_uint4(__float_as_uint(deg), __float_as_uint(cs), __float_as_uint(sn), (unsigned)g2);
+    const int idx = y * L.sw + x;
+    if (defined) q[atomicAdd(&qn, 1)] = make_uint2((unsigned)idx, ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16));
+    else P[idx] = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, (unsigned)g2);
   }
   int m = defined ? g2 : 0;
 #pragma unroll
   for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxg2 + f, m);
+  __syncthreads();
+  if ((int)threadIdx.x < qn) {
+    const uint2 e = q[threadIdx.x];
+    const int gx = (int)(short)(e.y & 0xffffu), gy = (int)e.y >> 16;
+    const float deg = fast_atan2_dev((float)gx, (float)(-gy));
+    const float af = (float)__dmul_rn((double)deg, PL_DEG_TO_RADS);
+    float sn, cs;
+    pl_sincosf_dev(af, &sn, &cs);
+    P[e.x] = make_uint4(__float_as_uint(deg), __float_as_uint(cs), __float_as_uint(sn), (unsigned)(gx * gx + gy * gy));
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1457,6 +1472,11 @@ int LineExtractor::configure(int W, int H, int batch) {
   P.rho = QUANT / std::sin(P.prec);
   P.log_nt = 5 * (std::log10((double)P.sw) + std::log10((double)P.sh)) / 2 + std::log10(11.0);
   P.min_reg_size = (int)(size_t)(-P.log_nt / std::log10(P.p));
+  {  // smallest gx^2 + gy^2 with modgrad = sqrt(g2 * 0.25) > rho (same double operations as ll_angle(); monotone in g2)
+    int g = 0;
+    while (!(std::sqrt((double)g * 0.25) > P.rho)) ++g;
+    P.g2_min = g;
+  }
   P.density_th = 0.7;
   P.log_eps = 0.0;
   P.max_lines = max_lines;

@@ -27,6 +27,7 @@ struct LineParams {
   double scale;        // 0.8
   double rho, prec, p, log_nt, density_th, log_eps;
   int min_reg_size;
+  int g2_min;          // smallest gx^2 + gy^2 whose gradient norm exceeds rho
   int max_lines;       // keep the strongest max_lines by response (0 = keep all)
   int rect_cap;        // capacity of the per-frame rectangle / segment lists
   int out_cap;         // capacity of the per-frame output (keylines kept)
