@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) k_lsd_scale(const __grid_constant__ LineP
 __device__ __forceinline__ double modgrad_of(int g2) { return sqrt(__dmul_rn((double)g2, 0.25)); }
 
 __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LineParams L, const uint8_t* __restrict__ scaled,
-                                                  uint4* __restrict__ pix, int* __restrict__ maxg2) {
+                                                  uint4* __restrict__ pix, float* __restrict__ degPlane,
+                                                  int* __restrict__ maxg2) {
   // Only ~1 pixel in 4 has a gradient above rho and needs the angle and its double-precision sin/cos.  The CTA's 32x8
   // tile first writes the records of the undefined pixels and queues the defined ones in shared memory; the queue is
   // then processed by full warps, so the double-precision pipe is not spent on mostly idle lanes.
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LinePa
   if (threadIdx.x == 0) qn = 0;
   __syncthreads();
   uint4* P = pix + (size_t)f * L.P;
+  float* DP = degPlane + (size_t)f * L.P;  // the angles alone, 4 B per pixel: what the rectangle scans of k_lsd_nfa read
   int g2 = 0;
   bool defined = false;
   if (x < L.sw && y < L.sh) {
@@ -150,7 +152,10 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LinePa
     }
     const int idx = y * L.sw + x;
     if (defined) q[atomicAdd(&qn, 1)] = make_uint2((unsigned)idx, ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16));
-    else P[idx] = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, (unsigned)g2);
+    else {
+      P[idx] = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, (unsigned)g2);
+      DP[idx] = NOTDEF_F;
+    }
   }
   int m = defined ? g2 : 0;
 #pragma unroll
@@ -165,6 +170,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LinePa
     float sn, cs;
     pl_sincosf_dev(af, &sn, &cs);
     P[e.x] = make_uint4(__float_as_uint(deg), __float_as_uint(cs), __float_as_uint(sn), (unsigned)(gx * gx + gy * gy));
+    DP[e.x] = deg;
   }
 }
 
@@ -940,7 +946,7 @@ __device__ __forceinline__ double lsd_ntheta(double theta, float deg) {
 // Row scan of rect_nfa(): counts the pixels of the rectangle (total) and, for up to 5 angular
 // tolerances at once, the aligned ones.  Warp-cooperative; results are warp-uniform.
 template <int NPREC>
-__device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* precs, const uint4* __restrict__ pix, int sw,
+__device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* precs, const float* __restrict__ pix, int sw,
                                int sh, int lane, int* total_out, int* alg_out) {
   const double hw = __dmul_rn(0.5, r.width);
   const double dyhw = __dmul_rn(r.dy, hw), dxhw = __dmul_rn(r.dx, hw);
@@ -975,10 +981,10 @@ __device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* prec
     int xe = (int)xb;
     if (xs < 0) xs = 0;
     if (xe > sw - 1) xe = sw - 1;
-    const uint4* row = pix + (size_t)yy * sw;
+    const float* row = pix + (size_t)yy * sw;
     for (int x = byRows ? xs : xs + lane; x <= xe; x += byRows ? 1 : 32) {
       ++total;
-      const double nt = lsd_ntheta(r.theta, __uint_as_float(__ldg(row + x).x));
+      const double nt = lsd_ntheta(r.theta, __ldg(row + x));
 #pragma unroll
       for (int j = 0; j < NPREC; ++j)
         if (nt <= precs[j]) ++alg[j];
@@ -998,9 +1004,9 @@ __device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* prec
 // rect_improve(): within a stage the five candidate rectangles do not depend on which of them is
 // accepted, so their pixel counts are gathered first and the five nfa() evaluations (the expensive
 // part: log-gamma, a binomial tail) run on five lanes at once; the accept chain is then replayed in order.
-__device__ void lsd_nfa_rect(const LineParams& L, const uint4* __restrict__ pixAll, const LsdRect* __restrict__ rectsAll,
+__device__ void lsd_nfa_rect(const LineParams& L, const float* __restrict__ pixAll, const LsdRect* __restrict__ rectsAll,
                              LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid, int f, int ri, int lane) {
-  const uint4* pix = pixAll + (size_t)f * L.P;
+  const float* pix = pixAll + (size_t)f * L.P;
   LsdRect rec = rectsAll[(size_t)f * L.rect_cap + ri];
   const double LOG_EPS = L.log_eps, LOG_NT = L.log_nt;
   const int sw = L.sw, sh = L.sh;
@@ -1103,7 +1109,7 @@ __device__ void lsd_nfa_rect(const LineParams& L, const uint4* __restrict__ pixA
 // counts are only known on the device and vary from ~50 to several hundred per frame; a grid sized for the capacity
 // would be 97 % empty CTAs, and rectangles that enter rect_improve cost ~25x the others, so small items matter.
 constexpr int NFA_GROUP = 4;
-__global__ void __launch_bounds__(256, 3) k_lsd_nfa(const __grid_constant__ LineParams L, const uint4* __restrict__ pixAll,
+__global__ void __launch_bounds__(256, 3) k_lsd_nfa(const __grid_constant__ LineParams L, const float* __restrict__ pixAll,
                                                  const LsdRect* __restrict__ rectsAll, const int* __restrict__ nrects,
                                                  LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1523,6 +1529,7 @@ int LineExtractor::configure(int W, int H, int batch) {
   PL_CUDA(cudaMemcpy(coef.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
   if ((rc = scaled.ensure(B * P.spitch * P.sh))) return rc;
   if ((rc = pix.ensure(B * P.P * sizeof(uint4)))) return rc;
+  if ((rc = degp.ensure(B * P.P * sizeof(float)))) return rc;
   if ((rc = rowhist.ensure(B * P.sh * LSD_BINS * sizeof(unsigned)))) return rc;
   if ((rc = binstart.ensure(B * LSD_BINS * sizeof(unsigned)))) return rc;
   if ((rc = maxg2.ensure(B * sizeof(int)))) return rc;
@@ -1568,7 +1575,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_grad", st);
   PL_CARVEOUT(k_lsd_grad);
-  k_lsd_grad<<<dim3(div_up(P.sw, 32), div_up(P.sh, 8), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(),
+  k_lsd_grad<<<dim3(div_up(P.sw, 32), div_up(P.sh, 8), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(), degp.as<float>(),
                                                                              maxg2.as<int>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_rowhist", st);
@@ -1605,7 +1612,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   uint8_t* rvalid = reinterpret_cast<uint8_t*>(rout + (size_t)cfgB * P.rect_cap);
   PL_STAGE_BEGIN(timer, "lsd_nfa", st);
   PL_CARVEOUT(k_lsd_nfa);
-  k_lsd_nfa<<<numSMs * 3, 256, 0, st>>>(P, pix.as<uint4>(), rects.as<LsdRect>(), nrects.as<int>(),
+  k_lsd_nfa<<<numSMs * 3, 256, 0, st>>>(P, degp.as<float>(), rects.as<LsdRect>(), nrects.as<int>(),
                                                                 rout, rvalid);
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_finish", st);
