@@ -207,6 +207,46 @@ def cpu_pairs_per_second(a, frames, threads):
     return time.perf_counter() - t0
 
 
+def opencv_primitives_fps(a, frames, threads):
+    """Independent reference point: the OpenCV calls the reference's path is made of, as shipped in cv2
+    (SIMD-optimised): 8-level resize pyramid, whole-level FAST at both thresholds' cheaper one, 7x7 blur per level,
+    LSD_REFINE_ADV, BFMatcher(HAMMING).knnMatch(k=2) of 1000 x 1000 rows per pair.  No quad-tree, orientation, rBRIEF or
+    LBD (cv2 has no ORB-SLAM extractor and no line_descriptor module here), so it is a LOWER bound on the CPU cost."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    from concurrent.futures import ThreadPoolExecutor
+    cv2.setNumThreads(1)
+    rng = np.random.default_rng(0)
+    d1 = rng.integers(0, 256, (a.nfeatures, 32)).astype(np.uint8)
+    d2 = rng.integers(0, 256, (a.nfeatures, 32)).astype(np.uint8)
+    tl = threading.local()
+
+    def task(p):
+        if not hasattr(tl, "lsd"):
+            tl.lsd = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV)
+            tl.fast = cv2.FastFeatureDetector_create(20, True)
+            tl.bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        for f in (2 * p, 2 * p + 1):
+            cur = frames[f]
+            for l in range(8):
+                if l:
+                    cur = cv2.resize(cur, (int(round(a.width / 1.2 ** l)), int(round(a.height / 1.2 ** l))), interpolation=cv2.INTER_LINEAR)
+                tl.fast.detect(cur)
+                cv2.GaussianBlur(cur, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+            tl.lsd.detect(frames[f])
+        tl.bf.knnMatch(d1, d2, k=2)
+
+    npairs = len(frames) // 2
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(task, range(min(npairs, threads))))  # untimed warm-up: detector creation, first-touch
+        t0 = time.perf_counter()
+        list(ex.map(task, range(npairs)))
+        dt = time.perf_counter() - t0
+    return len(frames) / dt
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -389,6 +429,11 @@ def run_ours(a):
             dt = cpu_pairs_per_second(a, frames[:sample], threads)
             cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "first %d frames (%d pairs) of the same batch, one frame pair per task, %d threads" % (sample, sample // 2, threads)}
+            ocv = opencv_primitives_fps(a, frames[:sample], threads)
+            if ocv:
+                cpu["opencv_primitives"] = {"value": ocv, "unit": UNIT,
+                                            "note": "cv2 4.13 resize+FAST+blur pyramid, LSD_REFINE_ADV, BFMatcher knn2 on the same sample and "
+                                                    "threads: a lower bound on the CPU cost (no quad-tree / orientation / rBRIEF / LBD)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
