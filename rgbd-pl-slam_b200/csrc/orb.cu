@@ -137,11 +137,24 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams 
   if ((sp & 3) == 0 && shift + pw <= pp) {
     const uint32_t* Sw = reinterpret_cast<const uint32_t*>(S - shift);
     const int nw = (shift + pw + 3) >> 2;
-    for (int yb = 0; yb < ph; yb += rpi)
-      for (int wb = 0; wb < nw; wb += 32) {
-        const int y = yb + r, w = wb + wl;
-        if (rowLane && y < ph && w < nw) PW[y * nwd + w] = __ldg(Sw + (size_t)y * (sp >> 2) + w);
+    const int spw = sp >> 2;
+    for (int wb = 0; wb < nw; wb += 32) {
+      const int w = wb + wl;
+      const bool on = rowLane && w < nw;
+      const uint32_t* src = Sw + (size_t)r * spw + w;  // this lane's column of words, rows r, r + rpi, ...
+      uint32_t* dst = PW + r * nwd + w;
+      // four rows per step: the loads are issued together, so a cell costs ~4 memory round trips instead of ~13
+      for (int y = r; y < ph; y += 4 * rpi) {
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (on && y + k * rpi < ph) ? __ldg(src + (size_t)k * rpi * spw) : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (on && y + k * rpi < ph) dst[k * rpi * nwd] = v[k];
+        src += (size_t)4 * rpi * spw;
+        dst += 4 * rpi * nwd;
       }
+    }
   } else {
     shift = 0;
     for (int y = 0; y < ph; ++y)
