@@ -100,3 +100,70 @@ def test_4k_frame_nfeatures_8000(oracle):
     for fld in okl.dtype.names:
         assert np.array_equal(kl[fld], okl[fld]), fld
     assert np.array_equal(ld, old) and np.array_equal(lf, olf)
+
+
+def test_full_size_batch_properties():
+    """BASELINE config C2 at its full size (256 frames = 128 pairs, 16 batches in flight), checked through properties that do
+    not need the CPU oracle on every frame: bitwise determinism across pipeline slots and submissions, independence of a
+    frame's result from the batch it travels in, level-major keypoint order inside every frame, and the kNN results
+    re-derived with independent torch arithmetic (Hamming distance of the reported neighbours, ordering d1 <= d2, and
+    minimality of d1 over the whole train set) for every query of every pair."""
+    import torch
+    import bench
+    import argparse
+    import plslam_b200 as pl
+    B, depth = 256, 16
+    a = argparse.Namespace(batch=B, width=640, height=480)
+    frames = bench.make_frames(a, 0)
+    d_images = torch.from_numpy(frames).cuda()
+    fe = pl.Frontend(depth=depth)
+    outs = [fe.alloc(B, device="cuda") for _ in range(depth)]
+    streams = [torch.cuda.Stream() for _ in range(depth)]
+    torch.cuda.synchronize()
+    for rep in range(2):  # 32 submissions: every slot is used twice
+        for k in range(depth):
+            fe.process_device(d_images, outs[k], True, stream=streams[k])
+    torch.cuda.synchronize()
+    fe.check_status()
+    ref = outs[0]
+    kc, lc = ref["kp_counts"].long(), ref["line_counts"].long()
+    assert int(kc.min()) > 900 and int(lc.min()) == 40
+    cap = ref["descriptors"].shape[1]
+    valid = (torch.arange(cap, device="cuda")[None, :] < kc[:, None])
+    lvalid = (torch.arange(ref["line_descriptors"].shape[1], device="cuda")[None, :] < lc[:, None])
+    for k in (1, 7, depth - 1):  # determinism across slots / submissions (valid rows only: the rest is never written)
+        o = outs[k]
+        assert torch.equal(o["kp_counts"], ref["kp_counts"]) and torch.equal(o["line_counts"], ref["line_counts"])
+        assert torch.equal(o["descriptors"][valid], ref["descriptors"][valid])
+        assert torch.equal(o["keypoints"][valid], ref["keypoints"][valid])
+        assert torch.equal(o["line_descriptors"][lvalid], ref["line_descriptors"][lvalid])
+        assert torch.equal(o["keylines"][lvalid], ref["keylines"][lvalid])
+        assert torch.equal(o["line_functions"][lvalid], ref["line_functions"][lvalid])
+    # batch independence: frames 10..13 alone give the same rows
+    fe2 = pl.Frontend()
+    small = fe2.alloc(4, device="cuda")
+    fe2.process_device(d_images[10:14].contiguous(), small, True)
+    torch.cuda.synchronize()
+    for j in range(4):
+        n = int(kc[10 + j])
+        assert int(small["kp_counts"][j]) == n
+        assert torch.equal(small["descriptors"][j, :n], ref["descriptors"][10 + j, :n])
+        assert torch.equal(small["keypoints"][j, :n], ref["keypoints"][10 + j, :n])
+        assert torch.equal(small["line_descriptors"][j, :40], ref["line_descriptors"][10 + j, :40])
+    # keypoints are level-major (octave is int32 word 5 of cv::KeyPoint) in every frame
+    octv = ref["keypoints"][:, :, 5].long()
+    octv = torch.where(valid, octv, torch.full_like(octv, 99))
+    assert bool((octv[:, 1:] >= octv[:, :-1]).all())
+    # kNN (k = 2) of every pair re-derived with torch
+    desc = ref["descriptors"]
+    m = ref["orb_matches"].long()
+    pop = torch.tensor([bin(i).count("1") for i in range(256)], device="cuda", dtype=torch.int16)
+    for p in range(0, B // 2, 8):
+        q, t = desc[2 * p, :kc[2 * p]], desc[2 * p + 1, :kc[2 * p + 1]]
+        d = pop[(q[:, None, :] ^ t[None, :, :]).long()].sum(-1)  # nq x nt Hamming distances
+        mm = m[p, :len(q)]
+        rows = torch.arange(len(q), device="cuda")
+        assert torch.equal(d[rows, mm[:, 0]].long(), mm[:, 1]) and torch.equal(d[rows, mm[:, 2]].long(), mm[:, 3])
+        s, _ = torch.sort(d.long(), dim=1)
+        assert torch.equal(s[:, 0], mm[:, 1]) and torch.equal(s[:, 1], mm[:, 3])
+        assert torch.equal(d.argmin(1), mm[:, 0])  # ties -> lowest index
