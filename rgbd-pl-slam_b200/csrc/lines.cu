@@ -296,6 +296,28 @@ struct GrowCtx {
   int sw, sh, P;
   int lane;
   bool prefetch;
+  // ---- CTA-per-frame mode (k_lsd_grow_mw): ordered speculative regions, see the kernel's header ----
+  unsigned* own;          // owner plane of the frame: MW_FREE or rank + 1 of the region that marked the pixel
+  unsigned myVal, baseVal;  // this region's tag; tags below baseVal are committed regions of earlier rounds
+  volatile int* poison;   // [slots] poison flags of the round (shared memory); mine is poison[slot]
+  const int* ranks;       // [slots] seed ranks of the round (shared memory)
+  int slot, nslots;
+  __device__ __forceinline__ bool mw_poisoned() const { return poison[slot] != 0; }
+  // May this region still test the pixel?  Not if a committed region or this region itself holds it.  A pixel held by
+  // another in-flight region stays a candidate: whether it is used only matters if it passes the alignment test, and
+  // then mw_take() settles it (a higher rank is robbed and poisoned, a lower rank poisons me).
+  __device__ __forceinline__ bool mw_available(unsigned ov) const { return ov >= baseVal && ov != myVal; }
+  __device__ __forceinline__ void mw_take(int id) const {
+    const unsigned old = atomicMin(own + id, myVal);
+    if (old == 0xffffffffu || old == myVal) return;
+    if (old > myVal) {  // robbed a higher in-flight region: it must not commit
+      for (int j = 0; j < nslots; ++j)
+        if ((unsigned)(ranks[j] + 1) == old) poison[j] = 1;
+    } else if (old >= baseVal) {
+      poison[slot] = 1;  // a lower in-flight region got there first
+    }
+  }
+  __device__ __forceinline__ void mw_release(int id) const { atomicCAS(own + id, myVal, 0xffffffffu); }
   __device__ __forceinline__ unsigned reg_get(int i) const { return i < REG_SMEM ? regS[i] : regG[i]; }
   __device__ __forceinline__ void reg_set(int i, unsigned v) const {
     if (i < REG_SMEM) regS[i] = v; else regG[i] = v;
@@ -397,6 +419,7 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
 // on which the two tests agree (plus the corrected decision of the first disagreeing lane).  A batch whose
 // decisions do not depend on the drift of the angle costs one round instead of one round per accepted pixel;
 // the result is identical to the sequential scan by construction.
+template <bool MW>
 __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_angle_out) {
   const int lane = C.lane;
   const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
@@ -411,7 +434,10 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
     sumdx = (float)c;
     sumdy = (float)s;
   }
-  if (lane == 0) *C.wptr(seed) = srec.w | USED_BIT;
+  if (lane == 0) {
+    if (MW) C.mw_take(seed);
+    else *C.wptr(seed) = srec.w | USED_BIT;
+  }
   __syncwarp();
   int n = 1;
   GP_DECL;
@@ -419,6 +445,10 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
   const int pt = lane >> 3, nb8 = lane & 7, nb = nb8 < 4 ? nb8 : nb8 + 1;
   const int ox = (nb % 3) - 1, oy = (nb / 3) - 1;
   for (int i = 0; i < n;) {
+    if (MW && (C.mw_poisoned() || n > C.P - 64)) {  // a poisoned region is discarded anyway: stop early
+      if (lane == 0) C.poison[C.slot] = 1;
+      break;
+    }
     const int m4 = min(4, n - i);
     GP_START();
     GP_CNT(9, 1);
@@ -430,8 +460,11 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
       const int nx = (int)(p & 0xffff) + ox, ny = (int)(p >> 16) + oy;
       if (nx >= 0 && ny >= 0 && nx < C.sw && ny < C.sh) {
         const int id = ny * C.sw + nx;
+        unsigned ov = 0;
+        if (MW) ov = __ldcg(C.own + id);  // owner words live in L2 (atomics), never in a possibly stale L1 line
         const uint4 r = C.pix[id];
-        if (!(r.w & USED_BIT) && __uint_as_float(r.x) != NOTDEF_F) {
+        const bool avail = MW ? (__uint_as_float(r.x) != NOTDEF_F && C.mw_available(ov)) : !(r.w & USED_BIT);
+        if (avail && __uint_as_float(r.x) != NOTDEF_F) {
           nidx = id;
           nxy = ((unsigned)ny << 16) | (unsigned)nx;
           w = r.w;
@@ -464,7 +497,8 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
           const int j0 = __ffs(m) - 1;
           if ((defm >> j0) == 1u) {
             if (lane == j0) {
-              *C.wptr(nidx) = w | USED_BIT;
+              if (MW) C.mw_take(nidx);
+              else *C.wptr(nidx) = w | USED_BIT;
               C.reg_set(n, nxy);
               if (C.prefetch) {
                 const int up = (nxy >> 16) > 0 ? nidx - C.sw : nidx, dn = (int)(nxy >> 16) < C.sh - 1 ? nidx + C.sw : nidx;
@@ -506,7 +540,8 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
           commit = (m & ((1u << b) - 1u)) | (m1 & (1u << b));
         }
         if ((commit >> lane) & 1u) {
-          *C.wptr(nidx) = w | USED_BIT;
+          if (MW) C.mw_take(nidx);
+          else *C.wptr(nidx) = w | USED_BIT;
           C.reg_set(n + __popc(commit & lt), nxy);
           if (C.prefetch) {
             // the 3x3 neighbourhood of the new region point is examined when the point reaches the scan front, a
@@ -659,6 +694,7 @@ __device__ __forceinline__ double rect_density(int n, const LsdRect& r) {
 }
 
 // refine() + reduce_region_radius(); returns false when the region must be dropped. *n_io = region size.
+template <bool MW>
 __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double prec, double p, LsdRect* rec,
                            double density_th, int variant) {
   const int lane = C.lane;
@@ -682,7 +718,8 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
       const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
       const int idx = py * C.sw + px;
       const uint4 r = C.pix[idx];
-      *C.wptr(idx) = r.w & ~USED_BIT;
+      if (MW) C.mw_release(idx);
+      else *C.wptr(idx) = r.w & ~USED_BIT;
       double flag = 0.0, v = 0.0;
       if (sqrt(dist_sq_dev(xc, yc, (double)px, (double)py)) < rec->width) {
         const double ang = __dmul_rn((double)__uint_as_float(r.x), PL_DEG_TO_RADS);
@@ -710,7 +747,11 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   const double tau = __dmul_rn(
       2.0, sqrt(__dadd_rn(__ddiv_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)), (double)cntN),
                           __dmul_rn(mean_angle, mean_angle))));
-  n = (variant & 1) ? lsd_region_grow_spec(C, tau, &reg_angle) : lsd_region_grow(C, tau, &reg_angle);
+  n = (MW || (variant & 1)) ? lsd_region_grow_spec<MW>(C, tau, &reg_angle) : lsd_region_grow(C, tau, &reg_angle);
+  if (MW && C.mw_poisoned()) {
+    *n_io = n;
+    return false;
+  }
   *n_io = n;
   if (n < 2) return false;
   lsd_region2rect(C, n, reg_angle, prec, p, rec);
@@ -730,8 +771,12 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
           const unsigned pxy = C.reg_get(i);
           const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
           if (dist_sq_dev(xc, yc, (double)px, (double)py) > radSq) {
-            unsigned* wp = C.wptr(py * C.sw + px);
-            *wp = *wp & ~USED_BIT;
+            if (MW) {
+              C.mw_release(py * C.sw + px);
+            } else {
+              unsigned* wp = C.wptr(py * C.sw + px);
+              *wp = *wp & ~USED_BIT;
+            }
             C.reg_set(i, C.reg_get(n - 1));
             C.reg_set(n - 1, pxy);
             --n;
@@ -751,8 +796,12 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
           const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
           far = dist_sq_dev(xc, yc, (double)px, (double)py) > radSq;
           if (far) {
-            unsigned* wp = C.wptr(py * C.sw + px);
-            *wp = *wp & ~USED_BIT;
+            if (MW) {
+              C.mw_release(py * C.sw + px);
+            } else {
+              unsigned* wp = C.wptr(py * C.sw + px);
+              *wp = *wp & ~USED_BIT;
+            }
             C.reg_set(i, pxy | FAR);
           }
         }
@@ -837,14 +886,14 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
       if (lane == 0) C.reg_set(0, ((unsigned)(seed / L.sw) << 16) | (unsigned)(seed % L.sw));
       __syncwarp();
       double reg_angle;
-      int n = (L.grow_variant & 1) ? lsd_region_grow_spec(C, L.prec, &reg_angle) : lsd_region_grow(C, L.prec, &reg_angle);
+      int n = (L.grow_variant & 1) ? lsd_region_grow_spec<false>(C, L.prec, &reg_angle) : lsd_region_grow(C, L.prec, &reg_angle);
       if (n < L.min_reg_size) continue;
       LsdRect rec;
       GP_START();
       lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
       GP_ADD(2);
       GP_START();
-      const bool keep = lsd_refine(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, L.grow_variant);
+      const bool keep = lsd_refine<false>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, L.grow_variant);
       GP_ADD(3);
       if (!keep) continue;
       if (nrect < L.rect_cap) {
@@ -863,6 +912,192 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
 #endif
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k_lsd_grow_mw: the same region growing with one CTA of MW_K warps per frame, for small batches and large frames
+// (a 4K frame holds ~25 000 regions; one warp per frame leaves the machine empty).  Regions are grown speculatively in
+// parallel and committed in seed order, which keeps the result identical to the sequential loop:
+//   * every round warp 0 picks the next MW_K free seeds of the sorted list; slot j gets rank = its seed's list index;
+//   * the `used` map is an owner plane: MW_FREE, or rank + 1 of the region that marked the pixel (tags below the first
+//     rank of the round belong to committed regions);
+//   * a region that takes a pixel held by a HIGHER in-flight rank robs it and poisons that slot; a region that tries
+//     to take a pixel held by a LOWER in-flight rank poisons itself (the sequential loop would have shown it that pixel
+//     as used); pixels that are merely examined and fail the alignment test create no dependence;
+//   * after a CTA barrier the longest prefix of un-poisoned slots commits (rectangles are emitted in rank order), the
+//     other slots clear their tags and their seeds are picked again; slot 0 can never be poisoned, so a round always
+//     commits at least one region.
+// ------------------------------------------------------------------------------------------
+// MW_K = warps (regions in flight) per frame: 8 for VGA-class frames, 24 (768 threads x 80 registers, 118 KB of dynamic
+// shared memory) for frames of a megapixel and more, where a round finds more independent regions
+constexpr int MW_DIST = 24;    // seeds closer than this (Chebyshev) with similar level-line angles count as one structure
+// heuristic only (it decides which seeds share a round, never the result): two seeds probably grow the same region
+__device__ __forceinline__ bool mw_same_structure(int x1, int y1, float deg1, int x2, int y2, float deg2) {
+  if (max(abs(x1 - x2), abs(y1 - y2)) >= MW_DIST) return false;
+  float d = fabsf(deg1 - deg2);
+  if (d > 180.f) d = 360.f - d;
+  return d <= 45.f;
+}
+constexpr int MW_SCAN = 8192;  // seeds scanned per round for the slots
+constexpr size_t mw_smem_bytes(int k) { return (sizeof(double) * 96 + sizeof(unsigned) * 1024) * (size_t)k; }  // stage + list head per warp
+template <int MW_K>
+__global__ void __launch_bounds__(32 * MW_K) k_lsd_grow_mw(const __grid_constant__ LineParams L, uint4* pixAll,
+                                                         unsigned* ownAll, const unsigned* __restrict__ seedsAll,
+                                                         const int* __restrict__ nseeds, unsigned* regAll,
+                                                         LsdRect* __restrict__ rectsAll, int* __restrict__ nrects,
+                                                         int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char mw_smem[];
+  double(*stage)[96] = reinterpret_cast<double(*)[96]>(mw_smem);
+  unsigned(*regS)[REG_SMEM] = reinterpret_cast<unsigned(*)[REG_SMEM]>(mw_smem + sizeof(double) * 96 * MW_K);
+  __shared__ LsdRect s_rect[MW_K];
+  __shared__ int s_rank[MW_K], s_poison[MW_K], s_has[MW_K], s_n[MW_K];
+  __shared__ int s_selx[MW_K], s_sely[MW_K];
+  __shared__ float s_sela[MW_K];
+  __shared__ int s_cursor, s_active, s_commit;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x;
+  GrowCtx C;
+#ifdef PLSLAM_GROW_PROF
+  long long prof[16];
+  for (int k = 0; k < 16; ++k) prof[k] = 0;
+  C.prof = prof;
+#endif
+  C.stage = stage[warp];
+  C.regS = regS[warp];
+  C.prefetch = false;
+  C.pix = pixAll + (size_t)f * L.P;
+  C.own = ownAll + (size_t)f * L.P;
+  C.regG = regAll + ((size_t)f * MW_K + warp) * L.P;
+  C.sw = L.sw;
+  C.sh = L.sh;
+  C.P = L.P;
+  C.lane = lane;
+  C.poison = s_poison;
+  C.ranks = s_rank;
+  C.slot = warp;
+  C.nslots = MW_K;
+  const unsigned* seeds = seedsAll + (size_t)f * L.P;
+  const int ns = nseeds[f];
+  LsdRect* rects = rectsAll + (size_t)f * L.rect_cap;
+  int nrect = 0;  // meaningful in thread 0
+  if (threadIdx.x == 0) s_cursor = 0;
+  while (true) {
+    __syncthreads();
+    if (warp == 0) {
+      // Slot 0 = the first free seed from the cursor; the other slots = the next free seeds that are not close to and
+      // aligned with a seed already picked.  Neighbouring seeds of the list usually sit on the same edge (same
+      // gradient bin, raster order) and would only grow the same region again.  A skipped seed keeps its place
+      // in the order: the commit step below makes sure it was absorbed by a committed region before anything behind it
+      // commits.
+      int found = 0;
+      const int scanEnd = min(ns, s_cursor + MW_SCAN);
+      for (int pos = s_cursor; pos < ns && (found == 0 || pos < scanEnd) && found < MW_K; pos += 32) {
+        const int i = pos + lane;
+        int sx = 0, sy = 0;
+        float sa = 0.f;
+        bool ok = false;
+        if (i < ns) {
+          const int sd = (int)seeds[i];
+          if (__ldcg(C.own + sd) == 0xffffffffu) {
+            sy = sd / L.sw;
+            sx = sd - sy * L.sw;
+            sa = __uint_as_float(C.pix[sd].x);
+            ok = true;
+            for (int k = 0; k < found; ++k) ok = ok && !mw_same_structure(sx, sy, sa, s_selx[k], s_sely[k], s_sela[k]);
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        while (m && found < MW_K) {
+          const int j = __ffs(m) - 1;
+          const int jx = __shfl_sync(0xffffffffu, sx, j), jy = __shfl_sync(0xffffffffu, sy, j);
+          const float ja = __shfl_sync(0xffffffffu, sa, j);
+          if (lane == 0) {
+            s_rank[found] = pos + j;
+            s_selx[found] = jx;
+            s_sely[found] = jy;
+            s_sela[found] = ja;
+          }
+          ++found;
+          ok = ok && lane > j && !mw_same_structure(sx, sy, sa, jx, jy, ja);
+          m = __ballot_sync(0xffffffffu, ok);
+        }
+        __syncwarp();
+      }
+      if (lane < MW_K) {
+        if (lane >= found) s_rank[lane] = -1;
+        s_poison[lane] = 0;
+        s_has[lane] = 0;
+        s_n[lane] = 0;
+      }
+      if (lane == 0) s_active = found;
+    }
+    __syncthreads();
+    const int active = s_active;
+    if (active == 0) break;
+    if (warp < active) {
+      const int rank = s_rank[warp];
+      const int seed = (int)seeds[rank];
+      C.myVal = (unsigned)rank + 1u;
+      C.baseVal = (unsigned)s_rank[0] + 1u;
+      if (lane == 0) C.reg_set(0, ((unsigned)(seed / L.sw) << 16) | (unsigned)(seed % L.sw));
+      __syncwarp();
+      double reg_angle;
+      int n = lsd_region_grow_spec<true>(C, L.prec, &reg_angle);
+      if (!C.mw_poisoned() && n >= L.min_reg_size) {
+        LsdRect rec;
+        lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
+        const bool keep = lsd_refine<true>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, 1);
+        if (keep && !C.mw_poisoned() && lane == 0) {
+          s_rect[warp] = rec;
+          s_has[warp] = 1;
+        }
+      }
+      if (lane == 0) s_n[warp] = n;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // longest committable prefix: un-poisoned slots, and every seed skipped in front of a slot must by now carry the
+      // tag of a lower-ranked (hence committed) region — otherwise the sequential loop would have grown it first
+      int c = 0;
+      while (c < active && !s_poison[c]) {
+        if (c > 0) {
+          const unsigned mine = (unsigned)s_rank[c] + 1u;
+          bool bad = false;
+          for (int i = s_rank[c - 1] + 1 + lane; i < s_rank[c]; i += 32) bad = bad || __ldcg(C.own + seeds[i]) >= mine;
+          if (__any_sync(0xffffffffu, bad)) break;
+        }
+        ++c;
+      }
+      if (lane == 0) s_commit = c;  // >= 1: nothing can poison the lowest rank and nothing is skipped in front of it
+#ifdef PLSLAM_GROW_PROF
+      if (lane == 0) {
+        atomicAdd(&g_grow_prof[5], 1ull);                                  // rounds
+        atomicAdd(&g_grow_prof[6], (unsigned long long)active);            // slots started
+        atomicAdd(&g_grow_prof[7], (unsigned long long)c);                 // slots committed
+        if (c < active) atomicAdd(&g_grow_prof[s_poison[c] ? 13 : 14], 1ull);  // stopped by poison / by a skipped free seed
+      }
+#endif
+    }
+    __syncthreads();
+    const int c = s_commit;
+    if (threadIdx.x == 0) {
+      for (int j = 0; j < c; ++j)
+        if (s_has[j]) {
+          if (nrect < L.rect_cap) rects[nrect] = s_rect[j];
+          else atomicMax(status, PLSLAM_ERR_OVERFLOW);
+          ++nrect;
+        }
+      s_cursor = s_rank[c - 1] + 1;
+    }
+    if (warp >= c && warp < active) {  // discarded: give the pixels back; the seed is picked again next round
+      const int n = s_n[warp];
+      for (int i = lane; i < n; i += 32) {
+        const unsigned pxy = C.reg_get(i) & 0x7fffffffu;
+        C.mw_release((int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff));
+      }
+    }
+  }
+  if (threadIdx.x == 0) nrects[f] = min(nrect, L.rect_cap);
+}
 
 // ------------------------------------------------------------------------------------------
 // k_lsd_nfa: rect_improve() / rect_nfa() / nfa(), one warp per rectangle.  The row scan is the one
@@ -1593,18 +1828,36 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
   P.batch = batch;
-  PL_CARVEOUT(k_lsd_grow);
-  // Residency cap: region growing is a long, register-heavy, latency-bound kernel (72 registers x 128 threads per CTA).
-  // Left alone, the CTAs of many batches in flight fill the register files and starve the streaming kernels of the
-  // other batches; dynamic shared memory that is never touched bounds the CTAs per SM (PLSLAM_GROW_SMEM_KB to tune).
-  static const int growPadKB = [] { const char* e = std::getenv("PLSLAM_GROW_SMEM_KB"); return e ? std::atoi(e) : 0; }();
-  static bool growAttr = false;
-  if (!growAttr && growPadKB > 0) {
-    PL_CUDA(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, growPadKB * 1024));
-    growAttr = true;
+  // Small batches / large frames: one CTA of MW_K warps per frame with ordered speculative regions (k_lsd_grow_mw);
+  // large batches of small frames: one warp per frame (no wasted speculation, many batches in flight fill the machine).
+  static const int growMode = [] { const char* e = std::getenv("PLSLAM_GROW_MODE"); return e ? std::atoi(e) : -1; }();  // -1 auto
+  const bool mw = growMode >= 0 ? growMode == 1 : batch <= numSMs;  // one CTA per SM at most
+  if (mw) {
+    int rc2;
+    if ((rc2 = owner.ensure((size_t)cfgB * P.P * sizeof(unsigned)))) return rc2;
+    const int mwK = P.P >= (1 << 20) ? 24 : 8;
+    if ((rc2 = regbuf.ensure((size_t)cfgB * mwK * P.P * sizeof(unsigned)))) return rc2;
+    PL_CUDA(cudaMemsetAsync(owner.p, 0xff, (size_t)batch * P.P * sizeof(unsigned), st));
+    if (P.P >= (1 << 20)) {
+      static bool attr24 = false;
+      if (!attr24) {
+        PL_CUDA(cudaFuncSetAttribute(k_lsd_grow_mw<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mw_smem_bytes(24)));
+        attr24 = true;
+      }
+      k_lsd_grow_mw<24><<<batch, 32 * 24, mw_smem_bytes(24), st>>>(P, pix.as<uint4>(), owner.as<unsigned>(), seeds.as<unsigned>(),
+                                                                 nseeds.as<int>(), regbuf.as<unsigned>(), rects.as<LsdRect>(),
+                                                                 nrects.as<int>(), status.as<int>());
+    } else {
+      k_lsd_grow_mw<8><<<batch, 32 * 8, mw_smem_bytes(8), st>>>(P, pix.as<uint4>(), owner.as<unsigned>(), seeds.as<unsigned>(),
+                                                               nseeds.as<int>(), regbuf.as<unsigned>(), rects.as<LsdRect>(),
+                                                               nrects.as<int>(), status.as<int>());
+    }
+  } else {
+    PL_CARVEOUT(k_lsd_grow);
+    k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(),
+                                                                      regbuf.as<unsigned>(), rects.as<LsdRect>(), nrects.as<int>(),
+                                                                      status.as<int>());
   }
-  k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, (size_t)growPadKB * 1024, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),
-                                          rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());
   PL_STAGE_END(timer, st);
   static const bool grow_only = std::getenv("PLSLAM_DEBUG_STOP_AFTER_GROW") != nullptr;  // profiling aid (tools/)
   if (grow_only) return PLSLAM_OK;

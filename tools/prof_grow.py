@@ -25,3 +25,6 @@ for n, x in zip(names, v):
     if n:
         print("  %-22s %12.0f" % (n, x))
 print("  seed scan+other (cycles) %10.0f" % (v[4] - v[0] - v[1] - v[2] - v[3] + 0))
+if buf[5]:
+    print("  CTA-per-frame mode: rounds %.0f, slots started %.2f and committed %.2f per round; rounds cut by poison %.0f, by a skipped free seed %.0f (per frame)"
+          % (v[5], buf[6] / buf[5], buf[7] / buf[5], v[13], v[14]))
