@@ -186,7 +186,10 @@ struct Frontend {
   int next = 0, lastSlot = 0;
   bool timing = false;
   Frontend(int nf, float sf, int nl, int ini, int mn, int max_lines, int depth) {
-    for (int i = 0; i < depth; ++i) slots.push_back(new Slot(nf, sf, nl, ini, mn, max_lines));
+    for (int i = 0; i < depth; ++i) {
+      slots.push_back(new Slot(nf, sf, nl, ini, mn, max_lines));
+      slots.back()->lines.batches_in_flight = depth;
+    }
   }
   ~Frontend() {
     for (Slot* s : slots) delete s;

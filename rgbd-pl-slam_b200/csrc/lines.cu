@@ -1831,7 +1831,8 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   // Small batches / large frames: one CTA of MW_K warps per frame with ordered speculative regions (k_lsd_grow_mw);
   // large batches of small frames: one warp per frame (no wasted speculation, many batches in flight fill the machine).
   static const int growMode = [] { const char* e = std::getenv("PLSLAM_GROW_MODE"); return e ? std::atoi(e) : -1; }();  // -1 auto
-  const bool mw = growMode >= 0 ? growMode == 1 : batch <= numSMs;  // one CTA per SM at most
+  // CTA-per-frame speculation pays when the whole GPU has at most one frame per SM to work on (all pipeline slots counted)
+  const bool mw = growMode >= 0 ? growMode == 1 : (long long)batch * batches_in_flight <= numSMs;
   if (mw) {
     int rc2;
     if ((rc2 = owner.ensure((size_t)cfgB * P.P * sizeof(unsigned)))) return rc2;

@@ -57,6 +57,7 @@ class LineExtractor {
 
   StageTimer* timer = nullptr;
   const int* device_status() const { return status.as<int>(); }
+  int batches_in_flight = 1;  // how many batches like this one the caller keeps on the GPU at once (pipeline depth)
   int max_lines = 40;  // lsdNFeatures of the PL-SLAM fork family
   int rect_cap = 4096;
 
