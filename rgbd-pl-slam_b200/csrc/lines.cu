@@ -929,13 +929,15 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
 // ------------------------------------------------------------------------------------------
 // MW_K = warps (regions in flight) per frame: 8 for VGA-class frames, 24 (768 threads x 80 registers, 118 KB of dynamic
 // shared memory) for frames of a megapixel and more, where a round finds more independent regions
-constexpr int MW_DIST = 24;    // seeds closer than this (Chebyshev) with similar level-line angles count as one structure
+constexpr int MW_DIST = 12;    // seeds closer than this (Chebyshev) with similar level-line angles count as one structure
 // heuristic only (it decides which seeds share a round, never the result): two seeds probably grow the same region
+__device__ int g_mw_dist = MW_DIST;
+__device__ float g_mw_ang = 25.f;
 __device__ __forceinline__ bool mw_same_structure(int x1, int y1, float deg1, int x2, int y2, float deg2) {
-  if (max(abs(x1 - x2), abs(y1 - y2)) >= MW_DIST) return false;
+  if (max(abs(x1 - x2), abs(y1 - y2)) >= g_mw_dist) return false;
   float d = fabsf(deg1 - deg2);
   if (d > 180.f) d = 360.f - d;
-  return d <= 45.f;
+  return d <= g_mw_ang;
 }
 constexpr int MW_SCAN = 8192;  // seeds scanned per round for the slots
 constexpr size_t mw_smem_bytes(int k) { return (sizeof(double) * 96 + sizeof(unsigned) * 1024) * (size_t)k; }  // stage + list head per warp
@@ -1835,6 +1837,12 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   const bool mw = growMode >= 0 ? growMode == 1 : (long long)batch * batches_in_flight <= numSMs;
   if (mw) {
     int rc2;
+    static bool mwTune = false;
+    if (!mwTune) {  // experiment knobs of the seed-spreading heuristic (never affect results)
+      mwTune = true;
+      if (const char* e = std::getenv("PLSLAM_MW_DIST")) { int v = std::atoi(e); cudaMemcpyToSymbol(g_mw_dist, &v, sizeof(v)); }
+      if (const char* e = std::getenv("PLSLAM_MW_ANG")) { float v = (float)std::atof(e); cudaMemcpyToSymbol(g_mw_ang, &v, sizeof(v)); }
+    }
     if ((rc2 = owner.ensure((size_t)cfgB * P.P * sizeof(unsigned)))) return rc2;
     const int mwK = P.P >= (1 << 20) ? 24 : 8;
     if ((rc2 = regbuf.ensure((size_t)cfgB * mwK * P.P * sizeof(unsigned)))) return rc2;
