@@ -140,7 +140,10 @@ struct Slot {
         return rc;
     }
     cudaStream_t st = sHost;
-    if (stride == (size_t)pitch * H) {
+    if (stride == (size_t)pitch * H && (size_t)pitch == dpitch) {
+      // densely packed frames on both sides: one linear copy (a 2-D copy of 122 880 rows is descriptor bound)
+      PL_CUDA(cudaMemcpyAsync(dIn.p, images, dstride * batch, cudaMemcpyHostToDevice, st));
+    } else if (stride == (size_t)pitch * H) {
       PL_CUDA(cudaMemcpy2DAsync(dIn.p, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, st));
     } else {
       for (int f = 0; f < batch; ++f)
