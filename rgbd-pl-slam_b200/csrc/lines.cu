@@ -1834,7 +1834,10 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   // large batches of small frames: one warp per frame (no wasted speculation, many batches in flight fill the machine).
   static const int growMode = [] { const char* e = std::getenv("PLSLAM_GROW_MODE"); return e ? std::atoi(e) : -1; }();  // -1 auto
   // CTA-per-frame speculation pays when the whole GPU has at most one frame per SM to work on (all pipeline slots counted)
-  const bool mw = growMode >= 0 ? growMode == 1 : (long long)batch * batches_in_flight <= numSMs;
+  // ... and when the per-slot region lists (K lists of P entries per frame) stay within 10 GB
+  const size_t mwListBytes = (size_t)std::max(batch, cfgB) * (P.P >= (1 << 20) ? 24 : 8) * P.P * sizeof(unsigned);
+  const bool mw = growMode >= 0 ? growMode == 1
+                                : ((long long)batch * batches_in_flight <= numSMs && mwListBytes <= ((size_t)10 << 30));
   if (mw) {
     int rc2;
     static bool mwTune = false;
