@@ -7,14 +7,18 @@
 // reproduces the oracle's PINNED mode bit for bit.
 //
 // Stage map (one launch per stage for the whole batch):
-//   k_lsd_scale    7x7 sigma-0.75 Gaussian + x0.8 INTER_LINEAR_EXACT, fused through shared memory
-//   k_lsd_grad     2x2 gradient, level-line angle (fastAtan2), per-pixel record {deg, cos, sin, g2}
+//   k_lsd_scale    7x7 sigma-0.75 Gaussian (dp4a) + x0.8 INTER_LINEAR_EXACT, fused through shared memory
+//   k_lsd_grad     2x2 gradient, level-line angle (fastAtan2), per-pixel record {deg, cos, sin, g2} + 4-byte angle plane
 //   k_lsd_rowhist / k_lsd_colscan / k_lsd_scatter   stable counting sort of the seeds (bin desc, raster)
-//   k_lsd_grow     region growing + rectangle fit + density refinement: one warp per frame, because
-//                  the greedy growth is sequential inside a frame (running region angle, shared
-//                  `used` map); lanes cooperate on neighbour tests and the `used` map lives in shared memory
-//   k_lsd_nfa      rect_improve / rect_nfa: one warp per rectangle (independent of `used`)
-//   k_lsd_finish   ordered compaction, KeyLine fields, strongest-N selection, LBD, line equations
+//   k_lsd_grow     region growing + rectangle fit + density refinement, one warp per frame: the greedy growth is
+//                  sequential inside a frame (running region angle, shared `used` map).  Lanes = 4 frontier points x 8
+//                  neighbours with in-batch speculation; the `used` flag lives in the pixel records.  This is the mode
+//                  for large batches (many batches in flight fill the machine).
+//   k_lsd_grow_mw  the same result with one CTA of 8 / 24 warps per frame (ordered speculative regions over an owner
+//                  plane), chosen when the GPU holds at most one frame per SM (single frames, small batches, 4K)
+//   k_lsd_nfa      rect_improve / rect_nfa: persistent grid, one warp per rectangle (independent of `used`)
+//   k_lsd_finish   ordered compaction, KeyLine fields, strongest-N selection, line equations
+//   k_lbd          LBD band descriptors, one CTA per kept line
 #include "lines.cuh"
 
 #include <algorithm>
