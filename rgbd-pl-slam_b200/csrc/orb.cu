@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ OrbParam
 // (X, Y border-local).  key = ((cellRow*256 + cellCol)*64 + yLocal)*64 + xLocal reproduces the
 // reference list order (cell-major, then FAST's row-major) without ordered writes.
 // ------------------------------------------------------------------------------------------
-constexpr int FAST_QUEUE_BYTES = 320;  // 160 queue entries: < 32 left over + up to 128 new per iteration
+constexpr int FAST_LIST_CAP = 512;                  // survivor list entries per cell (warp)
+constexpr int FAST_QUEUE_BYTES = 2 * FAST_LIST_CAP;  // u16 positions
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams P, OrbImages I,
                                               unsigned long long* __restrict__ cand, int* __restrict__ candCount,
                                               int* __restrict__ status) {
@@ -181,8 +182,12 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams 
   const int th0 = P.minTh;
   const unsigned th4 = (unsigned)th0 * 0x01010101u;
 
-  // pass 1: 4-point quick test at minThFAST (N/S and E/W compass pixels), survivors queued for the 16-arc score
-  int qn = 0;
+  // pass 1: 4-point quick test at minThFAST (N/S and E/W compass pixels); the survivors are appended to a list (in
+  // FAST's row-major order) and scored 32 at a time with the 16-arc test.  The list is kept for the later passes, which
+  // then only visit the ~25 % of pixels that can be corners; if it would overflow it degrades to a rolling queue
+  // and the later passes scan the whole cell.
+  int ns = 0, sc = 0;  // entries appended / scored
+  bool overflow = false;
   for (int yb = 3; yb < yEnd; yb += rpi)
     for (int wb = 0; wb < nwd; wb += 32) {
       const int y = yb + r, w = wb + wl;
@@ -198,27 +203,92 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams 
           pass = a & b & vm & 0x01010101u;
         }
       }
+      if (ns + 128 > FAST_LIST_CAP) {  // no room for a full iteration: score what is pending, restart as a queue
+        for (; sc < ns; sc += 32)
+          if (sc + lane < ns) {
+            const int q = queue[sc + lane];
+            score[q] = (uint8_t)fast_arc_score(patch + q, pp);
+          }
+        __syncwarp();
+        overflow = true;
+        ns = sc = 0;
+      }
       int tot;
-      int at = qn + lane_prefix(__popc(pass), &tot);
+      int at = ns + lane_prefix(__popc(pass), &tot);
       const int base = y * pp + 4 * w;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if ((pass >> (8 * k)) & 1u) queue[at++] = (unsigned short)(base + k);
-      qn += tot;
+      ns += tot;
       __syncwarp();
-      while (qn >= 32) {
-        const int q = queue[qn - 32 + lane];
+      while (ns - sc >= 32) {
+        const int q = queue[sc + lane];
         score[q] = (uint8_t)fast_arc_score(patch + q, pp);
-        qn -= 32;
+        sc += 32;
       }
       __syncwarp();
     }
-  if (lane < qn) {
-    const int q = queue[lane];
+  if (sc + lane < ns) {
+    const int q = queue[sc + lane];
     score[q] = (uint8_t)fast_arc_score(patch + q, pp);
   }
   __syncwarp();
 
+  if (!overflow) {
+    // pass 2 over the survivors: strict 3x3 local maxima of the raw score map (scores outside the detection area are
+    // 0); the maxima (score, else 0) go to the pixel tile, which is no longer read as pixels
+    int nHi = 0, nLo = 0;
+    for (int b0 = 0; b0 < ns; b0 += 32) {
+      int keep = 0;
+      if (b0 + lane < ns) {
+        const int q = queue[b0 + lane];
+        const uint8_t* sp8 = score + q;
+        const int c = sp8[0];
+        if (c > th0) {
+          const int m = max(max(max(sp8[-pp - 1], sp8[-pp]), max(sp8[-pp + 1], sp8[-1])),
+                            max(max(sp8[1], sp8[pp - 1]), max(sp8[pp], sp8[pp + 1])));
+          if (c > m) keep = c;
+        }
+        patch[q] = (uint8_t)keep;
+      }
+      nHi += __popc(__ballot_sync(FULL, keep > P.iniTh));
+      nLo += __popc(__ballot_sync(FULL, keep > 0));
+    }
+    __syncwarp();
+    const int thSel = nHi > 0 ? P.iniTh : th0;
+    const int nOut = nHi > 0 ? nHi : nLo;
+    if (nOut == 0) return;
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(candCount + f * ORB_MAXL + l, nOut);
+    slot = __shfl_sync(FULL, slot, 0);
+    if (slot + nOut > L.candCap) {
+      if (lane == 0) atomicMax(status, PLSLAM_ERR_OVERFLOW);
+      return;
+    }
+    unsigned long long* out = cand + (size_t)f * P.candFrameStride + L.candOff + slot;
+    // pass 3 over the survivors: emit the maxima above the selected threshold (list order = FAST's row-major order)
+    int wr = 0;
+    for (int b0 = 0; b0 < ns; b0 += 32) {
+      int q = 0, keep = 0;
+      if (b0 + lane < ns) {
+        q = queue[b0 + lane];
+        keep = patch[q];
+      }
+      const bool emit = keep > thSel;
+      const unsigned m = __ballot_sync(FULL, emit);
+      if (emit) {
+        const int y = q / pp, x = q - y * pp - shift;
+        const unsigned key = (((unsigned)(ci * 256 + cj) * 64u + (unsigned)y) * 64u + (unsigned)x);
+        const unsigned X = x + cj * L.wCell, Y = y + ci * L.hCell;
+        out[wr + __popc(m & lt)] =
+            ((unsigned long long)keep << 56) | ((unsigned long long)key << 28) | ((unsigned long long)Y << 14) | X;
+      }
+      wr += __popc(m);
+    }
+    return;
+  }
+
+  // survivor list overflowed (a very noisy cell): full-cell passes
   // pass 2: strict 3x3 local maxima of the raw score map (scores outside the detection area are 0); the maxima
   // (score, else 0) overwrite the pixel tile, which is no longer read as pixels
   const unsigned ini4 = (unsigned)P.iniTh * 0x01010101u;
