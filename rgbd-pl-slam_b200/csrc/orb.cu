@@ -702,16 +702,26 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams 
     }
     __syncthreads();
     if (rim) {
-      // reflect-101 halo outside the level (TMA wrote zeros there)
-      for (int i = threadIdx.x; i < BOX_H * (BT_W + 6); i += 256) {
-        const int yy = i / (BT_W + 6), xx = i - yy * (BT_W + 6);
-        int gx = tx + xx - 3, gy = ty + yy - 3;
-        if (gx >= 0 && gx < w && gy >= 0 && gy < h) continue;
-        gx = gx < 0 ? -gx : (gx >= w ? 2 * (w - 1) - gx : gx);
-        gy = gy < 0 ? -gy : (gy >= h ? 2 * (h - 1) - gy : gy);
-        gx = max(0, min(gx, w - 1));
-        gy = max(0, min(gy, h - 1));
-        raw[yy][BOX_XOFF + xx] = S[(size_t)gy * sp + gx];
+      // reflect-101 halo outside the level (TMA wrote zeros there).  Only the cells that can reach a valid output are
+      // patched: up to 3 rows above / below the level and up to 3 columns left / right of it; warp = row, lane = column.
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      auto refl = [](int g, int n) {
+        g = g < 0 ? -g : (g >= n ? 2 * (n - 1) - g : g);
+        return max(0, min(g, n - 1));
+      };
+      const int xxEnd = min(BT_W + 6, w + 3 - (tx - 3));  // columns beyond w + 2 feed no valid output
+      for (int yy = warp; yy < BOX_H; yy += 8) {
+        const int gy = ty + yy - 3;
+        if (gy >= h + 3) break;
+        const uint8_t* row = S + (size_t)refl(gy, h) * sp;
+        if (gy < 0 || gy >= h) {  // a whole row outside the level
+          for (int xx = lane; xx < xxEnd; xx += 32) raw[yy][BOX_XOFF + xx] = row[refl(tx + xx - 3, w)];
+        } else {                  // inside rows: only the columns left of 0 and right of w - 1
+          if (tx < 3 && lane < 3 - tx) raw[yy][BOX_XOFF + lane] = row[refl(tx + lane - 3, w)];
+          const int x0 = w - (tx - 3);  // first box column at or beyond w
+          if (x0 < BT_W + 6 && lane < 3 && x0 + lane < BT_W + 6 && x0 + lane >= 0)
+            raw[yy][BOX_XOFF + x0 + lane] = row[refl(w + lane, w)];
+        }
       }
     }
   } else {
