@@ -658,18 +658,17 @@ struct BlurMaps {
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams P, const BlurMaps* __restrict__ Mp,
-                                              OrbImages I, const int* __restrict__ lvlCnt) {
+                                              OrbImages I, const int* __restrict__ lvlCnt,
+                                              const unsigned* __restrict__ tileTab) {
   __shared__ __align__(128) uint8_t raw[BOX_H][BOX_W];
   __shared__ __align__(16) unsigned short hs[BOX_H][BT_W];
   __shared__ __align__(8) unsigned long long mbar;
   const int f = blockIdx.y;
-  int tile = blockIdx.x;
-  int l = 0;
-  while (l + 1 < P.nlevels && tile >= P.lv[l + 1].tileBase) ++l;
+  const unsigned tt = __ldg(tileTab + blockIdx.x);  // level << 28 | tile row << 14 | tile column (host table)
+  const int l = (int)(tt >> 28);
   if (lvlCnt[f * ORB_MAXL + l] == 0) return;  // the reference blurs only levels with keypoints
   const OrbLevel& L = P.lv[l];
-  tile -= L.tileBase;
-  const int tx = (tile % L.tilesX) * BT_W, ty = (tile / L.tilesX) * BT_H;
+  const int tx = (int)(tt & 0x3fffu) * BT_W, ty = (int)((tt >> 14) & 0x3fffu) * BT_H;
   const int w = L.w, h = L.h;
   int sp;
   const uint8_t* S = level_ptr(P, I, f, l, sp);
@@ -969,7 +968,7 @@ OrbExtractor::OrbExtractor(int nf, float sf, int nl, int ini, int mn)
 }
 
 OrbExtractor::~OrbExtractor() {
-  DevBuf* all[] = {&pyr, &blurred, &coef, &cand, &candCount, &knode, &lvlKp, &lvlCnt, &status, &blurMaps,
+  DevBuf* all[] = {&pyr, &blurred, &coef, &cand, &candCount, &knode, &lvlKp, &lvlCnt, &status, &blurMaps, &tileTab,
                    &stageIn, &stageKps, &stageDesc, &stageCnt};
   for (DevBuf* b : all) b->release();
   if (ownStream) cudaStreamDestroy(ownStream);
@@ -1090,6 +1089,18 @@ int OrbExtractor::configure(int W, int H, int batch) {
   }
   P.totalCells = cellBase;
   P.totalTiles = tileBase;
+  {  // blur tile table: one word per CTA instead of a level search and two integer divisions per thread
+    std::vector<unsigned> tab;
+    tab.reserve(tileBase);
+    for (int l = 0; l < nlevels; ++l) {
+      const int ty_n = div_up(P.lv[l].h, BT_H);
+      for (int ty = 0; ty < ty_n; ++ty)
+        for (int tx = 0; tx < P.lv[l].tilesX; ++tx) tab.push_back(((unsigned)l << 28) | ((unsigned)ty << 14) | (unsigned)tx);
+    }
+    int rct = tileTab.ensure(tab.size() * sizeof(unsigned));
+    if (rct) return rct;
+    PL_CUDA(cudaMemcpy(tileTab.p, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
   P.maxKp = kpOff;
   P.nodeCap = std::max(maxQuota + 8, 16);
   P.patchPitch = (int)align_up(maxPw + 3, 4);  // + 3: room for the alignment shift of the staged tile
@@ -1198,7 +1209,7 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
     if (rcm) return rcm;
     PL_CUDA(cudaMemcpyAsync(blurMaps.p, &M, sizeof(M), cudaMemcpyHostToDevice, st));
     PL_CARVEOUT(k_blur);
-    k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, blurMaps.as<BlurMaps>(), I, lvlCnt.as<int>());
+    k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, blurMaps.as<BlurMaps>(), I, lvlCnt.as<int>(), tileTab.as<unsigned>());
   }
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "orb_orient_desc", st);

@@ -84,7 +84,7 @@ class OrbExtractor {
   int last_pitch0 = 0, last_batch = 0;
   size_t last_stride0 = 0;
   size_t blurOff0 = 0, blurFrameStride = 0;
-  DevBuf pyr, blurred, coef, cand, candCount, knode, lvlKp, lvlCnt, status, blurMaps;
+  DevBuf pyr, blurred, coef, cand, candCount, knode, lvlKp, lvlCnt, status, blurMaps, tileTab;
   DevBuf stageIn, stageKps, stageDesc, stageCnt;
   cudaStream_t ownStream = nullptr;
   void* pinnedStatus = nullptr;
