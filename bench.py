@@ -28,6 +28,8 @@ for p in (ROOT, os.path.join(ROOT, "rgbd-pl-slam_b200")):
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 # keep stdout to the one JSON line: NCCL's version banner / debug output goes to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # the VERSION level prints its banner with a bare printf to stdout
 
 import numpy as np
 
