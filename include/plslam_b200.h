@@ -315,6 +315,13 @@ int plslam_frontend_process_host(plslam_frontend_t* h, const uint8_t* images, in
 int plslam_frontend_submit_host(plslam_frontend_t* h, const uint8_t* images, int batch, int width, int height, int pitch,
                                 size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs);
 int plslam_frontend_wait_host(plslam_frontend_t* h);
+/* Completion-ordered variant for deep pipelines: acquire_slot blocks until some slot's previous batch has finished and
+ * returns its index (0 .. depth-1); submit_host_slot enqueues on that slot.  The caller can keep one set of host output
+ * buffers per slot.  Work enqueued this way is ready to run at once, which keeps the copy engines' in-order queues from
+ * coupling the slots to each other. */
+int plslam_frontend_acquire_slot(plslam_frontend_t* h);
+int plslam_frontend_submit_host_slot(plslam_frontend_t* h, int slot, const uint8_t* images, int batch, int width, int height,
+                                     int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs);
 /* Per-stage device times (ms, CUDA events on the launching streams) of the last process call made after
  * plslam_frontend_enable_timing(h, 1).  names/ms hold up to `capacity` entries; returns the number of stages. */
 int plslam_frontend_enable_timing(plslam_frontend_t* h, int enable);

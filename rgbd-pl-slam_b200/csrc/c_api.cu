@@ -37,7 +37,7 @@ namespace plslam {
 int carveout_pct() {
   static const int v = [] {
     const char* e = std::getenv("PLSLAM_CARVEOUT");
-    return e ? std::atoi(e) : 50;
+    return e ? std::atoi(e) : 65;
   }();
   return v;
 }

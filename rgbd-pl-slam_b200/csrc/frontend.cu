@@ -4,12 +4,22 @@
 // stream: the latency-bound line kernels (one warp per frame) overlap the throughput-bound ORB kernels.
 #include <new>
 
+#include <chrono>
+#include <thread>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "lines.cuh"
 #include "orb.cuh"
 
 namespace plslam {
 namespace {
+
+// PLSLAM_TRACE_HOST=1: report enqueue calls that block the submitting thread for more than a millisecond
+inline bool trace_host() {
+  static const bool on = std::getenv("PLSLAM_TRACE_HOST") != nullptr;
+  return on;
+}
 
 __global__ void k_make_pair_jobs(const uint8_t* desc, const int32_t* counts, int capacity, int npairs, int32_t* out,
                                  plslam_knn_job_t* jobs) {
@@ -35,10 +45,11 @@ struct Slot {
   StageTimer tOrb, tLines;
   cudaStream_t sOrb = nullptr, sHost = nullptr;  // the line branch runs on the caller's stream, the ORB branch beside it
   cudaEvent_t evFork = nullptr, evOrb = nullptr, evLines = nullptr, evDone = nullptr;
+
   DevBuf jobsOrb, jobsLines;
   DevBuf dIn, dKps, dDesc, dKpCnt, dKl, dLdesc, dFuncs, dLCnt, dOrbM, dLineM;
   int* pinnedStatus = nullptr;
-  bool used = false, hostPending = false;
+  bool used = false, hostPending = false, h2dOnce = false;
   Slot(int nf, float sf, int nl, int ini, int mn, int max_lines) : orb(nf, sf, nl, ini, mn) { lines.set_max_lines(max_lines); }
   ~Slot() {
     DevBuf* all[] = {&jobsOrb, &jobsLines, &dIn, &dKps, &dDesc, &dKpCnt, &dKl, &dLdesc, &dFuncs, &dLCnt, &dOrbM, &dLineM};
@@ -85,11 +96,18 @@ struct Slot {
     PL_CUDA(cudaStreamWaitEvent(sOrb, evFork, 0));
     cudaStream_t sLines = st;  // every stream is a hardware connection: two per slot keep deep pipelines from aliasing queues
     // line branch first: its long sequential kernel should start as early as possible
+    const auto tA = std::chrono::steady_clock::now();
     rc = lines.extract_device(d_images, batch, W, H, pitch, stride, io.keylines, io.line_descriptors, io.line_functions,
                               lnCap, io.line_counts, sLines);
     if (rc) return rc;
+    const auto tB = std::chrono::steady_clock::now();
     rc = orb.extract_device(d_images, batch, W, H, pitch, stride, io.keypoints, io.descriptors, kpCap, io.kp_counts, sOrb);
     if (rc) return rc;
+    const auto tC = std::chrono::steady_clock::now();
+    if (trace_host()) {
+      const double a = std::chrono::duration<double, std::milli>(tB - tA).count(), b = std::chrono::duration<double, std::milli>(tC - tB).count();
+      if (a > 1.0 || b > 1.0) fprintf(stderr, "[plslam trace] enqueue lines %.2f ms, orb %.2f ms\n", a, b);
+    }
     if (match_pairs) {
       PL_STAGE_BEGIN(orb.timer, "match_orb_knn2", sOrb);
       rc = plslam_match_knn2_pairs_device(io.descriptors, io.kp_counts, kpCap, npairs, io.orb_matches,
@@ -117,6 +135,8 @@ struct Slot {
     PL_CUDA(cudaStreamSynchronize(st));
     if (pinnedStatus[0] != PLSLAM_OK || pinnedStatus[1] != PLSLAM_OK) {
       set_error("device status orb=%d lines=%d (internal fixed-capacity buffer overflow)", pinnedStatus[0], pinnedStatus[1]);
+      cudaMemsetAsync(const_cast<int*>(orb.device_status()), 0, sizeof(int), st);  // re-arm the sticky flags
+      cudaMemsetAsync(const_cast<int*>(lines.device_status()), 0, sizeof(int), st);
       return PLSLAM_ERR_OVERFLOW;
     }
     return PLSLAM_OK;
@@ -140,16 +160,21 @@ struct Slot {
         return rc;
     }
     cudaStream_t st = sHost;
-    if (stride == (size_t)pitch * H && (size_t)pitch == dpitch) {
+    static const int dbgSkip = [] { const char* e = std::getenv("PLSLAM_DEBUG_SKIP_COPIES"); return e ? std::atoi(e) : 0; }();  // profiling aid: 1 = H2D only on first use, 2 = no D2H
+    // (Measured: moving the upload to its own stream with a second staging buffer does not change the throughput,
+    // and background uploads do not slow the kernels; the upload stays on the slot's stream.)
+    uint8_t* dst = dIn.as<uint8_t>();
+    if ((dbgSkip & 1) && h2dOnce) {  // the staging buffer still holds the same frames
+    } else if (stride == (size_t)pitch * H && (size_t)pitch == dpitch) {
       // densely packed frames on both sides: one linear copy (a 2-D copy of 122 880 rows is descriptor bound)
-      PL_CUDA(cudaMemcpyAsync(dIn.p, images, dstride * batch, cudaMemcpyHostToDevice, st));
+      PL_CUDA(cudaMemcpyAsync(dst, images, dstride * batch, cudaMemcpyHostToDevice, st));
     } else if (stride == (size_t)pitch * H) {
-      PL_CUDA(cudaMemcpy2DAsync(dIn.p, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, st));
+      PL_CUDA(cudaMemcpy2DAsync(dst, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, st));
     } else {
       for (int f = 0; f < batch; ++f)
-        PL_CUDA(cudaMemcpy2DAsync(dIn.as<uint8_t>() + f * dstride, dpitch, images + f * stride, pitch, W, H,
-                                  cudaMemcpyHostToDevice, st));
+        PL_CUDA(cudaMemcpy2DAsync(dst + f * dstride, dpitch, images + f * stride, pitch, W, H, cudaMemcpyHostToDevice, st));
     }
+    h2dOnce = true;
     plslam_frontend_io_t d{};
     d.keypoints = dKps.as<plslam_keypoint_t>();
     d.descriptors = dDesc.as<uint8_t>();
@@ -160,8 +185,10 @@ struct Slot {
     d.line_counts = dLCnt.as<int32_t>();
     d.orb_matches = match_pairs ? dOrbM.as<int32_t>() : nullptr;
     d.line_matches = match_pairs ? dLineM.as<int32_t>() : nullptr;
-    rc = process_device(dIn.as<uint8_t>(), batch, W, H, (int)dpitch, dstride, d, match_pairs, st, timing);
+    rc = process_device(dst, batch, W, H, (int)dpitch, dstride, d, match_pairs, st, timing);
     if (rc) return rc;
+
+    if (!(dbgSkip & 2)) {
     PL_CUDA(cudaMemcpyAsync(io.keypoints, d.keypoints, (size_t)batch * kpCap * sizeof(plslam_keypoint_t), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaMemcpyAsync(io.descriptors, d.descriptors, (size_t)batch * kpCap * 32, cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaMemcpyAsync(io.kp_counts, d.kp_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
@@ -172,6 +199,7 @@ struct Slot {
     if (match_pairs) {
       PL_CUDA(cudaMemcpyAsync(io.orb_matches, d.orb_matches, (size_t)npairs * kpCap * 16, cudaMemcpyDeviceToHost, st));
       PL_CUDA(cudaMemcpyAsync(io.line_matches, d.line_matches, (size_t)npairs * lnCap * 16, cudaMemcpyDeviceToHost, st));
+    }
     }
     PL_CUDA(cudaEventRecord(evDone, st));
     hostPending = true;
@@ -188,6 +216,7 @@ struct Frontend {
   std::vector<Slot*> slots;
   int next = 0, lastSlot = 0;
   bool timing = false;
+
   Frontend(int nf, float sf, int nl, int ini, int mn, int max_lines, int depth) {
     for (int i = 0; i < depth; ++i) {
       slots.push_back(new Slot(nf, sf, nl, ini, mn, max_lines));
@@ -260,10 +289,36 @@ int plslam_frontend_process_device(plslam_frontend_t* h, const uint8_t* d_images
 int plslam_frontend_submit_host(plslam_frontend_t* h, const uint8_t* images, int batch, int width, int height, int pitch,
                                 size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs) {
   PL_CHECK_ARG(h && io);
+  // No host wait here: the slot's streams order this batch behind its previous one (staging buffers, workspaces), and
+  // the overflow flags are sticky until plslam_frontend_wait_host() reads them.  Blocking on the slot's previous batch
+  // would stall the one submitting thread while other slots sit idle.
   Slot& s = h->impl.take();
-  int rc = s.wait_host();  // the slot's previous host batch must have landed before its staging is reused
-  if (rc) return rc;
   return s.submit_host(images, batch, width, height, pitch, frame_stride, *io, match_pairs, h->impl.timing);
+}
+// Completion-ordered submission: acquire returns a slot whose previous batch has finished (polling the slots' completion
+// events), submit_host_slot enqueues on exactly that slot.  Every copy and kernel enqueued this way is ready to run, so the
+// copy engines' in-order queues never hold a batch behind another slot's unfinished one.
+int plslam_frontend_acquire_slot(plslam_frontend_t* h) {
+  if (!h) return -1;
+  Frontend& F = h->impl;
+  const int n = (int)F.slots.size();
+  for (;;) {
+    for (int k = 0; k < n; ++k) {
+      const int i = (F.next + k) % n;
+      Slot* s = F.slots[i];
+      if (!s->used || !s->evDone || cudaEventQuery(s->evDone) == cudaSuccess) {
+        F.next = (i + 1) % n;
+        return i;
+      }
+    }
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+}
+int plslam_frontend_submit_host_slot(plslam_frontend_t* h, int slot, const uint8_t* images, int batch, int width, int height,
+                                     int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs) {
+  PL_CHECK_ARG(h && io && slot >= 0 && slot < (int)h->impl.slots.size());
+  h->impl.lastSlot = slot;
+  return h->impl.slots[slot]->submit_host(images, batch, width, height, pitch, frame_stride, *io, match_pairs, h->impl.timing);
 }
 int plslam_frontend_wait_host(plslam_frontend_t* h) {
   PL_CHECK_ARG(h);

@@ -1785,6 +1785,7 @@ int LineExtractor::configure(int W, int H, int batch) {
   if ((rc = resp.ensure(B * P.rect_cap * sizeof(float)))) return rc;
   if ((rc = rowsum.ensure(B * P.out_cap * LBD_ROWS * 4 * sizeof(float)))) return rc;
   if ((rc = status.ensure(sizeof(int)))) return rc;
+  PL_CUDA(cudaMemset(status.p, 0, sizeof(int)));
   PL_CHECK_ARG(P.sw < 65536 && P.sh < 32768);
   PL_CARVEOUT(k_lsd_lgamma_table);
   k_lsd_lgamma_table<<<div_up(LGAMMA_TABLE, 256), 256>>>();
@@ -1808,7 +1809,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   }
   last_batch = batch;
   PL_CUDA(cudaMemsetAsync(maxg2.p, 0, (size_t)batch * sizeof(int), st));
-  PL_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), st));
+  // `status` is sticky: kernels only raise it, check_status() reads and re-arms it (several batches may be in flight)
   PL_STAGE_BEGIN(timer, "lsd_scale", st);
   PL_CARVEOUT(k_lsd_scale);
   k_lsd_scale<<<dim3(div_up(P.sw, ST_W), div_up(P.sh, ST_H), batch), 256, 0, st>>>(P, d_images, pitch, frame_stride,
@@ -1902,7 +1903,10 @@ int LineExtractor::check_status(cudaStream_t st) {
   PL_CUDA(cudaMemcpyAsync(pinnedStatus, status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   PL_CUDA(cudaStreamSynchronize(st));
   const int s = *reinterpret_cast<int*>(pinnedStatus);
-  if (s != PLSLAM_OK) set_error("device status %d (rectangle list overflow: raise rect_cap)", s);
+  if (s != PLSLAM_OK) {
+    set_error("device status %d (rectangle list overflow: raise rect_cap)", s);
+    cudaMemsetAsync(status.p, 0, sizeof(int), st);  // re-arm
+  }
   return s;
 }
 

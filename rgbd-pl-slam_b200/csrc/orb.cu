@@ -1122,6 +1122,7 @@ int OrbExtractor::configure(int W, int H, int batch) {
   if ((rc = lvlCnt.ensure((size_t)B * ORB_MAXL * sizeof(int)))) return rc;
   if ((rc = lvlKp.ensure((size_t)B * P.maxKp * sizeof(uint2)))) return rc;
   if ((rc = status.ensure(sizeof(int)))) return rc;
+  PL_CUDA(cudaMemset(status.p, 0, sizeof(int)));
   cfgW = W;
   cfgH = H;
   cfgB = B;
@@ -1157,7 +1158,7 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
   last_batch = batch;
 
   PL_CUDA(cudaMemsetAsync(candCount.p, 0, (size_t)batch * ORB_MAXL * sizeof(int), st));
-  PL_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), st));
+  // `status` is sticky: kernels only raise it, check_status() reads and re-arms it (several batches may be in flight)
   PL_STAGE_BEGIN(timer, "orb_pyramid(7 launches)", st);
   for (int l = 1; l < nlevels; ++l) {
     dim3 grid(div_up(P.lv[l].w, 128), div_up(P.lv[l].h, 8), batch);
@@ -1193,23 +1194,37 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
   }
   PL_STAGE_BEGIN(timer, "orb_blur", st);
   {
-    BlurMaps M;
-    std::memset(&M, 0, sizeof(M));
     bool k8 = true;
     for (int i = 0; i < 7; ++i) k8 = k8 && blurk[i] >= 0 && blurk[i] <= 255;
     PL_CHECK_ARG(k8);
-    for (int l = 0; l < nlevels; ++l) {
-      const void* base = l ? (const void*)(pyr.as<uint8_t>() + P.lv[l].off) : (const void*)d_images;
-      const size_t lp = l ? (size_t)P.lv[l].pitch : (size_t)pitch, ls = l ? (size_t)P.pyrFrameStride : frame_stride;
-      if (encode_level_map(&M.m[l], base, P.lv[l].w, P.lv[l].h, lp, ls, batch)) M.tmaMask |= 1u << l;
+    // The TMA descriptors only depend on the buffers and the frame geometry: re-encode and upload them when those
+    // change, not on every call.  (A cudaMemcpyAsync from pageable memory synchronises its stream first: done per
+    // call it stalled the submitting host thread behind the whole ORB branch of the slot.)
+    const uintptr_t key[6] = {(uintptr_t)d_images, (uintptr_t)pitch, (uintptr_t)frame_stride, (uintptr_t)batch,
+                              (uintptr_t)pyr.p, (uintptr_t)(W * 65536 + H)};
+    // two cached descriptor sets (the host path of the front-end alternates between two input staging buffers)
+    int slotIdx = -1;
+    for (int e = 0; e < 2; ++e)
+      if (std::memcmp(key, mapsKey[e], sizeof(key)) == 0) slotIdx = e;
+    if (slotIdx < 0) {
+      slotIdx = mapsNext;
+      mapsNext ^= 1;
+      BlurMaps M;
+      std::memset(&M, 0, sizeof(M));
+      for (int l = 0; l < nlevels; ++l) {
+        const void* base = l ? (const void*)(pyr.as<uint8_t>() + P.lv[l].off) : (const void*)d_images;
+        const size_t lp = l ? (size_t)P.lv[l].pitch : (size_t)pitch, ls = l ? (size_t)P.pyrFrameStride : frame_stride;
+        if (encode_level_map(&M.m[l], base, P.lv[l].w, P.lv[l].h, lp, ls, batch)) M.tmaMask |= 1u << l;
+      }
+      int rcm = blurMaps.ensure(2 * sizeof(BlurMaps));
+      if (rcm) return rcm;
+      if (mapsKey[slotIdx][0]) PL_CUDA(cudaStreamSynchronize(st));  // an earlier launch may still read the entry being replaced
+      PL_CUDA(cudaMemcpy(blurMaps.as<BlurMaps>() + slotIdx, &M, sizeof(M), cudaMemcpyHostToDevice));
+      std::memcpy(mapsKey[slotIdx], key, sizeof(key));
     }
-    // the descriptors live in global memory (TMA needs them in global/const/param space); pageable source: the
-    // runtime stages the 1.5 KB before cudaMemcpyAsync returns
-    int rcm = blurMaps.ensure(sizeof(BlurMaps));
-    if (rcm) return rcm;
-    PL_CUDA(cudaMemcpyAsync(blurMaps.p, &M, sizeof(M), cudaMemcpyHostToDevice, st));
+    const BlurMaps* dMaps = blurMaps.as<BlurMaps>() + slotIdx;
     PL_CARVEOUT(k_blur);
-    k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, blurMaps.as<BlurMaps>(), I, lvlCnt.as<int>(), tileTab.as<unsigned>());
+    k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, dMaps, I, lvlCnt.as<int>(), tileTab.as<unsigned>());
   }
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "orb_orient_desc", st);
@@ -1225,7 +1240,10 @@ int OrbExtractor::check_status(cudaStream_t st) {
   PL_CUDA(cudaMemcpyAsync(pinnedStatus, status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   PL_CUDA(cudaStreamSynchronize(st));
   const int s = *reinterpret_cast<int*>(pinnedStatus);
-  if (s != PLSLAM_OK) set_error("device status %d (internal candidate buffer overflow)", s);
+  if (s != PLSLAM_OK) {
+    set_error("device status %d (internal candidate buffer overflow)", s);
+    cudaMemsetAsync(status.p, 0, sizeof(int), st);  // re-arm
+  }
   return s;
 }
 

@@ -88,6 +88,8 @@ class OrbExtractor {
   DevBuf stageIn, stageKps, stageDesc, stageCnt;
   cudaStream_t ownStream = nullptr;
   void* pinnedStatus = nullptr;
+  uintptr_t mapsKey[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};  // what the cached TMA descriptor sets of k_blur were encoded for
+  int mapsNext = 0;
 };
 
 }  // namespace plslam

@@ -437,6 +437,21 @@ class Frontend:
         """Asynchronous process_host on the next pipeline slot; `out` is valid after wait_host()."""
         return self._host_call(lib().plslam_frontend_submit_host, images, out, match_pairs)
 
+    def acquire_slot(self):
+        """Blocks until a pipeline slot is idle and returns its index (keep one set of host output buffers per slot)."""
+        return lib().plslam_frontend_acquire_slot(self._h)
+
+    def submit_host_slot(self, slot, images, out, match_pairs=True):
+        """submit_host on the slot returned by acquire_slot()."""
+        B, H, W = images.shape
+        io = self._io(out)
+        ptr = images.data_ptr() if hasattr(images, "data_ptr") else images.ctypes.data
+        st0 = images.stride(0) if hasattr(images, "stride") else images.strides[0]
+        st1 = images.stride(1) if hasattr(images, "stride") else images.strides[1]
+        _check(lib().plslam_frontend_submit_host_slot(self._h, int(slot), C.c_void_p(ptr), B, W, H, st1, C.c_size_t(st0),
+                                                      C.byref(io), int(match_pairs)))
+        return out
+
     def wait_host(self):
         _check(lib().plslam_frontend_wait_host(self._h))
 
