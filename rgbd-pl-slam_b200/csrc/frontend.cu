@@ -164,7 +164,9 @@ struct Slot {
     // (Measured: moving the upload to its own stream with a second staging buffer does not change the throughput,
     // and background uploads do not slow the kernels; the upload stays on the slot's stream.)
     uint8_t* dst = dIn.as<uint8_t>();
-    if ((dbgSkip & 1) && h2dOnce) {  // the staging buffer still holds the same frames
+    if ((dbgSkip & 4) && h2dOnce) {  // re-upload one frame only: is the cost the bytes or the dependency?
+      PL_CUDA(cudaMemcpyAsync(dst, images, dstride, cudaMemcpyHostToDevice, st));
+    } else if ((dbgSkip & 1) && h2dOnce) {  // the staging buffer still holds the same frames
     } else if (stride == (size_t)pitch * H && (size_t)pitch == dpitch) {
       // densely packed frames on both sides: one linear copy (a 2-D copy of 122 880 rows is descriptor bound)
       PL_CUDA(cudaMemcpyAsync(dst, images, dstride * batch, cudaMemcpyHostToDevice, st));
