@@ -45,18 +45,24 @@ struct Slot {
   StageTimer tOrb, tLines;
   cudaStream_t sOrb = nullptr, sHost = nullptr;  // the line branch runs on the caller's stream, the ORB branch beside it
   cudaEvent_t evFork = nullptr, evOrb = nullptr, evLines = nullptr, evDone = nullptr;
+  // host path, optional (PLSLAM_UPLOAD_STREAM=1): two input staging buffers and a shared upload stream, so the upload of a
+  // slot's next batch runs while its current batch computes
+  cudaStream_t sUp = nullptr;  // owned by the Frontend
+  cudaEvent_t evUp[2] = {nullptr, nullptr}, evFree[2] = {nullptr, nullptr};
+  bool bufUsed[2] = {false, false};
+  int bufNext = 0;
 
   DevBuf jobsOrb, jobsLines;
-  DevBuf dIn, dKps, dDesc, dKpCnt, dKl, dLdesc, dFuncs, dLCnt, dOrbM, dLineM;
+  DevBuf dIn[2], dKps, dDesc, dKpCnt, dKl, dLdesc, dFuncs, dLCnt, dOrbM, dLineM;
   int* pinnedStatus = nullptr;
   bool used = false, hostPending = false, h2dOnce = false;
   Slot(int nf, float sf, int nl, int ini, int mn, int max_lines) : orb(nf, sf, nl, ini, mn) { lines.set_max_lines(max_lines); }
   ~Slot() {
-    DevBuf* all[] = {&jobsOrb, &jobsLines, &dIn, &dKps, &dDesc, &dKpCnt, &dKl, &dLdesc, &dFuncs, &dLCnt, &dOrbM, &dLineM};
+    DevBuf* all[] = {&jobsOrb, &jobsLines, &dIn[0], &dIn[1], &dKps, &dDesc, &dKpCnt, &dKl, &dLdesc, &dFuncs, &dLCnt, &dOrbM, &dLineM};
     for (DevBuf* b : all) b->release();
     if (sOrb) cudaStreamDestroy(sOrb);
     if (sHost) cudaStreamDestroy(sHost);
-    cudaEvent_t evs[] = {evFork, evOrb, evLines, evDone};
+    cudaEvent_t evs[] = {evFork, evOrb, evLines, evDone, evUp[0], evUp[1], evFree[0], evFree[1]};
     for (cudaEvent_t e : evs)
       if (e) cudaEventDestroy(e);
     if (pinnedStatus) cudaFreeHost(pinnedStatus);
@@ -69,6 +75,10 @@ struct Slot {
     PL_CUDA(cudaEventCreateWithFlags(&evOrb, cudaEventDisableTiming));
     PL_CUDA(cudaEventCreateWithFlags(&evLines, cudaEventDisableTiming));
     PL_CUDA(cudaEventCreateWithFlags(&evDone, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+      PL_CUDA(cudaEventCreateWithFlags(&evUp[b], cudaEventDisableTiming));
+      PL_CUDA(cudaEventCreateWithFlags(&evFree[b], cudaEventDisableTiming));
+    }
     PL_CUDA(cudaMallocHost((void**)&pinnedStatus, 64));
     return PLSLAM_OK;
   }
@@ -150,7 +160,9 @@ struct Slot {
     const int kpCap = orb.max_keypoints(), lnCap = lines.out_capacity();
     const int npairs = batch / 2;
     const size_t dpitch = align_up(W, 32), dstride = dpitch * H;
-    if ((rc = dIn.ensure(dstride * batch)) || (rc = dKps.ensure((size_t)batch * kpCap * sizeof(plslam_keypoint_t))) ||
+    const int b = sUp ? bufNext : 0;
+    if (sUp) bufNext ^= 1;
+    if ((rc = dIn[b].ensure(dstride * batch)) || (rc = dKps.ensure((size_t)batch * kpCap * sizeof(plslam_keypoint_t))) ||
         (rc = dDesc.ensure((size_t)batch * kpCap * 32)) || (rc = dKpCnt.ensure((size_t)batch * 4)) ||
         (rc = dKl.ensure((size_t)batch * lnCap * sizeof(plslam_keyline_t))) || (rc = dLdesc.ensure((size_t)batch * lnCap * 32)) ||
         (rc = dFuncs.ensure((size_t)batch * lnCap * 24)) || (rc = dLCnt.ensure((size_t)batch * 4)))
@@ -161,21 +173,26 @@ struct Slot {
     }
     cudaStream_t st = sHost;
     static const int dbgSkip = [] { const char* e = std::getenv("PLSLAM_DEBUG_SKIP_COPIES"); return e ? std::atoi(e) : 0; }();  // profiling aid: 1 = H2D only on first use, 2 = no D2H
-    // (Measured: moving the upload to its own stream with a second staging buffer does not change the throughput,
-    // and background uploads do not slow the kernels; the upload stays on the slot's stream.)
-    uint8_t* dst = dIn.as<uint8_t>();
-    if ((dbgSkip & 4) && h2dOnce) {  // re-upload one frame only: is the cost the bytes or the dependency?
-      PL_CUDA(cudaMemcpyAsync(dst, images, dstride, cudaMemcpyHostToDevice, st));
-    } else if ((dbgSkip & 1) && h2dOnce) {  // the staging buffer still holds the same frames
+    cudaStream_t up = sUp ? sUp : st;
+    if (sUp && bufUsed[b]) PL_CUDA(cudaStreamWaitEvent(up, evFree[b], 0));  // the batch that last read this buffer
+    uint8_t* dst = dIn[b].as<uint8_t>();
+    if ((dbgSkip & 4) && h2dOnce && bufUsed[b]) {  // re-upload one frame only: is the cost the bytes or the dependency?
+      PL_CUDA(cudaMemcpyAsync(dst, images, dstride, cudaMemcpyHostToDevice, up));
+    } else if ((dbgSkip & 1) && h2dOnce && bufUsed[b]) {  // the staging buffer still holds the same frames
     } else if (stride == (size_t)pitch * H && (size_t)pitch == dpitch) {
       // densely packed frames on both sides: one linear copy (a 2-D copy of 122 880 rows is descriptor bound)
-      PL_CUDA(cudaMemcpyAsync(dst, images, dstride * batch, cudaMemcpyHostToDevice, st));
+      PL_CUDA(cudaMemcpyAsync(dst, images, dstride * batch, cudaMemcpyHostToDevice, up));
     } else if (stride == (size_t)pitch * H) {
-      PL_CUDA(cudaMemcpy2DAsync(dst, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, st));
+      PL_CUDA(cudaMemcpy2DAsync(dst, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, up));
     } else {
       for (int f = 0; f < batch; ++f)
-        PL_CUDA(cudaMemcpy2DAsync(dst + f * dstride, dpitch, images + f * stride, pitch, W, H, cudaMemcpyHostToDevice, st));
+        PL_CUDA(cudaMemcpy2DAsync(dst + f * dstride, dpitch, images + f * stride, pitch, W, H, cudaMemcpyHostToDevice, up));
     }
+    if (sUp) {
+      PL_CUDA(cudaEventRecord(evUp[b], up));
+      PL_CUDA(cudaStreamWaitEvent(st, evUp[b], 0));
+    }
+    bufUsed[b] = true;
     h2dOnce = true;
     plslam_frontend_io_t d{};
     d.keypoints = dKps.as<plslam_keypoint_t>();
@@ -218,6 +235,16 @@ struct Frontend {
   std::vector<Slot*> slots;
   int next = 0, lastSlot = 0;
   bool timing = false;
+  // optional upload stream of the host path, shared by the slots (PLSLAM_UPLOAD_STREAM=1; measured: no gain, off by default)
+  cudaStream_t sUp = nullptr;
+  int ensure_upload_stream() {
+    static const bool enabled = [] { const char* e = std::getenv("PLSLAM_UPLOAD_STREAM"); return e && std::atoi(e) != 0; }();
+    if (enabled && !sUp && slots.size() > 1) {
+      PL_CUDA(cudaStreamCreateWithFlags(&sUp, cudaStreamNonBlocking));
+      for (Slot* s : slots) s->sUp = sUp;
+    }
+    return PLSLAM_OK;
+  }
 
   Frontend(int nf, float sf, int nl, int ini, int mn, int max_lines, int depth) {
     for (int i = 0; i < depth; ++i) {
@@ -227,6 +254,7 @@ struct Frontend {
   }
   ~Frontend() {
     for (Slot* s : slots) delete s;
+    if (sUp) cudaStreamDestroy(sUp);
   }
   Slot& take() {
     lastSlot = next;
@@ -294,6 +322,8 @@ int plslam_frontend_submit_host(plslam_frontend_t* h, const uint8_t* images, int
   // No host wait here: the slot's streams order this batch behind its previous one (staging buffers, workspaces), and
   // the overflow flags are sticky until plslam_frontend_wait_host() reads them.  Blocking on the slot's previous batch
   // would stall the one submitting thread while other slots sit idle.
+  int rcu = h->impl.ensure_upload_stream();
+  if (rcu) return rcu;
   Slot& s = h->impl.take();
   return s.submit_host(images, batch, width, height, pitch, frame_stride, *io, match_pairs, h->impl.timing);
 }
@@ -319,6 +349,8 @@ int plslam_frontend_acquire_slot(plslam_frontend_t* h) {
 int plslam_frontend_submit_host_slot(plslam_frontend_t* h, int slot, const uint8_t* images, int batch, int width, int height,
                                      int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs) {
   PL_CHECK_ARG(h && io && slot >= 0 && slot < (int)h->impl.slots.size());
+  int rcu = h->impl.ensure_upload_stream();
+  if (rcu) return rcu;
   h->impl.lastSlot = slot;
   return h->impl.slots[slot]->submit_host(images, batch, width, height, pitch, frame_stride, *io, match_pairs, h->impl.timing);
 }

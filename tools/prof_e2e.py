@@ -9,11 +9,11 @@ import plslam_b200 as pl
 import bench
 a = argparse.Namespace(batch=256, width=640, height=480)
 frames = bench.make_frames(a, 0)
-depth, steps = 16, 64
+depth, steps = int(os.environ.get('E2E_DEPTH', '16')), 64
 fe = pl.Frontend(depth=depth)
 h_images = torch.from_numpy(frames).pin_memory()
 h_outs = [fe.alloc(256, pinned=True) for _ in range(depth)]
-for k in range(depth): fe.submit_host(h_images, h_outs[k % depth], True)
+for k in range(2 * depth): fe.submit_host(h_images, h_outs[k % depth], True)
 fe.wait_host()
 lat = []
 t0 = time.perf_counter()
