@@ -28,13 +28,14 @@ def run(n, copies):
         fe.process_device(d_images, outs[k % depth], True, stream=streams[k % depth])
     for s in streams: main.wait_stream(s)
     main.wait_stream(up)
-def run_into_input(n):
-    """the upload overwrites the very buffer the kernels read (same bytes), ordered before the step like the host path"""
+def run_into_input(n, shift=0):
+    """an upload ordered before every step like the host path; shift = 0: into the buffer that step reads, shift = 8: into
+    the buffer another slot reads 8 steps later"""
     main = torch.cuda.current_stream()
     for s in streams: s.wait_stream(main)
     for k in range(n):
         with torch.cuda.stream(streams[k % depth]):
-            d_in[k % depth].copy_(h_images, non_blocking=True)
+            d_in[(k + shift) % depth].copy_(h_images, non_blocking=True)
         fe.process_device(d_in[k % depth], outs[k % depth], True, stream=streams[k % depth])
     for s in streams: main.wait_stream(s)
 d_in = [d_images.clone() for _ in range(depth)]
@@ -42,6 +43,9 @@ run_into_input(depth); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run_into_input(steps); e1.record(); torch.cuda.synchronize()
 print("upload into the input buffer of each step (torch streams, device API): %.2f ms/step" % (e0.elapsed_time(e1) / steps), flush=True)
+run_into_input(depth, 8); torch.cuda.synchronize()
+e0.record(); run_into_input(steps, 8); e1.record(); torch.cuda.synchronize()
+print("same uploads in the chain, but into a buffer read 8 steps later: %.2f ms/step" % (e0.elapsed_time(e1) / steps), flush=True)
 for copies in (0, 1):
     run(depth, copies); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
