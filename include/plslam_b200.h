@@ -322,6 +322,15 @@ int plslam_frontend_wait_host(plslam_frontend_t* h);
 int plslam_frontend_acquire_slot(plslam_frontend_t* h);
 int plslam_frontend_submit_host_slot(plslam_frontend_t* h, int slot, const uint8_t* images, int batch, int width, int height,
                                      int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs);
+/* Wave submission (the throughput form of the host path): `n_batches` (1 .. depth) batches of `batch` frames each enter the
+ * pipeline together.  images[i] / ios[i] are the host frames and host result buffers of batch i (pinned memory for
+ * asynchronous copies).  All uploads of the wave run back to back on an upload stream into input buffers the previous wave
+ * is not reading, every batch starts after the wave's last upload (the slots then run in phase, which is where the
+ * pipeline is fastest), results leave on a download stream.  Returns once everything is enqueued; the uploads of a wave
+ * overlap the kernels of the wave before it.  plslam_frontend_wait_host() returns when all results have landed.  The host
+ * buffers of a wave must stay untouched until then. */
+int plslam_frontend_submit_host_wave(plslam_frontend_t* h, const uint8_t* const* images, int n_batches, int batch, int width,
+                                     int height, int pitch, size_t frame_stride, const plslam_frontend_io_t* ios, int match_pairs);
 /* Per-stage device times (ms, CUDA events on the launching streams) of the last process call made after
  * plslam_frontend_enable_timing(h, 1).  names/ms hold up to `capacity` entries; returns the number of stages. */
 int plslam_frontend_enable_timing(plslam_frontend_t* h, int enable);

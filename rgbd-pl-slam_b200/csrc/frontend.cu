@@ -60,11 +60,17 @@ struct Slot {
   ~Slot() {
     DevBuf* all[] = {&jobsOrb, &jobsLines, &dIn[0], &dIn[1], &dKps, &dDesc, &dKpCnt, &dKl, &dLdesc, &dFuncs, &dLCnt, &dOrbM, &dLineM};
     for (DevBuf* b : all) b->release();
+    for (OutSet& o : wOut) {
+      DevBuf* w[] = {&o.kps, &o.desc, &o.kpCnt, &o.kl, &o.ldesc, &o.funcs, &o.lCnt, &o.orbM, &o.lineM};
+      for (DevBuf* b : w) b->release();
+    }
     if (sOrb) cudaStreamDestroy(sOrb);
     if (sHost) cudaStreamDestroy(sHost);
-    cudaEvent_t evs[] = {evFork, evOrb, evLines, evDone, evUp[0], evUp[1], evFree[0], evFree[1]};
+    cudaEvent_t evs[] = {evFork, evOrb, evLines, evDone, evUp[0], evUp[1], evFree[0], evFree[1], evRead[0], evRead[1], evDl[0], evDl[1]};
     for (cudaEvent_t e : evs)
       if (e) cudaEventDestroy(e);
+    if (evUpDone) cudaEventDestroy(evUpDone);
+    if (evDownDone) cudaEventDestroy(evDownDone);
     if (pinnedStatus) cudaFreeHost(pinnedStatus);
   }
   int init() {
@@ -224,6 +230,179 @@ struct Slot {
     hostPending = true;
     return PLSLAM_OK;
   }
+  // ---- host-scheduled path (plslam_frontend_acquire_slot / _submit_host_slot / _wait_host) ----
+  // A copy with dependent kernels behind it in the same stream costs about twice its duration of whole-pipeline time
+  // (DESIGN.md section 6).  Here copies run on a stream of their own, kernels on theirs, and the hand-over between the
+  // two is done by the host polling events, so no compute stream ever waits on a copy.
+  enum HostState { H_IDLE = 0, H_UPLOAD, H_COMPUTE, H_DOWNLOAD };
+  HostState hstate = H_IDLE;
+  cudaEvent_t evUpDone = nullptr, evDownDone = nullptr;
+  struct Task {
+    int batch = 0, W = 0, H = 0, match_pairs = 0;
+    size_t dpitch = 0, dstride = 0;
+    plslam_frontend_io_t io{};
+    bool timing = false;
+  } task;
+  int stage_upload(cudaStream_t sCopy, const uint8_t* images, int batch, int W, int H, int pitch, size_t stride,
+                   const plslam_frontend_io_t& io, int match_pairs, bool timing) {
+    int rc = init();
+    if (rc) return rc;
+    PL_CHECK_ARG(images && batch >= 1 && pitch >= W && hstate == H_IDLE);
+    if (!evUpDone) {
+      PL_CUDA(cudaEventCreateWithFlags(&evUpDone, cudaEventDisableTiming));
+      PL_CUDA(cudaEventCreateWithFlags(&evDownDone, cudaEventDisableTiming));
+    }
+    const int kpCap = orb.max_keypoints(), lnCap = lines.out_capacity();
+    const int npairs = batch / 2;
+    const size_t dpitch = align_up(W, 32), dstride = dpitch * H;
+    if ((rc = dIn[0].ensure(dstride * batch)) || (rc = dKps.ensure((size_t)batch * kpCap * sizeof(plslam_keypoint_t))) ||
+        (rc = dDesc.ensure((size_t)batch * kpCap * 32)) || (rc = dKpCnt.ensure((size_t)batch * 4)) ||
+        (rc = dKl.ensure((size_t)batch * lnCap * sizeof(plslam_keyline_t))) || (rc = dLdesc.ensure((size_t)batch * lnCap * 32)) ||
+        (rc = dFuncs.ensure((size_t)batch * lnCap * 24)) || (rc = dLCnt.ensure((size_t)batch * 4)))
+      return rc;
+    if (match_pairs) {
+      if ((rc = dOrbM.ensure((size_t)std::max(npairs, 1) * kpCap * 16)) || (rc = dLineM.ensure((size_t)std::max(npairs, 1) * lnCap * 16)))
+        return rc;
+    }
+    uint8_t* dst = dIn[0].as<uint8_t>();
+    if (stride == (size_t)pitch * H && (size_t)pitch == dpitch) {
+      PL_CUDA(cudaMemcpyAsync(dst, images, dstride * batch, cudaMemcpyHostToDevice, sCopy));
+    } else if (stride == (size_t)pitch * H) {
+      PL_CUDA(cudaMemcpy2DAsync(dst, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, sCopy));
+    } else {
+      for (int f = 0; f < batch; ++f)
+        PL_CUDA(cudaMemcpy2DAsync(dst + f * dstride, dpitch, images + f * stride, pitch, W, H, cudaMemcpyHostToDevice, sCopy));
+    }
+    PL_CUDA(cudaEventRecord(evUpDone, sCopy));
+    task.batch = batch; task.W = W; task.H = H; task.match_pairs = match_pairs;
+    task.dpitch = dpitch; task.dstride = dstride; task.io = io; task.timing = timing;
+    hstate = H_UPLOAD;
+    hostPending = true;
+    return PLSLAM_OK;
+  }
+  plslam_frontend_io_t device_io() {
+    plslam_frontend_io_t d{};
+    d.keypoints = dKps.as<plslam_keypoint_t>();
+    d.descriptors = dDesc.as<uint8_t>();
+    d.kp_counts = dKpCnt.as<int32_t>();
+    d.keylines = dKl.as<plslam_keyline_t>();
+    d.line_descriptors = dLdesc.as<uint8_t>();
+    d.line_functions = dFuncs.as<double>();
+    d.line_counts = dLCnt.as<int32_t>();
+    d.orb_matches = task.match_pairs ? dOrbM.as<int32_t>() : nullptr;
+    d.line_matches = task.match_pairs ? dLineM.as<int32_t>() : nullptr;
+    return d;
+  }
+  // advance this slot's batch by whatever stage has completed; returns a status code
+  int pump(cudaStream_t sCopy) {  // sCopy here: the download stream
+    if (hstate == H_UPLOAD && cudaEventQuery(evUpDone) == cudaSuccess) {
+      const plslam_frontend_io_t d = device_io();
+      int rc = process_device(dIn[0].as<uint8_t>(), task.batch, task.W, task.H, (int)task.dpitch, task.dstride, d, task.match_pairs,
+                              sHost, task.timing);
+      if (rc) return rc;
+      hstate = H_COMPUTE;
+    }
+    if (hstate == H_COMPUTE && cudaEventQuery(evDone) == cudaSuccess) {
+      const plslam_frontend_io_t d = device_io();
+      const plslam_frontend_io_t& io = task.io;
+      const int batch = task.batch, kpCap = orb.max_keypoints(), lnCap = lines.out_capacity(), npairs = batch / 2;
+      PL_CUDA(cudaMemcpyAsync(io.keypoints, d.keypoints, (size_t)batch * kpCap * sizeof(plslam_keypoint_t), cudaMemcpyDeviceToHost, sCopy));
+      PL_CUDA(cudaMemcpyAsync(io.descriptors, d.descriptors, (size_t)batch * kpCap * 32, cudaMemcpyDeviceToHost, sCopy));
+      PL_CUDA(cudaMemcpyAsync(io.kp_counts, d.kp_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, sCopy));
+      PL_CUDA(cudaMemcpyAsync(io.keylines, d.keylines, (size_t)batch * lnCap * sizeof(plslam_keyline_t), cudaMemcpyDeviceToHost, sCopy));
+      PL_CUDA(cudaMemcpyAsync(io.line_descriptors, d.line_descriptors, (size_t)batch * lnCap * 32, cudaMemcpyDeviceToHost, sCopy));
+      PL_CUDA(cudaMemcpyAsync(io.line_functions, d.line_functions, (size_t)batch * lnCap * 24, cudaMemcpyDeviceToHost, sCopy));
+      PL_CUDA(cudaMemcpyAsync(io.line_counts, d.line_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, sCopy));
+      if (task.match_pairs) {
+        PL_CUDA(cudaMemcpyAsync(io.orb_matches, d.orb_matches, (size_t)npairs * kpCap * 16, cudaMemcpyDeviceToHost, sCopy));
+        PL_CUDA(cudaMemcpyAsync(io.line_matches, d.line_matches, (size_t)npairs * lnCap * 16, cudaMemcpyDeviceToHost, sCopy));
+      }
+      PL_CUDA(cudaEventRecord(evDownDone, sCopy));
+      hstate = H_DOWNLOAD;
+    }
+    if (hstate == H_DOWNLOAD && cudaEventQuery(evDownDone) == cudaSuccess) hstate = H_IDLE;
+    return PLSLAM_OK;
+  }
+  // ---- wave path (plslam_frontend_submit_host_wave) ----
+  // The pipeline is fastest when its slots run in phase (every kernel type gets the whole machine in turn); an upload in
+  // front of every step staggers the slots by one copy each and costs ~2 copy durations per step.
+  // A wave = up to `depth` batches submitted together: their uploads run back to back on the upload stream into the input
+  // buffer set the previous wave is NOT reading, every slot starts after the wave's last upload, results leave on the
+  // download stream from the result set the previous wave is NOT using.
+  struct OutSet {
+    DevBuf kps, desc, kpCnt, kl, ldesc, funcs, lCnt, orbM, lineM;
+  };
+  OutSet wOut[2];
+  cudaEvent_t evRead[2] = {nullptr, nullptr}, evDl[2] = {nullptr, nullptr};
+  bool wUsed[2] = {false, false};
+  int wave_upload(int b, cudaStream_t sUpload, const uint8_t* images, int batch, int W, int H, int pitch, size_t stride,
+                  int match_pairs) {
+    int rc = init();
+    if (rc) return rc;
+    PL_CHECK_ARG(images && batch >= 1 && pitch >= W);
+    if (!evRead[0])
+      for (int i = 0; i < 2; ++i) {
+        PL_CUDA(cudaEventCreateWithFlags(&evRead[i], cudaEventDisableTiming));
+        PL_CUDA(cudaEventCreateWithFlags(&evDl[i], cudaEventDisableTiming));
+      }
+    const int kpCap = orb.max_keypoints(), lnCap = lines.out_capacity(), npairs = std::max(batch / 2, 1);
+    const size_t dpitch = align_up(W, 32), dstride = dpitch * H;
+    OutSet& o = wOut[b];
+    if ((rc = dIn[b].ensure(dstride * batch)) || (rc = o.kps.ensure((size_t)batch * kpCap * sizeof(plslam_keypoint_t))) ||
+        (rc = o.desc.ensure((size_t)batch * kpCap * 32)) || (rc = o.kpCnt.ensure((size_t)batch * 4)) ||
+        (rc = o.kl.ensure((size_t)batch * lnCap * sizeof(plslam_keyline_t))) || (rc = o.ldesc.ensure((size_t)batch * lnCap * 32)) ||
+        (rc = o.funcs.ensure((size_t)batch * lnCap * 24)) || (rc = o.lCnt.ensure((size_t)batch * 4)))
+      return rc;
+    if (match_pairs && ((rc = o.orbM.ensure((size_t)npairs * kpCap * 16)) || (rc = o.lineM.ensure((size_t)npairs * lnCap * 16)))) return rc;
+    if (wUsed[b]) PL_CUDA(cudaStreamWaitEvent(sUpload, evRead[b], 0));  // the buffer's previous reader (two waves ago)
+    uint8_t* dst = dIn[b].as<uint8_t>();
+    if (stride == (size_t)pitch * H && (size_t)pitch == dpitch) {
+      PL_CUDA(cudaMemcpyAsync(dst, images, dstride * batch, cudaMemcpyHostToDevice, sUpload));
+    } else if (stride == (size_t)pitch * H) {
+      PL_CUDA(cudaMemcpy2DAsync(dst, dpitch, images, pitch, W, (size_t)H * batch, cudaMemcpyHostToDevice, sUpload));
+    } else {
+      for (int f = 0; f < batch; ++f)
+        PL_CUDA(cudaMemcpy2DAsync(dst + f * dstride, dpitch, images + f * stride, pitch, W, H, cudaMemcpyHostToDevice, sUpload));
+    }
+    return PLSLAM_OK;
+  }
+  int wave_compute(int b, cudaEvent_t evWaveUp, cudaStream_t sDownload, int batch, int W, int H, const plslam_frontend_io_t& io,
+                   int match_pairs, bool timing) {
+    const int kpCap = orb.max_keypoints(), lnCap = lines.out_capacity(), npairs = batch / 2;
+    const size_t dpitch = align_up(W, 32), dstride = dpitch * H;
+    OutSet& o = wOut[b];
+    plslam_frontend_io_t d{};
+    d.keypoints = o.kps.as<plslam_keypoint_t>();
+    d.descriptors = o.desc.as<uint8_t>();
+    d.kp_counts = o.kpCnt.as<int32_t>();
+    d.keylines = o.kl.as<plslam_keyline_t>();
+    d.line_descriptors = o.ldesc.as<uint8_t>();
+    d.line_functions = o.funcs.as<double>();
+    d.line_counts = o.lCnt.as<int32_t>();
+    d.orb_matches = match_pairs ? o.orbM.as<int32_t>() : nullptr;
+    d.line_matches = match_pairs ? o.lineM.as<int32_t>() : nullptr;
+    PL_CUDA(cudaStreamWaitEvent(sHost, evWaveUp, 0));
+    if (wUsed[b]) PL_CUDA(cudaStreamWaitEvent(sHost, evDl[b], 0));  // this result set has left for the host
+    int rc = process_device(dIn[b].as<uint8_t>(), batch, W, H, (int)dpitch, dstride, d, match_pairs, sHost, timing);
+    if (rc) return rc;
+    PL_CUDA(cudaEventRecord(evRead[b], sHost));
+    PL_CUDA(cudaStreamWaitEvent(sDownload, evRead[b], 0));
+    PL_CUDA(cudaMemcpyAsync(io.keypoints, d.keypoints, (size_t)batch * kpCap * sizeof(plslam_keypoint_t), cudaMemcpyDeviceToHost, sDownload));
+    PL_CUDA(cudaMemcpyAsync(io.descriptors, d.descriptors, (size_t)batch * kpCap * 32, cudaMemcpyDeviceToHost, sDownload));
+    PL_CUDA(cudaMemcpyAsync(io.kp_counts, d.kp_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, sDownload));
+    PL_CUDA(cudaMemcpyAsync(io.keylines, d.keylines, (size_t)batch * lnCap * sizeof(plslam_keyline_t), cudaMemcpyDeviceToHost, sDownload));
+    PL_CUDA(cudaMemcpyAsync(io.line_descriptors, d.line_descriptors, (size_t)batch * lnCap * 32, cudaMemcpyDeviceToHost, sDownload));
+    PL_CUDA(cudaMemcpyAsync(io.line_functions, d.line_functions, (size_t)batch * lnCap * 24, cudaMemcpyDeviceToHost, sDownload));
+    PL_CUDA(cudaMemcpyAsync(io.line_counts, d.line_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, sDownload));
+    if (match_pairs) {
+      PL_CUDA(cudaMemcpyAsync(io.orb_matches, d.orb_matches, (size_t)npairs * kpCap * 16, cudaMemcpyDeviceToHost, sDownload));
+      PL_CUDA(cudaMemcpyAsync(io.line_matches, d.line_matches, (size_t)npairs * lnCap * 16, cudaMemcpyDeviceToHost, sDownload));
+    }
+    PL_CUDA(cudaEventRecord(evDl[b], sDownload));
+    wUsed[b] = true;
+    hostPending = true;
+    return PLSLAM_OK;
+  }
   int wait_host() {
     if (!hostPending) return PLSLAM_OK;
     hostPending = false;
@@ -235,6 +414,24 @@ struct Frontend {
   std::vector<Slot*> slots;
   int next = 0, lastSlot = 0;
   bool timing = false;
+  cudaStream_t sCopy = nullptr, sDown = nullptr;  // upload / download streams of the host-scheduled path
+  int ensure_copy_stream() {
+    if (!sCopy) PL_CUDA(cudaStreamCreateWithFlags(&sCopy, cudaStreamNonBlocking));
+    if (!sDown) PL_CUDA(cudaStreamCreateWithFlags(&sDown, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : evWave)
+      if (!e) PL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return PLSLAM_OK;
+  }
+  cudaEvent_t evWave[2] = {nullptr, nullptr};
+  unsigned waveIdx = 0;
+  int pump_all() {
+    int rc = PLSLAM_OK;
+    for (Slot* s : slots) {
+      const int r = s->pump(sDown);
+      if (r && !rc) rc = r;
+    }
+    return rc;
+  }
   // optional upload stream of the host path, shared by the slots (PLSLAM_UPLOAD_STREAM=1; measured: no gain, off by default)
   cudaStream_t sUp = nullptr;
   int ensure_upload_stream() {
@@ -255,6 +452,10 @@ struct Frontend {
   ~Frontend() {
     for (Slot* s : slots) delete s;
     if (sUp) cudaStreamDestroy(sUp);
+    if (sCopy) cudaStreamDestroy(sCopy);
+    if (sDown) cudaStreamDestroy(sDown);
+    for (cudaEvent_t e : evWave)
+      if (e) cudaEventDestroy(e);
   }
   Slot& take() {
     lastSlot = next;
@@ -333,30 +534,69 @@ int plslam_frontend_submit_host(plslam_frontend_t* h, const uint8_t* images, int
 int plslam_frontend_acquire_slot(plslam_frontend_t* h) {
   if (!h) return -1;
   Frontend& F = h->impl;
+  if (F.ensure_copy_stream()) return -1;
   const int n = (int)F.slots.size();
   for (;;) {
+    if (F.pump_all()) return -1;
     for (int k = 0; k < n; ++k) {
       const int i = (F.next + k) % n;
       Slot* s = F.slots[i];
-      if (!s->used || !s->evDone || cudaEventQuery(s->evDone) == cudaSuccess) {
+      if (s->hstate == Slot::H_IDLE && (!s->used || !s->evDone || cudaEventQuery(s->evDone) == cudaSuccess)) {
         F.next = (i + 1) % n;
         return i;
       }
     }
-    std::this_thread::sleep_for(std::chrono::microseconds(50));
+    std::this_thread::sleep_for(std::chrono::microseconds(20));
   }
 }
 int plslam_frontend_submit_host_slot(plslam_frontend_t* h, int slot, const uint8_t* images, int batch, int width, int height,
                                      int pitch, size_t frame_stride, const plslam_frontend_io_t* io, int match_pairs) {
   PL_CHECK_ARG(h && io && slot >= 0 && slot < (int)h->impl.slots.size());
-  int rcu = h->impl.ensure_upload_stream();
-  if (rcu) return rcu;
+  int rc = h->impl.ensure_copy_stream();
+  if (rc) return rc;
   h->impl.lastSlot = slot;
-  return h->impl.slots[slot]->submit_host(images, batch, width, height, pitch, frame_stride, *io, match_pairs, h->impl.timing);
+  rc = h->impl.slots[slot]->stage_upload(h->impl.sCopy, images, batch, width, height, pitch, frame_stride, *io, match_pairs,
+                                         h->impl.timing);
+  if (rc) return rc;
+  return h->impl.pump_all();
+}
+// Wave submission: n_batches (<= depth) batches enter the pipeline together and in phase (Slot::wave_*).  Returns once
+// everything is enqueued; the uploads of this wave overlap the kernels of the previous one.
+int plslam_frontend_submit_host_wave(plslam_frontend_t* h, const uint8_t* const* images, int n_batches, int batch, int width,
+                                     int height, int pitch, size_t frame_stride, const plslam_frontend_io_t* ios, int match_pairs) {
+  PL_CHECK_ARG(h && images && ios && n_batches >= 1 && n_batches <= (int)h->impl.slots.size());
+  Frontend& F = h->impl;
+  int rc = F.ensure_copy_stream();
+  if (rc) return rc;
+  for (int i = 0; i < n_batches; ++i) {
+    const plslam_frontend_io_t& io = ios[i];
+    PL_CHECK_ARG(io.keypoints && io.descriptors && io.kp_counts && io.keylines && io.line_descriptors && io.line_functions &&
+                 io.line_counts && (!match_pairs || (io.orb_matches && io.line_matches)));
+  }
+  const int b = (int)(F.waveIdx & 1u);
+  for (int i = 0; i < n_batches; ++i)
+    if ((rc = F.slots[i]->wave_upload(b, F.sCopy, images[i], batch, width, height, pitch, frame_stride, match_pairs))) return rc;
+  PL_CUDA(cudaEventRecord(F.evWave[b], F.sCopy));
+  for (int i = 0; i < n_batches; ++i)
+    if ((rc = F.slots[i]->wave_compute(b, F.evWave[b], F.sDown, batch, width, height, ios[i], match_pairs, F.timing))) return rc;
+  ++F.waveIdx;
+  F.lastSlot = n_batches - 1;
+  return PLSLAM_OK;
 }
 int plslam_frontend_wait_host(plslam_frontend_t* h) {
   PL_CHECK_ARG(h);
   int rc = PLSLAM_OK;
+  if (h->impl.sCopy) {  // host-scheduled batches: drive them to completion
+    for (;;) {
+      rc = h->impl.pump_all();
+      if (rc) return rc;
+      bool busy = false;
+      for (Slot* s : h->impl.slots) busy = busy || s->hstate != Slot::H_IDLE;
+      if (!busy) break;
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+  }
+  if (h->impl.sDown) PL_CUDA(cudaStreamSynchronize(h->impl.sDown));  // results of the wave path
   for (Slot* s : h->impl.slots) {
     const int r = s->wait_host();
     if (r && !rc) rc = r;

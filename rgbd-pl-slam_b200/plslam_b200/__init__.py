@@ -437,6 +437,21 @@ class Frontend:
         """Asynchronous process_host on the next pipeline slot; `out` is valid after wait_host()."""
         return self._host_call(lib().plslam_frontend_submit_host, images, out, match_pairs)
 
+    def submit_host_wave(self, images_list, outs, match_pairs=True):
+        """plslam_frontend_submit_host_wave: len(images_list) <= depth batches (pinned uint8 tensors [B, H, W]) enter the
+        pipeline together; outs[i] receives batch i after wait_host()."""
+        n = len(images_list)
+        assert n == len(outs) and n >= 1
+        B, H, W = images_list[0].shape
+        st0, st1 = images_list[0].stride(0), images_list[0].stride(1)
+        ptrs = (C.c_void_p * n)()
+        ios = (FrontendIO * n)()
+        for i, (im, out) in enumerate(zip(images_list, outs)):
+            assert tuple(im.shape) == (B, H, W) and im.stride(0) == st0 and im.stride(1) == st1 and im.stride(2) == 1
+            ptrs[i] = im.data_ptr()
+            ios[i] = self._io(out)
+        _check(lib().plslam_frontend_submit_host_wave(self._h, ptrs, n, B, W, H, st1, C.c_size_t(st0), ios, int(bool(match_pairs))))
+
     def acquire_slot(self):
         """Blocks until a pipeline slot is idle and returns its index (keep one set of host output buffers per slot)."""
         return lib().plslam_frontend_acquire_slot(self._h)

@@ -76,6 +76,23 @@ def test_full_bench_batch_all_paths(oracle):
     fe.wait_host()
     for k in (0, 3):
         _compare(oracle, pl, h_outs[k], ref, B, "host submission %d" % k)
+    # host-scheduled slots (copies on their own streams, hand-over by event polling), 5 submissions over 3 slots
+    s_outs = [fe.alloc(B, pinned=True) for _ in range(5)]
+    for k in range(5):
+        fe.submit_host_slot(fe.acquire_slot(), h_images, s_outs[k], True)
+    fe.wait_host()
+    for k in (0, 2, 4):
+        _compare(oracle, pl, s_outs[k], ref, B, "host-scheduled submission %d" % k)
+    # wave submission: 3 waves (3, 3 and 2 batches) over the 3 slots, uploads of a wave overlapping the wave before it
+    w_outs = [fe.alloc(B, pinned=True) for _ in range(8)]
+    for v in w_outs:
+        v["kp_counts"].fill_(-7)
+    fe.submit_host_wave([h_images] * 3, w_outs[0:3], True)
+    fe.submit_host_wave([h_images] * 3, w_outs[3:6], True)
+    fe.submit_host_wave([h_images] * 2, w_outs[6:8], True)
+    fe.wait_host()
+    for k in (0, 2, 4, 5, 7):
+        _compare(oracle, pl, w_outs[k], ref, B, "wave submission %d" % k)
     # synchronous host path from pageable memory
     out = fe.alloc(B)
     fe.process_host(frames, out, True)
