@@ -384,7 +384,7 @@ def run_ours(a):
     h_outs2 = [h_outs, [fe.alloc(a.batch, pinned=True) for _ in range(depth)]]
     e2e_modes = {}
     for mode in ("stream", "wave"):
-        host_steps(max(2, depth), mode)
+        host_steps(2 * depth if mode == "wave" else max(2, depth), mode)  # two waves: both buffer sets touched
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()

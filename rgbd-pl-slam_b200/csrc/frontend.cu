@@ -347,13 +347,16 @@ struct Slot {
       }
     const int kpCap = orb.max_keypoints(), lnCap = lines.out_capacity(), npairs = std::max(batch / 2, 1);
     const size_t dpitch = align_up(W, 32), dstride = dpitch * H;
-    OutSet& o = wOut[b];
-    if ((rc = dIn[b].ensure(dstride * batch)) || (rc = o.kps.ensure((size_t)batch * kpCap * sizeof(plslam_keypoint_t))) ||
-        (rc = o.desc.ensure((size_t)batch * kpCap * 32)) || (rc = o.kpCnt.ensure((size_t)batch * 4)) ||
-        (rc = o.kl.ensure((size_t)batch * lnCap * sizeof(plslam_keyline_t))) || (rc = o.ldesc.ensure((size_t)batch * lnCap * 32)) ||
-        (rc = o.funcs.ensure((size_t)batch * lnCap * 24)) || (rc = o.lCnt.ensure((size_t)batch * 4)))
-      return rc;
-    if (match_pairs && ((rc = o.orbM.ensure((size_t)npairs * kpCap * 16)) || (rc = o.lineM.ensure((size_t)npairs * lnCap * 16)))) return rc;
+    // both buffer sets at once: an allocation while the previous wave computes would stall the submitting thread
+    for (int i = 0; i < 2; ++i) {
+      OutSet& o = wOut[i];
+      if ((rc = dIn[i].ensure(dstride * batch)) || (rc = o.kps.ensure((size_t)batch * kpCap * sizeof(plslam_keypoint_t))) ||
+          (rc = o.desc.ensure((size_t)batch * kpCap * 32)) || (rc = o.kpCnt.ensure((size_t)batch * 4)) ||
+          (rc = o.kl.ensure((size_t)batch * lnCap * sizeof(plslam_keyline_t))) || (rc = o.ldesc.ensure((size_t)batch * lnCap * 32)) ||
+          (rc = o.funcs.ensure((size_t)batch * lnCap * 24)) || (rc = o.lCnt.ensure((size_t)batch * 4)))
+        return rc;
+      if (match_pairs && ((rc = o.orbM.ensure((size_t)npairs * kpCap * 16)) || (rc = o.lineM.ensure((size_t)npairs * lnCap * 16)))) return rc;
+    }
     if (wUsed[b]) PL_CUDA(cudaStreamWaitEvent(sUpload, evRead[b], 0));  // the buffer's previous reader (two waves ago)
     uint8_t* dst = dIn[b].as<uint8_t>();
     if (stride == (size_t)pitch * H && (size_t)pitch == dpitch) {
