@@ -427,6 +427,20 @@ int plslam_frame_post_host(const plslam_frame_calib_t* calib, const float bounds
                            int n, const float* depth, int cols, int rows, int depth_pitch, float* un_xy, float* uright,
                            float* depth_out, int32_t* grid_start, int32_t* grid_items);
 
+/* ------------------------------------------------------------------------------------------------
+ * On-disk formats either side of the path (host only, no device work).
+ * ------------------------------------------------------------------------------------------------ */
+/* LoadImages (Examples/RGB-D/rgbd_tum.cc:151-176): one entry per non-empty line "t_rgb rgb_file t_depth depth_file"; the RGB
+ * time stamp is the frame's.  A line that does not parse still yields an entry (0 / empty strings), as in the reference.
+ * Names are written as NUL-terminated strings `name_stride` bytes apart.  capacity == 0: only *count is returned. */
+int plslam_tum_load_associations(const char* path, double* timestamps, char* rgb_names, char* depth_names, int name_stride,
+                                 int capacity, int* count);
+/* One line of System::SaveTrajectoryTUM (include/System.h:104, lib/libORB_SLAM2.so@0x3df90): "t tx ty tz qx qy qz qw\n" for the
+ * camera pose Tcw (rows 0..2 of the 4x4 CV_32F matrix, row-major 3x4): Rwc = Rcw^T, twc = -Rwc tcw, quaternion of Rwc as
+ * Converter::toQuaternion (Eigen, double); fixed notation, 6 decimals for t, 9 for the rest. */
+int plslam_tum_pose_to_line(double timestamp, const float* Tcw_3x4, char* line, int capacity, int* length);
+int plslam_tum_save_trajectory(const char* path, const double* timestamps, const float* Tcw_3x4, int n);
+
 #ifdef __cplusplus
 }
 #endif

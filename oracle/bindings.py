@@ -443,3 +443,39 @@ def search_local_points(mp, fr, cam4, scale_factors, th, nnratio=0.8):
                                        n, _p(f["xy"]), _p(f["octave"]), _p(f["desc"]), _p(f["uright"]), _p(f["taken"]),
                                        _p(f["grid_start"]), _p(f["grid_items"]), _p(cam), _p(sf), th, nnratio, _p(match))
     return match[:n], cnt
+
+
+# ---- on-disk formats (tum_oracle.cc) ----
+NAME_STRIDE = 256
+
+
+def _names(buf, n):
+    return [buf[i * NAME_STRIDE:(i + 1) * NAME_STRIDE].split(b"\0", 1)[0].decode("latin-1") for i in range(n)]
+
+
+def tum_load_associations(path):
+    """LoadImages (rgbd_tum.cc:151-176) -> (timestamps float64 [n], rgb names, depth names)"""
+    L = lib()
+    n = L.oracle_tum_load(os.fsencode(path), None, None, None, NAME_STRIDE, 0)
+    if n < 0:
+        raise FileNotFoundError(path)
+    ts = np.empty(n, np.float64)
+    rgb, dep = C.create_string_buffer(max(n, 1) * NAME_STRIDE), C.create_string_buffer(max(n, 1) * NAME_STRIDE)
+    assert L.oracle_tum_load(os.fsencode(path), _p(ts), rgb, dep, NAME_STRIDE, n) == n
+    return ts, _names(rgb.raw, n), _names(dep.raw, n)
+
+
+def tum_pose(Tcw):
+    """-> float32 [7]: twc, quaternion x y z w of Rwc, as System::SaveTrajectoryTUM prints them"""
+    T = np.ascontiguousarray(np.asarray(Tcw, np.float32)[:3, :4])
+    out = np.empty(7, np.float32)
+    lib().oracle_tum_pose(_p(T), _p(out))
+    return out
+
+
+def tum_pose_line(timestamp, Tcw):
+    T = np.ascontiguousarray(np.asarray(Tcw, np.float32)[:3, :4])
+    buf = C.create_string_buffer(256)
+    n = lib().oracle_tum_pose_line(C.c_double(timestamp), _p(T), buf, 256)
+    assert n > 0
+    return buf.raw[:n].decode("ascii")

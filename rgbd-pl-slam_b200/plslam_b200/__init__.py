@@ -738,3 +738,37 @@ def search_local_points_host(mp, fr, cam4, scale_factors, th, nnratio=0.8):
     j.th = float(th); j.nnratio = float(nnratio); j.m = m; j.n = n
     _check(lib().plslam_match_local_points_host(C.byref(j), len(sf)))
     return out[:n], int(cnt[0])
+
+
+# ---- on-disk formats either side of the path (host only; include/plslam_b200.h, last section) ----
+TUM_NAME_STRIDE = 256
+
+
+def LoadImages(association_file):
+    """Examples/RGB-D/rgbd_tum.cc:151 LoadImages -> (vstrImageFilenamesRGB, vstrImageFilenamesD, vTimestamps)."""
+    path = os.fsencode(association_file)
+    n = C.c_int(0)
+    _check(lib().plslam_tum_load_associations(path, None, None, None, TUM_NAME_STRIDE, 0, C.byref(n)))
+    n = n.value
+    ts = np.empty(n, np.float64)
+    rgb, dep = C.create_string_buffer(max(n, 1) * TUM_NAME_STRIDE), C.create_string_buffer(max(n, 1) * TUM_NAME_STRIDE)
+    m = C.c_int(0)
+    _check(lib().plslam_tum_load_associations(path, _vp(ts), rgb, dep, TUM_NAME_STRIDE, n, C.byref(m)))
+    cut = lambda buf: [buf[i * TUM_NAME_STRIDE:(i + 1) * TUM_NAME_STRIDE].split(b"\0", 1)[0].decode("latin-1") for i in range(n)]
+    return cut(rgb.raw), cut(dep.raw), ts
+
+
+def trajectory_line(timestamp, Tcw):
+    """One line of System::SaveTrajectoryTUM for the camera pose Tcw (3x4 or 4x4 float32)."""
+    T = np.ascontiguousarray(np.asarray(Tcw, np.float32)[:3, :4])
+    buf, n = C.create_string_buffer(256), C.c_int(0)
+    _check(lib().plslam_tum_pose_to_line(C.c_double(timestamp), _vp(T), buf, 256, C.byref(n)))
+    return buf.raw[:n.value].decode("ascii")
+
+
+def SaveTrajectoryTUM(filename, timestamps, poses_Tcw):
+    """System::SaveTrajectoryTUM's file for per-frame camera poses Tcw [n, 3|4, 4]."""
+    ts = np.ascontiguousarray(timestamps, np.float64)
+    T = np.ascontiguousarray(np.asarray(poses_Tcw, np.float32)[:, :3, :4])
+    assert len(ts) == len(T)
+    _check(lib().plslam_tum_save_trajectory(os.fsencode(filename), _vp(ts), _vp(T), len(ts)))

@@ -9,6 +9,9 @@ Sources of truth, none of them this repository's own oracle:
   dbow2_ref.npz        the reference's OWN Thirdparty/DBoW2 sources (compiled into oracle/_ref/libdbow2_ref.so):
                        FORB::distance and ORBVocabulary::transform on a small vocabulary
   reference_binary.json  constants read from /root/reference/lib/libORB_SLAM2.so (rBRIEF pattern, matcher thresholds)
+  tum_io.json          the reference's own association lists (Examples/RGB-D/associations/*.txt) parsed with str.split /
+                       float(): entry count, digest, first and last entry of each; the trajectory line of the identity pose
+                       from cv2.gemm + Python's "%.9f"  (`python tests/golden/make_golden.py tum` writes only this file)
 
     python tests/golden/make_golden.py
 """
@@ -26,7 +29,32 @@ for p in (ROOT, os.path.join(ROOT, "rgbd-pl-slam_b200")):
     sys.path.insert(0, p)
 
 
+def tum_io():
+    import cv2
+    d = "/root/reference/Examples/RGB-D/associations"
+    out = {"associations": {}}
+    for name in sorted(os.listdir(d)):
+        ts, rgb, dep = [], [], []
+        for line in open(os.path.join(d, name), "rb").read().decode("latin-1").split("\n"):
+            if line == "":
+                continue
+            tok = line.split()
+            assert len(tok) == 4, (name, line)  # well-formed lists only: the split rule then equals the reference's extraction
+            ts.append(float(tok[0])); rgb.append(tok[1]); dep.append(tok[3])
+        h = hashlib.sha256()
+        for t, a, b in zip(ts, rgb, dep):
+            h.update(("%s|%s|%s\n" % (float(t).hex(), a, b)).encode())
+        out["associations"][name] = {"n": len(ts), "sha256": h.hexdigest(), "first": [ts[0].hex(), rgb[0], dep[0]],
+                                     "last": [ts[-1].hex(), rgb[-1], dep[-1]]}
+    twc = cv2.gemm(np.eye(3, dtype=np.float32), np.zeros((3, 1), np.float32), -1.0, None, 0.0).ravel()
+    out["identity_line"] = "%.6f %.9f %.9f %.9f %.9f %.9f %.9f %.9f\n" % ((0.0,) + tuple(float(x) for x in twc) + (0.0, 0.0, 0.0, 1.0))
+    json.dump(out, open(os.path.join(HERE, "tum_io.json"), "w"), indent=1)
+    print("tum_io.json:", {k: v["n"] for k, v in out["associations"].items()}, repr(out["identity_line"]))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "tum":
+        return tum_io()
     import cv2
     from plslam_b200.synth import synth_frame
     assert cv2.__version__.startswith("4.13"), cv2.__version__
@@ -108,3 +136,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if len(sys.argv) == 1:
+        tum_io()
