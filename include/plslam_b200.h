@@ -260,6 +260,45 @@ typedef struct plslam_local_job {
 int plslam_match_local_points_batch_device(const plslam_local_job_t* d_jobs, int njobs, int max_n, void* stream); /* max_n >= every job's n */
 int plslam_match_local_points_host(const plslam_local_job_t* job, int n_scale_levels);
 
+/* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vector<pair<size_t,size_t>>&
+ * vMatchedPairs, bool bOnlyStereo) (ORBmatcher.h:86, @0x86b30) with CheckDistEpipolarLine (ORBmatcher.h:89, @0x79b90).
+ * FeatureVectors as CSR sorted by node id, key-frame fields flattened.  vMatchedPairs = {(i, match12[i]) : match12[i] >= 0}
+ * in ascending i, as the reference collects them. */
+typedef struct plslam_tri_job {
+  const uint8_t* kf1_desc;    /* N1 x 32 : pKF1->mDescriptors */
+  const float* kf1_xy;        /* N1 x 2  : pKF1->mvKeysUn[i].pt */
+  const float* kf1_angle;     /* N1      : pKF1->mvKeysUn[i].angle */
+  const float* kf1_uright;    /* N1      : pKF1->mvuRight (>= 0 means stereo) */
+  const uint8_t* kf1_has_mp;  /* N1      : pKF1->GetMapPoint(i) != NULL */
+  const int32_t* kf1_nodes;   /* n1_nodes   : FeatureVector keys, ascending */
+  const int32_t* kf1_start;   /* n1_nodes+1 */
+  const int32_t* kf1_idx;
+  const uint8_t* kf2_desc;    /* N2 x 32 */
+  const float* kf2_xy;        /* N2 x 2 */
+  const float* kf2_angle;     /* N2 */
+  const int32_t* kf2_octave;  /* N2 : pKF2->mvKeysUn[i].octave */
+  const float* kf2_uright;    /* N2 */
+  const uint8_t* kf2_has_mp;  /* N2 */
+  const int32_t* kf2_nodes;
+  const int32_t* kf2_start;
+  const int32_t* kf2_idx;
+  const float* scale_factors; /* pKF2->mvScaleFactors */
+  const float* level_sigma2;  /* pKF2->mvLevelSigma2 */
+  int32_t* match12;           /* N1 : vMatches12 (KF2 feature matched to each KF1 feature, -1 = none) */
+  int32_t* nmatches;          /* 1  : return value */
+  float F12[9];               /* fundamental matrix, row-major CV_32F */
+  float ex, ey;               /* epipole of KF1's centre in KF2: plslam_match_epipole */
+  int32_t n1, n2, n1_nodes, n2_nodes;
+  int32_t only_stereo;        /* bOnlyStereo */
+  int32_t check_orientation;  /* mbCheckOrientation */
+} plslam_tri_job_t;
+int plslam_match_triangulation_batch_device(const plslam_tri_job_t* d_jobs, int njobs, int max_n, void* stream); /* max_n >= every job's n1 and n2 */
+int plslam_match_triangulation_host(const plslam_tri_job_t* job, int n_scale_levels); /* HOST pointers inside *job */
+/* The epipole as SearchForTriangulation computes it (@0x86b9c-0x86f8b): C2 = R2w * Cw + t2w, ex = fx * C2x / C2z + cx with
+ * the binary's rounding sequence.  R2w row-major 3x3 (pKF2->GetRotation()), t2w (GetTranslation()), Cw (pKF1->GetCameraCenter()). */
+int plslam_match_epipole(const float* R2w_3x3, const float* t2w, const float* Cw, float fx, float fy, float cx, float cy,
+                         float* ex, float* ey);
+
 /* Single-job convenience forms for the class veneers: every pointer inside *job is a HOST pointer; the call
  * uploads the arrays, runs the kernel and writes match_* / nmatches back.  n_grid_items = grid_start[64*48]. */
 int plslam_match_bow_host(const plslam_bow_job_t* job);

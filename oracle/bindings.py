@@ -479,3 +479,61 @@ def tum_pose_line(timestamp, Tcw):
     n = lib().oracle_tum_pose_line(C.c_double(timestamp), _p(T), buf, 256)
     assert n > 0
     return buf.raw[:n].decode("ascii")
+
+
+# ---- leaf functions pinned against the reference's machine code (tests/golden/reference_code.py) ----
+def radius_by_viewing_cos(v):
+    L = lib()
+    L.oracle_radius_by_viewing_cos.restype = C.c_float
+    L.oracle_radius_by_viewing_cos.argtypes = [C.c_float]
+    return float(L.oracle_radius_by_viewing_cos(float(v)))
+
+
+def three_maxima(sizes):
+    s = np.ascontiguousarray(sizes, np.int32)
+    out = np.full(3, -1, np.int32)
+    lib().oracle_three_maxima(_p(s), len(s), _p(out))
+    return tuple(int(x) for x in out)
+
+
+def check_dist_epipolar_line(kp1_xy, kp2_xy, F12, sigma2_kp2):
+    L = lib()
+    L.oracle_check_dist_epipolar_line.argtypes = [C.c_float] * 4 + [C.c_void_p, C.c_float]
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    return bool(L.oracle_check_dist_epipolar_line(float(kp1_xy[0]), float(kp1_xy[1]), float(kp2_xy[0]), float(kp2_xy[1]), _p(F),
+                                                  float(sigma2_kp2)))
+
+
+def epipole(R2w, t2w, Cw, fx, fy, cx, cy):
+    L = lib()
+    L.oracle_epipole.argtypes = [C.c_void_p] * 3 + [C.c_float] * 4 + [C.POINTER(C.c_float)] * 2
+    R, t, c = (np.ascontiguousarray(x, np.float32).ravel() for x in (R2w, t2w, Cw))
+    ex, ey = C.c_float(), C.c_float()
+    L.oracle_epipole(_p(R), _p(t), _p(c), fx, fy, cx, cy, C.byref(ex), C.byref(ey))
+    return ex.value, ey.value
+
+
+def search_for_triangulation(kf1, kf2, F12, ex, ey, scale_factors, level_sigma2, only_stereo=False, check_ori=True):
+    """kf*: dict desc (N,32) u8, xy (N,2) f32, angle, uright f32, has_mp u8, octave i32 (kf2), nodes/start/idx CSR
+    -> (match12 int32 [N1], nmatches)"""
+    g = lambda d, k, t: np.ascontiguousarray(d[k], t)
+    a = dict(desc=g(kf1, "desc", np.uint8), xy=g(kf1, "xy", np.float32), angle=g(kf1, "angle", np.float32),
+             uright=g(kf1, "uright", np.float32), has_mp=g(kf1, "has_mp", np.uint8), nodes=g(kf1, "nodes", np.int32),
+             start=g(kf1, "start", np.int32), idx=g(kf1, "idx", np.int32))
+    b = dict(desc=g(kf2, "desc", np.uint8), xy=g(kf2, "xy", np.float32), angle=g(kf2, "angle", np.float32),
+             octave=g(kf2, "octave", np.int32), uright=g(kf2, "uright", np.float32), has_mp=g(kf2, "has_mp", np.uint8),
+             nodes=g(kf2, "nodes", np.int32), start=g(kf2, "start", np.int32), idx=g(kf2, "idx", np.int32))
+    sf, sg = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    n1, n2 = len(a["desc"]), len(b["desc"])
+    m = np.empty(max(n1, 1), np.int32)
+    L = lib()
+    L.oracle_search_for_triangulation.argtypes = (
+        [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3 +
+        [C.c_void_p] * 3 + [C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p])
+    n = L.oracle_search_for_triangulation(
+        n1, _p(a["desc"]), _p(a["xy"]), _p(a["angle"]), _p(a["uright"]), _p(a["has_mp"]), len(a["nodes"]), _p(a["nodes"]),
+        _p(a["start"]), _p(a["idx"]), n2, _p(b["desc"]), _p(b["xy"]), _p(b["angle"]), _p(b["octave"]), _p(b["uright"]),
+        _p(b["has_mp"]), len(b["nodes"]), _p(b["nodes"]), _p(b["start"]), _p(b["idx"]), _p(sf), _p(sg), _p(F), ex, ey,
+        int(only_stereo), int(check_ori), _p(m))
+    return m[:n1], n

@@ -50,6 +50,11 @@ void compute_three_maxima(const std::vector<int>* histo, int L, int& ind1, int& 
   else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
 }
 
+// ORBmatcher::RadiusByViewingCos (@0x79b60): the float is widened and compared with the DOUBLE 0.998 (@0x126a00), so
+// 0.998f itself (= 0.99800002...) already gets the small radius.  Pinned by executing the reference's machine code
+// (tests/golden/reference_code.py).
+inline float radius_by_viewing_cos(float viewCos) { return (double)viewCos > 0.998 ? 2.5f : 4.0f; }
+
 inline int rot_bin(float a1, float a2) {
   const float factor = (float)HISTO_LENGTH / 360.0f;  // 0.0833333 @0x1269f8
   float rot = a1 - a2;
@@ -64,6 +69,13 @@ inline int rot_bin(float a1, float a2) {
 extern "C" {
 
 int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+float oracle_radius_by_viewing_cos(float v) { return radius_by_viewing_cos(v); }
+// ComputeThreeMaxima on bin populations; out3 must hold the caller's initial values (-1 in every reference call site)
+void oracle_three_maxima(const int* sizes, int L, int* out3) {
+  std::vector<std::vector<int>> h(L);
+  for (int i = 0; i < L; ++i) h[i].resize(sizes[i]);
+  compute_three_maxima(h.data(), L, out3[0], out3[1], out3[2]);
+}
 
 // BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2): per query the two nearest train rows, ties by lower
 // train index.  out: nq x 4 ints (idx1, dist1, idx2, dist2); missing entries are -1.
@@ -260,7 +272,7 @@ int oracle_search_local_points(int M, const uint8_t* mpValid, const float* mpPro
   for (int iMP = 0; iMP < M; ++iMP) {
     if (!mpValid[iMP]) continue;
     const int nPredictedLevel = mpLevel[iMP];
-    float r = mpViewCos[iMP] > 0.998f ? 2.5f : 4.0f;  // RadiusByViewingCos
+    float r = radius_by_viewing_cos(mpViewCos[iMP]);
     if (bFactor) r *= th;
     const float x = mpProj[3 * iMP], y = mpProj[3 * iMP + 1], xr = mpProj[3 * iMP + 2];
     const float radius = r * scaleFactors[nPredictedLevel];
@@ -309,6 +321,110 @@ int oracle_search_local_points(int M, const uint8_t* mpValid, const float* mpPro
       matchF[bestIdx] = iMP;
       if (mpObs[iMP]) taken[bestIdx] = 1;
       nmatches++;
+    }
+  }
+  return nmatches;
+}
+
+// ORBmatcher::CheckDistEpipolarLine(kp1, kp2, F12, pKF2) (ORBmatcher.h:89; machine code @0x79b90-0x79c32, compiled with FMA:
+// the fused operations below are the binary's — vfmadd231ss @0x79bb3, @0x79bbf, @0x79bcd, @0x79bf3, vfmadd132ss @0x79c00).
+// F: row-major 3x3 float.  3.84 is a double (@0x126a08), the comparison is made in double (@0x79c1b-0x79c2f).
+static bool check_dist_epipolar_line(float x1, float y1, float x2, float y2, const float* F, float sigma2_kp2) {
+  const float b = std::fmaf(x1, F[1], y1 * F[4]) + F[7];
+  const float a = std::fmaf(x1, F[0], y1 * F[3]) + F[6];
+  const float den = std::fmaf(a, a, b * b);
+  if (den == 0.0f) return false;
+  const float c = std::fmaf(y1, F[5], x1 * F[2]) + F[8];
+  const float num = c + std::fmaf(b, y2, a * x2);
+  const float dsqr = (num * num) / den;
+  return 3.84 * (double)sigma2_kp2 > (double)dsqr;
+}
+int oracle_check_dist_epipolar_line(float x1, float y1, float x2, float y2, const float* F, float sigma2_kp2) {
+  return check_dist_epipolar_line(x1, y1, x2, y2, F, sigma2_kp2) ? 1 : 0;
+}
+
+// The epipole of KF1's camera centre in KF2, as SearchForTriangulation computes it before its loops (@0x86b9c-0x86f8b):
+// C2 = R2w * Cw + t2w is one cv::gemm (3x3 by 3x1 CV_32F: small-matrix path, float sum, (double)s * 1 + (double)t * 1),
+// invz = 1.0f / C2z (@0x86ee0), ex = fma(invz, fx * C2x, cx) (@0x86eee-0x86ef2), ey likewise (@0x86f4a-0x86f8b).
+void oracle_epipole(const float* R2w, const float* t2w, const float* Cw, float fx, float fy, float cx, float cy, float* ex, float* ey) {
+  float C2[3];
+  for (int r = 0; r < 3; ++r) {
+    const float p0 = R2w[3 * r] * Cw[0], p1 = R2w[3 * r + 1] * Cw[1], p2 = R2w[3 * r + 2] * Cw[2];
+    const float s = (p0 + p1) + p2;
+    C2[r] = (float)((double)s * 1.0 + (double)t2w[r] * 1.0);
+  }
+  const float invz = 1.0f / C2[2];
+  *ex = std::fmaf(invz, fx * C2[0], cx);
+  *ey = std::fmaf(invz, fy * C2[1], cy);
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (ORBmatcher.h:86; @0x86b30).
+// Read from the binary: candidates only inside a shared vocabulary node (merge of the two FeatureVectors, lower_bound on
+// mismatch); KF1 features with a map point are skipped (@0x87836-0x8783e), with bOnlyStereo also those with mvuRight < 0
+// (@0x87869-0x87876); bestDist starts at TH_LOW = 50 (@0x87915); a KF2 feature is skipped when already matched
+// (vbMatched2 bit test @0x87977 — this build DOES set the bit on acceptance, @0x87bc9) or when it has a map point (@0x8797d),
+// with bOnlyStereo when mvuRight < 0 (@0x879a0-0x879a8); dist > 50 or dist > bestDist skips (@0x87a01-0x87a13: an equal
+// distance replaces the earlier candidate); when neither feature is stereo the candidate must be at least
+// sqrt(100 * mvScaleFactors[octave2]) away from the epipole: fma(dx, dx, dy * dy) against 100.0f * scale (@0x87a52-0x87a91);
+// CheckDistEpipolarLine decides (@0x87aaf).  Accepted: vMatches12[idx1] = bestIdx2, bit set, rotation histogram with
+// kp1.angle - kp2.angle (@0x87bf1-0x87c2d), ComputeThreeMaxima, pairs collected in idx1 order.
+// hasMP*: GetMapPoint(i) != NULL.  match12[N1] receives vMatches12.  Returns nmatches.
+int oracle_search_for_triangulation(int N1, const uint8_t* d1, const float* xy1, const float* ang1, const float* uright1,
+                                    const uint8_t* hasMP1, int nNodes1, const int* nodes1, const int* start1, const int* idx1v,
+                                    int N2, const uint8_t* d2, const float* xy2, const float* ang2, const int* oct2,
+                                    const float* uright2, const uint8_t* hasMP2, int nNodes2, const int* nodes2, const int* start2,
+                                    const int* idx2v, const float* scaleFactors2, const float* levelSigma2_2, const float* F12,
+                                    float ex, float ey, int onlyStereo, int checkOri, int* match12) {
+  for (int i = 0; i < N1; ++i) match12[i] = -1;
+  std::vector<uint8_t> matched2(N2, 0);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nmatches = 0;
+  int a = 0, b = 0;
+  while (a < nNodes1 && b < nNodes2) {
+    if (nodes1[a] == nodes2[b]) {
+      for (int i1 = start1[a]; i1 < start1[a + 1]; ++i1) {
+        const int idx1 = idx1v[i1];
+        if (hasMP1[idx1]) continue;
+        const bool bStereo1 = uright1[idx1] >= 0.0f;
+        if (onlyStereo && !bStereo1) continue;
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int i2 = start2[b]; i2 < start2[b + 1]; ++i2) {
+          const int idx2 = idx2v[i2];
+          if (matched2[idx2] || hasMP2[idx2]) continue;
+          const bool bStereo2 = uright2[idx2] >= 0.0f;
+          if (onlyStereo && !bStereo2) continue;
+          const int dist = descriptor_distance(d1 + 32 * idx1, d2 + 32 * idx2);
+          if (dist > TH_LOW || dist > bestDist) continue;
+          if (!bStereo1 && !bStereo2) {
+            const float distex = ex - xy2[2 * idx2], distey = ey - xy2[2 * idx2 + 1];
+            if (100.0f * scaleFactors2[oct2[idx2]] > std::fmaf(distex, distex, distey * distey)) continue;
+          }
+          if (check_dist_epipolar_line(xy1[2 * idx1], xy1[2 * idx1 + 1], xy2[2 * idx2], xy2[2 * idx2 + 1], F12,
+                                       levelSigma2_2[oct2[idx2]])) {
+            bestIdx2 = idx2;
+            bestDist = dist;
+          }
+        }
+        if (bestIdx2 >= 0) {
+          match12[idx1] = bestIdx2;
+          matched2[bestIdx2] = 1;
+          nmatches++;
+          if (checkOri) rotHist[rot_bin(ang1[idx1], ang2[bestIdx2])].push_back(idx1);
+        }
+      }
+      ++a; ++b;
+    } else if (nodes1[a] < nodes2[b]) {
+      a = (int)(std::lower_bound(nodes1, nodes1 + nNodes1, nodes2[b]) - nodes1);
+    } else {
+      b = (int)(std::lower_bound(nodes2, nodes2 + nNodes2, nodes1[a]) - nodes2);
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int j : rotHist[i]) { match12[j] = -1; nmatches--; }
     }
   }
   return nmatches;

@@ -181,6 +181,120 @@ __global__ void __launch_bounds__(32) k_bow(const plslam_bow_job_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (@0x86b30): greedy like SearchByBoW (a KF2 feature
+// matched by an earlier KF1 feature is skipped later: the vbMatched2 bit IS set in this build, @0x87bc9), so one warp walks
+// the KF1 features of a job in FeatureVector order and the lanes split the KF2 candidates of the shared node.  Within one
+// KF1 feature the sequential rule "dist <= bestDist replaces" has a closed form: every test but that one is independent of
+// the running state, so the winner is the smallest distance among the candidates passing them, the LAST one on ties.
+// CheckDistEpipolarLine (@0x79b90) with the binary's fused operations (__fmaf_rn where it has vfmadd).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool check_dist_epipolar_line_dev(float x1, float y1, float x2, float y2, const float* F, float sigma2) {
+  const float b = __fadd_rn(__fmaf_rn(x1, F[1], __fmul_rn(y1, F[4])), F[7]);
+  const float a = __fadd_rn(__fmaf_rn(x1, F[0], __fmul_rn(y1, F[3])), F[6]);
+  const float den = __fmaf_rn(a, a, __fmul_rn(b, b));
+  if (den == 0.0f) return false;
+  const float c = __fadd_rn(__fmaf_rn(y1, F[5], __fmul_rn(x1, F[2])), F[8]);
+  const float num = __fadd_rn(c, __fmaf_rn(b, y2, __fmul_rn(a, x2)));
+  const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+  return __dmul_rn(3.84, (double)sigma2) > (double)dsqr;
+}
+
+__global__ void __launch_bounds__(32) k_triangulation(const plslam_tri_job_t* __restrict__ jobs) {
+  extern __shared__ int smem_i[];
+  const plslam_tri_job_t& J = jobs[blockIdx.x];
+  const int lane = threadIdx.x;
+  const int N1 = J.n1, N2 = J.n2;
+  int* matched2 = smem_i;            // [N2]
+  int* entryIdx = matched2 + N2;     // [N1] accepted KF1 feature indices, in order
+  int* entryBin = entryIdx + N1;     // [N1]
+  __shared__ int hist[PLSLAM_HISTO_LENGTH];
+  __shared__ float F[9];
+  for (int i = lane; i < N2; i += 32) matched2[i] = 0;
+  for (int i = lane; i < N1; i += 32) J.match12[i] = -1;
+  if (lane < PLSLAM_HISTO_LENGTH) hist[lane] = 0;
+  if (lane < 9) F[lane] = J.F12[lane];
+  __syncwarp();
+  const float ex = J.ex, ey = J.ey;
+  const bool onlyStereo = J.only_stereo != 0;
+  int nmatches = 0, nentries = 0;
+  int a = 0, b = 0;
+  const uint4* D1 = reinterpret_cast<const uint4*>(J.kf1_desc);
+  const uint4* D2 = reinterpret_cast<const uint4*>(J.kf2_desc);
+  while (a < J.n1_nodes && b < J.n2_nodes) {
+    const int na = J.kf1_nodes[a], nb = J.kf2_nodes[b];
+    if (na == nb) {
+      const int fs = J.kf2_start[b], fe = J.kf2_start[b + 1];
+      for (int i1 = J.kf1_start[a]; i1 < J.kf1_start[a + 1]; ++i1) {
+        const int idx1 = J.kf1_idx[i1];
+        if (J.kf1_has_mp[idx1]) continue;
+        const bool bStereo1 = J.kf1_uright[idx1] >= 0.0f;
+        if (onlyStereo && !bStereo1) continue;
+        const uint4 a0 = D1[2 * idx1], a1 = D1[2 * idx1 + 1];
+        const float x1 = J.kf1_xy[2 * idx1], y1 = J.kf1_xy[2 * idx1 + 1];
+        // key = dist << 20 | (0xfffff - order): the minimum is the smallest distance, the last candidate on ties
+        unsigned k = 0xffffffffu;
+        for (int i2 = fs + lane; i2 < fe; i2 += 32) {
+          const int idx2 = J.kf2_idx[i2];
+          if (matched2[idx2] || J.kf2_has_mp[idx2]) continue;
+          const bool bStereo2 = J.kf2_uright[idx2] >= 0.0f;
+          if (onlyStereo && !bStereo2) continue;
+          const int dist = hamming256(a0, a1, D2[2 * idx2], D2[2 * idx2 + 1]);
+          if (dist > PLSLAM_TH_LOW) continue;
+          const float x2 = J.kf2_xy[2 * idx2], y2 = J.kf2_xy[2 * idx2 + 1];
+          const int oct2 = J.kf2_octave[idx2];
+          if (!bStereo1 && !bStereo2) {
+            const float dx = __fsub_rn(ex, x2), dy = __fsub_rn(ey, y2);
+            if (__fmul_rn(100.0f, J.scale_factors[oct2]) > __fmaf_rn(dx, dx, __fmul_rn(dy, dy))) continue;
+          }
+          if (!check_dist_epipolar_line_dev(x1, y1, x2, y2, F, J.level_sigma2[oct2])) continue;
+          const unsigned key = ((unsigned)dist << 20) | (0xfffffu - (unsigned)(i2 - fs));
+          k = min(k, key);
+        }
+        const unsigned g = warp_min_u32(k);
+        if (g == 0xffffffffu) continue;
+        const int bestIdx2 = J.kf2_idx[fs + (int)(0xfffffu - (g & 0xfffffu))];
+        if (lane == 0) {
+          J.match12[idx1] = bestIdx2;
+          matched2[bestIdx2] = 1;
+          if (J.check_orientation) {
+            const int bin = rot_bin_dev(J.kf1_angle[idx1], J.kf2_angle[bestIdx2]);
+            hist[bin]++;
+            entryIdx[nentries] = idx1;
+            entryBin[nentries] = bin;
+          }
+        }
+        ++nentries;
+        ++nmatches;
+        __syncwarp();
+      }
+      ++a;
+      ++b;
+    } else if (na < nb) {
+      while (a < J.n1_nodes && J.kf1_nodes[a] < nb) ++a;  // lower_bound
+    } else {
+      while (b < J.n2_nodes && J.kf2_nodes[b] < na) ++b;
+    }
+  }
+  __syncwarp();
+  if (J.check_orientation) {
+    int i1, i2, i3;
+    three_maxima_dev(hist, i1, i2, i3);
+    int removed = 0;
+    for (int e = lane; e < nentries; e += 32) {
+      const int bin = entryBin[e];
+      if (bin != i1 && bin != i2 && bin != i3) {
+        J.match12[entryIdx[e]] = -1;
+        ++removed;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, d);
+    nmatches -= removed;
+  }
+  if (lane == 0) *J.nmatches = nmatches;
+}
+
+// ------------------------------------------------------------------------------------------
 // SearchByProjection(CurrentFrame, LastFrame, th, bMono): one warp per frame pair walks the last
 // frame's map points in order (a current keypoint claimed by an earlier point is skipped later);
 // lanes split the grid cells of the search window, candidate order = [ix][iy][position in cell].
@@ -349,7 +463,7 @@ __global__ void __launch_bounds__(32) k_local_points(const plslam_local_job_t* _
   for (int i = 0; i < M; ++i) {
     if (!J.mp_valid[i]) continue;
     const int level = J.mp_level[i];
-    float r = J.mp_viewcos[i] > 0.998f ? 2.5f : 4.0f;
+    float r = (double)J.mp_viewcos[i] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos compares in double (@0x79b64-0x79b70)
     if (bFactor) r = __fmul_rn(r, J.th);
     const float x = J.mp_proj[3 * i], y = J.mp_proj[3 * i + 1], xr = J.mp_proj[3 * i + 2];
     const float radius = __fmul_rn(r, J.scale_factors[level]);
@@ -556,6 +670,75 @@ int plslam_match_bow_host(const plslam_bow_job_t* job) {
   int rc = plslam_match_bow_batch_device(dj, 1, std::max(job->n1, job->n2), nullptr);
   if (rc) return rc;
   PL_CUDA(cudaMemcpy(job->match_f, d.match_f, (size_t)job->n2 * 4, cudaMemcpyDeviceToHost));
+  PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int plslam_match_triangulation_batch_device(const plslam_tri_job_t* d_jobs, int njobs, int max_n, void* stream) {
+  PL_CHECK_ARG(d_jobs && njobs >= 1 && max_n >= 0);
+  const size_t smem = (size_t)max_n * 4 * 3;  // matched2[n2] + entryIdx[n1] + entryBin[n1]
+  PL_CHECK_ARG(smem <= 200 * 1024);
+  static bool attr = false;
+  if (!attr) {
+    PL_CUDA(cudaFuncSetAttribute(k_triangulation, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  PL_CARVEOUT(k_triangulation);
+  k_triangulation<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+// C2 = R2w * Cw + t2w through cv::gemm's small-matrix path (float sum, scaled and added in double), invz = 1 / C2z,
+// ex = fma(invz, fx * C2x, cx) — the sequence of @0x86b9c-0x86f8b.  Host scalar work, once per key-frame pair.
+int plslam_match_epipole(const float* R2w_3x3, const float* t2w, const float* Cw, float fx, float fy, float cx, float cy,
+                         float* ex, float* ey) {
+  PL_CHECK_ARG(R2w_3x3 && t2w && Cw && ex && ey);
+  float C2[3];
+  for (int r = 0; r < 3; ++r) {
+    float s = R2w_3x3[3 * r] * Cw[0];
+    s = s + R2w_3x3[3 * r + 1] * Cw[1];
+    s = s + R2w_3x3[3 * r + 2] * Cw[2];
+    C2[r] = (float)((double)s * 1.0 + (double)t2w[r] * 1.0);
+  }
+  const float invz = 1.0f / C2[2];
+  *ex = fmaf(invz, fx * C2[0], cx);
+  *ey = fmaf(invz, fy * C2[1], cy);
+  return PLSLAM_OK;
+}
+
+int plslam_match_triangulation_host(const plslam_tri_job_t* job, int n_scale_levels) {
+  PL_CHECK_ARG(job && job->match12 && job->nmatches && job->n1 >= 0 && job->n2 >= 0 && n_scale_levels >= 1);
+  Uploader U;
+  plslam_tri_job_t d = *job;
+  const int n1 = job->n1, n2 = job->n2, na = job->n1_nodes, nb = job->n2_nodes;
+  const int len1 = na ? job->kf1_start[na] : 0, len2 = nb ? job->kf2_start[nb] : 0;
+  d.kf1_desc = U.up(job->kf1_desc, (size_t)n1 * 32);
+  d.kf1_xy = U.up(job->kf1_xy, (size_t)n1 * 2);
+  d.kf1_angle = U.up(job->kf1_angle, n1);
+  d.kf1_uright = U.up(job->kf1_uright, n1);
+  d.kf1_has_mp = U.up(job->kf1_has_mp, n1);
+  d.kf1_nodes = U.up(job->kf1_nodes, na);
+  d.kf1_start = U.up(job->kf1_start, na + 1);
+  d.kf1_idx = U.up(job->kf1_idx, len1);
+  d.kf2_desc = U.up(job->kf2_desc, (size_t)n2 * 32);
+  d.kf2_xy = U.up(job->kf2_xy, (size_t)n2 * 2);
+  d.kf2_angle = U.up(job->kf2_angle, n2);
+  d.kf2_octave = U.up(job->kf2_octave, n2);
+  d.kf2_uright = U.up(job->kf2_uright, n2);
+  d.kf2_has_mp = U.up(job->kf2_has_mp, n2);
+  d.kf2_nodes = U.up(job->kf2_nodes, nb);
+  d.kf2_start = U.up(job->kf2_start, nb + 1);
+  d.kf2_idx = U.up(job->kf2_idx, len2);
+  d.scale_factors = U.up(job->scale_factors, n_scale_levels);
+  d.level_sigma2 = U.up(job->level_sigma2, n_scale_levels);
+  d.match12 = U.out<int32_t>(std::max(n1, 1));
+  d.nmatches = U.out<int32_t>(1);
+  const plslam_tri_job_t* dj = U.up(&d, 1);
+  if (U.err != cudaSuccess) { set_error("triangulation host path: %s", cudaGetErrorString(U.err)); return PLSLAM_ERR_CUDA; }
+  int rc = plslam_match_triangulation_batch_device(dj, 1, std::max(n1, n2), nullptr);
+  if (rc) return rc;
+  if (n1) PL_CUDA(cudaMemcpy(job->match12, d.match12, (size_t)n1 * 4, cudaMemcpyDeviceToHost));
   PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
   return PLSLAM_OK;
 }

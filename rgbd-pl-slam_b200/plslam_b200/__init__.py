@@ -306,7 +306,16 @@ class ProjJob(C.Structure):
                 ("n1", C.c_int32), ("n2", C.c_int32), ("mono", C.c_int32), ("check_orientation", C.c_int32)]
 
 
-assert C.sizeof(KnnJob) == 32 and C.sizeof(BowJob) == 128 and C.sizeof(ProjJob) == 304
+class TriJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("kf1_desc", "kf1_xy", "kf1_angle", "kf1_uright", "kf1_has_mp", "kf1_nodes", "kf1_start",
+                                          "kf1_idx", "kf2_desc", "kf2_xy", "kf2_angle", "kf2_octave", "kf2_uright", "kf2_has_mp",
+                                          "kf2_nodes", "kf2_start", "kf2_idx", "scale_factors", "level_sigma2", "match12",
+                                          "nmatches")] + \
+               [("F12", C.c_float * 9), ("ex", C.c_float), ("ey", C.c_float), ("n1", C.c_int32), ("n2", C.c_int32),
+                ("n1_nodes", C.c_int32), ("n2_nodes", C.c_int32), ("only_stereo", C.c_int32), ("check_orientation", C.c_int32)]
+
+
+assert C.sizeof(KnnJob) == 32 and C.sizeof(BowJob) == 128 and C.sizeof(ProjJob) == 304 and C.sizeof(TriJob) == 240
 
 
 def _jobs_to_device(jobs, device):
@@ -772,3 +781,46 @@ def SaveTrajectoryTUM(filename, timestamps, poses_Tcw):
     T = np.ascontiguousarray(np.asarray(poses_Tcw, np.float32)[:, :3, :4])
     assert len(ts) == len(T)
     _check(lib().plslam_tum_save_trajectory(os.fsencode(filename), _vp(ts), _vp(T), len(ts)))
+
+
+# ---- ORBmatcher::SearchForTriangulation (include/plslam_b200.h: plslam_tri_job_t) ----
+def epipole(R2w, t2w, Cw, fx, fy, cx, cy):
+    """The epipole of KF1's camera centre in KF2 with the reference's rounding sequence (plslam_match_epipole)."""
+    R, t, c = (np.ascontiguousarray(x, np.float32).ravel() for x in (R2w, t2w, Cw))
+    ex, ey = C.c_float(), C.c_float()
+    _check(lib().plslam_match_epipole(_vp(R), _vp(t), _vp(c), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                                      C.byref(ex), C.byref(ey)))
+    return ex.value, ey.value
+
+
+def _tri_job(kf1, kf2, F12, ex, ey, scale_factors, level_sigma2, only_stereo, check_ori, ptr):
+    """TriJob over the arrays of two key-frame dicts (layout of tests/matchdata.py: triangulation_case); returns (job, keep)."""
+    g = lambda d, k, t: np.ascontiguousarray(d[k], t)
+    keep = dict(a_desc=g(kf1, "desc", np.uint8), a_xy=g(kf1, "xy", np.float32), a_angle=g(kf1, "angle", np.float32),
+                a_uright=g(kf1, "uright", np.float32), a_has_mp=g(kf1, "has_mp", np.uint8), a_nodes=g(kf1, "nodes", np.int32),
+                a_start=g(kf1, "start", np.int32), a_idx=g(kf1, "idx", np.int32),
+                b_desc=g(kf2, "desc", np.uint8), b_xy=g(kf2, "xy", np.float32), b_angle=g(kf2, "angle", np.float32),
+                b_octave=g(kf2, "octave", np.int32), b_uright=g(kf2, "uright", np.float32), b_has_mp=g(kf2, "has_mp", np.uint8),
+                b_nodes=g(kf2, "nodes", np.int32), b_start=g(kf2, "start", np.int32), b_idx=g(kf2, "idx", np.int32),
+                sf=np.ascontiguousarray(scale_factors, np.float32), sg=np.ascontiguousarray(level_sigma2, np.float32))
+    n1, n2 = len(keep["a_desc"]), len(keep["b_desc"])
+    keep["m"], keep["n"] = np.full(max(n1, 1), -9, np.int32), np.zeros(1, np.int32)
+    p = ptr
+    j = TriJob(p(keep["a_desc"]), p(keep["a_xy"]), p(keep["a_angle"]), p(keep["a_uright"]), p(keep["a_has_mp"]), p(keep["a_nodes"]),
+               p(keep["a_start"]), p(keep["a_idx"]), p(keep["b_desc"]), p(keep["b_xy"]), p(keep["b_angle"]), p(keep["b_octave"]),
+               p(keep["b_uright"]), p(keep["b_has_mp"]), p(keep["b_nodes"]), p(keep["b_start"]), p(keep["b_idx"]), p(keep["sf"]),
+               p(keep["sg"]), p(keep["m"]), p(keep["n"]))
+    j.F12[:] = np.asarray(F12, np.float32).ravel().tolist()
+    j.ex, j.ey = float(ex), float(ey)
+    j.n1, j.n2, j.n1_nodes, j.n2_nodes = n1, n2, len(keep["a_nodes"]), len(keep["b_nodes"])
+    j.only_stereo, j.check_orientation = int(only_stereo), int(check_ori)
+    return j, keep
+
+
+def search_for_triangulation_host(kf1, kf2, F12, ex, ey, scale_factors, level_sigma2, only_stereo=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation on host arrays through plslam_match_triangulation_host
+    -> (vMatches12 int32 [N1], nmatches, vMatchedPairs [(i1, i2)])."""
+    j, keep = _tri_job(kf1, kf2, F12, ex, ey, scale_factors, level_sigma2, only_stereo, check_ori, lambda a: a.ctypes.data)
+    _check(lib().plslam_match_triangulation_host(C.byref(j), len(keep["sf"])))
+    m = keep["m"][:j.n1].copy()
+    return m, int(keep["n"][0]), [(int(i), int(v)) for i, v in enumerate(m) if v >= 0]

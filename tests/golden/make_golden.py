@@ -9,6 +9,9 @@ Sources of truth, none of them this repository's own oracle:
   dbow2_ref.npz        the reference's OWN Thirdparty/DBoW2 sources (compiled into oracle/_ref/libdbow2_ref.so):
                        FORB::distance and ORBVocabulary::transform on a small vocabulary
   reference_binary.json  constants read from /root/reference/lib/libORB_SLAM2.so (rBRIEF pattern, matcher thresholds)
+  reference_code.npz    outputs of the reference's OWN MACHINE CODE for four leaf functions of the matcher path
+                       (RadiusByViewingCos, CheckDistEpipolarLine, ComputeThreeMaxima, DescriptorDistance), executed from
+                       lib/libORB_SLAM2.so by tests/golden/reference_code.py  (`python tests/golden/make_golden.py refcode`)
   tum_io.json          the reference's own association lists (Examples/RGB-D/associations/*.txt) parsed with str.split /
                        float(): entry count, digest, first and last entry of each; the trajectory line of the identity pose
                        from cv2.gemm + Python's "%.9f"  (`python tests/golden/make_golden.py tum` writes only this file)
@@ -27,6 +30,84 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 for p in (ROOT, os.path.join(ROOT, "rgbd-pl-slam_b200")):
     sys.path.insert(0, p)
+
+
+def refcode():
+    sys.path.insert(0, HERE)
+    from reference_code import RefCode, SO
+    r = RefCode()
+    rng = np.random.default_rng(77)
+    out = {"so_sha256": np.array(hashlib.sha256(open(SO, "rb").read()).hexdigest())}
+    # RadiusByViewingCos: the floats around the threshold, and a spread
+    t = np.float32(0.998)
+    vals = [t]
+    for _ in range(4):
+        vals.append(np.nextafter(vals[-1], np.float32(2)))
+    lo = t
+    for _ in range(4):
+        lo = np.nextafter(lo, np.float32(-2)); vals.append(lo)
+    vals += list(rng.uniform(-1, 1, 64).astype(np.float32)) + [np.float32(1.0), np.float32(0.0)]
+    out["radius_in"] = np.array(vals, np.float32)
+    out["radius_out"] = np.array([r.radius_by_viewing_cos(float(v)) for v in vals], np.float32)
+    # DescriptorDistance
+    a = rng.integers(0, 256, (300, 32)).astype(np.uint8)
+    b = rng.integers(0, 256, (300, 32)).astype(np.uint8)
+    a[0] = 0; b[0] = 255; b[1] = a[1]; a[2] = 0; b[2] = 0; b[2, 31] = 0x80
+    out["dd_a"], out["dd_b"] = a, b
+    out["dd_out"] = np.array([r.descriptor_distance(x, y) for x, y in zip(a, b)], np.int32)
+    # ComputeThreeMaxima: random populations, ties, and the 0.1 * max thresholds
+    hists = [rng.integers(0, 40, 30) for _ in range(150)] + [rng.integers(0, 3, 30) for _ in range(50)]
+    for m1 in (10, 20, 30, 50, 100, 101):
+        for m2 in (m1 // 10 - 1, m1 // 10, m1 // 10 + 1, m1):
+            for m3 in (0, m1 // 10 - 1, m1 // 10, m1 // 10 + 1):
+                h = np.zeros(30, np.int64); pos = rng.permutation(30)[:3]
+                h[pos[0]], h[pos[1]], h[pos[2]] = m1, max(m2, 0), max(m3, 0)
+                hists.append(h)
+    hists.append(np.zeros(30, np.int64))
+    hists = np.array(hists, np.int32)
+    out["tm_in"] = hists
+    res = []
+    for h in hists:
+        i = r.compute_three_maxima([int(x) for x in h])
+        res.append([-1 if x == -7 else x for x in i])  # untouched outputs keep the callers' initial -1
+    out["tm_out"] = np.array(res, np.int32)
+    # CheckDistEpipolarLine: for random geometry, bisect kp2.y in float32 until the reference's answer flips between two
+    # ADJACENT floats, and keep both: any difference in the rounding sequence (the binary's FMA pattern) moves that boundary.
+    sig = np.array([1.2 ** (2 * l) for l in range(8)], np.float32)
+    cases = []
+    while len(cases) < 1500:
+        F = rng.standard_normal((3, 3)).astype(np.float32) * np.float32(10.0 ** rng.uniform(-4, 0))
+        if len(cases) % 50 == 0:
+            F[:, :2] = 0  # a = b = 0: den == 0 -> false
+        kp1 = rng.uniform(0, 640, 2).astype(np.float32)
+        x2 = np.float32(rng.uniform(0, 640)); octv = int(rng.integers(0, 8))
+        f = lambda y: r.check_dist_epipolar_line(kp1, (x2, np.float32(y)), octv, F, sig)
+        ys = np.linspace(-2000, 2000, 81).astype(np.float32)
+        v = [f(y) for y in ys]
+        flips = [i for i in range(80) if v[i] != v[i + 1]]
+        if not flips:
+            cases.append((F, kp1, x2, np.float32(rng.uniform(0, 480)), octv)); continue
+        for i in flips[:2]:
+            lo, hi = ys[i], ys[i + 1]
+            flo = v[i]
+            while np.nextafter(lo, hi) != hi:
+                mid = np.float32((np.float64(lo) + np.float64(hi)) / 2)
+                if mid == lo or mid == hi:
+                    break
+                if f(mid) == flo:
+                    lo = mid
+                else:
+                    hi = mid
+            cases.append((F, kp1, x2, lo, octv)); cases.append((F, kp1, x2, hi, octv))
+    out["ep_F"] = np.array([c[0] for c in cases], np.float32)
+    out["ep_kp1"] = np.array([c[1] for c in cases], np.float32)
+    out["ep_kp2"] = np.array([[c[2], c[3]] for c in cases], np.float32)
+    out["ep_oct"] = np.array([c[4] for c in cases], np.int32)
+    out["ep_sigma2"] = sig
+    out["ep_out"] = np.array([r.check_dist_epipolar_line(c[1], (c[2], c[3]), c[4], c[0], sig) for c in cases], np.uint8)
+    np.savez_compressed(os.path.join(HERE, "reference_code.npz"), **out)
+    print("reference_code.npz: %d radius, %d distances, %d histograms, %d epipolar cases (%d true)"
+          % (len(vals), len(a), len(hists), len(cases), int(out["ep_out"].sum())))
 
 
 def tum_io():
@@ -55,6 +136,8 @@ def tum_io():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "tum":
         return tum_io()
+    if len(sys.argv) > 1 and sys.argv[1] == "refcode":
+        return refcode()
     import cv2
     from plslam_b200.synth import synth_frame
     assert cv2.__version__.startswith("4.13"), cv2.__version__
@@ -138,3 +221,4 @@ if __name__ == "__main__":
     main()
     if len(sys.argv) == 1:
         tum_io()
+        refcode()

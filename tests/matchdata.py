@@ -88,3 +88,59 @@ def local_points_case(kps_map, desc_map, kps_cur, desc_cur, W=640, H=480, seed=0
               taken=(rng.random(n) < 0.05).astype(np.uint8), grid_start=gs, grid_items=gi)
     cam4 = np.array([mnx, mny, gwi, ghi], np.float32)
     return mp, fr, cam4
+
+
+def triangulation_case(kps, desc, seed=0, stereo_fraction=0.5, nbits=3, W=640, H=480, t21=(0.12, 0.01, 0.03)):
+    """LocalMapping::CreateNewMapPoints-like inputs for ORBmatcher::SearchForTriangulation: key frame 1 = the given features at
+    synthetic depths with the camera at the origin, key frame 2 = their projections after a small motion (noisy positions,
+    descriptors with a few flipped bits, shuffled) plus distractors.  F12 as LocalMapping::ComputeF12 builds it
+    (K^-T [t12]x R12 K^-1), the epipole from the same geometry.  Returns kf1, kf2, F12, (R2w, t2w, Cw), cam, scale_factors,
+    level_sigma2."""
+    rng = np.random.default_rng(seed)
+    n1 = len(kps)
+    fx = fy = np.float32(520.0); cx = np.float32(W / 2 - 0.5); cy = np.float32(H / 2 - 0.5)
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    z = 1.5 + 2.0 * rng.random(n1)
+    X1 = np.stack([(kps["x"] - cx) * z / fx, (kps["y"] - cy) * z / fy, z], 1).astype(np.float64)
+    ang = 0.03
+    R21 = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t21 = np.array(t21, np.float64)  # (0.005, 0.002, 0.15) puts the epipole inside the image
+    X2 = X1 @ R21.T + t21
+    oct1 = np.asarray(kps["octave"], np.int32)
+    x2 = np.stack([fx * X2[:, 0] / X2[:, 2] + cx, fy * X2[:, 1] / X2[:, 2] + cy], 1)
+    x2 += rng.normal(0, 0.6, x2.shape) * sf[oct1][:, None]
+    inside = (x2[:, 0] > 0) & (x2[:, 0] < W) & (x2[:, 1] > 0) & (x2[:, 1] < H) & (rng.random(n1) < 0.85)
+    src = np.flatnonzero(inside)
+    d2 = desc[src].copy()
+    for r in range(len(d2)):  # flip 0..40 random bits: distances on both sides of TH_LOW = 50
+        for bit in rng.choice(256, int(rng.integers(0, 41)), replace=False):
+            d2[r, bit >> 3] ^= np.uint8(1 << (bit & 7))
+    ndis = 150
+    dsrc = rng.integers(0, n1, ndis)
+    dd = desc[dsrc].copy()
+    for r in range(ndis):
+        for bit in rng.choice(256, int(rng.integers(10, 60)), replace=False):
+            dd[r, bit >> 3] ^= np.uint8(1 << (bit & 7))
+    xy2 = np.vstack([x2[src], np.stack([rng.uniform(0, W, ndis), rng.uniform(0, H, ndis)], 1)]).astype(np.float32)
+    desc2 = np.vstack([d2, dd])
+    oct2 = np.concatenate([oct1[src], rng.integers(0, 8, ndis)]).astype(np.int32)
+    ang2 = np.concatenate([np.asarray(kps["angle"], np.float32)[src] + rng.normal(0, 3, len(src)), rng.uniform(0, 360, ndis)])
+    wild = rng.random(len(ang2)) < 0.1
+    ang2 = np.mod(np.where(wild, rng.uniform(0, 360, len(ang2)), ang2), 360).astype(np.float32)
+    perm = rng.permutation(len(xy2))
+    xy2, desc2, oct2, ang2 = xy2[perm], np.ascontiguousarray(desc2[perm]), oct2[perm], ang2[perm]
+    n2 = len(xy2)
+    xy1 = np.stack([kps["x"], kps["y"]], 1).astype(np.float32)
+    ur = lambda x, n: np.where(rng.random(n) < stereo_fraction, x - 40.0 / (1.5 + 2 * rng.random(n)), -1).astype(np.float32)
+    nodes1, start1, idx1 = fake_feature_vector(desc, nbits, seed=seed + 100)
+    nodes2, start2, idx2 = fake_feature_vector(desc2, nbits, seed=seed + 100)
+    kf1 = dict(desc=np.ascontiguousarray(desc), xy=xy1, angle=np.asarray(kps["angle"], np.float32), uright=ur(xy1[:, 0], n1),
+               has_mp=(rng.random(n1) < 0.2).astype(np.uint8), nodes=nodes1, start=start1, idx=idx1)
+    kf2 = dict(desc=desc2, xy=xy2, angle=ang2, octave=oct2, uright=ur(xy2[:, 0], n2), has_mp=(rng.random(n2) < 0.2).astype(np.uint8),
+               nodes=nodes2, start=start2, idx=idx2)
+    R12, t12 = R21.T, -R21.T @ t21
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    F12 = (np.linalg.inv(K).T @ tx @ R12 @ np.linalg.inv(K)).astype(np.float32)
+    pose = (R21.astype(np.float32), t21.astype(np.float32), np.zeros(3, np.float32))
+    return kf1, kf2, F12, pose, (fx, fy, cx, cy), sf, (sf * sf).astype(np.float32)

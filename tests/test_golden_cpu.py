@@ -88,3 +88,34 @@ def test_product_host_pieces_against_golden():
     desc = g["desc"]
     d = np.array([pl.DescriptorDistance(a, b) for a, b in zip(desc[:200], desc[200:])], np.int32)
     assert np.array_equal(d, g["forb_distance"])
+
+
+def test_oracle_equals_the_reference_machine_code(oracle):
+    """tests/golden/reference_code.npz holds outputs of lib/libORB_SLAM2.so's own code for four leaf functions of the
+    matcher path (tests/golden/reference_code.py executes them); the epipolar cases are pairs of ADJACENT float32 inputs
+    on either side of the reference's decision boundary, so the rounding sequence (the binary's FMA pattern) is pinned."""
+    g = np.load(os.path.join(G, "reference_code.npz"))
+    for v, want in zip(g["radius_in"], g["radius_out"]):
+        assert oracle.radius_by_viewing_cos(v) == want, float(v)
+    assert oracle.radius_by_viewing_cos(np.float32(0.998)) == 2.5  # (double)0.998f > 0.998
+    for a, b, want in zip(g["dd_a"], g["dd_b"], g["dd_out"]):
+        assert oracle.descriptor_distance(a, b) == want
+    for h, want in zip(g["tm_in"], g["tm_out"]):
+        assert oracle.three_maxima(h) == tuple(int(x) for x in want), h
+    got = np.array([oracle.check_dist_epipolar_line(k1, k2, F, g["ep_sigma2"][o])
+                    for F, k1, k2, o in zip(g["ep_F"], g["ep_kp1"], g["ep_kp2"], g["ep_oct"])], np.uint8)
+    assert np.array_equal(got, g["ep_out"]), "%d of %d differ" % (int((got != g["ep_out"]).sum()), len(got))
+    assert 300 < int(g["ep_out"].sum()) < 1200
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/lib/libORB_SLAM2.so"), reason="build container only")
+def test_reference_machine_code_still_gives_the_golden_answers():
+    import hashlib
+    import sys
+    sys.path.insert(0, G)
+    from reference_code import RefCode, SO
+    g = np.load(os.path.join(G, "reference_code.npz"))
+    assert hashlib.sha256(open(SO, "rb").read()).hexdigest() == str(g["so_sha256"])
+    r = RefCode()
+    assert [r.descriptor_distance(a, b) for a, b in zip(g["dd_a"][:20], g["dd_b"][:20])] == list(g["dd_out"][:20])
+    assert [r.radius_by_viewing_cos(float(v)) for v in g["radius_in"][:9]] == list(g["radius_out"][:9])

@@ -54,3 +54,35 @@ def test_frame_grid_is_a_partition():
     start, items, _ = frame_grid(xy, 640, 480)
     assert start[-1] == len(items) <= 500 and len(start) == 64 * 48 + 1
     assert len(set(items.tolist())) == len(items)
+
+
+def test_search_for_triangulation_oracle_properties(oracle):
+    """Structure of ORBmatcher::SearchForTriangulation's result on synthetic two-view geometry (the arithmetic of its leaves is
+    pinned against the reference's machine code in test_golden_cpu.py)."""
+    import plslam_b200 as pl
+    from plslam_b200.synth import synth_frame
+    from matchdata import triangulation_case
+    kps, desc = oracle.OrbOracle().extract(synth_frame(21))
+    kf1, kf2, F12, (R2w, t2w, Cw), (fx, fy, cx, cy), sf, sg = triangulation_case(kps, desc, seed=1)
+    ex, ey = oracle.epipole(R2w, t2w, Cw, fx, fy, cx, cy)
+    assert (ex, ey) == pl.epipole(R2w, t2w, Cw, fx, fy, cx, cy)          # host scalar code of the product, no GPU needed
+    assert abs(ex - (fx * t2w[0] / t2w[2] + cx)) < 1e-2
+    node_of = lambda kf: {int(i): int(kf["nodes"][k]) for k in range(len(kf["nodes"])) for i in kf["idx"][kf["start"][k]:kf["start"][k + 1]]}
+    nd1, nd2 = node_of(kf1), node_of(kf2)
+    for only_stereo in (False, True):
+        m, n = oracle.search_for_triangulation(kf1, kf2, F12, ex, ey, sf, sg, only_stereo=only_stereo, check_ori=True)
+        m0, n0 = oracle.search_for_triangulation(kf1, kf2, F12, ex, ey, sf, sg, only_stereo=only_stereo, check_ori=False)
+        idx = np.flatnonzero(m >= 0)
+        assert n == len(idx) and n0 == int((m0 >= 0).sum()) and 30 < n <= n0
+        assert len(set(m[idx].tolist())) == len(idx)                       # a KF2 feature is matched once (vbMatched2)
+        assert set(idx.tolist()) <= set(np.flatnonzero(m0 >= 0).tolist())   # the rotation filter only removes
+        for i in idx:
+            j = int(m[i])
+            assert not kf1["has_mp"][i] and not kf2["has_mp"][j] and nd1[int(i)] == nd2[j]
+            assert oracle.descriptor_distance(kf1["desc"][i], kf2["desc"][j]) <= 50
+            assert oracle.check_dist_epipolar_line(kf1["xy"][i], kf2["xy"][j], F12, sg[kf2["octave"][j]])
+            if only_stereo:
+                assert kf1["uright"][i] >= 0 and kf2["uright"][j] >= 0
+            elif kf1["uright"][i] < 0 and kf2["uright"][j] < 0:
+                d = kf2["xy"][j] - np.array([ex, ey], np.float32)
+                assert float(d @ d) >= 100 * sf[kf2["octave"][j]] * (1 - 1e-5)
