@@ -12,6 +12,11 @@ Sources of truth, none of them this repository's own oracle:
   reference_code.npz    outputs of the reference's OWN MACHINE CODE for four leaf functions of the matcher path
                        (RadiusByViewingCos, CheckDistEpipolarLine, ComputeThreeMaxima, DescriptorDistance), executed from
                        lib/libORB_SLAM2.so by tests/golden/reference_code.py  (`python tests/golden/make_golden.py refcode`)
+  reference_library.npz  the reference library ITSELF, dlopen'ed over generated stub dependencies (reference_code.py:
+                       RefLibrary): constructor tables of ORB_SLAM2::ORBextractor for four parameter sets, and the outputs of
+                       ORBextractor::DistributeOctTree (run under a monotonic operator new, which fixes its pointer-valued
+                       tie-break to allocation order) for real FAST candidate lists and for lattices full of ties
+                       (`python tests/golden/make_golden.py reflib`, in a fresh process)
   tum_io.json          the reference's own association lists (Examples/RGB-D/associations/*.txt) parsed with str.split /
                        float(): entry count, digest, first and last entry of each; the trajectory line of the identity pose
                        from cv2.gemm + Python's "%.9f"  (`python tests/golden/make_golden.py tum` writes only this file)
@@ -110,6 +115,50 @@ def refcode():
           % (len(vals), len(a), len(hists), len(cases), int(out["ep_out"].sum())))
 
 
+def reflib():
+    sys.path.insert(0, HERE)
+    from reference_code import RefLibrary, SO
+    R = RefLibrary()  # first: the monotonic operator new must precede any global libstdc++
+    from oracle import bindings as orb  # only to produce realistic inputs (FAST candidates); outputs come from the reference
+    from plslam_b200.synth import synth_frame
+    out = {"so_sha256": np.array(hashlib.sha256(open(SO, "rb").read()).hexdigest())}
+    params = [(1000, 1.2, 8, 20, 7), (2000, 1.2, 8, 20, 7), (8000, 1.2, 8, 20, 7), (500, 1.5, 4, 12, 5)]
+    out["ctor_params"] = np.array(params, np.float64)
+    objs = []
+    for k, pr in enumerate(params):
+        obj, t = R.extractor(*pr)
+        objs.append(obj)
+        for name in ("quota", "umax", "scale", "inv_scale", "sigma2", "inv_sigma2", "pattern"):
+            out["ctor%d_%s" % (k, name)] = t[name]
+    rng = np.random.default_rng(5)
+    cases = []
+    o = orb.OrbOracle()
+    quota = o.tables()["quota"]
+    for seed in (0, 7):
+        o.extract(synth_frame(seed))
+        for l in (0, 1, 3, 5, 7):
+            h, w = o.level(l).shape
+            cases.append((o.candidates(l), 16, w - 16, 16, h - 16, int(quota[l])))
+    c0 = cases[0][0]
+    cases.append((c0, 16, 640 - 16, 16, 480 - 16, 50))       # far fewer features than candidates
+    cases.append((c0[:150], 16, 640 - 16, 16, 480 - 16, 217))  # more features than candidates
+    for step, N in ((8, 200), (16, 150), (5, 400)):           # lattices with equal responses: every node size ties
+        xs, ys = np.meshgrid(np.arange(0, 600, step), np.arange(0, 440, step))
+        pts = np.stack([xs.ravel(), ys.ravel(), np.full(xs.size, 30)], 1).astype(np.int32)
+        cases.append((pts[rng.permutation(len(pts))], 16, 640 - 16, 16, 480 - 16, N))
+    pts = np.stack([rng.integers(0, 300, 3000), rng.integers(0, 440, 3000), rng.integers(7, 60, 3000)], 1).astype(np.int32)
+    cases.append((pts, 16, 640 - 16, 16, 480 - 16, 300))      # everything in the left half
+    out["qt_n"] = np.array(len(cases))
+    for k, (c, x0, x1, y0, y1, N) in enumerate(cases):
+        idx, _ = R.distribute(objs[0], c, x0, x1, y0, y1, N, 0)
+        out["qt%d_in" % k] = np.ascontiguousarray(c, np.int32)
+        out["qt%d_args" % k] = np.array([x0, x1, y0, y1, N], np.int32)
+        out["qt%d_out" % k] = idx
+    np.savez_compressed(os.path.join(HERE, "reference_library.npz"), **out)
+    print("reference_library.npz: %d constructor tables, %d quad-tree cases, outputs of sizes %s"
+          % (len(params), len(cases), [len(out["qt%d_out" % k]) for k in range(len(cases))]))
+
+
 def tum_io():
     import cv2
     d = "/root/reference/Examples/RGB-D/associations"
@@ -138,6 +187,8 @@ def main():
         return tum_io()
     if len(sys.argv) > 1 and sys.argv[1] == "refcode":
         return refcode()
+    if len(sys.argv) > 1 and sys.argv[1] == "reflib":
+        return reflib()
     import cv2
     from plslam_b200.synth import synth_frame
     assert cv2.__version__.startswith("4.13"), cv2.__version__
@@ -222,3 +273,5 @@ if __name__ == "__main__":
     if len(sys.argv) == 1:
         tum_io()
         refcode()
+        import subprocess
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "reflib"])  # needs a fresh process

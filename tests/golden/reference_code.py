@@ -86,3 +86,139 @@ class RefCode:
         i1, i2, i3 = C.c_int(-7), C.c_int(-7), C.c_int(-7)
         self._maxima(None, C.addressof(vec), L, C.byref(i1), C.byref(i2), C.byref(i3))
         return i1.value, i2.value, i3.value
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The whole library, loaded.  dlopen() of lib/libORB_SLAM2.so fails only because its NEEDED libraries (OpenCV 3.3, Pangolin,
+# g2o, DBoW2, libGL) are absent.  build_stubs() generates, from the library's own dynamic symbol table, one stub object that
+# defines every undefined non-system symbol (functions: return 0; objects: zero bytes) plus an empty shared object for each
+# missing SONAME; with those loaded first the dynamic loader accepts the reference library as it is.  Every function whose
+# call graph stays inside libORB_SLAM2.so + libstdc++/libm/libc then runs unmodified: the ORBextractor constructor and
+# ORBextractor::DistributeOctTree (the quad-tree) are used below.  Nothing is patched and no reference byte is copied.
+# ----------------------------------------------------------------------------------------------------------------------
+STUB_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "oracle", "_ref", "refstub")
+_SYSTEM = ("libstdc++.so.6", "libm.so.6", "libgcc_s.so.1", "libpthread.so.0")
+
+
+BUMP_C = r"""
+/* operator new / delete with strictly increasing addresses and no reuse.  ORBextractor::DistributeOctTree sorts
+ * pair<int, ExtractorNode*>: equal node sizes are ordered by POINTER VALUE, so the reference's result depends on the state of
+ * the heap.  Under this allocator the pointer order is the allocation order, which makes the reference deterministic and is
+ * the instance of its behaviour the oracle restates (its `seq` tie-break). */
+#include <stddef.h>
+#include <sys/mman.h>
+static char* base;
+static size_t off;
+void* _Znwm(size_t n) {
+  if (!base) base = mmap(NULL, 1UL << 34, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  n = (n + 15) & ~(size_t)15;
+  void* p = base + off;
+  off += n ? n : 16;
+  return p;
+}
+void* _Znam(size_t n) { return _Znwm(n); }
+void _ZdlPv(void* p) { (void)p; }
+void _ZdaPv(void* p) { (void)p; }
+void _ZdlPvm(void* p, size_t n) { (void)p; (void)n; }
+"""
+
+
+def load_monotonic_new(out=STUB_DIR):
+    """Must run before anything loads libstdc++ with RTLD_GLOBAL: the first global definition of operator new wins."""
+    import subprocess
+    os.makedirs(out, exist_ok=True)
+    src = os.path.join(out, "bump.c")
+    open(src, "w").write(BUMP_C)
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", os.path.join(out, "libbumpnew.so"), src])
+    return C.CDLL(os.path.join(out, "libbumpnew.so"), mode=C.RTLD_GLOBAL)
+
+
+def build_stubs(so=SO, out=STUB_DIR):
+    import re
+    import subprocess
+    os.makedirs(out, exist_ok=True)
+    for lib in _SYSTEM:
+        C.CDLL(lib, mode=C.RTLD_GLOBAL)
+    me = C.CDLL(None)
+    funcs, objs = [], []
+    for line in subprocess.run(["readelf", "--dyn-syms", "-W", so], capture_output=True, text=True, check=True).stdout.splitlines():
+        p = line.split()
+        if len(p) < 8 or p[6] != "UND" or p[4] == "WEAK":
+            continue
+        name = p[7].split("@")[0]
+        if hasattr(me, name):
+            continue  # the process already provides it (libc, libm, libstdc++ ...)
+        (objs if p[3] == "OBJECT" else funcs).append(name)
+    with open(os.path.join(out, "stub.s"), "w") as f:
+        f.write(".text\nrefstub_fn:\n xorl %eax,%eax\n ret\n")
+        for n in funcs:
+            f.write(".globl %s\n.type %s,@function\n.set %s, refstub_fn\n" % (n, n, n))
+        f.write(".data\n.align 64\n")
+        for n in objs:
+            f.write(".globl %s\n.type %s,@object\n.size %s,1024\n%s:\n .zero 1024\n" % (n, n, n, n))
+        f.write('.section .note.GNU-stack,"",@progbits\n')
+    open(os.path.join(out, "empty.c"), "w").write("")
+    dyn = subprocess.run(["readelf", "-d", so], capture_output=True, text=True, check=True).stdout
+    needed = [l.split("[")[1].rstrip("]") for l in dyn.splitlines() if "(NEEDED)" in l]
+    needed = [n for n in needed if not re.match(r"lib(stdc\+\+|m|gcc_s|pthread|c)\.so", n)]
+    subprocess.check_call(["gcc", "-shared", "-o", os.path.join(out, "librefstub.so"), os.path.join(out, "stub.s"),
+                           "-Wl,-soname,librefstub.so"])
+    for n in needed:
+        subprocess.check_call(["gcc", "-shared", "-o", os.path.join(out, n), os.path.join(out, "empty.c"), "-Wl,-soname," + n])
+    return needed
+
+
+class RefLibrary:
+    """lib/libORB_SLAM2.so dlopen'ed over the stubs; call build_stubs() first (make_golden does)."""
+
+    KP = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"),
+                   ("class_id", "<i4")])
+
+    def __init__(self, so=SO, monotonic_new=True):
+        if monotonic_new:
+            self._bump = load_monotonic_new()
+        needed = build_stubs(so)
+        C.CDLL(os.path.join(STUB_DIR, "librefstub.so"), mode=C.RTLD_GLOBAL)
+        for n in needed:
+            C.CDLL(os.path.join(STUB_DIR, n), mode=C.RTLD_GLOBAL)
+        self.lib = C.CDLL(so, mode=C.RTLD_GLOBAL)
+        self._ctor = getattr(self.lib, "_ZN9ORB_SLAM212ORBextractorC1Eifiii")
+        self._ctor.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        self._ctor.restype = None
+        self._dist = getattr(self.lib, "_ZN9ORB_SLAM212ORBextractor17DistributeOctTreeERKSt6vectorIN2cv8KeyPointESaIS3_EERKiS9_S9_S9_S9_S9_")
+        self._dist.argtypes = [C.c_void_p] * 9
+        self._dist.restype = C.c_void_p
+
+    @staticmethod
+    def _vec(buf, off, dtype):
+        b, e = buf[off // 8], buf[off // 8 + 1]
+        n = (e - b) // np.dtype(dtype).itemsize
+        return np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint8)), ((e - b),)).view(dtype)[:n].copy() if n else np.empty(0, dtype)
+
+    def extractor(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        """Runs the reference constructor; returns (object memory, tables).  Layout from include/ORBextractor.h:85-110:
+        mvImagePyramid @0, pattern @0x18, nfeatures @0x30, scaleFactor (double) @0x38, nlevels @0x40, iniThFAST @0x44,
+        minThFAST @0x48, mnFeaturesPerLevel @0x50, umax @0x68, mvScaleFactor @0x80, mvInvScaleFactor @0x98, mvLevelSigma2 @0xb0,
+        mvInvLevelSigma2 @0xc8."""
+        obj = (C.c_uint64 * 64)()
+        self._ctor(C.addressof(obj), nfeatures, scale_factor, nlevels, ini_th, min_th)
+        t = dict(quota=self._vec(obj, 0x50, np.int32), umax=self._vec(obj, 0x68, np.int32), scale=self._vec(obj, 0x80, np.float32),
+                 inv_scale=self._vec(obj, 0x98, np.float32), sigma2=self._vec(obj, 0xb0, np.float32),
+                 inv_sigma2=self._vec(obj, 0xc8, np.float32), pattern=self._vec(obj, 0x18, np.int32).reshape(-1, 2),
+                 nfeatures=int(np.frombuffer(obj, np.int32, 1, 0x30)[0]), scale_factor=float(np.frombuffer(obj, np.float64, 1, 0x38)[0]),
+                 nlevels=int(np.frombuffer(obj, np.int32, 1, 0x40)[0]))
+        return obj, t
+
+    def distribute(self, obj, xyr, minX, maxX, minY, maxY, N, level=0):
+        """ORBextractor::DistributeOctTree on (x, y, response) rows; returns the input indices in output order."""
+        xyr = np.asarray(xyr)
+        keys = np.zeros(len(xyr), self.KP)
+        keys["x"], keys["y"], keys["response"] = xyr[:, 0], xyr[:, 1], xyr[:, 2]
+        keys["size"], keys["angle"], keys["class_id"] = 7, -1, np.arange(len(xyr))
+        vec = (C.c_uint64 * 3)(keys.ctypes.data, keys.ctypes.data + keys.nbytes, keys.ctypes.data + keys.nbytes)
+        ret = (C.c_uint64 * 3)()
+        ints = [C.c_int(v) for v in (minX, maxX, minY, maxY, N, level)]
+        self._dist(C.addressof(ret), C.addressof(obj), C.addressof(vec), *[C.addressof(i) for i in ints])
+        n = (ret[1] - ret[0]) // 28
+        out = np.ctypeslib.as_array(C.cast(ret[0], C.POINTER(C.c_uint8)), (n * 28,)).view(self.KP).copy() if n else np.empty(0, self.KP)
+        return out["class_id"].astype(np.int32), out

@@ -119,3 +119,22 @@ def test_reference_machine_code_still_gives_the_golden_answers():
     r = RefCode()
     assert [r.descriptor_distance(a, b) for a, b in zip(g["dd_a"][:20], g["dd_b"][:20])] == list(g["dd_out"][:20])
     assert [r.radius_by_viewing_cos(float(v)) for v in g["radius_in"][:9]] == list(g["radius_out"][:9])
+
+
+def test_oracle_equals_the_loaded_reference_library(oracle):
+    """tests/golden/reference_library.npz: outputs of lib/libORB_SLAM2.so itself (dlopen'ed over stub dependencies by
+    tests/golden/reference_code.py) — ORBextractor's constructor tables and ORBextractor::DistributeOctTree, the latter under a
+    monotonic allocator (its pair<int, ExtractorNode*> sort breaks ties by pointer value; allocation order is the instance
+    the oracle restates)."""
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    for k, pr in enumerate(g["ctor_params"]):
+        o = oracle.OrbOracle(int(pr[0]), float(pr[1]), int(pr[2]), int(pr[3]), int(pr[4]))
+        t = o.tables()
+        for name in ("quota", "scale", "inv_scale", "sigma2", "inv_sigma2", "umax"):
+            assert np.array_equal(t[name], g["ctor%d_%s" % (k, name)]), (k, name)
+        assert np.array_equal(np.asarray(oracle.orb_pattern(), np.int32).reshape(-1, 2)[:512], g["ctor%d_pattern" % k])
+    o = oracle.OrbOracle()
+    for k in range(int(g["qt_n"])):
+        x0, x1, y0, y1, N = (int(v) for v in g["qt%d_args" % k])
+        got = o.distribute(g["qt%d_in" % k], x0, x1, y0, y1, N)
+        assert np.array_equal(got, g["qt%d_out" % k]), "quad-tree case %d" % k
