@@ -154,9 +154,25 @@ def reflib():
         out["qt%d_in" % k] = np.ascontiguousarray(c, np.int32)
         out["qt%d_args" % k] = np.array([x0, x1, y0, y1, N], np.int32)
         out["qt%d_out" % k] = idx
+    # ORBextractor::ComputeKeyPointsOctTree + computeOrientation, run from the reference library on the oracle's pyramid levels
+    # of small frames (cv::FAST / cv::fastAtan2 supplied by the cv2-pinned shims of reference_code.py).  The fixture keeps the
+    # input FRAME (the pyramid is rebuilt by the oracle at test time) and the reference's per-level keypoints.
+    ck = []
+    for k, (seed, W, H, nf) in enumerate([(3, 320, 240, 500), (11, 400, 304, 1000), (12, 256, 200, 300)]):
+        img = synth_frame(seed, W, H)
+        oo = orb.OrbOracle(nf)
+        oo.extract(img)
+        obj, t = R.extractor(nf)
+        ref = R.compute_keypoints_oct_tree(obj, [oo.level(l) for l in range(8)])
+        out["ck%d_img" % k] = img
+        out["ck%d_nf" % k] = np.array(nf)
+        out["ck%d_counts" % k] = np.array([len(r) for r in ref], np.int32)
+        out["ck%d_kps" % k] = np.concatenate(ref)
+        ck.append(int(sum(len(r) for r in ref)))
+    out["ck_n"] = np.array(len(ck))
     np.savez_compressed(os.path.join(HERE, "reference_library.npz"), **out)
-    print("reference_library.npz: %d constructor tables, %d quad-tree cases, outputs of sizes %s"
-          % (len(params), len(cases), [len(out["qt%d_out" % k]) for k in range(len(cases))]))
+    print("reference_library.npz: %d constructor tables, %d quad-tree cases, outputs of sizes %s; ComputeKeyPointsOctTree on %d frames: %s keypoints"
+          % (len(params), len(cases), [len(out["qt%d_out" % k]) for k in range(len(cases))], len(ck), ck))
 
 
 def tum_io():

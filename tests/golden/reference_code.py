@@ -133,6 +133,100 @@ def load_monotonic_new(out=STUB_DIR):
     return C.CDLL(os.path.join(out, "libbumpnew.so"), mode=C.RTLD_GLOBAL)
 
 
+CVSHIM_CC = r"""
+// ABI-exact stand-ins for the five OpenCV 3.3 entry points ORBextractor::ComputeKeyPointsOctTree / computeOrientation call
+// (objdump of 0x75fa0-0x76da0 and 0x6fb10-0x70383): the sub-matrix constructor, cv::FAST, cv::fastAtan2 and the two release
+// helpers.  FAST and fastAtan2 are the oracle's restatements, which are pinned bit for bit against cv2 4.13
+// (tests/test_oracle_cv2.py, tests/golden/cv2_primitives.npz).  Symbol names are given literally, no OpenCV header exists here.
+#include <climits>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <new>
+extern "C" int oracle_fast9(const uint8_t* img, int w, int h, int step, int th, int* out, int cap);
+extern "C" float oracle_fast_atan2(float y, float x);
+namespace {
+struct Range { int start, end; };
+struct Mat {  // cv::Mat of OpenCV 3.x, 96 bytes
+  int flags, dims, rows, cols;
+  uint8_t* data;
+  const uint8_t *datastart, *dataend, *datalimit;
+  void* allocator;
+  void* u;
+  int* sizep;
+  size_t* stepp;
+  size_t stepbuf[2];
+};
+static_assert(sizeof(Mat) == 96, "cv::Mat layout");
+struct KeyPoint { float x, y, size, angle, response; int octave, class_id; };
+struct InputArray { int flags; void* obj; int w, h; };
+struct KpVector { KeyPoint *b, *e, *c; };
+const int CONTINUOUS_FLAG = 1 << 14, SUBMATRIX_FLAG = 1 << 15;
+}
+extern "C" {
+void shim_fastFree(void*) asm("_ZN2cv8fastFreeEPv");
+void shim_fastFree(void*) {}
+void shim_deallocate(Mat*) asm("_ZN2cv3Mat10deallocateEv");
+void shim_deallocate(Mat*) {}
+// Mat::Mat(const Mat& m, const Range& rowRange, const Range& colRange), 2-D case
+void shim_mat_ranges(Mat* self, const Mat* m, const Range* rr, const Range* cr) asm("_ZN2cv3MatC1ERKS0_RKNS_5RangeES5_");
+void shim_mat_ranges(Mat* self, const Mat* m, const Range* rr, const Range* cr) {
+  *self = *m;
+  self->sizep = &self->rows;
+  self->stepp = self->stepbuf;
+  self->stepbuf[0] = m->stepp[0];
+  self->stepbuf[1] = m->stepp[1];
+  const bool allR = rr->start == INT_MIN && rr->end == INT_MAX, allC = cr->start == INT_MIN && cr->end == INT_MAX;
+  if (!allR) {
+    self->rows = rr->end - rr->start;
+    self->data += self->stepbuf[0] * (size_t)rr->start;
+    self->flags |= SUBMATRIX_FLAG;
+  }
+  if (!allC) {
+    self->cols = cr->end - cr->start;
+    self->data += (size_t)cr->start * self->stepbuf[1];
+    if (self->cols < m->cols) self->flags &= ~CONTINUOUS_FLAG;
+    self->flags |= SUBMATRIX_FLAG;
+  }
+  if (self->rows == 1) self->flags |= CONTINUOUS_FLAG;
+  if (self->rows <= 0 || self->cols <= 0) self->rows = self->cols = 0;
+}
+// void cv::FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression)
+void shim_FAST(const InputArray* img, KpVector* kps, int threshold, bool nonmax) asm("_ZN2cv4FASTERKNS_11_InputArrayERSt6vectorINS_8KeyPointESaIS4_EEib");
+void shim_FAST(const InputArray* img, KpVector* kps, int threshold, bool nonmax) {
+  const Mat* m = (const Mat*)img->obj;
+  (void)nonmax;  // the reference passes true at both call sites
+  const int cap = m->rows * m->cols + 1;
+  int* tmp = (int*)::operator new(sizeof(int) * 3 * (size_t)cap);
+  const int n = m->rows > 0 && m->cols > 0 ? oracle_fast9(m->data, m->cols, m->rows, (int)m->stepp[0], threshold, tmp, cap) : 0;
+  KeyPoint* out = (KeyPoint*)::operator new(sizeof(KeyPoint) * (size_t)(n ? n : 1));
+  for (int i = 0; i < n; ++i) out[i] = KeyPoint{(float)tmp[3 * i], (float)tmp[3 * i + 1], 7.f, -1.f, (float)tmp[3 * i + 2], 0, -1};
+  ::operator delete(tmp);
+  if (kps->b) ::operator delete(kps->b);
+  kps->b = out;
+  kps->e = out + n;
+  kps->c = out + (n ? n : 1);
+}
+float shim_fastAtan2(float y, float x) asm("_ZN2cv9fastAtan2Eff");
+float shim_fastAtan2(float y, float x) { return oracle_fast_atan2(y, x); }
+}
+"""
+
+
+def load_cv_shims(out=STUB_DIR):
+    """The five OpenCV entry points of ComputeKeyPointsOctTree, backed by the oracle's cv2-pinned primitives; loaded with
+    RTLD_GLOBAL before the generic stubs so that these definitions win."""
+    import subprocess
+    os.makedirs(out, exist_ok=True)
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    oracle_dir = os.path.join(root, "oracle", "_build")
+    src = os.path.join(out, "cvshim.cc")
+    open(src, "w").write(CVSHIM_CC)
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", os.path.join(out, "libcvshim.so"), src,
+                           "-L" + oracle_dir, "-loracle", "-Wl,-rpath," + oracle_dir])
+    return C.CDLL(os.path.join(out, "libcvshim.so"), mode=C.RTLD_GLOBAL)
+
+
 def build_stubs(so=SO, out=STUB_DIR):
     import re
     import subprocess
@@ -177,6 +271,7 @@ class RefLibrary:
     def __init__(self, so=SO, monotonic_new=True):
         if monotonic_new:
             self._bump = load_monotonic_new()
+        self._shims = load_cv_shims()
         needed = build_stubs(so)
         C.CDLL(os.path.join(STUB_DIR, "librefstub.so"), mode=C.RTLD_GLOBAL)
         for n in needed:
@@ -188,6 +283,9 @@ class RefLibrary:
         self._dist = getattr(self.lib, "_ZN9ORB_SLAM212ORBextractor17DistributeOctTreeERKSt6vectorIN2cv8KeyPointESaIS3_EERKiS9_S9_S9_S9_S9_")
         self._dist.argtypes = [C.c_void_p] * 9
         self._dist.restype = C.c_void_p
+        self._ckp = getattr(self.lib, "_ZN9ORB_SLAM212ORBextractor23ComputeKeyPointsOctTreeERSt6vectorIS1_IN2cv8KeyPointESaIS3_EESaIS5_EE")
+        self._ckp.argtypes = [C.c_void_p, C.c_void_p]
+        self._ckp.restype = None
 
     @staticmethod
     def _vec(buf, off, dtype):
@@ -222,3 +320,37 @@ class RefLibrary:
         n = (ret[1] - ret[0]) // 28
         out = np.ctypeslib.as_array(C.cast(ret[0], C.POINTER(C.c_uint8)), (n * 28,)).view(self.KP).copy() if n else np.empty(0, self.KP)
         return out["class_id"].astype(np.int32), out
+
+    def compute_keypoints_oct_tree(self, obj, level_images):
+        """ORBextractor::ComputeKeyPointsOctTree(allKeypoints) on a pyramid supplied by the caller (one contiguous uint8 image
+        per level, written into the object's mvImagePyramid as header-only cv::Mat).  cv::FAST / cv::fastAtan2 are the shims
+        above.  Returns one KeyPoint array per level: level coordinates, size, octave and IC angle as the reference sets them."""
+        mats_begin = obj[0]
+        keep = []
+        for l, img in enumerate(level_images):
+            img = np.ascontiguousarray(img, np.uint8)
+            keep.append(img)
+            m = (C.c_uint64 * 12).from_address(mats_begin + 96 * l)
+            base = mats_begin + 96 * l
+            m[0] = (2 << 32) | (0x42FF0000 | (1 << 14))
+            m[1] = (img.shape[1] << 32) | img.shape[0]
+            m[2] = img.ctypes.data
+            m[3] = img.ctypes.data
+            m[4] = img.ctypes.data + img.nbytes
+            m[5] = img.ctypes.data + img.nbytes
+            m[6] = 0
+            m[7] = 0
+            m[8] = base + 8
+            m[9] = base + 0x50
+            m[10] = img.strides[0]
+            m[11] = 1
+        allk = (C.c_uint64 * 3)()
+        self._ckp(C.addressof(obj), C.addressof(allk))
+        n = (allk[1] - allk[0]) // 24
+        out = []
+        for l in range(n):
+            v = (C.c_uint64 * 3).from_address(allk[0] + 24 * l)
+            cnt = (v[1] - v[0]) // 28
+            out.append(np.ctypeslib.as_array(C.cast(v[0], C.POINTER(C.c_uint8)), (cnt * 28,)).view(self.KP).copy() if cnt
+                       else np.empty(0, self.KP))
+        return out

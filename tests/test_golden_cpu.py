@@ -138,3 +138,23 @@ def test_oracle_equals_the_loaded_reference_library(oracle):
         x0, x1, y0, y1, N = (int(v) for v in g["qt%d_args" % k])
         got = o.distribute(g["qt%d_in" % k], x0, x1, y0, y1, N)
         assert np.array_equal(got, g["qt%d_out" % k]), "quad-tree case %d" % k
+
+
+def test_oracle_keypoints_equal_the_reference_compute_keypoints_oct_tree(oracle):
+    """ORBextractor::ComputeKeyPointsOctTree + computeOrientation executed from lib/libORB_SLAM2.so (fixture
+    reference_library.npz, ck*): cell grid, threshold retry, quad-tree, border offsets, patch size, octave and IC angle of
+    every keypoint, in the reference's order.  The oracle's final keypoints are those scaled by mvScaleFactor[level]
+    (operator() does `keypoint->pt *= scale` for level > 0, @0x77d10)."""
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    for k in range(int(g["ck_n"])):
+        o = oracle.OrbOracle(int(g["ck%d_nf" % k]))
+        kps, _ = o.extract(g["ck%d_img" % k])
+        scale = o.tables()["scale"]
+        ref, counts = g["ck%d_kps" % k], g["ck%d_counts" % k]
+        assert len(kps) == len(ref) == int(counts.sum()) > 100
+        assert np.array_equal(kps["octave"], ref["octave"])
+        assert np.array_equal(np.bincount(kps["octave"], minlength=8), counts)
+        s = scale[ref["octave"]]
+        for name, want in (("x", np.where(ref["octave"] > 0, ref["x"] * s, ref["x"])), ("y", np.where(ref["octave"] > 0, ref["y"] * s, ref["y"])),
+                           ("angle", ref["angle"]), ("response", ref["response"]), ("size", ref["size"])):
+            assert np.array_equal(kps[name].view(np.uint32), want.astype(np.float32).view(np.uint32)), (k, name)
