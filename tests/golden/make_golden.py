@@ -170,9 +170,24 @@ def reflib():
         out["ck%d_kps" % k] = np.concatenate(ref)
         ck.append(int(sum(len(r) for r in ref)))
     out["ck_n"] = np.array(len(ck))
+    # The whole ORBextractor::operator() (pyramid, key points, blur, rBRIEF, scaling), the reference's own code end to end.
+    # Small frames are stored; the standard sizes are named by their synth_frame arguments (plslam_b200/synth.py).
+    ex = []
+    for k, (seed, W, H, nf, store) in enumerate([(3, 320, 240, 500, True), (13, 333, 250, 1000, True), (12, 256, 200, 300, True),
+                                                 (0, 640, 480, 1000, False), (5, 640, 480, 1000, False), (40, 1280, 720, 2000, False)]):
+        img = synth_frame(seed, W, H)
+        obj, t = R.extractor(nf)
+        kps, desc = R.extract(obj, img)
+        out["ex%d_args" % k] = np.array([seed, W, H, nf], np.int32)
+        if store:
+            out["ex%d_img" % k] = img
+        out["ex%d_img_sha256" % k] = np.array(hashlib.sha256(img.tobytes()).hexdigest())
+        out["ex%d_kps" % k], out["ex%d_desc" % k] = kps, desc
+        ex.append(len(kps))
+    out["ex_n"] = np.array(len(ex))
     np.savez_compressed(os.path.join(HERE, "reference_library.npz"), **out)
-    print("reference_library.npz: %d constructor tables, %d quad-tree cases, outputs of sizes %s; ComputeKeyPointsOctTree on %d frames: %s keypoints"
-          % (len(params), len(cases), [len(out["qt%d_out" % k]) for k in range(len(cases))], len(ck), ck))
+    print("reference_library.npz: %d constructor tables, %d quad-tree cases, outputs of sizes %s; ComputeKeyPointsOctTree on %d frames: %s keypoints; operator() on %d frames: %s keypoints"
+          % (len(params), len(cases), [len(out["qt%d_out" % k]) for k in range(len(cases))], len(ck), ck, len(ex), ex))
 
 
 def tum_io():

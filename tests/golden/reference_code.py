@@ -143,6 +143,10 @@ CVSHIM_CC = r"""
 #include <cstdint>
 #include <cstring>
 #include <new>
+#include <cstdio>
+#include <cstdlib>
+static const bool g_trace = std::getenv("REFSHIM_TRACE") != nullptr;
+#define TRACE(...) do { if (g_trace) { std::fprintf(stderr, __VA_ARGS__); std::fputc(10, stderr); } } while (0)
 extern "C" int oracle_fast9(const uint8_t* img, int w, int h, int step, int th, int* out, int cap);
 extern "C" float oracle_fast_atan2(float y, float x);
 namespace {
@@ -171,6 +175,7 @@ void shim_deallocate(Mat*) {}
 // Mat::Mat(const Mat& m, const Range& rowRange, const Range& colRange), 2-D case
 void shim_mat_ranges(Mat* self, const Mat* m, const Range* rr, const Range* cr) asm("_ZN2cv3MatC1ERKS0_RKNS_5RangeES5_");
 void shim_mat_ranges(Mat* self, const Mat* m, const Range* rr, const Range* cr) {
+  TRACE("Mat(m, rows %d..%d, cols %d..%d) of %dx%d", rr->start, rr->end, cr->start, cr->end, m->rows, m->cols);
   *self = *m;
   self->sizep = &self->rows;
   self->stepp = self->stepbuf;
@@ -194,6 +199,7 @@ void shim_mat_ranges(Mat* self, const Mat* m, const Range* rr, const Range* cr) 
 // void cv::FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression)
 void shim_FAST(const InputArray* img, KpVector* kps, int threshold, bool nonmax) asm("_ZN2cv4FASTERKNS_11_InputArrayERSt6vectorINS_8KeyPointESaIS4_EEib");
 void shim_FAST(const InputArray* img, KpVector* kps, int threshold, bool nonmax) {
+  TRACE("FAST th %d", threshold);
   const Mat* m = (const Mat*)img->obj;
   (void)nonmax;  // the reference passes true at both call sites
   const int cap = m->rows * m->cols + 1;
@@ -209,6 +215,193 @@ void shim_FAST(const InputArray* img, KpVector* kps, int threshold, bool nonmax)
 }
 float shim_fastAtan2(float y, float x) asm("_ZN2cv9fastAtan2Eff");
 float shim_fastAtan2(float y, float x) { return oracle_fast_atan2(y, x); }
+
+// ---- the further entry points of ORBextractor::operator() (0x76da0-0x782ee) and ComputePyramid (0x70430-0x70c53) ----
+// Every Mat made here has u == NULL: the reference's inlined release() then never calls deallocate(), memory is simply
+// not returned (the process is a fixture generator).
+static const int MAGIC = 0x42FF0000, TYPE_MASK = 0xFFF, KIND_MASK = 31 << 16, KIND_MAT = 1 << 16;
+static void mat_init_empty(Mat* m) {
+  std::memset(m, 0, sizeof(Mat));
+  m->flags = MAGIC;
+  m->sizep = &m->rows;
+  m->stepp = m->stepbuf;
+}
+static void mat_create(Mat* m, int rows, int cols, int type) {
+  if (m->data && m->dims == 2 && (m->flags & TYPE_MASK) == type && m->rows == rows && m->cols == cols) return;
+  if (type != 0) __builtin_trap();  // only CV_8UC1 occurs on this path
+  mat_init_empty(m);
+  m->flags = MAGIC | CONTINUOUS_FLAG | type;
+  m->dims = 2;
+  m->rows = rows;
+  m->cols = cols;
+  m->stepbuf[0] = (size_t)cols;
+  m->stepbuf[1] = 1;
+  const size_t total = (size_t)rows * cols;
+  m->data = (uint8_t*)::operator new(total ? total : 1);
+  std::memset(m->data, 0, total);
+  m->datastart = m->data;
+  m->dataend = m->datalimit = m->data + total;
+}
+static Mat* arr_mat(const InputArray* a) { return (a->flags & KIND_MASK) == KIND_MAT ? (Mat*)a->obj : nullptr; }
+
+void shim_mat_dtor(Mat*) asm("_ZN2cv3MatD1Ev");
+void shim_mat_dtor(Mat*) {}
+void shim_copySize(Mat*, const Mat*) asm("_ZN2cv3Mat8copySizeERKS0_");
+void shim_copySize(Mat*, const Mat*) {}
+void shim_mat_create(Mat* m, int d, const int* sizes, int type) asm("_ZN2cv3Mat6createEiPKii");
+void shim_mat_create(Mat* m, int d, const int* sizes, int type) {
+  TRACE("Mat::create %d x %d type %d", sizes[0], sizes[1], type);
+  if (d != 2) __builtin_trap();
+  mat_create(m, sizes[0], sizes[1], type & TYPE_MASK);
+}
+struct Rect { int x, y, w, h; };
+void shim_mat_rect(Mat* self, const Mat* m, const Rect* r) asm("_ZN2cv3MatC1ERKS0_RKNS_5Rect_IiEE");
+void shim_mat_rect(Mat* self, const Mat* m, const Rect* r) {
+  TRACE("Mat(m, Rect %d %d %d %d) of %dx%d", r->x, r->y, r->w, r->h, m->rows, m->cols);
+  *self = *m;
+  self->sizep = &self->rows;
+  self->stepp = self->stepbuf;
+  self->stepbuf[0] = m->stepp[0];
+  self->stepbuf[1] = m->stepp[1];
+  self->rows = r->h;
+  self->cols = r->w;
+  self->data += (size_t)r->y * self->stepbuf[0] + (size_t)r->x * self->stepbuf[1];
+  if (r->w < m->cols) self->flags &= ~CONTINUOUS_FLAG;
+  if (r->h == 1) self->flags |= CONTINUOUS_FLAG;
+  if (r->w < m->cols || r->h < m->rows) self->flags |= SUBMATRIX_FLAG;
+  if (self->rows <= 0 || self->cols <= 0) self->rows = self->cols = 0;
+}
+int shim_kind(const InputArray* a) asm("_ZNK2cv11_InputArray4kindEv");
+int shim_kind(const InputArray* a) {
+  TRACE("kind() flags %x", a->flags); return a->flags & KIND_MASK; }
+bool shim_empty(const InputArray* a) asm("_ZNK2cv11_InputArray5emptyEv");
+bool shim_empty(const InputArray* a) {
+  TRACE("empty() flags %x", a->flags);
+  const Mat* m = arr_mat(a);
+  return !m || !m->data || m->rows == 0 || m->cols == 0;
+}
+void shim_getMat(Mat* ret, const InputArray* a, int idx) asm("_ZNK2cv11_InputArray7getMat_Ei");
+void shim_getMat(Mat* ret, const InputArray* a, int idx) {
+  TRACE("getMat_(%d) flags %x", idx, a->flags);
+  (void)idx;
+  const Mat* m = arr_mat(a);
+  if (!m) { mat_init_empty(ret); return; }
+  *ret = *m;
+  ret->sizep = &ret->rows;
+  ret->stepp = ret->stepbuf;
+  ret->stepbuf[0] = m->stepp[0];
+  ret->stepbuf[1] = m->stepp[1];
+}
+void shim_out_create(const InputArray* a, int rows, int cols, int type, int i, bool allowT, int mask) asm("_ZNK2cv12_OutputArray6createEiiiibi");
+void shim_out_create(const InputArray* a, int rows, int cols, int type, int i, bool allowT, int mask) {
+  TRACE("OutputArray::create %d x %d type %d", rows, cols, type);
+  (void)i; (void)allowT; (void)mask;
+  Mat* m = arr_mat(a);
+  if (!m) __builtin_trap();
+  mat_create(m, rows, cols, type & TYPE_MASK);
+}
+void shim_out_release(const InputArray* a) asm("_ZNK2cv12_OutputArray7releaseEv");
+void shim_out_release(const InputArray* a) {
+  TRACE("OutputArray::release");
+  Mat* m = arr_mat(a);
+  if (m) mat_init_empty(m);
+}
+void shim_copyTo(const Mat* src, const InputArray* dst) asm("_ZNK2cv3Mat6copyToERKNS_12_OutputArrayE");
+void shim_copyTo(const Mat* src, const InputArray* dst) {
+  TRACE("copyTo %dx%d", src->rows, src->cols);
+  Mat* d = arr_mat(dst);
+  if (!d) __builtin_trap();
+  mat_create(d, src->rows, src->cols, src->flags & TYPE_MASK);
+  if (d->data == src->data) return;
+  for (int r = 0; r < src->rows; ++r) std::memcpy(d->data + (size_t)r * d->stepp[0], src->data + (size_t)r * src->stepp[0], (size_t)src->cols);
+}
+extern "C" void oracle_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstep, uint8_t* dst, int dw, int dh, int dstep);
+extern "C" void oracle_blur7_u8(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep, const int* k);
+// void cv::resize(InputArray src, OutputArray dst, Size dsize, double fx, double fy, int interpolation).  cv::Size_ has a
+// user-provided copy constructor in OpenCV 3.x, so the Itanium ABI passes it by invisible reference: a pointer to {w, h}
+void shim_resize(const InputArray* src, const InputArray* dst, const int* dsize, double fx, double fy, int interp) asm("_ZN2cv6resizeERKNS_11_InputArrayERKNS_12_OutputArrayENS_5Size_IiEEddi");
+void shim_resize(const InputArray* src, const InputArray* dst, const int* dsize, double fx, double fy, int interp) {
+  TRACE("resize -> %d x %d interp %d", dsize[0], dsize[1], interp);
+  (void)fx; (void)fy;
+  if (interp != 1) __builtin_trap();  // INTER_LINEAR at the one call site (@0x70b07)
+  const Mat* s = arr_mat(src);
+  Mat* d = arr_mat(dst);
+  const int dw = dsize[0], dh = dsize[1];
+  mat_create(d, dh, dw, s->flags & TYPE_MASK);  // same size already: the level's view into its bordered buffer is kept
+  oracle_resize_linear_u8(s->data, s->cols, s->rows, (int)s->stepp[0], d->data, dw, dh, (int)d->stepp[0]);
+}
+static int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+  return p;
+}
+// void cv::copyMakeBorder(InputArray src, OutputArray dst, int top, int bottom, int left, int right, int borderType, const Scalar&)
+void shim_copyMakeBorder(const InputArray* src, const InputArray* dst, int top, int bottom, int left, int right, int borderType, const void* value)
+    asm("_ZN2cv14copyMakeBorderERKNS_11_InputArrayERKNS_12_OutputArrayEiiiiiRKNS_7Scalar_IdEE");
+void shim_copyMakeBorder(const InputArray* src, const InputArray* dst, int top, int bottom, int left, int right, int borderType, const void* value) {
+  TRACE("copyMakeBorder %d %d %d %d type %d", top, bottom, left, right, borderType);
+  (void)value;
+  if ((borderType & ~16) != 4) __builtin_trap();  // BORDER_REFLECT_101, optionally | BORDER_ISOLATED
+  const Mat s = *arr_mat(src);                    // header copy: dst may be the buffer src is a view of
+  const size_t sstep = arr_mat(src)->stepp[0];
+  Mat* d = arr_mat(dst);
+  mat_create(d, s.rows + top + bottom, s.cols + left + right, s.flags & TYPE_MASK);
+  const size_t dstep = d->stepp[0];
+  uint8_t* centre = d->data + (size_t)top * dstep + left;
+  if (centre != s.data)
+    for (int r = 0; r < s.rows; ++r) std::memmove(centre + (size_t)r * dstep, s.data + (size_t)r * sstep, (size_t)s.cols);
+  for (int r = 0; r < s.rows; ++r) {
+    uint8_t* row = centre + (size_t)r * dstep;
+    for (int c = -left; c < 0; ++c) row[c] = row[reflect101(c, s.cols)];
+    for (int c = s.cols; c < s.cols + right; ++c) row[c] = row[reflect101(c, s.cols)];
+  }
+  for (int r = -top; r < s.rows + bottom; ++r) {
+    if (r >= 0 && r < s.rows) continue;
+    std::memcpy(d->data + (size_t)(r + top) * dstep, d->data + (size_t)(reflect101(r, s.rows) + top) * dstep, (size_t)(s.cols + left + right));
+  }
+}
+// void cv::GaussianBlur(InputArray src, OutputArray dst, Size ksize, double sigmaX, double sigmaY, int borderType)
+void shim_GaussianBlur(const InputArray* src, const InputArray* dst, const int* ksize, double sx, double sy, int borderType)
+    asm("_ZN2cv12GaussianBlurERKNS_11_InputArrayERKNS_12_OutputArrayENS_5Size_IiEEddi");
+void shim_GaussianBlur(const InputArray* src, const InputArray* dst, const int* ksize, double sx, double sy, int borderType) {
+  TRACE("GaussianBlur ksize %d x %d sigma %g %g border %d", ksize[0], ksize[1], sx, sy, borderType);
+  if (ksize[0] != 7 || ksize[1] != 7 || sx != 2.0 || sy != 2.0 || borderType != 4) __builtin_trap();  // the one call (@0x77487)
+  const Mat* s = arr_mat(src);
+  Mat* d = arr_mat(dst);
+  static const int k[7] = {18, 34, 48, 56, 48, 34, 18};  // getGaussianKernel(7, 2) in 8-bit fixed point, pinned against cv2
+  const size_t n = (size_t)s->rows * s->cols;
+  uint8_t* tmp = (uint8_t*)::operator new(n ? n : 1);
+  for (int r = 0; r < s->rows; ++r) std::memcpy(tmp + (size_t)r * s->cols, s->data + (size_t)r * s->stepp[0], (size_t)s->cols);
+  const int rows = s->rows, cols = s->cols, type = s->flags & TYPE_MASK;
+  mat_create(d, rows, cols, type);
+  oracle_blur7_u8(tmp, cols, rows, cols, d->data, (int)d->stepp[0], k);
+  ::operator delete(tmp);
+}
+// MatExpr cv::Mat::zeros(int rows, int cols, int type) and the MatOp whose assign() the caller invokes through vtable slot 3
+struct MatExpr { const void* op; int flags; int pad; Mat a, b, c; double alpha, beta; double s[4]; };
+static_assert(sizeof(MatExpr) == 352 && offsetof(MatExpr, c) == 0xd0, "cv::MatExpr layout");
+static void op_dtor(void*) {}
+static bool op_elementwise(const void*, const MatExpr*) { return false; }
+static void op_assign(const void*, const MatExpr* e, Mat* m, int type) {
+  TRACE("MatOp::assign into %dx%d", m->rows, m->cols);
+  (void)type;
+  mat_create(m, (int)e->alpha, (int)e->beta, e->flags & TYPE_MASK);
+  for (int r = 0; r < m->rows; ++r) std::memset(m->data + (size_t)r * m->stepp[0], 0, (size_t)m->cols);
+}
+static const void* const op_vtable[4] = {(const void*)op_dtor, (const void*)op_dtor, (const void*)op_elementwise, (const void*)op_assign};
+static const void* const op_object[1] = {op_vtable};
+void shim_zeros(MatExpr* ret, int rows, int cols, int type) asm("_ZN2cv3Mat5zerosEiii");
+void shim_zeros(MatExpr* ret, int rows, int cols, int type) {
+  TRACE("Mat::zeros %d x %d type %d", rows, cols, type);
+  std::memset(ret, 0, sizeof(MatExpr));
+  ret->op = op_object;
+  ret->flags = type & TYPE_MASK;
+  mat_init_empty(&ret->a);
+  mat_init_empty(&ret->b);
+  mat_init_empty(&ret->c);
+  ret->alpha = rows;
+  ret->beta = cols;
+}
 }
 """
 
@@ -286,6 +479,9 @@ class RefLibrary:
         self._ckp = getattr(self.lib, "_ZN9ORB_SLAM212ORBextractor23ComputeKeyPointsOctTreeERSt6vectorIS1_IN2cv8KeyPointESaIS3_EESaIS5_EE")
         self._ckp.argtypes = [C.c_void_p, C.c_void_p]
         self._ckp.restype = None
+        self._call = getattr(self.lib, "_ZN9ORB_SLAM212ORBextractorclERKN2cv11_InputArrayES4_RSt6vectorINS1_8KeyPointESaIS6_EERKNS1_12_OutputArrayE")
+        self._call.argtypes = [C.c_void_p] * 5
+        self._call.restype = None
 
     @staticmethod
     def _vec(buf, off, dtype):
@@ -354,3 +550,25 @@ class RefLibrary:
             out.append(np.ctypeslib.as_array(C.cast(v[0], C.POINTER(C.c_uint8)), (cnt * 28,)).view(self.KP).copy() if cnt
                        else np.empty(0, self.KP))
         return out
+
+    def extract(self, obj, image):
+        """ORBextractor::operator()(image, cv::Mat(), keypoints, descriptors) as Frame::ExtractORB calls it (Frame.h:67):
+        the reference's own code from pyramid to descriptors, OpenCV entry points supplied by the shims above.
+        Returns (keypoints, descriptors [n, 32] uint8)."""
+        img, keep = self_mat = RefCode._mat(np.ascontiguousarray(image, np.uint8))
+        img[0] = (2 << 32) | (0x42FF0000 | (1 << 14))
+        empty = (C.c_uint64 * 12)()
+        empty[0] = 0x42FF0000
+        empty[8], empty[9] = C.addressof(empty) + 8, C.addressof(empty) + 0x50
+        desc = (C.c_uint64 * 12)()
+        desc[0] = 0x42FF0000
+        desc[8], desc[9] = C.addressof(desc) + 8, C.addressof(desc) + 0x50
+        arr = lambda flags, m: (C.c_uint64 * 3)(flags, C.addressof(m), 0)
+        a_img, a_mask, a_desc = arr(0x01010000, img), arr(0x01010000, empty), arr(0x02010000, desc)
+        kv = (C.c_uint64 * 3)()
+        self._call(C.addressof(obj), C.addressof(a_img), C.addressof(a_mask), C.addressof(kv), C.addressof(a_desc))
+        n = (kv[1] - kv[0]) // 28
+        kps = np.ctypeslib.as_array(C.cast(kv[0], C.POINTER(C.c_uint8)), (n * 28,)).view(self.KP).copy() if n else np.empty(0, self.KP)
+        rows, cols = desc[1] & 0xffffffff, desc[1] >> 32
+        d = np.ctypeslib.as_array(C.cast(desc[2], C.POINTER(C.c_uint8)), (rows * cols,)).reshape(rows, cols).copy() if rows else np.empty((0, 32), np.uint8)
+        return kps, d

@@ -158,3 +158,29 @@ def test_oracle_keypoints_equal_the_reference_compute_keypoints_oct_tree(oracle)
         for name, want in (("x", np.where(ref["octave"] > 0, ref["x"] * s, ref["x"])), ("y", np.where(ref["octave"] > 0, ref["y"] * s, ref["y"])),
                            ("angle", ref["angle"]), ("response", ref["response"]), ("size", ref["size"])):
             assert np.array_equal(kps[name].view(np.uint32), want.astype(np.float32).view(np.uint32)), (k, name)
+
+
+def _reference_extractions():
+    from plslam_b200.synth import synth_frame
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    for k in range(int(g["ex_n"])):
+        seed, W, H, nf = (int(v) for v in g["ex%d_args" % k])
+        img = g["ex%d_img" % k] if "ex%d_img" % k in g.files else synth_frame(seed, W, H)
+        assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == str(g["ex%d_img_sha256" % k])
+        yield k, nf, img, g["ex%d_kps" % k], g["ex%d_desc" % k]
+
+
+def test_oracle_equals_the_reference_orb_extractor_end_to_end(oracle):
+    """ORB_SLAM2::ORBextractor::operator() executed from lib/libORB_SLAM2.so — the reference's own code from pyramid to
+    descriptors, OpenCV entry points replaced by ABI-exact shims over the cv2-pinned primitives (tests/golden/
+    reference_code.py) — on six frames (256x200 ... 1280x720, nFeatures 300 ... 2000): every keypoint field and every
+    descriptor byte of the oracle is identical, in the same order."""
+    n = 0
+    for k, nf, img, kps, desc in _reference_extractions():
+        ok, od = oracle.OrbOracle(nf).extract(img)
+        assert len(ok) == len(kps) > 200, k
+        for f in kps.dtype.names:
+            assert np.array_equal(ok[f].view(np.uint32), kps[f].view(np.uint32)), (k, f)
+        assert np.array_equal(od, desc), k
+        n += 1
+    assert n == 6

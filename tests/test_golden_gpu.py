@@ -52,3 +52,29 @@ def test_undistort_against_cv2():
     b = pl.frame_image_bounds(cal, 640, 480)
     m = p["undist_out"][:4]  # the four image corners
     assert np.array_equal(b, np.array([min(m[0, 0], m[2, 0]), max(m[1, 0], m[3, 0]), min(m[0, 1], m[1, 1]), max(m[2, 1], m[3, 1])], np.float32))
+
+
+def test_orb_extractor_equals_the_reference_library():
+    """The CUDA ORBextractor against outputs of the reference's OWN code: ORB_SLAM2::ORBextractor::operator() executed from
+    lib/libORB_SLAM2.so in the build container (tests/golden/reference_code.py; fixture reference_library.npz, ex*).
+    Standard frame sizes only (640x480 nFeatures 1000, 1280x720 nFeatures 2000)."""
+    import hashlib
+    import plslam_b200 as pl
+    from plslam_b200.synth import synth_frame
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    done = 0
+    for k in range(int(g["ex_n"])):
+        seed, W, H, nf = (int(v) for v in g["ex%d_args" % k])
+        if (W, H) not in ((640, 480), (1280, 720)):
+            continue
+        img = synth_frame(seed, W, H)
+        assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == str(g["ex%d_img_sha256" % k])
+        kps, desc = pl.ORBextractor(nfeatures=nf)(img)
+        ref = g["ex%d_kps" % k]
+        assert len(kps) == len(ref)
+        for f in ("x", "y", "size", "response", "octave"):
+            assert np.array_equal(kps[f], ref[f]), (k, f)
+        assert np.abs(kps["angle"] - ref["angle"]).max() <= 1e-4 and np.array_equal(kps["angle"], ref["angle"]), k
+        assert np.array_equal(desc, g["ex%d_desc" % k]), k
+        done += 1
+    assert done == 3
