@@ -537,3 +537,16 @@ def search_for_triangulation(kf1, kf2, F12, ex, ey, scale_factors, level_sigma2,
         _p(b["has_mp"]), len(b["nodes"]), _p(b["nodes"]), _p(b["start"]), _p(b["idx"]), _p(sf), _p(sg), _p(F), ex, ey,
         int(only_stereo), int(check_ori), _p(m))
     return m[:n1], n
+
+
+def get_features_in_area(x, y, r, min_level, max_level, cam4, grid_start, grid_items, xy, octave):
+    """Frame::GetFeaturesInArea on a CSR grid -> candidate indices in the reference's order"""
+    L = lib()
+    L.oracle_get_features_in_area.argtypes = [C.c_float] * 3 + [C.c_int] * 2 + [C.c_void_p] * 5 + [C.c_void_p, C.c_int]
+    cam = np.ascontiguousarray(cam4, np.float32)
+    gs, gi = np.ascontiguousarray(grid_start, np.int32), np.ascontiguousarray(grid_items, np.int32)
+    xy, octv = np.ascontiguousarray(xy, np.float32), np.ascontiguousarray(octave, np.int32)
+    out = np.empty(max(len(octv), 1), np.int32)
+    n = L.oracle_get_features_in_area(float(x), float(y), float(r), int(min_level), int(max_level), _p(cam), _p(gs), _p(gi), _p(xy),
+                                      _p(octv), _p(out), len(out))
+    return out[:n].copy()

@@ -55,6 +55,39 @@ void compute_three_maxima(const std::vector<int>* histo, int L, int& ind1, int& 
 // (tests/golden/reference_code.py).
 inline float radius_by_viewing_cos(float viewCos) { return (double)viewCos > 0.998 ? 2.5f : 4.0f; }
 
+// Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (include/Frame.h:113; machine code @0xfbc60): cell range by
+// floorf / ceilf of (x - mnMinX -/+ r) * mfGridElementWidthInv clamped to the 64 x 48 grid (@0xfbcc0-0xfbdd4), cells walked
+// [ix][iy], items in insertion order; level filter when minLevel > 0 or maxLevel >= 0 (@0xfbdda-0xfbdf9, @0xfc05d-0xfc06d);
+// a feature is a candidate when |dx| < r and |dy| < r (@0xfbf87-0xfbfb9).  Calls f(index) for each candidate in the
+// reference's order.  Pinned by running the reference's own function (tests/golden/reference_code.py).
+template <class F>
+inline void for_features_in_area(float x, float y, float r, int minLevel, int maxLevel, float mnMinX, float mnMinY, float gwi,
+                                 float ghi, const int* gridStart, const int* gridItems, const float* xy, const int* octave, F&& f) {
+  const int nMinCellX = std::max(0, (int)floorf((x - mnMinX - r) * gwi));
+  if (nMinCellX >= FRAME_GRID_COLS) return;
+  const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceilf((x - mnMinX + r) * gwi));
+  if (nMaxCellX < 0) return;
+  const int nMinCellY = std::max(0, (int)floorf((y - mnMinY - r) * ghi));
+  if (nMinCellY >= FRAME_GRID_ROWS) return;
+  const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceilf((y - mnMinY + r) * ghi));
+  if (nMaxCellY < 0) return;
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+    for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+      const int c = ix * FRAME_GRID_ROWS + iy;
+      for (int j = gridStart[c]; j < gridStart[c + 1]; ++j) {
+        const int i2 = gridItems[j];
+        if (bCheckLevels) {
+          if (octave[i2] < minLevel) continue;
+          if (maxLevel >= 0 && octave[i2] > maxLevel) continue;
+        }
+        const float distx = xy[2 * i2] - x, disty = xy[2 * i2 + 1] - y;
+        if (!(fabsf(distx) < r && fabsf(disty) < r)) continue;
+        f(i2);
+      }
+    }
+}
+
 inline int rot_bin(float a1, float a2) {
   const float factor = (float)HISTO_LENGTH / 360.0f;  // 0.0833333 @0x1269f8
   float rot = a1 - a2;
@@ -70,6 +103,17 @@ extern "C" {
 
 int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
 float oracle_radius_by_viewing_cos(float v) { return radius_by_viewing_cos(v); }
+// Frame::GetFeaturesInArea on a CSR grid; cam4 = mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv.  Returns the
+// number of candidates, the first `cap` of them in out.
+int oracle_get_features_in_area(float x, float y, float r, int minLevel, int maxLevel, const float* cam4, const int* gridStart,
+                                const int* gridItems, const float* xy, const int* octave, int* out, int cap) {
+  int n = 0;
+  for_features_in_area(x, y, r, minLevel, maxLevel, cam4[0], cam4[1], cam4[2], cam4[3], gridStart, gridItems, xy, octave, [&](int i) {
+    if (n < cap) out[n] = i;
+    ++n;
+  });
+  return n;
+}
 // ComputeThreeMaxima on bin populations; out3 must hold the caller's initial values (-1 in every reference call site)
 void oracle_three_maxima(const int* sizes, int L, int* out3) {
   std::vector<std::vector<int>> h(L);
@@ -198,39 +242,17 @@ int oracle_search_by_projection(int N1, const uint8_t* lastValid, const float* l
     if (bForward) { minLevel = nLastOctave; maxLevel = -1; }
     else if (bBackward) { minLevel = 0; maxLevel = nLastOctave; }
     else { minLevel = nLastOctave - 1; maxLevel = nLastOctave + 1; }
-    // Frame::GetFeaturesInArea(u, v, radius, minLevel, maxLevel)
-    const int nMinCellX = std::max(0, (int)floorf((u - mnMinX - radius) * gwi));
-    if (nMinCellX >= FRAME_GRID_COLS) continue;
-    const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceilf((u - mnMinX + radius) * gwi));
-    if (nMaxCellX < 0) continue;
-    const int nMinCellY = std::max(0, (int)floorf((v - mnMinY - radius) * ghi));
-    if (nMinCellY >= FRAME_GRID_ROWS) continue;
-    const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceilf((v - mnMinY + radius) * ghi));
-    if (nMaxCellY < 0) continue;
-    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
     int bestDist = 256, bestIdx2 = -1;
-    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
-      for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
-        const int c = ix * FRAME_GRID_ROWS + iy;
-        for (int j = gridStart[c]; j < gridStart[c + 1]; ++j) {
-          const int i2 = gridItems[j];
-          if (bCheckLevels) {
-            if (curOctave[i2] < minLevel) continue;
-            if (maxLevel >= 0 && curOctave[i2] > maxLevel) continue;
-          }
-          const float distx = curXY[2 * i2] - u, disty = curXY[2 * i2 + 1] - v;
-          if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
-          // candidate i2
-          if (taken[i2]) continue;
-          if (curURight[i2] > 0) {
-            const float ur = u - mbf * invzc;
-            const float er = fabsf(ur - curURight[i2]);
-            if (er > radius) continue;
-          }
-          const int dist = descriptor_distance(lastDesc + 32 * i, curDesc + 32 * i2);
-          if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
-        }
+    for_features_in_area(u, v, radius, minLevel, maxLevel, mnMinX, mnMinY, gwi, ghi, gridStart, gridItems, curXY, curOctave, [&](int i2) {
+      if (taken[i2]) return;
+      if (curURight[i2] > 0) {
+        const float ur = u - mbf * invzc;
+        const float er = fabsf(ur - curURight[i2]);
+        if (er > radius) return;
       }
+      const int dist = descriptor_distance(lastDesc + 32 * i, curDesc + 32 * i2);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    });
     if (bestDist <= TH_HIGH) {
       matchCur[bestIdx2] = i;
       if (lastObs[i]) taken[bestIdx2] = 1;
@@ -277,45 +299,25 @@ int oracle_search_local_points(int M, const uint8_t* mpValid, const float* mpPro
     const float x = mpProj[3 * iMP], y = mpProj[3 * iMP + 1], xr = mpProj[3 * iMP + 2];
     const float radius = r * scaleFactors[nPredictedLevel];
     const int minLevel = nPredictedLevel - 1, maxLevel = nPredictedLevel;
-    const int nMinCellX = std::max(0, (int)floorf((x - mnMinX - radius) * gwi));
-    if (nMinCellX >= FRAME_GRID_COLS) continue;
-    const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceilf((x - mnMinX + radius) * gwi));
-    if (nMaxCellX < 0) continue;
-    const int nMinCellY = std::max(0, (int)floorf((y - mnMinY - radius) * ghi));
-    if (nMinCellY >= FRAME_GRID_ROWS) continue;
-    const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceilf((y - mnMinY + radius) * ghi));
-    if (nMaxCellY < 0) continue;
-    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
     int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
-      for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
-        const int c = ix * FRAME_GRID_ROWS + iy;
-        for (int j = gridStart[c]; j < gridStart[c + 1]; ++j) {
-          const int idx = gridItems[j];
-          if (bCheckLevels) {
-            if (fOctave[idx] < minLevel) continue;
-            if (maxLevel >= 0 && fOctave[idx] > maxLevel) continue;
-          }
-          const float distx = fXY[2 * idx] - x, disty = fXY[2 * idx + 1] - y;
-          if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
-          if (taken[idx]) continue;
-          if (fURight[idx] > 0) {
-            const float er = fabsf(xr - fURight[idx]);
-            if (er > radius) continue;
-          }
-          const int dist = descriptor_distance(mpDesc + 32 * iMP, fDesc + 32 * idx);
-          if (dist < bestDist) {
-            bestDist2 = bestDist;
-            bestDist = dist;
-            bestLevel2 = bestLevel;
-            bestLevel = fOctave[idx];
-            bestIdx = idx;
-          } else if (dist < bestDist2) {
-            bestLevel2 = fOctave[idx];
-            bestDist2 = dist;
-          }
-        }
+    for_features_in_area(x, y, radius, minLevel, maxLevel, mnMinX, mnMinY, gwi, ghi, gridStart, gridItems, fXY, fOctave, [&](int idx) {
+      if (taken[idx]) return;
+      if (fURight[idx] > 0) {
+        const float er = fabsf(xr - fURight[idx]);
+        if (er > radius) return;
       }
+      const int dist = descriptor_distance(mpDesc + 32 * iMP, fDesc + 32 * idx);
+      if (dist < bestDist) {
+        bestDist2 = bestDist;
+        bestDist = dist;
+        bestLevel2 = bestLevel;
+        bestLevel = fOctave[idx];
+        bestIdx = idx;
+      } else if (dist < bestDist2) {
+        bestLevel2 = fOctave[idx];
+        bestDist2 = dist;
+      }
+    });
     if (bestDist <= TH_HIGH) {
       if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
       matchF[bestIdx] = iMP;

@@ -185,9 +185,24 @@ def reflib():
         out["ex%d_kps" % k], out["ex%d_desc" % k] = kps, desc
         ex.append(len(kps))
     out["ex_n"] = np.array(len(ex))
+    # Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea on a faked Frame (the reference's own grid and window search)
+    kps, _ = orb.OrbOracle().extract(synth_frame(2))
+    kps = kps.copy()
+    kps["x"] += rng.uniform(-45, 45, len(kps)).astype(np.float32)   # some keypoints fall outside the grid bounds
+    kps["y"] += rng.uniform(-45, 45, len(kps)).astype(np.float32)
+    bounds = (-11.5, 651.25, -9.75, 489.5)                           # undistorted-image bounds need not be integers
+    q = [(rng.uniform(-40, 700), rng.uniform(-40, 520), rng.uniform(1, 90), int(rng.integers(-1, 8)), int(rng.integers(-1, 8)))
+         for _ in range(600)]
+    q += [(x, y, r, -1, -1) for x in (-11.5, 0, 10.35, 651.25, 700) for y in (-9.75, 0, 489.5) for r in (0.5, 10.4, 100)]
+    start, items, res = R.frame_grid_queries(kps, bounds, q)
+    out["fg_kps"], out["fg_bounds"], out["fg_queries"] = kps, np.array(bounds, np.float32), np.array(q, np.float64)
+    out["fg_start"], out["fg_items"] = start, items
+    out["fg_res_len"] = np.array([len(r) for r in res], np.int32)
+    out["fg_res"] = np.concatenate(res).astype(np.int32)
     np.savez_compressed(os.path.join(HERE, "reference_library.npz"), **out)
-    print("reference_library.npz: %d constructor tables, %d quad-tree cases, outputs of sizes %s; ComputeKeyPointsOctTree on %d frames: %s keypoints; operator() on %d frames: %s keypoints"
-          % (len(params), len(cases), [len(out["qt%d_out" % k]) for k in range(len(cases))], len(ck), ck, len(ex), ex))
+    print("reference_library.npz: %d constructor tables, %d quad-tree cases, outputs of sizes %s; ComputeKeyPointsOctTree on %d frames: %s keypoints; operator() on %d frames: %s keypoints; grid of %d keypoints (%d inside), %d window queries with %d candidates"
+          % (len(params), len(cases), [len(out["qt%d_out" % k]) for k in range(len(cases))], len(ck), ck, len(ex), ex, len(kps),
+             len(items), len(q), len(out["fg_res"])))
 
 
 def tum_io():

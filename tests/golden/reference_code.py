@@ -572,3 +572,43 @@ class RefLibrary:
         rows, cols = desc[1] & 0xffffffff, desc[1] >> 32
         d = np.ctypeslib.as_array(C.cast(desc[2], C.POINTER(C.c_uint8)), (rows * cols,)).reshape(rows, cols).copy() if rows else np.empty((0, 32), np.uint8)
         return kps, d
+
+    # ---- Frame::AssignFeaturesToGrid (@0xf9120), Frame::PosInGrid (@0xf5fa0), Frame::GetFeaturesInArea (@0xfbc60) ----
+    # A Frame is faked as zeroed memory with the three members these functions read: N @0xec, mvKeysUn @0x120 (vector of
+    # 28-byte cv::KeyPoint), mGrid @0x2c8 (std::vector<size_t>[64][48]); offsets from the disassembly of GetFeaturesInArea.
+    def frame_grid_queries(self, kps_un, bounds, queries):
+        """bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY); queries = rows (x, y, r, minLevel, maxLevel).
+        Returns (grid CSR start [64*48+1], items, [candidate index arrays per query])."""
+        f32 = np.float32
+        st = lambda name: C.c_float.in_dll(self.lib, name)
+        minX, maxX, minY, maxY = (f32(v) for v in bounds)
+        st("_ZN9ORB_SLAM25Frame6mnMinXE").value, st("_ZN9ORB_SLAM25Frame6mnMaxXE").value = minX, maxX
+        st("_ZN9ORB_SLAM25Frame6mnMinYE").value, st("_ZN9ORB_SLAM25Frame6mnMaxYE").value = minY, maxY
+        st("_ZN9ORB_SLAM25Frame21mfGridElementWidthInvE").value = f32(64.0) / (maxX - minX)    # Frame ctor, @0xfa2e8
+        st("_ZN9ORB_SLAM25Frame22mfGridElementHeightInvE").value = f32(48.0) / (maxY - minY)
+        keys = np.ascontiguousarray(kps_un, self.KP)
+        frame = (C.c_uint64 * (0x13000 // 8))()
+        base = C.addressof(frame)
+        C.c_int32.from_address(base + 0xec).value = len(keys)
+        frame[0x120 // 8], frame[0x128 // 8], frame[0x130 // 8] = keys.ctypes.data, keys.ctypes.data + keys.nbytes, keys.ctypes.data + keys.nbytes
+        assign = getattr(self.lib, "_ZN9ORB_SLAM25Frame20AssignFeaturesToGridEv")
+        assign.argtypes, assign.restype = [C.c_void_p], None
+        assign(base)
+        start, items = np.zeros(64 * 48 + 1, np.int32), []
+        for c in range(64 * 48):
+            b, e = frame[(0x2c8 + 24 * c) // 8], frame[(0x2c8 + 24 * c) // 8 + 1]
+            n = (e - b) // 8
+            if n:
+                items += list(np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint64)), (n,)))
+            start[c + 1] = len(items)
+        area = getattr(self.lib, "_ZNK9ORB_SLAM25Frame17GetFeaturesInAreaERKfS2_S2_ii")
+        area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        area.restype = C.c_void_p
+        res = []
+        for x, y, r, lo, hi in queries:
+            ret = (C.c_uint64 * 3)()
+            fx, fy, fr = C.c_float(x), C.c_float(y), C.c_float(r)
+            area(C.addressof(ret), base, C.addressof(fx), C.addressof(fy), C.addressof(fr), int(lo), int(hi))
+            n = (ret[1] - ret[0]) // 8
+            res.append(np.ctypeslib.as_array(C.cast(ret[0], C.POINTER(C.c_uint64)), (n,)).astype(np.int32) if n else np.empty(0, np.int32))
+        return start, np.array(items, np.int32), res

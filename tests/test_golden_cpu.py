@@ -184,3 +184,24 @@ def test_oracle_equals_the_reference_orb_extractor_end_to_end(oracle):
         assert np.array_equal(od, desc), k
         n += 1
     assert n == 6
+
+
+def test_grid_and_window_search_equal_the_reference_frame_code(oracle):
+    """Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea executed from lib/libORB_SLAM2.so on a faked Frame
+    (fixture reference_library.npz, fg*): the oracle's grid (frame_oracle.cc) and its window search (the function both
+    SearchByProjection restatements use) reproduce the reference's cells and candidate lists, order included."""
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    kps, b = g["fg_kps"], g["fg_bounds"]
+    xy = np.stack([kps["x"], kps["y"]], 1).astype(np.float32)
+    calib = dict(fx=500.0, fy=500.0, cx=320.0, cy=240.0, k1=0.0, k2=0.0, p1=0.0, p2=0.0, k3=0.0, bf=40.0)  # k1 == 0: no undistortion
+    fp = oracle.frame_post(calib, np.array([b[0], b[1], b[2], b[3]], np.float32), xy, np.zeros((480, 640), np.float32))
+    assert np.array_equal(fp["grid_start"], g["fg_start"]) and np.array_equal(fp["grid_items"], g["fg_items"])
+    assert 0 < len(g["fg_items"]) < len(kps)  # some keypoints lie outside the bounds and are in no cell
+    cam4 = np.array([b[0], b[2], np.float32(64.0) / (b[1] - b[0]), np.float32(48.0) / (b[3] - b[2])], np.float32)
+    off = np.concatenate([[0], np.cumsum(g["fg_res_len"])])
+    octave = kps["octave"].astype(np.int32)
+    for k, (x, y, r, lo, hi) in enumerate(g["fg_queries"]):
+        got = oracle.get_features_in_area(np.float32(x), np.float32(y), np.float32(r), int(lo), int(hi), cam4, g["fg_start"],
+                                          g["fg_items"], xy, octave)
+        assert np.array_equal(got, g["fg_res"][off[k]:off[k + 1]]), (k, x, y, r, lo, hi)
+    assert int(g["fg_res_len"].sum()) > 3000
