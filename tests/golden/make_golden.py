@@ -185,6 +185,26 @@ def reflib():
         out["ex%d_kps" % k], out["ex%d_desc" % k] = kps, desc
         ex.append(len(kps))
     out["ex_n"] = np.array(len(ex))
+    # ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) — the local-map search — on faked Frame / MapPoint
+    # objects; inputs are rebuilt at test time from the same seeds (tests/matchdata.py: local_points_case)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from matchdata import local_points_case
+    from plslam_b200.synth import synth_pair
+    oo = orb.OrbOracle()
+    sf = oo.tables()["scale"]
+    lp = []
+    for seed in (1, 2):
+        a, b = synth_pair(seed)
+        (ka, da), (kb, db) = oo.extract(a), oo.extract(b)
+        for th, nnr, jit in ((1.0, 0.8, 2.0), (3.0, 0.8, 6.0), (1.0, 0.6, 1.0), (5.0, 0.9, 10.0)):
+            mpd, frd, cam4 = local_points_case(ka, da, kb, db, seed=10 * seed + int(th), jitter=jit)
+            m, n = R.search_local_points(mpd, frd, cam4, sf, th, nnr)
+            k = len(lp)
+            out["lp%d_args" % k] = np.array([seed, th, nnr, jit], np.float64)
+            out["lp%d_match" % k], out["lp%d_n" % k] = m, np.array(n)
+            lp.append(n)
+    out["lp_n"] = np.array(len(lp))
+    print("SearchByProjection(Frame&, MapPoints, th):", lp)
     # Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea on a faked Frame (the reference's own grid and window search)
     kps, _ = orb.OrbOracle().extract(synth_frame(2))
     kps = kps.copy()

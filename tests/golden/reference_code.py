@@ -612,3 +612,76 @@ class RefLibrary:
             n = (ret[1] - ret[0]) // 8
             res.append(np.ctypeslib.as_array(C.cast(ret[0], C.POINTER(C.c_uint64)), (n,)).astype(np.int32) if n else np.empty(0, np.int32))
         return start, np.array(items, np.int32), res
+
+    # ---- ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float th) (@0x79f10) on faked objects ----
+    # Offsets read from its disassembly and from MapPoint::isBad / Observations / GetDescriptor:
+    #   MapPoint: nObs @0x18, mTrackProjX/Y/XR @0x1c/0x20/0x24, mnTrackScaleLevel @0x28, mTrackViewCos @0x2c, mbTrackInView @0x30,
+    #             mDescriptor (cv::Mat) @0x1c8, mbBad @0x238, mutexes (zero bytes = unlocked)
+    #   Frame:    N @0xec, mvKeysUn @0x120, mvuRight @0x138, mDescriptors (cv::Mat) @0x1c8, mvpMapPoints @0x288, mGrid @0x2c8,
+    #             mvScaleFactors @0x12348
+    @staticmethod
+    def _mat_at(addr, arr):
+        m = (C.c_uint64 * 12).from_address(addr)
+        m[0] = (2 << 32) | (0x42FF0000 | (1 << 14))
+        m[1] = (arr.shape[1] << 32) | arr.shape[0]
+        m[2] = m[3] = arr.ctypes.data
+        m[4] = m[5] = arr.ctypes.data + arr.nbytes
+        m[6] = m[7] = 0
+        m[8], m[9] = addr + 8, addr + 0x50
+        m[10], m[11] = arr.strides[0], 1
+
+    def search_local_points(self, mp, fr, cam4, scale_factors, th, nnratio):
+        """Inputs in the layout of tests/matchdata.py: local_points_case.  Returns (match_f int32 [N] = map-point index assigned
+        to each keypoint or -1, nmatches) as oracle.search_local_points does."""
+        f32 = np.float32
+        st = lambda name: C.c_float.in_dll(self.lib, name)
+        st("_ZN9ORB_SLAM25Frame6mnMinXE").value, st("_ZN9ORB_SLAM25Frame6mnMinYE").value = f32(cam4[0]), f32(cam4[1])
+        st("_ZN9ORB_SLAM25Frame21mfGridElementWidthInvE").value = f32(cam4[2])
+        st("_ZN9ORB_SLAM25Frame22mfGridElementHeightInvE").value = f32(cam4[3])
+        M, N = len(mp["desc"]), len(fr["desc"])
+        keys = np.zeros(N, self.KP)
+        keys["x"], keys["y"], keys["octave"] = fr["xy"][:, 0], fr["xy"][:, 1], fr["octave"]
+        uright = np.ascontiguousarray(fr["uright"], np.float32)
+        fdesc = np.ascontiguousarray(fr["desc"], np.uint8)
+        mdesc = np.ascontiguousarray(mp["desc"], np.uint8)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        mps = (C.c_uint8 * (0x400 * (M + 1)))()          # M map points + one "already tracked" point for fr["taken"]
+        mbase = C.addressof(mps)
+        for i in range(M + 1):
+            a = mbase + 0x400 * i
+            if i < M:
+                C.c_int32.from_address(a + 0x18).value = 1 if mp["obs"][i] else 0
+                C.c_float.from_address(a + 0x1c).value = f32(mp["proj"][i, 0])
+                C.c_float.from_address(a + 0x20).value = f32(mp["proj"][i, 1])
+                C.c_float.from_address(a + 0x24).value = f32(mp["proj"][i, 2])
+                C.c_int32.from_address(a + 0x28).value = int(mp["level"][i])
+                C.c_float.from_address(a + 0x2c).value = f32(mp["viewcos"][i])
+                C.c_uint8.from_address(a + 0x30).value = 1 if mp["valid"][i] else 0
+                self._mat_at(a + 0x1c8, mdesc[i:i + 1])
+            else:
+                C.c_int32.from_address(a + 0x18).value = 1
+        vp = np.array([mbase + 0x400 * i for i in range(M)], np.uint64)
+        fmp = np.array([mbase + 0x400 * M if t else 0 for t in fr["taken"]], np.uint64)
+        frame = (C.c_uint64 * (0x12800 // 8))()
+        fb = C.addressof(frame)
+        C.c_int32.from_address(fb + 0xec).value = N
+        setv = lambda off, arr: (frame.__setitem__(off // 8, arr.ctypes.data), frame.__setitem__(off // 8 + 1, arr.ctypes.data + arr.nbytes),
+                                 frame.__setitem__(off // 8 + 2, arr.ctypes.data + arr.nbytes))
+        setv(0x120, keys); setv(0x138, uright); setv(0x288, fmp); setv(0x12348, sf)
+        self._mat_at(fb + 0x1c8, fdesc)
+        assign = getattr(self.lib, "_ZN9ORB_SLAM25Frame20AssignFeaturesToGridEv")
+        assign.argtypes, assign.restype = [C.c_void_p], None
+        assign(fb)
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher18SearchByProjectionERNS_5FrameERKSt6vectorIPNS_8MapPointESaIS5_EEf")
+        fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float], C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = f32(nnratio)
+        matcher[4] = 1
+        vec = (C.c_uint64 * 3)(vp.ctypes.data, vp.ctypes.data + vp.nbytes, vp.ctypes.data + vp.nbytes)
+        n = fn(C.addressof(matcher), fb, C.addressof(vec), f32(th))
+        out = np.full(N, -1, np.int32)
+        for i in range(N):
+            p = int(fmp[i])
+            if p and p != mbase + 0x400 * M:
+                out[i] = (p - mbase) // 0x400
+        return out, int(n)

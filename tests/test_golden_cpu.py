@@ -205,3 +205,27 @@ def test_grid_and_window_search_equal_the_reference_frame_code(oracle):
                                           g["fg_items"], xy, octave)
         assert np.array_equal(got, g["fg_res"][off[k]:off[k + 1]]), (k, x, y, r, lo, hi)
     assert int(g["fg_res_len"].sum()) > 3000
+
+
+def test_local_map_search_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (@0x79f10) executed from lib/libORB_SLAM2.so on
+    faked Frame / MapPoint objects (fixture reference_library.npz, lp*): the oracle assigns the same map point to every
+    keypoint and returns the same count."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import local_points_case
+    from plslam_b200.synth import synth_pair
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    o = oracle.OrbOracle()
+    sf = o.tables()["scale"]
+    feats = {}
+    for k in range(int(g["lp_n"])):
+        seed, th, nnr, jit = g["lp%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (o.extract(a), o.extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        mp, fr, cam4 = local_points_case(ka, da, kb, db, seed=10 * seed + int(th), jitter=float(jit))
+        m, n = oracle.search_local_points(mp, fr, cam4, sf, float(th), float(nnr))
+        assert n == int(g["lp%d_n" % k]) > 300 and np.array_equal(m, g["lp%d_match" % k]), k
