@@ -205,6 +205,26 @@ def reflib():
             lp.append(n)
     out["lp_n"] = np.array(len(lp))
     print("SearchByProjection(Frame&, MapPoints, th):", lp)
+    # ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches) on faked KeyFrame / Frame objects (real std::map feature vectors)
+    from matchdata import fake_feature_vector
+    bw = []
+    for seed in (1, 2):
+        a, b = synth_pair(seed)
+        (ka, da), (kb, db) = oo.extract(a), oo.extract(b)
+        r2 = np.random.default_rng(seed)
+        for nnr, ori, nbits in ((0.7, 1, 6), (0.9, 0, 6), (0.7, 1, 2), (0.6, 1, 4)):
+            kf = dict(desc=da, angle=np.ascontiguousarray(ka["angle"]), valid=(r2.random(len(da)) < 0.85).astype(np.uint8))
+            kf["nodes"], kf["start"], kf["idx"] = fake_feature_vector(da, nbits, seed=7)
+            ff = dict(desc=db, angle=np.ascontiguousarray(kb["angle"]))
+            ff["nodes"], ff["start"], ff["idx"] = fake_feature_vector(db, nbits, seed=7)
+            m, n = R.search_by_bow(kf, ff, nnr, bool(ori))
+            k = len(bw)
+            out["bw%d_args" % k] = np.array([seed, nnr, ori, nbits], np.float64)
+            out["bw%d_valid" % k] = kf["valid"]
+            out["bw%d_match" % k], out["bw%d_n" % k] = m, np.array(n)
+            bw.append(n)
+    out["bw_n"] = np.array(len(bw))
+    print("SearchByBoW(KeyFrame*, Frame&):", bw)
     # Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea on a faked Frame (the reference's own grid and window search)
     kps, _ = orb.OrbOracle().extract(synth_frame(2))
     kps = kps.copy()

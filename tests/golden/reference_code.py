@@ -143,6 +143,8 @@ CVSHIM_CC = r"""
 #include <cstdint>
 #include <cstring>
 #include <new>
+#include <map>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 static const bool g_trace = std::getenv("REFSHIM_TRACE") != nullptr;
@@ -391,6 +393,13 @@ static void op_assign(const void*, const MatExpr* e, Mat* m, int type) {
 static const void* const op_vtable[4] = {(const void*)op_dtor, (const void*)op_dtor, (const void*)op_elementwise, (const void*)op_assign};
 static const void* const op_object[1] = {op_vtable};
 void shim_zeros(MatExpr* ret, int rows, int cols, int type) asm("_ZN2cv3Mat5zerosEiii");
+// helper for the harness (not an OpenCV symbol): a DBoW2::FeatureVector (= std::map<unsigned, std::vector<unsigned>>, same
+// libstdc++ layout in GCC 5 and today) built in place from CSR arrays
+void refshim_build_featvec(void* where, const int* nodes, const int* start, const int* idx, int n);
+void refshim_build_featvec(void* where, const int* nodes, const int* start, const int* idx, int n) {
+  auto* m = new (where) std::map<unsigned int, std::vector<unsigned int>>();
+  for (int k = 0; k < n; ++k) (*m)[(unsigned)nodes[k]].assign(idx + start[k], idx + start[k + 1]);
+}
 void shim_zeros(MatExpr* ret, int rows, int cols, int type) {
   TRACE("Mat::zeros %d x %d type %d", rows, cols, type);
   std::memset(ret, 0, sizeof(MatExpr));
@@ -684,4 +693,49 @@ class RefLibrary:
             p = int(fmp[i])
             if p and p != mbase + 0x400 * M:
                 out[i] = (p - mbase) // 0x400
+        return out, int(n)
+
+    # ---- ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (@0x80150) ----
+    # KeyFrame: mvKeysUn @0x170, mDescriptors @0x1b8, mFeatVec @0x248, mvpMapPoints @0x520 (KeyFrame::GetMapPointMatches
+    # @0x9c4b0 copies it under the mutex @0x690).  Frame: N @0xec, mvKeys @0xf0, mFeatVec @0x198, mDescriptors @0x1c8.
+    def search_by_bow(self, kf, f, nnratio=0.7, check_ori=True):
+        """Inputs in the layout of oracle.search_by_bow.  Returns (match_f int32 [N2] = KF feature matched to each F feature or
+        -1, nmatches)."""
+        f32 = np.float32
+        n1, n2 = len(kf["desc"]), len(f["desc"])
+        k1, k2 = np.zeros(n1, self.KP), np.zeros(n2, self.KP)
+        k1["angle"], k2["angle"] = kf["angle"], f["angle"]
+        d1, d2 = np.ascontiguousarray(kf["desc"], np.uint8), np.ascontiguousarray(f["desc"], np.uint8)
+        mps = (C.c_uint8 * (0x400 * max(n1, 1)))()   # one zeroed (good, not bad) MapPoint per valid KF feature
+        mb = C.addressof(mps)
+        vp = np.array([mb + 0x400 * i if kf["valid"][i] else 0 for i in range(n1)], np.uint64)
+        kfo = (C.c_uint64 * (0x800 // 8))()
+        kb = C.addressof(kfo)
+        fro = (C.c_uint64 * (0x400 // 8))()
+        fb = C.addressof(fro)
+        def setv(obj, off, arr):
+            obj[off // 8], obj[off // 8 + 1], obj[off // 8 + 2] = arr.ctypes.data, arr.ctypes.data + arr.nbytes, arr.ctypes.data + arr.nbytes
+        setv(kfo, 0x170, k1); setv(kfo, 0x520, vp)
+        self._mat_at(kb + 0x1b8, d1)
+        C.c_int32.from_address(fb + 0xec).value = n2
+        setv(fro, 0xf0, k2)
+        self._mat_at(fb + 0x1c8, d2)
+        build = self._shims.refshim_build_featvec
+        build.argtypes, build.restype = [C.c_void_p] * 4 + [C.c_int], None
+        arrs = [np.ascontiguousarray(x, np.int32) for x in (kf["nodes"], kf["start"], kf["idx"], f["nodes"], f["start"], f["idx"])]
+        build(kb + 0x248, arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, len(arrs[0]))
+        build(fb + 0x198, arrs[3].ctypes.data, arrs[4].ctypes.data, arrs[5].ctypes.data, len(arrs[3]))
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher11SearchByBoWEPNS_8KeyFrameERNS_5FrameERSt6vectorIPNS_8MapPointESaIS7_EE")
+        fn.argtypes, fn.restype = [C.c_void_p] * 4, C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = f32(nnratio)
+        matcher[4] = 1 if check_ori else 0
+        res = (C.c_uint64 * 3)()
+        n = fn(C.addressof(matcher), kb, fb, C.addressof(res))
+        cnt = (res[1] - res[0]) // 8
+        ptrs = np.ctypeslib.as_array(C.cast(res[0], C.POINTER(C.c_uint64)), (cnt,)) if cnt else np.empty(0, np.uint64)
+        out = np.full(n2, -1, np.int32)
+        for i, p in enumerate(ptrs):
+            if p:
+                out[i] = (int(p) - mb) // 0x400
         return out, int(n)

@@ -229,3 +229,28 @@ def test_local_map_search_equals_the_reference_matcher(oracle):
         mp, fr, cam4 = local_points_case(ka, da, kb, db, seed=10 * seed + int(th), jitter=float(jit))
         m, n = oracle.search_local_points(mp, fr, cam4, sf, float(th), float(nnr))
         assert n == int(g["lp%d_n" % k]) > 300 and np.array_equal(m, g["lp%d_match" % k]), k
+
+
+def test_search_by_bow_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (@0x80150) executed from lib/libORB_SLAM2.so on faked
+    KeyFrame / Frame objects whose feature vectors are real std::map's (fixture reference_library.npz, bw*)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import fake_feature_vector
+    from plslam_b200.synth import synth_pair
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    o = oracle.OrbOracle()
+    feats = {}
+    for k in range(int(g["bw_n"])):
+        seed, nnr, ori, nbits = g["bw%d_args" % k]
+        seed, nbits = int(seed), int(nbits)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (o.extract(a), o.extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        kf = dict(desc=da, angle=np.ascontiguousarray(ka["angle"]), valid=g["bw%d_valid" % k])
+        kf["nodes"], kf["start"], kf["idx"] = fake_feature_vector(da, nbits, seed=7)
+        f = dict(desc=db, angle=np.ascontiguousarray(kb["angle"]))
+        f["nodes"], f["start"], f["idx"] = fake_feature_vector(db, nbits, seed=7)
+        m, n = oracle.search_by_bow(kf, f, float(nnr), bool(ori))
+        assert n == int(g["bw%d_n" % k]) > 200 and np.array_equal(m, g["bw%d_match" % k]), k
