@@ -205,6 +205,23 @@ def reflib():
             lp.append(n)
     out["lp_n"] = np.array(len(lp))
     print("SearchByProjection(Frame&, MapPoints, th):", lp)
+    # ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on faked Frame / MapPoint objects, cv::Mat expressions
+    # (-Rcw.t()*tcw, Rlw*twc+tlw, Rcw*x3Dw+tcw) evaluated by the expression shims with cv::gemm's arithmetic
+    from matchdata import projection_case
+    pj = []
+    for seed in (1, 2):
+        a, b = synth_pair(seed)
+        (ka, da), (kb, db) = oo.extract(a), oo.extract(b)
+        for motion in (0.02, 0.3, -0.3):
+            last, cur, cam, sf2, tc, tl = projection_case(ka, da, kb, db, sf, seed=seed, motion=motion)
+            for th, mono in ((7.0, 0), (15.0, 0), (15.0, 1)):
+                m, n = R.search_by_projection(last, cur, cam, sf, tc, tl, th, bool(mono), True)
+                k = len(pj)
+                out["pj%d_args" % k] = np.array([seed, motion, th, mono], np.float64)
+                out["pj%d_match" % k], out["pj%d_n" % k] = m, np.array(n)
+                pj.append(n)
+    out["pj_n"] = np.array(len(pj))
+    print("SearchByProjection(Frame&, Frame&):", pj)
     # ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches) on faked KeyFrame / Frame objects (real std::map feature vectors)
     from matchdata import fake_feature_vector
     bw = []

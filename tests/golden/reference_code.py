@@ -123,13 +123,22 @@ void _ZdlPvm(void* p, size_t n) { (void)p; (void)n; }
 """
 
 
+def _build_atomically(cmd, target):
+    """Link to a temporary name and rename: another process may have the previous file mapped (rewriting a mapped shared
+    object in place corrupts that process)."""
+    import subprocess
+    tmp = "%s.tmp.%d" % (target, os.getpid())
+    subprocess.check_call(cmd + ["-o", tmp])
+    os.replace(tmp, target)
+
+
 def load_monotonic_new(out=STUB_DIR):
     """Must run before anything loads libstdc++ with RTLD_GLOBAL: the first global definition of operator new wins."""
     import subprocess
     os.makedirs(out, exist_ok=True)
     src = os.path.join(out, "bump.c")
     open(src, "w").write(BUMP_C)
-    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", os.path.join(out, "libbumpnew.so"), src])
+    _build_atomically(["gcc", "-O1", "-shared", "-fPIC", src], os.path.join(out, "libbumpnew.so"))
     return C.CDLL(os.path.join(out, "libbumpnew.so"), mode=C.RTLD_GLOBAL)
 
 
@@ -230,15 +239,16 @@ static void mat_init_empty(Mat* m) {
 }
 static void mat_create(Mat* m, int rows, int cols, int type) {
   if (m->data && m->dims == 2 && (m->flags & TYPE_MASK) == type && m->rows == rows && m->cols == cols) return;
-  if (type != 0) __builtin_trap();  // only CV_8UC1 occurs on this path
+  if (type != 0 && type != 5) __builtin_trap();  // CV_8UC1 and CV_32FC1 are the only types on these paths
+  const size_t esz = type == 5 ? 4 : 1;
   mat_init_empty(m);
   m->flags = MAGIC | CONTINUOUS_FLAG | type;
   m->dims = 2;
   m->rows = rows;
   m->cols = cols;
-  m->stepbuf[0] = (size_t)cols;
-  m->stepbuf[1] = 1;
-  const size_t total = (size_t)rows * cols;
+  m->stepbuf[0] = (size_t)cols * esz;
+  m->stepbuf[1] = esz;
+  const size_t total = (size_t)rows * cols * esz;
   m->data = (uint8_t*)::operator new(total ? total : 1);
   std::memset(m->data, 0, total);
   m->datastart = m->data;
@@ -315,7 +325,8 @@ void shim_copyTo(const Mat* src, const InputArray* dst) {
   if (!d) __builtin_trap();
   mat_create(d, src->rows, src->cols, src->flags & TYPE_MASK);
   if (d->data == src->data) return;
-  for (int r = 0; r < src->rows; ++r) std::memcpy(d->data + (size_t)r * d->stepp[0], src->data + (size_t)r * src->stepp[0], (size_t)src->cols);
+  for (int r = 0; r < src->rows; ++r)
+    std::memcpy(d->data + (size_t)r * d->stepp[0], src->data + (size_t)r * src->stepp[0], (size_t)src->cols * src->stepp[1]);
 }
 extern "C" void oracle_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstep, uint8_t* dst, int dw, int dh, int dstep);
 extern "C" void oracle_blur7_u8(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep, const int* k);
@@ -411,6 +422,101 @@ void shim_zeros(MatExpr* ret, int rows, int cols, int type) {
   ret->alpha = rows;
   ret->beta = cols;
 }
+
+// ---- the matrix expressions of ORBmatcher::SearchByProjection(Frame&, const Frame&, ...) (@0x80d00): -Rcw.t()*tcw,
+// Rlw*twc+tlw, Rcw*x3Dw+tcw.  Expressions stay lazy as in OpenCV (MatExpr flags: 'T' = a^T * alpha, 'G' = alpha*op(a)*b + beta*c);
+// the evaluation in assign() is cv::gemm's for CV_32F: with no transpose flag and an inner dimension of 2..4 the small-matrix
+// path (float products summed left to right in float, then (double)sum*alpha + (double)c*beta), otherwise GEMMSingleMul (double
+// accumulator, (float)(sum*alpha [+ c*beta])).  The small-matrix arithmetic is pinned against cv2 4.13 (tests/test_tum_io_cpu.py).
+static float& at(const Mat* m, int r, int c) { return *(float*)(m->data + (size_t)r * m->stepp[0] + (size_t)c * 4); }
+static void hdr_copy(Mat* d, const Mat* s) {
+  *d = *s;
+  d->sizep = &d->rows;
+  d->stepp = d->stepbuf;
+  d->stepbuf[0] = s->stepp[0];
+  d->stepbuf[1] = s->stepp[1];
+}
+static void expr_assign(const void*, const MatExpr* e, Mat* m, int type) {
+  (void)type;
+  if ((e->flags >> 8) == 'Z') { op_assign(nullptr, e, m, type); return; }
+  if ((e->flags >> 8) != 'G') __builtin_trap();
+  const bool tA = (e->flags & 1) != 0;
+  const Mat *A = &e->a, *B = &e->b, *Cm = e->c.data ? &e->c : nullptr;
+  const int rows = tA ? A->cols : A->rows, len = tA ? A->rows : A->cols, cols = B->cols;
+  Mat D;
+  mat_init_empty(&D);
+  mat_create(&D, rows, cols, 5);
+  const bool small = !tA && len >= 2 && len <= 4 && (len == cols || len == rows);
+  for (int i = 0; i < rows; ++i)
+    for (int j = 0; j < cols; ++j) {
+      if (small) {
+        float t = at(A, i, 0) * at(B, 0, j);
+        for (int k = 1; k < len; ++k) t = t + at(A, i, k) * at(B, k, j);
+        at(&D, i, j) = (float)((double)t * e->alpha + (Cm ? (double)at(Cm, i, j) : 0.0) * (Cm ? e->beta : 0.0));
+      } else {
+        double s0 = 0;
+        for (int k = 0; k < len; ++k) s0 += (double)(tA ? at(A, k, i) : at(A, i, k)) * (double)at(B, k, j);
+        at(&D, i, j) = Cm ? (float)(s0 * e->alpha + (double)at(Cm, i, j) * e->beta) : (float)(s0 * e->alpha);
+      }
+    }
+  mat_create(m, rows, cols, 5);
+  for (int i = 0; i < rows; ++i) std::memcpy(m->data + (size_t)i * m->stepp[0], D.data + (size_t)i * D.stepp[0], (size_t)cols * 4);
+}
+static const void* const expr_vtable[4] = {(const void*)op_dtor, (const void*)op_dtor, (const void*)op_elementwise, (const void*)expr_assign};
+static const void* const expr_object[1] = {expr_vtable};
+static void expr_init(MatExpr* e, int kind, int tA) {
+  std::memset(e, 0, sizeof(MatExpr));
+  e->op = expr_object;
+  e->flags = (kind << 8) | tA;
+  mat_init_empty(&e->a);
+  mat_init_empty(&e->b);
+  mat_init_empty(&e->c);
+  e->alpha = 1;
+}
+void shim_t(MatExpr* ret, const Mat* m) asm("_ZNK2cv3Mat1tEv");
+void shim_t(MatExpr* ret, const Mat* m) {
+  TRACE("Mat::t()");
+  expr_init(ret, 'T', 1);
+  hdr_copy(&ret->a, m);
+}
+void shim_neg(MatExpr* ret, const MatExpr* e) asm("_ZN2cvngERKNS_7MatExprE");
+void shim_neg(MatExpr* ret, const MatExpr* e) {
+  TRACE("operator-(MatExpr)");
+  if ((e->flags >> 8) != 'T') __builtin_trap();
+  expr_init(ret, 'T', 1);
+  hdr_copy(&ret->a, &e->a);
+  ret->alpha = -e->alpha;
+}
+void shim_mul_em(MatExpr* ret, const MatExpr* e, const Mat* m) asm("_ZN2cvmlERKNS_7MatExprERKNS_3MatE");
+void shim_mul_em(MatExpr* ret, const MatExpr* e, const Mat* m) {
+  TRACE("operator*(MatExpr, Mat)");
+  if ((e->flags >> 8) != 'T') __builtin_trap();
+  expr_init(ret, 'G', 1);
+  hdr_copy(&ret->a, &e->a);
+  hdr_copy(&ret->b, m);
+  ret->alpha = e->alpha;
+}
+void shim_mul_mm(MatExpr* ret, const Mat* a, const Mat* b) asm("_ZN2cvmlERKNS_3MatES2_");
+void shim_mul_mm(MatExpr* ret, const Mat* a, const Mat* b) {
+  TRACE("operator*(Mat, Mat)");
+  expr_init(ret, 'G', 0);
+  hdr_copy(&ret->a, a);
+  hdr_copy(&ret->b, b);
+}
+void shim_add_em(MatExpr* ret, const MatExpr* e, const Mat* m) asm("_ZN2cvplERKNS_7MatExprERKNS_3MatE");
+void shim_add_em(MatExpr* ret, const MatExpr* e, const Mat* m) {
+  TRACE("operator+(MatExpr, Mat)");
+  if ((e->flags >> 8) != 'G' || e->c.data) __builtin_trap();
+  *ret = *e;
+  hdr_copy(&ret->a, &e->a);
+  hdr_copy(&ret->b, &e->b);
+  hdr_copy(&ret->c, m);
+  ret->beta = 1;
+}
+void shim_expr_dtor(MatExpr*) asm("_ZN2cv7MatExprD1Ev");
+void shim_expr_dtor(MatExpr*) {}
+void shim_expr_dtor2(MatExpr*) asm("_ZN2cv7MatExprD2Ev");
+void shim_expr_dtor2(MatExpr*) {}
 }
 """
 
@@ -424,8 +530,8 @@ def load_cv_shims(out=STUB_DIR):
     oracle_dir = os.path.join(root, "oracle", "_build")
     src = os.path.join(out, "cvshim.cc")
     open(src, "w").write(CVSHIM_CC)
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", os.path.join(out, "libcvshim.so"), src,
-                           "-L" + oracle_dir, "-loracle", "-Wl,-rpath," + oracle_dir])
+    _build_atomically(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", src, "-L" + oracle_dir, "-loracle",
+                       "-Wl,-rpath," + oracle_dir], os.path.join(out, "libcvshim.so"))
     return C.CDLL(os.path.join(out, "libcvshim.so"), mode=C.RTLD_GLOBAL)
 
 
@@ -457,10 +563,9 @@ def build_stubs(so=SO, out=STUB_DIR):
     dyn = subprocess.run(["readelf", "-d", so], capture_output=True, text=True, check=True).stdout
     needed = [l.split("[")[1].rstrip("]") for l in dyn.splitlines() if "(NEEDED)" in l]
     needed = [n for n in needed if not re.match(r"lib(stdc\+\+|m|gcc_s|pthread|c)\.so", n)]
-    subprocess.check_call(["gcc", "-shared", "-o", os.path.join(out, "librefstub.so"), os.path.join(out, "stub.s"),
-                           "-Wl,-soname,librefstub.so"])
+    _build_atomically(["gcc", "-shared", os.path.join(out, "stub.s"), "-Wl,-soname,librefstub.so"], os.path.join(out, "librefstub.so"))
     for n in needed:
-        subprocess.check_call(["gcc", "-shared", "-o", os.path.join(out, n), os.path.join(out, "empty.c"), "-Wl,-soname," + n])
+        _build_atomically(["gcc", "-shared", os.path.join(out, "empty.c"), "-Wl,-soname," + n], os.path.join(out, n))
     return needed
 
 
@@ -738,4 +843,80 @@ class RefLibrary:
         for i, p in enumerate(ptrs):
             if p:
                 out[i] = (int(p) - mb) // 0x400
+        return out, int(n)
+
+    # ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono) (@0x80d00) ----
+    # Further Frame members: mbf @0xe0, mb @0xe4, mvKeys @0xf0, mvbOutlier (vector<bool>) @0x2a0, mTcw (cv::Mat 4x4) @0x122c8;
+    # MapPoint::mWorldPos (cv::Mat 3x1) @0xd8 (MapPoint::GetWorldPos @0x91630).  Frame::fx/fy/cx/cy are static members.
+    @staticmethod
+    def _fmat_at(addr, arr):
+        m = (C.c_uint64 * 12).from_address(addr)
+        m[0] = (2 << 32) | (0x42FF0000 | (1 << 14) | 5)
+        m[1] = (arr.shape[1] << 32) | arr.shape[0]
+        m[2] = m[3] = arr.ctypes.data
+        m[4] = m[5] = arr.ctypes.data + arr.nbytes
+        m[6] = m[7] = 0
+        m[8], m[9] = addr + 8, addr + 0x50
+        m[10], m[11] = arr.strides[0], 4
+
+    def search_by_projection(self, last, cur, cam, scale_factors, tcw_cur, tcw_last, th, mono=False, check_ori=True):
+        """Inputs in the layout of oracle.search_by_projection (tests/matchdata.py: projection_case).  Returns (match_cur int32
+        [N2] = last-frame index assigned to each current keypoint or -1, nmatches)."""
+        f32 = np.float32
+        st = lambda name: C.c_float.in_dll(self.lib, name)
+        for name, v in zip(("2fx", "2fy", "2cx", "2cy"), cam[:4]):
+            st("_ZN9ORB_SLAM25Frame%sE" % name).value = f32(v)
+        st("_ZN9ORB_SLAM25Frame6mnMinXE").value, st("_ZN9ORB_SLAM25Frame6mnMaxXE").value = f32(cam[6]), f32(cam[7])
+        st("_ZN9ORB_SLAM25Frame6mnMinYE").value, st("_ZN9ORB_SLAM25Frame6mnMaxYE").value = f32(cam[8]), f32(cam[9])
+        st("_ZN9ORB_SLAM25Frame21mfGridElementWidthInvE").value = f32(cam[10])
+        st("_ZN9ORB_SLAM25Frame22mfGridElementHeightInvE").value = f32(cam[11])
+        n1, n2 = len(last["desc"]), len(cur["desc"])
+        ldesc, cdesc = np.ascontiguousarray(last["desc"], np.uint8), np.ascontiguousarray(cur["desc"], np.uint8)
+        xyz = np.ascontiguousarray(last["xyz"], np.float32)
+        mps = (C.c_uint8 * (0x400 * (n1 + 1)))()
+        mb_ = C.addressof(mps)
+        for i in range(n1):
+            a = mb_ + 0x400 * i
+            C.c_int32.from_address(a + 0x18).value = 1 if last["obs"][i] else 0
+            self._fmat_at(a + 0xd8, xyz[i].reshape(3, 1))
+            self._mat_at(a + 0x1c8, ldesc[i:i + 1])
+        C.c_int32.from_address(mb_ + 0x400 * n1 + 0x18).value = 1            # the "already tracked" point of cur["taken"]
+        lmp = np.array([mb_ + 0x400 * i if last["valid"][i] else 0 for i in range(n1)], np.uint64)
+        cmp_ = np.array([mb_ + 0x400 * n1 if t else 0 for t in cur["taken"]], np.uint64)
+        lk = np.zeros(n1, self.KP)
+        lk["octave"], lk["angle"] = last["octave"], last["angle"]
+        ck = np.zeros(n2, self.KP)
+        ck["x"], ck["y"], ck["octave"], ck["angle"] = cur["xy"][:, 0], cur["xy"][:, 1], cur["octave"], cur["angle"]
+        uright = np.ascontiguousarray(cur["uright"], np.float32)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        T = lambda t: np.ascontiguousarray(np.vstack([np.asarray(t, np.float32).reshape(3, 4), [[0, 0, 0, 1]]]).astype(np.float32))
+        Tc, Tl = T(tcw_cur), T(tcw_last)
+        outl = np.zeros((n1 + 63) // 64 + 1, np.uint64)
+        fl, fc = (C.c_uint64 * (0x12800 // 8))(), (C.c_uint64 * (0x12800 // 8))()
+        lb, cb = C.addressof(fl), C.addressof(fc)
+        def setv(obj, off, arr):
+            obj[off // 8], obj[off // 8 + 1], obj[off // 8 + 2] = arr.ctypes.data, arr.ctypes.data + arr.nbytes, arr.ctypes.data + arr.nbytes
+        C.c_int32.from_address(lb + 0xec).value = n1
+        setv(fl, 0xf0, lk); setv(fl, 0x120, lk); setv(fl, 0x288, lmp)
+        fl[0x2a0 // 8] = outl.ctypes.data                                      # vector<bool>::_M_start._M_p, all bits clear
+        self._fmat_at(lb + 0x122c8, Tl)
+        C.c_int32.from_address(cb + 0xec).value = n2
+        C.c_float.from_address(cb + 0xe0).value, C.c_float.from_address(cb + 0xe4).value = f32(cam[4]), f32(cam[5])
+        setv(fc, 0xf0, ck); setv(fc, 0x120, ck); setv(fc, 0x138, uright); setv(fc, 0x288, cmp_); setv(fc, 0x12348, sf)
+        self._mat_at(cb + 0x1c8, cdesc)
+        self._fmat_at(cb + 0x122c8, Tc)
+        assign = getattr(self.lib, "_ZN9ORB_SLAM25Frame20AssignFeaturesToGridEv")
+        assign.argtypes, assign.restype = [C.c_void_p], None
+        assign(cb)
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher18SearchByProjectionERNS_5FrameERKS1_fb")
+        fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_bool], C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = f32(0.9)
+        matcher[4] = 1 if check_ori else 0
+        n = fn(C.addressof(matcher), cb, lb, f32(th), bool(mono))
+        out = np.full(n2, -1, np.int32)
+        for i in range(n2):
+            p = int(cmp_[i])
+            if p and p != mb_ + 0x400 * n1:
+                out[i] = (p - mb_) // 0x400
         return out, int(n)

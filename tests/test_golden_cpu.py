@@ -254,3 +254,29 @@ def test_search_by_bow_equals_the_reference_matcher(oracle):
         f["nodes"], f["start"], f["idx"] = fake_feature_vector(db, nbits, seed=7)
         m, n = oracle.search_by_bow(kf, f, float(nnr), bool(ori))
         assert n == int(g["bw%d_n" % k]) > 200 and np.array_equal(m, g["bw%d_match" % k]), k
+
+
+def test_search_by_projection_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (@0x80d00, TrackWithMotionModel's matcher) executed from
+    lib/libORB_SLAM2.so on faked Frame / MapPoint objects, its cv::Mat expressions evaluated with cv::gemm's arithmetic
+    (fixture reference_library.npz, pj*): forward, backward and sideways motion, stereo and mono."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import projection_case
+    from plslam_b200.synth import synth_pair
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    o = oracle.OrbOracle()
+    sf = o.tables()["scale"]
+    feats, total = {}, 0
+    for k in range(int(g["pj_n"])):
+        seed, motion, th, mono = g["pj%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (o.extract(a), o.extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        last, cur, cam, _, tc, tl = projection_case(ka, da, kb, db, sf, seed=seed, motion=float(motion))
+        m, n = oracle.search_by_projection(last, cur, cam, sf, tc, tl, float(th), bool(mono), True)
+        assert n == int(g["pj%d_n" % k]) and np.array_equal(m, g["pj%d_match" % k]), k
+        total += n
+    assert total > 3000
