@@ -118,9 +118,18 @@ def refcode():
 def reflib():
     sys.path.insert(0, HERE)
     from reference_code import RefLibrary, SO
-    R = RefLibrary()  # first: the monotonic operator new must precede any global libstdc++
+    # Every synthetic frame is rendered BEFORE the reference library is loaded: its stub / shim objects define cv:: symbols
+    # with RTLD_GLOBAL, and plslam_b200.synth warps the second frame of a pair with cv2, whose lazily bound calls would then
+    # land in the shims (observed: a different second frame on every call, eventually a crash).
+    import plslam_b200.synth as _synth
+    _frames = {("f", a): _synth.synth_frame(*a) for a in [(0,), (7,), (2,), (21,), (22,), (24,), (3, 320, 240), (11, 400, 304),
+                                                            (12, 256, 200), (13, 333, 250), (0, 640, 480), (5, 640, 480),
+                                                            (40, 1280, 720)]}
+    _frames.update({("p", s): _synth.synth_pair(s) for s in (1, 2)})
+    synth_frame = lambda *a: _frames[("f", a)]
+    synth_pair = lambda s: _frames[("p", s)]
+    R = RefLibrary()  # the monotonic operator new must precede any global libstdc++
     from oracle import bindings as orb  # only to produce realistic inputs (FAST candidates); outputs come from the reference
-    from plslam_b200.synth import synth_frame
     out = {"so_sha256": np.array(hashlib.sha256(open(SO, "rb").read()).hexdigest())}
     params = [(1000, 1.2, 8, 20, 7), (2000, 1.2, 8, 20, 7), (8000, 1.2, 8, 20, 7), (500, 1.5, 4, 12, 5)]
     out["ctor_params"] = np.array(params, np.float64)
@@ -189,7 +198,6 @@ def reflib():
     # objects; inputs are rebuilt at test time from the same seeds (tests/matchdata.py: local_points_case)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from matchdata import local_points_case
-    from plslam_b200.synth import synth_pair
     oo = orb.OrbOracle()
     sf = oo.tables()["scale"]
     lp = []
@@ -222,6 +230,22 @@ def reflib():
                 pj.append(n)
     out["pj_n"] = np.array(len(pj))
     print("SearchByProjection(Frame&, Frame&):", pj)
+    # ORBmatcher::SearchForTriangulation on faked KeyFrame objects: the reference computes its own epipole through
+    # KeyFrame::GetCameraCenter / GetRotation / GetTranslation and the gemm shims, walks real std::map feature vectors
+    from matchdata import triangulation_case
+    tr = []
+    tri_cases = [(21, {}), (22, dict(stereo_fraction=0.0, t21=(0.005, 0.002, 0.15))), (24, dict(nbits=1))]
+    for seed, kw in tri_cases:
+        kps, desc = orb.OrbOracle().extract(synth_frame(seed))
+        kf1, kf2, F12, pose, cam, sft, sgt = triangulation_case(kps, desc, seed=seed, **kw)
+        for only, ori in ((0, 1), (0, 0), (1, 1)):
+            m, n, pairs = R.search_for_triangulation(kf1, kf2, F12, pose, cam, sft, sgt, bool(only), bool(ori))
+            k = len(tr)
+            out["tr%d_args" % k] = np.array([seed, only, ori, kw.get("stereo_fraction", 0.5), kw.get("nbits", 3)] + list(kw.get("t21", (0.12, 0.01, 0.03))), np.float64)
+            out["tr%d_match" % k], out["tr%d_n" % k] = m, np.array(n)
+            tr.append(n)
+    out["tr_n"] = np.array(len(tr))
+    print("SearchForTriangulation:", tr)
     # ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches) on faked KeyFrame / Frame objects (real std::map feature vectors)
     from matchdata import fake_feature_vector
     bw = []

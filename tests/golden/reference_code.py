@@ -570,7 +570,12 @@ def build_stubs(so=SO, out=STUB_DIR):
 
 
 class RefLibrary:
-    """lib/libORB_SLAM2.so dlopen'ed over the stubs; call build_stubs() first (make_golden does)."""
+    """lib/libORB_SLAM2.so dlopen'ed over the stubs and shims.
+
+    Process hygiene: the stub and shim objects are loaded RTLD_GLOBAL and define cv:: symbols and operator new/delete.  Any other
+    C++ library used LATER in the same process and bound lazily (cv2 above all) may resolve its calls to them.  Render inputs
+    with cv2-based code before constructing this object, use it in a dedicated process (tests/golden/make_golden.py reflib), and
+    never from the test-suite: the tests only read the fixtures it wrote."""
 
     KP = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"),
                    ("class_id", "<i4")])
@@ -920,3 +925,64 @@ class RefLibrary:
             if p and p != mb_ + 0x400 * n1:
                 out[i] = (p - mb_) // 0x400
         return out, int(n)
+
+    # ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (@0x86b30) ----
+    # KeyFrame: fx/fy/cx/cy @0x130..0x13c, N @0x154, mvKeysUn @0x170, mvuRight @0x188, mDescriptors @0x1b8, mFeatVec @0x248,
+    # mvScaleFactors @0x2e8, mvLevelSigma2 @0x300, Tcw (cv::Mat 4x4) @0x3a0, Ow (3x1) @0x460, mvpMapPoints @0x520 (offsets from
+    # the function and from KeyFrame::GetCameraCenter / GetRotation / GetTranslation / GetMapPoint).  cv::Mat F12 is passed by
+    # invisible reference (non-trivial copy constructor).
+    def search_for_triangulation(self, kf1, kf2, F12, pose, cam, scale_factors, level_sigma2, only_stereo=False, check_ori=True):
+        """Inputs as tests/matchdata.py: triangulation_case returns them; pose = (R2w, t2w, Cw).  The epipole is computed by the
+        reference itself.  Returns (vMatches12-equivalent int32 [N1], nmatches, pairs)."""
+        f32 = np.float32
+        R2w, t2w, Cw = pose
+        n1, n2 = len(kf1["desc"]), len(kf2["desc"])
+        keep = []
+        def make_kf(kf, n, Tcw, Ow):
+            o = (C.c_uint64 * (0x800 // 8))()
+            b = C.addressof(o)
+            keys = np.zeros(n, self.KP)
+            keys["x"], keys["y"], keys["angle"] = kf["xy"][:, 0], kf["xy"][:, 1], kf["angle"]
+            if "octave" in kf:
+                keys["octave"] = kf["octave"]
+            ur = np.ascontiguousarray(kf["uright"], np.float32)
+            d = np.ascontiguousarray(kf["desc"], np.uint8)
+            dummy = (C.c_uint8 * 0x400)()
+            mp = np.array([C.addressof(dummy) if h else 0 for h in kf["has_mp"]], np.uint64)
+            sfa, sga = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+            arrs = [np.ascontiguousarray(kf[k], np.int32) for k in ("nodes", "start", "idx")]
+            def setv(off, arr):
+                o[off // 8], o[off // 8 + 1], o[off // 8 + 2] = arr.ctypes.data, arr.ctypes.data + arr.nbytes, arr.ctypes.data + arr.nbytes
+            for off, v in zip((0x130, 0x134, 0x138, 0x13c), cam):
+                C.c_float.from_address(b + off).value = f32(v)
+            C.c_int32.from_address(b + 0x154).value = n
+            setv(0x170, keys); setv(0x188, ur); setv(0x520, mp); setv(0x2e8, sfa); setv(0x300, sga)
+            self._mat_at(b + 0x1b8, d)
+            self._fmat_at(b + 0x3a0, Tcw)
+            self._fmat_at(b + 0x460, Ow)
+            build = self._shims.refshim_build_featvec
+            build.argtypes, build.restype = [C.c_void_p] * 4 + [C.c_int], None
+            build(b + 0x248, arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, len(arrs[0]))
+            keep.extend([o, keys, ur, d, dummy, mp, sfa, sga, arrs, Tcw, Ow])
+            return b
+        T2 = np.ascontiguousarray(np.vstack([np.hstack([np.asarray(R2w, np.float32), np.asarray(t2w, np.float32).reshape(3, 1)]),
+                                             [[0, 0, 0, 1]]]).astype(np.float32))
+        eye = np.ascontiguousarray(np.eye(4, dtype=np.float32))
+        b1 = make_kf(kf1, n1, eye, np.ascontiguousarray(np.asarray(Cw, np.float32).reshape(3, 1)))
+        b2 = make_kf(kf2, n2, T2, np.zeros((3, 1), np.float32))
+        Fm = np.ascontiguousarray(np.asarray(F12, np.float32).reshape(3, 3))
+        fmat = (C.c_uint64 * 12)()
+        self._fmat_at(C.addressof(fmat), Fm)
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher22SearchForTriangulationEPNS_8KeyFrameES2_N2cv3MatERSt6vectorISt4pairImmESaIS7_EEb")
+        fn.argtypes, fn.restype = [C.c_void_p] * 5 + [C.c_bool], C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = f32(0.6)
+        matcher[4] = 1 if check_ori else 0
+        res = (C.c_uint64 * 3)()
+        n = fn(C.addressof(matcher), b1, b2, C.addressof(fmat), C.addressof(res), bool(only_stereo))
+        cnt = (res[1] - res[0]) // 16
+        pr = np.ctypeslib.as_array(C.cast(res[0], C.POINTER(C.c_uint64)), (cnt * 2,)).reshape(cnt, 2).astype(np.int64) if cnt else np.empty((0, 2), np.int64)
+        m = np.full(n1, -1, np.int32)
+        for i, j in pr:
+            m[i] = j
+        return m, int(n), [(int(i), int(j)) for i, j in pr]

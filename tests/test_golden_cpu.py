@@ -280,3 +280,28 @@ def test_search_by_projection_equals_the_reference_matcher(oracle):
         assert n == int(g["pj%d_n" % k]) and np.array_equal(m, g["pj%d_match" % k]), k
         total += n
     assert total > 3000
+
+
+def test_search_for_triangulation_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchForTriangulation (@0x86b30) executed from lib/libORB_SLAM2.so on faked KeyFrame objects — the reference
+    computes its own epipole through KeyFrame's pose getters — against the oracle fed with oracle.epipole (fixture
+    reference_library.npz, tr*).  The CUDA kernel is compared with the same oracle in tests/test_triangulation_gpu.py."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import triangulation_case
+    from plslam_b200.synth import synth_frame
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    cases, total = {}, 0
+    for k in range(int(g["tr_n"])):
+        a = g["tr%d_args" % k]
+        seed, only, ori, nbits = int(a[0]), bool(a[1]), bool(a[2]), int(a[4])
+        key = (seed, float(a[3]), nbits, tuple(a[5:8]))
+        if key not in cases:
+            kps, desc = oracle.OrbOracle().extract(synth_frame(seed))
+            cases[key] = triangulation_case(kps, desc, seed=seed, stereo_fraction=float(a[3]), nbits=nbits, t21=tuple(a[5:8]))
+        kf1, kf2, F12, pose, cam, sf, sg = cases[key]
+        ex, ey = oracle.epipole(*pose, *cam)
+        m, n = oracle.search_for_triangulation(kf1, kf2, F12, ex, ey, sf, sg, only, ori)
+        assert n == int(g["tr%d_n" % k]) and np.array_equal(m, g["tr%d_match" % k]), k
+        total += n
+    assert total > 1500
