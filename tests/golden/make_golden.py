@@ -230,6 +230,19 @@ def reflib():
                 pj.append(n)
     out["pj_n"] = np.array(len(pj))
     print("SearchByProjection(Frame&, Frame&):", pj)
+    # Frame::ComputeStereoFromRGBD on a faked Frame: distorted / undistorted keypoints, a float depth map with holes and negatives
+    r3 = np.random.default_rng(3)
+    nst = 3000
+    st_xy = np.stack([r3.uniform(0, 639.99, nst), r3.uniform(0, 479.99, nst)], 1).astype(np.float32)
+    st_un = (st_xy + r3.normal(0, 2.0, st_xy.shape)).astype(np.float32)
+    st_depth = (r3.uniform(0.3, 6, (480, 640)) * (r3.random((480, 640)) > 0.2)).astype(np.float32)
+    st_depth[r3.random((480, 640)) < 0.02] = -1.0
+    ur, dz = R.compute_stereo_from_rgbd(st_xy, st_un, st_depth, 40.0)
+    out["st_xy"], out["st_un"], out["st_depth"] = st_xy, st_un, st_depth.astype(np.float16).astype(np.float32)
+    ur, dz = R.compute_stereo_from_rgbd(st_xy, st_un, out["st_depth"], 40.0)  # on the stored (half-precision valued) map
+    out["st_uright"], out["st_z"] = ur, dz
+    out["st_depth"] = out["st_depth"].astype(np.float16)
+    print("ComputeStereoFromRGBD: %d of %d keypoints with depth" % (int((dz > 0).sum()), nst))
     # ORBmatcher::SearchForTriangulation on faked KeyFrame objects: the reference computes its own epipole through
     # KeyFrame::GetCameraCenter / GetRotation / GetTranslation and the gemm shims, walks real std::map feature vectors
     from matchdata import triangulation_case

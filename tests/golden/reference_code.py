@@ -986,3 +986,25 @@ class RefLibrary:
         for i, j in pr:
             m[i] = j
         return m, int(n), [(int(i), int(j)) for i, j in pr]
+
+    # ---- Frame::ComputeStereoFromRGBD(const cv::Mat& imDepth) (@0xf6860): mvuRight @0x138, mvDepth @0x150 from mvKeys @0xf0,
+    # mvKeysUn @0x120, mbf @0xe0 and the float depth map ----
+    def compute_stereo_from_rgbd(self, xy, un_xy, depth, mbf):
+        n = len(xy)
+        k, ku = np.zeros(n, self.KP), np.zeros(n, self.KP)
+        k["x"], k["y"] = xy[:, 0], xy[:, 1]
+        ku["x"], ku["y"] = un_xy[:, 0], un_xy[:, 1]
+        d = np.ascontiguousarray(depth, np.float32)
+        fr = (C.c_uint64 * (0x400 // 8))()
+        b = C.addressof(fr)
+        C.c_int32.from_address(b + 0xec).value = n
+        C.c_float.from_address(b + 0xe0).value = np.float32(mbf)
+        for off, arr in ((0xf0, k), (0x120, ku)):
+            fr[off // 8], fr[off // 8 + 1], fr[off // 8 + 2] = arr.ctypes.data, arr.ctypes.data + arr.nbytes, arr.ctypes.data + arr.nbytes
+        dm = (C.c_uint64 * 12)()
+        self._fmat_at(C.addressof(dm), d)
+        fn = getattr(self.lib, "_ZN9ORB_SLAM25Frame21ComputeStereoFromRGBDERKN2cv3MatE")
+        fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p], None
+        fn(b, C.addressof(dm))
+        get = lambda off: np.ctypeslib.as_array(C.cast(fr[off // 8], C.POINTER(C.c_float)), (n,)).copy()
+        return get(0x138), get(0x150)
