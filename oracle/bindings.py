@@ -550,3 +550,21 @@ def get_features_in_area(x, y, r, min_level, max_level, cam4, grid_start, grid_i
     n = L.oracle_get_features_in_area(float(x), float(y), float(r), int(min_level), int(max_level), _p(cam), _p(gs), _p(gi), _p(xy),
                                       _p(octv), _p(out), len(out))
     return out[:n].copy()
+
+
+def search_for_initialization(f1, f2, cam4, prev_matched, window_size=100, nnratio=0.9, check_ori=True):
+    """f1: dict xy, octave, angle, desc; f2: the same plus grid_start, grid_items -> (matches12 int32 [N1], nmatches, updated prev)"""
+    g = lambda d, k, t: np.ascontiguousarray(d[k], t)
+    a = [g(f1, "xy", np.float32), g(f1, "octave", np.int32), g(f1, "angle", np.float32), g(f1, "desc", np.uint8)]
+    b = [g(f2, "xy", np.float32), g(f2, "octave", np.int32), g(f2, "angle", np.float32), g(f2, "desc", np.uint8),
+         g(f2, "grid_start", np.int32), g(f2, "grid_items", np.int32)]
+    cam = np.ascontiguousarray(cam4, np.float32)
+    prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    n1, n2 = len(a[3]), len(b[3])
+    m = np.empty(max(n1, 1), np.int32)
+    L = lib()
+    L.oracle_search_for_initialization.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 6 + [C.c_void_p, C.c_void_p,
+                                                                                                                 C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = L.oracle_search_for_initialization(n1, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), n2, _p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]),
+                                           _p(b[4]), _p(b[5]), _p(cam), _p(prev), int(window_size), nnratio, int(check_ori), _p(m))
+    return m[:n1].copy(), n, prev

@@ -14,6 +14,7 @@
 // The pointer-based containers (MapPoint*, std::map FeatureVector, mGrid vectors) are flattened to
 // arrays/CSR; iteration orders are preserved.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -429,6 +430,63 @@ int oracle_search_for_triangulation(int N1, const uint8_t* d1, const float* xy1,
       for (int j : rotHist[i]) { match12[j] = -1; nmatches--; }
     }
   }
+  return nmatches;
+}
+
+// ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched, vector<int>& vnMatches12,
+// int windowSize) (ORBmatcher.h:82; @0x7db00) — the monocular-initialisation matcher.  Only level-0 key points of F1 are used;
+// candidates are F2's level-0 key points inside the window around vbPrevMatched[i1] (Frame::GetFeaturesInArea(x, y, windowSize,
+// 0, 0)); a candidate already matched with a distance <= the present one is skipped; best / second best by strict '<';
+// accepted when bestDist <= TH_LOW and bestDist < bestDist2 * mfNNratio; a re-matched F2 key point releases its earlier F1
+// partner; rotation histogram over accepted i1 (angle of F1 minus angle of F2), three-maxima filter; finally
+// vbPrevMatched[i1] = F2 position of every surviving match.  Order dependent (vMatchedDistance / vnMatches21), restated
+// sequentially.  Pinned by running the reference's own function (tests/golden/reference_code.py, fixture si*).
+// xy1/oct1/ang1: F1.mvKeysUn; F2 likewise with its grid as CSR; prevMatched: N1 x 2 floats, updated in place.
+int oracle_search_for_initialization(int N1, const float* xy1, const int* oct1, const float* ang1, const uint8_t* d1, int N2,
+                                     const float* xy2, const int* oct2, const float* ang2, const uint8_t* d2, const int* gridStart,
+                                     const int* gridItems, const float* cam4, float* prevMatched, int windowSize, float nnratio,
+                                     int checkOri, int* matches12) {
+  (void)xy1;
+  int nmatches = 0;
+  for (int i = 0; i < N1; ++i) matches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  std::vector<int> vMatchedDistance(N2, INT_MAX), vnMatches21(N2, -1);
+  for (int i1 = 0; i1 < N1; ++i1) {
+    const int level1 = oct1[i1];
+    if (level1 > 0) continue;
+    int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+    bool any = false;
+    for_features_in_area(prevMatched[2 * i1], prevMatched[2 * i1 + 1], (float)windowSize, level1, level1, cam4[0], cam4[1], cam4[2],
+                         cam4[3], gridStart, gridItems, xy2, oct2, [&](int i2) {
+                           any = true;
+                           const int dist = descriptor_distance(d1 + 32 * i1, d2 + 32 * i2);
+                           if (vMatchedDistance[i2] <= dist) return;
+                           if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                           else if (dist < bestDist2) { bestDist2 = dist; }
+                         });
+    if (!any) continue;
+    if (bestDist <= TH_LOW) {
+      if (bestDist < (float)bestDist2 * nnratio) {
+        if (vnMatches21[bestIdx2] >= 0) { matches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+        matches12[i1] = bestIdx2;
+        vnMatches21[bestIdx2] = i1;
+        vMatchedDistance[bestIdx2] = bestDist;
+        nmatches++;
+        if (checkOri) rotHist[rot_bin(ang1[i1], ang2[bestIdx2])].push_back(i1);
+      }
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i])
+        if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+    }
+  }
+  for (int i1 = 0; i1 < N1; ++i1)
+    if (matches12[i1] >= 0) { prevMatched[2 * i1] = xy2[2 * matches12[i1]]; prevMatched[2 * i1 + 1] = xy2[2 * matches12[i1] + 1]; }
   return nmatches;
 }
 

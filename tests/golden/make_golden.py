@@ -230,6 +230,26 @@ def reflib():
                 pj.append(n)
     out["pj_n"] = np.array(len(pj))
     print("SearchByProjection(Frame&, Frame&):", pj)
+    # ORBmatcher::SearchForInitialization (oracle only so far: the GPU kernel is a next-round item)
+    from matchdata import frame_grid
+    si = []
+    for seed in (1, 2):
+        a, b = synth_pair(seed)
+        (ka, da), (kb, db) = oo.extract(a), oo.extract(b)
+        mk = lambda k, d: dict(xy=np.stack([k["x"], k["y"]], 1).astype(np.float32), octave=k["octave"].astype(np.int32),
+                               angle=k["angle"].astype(np.float32), desc=d)
+        f1, f2 = mk(ka, da), mk(kb, db)
+        gs, gi, (mnx, mxx, mny, mxy, gwi, ghi) = frame_grid(f2["xy"], 640, 480)
+        f2["grid_start"], f2["grid_items"] = gs, gi
+        cam4 = np.array([mnx, mny, gwi, ghi], np.float32)
+        for win, nnr, ori in ((100, 0.9, 1), (30, 0.9, 1), (100, 0.6, 0)):
+            m, n, prev = R.search_for_initialization(f1, f2, cam4, f1["xy"].copy(), win, nnr, bool(ori))
+            k = len(si)
+            out["si%d_args" % k] = np.array([seed, win, nnr, ori], np.float64)
+            out["si%d_match" % k], out["si%d_n" % k], out["si%d_prev" % k] = m, np.array(n), prev
+            si.append(n)
+    out["si_n"] = np.array(len(si))
+    print("SearchForInitialization:", si)
     # Frame::ComputeStereoFromRGBD on a faked Frame: distorted / undistorted keypoints, a float depth map with holes and negatives
     r3 = np.random.default_rng(3)
     nst = 3000

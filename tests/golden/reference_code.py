@@ -1008,3 +1008,41 @@ class RefLibrary:
         fn(b, C.addressof(dm))
         get = lambda off: np.ctypeslib.as_array(C.cast(fr[off // 8], C.POINTER(C.c_float)), (n,)).copy()
         return get(0x138), get(0x150)
+
+    # ---- ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (@0x7db00) ----
+    def search_for_initialization(self, f1, f2, cam4, prev_matched, window_size=100, nnratio=0.9, check_ori=True):
+        f32 = np.float32
+        st = lambda name: C.c_float.in_dll(self.lib, name)
+        st("_ZN9ORB_SLAM25Frame6mnMinXE").value, st("_ZN9ORB_SLAM25Frame6mnMinYE").value = f32(cam4[0]), f32(cam4[1])
+        st("_ZN9ORB_SLAM25Frame21mfGridElementWidthInvE").value = f32(cam4[2])
+        st("_ZN9ORB_SLAM25Frame22mfGridElementHeightInvE").value = f32(cam4[3])
+        keep = []
+        def make(f):
+            n = len(f["desc"])
+            k = np.zeros(n, self.KP)
+            k["x"], k["y"], k["octave"], k["angle"] = f["xy"][:, 0], f["xy"][:, 1], f["octave"], f["angle"]
+            d = np.ascontiguousarray(f["desc"], np.uint8)
+            o = (C.c_uint64 * (0x12800 // 8))()
+            b = C.addressof(o)
+            C.c_int32.from_address(b + 0xec).value = n
+            for off in (0xf0, 0x120):
+                o[off // 8], o[off // 8 + 1], o[off // 8 + 2] = k.ctypes.data, k.ctypes.data + k.nbytes, k.ctypes.data + k.nbytes
+            self._mat_at(b + 0x1c8, d)
+            keep.extend([k, d, o])
+            return b
+        b1, b2 = make(f1), make(f2)
+        assign = getattr(self.lib, "_ZN9ORB_SLAM25Frame20AssignFeaturesToGridEv")
+        assign.argtypes, assign.restype = [C.c_void_p], None
+        assign(b2)
+        prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+        pv = (C.c_uint64 * 3)(prev.ctypes.data, prev.ctypes.data + prev.nbytes, prev.ctypes.data + prev.nbytes)
+        mv = (C.c_uint64 * 3)()
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher23SearchForInitializationERNS_5FrameES2_RSt6vectorIN2cv6Point_IfEESaIS6_EERS3_IiSaIiEEi")
+        fn.argtypes, fn.restype = [C.c_void_p] * 5 + [C.c_int], C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = f32(nnratio)
+        matcher[4] = 1 if check_ori else 0
+        n = fn(C.addressof(matcher), b1, b2, C.addressof(pv), C.addressof(mv), int(window_size))
+        cnt = (mv[1] - mv[0]) // 4
+        m = np.ctypeslib.as_array(C.cast(mv[0], C.POINTER(C.c_int32)), (cnt,)).copy()
+        return m, int(n), prev

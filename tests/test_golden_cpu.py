@@ -323,3 +323,31 @@ def test_rgbd_stereo_equals_the_reference_frame_code(oracle):
     assert np.array_equal(want.view(np.uint32), g["st_uright"].view(np.uint32))   # the reference's arithmetic, restated in numpy
     # and the oracle's own subtraction, on points whose undistorted position equals the distorted one
     assert np.array_equal(fp["uright"][has].view(np.uint32), (xy[has, 0] - np.float32(40.0) / g["st_z"][has]).astype(np.float32).view(np.uint32))
+
+
+def test_search_for_initialization_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchForInitialization (@0x7db00) executed from lib/libORB_SLAM2.so on faked Frames (fixture si*): matches,
+    count and the updated vbPrevMatched."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import frame_grid
+    from plslam_b200.synth import synth_pair
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    o = oracle.OrbOracle()
+    feats = {}
+    for k in range(int(g["si_n"])):
+        seed, win, nnr, ori = g["si%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            (ka, da), (kb, db) = o.extract(a), o.extract(b)
+            mk = lambda kk, d: dict(xy=np.stack([kk["x"], kk["y"]], 1).astype(np.float32), octave=kk["octave"].astype(np.int32),
+                                    angle=kk["angle"].astype(np.float32), desc=d)
+            f1, f2 = mk(ka, da), mk(kb, db)
+            gs, gi, (mnx, mxx, mny, mxy, gwi, ghi) = frame_grid(f2["xy"], 640, 480)
+            f2["grid_start"], f2["grid_items"] = gs, gi
+            feats[seed] = (f1, f2, np.array([mnx, mny, gwi, ghi], np.float32))
+        f1, f2, cam4 = feats[seed]
+        m, n, prev = oracle.search_for_initialization(f1, f2, cam4, f1["xy"].copy(), int(win), float(nnr), bool(ori))
+        assert n == int(g["si%d_n" % k]) > 50 and np.array_equal(m, g["si%d_match" % k]), k
+        assert np.array_equal(prev, g["si%d_prev" % k]), k
