@@ -250,6 +250,19 @@ def reflib():
             si.append(n)
     out["si_n"] = np.array(len(si))
     print("SearchForInitialization:", si)
+    # Frame::UndistortKeyPoints / ComputeImageBounds on a faked Frame (cv::undistortPoints = the cv2-pinned shim)
+    r4 = np.random.default_rng(4)
+    cal = [dict(fx=517.306408, fy=516.469215, cx=318.643040, cy=255.313989, k1=0.262383, k2=-0.953104, p1=-0.005358, p2=0.002628, k3=1.163314),
+           dict(fx=535.4, fy=539.2, cx=320.1, cy=247.6, k1=0.0, k2=0.0, p1=0.0, p2=0.0, k3=0.0),
+           dict(fx=520.9, fy=521.0, cx=325.1, cy=249.7, k1=0.2312, k2=-0.7849, p1=-0.0033, p2=-0.0001, k3=0.9172)]
+    for k, c in enumerate(cal):
+        xyu = np.stack([r4.uniform(0, 640, 1500), r4.uniform(0, 480, 1500)], 1).astype(np.float32)
+        un, bnd = R.undistort_and_bounds(xyu, c, 640, 480)
+        out["un%d_calib" % k] = np.array([c[n] for n in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3")], np.float64)
+        out["un%d_xy" % k], out["un%d_out" % k] = xyu, np.stack([un["x"], un["y"]], 1)
+        out["un%d_bounds" % k] = np.array(bnd, np.float32)
+    out["un_n"] = np.array(len(cal))
+    print("UndistortKeyPoints / ComputeImageBounds: %d calibrations" % len(cal))
     # Frame::ComputeStereoFromRGBD on a faked Frame: distorted / undistorted keypoints, a float depth map with holes and negatives
     r3 = np.random.default_rng(3)
     nst = 3000

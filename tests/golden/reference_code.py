@@ -239,8 +239,8 @@ static void mat_init_empty(Mat* m) {
 }
 static void mat_create(Mat* m, int rows, int cols, int type) {
   if (m->data && m->dims == 2 && (m->flags & TYPE_MASK) == type && m->rows == rows && m->cols == cols) return;
-  if (type != 0 && type != 5) __builtin_trap();  // CV_8UC1 and CV_32FC1 are the only types on these paths
-  const size_t esz = type == 5 ? 4 : 1;
+  static const size_t depth_size[8] = {1, 1, 2, 2, 4, 4, 8, 2};
+  const size_t esz = depth_size[type & 7] * (size_t)(((type >> 3) & 511) + 1);  // CV_8UC1, CV_32FC1, CV_32FC2 occur
   mat_init_empty(m);
   m->flags = MAGIC | CONTINUOUS_FLAG | type;
   m->dims = 2;
@@ -512,6 +512,47 @@ void shim_add_em(MatExpr* ret, const MatExpr* e, const Mat* m) {
   hdr_copy(&ret->b, &e->b);
   hdr_copy(&ret->c, m);
   ret->beta = 1;
+}
+// ---- Frame::UndistortKeyPoints (@0xf8630) / Frame::ComputeImageBounds (@0xf6010): Mat::reshape and cv::undistortPoints ----
+void shim_reshape(Mat* ret, const Mat* m, int new_cn, int new_rows) asm("_ZNK2cv3Mat7reshapeEii");
+void shim_reshape(Mat* ret, const Mat* m, int new_cn, int new_rows) {
+  TRACE("Mat::reshape(%d, %d) of %dx%d type %d", new_cn, new_rows, m->rows, m->cols, m->flags & TYPE_MASK);
+  if (new_rows != 0) __builtin_trap();
+  hdr_copy(ret, m);
+  const int type = m->flags & TYPE_MASK, depth = type & 7, cn = ((type >> 3) & 511) + 1;
+  if (new_cn == 0) new_cn = cn;
+  const int total_width = m->cols * cn;
+  if (total_width % new_cn) __builtin_trap();
+  static const size_t depth_size[8] = {1, 1, 2, 2, 4, 4, 8, 2};
+  ret->cols = total_width / new_cn;
+  ret->flags = (m->flags & ~TYPE_MASK) | depth | ((new_cn - 1) << 3);
+  ret->stepbuf[1] = depth_size[depth] * (size_t)new_cn;
+}
+extern "C" void oracle_undistort_points(const float* calib10, const float* xy, int n, float* out_xy);
+// void cv::undistortPoints(InputArray src, OutputArray dst, InputArray cameraMatrix, InputArray distCoeffs, InputArray R, InputArray P)
+// as the two callers use it: N x 1 CV_32FC2 in place, K and P the same 3x3 CV_32F matrix, 4 or 5 float coefficients, R empty.
+// The arithmetic is the oracle's restatement, pinned bit for bit against cv2 4.13 (tests/test_frame_cpu.py).
+void shim_undistortPoints(const InputArray* src, const InputArray* dst, const InputArray* Km, const InputArray* dm, const InputArray* Rm, const InputArray* Pm)
+    asm("_ZN2cv15undistortPointsERKNS_11_InputArrayERKNS_12_OutputArrayES2_S2_S2_S2_");
+void shim_undistortPoints(const InputArray* src, const InputArray* dst, const InputArray* Km, const InputArray* dm, const InputArray* Rm, const InputArray* Pm) {
+  const Mat *s = arr_mat(src), *K = arr_mat(Km), *D = arr_mat(dm), *P = arr_mat(Pm), *R = arr_mat(Rm);
+  Mat* d = arr_mat(dst);
+  TRACE("undistortPoints %dx%d type %d", s->rows, s->cols, s->flags & TYPE_MASK);
+  if (!s || !d || !K || !D || !P || (R && R->data) || (s->flags & TYPE_MASK) != 13 || s->cols != 1) __builtin_trap();
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      if (at(K, r, c) != at(P, r, c)) __builtin_trap();
+  const int nd = D->rows * D->cols;
+  float calib[10] = {at(K, 0, 0), at(K, 1, 1), at(K, 0, 2), at(K, 1, 2), 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nd && i < 5; ++i) calib[4 + i] = D->rows == 1 ? at(D, 0, i) : at(D, i, 0);
+  if (calib[4] == 0.0f) __builtin_trap();  // both callers test k1 themselves; the oracle entry point copies when k1 == 0
+  const int n = s->rows;
+  float* in = (float*)::operator new(sizeof(float) * 2 * (size_t)(n ? n : 1));
+  float* out = (float*)::operator new(sizeof(float) * 2 * (size_t)(n ? n : 1));
+  for (int i = 0; i < n; ++i) std::memcpy(in + 2 * i, s->data + (size_t)i * s->stepp[0], 8);
+  oracle_undistort_points(calib, in, n, out);
+  mat_create(d, n, 1, 13);
+  for (int i = 0; i < n; ++i) std::memcpy(d->data + (size_t)i * d->stepp[0], out + 2 * i, 8);
 }
 void shim_expr_dtor(MatExpr*) asm("_ZN2cv7MatExprD1Ev");
 void shim_expr_dtor(MatExpr*) {}
@@ -1046,3 +1087,34 @@ class RefLibrary:
         cnt = (mv[1] - mv[0]) // 4
         m = np.ctypeslib.as_array(C.cast(mv[0], C.POINTER(C.c_int32)), (cnt,)).copy()
         return m, int(n), prev
+
+    # ---- Frame::UndistortKeyPoints() (@0xf8630) and Frame::ComputeImageBounds(const cv::Mat&) (@0xf6010) ----
+    # Frame: mK (cv::Mat 3x3 CV_32F) @0x20, mDistCoef (4x1 or 5x1 CV_32F) @0x80, N @0xec, mvKeys @0xf0, mvKeysUn @0x120.
+    def undistort_and_bounds(self, xy, calib, cols, rows):
+        """calib: dict fx fy cx cy k1 k2 p1 p2 k3.  Returns (mvKeysUn xy float32 [n, 2], (mnMinX, mnMaxX, mnMinY, mnMaxY))."""
+        n = len(xy)
+        k = np.zeros(n, self.KP)
+        k["x"], k["y"], k["size"], k["octave"] = xy[:, 0], xy[:, 1], 31, 2
+        K = np.array([[calib["fx"], 0, calib["cx"]], [0, calib["fy"], calib["cy"]], [0, 0, 1]], np.float32)
+        D = np.array([[calib[c]] for c in ("k1", "k2", "p1", "p2", "k3")], np.float32)
+        fr = (C.c_uint64 * (0x400 // 8))()
+        b = C.addressof(fr)
+        C.c_int32.from_address(b + 0xec).value = n
+        fr[0xf0 // 8], fr[0xf0 // 8 + 1], fr[0xf0 // 8 + 2] = k.ctypes.data, k.ctypes.data + k.nbytes, k.ctypes.data + k.nbytes
+        self._fmat_at(b + 0x20, K)
+        self._fmat_at(b + 0x80, D)
+        fn = getattr(self.lib, "_ZN9ORB_SLAM25Frame18UndistortKeyPointsEv")
+        fn.argtypes, fn.restype = [C.c_void_p], None
+        fn(b)
+        cnt = (fr[0x128 // 8] - fr[0x120 // 8]) // 28
+        un = np.ctypeslib.as_array(C.cast(fr[0x120 // 8], C.POINTER(C.c_uint8)), (cnt * 28,)).view(self.KP).copy()
+        im = (C.c_uint64 * 12)()
+        dummy = np.zeros((rows, cols), np.uint8)
+        self._mat_at(C.addressof(im), dummy)
+        fb = getattr(self.lib, "_ZN9ORB_SLAM25Frame18ComputeImageBoundsERKN2cv3MatE")
+        fb.argtypes, fb.restype = [C.c_void_p, C.c_void_p], None
+        fb(b, C.addressof(im))
+        st = lambda name: float(C.c_float.in_dll(self.lib, name).value)
+        bounds = (st("_ZN9ORB_SLAM25Frame6mnMinXE"), st("_ZN9ORB_SLAM25Frame6mnMaxXE"), st("_ZN9ORB_SLAM25Frame6mnMinYE"),
+                  st("_ZN9ORB_SLAM25Frame6mnMaxYE"))
+        return un, bounds

@@ -351,3 +351,15 @@ def test_search_for_initialization_equals_the_reference_matcher(oracle):
         m, n, prev = oracle.search_for_initialization(f1, f2, cam4, f1["xy"].copy(), int(win), float(nnr), bool(ori))
         assert n == int(g["si%d_n" % k]) > 50 and np.array_equal(m, g["si%d_match" % k]), k
         assert np.array_equal(prev, g["si%d_prev" % k]), k
+
+
+def test_undistortion_and_bounds_equal_the_reference_frame_code(oracle):
+    """Frame::UndistortKeyPoints (@0xf8630) and Frame::ComputeImageBounds (@0xf6010) executed from lib/libORB_SLAM2.so on a faked
+    Frame (fixture un*; cv::undistortPoints served by the cv2-pinned restatement): the k1 == 0 shortcut, the N x 2 / 2-channel
+    round trip, the corner order and min/max choices of the bounds."""
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    for k in range(int(g["un_n"])):
+        c = dict(zip(("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3"), (float(v) for v in g["un%d_calib" % k])), bf=40.0)
+        assert np.array_equal(oracle.undistort_points(c, g["un%d_xy" % k]).view(np.uint32), g["un%d_out" % k].view(np.uint32)), k
+        assert np.array_equal(oracle.image_bounds(c, 640, 480), g["un%d_bounds" % k]), k
+    assert np.array_equal(g["un1_out"], g["un1_xy"])  # the undistorted calibration copies
