@@ -9,6 +9,10 @@
 //   ORBmatcher::ComputeThreeMaxima            @0x79c40
 //   LSDmatcher / LineSegment::LineSegmentMathch: cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) semantics
 //                                             (header evidence include/auxiliar.h:30-51; UNPINNED beyond that)
+// Parity status: DescriptorDistance, ComputeThreeMaxima, RadiusByViewingCos, CheckDistEpipolarLine, Frame::GetFeaturesInArea and
+// the whole functions SearchByProjection (both overloads), SearchByBoW, SearchForTriangulation and SearchForInitialization are
+// PINNED AGAINST THE REFERENCE'S OWN CODE, executed from lib/libORB_SLAM2.so on hand-laid-out Frame / KeyFrame / MapPoint
+// objects (tests/golden/reference_code.py; fixtures reference_code.npz / reference_library.npz; tests/test_golden_cpu.py).
 // Constants from the binary: TH_LOW=50, TH_HIGH=100, HISTO_LENGTH=30 (@0x1269e0-e8), histogram factor
 // HISTO_LENGTH/360 (@0x1269f8), secondary-bin cut 0.1 (@0x1269f0).
 // The pointer-based containers (MapPoint*, std::map FeatureVector, mGrid vectors) are flattened to

@@ -8,12 +8,15 @@
 // model of SURVEY.md Appendix B, which tests/test_oracle_cv2.py pins against
 // cv2 4.13 (resize, GaussianBlur, FAST, fastAtan2) bit for bit.
 //
-// Parity status: ORB side PINNED on the primitives against cv2 4.13 and on the
-// constructor tables / pattern against the reference binary's data; the four
-// documented definitions (DESIGN.md "Pinned choices") are: blur table (runtime
-// parameter, default = cv2 4.13 table), sin/cos definition (orb_sincos below),
-// FMA form of the rBRIEF rotation (as in the shipped binary), quad-tree tie-break
-// (size, creation sequence) instead of the reference's heap address.
+// Parity status: PINNED AGAINST THE REFERENCE ITSELF.  ORB_SLAM2::ORBextractor::operator() is executed from the shipped
+// lib/libORB_SLAM2.so (tests/golden/reference_code.py: the library is dlopen'ed over generated stub dependencies, its OpenCV
+// entry points served by ABI-exact shims over the cv2-pinned primitives) and this restatement reproduces every keypoint
+// field and descriptor byte, order included (fixtures tests/golden/reference_library.npz, tests/test_golden_cpu.py); the
+// constructor tables, DistributeOctTree and ComputeKeyPointsOctTree are pinned the same way on their own.  The primitives are
+// pinned against cv2 4.13.  Choices the reference leaves to its environment (DESIGN.md "Pinned choices"): blur table (runtime
+// parameter, default = cv2 4.13 table), sin/cos definition (orb_sincos below; coincides with this container's glibc on every
+// argument that occurred), quad-tree tie-break (size, creation sequence) = the reference's heap-address order under a
+// monotonic allocator.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load this library.  The product (rgbd-pl-slam_b200/) never does.
