@@ -5,6 +5,10 @@
 //
 // TEST INFRASTRUCTURE ONLY: never linked into the product.
 //
+// Parity status: UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD, AssignFeaturesToGrid / PosInGrid are PINNED
+// AGAINST THE REFERENCE'S OWN CODE, executed from lib/libORB_SLAM2.so on a faked Frame (tests/golden/reference_code.py;
+// fixtures un*, st*, fg* of tests/golden/reference_library.npz; tests/test_golden_cpu.py).
+//
 // cv::undistortPoints (called by UndistortKeyPoints and ComputeImageBounds with R = empty, P = mK) lives in OpenCV, which is
 // not vendored; its published algorithm is restated here (normalise, 5 fixed-point iterations of the Brown model in double,
 // re-project with K) and pinned bit-for-bit against cv2 4.13 in tests/test_frame_cpu.py.  Built with -ffp-contract=off.
