@@ -14,8 +14,8 @@
 //                  sequential inside a frame (running region angle, shared `used` map).  Lanes = 4 frontier points x 8
 //                  neighbours with in-batch speculation; the `used` flag lives in the pixel records.  This is the mode
 //                  for large batches (many batches in flight fill the machine).
-//   k_lsd_grow_mw  the same result with one CTA of 8 / 24 warps per frame (ordered speculative regions over an owner
-//                  plane), chosen when the GPU holds at most one frame per SM (single frames, small batches, 4K)
+//   k_lsd_grow_aw  the same result with one CTA of 8 / 16 / 32 warps per frame: regions grown speculatively in parallel
+//                  over an owner plane and retired in seed order through a reorder window (no round barriers)
 //   k_lsd_nfa      rect_improve / rect_nfa: persistent grid, one warp per rectangle (independent of `used`)
 //   k_lsd_finish   ordered compaction, KeyLine fields, strongest-N selection, line equations
 //   k_lbd          LBD band descriptors, one CTA per kept line
@@ -300,28 +300,78 @@ struct GrowCtx {
   int sw, sh, P;
   int lane;
   bool prefetch;
-  // ---- CTA-per-frame mode (k_lsd_grow_mw): ordered speculative regions, see the kernel's header ----
-  unsigned* own;          // owner plane of the frame: MW_FREE or rank + 1 of the region that marked the pixel
-  unsigned myVal, baseVal;  // this region's tag; tags below baseVal are committed regions of earlier rounds
-  volatile int* poison;   // [slots] poison flags of the round (shared memory); mine is poison[slot]
-  const int* ranks;       // [slots] seed ranks of the round (shared memory)
+  // ---- CTA-per-frame mode (k_lsd_grow_aw): ordered speculative regions, see the kernel's header ----
+  // Owner plane: one word per pixel.  MW_FREE, or (tag << 1) | released with tag = seed rank + 1 of the region that
+  // marked the pixel.  released = 1 is a TOMBSTONE: the region gave the pixel back (refine() un-marks, reduce_region_radius()
+  // drops far points) but its result still depends on having held it, so an older region that takes the pixel while the
+  // releasing region is in flight must still poison it.  Tombstones of retired regions read as free.
+  unsigned* own;
+  unsigned myVal;         // this region's mark: tag << 1
+  const volatile unsigned* headTag;  // shared memory: smallest tag that is not final yet (lower tags = retired regions)
+  volatile int* poison;   // [nslots] poison flags (shared memory); mine is poison[slot]
+  volatile int* blocker;  // [nslots] tag of the older region that poisoned the slot
+  const volatile int* ranks;  // [nslots] seed ranks of the regions in the window (shared memory; -1 = empty slot)
   int slot, nslots;
   __device__ __forceinline__ bool mw_poisoned() const { return poison[slot] != 0; }
-  // May this region still test the pixel?  Not if a committed region or this region itself holds it.  A pixel held by
-  // another in-flight region stays a candidate: whether it is used only matters if it passes the alignment test, and
-  // then mw_take() settles it (a higher rank is robbed and poisoned, a lower rank poisons me).
-  __device__ __forceinline__ bool mw_available(unsigned ov) const { return ov >= baseVal && ov != myVal; }
-  __device__ __forceinline__ void mw_take(int id) const {
-    const unsigned old = atomicMin(own + id, myVal);
-    if (old == 0xffffffffu || old == myVal) return;
-    if (old > myVal) {  // robbed a higher in-flight region: it must not commit
-      for (int j = 0; j < nslots; ++j)
-        if ((unsigned)(ranks[j] + 1) == old) poison[j] = 1;
-    } else if (old >= baseVal) {
-      poison[slot] = 1;  // a lower in-flight region got there first
-    }
+  // headTag read AFTER the owner word `dep` has arrived (address dependence): a tag observed in the owner plane was
+  // written after the scheduler published the head tag under which that region runs, so a region inserted in front of
+  // the window is never mistaken for a retired one.
+  __device__ __forceinline__ unsigned fresh_head(unsigned dep) const {
+    unsigned z;
+    asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(dep));
+    return *reinterpret_cast<const volatile unsigned*>(reinterpret_cast<const volatile char*>(headTag) + z);
   }
-  __device__ __forceinline__ void mw_release(int id) const { atomicCAS(own + id, myVal, 0xffffffffu); }
+  // May this region still test the pixel?  Not if a retired region or this region itself holds it.  A pixel held (or
+  // tombstoned) by another in-flight region stays a candidate: whether it is used only matters if it passes the alignment
+  // test, and then mw_take() settles it (a younger region is robbed and poisoned, an older one poisons me).
+  // `h0` = the head tag read BEFORE the owner word was loaded: the holder counts as retired only if its tag lies below the
+  // head tag both before and after the load (before: a region that was still running when the word was read, and may
+  // un-mark the pixel later, must not pass for retired because it retired meanwhile).
+  __device__ __forceinline__ bool mw_available(unsigned ov, unsigned h0) const {
+    if (ov == 0xffffffffu) return true;
+    if ((ov | 1u) == (myVal | 1u)) return (ov & 1u) != 0;  // mine: only what I released myself
+    if (ov & 1u) return true;                                // tombstone: free if its region retired, else mw_take decides
+    const unsigned t = ov >> 1;
+    return t >= h0 || t >= fresh_head(ov);
+  }
+  __device__ __forceinline__ void mw_poison_self(unsigned tag) const {
+    blocker[slot] = (int)tag;
+    poison[slot] = 1;
+  }
+  // Take pixel `id`, last seen holding `ov`.
+  __device__ __forceinline__ void mw_take(int id, unsigned ov) const {
+    unsigned exp = ov;
+    for (int it = 0; it < 64; ++it) {
+      if (exp != 0xffffffffu && exp < myVal) {  // a lower word is in place
+        const unsigned t = exp >> 1;
+        if ((exp & 1u) && t < fresh_head(exp)) {  // tombstone of a retired region: free, but atomicMin cannot replace it
+          const unsigned old = atomicCAS(own + id, exp, myVal);
+          if (old == exp) return;
+          exp = old;
+          continue;
+        }
+        mw_poison_self(t);  // an older region holds the pixel (or gave it back and is still in flight)
+        return;
+      }
+      const unsigned old = atomicMin(own + id, myVal);
+      if (old == 0xffffffffu || (old | 1u) == (myVal | 1u)) return;
+      if (old > myVal) {  // robbed a younger in-flight region (or its tombstone): it must not retire with this result
+        const unsigned t = old >> 1;
+        for (int j = 0; j < nslots; ++j)
+          if ((unsigned)(ranks[j] + 1) == t) {
+            blocker[j] = (int)(myVal >> 1);
+            poison[j] = 1;
+          }
+        return;
+      }
+      exp = old;  // an older word got there first
+    }
+    mw_poison_self(0);  // never seen: give up on this run, the region is grown again
+  }
+  // refine() / reduce_region_radius(): the pixel is free again, the tombstone keeps the dependence visible
+  __device__ __forceinline__ void mw_release(int id) const { atomicCAS(own + id, myVal, myVal | 1u); }
+  // a squashed run leaves no trace
+  __device__ __forceinline__ void mw_release_free(int id) const { atomicCAS(own + id, myVal, 0xffffffffu); }
   __device__ __forceinline__ unsigned reg_get(int i) const { return i < REG_SMEM ? regS[i] : regG[i]; }
   __device__ __forceinline__ void reg_set(int i, unsigned v) const {
     if (i < REG_SMEM) regS[i] = v; else regG[i] = v;
@@ -439,7 +489,7 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
     sumdy = (float)s;
   }
   if (lane == 0) {
-    if (MW) C.mw_take(seed);
+    if (MW) C.mw_take(seed, __ldcg(C.own + seed));
     else *C.wptr(seed) = srec.w | USED_BIT;
   }
   __syncwarp();
@@ -449,16 +499,15 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
   const int pt = lane >> 3, nb8 = lane & 7, nb = nb8 < 4 ? nb8 : nb8 + 1;
   const int ox = (nb % 3) - 1, oy = (nb / 3) - 1;
   for (int i = 0; i < n;) {
-    if (MW && (C.mw_poisoned() || n > C.P - 64)) {  // a poisoned region is discarded anyway: stop early
-      if (lane == 0) C.poison[C.slot] = 1;
-      break;
-    }
+    if (MW && C.mw_poisoned()) break;  // a poisoned region is discarded anyway: stop early
     const int m4 = min(4, n - i);
     GP_START();
     GP_CNT(9, 1);
     int nidx = -1;
-    unsigned nxy = 0, w = 0;
+    unsigned nxy = 0, w = 0, ovk = 0;
     float deg = NOTDEF_F, cs = 0.f, sn = 0.f;
+    unsigned h0 = 0;
+    if (MW) h0 = *C.headTag;
     if (pt < m4) {
       const unsigned p = i + 4 <= REG_SMEM ? C.regS[i + pt] : C.reg_get(i + pt);  // warp-uniform fast path
       const int nx = (int)(p & 0xffff) + ox, ny = (int)(p >> 16) + oy;
@@ -467,11 +516,12 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
         unsigned ov = 0;
         if (MW) ov = __ldcg(C.own + id);  // owner words live in L2 (atomics), never in a possibly stale L1 line
         const uint4 r = C.pix[id];
-        const bool avail = MW ? (__uint_as_float(r.x) != NOTDEF_F && C.mw_available(ov)) : !(r.w & USED_BIT);
+        const bool avail = MW ? (__uint_as_float(r.x) != NOTDEF_F && C.mw_available(ov, h0)) : !(r.w & USED_BIT);
         if (avail && __uint_as_float(r.x) != NOTDEF_F) {
           nidx = id;
           nxy = ((unsigned)ny << 16) | (unsigned)nx;
           w = r.w;
+          ovk = ov;
           deg = __uint_as_float(r.x);
           cs = __uint_as_float(r.y);
           sn = __uint_as_float(r.z);
@@ -501,7 +551,7 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
           const int j0 = __ffs(m) - 1;
           if ((defm >> j0) == 1u) {
             if (lane == j0) {
-              if (MW) C.mw_take(nidx);
+              if (MW) C.mw_take(nidx, ovk);
               else *C.wptr(nidx) = w | USED_BIT;
               C.reg_set(n, nxy);
               if (C.prefetch) {
@@ -544,7 +594,7 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
           commit = (m & ((1u << b) - 1u)) | (m1 & (1u << b));
         }
         if ((commit >> lane) & 1u) {
-          if (MW) C.mw_take(nidx);
+          if (MW) C.mw_take(nidx, ovk);
           else *C.wptr(nidx) = w | USED_BIT;
           C.reg_set(n + __popc(commit & lt), nxy);
           if (C.prefetch) {
@@ -917,24 +967,9 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
 }
 
 
-// ------------------------------------------------------------------------------------------
-// k_lsd_grow_mw: the same region growing with one CTA of MW_K warps per frame, for small batches and large frames
-// (a 4K frame holds ~25 000 regions; one warp per frame leaves the machine empty).  Regions are grown speculatively in
-// parallel and committed in seed order, which keeps the result identical to the sequential loop:
-//   * every round warp 0 picks the next MW_K free seeds of the sorted list; slot j gets rank = its seed's list index;
-//   * the `used` map is an owner plane: MW_FREE, or rank + 1 of the region that marked the pixel (tags below the first
-//     rank of the round belong to committed regions);
-//   * a region that takes a pixel held by a HIGHER in-flight rank robs it and poisons that slot; a region that tries
-//     to take a pixel held by a LOWER in-flight rank poisons itself (the sequential loop would have shown it that pixel
-//     as used); pixels that are merely examined and fail the alignment test create no dependence;
-//   * after a CTA barrier the longest prefix of un-poisoned slots commits (rectangles are emitted in rank order), the
-//     other slots clear their tags and their seeds are picked again; slot 0 can never be poisoned, so a round always
-//     commits at least one region.
-// ------------------------------------------------------------------------------------------
-// MW_K = warps (regions in flight) per frame: 8 for VGA-class frames, 24 (768 threads x 80 registers, 118 KB of dynamic
-// shared memory) for frames of a megapixel and more, where a round finds more independent regions
-constexpr int MW_DIST = 12;    // seeds closer than this (Chebyshev) with similar level-line angles count as one structure
-// heuristic only (it decides which seeds share a round, never the result): two seeds probably grow the same region
+// heuristic only (it decides which seeds are grown at the same time, never the result): two seeds closer than MW_DIST
+// (Chebyshev) with similar level-line angles probably grow the same region
+constexpr int MW_DIST = 12;
 __device__ int g_mw_dist = MW_DIST;
 __device__ float g_mw_ang = 25.f;
 __device__ __forceinline__ bool mw_same_structure(int x1, int y1, float deg1, int x2, int y2, float deg2) {
@@ -943,166 +978,539 @@ __device__ __forceinline__ bool mw_same_structure(int x1, int y1, float deg1, in
   if (d > 180.f) d = 360.f - d;
   return d <= g_mw_ang;
 }
-constexpr int MW_SCAN = 8192;  // seeds scanned per round for the slots
-constexpr size_t mw_smem_bytes(int k) { return (sizeof(double) * 96 + sizeof(unsigned) * 1024) * (size_t)k; }  // stage + list head per warp
-template <int MW_K>
-__global__ void __launch_bounds__(32 * MW_K) k_lsd_grow_mw(const __grid_constant__ LineParams L, uint4* pixAll,
-                                                         unsigned* ownAll, const unsigned* __restrict__ seedsAll,
-                                                         const int* __restrict__ nseeds, unsigned* regAll,
-                                                         LsdRect* __restrict__ rectsAll, int* __restrict__ nrects,
-                                                         int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char mw_smem[];
-  double(*stage)[96] = reinterpret_cast<double(*)[96]>(mw_smem);
-  unsigned(*regS)[REG_SMEM] = reinterpret_cast<unsigned(*)[REG_SMEM]>(mw_smem + sizeof(double) * 96 * MW_K);
-  __shared__ LsdRect s_rect[MW_K];
-  __shared__ int s_rank[MW_K], s_poison[MW_K], s_has[MW_K], s_n[MW_K];
-  __shared__ int s_selx[MW_K], s_sely[MW_K];
-  __shared__ float s_sela[MW_K];
-  __shared__ int s_cursor, s_active, s_commit;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x;
-  GrowCtx C;
-#ifdef PLSLAM_GROW_PROF
-  long long prof[16];
-  for (int k = 0; k < 16; ++k) prof[k] = 0;
-  C.prof = prof;
-#endif
-  C.stage = stage[warp];
-  C.regS = regS[warp];
-  C.prefetch = false;
-  C.pix = pixAll + (size_t)f * L.P;
-  C.own = ownAll + (size_t)f * L.P;
-  C.regG = regAll + ((size_t)f * MW_K + warp) * L.P;
-  C.sw = L.sw;
-  C.sh = L.sh;
-  C.P = L.P;
-  C.lane = lane;
-  C.poison = s_poison;
-  C.ranks = s_rank;
-  C.slot = warp;
-  C.nslots = MW_K;
-  const unsigned* seeds = seedsAll + (size_t)f * L.P;
-  const int ns = nseeds[f];
-  LsdRect* rects = rectsAll + (size_t)f * L.rect_cap;
-  int nrect = 0;  // meaningful in thread 0
-  if (threadIdx.x == 0) s_cursor = 0;
+
+// ------------------------------------------------------------------------------------------
+// k_lsd_grow_aw: region growing with one CTA per frame, K - 1 worker warps and one scheduler warp, NO round barriers.
+// Regions are grown speculatively in parallel and retired in seed order through a reorder window, which keeps the result
+// identical to the sequential loop of lsd.cpp over an owner plane (GrowCtx):
+//   * the scheduler walks the sorted seed list once (cursor).  A seed whose pixel is free and that does not look like
+//     part of a structure already being grown is ISSUED: it gets a window slot (tag = rank + 1) and enters the ready
+//     queue; every other seed is SKIPPED.  Workers pop the queue, grow the region (lsd_region_grow_spec<true>,
+//     region2rect, refine), publish DONE and take the next job at once;
+//   * window slots form a list ordered by rank.  The head retires when it is DONE and not poisoned, after the seeds
+//     skipped in front of it have been VALIDATED: each must carry the tag of a region that already retired (the
+//     sequential loop would have found it used).  Only skipped seeds that were not already held by a retired region
+//     when the cursor passed need the second look (dirtyFrom).  A skipped seed that is still free (or held by a
+//     younger region) is INSERTED as a new head in front of the waiting one: it must grow first;
+//   * tags below the head tag are final.  A region that takes a pixel held by a younger in-flight region robs it
+//     (atomicMin) and poisons that slot; a region that wants a pixel held by an older in-flight region poisons itself
+//     (blocker = that tag).  A poisoned region gives its pixels back (SQUASHED) and is re-issued once its blocker has
+//     retired; a region poisoned after it finished releases its pixels by scanning its bounding box for its tag;
+//   * the head can only be poisoned by an inserted older region, and every insertion retires before the next
+//     validation, so the kernel always makes progress; spin loops carry a watchdog that raises PLSLAM_ERR_INTERNAL.
+// ------------------------------------------------------------------------------------------
+enum { AW_FREE = 0, AW_READY = 1, AW_RUNNING = 2, AW_DONE = 3, AW_SQUASHED = 4 };
+constexpr int AW_ACT = 32;            // seeds of regions in flight remembered for the same-structure test
+constexpr int AW_NONE = 0x7fffffff;
+enum { AWS_ISSUED = 0, AWS_VOID, AWS_SQUASH_RUN, AWS_SQUASH_DONE, AWS_INSERT, AWS_RECTS, AWS_VALCHUNKS, AWS_SCHED_IDLE,
+       AWS_WORK_IDLE, AWS_BLOCKED_SEED, AWS_PICKCHUNKS, AWS_FRAMES, AWS_N };
+__device__ unsigned long long g_aw_stats[16];
+
+template <int W>
+struct AwState {
+  LsdRect rect[W];
+  int rank[W];        // seed rank of the slot's region, -1 = free slot
+  int state[W];
+  int poison[W];
+  int blocker[W];
+  int has[W];         // DONE: a rectangle was produced
+  int next[W];        // rank-ordered list of the slots in use
+  int dirtyFrom[W];   // first skipped seed in front of this slot that needs validation (AW_NONE: none)
+  int needRelease[W]; // poisoned after DONE: the next run starts by releasing the bounding box
+  int bb0[W], bb1[W]; // bounding box of the region's pixels: (y0 << 16) | x0, (y1 << 16) | x1
+  int freeStack[W];
+  int q[W];           // ready queue: slot + 1, 0 = empty
+  int actSlot[AW_ACT], actRank[AW_ACT], actX[AW_ACT], actY[AW_ACT];
+  float actA[AW_ACT];
+  unsigned qticket;
+  unsigned headTag;
+  int nActive, nSquashed, done, abort;
+  unsigned long long stats[AWS_N];
+};
+template <int K, int W>
+constexpr size_t aw_smem_bytes() {
+  return ((sizeof(AwState<W>) + 15) & ~size_t(15)) + (sizeof(double) * 96 + sizeof(unsigned) * REG_SMEM) * (size_t)(K - 1);
+}
+constexpr long long AW_WATCHDOG = 1ll << 24;  // polls (>= 40 ns each) without progress before the kernel gives up
+
+template <int K, int W>
+__device__ void aw_scheduler(AwState<W>& S, const LineParams& L, const uint4* __restrict__ pix, const unsigned* own,
+                             const unsigned* __restrict__ seeds, int ns, LsdRect* __restrict__ rects, int* nrectOut,
+                             int* status, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  volatile int* vstate = S.state;
+  volatile int* vpoison = S.poison;
+  volatile int* vblocker = S.blocker;
+  volatile int* vq = S.q;
+  volatile int* vrank = S.rank;
+  volatile unsigned* vhead = &S.headTag;
+  int head = -1, tail = -1, nfree = W, cursor = 0, valFrom = 0, gapDirty = AW_NONE, nrect = 0;
+  unsigned qtail = 0, headTag = 1u;
+  constexpr int MAXACT = K + 1;  // regions READY or RUNNING: the K - 1 workers never wait for the scheduler
+  long long idle = 0;
+#define AW_STAT(k, v) do { if (lane == 0) S.stats[k] += (v); } while (0)
+
+  auto push = [&](int s) {
+    if (lane == 0) {
+      vstate[s] = AW_READY;
+      atomicAdd(&S.nActive, 1);
+      __threadfence_block();
+      long long spins = 0;  // the entry was consumed long ago (at most W jobs exist, tickets are FIFO)
+      while (vq[qtail % W] != 0 && ++spins < AW_WATCHDOG) {}
+      if (spins >= AW_WATCHDOG) {
+        atomicMax(status, PLSLAM_ERR_INTERNAL);
+        *reinterpret_cast<volatile int*>(&S.abort) = 1;
+      }
+      vq[qtail % W] = s + 1;
+    }
+    ++qtail;
+    __syncwarp();
+  };
+  auto remember = [&](int s, int rank, int x, int y, float a) {  // same-structure table: reuse a dead entry
+    bool dead = true;
+    if (lane < AW_ACT) {
+      const int as = S.actSlot[lane];
+      if (as >= 0) {
+        const int st = vstate[as];
+        dead = !((st == AW_READY || st == AW_RUNNING) && vrank[as] == S.actRank[lane]);
+      }
+    }
+    const unsigned m = __ballot_sync(FULL, dead && lane < AW_ACT);
+    const int e = m ? __ffs(m) - 1 : 0;
+    if (lane == 0) {
+      S.actSlot[e] = s;
+      S.actRank[e] = rank;
+      S.actX[e] = x;
+      S.actY[e] = y;
+      S.actA[e] = a;
+    }
+    __syncwarp();
+  };
+  auto issue = [&](int rank, int x, int y, float a, int dirty, bool atHead) {
+    const int t = S.freeStack[nfree - 1];
+    --nfree;
+    if (lane == 0) {
+      vrank[t] = rank;
+      S.has[t] = 0;
+      S.needRelease[t] = 0;
+      S.dirtyFrom[t] = dirty;
+      vpoison[t] = 0;
+      vblocker[t] = 0;
+      if (atHead) {
+        S.next[t] = head;
+      } else {
+        S.next[t] = -1;
+        if (tail >= 0) S.next[tail] = t;
+      }
+    }
+    if (atHead || head < 0) {
+      headTag = (unsigned)rank + 1u;  // lowered by an insertion, raised when the window was empty
+      if (lane == 0) *vhead = headTag;
+      if (head < 0) tail = t;
+      head = t;
+    } else {
+      tail = t;
+    }
+    __syncwarp();
+    __threadfence_block();
+    remember(t, rank, x, y, a);
+    AW_STAT(AWS_ISSUED, 1);
+    push(t);
+  };
+  // first seed in [from, to) whose pixel is not HELD by a retired region (tag < limitTag; tombstones and MW_FREE have bit 0
+  // set), or -1
+  auto validate = [&](int from, int to, unsigned limitTag) {
+    int bad = -1;
+    for (int i0 = from; i0 < to && bad < 0; i0 += 32) {
+      const int i = i0 + lane;
+      bool fail = false;
+      if (i < to) {
+        const unsigned v = __ldcg(own + seeds[i]);
+        fail = (v & 1u) || (v >> 1) >= limitTag;  // free, given back, or held by a region that is not final
+      }
+      const unsigned m = __ballot_sync(FULL, fail);
+      if (m) bad = i0 + __ffs(m) - 1;
+      AW_STAT(AWS_VALCHUNKS, 1);
+    }
+    return bad;
+  };
+  auto insert = [&](int rank) {  // a skipped seed turned out to be free: it becomes the new head
+    const int sd = (int)seeds[rank];
+    const int y = sd / L.sw, x = sd - y * L.sw;
+    if (head >= 0 && lane == 0) S.dirtyFrom[head] = rank + 1;
+    __syncwarp();
+    issue(rank, x, y, __uint_as_float(pix[sd].x), AW_NONE, true);
+    valFrom = rank;  // everything in front of it was validated
+    AW_STAT(AWS_INSERT, 1);
+  };
+
   while (true) {
-    __syncthreads();
-    if (warp == 0) {
-      // Slot 0 = the first free seed from the cursor; the other slots = the next free seeds that are not close to and
-      // aligned with a seed already picked.  Neighbouring seeds of the list usually sit on the same edge (same
-      // gradient bin, raster order) and would only grow the same region again.  A skipped seed keeps its place
-      // in the order: the commit step below makes sure it was absorbed by a committed region before anything behind it
-      // commits.
-      int found = 0;
-      const int scanEnd = min(ns, s_cursor + MW_SCAN);
-      for (int pos = s_cursor; pos < ns && (found == 0 || pos < scanEnd) && found < MW_K; pos += 32) {
-        const int i = pos + lane;
-        int sx = 0, sy = 0;
-        float sa = 0.f;
-        bool ok = false;
-        if (i < ns) {
-          const int sd = (int)seeds[i];
-          if (__ldcg(C.own + sd) == 0xffffffffu) {
-            sy = sd / L.sw;
-            sx = sd - sy * L.sw;
-            sa = __uint_as_float(C.pix[sd].x);
-            ok = true;
-            for (int k = 0; k < found; ++k) ok = ok && !mw_same_structure(sx, sy, sa, s_selx[k], s_sely[k], s_sela[k]);
-          }
-        }
-        unsigned m = __ballot_sync(0xffffffffu, ok);
-        while (m && found < MW_K) {
-          const int j = __ffs(m) - 1;
-          const int jx = __shfl_sync(0xffffffffu, sx, j), jy = __shfl_sync(0xffffffffu, sy, j);
-          const float ja = __shfl_sync(0xffffffffu, sa, j);
-          if (lane == 0) {
-            s_rank[found] = pos + j;
-            s_selx[found] = jx;
-            s_sely[found] = jy;
-            s_sela[found] = ja;
-          }
-          ++found;
-          ok = ok && lane > j && !mw_same_structure(sx, sy, sa, jx, jy, ja);
-          m = __ballot_sync(0xffffffffu, ok);
-        }
-        __syncwarp();
+    bool progress = false, scan = false;
+    if (*reinterpret_cast<volatile int*>(&S.abort)) break;
+    // ---- retire in rank order ----
+    while (head >= 0) {
+      const int s = head;
+      const int st = vstate[s];
+      if (st != AW_DONE) break;
+      __threadfence_block();
+      if (vpoison[s]) {  // robbed by an older region after it had finished: re-issued by the scan below
+        scan = true;
+        break;
       }
-      if (lane < MW_K) {
-        if (lane >= found) s_rank[lane] = -1;
-        s_poison[lane] = 0;
-        s_has[lane] = 0;
-        s_n[lane] = 0;
+      const int myRank = vrank[s];
+      const int from = max(valFrom, S.dirtyFrom[s]);
+      const int bad = from < myRank ? validate(from, myRank, (unsigned)myRank + 1u) : -1;
+      if (bad >= 0) {
+        insert(bad);
+        progress = true;
+        break;
       }
-      if (lane == 0) s_active = found;
-    }
-    __syncthreads();
-    const int active = s_active;
-    if (active == 0) break;
-    if (warp < active) {
-      const int rank = s_rank[warp];
-      const int seed = (int)seeds[rank];
-      C.myVal = (unsigned)rank + 1u;
-      C.baseVal = (unsigned)s_rank[0] + 1u;
-      if (lane == 0) C.reg_set(0, ((unsigned)(seed / L.sw) << 16) | (unsigned)(seed % L.sw));
-      __syncwarp();
-      double reg_angle;
-      int n = lsd_region_grow_spec<true>(C, L.prec, &reg_angle);
-      if (!C.mw_poisoned() && n >= L.min_reg_size) {
-        LsdRect rec;
-        lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
-        const bool keep = lsd_refine<true>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, 1);
-        if (keep && !C.mw_poisoned() && lane == 0) {
-          s_rect[warp] = rec;
-          s_has[warp] = 1;
+      if (S.has[s]) {
+        if (nrect < L.rect_cap) {
+          if (lane < (int)(sizeof(LsdRect) / sizeof(double)))
+            reinterpret_cast<double*>(rects + nrect)[lane] = reinterpret_cast<const double*>(&S.rect[s])[lane];
+        } else if (lane == 0) {
+          atomicMax(status, PLSLAM_ERR_OVERFLOW);
         }
+        ++nrect;
+        AW_STAT(AWS_RECTS, 1);
       }
-      if (lane == 0) s_n[warp] = n;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      // longest committable prefix: un-poisoned slots, and every seed skipped in front of a slot must by now carry the
-      // tag of a lower-ranked (hence committed) region — otherwise the sequential loop would have grown it first
-      int c = 0;
-      while (c < active && !s_poison[c]) {
-        if (c > 0) {
-          const unsigned mine = (unsigned)s_rank[c] + 1u;
-          bool bad = false;
-          for (int i = s_rank[c - 1] + 1 + lane; i < s_rank[c]; i += 32) bad = bad || __ldcg(C.own + seeds[i]) >= mine;
-          if (__any_sync(0xffffffffu, bad)) break;
-        }
-        ++c;
-      }
-      if (lane == 0) s_commit = c;  // >= 1: nothing can poison the lowest rank and nothing is skipped in front of it
-#ifdef PLSLAM_GROW_PROF
+      valFrom = myRank + 1;
+      const int nx = S.next[s];
+      headTag = nx >= 0 ? (unsigned)vrank[nx] + 1u : (unsigned)max(cursor, myRank + 1) + 1u;
       if (lane == 0) {
-        atomicAdd(&g_grow_prof[5], 1ull);                                  // rounds
-        atomicAdd(&g_grow_prof[6], (unsigned long long)active);            // slots started
-        atomicAdd(&g_grow_prof[7], (unsigned long long)c);                 // slots committed
-        if (c < active) atomicAdd(&g_grow_prof[s_poison[c] ? 13 : 14], 1ull);  // stopped by poison / by a skipped free seed
+        vrank[s] = -1;
+        vstate[s] = AW_FREE;
+        S.freeStack[nfree] = s;
+        *vhead = headTag;
       }
-#endif
+      ++nfree;
+      head = nx;
+      if (head < 0) tail = -1;
+      __syncwarp();
+      progress = true;
     }
-    __syncthreads();
-    const int c = s_commit;
-    if (threadIdx.x == 0) {
-      for (int j = 0; j < c; ++j)
-        if (s_has[j]) {
-          if (nrect < L.rect_cap) rects[nrect] = s_rect[j];
-          else atomicMax(status, PLSLAM_ERR_OVERFLOW);
-          ++nrect;
+    // ---- poisoned regions run again once the region that blocked them has retired (or they are the head): squashed
+    //      ones have given their pixels back already, finished ones release by bounding box first ----
+    if (scan || progress || *reinterpret_cast<volatile int*>(&S.nSquashed) > 0) {
+      for (int b = 0; b < W; b += 32) {
+        const int s = b + lane;
+        int kind = 0;
+        if (s < W) {
+          const int st = vstate[s];
+          const bool go = (unsigned)vblocker[s] < headTag || s == head;
+          if (st == AW_SQUASHED && go) kind = 1;
+          else if (st == AW_DONE && vpoison[s] && go) kind = 2;
         }
-      s_cursor = s_rank[c - 1] + 1;
-    }
-    if (warp >= c && warp < active) {  // discarded: give the pixels back; the seed is picked again next round
-      const int n = s_n[warp];
-      for (int i = lane; i < n; i += 32) {
-        const unsigned pxy = C.reg_get(i) & 0x7fffffffu;
-        C.mw_release((int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff));
+        unsigned m = __ballot_sync(FULL, kind != 0);
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1u;
+          const int kj = __shfl_sync(FULL, kind, j);
+          if (lane == 0) {
+            if (kj == 1) atomicSub(&S.nSquashed, 1);
+            else S.needRelease[b + j] = 1;
+          }
+          if (kj == 2) AW_STAT(AWS_SQUASH_DONE, 1);
+          push(b + j);
+          progress = true;
+        }
       }
+    }
+    // ---- issue new regions from the cursor (a few chunks at a time: retirement must not wait for a long scan) ----
+    for (int chunks = 0; chunks < 8 && nfree > 1 && cursor < ns; ++chunks) {
+      int nAct = *reinterpret_cast<volatile int*>(&S.nActive);
+      if (nAct >= MAXACT) break;
+      const int i = cursor + lane;
+      const int sd = i < ns ? (int)seeds[i] : -1;
+      const unsigned ov = sd >= 0 ? __ldcg(own + sd) : 0u;
+      AW_STAT(AWS_PICKCHUNKS, 1);
+      const bool retired = (ov >> 1) < headTag;  // (MW_FREE >> 1 is above every tag)
+      const bool isFree = sd >= 0 && (ov & 1u) && (ov == 0xffffffffu || retired);  // free, or given back by a retired region
+      const bool fin = sd >= 0 && !(ov & 1u) && retired;                          // held by a retired region: skipped for good
+      int sx = 0, sy = 0;
+      float sa = 0.f;
+      bool ok = isFree;
+      // live entries of the same-structure table
+      bool live = false;
+      if (lane < AW_ACT) {
+        const int as = S.actSlot[lane];
+        if (as >= 0) {
+          const int st = vstate[as];
+          live = (st == AW_READY || st == AW_RUNNING) && vrank[as] == S.actRank[lane];
+        }
+      }
+      const unsigned liveM = __ballot_sync(FULL, live);
+      if (isFree) {
+        sy = sd / L.sw;
+        sx = sd - sy * L.sw;
+        sa = __uint_as_float(pix[sd].x);
+        for (unsigned r = liveM; r && ok; r &= r - 1u) {
+          const int e = __ffs(r) - 1;
+          ok = !mw_same_structure(sx, sy, sa, S.actX[e], S.actY[e], S.actA[e]);
+        }
+      }
+      unsigned m = __ballot_sync(FULL, ok);
+      const unsigned dirtyM = __ballot_sync(FULL, sd >= 0 && !fin);
+      int consumed = 0;
+      while (m && nfree > 1 && nAct < MAXACT) {
+        const int j = __ffs(m) - 1;
+        const unsigned between = dirtyM & ((1u << j) - 1u) & ~((1u << consumed) - 1u);
+        if (between) gapDirty = min(gapDirty, cursor + __ffs(between) - 1);
+        const int jx = __shfl_sync(FULL, sx, j), jy = __shfl_sync(FULL, sy, j);
+        const float ja = __shfl_sync(FULL, sa, j);
+        issue(cursor + j, jx, jy, ja, gapDirty, false);
+        gapDirty = AW_NONE;
+        consumed = j + 1;
+        ++nAct;
+        ok = ok && lane > j && !mw_same_structure(sx, sy, sa, jx, jy, ja);
+        m = __ballot_sync(FULL, ok);
+        progress = true;
+      }
+      if (!m) {  // the rest of the chunk is skipped
+        const unsigned rest = consumed < 32 ? dirtyM & ~((1u << consumed) - 1u) : 0u;
+        if (rest) gapDirty = min(gapDirty, cursor + __ffs(rest) - 1);
+        cursor = min(ns, cursor + 32);
+        progress = true;
+      } else {
+        cursor += consumed;
+        break;
+      }
+    }
+    // ---- the end: nothing in flight, list exhausted, tail of skipped seeds validated ----
+    if (head < 0 && cursor >= ns) {
+      const int from = max(valFrom, gapDirty);
+      const int bad = from < ns ? validate(from, ns, 0x7fffffffu) : -1;
+      if (bad < 0) break;
+      gapDirty = bad + 1;
+      insert(bad);
+      progress = true;
+    }
+    if (!progress) {
+      AW_STAT(AWS_SCHED_IDLE, 1);
+      __nanosleep(40);
+      if (++idle > AW_WATCHDOG) {
+        if (lane == 0) {
+          atomicMax(status, PLSLAM_ERR_INTERNAL);
+          *reinterpret_cast<volatile int*>(&S.abort) = 1;
+        }
+        break;
+      }
+    } else {
+      idle = 0;
     }
   }
-  if (threadIdx.x == 0) nrects[f] = min(nrect, L.rect_cap);
+  if (lane == 0) {
+    *nrectOut = min(nrect, L.rect_cap);
+    __threadfence_block();
+    *reinterpret_cast<volatile int*>(&S.done) = 1;
+  }
+#undef AW_STAT
+}
+
+template <int K, int W>
+__device__ void aw_worker(AwState<W>& S, GrowCtx& C, const LineParams& L, const unsigned* __restrict__ seeds, int* status) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = C.lane;
+  volatile int* vstate = S.state;
+  volatile int* vq = S.q;
+  volatile int* vrank = S.rank;
+  volatile int* vdone = &S.done;
+  volatile int* vabort = &S.abort;
+  while (true) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(&S.qticket, 1u);
+    t = __shfl_sync(FULL, t, 0);
+    int v = 0;
+    long long spins = 0;
+    while (true) {
+      if (lane == 0) v = vq[t % W];
+      v = __shfl_sync(FULL, v, 0);
+      if (v) break;
+      int stop = 0;
+      if (lane == 0) stop = *vdone | *vabort;
+      if (__shfl_sync(FULL, stop, 0)) return;
+      __nanosleep(40);
+      if (++spins > AW_WATCHDOG) {
+        if (lane == 0) {
+          atomicMax(status, PLSLAM_ERR_INTERNAL);
+          *vabort = 1;
+        }
+        return;
+      }
+    }
+    if (lane == 0) {
+      vq[t % W] = 0;
+      S.stats[AWS_WORK_IDLE] += (unsigned long long)spins;  // racy between workers: a statistic only
+    }
+    const int s = v - 1;
+    __threadfence_block();
+    const int rank = vrank[s];
+    const int seed = (int)seeds[rank];
+    C.myVal = ((unsigned)rank + 1u) << 1;
+    C.slot = s;
+    if (S.needRelease[s]) {  // the previous run finished and was robbed afterwards: its pixels still carry the tag
+      const int x0 = S.bb0[s] & 0xffff, y0 = S.bb0[s] >> 16, x1 = S.bb1[s] & 0xffff, y1 = S.bb1[s] >> 16;
+      const int bw = x1 - x0 + 1, tot = bw > 0 ? bw * (y1 - y0 + 1) : 0;
+      for (int k = lane; k < tot; k += 32) {
+        const int yy = y0 + k / bw, xx = x0 + k % bw;
+        const int id = yy * C.sw + xx;
+        if (__ldcg(C.own + id) == C.myVal) C.mw_release_free(id);
+      }
+    }
+    __threadfence();
+    if (lane == 0) {
+      S.needRelease[s] = 0;
+      C.blocker[s] = 0;
+      C.poison[s] = 0;
+      vstate[s] = AW_RUNNING;
+    }
+    __syncwarp();
+    int n = 0;
+    bool keep = false, squashed = false;
+    LsdRect rec;
+    const unsigned sh0 = *C.headTag;
+    const unsigned sov = __ldcg(C.own + seed);
+    const unsigned stag = sov >> 1;
+    const bool older = sov != 0xffffffffu && sov < C.myVal;
+    const bool olderInFlight = older && (stag >= sh0 || stag >= C.fresh_head(sov));
+    if (older && olderInFlight) {
+      // an older region in flight holds the seed (or gave it back): wait for its fate
+      squashed = true;
+      if (lane == 0) {
+        C.blocker[s] = (int)stag;
+        S.stats[AWS_BLOCKED_SEED] += 1;
+      }
+    } else if (older && !(sov & 1u)) {
+      // a retired region holds the seed: the sequential loop finds it used, there is no region
+      if (lane == 0) S.stats[AWS_VOID] += 1;
+    } else {
+      if (lane == 0) C.reg_set(0, ((unsigned)(seed / C.sw) << 16) | (unsigned)(seed % C.sw));
+      __syncwarp();
+      double reg_angle;
+      n = lsd_region_grow_spec<true>(C, L.prec, &reg_angle);
+      if (!C.mw_poisoned() && n >= L.min_reg_size) {
+        lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
+        keep = lsd_refine<true>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, 1);
+      }
+      if (C.mw_poisoned()) {
+        squashed = true;
+        for (int i = lane; i < n; i += 32) {
+          const unsigned pxy = C.reg_get(i) & 0x7fffffffu;
+          C.mw_release_free((int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff));
+        }
+        if (lane == 0) S.stats[AWS_SQUASH_RUN] += 1;
+      }
+    }
+    int bx0 = 0xffff, by0 = 0x7fff, bx1 = 0, by1 = 0;
+    if (!squashed) {
+      for (int i = lane; i < n; i += 32) {
+        const unsigned pxy = C.reg_get(i) & 0x7fffffffu;
+        const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+        bx0 = min(bx0, px);
+        bx1 = max(bx1, px);
+        by0 = min(by0, py);
+        by1 = max(by1, py);
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        bx0 = min(bx0, __shfl_xor_sync(FULL, bx0, d));
+        by0 = min(by0, __shfl_xor_sync(FULL, by0, d));
+        bx1 = max(bx1, __shfl_xor_sync(FULL, bx1, d));
+        by1 = max(by1, __shfl_xor_sync(FULL, by1, d));
+      }
+      if (n == 0) { bx0 = 1; bx1 = 0; by0 = 0; by1 = 0; }
+    }
+    __threadfence();  // owner-plane updates (releases are fire-and-forget) are performed before the state is published
+    if (lane == 0) {
+      if (squashed) {
+        atomicAdd(&S.nSquashed, 1);
+        __threadfence_block();
+        vstate[s] = AW_SQUASHED;
+      } else {
+        S.has[s] = keep ? 1 : 0;
+        if (keep) S.rect[s] = rec;
+        S.bb0[s] = (by0 << 16) | bx0;
+        S.bb1[s] = (by1 << 16) | bx1;
+        __threadfence_block();
+        vstate[s] = AW_DONE;
+      }
+      atomicSub(&S.nActive, 1);
+    }
+    __syncwarp();
+  }
+}
+
+template <int K, int W>
+__global__ void __launch_bounds__(32 * K) k_lsd_grow_aw(const __grid_constant__ LineParams L, uint4* pixAll, unsigned* ownAll,
+                                                       const unsigned* __restrict__ seedsAll,
+                                                       const int* __restrict__ nseeds, unsigned* regAll,
+                                                       LsdRect* __restrict__ rectsAll, int* __restrict__ nrects,
+                                                       int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char aw_smem[];
+  AwState<W>& S = *reinterpret_cast<AwState<W>*>(aw_smem);
+  unsigned char* wbase = aw_smem + ((sizeof(AwState<W>) + 15) & ~size_t(15));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x;
+  for (int i = threadIdx.x; i < W; i += 32 * K) {
+    S.rank[i] = -1;
+    S.state[i] = AW_FREE;
+    S.poison[i] = 0;
+    S.blocker[i] = 0;
+    S.has[i] = 0;
+    S.next[i] = -1;
+    S.dirtyFrom[i] = AW_NONE;
+    S.needRelease[i] = 0;
+    S.freeStack[i] = W - 1 - i;
+    S.q[i] = 0;
+  }
+  if (threadIdx.x < AW_ACT) S.actSlot[threadIdx.x] = -1;
+  if (threadIdx.x < AWS_N) S.stats[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    S.qticket = 0;
+    S.headTag = 1u;
+    S.nActive = 0;
+    S.nSquashed = 0;
+    S.done = 0;
+    S.abort = 0;
+  }
+  __syncthreads();
+  const unsigned* seeds = seedsAll + (size_t)f * L.P;
+  if (warp == 0) {
+    aw_scheduler<K, W>(S, L, pixAll + (size_t)f * L.P, ownAll + (size_t)f * L.P, seeds, nseeds[f],
+                       rectsAll + (size_t)f * L.rect_cap, nrects + f, status, lane);
+  } else {
+    GrowCtx C;
+#ifdef PLSLAM_GROW_PROF
+    long long prof[16];
+    for (int k = 0; k < 16; ++k) prof[k] = 0;
+    C.prof = prof;
+#endif
+    unsigned char* mine = wbase + (size_t)(warp - 1) * (sizeof(double) * 96 + sizeof(unsigned) * REG_SMEM);
+    C.stage = reinterpret_cast<double*>(mine);
+    C.regS = reinterpret_cast<unsigned*>(mine + sizeof(double) * 96);
+    C.prefetch = false;
+    C.pix = pixAll + (size_t)f * L.P;
+    C.own = ownAll + (size_t)f * L.P;
+    C.regG = regAll + ((size_t)f * K + warp) * L.P;
+    C.sw = L.sw;
+    C.sh = L.sh;
+    C.P = L.P;
+    C.lane = lane;
+    C.poison = S.poison;
+    C.blocker = S.blocker;
+    C.headTag = &S.headTag;
+    C.ranks = S.rank;
+    C.nslots = W;
+    C.slot = 0;
+    C.myVal = 0;
+    aw_worker<K, W>(S, C, L, seeds, status);
+  }
+  __syncthreads();
+  if (threadIdx.x < AWS_N) {
+    const unsigned long long v = threadIdx.x == AWS_FRAMES ? 1ull : S.stats[threadIdx.x];
+    if (v) atomicAdd(&g_aw_stats[threadIdx.x], v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1644,6 +2052,13 @@ __global__ void __launch_bounds__(96) k_lbd(const __grid_constant__ LineParams L
 }
 
 }  // namespace
+int debug_aw_stats(unsigned long long* out16) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return PLSLAM_ERR_CUDA;
+  if (cudaMemcpyFromSymbol(out16, g_aw_stats, sizeof(g_aw_stats)) != cudaSuccess) return PLSLAM_ERR_CUDA;
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyToSymbol(g_aw_stats, z, sizeof(z)) != cudaSuccess) return PLSLAM_ERR_CUDA;
+  return PLSLAM_OK;
+}
 #ifdef PLSLAM_GROW_PROF
 int debug_grow_prof(unsigned long long* out16) {
   cudaDeviceSynchronize();
@@ -1835,40 +2250,45 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
   P.batch = batch;
-  // Small batches / large frames: one CTA of MW_K warps per frame with ordered speculative regions (k_lsd_grow_mw);
-  // large batches of small frames: one warp per frame (no wasted speculation, many batches in flight fill the machine).
+  // PLSLAM_GROW_MODE: 0 = one warp per frame (k_lsd_grow), 2 = speculative multi-warp growing with in-order retirement
+  // (k_lsd_grow_aw); unset = automatic.  (Mode 1, the round-based predecessor of mode 2, is gone.)
   static const int growMode = [] { const char* e = std::getenv("PLSLAM_GROW_MODE"); return e ? std::atoi(e) : -1; }();  // -1 auto
-  // CTA-per-frame speculation pays when the whole GPU has at most one frame per SM to work on (all pipeline slots counted)
-  // ... and when the per-slot region lists (K lists of P entries per frame) stay within 10 GB
-  const size_t mwListBytes = (size_t)std::max(batch, cfgB) * (P.P >= (1 << 20) ? 24 : 8) * P.P * sizeof(unsigned);
-  const bool mw = growMode >= 0 ? growMode == 1
-                                : ((long long)batch * batches_in_flight <= numSMs && mwListBytes <= ((size_t)10 << 30));
-  if (mw) {
+  // speculation pays when the whole GPU has at most one frame per SM to work on (all pipeline slots counted)
+  // ... and when the per-worker region lists (K lists of P entries per frame) stay within 10 GB
+  const size_t awListBytes = (size_t)std::max(batch, cfgB) * 8 * P.P * sizeof(unsigned);
+  const bool aw = growMode >= 0 ? growMode != 0
+                                : ((long long)batch * batches_in_flight <= numSMs && awListBytes <= ((size_t)10 << 30));
+  static const int awKenv = [] { const char* e = std::getenv("PLSLAM_AW_K"); return e ? std::atoi(e) : 0; }();
+  if (aw) {
+    // async window: K warps per frame (1 scheduler + K - 1 workers); per-worker region lists of P entries
+    int awK = awKenv ? awKenv : ((long long)batch * batches_in_flight <= numSMs ? 32 : 8);
+    awK = awK >= 32 ? 32 : awK >= 16 ? 16 : 8;
     int rc2;
-    static bool mwTune = false;
-    if (!mwTune) {  // experiment knobs of the seed-spreading heuristic (never affect results)
-      mwTune = true;
+    static bool awTune = false;
+    if (!awTune) {  // experiment knobs of the seed-spreading heuristic (never affect results)
+      awTune = true;
       if (const char* e = std::getenv("PLSLAM_MW_DIST")) { int v = std::atoi(e); cudaMemcpyToSymbol(g_mw_dist, &v, sizeof(v)); }
       if (const char* e = std::getenv("PLSLAM_MW_ANG")) { float v = (float)std::atof(e); cudaMemcpyToSymbol(g_mw_ang, &v, sizeof(v)); }
     }
     if ((rc2 = owner.ensure((size_t)cfgB * P.P * sizeof(unsigned)))) return rc2;
-    const int mwK = P.P >= (1 << 20) ? 24 : 8;
-    if ((rc2 = regbuf.ensure((size_t)cfgB * mwK * P.P * sizeof(unsigned)))) return rc2;
+    if ((rc2 = regbuf.ensure((size_t)cfgB * awK * P.P * sizeof(unsigned)))) return rc2;
     PL_CUDA(cudaMemsetAsync(owner.p, 0xff, (size_t)batch * P.P * sizeof(unsigned), st));
-    if (P.P >= (1 << 20)) {
-      static bool attr24 = false;
-      if (!attr24) {
-        PL_CUDA(cudaFuncSetAttribute(k_lsd_grow_mw<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mw_smem_bytes(24)));
-        attr24 = true;
-      }
-      k_lsd_grow_mw<24><<<batch, 32 * 24, mw_smem_bytes(24), st>>>(P, pix.as<uint4>(), owner.as<unsigned>(), seeds.as<unsigned>(),
-                                                                 nseeds.as<int>(), regbuf.as<unsigned>(), rects.as<LsdRect>(),
-                                                                 nrects.as<int>(), status.as<int>());
-    } else {
-      k_lsd_grow_mw<8><<<batch, 32 * 8, mw_smem_bytes(8), st>>>(P, pix.as<uint4>(), owner.as<unsigned>(), seeds.as<unsigned>(),
-                                                               nseeds.as<int>(), regbuf.as<unsigned>(), rects.as<LsdRect>(),
-                                                               nrects.as<int>(), status.as<int>());
-    }
+#define PL_AW_LAUNCH(KK, WW)                                                                                                  \
+  do {                                                                                                                        \
+    static bool attr = false;                                                                                                 \
+    if (!attr) {                                                                                                              \
+      PL_CUDA(cudaFuncSetAttribute(k_lsd_grow_aw<KK, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,                        \
+                                   (int)aw_smem_bytes<KK, WW>()));                                                            \
+      attr = true;                                                                                                            \
+    }                                                                                                                         \
+    k_lsd_grow_aw<KK, WW><<<batch, 32 * KK, aw_smem_bytes<KK, WW>(), st>>>(                                                   \
+        P, pix.as<uint4>(), owner.as<unsigned>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),              \
+        rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());                                                             \
+  } while (0)
+    if (awK == 32) PL_AW_LAUNCH(32, 256);
+    else if (awK == 16) PL_AW_LAUNCH(16, 128);
+    else PL_AW_LAUNCH(8, 64);
+#undef PL_AW_LAUNCH
   } else {
     PL_CARVEOUT(k_lsd_grow);
     k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(),
@@ -1904,7 +2324,7 @@ int LineExtractor::check_status(cudaStream_t st) {
   PL_CUDA(cudaStreamSynchronize(st));
   const int s = *reinterpret_cast<int*>(pinnedStatus);
   if (s != PLSLAM_OK) {
-    set_error("device status %d (rectangle list overflow: raise rect_cap)", s);
+    set_error(s == PLSLAM_ERR_INTERNAL ? "device status %d (region-growing scheduler watchdog)" : "device status %d (rectangle list overflow: raise rect_cap)", s);
     cudaMemsetAsync(status.p, 0, sizeof(int), st);  // re-arm
   }
   return s;
@@ -1988,6 +2408,10 @@ int LineExtractor::copy_segments(int frame, LsdSegment* out, int capacity, int* 
 }
 
 }  // namespace plslam
+extern "C" int plslam_debug_grow_stats(unsigned long long* out16) {
+  if (!out16) return PLSLAM_ERR_INVALID;
+  return plslam::debug_aw_stats(out16);
+}
 #ifdef PLSLAM_GROW_PROF
 extern "C" int plslam_debug_grow_prof(unsigned long long* out16) { return plslam::debug_grow_prof(out16); }
 #endif
