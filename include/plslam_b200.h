@@ -152,11 +152,11 @@ int plslam_lines_scaled_size(const plslam_lines_t* h, int* width, int* height);
 int plslam_lines_copy_scaled(plslam_lines_t* h, int frame, uint8_t* out, size_t out_bytes);
 int plslam_lines_copy_level_lines(plslam_lines_t* h, int frame, float* degrees, int32_t* grad2, size_t count);
 int plslam_lines_copy_segments(plslam_lines_t* h, int frame, double* seg7, int capacity, int* n_out);
-/* Profiling aid: reads and clears the 16 device-side counters of the speculative region-growing scheduler
+/* Profiling aid: reads and clears the 32 device-side counters of the speculative region-growing scheduler
  * (k_lsd_grow_aw: regions issued / void / squashed while running / squashed after finishing / inserted, rectangles,
- * validation chunks, scheduler idle polls, worker idle polls, blocked seeds, pick chunks, frames).  Synchronises the
- * device.  Counters never influence a result. */
-int plslam_debug_grow_stats(unsigned long long* out16);
+ * validation chunks, scheduler idle polls, worker idle polls, blocked seeds, pick chunks, frames, then cycle
+ * accounting; names in tools/prof_aw.py).  Synchronises the device.  Counters never influence a result. */
+int plslam_debug_grow_stats(unsigned long long* out32);
 
 /* ------------------------------------------------------------------------------------------
  * Matchers — Hamming cores of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-141) and

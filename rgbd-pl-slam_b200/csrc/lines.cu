@@ -14,8 +14,8 @@
 //                  sequential inside a frame (running region angle, shared `used` map).  Lanes = 4 frontier points x 8
 //                  neighbours with in-batch speculation; the `used` flag lives in the pixel records.  This is the mode
 //                  for large batches (many batches in flight fill the machine).
-//   k_lsd_grow_aw  the same result with one CTA of 8 / 16 / 32 warps per frame: regions grown speculatively in parallel
-//                  over an owner plane and retired in seed order through a reorder window (no round barriers)
+//   k_lsd_grow_cw  the same result with one CTA of 8 / 16 / 32 warps per frame: jobs of 32 consecutive seeds run
+//                  speculatively in parallel over an owner plane and retire in order from a window (no round barriers)
 //   k_lsd_nfa      rect_improve / rect_nfa: persistent grid, one warp per rectangle (independent of `used`)
 //   k_lsd_finish   ordered compaction, KeyLine fields, strongest-N selection, line equations
 //   k_lbd          LBD band descriptors, one CTA per kept line
@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ Lin
 // k_lsd_grow: the sequential heart of LSD, one warp per frame.
 // ------------------------------------------------------------------------------------------
 constexpr int REG_SMEM = 1024;  // region-list entries kept in shared memory (larger regions spill to global)
+constexpr int CW_CH = 32;       // k_lsd_grow_cw: seeds per job (one chunk of the sorted seed list)
 constexpr unsigned USED_BIT = 0x80000000u;  // `used` flag of a pixel: bit 31 of its record's .w (gx^2+gy^2 < 2^20)
 
 // The `used` map lives in the pixel records themselves (global memory, L1-resident around the growing region),
@@ -300,43 +301,41 @@ struct GrowCtx {
   int sw, sh, P;
   int lane;
   bool prefetch;
-  // ---- CTA-per-frame mode (k_lsd_grow_aw): ordered speculative regions, see the kernel's header ----
+  // ---- CTA-per-frame mode (k_lsd_grow_cw): ordered speculative regions, see the kernel's header ----
   // Owner plane: one word per pixel.  MW_FREE, or (tag << 1) | released with tag = seed rank + 1 of the region that
   // marked the pixel.  released = 1 is a TOMBSTONE: the region gave the pixel back (refine() un-marks, reduce_region_radius()
   // drops far points) but its result still depends on having held it, so an older region that takes the pixel while the
   // releasing region is in flight must still poison it.  Tombstones of retired regions read as free.
+  // Jobs are chunks of CW_CH consecutive seeds; window slot of a tag = ((tag - 1) / CW_CH) % nslots.
   unsigned* own;
   unsigned myVal;         // this region's mark: tag << 1
-  const volatile unsigned* headTag;  // shared memory: smallest tag that is not final yet (lower tags = retired regions)
-  volatile int* poison;   // [nslots] poison flags (shared memory); mine is poison[slot]
-  volatile int* blocker;  // [nslots] tag of the older region that poisoned the slot
-  const volatile int* ranks;  // [nslots] seed ranks of the regions in the window (shared memory; -1 = empty slot)
+  unsigned jobLo, jobHi;  // tags of this job's seeds: [jobLo, jobHi]; its earlier regions are final from this region's view
+  const volatile unsigned* headTag;  // shared memory: smallest tag that is not final yet (only ever grows)
+  volatile int* poison;   // [nslots] poison flags of the window's jobs (shared memory); mine is poison[slot]
+  volatile int* blocker;  // [nslots] tag of the older region that poisoned the job
+  const volatile int* chunks;  // [nslots] chunk index each window slot holds (-1 = none)
+  int* poisonEv;          // shared counter of poison events: tells the scheduler to look at the window
   int slot, nslots;
+  int cap;                // entries left in this job's list stack behind the current region (scratch of refine())
   __device__ __forceinline__ bool mw_poisoned() const { return poison[slot] != 0; }
-  // headTag read AFTER the owner word `dep` has arrived (address dependence): a tag observed in the owner plane was
-  // written after the scheduler published the head tag under which that region runs, so a region inserted in front of
-  // the window is never mistaken for a retired one.
-  __device__ __forceinline__ unsigned fresh_head(unsigned dep) const {
-    unsigned z;
-    asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(dep));
-    return *reinterpret_cast<const volatile unsigned*>(reinterpret_cast<const volatile char*>(headTag) + z);
-  }
-  // May this region still test the pixel?  Not if a retired region or this region itself holds it.  A pixel held (or
+  // tag of a region that can no longer change what it holds, as far as this region is concerned: retired (below the
+  // head tag `h`), or an earlier region of this region's own job (the job runs its seeds one after the other)
+  __device__ __forceinline__ bool mw_settled(unsigned t, unsigned h) const { return t < h || (t >= jobLo && t < (myVal >> 1)); }
+  // May this region still test the pixel?  Not if a settled region or this region itself holds it.  A pixel held (or
   // tombstoned) by another in-flight region stays a candidate: whether it is used only matters if it passes the alignment
-  // test, and then mw_take() settles it (a younger region is robbed and poisoned, an older one poisons me).
-  // `h0` = the head tag read BEFORE the owner word was loaded: the holder counts as retired only if its tag lies below the
-  // head tag both before and after the load (before: a region that was still running when the word was read, and may
-  // un-mark the pixel later, must not pass for retired because it retired meanwhile).
+  // test, and then mw_take() settles it (a younger region is robbed and its job poisoned, an older one poisons my job).
+  // `h0` = the head tag read BEFORE the owner word was loaded: a holder that was still running when the word was read, and
+  // may un-mark the pixel later, must not pass for retired because it retired meanwhile.
   __device__ __forceinline__ bool mw_available(unsigned ov, unsigned h0) const {
     if (ov == 0xffffffffu) return true;
     if ((ov | 1u) == (myVal | 1u)) return (ov & 1u) != 0;  // mine: only what I released myself
-    if (ov & 1u) return true;                                // tombstone: free if its region retired, else mw_take decides
-    const unsigned t = ov >> 1;
-    return t >= h0 || t >= fresh_head(ov);
+    if (ov & 1u) return true;                                // tombstone: free if its region is settled, else mw_take decides
+    return !mw_settled(ov >> 1, h0);
   }
   __device__ __forceinline__ void mw_poison_self(unsigned tag) const {
     blocker[slot] = (int)tag;
     poison[slot] = 1;
+    atomicAdd(poisonEv, 1);
   }
   // Take pixel `id`, last seen holding `ov`.
   __device__ __forceinline__ void mw_take(int id, unsigned ov) const {
@@ -344,7 +343,7 @@ struct GrowCtx {
     for (int it = 0; it < 64; ++it) {
       if (exp != 0xffffffffu && exp < myVal) {  // a lower word is in place
         const unsigned t = exp >> 1;
-        if ((exp & 1u) && t < fresh_head(exp)) {  // tombstone of a retired region: free, but atomicMin cannot replace it
+        if ((exp & 1u) && mw_settled(t, *headTag)) {  // tombstone of a settled region: free, but atomicMin cannot replace it
           const unsigned old = atomicCAS(own + id, exp, myVal);
           if (old == exp) return;
           exp = old;
@@ -355,23 +354,23 @@ struct GrowCtx {
       }
       const unsigned old = atomicMin(own + id, myVal);
       if (old == 0xffffffffu || (old | 1u) == (myVal | 1u)) return;
-      if (old > myVal) {  // robbed a younger in-flight region (or its tombstone): it must not retire with this result
+      if (old > myVal) {  // robbed a younger in-flight region (or its tombstone): its job must not retire with this result
         const unsigned t = old >> 1;
-        for (int j = 0; j < nslots; ++j)
-          if ((unsigned)(ranks[j] + 1) == t) {
-            blocker[j] = (int)(myVal >> 1);
-            poison[j] = 1;
-          }
+        if (t <= jobHi) return;  // tombstone left by a squashed run of this very job
+        const int c = (int)((t - 1u) / CW_CH), j = c % nslots;
+        if (chunks[j] == c) {
+          blocker[j] = (int)(myVal >> 1);
+          poison[j] = 1;
+          atomicAdd(poisonEv, 1);
+        }
         return;
       }
       exp = old;  // an older word got there first
     }
-    mw_poison_self(0);  // never seen: give up on this run, the region is grown again
+    mw_poison_self(0);  // never seen: give up on this run, the job is run again
   }
   // refine() / reduce_region_radius(): the pixel is free again, the tombstone keeps the dependence visible
   __device__ __forceinline__ void mw_release(int id) const { atomicCAS(own + id, myVal, myVal | 1u); }
-  // a squashed run leaves no trace
-  __device__ __forceinline__ void mw_release_free(int id) const { atomicCAS(own + id, myVal, 0xffffffffu); }
   __device__ __forceinline__ unsigned reg_get(int i) const { return i < REG_SMEM ? regS[i] : regG[i]; }
   __device__ __forceinline__ void reg_set(int i, unsigned v) const {
     if (i < REG_SMEM) regS[i] = v; else regG[i] = v;
@@ -819,7 +818,7 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
     // The reference removes far points by swapping each with the current last element (that order defines the later
     // sums).  Equivalent closed form (checked exhaustively against the sequential loop): with n' points kept, the far
     // positions below n' in increasing order receive the kept points at or above n' in decreasing order.
-    if (n + (n >> 1) + 32 > C.P) {  // no room for the scratch list behind the region (never seen; kept for safety)
+    if (n + (n >> 1) + 32 > (MW ? C.cap : C.P)) {  // no room for the scratch list behind the region (rare; kept for safety)
       if (lane == 0) {
         for (int i = 0; i < n; ++i) {
           const unsigned pxy = C.reg_get(i);
@@ -967,329 +966,201 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
 }
 
 
-// heuristic only (it decides which seeds are grown at the same time, never the result): two seeds closer than MW_DIST
-// (Chebyshev) with similar level-line angles probably grow the same region
-constexpr int MW_DIST = 12;
-__device__ int g_mw_dist = MW_DIST;
-__device__ float g_mw_ang = 25.f;
-__device__ __forceinline__ bool mw_same_structure(int x1, int y1, float deg1, int x2, int y2, float deg2) {
-  if (max(abs(x1 - x2), abs(y1 - y2)) >= g_mw_dist) return false;
-  float d = fabsf(deg1 - deg2);
-  if (d > 180.f) d = 360.f - d;
-  return d <= g_mw_ang;
-}
-
 // ------------------------------------------------------------------------------------------
-// k_lsd_grow_aw: region growing with one CTA per frame, K - 1 worker warps and one scheduler warp, NO round barriers.
-// Regions are grown speculatively in parallel and retired in seed order through a reorder window, which keeps the result
-// identical to the sequential loop of lsd.cpp over an owner plane (GrowCtx):
-//   * the scheduler walks the sorted seed list once (cursor).  A seed whose pixel is free and that does not look like
-//     part of a structure already being grown is ISSUED: it gets a window slot (tag = rank + 1) and enters the ready
-//     queue; every other seed is SKIPPED.  Workers pop the queue, grow the region (lsd_region_grow_spec<true>,
-//     region2rect, refine), publish DONE and take the next job at once;
-//   * window slots form a list ordered by rank.  The head retires when it is DONE and not poisoned, after the seeds
-//     skipped in front of it have been VALIDATED: each must carry the tag of a region that already retired (the
-//     sequential loop would have found it used).  Only skipped seeds that were not already held by a retired region
-//     when the cursor passed need the second look (dirtyFrom).  A skipped seed that is still free (or held by a
-//     younger region) is INSERTED as a new head in front of the waiting one: it must grow first;
-//   * tags below the head tag are final.  A region that takes a pixel held by a younger in-flight region robs it
-//     (atomicMin) and poisons that slot; a region that wants a pixel held by an older in-flight region poisons itself
-//     (blocker = that tag).  A poisoned region gives its pixels back (SQUASHED) and is re-issued once its blocker has
-//     retired; a region poisoned after it finished releases its pixels by scanning its bounding box for its tag;
-//   * the head can only be poisoned by an inserted older region, and every insertion retires before the next
-//     validation, so the kernel always makes progress; spin loops carry a watchdog that raises PLSLAM_ERR_INTERNAL.
+// k_lsd_grow_cw: region growing with one CTA per frame: K - 1 worker warps and one retirement warp, NO round barriers.
+// The sorted seed list is cut into JOBS of CW_CH consecutive seeds.  A worker takes the next job (an atomic counter),
+// runs its seeds one after the other exactly like the sequential loop of lsd.cpp (region_grow, region2rect, refine) and
+// takes the next job at once; jobs of a frame run speculatively in parallel on the worker warps and RETIRE IN ORDER from a
+// ring of W window slots (slot = job % W), which keeps the result identical to the sequential loop:
+//   * a region marks its pixels in the owner plane with (tag << 1), tag = seed rank + 1 (GrowCtx).  Tags below the head
+//     tag (first seed of the oldest job in the window) are final;
+//   * a region that takes a pixel held or given back by a YOUNGER in-flight job robs it (atomicMin) and poisons that job;
+//     a region that wants a pixel held or given back by an OLDER in-flight job poisons its own job (blocker = that tag);
+//   * a seed that a job passes over because an older IN-FLIGHT region holds it makes the job dirty: when the job reaches
+//     the head of the window, each of its seeds from the first dirty one on must be held by a region that does not come
+//     after it (tag <= rank + 1), else the sequential loop would have grown it and the job runs again;
+//   * a poisoned job gives its pixels back (squashed while running: from its list stack; after it finished: from the copy
+//     of its lists in the frame's pool) and runs again once its blocker has retired, or at once when it is the head —
+//     the head has nothing older in flight, so its run is exact and the window always advances.
+// The retirement warp only watches the window (retire, validate, re-issue); seeds are scanned by the workers.
 // ------------------------------------------------------------------------------------------
-enum { AW_FREE = 0, AW_READY = 1, AW_RUNNING = 2, AW_DONE = 3, AW_SQUASHED = 4 };
-constexpr int AW_ACT = 32;            // seeds of regions in flight remembered for the same-structure test
-constexpr int AW_NONE = 0x7fffffff;
-enum { AWS_ISSUED = 0, AWS_VOID, AWS_SQUASH_RUN, AWS_SQUASH_DONE, AWS_INSERT, AWS_RECTS, AWS_VALCHUNKS, AWS_SCHED_IDLE,
-       AWS_WORK_IDLE, AWS_BLOCKED_SEED, AWS_PICKCHUNKS, AWS_FRAMES, AWS_N };
-__device__ unsigned long long g_aw_stats[16];
+enum { CW_EMPTY = 0, CW_RUNNING = 1, CW_DONE = 2, CW_SQUASHED = 3, CW_QUEUED = 4 };
+constexpr int CW_NONE = 0x7fffffff;
+constexpr int CW_RQN = 64;  // re-issue queue entries
+enum { CWS_JOBS = 0, CWS_REGIONS, CWS_SQUASH_RUN, CWS_SQUASH_DONE, CWS_REVALIDATE, CWS_RECTS, CWS_VALCHUNKS, CWS_SCHED_IDLE,
+       CWS_WORK_IDLE, CWS_DIRTY_JOBS, CWS_RERUNS, CWS_FRAMES,
+       // cycle accounting (clock64): wall time of the frame, and where workers / the retirement warp spent it
+       CWS_CYC_KERNEL, CWS_CYC_W_WAIT, CWS_CYC_W_DONE, CWS_CYC_W_SQUASH, CWS_CYC_W_EMPTY, CWS_CYC_S_RETIRE, CWS_CYC_S_SCAN,
+       CWS_CYC_S_IDLE, CWS_PIX_DONE, CWS_PIX_SQUASH, CWS_WINFULL, CWS_POOLFULL, CWS_N };
+__device__ unsigned long long g_aw_stats[32];
 
 template <int W>
-struct AwState {
-  LsdRect rect[W];
-  int rank[W];        // seed rank of the slot's region, -1 = free slot
+struct CwState {
+  int chunk[W];       // job (chunk index) the slot holds, -1 = none
   int state[W];
   int poison[W];
-  int blocker[W];
-  int has[W];         // DONE: a rectangle was produced
-  int next[W];        // rank-ordered list of the slots in use
-  int dirtyFrom[W];   // first skipped seed in front of this slot that needs validation (AW_NONE: none)
-  int needRelease[W]; // poisoned after DONE: the next run starts by releasing the bounding box
-  int bb0[W], bb1[W]; // bounding box of the region's pixels: (y0 << 16) | x0, (y1 << 16) | x1
-  int freeStack[W];
-  int q[W];           // ready queue: slot + 1, 0 = empty
-  int actSlot[AW_ACT], actRank[AW_ACT], actX[AW_ACT], actY[AW_ACT];
-  float actA[AW_ACT];
-  unsigned qticket;
+  int blocker[W];     // tag of the older region that poisoned the job
+  int dirtyFrom[W];   // first seed of the job that needs validation at retirement (CW_NONE: none)
+  int rectOff[W], rectCnt[W];  // the job's rectangles in the frame's rectangle pool
+  int listOff[W], listCnt[W];  // copy of the job's pixel lists in the frame's list pool (listCnt < 0: not stored)
+  int rq[CW_RQN];     // re-issue queue: slot + 1, 0 = empty
+  unsigned rqHead, rqTail;
   unsigned headTag;
-  int nActive, nSquashed, done, abort;
-  unsigned long long stats[AWS_N];
+  int headChunk, nextChunk;
+  int rectTop, listTop;
+  int nSquashed, poisonEv, done, abort;
+  unsigned long long stats[CWS_N];
 };
 template <int K, int W>
-constexpr size_t aw_smem_bytes() {
-  return ((sizeof(AwState<W>) + 15) & ~size_t(15)) + (sizeof(double) * 96 + sizeof(unsigned) * REG_SMEM) * (size_t)(K - 1);
+constexpr size_t cw_smem_bytes() {
+  return ((sizeof(CwState<W>) + 15) & ~size_t(15)) + (sizeof(double) * 96 + sizeof(unsigned) * REG_SMEM) * (size_t)(K - 1);
 }
-constexpr long long AW_WATCHDOG = 1ll << 24;  // polls (>= 40 ns each) without progress before the kernel gives up
+constexpr long long CW_WATCHDOG = 1ll << 21;  // polls (>= 40 ns each) without progress before the kernel gives up
+// internal consistency checks: a failure raises status 100 + code and stops the frame's CTA
+#define CW_ASSERT(cond, code)                                                   \
+  do {                                                                          \
+    if (!(cond)) {                                                              \
+      atomicMax(status, 100 + (code));                                          \
+      *reinterpret_cast<volatile int*>(&S.abort) = 1;                           \
+    }                                                                           \
+  } while (0)
 
 template <int K, int W>
-__device__ void aw_scheduler(AwState<W>& S, const LineParams& L, const uint4* __restrict__ pix, const unsigned* own,
-                             const unsigned* __restrict__ seeds, int ns, LsdRect* __restrict__ rects, int* nrectOut,
-                             int* status, int lane) {
+__device__ void cw_retire_warp(CwState<W>& S, const LineParams& L, const unsigned* own, const unsigned* __restrict__ seeds,
+                               int ns, int nChunks, const LsdRect* rectPool, LsdRect* __restrict__ rects, int* nrectOut,
+                               int* status, int lane) {
   const unsigned FULL = 0xffffffffu;
   volatile int* vstate = S.state;
   volatile int* vpoison = S.poison;
   volatile int* vblocker = S.blocker;
-  volatile int* vq = S.q;
-  volatile int* vrank = S.rank;
-  volatile unsigned* vhead = &S.headTag;
-  int head = -1, tail = -1, nfree = W, cursor = 0, valFrom = 0, gapDirty = AW_NONE, nrect = 0;
-  unsigned qtail = 0, headTag = 1u;
-  constexpr int MAXACT = K + 1;  // regions READY or RUNNING: the K - 1 workers never wait for the scheduler
+  volatile int* vchunk = S.chunk;
+  volatile int* vrq = S.rq;
+  volatile int* vnSquashed = &S.nSquashed;
+  volatile int* vpoisonEv = &S.poisonEv;
+  int head = 0, nrect = 0;
+  unsigned rqTail = 0;
   long long idle = 0;
-#define AW_STAT(k, v) do { if (lane == 0) S.stats[k] += (v); } while (0)
-
-  auto push = [&](int s) {
+  const long long tKernel = clock64();
+  long long tPhase = tKernel;
+  int lastEv = 0, lastSq = 0, waiting = 0;
+#define CW_STAT(k, v) do { if (lane == 0) S.stats[k] += (v); } while (0)
+  auto requeue = [&](int s) {  // the job of slot s runs again
     if (lane == 0) {
-      vstate[s] = AW_READY;
-      atomicAdd(&S.nActive, 1);
+      vstate[s] = CW_QUEUED;
       __threadfence_block();
-      long long spins = 0;  // the entry was consumed long ago (at most W jobs exist, tickets are FIFO)
-      while (vq[qtail % W] != 0 && ++spins < AW_WATCHDOG) {}
-      if (spins >= AW_WATCHDOG) {
-        atomicMax(status, PLSLAM_ERR_INTERNAL);
-        *reinterpret_cast<volatile int*>(&S.abort) = 1;
-      }
-      vq[qtail % W] = s + 1;
+      long long spins = 0;
+      while (vrq[rqTail % CW_RQN] != 0 && ++spins < CW_WATCHDOG) {}
+      CW_ASSERT(spins < CW_WATCHDOG, 1);
+      vrq[rqTail % CW_RQN] = s + 1;
+      __threadfence_block();
+      *reinterpret_cast<volatile unsigned*>(&S.rqTail) = rqTail + 1;
     }
-    ++qtail;
+    ++rqTail;
+    CW_STAT(CWS_RERUNS, 1);
     __syncwarp();
   };
-  auto remember = [&](int s, int rank, int x, int y, float a) {  // same-structure table: reuse a dead entry
-    bool dead = true;
-    if (lane < AW_ACT) {
-      const int as = S.actSlot[lane];
-      if (as >= 0) {
-        const int st = vstate[as];
-        dead = !((st == AW_READY || st == AW_RUNNING) && vrank[as] == S.actRank[lane]);
-      }
-    }
-    const unsigned m = __ballot_sync(FULL, dead && lane < AW_ACT);
-    const int e = m ? __ffs(m) - 1 : 0;
-    if (lane == 0) {
-      S.actSlot[e] = s;
-      S.actRank[e] = rank;
-      S.actX[e] = x;
-      S.actY[e] = y;
-      S.actA[e] = a;
-    }
-    __syncwarp();
-  };
-  auto issue = [&](int rank, int x, int y, float a, int dirty, bool atHead) {
-    const int t = S.freeStack[nfree - 1];
-    --nfree;
-    if (lane == 0) {
-      vrank[t] = rank;
-      S.has[t] = 0;
-      S.needRelease[t] = 0;
-      S.dirtyFrom[t] = dirty;
-      vpoison[t] = 0;
-      vblocker[t] = 0;
-      if (atHead) {
-        S.next[t] = head;
-      } else {
-        S.next[t] = -1;
-        if (tail >= 0) S.next[tail] = t;
-      }
-    }
-    if (atHead || head < 0) {
-      headTag = (unsigned)rank + 1u;  // lowered by an insertion, raised when the window was empty
-      if (lane == 0) *vhead = headTag;
-      if (head < 0) tail = t;
-      head = t;
-    } else {
-      tail = t;
-    }
-    __syncwarp();
-    __threadfence_block();
-    remember(t, rank, x, y, a);
-    AW_STAT(AWS_ISSUED, 1);
-    push(t);
-  };
-  // first seed in [from, to) whose pixel is not HELD by a retired region (tag < limitTag; tombstones and MW_FREE have bit 0
-  // set), or -1
-  auto validate = [&](int from, int to, unsigned limitTag) {
-    int bad = -1;
-    for (int i0 = from; i0 < to && bad < 0; i0 += 32) {
-      const int i = i0 + lane;
-      bool fail = false;
-      if (i < to) {
-        const unsigned v = __ldcg(own + seeds[i]);
-        fail = (v & 1u) || (v >> 1) >= limitTag;  // free, given back, or held by a region that is not final
-      }
-      const unsigned m = __ballot_sync(FULL, fail);
-      if (m) bad = i0 + __ffs(m) - 1;
-      AW_STAT(AWS_VALCHUNKS, 1);
-    }
-    return bad;
-  };
-  auto insert = [&](int rank) {  // a skipped seed turned out to be free: it becomes the new head
-    const int sd = (int)seeds[rank];
-    const int y = sd / L.sw, x = sd - y * L.sw;
-    if (head >= 0 && lane == 0) S.dirtyFrom[head] = rank + 1;
-    __syncwarp();
-    issue(rank, x, y, __uint_as_float(pix[sd].x), AW_NONE, true);
-    valFrom = rank;  // everything in front of it was validated
-    AW_STAT(AWS_INSERT, 1);
-  };
-
-  while (true) {
-    bool progress = false, scan = false;
+  while (head < nChunks) {
+    bool progress = false, retired = false, headPoisoned = false;
     if (*reinterpret_cast<volatile int*>(&S.abort)) break;
-    // ---- retire in rank order ----
-    while (head >= 0) {
-      const int s = head;
-      const int st = vstate[s];
-      if (st != AW_DONE) break;
+    // ---- retire in order ----
+    while (head < nChunks) {
+      const int s = head % W;
+      if (vchunk[s] != head || vstate[s] != CW_DONE) break;
       __threadfence_block();
       if (vpoison[s]) {  // robbed by an older region after it had finished: re-issued by the scan below
-        scan = true;
+        headPoisoned = true;
         break;
       }
-      const int myRank = vrank[s];
-      const int from = max(valFrom, S.dirtyFrom[s]);
-      const int bad = from < myRank ? validate(from, myRank, (unsigned)myRank + 1u) : -1;
-      if (bad >= 0) {
-        insert(bad);
-        progress = true;
-        break;
-      }
-      if (S.has[s]) {
-        if (nrect < L.rect_cap) {
-          if (lane < (int)(sizeof(LsdRect) / sizeof(double)))
-            reinterpret_cast<double*>(rects + nrect)[lane] = reinterpret_cast<const double*>(&S.rect[s])[lane];
-        } else if (lane == 0) {
-          atomicMax(status, PLSLAM_ERR_OVERFLOW);
+      const int a = head * CW_CH, b = min(ns, a + CW_CH);
+      const int from = S.dirtyFrom[s];
+      if (from < b) {
+        // every seed from the first dirty one on must be held by a region that does not come after it
+        const int i = from + lane;
+        bool fail = false;
+        if (i < b) {
+          const unsigned v = __ldcg(own + seeds[i]);
+          fail = (v & 1u) || (v >> 1) > (unsigned)i + 1u;
         }
-        ++nrect;
-        AW_STAT(AWS_RECTS, 1);
-      }
-      valFrom = myRank + 1;
-      const int nx = S.next[s];
-      headTag = nx >= 0 ? (unsigned)vrank[nx] + 1u : (unsigned)max(cursor, myRank + 1) + 1u;
-      if (lane == 0) {
-        vrank[s] = -1;
-        vstate[s] = AW_FREE;
-        S.freeStack[nfree] = s;
-        *vhead = headTag;
-      }
-      ++nfree;
-      head = nx;
-      if (head < 0) tail = -1;
-      __syncwarp();
-      progress = true;
-    }
-    // ---- poisoned regions run again once the region that blocked them has retired (or they are the head): squashed
-    //      ones have given their pixels back already, finished ones release by bounding box first ----
-    if (scan || progress || *reinterpret_cast<volatile int*>(&S.nSquashed) > 0) {
-      for (int b = 0; b < W; b += 32) {
-        const int s = b + lane;
-        int kind = 0;
-        if (s < W) {
-          const int st = vstate[s];
-          const bool go = (unsigned)vblocker[s] < headTag || s == head;
-          if (st == AW_SQUASHED && go) kind = 1;
-          else if (st == AW_DONE && vpoison[s] && go) kind = 2;
-        }
-        unsigned m = __ballot_sync(FULL, kind != 0);
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1u;
-          const int kj = __shfl_sync(FULL, kind, j);
+        CW_STAT(CWS_VALCHUNKS, 1);
+        if (__any_sync(FULL, fail)) {  // the sequential loop would have grown a seed this run passed over: run the job again
           if (lane == 0) {
-            if (kj == 1) atomicSub(&S.nSquashed, 1);
-            else S.needRelease[b + j] = 1;
+            vpoison[s] = 1;
+            vblocker[s] = 0;
           }
-          if (kj == 2) AW_STAT(AWS_SQUASH_DONE, 1);
-          push(b + j);
-          progress = true;
+          __syncwarp();
+          CW_STAT(CWS_REVALIDATE, 1);
+          headPoisoned = true;
+          break;
         }
       }
+      const int k = S.rectCnt[s], off = S.rectOff[s];
+      constexpr int RD = (int)(sizeof(LsdRect) / sizeof(double));
+      if (nrect + k <= L.rect_cap) {
+        for (int i = lane; i < k * RD; i += 32)
+          reinterpret_cast<double*>(rects + nrect)[i] = __ldcg(reinterpret_cast<const double*>(rectPool + off) + i);
+      } else if (lane == 0) {
+        atomicMax(status, PLSLAM_ERR_OVERFLOW);
+      }
+      nrect = min(nrect + k, L.rect_cap + 1);
+      CW_STAT(CWS_RECTS, k);
+      ++head;
+      if (lane == 0) {
+        vchunk[s] = -1;
+        vstate[s] = CW_EMPTY;
+        vpoison[s] = 0;
+        __threadfence_block();
+        *reinterpret_cast<volatile unsigned*>(&S.headTag) = (unsigned)min(head * CW_CH, ns) + 1u;
+        *reinterpret_cast<volatile int*>(&S.headChunk) = head;
+      }
+      __syncwarp();
+      progress = retired = true;
     }
-    // ---- issue new regions from the cursor (a few chunks at a time: retirement must not wait for a long scan) ----
-    for (int chunks = 0; chunks < 8 && nfree > 1 && cursor < ns; ++chunks) {
-      int nAct = *reinterpret_cast<volatile int*>(&S.nActive);
-      if (nAct >= MAXACT) break;
-      const int i = cursor + lane;
-      const int sd = i < ns ? (int)seeds[i] : -1;
-      const unsigned ov = sd >= 0 ? __ldcg(own + sd) : 0u;
-      AW_STAT(AWS_PICKCHUNKS, 1);
-      const bool retired = (ov >> 1) < headTag;  // (MW_FREE >> 1 is above every tag)
-      const bool isFree = sd >= 0 && (ov & 1u) && (ov == 0xffffffffu || retired);  // free, or given back by a retired region
-      const bool fin = sd >= 0 && !(ov & 1u) && retired;                          // held by a retired region: skipped for good
-      int sx = 0, sy = 0;
-      float sa = 0.f;
-      bool ok = isFree;
-      // live entries of the same-structure table
-      bool live = false;
-      if (lane < AW_ACT) {
-        const int as = S.actSlot[lane];
-        if (as >= 0) {
-          const int st = vstate[as];
-          live = (st == AW_READY || st == AW_RUNNING) && vrank[as] == S.actRank[lane];
+    { const long long t = clock64(); CW_STAT(CWS_CYC_S_RETIRE, t - tPhase); tPhase = t; }
+    // ---- poisoned jobs run again once the region that blocked them has retired, or at once at the head.  The window is
+    //      only scanned when something changed ----
+    {
+      const int ev = *vpoisonEv, sq = *vnSquashed;
+      if (headPoisoned || ev != lastEv || sq != lastSq || (waiting > 0 && retired)) {
+        lastEv = ev;
+        waiting = 0;
+        int requeued = 0;
+        const unsigned headTag = (unsigned)min(head * CW_CH, ns) + 1u;
+        for (int b0 = 0; b0 < W; b0 += 32) {
+          const int s = b0 + lane;
+          int kind = 0;
+          bool wait = false;
+          if (s < W) {
+            const int st = vstate[s];
+            const bool pz = st == CW_SQUASHED || (st == CW_DONE && vpoison[s]);
+            const bool go = (unsigned)vblocker[s] < headTag || vchunk[s] == head;
+            if (pz && go) kind = st == CW_SQUASHED ? 1 : 2;
+            wait = pz && !go;
+          }
+          waiting += __popc(__ballot_sync(FULL, wait));
+          unsigned m = __ballot_sync(FULL, kind != 0);
+          while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1u;
+            const int kj = __shfl_sync(FULL, kind, j);
+            if (kj == 1) {
+              if (lane == 0) atomicSub(&S.nSquashed, 1);
+              ++requeued;
+            } else {
+              CW_STAT(CWS_SQUASH_DONE, 1);
+            }
+            requeue(b0 + j);
+            progress = true;
+          }
         }
-      }
-      const unsigned liveM = __ballot_sync(FULL, live);
-      if (isFree) {
-        sy = sd / L.sw;
-        sx = sd - sy * L.sw;
-        sa = __uint_as_float(pix[sd].x);
-        for (unsigned r = liveM; r && ok; r &= r - 1u) {
-          const int e = __ffs(r) - 1;
-          ok = !mw_same_structure(sx, sy, sa, S.actX[e], S.actY[e], S.actA[e]);
-        }
-      }
-      unsigned m = __ballot_sync(FULL, ok);
-      const unsigned dirtyM = __ballot_sync(FULL, sd >= 0 && !fin);
-      int consumed = 0;
-      while (m && nfree > 1 && nAct < MAXACT) {
-        const int j = __ffs(m) - 1;
-        const unsigned between = dirtyM & ((1u << j) - 1u) & ~((1u << consumed) - 1u);
-        if (between) gapDirty = min(gapDirty, cursor + __ffs(between) - 1);
-        const int jx = __shfl_sync(FULL, sx, j), jy = __shfl_sync(FULL, sy, j);
-        const float ja = __shfl_sync(FULL, sa, j);
-        issue(cursor + j, jx, jy, ja, gapDirty, false);
-        gapDirty = AW_NONE;
-        consumed = j + 1;
-        ++nAct;
-        ok = ok && lane > j && !mw_same_structure(sx, sy, sa, jx, jy, ja);
-        m = __ballot_sync(FULL, ok);
-        progress = true;
-      }
-      if (!m) {  // the rest of the chunk is skipped
-        const unsigned rest = consumed < 32 ? dirtyM & ~((1u << consumed) - 1u) : 0u;
-        if (rest) gapDirty = min(gapDirty, cursor + __ffs(rest) - 1);
-        cursor = min(ns, cursor + 32);
-        progress = true;
-      } else {
-        cursor += consumed;
-        break;
+        lastSq = sq - requeued;  // a job squashed meanwhile makes the counter differ and triggers the next scan
       }
     }
-    // ---- the end: nothing in flight, list exhausted, tail of skipped seeds validated ----
-    if (head < 0 && cursor >= ns) {
-      const int from = max(valFrom, gapDirty);
-      const int bad = from < ns ? validate(from, ns, 0x7fffffffu) : -1;
-      if (bad < 0) break;
-      gapDirty = bad + 1;
-      insert(bad);
-      progress = true;
-    }
+    { const long long t = clock64(); CW_STAT(CWS_CYC_S_SCAN, t - tPhase); tPhase = t; }
     if (!progress) {
-      AW_STAT(AWS_SCHED_IDLE, 1);
+      CW_STAT(CWS_SCHED_IDLE, 1);
       __nanosleep(40);
-      if (++idle > AW_WATCHDOG) {
+      { const long long t = clock64(); CW_STAT(CWS_CYC_S_IDLE, t - tPhase); tPhase = t; }
+      if (++idle > CW_WATCHDOG) {
         if (lane == 0) {
           atomicMax(status, PLSLAM_ERR_INTERNAL);
           *reinterpret_cast<volatile int*>(&S.abort) = 1;
@@ -1300,38 +1171,73 @@ __device__ void aw_scheduler(AwState<W>& S, const LineParams& L, const uint4* __
       idle = 0;
     }
   }
+  CW_STAT(CWS_CYC_KERNEL, clock64() - tKernel);
   if (lane == 0) {
     *nrectOut = min(nrect, L.rect_cap);
     __threadfence_block();
     *reinterpret_cast<volatile int*>(&S.done) = 1;
   }
-#undef AW_STAT
+#undef CW_STAT
 }
 
+// One worker warp: take a job (re-issued ones first), run its seeds in order, publish, repeat.
 template <int K, int W>
-__device__ void aw_worker(AwState<W>& S, GrowCtx& C, const LineParams& L, const unsigned* __restrict__ seeds, int* status) {
+__device__ void cw_worker(CwState<W>& S, GrowCtx& C, const LineParams& L, const unsigned* __restrict__ seeds, int ns, int nChunks,
+                          unsigned* stackBase, int stackCap, unsigned* listPool, int listPoolCap, LsdRect* rectStage,
+                          LsdRect* rectPool, int* status) {
   const unsigned FULL = 0xffffffffu;
   const int lane = C.lane;
   volatile int* vstate = S.state;
-  volatile int* vq = S.q;
-  volatile int* vrank = S.rank;
+  volatile int* vchunk = S.chunk;
+  volatile int* vrq = S.rq;
   volatile int* vdone = &S.done;
   volatile int* vabort = &S.abort;
+  volatile int* vheadChunk = &S.headChunk;
+  int fresh = -1;  // a job taken from the counter that still waits for its window slot
+  bool freshLeft = true;
   while (true) {
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(&S.qticket, 1u);
-    t = __shfl_sync(FULL, t, 0);
-    int v = 0;
+    // ---- acquire ----
+    const long long tWait = clock64();
+    int s = -1, c = -1;
+    bool rerun = false;
     long long spins = 0;
     while (true) {
-      if (lane == 0) v = vq[t % W];
-      v = __shfl_sync(FULL, v, 0);
-      if (v) break;
-      int stop = 0;
-      if (lane == 0) stop = *vdone | *vabort;
+      int got = -1, gotC = -1, gotRerun = 0, stop = 0;
+      if (lane == 0) {
+        const unsigned h = *reinterpret_cast<volatile unsigned*>(&S.rqHead), tl = *reinterpret_cast<volatile unsigned*>(&S.rqTail);
+        if (h != tl) {
+          if (atomicCAS(&S.rqHead, h, h + 1u) == h) {
+            const int v = vrq[h % CW_RQN];
+            vrq[h % CW_RQN] = 0;
+            got = v - 1;
+            gotRerun = 1;
+            if (got >= 0 && got < W) gotC = vchunk[got];
+          }
+        } else {
+          if (fresh < 0 && freshLeft) {
+            fresh = atomicAdd(&S.nextChunk, 1);
+            if (fresh >= nChunks) { fresh = -1; freshLeft = false; }
+          }
+          if (fresh >= 0 && fresh < *vheadChunk + W) {
+            got = fresh % W;
+            gotC = fresh;
+            fresh = -1;
+          } else if (fresh >= 0) {
+            S.stats[CWS_WINFULL] += 1;  // racy between workers: a statistic only
+          }
+        }
+        stop = *vdone | *vabort;
+      }
+      got = __shfl_sync(FULL, got, 0);
+      if (got >= 0) {
+        s = got;
+        c = __shfl_sync(FULL, gotC, 0);
+        rerun = __shfl_sync(FULL, gotRerun, 0) != 0;
+        break;
+      }
       if (__shfl_sync(FULL, stop, 0)) return;
       __nanosleep(40);
-      if (++spins > AW_WATCHDOG) {
+      if (++spins > CW_WATCHDOG) {
         if (lane == 0) {
           atomicMax(status, PLSLAM_ERR_INTERNAL);
           *vabort = 1;
@@ -1339,146 +1245,218 @@ __device__ void aw_worker(AwState<W>& S, GrowCtx& C, const LineParams& L, const 
         return;
       }
     }
+    const long long tJob = clock64();
     if (lane == 0) {
-      vq[t % W] = 0;
-      S.stats[AWS_WORK_IDLE] += (unsigned long long)spins;  // racy between workers: a statistic only
+      atomicAdd(&S.stats[CWS_WORK_IDLE], (unsigned long long)spins);
+      atomicAdd(&S.stats[CWS_CYC_W_WAIT], (unsigned long long)(tJob - tWait));
     }
-    const int s = v - 1;
+    if ((unsigned)s >= (unsigned)W || c < 0 || c >= nChunks) {
+      CW_ASSERT(false, 2);
+      return;
+    }
     __threadfence_block();
-    const int rank = vrank[s];
-    const int seed = (int)seeds[rank];
-    C.myVal = ((unsigned)rank + 1u) << 1;
+    const int a = c * CW_CH, b = min(ns, a + CW_CH);
     C.slot = s;
-    if (S.needRelease[s]) {  // the previous run finished and was robbed afterwards: its pixels still carry the tag
-      const int x0 = S.bb0[s] & 0xffff, y0 = S.bb0[s] >> 16, x1 = S.bb1[s] & 0xffff, y1 = S.bb1[s] >> 16;
-      const int bw = x1 - x0 + 1, tot = bw > 0 ? bw * (y1 - y0 + 1) : 0;
-      for (int k = lane; k < tot; k += 32) {
-        const int yy = y0 + k / bw, xx = x0 + k % bw;
-        const int id = yy * C.sw + xx;
-        if (__ldcg(C.own + id) == C.myVal) C.mw_release_free(id);
+    C.jobLo = (unsigned)a + 1u;
+    C.jobHi = (unsigned)b;
+    // ---- a job that finished and was poisoned afterwards still holds its pixels: give them back (pool copy of its lists) ----
+    if (rerun && S.listCnt[s] != 0) {
+      const int cnt = S.listCnt[s], off = S.listOff[s];
+      CW_ASSERT(cnt > 0, 3);  // (a job whose lists did not fit the pool is never stored as DONE, see below)
+      for (int i = lane; i < cnt; i += 32) {
+        const unsigned pxy = listPool[off + i] & 0x7fffffffu;
+        const int id = (int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff);
+        const unsigned v = __ldcg(C.own + id);
+        if (!(v & 1u) && (v >> 1) >= C.jobLo && (v >> 1) <= C.jobHi) atomicCAS(C.own + id, v, 0xffffffffu);
       }
     }
     __threadfence();
     if (lane == 0) {
-      S.needRelease[s] = 0;
+      vchunk[s] = c;
+      S.listCnt[s] = 0;
+      S.rectCnt[s] = 0;
+      S.dirtyFrom[s] = CW_NONE;
       C.blocker[s] = 0;
       C.poison[s] = 0;
-      vstate[s] = AW_RUNNING;
+      __threadfence_block();
+      vstate[s] = CW_RUNNING;
     }
     __syncwarp();
-    int n = 0;
-    bool keep = false, squashed = false;
-    LsdRect rec;
-    const unsigned sh0 = *C.headTag;
-    const unsigned sov = __ldcg(C.own + seed);
-    const unsigned stag = sov >> 1;
-    const bool older = sov != 0xffffffffu && sov < C.myVal;
-    const bool olderInFlight = older && (stag >= sh0 || stag >= C.fresh_head(sov));
-    if (older && olderInFlight) {
-      // an older region in flight holds the seed (or gave it back): wait for its fate
-      squashed = true;
-      if (lane == 0) {
-        C.blocker[s] = (int)stag;
-        S.stats[AWS_BLOCKED_SEED] += 1;
+    // ---- run the job: its seeds in order, like the sequential loop ----
+    int sd = a + lane < b ? (int)seeds[a + lane] : -1;
+    int used = 0, nrectJob = 0, dirty = CW_NONE, nreg = 0;
+    bool squashed = false;
+    while (true) {
+      const unsigned h0 = *C.headTag;
+      const unsigned v = sd >= 0 ? __ldcg(C.own + sd) : 0u;
+      const unsigned t = v >> 1;
+      bool grow = false, isDirty = false;
+      if (sd >= 0) {
+        if (v == 0xffffffffu) grow = true;
+        else if (t < h0 || (t >= C.jobLo && t <= C.jobHi)) grow = (v & 1u) != 0;  // settled: given back = free, held = used
+        else if (t < C.jobLo) isDirty = true;  // an older region in flight holds it or gave it back: its fate decides
+        else grow = true;                      // a younger job's region: the take robs it
       }
-    } else if (older && !(sov & 1u)) {
-      // a retired region holds the seed: the sequential loop finds it used, there is no region
-      if (lane == 0) S.stats[AWS_VOID] += 1;
-    } else {
+      const unsigned gm = __ballot_sync(FULL, grow);
+      const unsigned dm = __ballot_sync(FULL, isDirty);
+      const int j = gm ? __ffs(gm) - 1 : 32;
+      const unsigned passedDirty = j < 32 ? dm & ((1u << j) - 1u) : dm;
+      if (passedDirty) dirty = min(dirty, a + __ffs(passedDirty) - 1);
+      if (!gm) break;
+      const int seed = __shfl_sync(FULL, sd, j);
+      if (lane <= j) sd = -1;
+      C.myVal = ((unsigned)(a + j) + 1u) << 1;
+      C.regG = stackBase + used;
+      C.cap = stackCap - used;
+      if (C.cap < 64) {  // the list stack of the job is full (cannot happen: a job's regions are disjoint, stack = P entries)
+        CW_ASSERT(false, 4);
+        squashed = true;
+        break;
+      }
       if (lane == 0) C.reg_set(0, ((unsigned)(seed / C.sw) << 16) | (unsigned)(seed % C.sw));
       __syncwarp();
       double reg_angle;
-      n = lsd_region_grow_spec<true>(C, L.prec, &reg_angle);
+      int n = lsd_region_grow_spec<true>(C, L.prec, &reg_angle);
+      ++nreg;
+      bool keep = false;
+      LsdRect rec;
       if (!C.mw_poisoned() && n >= L.min_reg_size) {
         lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
         keep = lsd_refine<true>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, 1);
       }
+      // the head of the list lives in shared memory: the stack keeps the whole list (release / pool copy)
+      for (int i = lane; i < min(n, REG_SMEM); i += 32) C.regG[i] = C.regS[i];
+      used += n;
       if (C.mw_poisoned()) {
         squashed = true;
-        for (int i = lane; i < n; i += 32) {
-          const unsigned pxy = C.reg_get(i) & 0x7fffffffu;
-          C.mw_release_free((int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff));
+        break;
+      }
+      if (keep) {
+        if (lane == 0) rectStage[nrectJob] = rec;
+        ++nrectJob;
+      }
+    }
+    __syncwarp();
+    if (squashed || C.mw_poisoned()) {
+      squashed = true;
+      // give every pixel still held by a region of this job back (MW_FREE: a squashed run leaves no trace but tombstones)
+      for (int i = lane; i < used; i += 32) {
+        const unsigned pxy = stackBase[i] & 0x7fffffffu;
+        const int id = (int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff);
+        const unsigned v = __ldcg(C.own + id);
+        if (!(v & 1u) && (v >> 1) >= C.jobLo && (v >> 1) <= C.jobHi) atomicCAS(C.own + id, v, 0xffffffffu);
+      }
+    } else {
+      // publish: rectangles and the lists (for a release after DONE) go to the frame's pools
+      int roff = 0, loff = 0;
+      if (lane == 0) {
+        if (nrectJob) roff = atomicAdd(&S.rectTop, nrectJob);
+        if (used) loff = atomicAdd(&S.listTop, used);
+      }
+      roff = __shfl_sync(FULL, roff, 0);
+      loff = __shfl_sync(FULL, loff, 0);
+      if (roff + nrectJob > L.rect_cap) {  // rectangle pool exhausted (runs that were squashed leak their entries)
+        if (lane == 0) atomicMax(status, PLSLAM_ERR_OVERFLOW);
+        nrectJob = 0;
+        roff = 0;
+      }
+      constexpr int RD = (int)(sizeof(LsdRect) / sizeof(double));
+      for (int i = lane; i < nrectJob * RD; i += 32)
+        reinterpret_cast<double*>(rectPool + roff)[i] = reinterpret_cast<const double*>(rectStage)[i];
+      bool stored = true;
+      if (used) {
+        if (loff + used <= listPoolCap) {
+          for (int i = lane; i < used; i += 32) listPool[loff + i] = stackBase[i];
+        } else {
+          stored = false;
         }
-        if (lane == 0) S.stats[AWS_SQUASH_RUN] += 1;
+      }
+      if (!stored) {
+        // list pool exhausted: the job cannot be released after DONE, so it only publishes once nothing older is in flight
+        if (lane == 0) S.stats[CWS_POOLFULL] += 1;
+        long long sp = 0;
+        while (*vheadChunk != c && !C.mw_poisoned() && !(*vabort) && ++sp < CW_WATCHDOG) __nanosleep(100);
+        if (C.mw_poisoned() || *vheadChunk != c) {
+          squashed = true;
+          for (int i = lane; i < used; i += 32) {
+            const unsigned pxy = stackBase[i] & 0x7fffffffu;
+            const int id = (int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff);
+            const unsigned v = __ldcg(C.own + id);
+            if (!(v & 1u) && (v >> 1) >= C.jobLo && (v >> 1) <= C.jobHi) atomicCAS(C.own + id, v, 0xffffffffu);
+          }
+        }
+      }
+      if (!squashed && lane == 0) {
+        S.rectOff[s] = roff;
+        S.rectCnt[s] = nrectJob;
+        S.listOff[s] = loff;
+        S.listCnt[s] = stored ? used : 0;
+        S.dirtyFrom[s] = dirty;
       }
     }
-    int bx0 = 0xffff, by0 = 0x7fff, bx1 = 0, by1 = 0;
-    if (!squashed) {
-      for (int i = lane; i < n; i += 32) {
-        const unsigned pxy = C.reg_get(i) & 0x7fffffffu;
-        const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
-        bx0 = min(bx0, px);
-        bx1 = max(bx1, px);
-        by0 = min(by0, py);
-        by1 = max(by1, py);
-      }
-#pragma unroll
-      for (int d = 16; d; d >>= 1) {
-        bx0 = min(bx0, __shfl_xor_sync(FULL, bx0, d));
-        by0 = min(by0, __shfl_xor_sync(FULL, by0, d));
-        bx1 = max(bx1, __shfl_xor_sync(FULL, bx1, d));
-        by1 = max(by1, __shfl_xor_sync(FULL, by1, d));
-      }
-      if (n == 0) { bx0 = 1; bx1 = 0; by0 = 0; by1 = 0; }
-    }
-    __threadfence();  // owner-plane updates (releases are fire-and-forget) are performed before the state is published
+    __threadfence();  // owner-plane updates (releases are fire-and-forget) and pool copies are performed before the state is published
     if (lane == 0) {
       if (squashed) {
-        atomicAdd(&S.nSquashed, 1);
+        vstate[s] = CW_SQUASHED;
         __threadfence_block();
-        vstate[s] = AW_SQUASHED;
+        atomicAdd(&S.nSquashed, 1);  // after the state: a retirement warp that sees the count also sees the state
+        atomicAdd(&S.stats[CWS_SQUASH_RUN], 1ull);
+        atomicAdd(&S.stats[CWS_PIX_SQUASH], (unsigned long long)used);
       } else {
-        S.has[s] = keep ? 1 : 0;
-        if (keep) S.rect[s] = rec;
-        S.bb0[s] = (by0 << 16) | bx0;
-        S.bb1[s] = (by1 << 16) | bx1;
         __threadfence_block();
-        vstate[s] = AW_DONE;
+        vstate[s] = CW_DONE;
+        atomicAdd(&S.stats[CWS_PIX_DONE], (unsigned long long)used);
+        if (dirty != CW_NONE) atomicAdd(&S.stats[CWS_DIRTY_JOBS], 1ull);
       }
-      atomicSub(&S.nActive, 1);
+      atomicAdd(&S.stats[CWS_JOBS], 1ull);
+      atomicAdd(&S.stats[CWS_REGIONS], (unsigned long long)nreg);
+      atomicAdd(&S.stats[squashed ? CWS_CYC_W_SQUASH : nreg ? CWS_CYC_W_DONE : CWS_CYC_W_EMPTY], (unsigned long long)(clock64() - tJob));
     }
     __syncwarp();
   }
 }
 
 template <int K, int W>
-__global__ void __launch_bounds__(32 * K) k_lsd_grow_aw(const __grid_constant__ LineParams L, uint4* pixAll, unsigned* ownAll,
+__global__ void __launch_bounds__(32 * K) k_lsd_grow_cw(const __grid_constant__ LineParams L, uint4* pixAll, unsigned* ownAll,
                                                        const unsigned* __restrict__ seedsAll,
-                                                       const int* __restrict__ nseeds, unsigned* regAll,
+                                                       const int* __restrict__ nseeds, unsigned* stackAll, unsigned* listPoolAll,
+                                                       LsdRect* rectStageAll, LsdRect* rectPoolAll,
                                                        LsdRect* __restrict__ rectsAll, int* __restrict__ nrects,
                                                        int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char aw_smem[];
-  AwState<W>& S = *reinterpret_cast<AwState<W>*>(aw_smem);
-  unsigned char* wbase = aw_smem + ((sizeof(AwState<W>) + 15) & ~size_t(15));
+  extern __shared__ __align__(16) unsigned char cw_smem[];
+  CwState<W>& S = *reinterpret_cast<CwState<W>*>(cw_smem);
+  unsigned char* wbase = cw_smem + ((sizeof(CwState<W>) + 15) & ~size_t(15));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x;
   for (int i = threadIdx.x; i < W; i += 32 * K) {
-    S.rank[i] = -1;
-    S.state[i] = AW_FREE;
+    S.chunk[i] = -1;
+    S.state[i] = CW_EMPTY;
     S.poison[i] = 0;
     S.blocker[i] = 0;
-    S.has[i] = 0;
-    S.next[i] = -1;
-    S.dirtyFrom[i] = AW_NONE;
-    S.needRelease[i] = 0;
-    S.freeStack[i] = W - 1 - i;
-    S.q[i] = 0;
+    S.dirtyFrom[i] = CW_NONE;
+    S.rectOff[i] = S.rectCnt[i] = S.listOff[i] = S.listCnt[i] = 0;
   }
-  if (threadIdx.x < AW_ACT) S.actSlot[threadIdx.x] = -1;
-  if (threadIdx.x < AWS_N) S.stats[threadIdx.x] = 0;
+  if (threadIdx.x < CW_RQN) S.rq[threadIdx.x] = 0;
+  if (threadIdx.x < CWS_N) S.stats[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
-    S.qticket = 0;
+    S.rqHead = S.rqTail = 0;
     S.headTag = 1u;
-    S.nActive = 0;
+    S.headChunk = 0;
+    S.nextChunk = 0;
+    S.rectTop = 0;
+    S.listTop = 0;
     S.nSquashed = 0;
+    S.poisonEv = 0;
     S.done = 0;
     S.abort = 0;
   }
   __syncthreads();
   const unsigned* seeds = seedsAll + (size_t)f * L.P;
+  const int ns = nseeds[f];
+  const int nChunks = (ns + CW_CH - 1) / CW_CH;
   if (warp == 0) {
-    aw_scheduler<K, W>(S, L, pixAll + (size_t)f * L.P, ownAll + (size_t)f * L.P, seeds, nseeds[f],
-                       rectsAll + (size_t)f * L.rect_cap, nrects + f, status, lane);
+    cw_retire_warp<K, W>(S, L, ownAll + (size_t)f * L.P, seeds, ns, nChunks, rectPoolAll + (size_t)f * L.rect_cap,
+                         rectsAll + (size_t)f * L.rect_cap, nrects + f, status, lane);
   } else {
     GrowCtx C;
 #ifdef PLSLAM_GROW_PROF
@@ -1492,23 +1470,30 @@ __global__ void __launch_bounds__(32 * K) k_lsd_grow_aw(const __grid_constant__ 
     C.prefetch = false;
     C.pix = pixAll + (size_t)f * L.P;
     C.own = ownAll + (size_t)f * L.P;
-    C.regG = regAll + ((size_t)f * K + warp) * L.P;
+    C.regG = nullptr;
+    C.cap = 0;
     C.sw = L.sw;
     C.sh = L.sh;
     C.P = L.P;
     C.lane = lane;
     C.poison = S.poison;
     C.blocker = S.blocker;
+    C.poisonEv = &S.poisonEv;
     C.headTag = &S.headTag;
-    C.ranks = S.rank;
+    C.chunks = S.chunk;
     C.nslots = W;
     C.slot = 0;
     C.myVal = 0;
-    aw_worker<K, W>(S, C, L, seeds, status);
+    C.jobLo = C.jobHi = 0;
+    // per worker: a list stack of 2 P entries (lists of the job's regions one after the other + refine() scratch) and a
+    // staging area of CW_CH rectangles; per frame: list pool of 2 P entries, rectangle pool of rect_cap entries
+    cw_worker<K, W>(S, C, L, seeds, ns, nChunks, stackAll + ((size_t)f * (K - 1) + (warp - 1)) * 2 * (size_t)L.P, 2 * L.P,
+                    listPoolAll + (size_t)f * 2 * (size_t)L.P, 2 * L.P,
+                    rectStageAll + ((size_t)f * (K - 1) + (warp - 1)) * CW_CH, rectPoolAll + (size_t)f * L.rect_cap, status);
   }
   __syncthreads();
-  if (threadIdx.x < AWS_N) {
-    const unsigned long long v = threadIdx.x == AWS_FRAMES ? 1ull : S.stats[threadIdx.x];
+  if (threadIdx.x < CWS_N) {
+    const unsigned long long v = threadIdx.x == CWS_FRAMES ? 1ull : S.stats[threadIdx.x];
     if (v) atomicAdd(&g_aw_stats[threadIdx.x], v);
   }
 }
@@ -2052,10 +2037,10 @@ __global__ void __launch_bounds__(96) k_lbd(const __grid_constant__ LineParams L
 }
 
 }  // namespace
-int debug_aw_stats(unsigned long long* out16) {
+int debug_aw_stats(unsigned long long* out32) {
   if (cudaDeviceSynchronize() != cudaSuccess) return PLSLAM_ERR_CUDA;
-  if (cudaMemcpyFromSymbol(out16, g_aw_stats, sizeof(g_aw_stats)) != cudaSuccess) return PLSLAM_ERR_CUDA;
-  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out32, g_aw_stats, sizeof(g_aw_stats)) != cudaSuccess) return PLSLAM_ERR_CUDA;
+  unsigned long long z[32] = {0};
   if (cudaMemcpyToSymbol(g_aw_stats, z, sizeof(z)) != cudaSuccess) return PLSLAM_ERR_CUDA;
   return PLSLAM_OK;
 }
@@ -2075,7 +2060,7 @@ int debug_grow_prof(unsigned long long* out16) {
 LineExtractor::LineExtractor() {}
 
 LineExtractor::~LineExtractor() {
-  DevBuf* all[] = {&scaled, &pix, &coef, &rowhist, &binstart, &maxg2, &seeds, &nseeds, &regbuf, &rects, &nrects,
+  DevBuf* all[] = {&listpool, &rectstage, &recttmp, &owner, &degp, &scaled, &pix, &coef, &rowhist, &binstart, &maxg2, &seeds, &nseeds, &regbuf, &rects, &nrects,
                    &rectout, &segs, &nsegs, &resp, &rowsum, &status, &stageIn, &stageKl, &stageDesc, &stageFuncs, &stageCnt};
   for (DevBuf* b : all) b->release();
   if (ownStream) cudaStreamDestroy(ownStream);
@@ -2251,44 +2236,40 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
   P.batch = batch;
   // PLSLAM_GROW_MODE: 0 = one warp per frame (k_lsd_grow), 2 = speculative multi-warp growing with in-order retirement
-  // (k_lsd_grow_aw); unset = automatic.  (Mode 1, the round-based predecessor of mode 2, is gone.)
+  // (k_lsd_grow_cw); unset = automatic.  PLSLAM_CW_K = warps per frame of mode 2 (8, 16 or 32).
   static const int growMode = [] { const char* e = std::getenv("PLSLAM_GROW_MODE"); return e ? std::atoi(e) : -1; }();  // -1 auto
-  // speculation pays when the whole GPU has at most one frame per SM to work on (all pipeline slots counted)
-  // ... and when the per-worker region lists (K lists of P entries per frame) stay within 10 GB
-  const size_t awListBytes = (size_t)std::max(batch, cfgB) * 8 * P.P * sizeof(unsigned);
-  const bool aw = growMode >= 0 ? growMode != 0
-                                : ((long long)batch * batches_in_flight <= numSMs && awListBytes <= ((size_t)10 << 30));
-  static const int awKenv = [] { const char* e = std::getenv("PLSLAM_AW_K"); return e ? std::atoi(e) : 0; }();
-  if (aw) {
-    // async window: K warps per frame (1 scheduler + K - 1 workers); per-worker region lists of P entries
-    int awK = awKenv ? awKenv : ((long long)batch * batches_in_flight <= numSMs ? 32 : 8);
-    awK = awK >= 32 ? 32 : awK >= 16 ? 16 : 8;
+  static const int cwKenv = [] { const char* e = std::getenv("PLSLAM_CW_K"); return e ? std::atoi(e) : 0; }();
+  int cwK = cwKenv ? cwKenv : ((long long)batch * batches_in_flight <= numSMs ? 32 : 8);
+  cwK = cwK >= 32 ? 32 : cwK >= 16 ? 16 : 8;
+  // per worker warp a list stack of 2 P entries, per frame a list pool of 2 P entries: mode 2 needs them within 24 GB
+  const size_t cwBytes = (size_t)std::max(batch, cfgB) * (2 * (size_t)(cwK - 1) + 2) * P.P * sizeof(unsigned);
+  const bool cw = growMode >= 0 ? growMode != 0
+                                : ((long long)batch * batches_in_flight <= numSMs && cwBytes <= ((size_t)24 << 30));
+  if (cw) {
     int rc2;
-    static bool awTune = false;
-    if (!awTune) {  // experiment knobs of the seed-spreading heuristic (never affect results)
-      awTune = true;
-      if (const char* e = std::getenv("PLSLAM_MW_DIST")) { int v = std::atoi(e); cudaMemcpyToSymbol(g_mw_dist, &v, sizeof(v)); }
-      if (const char* e = std::getenv("PLSLAM_MW_ANG")) { float v = (float)std::atof(e); cudaMemcpyToSymbol(g_mw_ang, &v, sizeof(v)); }
-    }
     if ((rc2 = owner.ensure((size_t)cfgB * P.P * sizeof(unsigned)))) return rc2;
-    if ((rc2 = regbuf.ensure((size_t)cfgB * awK * P.P * sizeof(unsigned)))) return rc2;
+    if ((rc2 = regbuf.ensure((size_t)cfgB * (cwK - 1) * 2 * P.P * sizeof(unsigned)))) return rc2;
+    if ((rc2 = listpool.ensure((size_t)cfgB * 2 * P.P * sizeof(unsigned)))) return rc2;
+    if ((rc2 = rectstage.ensure((size_t)cfgB * (cwK - 1) * CW_CH * sizeof(LsdRect)))) return rc2;
+    if ((rc2 = recttmp.ensure((size_t)cfgB * P.rect_cap * sizeof(LsdRect)))) return rc2;
     PL_CUDA(cudaMemsetAsync(owner.p, 0xff, (size_t)batch * P.P * sizeof(unsigned), st));
-#define PL_AW_LAUNCH(KK, WW)                                                                                                  \
+#define PL_CW_LAUNCH(KK, WW)                                                                                                  \
   do {                                                                                                                        \
     static bool attr = false;                                                                                                 \
     if (!attr) {                                                                                                              \
-      PL_CUDA(cudaFuncSetAttribute(k_lsd_grow_aw<KK, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,                        \
-                                   (int)aw_smem_bytes<KK, WW>()));                                                            \
+      PL_CUDA(cudaFuncSetAttribute(k_lsd_grow_cw<KK, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,                        \
+                                   (int)cw_smem_bytes<KK, WW>()));                                                            \
       attr = true;                                                                                                            \
     }                                                                                                                         \
-    k_lsd_grow_aw<KK, WW><<<batch, 32 * KK, aw_smem_bytes<KK, WW>(), st>>>(                                                   \
+    k_lsd_grow_cw<KK, WW><<<batch, 32 * KK, cw_smem_bytes<KK, WW>(), st>>>(                                                   \
         P, pix.as<uint4>(), owner.as<unsigned>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),              \
-        rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());                                                             \
+        listpool.as<unsigned>(), rectstage.as<LsdRect>(), recttmp.as<LsdRect>(), rects.as<LsdRect>(), nrects.as<int>(),       \
+        status.as<int>());                                                                                                    \
   } while (0)
-    if (awK == 32) PL_AW_LAUNCH(32, 256);
-    else if (awK == 16) PL_AW_LAUNCH(16, 128);
-    else PL_AW_LAUNCH(8, 64);
-#undef PL_AW_LAUNCH
+    if (cwK == 32) PL_CW_LAUNCH(32, 512);
+    else if (cwK == 16) PL_CW_LAUNCH(16, 256);
+    else PL_CW_LAUNCH(8, 256);
+#undef PL_CW_LAUNCH
   } else {
     PL_CARVEOUT(k_lsd_grow);
     k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(),
@@ -2324,7 +2305,7 @@ int LineExtractor::check_status(cudaStream_t st) {
   PL_CUDA(cudaStreamSynchronize(st));
   const int s = *reinterpret_cast<int*>(pinnedStatus);
   if (s != PLSLAM_OK) {
-    set_error(s == PLSLAM_ERR_INTERNAL ? "device status %d (region-growing scheduler watchdog)" : "device status %d (rectangle list overflow: raise rect_cap)", s);
+    set_error(s >= PLSLAM_ERR_INTERNAL ? "device status %d (region-growing scheduler: 5 = watchdog, 100 + n = consistency check n)" : "device status %d (rectangle list overflow: raise rect_cap)", s);
     cudaMemsetAsync(status.p, 0, sizeof(int), st);  // re-arm
   }
   return s;
@@ -2408,9 +2389,9 @@ int LineExtractor::copy_segments(int frame, LsdSegment* out, int capacity, int* 
 }
 
 }  // namespace plslam
-extern "C" int plslam_debug_grow_stats(unsigned long long* out16) {
-  if (!out16) return PLSLAM_ERR_INVALID;
-  return plslam::debug_aw_stats(out16);
+extern "C" int plslam_debug_grow_stats(unsigned long long* out32) {
+  if (!out32) return PLSLAM_ERR_INVALID;
+  return plslam::debug_aw_stats(out32);
 }
 #ifdef PLSLAM_GROW_PROF
 extern "C" int plslam_debug_grow_prof(unsigned long long* out16) { return plslam::debug_grow_prof(out16); }

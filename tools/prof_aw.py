@@ -14,8 +14,9 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "rgbd-pl-slam_b200"))
-STAT_NAMES = ["issued", "void", "squash_run", "squash_done", "insert", "rects", "valchunks", "sched_idle", "work_idle",
-              "blocked_seed", "pickchunks", "frames"]
+STAT_NAMES = ["jobs", "regions", "squash_run", "squash_done", "revalidate", "rects", "valchunks", "sched_idle", "work_idle",
+              "dirty_jobs", "reruns", "frames", "cyc_kernel", "cyc_w_wait", "cyc_w_done", "cyc_w_squash", "cyc_w_empty",
+              "cyc_s_retire", "cyc_s_scan", "cyc_s_idle", "pix_done", "pix_squash", "winfull", "poolfull"]
 
 
 def frames(gen, B, W, H):
@@ -54,7 +55,7 @@ def child(mode, K, B, W, H, gen, out):
     torch.cuda.synchronize()
     ls.check_status()
     L = pl.lib()
-    st = (C.c_ulonglong * 16)()
+    st = (C.c_ulonglong * 32)()
     L.plslam_debug_grow_stats.argtypes = [C.POINTER(C.c_ulonglong)]
     L.plslam_debug_grow_stats(st)
     stats = list(st)
@@ -83,11 +84,11 @@ def child(mode, K, B, W, H, gen, out):
 
 def run(mode, K, B, W, H, gen, tag):
     out = "/tmp/prof_aw_%s.npz" % tag
-    env = dict(os.environ, PLSLAM_GROW_MODE=str(mode), PLSLAM_AW_K=str(K), PLSLAM_DEBUG_STOP_AFTER_GROW="")
+    env = dict(os.environ, PLSLAM_GROW_MODE=str(mode), PLSLAM_CW_K=str(K), PLSLAM_DEBUG_STOP_AFTER_GROW="")
     env.pop("PLSLAM_DEBUG_STOP_AFTER_GROW")
     t0 = time.time()
     p = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(mode), str(K), str(B), str(W), str(H), gen, out],
-                       env=env, capture_output=True, text=True, timeout=600)
+                       env=env, capture_output=True, text=True, timeout=150)
     if p.returncode != 0:
         print("  mode %d K %d: FAILED rc=%d (%.0f s)\n%s" % (mode, K, p.returncode, time.time() - t0, (p.stderr or "")[-1500:]), flush=True)
         return None
@@ -136,6 +137,8 @@ if __name__ == "__main__":
                 s = r["stats"].astype(float)
                 fr = max(s[11], 1.0)
                 line += "  | per frame: " + " ".join("%s=%.0f" % (STAT_NAMES[i], s[i] / fr) for i in range(11))
+                line += "\n      kcycles/frame: " + " ".join("%s=%.0f" % (STAT_NAMES[i][4:], s[i] / fr / 1e3) for i in range(12, 20))
+                line += " | " + " ".join("%s=%.0f" % (STAT_NAMES[i], s[i] / fr) for i in range(20, 24))
             print(line, flush=True)
     print("prof_aw: %d problem(s)" % bad)
     sys.exit(1 if bad else 0)
