@@ -14,8 +14,8 @@
 //                  sequential inside a frame (running region angle, shared `used` map).  Lanes = 4 frontier points x 8
 //                  neighbours with in-batch speculation; the `used` flag lives in the pixel records.  This is the mode
 //                  for large batches (many batches in flight fill the machine).
-//   k_lsd_grow_cw  the same result with one CTA of 8 / 16 / 32 warps per frame: jobs of 32 consecutive seeds run
-//                  speculatively in parallel over an owner plane and retire in order from a window (no round barriers)
+//   k_lsd_grow_sw  the same result with one CTA of 8 / 16 / 32 warps per frame: regions grown speculatively in parallel
+//                  over an owner plane and retired in seed order through a window (no round barriers)
 //   k_lsd_nfa      rect_improve / rect_nfa: persistent grid, one warp per rectangle (independent of `used`)
 //   k_lsd_finish   ordered compaction, KeyLine fields, strongest-N selection, line equations
 //   k_lbd          LBD band descriptors, one CTA per kept line
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ Lin
 // k_lsd_grow: the sequential heart of LSD, one warp per frame.
 // ------------------------------------------------------------------------------------------
 constexpr int REG_SMEM = 1024;  // region-list entries kept in shared memory (larger regions spill to global)
-constexpr int CW_CH = 32;       // k_lsd_grow_cw: seeds per job (one chunk of the sorted seed list)
+constexpr int SW_G = 32;        // k_lsd_grow_sw: seeds per group (one warp-wide load of the sorted seed list)
 constexpr unsigned USED_BIT = 0x80000000u;  // `used` flag of a pixel: bit 31 of its record's .w (gx^2+gy^2 < 2^20)
 
 // The `used` map lives in the pixel records themselves (global memory, L1-resident around the growing region),
@@ -301,41 +301,40 @@ struct GrowCtx {
   int sw, sh, P;
   int lane;
   bool prefetch;
-  // ---- CTA-per-frame mode (k_lsd_grow_cw): ordered speculative regions, see the kernel's header ----
+  // ---- CTA-per-frame mode (k_lsd_grow_sw): ordered speculative regions, see the kernel's header ----
   // Owner plane: one word per pixel.  MW_FREE, or (tag << 1) | released with tag = seed rank + 1 of the region that
   // marked the pixel.  released = 1 is a TOMBSTONE: the region gave the pixel back (refine() un-marks, reduce_region_radius()
   // drops far points) but its result still depends on having held it, so an older region that takes the pixel while the
   // releasing region is in flight must still poison it.  Tombstones of retired regions read as free.
-  // Jobs are chunks of CW_CH consecutive seeds; window slot of a tag = ((tag - 1) / CW_CH) % nslots.
+  // Window slot of a tag = (tag - 1) % nslots (one slot per seed of the sorted list).
   unsigned* own;
   unsigned myVal;         // this region's mark: tag << 1
-  unsigned jobLo, jobHi;  // tags of this job's seeds: [jobLo, jobHi]; its earlier regions are final from this region's view
   const volatile unsigned* headTag;  // shared memory: smallest tag that is not final yet (only ever grows)
-  volatile int* poison;   // [nslots] poison flags of the window's jobs (shared memory); mine is poison[slot]
-  volatile int* blocker;  // [nslots] tag of the older region that poisoned the job
-  const volatile int* chunks;  // [nslots] chunk index each window slot holds (-1 = none)
-  int* poisonEv;          // shared counter of poison events: tells the scheduler to look at the window
+  int* poison;            // [nslots] poison flags of the window's seeds (shared memory); mine is poison[slot]
+  volatile int* blocker;  // [nslots] tag of the older region that poisoned the seed's region
+  int* plist;             // [nslots] ring of poisoned slots (slot + 1) for the retirement warp, 0 = not written yet
+  unsigned* plTail;
+  unsigned long long* pstat;  // 3 counters: poisoned by an older holder / an older tombstone / robbed a younger region
   int slot, nslots;
-  int cap;                // entries left in this job's list stack behind the current region (scratch of refine())
-  __device__ __forceinline__ bool mw_poisoned() const { return poison[slot] != 0; }
-  // tag of a region that can no longer change what it holds, as far as this region is concerned: retired (below the
-  // head tag `h`), or an earlier region of this region's own job (the job runs its seeds one after the other)
-  __device__ __forceinline__ bool mw_settled(unsigned t, unsigned h) const { return t < h || (t >= jobLo && t < (myVal >> 1)); }
-  // May this region still test the pixel?  Not if a settled region or this region itself holds it.  A pixel held (or
+  int cap;                // entries of this worker's list area (list + scratch of refine())
+  __device__ __forceinline__ bool mw_poisoned() const { return *reinterpret_cast<volatile int*>(poison + slot) != 0; }
+  __device__ __forceinline__ void mw_mark_poison(int j, unsigned tag) const {
+    blocker[j] = (int)tag;
+    if (atomicExch(poison + j, 1) == 0) {  // first poison of this run: tell the retirement warp
+      const unsigned e = atomicAdd(plTail, 1u);
+      *reinterpret_cast<volatile int*>(plist + e % (unsigned)nslots) = j + 1;
+    }
+  }
+  // May this region still test the pixel?  Not if a retired region or this region itself holds it.  A pixel held (or
   // tombstoned) by another in-flight region stays a candidate: whether it is used only matters if it passes the alignment
-  // test, and then mw_take() settles it (a younger region is robbed and its job poisoned, an older one poisons my job).
+  // test, and then mw_take() settles it (a younger region is robbed and poisoned, an older one poisons me).
   // `h0` = the head tag read BEFORE the owner word was loaded: a holder that was still running when the word was read, and
   // may un-mark the pixel later, must not pass for retired because it retired meanwhile.
   __device__ __forceinline__ bool mw_available(unsigned ov, unsigned h0) const {
     if (ov == 0xffffffffu) return true;
     if ((ov | 1u) == (myVal | 1u)) return (ov & 1u) != 0;  // mine: only what I released myself
-    if (ov & 1u) return true;                                // tombstone: free if its region is settled, else mw_take decides
-    return !mw_settled(ov >> 1, h0);
-  }
-  __device__ __forceinline__ void mw_poison_self(unsigned tag) const {
-    blocker[slot] = (int)tag;
-    poison[slot] = 1;
-    atomicAdd(poisonEv, 1);
+    if (ov & 1u) return true;                                // tombstone: free if its region retired, else mw_take decides
+    return (ov >> 1) >= h0;
   }
   // Take pixel `id`, last seen holding `ov`.
   __device__ __forceinline__ void mw_take(int id, unsigned ov) const {
@@ -343,31 +342,26 @@ struct GrowCtx {
     for (int it = 0; it < 64; ++it) {
       if (exp != 0xffffffffu && exp < myVal) {  // a lower word is in place
         const unsigned t = exp >> 1;
-        if ((exp & 1u) && mw_settled(t, *headTag)) {  // tombstone of a settled region: free, but atomicMin cannot replace it
+        if ((exp & 1u) && t < *headTag) {  // tombstone of a retired region: free, but atomicMin cannot replace it
           const unsigned old = atomicCAS(own + id, exp, myVal);
           if (old == exp) return;
           exp = old;
           continue;
         }
-        mw_poison_self(t);  // an older region holds the pixel (or gave it back and is still in flight)
+        atomicAdd(pstat + (exp & 1u), 1ull);
+        mw_mark_poison(slot, t);  // an older region holds the pixel (or gave it back and is still in flight)
         return;
       }
       const unsigned old = atomicMin(own + id, myVal);
       if (old == 0xffffffffu || (old | 1u) == (myVal | 1u)) return;
-      if (old > myVal) {  // robbed a younger in-flight region (or its tombstone): its job must not retire with this result
-        const unsigned t = old >> 1;
-        if (t <= jobHi) return;  // tombstone left by a squashed run of this very job
-        const int c = (int)((t - 1u) / CW_CH), j = c % nslots;
-        if (chunks[j] == c) {
-          blocker[j] = (int)(myVal >> 1);
-          poison[j] = 1;
-          atomicAdd(poisonEv, 1);
-        }
+      if (old > myVal) {  // robbed a younger in-flight region (or its tombstone): it must not retire with this result
+        atomicAdd(pstat + 2, 1ull);
+        mw_mark_poison((int)(((old >> 1) - 1u) % (unsigned)nslots), myVal >> 1);
         return;
       }
       exp = old;  // an older word got there first
     }
-    mw_poison_self(0);  // never seen: give up on this run, the job is run again
+    mw_mark_poison(slot, 0);  // never seen: give up on this run, the region is grown again
   }
   // refine() / reduce_region_radius(): the pixel is free again, the tombstone keeps the dependence visible
   __device__ __forceinline__ void mw_release(int id) const { atomicCAS(own + id, myVal, myVal | 1u); }
@@ -967,57 +961,66 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
 
 
 // ------------------------------------------------------------------------------------------
-// k_lsd_grow_cw: region growing with one CTA per frame: K - 1 worker warps and one retirement warp, NO round barriers.
-// The sorted seed list is cut into JOBS of CW_CH consecutive seeds.  A worker takes the next job (an atomic counter),
-// runs its seeds one after the other exactly like the sequential loop of lsd.cpp (region_grow, region2rect, refine) and
-// takes the next job at once; jobs of a frame run speculatively in parallel on the worker warps and RETIRE IN ORDER from a
-// ring of W window slots (slot = job % W), which keeps the result identical to the sequential loop:
-//   * a region marks its pixels in the owner plane with (tag << 1), tag = seed rank + 1 (GrowCtx).  Tags below the head
-//     tag (first seed of the oldest job in the window) are final;
-//   * a region that takes a pixel held or given back by a YOUNGER in-flight job robs it (atomicMin) and poisons that job;
-//     a region that wants a pixel held or given back by an OLDER in-flight job poisons its own job (blocker = that tag);
-//   * a seed that a job passes over because an older IN-FLIGHT region holds it makes the job dirty: when the job reaches
-//     the head of the window, each of its seeds from the first dirty one on must be held by a region that does not come
-//     after it (tag <= rank + 1), else the sequential loop would have grown it and the job runs again;
-//   * a poisoned job gives its pixels back (squashed while running: from its list stack; after it finished: from the copy
-//     of its lists in the frame's pool) and runs again once its blocker has retired, or at once when it is the head —
-//     the head has nothing older in flight, so its run is exact and the window always advances.
-// The retirement warp only watches the window (retire, validate, re-issue); seeds are scanned by the workers.
+// k_lsd_grow_sw: region growing with one CTA per frame: K - 1 worker warps and one retirement warp, NO round barriers.
+// Regions are grown speculatively in parallel and RETIRE IN SEED ORDER through a window of WS seeds (slot = rank % WS),
+// which keeps the result identical to the sequential loop of lsd.cpp:
+//   * a worker takes the next GROUP of 32 consecutive seeds (an atomic counter), classifies them with one look at the
+//     owner plane and grows the free ones one after the other (region_grow, region2rect, refine as in the sequential
+//     loop), so seeds of one edge that sit next to each other in the list are absorbed as they would be sequentially;
+//   * a region marks its pixels with (tag << 1), tag = seed rank + 1 (GrowCtx).  Tags below the head tag are final.  A
+//     region that takes a pixel held or given back by a YOUNGER in-flight region robs it (atomicMin) and poisons that
+//     region; a region that wants a pixel held or given back by an OLDER in-flight region poisons itself;
+//   * a seed is passed over (DIRTY) when an older region still in flight holds it, or when it lies on the level line of
+//     an older seed that is pending or being grown (same-edge heuristic: it will most likely be absorbed).  When a DIRTY
+//     seed reaches the head of the window it must be held by a region that does not come after it, else it is grown
+//     then — as the head, with nothing older in flight, i.e. exactly;
+//   * a poisoned region gives its pixels back (squashed while running: from its list; after it finished: from the copy
+//     of its list in the frame's pool) and is grown again once its blocker has retired, or at once at the head.
+// The retirement warp handles 32 seeds per step (states are per seed) and never looks at the seed list except to
+// validate DIRTY seeds; scanning is done by the workers.
 // ------------------------------------------------------------------------------------------
-enum { CW_EMPTY = 0, CW_RUNNING = 1, CW_DONE = 2, CW_SQUASHED = 3, CW_QUEUED = 4 };
-constexpr int CW_NONE = 0x7fffffff;
-constexpr int CW_RQN = 64;  // re-issue queue entries
-enum { CWS_JOBS = 0, CWS_REGIONS, CWS_SQUASH_RUN, CWS_SQUASH_DONE, CWS_REVALIDATE, CWS_RECTS, CWS_VALCHUNKS, CWS_SCHED_IDLE,
-       CWS_WORK_IDLE, CWS_DIRTY_JOBS, CWS_RERUNS, CWS_FRAMES,
+enum { SW_EMPTY = 0, SW_PENDING = 1, SW_RUNNING = 2, SW_DONE = 3, SW_DIRTY = 4, SW_SQUASHED = 5, SW_QUEUED = 6 };
+constexpr int SW_RQN = 128;  // re-issue queue entries (ranks)
+enum { SWS_GROUPS = 0, SWS_REGIONS, SWS_SQUASH_RUN, SWS_SQUASH_DONE, SWS_INSERT, SWS_RECTS, SWS_VALSTEPS, SWS_SCHED_IDLE,
+       SWS_WORK_IDLE, SWS_DIRTY, SWS_RERUNS, SWS_FRAMES,
        // cycle accounting (clock64): wall time of the frame, and where workers / the retirement warp spent it
-       CWS_CYC_KERNEL, CWS_CYC_W_WAIT, CWS_CYC_W_DONE, CWS_CYC_W_SQUASH, CWS_CYC_W_EMPTY, CWS_CYC_S_RETIRE, CWS_CYC_S_SCAN,
-       CWS_CYC_S_IDLE, CWS_PIX_DONE, CWS_PIX_SQUASH, CWS_WINFULL, CWS_POOLFULL, CWS_N };
+       SWS_CYC_KERNEL, SWS_CYC_W_WAIT, SWS_CYC_W_GROW, SWS_CYC_W_SQUASH, SWS_CYC_W_SCAN, SWS_CYC_S_RETIRE, SWS_CYC_S_PLIST,
+       SWS_CYC_S_IDLE, SWS_PIX_DONE, SWS_PIX_SQUASH, SWS_WINFULL, SWS_POOLFULL, SWS_HEUR_SKIP, SWS_P_HELD, SWS_P_TOMB, SWS_P_ROB,
+       SWS_N };
 __device__ unsigned long long g_aw_stats[32];
+// "same edge" heuristic (it decides which seeds are passed over for now, never the result): a seed closer than
+// g_sw_perp px to the level line through an older seed that is pending or being grown, within g_sw_along px along it, with
+// a level-line angle within g_sw_ang degrees, will most likely be absorbed by that seed's region
+__device__ float g_sw_perp = 4.f, g_sw_along = 300.f, g_sw_ang = 30.f;
 
-template <int W>
-struct CwState {
-  int chunk[W];       // job (chunk index) the slot holds, -1 = none
-  int state[W];
-  int poison[W];
-  int blocker[W];     // tag of the older region that poisoned the job
-  int dirtyFrom[W];   // first seed of the job that needs validation at retirement (CW_NONE: none)
-  int rectOff[W], rectCnt[W];  // the job's rectangles in the frame's rectangle pool
-  int listOff[W], listCnt[W];  // copy of the job's pixel lists in the frame's list pool (listCnt < 0: not stored)
-  int rq[CW_RQN];     // re-issue queue: slot + 1, 0 = empty
+template <int K, int WS>
+struct SwState {
+  int st[WS];         // per seed of the window
+  int poison[WS];
+  int blocker[WS];    // tag of the older region that poisoned the seed's region
+  int rect[WS];       // DONE: index of the region's rectangle in the frame's pool, -1 = none
+  int lstOff[WS], lstCnt[WS];  // DONE: copy of the region's pixel list in the frame's list pool
+  int plist[WS];      // ring of poisoned slots (slot + 1), written by whoever poisons
+  unsigned plTail;
+  // seeds that are pending or being grown, one row per worker warp: tag (0 = none), position, unit vector along the
+  // level line, level-line angle
+  unsigned pendTag[K - 1][32];
+  float pendX[K - 1][32], pendY[K - 1][32], pendC[K - 1][32], pendS[K - 1][32], pendD[K - 1][32];
+  int rq[SW_RQN];     // re-issue queue: rank + 1, 0 = empty
   unsigned rqHead, rqTail;
   unsigned headTag;
-  int headChunk, nextChunk;
+  int headRank, nextGroup;
   int rectTop, listTop;
-  int nSquashed, poisonEv, done, abort;
-  unsigned long long stats[CWS_N];
+  int done, abort;
+  unsigned long long stats[SWS_N];
 };
-template <int K, int W>
-constexpr size_t cw_smem_bytes() {
-  return ((sizeof(CwState<W>) + 15) & ~size_t(15)) + (sizeof(double) * 96 + sizeof(unsigned) * REG_SMEM) * (size_t)(K - 1);
+template <int K, int WS>
+constexpr size_t sw_smem_bytes() {
+  return ((sizeof(SwState<K, WS>) + 15) & ~size_t(15)) + (sizeof(double) * 96 + sizeof(unsigned) * REG_SMEM) * (size_t)(K - 1);
 }
-constexpr long long CW_WATCHDOG = 1ll << 21;  // polls (>= 40 ns each) without progress before the kernel gives up
+constexpr long long SW_WATCHDOG = 1ll << 21;  // polls (>= 40 ns each) without progress before the kernel gives up
 // internal consistency checks: a failure raises status 100 + code and stops the frame's CTA
-#define CW_ASSERT(cond, code)                                                   \
+#define SW_ASSERT(cond, code)                                                   \
   do {                                                                          \
     if (!(cond)) {                                                              \
       atomicMax(status, 100 + (code));                                          \
@@ -1025,142 +1028,174 @@ constexpr long long CW_WATCHDOG = 1ll << 21;  // polls (>= 40 ns each) without p
     }                                                                           \
   } while (0)
 
-template <int K, int W>
-__device__ void cw_retire_warp(CwState<W>& S, const LineParams& L, const unsigned* own, const unsigned* __restrict__ seeds,
-                               int ns, int nChunks, const LsdRect* rectPool, LsdRect* __restrict__ rects, int* nrectOut,
-                               int* status, int lane) {
-  const unsigned FULL = 0xffffffffu;
-  volatile int* vstate = S.state;
+template <int K, int WS>
+__device__ void sw_retire_warp(SwState<K, WS>& S, const LineParams& L, const unsigned* own, const unsigned* __restrict__ seeds,
+                               int ns, const LsdRect* rectPool, LsdRect* __restrict__ rects, int* nrectOut, int* status,
+                               int lane) {
+  const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+  volatile int* vst = S.st;
   volatile int* vpoison = S.poison;
   volatile int* vblocker = S.blocker;
-  volatile int* vchunk = S.chunk;
   volatile int* vrq = S.rq;
-  volatile int* vnSquashed = &S.nSquashed;
-  volatile int* vpoisonEv = &S.poisonEv;
-  int head = 0, nrect = 0;
-  unsigned rqTail = 0;
+  volatile int* vplist = S.plist;
+  int head = 0, nrect = 0;  // head = rank of the oldest seed that has not retired
+  unsigned rqTail = 0, plHead = 0, plSeenTail = 0;
+  int plSeenHead = -1;
   long long idle = 0;
   const long long tKernel = clock64();
   long long tPhase = tKernel;
-  int lastEv = 0, lastSq = 0, waiting = 0;
-#define CW_STAT(k, v) do { if (lane == 0) S.stats[k] += (v); } while (0)
-  auto requeue = [&](int s) {  // the job of slot s runs again
+#define SW_STAT(k, v) do { if (lane == 0) S.stats[k] += (v); } while (0)
+  auto requeue = [&](int rank) {  // the seed `rank` is grown (again) as a job of its own
     if (lane == 0) {
-      vstate[s] = CW_QUEUED;
+      vst[rank % WS] = SW_QUEUED;
       __threadfence_block();
       long long spins = 0;
-      while (vrq[rqTail % CW_RQN] != 0 && ++spins < CW_WATCHDOG) {}
-      CW_ASSERT(spins < CW_WATCHDOG, 1);
-      vrq[rqTail % CW_RQN] = s + 1;
+      while (vrq[rqTail % SW_RQN] != 0 && ++spins < SW_WATCHDOG) __nanosleep(20);
+      SW_ASSERT(spins < SW_WATCHDOG, 1);
+      vrq[rqTail % SW_RQN] = rank + 1;
       __threadfence_block();
       *reinterpret_cast<volatile unsigned*>(&S.rqTail) = rqTail + 1;
     }
     ++rqTail;
-    CW_STAT(CWS_RERUNS, 1);
+    SW_STAT(SWS_RERUNS, 1);
     __syncwarp();
   };
-  while (head < nChunks) {
-    bool progress = false, retired = false, headPoisoned = false;
+  while (head < ns) {
+    bool progress = false;
     if (*reinterpret_cast<volatile int*>(&S.abort)) break;
-    // ---- retire in order ----
-    while (head < nChunks) {
-      const int s = head % W;
-      if (vchunk[s] != head || vstate[s] != CW_DONE) break;
-      __threadfence_block();
-      if (vpoison[s]) {  // robbed by an older region after it had finished: re-issued by the scan below
-        headPoisoned = true;
-        break;
-      }
-      const int a = head * CW_CH, b = min(ns, a + CW_CH);
-      const int from = S.dirtyFrom[s];
-      if (from < b) {
-        // every seed from the first dirty one on must be held by a region that does not come after it
-        const int i = from + lane;
-        bool fail = false;
-        if (i < b) {
-          const unsigned v = __ldcg(own + seeds[i]);
-          fail = (v & 1u) || (v >> 1) > (unsigned)i + 1u;
-        }
-        CW_STAT(CWS_VALCHUNKS, 1);
-        if (__any_sync(FULL, fail)) {  // the sequential loop would have grown a seed this run passed over: run the job again
-          if (lane == 0) {
-            vpoison[s] = 1;
-            vblocker[s] = 0;
-          }
-          __syncwarp();
-          CW_STAT(CWS_REVALIDATE, 1);
-          headPoisoned = true;
-          break;
-        }
-      }
-      const int k = S.rectCnt[s], off = S.rectOff[s];
-      constexpr int RD = (int)(sizeof(LsdRect) / sizeof(double));
-      if (nrect + k <= L.rect_cap) {
-        for (int i = lane; i < k * RD; i += 32)
-          reinterpret_cast<double*>(rects + nrect)[i] = __ldcg(reinterpret_cast<const double*>(rectPool + off) + i);
-      } else if (lane == 0) {
-        atomicMax(status, PLSLAM_ERR_OVERFLOW);
-      }
-      nrect = min(nrect + k, L.rect_cap + 1);
-      CW_STAT(CWS_RECTS, k);
-      ++head;
-      if (lane == 0) {
-        vchunk[s] = -1;
-        vstate[s] = CW_EMPTY;
-        vpoison[s] = 0;
-        __threadfence_block();
-        *reinterpret_cast<volatile unsigned*>(&S.headTag) = (unsigned)min(head * CW_CH, ns) + 1u;
-        *reinterpret_cast<volatile int*>(&S.headChunk) = head;
-      }
-      __syncwarp();
-      progress = retired = true;
-    }
-    { const long long t = clock64(); CW_STAT(CWS_CYC_S_RETIRE, t - tPhase); tPhase = t; }
-    // ---- poisoned jobs run again once the region that blocked them has retired, or at once at the head.  The window is
-    //      only scanned when something changed ----
+    // ---- retire the longest prefix of the 32 oldest seeds that is finished and not poisoned ----
     {
-      const int ev = *vpoisonEv, sq = *vnSquashed;
-      if (headPoisoned || ev != lastEv || sq != lastSq || (waiting > 0 && retired)) {
-        lastEv = ev;
-        waiting = 0;
-        int requeued = 0;
-        const unsigned headTag = (unsigned)min(head * CW_CH, ns) + 1u;
-        for (int b0 = 0; b0 < W; b0 += 32) {
-          const int s = b0 + lane;
-          int kind = 0;
-          bool wait = false;
-          if (s < W) {
-            const int st = vstate[s];
-            const bool pz = st == CW_SQUASHED || (st == CW_DONE && vpoison[s]);
-            const bool go = (unsigned)vblocker[s] < headTag || vchunk[s] == head;
-            if (pz && go) kind = st == CW_SQUASHED ? 1 : 2;
-            wait = pz && !go;
+      const int rank = head + lane;
+      const bool valid = rank < ns;
+      const int s = rank % WS;
+      const int st = valid ? vst[s] : SW_EMPTY;
+      __threadfence_block();
+      const bool pz = valid && vpoison[s] != 0;
+      const bool fin = valid && (st == SW_DONE || st == SW_DIRTY) && !pz;
+      const unsigned finM = __ballot_sync(FULL, fin);
+      int prefix = __ffs(~finM) - 1;  // (finM == FULL gives 32 - 1 + 1: ffs(0) = 0 -> -1; handled below)
+      if (finM == FULL) prefix = 32;
+      // DIRTY seeds of the prefix: each must be held by a region that does not come after it
+      const bool chk = fin && st == SW_DIRTY && lane < prefix;
+      if (__any_sync(FULL, chk)) {
+        bool fail = false;
+        if (chk) {
+          const unsigned v = __ldcg(own + seeds[rank]);
+          fail = (v & 1u) || (v >> 1) > (unsigned)rank + 1u;
+        }
+        SW_STAT(SWS_VALSTEPS, 1);
+        const unsigned failM = __ballot_sync(FULL, fail);
+        if (failM) {  // the sequential loop would have grown this seed: it is grown now, as the head
+          const int f = __ffs(failM) - 1;
+          prefix = f;
+          if (lane == 0) {
+            S.lstCnt[(head + f) % WS] = 0;
+            vblocker[(head + f) % WS] = 0;
           }
-          waiting += __popc(__ballot_sync(FULL, wait));
-          unsigned m = __ballot_sync(FULL, kind != 0);
+          SW_STAT(SWS_INSERT, 1);
+          requeue(head + f);
+          progress = true;
+        }
+      }
+      if (prefix > 0) {
+        // rectangles of the retiring regions, in seed order
+        const int ri = (lane < prefix && st == SW_DONE) ? S.rect[s] : -1;
+        const unsigned rectM = __ballot_sync(FULL, ri >= 0);
+        constexpr int RD = (int)(sizeof(LsdRect) / sizeof(double));
+        int pos = nrect;
+        for (unsigned r = rectM; r; r &= r - 1u, ++pos) {
+          const int src = __shfl_sync(FULL, ri, __ffs(r) - 1);
+          if (pos < L.rect_cap) {
+            if (lane < RD) reinterpret_cast<double*>(rects + pos)[lane] = __ldcg(reinterpret_cast<const double*>(rectPool + src) + lane);
+          } else if (lane == 0) {
+            atomicMax(status, PLSLAM_ERR_OVERFLOW);
+          }
+        }
+        SW_STAT(SWS_RECTS, __popc(rectM));
+        nrect = pos;
+        if (lane < prefix) {
+          vpoison[s] = 0;
+          vst[s] = SW_EMPTY;
+        }
+        head += prefix;
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) {
+          *reinterpret_cast<volatile unsigned*>(&S.headTag) = (unsigned)head + 1u;
+          *reinterpret_cast<volatile int*>(&S.headRank) = head;
+        }
+        progress = true;
+      }
+      // the seed now at the head: poisoned or squashed -> grown again at once (nothing older is in flight any more)
+      if (head < ns) {
+        const int hs = head % WS;
+        const int hst = vst[hs];
+        const bool hpz = vpoison[hs] != 0;
+        if (hst == SW_SQUASHED || ((hst == SW_DONE || hst == SW_DIRTY) && hpz)) {
+          if (hst != SW_SQUASHED) SW_STAT(SWS_SQUASH_DONE, 1);
+          requeue(head);
+          progress = true;
+        }
+      }
+    }
+    { const long long t = clock64(); SW_STAT(SWS_CYC_S_RETIRE, t - tPhase); tPhase = t; }
+    // ---- poisoned regions behind the head are grown again once the region that blocked them has retired ----
+    {
+      // entries that must wait for their blocker go back to the ring; the ring is looked at again when a new entry has
+      // arrived or the head has moved since, not in a busy loop
+      const unsigned tl = *reinterpret_cast<volatile unsigned*>(&S.plTail);
+      if (tl != plHead && (tl != plSeenTail || head != plSeenHead)) {
+        unsigned repushed = 0;
+        while (plHead != tl) {
+          const unsigned todo = min(tl - plHead, 32u);
+          int e = 0;
+          if ((unsigned)lane < todo) {
+            long long spins = 0;
+            while ((e = vplist[(plHead + lane) % WS]) == 0 && ++spins < SW_WATCHDOG) {}
+            vplist[(plHead + lane) % WS] = 0;
+          }
+          plHead += todo;
+          const int s = e - 1;
+          int kind = 0;  // 1 requeue, 2 keep waiting
+          int rank = 0;
+          if (e > 0) {
+            const int st = vst[s];
+            const bool pz = vpoison[s] != 0;
+            rank = head + ((s - head % WS) + WS) % WS;
+            if (st == SW_SQUASHED || ((st == SW_DONE || st == SW_DIRTY) && pz)) {
+              kind = ((unsigned)vblocker[s] < (unsigned)head + 1u) ? 1 : 2;
+              if (rank == head) kind = 0;  // the head is handled above
+            } else if ((st == SW_RUNNING || st == SW_PENDING) && pz) {
+              kind = 2;  // its worker has not noticed yet
+            }
+          }
+          unsigned m = __ballot_sync(FULL, kind == 1);
           while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1u;
-            const int kj = __shfl_sync(FULL, kind, j);
-            if (kj == 1) {
-              if (lane == 0) atomicSub(&S.nSquashed, 1);
-              ++requeued;
-            } else {
-              CW_STAT(CWS_SQUASH_DONE, 1);
-            }
-            requeue(b0 + j);
+            const int rj = __shfl_sync(FULL, rank, j), sj = __shfl_sync(FULL, s, j);
+            const int stj = vst[sj];  // read again: two ring entries may name the same slot
+            if (!(stj == SW_SQUASHED || ((stj == SW_DONE || stj == SW_DIRTY) && vpoison[sj] != 0))) continue;
+            if (stj != SW_SQUASHED) SW_STAT(SWS_SQUASH_DONE, 1);
+            requeue(rj);
             progress = true;
           }
+          if (kind == 2) {
+            const unsigned p = atomicAdd(&S.plTail, 1u);
+            vplist[p % WS] = e;
+          }
+          repushed += __popc(__ballot_sync(FULL, kind == 2));
         }
-        lastSq = sq - requeued;  // a job squashed meanwhile makes the counter differ and triggers the next scan
+        plSeenTail = tl + repushed;  // a push by a worker meanwhile makes the tail differ and the ring is looked at again
+        plSeenHead = head;
       }
     }
-    { const long long t = clock64(); CW_STAT(CWS_CYC_S_SCAN, t - tPhase); tPhase = t; }
+    { const long long t = clock64(); SW_STAT(SWS_CYC_S_PLIST, t - tPhase); tPhase = t; }
     if (!progress) {
-      CW_STAT(CWS_SCHED_IDLE, 1);
+      SW_STAT(SWS_SCHED_IDLE, 1);
       __nanosleep(40);
-      { const long long t = clock64(); CW_STAT(CWS_CYC_S_IDLE, t - tPhase); tPhase = t; }
-      if (++idle > CW_WATCHDOG) {
+      { const long long t = clock64(); SW_STAT(SWS_CYC_S_IDLE, t - tPhase); tPhase = t; }
+      if (++idle > SW_WATCHDOG) {
         if (lane == 0) {
           atomicMax(status, PLSLAM_ERR_INTERNAL);
           *reinterpret_cast<volatile int*>(&S.abort) = 1;
@@ -1171,73 +1206,72 @@ __device__ void cw_retire_warp(CwState<W>& S, const LineParams& L, const unsigne
       idle = 0;
     }
   }
-  CW_STAT(CWS_CYC_KERNEL, clock64() - tKernel);
+  SW_STAT(SWS_CYC_KERNEL, clock64() - tKernel);
   if (lane == 0) {
     *nrectOut = min(nrect, L.rect_cap);
     __threadfence_block();
     *reinterpret_cast<volatile int*>(&S.done) = 1;
   }
-#undef CW_STAT
+#undef SW_STAT
 }
 
-// One worker warp: take a job (re-issued ones first), run its seeds in order, publish, repeat.
-template <int K, int W>
-__device__ void cw_worker(CwState<W>& S, GrowCtx& C, const LineParams& L, const unsigned* __restrict__ seeds, int ns, int nChunks,
-                          unsigned* stackBase, int stackCap, unsigned* listPool, int listPoolCap, LsdRect* rectStage,
-                          LsdRect* rectPool, int* status) {
+// One worker warp: take a job (re-issued seeds first, else the next group of 32 seeds), grow its free seeds in order,
+// publish every seed's state, repeat.
+template <int K, int WS>
+__device__ void sw_worker(SwState<K, WS>& S, GrowCtx& C, const LineParams& L, const unsigned* __restrict__ seeds, int ns,
+                          unsigned* listPool, int listPoolCap, LsdRect* rectPool, int* status) {
   const unsigned FULL = 0xffffffffu;
   const int lane = C.lane;
-  volatile int* vstate = S.state;
-  volatile int* vchunk = S.chunk;
+  volatile int* vst = S.st;
   volatile int* vrq = S.rq;
   volatile int* vdone = &S.done;
   volatile int* vabort = &S.abort;
-  volatile int* vheadChunk = &S.headChunk;
-  int fresh = -1;  // a job taken from the counter that still waits for its window slot
+  volatile int* vheadRank = &S.headRank;
+  const int me = (int)(threadIdx.x >> 5) - 1;  // my row of the table of pending seeds
+  const int nGroups = (ns + SW_G - 1) / SW_G;
+  int fresh = -1;  // a group taken from the counter that still waits for room in the window
   bool freshLeft = true;
   while (true) {
     // ---- acquire ----
     const long long tWait = clock64();
-    int s = -1, c = -1;
-    bool rerun = false;
+    int a = -1, cnt = 0;  // the job: seeds [a, a + cnt)
+    bool single = false;
     long long spins = 0;
     while (true) {
-      int got = -1, gotC = -1, gotRerun = 0, stop = 0;
+      int gotA = -1, gotSingle = 0, stop = 0;
       if (lane == 0) {
         const unsigned h = *reinterpret_cast<volatile unsigned*>(&S.rqHead), tl = *reinterpret_cast<volatile unsigned*>(&S.rqTail);
         if (h != tl) {
           if (atomicCAS(&S.rqHead, h, h + 1u) == h) {
-            const int v = vrq[h % CW_RQN];
-            vrq[h % CW_RQN] = 0;
-            got = v - 1;
-            gotRerun = 1;
-            if (got >= 0 && got < W) gotC = vchunk[got];
+            const int v = vrq[h % SW_RQN];
+            vrq[h % SW_RQN] = 0;
+            gotA = v - 1;
+            gotSingle = 1;
           }
         } else {
           if (fresh < 0 && freshLeft) {
-            fresh = atomicAdd(&S.nextChunk, 1);
-            if (fresh >= nChunks) { fresh = -1; freshLeft = false; }
+            fresh = atomicAdd(&S.nextGroup, 1);
+            if (fresh >= nGroups) { fresh = -1; freshLeft = false; }
           }
-          if (fresh >= 0 && fresh < *vheadChunk + W) {
-            got = fresh % W;
-            gotC = fresh;
+          if (fresh >= 0 && (fresh + 1) * SW_G <= *vheadRank + WS) {
+            gotA = fresh * SW_G;
             fresh = -1;
           } else if (fresh >= 0) {
-            S.stats[CWS_WINFULL] += 1;  // racy between workers: a statistic only
+            S.stats[SWS_WINFULL] += 1;  // racy between workers: a statistic only
           }
         }
         stop = *vdone | *vabort;
       }
-      got = __shfl_sync(FULL, got, 0);
-      if (got >= 0) {
-        s = got;
-        c = __shfl_sync(FULL, gotC, 0);
-        rerun = __shfl_sync(FULL, gotRerun, 0) != 0;
+      gotA = __shfl_sync(FULL, gotA, 0);
+      if (gotA >= 0) {
+        a = gotA;
+        single = __shfl_sync(FULL, gotSingle, 0) != 0;
+        cnt = single ? 1 : min(SW_G, ns - a);
         break;
       }
       if (__shfl_sync(FULL, stop, 0)) return;
       __nanosleep(40);
-      if (++spins > CW_WATCHDOG) {
+      if (++spins > SW_WATCHDOG) {
         if (lane == 0) {
           atomicMax(status, PLSLAM_ERR_INTERNAL);
           *vabort = 1;
@@ -1247,73 +1281,140 @@ __device__ void cw_worker(CwState<W>& S, GrowCtx& C, const LineParams& L, const 
     }
     const long long tJob = clock64();
     if (lane == 0) {
-      atomicAdd(&S.stats[CWS_WORK_IDLE], (unsigned long long)spins);
-      atomicAdd(&S.stats[CWS_CYC_W_WAIT], (unsigned long long)(tJob - tWait));
+      atomicAdd(&S.stats[SWS_WORK_IDLE], (unsigned long long)spins);
+      atomicAdd(&S.stats[SWS_CYC_W_WAIT], (unsigned long long)(tJob - tWait));
     }
-    if ((unsigned)s >= (unsigned)W || c < 0 || c >= nChunks) {
-      CW_ASSERT(false, 2);
+    if (a < 0 || a >= ns) {
+      SW_ASSERT(false, 2);
       return;
     }
     __threadfence_block();
-    const int a = c * CW_CH, b = min(ns, a + CW_CH);
-    C.slot = s;
-    C.jobLo = (unsigned)a + 1u;
-    C.jobHi = (unsigned)b;
-    // ---- a job that finished and was poisoned afterwards still holds its pixels: give them back (pool copy of its lists) ----
-    if (rerun && S.listCnt[s] != 0) {
-      const int cnt = S.listCnt[s], off = S.listOff[s];
-      CW_ASSERT(cnt > 0, 3);  // (a job whose lists did not fit the pool is never stored as DONE, see below)
-      for (int i = lane; i < cnt; i += 32) {
-        const unsigned pxy = listPool[off + i] & 0x7fffffffu;
-        const int id = (int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff);
-        const unsigned v = __ldcg(C.own + id);
-        if (!(v & 1u) && (v >> 1) >= C.jobLo && (v >> 1) <= C.jobHi) atomicCAS(C.own + id, v, 0xffffffffu);
+    const bool mineLane = lane < cnt;
+    const int rank = a + lane, slot = rank % WS;
+    const unsigned tagL = (unsigned)rank + 1u;
+    int sd = mineLane ? (int)seeds[rank] : -1;
+    if (single) {
+      // a region that finished and was poisoned afterwards still holds its pixels: give them back (pool copy of its list)
+      const int lc = S.lstCnt[a % WS], lo = S.lstOff[a % WS];
+      const unsigned mark = ((unsigned)a + 1u) << 1;
+      for (int i = lane; i < lc; i += 32) {
+        const unsigned pxy = listPool[lo + i] & 0x7fffffffu;
+        atomicCAS(C.own + (int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff), mark, 0xffffffffu);
       }
-    }
-    __threadfence();
-    if (lane == 0) {
-      vchunk[s] = c;
-      S.listCnt[s] = 0;
-      S.rectCnt[s] = 0;
-      S.dirtyFrom[s] = CW_NONE;
-      C.blocker[s] = 0;
-      C.poison[s] = 0;
-      __threadfence_block();
-      vstate[s] = CW_RUNNING;
+      __threadfence();
+      if (lane == 0) {
+        S.lstCnt[a % WS] = 0;
+        S.rect[a % WS] = -1;
+        C.blocker[a % WS] = 0;
+        *reinterpret_cast<volatile int*>(C.poison + a % WS) = 0;
+        __threadfence_block();
+        vst[a % WS] = SW_PENDING;
+      }
+    } else if (mineLane) {
+      S.lstCnt[slot] = 0;
+      S.rect[slot] = -1;
+      C.blocker[slot] = 0;
+      vst[slot] = SW_PENDING;  // (the slot was EMPTY with its poison flag cleared: the window had room for this group)
     }
     __syncwarp();
-    // ---- run the job: its seeds in order, like the sequential loop ----
-    int sd = a + lane < b ? (int)seeds[a + lane] : -1;
-    int used = 0, nrectJob = 0, dirty = CW_NONE, nreg = 0;
-    bool squashed = false;
+    // seed positions and level lines (same-edge heuristic)
+    float sxf = 0.f, syf = 0.f, sdeg = 0.f, scs = 0.f, ssn = 0.f;
+    if (sd >= 0) {
+      const uint4 r = C.pix[sd];
+      const int yy = sd / C.sw;
+      sxf = (float)(sd - yy * C.sw);
+      syf = (float)yy;
+      sdeg = __uint_as_float(r.x);
+      scs = __uint_as_float(r.y);
+      ssn = __uint_as_float(r.z);
+      S.pendX[me][lane] = sxf;
+      S.pendY[me][lane] = syf;
+      S.pendC[me][lane] = scs;
+      S.pendS[me][lane] = ssn;
+      S.pendD[me][lane] = sdeg;
+    }
+    bool published = false;  // pendTag row written (after the first classification: only seeds that look free)
+    int nreg = 0;
+    long long cycGrow = 0, cycSquash = 0;
+    // Pass 0 walks the job's seeds in order; seeds the same-edge heuristic holds back are looked at once more in pass 1,
+    // when the older seeds they waited for have most likely been grown (what is still held back then stays DIRTY).
+    unsigned deferM = 0;
+    int sdd = -1;
+    for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      if (!deferM) break;
+      sd = ((deferM >> lane) & 1u) ? sdd : -1;
+      published = false;
+    }
     while (true) {
       const unsigned h0 = *C.headTag;
       const unsigned v = sd >= 0 ? __ldcg(C.own + sd) : 0u;
       const unsigned t = v >> 1;
-      bool grow = false, isDirty = false;
+      // 0 = not mine / dropped, 1 = grow, 2 = used for good (held by a retired region), 3 = dirty (an older region in
+      // flight holds it or gave it back: its fate decides)
+      int cls = 0;
       if (sd >= 0) {
-        if (v == 0xffffffffu) grow = true;
-        else if (t < h0 || (t >= C.jobLo && t <= C.jobHi)) grow = (v & 1u) != 0;  // settled: given back = free, held = used
-        else if (t < C.jobLo) isDirty = true;  // an older region in flight holds it or gave it back: its fate decides
-        else grow = true;                      // a younger job's region: the take robs it
+        if (v == 0xffffffffu) cls = 1;
+        else if (t < h0) cls = (v & 1u) ? 1 : 2;
+        else if (t < tagL) cls = 3;
+        else cls = 1;  // mine from an earlier run (tombstone), or a younger region: the take robs it
       }
-      const unsigned gm = __ballot_sync(FULL, grow);
-      const unsigned dm = __ballot_sync(FULL, isDirty);
+      if (cls == 2) {
+        vst[slot] = SW_DONE;
+        sd = -1;
+      }
+      if (!published) {
+        *reinterpret_cast<volatile unsigned*>(&S.pendTag[me][lane]) = cls == 1 ? tagL : 0u;
+        published = true;
+      }
+      const unsigned gm = __ballot_sync(FULL, cls == 1);
       const int j = gm ? __ffs(gm) - 1 : 32;
-      const unsigned passedDirty = j < 32 ? dm & ((1u << j) - 1u) : dm;
-      if (passedDirty) dirty = min(dirty, a + __ffs(passedDirty) - 1);
+      if (cls == 3 && lane < j) {  // passed over
+        vst[slot] = SW_DIRTY;
+        sd = -1;
+        atomicAdd(&S.stats[SWS_DIRTY], 1ull);
+      }
       if (!gm) break;
       const int seed = __shfl_sync(FULL, sd, j);
-      if (lane <= j) sd = -1;
-      C.myVal = ((unsigned)(a + j) + 1u) << 1;
-      C.regG = stackBase + used;
-      C.cap = stackCap - used;
-      if (C.cap < 64) {  // the list stack of the job is full (cannot happen: a job's regions are disjoint, stack = P entries)
-        CW_ASSERT(false, 4);
-        squashed = true;
-        break;
+      const unsigned myTag = (unsigned)(a + j) + 1u;
+      const int mySlot = (a + j) % WS;
+      if (lane == j) {
+        sdd = sd;
+        sd = -1;
       }
-      if (lane == 0) C.reg_set(0, ((unsigned)(seed / C.sw) << 16) | (unsigned)(seed % C.sw));
+      {
+        // same-edge heuristic against the older seeds other workers have pending or are growing
+        const float jx = __shfl_sync(FULL, sxf, j), jy = __shfl_sync(FULL, syf, j), jd = __shfl_sync(FULL, sdeg, j);
+        bool hit = false;
+        for (int w = 0; w < K - 1 && !hit; ++w) {
+          if (w == me) continue;
+          const unsigned at = *reinterpret_cast<volatile unsigned*>(&S.pendTag[w][lane]);
+          if (at != 0u && at < myTag) {
+            const float dx = jx - S.pendX[w][lane], dy = jy - S.pendY[w][lane];
+            const float perp = fabsf(dx * S.pendS[w][lane] - dy * S.pendC[w][lane]);
+            const float along = fabsf(dx * S.pendC[w][lane] + dy * S.pendS[w][lane]);
+            float dd = fabsf(jd - S.pendD[w][lane]);
+            if (dd > 180.f) dd = 360.f - dd;
+            hit = perp < g_sw_perp && along < g_sw_along && dd < g_sw_ang;
+          }
+        }
+        if (__any_sync(FULL, hit)) {
+          if (lane == 0) {
+            *reinterpret_cast<volatile unsigned*>(&S.pendTag[me][j]) = 0u;
+            if (pass == 1) vst[mySlot] = SW_DIRTY;
+            atomicAdd(&S.stats[SWS_HEUR_SKIP], 1ull);
+          }
+          if (pass == 0) deferM |= 1u << j;
+          continue;
+        }
+      }
+      const long long tReg = clock64();
+      C.myVal = myTag << 1;
+      C.slot = mySlot;
+      if (lane == 0) {
+        vst[mySlot] = SW_RUNNING;
+        C.reg_set(0, ((unsigned)(seed / C.sw) << 16) | (unsigned)(seed % C.sw));
+      }
       __syncwarp();
       double reg_angle;
       int n = lsd_region_grow_spec<true>(C, L.prec, &reg_angle);
@@ -1324,139 +1425,109 @@ __device__ void cw_worker(CwState<W>& S, GrowCtx& C, const LineParams& L, const 
         lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
         keep = lsd_refine<true>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, 1);
       }
-      // the head of the list lives in shared memory: the stack keeps the whole list (release / pool copy)
-      for (int i = lane; i < min(n, REG_SMEM); i += 32) C.regG[i] = C.regS[i];
-      used += n;
-      if (C.mw_poisoned()) {
-        squashed = true;
-        break;
-      }
-      if (keep) {
-        if (lane == 0) rectStage[nrectJob] = rec;
-        ++nrectJob;
-      }
-    }
-    __syncwarp();
-    if (squashed || C.mw_poisoned()) {
-      squashed = true;
-      // give every pixel still held by a region of this job back (MW_FREE: a squashed run leaves no trace but tombstones)
-      for (int i = lane; i < used; i += 32) {
-        const unsigned pxy = stackBase[i] & 0x7fffffffu;
-        const int id = (int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff);
-        const unsigned v = __ldcg(C.own + id);
-        if (!(v & 1u) && (v >> 1) >= C.jobLo && (v >> 1) <= C.jobHi) atomicCAS(C.own + id, v, 0xffffffffu);
-      }
-    } else {
-      // publish: rectangles and the lists (for a release after DONE) go to the frame's pools
-      int roff = 0, loff = 0;
-      if (lane == 0) {
-        if (nrectJob) roff = atomicAdd(&S.rectTop, nrectJob);
-        if (used) loff = atomicAdd(&S.listTop, used);
-      }
-      roff = __shfl_sync(FULL, roff, 0);
-      loff = __shfl_sync(FULL, loff, 0);
-      if (roff + nrectJob > L.rect_cap) {  // rectangle pool exhausted (runs that were squashed leak their entries)
-        if (lane == 0) atomicMax(status, PLSLAM_ERR_OVERFLOW);
-        nrectJob = 0;
-        roff = 0;
-      }
-      constexpr int RD = (int)(sizeof(LsdRect) / sizeof(double));
-      for (int i = lane; i < nrectJob * RD; i += 32)
-        reinterpret_cast<double*>(rectPool + roff)[i] = reinterpret_cast<const double*>(rectStage)[i];
-      bool stored = true;
-      if (used) {
-        if (loff + used <= listPoolCap) {
-          for (int i = lane; i < used; i += 32) listPool[loff + i] = stackBase[i];
+      if (lane == 0) *reinterpret_cast<volatile unsigned*>(&S.pendTag[me][j]) = 0u;
+      bool squashed = C.mw_poisoned();
+      int roff = -1, loff = 0;
+      if (!squashed) {
+        // publish: the rectangle and the list (for a release after DONE) go to the frame's pools
+        if (lane == 0) {
+          if (keep) roff = atomicAdd(&S.rectTop, 1);
+          if (n) loff = atomicAdd(&S.listTop, n);
+        }
+        roff = __shfl_sync(FULL, roff, 0);
+        loff = __shfl_sync(FULL, loff, 0);
+        if (roff >= L.rect_cap) {  // rectangle pool exhausted (runs that were squashed leak their entries)
+          if (lane == 0) atomicMax(status, PLSLAM_ERR_OVERFLOW);
+          roff = -1;
+        }
+        if (roff >= 0 && lane == 0) rectPool[roff] = rec;
+        if (loff + n <= listPoolCap) {
+          for (int i = lane; i < n; i += 32) listPool[loff + i] = C.reg_get(i);
         } else {
-          stored = false;
+          // list pool exhausted: the region could not be released after DONE, so it only publishes as the head
+          if (lane == 0) S.stats[SWS_POOLFULL] += 1;
+          long long sp = 0;
+          while (*vheadRank != a + j && !C.mw_poisoned() && !(*vabort) && ++sp < SW_WATCHDOG) __nanosleep(100);
+          squashed = C.mw_poisoned() || *vheadRank != a + j;
+          loff = 0;
+          if (!squashed) n = 0;  // (published with an empty list: the head cannot be poisoned any more)
         }
       }
-      if (!stored) {
-        // list pool exhausted: the job cannot be released after DONE, so it only publishes once nothing older is in flight
-        if (lane == 0) S.stats[CWS_POOLFULL] += 1;
-        long long sp = 0;
-        while (*vheadChunk != c && !C.mw_poisoned() && !(*vabort) && ++sp < CW_WATCHDOG) __nanosleep(100);
-        if (C.mw_poisoned() || *vheadChunk != c) {
-          squashed = true;
-          for (int i = lane; i < used; i += 32) {
-            const unsigned pxy = stackBase[i] & 0x7fffffffu;
-            const int id = (int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff);
-            const unsigned v = __ldcg(C.own + id);
-            if (!(v & 1u) && (v >> 1) >= C.jobLo && (v >> 1) <= C.jobHi) atomicCAS(C.own + id, v, 0xffffffffu);
-          }
-        }
-      }
-      if (!squashed && lane == 0) {
-        S.rectOff[s] = roff;
-        S.rectCnt[s] = nrectJob;
-        S.listOff[s] = loff;
-        S.listCnt[s] = stored ? used : 0;
-        S.dirtyFrom[s] = dirty;
-      }
-    }
-    __threadfence();  // owner-plane updates (releases are fire-and-forget) and pool copies are performed before the state is published
-    if (lane == 0) {
       if (squashed) {
-        vstate[s] = CW_SQUASHED;
-        __threadfence_block();
-        atomicAdd(&S.nSquashed, 1);  // after the state: a retirement warp that sees the count also sees the state
-        atomicAdd(&S.stats[CWS_SQUASH_RUN], 1ull);
-        atomicAdd(&S.stats[CWS_PIX_SQUASH], (unsigned long long)used);
-      } else {
-        __threadfence_block();
-        vstate[s] = CW_DONE;
-        atomicAdd(&S.stats[CWS_PIX_DONE], (unsigned long long)used);
-        if (dirty != CW_NONE) atomicAdd(&S.stats[CWS_DIRTY_JOBS], 1ull);
+        for (int i = lane; i < n; i += 32) {
+          const unsigned pxy = C.reg_get(i) & 0x7fffffffu;
+          atomicCAS(C.own + (int)(pxy >> 16) * C.sw + (int)(pxy & 0xffff), C.myVal, 0xffffffffu);
+        }
       }
-      atomicAdd(&S.stats[CWS_JOBS], 1ull);
-      atomicAdd(&S.stats[CWS_REGIONS], (unsigned long long)nreg);
-      atomicAdd(&S.stats[squashed ? CWS_CYC_W_SQUASH : nreg ? CWS_CYC_W_DONE : CWS_CYC_W_EMPTY], (unsigned long long)(clock64() - tJob));
+      __threadfence();  // owner-plane updates (releases are fire-and-forget) and pool copies are performed before the state is published
+      if (lane == 0) {
+        if (squashed) {
+          vst[mySlot] = SW_SQUASHED;  // (its slot is in the poison ring: the retirement warp re-issues it)
+          atomicAdd(&S.stats[SWS_SQUASH_RUN], 1ull);
+          atomicAdd(&S.stats[SWS_PIX_SQUASH], (unsigned long long)n);
+        } else {
+          S.rect[mySlot] = roff;
+          S.lstOff[mySlot] = loff;
+          S.lstCnt[mySlot] = n;
+          __threadfence_block();
+          vst[mySlot] = SW_DONE;
+          atomicAdd(&S.stats[SWS_PIX_DONE], (unsigned long long)n);
+        }
+      }
+      (squashed ? cycSquash : cycGrow) += clock64() - tReg;
+      __syncwarp();
+    }
+    }
+    if (lane == 0) {
+      atomicAdd(&S.stats[SWS_GROUPS], single ? 0ull : 1ull);
+      atomicAdd(&S.stats[SWS_REGIONS], (unsigned long long)nreg);
+      atomicAdd(&S.stats[SWS_CYC_W_GROW], (unsigned long long)cycGrow);
+      atomicAdd(&S.stats[SWS_CYC_W_SQUASH], (unsigned long long)cycSquash);
+      atomicAdd(&S.stats[SWS_CYC_W_SCAN], (unsigned long long)(clock64() - tJob - cycGrow - cycSquash));
     }
     __syncwarp();
   }
 }
 
-template <int K, int W>
-__global__ void __launch_bounds__(32 * K) k_lsd_grow_cw(const __grid_constant__ LineParams L, uint4* pixAll, unsigned* ownAll,
+template <int K, int WS>
+__global__ void __launch_bounds__(32 * K) k_lsd_grow_sw(const __grid_constant__ LineParams L, uint4* pixAll, unsigned* ownAll,
                                                        const unsigned* __restrict__ seedsAll,
-                                                       const int* __restrict__ nseeds, unsigned* stackAll, unsigned* listPoolAll,
-                                                       LsdRect* rectStageAll, LsdRect* rectPoolAll,
-                                                       LsdRect* __restrict__ rectsAll, int* __restrict__ nrects,
-                                                       int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char cw_smem[];
-  CwState<W>& S = *reinterpret_cast<CwState<W>*>(cw_smem);
-  unsigned char* wbase = cw_smem + ((sizeof(CwState<W>) + 15) & ~size_t(15));
+                                                       const int* __restrict__ nseeds, unsigned* listAll, unsigned* listPoolAll,
+                                                       LsdRect* rectPoolAll, LsdRect* __restrict__ rectsAll,
+                                                       int* __restrict__ nrects, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char sw_smem[];
+  SwState<K, WS>& S = *reinterpret_cast<SwState<K, WS>*>(sw_smem);
+  unsigned char* wbase = sw_smem + ((sizeof(SwState<K, WS>) + 15) & ~size_t(15));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x;
-  for (int i = threadIdx.x; i < W; i += 32 * K) {
-    S.chunk[i] = -1;
-    S.state[i] = CW_EMPTY;
+  for (int i = threadIdx.x; i < WS; i += 32 * K) {
+    S.st[i] = SW_EMPTY;
     S.poison[i] = 0;
     S.blocker[i] = 0;
-    S.dirtyFrom[i] = CW_NONE;
-    S.rectOff[i] = S.rectCnt[i] = S.listOff[i] = S.listCnt[i] = 0;
+    S.rect[i] = -1;
+    S.lstOff[i] = S.lstCnt[i] = 0;
+    S.plist[i] = 0;
   }
-  if (threadIdx.x < CW_RQN) S.rq[threadIdx.x] = 0;
-  if (threadIdx.x < CWS_N) S.stats[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < (K - 1) * 32; i += 32 * K) S.pendTag[i / 32][i % 32] = 0u;
+  if (threadIdx.x < SW_RQN) S.rq[threadIdx.x] = 0;
+  if (threadIdx.x < SWS_N) S.stats[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
+    S.plTail = 0;
     S.rqHead = S.rqTail = 0;
     S.headTag = 1u;
-    S.headChunk = 0;
-    S.nextChunk = 0;
+    S.headRank = 0;
+    S.nextGroup = 0;
     S.rectTop = 0;
     S.listTop = 0;
-    S.nSquashed = 0;
-    S.poisonEv = 0;
     S.done = 0;
     S.abort = 0;
   }
   __syncthreads();
   const unsigned* seeds = seedsAll + (size_t)f * L.P;
   const int ns = nseeds[f];
-  const int nChunks = (ns + CW_CH - 1) / CW_CH;
   if (warp == 0) {
-    cw_retire_warp<K, W>(S, L, ownAll + (size_t)f * L.P, seeds, ns, nChunks, rectPoolAll + (size_t)f * L.rect_cap,
-                         rectsAll + (size_t)f * L.rect_cap, nrects + f, status, lane);
+    sw_retire_warp<K, WS>(S, L, ownAll + (size_t)f * L.P, seeds, ns, rectPoolAll + (size_t)f * L.rect_cap,
+                          rectsAll + (size_t)f * L.rect_cap, nrects + f, status, lane);
   } else {
     GrowCtx C;
 #ifdef PLSLAM_GROW_PROF
@@ -1470,30 +1541,29 @@ __global__ void __launch_bounds__(32 * K) k_lsd_grow_cw(const __grid_constant__ 
     C.prefetch = false;
     C.pix = pixAll + (size_t)f * L.P;
     C.own = ownAll + (size_t)f * L.P;
-    C.regG = nullptr;
-    C.cap = 0;
+    // per worker: a list area of 2 P entries (region list + refine() scratch); per frame: list pool of 2 P entries and
+    // rectangle pool of rect_cap entries
+    C.regG = listAll + ((size_t)f * (K - 1) + (warp - 1)) * 2 * (size_t)L.P;
+    C.cap = 2 * L.P;
     C.sw = L.sw;
     C.sh = L.sh;
     C.P = L.P;
     C.lane = lane;
     C.poison = S.poison;
     C.blocker = S.blocker;
-    C.poisonEv = &S.poisonEv;
+    C.plist = S.plist;
+    C.plTail = &S.plTail;
+    C.pstat = &S.stats[SWS_P_HELD];
     C.headTag = &S.headTag;
-    C.chunks = S.chunk;
-    C.nslots = W;
+    C.nslots = WS;
     C.slot = 0;
     C.myVal = 0;
-    C.jobLo = C.jobHi = 0;
-    // per worker: a list stack of 2 P entries (lists of the job's regions one after the other + refine() scratch) and a
-    // staging area of CW_CH rectangles; per frame: list pool of 2 P entries, rectangle pool of rect_cap entries
-    cw_worker<K, W>(S, C, L, seeds, ns, nChunks, stackAll + ((size_t)f * (K - 1) + (warp - 1)) * 2 * (size_t)L.P, 2 * L.P,
-                    listPoolAll + (size_t)f * 2 * (size_t)L.P, 2 * L.P,
-                    rectStageAll + ((size_t)f * (K - 1) + (warp - 1)) * CW_CH, rectPoolAll + (size_t)f * L.rect_cap, status);
+    sw_worker<K, WS>(S, C, L, seeds, ns, listPoolAll + (size_t)f * 2 * (size_t)L.P, 2 * L.P, rectPoolAll + (size_t)f * L.rect_cap,
+                     status);
   }
   __syncthreads();
-  if (threadIdx.x < CWS_N) {
-    const unsigned long long v = threadIdx.x == CWS_FRAMES ? 1ull : S.stats[threadIdx.x];
+  if (threadIdx.x < SWS_N) {
+    const unsigned long long v = threadIdx.x == SWS_FRAMES ? 1ull : S.stats[threadIdx.x];
     if (v) atomicAdd(&g_aw_stats[threadIdx.x], v);
   }
 }
@@ -2236,40 +2306,45 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
   P.batch = batch;
   // PLSLAM_GROW_MODE: 0 = one warp per frame (k_lsd_grow), 2 = speculative multi-warp growing with in-order retirement
-  // (k_lsd_grow_cw); unset = automatic.  PLSLAM_CW_K = warps per frame of mode 2 (8, 16 or 32).
+  // (k_lsd_grow_sw); unset = automatic.  PLSLAM_SW_K = warps per frame of mode 2 (8, 16 or 32).
   static const int growMode = [] { const char* e = std::getenv("PLSLAM_GROW_MODE"); return e ? std::atoi(e) : -1; }();  // -1 auto
-  static const int cwKenv = [] { const char* e = std::getenv("PLSLAM_CW_K"); return e ? std::atoi(e) : 0; }();
-  int cwK = cwKenv ? cwKenv : ((long long)batch * batches_in_flight <= numSMs ? 32 : 8);
-  cwK = cwK >= 32 ? 32 : cwK >= 16 ? 16 : 8;
-  // per worker warp a list stack of 2 P entries, per frame a list pool of 2 P entries: mode 2 needs them within 24 GB
-  const size_t cwBytes = (size_t)std::max(batch, cfgB) * (2 * (size_t)(cwK - 1) + 2) * P.P * sizeof(unsigned);
-  const bool cw = growMode >= 0 ? growMode != 0
-                                : ((long long)batch * batches_in_flight <= numSMs && cwBytes <= ((size_t)24 << 30));
-  if (cw) {
+  static const int swKenv = [] { const char* e = std::getenv("PLSLAM_SW_K"); return e ? std::atoi(e) : 0; }();
+  int swK = swKenv ? swKenv : ((long long)batch * batches_in_flight <= numSMs ? 32 : 8);
+  swK = swK >= 32 ? 32 : swK >= 16 ? 16 : 8;
+  // per worker warp a list area of 2 P entries, per frame a list pool of 2 P entries: mode 2 needs them within 24 GB
+  const size_t swBytes = (size_t)std::max(batch, cfgB) * (2 * (size_t)(swK - 1) + 2) * P.P * sizeof(unsigned);
+  const bool sw = growMode >= 0 ? growMode != 0
+                                : ((long long)batch * batches_in_flight <= numSMs && swBytes <= ((size_t)24 << 30));
+  if (sw) {
     int rc2;
+    static bool swTune = false;
+    if (!swTune) {  // experiment knobs of the same-edge heuristic (never affect results)
+      swTune = true;
+      if (const char* e = std::getenv("PLSLAM_SW_PERP")) { float v = (float)std::atof(e); cudaMemcpyToSymbol(g_sw_perp, &v, sizeof(v)); }
+      if (const char* e = std::getenv("PLSLAM_SW_ALONG")) { float v = (float)std::atof(e); cudaMemcpyToSymbol(g_sw_along, &v, sizeof(v)); }
+      if (const char* e = std::getenv("PLSLAM_SW_ANG")) { float v = (float)std::atof(e); cudaMemcpyToSymbol(g_sw_ang, &v, sizeof(v)); }
+    }
     if ((rc2 = owner.ensure((size_t)cfgB * P.P * sizeof(unsigned)))) return rc2;
-    if ((rc2 = regbuf.ensure((size_t)cfgB * (cwK - 1) * 2 * P.P * sizeof(unsigned)))) return rc2;
+    if ((rc2 = regbuf.ensure((size_t)cfgB * (swK - 1) * 2 * P.P * sizeof(unsigned)))) return rc2;
     if ((rc2 = listpool.ensure((size_t)cfgB * 2 * P.P * sizeof(unsigned)))) return rc2;
-    if ((rc2 = rectstage.ensure((size_t)cfgB * (cwK - 1) * CW_CH * sizeof(LsdRect)))) return rc2;
     if ((rc2 = recttmp.ensure((size_t)cfgB * P.rect_cap * sizeof(LsdRect)))) return rc2;
     PL_CUDA(cudaMemsetAsync(owner.p, 0xff, (size_t)batch * P.P * sizeof(unsigned), st));
-#define PL_CW_LAUNCH(KK, WW)                                                                                                  \
+#define PL_SW_LAUNCH(KK, WW)                                                                                                  \
   do {                                                                                                                        \
     static bool attr = false;                                                                                                 \
     if (!attr) {                                                                                                              \
-      PL_CUDA(cudaFuncSetAttribute(k_lsd_grow_cw<KK, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,                        \
-                                   (int)cw_smem_bytes<KK, WW>()));                                                            \
+      PL_CUDA(cudaFuncSetAttribute(k_lsd_grow_sw<KK, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,                        \
+                                   (int)sw_smem_bytes<KK, WW>()));                                                            \
       attr = true;                                                                                                            \
     }                                                                                                                         \
-    k_lsd_grow_cw<KK, WW><<<batch, 32 * KK, cw_smem_bytes<KK, WW>(), st>>>(                                                   \
+    k_lsd_grow_sw<KK, WW><<<batch, 32 * KK, sw_smem_bytes<KK, WW>(), st>>>(                                                   \
         P, pix.as<uint4>(), owner.as<unsigned>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),              \
-        listpool.as<unsigned>(), rectstage.as<LsdRect>(), recttmp.as<LsdRect>(), rects.as<LsdRect>(), nrects.as<int>(),       \
-        status.as<int>());                                                                                                    \
+        listpool.as<unsigned>(), recttmp.as<LsdRect>(), rects.as<LsdRect>(), nrects.as<int>(), status.as<int>());             \
   } while (0)
-    if (cwK == 32) PL_CW_LAUNCH(32, 512);
-    else if (cwK == 16) PL_CW_LAUNCH(16, 256);
-    else PL_CW_LAUNCH(8, 256);
-#undef PL_CW_LAUNCH
+    if (swK == 32) PL_SW_LAUNCH(32, 1024);
+    else if (swK == 16) PL_SW_LAUNCH(16, 1024);
+    else PL_SW_LAUNCH(8, 1024);
+#undef PL_SW_LAUNCH
   } else {
     PL_CARVEOUT(k_lsd_grow);
     k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(),

@@ -40,7 +40,7 @@ if __name__ == "__main__":
     outs = {}
     for mode in (0, 2):
         out = "/tmp/dbg_aw_%d.npz" % mode
-        env = dict(os.environ, PLSLAM_GROW_MODE=str(mode), PLSLAM_CW_K=str(K))
+        env = dict(os.environ, PLSLAM_GROW_MODE=str(mode), PLSLAM_SW_K=str(K))
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(B), gen, out, str(reps if mode else 1)], env=env,
                            capture_output=True, text=True, timeout=200)
         if p.returncode:

@@ -14,9 +14,10 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "rgbd-pl-slam_b200"))
-STAT_NAMES = ["jobs", "regions", "squash_run", "squash_done", "revalidate", "rects", "valchunks", "sched_idle", "work_idle",
-              "dirty_jobs", "reruns", "frames", "cyc_kernel", "cyc_w_wait", "cyc_w_done", "cyc_w_squash", "cyc_w_empty",
-              "cyc_s_retire", "cyc_s_scan", "cyc_s_idle", "pix_done", "pix_squash", "winfull", "poolfull"]
+STAT_NAMES = ["groups", "regions", "squash_run", "squash_done", "insert", "rects", "valsteps", "sched_idle", "work_idle",
+              "dirty", "reruns", "frames", "cyc_kernel", "cyc_w_wait", "cyc_w_grow", "cyc_w_squash", "cyc_w_scan",
+              "cyc_s_retire", "cyc_s_plist", "cyc_s_idle", "pix_done", "pix_squash", "winfull", "poolfull", "heur_skip",
+              "p_held", "p_tomb", "p_rob"]
 
 
 def frames(gen, B, W, H):
@@ -84,7 +85,7 @@ def child(mode, K, B, W, H, gen, out):
 
 def run(mode, K, B, W, H, gen, tag):
     out = "/tmp/prof_aw_%s.npz" % tag
-    env = dict(os.environ, PLSLAM_GROW_MODE=str(mode), PLSLAM_CW_K=str(K), PLSLAM_DEBUG_STOP_AFTER_GROW="")
+    env = dict(os.environ, PLSLAM_GROW_MODE=str(mode), PLSLAM_SW_K=str(K), PLSLAM_DEBUG_STOP_AFTER_GROW="")
     env.pop("PLSLAM_DEBUG_STOP_AFTER_GROW")
     t0 = time.time()
     p = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(mode), str(K), str(B), str(W), str(H), gen, out],
@@ -138,7 +139,7 @@ if __name__ == "__main__":
                 fr = max(s[11], 1.0)
                 line += "  | per frame: " + " ".join("%s=%.0f" % (STAT_NAMES[i], s[i] / fr) for i in range(11))
                 line += "\n      kcycles/frame: " + " ".join("%s=%.0f" % (STAT_NAMES[i][4:], s[i] / fr / 1e3) for i in range(12, 20))
-                line += " | " + " ".join("%s=%.0f" % (STAT_NAMES[i], s[i] / fr) for i in range(20, 24))
+                line += " | " + " ".join("%s=%.0f" % (STAT_NAMES[i], s[i] / fr) for i in range(20, 28))
             print(line, flush=True)
     print("prof_aw: %d problem(s)" % bad)
     sys.exit(1 if bad else 0)
