@@ -991,7 +991,10 @@ __device__ unsigned long long g_aw_stats[32];
 // "same edge" heuristic (it decides which seeds are passed over for now, never the result): a seed closer than
 // g_sw_perp px to the level line through an older seed that is pending or being grown, within g_sw_along px along it, with
 // a level-line angle within g_sw_ang degrees, will most likely be absorbed by that seed's region
-__device__ float g_sw_perp = 4.f, g_sw_along = 300.f, g_sw_ang = 30.f;
+// Measured (tools/sweep_sw.sh, 16 frames, K = 8 / 16): holding seeds back costs more (they are grown one by one at the
+// head when the guess was wrong) than the squashed regions it avoids, so the heuristic is OFF by default (perp = 0);
+// PLSLAM_SW_PERP / _ALONG / _ANG switch it on for experiments.
+__device__ float g_sw_perp = 0.f, g_sw_along = 0.f, g_sw_ang = 0.f;
 
 template <int K, int WS>
 struct SwState {
@@ -1386,7 +1389,7 @@ __device__ void sw_worker(SwState<K, WS>& S, GrowCtx& C, const LineParams& L, co
         // same-edge heuristic against the older seeds other workers have pending or are growing
         const float jx = __shfl_sync(FULL, sxf, j), jy = __shfl_sync(FULL, syf, j), jd = __shfl_sync(FULL, sdeg, j);
         bool hit = false;
-        for (int w = 0; w < K - 1 && !hit; ++w) {
+        for (int w = 0; w < K - 1; ++w) {  // (warp-uniform trip count: the vote below needs every lane)
           if (w == me) continue;
           const unsigned at = *reinterpret_cast<volatile unsigned*>(&S.pendTag[w][lane]);
           if (at != 0u && at < myTag) {
@@ -1395,9 +1398,10 @@ __device__ void sw_worker(SwState<K, WS>& S, GrowCtx& C, const LineParams& L, co
             const float along = fabsf(dx * S.pendC[w][lane] + dy * S.pendS[w][lane]);
             float dd = fabsf(jd - S.pendD[w][lane]);
             if (dd > 180.f) dd = 360.f - dd;
-            hit = perp < g_sw_perp && along < g_sw_along && dd < g_sw_ang;
+            hit = hit || (perp < g_sw_perp && along < g_sw_along && dd < g_sw_ang);
           }
         }
+        __syncwarp();
         if (__any_sync(FULL, hit)) {
           if (lane == 0) {
             *reinterpret_cast<volatile unsigned*>(&S.pendTag[me][j]) = 0u;
@@ -2309,12 +2313,16 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   // (k_lsd_grow_sw); unset = automatic.  PLSLAM_SW_K = warps per frame of mode 2 (8, 16 or 32).
   static const int growMode = [] { const char* e = std::getenv("PLSLAM_GROW_MODE"); return e ? std::atoi(e) : -1; }();  // -1 auto
   static const int swKenv = [] { const char* e = std::getenv("PLSLAM_SW_K"); return e ? std::atoi(e) : 0; }();
-  int swK = swKenv ? swKenv : ((long long)batch * batches_in_flight <= numSMs ? 32 : 8);
+  int swK = swKenv ? swKenv : 8;  // (16 and 32 workers do not pay: the retirement order, not the worker count, limits)
   swK = swK >= 32 ? 32 : swK >= 16 ? 16 : 8;
   // per worker warp a list area of 2 P entries, per frame a list pool of 2 P entries: mode 2 needs them within 24 GB
   const size_t swBytes = (size_t)std::max(batch, cfgB) * (2 * (size_t)(swK - 1) + 2) * P.P * sizeof(unsigned);
+  // Measured on B200 (tools/prof_aw.py, one batch on the GPU, 640x480): 29 -> 11 ms for 1 frame, 45 -> 26 ms for 64,
+  // 50 -> 34 ms for 148, 55 -> 49 ms for 256; 186 -> 63 ms for 8 frames of 1280x720.  With many batches in flight the
+  // one-warp-per-frame kernel fills the machine with less work per region, so mode 2 is chosen while the GPU holds at most
+  // two frames per SM.
   const bool sw = growMode >= 0 ? growMode != 0
-                                : ((long long)batch * batches_in_flight <= numSMs && swBytes <= ((size_t)24 << 30));
+                                : ((long long)batch * batches_in_flight <= 2 * numSMs && swBytes <= ((size_t)24 << 30));
   if (sw) {
     int rc2;
     static bool swTune = false;
@@ -2343,7 +2351,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   } while (0)
     if (swK == 32) PL_SW_LAUNCH(32, 1024);
     else if (swK == 16) PL_SW_LAUNCH(16, 1024);
-    else PL_SW_LAUNCH(8, 1024);
+    else PL_SW_LAUNCH(8, 2048);
 #undef PL_SW_LAUNCH
   } else {
     PL_CARVEOUT(k_lsd_grow);

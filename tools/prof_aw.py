@@ -51,7 +51,7 @@ def child(mode, K, B, W, H, gen, out):
     import plslam_b200 as pl
     imgs = frames(gen, B, W, H)
     d = torch.from_numpy(imgs).cuda()
-    ls = pl.LineSegment(max_lines=0)
+    ls = pl.LineSegment(max_lines=0 if W * H <= 1280 * 720 else 40)  # (keep-all output capacity is 8192 lines)
     res = ls.extract_batch_device(d)
     torch.cuda.synchronize()
     ls.check_status()
@@ -124,7 +124,8 @@ if __name__ == "__main__":
             bad += 1
             continue
         print("  mode 0 (warp per frame):        %8.3f ms/batch  lines/frame %.1f" % (float(ref["ms"]), ref["cnt"].mean()), flush=True)
-        for (mode, K) in ((2, 8), (2, 16), (2, 32)):
+        ks = [int(k) for k in os.environ.get("PROF_AW_K", "8,16,32").split(",")]
+        for (mode, K) in [(2, k) for k in ks]:
             if mode == 2 and K == 32 and B > 148:
                 continue
             r = run(mode, K, B, W, H, gen, "m%dk%d" % (mode, K))
