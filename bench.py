@@ -51,10 +51,38 @@ def parse():
     ap.add_argument("--depth", type=int, default=16, help="batches (steps) in flight per GPU: pipeline slots of the front-end")
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
-                    help="c2: extract + kNN matching (headline); c4: the same step plus ComputeBoW + SearchByBoW on every pair")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configs.  c2: 640x480 extract + kNN matching (headline); c3: 1280x720, nFeatures 2000, "
+                         "128 frames (64 pairs) per step; c4: c2 plus ComputeBoW + SearchByBoW on every pair; c5: 3840x2160, "
+                         "nFeatures 8000, 16 frames per step")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency block")
     ap.add_argument("--voc-levels", type=int, default=6, help="depth L of the synthetic k=10 vocabulary (ORBvoc.txt: 6)")
     return ap.parse_args()
+
+
+WORKLOAD_PRESETS = {  # (width, height, nfeatures, batch, depth) of BASELINE.json's configs 3 and 5
+    "c3": (1280, 720, 2000, 128, 4),
+    "c5": (3840, 2160, 8000, 16, 2),
+}
+
+
+def apply_workload(a):
+    if a.workload in WORKLOAD_PRESETS:
+        w, h, nf, b, d = WORKLOAD_PRESETS[a.workload]
+        defaults = parse_defaults()
+        if a.width == defaults.width and a.height == defaults.height:
+            a.width, a.height = w, h
+        if a.nfeatures == defaults.nfeatures:
+            a.nfeatures = nf
+        if a.batch == defaults.batch:
+            a.batch = b
+        if a.depth == defaults.depth:
+            a.depth = d
+    return a
+
+
+def parse_defaults():
+    return argparse.Namespace(width=640, height=480, nfeatures=1000, batch=256, depth=16)
 
 
 def workload_name(a):
@@ -62,7 +90,7 @@ def workload_name(a):
         a.width, a.height, a.batch, a.batch // 2, a.nfeatures, a.max_lines)
     if getattr(a, "workload", "c2") == "c4":
         return "C4: " + base + " + ComputeBoW (k=10 L=%d synthetic vocabulary) + SearchByBoW per pair" % a.voc_levels
-    return "C2: " + base
+    return getattr(a, "workload", "c2").upper() + ": " + base
 
 
 def broadcast_vocabulary(a, pl, dist, rank, world):
@@ -137,6 +165,64 @@ def algorithmic_bytes(a, kp_avg, cand_avg):
         "match_lbd_knn2": (2 * a.max_lines * 32 + a.max_lines * 16) // 2,
     }
     return stages
+
+
+def survey_bytes_per_frame(a, K):
+    """SURVEY.md section 8d's algorithmic bytes of one frame (ORB + LSD + LBD; 21.46 MB at 640x480, K = 1000)."""
+    W, H = a.width, a.height
+    inv = [1.0]
+    for _ in range(7):
+        inv.append(inv[-1] / 1.2)
+    A = [int(round(W * s)) * int(round(H * s)) for s in inv]
+    S = sum(A)
+    P = int(np.ceil(0.8 * W)) * int(np.ceil(0.8 * H))
+    orb = A[0] + sum(A[l - 1] + A[l] for l in range(1, 8)) + S + 2 * S + K * (709 + 4) + K * (512 + 32) + K * 28
+    lsd = 2 * W * H + (W * H + P) + (P + 16 * P + 12 * P) + 24 * P + 9 * P
+    lbd = W * H + 4 * W * H + 40 * (60 * 63 * 4 + 32)
+    return orb + lsd + lbd
+
+
+def single_frame_latency(a, frames, n=200):
+    """The drop-in call of the reference's Frame constructor: one ORBextractor::operator() + one
+    LineSegment::ExtractLineSegment per camera frame, through the C-ABI host entry points (pageable host image in, host
+    results out, synchronous), next to the same two calls of the CPU port on one thread."""
+    import plslam_b200 as pl
+    orb = pl.ORBextractor(a.nfeatures, 1.2, 8, 20, 7)
+    ls = pl.LineSegment(a.max_lines)
+    for i in range(5):
+        orb(frames[i % len(frames)])
+        ls.ExtractLineSegment(frames[i % len(frames)])
+    t_orb, t_ls = [], []
+    for i in range(n):
+        img = frames[i % len(frames)]
+        t0 = time.perf_counter()
+        orb(img)
+        t1 = time.perf_counter()
+        ls.ExtractLineSegment(img)
+        t2 = time.perf_counter()
+        t_orb.append((t1 - t0) * 1e3)
+        t_ls.append((t2 - t1) * 1e3)
+    tot = np.array(t_orb) + np.array(t_ls)
+    out = {"frames": n, "api": "plslam_orb_extract + plslam_lines_extract (ORBextractor::operator(), LineSegment::ExtractLineSegment), "
+                              "host image in, host results out, one frame per call",
+           "p50_ms": float(np.percentile(tot, 50)), "p99_ms": float(np.percentile(tot, 99)),
+           "orb_p50_ms": float(np.percentile(t_orb, 50)), "lines_p50_ms": float(np.percentile(t_ls, 50))}
+    try:
+        from oracle import bindings as ob
+        ob.build()
+        o = ob.OrbOracle(a.nfeatures, 1.2, 8, 20, 7)
+        m = min(6, len(frames))
+        t0 = time.perf_counter()
+        for i in range(m):
+            o.extract(frames[i])
+        t1 = time.perf_counter()
+        for i in range(m):
+            ob.extract_lines(frames[i], a.max_lines)
+        t2 = time.perf_counter()
+        out["cpu_port_1thread_ms"] = {"orb": (t1 - t0) / m * 1e3, "lines": (t2 - t1) / m * 1e3, "frames": m}
+    except Exception as e:  # the oracle is the checker: its absence must not lose the bench line
+        out["cpu_port_1thread_ms"] = "unavailable: %s" % e
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -254,7 +340,8 @@ def run_reference(a):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = a.cpu_sample or max(2 * threads, 16)
+    area = (a.width * a.height) / (640.0 * 480.0)  # bounded sample: about the same CPU work whatever the frame size
+    sample = a.cpu_sample or max(2, int(max(2 * threads, 16) / area))
     sample -= sample % 2
     a_s = argparse.Namespace(**vars(a))
     a_s.batch = sample
@@ -434,24 +521,56 @@ def run_ours(a):
             traffic = prof.get(dom)
         except Exception:
             pass
-        total_bytes = sum(stages.values()) * a.batch
         step_ms = dev_ms / a.steps
+        lat_sum = sum(acc.values())
+        # With `depth` batches in flight the stage times above are LATENCIES of one batch (they overlap with the kernels of
+        # the other batches); what a stage costs the pipeline at saturation is modelled as its share of the summed
+        # latencies times the measured step time.
+        sat_ms = {k: step_ms * v / lat_sum for k, v in acc.items()} if lat_sum > 0 else {}
+        survey_total = survey_bytes_per_frame(a, int(round(kp_avg))) * a.batch
+        # all-pairs Hamming is not an HBM problem: popc32 per second against the SM's integer rate
+        kq = int(round(kp_avg))
+        popc = None
+        if acc.get("match_orb_knn2"):
+            n_popc = (a.batch // 2) * kq * kq * 8
+            sm_mhz = (clocks.get("sm_mhz") or 1965.0)
+            popc_peak = 148 * 16 * sm_mhz * 1e6
+            popc = {"kernel": "match_orb_knn2", "popc32_per_launch": n_popc, "kernel_ms": acc["match_orb_knn2"],
+                    "achieved_popc32_per_s": n_popc / (acc["match_orb_knn2"] * 1e-3), "peak_popc32_per_s": popc_peak,
+                    "frac": n_popc / (acc["match_orb_knn2"] * 1e-3) / popc_peak,
+                    "peak_source": "nominal: 16 popc per clock per SM (CUDA arithmetic-throughput table) x 148 SMs x measured SM clock"}
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": acc[dom],
-                    "note": "k_lsd_grow is latency bound (sequential greedy region growing, one warp per frame), not HBM bound; "
-                            "see DESIGN.md",
-                    "pipeline": {"algorithmic_bytes_per_step": total_bytes, "achieved": total_bytes / (step_ms * 1e-3) / 1e9,
-                                 "frac": total_bytes / (step_ms * 1e-3) / 1e9 / peak},
+                    "kernel_ms_at_saturation_model": sat_ms.get(dom),
+                    "frac_at_saturation_model": (dom_bytes / (sat_ms[dom] * 1e-3) / 1e9 / peak) if sat_ms.get(dom) else None,
+                    "note": "lsd_grow (region growing) is latency bound (greedy growth is sequential inside a frame: one warp per "
+                            "frame when many batches are in flight, 8 warps per frame with in-order retirement for small batches), "
+                            "not HBM bound; kernel_ms is the latency of ONE batch with %d batches in flight elsewhere idle, the "
+                            "*_at_saturation_model figures spread the measured step time over the stages by latency share; see "
+                            "DESIGN.md" % depth,
+                    "pipeline": {"algorithmic_bytes_per_step": survey_total, "bytes_per_frame": survey_total // a.batch,
+                                 "source": "SURVEY.md 8d (21.46 MB per 640x480 frame)",
+                                 "achieved": survey_total / (step_ms * 1e-3) / 1e9,
+                                 "frac": survey_total / (step_ms * 1e-3) / 1e9 / peak},
+                    "popc": popc,
                     "stages_ms": {k: round(v, 4) for k, v in sorted(acc.items(), key=lambda kv: -kv[1])},
+                    "stages_ms_at_saturation_model": {k: round(v, 4) for k, v in sorted(sat_ms.items(), key=lambda kv: -kv[1])},
                     # algorithmic GB/s of every stage (same definition as `achieved`), one batch in flight, the ORB and
                     # line branches running side by side on two streams
                     "stages_gbs": {k: round(stages.get(k, 0) * a.batch / (v * 1e-3) / 1e9, 1)
                                    for k, v in sorted(acc.items(), key=lambda kv: -kv[1]) if v > 0}}
+        latency = None
+        if world == 1 and not a.no_latency:
+            try:
+                latency = single_frame_latency(a, frames)
+            except Exception as e:
+                latency = {"error": str(e)}
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample = a.cpu_sample or min(a.batch, max(4 * threads, 32))
+            area = (a.width * a.height) / (640.0 * 480.0)
+            sample = a.cpu_sample or min(a.batch, max(2, int(max(4 * threads, 32) / area)))
             sample -= sample % 2
             dt = cpu_pairs_per_second(a, frames[:sample], threads)
             cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
@@ -465,7 +584,7 @@ def run_ours(a):
                 "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": workload_name(a), "frames_per_gpu_per_step": a.batch,
-                           "cache": "inputs + intermediates (~7 MB/frame, ~1.8 GB/step) exceed the 126 MB L2; no flush needed",
+                           "cache": "inputs + intermediates (~12 MB per 640x480 frame, scaled with the frame area) exceed the 126 MB L2; no flush needed",
                            "steps_in_flight": depth, **voc_info,
                            "parallelism": "frames sharded over %d rank(s), no data-path collective" % world},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -475,7 +594,7 @@ def run_ours(a):
                                " (pinned host buffers; H2D, kernels and D2H of every step inside the timed region, up to `steps_in_flight` steps overlapped)" +
                                ("; the C4 extras (ComputeBoW + SearchByBoW) are device-path only and not part of this e2e figure" if c4 else "")},
                 "gpu_launches": world * a.steps * (fe.launches_per_call(True) + (5 if c4 else 0)),
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
                 "counts": {"keypoints_per_frame": kp_avg, "lines_per_frame": float(out["line_counts"].float().mean())}}
     if dist is not None:
         dist.barrier()
@@ -485,7 +604,7 @@ def run_ours(a):
 
 
 def main():
-    a = parse()
+    a = apply_workload(parse())
     if a.batch % 2:
         a.batch += 1
     if a.impl == "reference":

@@ -657,7 +657,9 @@ struct BlurMaps {
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams P, const BlurMaps* __restrict__ Mp,
+// The tensor maps travel as a __grid_constant__ kernel parameter (12 x 128 B): no device copy of them exists, so a caller
+// that cycles through any number of input buffers never waits for a descriptor upload.
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams P, const __grid_constant__ BlurMaps Mp,
                                               OrbImages I, const int* __restrict__ lvlCnt,
                                               const unsigned* __restrict__ tileTab) {
   __shared__ __align__(128) uint8_t raw[BOX_H][BOX_W];
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams 
   const int w = L.w, h = L.h;
   int sp;
   const uint8_t* S = level_ptr(P, I, f, l, sp);
-  const bool useTma = (Mp->tmaMask >> l) & 1u;
+  const bool useTma = (Mp.tmaMask >> l) & 1u;
   const bool rim = tx < 3 || ty < 3 || tx + BT_W + 3 > w || ty + BT_H + 3 > h;
   if (useTma) {
     if (threadIdx.x == 0) {
@@ -682,7 +684,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams 
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BOX_W * BOX_H) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"(smem_u32(&raw[0][0])), "l"(reinterpret_cast<unsigned long long>(&Mp->m[l])), "r"(tx - 16), "r"(ty - 3), "r"(f),
+          ::"r"(smem_u32(&raw[0][0])), "l"(reinterpret_cast<unsigned long long>(&Mp.m[l])), "r"(tx - 16), "r"(ty - 3), "r"(f),
             "r"(bar)
           : "memory");
     }
@@ -968,7 +970,7 @@ OrbExtractor::OrbExtractor(int nf, float sf, int nl, int ini, int mn)
 }
 
 OrbExtractor::~OrbExtractor() {
-  DevBuf* all[] = {&pyr, &blurred, &coef, &cand, &candCount, &knode, &lvlKp, &lvlCnt, &status, &blurMaps, &tileTab,
+  DevBuf* all[] = {&pyr, &blurred, &coef, &cand, &candCount, &knode, &lvlKp, &lvlCnt, &status, &tileTab,
                    &stageIn, &stageKps, &stageDesc, &stageCnt};
   for (DevBuf* b : all) b->release();
   if (ownStream) cudaStreamDestroy(ownStream);
@@ -1197,18 +1199,18 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
     bool k8 = true;
     for (int i = 0; i < 7; ++i) k8 = k8 && blurk[i] >= 0 && blurk[i] <= 255;
     PL_CHECK_ARG(k8);
-    // The TMA descriptors only depend on the buffers and the frame geometry: re-encode and upload them when those
-    // change, not on every call.  (A cudaMemcpyAsync from pageable memory synchronises its stream first: done per
-    // call it stalled the submitting host thread behind the whole ORB branch of the slot.)
+    // The TMA descriptors only depend on the buffers and the frame geometry: they are re-encoded (host only, ~1 us per
+    // level) when those change and passed to the kernel by value; four encoded sets are kept (input buffers the caller
+    // alternates between).
     const uintptr_t key[6] = {(uintptr_t)d_images, (uintptr_t)pitch, (uintptr_t)frame_stride, (uintptr_t)batch,
                               (uintptr_t)pyr.p, (uintptr_t)(W * 65536 + H)};
-    // two cached descriptor sets (the host path of the front-end alternates between two input staging buffers)
+    static_assert(sizeof(BlurMaps) <= sizeof(mapsCache[0]), "mapsCache entry too small");
     int slotIdx = -1;
-    for (int e = 0; e < 2; ++e)
+    for (int e = 0; e < 4; ++e)
       if (std::memcmp(key, mapsKey[e], sizeof(key)) == 0) slotIdx = e;
     if (slotIdx < 0) {
       slotIdx = mapsNext;
-      mapsNext ^= 1;
+      mapsNext = (mapsNext + 1) & 3;
       BlurMaps M;
       std::memset(&M, 0, sizeof(M));
       for (int l = 0; l < nlevels; ++l) {
@@ -1216,13 +1218,10 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
         const size_t lp = l ? (size_t)P.lv[l].pitch : (size_t)pitch, ls = l ? (size_t)P.pyrFrameStride : frame_stride;
         if (encode_level_map(&M.m[l], base, P.lv[l].w, P.lv[l].h, lp, ls, batch)) M.tmaMask |= 1u << l;
       }
-      int rcm = blurMaps.ensure(2 * sizeof(BlurMaps));
-      if (rcm) return rcm;
-      if (mapsKey[slotIdx][0]) PL_CUDA(cudaStreamSynchronize(st));  // an earlier launch may still read the entry being replaced
-      PL_CUDA(cudaMemcpy(blurMaps.as<BlurMaps>() + slotIdx, &M, sizeof(M), cudaMemcpyHostToDevice));
+      std::memcpy(mapsCache[slotIdx], &M, sizeof(M));
       std::memcpy(mapsKey[slotIdx], key, sizeof(key));
     }
-    const BlurMaps* dMaps = blurMaps.as<BlurMaps>() + slotIdx;
+    const BlurMaps& dMaps = *reinterpret_cast<const BlurMaps*>(mapsCache[slotIdx]);
     PL_CARVEOUT(k_blur);
     k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, dMaps, I, lvlCnt.as<int>(), tileTab.as<unsigned>());
   }

@@ -84,11 +84,12 @@ class OrbExtractor {
   int last_pitch0 = 0, last_batch = 0;
   size_t last_stride0 = 0;
   size_t blurOff0 = 0, blurFrameStride = 0;
-  DevBuf pyr, blurred, coef, cand, candCount, knode, lvlKp, lvlCnt, status, blurMaps, tileTab;
+  DevBuf pyr, blurred, coef, cand, candCount, knode, lvlKp, lvlCnt, status, tileTab;
   DevBuf stageIn, stageKps, stageDesc, stageCnt;
   cudaStream_t ownStream = nullptr;
   void* pinnedStatus = nullptr;
-  uintptr_t mapsKey[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};  // what the cached TMA descriptor sets of k_blur were encoded for
+  uintptr_t mapsKey[4][6] = {};  // what the cached TMA descriptor sets of k_blur were encoded for
+  alignas(64) unsigned char mapsCache[4][2048] = {};  // the encoded sets (host memory; passed to k_blur by value)
   int mapsNext = 0;
 };
 
