@@ -228,13 +228,16 @@ typedef struct plslam_proj_job {
   const int32_t* grid_start;   /* 64*48+1 : CSR of mGrid in [ix][iy] order */
   const int32_t* grid_items;
   const float* scale_factors;  /* mvScaleFactors */
-  int32_t* match_cur;          /* N2 : LastFrame index assigned to each current keypoint, -1 = none */
+  int32_t* match_cur;          /* N2 : LastFrame index assigned to each current keypoint, -1 = none (and, with
+                                  report_removed, -2 = assigned during the scan and taken away again by the rotation
+                                  check: the reference leaves CurrentFrame.mvpMapPoints[i] NULL there) */
   int32_t* nmatches;           /* 1 */
   float cam[12];               /* fx, fy, cx, cy, mbf, mb, mnMinX, mnMaxX, mnMinY, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv */
   float tcw_cur[12];           /* CurrentFrame.mTcw rows 0..2 (3x4 row-major) */
   float tcw_last[12];          /* LastFrame.mTcw */
   float th;
   int32_t n1, n2, mono, check_orientation;
+  int32_t report_removed;      /* 0: removed entries read -1 like never-assigned ones; 1: they read -2 */
 } plslam_proj_job_t;
 int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream);
 
@@ -390,7 +393,8 @@ int plslam_frontend_check_status(plslam_frontend_t* h, void* stream);
  * (include/Frame.h:80, @0xf84f0) uses: ORBVocabulary::loadFromTextFile (TemplatedVocabulary.h:1362-1448)
  * and the per-feature tree descent of transform() (TemplatedVocabulary.h:1242-1284).  The descent
  * (k Hamming distances per level) runs on the GPU; BowVector / FeatureVector assembly (std::map
- * accumulation and L1 normalisation, TemplatedVocabulary.h:1151-1217) is host work on the results.
+ * accumulation and L1 normalisation, TemplatedVocabulary.h:1151-1217): plslam_voc_bowvec_batch_device /
+ * plslam_voc_compute_bow_host.
  * ---------------------------------------------------------------------------------------- */
 typedef struct plslam_voc plslam_voc_t;
 
@@ -427,6 +431,17 @@ int plslam_voc_featvec_batch_device(const plslam_voc_t* h, const uint8_t* d_desc
                                     int capacity, int levelsup, int32_t* d_word, double* d_weight, int32_t* d_node,
                                     int32_t* d_fv_nodes, int32_t* d_fv_start, int32_t* d_fv_idx, int32_t* d_fv_count,
                                     void* stream);
+/* The other half of Frame::ComputeBoW (Frame.h:80,189: mBowVec): `if (w > 0) v.addWeight(id, w)` in feature order, then
+ * v.normalize(L1) (TemplatedVocabulary.h:1196-1217), for every frame of a batch on the outputs of
+ * plslam_voc_featvec_batch_device: d_bow_ids / d_bow_vals [frames][capacity] word ids ascending and their normalised
+ * weights (std::map iteration order), d_bow_count [frames]. */
+int plslam_voc_bowvec_batch_device(const int32_t* d_word, const double* d_weight, const int32_t* d_counts, int frames,
+                                   int capacity, int32_t* d_bow_ids, double* d_bow_vals, int32_t* d_bow_count, void* stream);
+/* Frame::ComputeBoW of one frame on host arrays (n x 32 descriptor bytes, n <= 16384): mBowVec as (bow_ids, bow_vals)
+ * [<= n] and mFeatVec as the CSR (fv_nodes [<= n], fv_start [<= n + 1], fv_idx [<= n]); descent, sort, accumulation and
+ * normalisation all run on the device. */
+int plslam_voc_compute_bow_host(const plslam_voc_t* h, const uint8_t* descriptors, int n, int levelsup, int32_t* bow_ids,
+                                double* bow_vals, int* n_bow, int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_idx, int* n_fv);
 /* ORBmatcher::SearchByBoW on the frame pairs of a batch without a host round trip (config C4): pair p matches
  * "keyframe" = frame 2p against frame 2p+1.  d_kf_valid [frames][capacity] = pMP && !pMP->isBad() per keyframe
  * feature.  d_match [npairs][capacity] (index into frame 2p per feature of frame 2p+1, -1 = none), d_nmatches [npairs].

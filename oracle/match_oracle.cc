@@ -209,7 +209,7 @@ int oracle_search_by_projection(int N1, const uint8_t* lastValid, const float* l
   int nmatches = 0;
   std::vector<int> rotHist[HISTO_LENGTH];
   // Rcw, tcw (row-major 3x4); twc = -Rcw^T tcw; tlc = Rlw twc + tlw.  cv::Mat products of CV_32F matrices go
-  // through cv::gemm, which accumulates in double and rounds once (alpha * sum + beta * C) to float.
+  // through cv::gemm.
   const float* Rc = TcwCur;  // Rc[r*4+c], t = Rc[r*4+3]
   float twc[3];
   for (int r = 0; r < 3; ++r) {
@@ -217,11 +217,14 @@ int oracle_search_by_projection(int N1, const uint8_t* lastValid, const float* l
     for (int k = 0; k < 3; ++k) s += (double)Rc[k * 4 + r] * (double)Rc[k * 4 + 3];
     twc[r] = (float)(-1.0 * s);
   }
+  // Rlw * twc + tlw and Rcw * x3Dw + tcw carry no transpose flag and have an inner dimension of 3: cv::gemm's small-matrix
+  // path (float products summed left to right in float, then (double)sum + (double)c rounded to float), as pinned for the
+  // epipole below; -Rcw.t() * tcw above carries a transpose flag: GEMMSingleMul, double accumulator.
   float tlc2;
   {
-    double s = 0;
-    for (int k = 0; k < 3; ++k) s += (double)TcwLast[2 * 4 + k] * (double)twc[k];
-    tlc2 = (float)(s + (double)TcwLast[2 * 4 + 3]);
+    const float p0 = TcwLast[8] * twc[0], p1 = TcwLast[9] * twc[1], p2 = TcwLast[10] * twc[2];
+    const float s = (p0 + p1) + p2;
+    tlc2 = (float)((double)s + (double)TcwLast[2 * 4 + 3]);
   }
   const bool bForward = tlc2 > mb && !bMono;
   const bool bBackward = -tlc2 > mb && !bMono;
@@ -230,15 +233,17 @@ int oracle_search_by_projection(int N1, const uint8_t* lastValid, const float* l
     const float* X = lastXYZ + 3 * i;
     float pc[3];
     for (int r = 0; r < 3; ++r) {
-      double s = 0;
-      for (int k = 0; k < 3; ++k) s += (double)Rc[r * 4 + k] * (double)X[k];
-      pc[r] = (float)(s + (double)Rc[r * 4 + 3]);
+      const float p0 = Rc[r * 4] * X[0], p1 = Rc[r * 4 + 1] * X[1], p2 = Rc[r * 4 + 2] * X[2];
+      const float s = (p0 + p1) + p2;
+      pc[r] = (float)((double)s + (double)Rc[r * 4 + 3]);
     }
     const float xc = pc[0], yc = pc[1];
-    const float invzc = (float)(1.0 / pc[2]);
+    // the binary's sequence (it was compiled with FMA): vdivss @0x81c92, vmulss + vfmadd213ss @0x81caf-0x81cba and
+    // @0x81cce-0x81cd9, vfnmadd132ss @0x81eb5 for ur below
+    const float invzc = 1.0f / pc[2];
     if (invzc < 0) continue;
-    float u = fx * xc * invzc + cx;
-    float v = fy * yc * invzc + cy;
+    float u = std::fmaf(xc * fx, invzc, cx);
+    float v = std::fmaf(yc * fy, invzc, cy);
     if (u < mnMinX || u > mnMaxX) continue;
     if (v < mnMinY || v > mnMaxY) continue;
     const int nLastOctave = lastOctave[i];
@@ -251,7 +256,7 @@ int oracle_search_by_projection(int N1, const uint8_t* lastValid, const float* l
     for_features_in_area(u, v, radius, minLevel, maxLevel, mnMinX, mnMinY, gwi, ghi, gridStart, gridItems, curXY, curOctave, [&](int i2) {
       if (taken[i2]) return;
       if (curURight[i2] > 0) {
-        const float ur = u - mbf * invzc;
+        const float ur = std::fmaf(-invzc, mbf, u);
         const float er = fabsf(ur - curURight[i2]);
         if (er > radius) return;
       }

@@ -160,6 +160,77 @@ __global__ void __launch_bounds__(256) k_featvec_csr(const int32_t* __restrict__
   }
 }
 
+// BowVector of each frame of a batch (`if (w > 0) v.addWeight(id, w)` in feature order, then v.normalize(L1):
+// TemplatedVocabulary.h:1196-1217, BowVector.cpp addWeight / normalize).  One CTA per frame: bitonic sort of
+// (word << 32 | i) keys, one thread per distinct word adds its weights in ascending feature order (the order addWeight
+// sees them), thread 0 adds the L1 norm in ascending word order (the map's iteration order), everybody divides.
+__global__ void __launch_bounds__(256) k_bowvec(const int32_t* __restrict__ word, const double* __restrict__ weight,
+                                                const int32_t* __restrict__ counts, int capacity, int npow2,
+                                                int32_t* __restrict__ bow_ids, double* __restrict__ bow_vals,
+                                                int32_t* __restrict__ bow_count) {
+  extern __shared__ unsigned long long fv_smem[];
+  unsigned long long* key = fv_smem;
+  int* head = reinterpret_cast<int*>(key + npow2);
+  int* warp_tmp = head + npow2;
+  __shared__ double s_norm;
+  const int f = blockIdx.x, t = threadIdx.x;
+  const int n = min(counts[f], capacity);
+  const size_t o = (size_t)f * capacity;
+  for (int i = t; i < npow2; i += 256) {
+    unsigned long long k = ~0ull;
+    if (i < n && weight[o + i] > 0) k = ((unsigned long long)(unsigned)word[o + i] << 32) | (unsigned)i;
+    key[i] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < npow2; i += 256) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = key[i], b = key[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            key[i] = b;
+            key[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = t; i < npow2; i += 256) {
+    const unsigned long long k = key[i];
+    head[i] = (k != ~0ull && (i == 0 || (unsigned)(key[i - 1] >> 32) != (unsigned)(k >> 32))) ? 1 : 0;
+  }
+  __syncthreads();
+  const int nuniq = block_scan_excl(head, npow2, warp_tmp);  // head[i] = rank of the word of entry i (at head entries)
+  int32_t* ID = bow_ids + o;
+  double* V = bow_vals + o;
+  for (int i = t; i < npow2; i += 256) {
+    const unsigned long long k = key[i];
+    if (k == ~0ull) continue;
+    const unsigned w = (unsigned)(k >> 32);
+    if (i != 0 && (unsigned)(key[i - 1] >> 32) == w) continue;
+    double sum = 0.0;  // map[word] = w0, then += w1, ... in feature order
+    for (int j = i; j < npow2 && key[j] != ~0ull && (unsigned)(key[j] >> 32) == w; ++j) {
+      const double wj = weight[o + (unsigned)key[j]];
+      sum = j == i ? wj : __dadd_rn(sum, wj);
+    }
+    ID[head[i]] = (int32_t)w;
+    V[head[i]] = sum;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double norm = 0.0;
+    for (int r = 0; r < nuniq; ++r) norm = __dadd_rn(norm, fabs(V[r]));
+    s_norm = norm;
+    bow_count[f] = nuniq;
+  }
+  __syncthreads();
+  const double norm = s_norm;
+  if (norm > 0.0)
+    for (int r = t; r < nuniq; r += 256) V[r] = __ddiv_rn(V[r], norm);
+}
+
 __global__ void k_kp_angles(const plslam_keypoint_t* __restrict__ kps, size_t n, float* __restrict__ angle) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) angle[i] = kps[i].angle;
@@ -430,6 +501,79 @@ int plslam_voc_featvec_batch_device(const plslam_voc_t* h, const uint8_t* d_desc
   k_featvec_csr<<<frames, 256, smem, st>>>(d_node, d_weight, d_counts, capacity, npow2, d_fv_nodes, d_fv_start, d_fv_idx,
                                            d_fv_count);
   PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_voc_bowvec_batch_device(const int32_t* d_word, const double* d_weight, const int32_t* d_counts, int frames,
+                                   int capacity, int32_t* d_bow_ids, double* d_bow_vals, int32_t* d_bow_count, void* stream) {
+  PL_CHECK_ARG(d_word && d_weight && d_counts && d_bow_ids && d_bow_vals && d_bow_count);
+  PL_CHECK_ARG(frames >= 1 && frames <= 65535 && capacity >= 1 && capacity <= 16384);
+  int npow2 = 32;
+  while (npow2 < capacity) npow2 <<= 1;
+  const size_t smem = (size_t)npow2 * 12 + 33 * 4;
+  int dev = 0;
+  PL_CUDA(cudaGetDevice(&dev));
+  static bool attr[64] = {};
+  if (dev < 64 && !attr[dev]) {
+    PL_CUDA(cudaFuncSetAttribute(k_bowvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr[dev] = true;
+  }
+  PL_CARVEOUT(k_bowvec);
+  k_bowvec<<<frames, 256, smem, (cudaStream_t)stream>>>(d_word, d_weight, d_counts, capacity, npow2, d_bow_ids, d_bow_vals,
+                                                        d_bow_count);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_voc_compute_bow_host(const plslam_voc_t* h, const uint8_t* descriptors, int n, int levelsup, int32_t* bow_ids,
+                                double* bow_vals, int* n_bow, int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_idx, int* n_fv) {
+  PL_CHECK_ARG(h && n >= 0 && n <= 16384 && n_bow && n_fv);
+  *n_bow = *n_fv = 0;
+  if (n == 0) {
+    if (fv_start) fv_start[0] = 0;
+    return PLSLAM_OK;
+  }
+  PL_CHECK_ARG(descriptors && bow_ids && bow_vals && fv_nodes && fv_start && fv_idx);
+  DevBuf all;
+  // one allocation: desc | count | word | node | fv_nodes | fv_idx | bow_ids | fv_start | counts(2) | weight | bow_vals
+  const size_t N = (size_t)n;
+  const size_t offWord = align_up(N * 32 + 4, 16), offNode = offWord + N * 4, offFvN = offNode + N * 4, offFvI = offFvN + N * 4,
+               offBowI = offFvI + N * 4, offFvS = offBowI + N * 4, offCnt = offFvS + (N + 1) * 4,
+               offW = align_up(offCnt + 8, 16), offBowV = offW + N * 8, total = offBowV + N * 8;
+  int rc = all.ensure(total);
+  if (rc) return rc;
+  uint8_t* B = all.as<uint8_t>();
+  int32_t* dCount = reinterpret_cast<int32_t*>(B + N * 32);
+  cudaError_t e = cudaMemcpy(B, descriptors, N * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dCount, &n, 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = plslam_voc_featvec_batch_device(h, B, dCount, 1, n, levelsup, reinterpret_cast<int32_t*>(B + offWord),
+                                         reinterpret_cast<double*>(B + offW), reinterpret_cast<int32_t*>(B + offNode),
+                                         reinterpret_cast<int32_t*>(B + offFvN), reinterpret_cast<int32_t*>(B + offFvS),
+                                         reinterpret_cast<int32_t*>(B + offFvI), reinterpret_cast<int32_t*>(B + offCnt), nullptr);
+    if (!rc)
+      rc = plslam_voc_bowvec_batch_device(reinterpret_cast<int32_t*>(B + offWord), reinterpret_cast<double*>(B + offW), dCount, 1, n,
+                                          reinterpret_cast<int32_t*>(B + offBowI), reinterpret_cast<double*>(B + offBowV),
+                                          reinterpret_cast<int32_t*>(B + offCnt) + 1, nullptr);
+    int32_t cnt[2] = {0, 0};
+    if (!rc) {
+      e = cudaMemcpy(cnt, B + offCnt, 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(fv_nodes, B + offFvN, (size_t)cnt[0] * 4, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(fv_start, B + offFvS, ((size_t)cnt[0] + 1) * 4, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess && cnt[0]) {
+        int32_t last = 0;
+        e = cudaMemcpy(&last, B + offFvS + (size_t)cnt[0] * 4, 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(fv_idx, B + offFvI, (size_t)last * 4, cudaMemcpyDeviceToHost);
+      }
+      if (e == cudaSuccess) e = cudaMemcpy(bow_ids, B + offBowI, (size_t)cnt[1] * 4, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(bow_vals, B + offBowV, (size_t)cnt[1] * 8, cudaMemcpyDeviceToHost);
+      *n_fv = cnt[0];
+      *n_bow = cnt[1];
+    }
+  }
+  all.release();
+  if (rc) return rc;
+  if (e != cudaSuccess) { set_error("ComputeBoW host path: %s", cudaGetErrorString(e)); return PLSLAM_ERR_CUDA; }
   return PLSLAM_OK;
 }
 

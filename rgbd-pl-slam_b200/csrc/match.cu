@@ -323,12 +323,14 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
     for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)Rc[k * 4 + r], (double)Rc[k * 4 + 3]));
     twc[r] = (float)__dmul_rn(-1.0, s);
   }
+  // Rlw * twc + tlw and Rcw * x3Dw + tcw are cv::gemm calls without a transpose flag and an inner dimension of 3: the
+  // small-matrix path (float products summed left to right in float, then (double)sum + (double)c rounded to float).
+  // -Rcw.t() * tcw above carries a transpose flag: GEMMSingleMul, double accumulator.
   float tlc2;
   {
-    double s = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)J.tcw_last[8 + k], (double)twc[k]));
-    tlc2 = (float)__dadd_rn(s, (double)J.tcw_last[11]);
+    const float p0 = __fmul_rn(J.tcw_last[8], twc[0]), p1 = __fmul_rn(J.tcw_last[9], twc[1]), p2 = __fmul_rn(J.tcw_last[10], twc[2]);
+    const float s = __fadd_rn(__fadd_rn(p0, p1), p2);
+    tlc2 = (float)__dadd_rn((double)s, (double)J.tcw_last[11]);
   }
   const bool bForward = tlc2 > mb && !J.mono;
   const bool bBackward = -tlc2 > mb && !J.mono;
@@ -341,15 +343,15 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
     float pc[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      double s = 0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)Rc[r * 4 + k], (double)X[k]));
-      pc[r] = (float)__dadd_rn(s, (double)Rc[r * 4 + 3]);
+      const float p0 = __fmul_rn(Rc[r * 4], X[0]), p1 = __fmul_rn(Rc[r * 4 + 1], X[1]), p2 = __fmul_rn(Rc[r * 4 + 2], X[2]);
+      const float s = __fadd_rn(__fadd_rn(p0, p1), p2);
+      pc[r] = (float)__dadd_rn((double)s, (double)Rc[r * 4 + 3]);
     }
-    const float invzc = (float)__ddiv_rn(1.0, (double)pc[2]);
+    // the binary's sequence: vdivss @0x81c92 (float division), vmulss + vfmadd213ss @0x81caf-0x81cba / @0x81cce-0x81cd9
+    const float invzc = __fdiv_rn(1.0f, pc[2]);
     if (invzc < 0) continue;
-    const float u = __fadd_rn(__fmul_rn(__fmul_rn(fx, pc[0]), invzc), cx);
-    const float v = __fadd_rn(__fmul_rn(__fmul_rn(fy, pc[1]), invzc), cy);
+    const float u = __fmaf_rn(__fmul_rn(pc[0], fx), invzc, cx);
+    const float v = __fmaf_rn(__fmul_rn(pc[1], fy), invzc, cy);
     if (u < mnMinX || u > mnMaxX) continue;
     if (v < mnMinY || v > mnMaxY) continue;
     const int oct = J.last_octave[i];
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
     const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
     const int ncy = nMaxCellY - nMinCellY + 1, ncells = (nMaxCellX - nMinCellX + 1) * ncy;
     const uint4 a0 = DL[2 * i], a1 = DL[2 * i + 1];
-    const float ur = __fsub_rn(u, __fmul_rn(mbf, invzc));
+    const float ur = __fmaf_rn(-invzc, mbf, u);  // vfnmadd132ss @0x81eb5
     unsigned best = 0xffffffffu;  // dist << 22 | cellRank << 8 | pos  (cellRank < 2^14, pos < 2^8)
     int bestI2 = -1;
     for (int c = lane; c < ncells; c += 32) {
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
     for (int e = lane; e < nentries; e += 32) {
       const int bin = entryBin[e];
       if (bin != i1 && bin != i2 && bin != i3) {
-        matchCur[entryIdx[e]] = -1;
+        matchCur[entryIdx[e]] = J.report_removed ? -2 : -1;
         ++removed;
       }
     }

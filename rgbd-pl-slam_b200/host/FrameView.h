@@ -32,7 +32,7 @@ struct FrameView {
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
   cv::Mat mDescriptors;                        // N x 32
   std::vector<float> mvuRight;
-  std::vector<float> mvScaleFactors;
+  std::vector<float> mvScaleFactors, mvLevelSigma2;
   FeatureVectorView mFeatVec;
   // per-feature map point state
   std::vector<uint8_t> hasMapPoint;            // mvpMapPoints[i] != NULL (KeyFrame: && !isBad())

@@ -22,11 +22,24 @@ int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) { return 
 
 float ORBmatcher::RadiusByViewingCos(const float& viewCos) { return viewCos > 0.998 ? 2.5f : 4.0f; }  // @0x79b60
 
+// every array of a view must cover its features: a short or unfilled vector would be read out of bounds by the upload
+static void need(bool ok, const char* what) {
+  if (!ok) throw std::invalid_argument(std::string("ORBmatcher: ") + what);
+}
+
 int ORBmatcher::SearchByProjection(FrameView& Cur, const FrameView& Last, const float th, const bool bMono,
-                                   std::vector<int>& vnMatches) {
+                                   std::vector<int>& vnMatches, bool reportRemoved) {
   const int n1 = (int)Last.mvKeysUn.size(), n2 = (int)Cur.mvKeysUn.size();
   vnMatches.assign(n2, -1);
   if (n1 == 0 || n2 == 0) return 0;
+  need((int)Last.mvKeys.size() == n1 && (int)Last.hasMapPoint.size() == n1 && (int)Last.mapPointObserved.size() == n1 &&
+           (Last.mvbOutlier.empty() || (int)Last.mvbOutlier.size() == n1) && Last.mapPointWorldPos.size() == (size_t)n1 * 3 &&
+           Last.mapPointDescriptor.rows >= n1 && Last.mapPointDescriptor.cols == 32,
+       "LastFrame view: mvKeys / hasMapPoint / mapPointObserved / mvbOutlier / mapPointWorldPos / mapPointDescriptor do not cover its N features");
+  need((int)Cur.mvuRight.size() == n2 && (int)Cur.mapPointObserved.size() == n2 && Cur.mDescriptors.rows >= n2 &&
+           Cur.mDescriptors.cols == 32 && Cur.gridStart.size() == 64 * 48 + 1 &&
+           (int)Cur.gridItems.size() == Cur.gridStart.back() && !Cur.mvScaleFactors.empty(),
+       "CurrentFrame view: mvuRight (fill with -1 for monocular frames) / mapPointObserved / mDescriptors / grid / mvScaleFactors incomplete");
   std::vector<uint8_t> valid(n1);
   std::vector<int32_t> loct(n1), coct(n2);
   std::vector<float> lang(n1), cang(n2), cxy((size_t)n2 * 2);
@@ -55,6 +68,7 @@ int ORBmatcher::SearchByProjection(FrameView& Cur, const FrameView& Last, const 
   std::memcpy(j.tcw_cur, Cur.mTcw, sizeof(j.tcw_cur));
   std::memcpy(j.tcw_last, Last.mTcw, sizeof(j.tcw_last));
   j.th = th; j.n1 = n1; j.n2 = n2; j.mono = bMono; j.check_orientation = mbCheckOrientation;
+  j.report_removed = reportRemoved ? 1 : 0;
   check(plslam_match_projection_host(&j, (int)Cur.mvScaleFactors.size()), "SearchByProjection");
   return nm;
 }
@@ -63,6 +77,12 @@ int ORBmatcher::SearchByProjection(FrameView& F, const MapPointsView& MP, const 
   const int m = (int)MP.inViewAndGood.size(), n = (int)F.mvKeysUn.size();
   vnMatches.assign(n, -1);
   if (m == 0 || n == 0) return 0;
+  need(MP.trackProj.size() == (size_t)m * 3 && (int)MP.trackScaleLevel.size() == m && (int)MP.trackViewCos.size() == m &&
+           (int)MP.observed.size() == m && MP.descriptors.rows >= m && MP.descriptors.cols == 32,
+       "MapPointsView arrays do not cover its M map points");
+  need((int)F.mvuRight.size() == n && (int)F.mapPointObserved.size() == n && F.mDescriptors.rows >= n && F.mDescriptors.cols == 32 &&
+           F.gridStart.size() == 64 * 48 + 1 && (int)F.gridItems.size() == F.gridStart.back() && !F.mvScaleFactors.empty(),
+       "Frame view: mvuRight (fill with -1 for monocular frames) / mapPointObserved / mDescriptors / grid / mvScaleFactors incomplete");
   std::vector<int32_t> oct(n);
   std::vector<float> xy((size_t)n * 2);
   for (int i = 0; i < n; ++i) {
@@ -87,6 +107,10 @@ int ORBmatcher::SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>&
   const int n1 = (int)KF.mvKeysUn.size(), n2 = (int)F.mvKeys.size();
   vnMatches.assign(n2, -1);
   if (n1 == 0 || n2 == 0) return 0;
+  need((int)KF.hasMapPoint.size() == n1 && KF.mDescriptors.rows >= n1 && KF.mDescriptors.cols == 32 && F.mDescriptors.rows >= n2 &&
+           F.mDescriptors.cols == 32 && KF.mFeatVec.start.size() == KF.mFeatVec.nodes.size() + 1 &&
+           F.mFeatVec.start.size() == F.mFeatVec.nodes.size() + 1,
+       "SearchByBoW views: hasMapPoint / mDescriptors / mFeatVec incomplete");
   std::vector<float> a1(n1), a2(n2);
   for (int i = 0; i < n1; ++i) a1[i] = KF.mvKeysUn[i].angle;
   for (int i = 0; i < n2; ++i) a2[i] = F.mvKeys[i].angle;
@@ -100,6 +124,48 @@ int ORBmatcher::SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>&
   j.n1 = n1; j.n2 = n2; j.n_kf_nodes = (int)KF.mFeatVec.nodes.size(); j.n_f_nodes = (int)F.mFeatVec.nodes.size();
   j.nnratio = mfNNratio; j.check_orientation = mbCheckOrientation;
   check(plslam_match_bow_host(&j), "SearchByBoW");
+  return nm;
+}
+
+void ORBmatcher::Epipole(const float R2w[9], const float t2w[3], const float Cw[3], float fx, float fy, float cx, float cy,
+                         float* ex, float* ey) {
+  check(plslam_match_epipole(R2w, t2w, Cw, fx, fy, cx, cy, ex, ey), "Epipole");
+}
+
+int ORBmatcher::SearchForTriangulation(const FrameView& KF1, const FrameView& KF2, const float F12[9], float ex, float ey,
+                                       const bool bOnlyStereo, std::vector<int>& vnMatches12) {
+  const int n1 = (int)KF1.mvKeysUn.size(), n2 = (int)KF2.mvKeysUn.size();
+  vnMatches12.assign(n1, -1);
+  if (n1 == 0 || n2 == 0) return 0;
+  need((int)KF1.mvuRight.size() == n1 && (int)KF1.hasMapPoint.size() == n1 && KF1.mDescriptors.rows >= n1 &&
+           (int)KF2.mvuRight.size() == n2 && (int)KF2.hasMapPoint.size() == n2 && KF2.mDescriptors.rows >= n2 &&
+           KF1.mFeatVec.start.size() == KF1.mFeatVec.nodes.size() + 1 && KF2.mFeatVec.start.size() == KF2.mFeatVec.nodes.size() + 1 &&
+           !KF2.mvScaleFactors.empty() && KF2.mvLevelSigma2.size() == KF2.mvScaleFactors.size(),
+       "SearchForTriangulation views: mvuRight / hasMapPoint / mDescriptors / mFeatVec / mvScaleFactors / mvLevelSigma2 incomplete");
+  std::vector<float> xy1((size_t)n1 * 2), a1(n1), xy2((size_t)n2 * 2), a2(n2);
+  std::vector<int32_t> o2(n2);
+  for (int i = 0; i < n1; ++i) {
+    xy1[2 * i] = KF1.mvKeysUn[i].pt.x; xy1[2 * i + 1] = KF1.mvKeysUn[i].pt.y; a1[i] = KF1.mvKeysUn[i].angle;
+  }
+  for (int i = 0; i < n2; ++i) {
+    xy2[2 * i] = KF2.mvKeysUn[i].pt.x; xy2[2 * i + 1] = KF2.mvKeysUn[i].pt.y; a2[i] = KF2.mvKeysUn[i].angle;
+    o2[i] = KF2.mvKeysUn[i].octave;
+  }
+  int32_t nm = 0;
+  plslam_tri_job_t j{};
+  j.kf1_desc = KF1.mDescriptors.data; j.kf1_xy = xy1.data(); j.kf1_angle = a1.data(); j.kf1_uright = KF1.mvuRight.data();
+  j.kf1_has_mp = KF1.hasMapPoint.data(); j.kf1_nodes = KF1.mFeatVec.nodes.data(); j.kf1_start = KF1.mFeatVec.start.data();
+  j.kf1_idx = KF1.mFeatVec.idx.data();
+  j.kf2_desc = KF2.mDescriptors.data; j.kf2_xy = xy2.data(); j.kf2_angle = a2.data(); j.kf2_octave = o2.data();
+  j.kf2_uright = KF2.mvuRight.data(); j.kf2_has_mp = KF2.hasMapPoint.data(); j.kf2_nodes = KF2.mFeatVec.nodes.data();
+  j.kf2_start = KF2.mFeatVec.start.data(); j.kf2_idx = KF2.mFeatVec.idx.data();
+  j.scale_factors = KF2.mvScaleFactors.data(); j.level_sigma2 = KF2.mvLevelSigma2.data();
+  j.match12 = vnMatches12.data(); j.nmatches = &nm;
+  std::memcpy(j.F12, F12, sizeof(j.F12));
+  j.ex = ex; j.ey = ey;
+  j.n1 = n1; j.n2 = n2; j.n1_nodes = (int)KF1.mFeatVec.nodes.size(); j.n2_nodes = (int)KF2.mFeatVec.nodes.size();
+  j.only_stereo = bOnlyStereo; j.check_orientation = mbCheckOrientation;
+  check(plslam_match_triangulation_host(&j, (int)KF2.mvScaleFactors.size()), "SearchForTriangulation");
   return nm;
 }
 

@@ -1,9 +1,14 @@
 // ORBmatcher.h — drop-in surface of the reference's include/ORBmatcher.h:37-141 for the Hamming cores on the hot
-// path: DescriptorDistance (:44), SearchByProjection(Frame&, const Frame&, th, bMono) (:78), SearchByProjection(Frame&, const vector<MapPoint*>&, th) (:61) and
-// SearchByBoW(KeyFrame*, Frame&, matches) (:104).  Frames are passed as FrameView (see FrameView.h).
+// path: DescriptorDistance (:44), SearchByProjection(Frame&, const Frame&, th, bMono) (:78), SearchByProjection(Frame&, const
+// vector<MapPoint*>&, th) (:61), SearchByBoW(KeyFrame*, Frame&, matches) (:104) and SearchForTriangulation (:111).
+// Two forms of each: the reference's EXACT signatures as member templates over the caller's Frame / KeyFrame / MapPoint
+// classes (with the reference's own headers included, Tracking / LocalMapping call them unchanged; definitions in
+// ORBmatcher_impl.h), and the flattened FrameView forms they are built on (see FrameView.h).
 #ifndef PLSLAM_ORBMATCHER_H
 #define PLSLAM_ORBMATCHER_H
 
+#include <cstddef>
+#include <utility>
 #include <vector>
 
 #include "FrameView.h"
@@ -18,10 +23,33 @@ class ORBmatcher {
   // Computes the Hamming distance between two ORB descriptors
   static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
 
+  // ---- the reference's signatures (ORBmatcher.h:61, :78, :104, :111).  FrameT / KeyFrameT / MapPointT are the
+  //      caller's ORB_SLAM2::Frame / KeyFrame / MapPoint: the members read and written are the ones the reference's
+  //      functions read and write (Frame: N, mvKeys, mvKeysUn, mvuRight, mDescriptors, mvpMapPoints, mvbOutlier, mGrid,
+  //      fx fy cx cy, mnMinX.., mfGridElement*Inv, mbf, mb, mTcw, mvScaleFactors, mFeatVec; MapPoint: isBad, Observations,
+  //      GetWorldPos, GetDescriptor, mbTrackInView, mTrackProjX/Y/XR, mnTrackScaleLevel, mTrackViewCos; KeyFrame:
+  //      GetMapPointMatches, GetMapPoint, GetRotation, GetTranslation, GetCameraCenter, fx fy cx cy, mvKeysUn, mvuRight,
+  //      mDescriptors, mFeatVec, mvScaleFactors, mvLevelSigma2) ----
+  // Search matches between Frame keypoints and projected MapPoints. Returns number of matches (Tracking::SearchLocalPoints)
+  template <class FrameT, class MapPointT>
+  int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, const float th = 3);
+  // Project MapPoints tracked in last frame into the current frame and search matches (Tracking::TrackWithMotionModel)
+  template <class FrameT>
+  int SearchByProjection(FrameT& CurrentFrame, const FrameT& LastFrame, const float th, const bool bMono);
+  // Search matches between MapPoints in a KeyFrame and ORB in a Frame (Relocalisation, TrackReferenceKeyFrame)
+  template <class KeyFrameT, class FrameT, class MapPointT>
+  int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches);
+  // Matching to triangulate new MapPoints. Check Epipolar Constraint (LocalMapping::CreateNewMapPoints)
+  template <class KeyFrameT>
+  int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, cv::Mat F12,
+                             std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo);
+
+  // ---- flattened forms ----
   // Project MapPoints tracked in last frame into the current frame and search matches (Tracking).
-  // vnMatches[i2] = index in LastFrame matched to current keypoint i2, or -1.  Returns the number of matches.
+  // vnMatches[i2] = index in LastFrame matched to current keypoint i2, or -1 (-2 with reportRemoved: assigned during the
+  // scan and taken away again by the rotation-consistency check, where the reference leaves NULL).  Returns the number of matches.
   int SearchByProjection(FrameView& CurrentFrame, const FrameView& LastFrame, const float th, const bool bMono,
-                         std::vector<int>& vnMatches);
+                         std::vector<int>& vnMatches, bool reportRemoved = false);
 
   // Search matches between Frame keypoints and projected MapPoints (Tracking::SearchLocalPoints; ORBmatcher.h:61).
   // vnMatches[i] = index in vpMapPoints assigned to F's keypoint i, or -1.  Returns the number of matches.
@@ -30,6 +58,15 @@ class ORBmatcher {
   // Brute force constrained to ORB that belong to the same vocabulary node (Relocalisation / TrackReferenceKeyFrame).
   // vnMatches[iF] = index in the KeyFrame matched to F's feature iF, or -1.
   int SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>& vnMatches);
+
+  // SearchForTriangulation on views: KF1 / KF2 need mvKeysUn, mvuRight, mDescriptors, mFeatVec, hasMapPoint; KF2 also
+  // mvScaleFactors and mvLevelSigma2; (ex, ey) = the epipole of KF1's centre in KF2 (Epipole below).
+  // vnMatches12[i1] = KF2 feature matched to KF1 feature i1, or -1.
+  int SearchForTriangulation(const FrameView& KF1, const FrameView& KF2, const float F12[9], float ex, float ey,
+                             const bool bOnlyStereo, std::vector<int>& vnMatches12);
+  // C2 = R2w * Cw + t2w projected with KF2's intrinsics, with the binary's rounding sequence (@0x86b9c-0x86f8b)
+  static void Epipole(const float R2w[9], const float t2w[3], const float Cw[3], float fx, float fy, float cx, float cy,
+                      float* ex, float* ey);
 
  public:
   static const int TH_LOW;
@@ -43,4 +80,6 @@ class ORBmatcher {
 };
 
 }  // namespace ORB_SLAM2
+
+#include "ORBmatcher_impl.h"
 #endif

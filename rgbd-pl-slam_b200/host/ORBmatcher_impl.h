@@ -1,0 +1,198 @@
+// ORBmatcher_impl.h — the reference-signature member templates of ORB_SLAM2::ORBmatcher (declared in ORBmatcher.h):
+// each flattens the members the reference's function reads into a FrameView / MapPointsView, calls the flattened form
+// (one C-ABI call, one kernel) and writes the result where the reference writes it.  Included by ORBmatcher.h.
+#pragma once
+#include <stdexcept>
+#include <string>
+
+namespace ORB_SLAM2 {
+namespace dropin {
+
+// DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>) -> CSR, keys ascending as the map iterates
+template <class FeatVec>
+inline void flatten_featvec(const FeatVec& fv, FeatureVectorView* out) {
+  out->nodes.clear();
+  out->start.clear();
+  out->idx.clear();
+  out->start.push_back(0);
+  for (typename FeatVec::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+    out->nodes.push_back((int32_t)it->first);
+    for (size_t k = 0; k < it->second.size(); ++k) out->idx.push_back((int32_t)it->second[k]);
+    out->start.push_back((int32_t)out->idx.size());
+  }
+}
+
+// every array of a view must cover its N features: an unfilled member would be read out of bounds by the upload
+inline void require(bool ok, const char* what) {
+  if (!ok) throw std::invalid_argument(std::string("ORBmatcher: ") + what);
+}
+
+// The features, grid, bounds, intrinsics and pose of a Frame.  Map-point state is filled by the callers (it differs).
+template <class FrameT>
+inline void view_of_frame(const FrameT& F, FrameView* V, bool withGrid) {
+  V->mvKeys = F.mvKeys;
+  V->mvKeysUn = F.mvKeysUn;
+  V->mDescriptors = F.mDescriptors;
+  V->mvuRight = F.mvuRight;
+  V->mvScaleFactors = F.mvScaleFactors;
+  const size_t n = F.mvKeysUn.size();
+  require(F.mvKeys.size() == n && F.mvuRight.size() == n && (size_t)F.mDescriptors.rows == n && F.mvpMapPoints.size() == n,
+          "Frame members (mvKeys, mvKeysUn, mvuRight, mDescriptors, mvpMapPoints) differ in length");
+  if (withGrid) {
+    V->gridStart.assign(1, 0);
+    V->gridItems.clear();
+    for (int ix = 0; ix < 64; ++ix)
+      for (int iy = 0; iy < 48; ++iy) {
+        for (size_t k = 0; k < F.mGrid[ix][iy].size(); ++k) V->gridItems.push_back((int32_t)F.mGrid[ix][iy][k]);
+        V->gridStart.push_back((int32_t)V->gridItems.size());
+      }
+    V->mnMinX = FrameT::mnMinX; V->mnMaxX = FrameT::mnMaxX; V->mnMinY = FrameT::mnMinY; V->mnMaxY = FrameT::mnMaxY;
+    V->mfGridElementWidthInv = FrameT::mfGridElementWidthInv;
+    V->mfGridElementHeightInv = FrameT::mfGridElementHeightInv;
+  }
+  V->fx = FrameT::fx; V->fy = FrameT::fy; V->cx = FrameT::cx; V->cy = FrameT::cy;
+  V->mbf = F.mbf; V->mb = F.mb;
+  if (!F.mTcw.empty())
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) V->mTcw[4 * r + c] = F.mTcw.template at<float>(r, c);
+}
+
+}  // namespace dropin
+
+// ORBmatcher.h:78 (@0x80d00)
+template <class FrameT>
+int ORBmatcher::SearchByProjection(FrameT& CurrentFrame, const FrameT& LastFrame, const float th, const bool bMono) {
+  FrameView cur, last;
+  dropin::view_of_frame(CurrentFrame, &cur, true);
+  dropin::view_of_frame(LastFrame, &last, false);
+  const int n1 = (int)last.mvKeysUn.size(), n2 = (int)cur.mvKeysUn.size();
+  dropin::require(LastFrame.mvbOutlier.size() == (size_t)n1, "LastFrame.mvbOutlier differs in length");
+  last.hasMapPoint.assign(n1, 0);
+  last.mapPointObserved.assign(n1, 0);
+  last.mvbOutlier.assign(n1, 0);
+  last.mapPointWorldPos.assign((size_t)n1 * 3, 0.f);
+  last.mapPointDescriptor.create(n1 > 0 ? n1 : 1, 32, CV_8U);
+  for (int i = 0; i < n1; ++i) {
+    auto* pMP = LastFrame.mvpMapPoints[i];
+    last.mvbOutlier[i] = LastFrame.mvbOutlier[i] ? 1 : 0;
+    if (!pMP) continue;
+    last.hasMapPoint[i] = 1;
+    last.mapPointObserved[i] = pMP->Observations() > 0;
+    const cv::Mat x3Dw = pMP->GetWorldPos();
+    for (int k = 0; k < 3; ++k) last.mapPointWorldPos[3 * (size_t)i + k] = x3Dw.template at<float>(k);
+    const cv::Mat d = pMP->GetDescriptor();
+    std::memcpy(last.mapPointDescriptor.ptr(i), d.ptr(0), 32);
+  }
+  cur.mapPointObserved.assign(n2, 0);
+  for (int i = 0; i < n2; ++i)
+    if (CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations() > 0) cur.mapPointObserved[i] = 1;
+  std::vector<int> m;
+  const int n = SearchByProjection(cur, last, th, bMono, m, true);
+  for (int i2 = 0; i2 < n2; ++i2) {
+    if (m[i2] >= 0) CurrentFrame.mvpMapPoints[i2] = LastFrame.mvpMapPoints[m[i2]];
+    else if (m[i2] == -2) CurrentFrame.mvpMapPoints[i2] = nullptr;  // assigned, then removed by the rotation check
+  }
+  return n;
+}
+
+// ORBmatcher.h:61 (@0x79f10)
+template <class FrameT, class MapPointT>
+int ORBmatcher::SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, const float th) {
+  FrameView f;
+  dropin::view_of_frame(F, &f, true);
+  const int n = (int)f.mvKeysUn.size(), m = (int)vpMapPoints.size();
+  f.mapPointObserved.assign(n, 0);
+  for (int i = 0; i < n; ++i)
+    if (F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0) f.mapPointObserved[i] = 1;
+  MapPointsView mp;
+  mp.inViewAndGood.assign(m, 0);
+  mp.trackProj.assign((size_t)m * 3, 0.f);
+  mp.trackScaleLevel.assign(m, 0);
+  mp.trackViewCos.assign(m, 0.f);
+  mp.observed.assign(m, 0);
+  mp.descriptors.create(m > 0 ? m : 1, 32, CV_8U);
+  for (int i = 0; i < m; ++i) {
+    MapPointT* pMP = vpMapPoints[i];
+    if (!pMP || !pMP->mbTrackInView || pMP->isBad()) continue;
+    mp.inViewAndGood[i] = 1;
+    mp.trackProj[3 * (size_t)i] = pMP->mTrackProjX;
+    mp.trackProj[3 * (size_t)i + 1] = pMP->mTrackProjY;
+    mp.trackProj[3 * (size_t)i + 2] = pMP->mTrackProjXR;
+    mp.trackScaleLevel[i] = pMP->mnTrackScaleLevel;
+    mp.trackViewCos[i] = pMP->mTrackViewCos;
+    mp.observed[i] = pMP->Observations() > 0;
+    const cv::Mat d = pMP->GetDescriptor();
+    std::memcpy(mp.descriptors.ptr(i), d.ptr(0), 32);
+  }
+  std::vector<int> match;
+  const int nm = SearchByProjection(f, mp, th, match);
+  for (int i = 0; i < n; ++i)
+    if (match[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[match[i]];
+  return nm;
+}
+
+// ORBmatcher.h:104 (@0x80150)
+template <class KeyFrameT, class FrameT, class MapPointT>
+int ORBmatcher::SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {
+  const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+  vpMapPointMatches = std::vector<MapPointT*>(F.N, static_cast<MapPointT*>(nullptr));
+  FrameView kf, f;
+  kf.mvKeysUn = pKF->mvKeysUn;
+  kf.mDescriptors = pKF->mDescriptors;
+  const size_t n1 = kf.mvKeysUn.size();
+  dropin::require(vpMapPointsKF.size() == n1 && (size_t)pKF->mDescriptors.rows == n1, "KeyFrame members differ in length");
+  kf.hasMapPoint.assign(n1, 0);
+  for (size_t i = 0; i < n1; ++i) kf.hasMapPoint[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
+  dropin::flatten_featvec(pKF->mFeatVec, &kf.mFeatVec);
+  f.mvKeys = F.mvKeys;
+  f.mDescriptors = F.mDescriptors;
+  dropin::require((size_t)F.mDescriptors.rows == F.mvKeys.size(), "Frame members differ in length");
+  dropin::flatten_featvec(F.mFeatVec, &f.mFeatVec);
+  std::vector<int> match;
+  const int nm = SearchByBoW(kf, f, match);
+  for (size_t i = 0; i < match.size(); ++i)
+    if (match[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[match[i]];
+  return nm;
+}
+
+// ORBmatcher.h:111 (@0x86b30)
+template <class KeyFrameT>
+int ORBmatcher::SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, cv::Mat F12,
+                                       std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
+  FrameView v[2];
+  KeyFrameT* kfs[2] = {pKF1, pKF2};
+  for (int s = 0; s < 2; ++s) {
+    KeyFrameT* kf = kfs[s];
+    v[s].mvKeysUn = kf->mvKeysUn;
+    v[s].mvuRight = kf->mvuRight;
+    v[s].mDescriptors = kf->mDescriptors;
+    const size_t n = v[s].mvKeysUn.size();
+    dropin::require(kf->mvuRight.size() == n && (size_t)kf->mDescriptors.rows == n, "KeyFrame members differ in length");
+    v[s].hasMapPoint.assign(n, 0);
+    for (size_t i = 0; i < n; ++i) v[s].hasMapPoint[i] = kf->GetMapPoint(i) != nullptr;
+    dropin::flatten_featvec(kf->mFeatVec, &v[s].mFeatVec);
+  }
+  v[1].mvScaleFactors = pKF2->mvScaleFactors;
+  v[1].mvLevelSigma2 = pKF2->mvLevelSigma2;
+  // epipole in the second image: C2 = R2w * Cw + t2w
+  const cv::Mat Cw = pKF1->GetCameraCenter(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+  float R[9], t[3], C[3], F[9], ex, ey;
+  for (int r = 0; r < 3; ++r) {
+    t[r] = t2w.template at<float>(r);
+    C[r] = Cw.template at<float>(r);
+    for (int c = 0; c < 3; ++c) {
+      R[3 * r + c] = R2w.template at<float>(r, c);
+      F[3 * r + c] = F12.template at<float>(r, c);
+    }
+  }
+  Epipole(R, t, C, pKF2->fx, pKF2->fy, pKF2->cx, pKF2->cy, &ex, &ey);
+  std::vector<int> m12;
+  const int nm = SearchForTriangulation(v[0], v[1], F, ex, ey, bOnlyStereo, m12);
+  vMatchedPairs.clear();
+  vMatchedPairs.reserve(nm);
+  for (size_t i = 0; i < m12.size(); ++i)
+    if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
+  return nm;
+}
+
+}  // namespace ORB_SLAM2

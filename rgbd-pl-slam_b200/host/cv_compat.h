@@ -16,6 +16,7 @@
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 
 namespace cv {
 
@@ -38,31 +39,40 @@ struct DMatch {
   DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
 };
 
-// 8-bit single-channel matrix with shared ownership (enough of cv::Mat for images and descriptor blocks)
+// single-channel matrix with shared ownership (enough of cv::Mat for images, descriptor blocks and the small CV_32F pose
+// matrices the matchers read: CV_8U and CV_32F)
 class Mat {
  public:
   int rows = 0, cols = 0;
-  size_t step = 0;
+  size_t step = 0;  // bytes per row
   uint8_t* data = nullptr;
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
-  Mat(int r, int c, int /*type*/, void* ext, size_t st = 0) : rows(r), cols(c), step(st ? st : (size_t)c), data((uint8_t*)ext) {}
-  void create(int r, int c, int /*type*/) {
-    if (r == rows && c == cols && own_) return;
-    rows = r; cols = c; step = (size_t)c;
-    own_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * c > 0 ? (size_t)r * c : 1], std::default_delete<uint8_t[]>());
+  Mat(int r, int c, int type, void* ext, size_t st = 0) : rows(r), cols(c), step(st ? st : (size_t)c * esz(type)), data((uint8_t*)ext), type_(type) {}
+  void create(int r, int c, int type) {
+    if (r == rows && c == cols && type == type_ && own_) return;
+    rows = r; cols = c; type_ = type; step = (size_t)c * esz(type);
+    const size_t bytes = (size_t)r * step;
+    own_ = std::shared_ptr<uint8_t>(new uint8_t[bytes > 0 ? bytes : 1], std::default_delete<uint8_t[]>());
     data = own_.get();
   }
   void release() { rows = cols = 0; step = 0; data = nullptr; own_.reset(); }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-  int type() const { return CV_8UC1; }
+  int type() const { return type_; }
+  size_t elemSize() const { return esz(type_); }
   uint8_t* ptr(int r = 0) { return data + (size_t)r * step; }
   const uint8_t* ptr(int r = 0) const { return data + (size_t)r * step; }
   template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
   template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
-  Mat row(int r) const { Mat m; m.rows = 1; m.cols = cols; m.step = step; m.data = data + (size_t)r * step; m.own_ = own_; return m; }
-  Mat clone() const { Mat m(rows, cols, CV_8U); for (int r = 0; r < rows; ++r) std::memcpy(m.ptr(r), ptr(r), cols); return m; }
+  template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
+  template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
+  template <typename T> T& at(int i) { return rows == 1 ? ptr<T>(0)[i] : ptr<T>(i)[0]; }
+  template <typename T> const T& at(int i) const { return rows == 1 ? ptr<T>(0)[i] : ptr<T>(i)[0]; }
+  Mat row(int r) const { Mat m; m.rows = 1; m.cols = cols; m.step = step; m.type_ = type_; m.data = data + (size_t)r * step; m.own_ = own_; return m; }
+  Mat clone() const { Mat m(rows, cols, type_); for (int r = 0; r < rows; ++r) std::memcpy(m.ptr(r), ptr(r), (size_t)cols * esz(type_)); return m; }
  private:
+  static size_t esz(int type) { return type == 5 ? 4 : 1; }
+  int type_ = 0;
   std::shared_ptr<uint8_t> own_;
 };
 

@@ -1,0 +1,365 @@
+// dropin_matchers_demo.cc — ORB_SLAM2::ORBmatcher called through the REFERENCE'S signatures (include/ORBmatcher.h:61, :78,
+// :104, :111) on mock Frame / KeyFrame / MapPoint classes that carry the member names of the reference's
+// include/Frame.h, KeyFrame.h and MapPoint.h (the real classes are pointer graphs guarded by mutexes, outside the hot
+// path).  tests/test_dropin_gpu.py writes the array form of four matcher cases into a directory, this program builds the
+// object form, calls the matcher the way Tracking / LocalMapping do, and writes what the calls left in the objects;
+// the test compares that with the flattened C-ABI calls on the same arrays.
+//   dropin_matchers_demo <dir>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ORBmatcher.h"
+
+namespace DBoW2 {
+typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;  // DBoW2/FeatureVector.h
+}
+
+namespace ORB_SLAM2 {
+
+class MapPoint {  // include/MapPoint.h: the members the matchers touch
+ public:
+  cv::Mat GetWorldPos() { return mWorldPos.clone(); }
+  cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+  int Observations() { return nObs; }
+  bool isBad() { return mbBad; }
+  // Variables used by the tracking
+  float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0;
+  bool mbTrackInView = false;
+  int mnTrackScaleLevel = 0;
+  float mTrackViewCos = 0;
+  // (protected in the reference)
+  cv::Mat mWorldPos, mDescriptor;
+  int nObs = 0;
+  bool mbBad = false;
+  int id = -1;  // demo only: position in the vector it came from
+};
+
+class Frame {  // include/Frame.h
+ public:
+  static float fx, fy, cx, cy;
+  float mbf = 0, mb = 0;
+  int N = 0;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+  std::vector<float> mvuRight;
+  DBoW2::FeatureVector mFeatVec;
+  cv::Mat mDescriptors;
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<bool> mvbOutlier;
+  static float mfGridElementWidthInv, mfGridElementHeightInv;
+  std::vector<std::size_t> mGrid[64][48];
+  cv::Mat mTcw;
+  std::vector<float> mvScaleFactors;
+  static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+};
+float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX,
+    Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+
+class KeyFrame {  // include/KeyFrame.h
+ public:
+  std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+  cv::Mat GetRotation() { return R.clone(); }
+  cv::Mat GetTranslation() { return t.clone(); }
+  cv::Mat GetCameraCenter() { return Ow.clone(); }
+  float fx = 0, fy = 0, cx = 0, cy = 0;
+  std::vector<cv::KeyPoint> mvKeysUn;
+  std::vector<float> mvuRight;
+  cv::Mat mDescriptors;
+  DBoW2::FeatureVector mFeatVec;
+  std::vector<float> mvScaleFactors, mvLevelSigma2;
+  std::vector<MapPoint*> mvpMapPoints;
+  cv::Mat R, t, Ow;
+};
+
+}  // namespace ORB_SLAM2
+
+using namespace ORB_SLAM2;
+
+static std::string g_dir;
+template <class T>
+static std::vector<T> load(const std::string& name) {
+  std::ifstream f(g_dir + "/" + name, std::ios::binary | std::ios::ate);
+  if (!f) {
+    std::fprintf(stderr, "missing %s\n", name.c_str());
+    std::exit(2);
+  }
+  const size_t bytes = (size_t)f.tellg();
+  std::vector<T> v(bytes / sizeof(T));
+  f.seekg(0);
+  f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
+  return v;
+}
+template <class T>
+static void save(const std::string& name, const std::vector<T>& v) {
+  std::ofstream f(g_dir + "/" + name, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
+}
+static cv::Mat mat_u8(const std::vector<uint8_t>& d, int rows) {
+  cv::Mat m(rows > 0 ? rows : 1, 32, CV_8U);
+  if (rows) std::memcpy(m.data, d.data(), (size_t)rows * 32);
+  m.rows = rows;
+  return m;
+}
+static cv::Mat mat_f(const float* p, int r, int c) {
+  cv::Mat m(r, c, CV_32F);
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < c; ++j) m.at<float>(i, j) = p[i * c + j];
+  return m;
+}
+static cv::Mat desc_row(const std::vector<uint8_t>& d, int i) {
+  cv::Mat m(1, 32, CV_8U);
+  std::memcpy(m.data, d.data() + (size_t)i * 32, 32);
+  return m;
+}
+static DBoW2::FeatureVector featvec(const std::vector<int32_t>& nodes, const std::vector<int32_t>& start, const std::vector<int32_t>& idx) {
+  DBoW2::FeatureVector fv;
+  for (size_t k = 0; k < nodes.size(); ++k)
+    for (int j = start[k]; j < start[k + 1]; ++j) fv[(unsigned)nodes[k]].push_back((unsigned)idx[j]);
+  return fv;
+}
+static void fill_grid(Frame& F, const std::vector<int32_t>& gs, const std::vector<int32_t>& gi) {
+  for (int ix = 0; ix < 64; ++ix)
+    for (int iy = 0; iy < 48; ++iy) {
+      F.mGrid[ix][iy].clear();
+      for (int j = gs[ix * 48 + iy]; j < gs[ix * 48 + iy + 1]; ++j) F.mGrid[ix][iy].push_back((size_t)gi[j]);
+    }
+}
+static std::vector<MapPoint*> g_pool;
+static MapPoint* new_mp() {
+  g_pool.push_back(new MapPoint());
+  return g_pool.back();
+}
+
+// ---- TrackWithMotionModel: matcher.SearchByProjection(mCurrentFrame, mLastFrame, th, mSensor == MONOCULAR) ----
+static void case_projection() {
+  const auto valid = load<uint8_t>("pj_last_valid"), obs = load<uint8_t>("pj_last_obs"), ldesc = load<uint8_t>("pj_last_desc");
+  const auto xyz = load<float>("pj_last_xyz"), lang = load<float>("pj_last_angle");
+  const auto loct = load<int32_t>("pj_last_octave");
+  const auto cxy = load<float>("pj_cur_xy"), cang = load<float>("pj_cur_angle"), cur = load<float>("pj_cur_uright");
+  const auto coct = load<int32_t>("pj_cur_octave"), gs = load<int32_t>("pj_cur_grid_start"), gi = load<int32_t>("pj_cur_grid_items");
+  const auto cdesc = load<uint8_t>("pj_cur_desc"), taken = load<uint8_t>("pj_cur_taken");
+  const auto cam = load<float>("pj_cam"), sf = load<float>("pj_sf"), tc = load<float>("pj_tc"), tl = load<float>("pj_tl"),
+             par = load<float>("pj_par");  // th, mono
+  const int n1 = (int)valid.size(), n2 = (int)taken.size();
+  Frame::fx = cam[0]; Frame::fy = cam[1]; Frame::cx = cam[2]; Frame::cy = cam[3];
+  Frame::mnMinX = cam[6]; Frame::mnMaxX = cam[7]; Frame::mnMinY = cam[8]; Frame::mnMaxY = cam[9];
+  Frame::mfGridElementWidthInv = cam[10]; Frame::mfGridElementHeightInv = cam[11];
+  Frame Last, Cur;
+  Last.N = n1; Last.mbf = Cur.mbf = cam[4]; Last.mb = Cur.mb = cam[5];
+  Last.mvKeys.resize(n1); Last.mvKeysUn.resize(n1); Last.mvuRight.assign(n1, -1.f); Last.mvpMapPoints.assign(n1, nullptr);
+  Last.mvbOutlier.assign(n1, false);
+  Last.mDescriptors = mat_u8(ldesc, n1);
+  for (int i = 0; i < n1; ++i) {
+    Last.mvKeys[i].octave = Last.mvKeysUn[i].octave = loct[i];
+    Last.mvKeys[i].angle = Last.mvKeysUn[i].angle = lang[i];
+    // valid = mvpMapPoints[i] && !mvbOutlier[i]: invalid ones alternate between "no map point" and "outlier"
+    if (valid[i] || (i & 1)) {
+      MapPoint* p = new_mp();
+      p->id = i;
+      p->mWorldPos = mat_f(&xyz[3 * (size_t)i], 3, 1);
+      p->mDescriptor = desc_row(ldesc, i);
+      p->nObs = obs[i] ? 2 : 0;
+      Last.mvpMapPoints[i] = p;
+      if (!valid[i]) Last.mvbOutlier[i] = true;
+    }
+  }
+  float T[16] = {0};
+  std::memcpy(T, tl.data(), 12 * sizeof(float)); T[15] = 1;
+  Last.mTcw = mat_f(T, 4, 4);
+  Last.mvScaleFactors = sf;
+  Cur.N = n2;
+  Cur.mvKeys.resize(n2); Cur.mvKeysUn.resize(n2); Cur.mvuRight = cur; Cur.mvpMapPoints.assign(n2, nullptr); Cur.mvbOutlier.assign(n2, false);
+  Cur.mDescriptors = mat_u8(cdesc, n2);
+  std::vector<MapPoint*> before(n2, nullptr);
+  for (int i = 0; i < n2; ++i) {
+    Cur.mvKeysUn[i].pt = cv::Point2f(cxy[2 * i], cxy[2 * i + 1]);
+    Cur.mvKeys[i].pt = Cur.mvKeysUn[i].pt;
+    Cur.mvKeys[i].octave = Cur.mvKeysUn[i].octave = coct[i];
+    Cur.mvKeys[i].angle = Cur.mvKeysUn[i].angle = cang[i];
+    // taken = mvpMapPoints[i] && Observations() > 0; a few more carry a map point nobody observes yet (may be replaced)
+    if (taken[i] || i % 7 == 0) {
+      MapPoint* p = new_mp();
+      p->nObs = taken[i] ? 1 : 0;
+      Cur.mvpMapPoints[i] = before[i] = p;
+    }
+  }
+  std::memcpy(T, tc.data(), 12 * sizeof(float));
+  Cur.mTcw = mat_f(T, 4, 4);
+  Cur.mvScaleFactors = sf;
+  fill_grid(Cur, gs, gi);
+
+  ORBmatcher matcher(0.9f, true);
+  const int nmatches = matcher.SearchByProjection(Cur, Last, par[0], par[1] != 0.f);
+
+  std::vector<int32_t> out(n2 + 1);
+  for (int i = 0; i < n2; ++i) {
+    MapPoint* p = Cur.mvpMapPoints[i];
+    out[i] = !p ? (before[i] ? -2 : -1) : (p == before[i] ? -1 : p->id);  // -2: had a map point, NULL now
+  }
+  out[n2] = nmatches;
+  save("pj_out", out);
+}
+
+// ---- Tracking::SearchLocalPoints: matcher.SearchByProjection(mCurrentFrame, mvpLocalMapPoints, th) ----
+static void case_local() {
+  const auto valid = load<uint8_t>("lp_mp_valid"), obs = load<uint8_t>("lp_mp_obs"), mdesc = load<uint8_t>("lp_mp_desc");
+  const auto proj = load<float>("lp_mp_proj"), vcos = load<float>("lp_mp_viewcos");
+  const auto level = load<int32_t>("lp_mp_level");
+  const auto xy = load<float>("lp_fr_xy"), ur = load<float>("lp_fr_uright");
+  const auto oct = load<int32_t>("lp_fr_octave"), gs = load<int32_t>("lp_fr_grid_start"), gi = load<int32_t>("lp_fr_grid_items");
+  const auto fdesc = load<uint8_t>("lp_fr_desc"), taken = load<uint8_t>("lp_fr_taken");
+  const auto cam4 = load<float>("lp_cam4"), sf = load<float>("lp_sf"), par = load<float>("lp_par");  // th, nnratio
+  const int m = (int)valid.size(), n = (int)taken.size();
+  Frame::mnMinX = cam4[0]; Frame::mnMinY = cam4[1]; Frame::mfGridElementWidthInv = cam4[2]; Frame::mfGridElementHeightInv = cam4[3];
+  Frame F;
+  F.N = n;
+  F.mvKeys.resize(n); F.mvKeysUn.resize(n); F.mvuRight = ur; F.mvpMapPoints.assign(n, nullptr); F.mvbOutlier.assign(n, false);
+  F.mDescriptors = mat_u8(fdesc, n);
+  F.mvScaleFactors = sf;
+  std::vector<MapPoint*> before(n, nullptr);
+  for (int i = 0; i < n; ++i) {
+    F.mvKeysUn[i].pt = cv::Point2f(xy[2 * i], xy[2 * i + 1]);
+    F.mvKeysUn[i].octave = oct[i];
+    F.mvKeys[i] = F.mvKeysUn[i];
+    if (taken[i]) {
+      MapPoint* p = new_mp();
+      p->nObs = 1;
+      F.mvpMapPoints[i] = before[i] = p;
+    }
+  }
+  fill_grid(F, gs, gi);
+  std::vector<MapPoint*> vp(m, nullptr);
+  for (int i = 0; i < m; ++i) {
+    MapPoint* p = new_mp();
+    p->id = i;
+    // valid = mbTrackInView && !isBad(): invalid ones alternate between the two reasons
+    p->mbTrackInView = valid[i] || (i & 1);
+    p->mbBad = !valid[i] && (i & 1);
+    p->mTrackProjX = proj[3 * (size_t)i]; p->mTrackProjY = proj[3 * (size_t)i + 1]; p->mTrackProjXR = proj[3 * (size_t)i + 2];
+    p->mnTrackScaleLevel = level[i];
+    p->mTrackViewCos = vcos[i];
+    p->mDescriptor = desc_row(mdesc, i);
+    p->nObs = obs[i] ? 3 : 0;
+    vp[i] = p;
+  }
+  ORBmatcher matcher(par[1], true);
+  const int nmatches = matcher.SearchByProjection(F, vp, par[0]);
+  std::vector<int32_t> out(n + 1);
+  for (int i = 0; i < n; ++i) out[i] = (F.mvpMapPoints[i] && F.mvpMapPoints[i] != before[i]) ? F.mvpMapPoints[i]->id : -1;
+  out[n] = nmatches;
+  save("lp_out", out);
+}
+
+// ---- Tracking::TrackReferenceKeyFrame: matcher.SearchByBoW(mpReferenceKF, mCurrentFrame, vpMapPointMatches) ----
+static void case_bow() {
+  const auto kdesc = load<uint8_t>("bw_kf_desc"), kvalid = load<uint8_t>("bw_kf_valid"), fdesc = load<uint8_t>("bw_f_desc");
+  const auto kang = load<float>("bw_kf_angle"), fang = load<float>("bw_f_angle"), par = load<float>("bw_par");  // nnratio, ori
+  const int n1 = (int)kvalid.size(), n2 = (int)fang.size();
+  KeyFrame KF;
+  KF.mvKeysUn.resize(n1); KF.mvuRight.assign(n1, -1.f); KF.mvpMapPoints.assign(n1, nullptr);
+  KF.mDescriptors = mat_u8(kdesc, n1);
+  for (int i = 0; i < n1; ++i) {
+    KF.mvKeysUn[i].angle = kang[i];
+    // valid = map point exists and is not bad: invalid ones alternate between NULL and a bad point
+    if (kvalid[i] || (i & 1)) {
+      MapPoint* p = new_mp();
+      p->id = i;
+      p->mbBad = !kvalid[i];
+      KF.mvpMapPoints[i] = p;
+    }
+  }
+  KF.mFeatVec = featvec(load<int32_t>("bw_kf_nodes"), load<int32_t>("bw_kf_start"), load<int32_t>("bw_kf_idx"));
+  Frame F;
+  F.N = n2;
+  F.mvKeys.resize(n2); F.mvKeysUn.resize(n2); F.mvuRight.assign(n2, -1.f); F.mvpMapPoints.assign(n2, nullptr);
+  F.mDescriptors = mat_u8(fdesc, n2);
+  for (int i = 0; i < n2; ++i) F.mvKeys[i].angle = F.mvKeysUn[i].angle = fang[i];
+  F.mFeatVec = featvec(load<int32_t>("bw_f_nodes"), load<int32_t>("bw_f_start"), load<int32_t>("bw_f_idx"));
+  ORBmatcher matcher(par[0], par[1] != 0.f);
+  std::vector<MapPoint*> vpMapPointMatches;
+  const int nmatches = matcher.SearchByBoW(&KF, F, vpMapPointMatches);
+  std::vector<int32_t> out(n2 + 1);
+  for (int i = 0; i < n2; ++i) out[i] = vpMapPointMatches[i] ? vpMapPointMatches[i]->id : -1;
+  out[n2] = nmatches;
+  save("bw_out", out);
+}
+
+// ---- LocalMapping::CreateNewMapPoints: matcher.SearchForTriangulation(mpCurrentKeyFrame, pKF2, F12, vMatchedIndices, false) ----
+static void case_triangulation() {
+  const auto par = load<float>("tr_par");  // fx fy cx cy only_stereo ori
+  const auto F12 = load<float>("tr_F12"), R2w = load<float>("tr_R2w"), t2w = load<float>("tr_t2w"), Cw = load<float>("tr_Cw");
+  const auto sf = load<float>("tr_sf"), sg = load<float>("tr_sg");
+  KeyFrame K[2];
+  for (int s = 0; s < 2; ++s) {
+    const std::string p = s ? "tr_kf2_" : "tr_kf1_";
+    const auto desc = load<uint8_t>(p + "desc"), has = load<uint8_t>(p + "has_mp");
+    const auto xy = load<float>(p + "xy"), ang = load<float>(p + "angle"), ur = load<float>(p + "uright");
+    const int n = (int)has.size();
+    K[s].mvKeysUn.resize(n);
+    K[s].mvuRight = ur;
+    K[s].mDescriptors = mat_u8(desc, n);
+    K[s].mvpMapPoints.assign(n, nullptr);
+    std::vector<int32_t> oct;
+    if (s) oct = load<int32_t>(p + "octave");
+    for (int i = 0; i < n; ++i) {
+      K[s].mvKeysUn[i].pt = cv::Point2f(xy[2 * i], xy[2 * i + 1]);
+      K[s].mvKeysUn[i].angle = ang[i];
+      if (s) K[s].mvKeysUn[i].octave = oct[i];
+      if (has[i]) K[s].mvpMapPoints[i] = new_mp();
+    }
+    K[s].mFeatVec = featvec(load<int32_t>(p + "nodes"), load<int32_t>(p + "start"), load<int32_t>(p + "idx"));
+    K[s].fx = par[0]; K[s].fy = par[1]; K[s].cx = par[2]; K[s].cy = par[3];
+    K[s].mvScaleFactors = sf;
+    K[s].mvLevelSigma2 = sg;
+  }
+  K[0].Ow = mat_f(Cw.data(), 3, 1);
+  K[1].R = mat_f(R2w.data(), 3, 3);
+  K[1].t = mat_f(t2w.data(), 3, 1);
+  ORBmatcher matcher(0.6f, par[5] != 0.f);
+  std::vector<std::pair<size_t, size_t> > vMatchedIndices;
+  const int nmatches = matcher.SearchForTriangulation(&K[0], &K[1], mat_f(F12.data(), 3, 3), vMatchedIndices, par[4] != 0.f);
+  std::vector<int32_t> out;
+  for (auto& pr : vMatchedIndices) {
+    out.push_back((int32_t)pr.first);
+    out.push_back((int32_t)pr.second);
+  }
+  out.push_back(nmatches);
+  save("tr_out", out);
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    std::fprintf(stderr, "usage: %s <dir>\n", argv[0]);
+    return 2;
+  }
+  g_dir = argv[1];
+  try {
+    case_projection();
+    case_local();
+    case_bow();
+    case_triangulation();
+    // an unfilled member must be reported, not read out of bounds
+    Frame bad, last;
+    bad.mvKeysUn.resize(4);
+    bool thrown = false;
+    try {
+      ORBmatcher(0.9f, true).SearchByProjection(bad, last, 7.f, false);
+    } catch (const std::invalid_argument&) {
+      thrown = true;
+    }
+    if (!thrown) {
+      std::fprintf(stderr, "missing length check\n");
+      return 1;
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  for (MapPoint* p : g_pool) delete p;
+  std::printf("ok\n");
+  return 0;
+}

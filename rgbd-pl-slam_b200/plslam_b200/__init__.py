@@ -303,7 +303,8 @@ class ProjJob(C.Structure):
                                           "cur_xy", "cur_octave", "cur_angle", "cur_desc", "cur_uright", "cur_taken",
                                           "grid_start", "grid_items", "scale_factors", "match_cur", "nmatches")] + \
                [("cam", C.c_float * 12), ("tcw_cur", C.c_float * 12), ("tcw_last", C.c_float * 12), ("th", C.c_float),
-                ("n1", C.c_int32), ("n2", C.c_int32), ("mono", C.c_int32), ("check_orientation", C.c_int32)]
+                ("n1", C.c_int32), ("n2", C.c_int32), ("mono", C.c_int32), ("check_orientation", C.c_int32),
+                ("report_removed", C.c_int32)]
 
 
 class TriJob(C.Structure):
@@ -584,13 +585,37 @@ class ORBVocabulary:
         return word, weight, node
 
     def transform(self, desc, levelsup=4):
-        """-> dict(bow_ids, bow_vals, fv_nodes, fv_start, fv_idx): BowVector and FeatureVector in std::map order."""
-        word, weight, node = self.transform_features(desc, levelsup)
-        return assemble_bow(word, weight, node)
+        """Frame::ComputeBoW of one frame -> dict(bow_ids, bow_vals, fv_nodes, fv_start, fv_idx): BowVector and FeatureVector
+        in std::map order, assembled on the device (plslam_voc_compute_bow_host)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        ids = np.empty(max(n, 1), np.int32); vals = np.empty(max(n, 1), np.float64)
+        fn = np.empty(max(n, 1), np.int32); fs = np.zeros(n + 1, np.int32); fi = np.empty(max(n, 1), np.int32)
+        nb, nf = C.c_int(0), C.c_int(0)
+        _check(lib().plslam_voc_compute_bow_host(self._h, _vp(desc), n, int(levelsup), _vp(ids), _vp(vals), C.byref(nb), _vp(fn),
+                                                 _vp(fs), _vp(fi), C.byref(nf)))
+        nb, nf = nb.value, nf.value
+        return dict(bow_ids=ids[:nb].astype(np.uint32), bow_vals=vals[:nb].copy(), fv_nodes=fn[:nf].astype(np.uint32),
+                    fv_start=fs[:nf + 1].copy(), fv_idx=fi[:fs[nf]].astype(np.uint32))
+
+    def bowvec_batch_device(self, fv, d_counts, out=None, stream=None):
+        """mBowVec of every frame of a batch from the outputs of featvec_batch_device -> dict(bow_ids, bow_vals [B][cap],
+        bow_count [B]) on the device."""
+        import torch
+        B, cap = fv["word"].shape
+        dev = fv["word"].device
+        if out is None:
+            out = dict(bow_ids=torch.empty((B, cap), dtype=torch.int32, device=dev),
+                       bow_vals=torch.empty((B, cap), dtype=torch.float64, device=dev),
+                       bow_count=torch.empty((B,), dtype=torch.int32, device=dev))
+        _check(lib().plslam_voc_bowvec_batch_device(_vp(fv["word"]), _vp(fv["weight"]), _vp(d_counts), B, cap, _vp(out["bow_ids"]),
+                                                    _vp(out["bow_vals"]), _vp(out["bow_count"]), _stream_ptr(stream)))
+        return out
 
 
 def assemble_bow(word, weight, node):
-    """BowVector::addWeight in feature order + normalize(L1); FeatureVector::addFeature (TemplatedVocabulary.h:1151-1217)."""
+    """Host restatement of the assembly (BowVector::addWeight in feature order + normalize(L1); FeatureVector::addFeature,
+    TemplatedVocabulary.h:1151-1217): test helper only — ORBVocabulary.transform() runs the device kernels."""
     bow, fv = {}, {}
     for i in range(len(word)):
         w = float(weight[i])
@@ -676,7 +701,8 @@ def frame_post_host(calib, bounds, keypoints, depth):
     return dict(un_xy=un, uright=ur, depth=z, grid_start=gs, grid_items=gi[:gs[-1]])
 
 
-def search_by_projection_host(last, cur, cam, scale_factors, tcw_cur, tcw_last, th, mono=False, check_ori=True):
+def search_by_projection_host(last, cur, cam, scale_factors, tcw_cur, tcw_last, th, mono=False, check_ori=True,
+                              report_removed=False):
     """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on host arrays (dict layout of tests/matchdata.py)
     through plslam_match_projection_host -> (match_cur, nmatches)."""
     keep = {k: np.ascontiguousarray(v) for k, v in list(last.items()) + [("c_" + k, v) for k, v in cur.items()]}
@@ -691,6 +717,7 @@ def search_by_projection_host(last, cur, cam, scale_factors, tcw_cur, tcw_last, 
     j.tcw_cur[:] = np.asarray(tcw_cur, np.float32).ravel().tolist()
     j.tcw_last[:] = np.asarray(tcw_last, np.float32).ravel().tolist()
     j.th = float(th); j.n1 = n1; j.n2 = n2; j.mono = int(mono); j.check_orientation = int(check_ori)
+    j.report_removed = int(report_removed)
     _check(lib().plslam_match_projection_host(C.byref(j), len(sf)))
     return m[:n2], int(n[0])
 

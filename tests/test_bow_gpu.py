@@ -103,6 +103,7 @@ def test_c4_device_chain_extract_bow_search(oracle, voc):
     ex = pl.ORBextractor()
     d_kps, d_desc, d_cnt = ex.extract_batch_device(torch.from_numpy(imgs).cuda())
     fv = V.featvec_batch_device(d_desc, d_cnt, levelsup=2)
+    bv = V.bowvec_batch_device(fv, d_cnt)  # Frame::mBowVec of every frame, accumulated and normalised on the device
     res = pl.bow_pairs_device(d_kps, d_desc, d_cnt, fv, nnratio=0.7, check_ori=True)
     torch.cuda.synchronize()
     cnt = d_cnt.cpu().numpy()
@@ -118,6 +119,10 @@ def test_c4_device_chain_extract_bow_search(oracle, voc):
         assert np.array_equal(fv["fv_start"][f, :nn + 1].cpu().numpy(), t["fv_start"])
         m = int(t["fv_start"][-1])
         assert np.array_equal(fv["fv_idx"][f, :m].cpu().numpy(), t["fv_idx"].astype(np.int32))
+        nb = int(bv["bow_count"][f])
+        assert nb == len(t["bow_ids"])
+        assert np.array_equal(bv["bow_ids"][f, :nb].cpu().numpy(), t["bow_ids"].astype(np.int32))
+        assert np.array_equal(bv["bow_vals"][f, :nb].cpu().numpy(), t["bow_vals"])  # bit-identical doubles
         feats.append((k, d, t))
     total = 0
     for p in range(3):

@@ -54,3 +54,82 @@ def test_cpp_classes_match_oracle(oracle, tmp_path):
         x = np.sort(np.asarray(x, np.float64)); m = x[len(x) // 2]
         return 1.4826 * np.sort(np.abs(x - m))[len(x) // 2]
     assert mads[0] == mad(knn[:, 1]) and mads[1] == mad(knn[:, 3] - knn[:, 1])
+
+
+def test_matchers_through_the_reference_signatures(oracle, tmp_path):
+    """ORB_SLAM2::ORBmatcher called with the reference's own signatures (include/ORBmatcher.h:61, :78, :104, :111) on mock
+    Frame / KeyFrame / MapPoint classes carrying the reference's member names (host/dropin_matchers_demo.cc): what the
+    calls leave in the objects (mvpMapPoints, vpMapPointMatches, vMatchedPairs, return values) must equal the flattened
+    C-ABI calls on the same arrays — which tests/test_golden_gpu.py pins against the reference's machine code."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import plslam_b200 as pl
+    from matchdata import fake_feature_vector, local_points_case, projection_case, triangulation_case
+    from plslam_b200.synth import synth_frame, synth_pair
+    demo = os.path.join(ROOT, "rgbd-pl-slam_b200", "host", "dropin_matchers_demo")
+    assert os.path.exists(demo), "build the veneer: make -C rgbd-pl-slam_b200/host"
+    d = tmp_path
+
+    def put(name, a, dtype=None):
+        np.ascontiguousarray(a, dtype).tofile(d / name)
+
+    orc = oracle.OrbOracle()
+    sf = orc.tables()["scale"]
+    a, b = synth_pair(21)
+    (ka, da), (kb, db) = orc.extract(a), orc.extract(b)
+    # TrackWithMotionModel
+    last, cur, cam, _, tc, tl = projection_case(ka, da, kb, db, sf, seed=21, motion=0.02)
+    for k, v in last.items():
+        put("pj_last_" + k, v)
+    for k, v in cur.items():
+        put("pj_cur_" + k, v)
+    put("pj_cam", cam, np.float32); put("pj_sf", sf, np.float32); put("pj_tc", tc, np.float32); put("pj_tl", tl, np.float32)
+    put("pj_par", [7.0, 0.0], np.float32)
+    # SearchLocalPoints
+    mp, fr, cam4 = local_points_case(ka, da, kb, db, seed=5, jitter=3.0)
+    for k, v in mp.items():
+        put("lp_mp_" + k, v)
+    for k, v in fr.items():
+        put("lp_fr_" + k, v)
+    put("lp_cam4", cam4, np.float32); put("lp_sf", sf, np.float32); put("lp_par", [3.0, 0.8], np.float32)
+    # TrackReferenceKeyFrame
+    rng = np.random.default_rng(3)
+    kf = dict(desc=da, angle=np.ascontiguousarray(ka["angle"]), valid=(rng.random(len(da)) < 0.85).astype(np.uint8))
+    kf["nodes"], kf["start"], kf["idx"] = fake_feature_vector(da, seed=7)
+    f = dict(desc=db, angle=np.ascontiguousarray(kb["angle"]))
+    f["nodes"], f["start"], f["idx"] = fake_feature_vector(db, seed=7)
+    for k, v in kf.items():
+        put("bw_kf_" + k, v)
+    for k, v in f.items():
+        put("bw_f_" + k, v)
+    put("bw_par", [0.7, 1.0], np.float32)
+    # CreateNewMapPoints
+    kps, desc = orc.extract(synth_frame(33))
+    kf1, kf2, F12, pose, camt, sft, sg = triangulation_case(kps, desc, seed=33, stereo_fraction=0.5)
+    for k, v in kf1.items():
+        put("tr_kf1_" + k, v)
+    for k, v in kf2.items():
+        put("tr_kf2_" + k, v)
+    put("tr_F12", F12, np.float32); put("tr_R2w", pose[0], np.float32); put("tr_t2w", pose[1], np.float32); put("tr_Cw", pose[2], np.float32)
+    put("tr_sf", sft, np.float32); put("tr_sg", sg, np.float32); put("tr_par", list(camt) + [0.0, 1.0], np.float32)
+
+    r = subprocess.run([demo, str(d)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+    # expectations: the flattened calls on the same arrays
+    m, n = pl.search_by_projection_host(last, cur, cam, sf, tc, tl, 7.0, False, True, report_removed=True)
+    out = np.fromfile(d / "pj_out", np.int32)
+    had = (np.arange(len(m)) % 7 == 0) & (cur["taken"] == 0)  # the demo's unobserved map points
+    want = np.where(m >= 0, m, np.where((m == -2) & had, -2, -1))
+    assert out[-1] == n > 50 and np.array_equal(out[:-1], want)
+    m, n = pl.search_local_points_host(mp, fr, cam4, sf, 3.0, 0.8)
+    out = np.fromfile(d / "lp_out", np.int32)
+    assert out[-1] == n > 100 and np.array_equal(out[:-1], m)
+    em, en = oracle.search_by_bow(kf, f, 0.7, True)  # (the kernel equals the oracle: tests/test_match_gpu.py)
+    out = np.fromfile(d / "bw_out", np.int32)
+    assert out[-1] == en > 50 and np.array_equal(out[:-1], em)
+    ex, ey = pl.epipole(*pose, *camt)
+    m12, n12, pairs = pl.search_for_triangulation_host(kf1, kf2, F12, ex, ey, sft, sg, False, True)
+    out = np.fromfile(d / "tr_out", np.int32)
+    assert out[-1] == n12 > 50
+    assert np.array_equal(out[:-1].reshape(-1, 2), np.asarray(pairs, np.int32).reshape(-1, 2))

@@ -282,6 +282,25 @@ def test_search_by_projection_equals_the_reference_matcher(oracle):
     assert total > 3000
 
 
+def test_search_by_projection_window_edge_cases_equal_the_reference_matcher(oracle):
+    """The same function on projection_boundary.npz: current key points planted within one ulp of the search window's edge
+    (in x, and in the stereo coordinate), where an evaluation of the projection other than the binary's — float division
+    @0x81c92, fused multiply-adds @0x81cba / @0x81cd9 / @0x81eb5, cv::gemm's float sums — decides differently (the double
+    evaluation of round 1 fails every one of these cases).  Expected results: the reference's own code
+    (tests/golden/make_projection_boundary.py)."""
+    g = np.load(os.path.join(G, "projection_boundary.npz"))
+    planted = 0
+    for k in range(int(g["n"])):
+        last = {n[len("c%d_last_" % k):]: g[n] for n in g.files if n.startswith("c%d_last_" % k)}
+        cur = {n[len("c%d_cur_" % k):]: g[n] for n in g.files if n.startswith("c%d_cur_" % k)}
+        a = g["c%d_args" % k]
+        m, n = oracle.search_by_projection(last, cur, g["c%d_cam" % k], g["c%d_sf" % k], g["c%d_tc" % k], g["c%d_tl" % k],
+                                           float(a[2]), bool(a[3]), True)
+        assert n == int(g["c%d_n" % k]) and np.array_equal(m, g["c%d_match" % k]), k
+        planted += int(a[4])
+    assert planted > 2000
+
+
 def test_search_for_triangulation_equals_the_reference_matcher(oracle):
     """ORBmatcher::SearchForTriangulation (@0x86b30) executed from lib/libORB_SLAM2.so on faked KeyFrame objects — the reference
     computes its own epipole through KeyFrame's pose getters — against the oracle fed with oracle.epipole (fixture

@@ -78,3 +78,131 @@ def test_orb_extractor_equals_the_reference_library():
         assert np.array_equal(desc, g["ex%d_desc" % k]), k
         done += 1
     assert done == 3
+
+
+# ------------------------------------------------------------------------------------------------
+# The matcher KERNELS directly against outputs of the reference's own machine code (reference_library.npz,
+# projection_boundary.npz): the inputs are rebuilt from the seeds with the CUDA extractor (it equals the oracle bit for
+# bit, tests/test_orb_gpu.py), no oracle call is involved.
+# ------------------------------------------------------------------------------------------------
+def _features(seed, cache={}):
+    import plslam_b200 as pl
+    from plslam_b200.synth import synth_pair
+    if seed not in cache:
+        a, b = synth_pair(seed)
+        ex = pl.ORBextractor()
+        cache[seed] = (ex(a), ex(b))
+    return cache[seed]
+
+
+def _scale_factors():
+    import plslam_b200 as pl
+    return np.asarray(pl.ORBextractor().GetScaleFactors(), np.float32)
+
+
+def test_k_projection_equals_the_reference_matcher():
+    """k_projection (ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono), @0x80d00) on the pj* fixtures."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import plslam_b200 as pl
+    from matchdata import projection_case
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    sf = _scale_factors()
+    total = 0
+    for k in range(int(g["pj_n"])):
+        seed, motion, th, mono = g["pj%d_args" % k]
+        (ka, da), (kb, db) = _features(int(seed))
+        last, cur, cam, _, tc, tl = projection_case(ka, da, kb, db, sf, seed=int(seed), motion=float(motion))
+        m, n = pl.search_by_projection_host(last, cur, cam, sf, tc, tl, float(th), bool(mono), True)
+        assert n == int(g["pj%d_n" % k]) and np.array_equal(m, g["pj%d_match" % k]), k
+        total += n
+    assert total > 3000
+
+
+def test_k_projection_on_window_edge_cases_equals_the_reference_matcher():
+    """k_projection on projection_boundary.npz: current key points planted within one ulp of the search window's edge, where
+    an evaluation of the projection that is not the binary's (float division, fused multiply-adds, float gemm sums) decides
+    differently; expected results come from the reference's own code (tests/golden/make_projection_boundary.py)."""
+    import plslam_b200 as pl
+    g = np.load(os.path.join(G, "projection_boundary.npz"))
+    planted = 0
+    for k in range(int(g["n"])):
+        last = {n[len("c%d_last_" % k):]: g[n] for n in g.files if n.startswith("c%d_last_" % k)}
+        cur = {n[len("c%d_cur_" % k):]: g[n] for n in g.files if n.startswith("c%d_cur_" % k)}
+        a = g["c%d_args" % k]
+        m, n = pl.search_by_projection_host(last, cur, g["c%d_cam" % k], g["c%d_sf" % k], g["c%d_tc" % k], g["c%d_tl" % k],
+                                            float(a[2]), bool(a[3]), True)
+        assert n == int(g["c%d_n" % k]) and np.array_equal(m, g["c%d_match" % k]), k
+        planted += int(a[4])
+    assert planted > 2000
+
+
+def test_k_local_points_equals_the_reference_matcher():
+    """k_local_points (ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), @0x79f10) on the lp* fixtures."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import plslam_b200 as pl
+    from matchdata import local_points_case
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    sf = _scale_factors()
+    for k in range(int(g["lp_n"])):
+        seed, th, nnr, jit = g["lp%d_args" % k]
+        (ka, da), (kb, db) = _features(int(seed))
+        mp, fr, cam4 = local_points_case(ka, da, kb, db, seed=10 * int(seed) + int(th), jitter=float(jit))
+        m, n = pl.search_local_points_host(mp, fr, cam4, sf, float(th), float(nnr))
+        assert n == int(g["lp%d_n" % k]) > 300 and np.array_equal(m, g["lp%d_match" % k]), k
+
+
+def test_k_bow_equals_the_reference_matcher():
+    """k_bow (ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), @0x80150) on the bw* fixtures."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import plslam_b200 as pl
+    from matchdata import fake_feature_vector
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    jobs, keep = [], []
+    for k in range(int(g["bw_n"])):
+        seed, nnr, ori, nbits = g["bw%d_args" % k]
+        (ka, da), (kb, db) = _features(int(seed))
+        kf = dict(desc=da, angle=np.ascontiguousarray(ka["angle"]), valid=g["bw%d_valid" % k])
+        kf["nodes"], kf["start"], kf["idx"] = fake_feature_vector(da, int(nbits), seed=7)
+        f = dict(desc=db, angle=np.ascontiguousarray(kb["angle"]))
+        f["nodes"], f["start"], f["idx"] = fake_feature_vector(db, int(nbits), seed=7)
+        d, e = {n: dev(v) for n, v in kf.items()}, {n: dev(v) for n, v in f.items()}
+        m = torch.empty(len(db), dtype=torch.int32, device="cuda")
+        n = torch.zeros(1, dtype=torch.int32, device="cuda")
+        keep.append((d, e, m, n))
+        jobs.append(pl.BowJob(d["desc"].data_ptr(), d["angle"].data_ptr(), d["valid"].data_ptr(), d["nodes"].data_ptr(),
+                              d["start"].data_ptr(), d["idx"].data_ptr(), e["desc"].data_ptr(), e["angle"].data_ptr(),
+                              e["nodes"].data_ptr(), e["start"].data_ptr(), e["idx"].data_ptr(), m.data_ptr(), n.data_ptr(),
+                              len(da), len(db), len(kf["nodes"]), len(f["nodes"]), float(nnr), int(ori)))
+    pl.bow_batch_device(jobs, max(max(j.n1, j.n2) for j in jobs), "cuda")
+    torch.cuda.synchronize()
+    for k, (_, _, m, n) in enumerate(keep):
+        assert int(n) == int(g["bw%d_n" % k]) > 200 and np.array_equal(m.cpu().numpy(), g["bw%d_match" % k]), k
+
+
+def test_k_triangulation_equals_the_reference_matcher():
+    """k_triangulation (ORBmatcher::SearchForTriangulation, @0x86b30, epipole included) on the tr* fixtures."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import plslam_b200 as pl
+    from matchdata import triangulation_case
+    from plslam_b200.synth import synth_frame
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    cases, total = {}, 0
+    for k in range(int(g["tr_n"])):
+        a = g["tr%d_args" % k]
+        seed, only, ori, nbits = int(a[0]), bool(a[1]), bool(a[2]), int(a[4])
+        key = (seed, float(a[3]), nbits, tuple(a[5:8]))
+        if key not in cases:
+            kps, desc = pl.ORBextractor()(synth_frame(seed))
+            cases[key] = triangulation_case(kps, desc, seed=seed, stereo_fraction=float(a[3]), nbits=nbits, t21=tuple(a[5:8]))
+        kf1, kf2, F12, pose, cam, sf, sg = cases[key]
+        ex, ey = pl.epipole(*pose, *cam)
+        m, n, _ = pl.search_for_triangulation_host(kf1, kf2, F12, ex, ey, sf, sg, only, ori)
+        assert n == int(g["tr%d_n" % k]) and np.array_equal(m, g["tr%d_match" % k]), k
+        total += n
+    assert total > 1500
