@@ -492,10 +492,9 @@ int plslam_voc_featvec_batch_device(const plslam_voc_t* h, const uint8_t* d_desc
   int npow2 = 32;
   while (npow2 < capacity) npow2 <<= 1;
   const size_t smem = (size_t)npow2 * 12 + 33 * 4;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     PL_CUDA(cudaFuncSetAttribute(k_featvec_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   PL_CARVEOUT(k_featvec_csr);
   k_featvec_csr<<<frames, 256, smem, st>>>(d_node, d_weight, d_counts, capacity, npow2, d_fv_nodes, d_fv_start, d_fv_idx,
@@ -511,13 +510,8 @@ int plslam_voc_bowvec_batch_device(const int32_t* d_word, const double* d_weight
   int npow2 = 32;
   while (npow2 < capacity) npow2 <<= 1;
   const size_t smem = (size_t)npow2 * 12 + 33 * 4;
-  int dev = 0;
-  PL_CUDA(cudaGetDevice(&dev));
-  static bool attr[64] = {};
-  if (dev < 64 && !attr[dev]) {
-    PL_CUDA(cudaFuncSetAttribute(k_bowvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr[dev] = true;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first()) PL_CUDA(cudaFuncSetAttribute(k_bowvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PL_CARVEOUT(k_bowvec);
   k_bowvec<<<frames, 256, smem, (cudaStream_t)stream>>>(d_word, d_weight, d_counts, capacity, npow2, d_bow_ids, d_bow_vals,
                                                         d_bow_count);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -37,14 +38,24 @@ void set_error(const char* fmt, ...);
 // beside the long region-growing kernels of other batches.  PLSLAM_CARVEOUT (percent of shared memory, -1 = leave
 // the driver's per-kernel choice) overrides the default.
 int carveout_pct();
+// cudaFuncSetAttribute applies to the CURRENT device only: a flag per call site AND device (thread-safe), so that a second
+// GPU used from the same process gets its opt-in to large dynamic shared memory and its carve-out preference too.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done[2];
+  PerDeviceOnce() { done[0] = 0; done[1] = 0; }
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return true;
+    d &= 127;
+    const unsigned long long bit = 1ull << (d & 63);
+    return !(done[d >> 6].fetch_or(bit) & bit);
+  }
+};
 #define PL_CARVEOUT(kernel)                                                                                   \
   do {                                                                                                        \
-    static bool _pl_done = false;                                                                             \
-    if (!_pl_done) {                                                                                          \
-      if (::plslam::carveout_pct() >= 0)                                                                      \
-        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ::plslam::carveout_pct()); \
-      _pl_done = true;                                                                                        \
-    }                                                                                                         \
+    static ::plslam::PerDeviceOnce _pl_once;                                                                  \
+    if (_pl_once.first() && ::plslam::carveout_pct() >= 0)                                                    \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ::plslam::carveout_pct()); \
   } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -212,6 +212,9 @@ struct Slot {
     d.line_matches = match_pairs ? dLineM.as<int32_t>() : nullptr;
     rc = process_device(dst, batch, W, H, (int)dpitch, dstride, d, match_pairs, st, timing);
     if (rc) return rc;
+    // the kernels that read dIn[b] are all enqueued (process_device joins its two branches back into st): the next upload
+    // into this buffer waits for this event
+    if (sUp) PL_CUDA(cudaEventRecord(evFree[b], st));
 
     if (!(dbgSkip & 2)) {
     PL_CUDA(cudaMemcpyAsync(io.keypoints, d.keypoints, (size_t)batch * kpCap * sizeof(plslam_keypoint_t), cudaMemcpyDeviceToHost, st));

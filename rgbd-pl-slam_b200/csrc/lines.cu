@@ -2259,11 +2259,19 @@ int LineExtractor::configure(int W, int H, int batch) {
   if ((rc = resp.ensure(B * P.rect_cap * sizeof(float)))) return rc;
   if ((rc = rowsum.ensure(B * P.out_cap * LBD_ROWS * 4 * sizeof(float)))) return rc;
   if ((rc = status.ensure(sizeof(int)))) return rc;
-  PL_CUDA(cudaMemset(status.p, 0, sizeof(int)));
+  if (!statusArmed) {  // the status word is sticky (kernels only raise it): cleared when it is created, never on a reconfigure
+    PL_CUDA(cudaMemset(status.p, 0, sizeof(int)));
+    statusArmed = true;
+  }
   PL_CHECK_ARG(P.sw < 65536 && P.sh < 32768);
-  PL_CARVEOUT(k_lsd_lgamma_table);
-  k_lsd_lgamma_table<<<div_up(LGAMMA_TABLE, 256), 256>>>();
-  PL_CUDA(cudaDeviceSynchronize());
+  {  // the log-gamma table is a __device__ global shared by every extractor of the process: built once per device
+    static PerDeviceOnce tab;
+    if (tab.first()) {
+      PL_CARVEOUT(k_lsd_lgamma_table);
+      k_lsd_lgamma_table<<<div_up(LGAMMA_TABLE, 256), 256>>>();
+      PL_CUDA(cudaDeviceSynchronize());
+    }
+  }
   cfgW = W;
   cfgH = H;
   cfgB = (int)B;
@@ -2339,11 +2347,10 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
     PL_CUDA(cudaMemsetAsync(owner.p, 0xff, (size_t)batch * P.P * sizeof(unsigned), st));
 #define PL_SW_LAUNCH(KK, WW)                                                                                                  \
   do {                                                                                                                        \
-    static bool attr = false;                                                                                                 \
-    if (!attr) {                                                                                                              \
+    static PerDeviceOnce attr;                                                                                                \
+    if (attr.first()) {                                                                                                       \
       PL_CUDA(cudaFuncSetAttribute(k_lsd_grow_sw<KK, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,                        \
                                    (int)sw_smem_bytes<KK, WW>()));                                                            \
-      attr = true;                                                                                                            \
     }                                                                                                                         \
     k_lsd_grow_sw<KK, WW><<<batch, 32 * KK, sw_smem_bytes<KK, WW>(), st>>>(                                                   \
         P, pix.as<uint4>(), owner.as<unsigned>(), seeds.as<unsigned>(), nseeds.as<int>(), regbuf.as<unsigned>(),              \

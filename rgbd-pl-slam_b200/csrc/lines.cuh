@@ -70,6 +70,7 @@ class LineExtractor {
   DevBuf stageIn, stageKl, stageDesc, stageFuncs, stageCnt;
   cudaStream_t ownStream = nullptr;
   void* pinnedStatus = nullptr;
+  bool statusArmed = false;
 };
 
 }  // namespace plslam

@@ -592,11 +592,10 @@ int plslam_match_bow_batch_device(const plslam_bow_job_t* d_jobs, int njobs, int
   // shared: matchF[n2] + entryIdx[n1] + entryBin[n1]; n1 is bounded by the caller's max_n2-style capacity
   const size_t smem = (size_t)max_n2 * 4 * 3;
   PL_CHECK_ARG(smem <= 200 * 1024);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     PL_CUDA(cudaFuncSetAttribute(k_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PL_CUDA(cudaFuncSetAttribute(k_projection, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   PL_CARVEOUT(k_bow);
   k_bow<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
@@ -608,11 +607,10 @@ int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int nj
   PL_CHECK_ARG(d_jobs && njobs >= 1 && max_n1 >= 0 && max_n2 >= 0);
   const size_t smem = (size_t)max_n2 * 4 + (size_t)max_n1 * 8 + (size_t)max_n2 + 16;
   PL_CHECK_ARG(smem <= 200 * 1024);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     PL_CUDA(cudaFuncSetAttribute(k_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PL_CUDA(cudaFuncSetAttribute(k_projection, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   PL_CARVEOUT(k_projection);
   k_projection<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
@@ -680,10 +678,9 @@ int plslam_match_triangulation_batch_device(const plslam_tri_job_t* d_jobs, int 
   PL_CHECK_ARG(d_jobs && njobs >= 1 && max_n >= 0);
   const size_t smem = (size_t)max_n * 4 * 3;  // matched2[n2] + entryIdx[n1] + entryBin[n1]
   PL_CHECK_ARG(smem <= 200 * 1024);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     PL_CUDA(cudaFuncSetAttribute(k_triangulation, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   PL_CARVEOUT(k_triangulation);
   k_triangulation<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
@@ -781,10 +778,9 @@ int plslam_match_local_points_batch_device(const plslam_local_job_t* d_jobs, int
   PL_CHECK_ARG(d_jobs && njobs >= 1 && max_n >= 0);
   const size_t smem = (size_t)max_n * 5 + 16;  // matchF[n] ints + taken[n] bytes
   PL_CHECK_ARG(smem <= 200 * 1024);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     PL_CUDA(cudaFuncSetAttribute(k_local_points, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   PL_CARVEOUT(k_local_points);
   k_local_points<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ OrbParam
 // maxima are found once and the threshold only selects among them.
 //
 // Candidate record (64 bit): [63:56] response+1 (=s), [55:28] list-order key, [27:14] Y, [13:0] X
-// (X, Y border-local).  key = ((cellRow*256 + cellCol)*64 + yLocal)*64 + xLocal reproduces the
+// (X, Y border-local).  key = ((cellRow*nCols + cellCol)*(hCell+6) + yLocal)*(wCell+6) + xLocal reproduces the
 // reference list order (cell-major, then FAST's row-major) without ordered writes.
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_LIST_CAP = 512;                  // survivor list entries per cell (warp)
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams 
       const unsigned m = __ballot_sync(FULL, emit);
       if (emit) {
         const int y = q / pp, x = q - y * pp - shift;
-        const unsigned key = (((unsigned)(ci * 256 + cj) * 64u + (unsigned)y) * 64u + (unsigned)x);
+        const unsigned key = (((unsigned)(ci * L.nCols + cj) * (unsigned)(L.hCell + 6) + (unsigned)y) * (unsigned)(L.wCell + 6) + (unsigned)x);
         const unsigned X = x + cj * L.wCell, Y = y + ci * L.hCell;
         out[wr + __popc(m & lt)] =
             ((unsigned long long)keep << 56) | ((unsigned long long)key << 28) | ((unsigned long long)Y << 14) | X;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbParams 
         if ((e >> (8 * k)) & 1u) {
           const int x = 4 * w + k - shift;
           const unsigned keep = (kw >> (8 * k)) & 0xffu;
-          const unsigned key = (((unsigned)(ci * 256 + cj) * 64u + (unsigned)y) * 64u + (unsigned)x);
+          const unsigned key = (((unsigned)(ci * L.nCols + cj) * (unsigned)(L.hCell + 6) + (unsigned)y) * (unsigned)(L.wCell + 6) + (unsigned)x);
           const unsigned X = x + cj * L.wCell, Y = y + ci * L.hCell;
           out[at++] = ((unsigned long long)keep << 56) | ((unsigned long long)key << 28) | ((unsigned long long)Y << 14) | X;
         }
@@ -629,7 +629,10 @@ __global__ void __launch_bounds__(256) k_quadtree(const __grid_constant__ OrbPar
     const unsigned long long v = best[i];
     const unsigned key = 0x0fffffffu - (unsigned)(v & 0x0fffffffull);
     const int s = (int)(v >> 28);
-    const int xl = key & 63, yl = (key >> 6) & 63, cj = (key >> 12) & 255, ci = key >> 20;
+    const unsigned wSpan = (unsigned)(L.wCell + 6), hSpan = (unsigned)(L.hCell + 6);
+    const int xl = (int)(key % wSpan), yl = (int)((key / wSpan) % hSpan);
+    const unsigned cellIdx = key / (wSpan * hSpan);
+    const int cj = (int)(cellIdx % (unsigned)L.nCols), ci = (int)(cellIdx / (unsigned)L.nCols);
     const int X = xl + cj * L.wCell + ORB_MINB, Y = yl + ci * L.hCell + ORB_MINB;
     out[i] = make_uint2((unsigned)X | ((unsigned)Y << 16), (unsigned)(s - 1));
   }
@@ -1042,7 +1045,10 @@ int OrbExtractor::configure(int W, int H, int batch) {
       L.nCols = L.nRows = 0;
       L.wCell = L.hCell = 1;
     }
-    PL_CHECK_ARG(L.nCols < 256 && L.nRows < 256 && L.wCell + 6 <= 64 && L.hCell + 6 <= 64);
+    // a level with a single column (row) of cells has cells of up to 59 px; the list-order key is mixed-radix over
+    // (cell, y, x) and must fit its 28 bits, the staged tile its shared memory
+    PL_CHECK_ARG(L.wCell + 6 <= 128 && L.hCell + 6 <= 128);
+    PL_CHECK_ARG((unsigned long long)std::max(L.nCols * L.nRows, 1) * (L.wCell + 6) * (L.hCell + 6) < (1ull << 28));
     maxPw = std::max(maxPw, L.wCell + 6);
     maxPh = std::max(maxPh, L.hCell + 6);
     L.cellBase = cellBase;
@@ -1170,11 +1176,10 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
   PL_STAGE_END(timer, st);
   {
     const size_t smem = 8 * (2 * (size_t)P.patchPitch * P.patchRows + FAST_QUEUE_BYTES);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
       PL_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       PL_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
     }
     PL_STAGE_BEGIN(timer, "orb_fast", st);
     PL_CARVEOUT(k_fast);

@@ -42,7 +42,9 @@ def test_stages_and_end_to_end_640x480(oracle):
     assert len(g_kps) >= 1000
 
 
-@pytest.mark.parametrize("shape", [(480, 640), (720, 1280), (250, 333)])
+# (303, 401): level 7 is 112 x 85, one ROW of FAST cells 59 px high (cells wider than 58 px were rejected in round 1);
+# (200, 270): single rows / columns of cells on several levels
+@pytest.mark.parametrize("shape", [(480, 640), (720, 1280), (250, 333), (303, 401), (200, 270)])
 def test_batch_parity(oracle, shape):
     from plslam_b200.synth import synth_frame
     H, W = shape
