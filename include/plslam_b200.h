@@ -152,6 +152,12 @@ int plslam_lines_scaled_size(const plslam_lines_t* h, int* width, int* height);
 int plslam_lines_copy_scaled(plslam_lines_t* h, int frame, uint8_t* out, size_t out_bytes);
 int plslam_lines_copy_level_lines(plslam_lines_t* h, int frame, float* degrees, int32_t* grad2, size_t count);
 int plslam_lines_copy_segments(plslam_lines_t* h, int frame, double* seg7, int capacity, int* n_out);
+/* BinaryDescriptor::compute(image, keylines, descriptors) (OpenCV-contrib line_descriptor; the second half of
+ * LineSegment::ExtractLineSegment, include/ExtractLineSegment.h:38): the 32 LBD bytes of each of n GIVEN key lines of a
+ * host image (only the KeyLine fields the descriptor reads matter: sPointInOctave / ePointInOctave, angle, numOfPixels).
+ * Host pointers; synchronous. */
+int plslam_lines_compute_lbd(plslam_lines_t* h, const uint8_t* image, int width, int height, int pitch,
+                             const plslam_keyline_t* keylines, int n, uint8_t* descriptors);
 /* Profiling aid: reads and clears the 32 device-side counters of the speculative region-growing scheduler
  * (k_lsd_grow_aw: regions issued / void / squashed while running / squashed after finishing / inserted, rectangles,
  * validation chunks, scheduler idle polls, worker idle polls, blocked seeds, pick chunks, frames, then cycle
@@ -268,6 +274,29 @@ typedef struct plslam_local_job {
 } plslam_local_job_t;
 int plslam_match_local_points_batch_device(const plslam_local_job_t* d_jobs, int njobs, int max_n, void* stream); /* max_n >= every job's n */
 int plslam_match_local_points_host(const plslam_local_job_t* job, int n_scale_levels);
+
+/* ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched, vector<int>& vnMatches12,
+ * int windowSize) (ORBmatcher.h:108, @0x7db00) — the monocular-initialisation matcher, including
+ * Frame::GetFeaturesInArea(x, y, windowSize, 0, 0) on F2's grid.  Only level-0 key points of F1 take part. */
+typedef struct plslam_init_job {
+  const int32_t* f1_octave;    /* N1 : F1.mvKeysUn[i].octave */
+  const float* f1_angle;       /* N1 : F1.mvKeysUn[i].angle */
+  const uint8_t* f1_desc;      /* N1 x 32 */
+  const float* f2_xy;          /* N2 x 2 : F2.mvKeysUn[i].pt */
+  const float* f2_angle;       /* N2 */
+  const int32_t* f2_octave;    /* N2 : F2.mvKeysUn[i].octave (only level 0 is searched) */
+  const uint8_t* f2_desc;      /* N2 x 32 */
+  const int32_t* grid_start;   /* 64*48+1 : CSR of F2.mGrid in [ix][iy] order */
+  const int32_t* grid_items;
+  float* prev_matched;         /* N1 x 2 : vbPrevMatched, read as the window centres and updated in place for the matches */
+  int32_t* match12;            /* N1 : vnMatches12 (F2 key point matched to each F1 key point, -1 = none) */
+  int32_t* nmatches;           /* 1  : return value */
+  float cam[4];                /* F2: mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv */
+  float nnratio;               /* mfNNratio */
+  int32_t window_size, n1, n2, check_orientation;
+} plslam_init_job_t;
+int plslam_match_initialization_batch_device(const plslam_init_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream);
+int plslam_match_initialization_host(const plslam_init_job_t* job); /* HOST pointers inside *job */
 
 /* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vector<pair<size_t,size_t>>&
  * vMatchedPairs, bool bOnlyStereo) (ORBmatcher.h:86, @0x86b30) with CheckDistEpipolarLine (ORBmatcher.h:89, @0x79b90).

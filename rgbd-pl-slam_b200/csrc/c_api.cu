@@ -207,6 +207,11 @@ int plslam_lines_copy_level_lines(plslam_lines_t* h, int frame, float* degrees, 
   PL_CHECK_ARG(h);
   return h->impl.copy_angles(frame, degrees, grad2, count);
 }
+int plslam_lines_compute_lbd(plslam_lines_t* h, const uint8_t* image, int width, int height, int pitch,
+                             const plslam_keyline_t* keylines, int n, uint8_t* descriptors) {
+  PL_CHECK_ARG(h);
+  return h->impl.compute_lbd_host(image, width, height, pitch, keylines, n, descriptors);
+}
 int plslam_lines_copy_segments(plslam_lines_t* h, int frame, double* seg7, int capacity, int* n_out) {
   PL_CHECK_ARG(h && n_out);
   std::vector<LsdSegment> v(capacity > 0 ? capacity : 1);

@@ -2440,6 +2440,42 @@ int LineExtractor::extract_host(const uint8_t* images, int batch, int W, int H, 
   return PLSLAM_OK;
 }
 
+// BinaryDescriptor::compute(image, keylines, descriptors) of OpenCV-contrib line_descriptor, as ExtractLineSegment calls
+// it (reference include/ExtractLineSegment.h:38): the LBD bytes of GIVEN key lines (host arrays in, host bytes out).
+int LineExtractor::compute_lbd_host(const uint8_t* image, int W, int H, int pitch, const plslam_keyline_t* keylines, int n,
+                                    uint8_t* desc) {
+  PL_CHECK_ARG(image && pitch >= W && n >= 0);
+  if (n == 0) return PLSLAM_OK;
+  PL_CHECK_ARG(keylines && desc && n <= 65535);
+  int rc = configure(W, H, 1);
+  if (rc) return rc;
+  const size_t dpitch = align_up(W, 32);
+  DevBuf dImg, dKl, dDesc, dCnt;
+  if ((rc = dImg.ensure(dpitch * H)) || (rc = dKl.ensure((size_t)n * sizeof(plslam_keyline_t))) || (rc = dDesc.ensure((size_t)n * 32)) ||
+      (rc = dCnt.ensure(sizeof(int)))) {
+    dImg.release(); dKl.release(); dDesc.release(); dCnt.release();
+    return rc;
+  }
+  cudaStream_t st = ownStream;
+  cudaError_t e = cudaMemcpy2DAsync(dImg.p, dpitch, image, pitch, W, H, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dKl.p, keylines, (size_t)n * sizeof(plslam_keyline_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dCnt.p, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    PL_CARVEOUT(k_lbd);
+    k_lbd<<<dim3(n, 1), 96, 0, st>>>(P, dImg.as<uint8_t>(), (int)dpitch, dpitch * H, dKl.as<plslam_keyline_t>(), dCnt.as<int>(),
+                                    dDesc.as<uint8_t>(), n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(desc, dDesc.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  dImg.release(); dKl.release(); dDesc.release(); dCnt.release();
+  if (e != cudaSuccess) {
+    set_error("compute_lbd: %s", cudaGetErrorString(e));
+    return PLSLAM_ERR_CUDA;
+  }
+  return PLSLAM_OK;
+}
+
 int LineExtractor::scaled_size(int* w, int* h) const {
   PL_CHECK_ARG(cfgW > 0);
   *w = P.sw;

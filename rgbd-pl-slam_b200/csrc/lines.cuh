@@ -54,6 +54,7 @@ class LineExtractor {
   int copy_scaled(int frame, uint8_t* out, size_t bytes);
   int copy_angles(int frame, float* deg_out, int32_t* g2_out, size_t n);
   int copy_segments(int frame, LsdSegment* out, int capacity, int* n_out);
+  int compute_lbd_host(const uint8_t* image, int W, int H, int pitch, const plslam_keyline_t* keylines, int n, uint8_t* desc);
 
   StageTimer* timer = nullptr;
   const int* device_status() const { return status.as<int>(); }

@@ -531,6 +531,113 @@ __global__ void __launch_bounds__(32) k_local_points(const plslam_local_job_t* _
   if (lane == 0) *J.nmatches = nmatches;
 }
 
+// ------------------------------------------------------------------------------------------
+// SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.h:108, @0x7db00), the monocular
+// initialisation matcher: one warp per frame pair walks F1's level-0 key points in order (a re-matched F2 key point
+// releases its earlier partner, so the scan is order dependent); lanes split the grid cells of the window around
+// vbPrevMatched[i1].  Sequential best / second-best with strict '<' over the candidates in [ix][iy][position] order =
+// the two smallest (distance, order) keys; a candidate whose recorded distance is <= the present one is skipped.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_search_init(const plslam_init_job_t* __restrict__ jobs) {
+  extern __shared__ int smem_i[];
+  const plslam_init_job_t& J = jobs[blockIdx.x];
+  const int lane = threadIdx.x;
+  const int N1 = J.n1, N2 = J.n2;
+  int* match12 = smem_i;             // [N1]
+  int* match21 = match12 + N1;       // [N2]
+  int* matchedDist = match21 + N2;   // [N2]
+  int* entryBin = matchedDist + N2;  // [N1] rotation-histogram bin of i1 (-1: never accepted)
+  __shared__ int hist[PLSLAM_HISTO_LENGTH];
+  for (int i = lane; i < N1; i += 32) { match12[i] = -1; entryBin[i] = -1; }
+  for (int i = lane; i < N2; i += 32) { match21[i] = -1; matchedDist[i] = 0x7fffffff; }
+  if (lane < PLSLAM_HISTO_LENGTH) hist[lane] = 0;
+  __syncwarp();
+  const float mnMinX = J.cam[0], mnMinY = J.cam[1], gwi = J.cam[2], ghi = J.cam[3];
+  const float radius = (float)J.window_size;
+  const uint4* D1 = reinterpret_cast<const uint4*>(J.f1_desc);
+  const uint4* D2 = reinterpret_cast<const uint4*>(J.f2_desc);
+  int nmatches = 0;
+  for (int i1 = 0; i1 < N1; ++i1) {
+    if (J.f1_octave[i1] > 0) continue;
+    const float x = J.prev_matched[2 * i1], y = J.prev_matched[2 * i1 + 1];
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, mnMinX), radius), gwi)));
+    if (nMinCellX >= PLSLAM_GRID_COLS) continue;
+    const int nMaxCellX = min(PLSLAM_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, mnMinX), radius), gwi)));
+    if (nMaxCellX < 0) continue;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, mnMinY), radius), ghi)));
+    if (nMinCellY >= PLSLAM_GRID_ROWS) continue;
+    const int nMaxCellY = min(PLSLAM_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, mnMinY), radius), ghi)));
+    if (nMaxCellY < 0) continue;
+    const int ncy = nMaxCellY - nMinCellY + 1, ncells = (nMaxCellX - nMinCellX + 1) * ncy;
+    const uint4 a0 = D1[2 * i1], a1 = D1[2 * i1 + 1];
+    // GetFeaturesInArea(x, y, windowSize, 0, 0): maxLevel = 0 >= 0 => bCheckLevels, only level-0 key points of F2 pass
+    unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;
+    int c1 = -1;
+    for (int c = lane; c < ncells; c += 32) {
+      const int ix = nMinCellX + c / ncy, iy = nMinCellY + c % ncy;
+      const int cell = ix * PLSLAM_GRID_ROWS + iy;
+      const int s0 = J.grid_start[cell], s1 = J.grid_start[cell + 1];
+      for (int j = s0; j < s1; ++j) {
+        const int i2 = J.grid_items[j];
+        if (J.f2_octave[i2] != 0) continue;
+        const float distx = __fsub_rn(J.f2_xy[2 * i2], x), disty = __fsub_rn(J.f2_xy[2 * i2 + 1], y);
+        if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
+        const int dist = hamming256(a0, a1, D2[2 * i2], D2[2 * i2 + 1]);
+        if (matchedDist[i2] <= dist) continue;
+        const unsigned key = ((unsigned)dist << 22) | ((unsigned)c << 8) | (unsigned)min(j - s0, 255);
+        if (key < k1) { k2 = k1; k1 = key; c1 = i2; }
+        else if (key < k2) { k2 = key; }
+      }
+    }
+    const unsigned g1 = warp_min_u32(k1);
+    if (g1 == 0xffffffffu) continue;  // (an empty window, or only candidates that are matched better already)
+    const int bestDist = (int)(g1 >> 22);
+    if (bestDist > PLSLAM_TH_LOW) continue;
+    const int src1 = __ffs(__ballot_sync(0xffffffffu, k1 == g1)) - 1;
+    const int bestIdx2 = __shfl_sync(0xffffffffu, c1, src1);
+    const unsigned mine2 = lane == src1 ? k2 : k1;
+    const unsigned g2 = warp_min_u32(mine2);
+    // bestDist2 stays INT_MAX without a runner-up: (float)INT_MAX * nnratio is far above any distance
+    const float lim = g2 == 0xffffffffu ? __fmul_rn(2147483648.f, J.nnratio) : __fmul_rn((float)(int)(g2 >> 22), J.nnratio);
+    if (!((float)bestDist < lim)) continue;
+    if (lane == 0) {
+      const int old = match21[bestIdx2];
+      if (old >= 0) match12[old] = -1;
+      match12[i1] = bestIdx2;
+      match21[bestIdx2] = i1;
+      matchedDist[bestIdx2] = bestDist;
+      if (J.check_orientation) {
+        const int bin = rot_bin_dev(J.f1_angle[i1], J.f2_angle[bestIdx2]);
+        hist[bin]++;
+        entryBin[i1] = bin;
+      }
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  if (J.check_orientation) {
+    int b1, b2, b3;
+    three_maxima_dev(hist, b1, b2, b3);
+    for (int i = lane; i < N1; i += 32) {
+      const int bin = entryBin[i];
+      if (bin >= 0 && bin != b1 && bin != b2 && bin != b3) match12[i] = -1;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < N1; i += 32) {
+    const int m = match12[i];
+    J.match12[i] = m;
+    if (m >= 0) {
+      ++nmatches;
+      J.prev_matched[2 * i] = J.f2_xy[2 * m];
+      J.prev_matched[2 * i + 1] = J.f2_xy[2 * m + 1];
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) nmatches += __shfl_xor_sync(0xffffffffu, nmatches, d);
+  if (lane == 0) *J.nmatches = nmatches;
+}
+
 }  // namespace
 }  // namespace plslam
 
@@ -815,6 +922,46 @@ int plslam_match_local_points_host(const plslam_local_job_t* job, int n_scale_le
   int rc = plslam_match_local_points_batch_device(dj, 1, n, nullptr);
   if (rc) return rc;
   PL_CUDA(cudaMemcpy(job->match_f, d.match_f, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int plslam_match_initialization_batch_device(const plslam_init_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream) {
+  PL_CHECK_ARG(d_jobs && njobs >= 1 && njobs <= 65535 && max_n1 >= 0 && max_n2 >= 0);
+  const size_t smem = ((size_t)2 * max_n1 + 2 * (size_t)max_n2) * 4;
+  PL_CHECK_ARG(smem <= 200 * 1024);
+  static PerDeviceOnce attr;
+  if (attr.first()) PL_CUDA(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PL_CARVEOUT(k_search_init);
+  k_search_init<<<njobs, 32, smem, (cudaStream_t)stream>>>(d_jobs);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_match_initialization_host(const plslam_init_job_t* job) {
+  PL_CHECK_ARG(job && job->match12 && job->nmatches && job->prev_matched && job->n1 >= 0 && job->n2 >= 0);
+  Uploader U;
+  plslam_init_job_t d = *job;
+  const int n1 = job->n1, n2 = job->n2, ncell = PLSLAM_GRID_COLS * PLSLAM_GRID_ROWS;
+  const int nitems = job->grid_start[ncell];
+  d.f1_octave = U.up(job->f1_octave, n1);
+  d.f1_angle = U.up(job->f1_angle, n1);
+  d.f1_desc = U.up(job->f1_desc, (size_t)n1 * 32);
+  d.f2_xy = U.up(job->f2_xy, (size_t)n2 * 2);
+  d.f2_angle = U.up(job->f2_angle, n2);
+  d.f2_octave = U.up(job->f2_octave, n2);
+  d.f2_desc = U.up(job->f2_desc, (size_t)n2 * 32);
+  d.grid_start = U.up(job->grid_start, ncell + 1);
+  d.grid_items = U.up(job->grid_items, nitems);
+  d.prev_matched = const_cast<float*>(U.up(job->prev_matched, (size_t)n1 * 2));
+  d.match12 = U.out<int32_t>(n1);
+  d.nmatches = U.out<int32_t>(1);
+  const plslam_init_job_t* dj = U.up(&d, 1);
+  if (U.err != cudaSuccess) { set_error("initialization host path: %s", cudaGetErrorString(U.err)); return PLSLAM_ERR_CUDA; }
+  int rc = plslam_match_initialization_batch_device(dj, 1, n1, n2, nullptr);
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpy(job->match12, d.match12, (size_t)n1 * 4, cudaMemcpyDeviceToHost));
+  PL_CUDA(cudaMemcpy(job->prev_matched, d.prev_matched, (size_t)n1 * 8, cudaMemcpyDeviceToHost));
   PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
   return PLSLAM_OK;
 }

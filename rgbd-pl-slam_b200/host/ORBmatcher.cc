@@ -127,6 +127,37 @@ int ORBmatcher::SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>&
   return nm;
 }
 
+int ORBmatcher::SearchForInitialization(const FrameView& F1, const FrameView& F2, std::vector<cv::Point2f>& vbPrevMatched,
+                                        std::vector<int>& vnMatches12, int windowSize) {
+  const int n1 = (int)F1.mvKeysUn.size(), n2 = (int)F2.mvKeysUn.size();
+  vnMatches12.assign(n1, -1);
+  if (n1 == 0 || n2 == 0) return 0;
+  need((int)vbPrevMatched.size() == n1 && F1.mDescriptors.rows >= n1 && F2.mDescriptors.rows >= n2 &&
+           F2.gridStart.size() == 64 * 48 + 1 && (int)F2.gridItems.size() == F2.gridStart.back(),
+       "SearchForInitialization views: vbPrevMatched / mDescriptors / grid incomplete");
+  std::vector<int32_t> o1(n1), o2(n2);
+  std::vector<float> a1(n1), a2(n2), xy2((size_t)n2 * 2), prev((size_t)n1 * 2);
+  for (int i = 0; i < n1; ++i) {
+    o1[i] = F1.mvKeysUn[i].octave; a1[i] = F1.mvKeysUn[i].angle;
+    prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y;
+  }
+  for (int i = 0; i < n2; ++i) {
+    o2[i] = F2.mvKeysUn[i].octave; a2[i] = F2.mvKeysUn[i].angle;
+    xy2[2 * i] = F2.mvKeysUn[i].pt.x; xy2[2 * i + 1] = F2.mvKeysUn[i].pt.y;
+  }
+  int32_t nm = 0;
+  plslam_init_job_t j{};
+  j.f1_octave = o1.data(); j.f1_angle = a1.data(); j.f1_desc = F1.mDescriptors.data;
+  j.f2_xy = xy2.data(); j.f2_angle = a2.data(); j.f2_octave = o2.data(); j.f2_desc = F2.mDescriptors.data;
+  j.grid_start = F2.gridStart.data(); j.grid_items = F2.gridItems.data();
+  j.prev_matched = prev.data(); j.match12 = vnMatches12.data(); j.nmatches = &nm;
+  j.cam[0] = F2.mnMinX; j.cam[1] = F2.mnMinY; j.cam[2] = F2.mfGridElementWidthInv; j.cam[3] = F2.mfGridElementHeightInv;
+  j.nnratio = mfNNratio; j.window_size = windowSize; j.n1 = n1; j.n2 = n2; j.check_orientation = mbCheckOrientation;
+  check(plslam_match_initialization_host(&j), "SearchForInitialization");
+  for (int i = 0; i < n1; ++i) vbPrevMatched[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]);
+  return nm;
+}
+
 void ORBmatcher::Epipole(const float R2w[9], const float t2w[3], const float Cw[3], float fx, float fy, float cx, float cy,
                          float* ex, float* ey) {
   check(plslam_match_epipole(R2w, t2w, Cw, fx, fy, cx, cy, ex, ey), "Epipole");

@@ -39,6 +39,10 @@ class ORBmatcher {
   // Search matches between MapPoints in a KeyFrame and ORB in a Frame (Relocalisation, TrackReferenceKeyFrame)
   template <class KeyFrameT, class FrameT, class MapPointT>
   int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches);
+  // Matching for the Map Initialization (only used in the monocular case) (ORBmatcher.h:108)
+  template <class FrameT>
+  int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                              int windowSize = 10);
   // Matching to triangulate new MapPoints. Check Epipolar Constraint (LocalMapping::CreateNewMapPoints)
   template <class KeyFrameT>
   int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, cv::Mat F12,
@@ -58,6 +62,10 @@ class ORBmatcher {
   // Brute force constrained to ORB that belong to the same vocabulary node (Relocalisation / TrackReferenceKeyFrame).
   // vnMatches[iF] = index in the KeyFrame matched to F's feature iF, or -1.
   int SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>& vnMatches);
+
+  // SearchForInitialization on views: F1 needs mvKeysUn and mDescriptors, F2 also its grid and bounds
+  int SearchForInitialization(const FrameView& F1, const FrameView& F2, std::vector<cv::Point2f>& vbPrevMatched,
+                              std::vector<int>& vnMatches12, int windowSize);
 
   // SearchForTriangulation on views: KF1 / KF2 need mvKeysUn, mvuRight, mDescriptors, mFeatVec, hasMapPoint; KF2 also
   // mvScaleFactors and mvLevelSigma2; (ex, ey) = the epipole of KF1's centre in KF2 (Epipole below).

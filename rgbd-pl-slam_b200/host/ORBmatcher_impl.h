@@ -155,6 +155,18 @@ int ORBmatcher::SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& 
   return nm;
 }
 
+// ORBmatcher.h:108 (@0x7db00)
+template <class FrameT>
+int ORBmatcher::SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<cv::Point2f>& vbPrevMatched,
+                                        std::vector<int>& vnMatches12, int windowSize) {
+  FrameView f1, f2;
+  f1.mvKeysUn = F1.mvKeysUn;
+  f1.mDescriptors = F1.mDescriptors;
+  dropin::require((size_t)F1.mDescriptors.rows == F1.mvKeysUn.size(), "F1 members differ in length");
+  dropin::view_of_frame(F2, &f2, true);
+  return SearchForInitialization(f1, f2, vbPrevMatched, vnMatches12, windowSize);
+}
+
 // ORBmatcher.h:111 (@0x86b30)
 template <class KeyFrameT>
 int ORBmatcher::SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, cv::Mat F12,

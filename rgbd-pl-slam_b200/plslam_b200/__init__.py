@@ -248,6 +248,15 @@ class LineSegment:
                                                        cap, _vp(counts), _stream_ptr(stream)))
         return out
 
+    def compute_lbd(self, img, keylines):
+        """BinaryDescriptor::compute on given key lines (KEYLINE_DTYPE array) -> [n, 32] LBD bytes."""
+        img = np.ascontiguousarray(img, np.uint8)
+        kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+        desc = np.empty((len(kl), 32), np.uint8)
+        _check(lib().plslam_lines_compute_lbd(self._h, _vp(img), img.shape[1], img.shape[0], img.strides[0], _vp(kl), len(kl),
+                                              _vp(desc)))
+        return desc
+
     def check_status(self, stream=None):
         _check(lib().plslam_lines_check_status(self._h, _stream_ptr(stream)))
 
@@ -778,6 +787,29 @@ def search_local_points_host(mp, fr, cam4, scale_factors, th, nnratio=0.8):
 
 # ---- on-disk formats either side of the path (host only; include/plslam_b200.h, last section) ----
 TUM_NAME_STRIDE = 256
+
+
+class InitJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("f1_octave", "f1_angle", "f1_desc", "f2_xy", "f2_angle", "f2_octave", "f2_desc", "grid_start",
+                                          "grid_items", "prev_matched", "match12", "nmatches")] + \
+               [("cam", C.c_float * 4), ("nnratio", C.c_float), ("window_size", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32),
+                ("check_orientation", C.c_int32)]
+
+
+def search_for_initialization_host(f1, f2, cam4, prev_matched, window_size=100, nnratio=0.9, check_ori=True):
+    """ORBmatcher::SearchForInitialization on host arrays (dict layout of tests/matchdata.py) through
+    plslam_match_initialization_host -> (vnMatches12, nmatches, updated vbPrevMatched)."""
+    keep = {k: np.ascontiguousarray(v) for k, v in list(f1.items()) + [("2_" + k, v) for k, v in f2.items()]}
+    n1, n2 = len(f1["desc"]), len(f2["desc"])
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m, n = np.empty(max(n1, 1), np.int32), np.zeros(1, np.int32)
+    p = lambda a: a.ctypes.data
+    j = InitJob(p(keep["octave"]), p(keep["angle"]), p(keep["desc"]), p(keep["2_xy"]), p(keep["2_angle"]), p(keep["2_octave"]), p(keep["2_desc"]),
+                p(keep["2_grid_start"]), p(keep["2_grid_items"]), p(prev), p(m), p(n))
+    j.cam[:] = np.asarray(cam4, np.float32).tolist()
+    j.nnratio = float(nnratio); j.window_size = int(window_size); j.n1 = n1; j.n2 = n2; j.check_orientation = int(check_ori)
+    _check(lib().plslam_match_initialization_host(C.byref(j)))
+    return m[:n1], int(n[0]), prev
 
 
 def LoadImages(association_file):

@@ -206,3 +206,29 @@ def test_k_triangulation_equals_the_reference_matcher():
         assert n == int(g["tr%d_n" % k]) and np.array_equal(m, g["tr%d_match" % k]), k
         total += n
     assert total > 1500
+
+
+def test_k_search_init_equals_the_reference_matcher():
+    """k_search_init (ORBmatcher::SearchForInitialization, @0x7db00) on the si* fixtures: vnMatches12, the return value and the
+    updated vbPrevMatched."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import plslam_b200 as pl
+    from matchdata import frame_grid
+    g = np.load(os.path.join(G, "reference_library.npz"))
+    feats = {}
+    for k in range(int(g["si_n"])):
+        seed, win, nnr, ori = g["si%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            (ka, da), (kb, db) = _features(seed)
+            mk = lambda kk, d: dict(xy=np.stack([kk["x"], kk["y"]], 1).astype(np.float32), octave=kk["octave"].astype(np.int32),
+                                    angle=kk["angle"].astype(np.float32), desc=d)
+            f1, f2 = mk(ka, da), mk(kb, db)
+            gs, gi, (mnx, mxx, mny, mxy, gwi, ghi) = frame_grid(f2["xy"], 640, 480)
+            f2["grid_start"], f2["grid_items"] = gs, gi
+            feats[seed] = (f1, f2, np.array([mnx, mny, gwi, ghi], np.float32))
+        f1, f2, cam4 = feats[seed]
+        m, n, prev = pl.search_for_initialization_host(f1, f2, cam4, f1["xy"].copy(), int(win), float(nnr), bool(ori))
+        assert n == int(g["si%d_n" % k]) > 50 and np.array_equal(m, g["si%d_match" % k]), k
+        assert np.array_equal(prev, g["si%d_prev" % k]), k
