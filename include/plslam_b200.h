@@ -211,6 +211,12 @@ typedef struct plslam_bow_job {
   int32_t n1, n2, n_kf_nodes, n_f_nodes;
   float nnratio;            /* mfNNratio */
   int32_t check_orientation;/* mbCheckOrientation */
+  /* ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (ORBmatcher.h:105, @0x82cc0)
+   * is the same walk with the second key frame in the role of F: its features need a good map point too (f_valid, NULL
+   * = all valid) and the distance test is strict (strict_low: bestDist1 < TH_LOW, cmpl $0x31 @0x83490).  match_f is
+   * then indexed by KF2; vpMatches12[match_f[i2]] = KF2's map point i2 (plslam_match_bow_kfkf_host inverts it). */
+  const uint8_t* f_valid;
+  int32_t strict_low;
 } plslam_bow_job_t;
 int plslam_match_bow_batch_device(const plslam_bow_job_t* d_jobs, int njobs, int max_n, void* stream); /* max_n >= every job's n1 and n2 */
 
@@ -340,6 +346,9 @@ int plslam_match_epipole(const float* R2w_3x3, const float* t2w, const float* Cw
 /* Single-job convenience forms for the class veneers: every pointer inside *job is a HOST pointer; the call
  * uploads the arrays, runs the kernel and writes match_* / nmatches back.  n_grid_items = grid_start[64*48]. */
 int plslam_match_bow_host(const plslam_bow_job_t* job);
+/* SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12): kf_* = pKF1, f_* = pKF2 (f_valid required); match12 [n1] receives the
+ * KF2 feature assigned to each KF1 feature (-1 = none).  job->match_f is scratch [n2]. */
+int plslam_match_bow_kfkf_host(const plslam_bow_job_t* job, int32_t* match12);
 int plslam_match_projection_host(const plslam_proj_job_t* job, int n_scale_levels);
 
 /* Pair matching on the batched extractor outputs without a host round trip: for p in [0, npairs)

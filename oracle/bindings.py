@@ -261,6 +261,22 @@ def search_by_bow(kf, f, nnratio=0.7, check_ori=True):
     return match, n
 
 
+def search_by_bow_kfkf(kf1, kf2, nnratio=0.75, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) -> (match12 int32 [N1], nmatches)."""
+    n1, n2 = len(kf1["desc"]), len(kf2["desc"])
+    m = np.empty(max(n1, 1), np.int32)
+    a = [np.ascontiguousarray(x) for x in (kf1["desc"], np.asarray(kf1["angle"], np.float32), np.asarray(kf1["valid"], np.uint8),
+                                           np.asarray(kf1["nodes"], np.int32), np.asarray(kf1["start"], np.int32), np.asarray(kf1["idx"], np.int32),
+                                           kf2["desc"], np.asarray(kf2["angle"], np.float32), np.asarray(kf2["valid"], np.uint8),
+                                           np.asarray(kf2["nodes"], np.int32), np.asarray(kf2["start"], np.int32), np.asarray(kf2["idx"], np.int32))]
+    L = lib()
+    L.oracle_search_by_bow_kfkf.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_void_p] * 3 + \
+        [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_void_p]
+    n = L.oracle_search_by_bow_kfkf(_p(a[0]), _p(a[1]), _p(a[2]), n1, len(a[3]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]),
+                                    _p(a[8]), n2, len(a[9]), _p(a[9]), _p(a[10]), _p(a[11]), nnratio, int(check_ori), _p(m))
+    return m[:n1], n
+
+
 def search_by_projection(last, cur, cam, scale_factors, tcw_cur, tcw_last, th, mono=False, check_ori=True):
     n1, n2 = len(last["desc"]), len(cur["desc"])
     match = np.empty(n2, np.int32)

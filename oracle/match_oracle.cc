@@ -189,6 +189,60 @@ int oracle_search_by_bow(const uint8_t* dKF, const float* angKF, const uint8_t* 
   return nmatches;
 }
 
+// SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (ORBmatcher.h:105; @0x82cc0, loop closing).
+// Same walk over the shared vocabulary nodes as the key-frame / frame form above, with three differences read from the
+// binary: KF2 features need a good map point as well (valid2) and are skipped once matched (vbMatched2), the distance
+// test is bestDist1 < TH_LOW (cmpl $0x31 @0x83490, against $0x32 @0x808e0 in the other form), and the result is indexed
+// by KF1: match12[i1] = KF2 feature whose map point is assigned to KF1 feature i1 (-1 = none).  Returns nmatches.
+int oracle_search_by_bow_kfkf(const uint8_t* d1, const float* ang1, const uint8_t* valid1, int N1, int nNodes1, const int* nodes1,
+                              const int* start1, const int* idx1, const uint8_t* d2, const float* ang2, const uint8_t* valid2,
+                              int N2, int nNodes2, const int* nodes2, const int* start2, const int* idx2, float nnratio,
+                              int checkOri, int* match12) {
+  for (int i = 0; i < N1; ++i) match12[i] = -1;
+  std::vector<uint8_t> matched2(N2, 0);
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int a = 0, b = 0;
+  while (a < nNodes1 && b < nNodes2) {
+    if (nodes1[a] == nodes2[b]) {
+      for (int i1 = start1[a]; i1 < start1[a + 1]; ++i1) {
+        const int r1 = idx1[i1];
+        if (!valid1[r1]) continue;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int i2 = start2[b]; i2 < start2[b + 1]; ++i2) {
+          const int r2 = idx2[i2];
+          if (matched2[r2] || !valid2[r2]) continue;
+          const int dist = descriptor_distance(d1 + 32 * r1, d2 + 32 * r2);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = r2; }
+          else if (dist < bestDist2) { bestDist2 = dist; }
+        }
+        if (bestDist1 < TH_LOW) {
+          if ((float)bestDist1 < nnratio * (float)bestDist2) {
+            match12[r1] = bestIdx2;
+            matched2[bestIdx2] = 1;
+            if (checkOri) rotHist[rot_bin(ang1[r1], ang2[bestIdx2])].push_back(r1);
+            nmatches++;
+          }
+        }
+      }
+      ++a; ++b;
+    } else if (nodes1[a] < nodes2[b]) {
+      a = (int)(std::lower_bound(nodes1, nodes1 + nNodes1, nodes2[b]) - nodes1);
+    } else {
+      b = (int)(std::lower_bound(nodes2, nodes2 + nNodes2, nodes1[a]) - nodes2);
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int j : rotHist[i]) { match12[j] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
 // SearchByProjection(CurrentFrame, LastFrame, th, bMono).
 // Last frame: N1 points with lastValid[i] = (pMP && !outlier), world position (x,y,z), representative
 // descriptor, mvKeys[i].octave, mvKeysUn[i].angle, lastObs[i] = (pMP->Observations() > 0).

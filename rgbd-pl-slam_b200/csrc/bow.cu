@@ -264,6 +264,8 @@ __global__ void k_make_bow_jobs(int npairs, int capacity, const uint8_t* desc, c
   j.n_f_nodes = fv_count[2 * p + 1];
   j.nnratio = nnratio;
   j.check_orientation = check_ori;
+  j.f_valid = nullptr;
+  j.strict_low = 0;
   jobs[p] = j;
 }
 

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(32) k_bow(const plslam_bow_job_t* __restrict__
         for (int iF = fs + lane; iF < fe; iF += 32) {
           const int realIdxF = J.f_idx[iF];
           if (matchF[realIdxF] >= 0) continue;
+          if (J.f_valid && !J.f_valid[realIdxF]) continue;  // key frame / key frame form: KF2's map point must be good
           const int dist = hamming256(a0, a1, DF[2 * realIdxF], DF[2 * realIdxF + 1]);
           const unsigned key = ((unsigned)dist << 20) | (unsigned)(iF - fs);
           if (key < k1) { k2 = k1; k1 = key; }
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(32) k_bow(const plslam_bow_job_t* __restrict__
         if (g1 == 0xffffffffu) continue;
         const int bestDist1 = (int)(g1 >> 20);
         const int bestDist2 = g2 == 0xffffffffu ? 256 : (int)(g2 >> 20);
-        if (bestDist1 <= PLSLAM_TH_LOW && (float)bestDist1 < __fmul_rn(J.nnratio, (float)bestDist2)) {
+        if (bestDist1 <= PLSLAM_TH_LOW - (J.strict_low ? 1 : 0) && (float)bestDist1 < __fmul_rn(J.nnratio, (float)bestDist2)) {
           const int bestIdxF = J.f_idx[fs + (int)(g1 & 0xfffffu)];
           if (lane == 0) {
             matchF[bestIdxF] = realIdxKF;
@@ -770,6 +771,7 @@ int plslam_match_bow_host(const plslam_bow_job_t* job) {
   d.f_nodes = U.up(job->f_nodes, nf);
   d.f_start = U.up(job->f_start, nf + 1);
   d.f_idx = U.up(job->f_idx, lenF);
+  if (job->f_valid) d.f_valid = U.up(job->f_valid, job->n2);
   d.match_f = U.out<int32_t>(job->n2);
   d.nmatches = U.out<int32_t>(1);
   const plslam_bow_job_t* dj = U.up(&d, 1);
@@ -778,6 +780,18 @@ int plslam_match_bow_host(const plslam_bow_job_t* job) {
   if (rc) return rc;
   PL_CUDA(cudaMemcpy(job->match_f, d.match_f, (size_t)job->n2 * 4, cudaMemcpyDeviceToHost));
   PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int plslam_match_bow_kfkf_host(const plslam_bow_job_t* job, int32_t* match12) {
+  PL_CHECK_ARG(job && match12 && job->f_valid && job->match_f);
+  plslam_bow_job_t j = *job;
+  j.strict_low = 1;
+  int rc = plslam_match_bow_host(&j);
+  if (rc) return rc;
+  for (int i = 0; i < job->n1; ++i) match12[i] = -1;
+  for (int i2 = 0; i2 < job->n2; ++i2)
+    if (job->match_f[i2] >= 0) match12[job->match_f[i2]] = i2;  // a KF2 feature is matched at most once, a KF1 feature too
   return PLSLAM_OK;
 }
 

@@ -127,6 +127,31 @@ int ORBmatcher::SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>&
   return nm;
 }
 
+int ORBmatcher::SearchByBoW(const FrameView& KF1, const FrameView& KF2, std::vector<int>& vnMatches12, int) {
+  const int n1 = (int)KF1.mvKeysUn.size(), n2 = (int)KF2.mvKeysUn.size();
+  vnMatches12.assign(n1, -1);
+  if (n1 == 0 || n2 == 0) return 0;
+  need((int)KF1.hasMapPoint.size() == n1 && (int)KF2.hasMapPoint.size() == n2 && KF1.mDescriptors.rows >= n1 &&
+           KF1.mDescriptors.cols == 32 && KF2.mDescriptors.rows >= n2 && KF2.mDescriptors.cols == 32 &&
+           KF1.mFeatVec.start.size() == KF1.mFeatVec.nodes.size() + 1 && KF2.mFeatVec.start.size() == KF2.mFeatVec.nodes.size() + 1,
+       "SearchByBoW(KF, KF) views: hasMapPoint / mDescriptors / mFeatVec incomplete");
+  std::vector<float> a1(n1), a2(n2);
+  for (int i = 0; i < n1; ++i) a1[i] = KF1.mvKeysUn[i].angle;
+  for (int i = 0; i < n2; ++i) a2[i] = KF2.mvKeysUn[i].angle;
+  std::vector<int32_t> scratch(n2);
+  int32_t nm = 0;
+  plslam_bow_job_t j{};
+  j.kf_desc = KF1.mDescriptors.data; j.kf_angle = a1.data(); j.kf_valid = KF1.hasMapPoint.data();
+  j.kf_nodes = KF1.mFeatVec.nodes.data(); j.kf_start = KF1.mFeatVec.start.data(); j.kf_idx = KF1.mFeatVec.idx.data();
+  j.f_desc = KF2.mDescriptors.data; j.f_angle = a2.data(); j.f_valid = KF2.hasMapPoint.data();
+  j.f_nodes = KF2.mFeatVec.nodes.data(); j.f_start = KF2.mFeatVec.start.data(); j.f_idx = KF2.mFeatVec.idx.data();
+  j.match_f = scratch.data(); j.nmatches = &nm;
+  j.n1 = n1; j.n2 = n2; j.n_kf_nodes = (int)KF1.mFeatVec.nodes.size(); j.n_f_nodes = (int)KF2.mFeatVec.nodes.size();
+  j.nnratio = mfNNratio; j.check_orientation = mbCheckOrientation;
+  check(plslam_match_bow_kfkf_host(&j, vnMatches12.data()), "SearchByBoW(KF, KF)");
+  return nm;
+}
+
 int ORBmatcher::SearchForInitialization(const FrameView& F1, const FrameView& F2, std::vector<cv::Point2f>& vbPrevMatched,
                                         std::vector<int>& vnMatches12, int windowSize) {
   const int n1 = (int)F1.mvKeysUn.size(), n2 = (int)F2.mvKeysUn.size();

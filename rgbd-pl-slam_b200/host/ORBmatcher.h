@@ -39,6 +39,9 @@ class ORBmatcher {
   // Search matches between MapPoints in a KeyFrame and ORB in a Frame (Relocalisation, TrackReferenceKeyFrame)
   template <class KeyFrameT, class FrameT, class MapPointT>
   int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches);
+  // Search matches between the MapPoints of two key frames by vocabulary node (LoopClosing) (ORBmatcher.h:105)
+  template <class KeyFrameT, class MapPointT>
+  int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12);
   // Matching for the Map Initialization (only used in the monocular case) (ORBmatcher.h:108)
   template <class FrameT>
   int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
@@ -62,6 +65,10 @@ class ORBmatcher {
   // Brute force constrained to ORB that belong to the same vocabulary node (Relocalisation / TrackReferenceKeyFrame).
   // vnMatches[iF] = index in the KeyFrame matched to F's feature iF, or -1.
   int SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>& vnMatches);
+
+  // Key frame / key frame form (ORBmatcher.h:105): both views need mvKeysUn, mDescriptors, mFeatVec and hasMapPoint
+  // (map point present and not bad).  vnMatches12[i1] = KF2 feature whose map point goes to KF1's feature i1, or -1.
+  int SearchByBoW(const FrameView& KF1, const FrameView& KF2, std::vector<int>& vnMatches12, int /*tag: KF-KF*/);
 
   // SearchForInitialization on views: F1 needs mvKeysUn and mDescriptors, F2 also its grid and bounds
   int SearchForInitialization(const FrameView& F1, const FrameView& F2, std::vector<cv::Point2f>& vbPrevMatched,

@@ -155,6 +155,30 @@ int ORBmatcher::SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& 
   return nm;
 }
 
+// ORBmatcher.h:105 (@0x82cc0)
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12) {
+  FrameView v[2];
+  KeyFrameT* kfs[2] = {pKF1, pKF2};
+  std::vector<MapPointT*> mps[2];
+  for (int s = 0; s < 2; ++s) {
+    mps[s] = kfs[s]->GetMapPointMatches();
+    v[s].mvKeysUn = kfs[s]->mvKeysUn;
+    v[s].mDescriptors = kfs[s]->mDescriptors;
+    const size_t n = v[s].mvKeysUn.size();
+    dropin::require(mps[s].size() == n && (size_t)kfs[s]->mDescriptors.rows == n, "KeyFrame members differ in length");
+    v[s].hasMapPoint.assign(n, 0);
+    for (size_t i = 0; i < n; ++i) v[s].hasMapPoint[i] = mps[s][i] && !mps[s][i]->isBad();
+    dropin::flatten_featvec(kfs[s]->mFeatVec, &v[s].mFeatVec);
+  }
+  vpMatches12 = std::vector<MapPointT*>(mps[0].size(), static_cast<MapPointT*>(nullptr));
+  std::vector<int> m12;
+  const int nm = SearchByBoW(v[0], v[1], m12, 0);
+  for (size_t i = 0; i < m12.size(); ++i)
+    if (m12[i] >= 0) vpMatches12[i] = mps[1][m12[i]];
+  return nm;
+}
+
 // ORBmatcher.h:108 (@0x7db00)
 template <class FrameT>
 int ORBmatcher::SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<cv::Point2f>& vbPrevMatched,

@@ -288,6 +288,38 @@ static void case_bow() {
   save("bw_out", out);
 }
 
+// ---- LoopClosing::ComputeSim3: matcher.SearchByBoW(mpCurrentKF, pKF, vvpMapPointMatches[i]) ----
+static void case_bow_keyframes() {
+  const auto par = load<float>("bk_par");  // nnratio, ori
+  KeyFrame K[2];
+  for (int s = 0; s < 2; ++s) {
+    const std::string p = s ? "bk_kf2_" : "bk_kf1_";
+    const auto desc = load<uint8_t>(p + "desc"), valid = load<uint8_t>(p + "valid");
+    const auto ang = load<float>(p + "angle");
+    const int n = (int)valid.size();
+    K[s].mvKeysUn.resize(n); K[s].mvuRight.assign(n, -1.f); K[s].mvpMapPoints.assign(n, nullptr);
+    K[s].mDescriptors = mat_u8(desc, n);
+    for (int i = 0; i < n; ++i) {
+      K[s].mvKeysUn[i].angle = ang[i];
+      if (valid[i] || (i & 1)) {  // invalid = NULL or bad, alternating
+        MapPoint* mp = new_mp();
+        mp->id = i;
+        mp->mbBad = !valid[i];
+        K[s].mvpMapPoints[i] = mp;
+      }
+    }
+    K[s].mFeatVec = featvec(load<int32_t>(p + "nodes"), load<int32_t>(p + "start"), load<int32_t>(p + "idx"));
+  }
+  ORBmatcher matcher(par[0], par[1] != 0.f);
+  std::vector<MapPoint*> vpMatches12;
+  const int nmatches = matcher.SearchByBoW(&K[0], &K[1], vpMatches12);
+  const int n1 = (int)K[0].mvKeysUn.size();
+  std::vector<int32_t> out(n1 + 1);
+  for (int i = 0; i < n1; ++i) out[i] = vpMatches12[i] ? vpMatches12[i]->id : -1;
+  out[n1] = nmatches;
+  save("bk_out", out);
+}
+
 // ---- LocalMapping::CreateNewMapPoints: matcher.SearchForTriangulation(mpCurrentKeyFrame, pKF2, F12, vMatchedIndices, false) ----
 static void case_triangulation() {
   const auto par = load<float>("tr_par");  // fx fy cx cy only_stereo ori
@@ -341,6 +373,7 @@ int main(int argc, char** argv) {
     case_projection();
     case_local();
     case_bow();
+    case_bow_keyframes();
     case_triangulation();
     // an unfilled member must be reported, not read out of bounds
     Frame bad, last;

@@ -304,7 +304,7 @@ class BowJob(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("kf_desc", "kf_angle", "kf_valid", "kf_nodes", "kf_start", "kf_idx", "f_desc",
                                           "f_angle", "f_nodes", "f_start", "f_idx", "match_f", "nmatches")] + \
                [("n1", C.c_int32), ("n2", C.c_int32), ("n_kf_nodes", C.c_int32), ("n_f_nodes", C.c_int32),
-                ("nnratio", C.c_float), ("check_orientation", C.c_int32)]
+                ("nnratio", C.c_float), ("check_orientation", C.c_int32), ("f_valid", C.c_void_p), ("strict_low", C.c_int32)]
 
 
 class ProjJob(C.Structure):
@@ -325,7 +325,7 @@ class TriJob(C.Structure):
                 ("n1_nodes", C.c_int32), ("n2_nodes", C.c_int32), ("only_stereo", C.c_int32), ("check_orientation", C.c_int32)]
 
 
-assert C.sizeof(KnnJob) == 32 and C.sizeof(BowJob) == 128 and C.sizeof(ProjJob) == 304 and C.sizeof(TriJob) == 240
+assert C.sizeof(KnnJob) == 32 and C.sizeof(BowJob) == 144 and C.sizeof(ProjJob) == 304 and C.sizeof(TriJob) == 240
 
 
 def _jobs_to_device(jobs, device):
@@ -750,6 +750,22 @@ def bow_pairs_device(d_kps, d_desc, d_counts, fv, d_kf_valid=None, nnratio=0.7, 
                                                C.c_float(nnratio), int(check_ori), _vp(out["_angle"]), _vp(out["_jobs"]),
                                                _vp(out["match"]), _vp(out["nmatches"]), _stream_ptr(stream)))
     return out
+
+
+def search_by_bow_kfkf_host(kf1, kf2, nnratio=0.75, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) on host arrays (dicts desc, angle, valid, nodes, start, idx)
+    through plslam_match_bow_kfkf_host -> (match12 int32 [N1], nmatches)."""
+    n1, n2 = len(kf1["desc"]), len(kf2["desc"])
+    keep = []
+    def a(x, dt):
+        x = np.ascontiguousarray(x, dt); keep.append(x); return x.ctypes.data
+    mf = np.empty(max(n2, 1), np.int32); m12 = np.empty(max(n1, 1), np.int32); nm = np.zeros(1, np.int32)
+    j = BowJob(a(kf1["desc"], np.uint8), a(kf1["angle"], np.float32), a(kf1["valid"], np.uint8), a(kf1["nodes"], np.int32),
+               a(kf1["start"], np.int32), a(kf1["idx"], np.int32), a(kf2["desc"], np.uint8), a(kf2["angle"], np.float32),
+               a(kf2["nodes"], np.int32), a(kf2["start"], np.int32), a(kf2["idx"], np.int32), mf.ctypes.data, nm.ctypes.data,
+               n1, n2, len(kf1["nodes"]), len(kf2["nodes"]), float(nnratio), int(check_ori), a(kf2["valid"], np.uint8), 1)
+    _check(lib().plslam_match_bow_kfkf_host(C.byref(j), _vp(m12)))
+    return m12[:n1], int(nm[0])
 
 
 class LocalJob(C.Structure):

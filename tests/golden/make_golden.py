@@ -332,6 +332,41 @@ def reflib():
              len(items), len(q), len(out["fg_res"])))
 
 
+def reflib2():
+    """Round-2 additions, kept in their own file (reference_library2.npz) so that reference_library.npz stays byte-identical:
+    further ORBmatcher overloads executed from lib/libORB_SLAM2.so on faked objects."""
+    sys.path.insert(0, HERE)
+    from reference_code import RefLibrary, SO
+    import plslam_b200.synth as _synth
+    _pairs = {s: _synth.synth_pair(s) for s in (1, 2)}   # rendered before the library is loaded (see reflib)
+    R = RefLibrary()
+    from oracle import bindings as orb
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from matchdata import fake_feature_vector
+    out = {"so_sha256": np.array(hashlib.sha256(open(SO, "rb").read()).hexdigest())}
+    oo = orb.OrbOracle()
+    feats = {s: (oo.extract(_pairs[s][0]), oo.extract(_pairs[s][1])) for s in (1, 2)}
+    # ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (loop closing) on faked KeyFrames
+    bk = []
+    for seed in (1, 2):
+        (ka, da), (kb, db) = feats[seed]
+        r2 = np.random.default_rng(100 + seed)
+        for nnr, ori, nbits in ((0.75, 1, 6), (0.9, 0, 6), (0.75, 1, 2), (0.6, 1, 4)):
+            kf1 = dict(desc=da, angle=np.ascontiguousarray(ka["angle"]), valid=(r2.random(len(da)) < 0.85).astype(np.uint8))
+            kf1["nodes"], kf1["start"], kf1["idx"] = fake_feature_vector(da, nbits, seed=7)
+            kf2 = dict(desc=db, angle=np.ascontiguousarray(kb["angle"]), valid=(r2.random(len(db)) < 0.85).astype(np.uint8))
+            kf2["nodes"], kf2["start"], kf2["idx"] = fake_feature_vector(db, nbits, seed=7)
+            m, n = R.search_by_bow_kfkf(kf1, kf2, nnr, bool(ori))
+            k = len(bk)
+            out["bk%d_args" % k] = np.array([seed, nnr, ori, nbits], np.float64)
+            out["bk%d_valid1" % k], out["bk%d_valid2" % k] = kf1["valid"], kf2["valid"]
+            out["bk%d_match" % k], out["bk%d_n" % k] = m, np.array(n)
+            bk.append(n)
+    out["bk_n"] = np.array(len(bk))
+    print("SearchByBoW(KeyFrame*, KeyFrame*):", bk)
+    np.savez_compressed(os.path.join(HERE, "reference_library2.npz"), **out)
+
+
 def tum_io():
     import cv2
     d = "/root/reference/Examples/RGB-D/associations"
@@ -362,6 +397,8 @@ def main():
         return refcode()
     if len(sys.argv) > 1 and sys.argv[1] == "reflib":
         return reflib()
+    if len(sys.argv) > 1 and sys.argv[1] == "reflib2":
+        return reflib2()
     import cv2
     from plslam_b200.synth import synth_frame
     assert cv2.__version__.startswith("4.13"), cv2.__version__

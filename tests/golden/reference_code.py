@@ -891,6 +891,48 @@ class RefLibrary:
                 out[i] = (int(p) - mb) // 0x400
         return out, int(n)
 
+    # ---- ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (@0x82cc0, loop closing) ----
+    def search_by_bow_kfkf(self, kf1, kf2, nnratio=0.75, check_ori=True):
+        """kf1 / kf2: dict(desc, angle, valid, nodes, start, idx) (valid = map point exists and is not bad).  Returns
+        (match12 int32 [N1] = KF2 feature whose map point was assigned to KF1 feature i1, or -1; nmatches)."""
+        f32 = np.float32
+        keep = []
+        def make(kf):
+            n = len(kf["desc"])
+            k = np.zeros(n, self.KP)
+            k["angle"] = kf["angle"]
+            d = np.ascontiguousarray(kf["desc"], np.uint8)
+            mps = (C.c_uint8 * (0x400 * max(n, 1)))()
+            mb = C.addressof(mps)
+            vp = np.array([mb + 0x400 * i if kf["valid"][i] else 0 for i in range(n)], np.uint64)
+            o = (C.c_uint64 * (0x800 // 8))()
+            b = C.addressof(o)
+            o[0x170 // 8], o[0x170 // 8 + 1], o[0x170 // 8 + 2] = k.ctypes.data, k.ctypes.data + k.nbytes, k.ctypes.data + k.nbytes
+            o[0x520 // 8], o[0x520 // 8 + 1], o[0x520 // 8 + 2] = vp.ctypes.data, vp.ctypes.data + vp.nbytes, vp.ctypes.data + vp.nbytes
+            self._mat_at(b + 0x1b8, d)
+            arrs = [np.ascontiguousarray(kf[x], np.int32) for x in ("nodes", "start", "idx")]
+            build = self._shims.refshim_build_featvec
+            build.argtypes, build.restype = [C.c_void_p] * 4 + [C.c_int], None
+            build(b + 0x248, arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, len(arrs[0]))
+            keep.extend([k, d, mps, vp, o, arrs])
+            return b, mb, n
+        b1, mb1, n1 = make(kf1)
+        b2, mb2, n2 = make(kf2)
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher11SearchByBoWEPNS_8KeyFrameES2_RSt6vectorIPNS_8MapPointESaIS5_EE")
+        fn.argtypes, fn.restype = [C.c_void_p] * 4, C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = f32(nnratio)
+        matcher[4] = 1 if check_ori else 0
+        res = (C.c_uint64 * 3)()
+        n = fn(C.addressof(matcher), b1, b2, C.addressof(res))
+        cnt = (res[1] - res[0]) // 8
+        ptrs = np.ctypeslib.as_array(C.cast(res[0], C.POINTER(C.c_uint64)), (cnt,)) if cnt else np.empty(0, np.uint64)
+        out = np.full(n1, -1, np.int32)
+        for i, p in enumerate(ptrs):
+            if p:
+                out[i] = (int(p) - mb2) // 0x400
+        return out, int(n)
+
     # ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono) (@0x80d00) ----
     # Further Frame members: mbf @0xe0, mb @0xe4, mvKeys @0xf0, mvbOutlier (vector<bool>) @0x2a0, mTcw (cv::Mat 4x4) @0x122c8;
     # MapPoint::mWorldPos (cv::Mat 3x1) @0xd8 (MapPoint::GetWorldPos @0x91630).  Frame::fx/fy/cx/cy are static members.

@@ -103,6 +103,13 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
     for k, v in f.items():
         put("bw_f_" + k, v)
     put("bw_par", [0.7, 1.0], np.float32)
+    # LoopClosing::ComputeSim3
+    kfb = dict(f, valid=(rng.random(len(db)) < 0.85).astype(np.uint8))
+    for k, v in kf.items():
+        put("bk_kf1_" + k, v)
+    for k, v in kfb.items():
+        put("bk_kf2_" + k, v)
+    put("bk_par", [0.75, 1.0], np.float32)
     # CreateNewMapPoints
     kps, desc = orc.extract(synth_frame(33))
     kf1, kf2, F12, pose, camt, sft, sg = triangulation_case(kps, desc, seed=33, stereo_fraction=0.5)
@@ -127,6 +134,9 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
     assert out[-1] == n > 100 and np.array_equal(out[:-1], m)
     em, en = oracle.search_by_bow(kf, f, 0.7, True)  # (the kernel equals the oracle: tests/test_match_gpu.py)
     out = np.fromfile(d / "bw_out", np.int32)
+    assert out[-1] == en > 50 and np.array_equal(out[:-1], em)
+    em, en = oracle.search_by_bow_kfkf(kf, kfb, 0.75, True)  # (kernel vs reference code: tests/test_golden_gpu.py, bk*)
+    out = np.fromfile(d / "bk_out", np.int32)
     assert out[-1] == en > 50 and np.array_equal(out[:-1], em)
     ex, ey = pl.epipole(*pose, *camt)
     m12, n12, pairs = pl.search_for_triangulation_host(kf1, kf2, F12, ex, ey, sft, sg, False, True)

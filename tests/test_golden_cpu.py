@@ -256,6 +256,36 @@ def test_search_by_bow_equals_the_reference_matcher(oracle):
         assert n == int(g["bw%d_n" % k]) > 200 and np.array_equal(m, g["bw%d_match" % k]), k
 
 
+def _kfkf_cases(g, extract):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import fake_feature_vector
+    from plslam_b200.synth import synth_pair
+    feats = {}
+    for k in range(int(g["bk_n"])):
+        seed, nnr, ori, nbits = g["bk%d_args" % k]
+        seed, nbits = int(seed), int(nbits)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (extract(a), extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        kf1 = dict(desc=da, angle=np.ascontiguousarray(ka["angle"]), valid=g["bk%d_valid1" % k])
+        kf1["nodes"], kf1["start"], kf1["idx"] = fake_feature_vector(da, nbits, seed=7)
+        kf2 = dict(desc=db, angle=np.ascontiguousarray(kb["angle"]), valid=g["bk%d_valid2" % k])
+        kf2["nodes"], kf2["start"], kf2["idx"] = fake_feature_vector(db, nbits, seed=7)
+        yield k, kf1, kf2, float(nnr), bool(ori)
+
+
+def test_search_by_bow_keyframes_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (@0x82cc0, loop closing) executed from
+    lib/libORB_SLAM2.so on two faked KeyFrames (fixture reference_library2.npz, bk*)."""
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    o = oracle.OrbOracle()
+    for k, kf1, kf2, nnr, ori in _kfkf_cases(g, o.extract):
+        m, n = oracle.search_by_bow_kfkf(kf1, kf2, nnr, ori)
+        assert n == int(g["bk%d_n" % k]) > 150 and np.array_equal(m, g["bk%d_match" % k]), k
+
+
 def test_search_by_projection_equals_the_reference_matcher(oracle):
     """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (@0x80d00, TrackWithMotionModel's matcher) executed from
     lib/libORB_SLAM2.so on faked Frame / MapPoint objects, its cv::Mat expressions evaluated with cv::gemm's arithmetic

@@ -184,6 +184,21 @@ def test_k_bow_equals_the_reference_matcher():
         assert int(n) == int(g["bw%d_n" % k]) > 200 and np.array_equal(m.cpu().numpy(), g["bw%d_match" % k]), k
 
 
+def test_k_bow_keyframes_equals_the_reference_matcher():
+    """k_bow in its key frame / key frame form (ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), @0x82cc0) on the
+    bk* fixtures of reference_library2.npz, through plslam_match_bow_kfkf_host."""
+    import plslam_b200 as pl
+    from test_golden_cpu import _kfkf_cases
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    ex = pl.ORBextractor()
+    done = 0
+    for k, kf1, kf2, nnr, ori in _kfkf_cases(g, ex):
+        m, n = pl.search_by_bow_kfkf_host(kf1, kf2, nnr, ori)
+        assert n == int(g["bk%d_n" % k]) > 150 and np.array_equal(m, g["bk%d_match" % k]), k
+        done += 1
+    assert done == 8
+
+
 def test_k_triangulation_equals_the_reference_matcher():
     """k_triangulation (ORBmatcher::SearchForTriangulation, @0x86b30, epipole included) on the tr* fixtures."""
     import sys
