@@ -638,8 +638,8 @@ int plslam_frontend_stage_times(plslam_frontend_t* h, const char** names, float*
 }
 int plslam_frontend_launches_per_call(const plslam_frontend_t* h, int match_pairs) {
   if (!h) return 0;
-  // ORB: (nlevels-1) resize + fast + quadtree + blur + orient_desc; lines: 9 kernels; matching: 2 x (jobs + knn2)
-  return (h->impl.slots[0]->orb.nlevels - 1) + 4 + 9 + (match_pairs ? 4 : 0);
+  // ORB: (nlevels-1) resize + fast + quadtree + blur + orient_desc; lines: 10 kernels; matching: 2 x (jobs + knn2)
+  return (h->impl.slots[0]->orb.nlevels - 1) + 4 + 10 + (match_pairs ? 4 : 0);
 }
 
 }  // extern "C"

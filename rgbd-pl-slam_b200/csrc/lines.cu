@@ -129,7 +129,7 @@ __device__ __forceinline__ double modgrad_of(int g2) { return sqrt(__dmul_rn((do
 
 __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LineParams L, const uint8_t* __restrict__ scaled,
                                                   uint4* __restrict__ pix, float* __restrict__ degPlane,
-                                                  int* __restrict__ maxg2) {
+                                                  int* __restrict__ maxg2, unsigned* __restrict__ bmAll) {
   // Only ~1 pixel in 4 has a gradient above rho and needs the angle and its double-precision sin/cos.  The CTA's 32x8
   // tile first writes the records of the undefined pixels and queues the defined ones in shared memory; the queue is
   // then processed by full warps, so the double-precision pipe is not spent on mostly idle lanes.
@@ -159,6 +159,23 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LinePa
     else {
       P[idx] = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, (unsigned)g2);
       DP[idx] = NOTDEF_F;
+    }
+  }
+  if (bmAll) {
+    // bitmap of the pixels that can never join a region (no defined angle): bit (idx & 31) of word (idx >> 5), zeroed by the
+    // caller.  A warp holds 32 consecutive pixels of one row = 32 consecutive bits, which straddle two words unless the row
+    // starts word-aligned.
+    const unsigned und = __ballot_sync(0xffffffffu, x < L.sw && y < L.sh && !defined);
+    if ((threadIdx.x & 31) == 0 && y < L.sh) {
+      const int bmWords = (L.P + 31) / 32;
+      unsigned* bm = bmAll + (size_t)f * ((bmWords + 3) / 4 * 4);
+      const int i0 = y * L.sw + blockIdx.x * 32, sft = i0 & 31;
+      if ((L.sw & 31) == 0) {
+        bm[i0 >> 5] = und;  // rows are whole words: this warp is the only writer (no memset needed)
+      } else if (und) {
+        atomicOr(bm + (i0 >> 5), und << sft);
+        if (sft && (und >> (32 - sft))) atomicOr(bm + (i0 >> 5) + 1, und >> (32 - sft));
+      }
     }
   }
   int m = defined ? g2 : 0;
@@ -272,6 +289,9 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ Lin
 // ------------------------------------------------------------------------------------------
 constexpr int REG_SMEM = 1024;  // region-list entries kept in shared memory (larger regions spill to global)
 constexpr int SW_G = 32;        // k_lsd_grow_sw: seeds per group (one warp-wide load of the sorted seed list)
+// where region growing keeps the `used` map: in the pixel records (first version, kept for comparison), in a per-frame bitmap
+// in shared or global memory (one warp per frame), or in the owner plane of the CTA-per-frame mode
+enum { GM_REC = 0, GM_BMS = 1, GM_BMG = 2, GM_MW = 3 };
 constexpr unsigned USED_BIT = 0x80000000u;  // `used` flag of a pixel: bit 31 of its record's .w (gx^2+gy^2 < 2^20)
 
 // The `used` map lives in the pixel records themselves (global memory, L1-resident around the growing region),
@@ -301,6 +321,11 @@ struct GrowCtx {
   int sw, sh, P;
   int lane;
   bool prefetch;
+  bool prefetch2;     // bitmap modes: prefetch only the record sectors of neighbours that are still available
+  // ---- bitmap modes (GM_BMS / GM_BMG): one bit per pixel, bit (idx & 31) of word (idx >> 5), set = the pixel cannot join a
+  // region any more (no defined angle, or used).  k_lsd_grad writes the undefined bits; the growing warp sets and clears the
+  // rest.  GM_BMS keeps the frame's bitmap in shared memory (24 KB at 640x480), GM_BMG in global memory (read through L2).
+  unsigned* bm;
   // ---- CTA-per-frame mode (k_lsd_grow_sw): ordered speculative regions, see the kernel's header ----
   // Owner plane: one word per pixel.  MW_FREE, or (tag << 1) | released with tag = seed rank + 1 of the region that
   // marked the pixel.  released = 1 is a TOMBSTONE: the region gave the pixel back (refine() un-marks, reduce_region_radius()
@@ -370,6 +395,49 @@ struct GrowCtx {
     if (i < REG_SMEM) regS[i] = v; else regG[i] = v;
   }
   __device__ __forceinline__ unsigned* wptr(int idx) const { return reinterpret_cast<unsigned*>(pix + idx) + 3; }
+  template <int M>
+  __device__ __forceinline__ unsigned bm_word(int w) const {
+    if (M == GM_BMS) {
+      unsigned v;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(bm + w)) : "memory");
+      return v;
+    }
+    return __ldcg(bm + w);
+  }
+  template <int M>
+  __device__ __forceinline__ bool bm_test(int idx) const { return (bm_word<M>(idx >> 5) >> (idx & 31)) & 1u; }
+  template <int M>
+  __device__ __forceinline__ void bm_set(int idx) const {
+    if (M == GM_BMS)
+      asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bm + (idx >> 5))), "r"(1u << (idx & 31)) : "memory");
+    else
+      atomicOr(bm + (idx >> 5), 1u << (idx & 31));
+  }
+  template <int M>
+  __device__ __forceinline__ void bm_clear(int idx) const {
+    if (M == GM_BMS)
+      asm volatile("red.shared.and.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bm + (idx >> 5))), "r"(~(1u << (idx & 31))) : "memory");
+    else
+      atomicAnd(bm + (idx >> 5), ~(1u << (idx & 31)));
+  }
+  // Bitmap modes: pull the record sectors (32 B = two 16-byte records) of the still available neighbours of a new region point
+  // towards L1; they are loaded when the point reaches the scan front, a batch or more from now.
+  template <int M>
+  __device__ __forceinline__ void bm_prefetch_around(int idx, unsigned xy) const {
+    const int y = (int)(xy >> 16);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      if (y + dy < 0 || y + dy >= sh) continue;
+      int id0 = idx + dy * sw - 1;  // records id0, id0 + 1, id0 + 2 (at the image border one of them belongs to another row: harmless)
+      id0 = max(0, min(id0, P - 3));
+      const unsigned w0 = bm_word<M>(id0 >> 5), w1 = bm_word<M>((id0 + 2) >> 5);
+      const unsigned av = ~__funnelshift_r(w0, w1, id0 & 31) & 7u;
+      const unsigned inA = (id0 & 1) ? 1u : 3u;  // which of the three records share the first sector
+      const uint4* q = pix + id0;
+      if (av & inA) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+      if (av & (7u ^ inA)) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 2));
+    }
+  }
 };
 
 __device__ __forceinline__ bool lsd_aligned(double theta, float deg, double prec) {
@@ -394,7 +462,9 @@ __device__ __forceinline__ bool lsd_aligned_rad(double theta, double a, double p
 }
 
 // region_grow(): returns the region size; reg[0] must already hold the seed pixel.
+template <int M>
 __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_out) {
+  constexpr bool BM = M == GM_BMS || M == GM_BMG;
   const int lane = C.lane;
   const unsigned seedxy = C.reg_get(0);
   const int seed = (int)(seedxy >> 16) * C.sw + (int)(seedxy & 0xffff);
@@ -407,7 +477,10 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
     sumdx = (float)c;
     sumdy = (float)s;
   }
-  if (lane == 0) *C.wptr(seed) = srec.w | USED_BIT;
+  if (lane == 0) {
+    if (BM) C.bm_set<M>(seed);
+    else *C.wptr(seed) = srec.w | USED_BIT;
+  }
   __syncwarp();
   int n = 1;
   for (int i = 0; i < n;) {
@@ -424,12 +497,14 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
       if (nx >= 0 && ny >= 0 && nx < C.sw && ny < C.sh) {
         nidx = ny * C.sw + nx;
         nxy = ((unsigned)ny << 16) | (unsigned)nx;
-        const uint4 r = C.pix[nidx];
-        w = r.w;
-        if (!(w & USED_BIT)) {
-          deg = __uint_as_float(r.x);
-          cs = __uint_as_float(r.y);
-          sn = __uint_as_float(r.z);
+        if (!BM || !C.bm_test<M>(nidx)) {
+          const uint4 r = C.pix[nidx];
+          w = r.w;
+          if (BM || !(w & USED_BIT)) {
+            deg = __uint_as_float(r.x);
+            cs = __uint_as_float(r.y);
+            sn = __uint_as_float(r.z);
+          }
         }
       }
     }
@@ -441,7 +516,8 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
       const int j = __ffs(mask) - 1;
       const int aidx = __shfl_sync(0xffffffffu, nidx, j);
       if (lane == j) {
-        *C.wptr(nidx) = w | USED_BIT;
+        if (BM) C.bm_set<M>(nidx);
+        else *C.wptr(nidx) = w | USED_BIT;
         C.reg_set(n, nxy);
       }
       ++n;
@@ -466,8 +542,9 @@ __device__ int lsd_region_grow(const GrowCtx& C, double prec, double* reg_angle_
 // on which the two tests agree (plus the corrected decision of the first disagreeing lane).  A batch whose
 // decisions do not depend on the drift of the angle costs one round instead of one round per accepted pixel;
 // the result is identical to the sequential scan by construction.
-template <bool MW>
+template <int M>
 __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_angle_out) {
+  constexpr bool MW = M == GM_MW, BM = M == GM_BMS || M == GM_BMG;
   const int lane = C.lane;
   const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
   const unsigned seedxy = C.reg_get(0);
@@ -483,6 +560,7 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
   }
   if (lane == 0) {
     if (MW) C.mw_take(seed, __ldcg(C.own + seed));
+    else if (BM) C.bm_set<M>(seed);
     else *C.wptr(seed) = srec.w | USED_BIT;
   }
   __syncwarp();
@@ -506,18 +584,29 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
       const int nx = (int)(p & 0xffff) + ox, ny = (int)(p >> 16) + oy;
       if (nx >= 0 && ny >= 0 && nx < C.sw && ny < C.sh) {
         const int id = ny * C.sw + nx;
-        unsigned ov = 0;
-        if (MW) ov = __ldcg(C.own + id);  // owner words live in L2 (atomics), never in a possibly stale L1 line
-        const uint4 r = C.pix[id];
-        const bool avail = MW ? (__uint_as_float(r.x) != NOTDEF_F && C.mw_available(ov, h0)) : !(r.w & USED_BIT);
-        if (avail && __uint_as_float(r.x) != NOTDEF_F) {
-          nidx = id;
-          nxy = ((unsigned)ny << 16) | (unsigned)nx;
-          w = r.w;
-          ovk = ov;
-          deg = __uint_as_float(r.x);
-          cs = __uint_as_float(r.y);
-          sn = __uint_as_float(r.z);
+        if (BM) {
+          if (!C.bm_test<M>(id)) {  // defined and not used: only these records are loaded at all
+            const uint4 r = C.pix[id];
+            nidx = id;
+            nxy = ((unsigned)ny << 16) | (unsigned)nx;
+            deg = __uint_as_float(r.x);
+            cs = __uint_as_float(r.y);
+            sn = __uint_as_float(r.z);
+          }
+        } else {
+          unsigned ov = 0;
+          if (MW) ov = __ldcg(C.own + id);  // owner words live in L2 (atomics), never in a possibly stale L1 line
+          const uint4 r = C.pix[id];
+          const bool avail = MW ? (__uint_as_float(r.x) != NOTDEF_F && C.mw_available(ov, h0)) : !(r.w & USED_BIT);
+          if (avail && __uint_as_float(r.x) != NOTDEF_F) {
+            nidx = id;
+            nxy = ((unsigned)ny << 16) | (unsigned)nx;
+            w = r.w;
+            ovk = ov;
+            deg = __uint_as_float(r.x);
+            cs = __uint_as_float(r.y);
+            sn = __uint_as_float(r.z);
+          }
         }
       }
     }
@@ -545,9 +634,12 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
           if ((defm >> j0) == 1u) {
             if (lane == j0) {
               if (MW) C.mw_take(nidx, ovk);
+              else if (BM) C.bm_set<M>(nidx);
               else *C.wptr(nidx) = w | USED_BIT;
               C.reg_set(n, nxy);
-              if (C.prefetch) {
+              if (BM && C.prefetch2) {
+                C.bm_prefetch_around<M>(nidx, nxy);
+              } else if (C.prefetch) {
                 const int up = (nxy >> 16) > 0 ? nidx - C.sw : nidx, dn = (int)(nxy >> 16) < C.sh - 1 ? nidx + C.sw : nidx;
                 const uint4* q = C.pix + nidx;
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (up - nidx)));
@@ -588,9 +680,12 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
         }
         if ((commit >> lane) & 1u) {
           if (MW) C.mw_take(nidx, ovk);
+          else if (BM) C.bm_set<M>(nidx);
           else *C.wptr(nidx) = w | USED_BIT;
           C.reg_set(n + __popc(commit & lt), nxy);
-          if (C.prefetch) {
+          if (BM && C.prefetch2) {
+            C.bm_prefetch_around<M>(nidx, nxy);
+          } else if (C.prefetch) {
             // the 3x3 neighbourhood of the new region point is examined when the point reaches the scan front, a
             // few batches from now: pull the lines holding its three record rows towards L1
             const int up = (nxy >> 16) > 0 ? nidx - C.sw : nidx, dn = (int)(nxy >> 16) < C.sh - 1 ? nidx + C.sw : nidx;
@@ -741,9 +836,10 @@ __device__ __forceinline__ double rect_density(int n, const LsdRect& r) {
 }
 
 // refine() + reduce_region_radius(); returns false when the region must be dropped. *n_io = region size.
-template <bool MW>
+template <int M>
 __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double prec, double p, LsdRect* rec,
                            double density_th, int variant) {
+  constexpr bool MW = M == GM_MW, BM = M == GM_BMS || M == GM_BMG;
   const int lane = C.lane;
   int n = *n_io;
   double density = rect_density(n, *rec);
@@ -766,6 +862,7 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
       const int idx = py * C.sw + px;
       const uint4 r = C.pix[idx];
       if (MW) C.mw_release(idx);
+      else if (BM) C.bm_clear<M>(idx);
       else *C.wptr(idx) = r.w & ~USED_BIT;
       double flag = 0.0, v = 0.0;
       if (sqrt(dist_sq_dev(xc, yc, (double)px, (double)py)) < rec->width) {
@@ -794,7 +891,8 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   const double tau = __dmul_rn(
       2.0, sqrt(__dadd_rn(__ddiv_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)), (double)cntN),
                           __dmul_rn(mean_angle, mean_angle))));
-  n = (MW || (variant & 1)) ? lsd_region_grow_spec<MW>(C, tau, &reg_angle) : lsd_region_grow(C, tau, &reg_angle);
+  if (BM) __syncwarp();  // the cleared bits are read by the growth that follows
+  n = (MW || (variant & 1)) ? lsd_region_grow_spec<M>(C, tau, &reg_angle) : lsd_region_grow<M>(C, tau, &reg_angle);
   if (MW && C.mw_poisoned()) {
     *n_io = n;
     return false;
@@ -820,6 +918,8 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
           if (dist_sq_dev(xc, yc, (double)px, (double)py) > radSq) {
             if (MW) {
               C.mw_release(py * C.sw + px);
+            } else if (BM) {
+              C.bm_clear<M>(py * C.sw + px);
             } else {
               unsigned* wp = C.wptr(py * C.sw + px);
               *wp = *wp & ~USED_BIT;
@@ -845,6 +945,8 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
           if (far) {
             if (MW) {
               C.mw_release(py * C.sw + px);
+            } else if (BM) {
+              C.bm_clear<M>(py * C.sw + px);
             } else {
               unsigned* wp = C.wptr(py * C.sw + px);
               *wp = *wp & ~USED_BIT;
@@ -888,20 +990,42 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   return true;
 }
 
-constexpr int GROW_WARPS = 4;  // frames per CTA (one warp each): keeps the long-running kernel from holding every CTA slot of an SM
+constexpr int GROW_WARPS = 4;  // frames per CTA at most (one warp each): keeps the long-running kernel from holding every CTA slot of an SM
+// dynamic shared memory per frame: staging doubles, the head of the region list, and in GM_BMS the frame's bitmap
+__host__ __device__ inline size_t grow_smem_per_frame(int P, bool bitmap) {
+  return 96 * sizeof(double) + REG_SMEM * sizeof(unsigned) + (bitmap ? (size_t)((P + 31) / 32 + 3) / 4 * 16 : 0);
+}
+template <int M>
 __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_constant__ LineParams L, uint4* pixAll,
-                                                 const unsigned* __restrict__ seedsAll, const int* __restrict__ nseeds,
-                                                 unsigned* regAll, LsdRect* __restrict__ rectsAll,
-                                                 int* __restrict__ nrects, int* __restrict__ status) {
-  __shared__ double stage[GROW_WARPS][96];
-  __shared__ unsigned regS[GROW_WARPS][REG_SMEM];
+                                                 unsigned* bmAll, const unsigned* __restrict__ seedsAll,
+                                                 const int* __restrict__ nseeds, unsigned* regAll,
+                                                 LsdRect* __restrict__ rectsAll, int* __restrict__ nrects,
+                                                 int* __restrict__ status) {
+  constexpr bool BM = M == GM_BMS || M == GM_BMG;
+  extern __shared__ __align__(16) unsigned char grow_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x * GROW_WARPS + warp;
+  const int f = blockIdx.x * (blockDim.x >> 5) + warp;
   if (f >= L.batch) return;
+  unsigned char* mySmem = grow_smem + (size_t)warp * grow_smem_per_frame(L.P, M == GM_BMS);
   GrowCtx C;
-  C.stage = stage[warp];
-  C.regS = regS[warp];
+  C.stage = reinterpret_cast<double*>(mySmem);
+  C.regS = reinterpret_cast<unsigned*>(mySmem + 96 * sizeof(double));
+  C.bm = nullptr;
+  if (BM) {
+    const int bmWords = (L.P + 31) / 32;
+    unsigned* gbm = bmAll + (size_t)f * ((bmWords + 3) / 4 * 4);
+    if (M == GM_BMS) {
+      uint4* dst = reinterpret_cast<uint4*>(C.regS + REG_SMEM);
+      const uint4* src = reinterpret_cast<const uint4*>(gbm);
+      for (int i = lane; i < (bmWords + 3) / 4; i += 32) dst[i] = __ldcs(src + i);
+      C.bm = reinterpret_cast<unsigned*>(dst);
+      __syncwarp();
+    } else {
+      C.bm = gbm;
+    }
+  }
   C.prefetch = (L.grow_variant & 2) != 0;
+  C.prefetch2 = (L.grow_variant & 4) != 0;
   C.pix = pixAll + (size_t)f * L.P;
   C.regG = regAll + (size_t)f * L.P;
   C.sw = L.sw;
@@ -924,7 +1048,7 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
     int s = snext;
     snext = base + 32 + lane < ns ? (int)seeds[base + 32 + lane] : -1;  // prefetch the next chunk of seeds
     while (true) {
-      const bool unused = s >= 0 && !(*C.wptr(s) & USED_BIT);
+      const bool unused = s >= 0 && (BM ? !C.bm_test<M>(s) : !(*C.wptr(s) & USED_BIT));
       const unsigned m = __ballot_sync(0xffffffffu, unused);
       if (!m) break;
       const int j = __ffs(m) - 1;
@@ -933,14 +1057,14 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
       if (lane == 0) C.reg_set(0, ((unsigned)(seed / L.sw) << 16) | (unsigned)(seed % L.sw));
       __syncwarp();
       double reg_angle;
-      int n = (L.grow_variant & 1) ? lsd_region_grow_spec<false>(C, L.prec, &reg_angle) : lsd_region_grow(C, L.prec, &reg_angle);
+      int n = (L.grow_variant & 1) ? lsd_region_grow_spec<M>(C, L.prec, &reg_angle) : lsd_region_grow<M>(C, L.prec, &reg_angle);
       if (n < L.min_reg_size) continue;
       LsdRect rec;
       GP_START();
       lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
       GP_ADD(2);
       GP_START();
-      const bool keep = lsd_refine<false>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, L.grow_variant);
+      const bool keep = lsd_refine<M>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, L.grow_variant);
       GP_ADD(3);
       if (!keep) continue;
       if (nrect < L.rect_cap) {
@@ -1421,13 +1545,13 @@ __device__ void sw_worker(SwState<K, WS>& S, GrowCtx& C, const LineParams& L, co
       }
       __syncwarp();
       double reg_angle;
-      int n = lsd_region_grow_spec<true>(C, L.prec, &reg_angle);
+      int n = lsd_region_grow_spec<GM_MW>(C, L.prec, &reg_angle);
       ++nreg;
       bool keep = false;
       LsdRect rec;
       if (!C.mw_poisoned() && n >= L.min_reg_size) {
         lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
-        keep = lsd_refine<true>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, 1);
+        keep = lsd_refine<GM_MW>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, 1);
       }
       if (lane == 0) *reinterpret_cast<volatile unsigned*>(&S.pendTag[me][j]) = 0u;
       bool squashed = C.mw_poisoned();
@@ -1813,22 +1937,50 @@ __device__ void lsd_nfa_rect(const LineParams& L, const float* __restrict__ pixA
   }
 }
 
-// Persistent launch: a fixed grid of warps strides over (frame, group of NFA_GROUP rectangles) items.  The rectangle
-// counts are only known on the device and vary from ~50 to several hundred per frame; a grid sized for the capacity
-// would be 97 % empty CTAs, and rectangles that enter rect_improve cost ~25x the others, so small items matter.
-constexpr int NFA_GROUP = 4;
+// Persistent launch with a work queue: rectangle counts are only known on the device (~50 to several hundred per frame) and
+// a rectangle that enters rect_improve costs ~25x one that is meaningful at once, so a static assignment leaves most warps
+// idle while a few finish their heavy rectangles.  k_lsd_nfa_prefix lays the rectangles of the batch out as one list
+// (exclusive prefix of the per-frame counts) and clears the queue head; every warp of k_lsd_nfa then takes the next
+// rectangle with an atomic increment until the list is empty.  Rectangles are taken in frame order, which keeps a frame's
+// angle plane in L2 while its rectangles are evaluated.
+__global__ void __launch_bounds__(32) k_lsd_nfa_prefix(int batch, const int* __restrict__ nrects, int* __restrict__ prefix,
+                                                       int* __restrict__ head) {
+  const int lane = threadIdx.x;
+  int run = 0;
+  for (int base = 0; base < batch; base += 32) {
+    const int v = base + lane < batch ? nrects[base + lane] : 0;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (base + lane < batch) prefix[base + lane] = run + inc - v;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) {
+    prefix[batch] = run;
+    *head = 0;
+  }
+}
+
 __global__ void __launch_bounds__(256, 3) k_lsd_nfa(const __grid_constant__ LineParams L, const float* __restrict__ pixAll,
-                                                 const LsdRect* __restrict__ rectsAll, const int* __restrict__ nrects,
-                                                 LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * 8, wid = blockIdx.x * 8 + warp;
-  const int groups = (L.rect_cap + NFA_GROUP - 1) / NFA_GROUP;
-  const long long nitems = (long long)L.batch * groups;
-  for (long long item = wid; item < nitems; item += nwarps) {
-    const int f = (int)(item / groups), g = (int)(item % groups);
-    const int n = __ldg(nrects + f);
-    for (int ri = g * NFA_GROUP; ri < min(n, (g + 1) * NFA_GROUP); ++ri)
-      lsd_nfa_rect(L, pixAll, rectsAll, rectOut, rectValid, f, ri, lane);
+                                                 const LsdRect* __restrict__ rectsAll, const int* __restrict__ prefix,
+                                                 int* __restrict__ head, LsdSegment* __restrict__ rectOut,
+                                                 uint8_t* __restrict__ rectValid) {
+  const int lane = threadIdx.x & 31;
+  const int total = __ldg(prefix + L.batch);
+  while (true) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(head, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    int lo = 0, hi = L.batch;  // the frame of the item: largest f with prefix[f] <= item
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid;
+    }
+    lsd_nfa_rect(L, pixAll, rectsAll, rectOut, rectValid, lo, item - __ldg(prefix + lo), lane);
   }
 }
 
@@ -1984,7 +2136,19 @@ __global__ void __launch_bounds__(256) k_lsd_finish(const __grid_constant__ Line
 // reference); then thread = one of the 72 (band, statistic) accumulators, each summing its <= 21 row
 // contributions in row order; thread 0 normalises, clamps and binarises.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(96) k_lbd(const __grid_constant__ LineParams L, const uint8_t* __restrict__ img, int pitch,
+// Sobel taps of one position straight from the image (safety net of k_lbd when a chunk's box does not fit its tile)
+__device__ __noinline__ void lbd_taps_global(const uint8_t* I, int pitch, int x, int y, int xm, int xp, int ym, int yp, int* dx,
+                                             int* dy) {
+  const uint8_t* r0 = I + (size_t)ym * pitch;
+  const uint8_t* r1 = I + (size_t)y * pitch;
+  const uint8_t* r2 = I + (size_t)yp * pitch;
+  const int a = r0[xm], b = r0[x], c = r0[xp], d = r1[xm], e = r1[xp], g = r2[xm], h = r2[x], i = r2[xp];
+  *dx = (c - a) + 2 * (e - d) + (i - g);
+  *dy = (g - a) + 2 * (h - b) + (i - c);
+}
+
+constexpr int LBD_THREADS = 64;
+__global__ void __launch_bounds__(LBD_THREADS) k_lbd(const __grid_constant__ LineParams L, const uint8_t* __restrict__ img, int pitch,
                                             size_t frame_stride, const plslam_keyline_t* __restrict__ keylines,
                                             const int* __restrict__ counts, uint8_t* __restrict__ desc, int capacity) {
   __shared__ float rowsum[LBD_ROWS][4];
@@ -1993,53 +2157,119 @@ __global__ void __launch_bounds__(96) k_lbd(const __grid_constant__ LineParams L
   if (r >= counts[f]) return;
   const uint8_t* I = img + (size_t)f * frame_stride;
   const plslam_keyline_t kl = keylines[(size_t)f * capacity + r];
-  if (t < LBD_ROWS) {
-    const int hID = t;
-    const short lengthOfLSP = (short)kl.numOfPixels;
-    const short halfWidth = (lengthOfLSP - 1) / 2, halfHeight = (LBD_ROWS - 1) / 2;
+  // Thread hID < 63 owns row hID of the line support region.  The walk along a row is a chain of float additions (the
+  // positions and the four sums), so it stays sequential per row; the image is what the rows share.  The line is cut into
+  // chunks of LBD_CH steps: every row first advances its positions through the chunk, rows 0 and 62 publish the bounding
+  // box (positions are monotone in the row index, so the two outer rows bound all of them), the CTA copies that box of
+  // the image (+1 pixel for the Sobel taps, at most 76 x 76 bytes for 32 steps x 63 rows at any angle) into shared memory
+  // with coalesced row loads, and the rows then take their Sobel taps from the tile.  BORDER_REFLECT_101 is folded into
+  // the tap indices (x - 1 -> 1 at x = 0, x + 1 -> W - 2 at x = W - 1), which stay inside the box.
+  constexpr int LBD_CH = 32, LBD_TILE = 80, LBD_TROWS = 76;  // tile pitch 80: the box is widened to whole 4-byte words
+  __shared__ __align__(16) uint8_t tile[LBD_TILE * LBD_TROWS];
+  const bool wordLoads = ((reinterpret_cast<uintptr_t>(I) | (uintptr_t)pitch) & 3u) == 0;
+  __shared__ int boxS[2][4];
+  const bool rowThread = t < LBD_ROWS;
+  const int hID = t;
+  const int lengthOfLSP = (int)(short)kl.numOfPixels;
+  const int W = L.W, H = L.H;
+  float dL0, dL1;
+  {
+    double sn_, cs_;
+    pl_sincos_dev((double)kl.angle, &sn_, &cs_);
+    dL0 = (float)cs_;
+    dL1 = (float)sn_;
+  }
+  const float dO0 = -dL1, dO1 = dL0;
+  float sCorX = 0.f, sCorY = 0.f;
+  if (rowThread) {
+    const short halfWidth = (short)((lengthOfLSP - 1) / 2), halfHeight = (LBD_ROWS - 1) / 2;
     const float midX = (float)__dmul_rn(0.5, (double)__fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
     const float midY = (float)__dmul_rn(0.5, (double)__fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
-    float dL0, dL1;
-    {
-      double s, c;
-      pl_sincos_dev((double)kl.angle, &s, &c);
-      dL0 = (float)c;
-      dL1 = (float)s;
-    }
-    const float dO0 = -dL1, dO1 = dL0;
     // sCor0 after hID row steps (each step: sCorX0 -= dL[1]; sCorY0 += dL[0])
-    float sx0 = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, (float)halfHeight)), midX);
-    float sy0 = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, (float)halfHeight)), midY);
+    sCorX = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, (float)halfHeight)), midX);
+    sCorY = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, (float)halfHeight)), midY);
     for (int k = 0; k < hID; ++k) {
-      sx0 = __fsub_rn(sx0, dL1);
-      sy0 = __fadd_rn(sy0, dL0);
+      sCorX = __fsub_rn(sCorX, dL1);
+      sCorY = __fadd_rn(sCorY, dL0);
     }
-    float sCorX = sx0, sCorY = sy0;
-    float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
-    const int W = L.W, H = L.H;
-    for (short wID = 0; wID < lengthOfLSP; ++wID) {
-      short tc = (short)roundf(sCorX);
-      const int x = (tc < 0) ? 0 : (tc > W - 1) ? W - 1 : tc;
-      tc = (short)roundf(sCorY);
-      const int y = (tc < 0) ? 0 : (tc > H - 1) ? H - 1 : tc;
-      int dx, dy;
-      if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {  // interior: no border reflection
-        const uint8_t* r1 = I + (size_t)y * pitch + x;
-        const uint8_t* r0 = r1 - pitch;
-        const uint8_t* r2 = r1 + pitch;
-        const int a = r0[-1], b = r0[0], c = r0[1], d = r1[-1], e = r1[1], g = r2[-1], h = r2[0], i = r2[1];
-        dx = (c - a) + 2 * (e - d) + (i - g);
-        dy = (g - a) + 2 * (h - b) + (i - c);
-      } else {
-        sobel_at_dev(I, W, H, pitch, x, y, dx, dy);
+  }
+  float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
+  const int xlo = W > 1 ? 1 : 0, xhi = W > 1 ? W - 2 : 0, ylo = H > 1 ? 1 : 0, yhi = H > 1 ? H - 2 : 0;
+  for (int w0 = 0; w0 < lengthOfLSP; w0 += LBD_CH) {
+    const int nst = min(LBD_CH, lengthOfLSP - w0);
+    unsigned pos[LBD_CH];  // (y << 16) | x of this row's steps
+    int mnx = 0x7fff, mxx = 0, mny = 0x7fff, mxy = 0;
+    if (rowThread) {
+#pragma unroll
+      for (int u = 0; u < LBD_CH; ++u) {
+        short tc = (short)roundf(sCorX);
+        const int x = (tc < 0) ? 0 : (tc > W - 1) ? W - 1 : tc;
+        tc = (short)roundf(sCorY);
+        const int y = (tc < 0) ? 0 : (tc > H - 1) ? H - 1 : tc;
+        pos[u] = ((unsigned)y << 16) | (unsigned)x;
+        if (u < nst) {
+          sCorX = __fadd_rn(sCorX, dL0);
+          sCorY = __fadd_rn(sCorY, dL1);
+          mnx = min(mnx, x); mxx = max(mxx, x);
+          mny = min(mny, y); mxy = max(mxy, y);
+        }
       }
-      const float gDL = __fadd_rn(__fmul_rn((float)dx, dL0), __fmul_rn((float)dy, dL1));
-      const float gDO = __fadd_rn(__fmul_rn((float)dx, dO0), __fmul_rn((float)dy, dO1));
-      if (gDL > 0) pgdL = __fadd_rn(pgdL, gDL); else ngdL = __fsub_rn(ngdL, gDL);
-      if (gDO > 0) pgdO = __fadd_rn(pgdO, gDO); else ngdO = __fsub_rn(ngdO, gDO);
-      sCorX = __fadd_rn(sCorX, dL0);
-      sCorY = __fadd_rn(sCorY, dL1);
+      if (hID == 0 || hID == LBD_ROWS - 1) {
+        int* bs = boxS[hID ? 1 : 0];
+        bs[0] = mnx; bs[1] = mxx; bs[2] = mny; bs[3] = mxy;
+      }
     }
+    __syncthreads();
+    int bx0 = max(0, min(boxS[0][0], boxS[1][0]) - 1);
+    const int bx1 = min(W - 1, max(boxS[0][1], boxS[1][1]) + 1);
+    const int by0 = max(0, min(boxS[0][2], boxS[1][2]) - 1), by1 = min(H - 1, max(boxS[0][3], boxS[1][3]) + 1);
+    if (wordLoads) bx0 &= ~3;
+    const int tw = bx1 - bx0 + 1, th = by1 - by0 + 1;
+    const bool tiled = tw <= LBD_TILE && th <= LBD_TROWS;  // always, by the bound above; the global path is the safety net
+    if (tiled) {
+      if (wordLoads) {
+        // a row of the box is at most 20 words: two rows per warp step when it is at most 16
+        const int twords = (tw + 3) >> 2, lane = t & 31, warp = t >> 5;
+        const int rpw = twords <= 16 ? 2 : 1, col = rpw == 2 ? (lane & 15) : lane, sub = rpw == 2 ? (lane >> 4) : 0;
+        for (int ty = warp * rpw + sub; ty < th; ty += (LBD_THREADS / 32) * rpw)
+          if (col < twords)
+            reinterpret_cast<unsigned*>(tile + ty * LBD_TILE)[col] =
+                __ldg(reinterpret_cast<const unsigned*>(I + (size_t)(by0 + ty) * pitch + bx0) + col);
+      } else {
+        for (int ty = t >> 5; ty < th; ty += LBD_THREADS / 32) {
+          const uint8_t* src = I + (size_t)(by0 + ty) * pitch + bx0;
+          for (int tx = t & 31; tx < tw; tx += 32) tile[ty * LBD_TILE + tx] = __ldg(src + tx);
+        }
+      }
+    }
+    __syncthreads();
+    if (rowThread) {
+#pragma unroll
+      for (int u = 0; u < LBD_CH; ++u) {
+        if (u < nst) {
+          const int x = (int)(pos[u] & 0xffffu), y = (int)(pos[u] >> 16);
+          const int xm = x > 0 ? x - 1 : xlo, xp = x < W - 1 ? x + 1 : xhi;
+          const int ym = y > 0 ? y - 1 : ylo, yp = y < H - 1 ? y + 1 : yhi;
+          int dx, dy;
+          if (tiled) {
+            const uint8_t* r0 = tile + (ym - by0) * LBD_TILE - bx0;
+            const uint8_t* r1 = tile + (y - by0) * LBD_TILE - bx0;
+            const uint8_t* r2 = tile + (yp - by0) * LBD_TILE - bx0;
+            const int a = r0[xm], b = r0[x], c = r0[xp], d = r1[xm], e = r1[xp], g = r2[xm], h = r2[x], i = r2[xp];
+            dx = (c - a) + 2 * (e - d) + (i - g);
+            dy = (g - a) + 2 * (h - b) + (i - c);
+          } else {
+            lbd_taps_global(I, pitch, x, y, xm, xp, ym, yp, &dx, &dy);
+          }
+          const float gDL = __fadd_rn(__fmul_rn((float)dx, dL0), __fmul_rn((float)dy, dL1));
+          const float gDO = __fadd_rn(__fmul_rn((float)dx, dO0), __fmul_rn((float)dy, dO1));
+          if (gDL > 0) pgdL = __fadd_rn(pgdL, gDL); else ngdL = __fsub_rn(ngdL, gDL);
+          if (gDO > 0) pgdO = __fadd_rn(pgdO, gDO); else ngdO = __fsub_rn(ngdO, gDO);
+        }
+      }
+    }
+  }
+  if (rowThread) {
     const float cg = L.gaussG[hID];
     rowsum[hID][0] = __fmul_rn(cg, pgdL);
     rowsum[hID][1] = __fmul_rn(cg, ngdL);
@@ -2047,9 +2277,9 @@ __global__ void __launch_bounds__(96) k_lbd(const __grid_constant__ LineParams L
     rowsum[hID][3] = __fmul_rn(cg, ngdO);
   }
   __syncthreads();
-  if (t < LBD_BANDS * 8) {
+  for (int tt = t; tt < LBD_BANDS * 8; tt += LBD_THREADS) {
     // accumulator (band b, statistic q): q = 0 pgdL, 1 ngdL, 2 pgdL^2, 3 ngdL^2, 4 pgdO, 5 ngdO, 6 pgdO^2, 7 ngdO^2
-    const int b = t >> 3, q = t & 7;
+    const int b = tt >> 3, q = tt & 7;
     const int src = (q & 1) + ((q & 4) ? 2 : 0);  // which of the 4 row sums
     const bool sq = (q & 2) != 0;
     float acc = 0.f;
@@ -2253,6 +2483,7 @@ int LineExtractor::configure(int W, int H, int batch) {
   if ((rc = regbuf.ensure(B * P.P * sizeof(unsigned)))) return rc;
   if ((rc = rects.ensure(B * P.rect_cap * sizeof(LsdRect)))) return rc;
   if ((rc = nrects.ensure(B * sizeof(int)))) return rc;
+  if ((rc = nfaq.ensure((B + 2) * sizeof(int)))) return rc;  // k_lsd_nfa's work list: prefix[B + 1] and the queue head
   if ((rc = rectout.ensure(B * P.rect_cap * (sizeof(LsdSegment) + 1)))) return rc;
   if ((rc = segs.ensure(B * P.rect_cap * sizeof(LsdSegment)))) return rc;
   if ((rc = nsegs.ensure(B * sizeof(int)))) return rc;
@@ -2299,8 +2530,24 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_grad", st);
   PL_CARVEOUT(k_lsd_grad);
+  // Where the one-warp-per-frame kernel keeps the `used` map (experiment switch PLSLAM_GROW_USED: 0 = in the pixel records
+  // (default), 1 = bitmap in shared memory, 2 = bitmap in global memory).  Measured on B200, 640x480 (tools/r02_bm_ab.sh,
+  // gpurun_out/r02_bm_ab.log): the bitmaps cut the kernel's loads to the records of available pixels only, yet one batch of
+  // 256 frames takes 47.4 ms (shared) / 57.2 ms (global) against 49.5 ms, and with 16 batches in flight the shared bitmap
+  // (24 KB per frame: 4 frames per SM instead of ~20) falls from 17.8 k to 11.7 k frames/s, the global one to 17.0 k: the
+  // kernel is bound by its dependent instruction chain, not by the records it loads.
+  static const int usedEnv = [] { const char* e = std::getenv("PLSLAM_GROW_USED"); return e ? std::atoi(e) : -1; }();
+  static const int gwEnv = [] { const char* e = std::getenv("PLSLAM_GROW_GW"); return e ? std::atoi(e) : 0; }();
+  const size_t bmStride = (size_t)((P.P + 31) / 32 + 3) / 4 * 4;  // words per frame
+  int usedMode = usedEnv >= 0 && usedEnv <= GM_BMG ? usedEnv : GM_REC;
+  if (usedMode == GM_BMS && grow_smem_per_frame(P.P, true) > 200 * 1024) usedMode = GM_BMG;
+  if (usedMode != GM_REC) {
+    int rcb;
+    if ((rcb = ubm.ensure((size_t)std::max(batch, cfgB) * bmStride * sizeof(unsigned)))) return rcb;
+    if (P.sw % 32) PL_CUDA(cudaMemsetAsync(ubm.p, 0, (size_t)batch * bmStride * sizeof(unsigned), st));
+  }
   k_lsd_grad<<<dim3(div_up(P.sw, 32), div_up(P.sh, 8), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(), degp.as<float>(),
-                                                                             maxg2.as<int>());
+                                                                             maxg2.as<int>(), usedMode != GM_REC ? ubm.as<unsigned>() : nullptr);
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_rowhist", st);
   PL_CARVEOUT(k_lsd_rowhist);
@@ -2361,10 +2608,25 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
     else PL_SW_LAUNCH(8, 2048);
 #undef PL_SW_LAUNCH
   } else {
-    PL_CARVEOUT(k_lsd_grow);
-    k_lsd_grow<<<div_up(batch, GROW_WARPS), 32 * GROW_WARPS, 0, st>>>(P, pix.as<uint4>(), seeds.as<unsigned>(), nseeds.as<int>(),
-                                                                      regbuf.as<unsigned>(), rects.as<LsdRect>(), nrects.as<int>(),
-                                                                      status.as<int>());
+    // frames per CTA: 4 unless the bitmaps in shared memory would push a CTA beyond a quarter of the SM
+    const size_t perFrame = grow_smem_per_frame(P.P, usedMode == GM_BMS);
+    int gw = gwEnv ? std::min(std::max(gwEnv, 1), GROW_WARPS) : GROW_WARPS;
+    while (gw > 1 && perFrame * gw > 60 * 1024) gw >>= 1;
+#define PL_GROW_LAUNCH(MODE)                                                                                                  \
+  do {                                                                                                                        \
+    static PerDeviceOnce attr;                                                                                                \
+    if (attr.first())                                                                                                         \
+      PL_CUDA(cudaFuncSetAttribute(k_lsd_grow<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));               \
+    PL_CARVEOUT(k_lsd_grow<MODE>);                                                                                            \
+    k_lsd_grow<MODE><<<div_up(batch, gw), 32 * gw, perFrame * gw, st>>>(P, pix.as<uint4>(), ubm.as<unsigned>(),               \
+                                                                        seeds.as<unsigned>(), nseeds.as<int>(),               \
+                                                                        regbuf.as<unsigned>(), rects.as<LsdRect>(),           \
+                                                                        nrects.as<int>(), status.as<int>());                  \
+  } while (0)
+    if (usedMode == GM_BMS) PL_GROW_LAUNCH(GM_BMS);
+    else if (usedMode == GM_BMG) PL_GROW_LAUNCH(GM_BMG);
+    else PL_GROW_LAUNCH(GM_REC);
+#undef PL_GROW_LAUNCH
   }
   PL_STAGE_END(timer, st);
   static const bool grow_only = std::getenv("PLSLAM_DEBUG_STOP_AFTER_GROW") != nullptr;  // profiling aid (tools/)
@@ -2373,8 +2635,9 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   uint8_t* rvalid = reinterpret_cast<uint8_t*>(rout + (size_t)cfgB * P.rect_cap);
   PL_STAGE_BEGIN(timer, "lsd_nfa", st);
   PL_CARVEOUT(k_lsd_nfa);
-  k_lsd_nfa<<<numSMs * 3, 256, 0, st>>>(P, degp.as<float>(), rects.as<LsdRect>(), nrects.as<int>(),
-                                                                rout, rvalid);
+  k_lsd_nfa_prefix<<<1, 32, 0, st>>>(batch, nrects.as<int>(), nfaq.as<int>(), nfaq.as<int>() + batch + 1);
+  k_lsd_nfa<<<numSMs * 3, 256, 0, st>>>(P, degp.as<float>(), rects.as<LsdRect>(), nfaq.as<int>(), nfaq.as<int>() + batch + 1,
+                                        rout, rvalid);
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_finish", st);
   PL_CARVEOUT(k_lsd_finish);
@@ -2384,7 +2647,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lbd", st);
   PL_CARVEOUT(k_lbd);
-  k_lbd<<<dim3(P.out_cap, batch), 96, 0, st>>>(P, d_images, pitch, frame_stride, d_keylines, d_counts, d_desc, capacity);
+  k_lbd<<<dim3(P.out_cap, batch), LBD_THREADS, 0, st>>>(P, d_images, pitch, frame_stride, d_keylines, d_counts, d_desc, capacity);
   PL_STAGE_END(timer, st);
   PL_CUDA(cudaGetLastError());
   return PLSLAM_OK;
@@ -2462,7 +2725,7 @@ int LineExtractor::compute_lbd_host(const uint8_t* image, int W, int H, int pitc
   if (e == cudaSuccess) e = cudaMemcpyAsync(dCnt.p, &n, sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
     PL_CARVEOUT(k_lbd);
-    k_lbd<<<dim3(n, 1), 96, 0, st>>>(P, dImg.as<uint8_t>(), (int)dpitch, dpitch * H, dKl.as<plslam_keyline_t>(), dCnt.as<int>(),
+    k_lbd<<<dim3(n, 1), LBD_THREADS, 0, st>>>(P, dImg.as<uint8_t>(), (int)dpitch, dpitch * H, dKl.as<plslam_keyline_t>(), dCnt.as<int>(),
                                     dDesc.as<uint8_t>(), n);
     e = cudaGetLastError();
   }

@@ -32,7 +32,7 @@ struct LineParams {
   int rect_cap;        // capacity of the per-frame rectangle / segment lists
   int out_cap;         // capacity of the per-frame output (keylines kept)
   int batch;           // frames of the current launch
-  int grow_variant;    // k_lsd_grow neighbour scan: 0 = one accept per round, 1 = in-batch speculation
+  int grow_variant;    // k_lsd_grow: bit 0 in-batch speculation, bit 1 L1 prefetch of a new point's rows, bit 2 bitmap-guided prefetch
   float gaussL[LBD_W * 3], gaussG[LBD_ROWS];
 };
 
@@ -66,7 +66,7 @@ class LineExtractor {
   int configure(int W, int H, int batch);
   int device = -1, numSMs = 148, cfgW = 0, cfgH = 0, cfgB = 0, last_batch = 0;
   LineParams P{};
-  DevBuf scaled, pix, degp, owner, recttmp, listpool, rectstage, coef, rowhist, binstart, maxg2, seeds, nseeds, regbuf, rects, nrects, rectout, segs, nsegs, resp,
+  DevBuf scaled, pix, degp, ubm, owner, recttmp, listpool, rectstage, coef, rowhist, binstart, maxg2, seeds, nseeds, regbuf, rects, nrects, nfaq, rectout, segs, nsegs, resp,
       rowsum, status;
   DevBuf stageIn, stageKl, stageDesc, stageFuncs, stageCnt;
   cudaStream_t ownStream = nullptr;
