@@ -250,6 +250,17 @@ typedef struct plslam_proj_job {
   float th;
   int32_t n1, n2, mono, check_orientation;
   int32_t report_removed;      /* 0: removed entries read -1 like never-assigned ones; 1: they read -2 */
+  /* mode 1 = ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, float th,
+   * int ORBdist) (ORBmatcher.h:82, @0x7e8c0; Tracking::Relocalization): the "last" arrays describe the KEY FRAME's map points
+   * (last_valid = pMP && !isBad() && !sAlreadyFound.count(pMP); last_angle = pKF->mvKeysUn[i].angle; last_octave, last_obs,
+   * cur_uright, tcw_last, mono unused), last_dist_range = (mfMinDistance, mfMaxDistance) per point, cur_taken =
+   * CurrentFrame.mvpMapPoints[i] != NULL.  The search level is MapPoint::PredictScale(dist3D, &CurrentFrame) (@0x8fc20) from
+   * log_scale_factor = mfLogScaleFactor and n_levels = mnScaleLevels, the window spans levels level-1 .. level+1, every
+   * assigned key point is closed to later points, and the acceptance threshold is orb_dist.  mode 0 = the frame / frame form. */
+  const float* last_dist_range; /* N1 x 2, mode 1 only; NULL = the caller made the distance test and passes the predicted levels
+                                   (pMP->PredictScale(dist3D, &CurrentFrame)) in last_octave */
+  int32_t mode, orb_dist, n_levels;
+  float log_scale_factor;
 } plslam_proj_job_t;
 int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream);
 
@@ -350,6 +361,9 @@ int plslam_match_bow_host(const plslam_bow_job_t* job);
  * KF2 feature assigned to each KF1 feature (-1 = none).  job->match_f is scratch [n2]. */
 int plslam_match_bow_kfkf_host(const plslam_bow_job_t* job, int32_t* match12);
 int plslam_match_projection_host(const plslam_proj_job_t* job, int n_scale_levels);
+/* MapPoint::PredictScale(currentDist, pF / pKF) (@0x8fc20 / @0x8fb60) as the matcher kernels evaluate it (a one-thread kernel
+ * on the current device: the arithmetic is the device's, so the two agree by construction); -1 on a CUDA error */
+int plslam_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);
 
 /* Pair matching on the batched extractor outputs without a host round trip: for p in [0, npairs)
  * query = frame (2p), train = frame (2p+1) of a [frames][capacity][32] descriptor block whose valid

@@ -277,6 +277,38 @@ def search_by_bow_kfkf(kf1, kf2, nnratio=0.75, check_ori=True):
     return m[:n1], n
 
 
+def logf(x):
+    L = lib()
+    L.oracle_logf.argtypes, L.oracle_logf.restype = [C.c_float], C.c_float
+    return L.oracle_logf(x)
+
+
+def predict_scale(max_distance, dist, log_scale_factor, n_levels):
+    L = lib()
+    L.oracle_predict_scale.argtypes, L.oracle_predict_scale.restype = [C.c_float, C.c_float, C.c_float, C.c_int], C.c_int
+    return L.oracle_predict_scale(max_distance, dist, log_scale_factor, n_levels)
+
+
+def search_by_projection_kf(kf, cur, cam, scale_factors, log_scale_factor, tcw_cur, th, orb_dist, check_ori=True):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist) (layout: tests/matchdata.py
+    relocalisation_case) -> (match_cur int32 [N2], nmatches)."""
+    m, n2 = len(kf["desc"]), len(cur["desc"])
+    match = np.empty(max(n2, 1), np.int32)
+    a = [np.ascontiguousarray(kf["valid"], np.uint8), np.ascontiguousarray(kf["xyz"], np.float32), np.ascontiguousarray(kf["desc"], np.uint8),
+         np.ascontiguousarray(kf["dist_range"], np.float32), np.ascontiguousarray(kf["angle"], np.float32)]
+    b = [np.ascontiguousarray(cur["xy"], np.float32), np.ascontiguousarray(cur["octave"], np.int32), np.ascontiguousarray(cur["angle"], np.float32),
+         np.ascontiguousarray(cur["desc"], np.uint8), np.ascontiguousarray(cur["taken"], np.uint8),
+         np.ascontiguousarray(cur["grid_start"], np.int32), np.ascontiguousarray(cur["grid_items"], np.int32)]
+    c = [np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(tcw_cur, np.float32).reshape(12)]
+    L = lib()
+    L.oracle_search_by_projection_kf.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_float, C.c_void_p,
+                                                                                                      C.c_float, C.c_int, C.c_int, C.c_void_p]
+    L.oracle_search_by_projection_kf.restype = C.c_int
+    n = L.oracle_search_by_projection_kf(m, *[_p(x) for x in a], n2, *[_p(x) for x in b], _p(c[0]), _p(c[1]), len(c[1]),
+                                         float(log_scale_factor), _p(c[2]), float(th), int(orb_dist), int(check_ori), _p(match))
+    return match[:n2], n
+
+
 def search_by_projection(last, cur, cam, scale_factors, tcw_cur, tcw_last, th, mono=False, check_ori=True):
     n1, n2 = len(last["desc"]), len(cur["desc"])
     match = np.empty(n2, np.int32)

@@ -102,6 +102,57 @@ inline int rot_bin(float a1, float a2) {
   return bin;
 }
 
+// logf as glibc >= 2.27 computes it (sysdeps/ieee754/flt-32/e_logf.c: 16-entry table of 1/c and log(c), degree-3 polynomial in
+// double, one rounding to float).  MapPoint::PredictScale (@0x8fb60 / @0x8fc20) calls logf from the C library the binary is
+// loaded with; the restatement is pinned against this container's glibc 2.39 bit for bit (tests/test_oracle_match_cpu.py,
+// table read back from libm.so.6).  Special cases (zero, negative, inf, nan, subnormal) follow the same source.
+static const double LOGF_TAB[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+inline float pl_logf(float x) {
+  uint32_t ix;
+  std::memcpy(&ix, &x, 4);
+  if (ix == 0x3f800000u) return 0.0f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+    if (ix * 2 == 0) return -INFINITY;
+    if (ix == 0x7f800000u) return x;
+    if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return NAN;
+    const float xs = x * 0x1p23f;  // subnormal: normalise
+    std::memcpy(&ix, &xs, 4);
+    ix -= 23u << 23;
+  }
+  const uint32_t tmp = ix - 0x3f330000u;
+  const int i = (int)((tmp >> 19) % 16);
+  const int k = (int32_t)tmp >> 23;
+  const uint32_t iz = ix - (tmp & (0x1ffu << 23));
+  float zf;
+  std::memcpy(&zf, &iz, 4);
+  const double z = (double)zf;
+  const double r = z * LOGF_TAB[i][0] - 1;
+  const double y0 = LOGF_TAB[i][1] + (double)k * 0x1.62e42fefa39efp-1;
+  const double r2 = r * r;
+  double y = 0x1.5575b0be00b6ap-2 * r + -0x1.ffffef20a4123p-2;
+  y = -0x1.00ea348b88334p-2 * r2 + y;
+  y = y * r2 + (y0 + r);
+  return (float)y;
+}
+
+// MapPoint::PredictScale(const float& currentDist, Frame* / KeyFrame*) (@0x8fc20 / @0x8fb60): ratio = mfMaxDistance / dist
+// (vdivss), ceilf(logf(ratio) / mfLogScaleFactor) truncated to int, clamped to [0, mnScaleLevels - 1].
+inline int predict_scale(float maxDistance, float dist, float logScaleFactor, int nLevels) {
+  const float ratio = maxDistance / dist;
+  int nScale = (int)ceilf(pl_logf(ratio) / logScaleFactor);
+  if (nScale < 0) nScale = 0;
+  else if (nScale >= nLevels) nScale = nLevels - 1;
+  return nScale;
+}
+
 }  // namespace
 
 extern "C" {
@@ -322,6 +373,103 @@ int oracle_search_by_projection(int N1, const uint8_t* lastValid, const float* l
       if (lastObs[i]) taken[bestIdx2] = 1;
       nmatches++;
       if (checkOri) rotHist[rot_bin(lastAngle[i], curAngle[bestIdx2])].push_back(bestIdx2);
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int j : rotHist[i]) { matchCur[j] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
+float oracle_logf(float x) { return pl_logf(x); }
+// number of floats in [first, first + count * stride) (bit patterns) on which the restated logf differs from the C library's
+int oracle_logf_mismatches(uint32_t first, uint32_t count, uint32_t stride) {
+  int bad = 0;
+  for (uint32_t k = 0; k < count; ++k) {
+    const uint32_t b = first + k * stride;
+    float x;
+    std::memcpy(&x, &b, 4);
+    const float a = pl_logf(x), c = ::logf(x);
+    if (std::memcmp(&a, &c, 4) != 0 && !(a != a && c != c)) ++bad;
+  }
+  return bad;
+}
+int oracle_predict_scale(float maxDistance, float dist, float logScaleFactor, int nLevels) {
+  return predict_scale(maxDistance, dist, logScaleFactor, nLevels);
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, float th, int ORBdist)
+// (ORBmatcher.h:82; @0x7e8c0, Tracking::Relocalization).  Read from the binary: Ow = -Rcw.t() * tcw (@0x7ebec-0x7ec2b);
+// per map point of the key frame that exists, is not bad and is not in sAlreadyFound (@0x7ef24-0x7ef84): x3Dc = Rcw * x3Dw +
+// tcw (gemm, @0x7efaa-0x7efc0), invzc = 1.0f / zc (vdivss @0x7f4cd, no sign test), u = fma(xc * fx, invzc, cx), v likewise
+// (@0x7f4d1-0x7f4fb), image-bounds test (@0x7f513-0x7f542); PO = x3Dw - Ow, dist3D = (float)cv::norm(PO) (@0x7f96e-0x7fa81:
+// squares summed in double in element order, sqrt), rejected when 0.8f * mfMinDistance > dist3D or dist3D > 1.2f *
+// mfMaxDistance (@0x7faaa-0x7fab8); level = PredictScale(dist3D, &CurrentFrame) (@0x7fc3f); radius = th * mvScaleFactors[level]
+// (@0x7fc6f); GetFeaturesInArea(u, v, radius, level - 1, level + 1) (@0x7fc8e); a candidate is skipped when the frame's feature
+// already has a map point (@0x7fd5c); best = strictly smaller distance (@0x7fdba); accepted when bestDist <= ORBdist
+// (@0x7fdf2); rotation histogram of pKF->mvKeysUn[i].angle - CurrentFrame.mvKeysUn[best].angle (@0x7fe65-0x7fe98).
+// mpValid[i] = pMP && !pMP->isBad() && !sAlreadyFound.count(pMP); mpDistRange = (mfMinDistance, mfMaxDistance) per point;
+// curTaken[i2] = CurrentFrame.mvpMapPoints[i2] != NULL on entry; cam = {fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY, gwi, ghi}.
+// matchCur[N2] receives the key-frame index assigned to each current keypoint (-1 = none).  Returns nmatches.
+int oracle_search_by_projection_kf(int M, const uint8_t* mpValid, const float* mpXYZ, const uint8_t* mpDesc,
+                                   const float* mpDistRange, const float* kfAngle, int N2, const float* curXY,
+                                   const int* curOctave, const float* curAngle, const uint8_t* curDesc, const uint8_t* curTaken,
+                                   const int* gridStart, const int* gridItems, const float* cam, const float* scaleFactors,
+                                   int nLevels, float logScaleFactor, const float* TcwCur, float th, int ORBdist, int checkOri,
+                                   int* matchCur) {
+  const float fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+  const float mnMinX = cam[4], mnMaxX = cam[5], mnMinY = cam[6], mnMaxY = cam[7], gwi = cam[8], ghi = cam[9];
+  std::vector<uint8_t> taken(curTaken, curTaken + N2);
+  for (int i = 0; i < N2; ++i) matchCur[i] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float* Rc = TcwCur;
+  float Ow[3];
+  for (int r = 0; r < 3; ++r) {  // transpose flag: GEMMSingleMul, double accumulator
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += (double)Rc[k * 4 + r] * (double)Rc[k * 4 + 3];
+    Ow[r] = (float)(-1.0 * s);
+  }
+  for (int i = 0; i < M; i++) {
+    if (!mpValid[i]) continue;
+    const float* X = mpXYZ + 3 * i;
+    float pc[3];
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = Rc[r * 4] * X[0], p1 = Rc[r * 4 + 1] * X[1], p2 = Rc[r * 4 + 2] * X[2];
+      const float s = (p0 + p1) + p2;
+      pc[r] = (float)((double)s + (double)Rc[r * 4 + 3]);
+    }
+    const float invzc = 1.0f / pc[2];
+    const float u = std::fmaf(pc[0] * fx, invzc, cx);
+    const float v = std::fmaf(pc[1] * fy, invzc, cy);
+    if (u < mnMinX || u > mnMaxX) continue;
+    if (v < mnMinY || v > mnMaxY) continue;
+    double n2 = 0;
+    for (int r = 0; r < 3; ++r) {
+      const float d = X[r] - Ow[r];
+      n2 += (double)d * (double)d;
+    }
+    const float dist3D = (float)std::sqrt(n2);
+    const float maxDistance = 1.2f * mpDistRange[2 * i + 1], minDistance = 0.8f * mpDistRange[2 * i];
+    if (minDistance > dist3D || dist3D > maxDistance) continue;
+    const int level = predict_scale(mpDistRange[2 * i + 1], dist3D, logScaleFactor, nLevels);
+    const float radius = th * scaleFactors[level];
+    int bestDist = 256, bestIdx2 = -1;
+    for_features_in_area(u, v, radius, level - 1, level + 1, mnMinX, mnMinY, gwi, ghi, gridStart, gridItems, curXY, curOctave, [&](int i2) {
+      if (taken[i2]) return;
+      const int dist = descriptor_distance(mpDesc + 32 * i, curDesc + 32 * i2);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    });
+    if (bestIdx2 >= 0 && bestDist <= ORBdist) {
+      matchCur[bestIdx2] = i;
+      taken[bestIdx2] = 1;
+      nmatches++;
+      if (checkOri) rotHist[rot_bin(kfAngle[i], curAngle[bestIdx2])].push_back(bestIdx2);
     }
   }
   if (checkOri) {

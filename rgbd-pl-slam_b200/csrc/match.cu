@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "pl_math.cuh"
 
 namespace plslam {
 namespace {
@@ -300,6 +301,20 @@ __global__ void __launch_bounds__(32) k_triangulation(const plslam_tri_job_t* __
 // frame's map points in order (a current keypoint claimed by an earlier point is skipped later);
 // lanes split the grid cells of the search window, candidate order = [ix][iy][position in cell].
 // ------------------------------------------------------------------------------------------
+// MapPoint::PredictScale (@0x8fc20 / @0x8fb60): ceilf(logf(mfMaxDistance / dist) / mfLogScaleFactor) clamped to the pyramid
+__host__ __device__ __forceinline__ int predict_scale_clamp(float q, int nLevels) {
+  int nScale = (int)ceilf(q);
+  if (nScale < 0) nScale = 0;
+  else if (nScale >= nLevels) nScale = nLevels - 1;
+  return nScale;
+}
+__device__ __forceinline__ int predict_scale_dev(float maxDistance, float dist, float logScaleFactor, int nLevels) {
+  return predict_scale_clamp(__fdiv_rn(pl_logf_dev(__fdiv_rn(maxDistance, dist)), logScaleFactor), nLevels);
+}
+__global__ void k_predict_scale(float maxDistance, float dist, float logScaleFactor, int nLevels, int* out) {
+  *out = predict_scale_dev(maxDistance, dist, logScaleFactor, nLevels);
+}
+
 __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __restrict__ jobs) {
   extern __shared__ int smem_i[];
   const plslam_proj_job_t& J = jobs[blockIdx.x];
@@ -333,8 +348,10 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
     const float s = __fadd_rn(__fadd_rn(p0, p1), p2);
     tlc2 = (float)__dadd_rn((double)s, (double)J.tcw_last[11]);
   }
-  const bool bForward = tlc2 > mb && !J.mono;
-  const bool bBackward = -tlc2 > mb && !J.mono;
+  const bool kfMode = J.mode == 1;  // SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist): see the job struct
+  const bool bForward = tlc2 > mb && !J.mono && !kfMode;
+  const bool bBackward = -tlc2 > mb && !J.mono && !kfMode;
+  const int accept = kfMode ? J.orb_dist : PLSLAM_TH_HIGH;
   int nmatches = 0, nentries = 0;
   const uint4* DL = reinterpret_cast<const uint4*>(J.last_desc);
   const uint4* DC = reinterpret_cast<const uint4*>(J.cur_desc);
@@ -350,12 +367,29 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
     }
     // the binary's sequence: vdivss @0x81c92 (float division), vmulss + vfmadd213ss @0x81caf-0x81cba / @0x81cce-0x81cd9
     const float invzc = __fdiv_rn(1.0f, pc[2]);
-    if (invzc < 0) continue;
+    if (!kfMode && invzc < 0) continue;  // (the key-frame form has no sign test: @0x7f4cd)
     const float u = __fmaf_rn(__fmul_rn(pc[0], fx), invzc, cx);
     const float v = __fmaf_rn(__fmul_rn(pc[1], fy), invzc, cy);
     if (u < mnMinX || u > mnMaxX) continue;
     if (v < mnMinY || v > mnMaxY) continue;
-    const int oct = J.last_octave[i];
+    int oct;
+    if (kfMode && !J.last_dist_range) {
+      oct = J.last_octave[i];  // the caller ran the distance test and MapPoint::PredictScale itself (reference-signature veneer)
+    } else if (kfMode) {
+      // PO = x3Dw - Ow (float), dist3D = (float)cv::norm(PO): squares summed in double in element order (@0x7f96e-0x7fa81)
+      double n2 = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double d = (double)__fsub_rn(X[r], twc[r]);
+        n2 = __dadd_rn(n2, __dmul_rn(d, d));
+      }
+      const float dist3D = (float)sqrt(n2);
+      const float dMin = J.last_dist_range[2 * i], dMax = J.last_dist_range[2 * i + 1];
+      if (__fmul_rn(0.8f, dMin) > dist3D || dist3D > __fmul_rn(1.2f, dMax)) continue;
+      oct = predict_scale_dev(dMax, dist3D, J.log_scale_factor, J.n_levels);
+    } else {
+      oct = J.last_octave[i];
+    }
     const float radius = __fmul_rn(J.th, J.scale_factors[oct]);
     int minLevel, maxLevel;
     if (bForward) { minLevel = oct; maxLevel = -1; }
@@ -389,9 +423,11 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
         const float distx = __fsub_rn(J.cur_xy[2 * i2], u), disty = __fsub_rn(J.cur_xy[2 * i2 + 1], v);
         if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
         if (taken[i2]) continue;
-        const float ur2 = J.cur_uright[i2];
-        if (ur2 > 0) {
-          if (fabsf(__fsub_rn(ur, ur2)) > radius) continue;
+        if (!kfMode) {
+          const float ur2 = J.cur_uright[i2];
+          if (ur2 > 0) {
+            if (fabsf(__fsub_rn(ur, ur2)) > radius) continue;
+          }
         }
         const int dist = hamming256(a0, a1, DC[2 * i2], DC[2 * i2 + 1]);
         const unsigned key = ((unsigned)dist << 22) | ((unsigned)c << 8) | (unsigned)min(j - s0, 255);
@@ -401,12 +437,12 @@ __global__ void __launch_bounds__(32) k_projection(const plslam_proj_job_t* __re
     const unsigned g = warp_min_u32(best);
     if (g == 0xffffffffu) continue;
     const int bestDist = (int)(g >> 22);
-    if (bestDist <= PLSLAM_TH_HIGH) {
+    if (bestDist <= accept) {
       const unsigned src = __ballot_sync(0xffffffffu, best == g);
       const int bestIdx2 = __shfl_sync(0xffffffffu, bestI2, __ffs(src) - 1);
       if (lane == 0) {
         matchCur[bestIdx2] = i;
-        if (J.last_obs[i]) taken[bestIdx2] = 1;
+        if (kfMode || J.last_obs[i]) taken[bestIdx2] = 1;
         if (J.check_orientation) {
           const int bin = rot_bin_dev(J.last_angle[i], J.cur_angle[bestIdx2]);
           hist[bin]++;
@@ -872,14 +908,17 @@ int plslam_match_projection_host(const plslam_proj_job_t* job, int n_scale_level
   d.last_valid = U.up(job->last_valid, n1);
   d.last_xyz = U.up(job->last_xyz, (size_t)n1 * 3);
   d.last_desc = U.up(job->last_desc, (size_t)n1 * 32);
-  d.last_octave = U.up(job->last_octave, n1);
+  const bool kfMode = job->mode == 1;
+  PL_CHECK_ARG(!kfMode || job->last_octave || (job->last_dist_range && job->n_levels >= 1 && job->n_levels <= n_scale_levels));
+  d.last_octave = job->last_octave ? U.up(job->last_octave, n1) : nullptr;
   d.last_angle = U.up(job->last_angle, n1);
-  d.last_obs = U.up(job->last_obs, n1);
+  d.last_obs = kfMode ? nullptr : U.up(job->last_obs, n1);
+  d.last_dist_range = kfMode && job->last_dist_range ? U.up(job->last_dist_range, (size_t)n1 * 2) : nullptr;
   d.cur_xy = U.up(job->cur_xy, (size_t)n2 * 2);
   d.cur_octave = U.up(job->cur_octave, n2);
   d.cur_angle = U.up(job->cur_angle, n2);
   d.cur_desc = U.up(job->cur_desc, (size_t)n2 * 32);
-  d.cur_uright = U.up(job->cur_uright, n2);
+  d.cur_uright = kfMode ? nullptr : U.up(job->cur_uright, n2);
   d.cur_taken = U.up(job->cur_taken, n2);
   d.grid_start = U.up(job->grid_start, ncell + 1);
   d.grid_items = U.up(job->grid_items, nitems);
@@ -893,6 +932,17 @@ int plslam_match_projection_host(const plslam_proj_job_t* job, int n_scale_level
   PL_CUDA(cudaMemcpy(job->match_cur, d.match_cur, (size_t)n2 * 4, cudaMemcpyDeviceToHost));
   PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
   return PLSLAM_OK;
+}
+
+int plslam_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels) {
+  // one-thread kernel: the arithmetic is the device's (pl_logf_dev), so the veneer and the matcher kernels agree by construction
+  int* d = nullptr;
+  int h = -1;
+  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return -1;
+  k_predict_scale<<<1, 1>>>(max_distance, current_dist, log_scale_factor, n_levels, d);
+  if (cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) h = -1;
+  cudaFree(d);
+  return h;
 }
 
 int plslam_match_local_points_batch_device(const plslam_local_job_t* d_jobs, int njobs, int max_n, void* stream) {

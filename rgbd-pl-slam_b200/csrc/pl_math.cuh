@@ -121,6 +121,41 @@ __device__ __forceinline__ float pl_atan2f_dev(float yf, float xf) {
   return (float)a;
 }
 
+// logf as glibc >= 2.27 computes it (table of 1/c and log(c), degree-3 polynomial in double, one rounding to float): what
+// MapPoint::PredictScale (reference lib/libORB_SLAM2.so@0x8fc7b) gets from the C library; twin of oracle/match_oracle.cc pl_logf.
+__device__ __forceinline__ float pl_logf_dev(float x) {
+  const double T[16][2] = {
+      {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+      {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+      {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+      {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+      {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+      {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+      {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+      {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+  unsigned ix = __float_as_uint(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+    if (ix * 2 == 0) return __uint_as_float(0xff800000u);
+    if (ix == 0x7f800000u) return x;
+    if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return __uint_as_float(0x7fc00000u);
+    ix = __float_as_uint(__fmul_rn(x, 8388608.0f));
+    ix -= 23u << 23;
+  }
+  const unsigned tmp = ix - 0x3f330000u;
+  const int i = (int)((tmp >> 19) & 15u);
+  const int k = (int)tmp >> 23;
+  const unsigned iz = ix - (tmp & (0x1ffu << 23));
+  const double z = (double)__uint_as_float(iz);
+  const double r = __dsub_rn(__dmul_rn(z, T[i][0]), 1.0);
+  const double y0 = __dadd_rn(T[i][1], __dmul_rn((double)k, 0x1.62e42fefa39efp-1));
+  const double r2 = __dmul_rn(r, r);
+  double y = __dadd_rn(__dmul_rn(0x1.5575b0be00b6ap-2, r), -0x1.ffffef20a4123p-2);
+  y = __dadd_rn(__dmul_rn(-0x1.00ea348b88334p-2, r2), y);
+  y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+  return (float)y;
+}
+
 __device__ __forceinline__ int reflect101_dev(int i, int n) {
   if (n == 1) return 0;
   while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;

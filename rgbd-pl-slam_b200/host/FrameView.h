@@ -27,6 +27,16 @@ struct MapPointsView {
   std::vector<uint8_t> observed;        // Observations() > 0
 };
 
+// The map points of a key frame as ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist) reads them
+// (reference include/ORBmatcher.h:82), in the order of pKF->GetMapPointMatches().
+struct KeyFramePointsView {
+  std::vector<uint8_t> valid;      // pMP && !pMP->isBad() && !sAlreadyFound.count(pMP) && dist3D inside the invariance range
+  std::vector<float> worldPos;     // M x 3: GetWorldPos()
+  cv::Mat descriptors;             // M x 32: GetDescriptor()
+  std::vector<float> angle;        // pKF->mvKeysUn[i].angle
+  std::vector<int32_t> level;      // pMP->PredictScale(dist3D, &CurrentFrame)
+};
+
 struct FrameView {
   // features
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn;

@@ -73,6 +73,43 @@ int ORBmatcher::SearchByProjection(FrameView& Cur, const FrameView& Last, const 
   return nm;
 }
 
+int ORBmatcher::SearchByProjection(FrameView& Cur, const KeyFramePointsView& KF, const float th, const int ORBdist,
+                                   std::vector<int>& vnMatches) {
+  const int m = (int)KF.valid.size(), n2 = (int)Cur.mvKeysUn.size();
+  vnMatches.assign(n2, -1);
+  if (m == 0 || n2 == 0) return 0;
+  need(KF.worldPos.size() == (size_t)m * 3 && (int)KF.angle.size() == m && (int)KF.level.size() == m && KF.descriptors.rows >= m &&
+           KF.descriptors.cols == 32,
+       "KeyFramePointsView arrays do not cover its M map points");
+  need((int)Cur.hasMapPoint.size() == n2 && Cur.mDescriptors.rows >= n2 && Cur.mDescriptors.cols == 32 &&
+           Cur.gridStart.size() == 64 * 48 + 1 && (int)Cur.gridItems.size() == Cur.gridStart.back() && !Cur.mvScaleFactors.empty(),
+       "Frame view: hasMapPoint / mDescriptors / grid / mvScaleFactors incomplete");
+  for (int i = 0; i < m; ++i)
+    need(!KF.valid[i] || (KF.level[i] >= 0 && KF.level[i] < (int)Cur.mvScaleFactors.size()), "KeyFramePointsView level out of range");
+  std::vector<float> cxy((size_t)n2 * 2), cang(n2);
+  std::vector<int32_t> coct(n2);
+  for (int i = 0; i < n2; ++i) {
+    cxy[2 * i] = Cur.mvKeysUn[i].pt.x; cxy[2 * i + 1] = Cur.mvKeysUn[i].pt.y;
+    coct[i] = Cur.mvKeysUn[i].octave; cang[i] = Cur.mvKeysUn[i].angle;
+  }
+  int32_t nm = 0;
+  plslam_proj_job_t j{};
+  j.last_valid = KF.valid.data(); j.last_xyz = KF.worldPos.data(); j.last_desc = KF.descriptors.data;
+  j.last_octave = KF.level.data(); j.last_angle = KF.angle.data();
+  j.cur_xy = cxy.data(); j.cur_octave = coct.data(); j.cur_angle = cang.data(); j.cur_desc = Cur.mDescriptors.data;
+  j.cur_taken = Cur.hasMapPoint.data();
+  j.grid_start = Cur.gridStart.data(); j.grid_items = Cur.gridItems.data(); j.scale_factors = Cur.mvScaleFactors.data();
+  j.match_cur = vnMatches.data(); j.nmatches = &nm;
+  const float cam[12] = {Cur.fx, Cur.fy, Cur.cx, Cur.cy, 0.f, 0.f, Cur.mnMinX, Cur.mnMaxX, Cur.mnMinY, Cur.mnMaxY,
+                         Cur.mfGridElementWidthInv, Cur.mfGridElementHeightInv};
+  std::memcpy(j.cam, cam, sizeof(cam));
+  std::memcpy(j.tcw_cur, Cur.mTcw, sizeof(j.tcw_cur));
+  j.th = th; j.n1 = m; j.n2 = n2; j.check_orientation = mbCheckOrientation;
+  j.mode = 1; j.orb_dist = ORBdist; j.n_levels = (int)Cur.mvScaleFactors.size();
+  check(plslam_match_projection_host(&j, (int)Cur.mvScaleFactors.size()), "SearchByProjection(Frame, KeyFrame)");
+  return nm;
+}
+
 int ORBmatcher::SearchByProjection(FrameView& F, const MapPointsView& MP, const float th, std::vector<int>& vnMatches) {
   const int m = (int)MP.inViewAndGood.size(), n = (int)F.mvKeysUn.size();
   vnMatches.assign(n, -1);

@@ -9,6 +9,7 @@
 
 #include <cstddef>
 #include <utility>
+#include <set>
 #include <vector>
 
 #include "FrameView.h"
@@ -36,6 +37,12 @@ class ORBmatcher {
   // Project MapPoints tracked in last frame into the current frame and search matches (Tracking::TrackWithMotionModel)
   template <class FrameT>
   int SearchByProjection(FrameT& CurrentFrame, const FrameT& LastFrame, const float th, const bool bMono);
+  // Project MapPoints seen in KeyFrame into the Frame and search matches (Tracking::Relocalization) (ORBmatcher.h:82).
+  // Further members read: Frame::mfLogScaleFactor / mnScaleLevels through pMP->PredictScale(dist, &CurrentFrame),
+  // MapPoint::GetMinDistanceInvariance / GetMaxDistanceInvariance.
+  template <class FrameT, class KeyFrameT, class MapPointT>
+  int SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const std::set<MapPointT*>& sAlreadyFound, const float th,
+                         const int ORBdist);
   // Search matches between MapPoints in a KeyFrame and ORB in a Frame (Relocalisation, TrackReferenceKeyFrame)
   template <class KeyFrameT, class FrameT, class MapPointT>
   int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches);
@@ -61,6 +68,13 @@ class ORBmatcher {
   // Search matches between Frame keypoints and projected MapPoints (Tracking::SearchLocalPoints; ORBmatcher.h:61).
   // vnMatches[i] = index in vpMapPoints assigned to F's keypoint i, or -1.  Returns the number of matches.
   int SearchByProjection(FrameView& F, const MapPointsView& vpMapPoints, const float th, std::vector<int>& vnMatches);
+
+  // Key-frame form (ORBmatcher.h:82) on views: KF.valid = map point present, good and not already found; KF.level = the
+  // search level of each point (PredictScale), points outside their scale-invariance range marked invalid; CurrentFrame needs
+  // mvKeysUn, mDescriptors, hasMapPoint (mvpMapPoints[i] != NULL), grid, bounds, intrinsics, pose, mvScaleFactors.
+  // vnMatches[i2] = key-frame index assigned to current keypoint i2, or -1.
+  int SearchByProjection(FrameView& CurrentFrame, const KeyFramePointsView& KF, const float th, const int ORBdist,
+                         std::vector<int>& vnMatches);
 
   // Brute force constrained to ORB that belong to the same vocabulary node (Relocalisation / TrackReferenceKeyFrame).
   // vnMatches[iF] = index in the KeyFrame matched to F's feature iF, or -1.

@@ -2,6 +2,7 @@
 // each flattens the members the reference's function reads into a FrameView / MapPointsView, calls the flattened form
 // (one C-ABI call, one kernel) and writes the result where the reference writes it.  Included by ORBmatcher.h.
 #pragma once
+#include <cmath>
 #include <stdexcept>
 #include <string>
 
@@ -128,6 +129,59 @@ int ORBmatcher::SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpM
   const int nm = SearchByProjection(f, mp, th, match);
   for (int i = 0; i < n; ++i)
     if (match[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[match[i]];
+  return nm;
+}
+
+// ORBmatcher.h:82 (@0x7e8c0).  The camera centre and the distance of a point from it are evaluated here with the arithmetic of
+// the reference (Ow = -Rcw.t() * tcw: gemm with a transpose flag, double accumulator; PO = x3Dw - Ow in float; cv::norm:
+// squares summed in double, sqrt), so that the invariance test and pMP->PredictScale() see the value the reference gives them.
+template <class FrameT, class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const std::set<MapPointT*>& sAlreadyFound, const float th,
+                                   const int ORBdist) {
+  FrameView cur;
+  dropin::view_of_frame(CurrentFrame, &cur, true);
+  const int n2 = (int)cur.mvKeysUn.size();
+  cur.hasMapPoint.assign(n2, 0);
+  for (int i = 0; i < n2; ++i) cur.hasMapPoint[i] = CurrentFrame.mvpMapPoints[i] != nullptr;
+  const std::vector<MapPointT*> vpMPs = pKF->GetMapPointMatches();
+  const int m = (int)vpMPs.size();
+  dropin::require(pKF->mvKeysUn.size() == (size_t)m, "KeyFrame members differ in length");
+  float Ow[3];
+  for (int r = 0; r < 3; ++r) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += (double)cur.mTcw[4 * k + r] * (double)cur.mTcw[4 * k + 3];
+    Ow[r] = (float)(-1.0 * s);
+  }
+  KeyFramePointsView kv;
+  kv.valid.assign(m, 0);
+  kv.worldPos.assign((size_t)m * 3, 0.f);
+  kv.descriptors.create(m > 0 ? m : 1, 32, CV_8U);
+  kv.angle.assign(m, 0.f);
+  kv.level.assign(m, 0);
+  for (int i = 0; i < m; ++i) {
+    MapPointT* pMP = vpMPs[i];
+    kv.angle[i] = pKF->mvKeysUn[i].angle;
+    if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+    const cv::Mat x3Dw = pMP->GetWorldPos();
+    double n2sum = 0;
+    for (int k = 0; k < 3; ++k) {
+      const float x = x3Dw.template at<float>(k);
+      kv.worldPos[3 * (size_t)i + k] = x;
+      const float d = x - Ow[k];
+      n2sum += (double)d * (double)d;
+    }
+    const float dist3D = (float)std::sqrt(n2sum);
+    const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+    if (dist3D < minDistance || dist3D > maxDistance) continue;
+    kv.level[i] = pMP->PredictScale(dist3D, &CurrentFrame);
+    const cv::Mat d = pMP->GetDescriptor();
+    std::memcpy(kv.descriptors.ptr(i), d.ptr(0), 32);
+    kv.valid[i] = 1;
+  }
+  std::vector<int> match;
+  const int nm = SearchByProjection(cur, kv, th, ORBdist, match);
+  for (int i2 = 0; i2 < n2; ++i2)
+    if (match[i2] >= 0) CurrentFrame.mvpMapPoints[i2] = vpMPs[match[i2]];
   return nm;
 }
 

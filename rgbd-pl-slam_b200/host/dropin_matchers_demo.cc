@@ -9,9 +9,11 @@
 #include <cstdlib>
 #include <fstream>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
+#include "../../include/plslam_b200.h"
 #include "ORBmatcher.h"
 
 namespace DBoW2 {
@@ -20,8 +22,13 @@ typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;  // DB
 
 namespace ORB_SLAM2 {
 
+class Frame;
 class MapPoint {  // include/MapPoint.h: the members the matchers touch
  public:
+  float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
+  float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
+  int PredictScale(const float& currentDist, Frame* pF);
+  float mfMinDistance = 0, mfMaxDistance = 0;  // (protected in the reference)
   cv::Mat GetWorldPos() { return mWorldPos.clone(); }
   cv::Mat GetDescriptor() { return mDescriptor.clone(); }
   int Observations() { return nObs; }
@@ -52,9 +59,15 @@ class Frame {  // include/Frame.h
   static float mfGridElementWidthInv, mfGridElementHeightInv;
   std::vector<std::size_t> mGrid[64][48];
   cv::Mat mTcw;
+  int mnScaleLevels = 0;
+  float mfLogScaleFactor = 0;
   std::vector<float> mvScaleFactors;
   static float mnMinX, mnMaxX, mnMinY, mnMaxY;
 };
+// MapPoint.cc of the reference stays on the CPU; the demo's stand-in evaluates the same formula (@0x8fc20)
+int MapPoint::PredictScale(const float& currentDist, Frame* pF) {
+  return plslam_predict_scale(mfMaxDistance, currentDist, pF->mfLogScaleFactor, pF->mnScaleLevels);
+}
 float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX,
     Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 
@@ -288,6 +301,64 @@ static void case_bow() {
   save("bw_out", out);
 }
 
+// ---- Tracking::Relocalization: matcher2.SearchByProjection(mCurrentFrame, vpCandidateKFs[i], sFound, 10, 100) ----
+static void case_relocalisation() {
+  const auto state = load<uint8_t>("rk_kf_state"), kdesc = load<uint8_t>("rk_kf_desc"), cdesc = load<uint8_t>("rk_cur_desc");
+  const auto xyz = load<float>("rk_kf_xyz"), rng = load<float>("rk_kf_dist_range"), kang = load<float>("rk_kf_angle");
+  const auto cxy = load<float>("rk_cur_xy"), cang = load<float>("rk_cur_angle"), cam = load<float>("rk_cam"), sf = load<float>("rk_sf");
+  const auto coct = load<int32_t>("rk_cur_octave"), gs = load<int32_t>("rk_cur_grid_start"), gi = load<int32_t>("rk_cur_grid_items");
+  const auto taken = load<uint8_t>("rk_cur_taken");
+  const auto tc = load<float>("rk_tc"), par = load<float>("rk_par");  // th, ORBdist, logScaleFactor
+  const int m = (int)state.size(), n2 = (int)taken.size();
+  KeyFrame KF;
+  KF.mvKeysUn.resize(m); KF.mvpMapPoints.assign(m, nullptr);
+  std::set<MapPoint*> sFound;
+  for (int i = 0; i < m; ++i) {
+    KF.mvKeysUn[i].angle = kang[i];
+    if (!state[i]) continue;
+    MapPoint* p = new_mp();
+    p->id = i;
+    p->mbBad = state[i] == 2;
+    p->mWorldPos = mat_f(&xyz[3 * (size_t)i], 3, 1);
+    p->mDescriptor = desc_row(kdesc, i);
+    p->mfMinDistance = rng[2 * i];
+    p->mfMaxDistance = rng[2 * i + 1];
+    KF.mvpMapPoints[i] = p;
+    if (state[i] == 3) sFound.insert(p);
+  }
+  Frame F;
+  F.N = n2;
+  Frame::fx = cam[0]; Frame::fy = cam[1]; Frame::cx = cam[2]; Frame::cy = cam[3];
+  Frame::mnMinX = cam[4]; Frame::mnMaxX = cam[5]; Frame::mnMinY = cam[6]; Frame::mnMaxY = cam[7];
+  Frame::mfGridElementWidthInv = cam[8]; Frame::mfGridElementHeightInv = cam[9];
+  F.mvKeys.resize(n2); F.mvKeysUn.resize(n2); F.mvuRight.assign(n2, -1.f); F.mvpMapPoints.assign(n2, nullptr);
+  F.mDescriptors = mat_u8(cdesc, n2);
+  MapPoint* other = new_mp();
+  for (int i = 0; i < n2; ++i) {
+    F.mvKeysUn[i].pt = cv::Point2f(cxy[2 * i], cxy[2 * i + 1]);
+    F.mvKeysUn[i].octave = coct[i];
+    F.mvKeysUn[i].angle = cang[i];
+    F.mvKeys[i] = F.mvKeysUn[i];
+    if (taken[i]) F.mvpMapPoints[i] = other;
+  }
+  for (int ix = 0; ix < 64; ++ix)
+    for (int iy = 0; iy < 48; ++iy)
+      for (int k = gs[ix * 48 + iy]; k < gs[ix * 48 + iy + 1]; ++k) F.mGrid[ix][iy].push_back((size_t)gi[k]);
+  float T[16] = {0};
+  for (int k = 0; k < 12; ++k) T[k] = tc[k];
+  T[15] = 1.f;
+  F.mTcw = mat_f(T, 4, 4);
+  F.mvScaleFactors = sf;
+  F.mnScaleLevels = (int)sf.size();
+  F.mfLogScaleFactor = par[2];
+  ORBmatcher matcher2(0.9f, true);
+  const int nmatches = matcher2.SearchByProjection(F, &KF, sFound, par[0], (int)par[1]);
+  std::vector<int32_t> out(n2 + 1);
+  for (int i = 0; i < n2; ++i) out[i] = (F.mvpMapPoints[i] && F.mvpMapPoints[i] != other) ? F.mvpMapPoints[i]->id : -1;
+  out[n2] = nmatches;
+  save("rk_out", out);
+}
+
 // ---- LoopClosing::ComputeSim3: matcher.SearchByBoW(mpCurrentKF, pKF, vvpMapPointMatches[i]) ----
 static void case_bow_keyframes() {
   const auto par = load<float>("bk_par");  // nnratio, ori
@@ -374,6 +445,7 @@ int main(int argc, char** argv) {
     case_local();
     case_bow();
     case_bow_keyframes();
+    case_relocalisation();
     case_triangulation();
     // an unfilled member must be reported, not read out of bounds
     Frame bad, last;

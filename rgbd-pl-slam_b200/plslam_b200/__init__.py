@@ -313,7 +313,8 @@ class ProjJob(C.Structure):
                                           "grid_start", "grid_items", "scale_factors", "match_cur", "nmatches")] + \
                [("cam", C.c_float * 12), ("tcw_cur", C.c_float * 12), ("tcw_last", C.c_float * 12), ("th", C.c_float),
                 ("n1", C.c_int32), ("n2", C.c_int32), ("mono", C.c_int32), ("check_orientation", C.c_int32),
-                ("report_removed", C.c_int32)]
+                ("report_removed", C.c_int32), ("last_dist_range", C.c_void_p), ("mode", C.c_int32), ("orb_dist", C.c_int32),
+                ("n_levels", C.c_int32), ("log_scale_factor", C.c_float)]
 
 
 class TriJob(C.Structure):
@@ -325,7 +326,7 @@ class TriJob(C.Structure):
                 ("n1_nodes", C.c_int32), ("n2_nodes", C.c_int32), ("only_stereo", C.c_int32), ("check_orientation", C.c_int32)]
 
 
-assert C.sizeof(KnnJob) == 32 and C.sizeof(BowJob) == 144 and C.sizeof(ProjJob) == 304 and C.sizeof(TriJob) == 240
+assert C.sizeof(KnnJob) == 32 and C.sizeof(BowJob) == 144 and C.sizeof(ProjJob) == 328 and C.sizeof(TriJob) == 240
 
 
 def _jobs_to_device(jobs, device):
@@ -729,6 +730,39 @@ def search_by_projection_host(last, cur, cam, scale_factors, tcw_cur, tcw_last, 
     j.report_removed = int(report_removed)
     _check(lib().plslam_match_projection_host(C.byref(j), len(sf)))
     return m[:n2], int(n[0])
+
+
+def search_by_projection_kf_host(kf, cur, cam, scale_factors, log_scale_factor, tcw_cur, th, orb_dist, check_ori=True):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist) (relocalisation) on host arrays (layout of
+    tests/matchdata.py: relocalisation_case; cam = fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY, gridWInv, gridHInv) through
+    plslam_match_projection_host with mode 1 -> (match_cur int32 [N2], nmatches)."""
+    m, n2 = len(kf["desc"]), len(cur["desc"])
+    keep = []
+    def a(x, dt):
+        x = np.ascontiguousarray(x, dt); keep.append(x); return x.ctypes.data
+    match = np.empty(max(n2, 1), np.int32); nm = np.zeros(1, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    j = ProjJob()
+    j.last_valid, j.last_xyz, j.last_desc = a(kf["valid"], np.uint8), a(kf["xyz"], np.float32), a(kf["desc"], np.uint8)
+    j.last_angle, j.last_dist_range = a(kf["angle"], np.float32), a(kf["dist_range"], np.float32)
+    j.cur_xy, j.cur_octave, j.cur_angle = a(cur["xy"], np.float32), a(cur["octave"], np.int32), a(cur["angle"], np.float32)
+    j.cur_desc, j.cur_taken = a(cur["desc"], np.uint8), a(cur["taken"], np.uint8)
+    j.grid_start, j.grid_items, j.scale_factors = a(cur["grid_start"], np.int32), a(cur["grid_items"], np.int32), sf.ctypes.data
+    j.match_cur, j.nmatches = match.ctypes.data, nm.ctypes.data
+    c = np.asarray(cam, np.float32)
+    j.cam = (C.c_float * 12)(c[0], c[1], c[2], c[3], 0.0, 0.0, c[4], c[5], c[6], c[7], c[8], c[9])
+    j.tcw_cur = (C.c_float * 12)(*np.asarray(tcw_cur, np.float32).reshape(12))
+    j.th, j.n1, j.n2, j.mono, j.check_orientation, j.report_removed = float(th), m, n2, 0, int(check_ori), 0
+    j.mode, j.orb_dist, j.n_levels, j.log_scale_factor = 1, int(orb_dist), len(sf), float(log_scale_factor)
+    _check(lib().plslam_match_projection_host(C.byref(j), len(sf)))
+    return match[:n2], int(nm[0])
+
+
+def predict_scale(max_distance, dist, log_scale_factor, n_levels):
+    """MapPoint::PredictScale as the matcher kernels evaluate it."""
+    f = lib().plslam_predict_scale
+    f.argtypes, f.restype = [C.c_float, C.c_float, C.c_float, C.c_int], C.c_int
+    return f(max_distance, dist, log_scale_factor, n_levels)
 
 
 def bow_pairs_device(d_kps, d_desc, d_counts, fv, d_kf_valid=None, nnratio=0.7, check_ori=True, out=None, stream=None):

@@ -364,6 +364,23 @@ def reflib2():
             bk.append(n)
     out["bk_n"] = np.array(len(bk))
     print("SearchByBoW(KeyFrame*, KeyFrame*):", bk)
+    # ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist) (relocalisation) on a faked KeyFrame /
+    # Frame / MapPoints and a real std::set; MapPoint::PredictScale, isBad, GetWorldPos ... run from the library as well
+    from matchdata import relocalisation_case
+    sf = oo.tables()["scale"]
+    rk = []
+    for seed in (1, 2):
+        (ka, da), (kb, db) = feats[seed]
+        for motion in (0.03, 0.25, -0.25):
+            kf, cur, cam, sf2, lsf, tcw = relocalisation_case(ka, da, kb, db, sf, seed=seed, motion=motion)
+            for th, od, ori in ((10.0, 100, 1), (3.0, 64, 1), (10.0, 100, 0)):
+                m, n = R.search_by_projection_kf(kf, cur, cam, sf, lsf, tcw, th, od, bool(ori))
+                k = len(rk)
+                out["rk%d_args" % k] = np.array([seed, motion, th, od, ori], np.float64)
+                out["rk%d_match" % k], out["rk%d_n" % k] = m, np.array(n)
+                rk.append(n)
+    out["rk_n"] = np.array(len(rk))
+    print("SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist):", rk)
     np.savez_compressed(os.path.join(HERE, "reference_library2.npz"), **out)
 
 

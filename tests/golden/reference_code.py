@@ -153,6 +153,8 @@ CVSHIM_CC = r"""
 #include <cstring>
 #include <new>
 #include <map>
+#include <set>
+#include <cmath>
 #include <vector>
 #include <cstdio>
 #include <cstdlib>
@@ -439,6 +441,18 @@ static void hdr_copy(Mat* d, const Mat* s) {
 static void expr_assign(const void*, const MatExpr* e, Mat* m, int type) {
   (void)type;
   if ((e->flags >> 8) == 'Z') { op_assign(nullptr, e, m, type); return; }
+  if ((e->flags >> 8) == 'S') {  // a - b, element by element in float (cv::subtract on CV_32F)
+    const Mat *A = &e->a, *B = &e->b;
+    if (A->rows != B->rows || A->cols != B->cols) __builtin_trap();
+    Mat D;
+    mat_init_empty(&D);
+    mat_create(&D, A->rows, A->cols, 5);
+    for (int i = 0; i < A->rows; ++i)
+      for (int j = 0; j < A->cols; ++j) at(&D, i, j) = at(A, i, j) - at(B, i, j);
+    mat_create(m, A->rows, A->cols, 5);
+    for (int i = 0; i < A->rows; ++i) std::memcpy(m->data + (size_t)i * m->stepp[0], D.data + (size_t)i * D.stepp[0], (size_t)A->cols * 4);
+    return;
+  }
   if ((e->flags >> 8) != 'G') __builtin_trap();
   const bool tA = (e->flags & 1) != 0;
   const Mat *A = &e->a, *B = &e->b, *Cm = e->c.data ? &e->c : nullptr;
@@ -512,6 +526,45 @@ void shim_add_em(MatExpr* ret, const MatExpr* e, const Mat* m) {
   hdr_copy(&ret->b, &e->b);
   hdr_copy(&ret->c, m);
   ret->beta = 1;
+}
+// ---- ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist) (@0x7e8c0): PO = x3Dw - Ow, cv::norm(PO) ----
+void shim_sub_mm(MatExpr* ret, const Mat* a, const Mat* b) asm("_ZN2cvmiERKNS_3MatES2_");
+void shim_sub_mm(MatExpr* ret, const Mat* a, const Mat* b) {
+  TRACE("operator-(Mat, Mat)");
+  expr_init(ret, 'S', 0);
+  hdr_copy(&ret->a, a);
+  hdr_copy(&ret->b, b);
+}
+static InputArray g_noarray = {0, nullptr, 0, 0};
+const InputArray* shim_noArray() asm("_ZN2cv7noArrayEv");
+const InputArray* shim_noArray() { return &g_noarray; }
+// cv::norm(src, NORM_L2, noArray()) of a continuous CV_32F array: normL2_32f = squares accumulated in double in element
+// order (the generic normL2Sqr<float, double> loop: v0*v0 + v1*v1 + v2*v2 + v3*v3 per group of four, then one by one), sqrt
+double shim_norm(const InputArray* src, int normType, const InputArray* mask) asm("_ZN2cv4normERKNS_11_InputArrayEiS2_");
+double shim_norm(const InputArray* src, int normType, const InputArray* mask) {
+  const Mat* m = arr_mat(src);
+  TRACE("norm type %d", normType);
+  if (!m || normType != 4 || (mask && mask->obj) || (m->flags & TYPE_MASK) != 5) __builtin_trap();
+  std::vector<float> v;
+  for (int i = 0; i < m->rows; ++i)
+    for (int j = 0; j < m->cols; ++j) v.push_back(at(m, i, j));
+  double s = 0;
+  size_t i = 0;
+  for (; i + 4 <= v.size(); i += 4) {
+    const double v0 = v[i], v1 = v[i + 1], v2 = v[i + 2], v3 = v[i + 3];
+    s += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
+  }
+  for (; i < v.size(); ++i) {
+    const double x = v[i];
+    s += x * x;
+  }
+  return std::sqrt(s);
+}
+// helper for the harness (not an OpenCV symbol): a std::set<void*> built in place from an array of pointers
+void refshim_build_ptrset(void* where, void* const* ptrs, int n);
+void refshim_build_ptrset(void* where, void* const* ptrs, int n) {
+  auto* st = new (where) std::set<void*>();
+  for (int k = 0; k < n; ++k) st->insert(ptrs[k]);
 }
 // ---- Frame::UndistortKeyPoints (@0xf8630) / Frame::ComputeImageBounds (@0xf6010): Mat::reshape and cv::undistortPoints ----
 void shim_reshape(Mat* ret, const Mat* m, int new_cn, int new_rows) asm("_ZNK2cv3Mat7reshapeEii");
@@ -1006,6 +1059,74 @@ class RefLibrary:
         for i in range(n2):
             p = int(cmp_[i])
             if p and p != mb_ + 0x400 * n1:
+                out[i] = (p - mb_) // 0x400
+        return out, int(n)
+
+    # ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist) ----
+    # (@0x7e8c0, Tracking::Relocalization).  Further members: MapPoint::mbBad @0x238, mfMinDistance @0x248, mfMaxDistance @0x24c;
+    # Frame::mnScaleLevels @0x12338, mfLogScaleFactor @0x12340; KeyFrame::mvpMapPoints @0x520 (GetMapPointMatches, mutex @0x690).
+    def search_by_projection_kf(self, kf, cur, cam, scale_factors, log_scale_factor, tcw_cur, th, orb_dist, check_ori=True):
+        """kf: dict(state uint8 [M] (0 = no map point, 1 = good, 2 = bad, 3 = in sAlreadyFound), xyz [M,3], desc [M,32],
+        dist_range [M,2] (mfMinDistance, mfMaxDistance), angle [M]); cur: dict(xy, octave, angle, desc, taken (mvpMapPoints[i] != NULL));
+        cam = (fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY, gridWInv, gridHInv).  Returns (match_cur int32 [N2], nmatches)."""
+        f32 = np.float32
+        st = lambda name: C.c_float.in_dll(self.lib, name)
+        for name, v in zip(("2fx", "2fy", "2cx", "2cy"), cam[:4]):
+            st("_ZN9ORB_SLAM25Frame%sE" % name).value = f32(v)
+        st("_ZN9ORB_SLAM25Frame6mnMinXE").value, st("_ZN9ORB_SLAM25Frame6mnMaxXE").value = f32(cam[4]), f32(cam[5])
+        st("_ZN9ORB_SLAM25Frame6mnMinYE").value, st("_ZN9ORB_SLAM25Frame6mnMaxYE").value = f32(cam[6]), f32(cam[7])
+        st("_ZN9ORB_SLAM25Frame21mfGridElementWidthInvE").value = f32(cam[8])
+        st("_ZN9ORB_SLAM25Frame22mfGridElementHeightInvE").value = f32(cam[9])
+        m, n2 = len(kf["desc"]), len(cur["desc"])
+        kdesc, cdesc = np.ascontiguousarray(kf["desc"], np.uint8), np.ascontiguousarray(cur["desc"], np.uint8)
+        xyz = np.ascontiguousarray(kf["xyz"], np.float32)
+        rng_ = np.ascontiguousarray(kf["dist_range"], np.float32)
+        mps = (C.c_uint8 * (0x400 * (m + 1)))()
+        mb_ = C.addressof(mps)
+        for i in range(m):
+            a = mb_ + 0x400 * i
+            self._fmat_at(a + 0xd8, xyz[i].reshape(3, 1))
+            self._mat_at(a + 0x1c8, kdesc[i:i + 1])
+            C.c_uint8.from_address(a + 0x238).value = 1 if kf["state"][i] == 2 else 0
+            C.c_float.from_address(a + 0x248).value = rng_[i, 0]
+            C.c_float.from_address(a + 0x24c).value = rng_[i, 1]
+        kmp = np.array([mb_ + 0x400 * i if kf["state"][i] else 0 for i in range(m)], np.uint64)
+        found = np.array([mb_ + 0x400 * i for i in range(m) if kf["state"][i] == 3], np.uint64)
+        cmp_ = np.array([mb_ + 0x400 * m if t else 0 for t in cur["taken"]], np.uint64)
+        kk = np.zeros(m, self.KP)
+        kk["angle"] = kf["angle"]
+        ck = np.zeros(n2, self.KP)
+        ck["x"], ck["y"], ck["octave"], ck["angle"] = cur["xy"][:, 0], cur["xy"][:, 1], cur["octave"], cur["angle"]
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        Tc = np.ascontiguousarray(np.vstack([np.asarray(tcw_cur, np.float32).reshape(3, 4), [[0, 0, 0, 1]]]).astype(np.float32))
+        fk, fc = (C.c_uint64 * (0x800 // 8))(), (C.c_uint64 * (0x12800 // 8))()
+        kb, cb = C.addressof(fk), C.addressof(fc)
+        def setv(obj, off, arr):
+            obj[off // 8], obj[off // 8 + 1], obj[off // 8 + 2] = arr.ctypes.data, arr.ctypes.data + arr.nbytes, arr.ctypes.data + arr.nbytes
+        setv(fk, 0x170, kk); setv(fk, 0x520, kmp)
+        C.c_int32.from_address(cb + 0xec).value = n2
+        setv(fc, 0xf0, ck); setv(fc, 0x120, ck); setv(fc, 0x288, cmp_); setv(fc, 0x12348, sf)
+        C.c_int32.from_address(cb + 0x12338).value = len(sf)
+        C.c_float.from_address(cb + 0x12340).value = f32(log_scale_factor)
+        self._mat_at(cb + 0x1c8, cdesc)
+        self._fmat_at(cb + 0x122c8, Tc)
+        assign = getattr(self.lib, "_ZN9ORB_SLAM25Frame20AssignFeaturesToGridEv")
+        assign.argtypes, assign.restype = [C.c_void_p], None
+        assign(cb)
+        pset = (C.c_uint64 * 8)()
+        bs = self._shims.refshim_build_ptrset
+        bs.argtypes, bs.restype = [C.c_void_p, C.c_void_p, C.c_int], None
+        bs(C.addressof(pset), found.ctypes.data if len(found) else None, len(found))
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher18SearchByProjectionERNS_5FrameEPNS_8KeyFrameERKSt3setIPNS_8MapPointESt4lessIS7_ESaIS7_EEfi")
+        fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int], C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = f32(0.9)
+        matcher[4] = 1 if check_ori else 0
+        n = fn(C.addressof(matcher), cb, kb, C.addressof(pset), f32(th), int(orb_dist))
+        out = np.full(n2, -1, np.int32)
+        for i in range(n2):
+            p = int(cmp_[i])
+            if p and p != mb_ + 0x400 * m:
                 out[i] = (p - mb_) // 0x400
         return out, int(n)
 

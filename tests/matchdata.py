@@ -144,3 +144,33 @@ def triangulation_case(kps, desc, seed=0, stereo_fraction=0.5, nbits=3, W=640, H
     F12 = (np.linalg.inv(K).T @ tx @ R12 @ np.linalg.inv(K)).astype(np.float32)
     pose = (R21.astype(np.float32), t21.astype(np.float32), np.zeros(3, np.float32))
     return kf1, kf2, F12, pose, (fx, fy, cx, cy), sf, (sf * sf).astype(np.float32)
+
+
+def relocalisation_case(kps_kf, desc_kf, kps_cur, desc_cur, scale_factors, W=640, H=480, seed=0, motion=0.05):
+    """Tracking::Relocalization-like inputs for ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist):
+    the key frame's map points = its keypoints back-projected at synthetic depths (key frame at the origin), with the scale
+    invariance range MapPoint::UpdateNormalAndDepth would give them (some pushed out of range); the current frame a small
+    motion away, some of its features already holding a map point."""
+    rng = np.random.default_rng(seed)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    fx = fy = np.float32(520.0); cx = np.float32(W / 2 - 0.5); cy = np.float32(H / 2 - 0.5)
+    m, n2 = len(kps_kf), len(kps_cur)
+    z = (1.5 + rng.random(m) * 2.0).astype(np.float32)
+    xyz = np.stack([(kps_kf["x"] - cx) * z / fx, (kps_kf["y"] - cy) * z / fy, z], 1).astype(np.float32)
+    dist = np.linalg.norm(xyz.astype(np.float64), axis=1)
+    dmax = (dist * sf[kps_kf["octave"]] * rng.uniform(0.6, 1.5, m)).astype(np.float32)
+    dmin = (dmax / sf[-1]).astype(np.float32)
+    ang = 0.015
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    tcw = np.hstack([R, np.array([[motion], [0.004], [-motion * 1.5]])]).astype(np.float32)
+    xy = np.stack([kps_cur["x"], kps_cur["y"]], 1).astype(np.float32)
+    gs, gi, (mnx, mxx, mny, mxy, gwi, ghi) = frame_grid(xy, W, H)
+    state = rng.choice(np.array([0, 1, 2, 3], np.uint8), m, p=[0.1, 0.75, 0.05, 0.1]).astype(np.uint8)
+    kf = dict(state=state, valid=(state == 1).astype(np.uint8), xyz=np.ascontiguousarray(xyz), desc=np.ascontiguousarray(desc_kf),
+              dist_range=np.ascontiguousarray(np.stack([dmin, dmax], 1)), angle=np.ascontiguousarray(kps_kf["angle"], np.float32))
+    cur = dict(xy=np.ascontiguousarray(xy), octave=np.ascontiguousarray(kps_cur["octave"], np.int32),
+               angle=np.ascontiguousarray(kps_cur["angle"], np.float32), desc=np.ascontiguousarray(desc_cur),
+               taken=(rng.random(n2) < 0.05).astype(np.uint8), grid_start=gs, grid_items=gi)
+    cam = np.array([fx, fy, cx, cy, mnx, mxx, mny, mxy, gwi, ghi], np.float32)
+    log_sf = np.float32(np.log(np.float32(1.2)))
+    return kf, cur, cam, sf, log_sf, tcw

@@ -110,6 +110,15 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
     for k, v in kfb.items():
         put("bk_kf2_" + k, v)
     put("bk_par", [0.75, 1.0], np.float32)
+    # Relocalization
+    from matchdata import relocalisation_case
+    rkf, rcur, rcam, rsf, rlsf, rtc = relocalisation_case(ka, da, kb, db, sf, seed=21, motion=0.03)
+    for k, v in rkf.items():
+        put("rk_kf_" + k, v)
+    for k, v in rcur.items():
+        put("rk_cur_" + k, v)
+    put("rk_cam", rcam, np.float32); put("rk_sf", rsf, np.float32); put("rk_tc", rtc, np.float32)
+    put("rk_par", [10.0, 100.0, float(rlsf)], np.float32)
     # CreateNewMapPoints
     kps, desc = orc.extract(synth_frame(33))
     kf1, kf2, F12, pose, camt, sft, sg = triangulation_case(kps, desc, seed=33, stereo_fraction=0.5)
@@ -138,6 +147,9 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
     em, en = oracle.search_by_bow_kfkf(kf, kfb, 0.75, True)  # (kernel vs reference code: tests/test_golden_gpu.py, bk*)
     out = np.fromfile(d / "bk_out", np.int32)
     assert out[-1] == en > 50 and np.array_equal(out[:-1], em)
+    m, n = pl.search_by_projection_kf_host(rkf, rcur, rcam, rsf, rlsf, rtc, 10.0, 100, True)  # (pinned: test_golden_gpu.py, rk*)
+    out = np.fromfile(d / "rk_out", np.int32)
+    assert out[-1] == n > 100 and np.array_equal(out[:-1], m)
     ex, ey = pl.epipole(*pose, *camt)
     m12, n12, pairs = pl.search_for_triangulation_host(kf1, kf2, F12, ex, ey, sft, sg, False, True)
     out = np.fromfile(d / "tr_out", np.int32)

@@ -286,6 +286,53 @@ def test_search_by_bow_keyframes_equals_the_reference_matcher(oracle):
         assert n == int(g["bk%d_n" % k]) > 150 and np.array_equal(m, g["bk%d_match" % k]), k
 
 
+def _reloc_cases(g, extract, scale_factors):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import relocalisation_case
+    from plslam_b200.synth import synth_pair
+    feats = {}
+    for k in range(int(g["rk_n"])):
+        seed, motion, th, od, ori = g["rk%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (extract(a), extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        kf, cur, cam, sf, lsf, tcw = relocalisation_case(ka, da, kb, db, scale_factors, seed=seed, motion=float(motion))
+        yield k, kf, cur, cam, sf, lsf, tcw, float(th), int(od), bool(ori)
+
+
+def test_search_by_projection_keyframe_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist) (@0x7e8c0, relocalisation) executed
+    from lib/libORB_SLAM2.so on a faked Frame / KeyFrame / MapPoints with a real std::set; MapPoint::PredictScale (logf of the C
+    library), isBad, GetWorldPos and Frame::GetFeaturesInArea are the library's own (fixture reference_library2.npz, rk*)."""
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    o = oracle.OrbOracle()
+    total = 0
+    for k, kf, cur, cam, sf, lsf, tcw, th, od, ori in _reloc_cases(g, o.extract, o.tables()["scale"]):
+        m, n = oracle.search_by_projection_kf(kf, cur, cam, sf, lsf, tcw, th, od, ori)
+        assert n == int(g["rk%d_n" % k]) and np.array_equal(m, g["rk%d_match" % k]), k
+        total += n
+    assert total > 1500
+
+
+def test_logf_and_predict_scale(oracle):
+    """The restated glibc logf equals the C library's on a sweep of bit patterns (PredictScale calls logf, @0x8fc7b), and
+    PredictScale clamps to [0, nLevels - 1]."""
+    import ctypes as C
+    L = oracle.lib()
+    L.oracle_logf_mismatches.argtypes, L.oracle_logf_mismatches.restype = [C.c_uint32] * 3, C.c_int
+    assert L.oracle_logf_mismatches(0x00800000, (0x7f800000 - 0x00800000) // 997, 997) == 0
+    assert L.oracle_logf_mismatches(0x3f000000, 1 << 22, 3) == 0      # [0.5, ...) densely
+    assert L.oracle_logf_mismatches(1, 5000, 1601) == 0               # subnormals
+    lsf = float(np.log(np.float32(1.2)))
+    assert oracle.predict_scale(10.0, 10.0, lsf, 8) == 0
+    assert oracle.predict_scale(10.0, 20.0, lsf, 8) == 0              # ratio < 1: negative level clamps to 0
+    assert oracle.predict_scale(10.0, 10.0 / 1.2 ** 3.5, lsf, 8) == 4
+    assert oracle.predict_scale(10.0, 0.01, lsf, 8) == 7
+
+
 def test_search_by_projection_equals_the_reference_matcher(oracle):
     """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (@0x80d00, TrackWithMotionModel's matcher) executed from
     lib/libORB_SLAM2.so on faked Frame / MapPoint objects, its cv::Mat expressions evaluated with cv::gemm's arithmetic

@@ -199,6 +199,27 @@ def test_k_bow_keyframes_equals_the_reference_matcher():
     assert done == 8
 
 
+def test_k_projection_keyframe_mode_equals_the_reference_matcher():
+    """k_projection in its key-frame mode (ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist),
+    @0x7e8c0) on the rk* fixtures of reference_library2.npz; the device PredictScale (restated glibc logf) against the
+    oracle's on a sweep of distances."""
+    import plslam_b200 as pl
+    from oracle import bindings as ob
+    from test_golden_cpu import _reloc_cases
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    ex = pl.ORBextractor()
+    total = 0
+    for k, kf, cur, cam, sf, lsf, tcw, th, od, ori in _reloc_cases(g, ex, _scale_factors()):
+        m, n = pl.search_by_projection_kf_host(kf, cur, cam, sf, lsf, tcw, th, od, ori)
+        assert n == int(g["rk%d_n" % k]) and np.array_equal(m, g["rk%d_match" % k]), k
+        total += n
+    assert total > 1500
+    lsf = float(np.log(np.float32(1.2)))
+    rng = np.random.default_rng(9)
+    for d in list(rng.uniform(0.05, 30.0, 200)) + [10.0 / 1.2 ** e for e in range(-2, 10)]:
+        assert pl.predict_scale(10.0, float(d), lsf, 8) == ob.predict_scale(10.0, float(d), lsf, 8), d
+
+
 def test_k_triangulation_equals_the_reference_matcher():
     """k_triangulation (ORBmatcher::SearchForTriangulation, @0x86b30, epipole included) on the tr* fixtures."""
     import sys
