@@ -5,7 +5,10 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'rgbd-pl-slam_b2
 import numpy as np, torch
 import plslam_b200 as pl
 from plslam_b200.synth import synth_frame, synth_pair, synth_vocabulary_arrays, synth_depth
-for (W, H, B) in ((333, 250, 2), (640, 480, 4), (401, 303, 2)):
+SIZES = ((333, 250, 2), (640, 480, 4), (401, 303, 2))
+if os.environ.get("SAN_SMALL"):
+    SIZES = ((333, 250, 2), (270, 200, 2))
+for (W, H, B) in SIZES:
     imgs = np.stack([synth_frame(i, W, H) for i in range(B)])
     fe = pl.Frontend(depth=2)
     out = fe.alloc(B, device="cuda")
