@@ -539,6 +539,27 @@ int plslam_frame_post_host(const plslam_frame_calib_t* calib, const float bounds
                            int n, const float* depth, int cols, int rows, int depth_pitch, float* un_xy, float* uright,
                            float* depth_out, int32_t* grid_start, int32_t* grid_items);
 
+/* Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (reference include/Frame.h "isInFrustum", lib/libORB_SLAM2.so@0xf5190)
+ * for all local map points of a frame at once: what Tracking::SearchLocalPoints runs per point before
+ * ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th); the outputs are the mTrack* fields that matcher reads
+ * (plslam_local_job_t: mp_valid = in_view && !isBad(), mp_proj, mp_level, mp_viewcos), one thread per map point. */
+typedef struct plslam_frustum_job {
+  const float* mp_xyz;         /* M x 3 : pMP->GetWorldPos() */
+  const float* mp_normal;      /* M x 3 : pMP->GetNormal() */
+  const float* mp_dist_range;  /* M x 2 : mfMinDistance, mfMaxDistance (the invariance range is 0.8f * min .. 1.2f * max) */
+  uint8_t* in_view;            /* M : mbTrackInView (the return value) */
+  float* proj;                 /* M x 3 : mTrackProjX, mTrackProjY, mTrackProjXR (0 where not in view) */
+  int32_t* level;              /* M : mnTrackScaleLevel */
+  float* viewcos;              /* M : mTrackViewCos */
+  float cam[8];                /* fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY */
+  float tcw[12];               /* mRcw | mtcw, rows 0..2 of the pose */
+  float ow[3];                 /* mOw */
+  float mbf, log_scale_factor, viewing_cos_limit;
+  int32_t n_levels, m;
+} plslam_frustum_job_t;
+int plslam_frame_is_in_frustum_batch_device(const plslam_frustum_job_t* d_jobs, int njobs, int max_m, void* stream);
+int plslam_frame_is_in_frustum_host(const plslam_frustum_job_t* job); /* HOST pointers inside *job */
+
 /* ------------------------------------------------------------------------------------------------
  * On-disk formats either side of the path (host only, no device work).
  * ------------------------------------------------------------------------------------------------ */

@@ -289,6 +289,21 @@ def predict_scale(max_distance, dist, log_scale_factor, n_levels):
     return L.oracle_predict_scale(max_distance, dist, log_scale_factor, n_levels)
 
 
+def is_in_frustum(xyz, normal, dist_range, cam8, tcw, ow, mbf, log_scale_factor, n_levels, cos_limit):
+    """Frame::isInFrustum over M map points -> dict(in_view, proj [M,3], level, viewcos)."""
+    m = len(xyz)
+    a = [np.ascontiguousarray(xyz, np.float32), np.ascontiguousarray(normal, np.float32), np.ascontiguousarray(dist_range, np.float32),
+         np.ascontiguousarray(cam8, np.float32), np.ascontiguousarray(tcw, np.float32).reshape(12), np.ascontiguousarray(ow, np.float32).reshape(3)]
+    out = dict(in_view=np.zeros(max(m, 1), np.uint8), proj=np.zeros((max(m, 1), 3), np.float32), level=np.zeros(max(m, 1), np.int32),
+               viewcos=np.zeros(max(m, 1), np.float32))
+    L = lib()
+    L.oracle_is_in_frustum.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_int, C.c_float] + [C.c_void_p] * 4
+    L.oracle_is_in_frustum.restype = None
+    L.oracle_is_in_frustum(m, *[_p(x) for x in a], float(mbf), float(log_scale_factor), int(n_levels), float(cos_limit),
+                           _p(out["in_view"]), _p(out["proj"]), _p(out["level"]), _p(out["viewcos"]))
+    return {k: v[:m] for k, v in out.items()}
+
+
 def search_by_projection_kf(kf, cur, cam, scale_factors, log_scale_factor, tcw_cur, th, orb_dist, check_ori=True):
     """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist) (layout: tests/matchdata.py
     relocalisation_case) -> (match_cur int32 [N2], nmatches)."""

@@ -483,6 +483,58 @@ int oracle_search_by_projection_kf(int M, const uint8_t* mpValid, const float* m
   return nmatches;
 }
 
+// Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (include/Frame.h:107-ish "isInFrustum"; @0xf5190), what
+// Tracking::SearchLocalPoints runs on every local map point before ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)
+// (it fills the mTrack* fields that matcher reads).  Read from the binary: Pc = mRcw * P + mtcw (gemm small path); PcZ < 0
+// rejects (@0xf5740; zero passes); invz = 1.0f / PcZ (vdivss @0xf5759); u = fma(PcX * fx, invz, cx), v likewise (@0xf5761-
+// 0xf57c0); bounds tests; PO = P - mOw; dist = (float)cv::norm(PO); 0.8f * mfMinDistance > dist or dist > 1.2f * mfMaxDistance
+// rejects (@0xf5b15-0xf5b21); viewCos = (float)(PO.dot(Pn) / (double)dist) (dot in double, vdivsd @0xf5da6); viewingCosLimit >
+// viewCos rejects (@0xf5dae); level = PredictScale(dist, this); mTrackProjXR = fma(-invz, mbf, u) (vfnmadd132ss @0xf5dec).
+// cam = {fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY}; Tcw 3x4 row-major (mRcw | mtcw); Ow = mOw.  Rejected points keep
+// inView = 0 and zeros in the other outputs.
+void oracle_is_in_frustum(int M, const float* xyz, const float* normal, const float* distRange, const float* cam,
+                          const float* Tcw, const float* Ow, float mbf, float logScaleFactor, int nLevels, float cosLimit,
+                          uint8_t* inView, float* proj, int* level, float* viewCos) {
+  const float fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3], mnMinX = cam[4], mnMaxX = cam[5], mnMinY = cam[6], mnMaxY = cam[7];
+  for (int i = 0; i < M; ++i) {
+    inView[i] = 0;
+    proj[3 * i] = proj[3 * i + 1] = proj[3 * i + 2] = 0.f;
+    level[i] = 0;
+    viewCos[i] = 0.f;
+    const float* X = xyz + 3 * i;
+    float pc[3];
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = Tcw[r * 4] * X[0], p1 = Tcw[r * 4 + 1] * X[1], p2 = Tcw[r * 4 + 2] * X[2];
+      const float s = (p0 + p1) + p2;
+      pc[r] = (float)((double)s + (double)Tcw[r * 4 + 3]);
+    }
+    if (pc[2] < 0.0f) continue;
+    const float invz = 1.0f / pc[2];
+    const float u = std::fmaf(pc[0] * fx, invz, cx);
+    if (u < mnMinX || u > mnMaxX) continue;
+    const float v = std::fmaf(pc[1] * fy, invz, cy);
+    if (v < mnMinY || v > mnMaxY) continue;
+    float PO[3];
+    double n2 = 0;
+    for (int r = 0; r < 3; ++r) {
+      PO[r] = X[r] - Ow[r];
+      n2 += (double)PO[r] * (double)PO[r];
+    }
+    const float dist = (float)std::sqrt(n2);
+    if (0.8f * distRange[2 * i] > dist || dist > 1.2f * distRange[2 * i + 1]) continue;
+    double dot = 0;
+    for (int r = 0; r < 3; ++r) dot += (double)PO[r] * (double)normal[3 * i + r];
+    const float vc = (float)(dot / (double)dist);
+    if (cosLimit > vc) continue;
+    level[i] = predict_scale(distRange[2 * i + 1], dist, logScaleFactor, nLevels);
+    inView[i] = 1;
+    proj[3 * i] = u;
+    proj[3 * i + 1] = v;
+    proj[3 * i + 2] = std::fmaf(-invz, mbf, u);
+    viewCos[i] = vc;
+  }
+}
+
 // ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (reference
 // include/ORBmatcher.h:61; lib/libORB_SLAM2.so@0x79f10, called by Tracking::SearchLocalPoints).  Read from the binary:
 // mbTrackInView (+0x30) / isBad() gate @0x79fab-0x79fbc; RadiusByViewingCos(&mTrackViewCos) @0x79fd9 (2.5 / 4.0, @0x79b60);

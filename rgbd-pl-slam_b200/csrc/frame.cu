@@ -13,6 +13,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "pl_math.cuh"
 
 namespace plslam {
 namespace {
@@ -166,6 +167,64 @@ int make_params(const plslam_frame_calib_t* calib, const float* bounds4, int col
   return PLSLAM_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Frame::isInFrustum (@0xf5190) over the local map points of a frame: thread = map point.  Arithmetic as read from the binary
+// (see oracle/match_oracle.cc oracle_is_in_frustum): gemm small path for Pc, float division, fused projections, cv::norm and
+// Mat::dot in double, PredictScale with the C library's logf.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_is_in_frustum(const plslam_frustum_job_t* __restrict__ jobs) {
+  const plslam_frustum_job_t& J = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= J.m) return;
+  const float fx = J.cam[0], fy = J.cam[1], cx = J.cam[2], cy = J.cam[3];
+  const float mnMinX = J.cam[4], mnMaxX = J.cam[5], mnMinY = J.cam[6], mnMaxY = J.cam[7];
+  uint8_t inView = 0;
+  float u = 0.f, v = 0.f, ur = 0.f, vc = 0.f;
+  int level = 0;
+  do {
+    const float* X = J.mp_xyz + 3 * (size_t)i;
+    float pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = __fmul_rn(J.tcw[r * 4], X[0]), p1 = __fmul_rn(J.tcw[r * 4 + 1], X[1]), p2 = __fmul_rn(J.tcw[r * 4 + 2], X[2]);
+      pc[r] = (float)__dadd_rn((double)__fadd_rn(__fadd_rn(p0, p1), p2), (double)J.tcw[r * 4 + 3]);
+    }
+    if (pc[2] < 0.0f) break;
+    const float invz = __fdiv_rn(1.0f, pc[2]);
+    const float uu = __fmaf_rn(__fmul_rn(pc[0], fx), invz, cx);
+    if (uu < mnMinX || uu > mnMaxX) break;
+    const float vv = __fmaf_rn(__fmul_rn(pc[1], fy), invz, cy);
+    if (vv < mnMinY || vv > mnMaxY) break;
+    float PO[3];
+    double n2 = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      PO[r] = __fsub_rn(X[r], J.ow[r]);
+      n2 = __dadd_rn(n2, __dmul_rn((double)PO[r], (double)PO[r]));
+    }
+    const float dist = (float)sqrt(n2);
+    const float dMin = J.mp_dist_range[2 * (size_t)i], dMax = J.mp_dist_range[2 * (size_t)i + 1];
+    if (__fmul_rn(0.8f, dMin) > dist || dist > __fmul_rn(1.2f, dMax)) break;
+    double dot = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) dot = __dadd_rn(dot, __dmul_rn((double)PO[r], (double)J.mp_normal[3 * (size_t)i + r]));
+    const float c = (float)__ddiv_rn(dot, (double)dist);
+    if (J.viewing_cos_limit > c) break;
+    level = predict_scale_dev(dMax, dist, J.log_scale_factor, J.n_levels);
+    inView = 1;
+    u = uu;
+    v = vv;
+    ur = __fmaf_rn(-invz, J.mbf, uu);
+    vc = c;
+  } while (false);
+  J.in_view[i] = inView;
+  J.proj[3 * (size_t)i] = u;
+  J.proj[3 * (size_t)i + 1] = v;
+  J.proj[3 * (size_t)i + 2] = ur;
+  J.level[i] = level;
+  J.viewcos[i] = vc;
+}
+
 }  // namespace
 }  // namespace plslam
 
@@ -240,6 +299,52 @@ int plslam_frame_post_host(const plslam_frame_calib_t* calib, const float bounds
   }
   PL_CUDA(cudaMemcpy(grid_start, gs.p, (size_t)(NCELL + 1) * 4, cudaMemcpyDeviceToHost));
   if (n) PL_CUDA(cudaMemcpy(grid_items, gi.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int plslam_frame_is_in_frustum_batch_device(const plslam_frustum_job_t* d_jobs, int njobs, int max_m, void* stream) {
+  PL_CHECK_ARG(d_jobs && njobs >= 1 && njobs <= 65535 && max_m >= 0);
+  if (max_m == 0) return PLSLAM_OK;
+  PL_CARVEOUT(k_is_in_frustum);
+  k_is_in_frustum<<<dim3(div_up(max_m, 256), njobs), 256, 0, (cudaStream_t)stream>>>(d_jobs);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_frame_is_in_frustum_host(const plslam_frustum_job_t* job) {
+  PL_CHECK_ARG(job && job->m >= 0 && job->n_levels >= 1);
+  const int m = job->m;
+  if (m == 0) return PLSLAM_OK;
+  PL_CHECK_ARG(job->mp_xyz && job->mp_normal && job->mp_dist_range && job->in_view && job->proj && job->level && job->viewcos);
+  DevBuf in, out, dj;
+  const size_t inBytes = (size_t)m * 8 * sizeof(float), outBytes = (size_t)m * (1 + 12 + 4 + 4);
+  int rc;
+  if ((rc = in.ensure(inBytes)) || (rc = out.ensure(align_up(outBytes, 16) + 64)) || (rc = dj.ensure(sizeof(plslam_frustum_job_t)))) {
+    in.release(); out.release(); dj.release();
+    return rc;
+  }
+  float* dIn = in.as<float>();
+  plslam_frustum_job_t d = *job;
+  d.mp_xyz = dIn; d.mp_normal = dIn + 3 * (size_t)m; d.mp_dist_range = dIn + 6 * (size_t)m;
+  d.proj = out.as<float>(); d.viewcos = d.proj + 3 * (size_t)m;
+  d.level = reinterpret_cast<int32_t*>(d.viewcos + m); d.in_view = reinterpret_cast<uint8_t*>(d.level + m);
+  cudaError_t e = cudaMemcpy(dIn, job->mp_xyz, (size_t)m * 12, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dIn + 3 * (size_t)m, job->mp_normal, (size_t)m * 12, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dIn + 6 * (size_t)m, job->mp_dist_range, (size_t)m * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dj.p, &d, sizeof(d), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = plslam_frame_is_in_frustum_batch_device(dj.as<plslam_frustum_job_t>(), 1, m, nullptr);
+    if (rc) { in.release(); out.release(); dj.release(); return rc; }
+    e = cudaMemcpy(job->proj, d.proj, (size_t)m * 12, cudaMemcpyDeviceToHost);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(job->viewcos, d.viewcos, (size_t)m * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(job->level, d.level, (size_t)m * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(job->in_view, d.in_view, (size_t)m, cudaMemcpyDeviceToHost);
+  in.release(); out.release(); dj.release();
+  if (e != cudaSuccess) {
+    set_error("is_in_frustum host path: %s", cudaGetErrorString(e));
+    return PLSLAM_ERR_CUDA;
+  }
   return PLSLAM_OK;
 }
 

@@ -301,16 +301,6 @@ __global__ void __launch_bounds__(32) k_triangulation(const plslam_tri_job_t* __
 // frame's map points in order (a current keypoint claimed by an earlier point is skipped later);
 // lanes split the grid cells of the search window, candidate order = [ix][iy][position in cell].
 // ------------------------------------------------------------------------------------------
-// MapPoint::PredictScale (@0x8fc20 / @0x8fb60): ceilf(logf(mfMaxDistance / dist) / mfLogScaleFactor) clamped to the pyramid
-__host__ __device__ __forceinline__ int predict_scale_clamp(float q, int nLevels) {
-  int nScale = (int)ceilf(q);
-  if (nScale < 0) nScale = 0;
-  else if (nScale >= nLevels) nScale = nLevels - 1;
-  return nScale;
-}
-__device__ __forceinline__ int predict_scale_dev(float maxDistance, float dist, float logScaleFactor, int nLevels) {
-  return predict_scale_clamp(__fdiv_rn(pl_logf_dev(__fdiv_rn(maxDistance, dist)), logScaleFactor), nLevels);
-}
 __global__ void k_predict_scale(float maxDistance, float dist, float logScaleFactor, int nLevels, int* out) {
   *out = predict_scale_dev(maxDistance, dist, logScaleFactor, nLevels);
 }

@@ -156,6 +156,14 @@ __device__ __forceinline__ float pl_logf_dev(float x) {
   return (float)y;
 }
 
+// MapPoint::PredictScale (@0x8fc20 / @0x8fb60): ceilf(logf(mfMaxDistance / dist) / mfLogScaleFactor) clamped to the pyramid
+__device__ __forceinline__ int predict_scale_dev(float maxDistance, float dist, float logScaleFactor, int nLevels) {
+  int nScale = (int)ceilf(__fdiv_rn(pl_logf_dev(__fdiv_rn(maxDistance, dist)), logScaleFactor));
+  if (nScale < 0) nScale = 0;
+  else if (nScale >= nLevels) nScale = nLevels - 1;
+  return nScale;
+}
+
 __device__ __forceinline__ int reflect101_dev(int i, int n) {
   if (n == 1) return 0;
   while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;

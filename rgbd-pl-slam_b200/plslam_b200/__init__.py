@@ -758,6 +758,29 @@ def search_by_projection_kf_host(kf, cur, cam, scale_factors, log_scale_factor, 
     return match[:n2], int(nm[0])
 
 
+class FrustumJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("mp_xyz", "mp_normal", "mp_dist_range", "in_view", "proj", "level", "viewcos")] + \
+               [("cam", C.c_float * 8), ("tcw", C.c_float * 12), ("ow", C.c_float * 3), ("mbf", C.c_float), ("log_scale_factor", C.c_float),
+                ("viewing_cos_limit", C.c_float), ("n_levels", C.c_int32), ("m", C.c_int32)]
+
+
+def is_in_frustum_host(xyz, normal, dist_range, cam8, tcw, ow, mbf, log_scale_factor, n_levels, cos_limit):
+    """Frame::isInFrustum over M map points (host arrays) through plslam_frame_is_in_frustum_host ->
+    dict(in_view uint8 [M], proj float32 [M,3], level int32 [M], viewcos float32 [M])."""
+    m = len(xyz)
+    x = np.ascontiguousarray(xyz, np.float32); nv = np.ascontiguousarray(normal, np.float32); dr = np.ascontiguousarray(dist_range, np.float32)
+    out = dict(in_view=np.zeros(max(m, 1), np.uint8), proj=np.zeros((max(m, 1), 3), np.float32), level=np.zeros(max(m, 1), np.int32),
+               viewcos=np.zeros(max(m, 1), np.float32))
+    j = FrustumJob(x.ctypes.data, nv.ctypes.data, dr.ctypes.data, out["in_view"].ctypes.data, out["proj"].ctypes.data,
+                   out["level"].ctypes.data, out["viewcos"].ctypes.data)
+    j.cam = (C.c_float * 8)(*np.asarray(cam8, np.float32))
+    j.tcw = (C.c_float * 12)(*np.asarray(tcw, np.float32).reshape(12))
+    j.ow = (C.c_float * 3)(*np.asarray(ow, np.float32).reshape(3))
+    j.mbf, j.log_scale_factor, j.viewing_cos_limit, j.n_levels, j.m = float(mbf), float(log_scale_factor), float(cos_limit), int(n_levels), m
+    _check(lib().plslam_frame_is_in_frustum_host(C.byref(j)))
+    return {k: v[:m] for k, v in out.items()}
+
+
 def predict_scale(max_distance, dist, log_scale_factor, n_levels):
     """MapPoint::PredictScale as the matcher kernels evaluate it."""
     f = lib().plslam_predict_scale

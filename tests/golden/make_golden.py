@@ -381,6 +381,20 @@ def reflib2():
                 rk.append(n)
     out["rk_n"] = np.array(len(rk))
     print("SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist):", rk)
+    # Frame::isInFrustum on a faked Frame and faked MapPoints (GetWorldPos, GetNormal, the invariance range and PredictScale are
+    # the library's own); the outputs are what the function leaves in the map points
+    from matchdata import frustum_case
+    fz = []
+    for k, (seed, motion, lim) in enumerate(((1, 0.1, 0.5), (2, -0.3, 0.5), (3, 0.0, 0.8))):
+        c = frustum_case(3000, seed=seed, motion=motion)
+        r = R.is_in_frustum(c["xyz"], c["normal"], c["dist_range"], c["cam8"], c["tcw"], c["ow"], c["mbf"], c["log_sf"], c["n_levels"], lim)
+        out["fz%d_args" % k] = np.array([seed, motion, lim], np.float64)
+        out["fz%d_ow" % k] = c["ow"]
+        for name, v in r.items():
+            out["fz%d_%s" % (k, name)] = v
+        fz.append(int(r["in_view"].sum()))
+    out["fz_n"] = np.array(len(fz))
+    print("Frame::isInFrustum: in view", fz, "of 3000")
     np.savez_compressed(os.path.join(HERE, "reference_library2.npz"), **out)
 
 

@@ -560,6 +560,23 @@ double shim_norm(const InputArray* src, int normType, const InputArray* mask) {
   }
   return std::sqrt(s);
 }
+// Mat::dot of two continuous CV_32F arrays: dotProd_32f = products and sum in double, in element order (four per group, then
+// one by one); Frame::isInFrustum (@0xf5d8d) takes PO.dot(Pn) of two 3x1 vectors
+double shim_dot(const Mat* self, const InputArray* other) asm("_ZNK2cv3Mat3dotERKNS_11_InputArrayE");
+double shim_dot(const Mat* self, const InputArray* other) {
+  const Mat* m = arr_mat(other);
+  TRACE("Mat::dot");
+  if (!m || (self->flags & TYPE_MASK) != 5 || (m->flags & TYPE_MASK) != 5 || self->rows != m->rows || self->cols != m->cols) __builtin_trap();
+  std::vector<float> a, b;
+  for (int i = 0; i < m->rows; ++i)
+    for (int j = 0; j < m->cols; ++j) { a.push_back(at(self, i, j)); b.push_back(at(m, i, j)); }
+  double r = 0;
+  size_t i = 0;
+  for (; i + 4 <= a.size(); i += 4)
+    r += (double)a[i] * b[i] + (double)a[i + 1] * b[i + 1] + (double)a[i + 2] * b[i + 2] + (double)a[i + 3] * b[i + 3];
+  for (; i < a.size(); ++i) r += (double)a[i] * b[i];
+  return r;
+}
 // helper for the harness (not an OpenCV symbol): a std::set<void*> built in place from an array of pointers
 void refshim_build_ptrset(void* where, void* const* ptrs, int n);
 void refshim_build_ptrset(void* where, void* const* ptrs, int n) {
@@ -1129,6 +1146,49 @@ class RefLibrary:
             if p and p != mb_ + 0x400 * m:
                 out[i] = (p - mb_) // 0x400
         return out, int(n)
+
+    # ---- Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (@0xf5190; Tracking::SearchLocalPoints calls it per local map point) ----
+    # Frame: mRcw (3x3) @0x123a8, mtcw (3x1) @0x12408, mOw (3x1) @0x124c8, mbf @0xe0, mnScaleLevels @0x12338, mfLogScaleFactor @0x12340;
+    # MapPoint: mWorldPos @0xd8, mNormalVector @0x168, mfMinDistance @0x248, mfMaxDistance @0x24c; outputs mTrackProjX @0x1c,
+    # mTrackProjY @0x20, mTrackProjXR @0x24, mnTrackScaleLevel @0x28, mTrackViewCos @0x2c, mbTrackInView @0x30.
+    def is_in_frustum(self, xyz, normal, dist_range, cam, tcw, ow, mbf, log_scale_factor, n_levels, cos_limit):
+        """cam = (fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY).  Returns dict(in_view uint8 [M], proj float32 [M,3] (u, v, ur),
+        level int32 [M], viewcos float32 [M]) as the reference's function leaves them in the map points (untouched fields read 0)."""
+        f32 = np.float32
+        st = lambda name: C.c_float.in_dll(self.lib, name)
+        for name, v in zip(("2fx", "2fy", "2cx", "2cy"), cam[:4]):
+            st("_ZN9ORB_SLAM25Frame%sE" % name).value = f32(v)
+        st("_ZN9ORB_SLAM25Frame6mnMinXE").value, st("_ZN9ORB_SLAM25Frame6mnMaxXE").value = f32(cam[4]), f32(cam[5])
+        st("_ZN9ORB_SLAM25Frame6mnMinYE").value, st("_ZN9ORB_SLAM25Frame6mnMaxYE").value = f32(cam[6]), f32(cam[7])
+        m = len(xyz)
+        xyz = np.ascontiguousarray(xyz, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+        rng_ = np.ascontiguousarray(dist_range, np.float32)
+        T = np.asarray(tcw, np.float32).reshape(3, 4)
+        R = np.ascontiguousarray(T[:, :3]); t = np.ascontiguousarray(T[:, 3:4]); O = np.ascontiguousarray(np.asarray(ow, np.float32).reshape(3, 1))
+        fr = (C.c_uint64 * (0x12800 // 8))()
+        fb = C.addressof(fr)
+        self._fmat_at(fb + 0x123a8, R); self._fmat_at(fb + 0x12408, t); self._fmat_at(fb + 0x124c8, O)
+        C.c_float.from_address(fb + 0xe0).value = f32(mbf)
+        C.c_int32.from_address(fb + 0x12338).value = int(n_levels)
+        C.c_float.from_address(fb + 0x12340).value = f32(log_scale_factor)
+        fn = getattr(self.lib, "_ZN9ORB_SLAM25Frame11isInFrustumEPNS_8MapPointEf")
+        fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p, C.c_float], C.c_bool
+        out = dict(in_view=np.zeros(m, np.uint8), proj=np.zeros((m, 3), np.float32), level=np.zeros(m, np.int32), viewcos=np.zeros(m, np.float32))
+        mp = (C.c_uint8 * 0x400)()
+        a = C.addressof(mp)
+        for i in range(m):
+            C.memset(a, 0, 0x400)
+            self._fmat_at(a + 0xd8, xyz[i].reshape(3, 1))
+            self._fmat_at(a + 0x168, normal[i].reshape(3, 1))
+            C.c_float.from_address(a + 0x248).value = rng_[i, 0]
+            C.c_float.from_address(a + 0x24c).value = rng_[i, 1]
+            r = fn(fb, a, f32(cos_limit))
+            assert bool(r) == bool(mp[0x30])
+            out["in_view"][i] = mp[0x30]
+            out["proj"][i] = (C.c_float.from_address(a + 0x1c).value, C.c_float.from_address(a + 0x20).value, C.c_float.from_address(a + 0x24).value)
+            out["level"][i] = C.c_int32.from_address(a + 0x28).value
+            out["viewcos"][i] = C.c_float.from_address(a + 0x2c).value
+        return out
 
     # ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (@0x86b30) ----
     # KeyFrame: fx/fy/cx/cy @0x130..0x13c, N @0x154, mvKeysUn @0x170, mvuRight @0x188, mDescriptors @0x1b8, mFeatVec @0x248,

@@ -174,3 +174,30 @@ def relocalisation_case(kps_kf, desc_kf, kps_cur, desc_cur, scale_factors, W=640
     cam = np.array([fx, fy, cx, cy, mnx, mxx, mny, mxy, gwi, ghi], np.float32)
     log_sf = np.float32(np.log(np.float32(1.2)))
     return kf, cur, cam, sf, log_sf, tcw
+
+
+def frustum_case(n=3000, W=640, H=480, seed=0, motion=0.1):
+    """Tracking::SearchLocalPoints-like inputs for Frame::isInFrustum: local map points scattered in and around the view frustum
+    (some behind the camera, outside the image, out of their scale-invariance range or seen from too oblique an angle)."""
+    rng = np.random.default_rng(seed)
+    fx = fy = np.float32(520.0); cx = np.float32(W / 2 - 0.5); cy = np.float32(H / 2 - 0.5)
+    ang = 0.05
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([[motion], [0.01], [-motion]])
+    tcw = np.hstack([R, t]).astype(np.float32)
+    Rf, tf = tcw[:, :3].astype(np.float64), tcw[:, 3].astype(np.float64)
+    ow = (-(Rf.T @ tf)).astype(np.float32)          # (the fixture stores it: Frame::mOw is an input of isInFrustum)
+    z = rng.uniform(-1.0, 6.0, n)
+    x = rng.uniform(-1.3, 1.3, n) * np.abs(z) * (W / 2) / fx
+    y = rng.uniform(-1.3, 1.3, n) * np.abs(z) * (H / 2) / fy
+    xyz = np.stack([x, y, z], 1).astype(np.float32)
+    d = np.linalg.norm(xyz.astype(np.float64) - ow.astype(np.float64), axis=1)
+    dmax = (d * rng.uniform(0.5, 4.0, n)).astype(np.float32)
+    dmin = (dmax / np.float32(1.2) ** 7 * rng.uniform(0.5, 1.5, n)).astype(np.float32)
+    po = xyz.astype(np.float64) - ow.astype(np.float64)
+    nrm = po / np.maximum(np.linalg.norm(po, axis=1, keepdims=True), 1e-9)
+    nrm = nrm + rng.normal(0, 0.7, nrm.shape)
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    cam8 = np.array([fx, fy, cx, cy, 0, W, 0, H], np.float32)
+    return dict(xyz=np.ascontiguousarray(xyz), normal=np.ascontiguousarray(nrm), dist_range=np.ascontiguousarray(np.stack([dmin, dmax], 1)),
+                cam8=cam8, tcw=tcw, ow=ow, mbf=np.float32(40.0), log_sf=np.float32(np.log(np.float32(1.2))), n_levels=8)

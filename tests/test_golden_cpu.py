@@ -317,6 +317,30 @@ def test_search_by_projection_keyframe_equals_the_reference_matcher(oracle):
     assert total > 1500
 
 
+def _frustum_cases(g):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import frustum_case
+    for k in range(int(g["fz_n"])):
+        seed, motion, lim = g["fz%d_args" % k]
+        c = frustum_case(3000, seed=int(seed), motion=float(motion))
+        assert np.array_equal(c["ow"], g["fz%d_ow" % k])
+        yield k, c, float(lim)
+
+
+def test_is_in_frustum_equals_the_reference(oracle):
+    """Frame::isInFrustum (@0xf5190) executed from lib/libORB_SLAM2.so on a faked Frame and 3 x 3000 faked MapPoints: the
+    in-view flag, mTrackProjX / Y / XR, mnTrackScaleLevel and mTrackViewCos it leaves in each point (fixture fz*)."""
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    seen = 0
+    for k, c, lim in _frustum_cases(g):
+        r = oracle.is_in_frustum(c["xyz"], c["normal"], c["dist_range"], c["cam8"], c["tcw"], c["ow"], c["mbf"], c["log_sf"], c["n_levels"], lim)
+        for name in ("in_view", "proj", "level", "viewcos"):
+            assert np.array_equal(r[name], g["fz%d_%s" % (k, name)]), (k, name)
+        seen += int(r["in_view"].sum())
+    assert seen > 2000
+
+
 def test_logf_and_predict_scale(oracle):
     """The restated glibc logf equals the C library's on a sweep of bit patterns (PredictScale calls logf, @0x8fc7b), and
     PredictScale clamps to [0, nLevels - 1]."""

@@ -220,6 +220,22 @@ def test_k_projection_keyframe_mode_equals_the_reference_matcher():
         assert pl.predict_scale(10.0, float(d), lsf, 8) == ob.predict_scale(10.0, float(d), lsf, 8), d
 
 
+def test_k_is_in_frustum_equals_the_reference():
+    """k_is_in_frustum (Frame::isInFrustum, @0xf5190) on the fz* fixtures: 3 x 3000 map points, every field the reference's
+    function leaves in a MapPoint."""
+    import plslam_b200 as pl
+    from test_golden_cpu import _frustum_cases
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    seen = 0
+    for k, c, lim in _frustum_cases(g):
+        r = pl.is_in_frustum_host(c["xyz"], c["normal"], c["dist_range"], c["cam8"], c["tcw"], c["ow"], c["mbf"], c["log_sf"], c["n_levels"], lim)
+        for name in ("in_view", "proj", "level", "viewcos"):
+            assert np.array_equal(r[name], g["fz%d_%s" % (k, name)]), (k, name)
+        seen += int(r["in_view"].sum())
+    assert seen > 2000
+    assert len(pl.is_in_frustum_host(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 2)), c["cam8"], c["tcw"], c["ow"], 40.0, c["log_sf"], 8, 0.5)["in_view"]) == 0
+
+
 def test_k_triangulation_equals_the_reference_matcher():
     """k_triangulation (ORBmatcher::SearchForTriangulation, @0x86b30, epipole included) on the tr* fixtures."""
     import sys
