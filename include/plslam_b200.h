@@ -264,6 +264,39 @@ typedef struct plslam_proj_job {
 } plslam_proj_job_t;
 int plslam_match_projection_batch_device(const plslam_proj_job_t* d_jobs, int njobs, int max_n1, int max_n2, void* stream);
 
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched,
+ * int th) (ORBmatcher.h:86, @0x880f0; LoopClosing::ComputeSim3 / SearchAndFuse) including KeyFrame::GetFeaturesInArea (@0x96fe0),
+ * KeyFrame::IsInImage (@0x97480) and MapPoint::PredictScale(dist, pKF) (@0x8fb60): map points projected into a key frame with a
+ * similarity transform.  One warp per job walks the points in order (a key-frame feature assigned to an earlier point is closed
+ * to later ones). */
+typedef struct plslam_kfproj_job {
+  /* vpPoints */
+  const uint8_t* mp_valid;      /* M : !pMP->isBad() && pMP is not in vpMatched on entry */
+  const float* mp_xyz;          /* M x 3 : GetWorldPos() */
+  const float* mp_normal;       /* M x 3 : GetNormal() */
+  const float* mp_dist_range;   /* M x 2 : mfMinDistance, mfMaxDistance */
+  const uint8_t* mp_desc;       /* M x 32 : GetDescriptor() */
+  const int32_t* mp_level;      /* M or NULL.  Not NULL: the caller made the scale-invariance and viewing-angle tests itself
+                                   (folded into mp_valid) and passes pMP->PredictScale(dist, pKF); mp_normal / mp_dist_range unused */
+  /* pKF */
+  const float* kf_xy;           /* N x 2 : mvKeysUn[i].pt */
+  const int32_t* kf_octave;     /* N */
+  const uint8_t* kf_desc;       /* N x 32 */
+  const uint8_t* kf_matched;    /* N : vpMatched[i] != NULL on entry */
+  const int32_t* grid_start;    /* grid_cols * grid_rows + 1 : CSR of KeyFrame::mGrid in [ix][iy] order */
+  const int32_t* grid_items;
+  const float* scale_factors;   /* pKF->mvScaleFactors */
+  int32_t* match_kf;            /* N : index into vpPoints newly assigned to each key-frame feature, -1 = none */
+  int32_t* nmatches;            /* 1 */
+  float scw[12];                /* rows 0..2 of Scw = [s R | s t] */
+  float cam[4];                 /* pKF->fx, fy, cx, cy */
+  int32_t bounds[4];            /* pKF->mnMinX, mnMinY, mnMaxX, mnMaxY (int members of KeyFrame) */
+  float grid_width_inv, grid_height_inv, log_scale_factor;
+  int32_t grid_cols, grid_rows, n_levels, th, m, n;
+} plslam_kfproj_job_t;
+int plslam_match_kf_projection_batch_device(const plslam_kfproj_job_t* d_jobs, int njobs, int max_n, void* stream); /* max_n >= every job's n */
+int plslam_match_kf_projection_host(const plslam_kfproj_job_t* job); /* HOST pointers inside *job */
+
 /* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (ORBmatcher.h:61,
  * @0x79f10) — the local-map search of Tracking::SearchLocalPoints, including Frame::GetFeaturesInArea and
  * RadiusByViewingCos (@0x79b60).  The map-point fields it reads (filled by Frame::isInFrustum in the reference) are

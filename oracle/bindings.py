@@ -289,6 +289,30 @@ def predict_scale(max_distance, dist, log_scale_factor, n_levels):
     return L.oracle_predict_scale(max_distance, dist, log_scale_factor, n_levels)
 
 
+def search_by_projection_sim3(kf, mp, scw, matched_in, th):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (layout: tests/matchdata.py loop_projection_case)
+    -> (match_kf int32 [N]: map-point index newly assigned to each key-frame feature or -1, nmatches)."""
+    m, n = len(mp["desc"]), len(kf["desc"])
+    matched_in = np.asarray(matched_in, np.int32)
+    found = np.zeros(m, bool)
+    found[matched_in[matched_in >= 0]] = True
+    valid = np.ascontiguousarray((np.asarray(mp["state"]) == 1) & ~found, np.uint8)
+    a = [valid, np.ascontiguousarray(mp["xyz"], np.float32), np.ascontiguousarray(mp["normal"], np.float32),
+         np.ascontiguousarray(mp["dist_range"], np.float32), np.ascontiguousarray(mp["desc"], np.uint8)]
+    b = [np.ascontiguousarray(kf["xy"], np.float32), np.ascontiguousarray(kf["octave"], np.int32), np.ascontiguousarray(kf["desc"], np.uint8),
+         np.ascontiguousarray(matched_in >= 0, np.uint8), np.ascontiguousarray(kf["grid_start"], np.int32), np.ascontiguousarray(kf["grid_items"], np.int32)]
+    c = [np.ascontiguousarray(scw, np.float32).reshape(12), np.ascontiguousarray(kf["cam4"], np.float32), np.ascontiguousarray(kf["bounds4"], np.int32)]
+    sf = np.ascontiguousarray(kf["scale_factors"], np.float32)
+    out = np.empty(max(n, 1), np.int32)
+    L = lib()
+    L.oracle_search_by_projection_sim3.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + \
+        [C.c_void_p] * 3 + [C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    L.oracle_search_by_projection_sim3.restype = C.c_int
+    nm = L.oracle_search_by_projection_sim3(m, *[_p(x) for x in a], n, *[_p(x) for x in b], 64, 48, *[_p(x) for x in c], float(kf["gwi"]),
+                                            float(kf["ghi"]), _p(sf), len(sf), float(kf["log_sf"]), int(th), _p(out))
+    return out[:n], nm
+
+
 def is_in_frustum(xyz, normal, dist_range, cam8, tcw, ow, mbf, log_scale_factor, n_levels, cos_limit):
     """Frame::isInFrustum over M map points -> dict(in_view, proj [M,3], level, viewcos)."""
     m = len(xyz)

@@ -483,6 +483,112 @@ int oracle_search_by_projection_kf(int M, const uint8_t* mpValid, const float* m
   return nmatches;
 }
 
+}  // extern "C"
+namespace {
+// KeyFrame::GetFeaturesInArea(x, y, r) (@0x96fe0): the key frame's grid (mnGridCols x mnGridRows, CSR in [ix][iy] order), integer
+// bounds converted to float, no level filter; a feature is a candidate when |dx| < r and |dy| < r.
+template <class F>
+inline void for_kf_features_in_area(float x, float y, float r, int mnMinX, int mnMinY, float gwi, float ghi, int cols, int rows,
+                                    const int* gridStart, const int* gridItems, const float* xy, F&& f) {
+  const int nMinCellX = std::max(0, (int)floorf((x - (float)mnMinX - r) * gwi));
+  if (nMinCellX >= cols) return;
+  const int nMaxCellX = std::min(cols - 1, (int)ceilf((x - (float)mnMinX + r) * gwi));
+  if (nMaxCellX < 0) return;
+  const int nMinCellY = std::max(0, (int)floorf((y - (float)mnMinY - r) * ghi));
+  if (nMinCellY >= rows) return;
+  const int nMaxCellY = std::min(rows - 1, (int)ceilf((y - (float)mnMinY + r) * ghi));
+  if (nMaxCellY < 0) return;
+  for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+    for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+      const int c = ix * rows + iy;
+      for (int j = gridStart[c]; j < gridStart[c + 1]; ++j) {
+        const int i2 = gridItems[j];
+        const float distx = xy[2 * i2] - x, disty = xy[2 * i2 + 1] - y;
+        if (fabsf(distx) < r && fabsf(disty) < r) f(i2);
+      }
+    }
+}
+
+}  // namespace
+extern "C" {
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th)
+// (ORBmatcher.h:86; @0x880f0, LoopClosing).  Read from the binary: scw = (float)sqrt(sRcw.row(0).dot(sRcw.row(0))) (dot in double,
+// vsqrtsd @0x8836b); Rcw = sRcw / scw and tcw = Scw.col(3) / scw are cv::operator/(Mat, double) (@0x884fb, @0x886ab), which OpenCV
+// evaluates as a scaled conversion: every element TIMES (float)(1.0 / (double)scw); Ow = -Rcw.t() * tcw; per map point that is
+// not bad and not already in vpMatched: p3Dc = Rcw * p3Dw + tcw (gemm), z < 0 rejects (@0x890d9), invz = 1.0f / z, x = X * invz,
+// u = fma(x, fx, cx), v likewise (@0x890f0-0x89160), KeyFrame::IsInImage (u >= mnMinX && u < mnMaxX ..., int bounds), the
+// scale-invariance range, PO.dot(Pn) < 0.5 * dist rejects (doubles, @0x89acc), level = PredictScale(dist, pKF), radius =
+// (float)th * mvScaleFactors[level] (@0x89b22), KeyFrame::GetFeaturesInArea(u, v, radius); a candidate is skipped when already
+// matched or when its octave is outside [level - 1, level] (@0x89c1c-0x89c54); best = strictly smaller distance; accepted when
+// bestDist <= TH_LOW (@0x89daf).  mpValid[i] = !isBad() && pMP not in vpMatched on entry; kfMatched[i] = vpMatched[i] != NULL on entry.
+// matchKF[N] receives the map-point index newly assigned to each key-frame feature (-1 = none).  Returns nmatches.
+int oracle_search_by_projection_sim3(int M, const uint8_t* mpValid, const float* mpXYZ, const float* mpNormal,
+                                     const float* mpDistRange, const uint8_t* mpDesc, int N, const float* kfXY, const int* kfOctave,
+                                     const uint8_t* kfDesc, const uint8_t* kfMatched, const int* gridStart, const int* gridItems,
+                                     int gridCols, int gridRows, const float* Scw, const float* cam4, const int* bounds4, float gwi,
+                                     float ghi, const float* scaleFactors, int nLevels, float logScaleFactor, int th, int* matchKF) {
+  const float fx = cam4[0], fy = cam4[1], cx = cam4[2], cy = cam4[3];
+  const int mnMinX = bounds4[0], mnMinY = bounds4[1], mnMaxX = bounds4[2], mnMaxY = bounds4[3];
+  std::vector<uint8_t> matched(kfMatched, kfMatched + N);
+  for (int i = 0; i < N; ++i) matchKF[i] = -1;
+  double dot0 = 0;
+  for (int k = 0; k < 3; ++k) dot0 += (double)Scw[k] * (double)Scw[k];
+  const float scw = (float)std::sqrt(dot0);
+  const float inv = (float)(1.0 / (double)scw);
+  float T[12];  // Rcw | tcw
+  for (int k = 0; k < 12; ++k) T[k] = Scw[k] * inv + 0.0f;
+  float Ow[3];
+  for (int r = 0; r < 3; ++r) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += (double)T[k * 4 + r] * (double)T[k * 4 + 3];
+    Ow[r] = (float)(-1.0 * s);
+  }
+  int nmatches = 0;
+  for (int i = 0; i < M; ++i) {
+    if (!mpValid[i]) continue;
+    const float* X = mpXYZ + 3 * i;
+    float pc[3];
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = T[r * 4] * X[0], p1 = T[r * 4 + 1] * X[1], p2 = T[r * 4 + 2] * X[2];
+      const float s = (p0 + p1) + p2;
+      pc[r] = (float)((double)s + (double)T[r * 4 + 3]);
+    }
+    if (pc[2] < 0.0f) continue;
+    const float invz = 1.0f / pc[2];
+    const float x = pc[0] * invz, y = pc[1] * invz;
+    const float u = std::fmaf(x, fx, cx), v = std::fmaf(y, fy, cy);
+    if (!(u >= (float)mnMinX && u < (float)mnMaxX && v >= (float)mnMinY && v < (float)mnMaxY)) continue;
+    float PO[3];
+    double n2 = 0;
+    for (int r = 0; r < 3; ++r) {
+      PO[r] = X[r] - Ow[r];
+      n2 += (double)PO[r] * (double)PO[r];
+    }
+    const float dist = (float)std::sqrt(n2);
+    if (dist < 0.8f * mpDistRange[2 * i] || dist > 1.2f * mpDistRange[2 * i + 1]) continue;
+    double dot = 0;
+    for (int r = 0; r < 3; ++r) dot += (double)PO[r] * (double)mpNormal[3 * i + r];
+    if (dot < 0.5 * (double)dist) continue;
+    const int level = predict_scale(mpDistRange[2 * i + 1], dist, logScaleFactor, nLevels);
+    const float radius = (float)th * scaleFactors[level];
+    int bestDist = 256, bestIdx = -1;
+    for_kf_features_in_area(u, v, radius, mnMinX, mnMinY, gwi, ghi, gridCols, gridRows, gridStart, gridItems, kfXY, [&](int idx) {
+      if (matched[idx]) return;
+      const int kpLevel = kfOctave[idx];
+      if (kpLevel < level - 1 || kpLevel > level) return;
+      const int d = descriptor_distance(mpDesc + 32 * i, kfDesc + 32 * idx);
+      if (d < bestDist) { bestDist = d; bestIdx = idx; }
+    });
+    if (bestDist <= TH_LOW) {
+      matchKF[bestIdx] = i;
+      matched[bestIdx] = 1;
+      nmatches++;
+    }
+  }
+  return nmatches;
+}
+
 // Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (include/Frame.h:107-ish "isInFrustum"; @0xf5190), what
 // Tracking::SearchLocalPoints runs on every local map point before ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)
 // (it fills the mTrack* fields that matcher reads).  Read from the binary: Pc = mRcw * P + mtcw (gemm small path); PcZ < 0

@@ -37,6 +37,25 @@ struct KeyFramePointsView {
   std::vector<int32_t> level;      // pMP->PredictScale(dist3D, &CurrentFrame)
 };
 
+// Key frame and map points as ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) reads them
+// (reference include/ORBmatcher.h:86).
+struct KeyFrameGridView {
+  std::vector<cv::KeyPoint> mvKeysUn;
+  cv::Mat mDescriptors;                        // N x 32
+  std::vector<float> mvScaleFactors;
+  std::vector<int32_t> gridStart, gridItems;   // KeyFrame::mGrid[mnGridCols][mnGridRows] as CSR in [ix][iy] order
+  int mnGridCols = 64, mnGridRows = 48;
+  float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+  int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+  float fx = 0, fy = 0, cx = 0, cy = 0;
+};
+struct LoopPointsView {
+  std::vector<uint8_t> valid;      // !isBad() && not in vpMatched on entry && inside the invariance range && PO.dot(Pn) >= 0.5 * dist
+  std::vector<float> worldPos;     // M x 3
+  cv::Mat descriptors;             // M x 32
+  std::vector<int32_t> level;      // pMP->PredictScale(dist, pKF)
+};
+
 struct FrameView {
   // features
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn;

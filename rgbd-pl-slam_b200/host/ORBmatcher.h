@@ -43,6 +43,12 @@ class ORBmatcher {
   template <class FrameT, class KeyFrameT, class MapPointT>
   int SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const std::set<MapPointT*>& sAlreadyFound, const float th,
                          const int ORBdist);
+  // Project MapPoints using a Similarity Transformation and search matches (LoopClosing) (ORBmatcher.h:86).  pKF->mGrid is
+  // protected in the reference's KeyFrame.h: the template reads it through `pKF->mGrid`, i.e. it needs ORBmatcher befriended
+  // there or a public accessor.
+  template <class KeyFrameT, class MapPointT>
+  int SearchByProjection(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched,
+                         int th);
   // Search matches between MapPoints in a KeyFrame and ORB in a Frame (Relocalisation, TrackReferenceKeyFrame)
   template <class KeyFrameT, class FrameT, class MapPointT>
   int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches);
@@ -75,6 +81,11 @@ class ORBmatcher {
   // vnMatches[i2] = key-frame index assigned to current keypoint i2, or -1.
   int SearchByProjection(FrameView& CurrentFrame, const KeyFramePointsView& KF, const float th, const int ORBdist,
                          std::vector<int>& vnMatches);
+
+  // Loop-closing form (ORBmatcher.h:86) on views: Scw = rows 0..2 of the 4x4 similarity; matchedOnEntry[i] = vpMatched[i] != NULL;
+  // vnMatches[i] = index into the points newly assigned to key-frame feature i, or -1.
+  int SearchByProjection(const KeyFrameGridView& KF, const float Scw[12], const LoopPointsView& P,
+                         const std::vector<uint8_t>& matchedOnEntry, int th, std::vector<int>& vnMatches);
 
   // Brute force constrained to ORB that belong to the same vocabulary node (Relocalisation / TrackReferenceKeyFrame).
   // vnMatches[iF] = index in the KeyFrame matched to F's feature iF, or -1.

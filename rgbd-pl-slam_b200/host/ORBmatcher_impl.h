@@ -185,6 +185,82 @@ int ORBmatcher::SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const s
   return nm;
 }
 
+// ORBmatcher.h:86 (@0x880f0).  The similarity is taken apart here with the reference's arithmetic (scale from the first row of
+// sRcw, dot in double; every element times (float)(1.0 / scw), as cv::operator/(Mat, double) evaluates; Ow through the
+// double-accumulating product), so that the invariance test, the viewing-angle test and pMP->PredictScale() see the reference's
+// distance; the kernel repeats the same decomposition for the projections.
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchByProjection(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints,
+                                   std::vector<MapPointT*>& vpMatched, int th) {
+  KeyFrameGridView kv;
+  kv.mvKeysUn = pKF->mvKeysUn;
+  kv.mDescriptors = pKF->mDescriptors;
+  kv.mvScaleFactors = pKF->mvScaleFactors;
+  kv.mnGridCols = pKF->mnGridCols; kv.mnGridRows = pKF->mnGridRows;
+  kv.mfGridElementWidthInv = pKF->mfGridElementWidthInv; kv.mfGridElementHeightInv = pKF->mfGridElementHeightInv;
+  kv.mnMinX = pKF->mnMinX; kv.mnMinY = pKF->mnMinY; kv.mnMaxX = pKF->mnMaxX; kv.mnMaxY = pKF->mnMaxY;
+  kv.fx = pKF->fx; kv.fy = pKF->fy; kv.cx = pKF->cx; kv.cy = pKF->cy;
+  const int n = (int)kv.mvKeysUn.size(), m = (int)vpPoints.size();
+  dropin::require((int)vpMatched.size() == n && pKF->mDescriptors.rows == n, "KeyFrame members / vpMatched differ in length");
+  kv.gridStart.assign(1, 0);
+  for (int ix = 0; ix < kv.mnGridCols; ++ix)
+    for (int iy = 0; iy < kv.mnGridRows; ++iy) {
+      for (size_t k = 0; k < pKF->mGrid[ix][iy].size(); ++k) kv.gridItems.push_back((int32_t)pKF->mGrid[ix][iy][k]);
+      kv.gridStart.push_back((int32_t)kv.gridItems.size());
+    }
+  float S[12];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) S[4 * r + c] = Scw.template at<float>(r, c);
+  double d0 = 0;
+  for (int k = 0; k < 3; ++k) d0 += (double)S[k] * (double)S[k];
+  const float scw = (float)std::sqrt(d0);
+  const float inv = (float)(1.0 / (double)scw);
+  float T[12], Ow[3];
+  for (int k = 0; k < 12; ++k) { volatile float p = S[k] * inv; T[k] = p + 0.0f; }
+  for (int r = 0; r < 3; ++r) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += (double)T[4 * k + r] * (double)T[4 * k + 3];
+    Ow[r] = (float)(-1.0 * s);
+  }
+  std::set<MapPointT*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+  spAlreadyFound.erase(static_cast<MapPointT*>(nullptr));
+  std::vector<uint8_t> matchedOnEntry(n, 0);
+  for (int i = 0; i < n; ++i) matchedOnEntry[i] = vpMatched[i] != nullptr;
+  LoopPointsView pv;
+  pv.valid.assign(m, 0);
+  pv.worldPos.assign((size_t)m * 3, 0.f);
+  pv.descriptors.create(m > 0 ? m : 1, 32, CV_8U);
+  pv.level.assign(m, 0);
+  for (int i = 0; i < m; ++i) {
+    MapPointT* pMP = vpPoints[i];
+    if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+    const cv::Mat p3Dw = pMP->GetWorldPos();
+    float PO[3];
+    double n2 = 0;
+    for (int k = 0; k < 3; ++k) {
+      const float x = p3Dw.template at<float>(k);
+      pv.worldPos[3 * (size_t)i + k] = x;
+      PO[k] = x - Ow[k];
+      n2 += (double)PO[k] * (double)PO[k];
+    }
+    const float dist = (float)std::sqrt(n2);
+    if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+    const cv::Mat Pn = pMP->GetNormal();
+    double dot = 0;
+    for (int k = 0; k < 3; ++k) dot += (double)PO[k] * (double)Pn.template at<float>(k);
+    if (dot < 0.5 * (double)dist) continue;
+    pv.level[i] = pMP->PredictScale(dist, pKF);
+    const cv::Mat d = pMP->GetDescriptor();
+    std::memcpy(pv.descriptors.ptr(i), d.ptr(0), 32);
+    pv.valid[i] = 1;
+  }
+  std::vector<int> match;
+  const int nm = SearchByProjection(kv, S, pv, matchedOnEntry, th, match);
+  for (int i = 0; i < n; ++i)
+    if (match[i] >= 0) vpMatched[i] = vpPoints[match[i]];
+  return nm;
+}
+
 // ORBmatcher.h:104 (@0x80150)
 template <class KeyFrameT, class FrameT, class MapPointT>
 int ORBmatcher::SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {

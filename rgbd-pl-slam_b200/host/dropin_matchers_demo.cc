@@ -23,8 +23,12 @@ typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;  // DB
 namespace ORB_SLAM2 {
 
 class Frame;
+class KeyFrame;
 class MapPoint {  // include/MapPoint.h: the members the matchers touch
  public:
+  cv::Mat GetNormal() { return mNormalVector.clone(); }
+  int PredictScale(const float& currentDist, KeyFrame* pKF);
+  cv::Mat mNormalVector;  // (protected in the reference)
   float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
   float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
   int PredictScale(const float& currentDist, Frame* pF);
@@ -86,7 +90,16 @@ class KeyFrame {  // include/KeyFrame.h
   std::vector<float> mvScaleFactors, mvLevelSigma2;
   std::vector<MapPoint*> mvpMapPoints;
   cv::Mat R, t, Ow;
+  int mnGridCols = 64, mnGridRows = 48;
+  float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+  int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+  int mnScaleLevels = 0;
+  float mfLogScaleFactor = 0;
+  std::vector<std::vector<std::vector<size_t> > > mGrid;  // (protected in the reference: see ORBmatcher.h)
 };
+int MapPoint::PredictScale(const float& currentDist, KeyFrame* pKF) {
+  return plslam_predict_scale(mfMaxDistance, currentDist, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
+}
 
 }  // namespace ORB_SLAM2
 
@@ -359,6 +372,58 @@ static void case_relocalisation() {
   save("rk_out", out);
 }
 
+// ---- LoopClosing::ComputeSim3: matcher.SearchByProjection(mpCurrentKF, mScw, mvpLoopMapPoints, mvpCurrentMatchedPoints, 10) ----
+static void case_loop_projection() {
+  const auto state = load<uint8_t>("lc_mp_state"), mdesc = load<uint8_t>("lc_mp_desc"), kdesc = load<uint8_t>("lc_kf_desc");
+  const auto xyz = load<float>("lc_mp_xyz"), nrm = load<float>("lc_mp_normal"), rng = load<float>("lc_mp_dist_range");
+  const auto kxy = load<float>("lc_kf_xy"), cam4 = load<float>("lc_kf_cam4"), sf = load<float>("lc_kf_scale_factors"), scw = load<float>("lc_scw");
+  const auto koct = load<int32_t>("lc_kf_octave"), gs = load<int32_t>("lc_kf_grid_start"), gi = load<int32_t>("lc_kf_grid_items"),
+             bounds = load<int32_t>("lc_kf_bounds4"), mi = load<int32_t>("lc_matched_in");
+  const auto par = load<float>("lc_par");  // th, gwi, ghi, logScaleFactor
+  const int m = (int)state.size(), n = (int)koct.size();
+  KeyFrame KF;
+  KF.mvKeysUn.resize(n);
+  for (int i = 0; i < n; ++i) {
+    KF.mvKeysUn[i].pt = cv::Point2f(kxy[2 * i], kxy[2 * i + 1]);
+    KF.mvKeysUn[i].octave = koct[i];
+  }
+  KF.mDescriptors = mat_u8(kdesc, n);
+  KF.mvScaleFactors = sf;
+  KF.mnScaleLevels = (int)sf.size();
+  KF.mfLogScaleFactor = par[3];
+  KF.fx = cam4[0]; KF.fy = cam4[1]; KF.cx = cam4[2]; KF.cy = cam4[3];
+  KF.mnMinX = bounds[0]; KF.mnMinY = bounds[1]; KF.mnMaxX = bounds[2]; KF.mnMaxY = bounds[3];
+  KF.mfGridElementWidthInv = par[1]; KF.mfGridElementHeightInv = par[2];
+  KF.mGrid.assign(64, std::vector<std::vector<size_t> >(48));
+  for (int ix = 0; ix < 64; ++ix)
+    for (int iy = 0; iy < 48; ++iy)
+      for (int k = gs[ix * 48 + iy]; k < gs[ix * 48 + iy + 1]; ++k) KF.mGrid[ix][iy].push_back((size_t)gi[k]);
+  std::vector<MapPoint*> vpPoints(m);
+  for (int i = 0; i < m; ++i) {
+    MapPoint* p = new_mp();
+    p->id = i;
+    p->mbBad = state[i] == 2;
+    p->mWorldPos = mat_f(&xyz[3 * (size_t)i], 3, 1);
+    p->mNormalVector = mat_f(&nrm[3 * (size_t)i], 3, 1);
+    p->mDescriptor = desc_row(mdesc, i);
+    p->mfMinDistance = rng[2 * i];
+    p->mfMaxDistance = rng[2 * i + 1];
+    vpPoints[i] = p;
+  }
+  std::vector<MapPoint*> vpMatched(n, nullptr);
+  for (int i = 0; i < n; ++i)
+    if (mi[i] >= 0) vpMatched[i] = vpPoints[mi[i]];
+  float S[16] = {0};
+  for (int k = 0; k < 12; ++k) S[k] = scw[k];
+  S[15] = 1.f;
+  ORBmatcher matcher(0.75f, true);
+  const int nmatches = matcher.SearchByProjection(&KF, mat_f(S, 4, 4), vpPoints, vpMatched, (int)par[0]);
+  std::vector<int32_t> out(n + 1);
+  for (int i = 0; i < n; ++i) out[i] = (vpMatched[i] && mi[i] < 0) ? vpMatched[i]->id : -1;
+  out[n] = nmatches;
+  save("lc_out", out);
+}
+
 // ---- LoopClosing::ComputeSim3: matcher.SearchByBoW(mpCurrentKF, pKF, vvpMapPointMatches[i]) ----
 static void case_bow_keyframes() {
   const auto par = load<float>("bk_par");  // nnratio, ori
@@ -446,6 +511,7 @@ int main(int argc, char** argv) {
     case_bow();
     case_bow_keyframes();
     case_relocalisation();
+    case_loop_projection();
     case_triangulation();
     // an unfilled member must be reported, not read out of bounds
     Frame bad, last;

@@ -758,6 +758,44 @@ def search_by_projection_kf_host(kf, cur, cam, scale_factors, log_scale_factor, 
     return match[:n2], int(nm[0])
 
 
+class KfProjJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("mp_valid", "mp_xyz", "mp_normal", "mp_dist_range", "mp_desc", "mp_level", "kf_xy", "kf_octave",
+                                          "kf_desc", "kf_matched", "grid_start", "grid_items", "scale_factors", "match_kf", "nmatches")] + \
+               [("scw", C.c_float * 12), ("cam", C.c_float * 4), ("bounds", C.c_int32 * 4), ("grid_width_inv", C.c_float),
+                ("grid_height_inv", C.c_float), ("log_scale_factor", C.c_float), ("grid_cols", C.c_int32), ("grid_rows", C.c_int32),
+                ("n_levels", C.c_int32), ("th", C.c_int32), ("m", C.c_int32), ("n", C.c_int32)]
+
+
+def search_by_projection_sim3_host(kf, mp, scw, matched_in, th):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) on host arrays (layout: tests/matchdata.py
+    loop_projection_case) through plslam_match_kf_projection_host -> (match_kf int32 [N]: map-point index newly assigned to each
+    key-frame feature or -1, nmatches)."""
+    m, n = len(mp["desc"]), len(kf["desc"])
+    matched_in = np.asarray(matched_in, np.int32)
+    found = np.zeros(m, bool)
+    found[matched_in[matched_in >= 0]] = True
+    keep = []
+    def a(x, dt):
+        x = np.ascontiguousarray(x, dt); keep.append(x); return x.ctypes.data
+    sf = np.ascontiguousarray(kf["scale_factors"], np.float32)
+    out = np.empty(max(n, 1), np.int32); nm = np.zeros(1, np.int32)
+    j = KfProjJob()
+    j.mp_valid = a((np.asarray(mp["state"]) == 1) & ~found, np.uint8)
+    j.mp_xyz, j.mp_normal, j.mp_dist_range = a(mp["xyz"], np.float32), a(mp["normal"], np.float32), a(mp["dist_range"], np.float32)
+    j.mp_desc = a(mp["desc"], np.uint8)
+    j.kf_xy, j.kf_octave, j.kf_desc = a(kf["xy"], np.float32), a(kf["octave"], np.int32), a(kf["desc"], np.uint8)
+    j.kf_matched = a(matched_in >= 0, np.uint8)
+    j.grid_start, j.grid_items, j.scale_factors = a(kf["grid_start"], np.int32), a(kf["grid_items"], np.int32), sf.ctypes.data
+    j.match_kf, j.nmatches = out.ctypes.data, nm.ctypes.data
+    j.scw = (C.c_float * 12)(*np.asarray(scw, np.float32).reshape(12))
+    j.cam = (C.c_float * 4)(*np.asarray(kf["cam4"], np.float32))
+    j.bounds = (C.c_int32 * 4)(*[int(v) for v in kf["bounds4"]])
+    j.grid_width_inv, j.grid_height_inv, j.log_scale_factor = float(kf["gwi"]), float(kf["ghi"]), float(kf["log_sf"])
+    j.grid_cols, j.grid_rows, j.n_levels, j.th, j.m, j.n = 64, 48, len(sf), int(th), m, n
+    _check(lib().plslam_match_kf_projection_host(C.byref(j)))
+    return out[:n], int(nm[0])
+
+
 class FrustumJob(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("mp_xyz", "mp_normal", "mp_dist_range", "in_view", "proj", "level", "viewcos")] + \
                [("cam", C.c_float * 8), ("tcw", C.c_float * 12), ("ow", C.c_float * 3), ("mbf", C.c_float), ("log_scale_factor", C.c_float),

@@ -381,6 +381,23 @@ def reflib2():
                 rk.append(n)
     out["rk_n"] = np.array(len(rk))
     print("SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist):", rk)
+    # ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (loop closing) on a faked KeyFrame (its grid a real
+    # vector<vector<vector<size_t>>>), faked MapPoints and a similarity matrix with scale != 1
+    from matchdata import loop_projection_case
+    lc = []
+    for seed in (1, 2):
+        (ka, da), (kb, db) = feats[seed]
+        for motion, scale, th in ((0.02, 1.0, 10), (0.02, 1.7, 10), (-0.15, 0.6, 10), (0.02, 1.0, 3)):
+            kf, mp, scw, mi = loop_projection_case(ka, da, kb, db, sf, seed=seed, motion=motion, scale=scale)
+            m_out, n = R.search_by_projection_sim3(kf, mp, scw, mi, th)
+            k = len(lc)
+            out["lc%d_args" % k] = np.array([seed, motion, scale, th], np.float64)
+            newly = np.where((mi < 0) & (m_out >= 0), m_out, -1).astype(np.int32)
+            assert np.array_equal(m_out[mi >= 0], mi[mi >= 0])          # entries matched on entry are left alone
+            out["lc%d_match" % k], out["lc%d_n" % k] = newly, np.array(n)
+            lc.append(n)
+    out["lc_n"] = np.array(len(lc))
+    print("SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th):", lc)
     # Frame::isInFrustum on a faked Frame and faked MapPoints (GetWorldPos, GetNormal, the invariance range and PredictScale are
     # the library's own); the outputs are what the function leaves in the map points
     from matchdata import frustum_case

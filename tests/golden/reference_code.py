@@ -453,6 +453,21 @@ static void expr_assign(const void*, const MatExpr* e, Mat* m, int type) {
     for (int i = 0; i < A->rows; ++i) std::memcpy(m->data + (size_t)i * m->stepp[0], D.data + (size_t)i * D.stepp[0], (size_t)A->cols * 4);
     return;
   }
+  if ((e->flags >> 8) == 'D') {  // a / s = MatOp_AddEx(a, alpha = 1./s): convertTo with a scale, cvtScale_<float, float, float>:
+    const Mat* A = &e->a;         // dst = src * (float)alpha + (float)0
+    const float scale = (float)e->alpha, shift = 0.0f;
+    Mat D;
+    mat_init_empty(&D);
+    mat_create(&D, A->rows, A->cols, 5);
+    for (int i = 0; i < A->rows; ++i)
+      for (int j = 0; j < A->cols; ++j) {
+        volatile float prod = at(A, i, j) * scale;  // two roundings, as the SIMD mul + add of OpenCV 3.3's cvtScale
+        at(&D, i, j) = prod + shift;
+      }
+    mat_create(m, A->rows, A->cols, 5);
+    for (int i = 0; i < A->rows; ++i) std::memcpy(m->data + (size_t)i * m->stepp[0], D.data + (size_t)i * D.stepp[0], (size_t)A->cols * 4);
+    return;
+  }
   if ((e->flags >> 8) != 'G') __builtin_trap();
   const bool tA = (e->flags & 1) != 0;
   const Mat *A = &e->a, *B = &e->b, *Cm = e->c.data ? &e->c : nullptr;
@@ -576,6 +591,24 @@ double shim_dot(const Mat* self, const InputArray* other) {
     r += (double)a[i] * b[i] + (double)a[i + 1] * b[i + 1] + (double)a[i + 2] * b[i + 2] + (double)a[i + 3] * b[i + 3];
   for (; i < a.size(); ++i) r += (double)a[i] * b[i];
   return r;
+}
+// ---- ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (@0x880f0): sRcw / scw, tcw / scw ----
+void shim_div_ms(MatExpr* ret, const Mat* a, double s) asm("_ZN2cvdvERKNS_3MatEd");
+void shim_div_ms(MatExpr* ret, const Mat* a, double s) {
+  TRACE("operator/(Mat, double %g)", s);
+  expr_init(ret, 'D', 0);
+  hdr_copy(&ret->a, a);
+  ret->alpha = 1. / s;
+}
+// helper for the harness: KeyFrame::mGrid = std::vector<std::vector<std::vector<size_t>>> [cols][rows] built in place from CSR
+void refshim_build_kfgrid(void* where, int cols, int rows, const int* start, const int* items);
+void refshim_build_kfgrid(void* where, int cols, int rows, const int* start, const int* items) {
+  auto* g = new (where) std::vector<std::vector<std::vector<size_t>>>((size_t)cols);
+  for (int ix = 0; ix < cols; ++ix) {
+    (*g)[ix].resize((size_t)rows);
+    for (int iy = 0; iy < rows; ++iy)
+      for (int k = start[ix * rows + iy]; k < start[ix * rows + iy + 1]; ++k) (*g)[ix][iy].push_back((size_t)items[k]);
+  }
 }
 // helper for the harness (not an OpenCV symbol): a std::set<void*> built in place from an array of pointers
 void refshim_build_ptrset(void* where, void* const* ptrs, int n);
@@ -1189,6 +1222,84 @@ class RefLibrary:
             out["level"][i] = C.c_int32.from_address(a + 0x28).value
             out["viewcos"][i] = C.c_float.from_address(a + 0x2c).value
         return out
+
+    # ---- ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th) ----
+    # (@0x880f0, LoopClosing::ComputeSim3 / SearchAndFuse).  KeyFrame members: mnGridCols @0x18, mnGridRows @0x1c,
+    # mfGridElementWidthInv @0x20, mfGridElementHeightInv @0x24, fx fy cx cy @0x130.., N @0x154, mvKeysUn @0x170, mDescriptors @0x1b8,
+    # mnScaleLevels @0x2d8, mfLogScaleFactor @0x2e0, mvScaleFactors @0x2e8, mnMinX mnMinY mnMaxX mnMaxY (int) @0x330.., mGrid @0x548
+    # (KeyFrame::GetFeaturesInArea @0x96fe0, IsInImage @0x97480, MapPoint::PredictScale(dist, KeyFrame*) @0x8fb60).
+    def make_keyframe(self, kf, keep):
+        """kf: dict(xy, octave, desc, grid_start, grid_items, cam4, bounds4 (int: minx, miny, maxx, maxy), gwi, ghi, scale_factors,
+        log_sf [, angle, uright]) -> address of a faked KeyFrame."""
+        n = len(kf["desc"])
+        k = np.zeros(n, self.KP)
+        k["x"], k["y"], k["octave"] = kf["xy"][:, 0], kf["xy"][:, 1], kf["octave"]
+        if "angle" in kf:
+            k["angle"] = kf["angle"]
+        d = np.ascontiguousarray(kf["desc"], np.uint8)
+        sf = np.ascontiguousarray(kf["scale_factors"], np.float32)
+        o = (C.c_uint64 * (0x800 // 8))()
+        b = C.addressof(o)
+        def setv(off, arr):
+            o[off // 8], o[off // 8 + 1], o[off // 8 + 2] = arr.ctypes.data, arr.ctypes.data + arr.nbytes, arr.ctypes.data + arr.nbytes
+        C.c_int32.from_address(b + 0x18).value, C.c_int32.from_address(b + 0x1c).value = 64, 48
+        C.c_float.from_address(b + 0x20).value, C.c_float.from_address(b + 0x24).value = np.float32(kf["gwi"]), np.float32(kf["ghi"])
+        for i in range(4):
+            C.c_float.from_address(b + 0x130 + 4 * i).value = np.float32(kf["cam4"][i])
+            C.c_int32.from_address(b + 0x330 + 4 * i).value = int(kf["bounds4"][i])
+        C.c_int32.from_address(b + 0x154).value = n
+        setv(0x170, k); setv(0x2e8, sf)
+        self._mat_at(b + 0x1b8, d)
+        C.c_int32.from_address(b + 0x2d8).value = len(sf)
+        C.c_float.from_address(b + 0x2e0).value = np.float32(kf["log_sf"])
+        gs, gi = np.ascontiguousarray(kf["grid_start"], np.int32), np.ascontiguousarray(kf["grid_items"], np.int32)
+        bg = self._shims.refshim_build_kfgrid
+        bg.argtypes, bg.restype = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p], None
+        bg(b + 0x548, 64, 48, gs.ctypes.data, gi.ctypes.data)
+        keep.extend([k, d, sf, o, gs, gi])
+        return b
+
+    def make_map_points(self, mp, keep):
+        """mp: dict(state (1 good, 2 bad), xyz, normal, dist_range, desc) -> (base address of M faked MapPoints 0x400 bytes apart, buffer)."""
+        m = len(mp["desc"])
+        xyz = np.ascontiguousarray(mp["xyz"], np.float32); nrm = np.ascontiguousarray(mp["normal"], np.float32)
+        rng_ = np.ascontiguousarray(mp["dist_range"], np.float32); desc = np.ascontiguousarray(mp["desc"], np.uint8)
+        buf = (C.c_uint8 * (0x400 * (m + 1)))()
+        base = C.addressof(buf)
+        for i in range(m):
+            a = base + 0x400 * i
+            self._fmat_at(a + 0xd8, xyz[i].reshape(3, 1))
+            self._fmat_at(a + 0x168, nrm[i].reshape(3, 1))
+            self._mat_at(a + 0x1c8, desc[i:i + 1])
+            C.c_uint8.from_address(a + 0x238).value = 1 if mp["state"][i] == 2 else 0
+            C.c_float.from_address(a + 0x248).value = rng_[i, 0]
+            C.c_float.from_address(a + 0x24c).value = rng_[i, 1]
+        keep.extend([xyz, nrm, rng_, desc, buf])
+        return base
+
+    def search_by_projection_sim3(self, kf, mp, scw, matched_in, th):
+        """kf / mp as in make_keyframe / make_map_points; scw: 3x4 (rows of Scw); matched_in int32 [N]: index into the map points
+        already matched to a key-frame feature (-1 = none).  Returns (matched int32 [N] after the call, nmatches)."""
+        keep = []
+        kb = self.make_keyframe(kf, keep)
+        base = self.make_map_points(mp, keep)
+        m, n = len(mp["desc"]), len(kf["desc"])
+        vp = np.array([base + 0x400 * i for i in range(m)], np.uint64)
+        vm = np.array([base + 0x400 * int(j) if j >= 0 else 0 for j in matched_in], np.uint64)
+        S = np.ascontiguousarray(np.vstack([np.asarray(scw, np.float32).reshape(3, 4), [[0, 0, 0, 1]]]).astype(np.float32))
+        smat = (C.c_uint64 * 12)()
+        self._fmat_at(C.addressof(smat), S)
+        v1, v2 = (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
+        v1[0], v1[1], v1[2] = vp.ctypes.data, vp.ctypes.data + vp.nbytes, vp.ctypes.data + vp.nbytes
+        v2[0], v2[1], v2[2] = vm.ctypes.data, vm.ctypes.data + vm.nbytes, vm.ctypes.data + vm.nbytes
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher18SearchByProjectionEPNS_8KeyFrameEN2cv3MatERKSt6vectorIPNS_8MapPointESaIS7_EERS9_i")
+        fn.argtypes, fn.restype = [C.c_void_p] * 5 + [C.c_int], C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = np.float32(0.75)
+        matcher[4] = 1
+        nm = fn(C.addressof(matcher), kb, C.addressof(smat), C.addressof(v1), C.addressof(v2), int(th))
+        out = np.array([(int(p) - base) // 0x400 if p else -1 for p in vm], np.int32)
+        return out, int(nm)
 
     # ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (@0x86b30) ----
     # KeyFrame: fx/fy/cx/cy @0x130..0x13c, N @0x154, mvKeysUn @0x170, mvuRight @0x188, mDescriptors @0x1b8, mFeatVec @0x248,

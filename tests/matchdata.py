@@ -201,3 +201,45 @@ def frustum_case(n=3000, W=640, H=480, seed=0, motion=0.1):
     cam8 = np.array([fx, fy, cx, cy, 0, W, 0, H], np.float32)
     return dict(xyz=np.ascontiguousarray(xyz), normal=np.ascontiguousarray(nrm), dist_range=np.ascontiguousarray(np.stack([dmin, dmax], 1)),
                 cam8=cam8, tcw=tcw, ow=ow, mbf=np.float32(40.0), log_sf=np.float32(np.log(np.float32(1.2))), n_levels=8)
+
+
+def loop_projection_case(kps_kf, desc_kf, kps_src, desc_src, scale_factors, W=640, H=480, seed=0, motion=0.05, scale=1.0):
+    """LoopClosing-like inputs for ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th): the map points are the
+    OTHER frame's features placed at synthetic depths so that they project near their true position in the key frame (jitter),
+    with normals, scale-invariance ranges and a similarity Scw = [s R | s t]; some key-frame features are matched on entry."""
+    rng = np.random.default_rng(seed)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    fx = fy = np.float32(520.0); cx = np.float32(W / 2 - 0.5); cy = np.float32(H / 2 - 0.5)
+    n, m = len(kps_kf), len(kps_src)
+    ang = 0.02
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([motion, 0.004, -motion * 1.5])
+    # camera-frame points seen near the source features' pixels (+3 px shift of the synthetic pair, jitter), then to world
+    z = (1.5 + rng.random(m) * 2.0)
+    u = kps_src["x"].astype(np.float64) - 3.0 + rng.normal(0, 2.0, m)
+    v = kps_src["y"].astype(np.float64) - 3.0 + rng.normal(0, 2.0, m)
+    pc = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)
+    z[rng.random(m) < 0.03] *= -1.0                                    # a few behind the camera
+    pc[:, 2] = z
+    xyz = ((pc - t) @ R).astype(np.float32)                            # Pw = R^T (Pc - t)
+    ow = -(R.T @ t)
+    po = xyz.astype(np.float64) - ow
+    d = np.linalg.norm(po, axis=1)
+    dmax = (d * sf[np.clip(kps_src["octave"], 0, len(sf) - 1)] * rng.uniform(0.7, 1.4, m)).astype(np.float32)
+    dmin = (dmax / sf[-1]).astype(np.float32)
+    nrm = po / np.maximum(d[:, None], 1e-9) + rng.normal(0, 0.5, po.shape)
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    scw = (np.hstack([R, t[:, None]]) * scale).astype(np.float32)
+    xy = np.stack([kps_kf["x"], kps_kf["y"]], 1).astype(np.float32)
+    gs, gi, (mnx, mxx, mny, mxy, gwi, ghi) = frame_grid(xy, W, H)
+    kf = dict(xy=np.ascontiguousarray(xy), octave=np.ascontiguousarray(kps_kf["octave"], np.int32), desc=np.ascontiguousarray(desc_kf),
+              angle=np.ascontiguousarray(kps_kf["angle"], np.float32), grid_start=gs, grid_items=gi,
+              cam4=np.array([fx, fy, cx, cy], np.float32), bounds4=np.array([0, 0, W, H], np.int32), gwi=gwi, ghi=ghi,
+              scale_factors=sf, log_sf=np.float32(np.log(np.float32(1.2))))
+    state = rng.choice(np.array([1, 2], np.uint8), m, p=[0.93, 0.07]).astype(np.uint8)
+    mp = dict(state=state, xyz=np.ascontiguousarray(xyz), normal=np.ascontiguousarray(nrm),
+              dist_range=np.ascontiguousarray(np.stack([dmin, dmax], 1)), desc=np.ascontiguousarray(desc_src))
+    matched_in = np.full(n, -1, np.int32)
+    pre = rng.choice(n, n // 10, replace=False)
+    matched_in[pre] = rng.choice(m, len(pre), replace=False)          # already matched: those map points are "already found"
+    return kf, mp, scw, matched_in

@@ -119,6 +119,16 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
         put("rk_cur_" + k, v)
     put("rk_cam", rcam, np.float32); put("rk_sf", rsf, np.float32); put("rk_tc", rtc, np.float32)
     put("rk_par", [10.0, 100.0, float(rlsf)], np.float32)
+    # LoopClosing::ComputeSim3 (projection with a similarity)
+    from matchdata import loop_projection_case
+    lkf, lmp, lscw, lmi = loop_projection_case(ka, da, kb, db, sf, seed=21, motion=0.02, scale=1.3)
+    for k, v in lkf.items():
+        if k not in ("gwi", "ghi", "log_sf"):
+            put("lc_kf_" + k, v)
+    for k, v in lmp.items():
+        put("lc_mp_" + k, v)
+    put("lc_scw", lscw, np.float32); put("lc_matched_in", lmi, np.int32)
+    put("lc_par", [10.0, float(lkf["gwi"]), float(lkf["ghi"]), float(lkf["log_sf"])], np.float32)
     # CreateNewMapPoints
     kps, desc = orc.extract(synth_frame(33))
     kf1, kf2, F12, pose, camt, sft, sg = triangulation_case(kps, desc, seed=33, stereo_fraction=0.5)
@@ -149,6 +159,9 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
     assert out[-1] == en > 50 and np.array_equal(out[:-1], em)
     m, n = pl.search_by_projection_kf_host(rkf, rcur, rcam, rsf, rlsf, rtc, 10.0, 100, True)  # (pinned: test_golden_gpu.py, rk*)
     out = np.fromfile(d / "rk_out", np.int32)
+    assert out[-1] == n > 100 and np.array_equal(out[:-1], m)
+    m, n = pl.search_by_projection_sim3_host(lkf, lmp, lscw, lmi, 10)  # (pinned: test_golden_gpu.py, lc*)
+    out = np.fromfile(d / "lc_out", np.int32)
     assert out[-1] == n > 100 and np.array_equal(out[:-1], m)
     ex, ey = pl.epipole(*pose, *camt)
     m12, n12, pairs = pl.search_for_triangulation_host(kf1, kf2, F12, ex, ey, sft, sg, False, True)

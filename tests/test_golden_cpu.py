@@ -317,6 +317,37 @@ def test_search_by_projection_keyframe_equals_the_reference_matcher(oracle):
     assert total > 1500
 
 
+def _loop_cases(g, extract, scale_factors):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import loop_projection_case
+    from plslam_b200.synth import synth_pair
+    feats = {}
+    for k in range(int(g["lc_n"])):
+        seed, motion, scale, th = g["lc%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (extract(a), extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        kf, mp, scw, mi = loop_projection_case(ka, da, kb, db, scale_factors, seed=seed, motion=float(motion), scale=float(scale))
+        yield k, kf, mp, scw, mi, int(th)
+
+
+def test_search_by_projection_sim3_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (@0x880f0, loop closing) executed from
+    lib/libORB_SLAM2.so on a faked KeyFrame (real nested-vector grid) and faked MapPoints, similarity scales 0.6 / 1 / 1.7;
+    KeyFrame::GetFeaturesInArea, IsInImage and MapPoint::PredictScale(dist, KeyFrame*) are the library's own (fixture lc*)."""
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    o = oracle.OrbOracle()
+    total = 0
+    for k, kf, mp, scw, mi, th in _loop_cases(g, o.extract, o.tables()["scale"]):
+        m, n = oracle.search_by_projection_sim3(kf, mp, scw, mi, th)
+        assert n == int(g["lc%d_n" % k]) and np.array_equal(m, g["lc%d_match" % k]), k
+        total += n
+    assert total > 1500
+
+
 def _frustum_cases(g):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

@@ -220,6 +220,21 @@ def test_k_projection_keyframe_mode_equals_the_reference_matcher():
         assert pl.predict_scale(10.0, float(d), lsf, 8) == ob.predict_scale(10.0, float(d), lsf, 8), d
 
 
+def test_k_kf_projection_equals_the_reference_matcher():
+    """k_kf_projection (ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th), @0x880f0) on the lc*
+    fixtures of reference_library2.npz (similarity scales 0.6 / 1 / 1.7)."""
+    import plslam_b200 as pl
+    from test_golden_cpu import _loop_cases
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    ex = pl.ORBextractor()
+    total = 0
+    for k, kf, mp, scw, mi, th in _loop_cases(g, ex, _scale_factors()):
+        m, n = pl.search_by_projection_sim3_host(kf, mp, scw, mi, th)
+        assert n == int(g["lc%d_n" % k]) and np.array_equal(m, g["lc%d_match" % k]), k
+        total += n
+    assert total > 1500
+
+
 def test_k_is_in_frustum_equals_the_reference():
     """k_is_in_frustum (Frame::isInFrustum, @0xf5190) on the fz* fixtures: 3 x 3000 map points, every field the reference's
     function leaves in a MapPoint."""
