@@ -297,6 +297,37 @@ typedef struct plslam_kfproj_job {
 int plslam_match_kf_projection_batch_device(const plslam_kfproj_job_t* d_jobs, int njobs, int max_n, void* stream); /* max_n >= every job's n */
 int plslam_match_kf_projection_host(const plslam_kfproj_job_t* job); /* HOST pointers inside *job */
 
+/* The matching core of ORBmatcher::Fuse (ORBmatcher.h:119 Fuse(pKF, vpMapPoints, th), @0x7a500, LocalMapping::SearchInNeighbors;
+ * ORBmatcher.h:122 Fuse(pKF, Scw, vpPoints, th, vpReplacePoint), @0x7bb20, LoopClosing::SearchAndFuse): for every candidate map
+ * point the key-frame feature it would be fused into.  Fuse keeps no matched flags, so the points are independent: one warp per
+ * map point.  What depends on the order is the map-graph bookkeeping after each match (pMPinKF->Replace / AddObservation /
+ * AddMapPoint, or vpReplacePoint[i] = pMPinKF), which stays with the caller (host veneer), replayed in order over best_idx. */
+typedef struct plslam_fuse_job {
+  const uint8_t* mp_valid;      /* M : pMP && !isBad() && !IsInKeyFrame(pKF) (with Scw: && not in pKF->GetMapPoints()) */
+  const float* mp_xyz;          /* M x 3 */
+  const float* mp_normal;       /* M x 3 */
+  const float* mp_dist_range;   /* M x 2 : mfMinDistance, mfMaxDistance */
+  const uint8_t* mp_desc;       /* M x 32 */
+  const int32_t* mp_level;      /* M or NULL, as in plslam_kfproj_job_t */
+  const float* kf_xy;           /* N x 2 */
+  const int32_t* kf_octave;     /* N */
+  const float* kf_uright;       /* N : pKF->mvuRight (chi-square test of the rigid form; unused with Scw) */
+  const uint8_t* kf_desc;       /* N x 32 */
+  const int32_t* grid_start;    /* grid_cols * grid_rows + 1 */
+  const int32_t* grid_items;
+  const float* scale_factors;   /* pKF->mvScaleFactors */
+  const float* inv_level_sigma2;/* pKF->mvInvLevelSigma2 (rigid form) */
+  int32_t* best_idx;            /* M : key-frame feature, -1 = no match */
+  float pose[12];               /* use_scw = 0: Rcw | tcw (pKF->GetRotation(), GetTranslation()); 1: rows 0..2 of Scw */
+  float ow[3];                  /* use_scw = 0: pKF->GetCameraCenter(); 1: ignored (derived from Scw as the reference does) */
+  float cam[5];                 /* fx, fy, cx, cy, mbf */
+  int32_t bounds[4];            /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+  float grid_width_inv, grid_height_inv, log_scale_factor, th;
+  int32_t grid_cols, grid_rows, n_levels, use_scw, m, n;
+} plslam_fuse_job_t;
+int plslam_match_fuse_search_batch_device(const plslam_fuse_job_t* d_jobs, int njobs, int max_m, void* stream);
+int plslam_match_fuse_search_host(const plslam_fuse_job_t* job); /* HOST pointers inside *job */
+
 /* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (ORBmatcher.h:61,
  * @0x79f10) — the local-map search of Tracking::SearchLocalPoints, including Frame::GetFeaturesInArea and
  * RadiusByViewingCos (@0x79b60).  The map-point fields it reads (filled by Frame::isInFrustum in the reference) are

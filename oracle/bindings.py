@@ -313,6 +313,104 @@ def search_by_projection_sim3(kf, mp, scw, matched_in, th):
     return out[:n], nm
 
 
+def fuse_search(kf, mp, th):
+    """Matching core of ORBmatcher::Fuse(pKF, vpMapPoints, th) (layout: tests/matchdata.py fuse_case) -> best_idx int32 [M]
+    (key-frame feature each map point would be fused into, -1 = none)."""
+    m, n = len(mp["desc"]), len(kf["desc"])
+    valid = np.ascontiguousarray(np.asarray(mp["state"]) == 1, np.uint8)
+    a = [valid, np.ascontiguousarray(mp["xyz"], np.float32), np.ascontiguousarray(mp["normal"], np.float32),
+         np.ascontiguousarray(mp["dist_range"], np.float32), np.ascontiguousarray(mp["desc"], np.uint8)]
+    b = [np.ascontiguousarray(kf["xy"], np.float32), np.ascontiguousarray(kf["octave"], np.int32), np.ascontiguousarray(kf["uright"], np.float32),
+         np.ascontiguousarray(kf["desc"], np.uint8), np.ascontiguousarray(kf["grid_start"], np.int32), np.ascontiguousarray(kf["grid_items"], np.int32)]
+    c = [np.ascontiguousarray(kf["tcw"], np.float32).reshape(12), np.ascontiguousarray(kf["ow"], np.float32).reshape(3),
+         np.ascontiguousarray(list(kf["cam4"]) + [kf["mbf"]], np.float32), np.ascontiguousarray(kf["bounds4"], np.int32)]
+    sf = np.ascontiguousarray(kf["scale_factors"], np.float32); inv = np.ascontiguousarray(kf["inv_level_sigma2"], np.float32)
+    out = np.empty(max(m, 1), np.int32)
+    L = lib()
+    L.oracle_fuse_search.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 4 + \
+        [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    L.oracle_fuse_search.restype = None
+    L.oracle_fuse_search(m, *[_p(x) for x in a], n, *[_p(x) for x in b], 64, 48, *[_p(x) for x in c], float(kf["gwi"]), float(kf["ghi"]),
+                         _p(sf), _p(inv), len(sf), float(kf["log_sf"]), float(th), _p(out))
+    return out[:m]
+
+
+def fuse_search_sim3(kf, mp, scw, th):
+    """Matching core of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) -> best_idx int32 [M]."""
+    m, n = len(mp["desc"]), len(kf["desc"])
+    valid = np.ascontiguousarray(np.asarray(mp["state"]) == 1, np.uint8)
+    a = [valid, np.ascontiguousarray(mp["xyz"], np.float32), np.ascontiguousarray(mp["normal"], np.float32),
+         np.ascontiguousarray(mp["dist_range"], np.float32), np.ascontiguousarray(mp["desc"], np.uint8)]
+    b = [np.ascontiguousarray(kf["xy"], np.float32), np.ascontiguousarray(kf["octave"], np.int32), np.ascontiguousarray(kf["desc"], np.uint8),
+         np.ascontiguousarray(kf["grid_start"], np.int32), np.ascontiguousarray(kf["grid_items"], np.int32)]
+    c = [np.ascontiguousarray(scw, np.float32).reshape(12), np.ascontiguousarray(kf["cam4"], np.float32), np.ascontiguousarray(kf["bounds4"], np.int32)]
+    sf = np.ascontiguousarray(kf["scale_factors"], np.float32)
+    out = np.empty(max(m, 1), np.int32)
+    L = lib()
+    L.oracle_fuse_search_sim3.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + \
+        [C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    L.oracle_fuse_search_sim3.restype = None
+    L.oracle_fuse_search_sim3(m, *[_p(x) for x in a], n, *[_p(x) for x in b], 64, 48, *[_p(x) for x in c], float(kf["gwi"]), float(kf["ghi"]),
+                              _p(sf), len(sf), float(kf["log_sf"]), float(th), _p(out))
+    return out[:m]
+
+
+def fuse_replay_sim3(best_idx, mp, kf_points):
+    """Bookkeeping of Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) over precomputed matches -> (nFused, log, replace int32 [M]:
+    pool index M + feature of the key frame's point that should replace map point i, -1 = none)."""
+    m, n = len(best_idx), len(kf_points["has"])
+    slot = [m + i if kf_points["has"][i] else -1 for i in range(n)]
+    kbad = np.asarray(kf_points["bad"], bool)
+    ur = kf_points["uright"]
+    replace = np.full(m, -1, np.int32)
+    log, nf = [], 0
+    for i in range(m):
+        if mp["state"][i] != 1 or best_idx[i] < 0:
+            continue
+        idx = int(best_idx[i])
+        p = slot[idx]
+        if p >= 0:
+            if p >= m and not kbad[p - m]:
+                replace[i] = p
+            elif p < m:                       # a point added earlier in this call (never bad here)
+                replace[i] = p
+        else:
+            log.append((1, i, idx)); log.append((2, i, idx)); slot[idx] = i
+        nf += 1
+    return nf, log, replace
+
+
+def fuse_replay(best_idx, mp, kf_points):
+    """The bookkeeping of ORBmatcher::Fuse replayed over precomputed matches, against the harness stubs of
+    tests/golden/reference_code.py (AddObservation adds 2 observations for a stereo feature, Replace marks the replaced point bad
+    and redirects the key frame's slots): -> (nFused, log) in the format of RefLibrary.fuse."""
+    m = len(best_idx)
+    n = len(kf_points["has"])
+    slot = [m + i if kf_points["has"][i] else -1 for i in range(n)]        # point index held by each key-frame feature
+    bad = list(np.asarray(mp["state"]) == 2) + list(np.asarray(kf_points["bad"], bool))
+    nobs = list(np.asarray(mp["nobs"])) + list(np.asarray(kf_points["nobs"]))
+    inkf = list(np.asarray(mp["state"]) == 3)
+    ur = kf_points["uright"]
+    log, nf = [], 0
+    for i in range(m):
+        if mp["state"][i] == 0 or bad[i] or inkf[i] or best_idx[i] < 0:
+            continue
+        idx = int(best_idx[i])
+        p = slot[idx]
+        if p >= 0:
+            if not bad[p]:
+                if nobs[p] > nobs[i]:
+                    log.append((3, i, p)); bad[i] = True
+                else:
+                    log.append((3, p, i)); bad[p] = True
+                    slot = [i if q == p else q for q in slot]
+        else:
+            log.append((1, i, idx)); nobs[i] += 2 if ur[idx] >= 0 else 1; inkf[i] = True
+            log.append((2, i, idx)); slot[idx] = i
+        nf += 1
+    return nf, log
+
+
 def is_in_frustum(xyz, normal, dist_range, cam8, tcw, ow, mbf, log_scale_factor, n_levels, cos_limit):
     """Frame::isInFrustum over M map points -> dict(in_view, proj [M,3], level, viewcos)."""
     m = len(xyz)

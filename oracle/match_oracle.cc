@@ -589,6 +589,136 @@ int oracle_search_by_projection_sim3(int M, const uint8_t* mpValid, const float*
   return nmatches;
 }
 
+// The matching core of ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th) (ORBmatcher.h:119;
+// @0x7a500, LocalMapping::SearchInNeighbors): for every candidate map point the key-frame feature it would be fused into.  The
+// points are independent here (Fuse keeps no matched flags); what depends on the order is the map-graph bookkeeping that follows
+// each match (Replace / AddObservation / AddMapPoint), which stays with the caller.  Read from the binary: p3Dc = Rcw * p3Dw +
+// tcw (gemm), z < 0 rejects, invz = 1.0f / z, x = X * invz, u = fma(x, fx, cx), v = fma(fy, y, cy) (@0x7ab66-0x7abf0),
+// KeyFrame::IsInImage, ur = fma(-bf, invz, u) (@0x7b63e), the invariance range, PO.dot(Pn) < 0.5 * dist rejects (@0x7b4c6), level =
+// PredictScale(dist, pKF), radius = th * mvScaleFactors[level] (@0x7b515), KeyFrame::GetFeaturesInArea; a candidate needs its octave
+// in [level - 1, level] (@0x7b5e1-0x7b5ef) and a reprojection error below the chi-square bound: stereo (mvuRight >= 0) e2 =
+// fma(er, er, fma(ex, ex, ey * ey)) with e2 * mvInvLevelSigma2[octave] > 7.8 rejecting, mono e2 = fma(ex, ex, ey * ey) against 5.99
+// (products in float, comparison in double, @0x7b645-0x7b668, @0x7b961-0x7b97b); best = strictly smaller distance; a match needs
+// bestDist <= TH_LOW.  mpValid[i] = pMP && !isBad() && !IsInKeyFrame(pKF).  Tcw = Rcw | tcw (3x4), cam5 = fx fy cx cy mbf.
+void oracle_fuse_search(int M, const uint8_t* mpValid, const float* mpXYZ, const float* mpNormal, const float* mpDistRange,
+                        const uint8_t* mpDesc, int N, const float* kfXY, const int* kfOctave, const float* kfURight,
+                        const uint8_t* kfDesc, const int* gridStart, const int* gridItems, int gridCols, int gridRows,
+                        const float* Tcw, const float* Ow, const float* cam5, const int* bounds4, float gwi, float ghi,
+                        const float* scaleFactors, const float* invLevelSigma2, int nLevels, float logScaleFactor, float th,
+                        int* bestIdxOut) {
+  (void)N;
+  const float fx = cam5[0], fy = cam5[1], cx = cam5[2], cy = cam5[3], bf = cam5[4];
+  const int mnMinX = bounds4[0], mnMinY = bounds4[1], mnMaxX = bounds4[2], mnMaxY = bounds4[3];
+  for (int i = 0; i < M; ++i) {
+    bestIdxOut[i] = -1;
+    if (!mpValid[i]) continue;
+    const float* X = mpXYZ + 3 * i;
+    float pc[3];
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = Tcw[r * 4] * X[0], p1 = Tcw[r * 4 + 1] * X[1], p2 = Tcw[r * 4 + 2] * X[2];
+      const float s = (p0 + p1) + p2;
+      pc[r] = (float)((double)s + (double)Tcw[r * 4 + 3]);
+    }
+    if (pc[2] < 0.0f) continue;
+    const float invz = 1.0f / pc[2];
+    const float x = pc[0] * invz, y = pc[1] * invz;
+    const float u = std::fmaf(x, fx, cx), v = std::fmaf(fy, y, cy);
+    if (!(u >= (float)mnMinX && u < (float)mnMaxX && v >= (float)mnMinY && v < (float)mnMaxY)) continue;
+    const float ur = std::fmaf(-bf, invz, u);
+    float PO[3];
+    double n2 = 0;
+    for (int r = 0; r < 3; ++r) {
+      PO[r] = X[r] - Ow[r];
+      n2 += (double)PO[r] * (double)PO[r];
+    }
+    const float dist = (float)std::sqrt(n2);
+    if (dist < 0.8f * mpDistRange[2 * i] || dist > 1.2f * mpDistRange[2 * i + 1]) continue;
+    double dot = 0;
+    for (int r = 0; r < 3; ++r) dot += (double)PO[r] * (double)mpNormal[3 * i + r];
+    if (dot < 0.5 * (double)dist) continue;
+    const int level = predict_scale(mpDistRange[2 * i + 1], dist, logScaleFactor, nLevels);
+    const float radius = th * scaleFactors[level];
+    int bestDist = 256, bestIdx = -1;
+    for_kf_features_in_area(u, v, radius, mnMinX, mnMinY, gwi, ghi, gridCols, gridRows, gridStart, gridItems, kfXY, [&](int idx) {
+      const int kpLevel = kfOctave[idx];
+      if (kpLevel < level - 1 || kpLevel > level) return;
+      const float ex = u - kfXY[2 * idx], ey = v - kfXY[2 * idx + 1];
+      if (kfURight[idx] >= 0) {
+        const float er = ur - kfURight[idx];
+        const float e2 = std::fmaf(er, er, std::fmaf(ex, ex, ey * ey));
+        if ((double)(e2 * invLevelSigma2[kpLevel]) > 7.8) return;
+      } else {
+        const float e2 = std::fmaf(ex, ex, ey * ey);
+        if ((double)(e2 * invLevelSigma2[kpLevel]) > 5.99) return;
+      }
+      const int d = descriptor_distance(mpDesc + 32 * i, kfDesc + 32 * idx);
+      if (d < bestDist) { bestDist = d; bestIdx = idx; }
+    });
+    if (bestDist <= TH_LOW) bestIdxOut[i] = bestIdx;
+  }
+}
+
+// The matching core of ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th,
+// vector<MapPoint*>& vpReplacePoint) (ORBmatcher.h:122; @0x7bb20, LoopClosing::SearchAndFuse): the similarity is taken apart as in
+// SearchByProjection(KeyFrame*, Scw, ...) above, the per-point tests are those of the rigid Fuse without the chi-square test and
+// without ur (u = fma(x, fx, cx), v = fma(y, fy, cy) @0x7caac-0x7cabe; 0.5 * dist @0x7d429; th * mvScaleFactors[level] @0x7d47a;
+// bestDist <= TH_LOW @0x7d6fc).  mpValid[i] = !isBad() && pMP not among pKF->GetMapPoints().
+void oracle_fuse_search_sim3(int M, const uint8_t* mpValid, const float* mpXYZ, const float* mpNormal, const float* mpDistRange,
+                             const uint8_t* mpDesc, int N, const float* kfXY, const int* kfOctave, const uint8_t* kfDesc,
+                             const int* gridStart, const int* gridItems, int gridCols, int gridRows, const float* Scw,
+                             const float* cam4, const int* bounds4, float gwi, float ghi, const float* scaleFactors, int nLevels,
+                             float logScaleFactor, float th, int* bestIdxOut) {
+  (void)N;
+  const float fx = cam4[0], fy = cam4[1], cx = cam4[2], cy = cam4[3];
+  const int mnMinX = bounds4[0], mnMinY = bounds4[1], mnMaxX = bounds4[2], mnMaxY = bounds4[3];
+  double dot0 = 0;
+  for (int k = 0; k < 3; ++k) dot0 += (double)Scw[k] * (double)Scw[k];
+  const float inv = (float)(1.0 / (double)(float)std::sqrt(dot0));
+  float T[12], Ow[3];
+  for (int k = 0; k < 12; ++k) T[k] = Scw[k] * inv + 0.0f;
+  for (int r = 0; r < 3; ++r) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += (double)T[k * 4 + r] * (double)T[k * 4 + 3];
+    Ow[r] = (float)(-1.0 * s);
+  }
+  for (int i = 0; i < M; ++i) {
+    bestIdxOut[i] = -1;
+    if (!mpValid[i]) continue;
+    const float* X = mpXYZ + 3 * i;
+    float pc[3];
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = T[r * 4] * X[0], p1 = T[r * 4 + 1] * X[1], p2 = T[r * 4 + 2] * X[2];
+      const float s = (p0 + p1) + p2;
+      pc[r] = (float)((double)s + (double)T[r * 4 + 3]);
+    }
+    if (pc[2] < 0.0f) continue;
+    const float invz = 1.0f / pc[2];
+    const float u = std::fmaf(pc[0] * invz, fx, cx), v = std::fmaf(pc[1] * invz, fy, cy);
+    if (!(u >= (float)mnMinX && u < (float)mnMaxX && v >= (float)mnMinY && v < (float)mnMaxY)) continue;
+    float PO[3];
+    double n2 = 0;
+    for (int r = 0; r < 3; ++r) {
+      PO[r] = X[r] - Ow[r];
+      n2 += (double)PO[r] * (double)PO[r];
+    }
+    const float dist = (float)std::sqrt(n2);
+    if (dist < 0.8f * mpDistRange[2 * i] || dist > 1.2f * mpDistRange[2 * i + 1]) continue;
+    double dot = 0;
+    for (int r = 0; r < 3; ++r) dot += (double)PO[r] * (double)mpNormal[3 * i + r];
+    if (dot < 0.5 * (double)dist) continue;
+    const int level = predict_scale(mpDistRange[2 * i + 1], dist, logScaleFactor, nLevels);
+    const float radius = th * scaleFactors[level];
+    int bestDist = 256, bestIdx = -1;
+    for_kf_features_in_area(u, v, radius, mnMinX, mnMinY, gwi, ghi, gridCols, gridRows, gridStart, gridItems, kfXY, [&](int idx) {
+      const int kpLevel = kfOctave[idx];
+      if (kpLevel < level - 1 || kpLevel > level) return;
+      const int d = descriptor_distance(mpDesc + 32 * i, kfDesc + 32 * idx);
+      if (d < bestDist) { bestDist = d; bestIdx = idx; }
+    });
+    if (bestDist <= TH_LOW) bestIdxOut[i] = bestIdx;
+  }
+}
+
 // Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (include/Frame.h:107-ish "isInFrustum"; @0xf5190), what
 // Tracking::SearchLocalPoints runs on every local map point before ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)
 // (it fills the mTrack* fields that matcher reads).  Read from the binary: Pc = mRcw * P + mtcw (gemm small path); PcZ < 0

@@ -588,6 +588,125 @@ __global__ void __launch_bounds__(32) k_kf_projection(const plslam_kfproj_job_t*
 }
 
 // ------------------------------------------------------------------------------------------
+// The matching core of ORBmatcher::Fuse (@0x7a500 rigid pose with the chi-square tests, @0x7bb20 similarity): the map points are
+// independent, so one WARP per map point (8 per CTA, blockIdx.y = job); lanes split the cells of KeyFrame::GetFeaturesInArea.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fuse_search(const plslam_fuse_job_t* __restrict__ jobs) {
+  const plslam_fuse_job_t& J = jobs[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= J.m) return;
+  int result = -1;
+  do {
+    if (!J.mp_valid[i]) break;
+    const float fx = J.cam[0], fy = J.cam[1], cx = J.cam[2], cy = J.cam[3], bf = J.cam[4];
+    const float mnMinX = (float)J.bounds[0], mnMinY = (float)J.bounds[1], mnMaxX = (float)J.bounds[2], mnMaxY = (float)J.bounds[3];
+    const float gwi = J.grid_width_inv, ghi = J.grid_height_inv;
+    const int cols = J.grid_cols, rows = J.grid_rows;
+    float T[12], Ow[3];
+    if (J.use_scw) {
+      double d0 = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d0 = __dadd_rn(d0, __dmul_rn((double)J.pose[k], (double)J.pose[k]));
+      const float inv = (float)__ddiv_rn(1.0, (double)(float)sqrt(d0));
+#pragma unroll
+      for (int k = 0; k < 12; ++k) T[k] = __fadd_rn(__fmul_rn(J.pose[k], inv), 0.0f);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)T[k * 4 + r], (double)T[k * 4 + 3]));
+        Ow[r] = (float)__dmul_rn(-1.0, s);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) T[k] = J.pose[k];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) Ow[r] = J.ow[r];
+    }
+    const float* X = J.mp_xyz + 3 * (size_t)i;
+    float pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = __fmul_rn(T[r * 4], X[0]), p1 = __fmul_rn(T[r * 4 + 1], X[1]), p2 = __fmul_rn(T[r * 4 + 2], X[2]);
+      pc[r] = (float)__dadd_rn((double)__fadd_rn(__fadd_rn(p0, p1), p2), (double)T[r * 4 + 3]);
+    }
+    if (pc[2] < 0.0f) break;
+    const float invz = __fdiv_rn(1.0f, pc[2]);
+    const float u = __fmaf_rn(__fmul_rn(pc[0], invz), fx, cx), v = __fmaf_rn(fy, __fmul_rn(pc[1], invz), cy);
+    if (!(u >= mnMinX && u < mnMaxX && v >= mnMinY && v < mnMaxY)) break;
+    const float ur = __fmaf_rn(-bf, invz, u);
+    int level;
+    if (J.mp_level) {
+      level = J.mp_level[i];
+    } else {
+      float PO[3];
+      double n2 = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        PO[r] = __fsub_rn(X[r], Ow[r]);
+        n2 = __dadd_rn(n2, __dmul_rn((double)PO[r], (double)PO[r]));
+      }
+      const float dist = (float)sqrt(n2);
+      const float dMin = J.mp_dist_range[2 * (size_t)i], dMax = J.mp_dist_range[2 * (size_t)i + 1];
+      if (dist < __fmul_rn(0.8f, dMin) || dist > __fmul_rn(1.2f, dMax)) break;
+      double dot = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) dot = __dadd_rn(dot, __dmul_rn((double)PO[r], (double)J.mp_normal[3 * (size_t)i + r]));
+      if (dot < __dmul_rn(0.5, (double)dist)) break;
+      level = predict_scale_dev(dMax, dist, J.log_scale_factor, J.n_levels);
+    }
+    const float radius = __fmul_rn(J.th, J.scale_factors[level]);
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, mnMinX), radius), gwi)));
+    if (nMinCellX >= cols) break;
+    const int nMaxCellX = min(cols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, mnMinX), radius), gwi)));
+    if (nMaxCellX < 0) break;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, mnMinY), radius), ghi)));
+    if (nMinCellY >= rows) break;
+    const int nMaxCellY = min(rows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, mnMinY), radius), ghi)));
+    if (nMaxCellY < 0) break;
+    const int ncy = nMaxCellY - nMinCellY + 1, ncells = (nMaxCellX - nMinCellX + 1) * ncy;
+    const uint4* DM = reinterpret_cast<const uint4*>(J.mp_desc);
+    const uint4* DK = reinterpret_cast<const uint4*>(J.kf_desc);
+    const uint4 a0 = DM[2 * (size_t)i], a1 = DM[2 * (size_t)i + 1];
+    unsigned best = 0xffffffffu;  // dist << 22 | cellRank << 8 | pos
+    int bestI = -1;
+    for (int c = lane; c < ncells; c += 32) {
+      const int ix = nMinCellX + c / ncy, iy = nMinCellY + c % ncy;
+      const int cell = ix * rows + iy;
+      const int s0 = J.grid_start[cell], s1 = J.grid_start[cell + 1];
+      for (int j = s0; j < s1; ++j) {
+        const int idx = J.grid_items[j];
+        const float kx = J.kf_xy[2 * idx], ky = J.kf_xy[2 * idx + 1];
+        if (!(fabsf(__fsub_rn(kx, u)) < radius && fabsf(__fsub_rn(ky, v)) < radius)) continue;
+        const int kpLevel = J.kf_octave[idx];
+        if (kpLevel < level - 1 || kpLevel > level) continue;
+        if (!J.use_scw) {
+          const float ex = __fsub_rn(u, kx), ey = __fsub_rn(v, ky);
+          const float kr = J.kf_uright[idx];
+          float e2 = __fmaf_rn(ex, ex, __fmul_rn(ey, ey));
+          double bound = 5.99;
+          if (kr >= 0) {
+            const float er = __fsub_rn(ur, kr);
+            e2 = __fmaf_rn(er, er, e2);
+            bound = 7.8;
+          }
+          if ((double)__fmul_rn(e2, J.inv_level_sigma2[kpLevel]) > bound) continue;
+        }
+        const int d = hamming256(a0, a1, DK[2 * idx], DK[2 * idx + 1]);
+        const unsigned key = ((unsigned)d << 22) | ((unsigned)c << 8) | (unsigned)min(j - s0, 255);
+        if (key < best) { best = key; bestI = idx; }
+      }
+    }
+    const unsigned g = warp_min_u32(best);
+    if (g == 0xffffffffu || (int)(g >> 22) > PLSLAM_TH_LOW) break;
+    const unsigned src = __ballot_sync(0xffffffffu, best == g);
+    result = __shfl_sync(0xffffffffu, bestI, __ffs(src) - 1);
+  } while (false);
+  if (lane == 0) J.best_idx[i] = result;
+}
+
+// ------------------------------------------------------------------------------------------
 // SearchByProjection(Frame &F, const vector<MapPoint*>&, th) (@0x79f10, Tracking::SearchLocalPoints): one warp per
 // frame walks the local map points in order (a keypoint assigned to an observed map point is skipped later); lanes
 // split the grid cells of the search window.  The reference's best / second-best update over the candidates in
@@ -1087,6 +1206,46 @@ int plslam_match_kf_projection_host(const plslam_kfproj_job_t* job) {
   if (rc) return rc;
   if (n) PL_CUDA(cudaMemcpy(job->match_kf, d.match_kf, (size_t)n * 4, cudaMemcpyDeviceToHost));
   PL_CUDA(cudaMemcpy(job->nmatches, d.nmatches, 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int plslam_match_fuse_search_batch_device(const plslam_fuse_job_t* d_jobs, int njobs, int max_m, void* stream) {
+  PL_CHECK_ARG(d_jobs && njobs >= 1 && njobs <= 65535 && max_m >= 0);
+  if (max_m == 0) return PLSLAM_OK;
+  PL_CARVEOUT(k_fuse_search);
+  k_fuse_search<<<dim3(div_up(max_m, 8), njobs), 256, 0, (cudaStream_t)stream>>>(d_jobs);
+  PL_CUDA(cudaGetLastError());
+  return PLSLAM_OK;
+}
+
+int plslam_match_fuse_search_host(const plslam_fuse_job_t* job) {
+  PL_CHECK_ARG(job && job->best_idx && job->m >= 0 && job->n >= 0 && job->n_levels >= 1 && job->grid_cols >= 1 && job->grid_rows >= 1 &&
+               job->grid_start && (job->mp_level || (job->mp_normal && job->mp_dist_range)) && (job->use_scw || (job->kf_uright && job->inv_level_sigma2)));
+  Uploader U;
+  plslam_fuse_job_t d = *job;
+  const int m = job->m, n = job->n, ncell = job->grid_cols * job->grid_rows;
+  if (m == 0) return PLSLAM_OK;
+  const int nitems = job->grid_start[ncell];
+  d.mp_valid = U.up(job->mp_valid, m);
+  d.mp_xyz = U.up(job->mp_xyz, (size_t)m * 3);
+  d.mp_normal = job->mp_level ? nullptr : U.up(job->mp_normal, (size_t)m * 3);
+  d.mp_dist_range = job->mp_level ? nullptr : U.up(job->mp_dist_range, (size_t)m * 2);
+  d.mp_level = job->mp_level ? U.up(job->mp_level, m) : nullptr;
+  d.mp_desc = U.up(job->mp_desc, (size_t)m * 32);
+  d.kf_xy = U.up(job->kf_xy, (size_t)n * 2);
+  d.kf_octave = U.up(job->kf_octave, n);
+  d.kf_uright = job->kf_uright ? U.up(job->kf_uright, n) : nullptr;
+  d.kf_desc = U.up(job->kf_desc, (size_t)n * 32);
+  d.grid_start = U.up(job->grid_start, ncell + 1);
+  d.grid_items = U.up(job->grid_items, nitems);
+  d.scale_factors = U.up(job->scale_factors, job->n_levels);
+  d.inv_level_sigma2 = job->inv_level_sigma2 ? U.up(job->inv_level_sigma2, job->n_levels) : nullptr;
+  d.best_idx = U.out<int32_t>(m);
+  const plslam_fuse_job_t* dj = U.up(&d, 1);
+  if (U.err != cudaSuccess) { set_error("fuse host path: %s", cudaGetErrorString(U.err)); return PLSLAM_ERR_CUDA; }
+  int rc = plslam_match_fuse_search_batch_device(dj, 1, m, nullptr);
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpy(job->best_idx, d.best_idx, (size_t)m * 4, cudaMemcpyDeviceToHost));
   return PLSLAM_OK;
 }
 

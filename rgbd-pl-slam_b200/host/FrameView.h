@@ -48,6 +48,9 @@ struct KeyFrameGridView {
   float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
   int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
   float fx = 0, fy = 0, cx = 0, cy = 0;
+  // read by ORBmatcher::Fuse(pKF, vpMapPoints, th) on top (reprojection-error test): empty otherwise
+  std::vector<float> mvuRight, mvInvLevelSigma2;
+  float mbf = 0;
 };
 struct LoopPointsView {
   std::vector<uint8_t> valid;      // !isBad() && not in vpMatched on entry && inside the invariance range && PO.dot(Pn) >= 0.5 * dist

@@ -49,6 +49,16 @@ class ORBmatcher {
   template <class KeyFrameT, class MapPointT>
   int SearchByProjection(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched,
                          int th);
+  // Project MapPoints into KeyFrame and search for duplicated MapPoints (LocalMapping::SearchInNeighbors) (ORBmatcher.h:119), and
+  // the variant with a Similarity Transformation (LoopClosing::SearchAndFuse) (ORBmatcher.h:122).  The matching of all candidates
+  // is ONE kernel (the points are independent); the map-graph bookkeeping that follows each match — pMPinKF->Replace(pMP) /
+  // pMP->Replace(pMPinKF) / AddObservation + AddMapPoint, or vpReplacePoint[i] = pMPinKF — is replayed here in the reference's
+  // order on the caller's objects.  Further members read: pKF->mvuRight, mvInvLevelSigma2, mbf, GetRotation / GetTranslation /
+  // GetCameraCenter, GetMapPoint, GetMapPoints; pMP->IsInKeyFrame, Observations.
+  template <class KeyFrameT, class MapPointT>
+  int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, const float th = 3.0);
+  template <class KeyFrameT, class MapPointT>
+  int Fuse(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, float th, std::vector<MapPointT*>& vpReplacePoint);
   // Search matches between MapPoints in a KeyFrame and ORB in a Frame (Relocalisation, TrackReferenceKeyFrame)
   template <class KeyFrameT, class FrameT, class MapPointT>
   int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches);
@@ -86,6 +96,11 @@ class ORBmatcher {
   // vnMatches[i] = index into the points newly assigned to key-frame feature i, or -1.
   int SearchByProjection(const KeyFrameGridView& KF, const float Scw[12], const LoopPointsView& P,
                          const std::vector<uint8_t>& matchedOnEntry, int th, std::vector<int>& vnMatches);
+
+  // Matching core of Fuse on views: pose = Rcw | tcw with ow = camera centre (useScw = false, KF needs mvuRight / mvInvLevelSigma2 /
+  // mbf) or rows 0..2 of Scw (useScw = true).  vnBestIdx[i] = key-frame feature map point i would be fused into, or -1.
+  void FuseSearch(const KeyFrameGridView& KF, const float pose[12], const float ow[3], bool useScw, const LoopPointsView& P, float th,
+                  std::vector<int>& vnBestIdx);
 
   // Brute force constrained to ORB that belong to the same vocabulary node (Relocalisation / TrackReferenceKeyFrame).
   // vnMatches[iF] = index in the KeyFrame matched to F's feature iF, or -1.

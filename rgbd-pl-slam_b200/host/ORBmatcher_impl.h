@@ -58,6 +58,72 @@ inline void view_of_frame(const FrameT& F, FrameView* V, bool withGrid) {
       for (int c = 0; c < 4; ++c) V->mTcw[4 * r + c] = F.mTcw.template at<float>(r, c);
 }
 
+// What the key-frame projection matchers read of a KeyFrame (pKF->mGrid is protected in the reference's KeyFrame.h: befriend
+// ORBmatcher there or add a const accessor).
+template <class KeyFrameT>
+inline void view_of_keyframe_grid(KeyFrameT* pKF, KeyFrameGridView* kv) {
+  kv->mvKeysUn = pKF->mvKeysUn;
+  kv->mDescriptors = pKF->mDescriptors;
+  kv->mvScaleFactors = pKF->mvScaleFactors;
+  kv->mnGridCols = pKF->mnGridCols; kv->mnGridRows = pKF->mnGridRows;
+  kv->mfGridElementWidthInv = pKF->mfGridElementWidthInv; kv->mfGridElementHeightInv = pKF->mfGridElementHeightInv;
+  kv->mnMinX = pKF->mnMinX; kv->mnMinY = pKF->mnMinY; kv->mnMaxX = pKF->mnMaxX; kv->mnMaxY = pKF->mnMaxY;
+  kv->fx = pKF->fx; kv->fy = pKF->fy; kv->cx = pKF->cx; kv->cy = pKF->cy;
+  require((size_t)pKF->mDescriptors.rows == kv->mvKeysUn.size(), "KeyFrame members differ in length");
+  kv->gridStart.assign(1, 0);
+  kv->gridItems.clear();
+  for (int ix = 0; ix < kv->mnGridCols; ++ix)
+    for (int iy = 0; iy < kv->mnGridRows; ++iy) {
+      for (size_t k = 0; k < pKF->mGrid[ix][iy].size(); ++k) kv->gridItems.push_back((int32_t)pKF->mGrid[ix][iy][k]);
+      kv->gridStart.push_back((int32_t)kv->gridItems.size());
+    }
+}
+
+// Scw = [s R | s t] taken apart with the reference's arithmetic: s from the first row (dot in double), every element times
+// (float)(1.0 / s) as cv::operator/(Mat, double) evaluates, Ow = -Rcw.t() * tcw through the double-accumulating product
+inline void decompose_sim3(const float S[12], float T[12], float Ow[3]) {
+  double d0 = 0;
+  for (int k = 0; k < 3; ++k) d0 += (double)S[k] * (double)S[k];
+  const float inv = (float)(1.0 / (double)(float)std::sqrt(d0));
+  for (int k = 0; k < 12; ++k) { volatile float p = S[k] * inv; T[k] = p + 0.0f; }
+  for (int r = 0; r < 3; ++r) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += (double)T[4 * k + r] * (double)T[4 * k + 3];
+    Ow[r] = (float)(-1.0 * s);
+  }
+}
+
+// One candidate map point of the key-frame projection matchers: the distance from the camera centre with the reference's
+// arithmetic, the scale-invariance and viewing-angle tests, pMP->PredictScale; fills row i of the view when the point passes
+template <class KeyFrameT, class MapPointT>
+inline void loop_point(MapPointT* pMP, KeyFrameT* pKF, const float Ow[3], int i, LoopPointsView* pv) {
+  const cv::Mat p3Dw = pMP->GetWorldPos();
+  float PO[3];
+  double n2 = 0;
+  for (int k = 0; k < 3; ++k) {
+    const float x = p3Dw.template at<float>(k);
+    pv->worldPos[3 * (size_t)i + k] = x;
+    PO[k] = x - Ow[k];
+    n2 += (double)PO[k] * (double)PO[k];
+  }
+  const float dist = (float)std::sqrt(n2);
+  if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) return;
+  const cv::Mat Pn = pMP->GetNormal();
+  double dot = 0;
+  for (int k = 0; k < 3; ++k) dot += (double)PO[k] * (double)Pn.template at<float>(k);
+  if (dot < 0.5 * (double)dist) return;
+  pv->level[i] = pMP->PredictScale(dist, pKF);
+  const cv::Mat d = pMP->GetDescriptor();
+  std::memcpy(pv->descriptors.ptr(i), d.ptr(0), 32);
+  pv->valid[i] = 1;
+}
+inline void init_loop_points(int m, LoopPointsView* pv) {
+  pv->valid.assign(m, 0);
+  pv->worldPos.assign((size_t)m * 3, 0.f);
+  pv->descriptors.create(m > 0 ? m : 1, 32, CV_8U);
+  pv->level.assign(m, 0);
+}
+
 }  // namespace dropin
 
 // ORBmatcher.h:78 (@0x80d00)
@@ -193,72 +259,114 @@ template <class KeyFrameT, class MapPointT>
 int ORBmatcher::SearchByProjection(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints,
                                    std::vector<MapPointT*>& vpMatched, int th) {
   KeyFrameGridView kv;
-  kv.mvKeysUn = pKF->mvKeysUn;
-  kv.mDescriptors = pKF->mDescriptors;
-  kv.mvScaleFactors = pKF->mvScaleFactors;
-  kv.mnGridCols = pKF->mnGridCols; kv.mnGridRows = pKF->mnGridRows;
-  kv.mfGridElementWidthInv = pKF->mfGridElementWidthInv; kv.mfGridElementHeightInv = pKF->mfGridElementHeightInv;
-  kv.mnMinX = pKF->mnMinX; kv.mnMinY = pKF->mnMinY; kv.mnMaxX = pKF->mnMaxX; kv.mnMaxY = pKF->mnMaxY;
-  kv.fx = pKF->fx; kv.fy = pKF->fy; kv.cx = pKF->cx; kv.cy = pKF->cy;
+  dropin::view_of_keyframe_grid(pKF, &kv);
   const int n = (int)kv.mvKeysUn.size(), m = (int)vpPoints.size();
-  dropin::require((int)vpMatched.size() == n && pKF->mDescriptors.rows == n, "KeyFrame members / vpMatched differ in length");
-  kv.gridStart.assign(1, 0);
-  for (int ix = 0; ix < kv.mnGridCols; ++ix)
-    for (int iy = 0; iy < kv.mnGridRows; ++iy) {
-      for (size_t k = 0; k < pKF->mGrid[ix][iy].size(); ++k) kv.gridItems.push_back((int32_t)pKF->mGrid[ix][iy][k]);
-      kv.gridStart.push_back((int32_t)kv.gridItems.size());
-    }
-  float S[12];
+  dropin::require((int)vpMatched.size() == n, "vpMatched and the key frame's features differ in length");
+  float S[12], T[12], Ow[3];
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 4; ++c) S[4 * r + c] = Scw.template at<float>(r, c);
-  double d0 = 0;
-  for (int k = 0; k < 3; ++k) d0 += (double)S[k] * (double)S[k];
-  const float scw = (float)std::sqrt(d0);
-  const float inv = (float)(1.0 / (double)scw);
-  float T[12], Ow[3];
-  for (int k = 0; k < 12; ++k) { volatile float p = S[k] * inv; T[k] = p + 0.0f; }
-  for (int r = 0; r < 3; ++r) {
-    double s = 0;
-    for (int k = 0; k < 3; ++k) s += (double)T[4 * k + r] * (double)T[4 * k + 3];
-    Ow[r] = (float)(-1.0 * s);
-  }
+  dropin::decompose_sim3(S, T, Ow);
   std::set<MapPointT*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
   spAlreadyFound.erase(static_cast<MapPointT*>(nullptr));
   std::vector<uint8_t> matchedOnEntry(n, 0);
   for (int i = 0; i < n; ++i) matchedOnEntry[i] = vpMatched[i] != nullptr;
   LoopPointsView pv;
-  pv.valid.assign(m, 0);
-  pv.worldPos.assign((size_t)m * 3, 0.f);
-  pv.descriptors.create(m > 0 ? m : 1, 32, CV_8U);
-  pv.level.assign(m, 0);
+  dropin::init_loop_points(m, &pv);
   for (int i = 0; i < m; ++i) {
     MapPointT* pMP = vpPoints[i];
     if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
-    const cv::Mat p3Dw = pMP->GetWorldPos();
-    float PO[3];
-    double n2 = 0;
-    for (int k = 0; k < 3; ++k) {
-      const float x = p3Dw.template at<float>(k);
-      pv.worldPos[3 * (size_t)i + k] = x;
-      PO[k] = x - Ow[k];
-      n2 += (double)PO[k] * (double)PO[k];
-    }
-    const float dist = (float)std::sqrt(n2);
-    if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
-    const cv::Mat Pn = pMP->GetNormal();
-    double dot = 0;
-    for (int k = 0; k < 3; ++k) dot += (double)PO[k] * (double)Pn.template at<float>(k);
-    if (dot < 0.5 * (double)dist) continue;
-    pv.level[i] = pMP->PredictScale(dist, pKF);
-    const cv::Mat d = pMP->GetDescriptor();
-    std::memcpy(pv.descriptors.ptr(i), d.ptr(0), 32);
-    pv.valid[i] = 1;
+    dropin::loop_point(pMP, pKF, Ow, i, &pv);
   }
   std::vector<int> match;
   const int nm = SearchByProjection(kv, S, pv, matchedOnEntry, th, match);
   for (int i = 0; i < n; ++i)
     if (match[i] >= 0) vpMatched[i] = vpPoints[match[i]];
   return nm;
+}
+
+// ORBmatcher.h:119 (@0x7a500)
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, const float th) {
+  KeyFrameGridView kv;
+  dropin::view_of_keyframe_grid(pKF, &kv);
+  kv.mvuRight = pKF->mvuRight;
+  kv.mvInvLevelSigma2 = pKF->mvInvLevelSigma2;
+  kv.mbf = pKF->mbf;
+  const cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), OwM = pKF->GetCameraCenter();
+  float T[12], Ow[3];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T[4 * r + c] = Rcw.template at<float>(r, c);
+    T[4 * r + 3] = tcw.template at<float>(r);
+    Ow[r] = OwM.template at<float>(r);
+  }
+  const int m = (int)vpMapPoints.size();
+  LoopPointsView pv;
+  dropin::init_loop_points(m, &pv);
+  for (int i = 0; i < m; ++i) {
+    MapPointT* pMP = vpMapPoints[i];
+    if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+    dropin::loop_point(pMP, pKF, Ow, i, &pv);
+  }
+  std::vector<int> best;
+  FuseSearch(kv, T, Ow, false, pv, th, best);
+  int nFused = 0;
+  for (int i = 0; i < m; ++i) {
+    if (best[i] < 0) continue;
+    MapPointT* pMP = vpMapPoints[i];
+    if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;  // the bookkeeping of an earlier point may have changed it
+    const size_t bestIdx = (size_t)best[i];
+    MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx);
+    if (pMPinKF) {
+      if (!pMPinKF->isBad()) {
+        if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+        else pMPinKF->Replace(pMP);
+      }
+    } else {
+      pMP->AddObservation(pKF, bestIdx);
+      pKF->AddMapPoint(pMP, bestIdx);
+    }
+    nFused++;
+  }
+  return nFused;
+}
+
+// ORBmatcher.h:122 (@0x7bb20)
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::Fuse(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, float th,
+                     std::vector<MapPointT*>& vpReplacePoint) {
+  KeyFrameGridView kv;
+  dropin::view_of_keyframe_grid(pKF, &kv);
+  float S[12], T[12], Ow[3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) S[4 * r + c] = Scw.template at<float>(r, c);
+  dropin::decompose_sim3(S, T, Ow);
+  const std::set<MapPointT*> spAlreadyFound = pKF->GetMapPoints();
+  const int m = (int)vpPoints.size();
+  dropin::require((int)vpReplacePoint.size() == m, "vpReplacePoint and vpPoints differ in length");
+  LoopPointsView pv;
+  dropin::init_loop_points(m, &pv);
+  for (int i = 0; i < m; ++i) {
+    MapPointT* pMP = vpPoints[i];
+    if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+    dropin::loop_point(pMP, pKF, Ow, i, &pv);
+  }
+  std::vector<int> best;
+  FuseSearch(kv, S, nullptr, true, pv, th, best);
+  int nFused = 0;
+  for (int i = 0; i < m; ++i) {
+    if (best[i] < 0) continue;
+    MapPointT* pMP = vpPoints[i];
+    const size_t bestIdx = (size_t)best[i];
+    MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx);
+    if (pMPinKF) {
+      if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;
+    } else {
+      pMP->AddObservation(pKF, bestIdx);
+      pKF->AddMapPoint(pMP, bestIdx);
+    }
+    nFused++;
+  }
+  return nFused;
 }
 
 // ORBmatcher.h:104 (@0x80150)

@@ -27,6 +27,12 @@ class KeyFrame;
 class MapPoint {  // include/MapPoint.h: the members the matchers touch
  public:
   cv::Mat GetNormal() { return mNormalVector.clone(); }
+  // map-graph bookkeeping called by ORBmatcher::Fuse: the demo's stand-ins log the call and apply the minimum effect a later
+  // iteration can observe, exactly like the stand-ins of tests/golden/reference_code.py under which the reference's Fuse was run
+  bool IsInKeyFrame(KeyFrame*) { return inKF; }
+  void AddObservation(KeyFrame* pKF, size_t idx);
+  void Replace(MapPoint* pMP);
+  bool inKF = false;
   int PredictScale(const float& currentDist, KeyFrame* pKF);
   cv::Mat mNormalVector;  // (protected in the reference)
   float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
@@ -96,7 +102,33 @@ class KeyFrame {  // include/KeyFrame.h
   int mnScaleLevels = 0;
   float mfLogScaleFactor = 0;
   std::vector<std::vector<std::vector<size_t> > > mGrid;  // (protected in the reference: see ORBmatcher.h)
+  std::vector<float> mvInvLevelSigma2;
+  float mbf = 0;
+  void AddMapPoint(MapPoint* pMP, const size_t& idx);
+  std::set<MapPoint*> GetMapPoints() {
+    std::set<MapPoint*> s;
+    for (MapPoint* p : mvpMapPoints)
+      if (p && !p->isBad()) s.insert(p);
+    return s;
+  }
 };
+static std::vector<int32_t> g_log;
+static KeyFrame* g_fuse_kf = nullptr;
+void MapPoint::AddObservation(KeyFrame* pKF, size_t idx) {
+  g_log.push_back(1); g_log.push_back(id); g_log.push_back((int32_t)idx);
+  nObs += pKF->mvuRight[idx] >= 0 ? 2 : 1;
+  inKF = true;
+}
+void MapPoint::Replace(MapPoint* pMP) {
+  g_log.push_back(3); g_log.push_back(id); g_log.push_back(pMP->id);
+  mbBad = true;
+  for (MapPoint*& q : g_fuse_kf->mvpMapPoints)
+    if (q == this) q = pMP;
+}
+void KeyFrame::AddMapPoint(MapPoint* pMP, const size_t& idx) {
+  g_log.push_back(2); g_log.push_back(pMP->id); g_log.push_back((int32_t)idx);
+  mvpMapPoints[idx] = pMP;
+}
 int MapPoint::PredictScale(const float& currentDist, KeyFrame* pKF) {
   return plslam_predict_scale(mfMaxDistance, currentDist, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
 }
@@ -424,6 +456,83 @@ static void case_loop_projection() {
   save("lc_out", out);
 }
 
+// ---- LocalMapping::SearchInNeighbors: matcher.Fuse(pKFi, vpMapPointMatches) / LoopClosing::SearchAndFuse: matcher.Fuse(pKF, cvScw,
+//      mvpLoopMapPoints, 4, vpReplacePoints) ----
+static void case_fuse(const std::string& pfx, bool sim3) {
+  const auto state = load<uint8_t>(pfx + "mp_state"), mdesc = load<uint8_t>(pfx + "mp_desc"), kdesc = load<uint8_t>(pfx + "kf_desc");
+  const auto xyz = load<float>(pfx + "mp_xyz"), nrm = load<float>(pfx + "mp_normal"), rng = load<float>(pfx + "mp_dist_range");
+  const auto kxy = load<float>(pfx + "kf_xy"), cam4 = load<float>(pfx + "kf_cam4"), sf = load<float>(pfx + "kf_scale_factors");
+  const auto ur = load<float>(pfx + "kf_uright"), inv = load<float>(pfx + "kf_inv_level_sigma2"), tcw = load<float>(pfx + "kf_tcw"),
+             ow = load<float>(pfx + "kf_ow");
+  const auto koct = load<int32_t>(pfx + "kf_octave"), gs = load<int32_t>(pfx + "kf_grid_start"), gi = load<int32_t>(pfx + "kf_grid_items"),
+             bounds = load<int32_t>(pfx + "kf_bounds4"), mnobs = load<int32_t>(pfx + "mp_nobs"), knobs = load<int32_t>(pfx + "kp_nobs");
+  const auto khas = load<uint8_t>(pfx + "kp_has"), kbad = load<uint8_t>(pfx + "kp_bad");
+  const auto par = load<float>(pfx + "par");  // th, gwi, ghi, logScaleFactor, mbf
+  const int m = (int)state.size(), n = (int)koct.size();
+  KeyFrame KF;
+  g_fuse_kf = &KF;
+  g_log.clear();
+  KF.mvKeysUn.resize(n);
+  for (int i = 0; i < n; ++i) {
+    KF.mvKeysUn[i].pt = cv::Point2f(kxy[2 * i], kxy[2 * i + 1]);
+    KF.mvKeysUn[i].octave = koct[i];
+  }
+  KF.mDescriptors = mat_u8(kdesc, n);
+  KF.mvScaleFactors = sf; KF.mvInvLevelSigma2 = inv; KF.mvuRight = ur; KF.mbf = par[4];
+  KF.mnScaleLevels = (int)sf.size(); KF.mfLogScaleFactor = par[3];
+  KF.fx = cam4[0]; KF.fy = cam4[1]; KF.cx = cam4[2]; KF.cy = cam4[3];
+  KF.mnMinX = bounds[0]; KF.mnMinY = bounds[1]; KF.mnMaxX = bounds[2]; KF.mnMaxY = bounds[3];
+  KF.mfGridElementWidthInv = par[1]; KF.mfGridElementHeightInv = par[2];
+  KF.mGrid.assign(64, std::vector<std::vector<size_t> >(48));
+  for (int ix = 0; ix < 64; ++ix)
+    for (int iy = 0; iy < 48; ++iy)
+      for (int k = gs[ix * 48 + iy]; k < gs[ix * 48 + iy + 1]; ++k) KF.mGrid[ix][iy].push_back((size_t)gi[k]);
+  float R9[9], t3[3];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) R9[3 * r + c] = tcw[4 * r + c];
+    t3[r] = tcw[4 * r + 3];
+  }
+  KF.R = mat_f(R9, 3, 3); KF.t = mat_f(t3, 3, 1); KF.Ow = mat_f(ow.data(), 3, 1);
+  KF.mvpMapPoints.assign(n, nullptr);
+  for (int i = 0; i < n; ++i)
+    if (khas[i]) {
+      MapPoint* p = new_mp();
+      p->id = m + i; p->mbBad = kbad[i] != 0; p->nObs = knobs[i];
+      KF.mvpMapPoints[i] = p;
+    }
+  std::vector<int32_t> alias;
+  if (sim3) alias = load<int32_t>(pfx + "mp_alias");
+  std::vector<MapPoint*> vp(m, nullptr);
+  for (int i = 0; i < m; ++i) {
+    if (state[i] == 0) continue;
+    if (state[i] == 4) { vp[i] = KF.mvpMapPoints[alias[i]]; continue; }
+    MapPoint* p = new_mp();
+    p->id = i; p->mbBad = state[i] == 2; p->inKF = state[i] == 3; p->nObs = mnobs[i];
+    p->mWorldPos = mat_f(&xyz[3 * (size_t)i], 3, 1);
+    p->mNormalVector = mat_f(&nrm[3 * (size_t)i], 3, 1);
+    p->mDescriptor = desc_row(mdesc, i);
+    p->mfMinDistance = rng[2 * i]; p->mfMaxDistance = rng[2 * i + 1];
+    vp[i] = p;
+  }
+  ORBmatcher matcher(0.6f, true);
+  int nFused;
+  std::vector<int32_t> out;
+  if (sim3) {
+    const auto scw = load<float>(pfx + "kf_scw");
+    float S[16] = {0};
+    for (int k = 0; k < 12; ++k) S[k] = scw[k];
+    S[15] = 1.f;
+    std::vector<MapPoint*> vpReplace(m, nullptr);
+    nFused = matcher.Fuse(&KF, mat_f(S, 4, 4), vp, par[0], vpReplace);
+    for (int i = 0; i < m; ++i) out.push_back(vpReplace[i] ? vpReplace[i]->id : -1);
+  } else {
+    nFused = matcher.Fuse(&KF, vp, par[0]);
+  }
+  out.push_back(nFused);
+  save(pfx + "out", out);
+  save(pfx + "log", g_log);
+}
+
 // ---- LoopClosing::ComputeSim3: matcher.SearchByBoW(mpCurrentKF, pKF, vvpMapPointMatches[i]) ----
 static void case_bow_keyframes() {
   const auto par = load<float>("bk_par");  // nnratio, ori
@@ -512,6 +621,8 @@ int main(int argc, char** argv) {
     case_bow_keyframes();
     case_relocalisation();
     case_loop_projection();
+    case_fuse("fu_", false);
+    case_fuse("fs_", true);
     case_triangulation();
     // an unfilled member must be reported, not read out of bounds
     Frame bad, last;

@@ -796,6 +796,41 @@ def search_by_projection_sim3_host(kf, mp, scw, matched_in, th):
     return out[:n], int(nm[0])
 
 
+class FuseJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("mp_valid", "mp_xyz", "mp_normal", "mp_dist_range", "mp_desc", "mp_level", "kf_xy", "kf_octave",
+                                          "kf_uright", "kf_desc", "grid_start", "grid_items", "scale_factors", "inv_level_sigma2", "best_idx")] + \
+               [("pose", C.c_float * 12), ("ow", C.c_float * 3), ("cam", C.c_float * 5), ("bounds", C.c_int32 * 4), ("grid_width_inv", C.c_float),
+                ("grid_height_inv", C.c_float), ("log_scale_factor", C.c_float), ("th", C.c_float), ("grid_cols", C.c_int32),
+                ("grid_rows", C.c_int32), ("n_levels", C.c_int32), ("use_scw", C.c_int32), ("m", C.c_int32), ("n", C.c_int32)]
+
+
+def fuse_search_host(kf, mp, th, scw=None):
+    """Matching core of ORBmatcher::Fuse on host arrays (layout: tests/matchdata.py fuse_case): the rigid form (pKF's pose, chi-square
+    tests) or, with scw, the similarity form -> best_idx int32 [M] (key-frame feature each map point would be fused into, -1 = none)."""
+    m, n = len(mp["desc"]), len(kf["desc"])
+    keep = []
+    def a(x, dt):
+        x = np.ascontiguousarray(x, dt); keep.append(x); return x.ctypes.data
+    sf = np.ascontiguousarray(kf["scale_factors"], np.float32)
+    out = np.empty(max(m, 1), np.int32)
+    j = FuseJob()
+    j.mp_valid = a(np.asarray(mp["state"]) == 1, np.uint8)
+    j.mp_xyz, j.mp_normal, j.mp_dist_range = a(mp["xyz"], np.float32), a(mp["normal"], np.float32), a(mp["dist_range"], np.float32)
+    j.mp_desc = a(mp["desc"], np.uint8)
+    j.kf_xy, j.kf_octave, j.kf_desc = a(kf["xy"], np.float32), a(kf["octave"], np.int32), a(kf["desc"], np.uint8)
+    j.kf_uright, j.inv_level_sigma2 = a(kf["uright"], np.float32), a(kf["inv_level_sigma2"], np.float32)
+    j.grid_start, j.grid_items, j.scale_factors = a(kf["grid_start"], np.int32), a(kf["grid_items"], np.int32), sf.ctypes.data
+    j.best_idx = out.ctypes.data
+    j.pose = (C.c_float * 12)(*np.asarray(kf["tcw"] if scw is None else scw, np.float32).reshape(12))
+    j.ow = (C.c_float * 3)(*np.asarray(kf["ow"], np.float32).reshape(3))
+    j.cam = (C.c_float * 5)(*(list(np.asarray(kf["cam4"], np.float32)) + [float(kf["mbf"])]))
+    j.bounds = (C.c_int32 * 4)(*[int(v) for v in kf["bounds4"]])
+    j.grid_width_inv, j.grid_height_inv, j.log_scale_factor, j.th = float(kf["gwi"]), float(kf["ghi"]), float(kf["log_sf"]), float(th)
+    j.grid_cols, j.grid_rows, j.n_levels, j.use_scw, j.m, j.n = 64, 48, len(sf), 0 if scw is None else 1, m, n
+    _check(lib().plslam_match_fuse_search_host(C.byref(j)))
+    return out[:m]
+
+
 class FrustumJob(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("mp_xyz", "mp_normal", "mp_dist_range", "in_view", "proj", "level", "viewcos")] + \
                [("cam", C.c_float * 8), ("tcw", C.c_float * 12), ("ow", C.c_float * 3), ("mbf", C.c_float), ("log_scale_factor", C.c_float),

@@ -398,6 +398,34 @@ def reflib2():
             lc.append(n)
     out["lc_n"] = np.array(len(lc))
     print("SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th):", lc)
+    # ORBmatcher::Fuse(pKF, vpMapPoints, th): the library's function with its four map-graph callees (AddObservation, AddMapPoint,
+    # Replace, IsInKeyFrame) replaced by logging stand-ins; the fixture is the call log
+    from matchdata import fuse_case
+    fu = []
+    for seed in (1, 2):
+        (ka, da), (kb, db) = feats[seed]
+        for motion, th in ((0.02, 3.0), (0.02, 1.5), (-0.1, 4.0)):
+            kf, mp, kp_ = fuse_case(ka, da, kb, db, sf, seed=seed, motion=motion)
+            nf, log = R.fuse(kf, mp, kp_, th)
+            k = len(fu)
+            out["fu%d_args" % k] = np.array([seed, motion, th], np.float64)
+            out["fu%d_log" % k], out["fu%d_n" % k] = np.array(log, np.int32).reshape(-1, 3), np.array(nf)
+            fu.append((nf, len(log)))
+    # Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (loop closing): same stand-ins; the fixture is the call log and vpReplacePoint
+    fs = []
+    for seed in (1, 2):
+        (ka, da), (kb, db) = feats[seed]
+        for motion, scale, th in ((0.02, 1.0, 4.0), (0.02, 1.6, 4.0), (-0.1, 0.7, 2.0)):
+            kf, mp, kp_ = fuse_case(ka, da, kb, db, sf, seed=seed, motion=motion, scale=scale, sim3=True)
+            nf, log, rep_ = R.fuse(kf, mp, kp_, th, scw=kf["scw"])
+            k = len(fs)
+            out["fs%d_args" % k] = np.array([seed, motion, scale, th], np.float64)
+            out["fs%d_log" % k], out["fs%d_n" % k], out["fs%d_replace" % k] = np.array(log, np.int32).reshape(-1, 3), np.array(nf), rep_
+            fs.append((nf, len(log), int((rep_ >= 0).sum())))
+    out["fs_n"] = np.array(len(fs))
+    print("Fuse(pKF, Scw, vpPoints, th, vpReplacePoint): (nFused, logged calls, replacements)", fs)
+    out["fu_n"] = np.array(len(fu))
+    print("Fuse(pKF, vpMapPoints, th): (nFused, logged calls)", fu)
     # Frame::isInFrustum on a faked Frame and faked MapPoints (GetWorldPos, GetNormal, the invariance range and PredictScale are
     # the library's own); the outputs are what the function leaves in the map points
     from matchdata import frustum_case

@@ -610,6 +610,43 @@ void refshim_build_kfgrid(void* where, int cols, int rows, const int* start, con
       for (int k = start[ix * rows + iy]; k < start[ix * rows + iy + 1]; ++k) (*g)[ix][iy].push_back((size_t)items[k]);
   }
 }
+// ---- ORBmatcher::Fuse (@0x7a500, @0x7bb20): the map-graph side effects are the reference's CPU control plane; what is pinned is
+// the matching decision.  The four functions below REPLACE the library's own (same mangled names; this object precedes the
+// library in the global lookup order, and the library calls them through its PLT): they log the call and apply the minimum
+// effect later iterations can observe (the key frame's slot, the bad flag, the observation count, "is in this key frame").
+static std::vector<long> g_fuse_log;
+static char* g_fuse_kf = nullptr;
+void refshim_fuse_begin(void* kf) { g_fuse_kf = (char*)kf; g_fuse_log.clear(); }
+int refshim_fuse_log(long* out, int cap) {
+  const int n = (int)g_fuse_log.size();
+  for (int i = 0; i < n && i < cap; ++i) out[i] = g_fuse_log[i];
+  return n;
+}
+void stub_AddObservation(char* self, char* kf, unsigned long idx) asm("_ZN9ORB_SLAM28MapPoint14AddObservationEPNS_8KeyFrameEm");
+void stub_AddObservation(char* self, char* kf, unsigned long idx) {
+  g_fuse_log.push_back(1); g_fuse_log.push_back((long)self); g_fuse_log.push_back((long)idx);
+  const float* ur = *(const float**)(kf + 0x188);
+  *(int*)(self + 0x18) += (ur && ur[idx] >= 0) ? 2 : 1;
+  self[0x3f0] = 1;  // harness flag: IsInKeyFrame(this key frame)
+}
+void stub_AddMapPoint(char* kf, char* mp, const unsigned long* idx) asm("_ZN9ORB_SLAM28KeyFrame11AddMapPointEPNS_8MapPointERKm");
+void stub_AddMapPoint(char* kf, char* mp, const unsigned long* idx) {
+  g_fuse_log.push_back(2); g_fuse_log.push_back((long)mp); g_fuse_log.push_back((long)*idx);
+  (*(char***)(kf + 0x520))[*idx] = mp;
+}
+void stub_Replace(char* self, char* other) asm("_ZN9ORB_SLAM28MapPoint7ReplaceEPS0_");
+void stub_Replace(char* self, char* other) {
+  g_fuse_log.push_back(3); g_fuse_log.push_back((long)self); g_fuse_log.push_back((long)other);
+  self[0x238] = 1;
+  if (g_fuse_kf) {
+    char** b = *(char***)(g_fuse_kf + 0x520);
+    char** e = *(char***)(g_fuse_kf + 0x528);
+    for (; b != e; ++b)
+      if (*b == self) *b = other;
+  }
+}
+bool stub_IsInKeyFrame(char* self, char* kf) asm("_ZN9ORB_SLAM28MapPoint12IsInKeyFrameEPNS_8KeyFrameE");
+bool stub_IsInKeyFrame(char* self, char*) { return self[0x3f0] != 0; }
 // helper for the harness (not an OpenCV symbol): a std::set<void*> built in place from an array of pointers
 void refshim_build_ptrset(void* where, void* const* ptrs, int n);
 void refshim_build_ptrset(void* where, void* const* ptrs, int n) {
@@ -1257,6 +1294,15 @@ class RefLibrary:
         bg.argtypes, bg.restype = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p], None
         bg(b + 0x548, 64, 48, gs.ctypes.data, gi.ctypes.data)
         keep.extend([k, d, sf, o, gs, gi])
+        if "uright" in kf:   # the members ORBmatcher::Fuse reads on top: mbf @0x148, mvuRight @0x188, mvInvLevelSigma2 @0x318, Tcw @0x3a0,
+            ur = np.ascontiguousarray(kf["uright"], np.float32)           # Ow @0x460, mvpMapPoints @0x520
+            inv = np.ascontiguousarray(kf["inv_level_sigma2"], np.float32)
+            T = np.ascontiguousarray(np.vstack([np.asarray(kf["tcw"], np.float32).reshape(3, 4), [[0, 0, 0, 1]]]).astype(np.float32))
+            O = np.ascontiguousarray(np.asarray(kf["ow"], np.float32).reshape(3, 1))
+            C.c_float.from_address(b + 0x148).value = np.float32(kf["mbf"])
+            setv(0x188, ur); setv(0x318, inv)
+            self._fmat_at(b + 0x3a0, T); self._fmat_at(b + 0x460, O)
+            keep.extend([ur, inv, T, O])
         return b
 
     def make_map_points(self, mp, keep):
@@ -1300,6 +1346,71 @@ class RefLibrary:
         nm = fn(C.addressof(matcher), kb, C.addressof(smat), C.addressof(v1), C.addressof(v2), int(th))
         out = np.array([(int(p) - base) // 0x400 if p else -1 for p in vm], np.int32)
         return out, int(nm)
+
+    # ---- ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, float th) (@0x7a500, LocalMapping::SearchInNeighbors) ----
+    def fuse(self, kf, mp, kf_points, th, scw=None):
+        """kf as make_keyframe (with uright, inv_level_sigma2, tcw, ow, mbf); mp as make_map_points plus state 0 = NULL entry, 3 = already
+        in this key frame, and nobs [M]; kf_points int32 [N]: index (into an extra pool of M2 = N key-frame points appended after the
+        map points) of the map point each key-frame feature holds, -1 = none, with kf_nobs [N] their observation counts and kf_bad [N].
+        Returns (nFused, log) with log = list of (kind, a, b): 1 AddObservation(mp a, idx b), 2 AddMapPoint(mp a, idx b),
+        3 Replace(point a by point b); point indices >= M denote the key frame's own points (M + feature index)."""
+        keep = []
+        kb = self.make_keyframe(kf, keep)
+        m, n = len(mp["desc"]), len(kf["desc"])
+        # map points 0..M-1, then one faked point per key-frame feature (M + i)
+        pool = dict(state=np.concatenate([np.where(np.asarray(mp["state"]) == 2, 2, 1), np.where(np.asarray(kf_points["bad"]), 2, 1)]).astype(np.uint8),
+                    xyz=np.vstack([mp["xyz"], np.zeros((n, 3), np.float32)]), normal=np.vstack([mp["normal"], np.zeros((n, 3), np.float32)]),
+                    dist_range=np.vstack([mp["dist_range"], np.ones((n, 2), np.float32)]), desc=np.vstack([mp["desc"], np.zeros((n, 32), np.uint8)]))
+        base = self.make_map_points(pool, keep)
+        for i in range(m):
+            C.c_int32.from_address(base + 0x400 * i + 0x18).value = int(mp["nobs"][i])
+            C.c_uint8.from_address(base + 0x400 * i + 0x3f0).value = 1 if mp["state"][i] == 3 else 0
+        for i in range(n):
+            C.c_int32.from_address(base + 0x400 * (m + i) + 0x18).value = int(kf_points["nobs"][i])
+        vp = np.array([base + 0x400 * i if mp["state"][i] else 0 for i in range(m)], np.uint64)
+        kmp = np.array([base + 0x400 * (m + i) if kf_points["has"][i] else 0 for i in range(n)], np.uint64)
+        o = (C.c_uint64 * 3).from_address(kb + 0x520)
+        o[0], o[1], o[2] = kmp.ctypes.data, kmp.ctypes.data + kmp.nbytes, kmp.ctypes.data + kmp.nbytes
+        v1 = (C.c_uint64 * 3)()
+        v1[0], v1[1], v1[2] = vp.ctypes.data, vp.ctypes.data + vp.nbytes, vp.ctypes.data + vp.nbytes
+        begin = self._shims.refshim_fuse_begin
+        begin.argtypes, begin.restype = [C.c_void_p], None
+        begin(kb)
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = np.float32(0.6)
+        matcher[4] = 1
+        replace = None
+        if scw is None:
+            fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher4FuseEPNS_8KeyFrameERKSt6vectorIPNS_8MapPointESaIS5_EEf")
+            fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float], C.c_int
+            nf = fn(C.addressof(matcher), kb, C.addressof(v1), np.float32(th))
+        else:
+            # Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint) (@0x7bb20):
+            # entries with state 4 alias a map point the key frame already holds (pKF->GetMapPoints() makes them "already found")
+            for i in range(m):
+                if mp["state"][i] == 4:
+                    vp[i] = base + 0x400 * (m + int(mp["alias"][i]))
+            S = np.ascontiguousarray(np.vstack([np.asarray(scw, np.float32).reshape(3, 4), [[0, 0, 0, 1]]]).astype(np.float32))
+            smat = (C.c_uint64 * 12)()
+            self._fmat_at(C.addressof(smat), S)
+            rp = np.zeros(m, np.uint64)
+            v2 = (C.c_uint64 * 3)()
+            v2[0], v2[1], v2[2] = rp.ctypes.data, rp.ctypes.data + rp.nbytes, rp.ctypes.data + rp.nbytes
+            fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher4FuseEPNS_8KeyFrameEN2cv3MatERKSt6vectorIPNS_8MapPointESaIS7_EEfRS9_")
+            fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p], C.c_int
+            nf = fn(C.addressof(matcher), kb, C.addressof(smat), C.addressof(v1), np.float32(th), C.addressof(v2))
+            replace = np.array([(int(p) - base) // 0x400 if p else -1 for p in rp], np.int32)
+        getlog = self._shims.refshim_fuse_log
+        getlog.argtypes, getlog.restype = [C.c_void_p, C.c_int], C.c_int
+        buf = (C.c_long * (9 * (m + 1)))()
+        cnt = getlog(buf, len(buf))
+        log = []
+        for k in range(0, cnt, 3):
+            kind, a_, b_ = buf[k], buf[k + 1], buf[k + 2]
+            ai = (a_ - base) // 0x400
+            bi = (b_ - base) // 0x400 if kind == 3 else b_
+            log.append((int(kind), int(ai), int(bi)))
+        return (int(nf), log) if scw is None else (int(nf), log, replace)
 
     # ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (@0x86b30) ----
     # KeyFrame: fx/fy/cx/cy @0x130..0x13c, N @0x154, mvKeysUn @0x170, mvuRight @0x188, mDescriptors @0x1b8, mFeatVec @0x248,

@@ -243,3 +243,35 @@ def loop_projection_case(kps_kf, desc_kf, kps_src, desc_src, scale_factors, W=64
     pre = rng.choice(n, n // 10, replace=False)
     matched_in[pre] = rng.choice(m, len(pre), replace=False)          # already matched: those map points are "already found"
     return kf, mp, scw, matched_in
+
+
+def fuse_case(kps_kf, desc_kf, kps_src, desc_src, scale_factors, W=640, H=480, seed=0, motion=0.05, scale=1.0, sim3=False):
+    """LocalMapping::SearchInNeighbors-like inputs for ORBmatcher::Fuse(pKF, vpMapPoints, th): loop_projection_case with a rigid
+    pose, plus what Fuse reads on top (mvuRight, mvInvLevelSigma2, mbf), NULL / bad / already-in-key-frame candidates with
+    observation counts, and the map points the key frame already holds."""
+    kf, mp, scw, _ = loop_projection_case(kps_kf, desc_kf, kps_src, desc_src, scale_factors, W, H, seed=seed, motion=motion, scale=scale)
+    rng = np.random.default_rng(seed + 500)
+    n, m = len(kps_kf), len(kps_src)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    bf = np.float32(40.0)
+    kf["uright"] = np.where(rng.random(n) < 0.7, kf["xy"][:, 0] - bf / (1.5 + rng.random(n) * 2.0), -1).astype(np.float32)
+    kf["inv_level_sigma2"] = (np.float32(1.0) / (sf * sf)).astype(np.float32)
+    kf["mbf"] = bf
+    kf["tcw"] = scw.astype(np.float32)
+    R, t = scw[:, :3].astype(np.float64), scw[:, 3].astype(np.float64)
+    kf["ow"] = (-(R.T @ t)).astype(np.float32)
+    st = mp["state"].copy()
+    r = rng.random(m)
+    st[r < 0.05] = 0
+    st[(r >= 0.05) & (r < 0.10)] = 3
+    mp["state"] = st
+    mp["nobs"] = rng.integers(1, 9, m).astype(np.int32)
+    kf_points = dict(has=(rng.random(n) < 0.6).astype(np.uint8), nobs=rng.integers(1, 9, n).astype(np.int32),
+                     bad=(rng.random(n) < 0.05).astype(np.uint8), uright=kf["uright"])
+    if sim3:   # Fuse(pKF, Scw, ...): no NULL candidates, no IsInKeyFrame test; some candidates ARE points the key frame already holds
+        kf["scw"] = scw.astype(np.float32)
+        st = np.where(st == 0, 1, np.where(st == 3, 4, st)).astype(np.uint8)
+        good = np.flatnonzero((kf_points["has"] == 1) & (kf_points["bad"] == 0))
+        mp["alias"] = rng.choice(good, m).astype(np.int32)
+        mp["state"] = st
+    return kf, mp, kf_points

@@ -129,6 +129,18 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
         put("lc_mp_" + k, v)
     put("lc_scw", lscw, np.float32); put("lc_matched_in", lmi, np.int32)
     put("lc_par", [10.0, float(lkf["gwi"]), float(lkf["ghi"]), float(lkf["log_sf"])], np.float32)
+    # LocalMapping::SearchInNeighbors / LoopClosing::SearchAndFuse
+    from matchdata import fuse_case
+    fcases = {"fu_": fuse_case(ka, da, kb, db, sf, seed=21, motion=0.02), "fs_": fuse_case(ka, da, kb, db, sf, seed=22, motion=0.02, scale=1.4, sim3=True)}
+    for pfx, (fkf, fmp, fkp) in fcases.items():
+        for k, v in fkf.items():
+            if k not in ("gwi", "ghi", "log_sf", "mbf"):
+                put(pfx + "kf_" + k, v)
+        for k, v in fmp.items():
+            put(pfx + "mp_" + k, v)
+        for k in ("has", "nobs", "bad"):
+            put(pfx + "kp_" + k, fkp[k])
+        put(pfx + "par", [3.0 if pfx == "fu_" else 4.0, float(fkf["gwi"]), float(fkf["ghi"]), float(fkf["log_sf"]), float(fkf["mbf"])], np.float32)
     # CreateNewMapPoints
     kps, desc = orc.extract(synth_frame(33))
     kf1, kf2, F12, pose, camt, sft, sg = triangulation_case(kps, desc, seed=33, stereo_fraction=0.5)
@@ -163,6 +175,15 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
     m, n = pl.search_by_projection_sim3_host(lkf, lmp, lscw, lmi, 10)  # (pinned: test_golden_gpu.py, lc*)
     out = np.fromfile(d / "lc_out", np.int32)
     assert out[-1] == n > 100 and np.array_equal(out[:-1], m)
+    fkf, fmp, fkp = fcases["fu_"]   # (pinned: test_golden_gpu.py, fu* / fs*)
+    nf, log = oracle.fuse_replay(pl.fuse_search_host(fkf, fmp, 3.0), fmp, fkp)
+    assert int(np.fromfile(d / "fu_out", np.int32)[-1]) == nf > 50
+    assert np.array_equal(np.fromfile(d / "fu_log", np.int32).reshape(-1, 3), np.array(log, np.int32).reshape(-1, 3))
+    fkf, fmp, fkp = fcases["fs_"]
+    nf, log, rep = oracle.fuse_replay_sim3(pl.fuse_search_host(fkf, fmp, 4.0, scw=fkf["scw"]), fmp, fkp)
+    out = np.fromfile(d / "fs_out", np.int32)
+    assert out[-1] == nf > 50 and np.array_equal(out[:-1], rep)
+    assert np.array_equal(np.fromfile(d / "fs_log", np.int32).reshape(-1, 3), np.array(log, np.int32).reshape(-1, 3))
     ex, ey = pl.epipole(*pose, *camt)
     m12, n12, pairs = pl.search_for_triangulation_host(kf1, kf2, F12, ex, ey, sft, sg, False, True)
     out = np.fromfile(d / "tr_out", np.int32)

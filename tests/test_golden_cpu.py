@@ -348,6 +348,74 @@ def test_search_by_projection_sim3_equals_the_reference_matcher(oracle):
     assert total > 1500
 
 
+def _fuse_cases(g, extract, scale_factors):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import fuse_case
+    from plslam_b200.synth import synth_pair
+    feats = {}
+    for k in range(int(g["fu_n"])):
+        seed, motion, th = g["fu%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (extract(a), extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        kf, mp, kp_ = fuse_case(ka, da, kb, db, scale_factors, seed=seed, motion=float(motion))
+        yield k, kf, mp, kp_, float(th)
+
+
+def test_fuse_equals_the_reference_matcher(oracle):
+    """ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (@0x7a500) executed from lib/libORB_SLAM2.so on a faked KeyFrame
+    and faked MapPoints, its four map-graph callees replaced by logging stand-ins: the sequence of AddObservation / AddMapPoint /
+    Replace calls (which point, which key-frame feature, which direction) and nFused must follow from the oracle's matching core
+    plus the replay of the bookkeeping (fixture fu*)."""
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    o = oracle.OrbOracle()
+    total = 0
+    for k, kf, mp, kp_, th in _fuse_cases(g, o.extract, o.tables()["scale"]):
+        best = oracle.fuse_search(kf, mp, th)
+        nf, log = oracle.fuse_replay(best, mp, kp_)
+        assert nf == int(g["fu%d_n" % k]), k
+        assert np.array_equal(np.array(log, np.int32).reshape(-1, 3), g["fu%d_log" % k]), k
+        total += nf
+    assert total > 500
+
+
+def _fuse_sim3_cases(g, extract, scale_factors):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import fuse_case
+    from plslam_b200.synth import synth_pair
+    feats = {}
+    for k in range(int(g["fs_n"])):
+        seed, motion, scale, th = g["fs%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (extract(a), extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        kf, mp, kp_ = fuse_case(ka, da, kb, db, scale_factors, seed=seed, motion=float(motion), scale=float(scale), sim3=True)
+        yield k, kf, mp, kp_, float(th)
+
+
+def test_fuse_sim3_equals_the_reference_matcher(oracle):
+    """ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (@0x7bb20, LoopClosing::SearchAndFuse) executed from
+    lib/libORB_SLAM2.so (same stand-ins as above; pKF->GetMapPoints() is the library's): call log, vpReplacePoint and nFused must
+    follow from the oracle's matching core plus the replay (fixture fs*, similarity scales 0.7 / 1 / 1.6)."""
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    o = oracle.OrbOracle()
+    total = 0
+    for k, kf, mp, kp_, th in _fuse_sim3_cases(g, o.extract, o.tables()["scale"]):
+        best = oracle.fuse_search_sim3(kf, mp, kf["scw"], th)
+        nf, log, rep = oracle.fuse_replay_sim3(best, mp, kp_)
+        assert nf == int(g["fs%d_n" % k]), k
+        assert np.array_equal(np.array(log, np.int32).reshape(-1, 3), g["fs%d_log" % k]), k
+        assert np.array_equal(rep, g["fs%d_replace" % k]), k
+        total += nf
+    assert total > 1000
+
+
 def _frustum_cases(g):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

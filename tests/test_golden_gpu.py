@@ -235,6 +235,28 @@ def test_k_kf_projection_equals_the_reference_matcher():
     assert total > 1500
 
 
+def test_k_fuse_search_equals_the_reference_matcher():
+    """k_fuse_search (the matching core of both ORBmatcher::Fuse overloads, @0x7a500 / @0x7bb20) on the fu* and fs* fixtures: the
+    reference's sequence of AddObservation / AddMapPoint / Replace calls, vpReplacePoint and nFused follow from the kernel's
+    per-point matches plus the replay of the bookkeeping."""
+    import plslam_b200 as pl
+    from oracle import bindings as ob
+    from test_golden_cpu import _fuse_cases, _fuse_sim3_cases
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    ex = pl.ORBextractor()
+    total = 0
+    for k, kf, mp, kp_, th in _fuse_cases(g, ex, _scale_factors()):
+        nf, log = ob.fuse_replay(pl.fuse_search_host(kf, mp, th), mp, kp_)
+        assert nf == int(g["fu%d_n" % k]) and np.array_equal(np.array(log, np.int32).reshape(-1, 3), g["fu%d_log" % k]), k
+        total += nf
+    for k, kf, mp, kp_, th in _fuse_sim3_cases(g, ex, _scale_factors()):
+        nf, log, rep = ob.fuse_replay_sim3(pl.fuse_search_host(kf, mp, th, scw=kf["scw"]), mp, kp_)
+        assert nf == int(g["fs%d_n" % k]) and np.array_equal(np.array(log, np.int32).reshape(-1, 3), g["fs%d_log" % k]), k
+        assert np.array_equal(rep, g["fs%d_replace" % k]), k
+        total += nf
+    assert total > 1500
+
+
 def test_k_is_in_frustum_equals_the_reference():
     """k_is_in_frustum (Frame::isInFrustum, @0xf5190) on the fz* fixtures: 3 x 3000 map points, every field the reference's
     function leaves in a MapPoint."""
