@@ -318,7 +318,11 @@ typedef struct plslam_fuse_job {
   const float* scale_factors;   /* pKF->mvScaleFactors */
   const float* inv_level_sigma2;/* pKF->mvInvLevelSigma2 (rigid form) */
   int32_t* best_idx;            /* M : key-frame feature, -1 = no match */
-  float pose[12];               /* use_scw = 0: Rcw | tcw (pKF->GetRotation(), GetTranslation()); 1: rows 0..2 of Scw */
+  float pose[12];               /* use_scw = 0: Rcw | tcw (pKF->GetRotation(), GetTranslation()); 1: rows 0..2 of Scw; 2: see pose2 */
+  float pose2[12];              /* use_scw = 2 (one direction of ORBmatcher::SearchBySim3, ORBmatcher.h:116, @0x838b0): the points are
+                                   taken into their own key frame's camera with pose (R?w | t?w), then into the OTHER camera with
+                                   pose2 (sR21 | t21 or sR12 | t12); the distance is the norm of that last vector, there is no
+                                   viewing-angle test, candidates compete from INT_MAX and a match needs bestDist <= TH_HIGH */
   float ow[3];                  /* use_scw = 0: pKF->GetCameraCenter(); 1: ignored (derived from Scw as the reference does) */
   float cam[5];                 /* fx, fy, cx, cy, mbf */
   int32_t bounds[4];            /* mnMinX, mnMinY, mnMaxX, mnMaxY */
@@ -327,6 +331,9 @@ typedef struct plslam_fuse_job {
 } plslam_fuse_job_t;
 int plslam_match_fuse_search_batch_device(const plslam_fuse_job_t* d_jobs, int njobs, int max_m, void* stream);
 int plslam_match_fuse_search_host(const plslam_fuse_job_t* job); /* HOST pointers inside *job */
+/* sR12 = s12 * R12, sR21 = (1.0 / s12) * R12.t(), t21 = -sR21 * t12 as the reference's cv::Mat expressions evaluate (@0x83a8e:
+ * every element times (float)alpha, the product through gemm with scale -1); R12 row-major 3x3.  Host arithmetic, no GPU. */
+void plslam_sim3_transforms(float s12, const float* R12, const float* t12, float* sR12, float* sR21, float* t21);
 
 /* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (ORBmatcher.h:61,
  * @0x79f10) — the local-map search of Tracking::SearchLocalPoints, including Frame::GetFeaturesInArea and

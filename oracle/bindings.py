@@ -335,6 +335,38 @@ def fuse_search(kf, mp, th):
     return out[:m]
 
 
+def sim3_inputs(kf1, kf2, mp1, mp2, matched_in):
+    """The flattened arrays both the oracle and the C-ABI take for SearchBySim3 (layout: tests/matchdata.py sim3_case)."""
+    n1, n2 = len(kf1["desc"]), len(kf2["desc"])
+    matched_in = np.asarray(matched_in, np.int32)
+    m1 = np.ascontiguousarray(matched_in >= 0, np.uint8)
+    m2 = np.zeros(n2, np.uint8)
+    m2[matched_in[matched_in >= 0]] = 1          # (GetIndexInKeyFrame(pKF2) of a KF2 point is its feature index)
+    def side(kf, mp, m):
+        return [np.ascontiguousarray(np.asarray(mp["state"]) == 1, np.uint8), m, np.ascontiguousarray(mp["xyz"], np.float32),
+                np.ascontiguousarray(mp["dist_range"], np.float32), np.ascontiguousarray(mp["desc"], np.uint8),
+                np.ascontiguousarray(kf["xy"], np.float32), np.ascontiguousarray(kf["octave"], np.int32), np.ascontiguousarray(kf["desc"], np.uint8),
+                np.ascontiguousarray(kf["grid_start"], np.int32), np.ascontiguousarray(kf["grid_items"], np.int32),
+                np.ascontiguousarray(kf["tcw"], np.float32).reshape(12), np.ascontiguousarray(kf["cam4"], np.float32),
+                np.ascontiguousarray(kf["bounds4"], np.int32)]
+    return n1, n2, side(kf1, mp1, m1), side(kf2, mp2, m2)
+
+
+def search_by_sim3(kf1, kf2, mp1, mp2, s12, R12, t12, th, matched_in):
+    """ORBmatcher::SearchBySim3 -> (match12 int32 [N1]: KF2 feature newly matched to each KF1 feature or -1, nFound)."""
+    n1, n2, a, b = sim3_inputs(kf1, kf2, mp1, mp2, matched_in)
+    sf = np.ascontiguousarray(kf1["scale_factors"], np.float32)
+    R = np.ascontiguousarray(R12, np.float32).reshape(9); t = np.ascontiguousarray(t12, np.float32).reshape(3)
+    out = np.empty(max(n1, 1), np.int32)
+    L = lib()
+    L.oracle_search_by_sim3.argtypes = [C.c_int] + [C.c_void_p] * 13 + [C.c_int] + [C.c_void_p] * 13 + [C.c_float, C.c_float, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    L.oracle_search_by_sim3.restype = C.c_int
+    nf = L.oracle_search_by_sim3(n1, *[_p(x) for x in a], n2, *[_p(x) for x in b], float(kf1["gwi"]), float(kf1["ghi"]), 64, 48, _p(sf), len(sf),
+                                 float(kf1["log_sf"]), float(s12), _p(R), _p(t), float(th), _p(out))
+    return out[:n1], nf
+
+
 def fuse_search_sim3(kf, mp, scw, th):
     """Matching core of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) -> best_idx int32 [M]."""
     m, n = len(mp["desc"]), len(kf["desc"])

@@ -719,6 +719,93 @@ void oracle_fuse_search_sim3(int M, const uint8_t* mpValid, const float* mpXYZ, 
   }
 }
 
+// ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+// const cv::Mat& t12, const float th) (ORBmatcher.h:116; @0x838b0, LoopClosing::ComputeSim3).  Read from the binary: sR12 = s12 *
+// R12 and sR21 = (1.0 / s12) * R12.t() are scaled conversions (every element times (float)alpha; 1.0 / s12 in double, @0x83a8e),
+// t21 = -sR21 * t12 is a gemm with scale -1; per map point of one key frame that exists, is not bad and is not matched on entry:
+// p3Dc = R?w * p3Dw + t?w, then into the other camera with sR21 / t21 (or sR12 / t12), z < 0 rejects, u = fma(x, fx, cx) with the
+// OTHER key frame's intrinsics, IsInImage, dist3D = (float)cv::norm(p3Dc in the other camera) inside the invariance range,
+// PredictScale, radius = th * mvScaleFactors[level], GetFeaturesInArea, octave in [level - 1, level], best = strictly smaller
+// distance starting from INT_MAX, accepted when bestDist <= TH_HIGH (@0x86692, @0x866e9); a pair is kept when both directions
+// agree.  matched1[i] = vpMatches12[i] != NULL on entry, matched2 = the KF2 features those points are observed at.
+// Returns nFound; match12[N1] = KF2 feature newly matched to KF1 feature i (-1 = none).
+static void sim3_direction(int N, const uint8_t* valid, const uint8_t* already, const float* xyz, const float* distRange,
+                           const uint8_t* desc, const float* Tw, const float* sR, const float* tt, const float* camO,
+                           const int* boundsO, float gwi, float ghi, int cols, int rows, const int* gridStart, const int* gridItems,
+                           const float* xyO, const int* octO, const uint8_t* descO, const float* scaleFactors, int nLevels,
+                           float logScaleFactor, float th, int* match) {
+  const float fx = camO[0], fy = camO[1], cx = camO[2], cy = camO[3];
+  for (int i = 0; i < N; ++i) {
+    match[i] = -1;
+    if (!valid[i] || already[i]) continue;
+    const float* X = xyz + 3 * i;
+    float pa[3], pb[3];
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = Tw[r * 4] * X[0], p1 = Tw[r * 4 + 1] * X[1], p2 = Tw[r * 4 + 2] * X[2];
+      pa[r] = (float)((double)((p0 + p1) + p2) + (double)Tw[r * 4 + 3]);
+    }
+    for (int r = 0; r < 3; ++r) {
+      const float p0 = sR[r * 3] * pa[0], p1 = sR[r * 3 + 1] * pa[1], p2 = sR[r * 3 + 2] * pa[2];
+      pb[r] = (float)((double)((p0 + p1) + p2) + (double)tt[r]);
+    }
+    if (pb[2] < 0.0f) continue;
+    const float invz = 1.0f / pb[2];
+    const float u = std::fmaf(pb[0] * invz, fx, cx), v = std::fmaf(pb[1] * invz, fy, cy);
+    if (!(u >= (float)boundsO[0] && u < (float)boundsO[2] && v >= (float)boundsO[1] && v < (float)boundsO[3])) continue;
+    double n2 = 0;
+    for (int r = 0; r < 3; ++r) n2 += (double)pb[r] * (double)pb[r];
+    const float dist = (float)std::sqrt(n2);
+    if (dist < 0.8f * distRange[2 * i] || dist > 1.2f * distRange[2 * i + 1]) continue;
+    const int level = predict_scale(distRange[2 * i + 1], dist, logScaleFactor, nLevels);
+    const float radius = th * scaleFactors[level];
+    int bestDist = INT_MAX, bestIdx = -1;
+    for_kf_features_in_area(u, v, radius, boundsO[0], boundsO[1], gwi, ghi, cols, rows, gridStart, gridItems, xyO, [&](int idx) {
+      if (octO[idx] < level - 1 || octO[idx] > level) return;
+      const int d = descriptor_distance(desc + 32 * i, descO + 32 * idx);
+      if (d < bestDist) { bestDist = d; bestIdx = idx; }
+    });
+    if (bestDist <= TH_HIGH) match[i] = bestIdx;
+  }
+}
+// the three derived transforms, as OpenCV evaluates the reference's expressions (see above)
+void oracle_sim3_transforms(float s12, const float* R12, const float* t12, float* sR12, float* sR21, float* t21) {
+  const float a12 = (float)(double)s12, a21 = (float)(1.0 / (double)s12);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      sR12[3 * i + j] = R12[3 * i + j] * a12 + 0.0f;
+      sR21[3 * i + j] = R12[3 * j + i] * a21 + 0.0f;
+    }
+  for (int i = 0; i < 3; ++i) {
+    const float p0 = sR21[3 * i] * t12[0], p1 = sR21[3 * i + 1] * t12[1], p2 = sR21[3 * i + 2] * t12[2];
+    t21[i] = (float)((double)((p0 + p1) + p2) * -1.0);
+  }
+}
+int oracle_search_by_sim3(int N1, const uint8_t* valid1, const uint8_t* matched1, const float* xyz1, const float* range1,
+                          const uint8_t* mdesc1, const float* kxy1, const int* koct1, const uint8_t* kdesc1, const int* gs1,
+                          const int* gi1, const float* T1w, const float* cam1, const int* bounds1, int N2, const uint8_t* valid2,
+                          const uint8_t* matched2, const float* xyz2, const float* range2, const uint8_t* mdesc2, const float* kxy2,
+                          const int* koct2, const uint8_t* kdesc2, const int* gs2, const int* gi2, const float* T2w,
+                          const float* cam2, const int* bounds2, float gwi, float ghi, int cols, int rows, const float* scaleFactors,
+                          int nLevels, float logScaleFactor, float s12, const float* R12, const float* t12, float th, int* match12) {
+  float sR12[9], sR21[9], t21[3];
+  oracle_sim3_transforms(s12, R12, t12, sR12, sR21, t21);
+  std::vector<int> m1(std::max(N1, 1)), m2(std::max(N2, 1));
+  sim3_direction(N1, valid1, matched1, xyz1, range1, mdesc1, T1w, sR21, t21, cam2, bounds2, gwi, ghi, cols, rows, gs2, gi2, kxy2, koct2,
+                 kdesc2, scaleFactors, nLevels, logScaleFactor, th, m1.data());
+  sim3_direction(N2, valid2, matched2, xyz2, range2, mdesc2, T2w, sR12, t12, cam1, bounds1, gwi, ghi, cols, rows, gs1, gi1, kxy1, koct1,
+                 kdesc1, scaleFactors, nLevels, logScaleFactor, th, m2.data());
+  int nFound = 0;
+  for (int i1 = 0; i1 < N1; ++i1) {
+    match12[i1] = -1;
+    const int idx2 = m1[i1];
+    if (idx2 >= 0 && m2[idx2] == i1) {
+      match12[i1] = idx2;
+      nFound++;
+    }
+  }
+  return nFound;
+}
+
 // Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (include/Frame.h:107-ish "isInFrustum"; @0xf5190), what
 // Tracking::SearchLocalPoints runs on every local map point before ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)
 // (it fills the mTrack* fields that matcher reads).  Read from the binary: Pc = mRcw * P + mtcw (gemm small path); PcZ < 0

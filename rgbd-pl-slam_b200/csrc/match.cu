@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(256) k_fuse_search(const plslam_fuse_job_t* __
     const float gwi = J.grid_width_inv, ghi = J.grid_height_inv;
     const int cols = J.grid_cols, rows = J.grid_rows;
     float T[12], Ow[3];
-    if (J.use_scw) {
+    if (J.use_scw == 1) {
       double d0 = 0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) d0 = __dadd_rn(d0, __dmul_rn((double)J.pose[k], (double)J.pose[k]));
@@ -624,12 +624,24 @@ __global__ void __launch_bounds__(256) k_fuse_search(const plslam_fuse_job_t* __
 #pragma unroll
       for (int r = 0; r < 3; ++r) Ow[r] = J.ow[r];
     }
+    const bool sim3 = J.use_scw == 2;
+    const int accept = sim3 ? PLSLAM_TH_HIGH : PLSLAM_TH_LOW;
     const float* X = J.mp_xyz + 3 * (size_t)i;
     float pc[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const float p0 = __fmul_rn(T[r * 4], X[0]), p1 = __fmul_rn(T[r * 4 + 1], X[1]), p2 = __fmul_rn(T[r * 4 + 2], X[2]);
       pc[r] = (float)__dadd_rn((double)__fadd_rn(__fadd_rn(p0, p1), p2), (double)T[r * 4 + 3]);
+    }
+    if (sim3) {  // into the other key frame's camera
+      float pb[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float p0 = __fmul_rn(J.pose2[r * 4], pc[0]), p1 = __fmul_rn(J.pose2[r * 4 + 1], pc[1]), p2 = __fmul_rn(J.pose2[r * 4 + 2], pc[2]);
+        pb[r] = (float)__dadd_rn((double)__fadd_rn(__fadd_rn(p0, p1), p2), (double)J.pose2[r * 4 + 3]);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) pc[r] = pb[r];
     }
     if (pc[2] < 0.0f) break;
     const float invz = __fdiv_rn(1.0f, pc[2]);
@@ -639,6 +651,14 @@ __global__ void __launch_bounds__(256) k_fuse_search(const plslam_fuse_job_t* __
     int level;
     if (J.mp_level) {
       level = J.mp_level[i];
+    } else if (sim3) {
+      double n2 = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) n2 = __dadd_rn(n2, __dmul_rn((double)pc[r], (double)pc[r]));
+      const float dist = (float)sqrt(n2);
+      const float dMin = J.mp_dist_range[2 * (size_t)i], dMax = J.mp_dist_range[2 * (size_t)i + 1];
+      if (dist < __fmul_rn(0.8f, dMin) || dist > __fmul_rn(1.2f, dMax)) break;
+      level = predict_scale_dev(dMax, dist, J.log_scale_factor, J.n_levels);
     } else {
       float PO[3];
       double n2 = 0;
@@ -681,7 +701,7 @@ __global__ void __launch_bounds__(256) k_fuse_search(const plslam_fuse_job_t* __
         if (!(fabsf(__fsub_rn(kx, u)) < radius && fabsf(__fsub_rn(ky, v)) < radius)) continue;
         const int kpLevel = J.kf_octave[idx];
         if (kpLevel < level - 1 || kpLevel > level) continue;
-        if (!J.use_scw) {
+        if (J.use_scw == 0) {
           const float ex = __fsub_rn(u, kx), ey = __fsub_rn(v, ky);
           const float kr = J.kf_uright[idx];
           float e2 = __fmaf_rn(ex, ex, __fmul_rn(ey, ey));
@@ -699,7 +719,7 @@ __global__ void __launch_bounds__(256) k_fuse_search(const plslam_fuse_job_t* __
       }
     }
     const unsigned g = warp_min_u32(best);
-    if (g == 0xffffffffu || (int)(g >> 22) > PLSLAM_TH_LOW) break;
+    if (g == 0xffffffffu || (int)(g >> 22) > accept) break;
     const unsigned src = __ballot_sync(0xffffffffu, best == g);
     result = __shfl_sync(0xffffffffu, bestI, __ffs(src) - 1);
   } while (false);
@@ -1220,7 +1240,8 @@ int plslam_match_fuse_search_batch_device(const plslam_fuse_job_t* d_jobs, int n
 
 int plslam_match_fuse_search_host(const plslam_fuse_job_t* job) {
   PL_CHECK_ARG(job && job->best_idx && job->m >= 0 && job->n >= 0 && job->n_levels >= 1 && job->grid_cols >= 1 && job->grid_rows >= 1 &&
-               job->grid_start && (job->mp_level || (job->mp_normal && job->mp_dist_range)) && (job->use_scw || (job->kf_uright && job->inv_level_sigma2)));
+               job->grid_start && (job->mp_level || (job->mp_dist_range && (job->mp_normal || job->use_scw == 2))) &&
+               (job->use_scw || (job->kf_uright && job->inv_level_sigma2)));
   Uploader U;
   plslam_fuse_job_t d = *job;
   const int m = job->m, n = job->n, ncell = job->grid_cols * job->grid_rows;
@@ -1228,7 +1249,7 @@ int plslam_match_fuse_search_host(const plslam_fuse_job_t* job) {
   const int nitems = job->grid_start[ncell];
   d.mp_valid = U.up(job->mp_valid, m);
   d.mp_xyz = U.up(job->mp_xyz, (size_t)m * 3);
-  d.mp_normal = job->mp_level ? nullptr : U.up(job->mp_normal, (size_t)m * 3);
+  d.mp_normal = (job->mp_level || !job->mp_normal) ? nullptr : U.up(job->mp_normal, (size_t)m * 3);
   d.mp_dist_range = job->mp_level ? nullptr : U.up(job->mp_dist_range, (size_t)m * 2);
   d.mp_level = job->mp_level ? U.up(job->mp_level, m) : nullptr;
   d.mp_desc = U.up(job->mp_desc, (size_t)m * 32);
@@ -1247,6 +1268,22 @@ int plslam_match_fuse_search_host(const plslam_fuse_job_t* job) {
   if (rc) return rc;
   PL_CUDA(cudaMemcpy(job->best_idx, d.best_idx, (size_t)m * 4, cudaMemcpyDeviceToHost));
   return PLSLAM_OK;
+}
+
+void plslam_sim3_transforms(float s12, const float* R12, const float* t12, float* sR12, float* sR21, float* t21) {
+  const float a12 = (float)(double)s12, a21 = (float)(1.0 / (double)s12);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      volatile float p = R12[3 * i + j] * a12, q = R12[3 * j + i] * a21;  // two roundings each: product, then + 0.0f
+      sR12[3 * i + j] = p + 0.0f;
+      sR21[3 * i + j] = q + 0.0f;
+    }
+  for (int i = 0; i < 3; ++i) {
+    volatile float p0 = sR21[3 * i] * t12[0], p1 = sR21[3 * i + 1] * t12[1], p2 = sR21[3 * i + 2] * t12[2];
+    volatile float s01 = p0 + p1;
+    volatile float s = s01 + p2;
+    t21[i] = (float)((double)s * -1.0);
+  }
 }
 
 int plslam_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels) {

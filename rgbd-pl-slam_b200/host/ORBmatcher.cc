@@ -178,6 +178,43 @@ void ORBmatcher::FuseSearch(const KeyFrameGridView& KF, const float pose[12], co
   check(plslam_match_fuse_search_host(&j), "Fuse");
 }
 
+void ORBmatcher::Sim3Transforms(float s12, const float R12[9], const float t12[3], float sR12[9], float sR21[9], float t21[3]) {
+  plslam_sim3_transforms(s12, R12, t12, sR12, sR21, t21);
+}
+
+void ORBmatcher::Sim3Search(const KeyFrameGridView& KF, const float poseOwn[12], const float pose2[12], const LoopPointsView& P,
+                            float th, std::vector<int>& vnBestIdx) {
+  const int m = (int)P.valid.size(), n = (int)KF.mvKeysUn.size();
+  vnBestIdx.assign(m, -1);
+  if (m == 0 || n == 0) return;
+  need(P.worldPos.size() == (size_t)m * 3 && (int)P.level.size() == m && P.descriptors.rows >= m && P.descriptors.cols == 32,
+       "LoopPointsView arrays do not cover its M map points");
+  need(KF.mDescriptors.rows >= n && KF.mDescriptors.cols == 32 && !KF.mvScaleFactors.empty() &&
+           KF.gridStart.size() == (size_t)KF.mnGridCols * KF.mnGridRows + 1 && (int)KF.gridItems.size() == KF.gridStart.back(),
+       "KeyFrameGridView: mDescriptors / grid / mvScaleFactors incomplete");
+  for (int i = 0; i < m; ++i)
+    need(!P.valid[i] || (P.level[i] >= 0 && P.level[i] < (int)KF.mvScaleFactors.size()), "LoopPointsView level out of range");
+  std::vector<float> xy((size_t)n * 2);
+  std::vector<int32_t> oct(n);
+  for (int i = 0; i < n; ++i) {
+    xy[2 * i] = KF.mvKeysUn[i].pt.x; xy[2 * i + 1] = KF.mvKeysUn[i].pt.y;
+    oct[i] = KF.mvKeysUn[i].octave;
+  }
+  plslam_fuse_job_t j{};
+  j.mp_valid = P.valid.data(); j.mp_xyz = P.worldPos.data(); j.mp_desc = P.descriptors.data; j.mp_level = P.level.data();
+  j.kf_xy = xy.data(); j.kf_octave = oct.data(); j.kf_desc = KF.mDescriptors.data;
+  j.grid_start = KF.gridStart.data(); j.grid_items = KF.gridItems.data(); j.scale_factors = KF.mvScaleFactors.data();
+  j.best_idx = vnBestIdx.data();
+  std::memcpy(j.pose, poseOwn, sizeof(j.pose));
+  std::memcpy(j.pose2, pose2, sizeof(j.pose2));
+  j.cam[0] = KF.fx; j.cam[1] = KF.fy; j.cam[2] = KF.cx; j.cam[3] = KF.cy;
+  j.bounds[0] = KF.mnMinX; j.bounds[1] = KF.mnMinY; j.bounds[2] = KF.mnMaxX; j.bounds[3] = KF.mnMaxY;
+  j.grid_width_inv = KF.mfGridElementWidthInv; j.grid_height_inv = KF.mfGridElementHeightInv; j.th = th;
+  j.grid_cols = KF.mnGridCols; j.grid_rows = KF.mnGridRows; j.n_levels = (int)KF.mvScaleFactors.size(); j.use_scw = 2;
+  j.m = m; j.n = n;
+  check(plslam_match_fuse_search_host(&j), "SearchBySim3");
+}
+
 int ORBmatcher::SearchByProjection(FrameView& F, const MapPointsView& MP, const float th, std::vector<int>& vnMatches) {
   const int m = (int)MP.inViewAndGood.size(), n = (int)F.mvKeysUn.size();
   vnMatches.assign(n, -1);

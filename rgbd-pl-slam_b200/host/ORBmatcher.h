@@ -59,6 +59,12 @@ class ORBmatcher {
   int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, const float th = 3.0);
   template <class KeyFrameT, class MapPointT>
   int Fuse(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, float th, std::vector<MapPointT*>& vpReplacePoint);
+  // Search matches between MapPoints seen in KF1 and KF2 transforming by a Sim3 [s12*R12|t12] (LoopClosing::ComputeSim3)
+  // (ORBmatcher.h:116).  Both directions run on the device; the transforms, the invariance test, PredictScale and the
+  // agreement pass are evaluated here.  Further members read: pMP->GetIndexInKeyFrame(pKF2).
+  template <class KeyFrameT, class MapPointT>
+  int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                   const cv::Mat& t12, const float th);
   // Search matches between MapPoints in a KeyFrame and ORB in a Frame (Relocalisation, TrackReferenceKeyFrame)
   template <class KeyFrameT, class FrameT, class MapPointT>
   int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches);
@@ -102,6 +108,11 @@ class ORBmatcher {
   void FuseSearch(const KeyFrameGridView& KF, const float pose[12], const float ow[3], bool useScw, const LoopPointsView& P, float th,
                   std::vector<int>& vnBestIdx);
 
+  // One direction of SearchBySim3 on views: the points (world coordinates) go into their own key frame's camera with poseOwn
+  // (R?w | t?w) and into the other camera with pose2 (sR | t); KFother is the key frame they are searched in.
+  void Sim3Search(const KeyFrameGridView& KFother, const float poseOwn[12], const float pose2[12], const LoopPointsView& P, float th,
+                  std::vector<int>& vnBestIdx);
+
   // Brute force constrained to ORB that belong to the same vocabulary node (Relocalisation / TrackReferenceKeyFrame).
   // vnMatches[iF] = index in the KeyFrame matched to F's feature iF, or -1.
   int SearchByBoW(const FrameView& KF, FrameView& F, std::vector<int>& vnMatches);
@@ -119,6 +130,8 @@ class ORBmatcher {
   // vnMatches12[i1] = KF2 feature matched to KF1 feature i1, or -1.
   int SearchForTriangulation(const FrameView& KF1, const FrameView& KF2, const float F12[9], float ex, float ey,
                              const bool bOnlyStereo, std::vector<int>& vnMatches12);
+  // sR12 = s12 * R12, sR21 = (1.0 / s12) * R12.t(), t21 = -sR21 * t12 as the reference's cv::Mat expressions evaluate (@0x83a8e)
+  static void Sim3Transforms(float s12, const float R12[9], const float t12[3], float sR12[9], float sR21[9], float t21[3]);
   // C2 = R2w * Cw + t2w projected with KF2's intrinsics, with the binary's rounding sequence (@0x86b9c-0x86f8b)
   static void Epipole(const float R2w[9], const float t2w[3], const float Cw[3], float fx, float fy, float cx, float cy,
                       float* ex, float* ey);

@@ -369,6 +369,100 @@ int ORBmatcher::Fuse(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>&
   return nFused;
 }
 
+// ORBmatcher.h:116 (@0x838b0)
+namespace dropin {
+// a * x + b for a 3x4 [A | b] and a 3-vector, as cv::gemm's small-matrix path evaluates it (float products summed left to right,
+// then (double)sum + (double)b rounded to float)
+inline void affine3(const float T[12], const float x[3], float y[3]) {
+  for (int r = 0; r < 3; ++r) {
+    volatile float p0 = T[4 * r] * x[0], p1 = T[4 * r + 1] * x[1], p2 = T[4 * r + 2] * x[2];
+    volatile float s01 = p0 + p1;
+    volatile float s = s01 + p2;
+    y[r] = (float)((double)s + (double)T[4 * r + 3]);
+  }
+}
+template <class KeyFrameT, class MapPointT>
+inline void sim3_points(const std::vector<MapPointT*>& vp, const std::vector<uint8_t>& already, const float Tw[12], const float T2[12],
+                        KeyFrameT* pKFother, LoopPointsView* pv) {
+  const int n = (int)vp.size();
+  init_loop_points(n, pv);
+  for (int i = 0; i < n; ++i) {
+    MapPointT* pMP = vp[i];
+    if (!pMP || already[i] || pMP->isBad()) continue;
+    const cv::Mat p3Dw = pMP->GetWorldPos();
+    float X[3], pa[3], pb[3];
+    for (int k = 0; k < 3; ++k) X[k] = pv->worldPos[3 * (size_t)i + k] = p3Dw.template at<float>(k);
+    affine3(Tw, X, pa);
+    affine3(T2, pa, pb);
+    double n2 = 0;
+    for (int k = 0; k < 3; ++k) n2 += (double)pb[k] * (double)pb[k];
+    const float dist3D = (float)std::sqrt(n2);
+    if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+    pv->level[i] = pMP->PredictScale(dist3D, pKFother);
+    const cv::Mat d = pMP->GetDescriptor();
+    std::memcpy(pv->descriptors.ptr(i), d.ptr(0), 32);
+    pv->valid[i] = 1;
+  }
+}
+}  // namespace dropin
+
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float& s12,
+                             const cv::Mat& R12, const cv::Mat& t12, const float th) {
+  KeyFrameGridView kv1, kv2;
+  dropin::view_of_keyframe_grid(pKF1, &kv1);
+  dropin::view_of_keyframe_grid(pKF2, &kv2);
+  KeyFrameT* kfs[2] = {pKF1, pKF2};
+  float Tw[2][12];
+  for (int s = 0; s < 2; ++s) {
+    const cv::Mat R = kfs[s]->GetRotation(), t = kfs[s]->GetTranslation();
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) Tw[s][4 * r + c] = R.template at<float>(r, c);
+      Tw[s][4 * r + 3] = t.template at<float>(r);
+    }
+  }
+  float R9[9], t3[3], sR12[9], sR21[9], t21[3];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) R9[3 * r + c] = R12.template at<float>(r, c);
+    t3[r] = t12.template at<float>(r);
+  }
+  Sim3Transforms(s12, R9, t3, sR12, sR21, t21);
+  float T21[12], T12[12];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) { T21[4 * r + c] = sR21[3 * r + c]; T12[4 * r + c] = sR12[3 * r + c]; }
+    T21[4 * r + 3] = t21[r];
+    T12[4 * r + 3] = t3[r];
+  }
+  const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+  const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+  dropin::require((int)vpMatches12.size() == N1 && (int)kv1.mvKeysUn.size() == N1 && (int)kv2.mvKeysUn.size() == N2,
+                  "vpMatches12 / key-frame members differ in length");
+  std::vector<uint8_t> vbAlreadyMatched1(N1, 0), vbAlreadyMatched2(N2, 0);
+  for (int i = 0; i < N1; ++i) {
+    MapPointT* pMP = vpMatches12[i];
+    if (pMP) {
+      vbAlreadyMatched1[i] = 1;
+      const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+      if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = 1;
+    }
+  }
+  LoopPointsView p1, p2;
+  dropin::sim3_points(vpMapPoints1, vbAlreadyMatched1, Tw[0], T21, pKF2, &p1);
+  dropin::sim3_points(vpMapPoints2, vbAlreadyMatched2, Tw[1], T12, pKF1, &p2);
+  std::vector<int> vnMatch1, vnMatch2;
+  Sim3Search(kv2, Tw[0], T21, p1, th, vnMatch1);
+  Sim3Search(kv1, Tw[1], T12, p2, th, vnMatch2);
+  int nFound = 0;
+  for (int i1 = 0; i1 < N1; ++i1) {
+    const int idx2 = vnMatch1[i1];
+    if (idx2 >= 0 && vnMatch2[idx2] == i1) {
+      vpMatches12[i1] = vpMapPoints2[idx2];
+      nFound++;
+    }
+  }
+  return nFound;
+}
+
 // ORBmatcher.h:104 (@0x80150)
 template <class KeyFrameT, class FrameT, class MapPointT>
 int ORBmatcher::SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {

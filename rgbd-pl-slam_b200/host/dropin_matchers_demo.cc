@@ -30,6 +30,8 @@ class MapPoint {  // include/MapPoint.h: the members the matchers touch
   // map-graph bookkeeping called by ORBmatcher::Fuse: the demo's stand-ins log the call and apply the minimum effect a later
   // iteration can observe, exactly like the stand-ins of tests/golden/reference_code.py under which the reference's Fuse was run
   bool IsInKeyFrame(KeyFrame*) { return inKF; }
+  int GetIndexInKeyFrame(KeyFrame*) { return idxInKF2; }
+  int idxInKF2 = -1;  // demo: where the second key frame of case_sim3 observes this point
   void AddObservation(KeyFrame* pKF, size_t idx);
   void Replace(MapPoint* pMP);
   bool inKF = false;
@@ -533,6 +535,66 @@ static void case_fuse(const std::string& pfx, bool sim3) {
   save(pfx + "log", g_log);
 }
 
+// ---- LoopClosing::ComputeSim3: matcher.SearchBySim3(mpCurrentKF, pKF, vpMapPointMatches, s, R, t, 7.5) ----
+static void case_sim3() {
+  const auto par = load<float>("s3_par");  // th, gwi, ghi, logScaleFactor, s12
+  const auto R12 = load<float>("s3_R12"), t12 = load<float>("s3_t12");
+  const auto mi = load<int32_t>("s3_matched_in");
+  KeyFrame K[2];
+  for (int s = 0; s < 2; ++s) {
+    const std::string p = s ? "s3_kf2_" : "s3_kf1_", q = s ? "s3_mp2_" : "s3_mp1_";
+    const auto kdesc = load<uint8_t>(p + "desc"), state = load<uint8_t>(q + "state"), mdesc = load<uint8_t>(q + "desc");
+    const auto kxy = load<float>(p + "xy"), cam4 = load<float>(p + "cam4"), sf = load<float>(p + "scale_factors"), tcw = load<float>(p + "tcw");
+    const auto xyz = load<float>(q + "xyz"), rng = load<float>(q + "dist_range");
+    const auto koct = load<int32_t>(p + "octave"), gs = load<int32_t>(p + "grid_start"), gi = load<int32_t>(p + "grid_items"),
+               bounds = load<int32_t>(p + "bounds4");
+    const int n = (int)koct.size();
+    KeyFrame& KF = K[s];
+    KF.mvKeysUn.resize(n);
+    for (int i = 0; i < n; ++i) {
+      KF.mvKeysUn[i].pt = cv::Point2f(kxy[2 * i], kxy[2 * i + 1]);
+      KF.mvKeysUn[i].octave = koct[i];
+    }
+    KF.mDescriptors = mat_u8(kdesc, n);
+    KF.mvScaleFactors = sf; KF.mnScaleLevels = (int)sf.size(); KF.mfLogScaleFactor = par[3];
+    KF.fx = cam4[0]; KF.fy = cam4[1]; KF.cx = cam4[2]; KF.cy = cam4[3];
+    KF.mnMinX = bounds[0]; KF.mnMinY = bounds[1]; KF.mnMaxX = bounds[2]; KF.mnMaxY = bounds[3];
+    KF.mfGridElementWidthInv = par[1]; KF.mfGridElementHeightInv = par[2];
+    KF.mGrid.assign(64, std::vector<std::vector<size_t> >(48));
+    for (int ix = 0; ix < 64; ++ix)
+      for (int iy = 0; iy < 48; ++iy)
+        for (int k = gs[ix * 48 + iy]; k < gs[ix * 48 + iy + 1]; ++k) KF.mGrid[ix][iy].push_back((size_t)gi[k]);
+    float R9[9], t3[3];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) R9[3 * r + c] = tcw[4 * r + c];
+      t3[r] = tcw[4 * r + 3];
+    }
+    KF.R = mat_f(R9, 3, 3); KF.t = mat_f(t3, 3, 1);
+    KF.mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+      if (!state[i]) continue;
+      MapPoint* mp = new_mp();
+      mp->id = i; mp->mbBad = state[i] == 2;
+      mp->mWorldPos = mat_f(&xyz[3 * (size_t)i], 3, 1);
+      mp->mDescriptor = desc_row(mdesc, i);
+      mp->mfMinDistance = rng[2 * i]; mp->mfMaxDistance = rng[2 * i + 1];
+      if (s) mp->idxInKF2 = i;
+      KF.mvpMapPoints[i] = mp;
+    }
+  }
+  const int n1 = (int)K[0].mvKeysUn.size();
+  std::vector<MapPoint*> vpMatches12(n1, nullptr);
+  for (int i = 0; i < n1; ++i)
+    if (mi[i] >= 0) vpMatches12[i] = K[1].mvpMapPoints[mi[i]];
+  ORBmatcher matcher(0.75f, true);
+  const float s12 = par[4];
+  const int nFound = matcher.SearchBySim3(&K[0], &K[1], vpMatches12, s12, mat_f(R12.data(), 3, 3), mat_f(t12.data(), 3, 1), par[0]);
+  std::vector<int32_t> out(n1 + 1);
+  for (int i = 0; i < n1; ++i) out[i] = (vpMatches12[i] && mi[i] < 0) ? vpMatches12[i]->id : -1;
+  out[n1] = nFound;
+  save("s3_out", out);
+}
+
 // ---- LoopClosing::ComputeSim3: matcher.SearchByBoW(mpCurrentKF, pKF, vvpMapPointMatches[i]) ----
 static void case_bow_keyframes() {
   const auto par = load<float>("bk_par");  // nnratio, ori
@@ -623,6 +685,7 @@ int main(int argc, char** argv) {
     case_loop_projection();
     case_fuse("fu_", false);
     case_fuse("fs_", true);
+    case_sim3();
     case_triangulation();
     // an unfilled member must be reported, not read out of bounds
     Frame bad, last;

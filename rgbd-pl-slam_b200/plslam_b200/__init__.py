@@ -799,7 +799,7 @@ def search_by_projection_sim3_host(kf, mp, scw, matched_in, th):
 class FuseJob(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("mp_valid", "mp_xyz", "mp_normal", "mp_dist_range", "mp_desc", "mp_level", "kf_xy", "kf_octave",
                                           "kf_uright", "kf_desc", "grid_start", "grid_items", "scale_factors", "inv_level_sigma2", "best_idx")] + \
-               [("pose", C.c_float * 12), ("ow", C.c_float * 3), ("cam", C.c_float * 5), ("bounds", C.c_int32 * 4), ("grid_width_inv", C.c_float),
+               [("pose", C.c_float * 12), ("pose2", C.c_float * 12), ("ow", C.c_float * 3), ("cam", C.c_float * 5), ("bounds", C.c_int32 * 4), ("grid_width_inv", C.c_float),
                 ("grid_height_inv", C.c_float), ("log_scale_factor", C.c_float), ("th", C.c_float), ("grid_cols", C.c_int32),
                 ("grid_rows", C.c_int32), ("n_levels", C.c_int32), ("use_scw", C.c_int32), ("m", C.c_int32), ("n", C.c_int32)]
 
@@ -829,6 +829,57 @@ def fuse_search_host(kf, mp, th, scw=None):
     j.grid_cols, j.grid_rows, j.n_levels, j.use_scw, j.m, j.n = 64, 48, len(sf), 0 if scw is None else 1, m, n
     _check(lib().plslam_match_fuse_search_host(C.byref(j)))
     return out[:m]
+
+
+def sim3_transforms(s12, R12, t12):
+    """sR12, sR21, t21 of ORBmatcher::SearchBySim3 with the reference's arithmetic (plslam_sim3_transforms)."""
+    R = np.ascontiguousarray(R12, np.float32).reshape(9); t = np.ascontiguousarray(t12, np.float32).reshape(3)
+    sR12, sR21, t21 = np.empty(9, np.float32), np.empty(9, np.float32), np.empty(3, np.float32)
+    f = lib().plslam_sim3_transforms
+    f.argtypes, f.restype = [C.c_float] + [C.c_void_p] * 5, None
+    f(float(s12), _vp(R), _vp(t), _vp(sR12), _vp(sR21), _vp(t21))
+    return sR12.reshape(3, 3), sR21.reshape(3, 3), t21
+
+
+def search_by_sim3_host(kf1, kf2, mp1, mp2, s12, R12, t12, th, matched_in):
+    """ORBmatcher::SearchBySim3 on host arrays (layout: tests/matchdata.py sim3_case): the two directions through
+    plslam_match_fuse_search_host (use_scw = 2), the agreement pass here -> (match12 int32 [N1], nFound)."""
+    n1, n2 = len(kf1["desc"]), len(kf2["desc"])
+    matched_in = np.asarray(matched_in, np.int32)
+    already1 = matched_in >= 0
+    already2 = np.zeros(n2, bool)
+    already2[matched_in[already1]] = True
+    sR12, sR21, t21 = sim3_transforms(s12, R12, t12)
+    t12 = np.asarray(t12, np.float32).reshape(3)
+    def direction(kf_own, mp, already, kf_other, sR, tt):
+        m, n = len(mp["desc"]), len(kf_other["desc"])
+        keep = []
+        def a(x, dt):
+            x = np.ascontiguousarray(x, dt); keep.append(x); return x.ctypes.data
+        sf = np.ascontiguousarray(kf_other["scale_factors"], np.float32)
+        out = np.empty(max(m, 1), np.int32)
+        j = FuseJob()
+        j.mp_valid = a((np.asarray(mp["state"]) == 1) & ~already, np.uint8)
+        j.mp_xyz, j.mp_dist_range, j.mp_desc = a(mp["xyz"], np.float32), a(mp["dist_range"], np.float32), a(mp["desc"], np.uint8)
+        j.kf_xy, j.kf_octave, j.kf_desc = a(kf_other["xy"], np.float32), a(kf_other["octave"], np.int32), a(kf_other["desc"], np.uint8)
+        j.grid_start, j.grid_items, j.scale_factors = a(kf_other["grid_start"], np.int32), a(kf_other["grid_items"], np.int32), sf.ctypes.data
+        j.best_idx = out.ctypes.data
+        j.pose = (C.c_float * 12)(*np.asarray(kf_own["tcw"], np.float32).reshape(12))
+        j.pose2 = (C.c_float * 12)(*np.hstack([sR, np.asarray(tt, np.float32).reshape(3, 1)]).astype(np.float32).reshape(12))
+        j.cam = (C.c_float * 5)(*(list(np.asarray(kf_other["cam4"], np.float32)) + [0.0]))
+        j.bounds = (C.c_int32 * 4)(*[int(v) for v in kf_other["bounds4"]])
+        j.grid_width_inv, j.grid_height_inv = float(kf_other["gwi"]), float(kf_other["ghi"])
+        j.log_scale_factor, j.th = float(kf_other["log_sf"]), float(th)
+        j.grid_cols, j.grid_rows, j.n_levels, j.use_scw, j.m, j.n = 64, 48, len(sf), 2, m, n
+        _check(lib().plslam_match_fuse_search_host(C.byref(j)))
+        return out[:m]
+    m1 = direction(kf1, mp1, already1, kf2, sR21, t21)
+    m2 = direction(kf2, mp2, already2, kf1, sR12, t12)
+    match12 = np.full(n1, -1, np.int32)
+    ok = (m1 >= 0)
+    ok[ok] = m2[m1[ok]] == np.flatnonzero(ok)
+    match12[ok] = m1[ok]
+    return match12, int(ok.sum())
 
 
 class FrustumJob(C.Structure):

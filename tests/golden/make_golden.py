@@ -426,6 +426,21 @@ def reflib2():
     print("Fuse(pKF, Scw, vpPoints, th, vpReplacePoint): (nFused, logged calls, replacements)", fs)
     out["fu_n"] = np.array(len(fu))
     print("Fuse(pKF, vpMapPoints, th): (nFused, logged calls)", fu)
+    # ORBmatcher::SearchBySim3 on two faked KeyFrames with their own faked map points
+    from matchdata import sim3_case
+    s3 = []
+    for seed in (1, 2):
+        (ka, da), (kb, db) = feats[seed]
+        for s12, th in ((1.0, 7.5), (1.3, 7.5), (0.8, 3.0)):
+            kf1, kf2, mp1, mp2, sv, R12, t12, mi = sim3_case(ka, da, kb, db, sf, seed=seed, s12=s12)
+            m_out, n = R.search_by_sim3(kf1, kf2, mp1, mp2, sv, R12, t12, th, mi)
+            k = len(s3)
+            out["s3%d_args" % k] = np.array([seed, s12, th], np.float64)
+            assert np.array_equal(m_out[mi >= 0], mi[mi >= 0])
+            out["s3%d_match" % k], out["s3%d_n" % k] = np.where(mi < 0, m_out, -1).astype(np.int32), np.array(n)
+            s3.append(n)
+    out["s3_n"] = np.array(len(s3))
+    print("SearchBySim3:", s3)
     # Frame::isInFrustum on a faked Frame and faked MapPoints (GetWorldPos, GetNormal, the invariance range and PredictScale are
     # the library's own); the outputs are what the function leaves in the map points
     from matchdata import frustum_case

@@ -453,6 +453,27 @@ static void expr_assign(const void*, const MatExpr* e, Mat* m, int type) {
     for (int i = 0; i < A->rows; ++i) std::memcpy(m->data + (size_t)i * m->stepp[0], D.data + (size_t)i * D.stepp[0], (size_t)A->cols * 4);
     return;
   }
+  if ((e->flags >> 8) == 'A' || (e->flags >> 8) == 'T') {
+    // 'A': s * a or -a = MatOp_AddEx(a, alpha): convertTo with a scale, dst = src * (float)alpha + (float)0.
+    // 'T': alpha * a.t() = MatOp_T: transpose, then (alpha != 1) the same scaled conversion.
+    const Mat* A = &e->a;
+    const bool tr = (e->flags >> 8) == 'T';
+    const int rows = tr ? A->cols : A->rows, cols = tr ? A->rows : A->cols;
+    const float scale = (float)e->alpha;
+    Mat D;
+    mat_init_empty(&D);
+    mat_create(&D, rows, cols, 5);
+    for (int i = 0; i < rows; ++i)
+      for (int j = 0; j < cols; ++j) {
+        const float v = tr ? at(A, j, i) : at(A, i, j);
+        if (tr && e->alpha == 1) { at(&D, i, j) = v; continue; }
+        volatile float prod = v * scale;
+        at(&D, i, j) = prod + 0.0f;
+      }
+    mat_create(m, rows, cols, 5);
+    for (int i = 0; i < rows; ++i) std::memcpy(m->data + (size_t)i * m->stepp[0], D.data + (size_t)i * D.stepp[0], (size_t)cols * 4);
+    return;
+  }
   if ((e->flags >> 8) == 'D') {  // a / s = MatOp_AddEx(a, alpha = 1./s): convertTo with a scale, cvtScale_<float, float, float>:
     const Mat* A = &e->a;         // dst = src * (float)alpha + (float)0
     const float scale = (float)e->alpha, shift = 0.0f;
@@ -519,8 +540,9 @@ void shim_neg(MatExpr* ret, const MatExpr* e) {
 void shim_mul_em(MatExpr* ret, const MatExpr* e, const Mat* m) asm("_ZN2cvmlERKNS_7MatExprERKNS_3MatE");
 void shim_mul_em(MatExpr* ret, const MatExpr* e, const Mat* m) {
   TRACE("operator*(MatExpr, Mat)");
-  if ((e->flags >> 8) != 'T') __builtin_trap();
-  expr_init(ret, 'G', 1);
+  // MatOp::matmul: a transposed operand becomes GEMM_A_T with scale = alpha; a scaled operand (-a, s * a) GEMM with scale = alpha
+  if ((e->flags >> 8) != 'T' && (e->flags >> 8) != 'A') __builtin_trap();
+  expr_init(ret, 'G', (e->flags >> 8) == 'T' ? 1 : 0);
   hdr_copy(&ret->a, &e->a);
   hdr_copy(&ret->b, m);
   ret->alpha = e->alpha;
@@ -592,6 +614,32 @@ double shim_dot(const Mat* self, const InputArray* other) {
   for (; i < a.size(); ++i) r += (double)a[i] * b[i];
   return r;
 }
+// ---- ORBmatcher::SearchBySim3 (@0x838b0): s12 * R12, (1.0 / s12) * R12.t(), -sR21 * t12 ----
+void shim_mul_dm(MatExpr* ret, double s, const Mat* a) asm("_ZN2cvmlEdRKNS_3MatE");
+void shim_mul_dm(MatExpr* ret, double s, const Mat* a) {
+  TRACE("operator*(double %g, Mat)", s);
+  expr_init(ret, 'A', 0);
+  hdr_copy(&ret->a, a);
+  ret->alpha = s;
+}
+void shim_mul_de(MatExpr* ret, double s, const MatExpr* e) asm("_ZN2cvmlEdRKNS_7MatExprE");
+void shim_mul_de(MatExpr* ret, double s, const MatExpr* e) {
+  TRACE("operator*(double %g, MatExpr)", s);
+  if ((e->flags >> 8) != 'T') __builtin_trap();
+  expr_init(ret, 'T', 1);
+  hdr_copy(&ret->a, &e->a);
+  ret->alpha = e->alpha * s;
+}
+void shim_neg_m(MatExpr* ret, const Mat* a) asm("_ZN2cvngERKNS_3MatE");
+void shim_neg_m(MatExpr* ret, const Mat* a) {
+  TRACE("operator-(Mat)");
+  expr_init(ret, 'A', 0);
+  hdr_copy(&ret->a, a);
+  ret->alpha = -1;
+}
+// MapPoint::GetIndexInKeyFrame replaced for the harness: the index is a field of the faked map point (+0x3f4, -1 = not observed)
+int stub_GetIndexInKeyFrame(char* self, char* kf) asm("_ZN9ORB_SLAM28MapPoint18GetIndexInKeyFrameEPNS_8KeyFrameE");
+int stub_GetIndexInKeyFrame(char* self, char*) { return *(int*)(self + 0x3f4); }
 // ---- ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (@0x880f0): sRcw / scw, tcw / scw ----
 void shim_div_ms(MatExpr* ret, const Mat* a, double s) asm("_ZN2cvdvERKNS_3MatEd");
 void shim_div_ms(MatExpr* ret, const Mat* a, double s) {
@@ -1411,6 +1459,44 @@ class RefLibrary:
             bi = (b_ - base) // 0x400 if kind == 3 else b_
             log.append((int(kind), int(ai), int(bi)))
         return (int(nf), log) if scw is None else (int(nf), log, replace)
+
+    # ---- ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (@0x838b0, LoopClosing::ComputeSim3) ----
+    def search_by_sim3(self, kf1, kf2, mp1, mp2, s12, R12, t12, th, matched_in):
+        """kf1 / kf2 as make_keyframe (with tcw); mp1 / mp2: the key frames' own map points, one per feature (state 0 = none, 1 good,
+        2 bad); matched_in int32 [N1]: feature of KF2 whose map point is already in vpMatches12[i] (-1 = none).  Returns
+        (vpMatches12 as indices into KF2's features, nFound)."""
+        keep = []
+        for kf in (kf1, kf2):
+            kf.setdefault("uright", np.full(len(kf["desc"]), -1, np.float32))
+            kf.setdefault("inv_level_sigma2", np.ones(len(kf["scale_factors"]), np.float32))
+            kf.setdefault("ow", np.zeros(3, np.float32)); kf.setdefault("mbf", 0.0)
+        b1, b2 = self.make_keyframe(kf1, keep), self.make_keyframe(kf2, keep)
+        n1, n2 = len(kf1["desc"]), len(kf2["desc"])
+        base1, base2 = self.make_map_points(mp1, keep), self.make_map_points(mp2, keep)
+        for i in range(n1):
+            C.c_int32.from_address(base1 + 0x400 * i + 0x3f4).value = -1
+        for i in range(n2):
+            C.c_int32.from_address(base2 + 0x400 * i + 0x3f4).value = i      # KF2's own points are observed in KF2 at their index
+        v1 = np.array([base1 + 0x400 * i if mp1["state"][i] else 0 for i in range(n1)], np.uint64)
+        v2 = np.array([base2 + 0x400 * i if mp2["state"][i] else 0 for i in range(n2)], np.uint64)
+        for b, v in ((b1, v1), (b2, v2)):
+            o = (C.c_uint64 * 3).from_address(b + 0x520)
+            o[0], o[1], o[2] = v.ctypes.data, v.ctypes.data + v.nbytes, v.ctypes.data + v.nbytes
+        vm = np.array([base2 + 0x400 * int(j) if j >= 0 else 0 for j in matched_in], np.uint64)
+        vv = (C.c_uint64 * 3)()
+        vv[0], vv[1], vv[2] = vm.ctypes.data, vm.ctypes.data + vm.nbytes, vm.ctypes.data + vm.nbytes
+        Rm = np.ascontiguousarray(R12, np.float32).reshape(3, 3); tm = np.ascontiguousarray(t12, np.float32).reshape(3, 1)
+        rmat, tmat = (C.c_uint64 * 12)(), (C.c_uint64 * 12)()
+        self._fmat_at(C.addressof(rmat), Rm); self._fmat_at(C.addressof(tmat), tm)
+        sv, thv = C.c_float(np.float32(s12)), np.float32(th)
+        fn = getattr(self.lib, "_ZN9ORB_SLAM210ORBmatcher12SearchBySim3EPNS_8KeyFrameES2_RSt6vectorIPNS_8MapPointESaIS5_EERKfRKN2cv3MatESE_f")
+        fn.argtypes, fn.restype = [C.c_void_p] * 7 + [C.c_float], C.c_int
+        matcher = (C.c_uint8 * 8)()
+        C.c_float.from_address(C.addressof(matcher)).value = np.float32(0.75)
+        matcher[4] = 1
+        nf = fn(C.addressof(matcher), b1, b2, C.addressof(vv), C.addressof(sv), C.addressof(rmat), C.addressof(tmat), thv)
+        out = np.array([(int(p) - base2) // 0x400 if p else -1 for p in vm], np.int32)
+        return out, int(nf)
 
     # ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (@0x86b30) ----
     # KeyFrame: fx/fy/cx/cy @0x130..0x13c, N @0x154, mvKeysUn @0x170, mvuRight @0x188, mDescriptors @0x1b8, mFeatVec @0x248,

@@ -275,3 +275,48 @@ def fuse_case(kps_kf, desc_kf, kps_src, desc_src, scale_factors, W=640, H=480, s
         mp["alias"] = rng.choice(good, m).astype(np.int32)
         mp["state"] = st
     return kf, mp, kf_points
+
+
+def sim3_case(kps1, desc1, kps2, desc2, scale_factors, W=640, H=480, seed=0, s12=1.2):
+    """LoopClosing::ComputeSim3-like inputs for ORBmatcher::SearchBySim3: two key frames with their own map points (one per
+    feature, some missing or bad) and a similarity (s12, R12, t12) from camera 2 to camera 1 under which the points of each key
+    frame project near the corresponding features of the other (the synthetic pair differs by ~3 px)."""
+    rng = np.random.default_rng(seed + 900)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    fx = fy = np.float32(520.0); cx = np.float32(W / 2 - 0.5); cy = np.float32(H / 2 - 0.5)
+    def rot(ax, ang):
+        c, s_ = np.cos(ang), np.sin(ang)
+        return np.array([[c, 0, s_], [0, 1, 0], [-s_, 0, c]]) if ax == 1 else np.array([[1, 0, 0], [0, c, -s_], [0, s_, c]])
+    R12 = rot(1, 0.03) @ rot(0, -0.02); t12 = np.array([0.05, -0.02, 0.04])
+    R1w, t1w = rot(1, 0.2), np.array([0.3, 0.1, -0.2])
+    R2w, t2w = rot(0, -0.1), np.array([-0.1, 0.2, 0.1])
+    def kf_of(kps, desc, R, t):
+        xy = np.stack([kps["x"], kps["y"]], 1).astype(np.float32)
+        gs, gi, (mnx, mxx, mny, mxy, gwi, ghi) = frame_grid(xy, W, H)
+        return dict(xy=np.ascontiguousarray(xy), octave=np.ascontiguousarray(kps["octave"], np.int32), desc=np.ascontiguousarray(desc),
+                    grid_start=gs, grid_items=gi, cam4=np.array([fx, fy, cx, cy], np.float32), bounds4=np.array([0, 0, W, H], np.int32),
+                    gwi=gwi, ghi=ghi, scale_factors=sf, log_sf=np.float32(np.log(np.float32(1.2))),
+                    tcw=np.hstack([R, t[:, None]]).astype(np.float32))
+    kf1, kf2 = kf_of(kps1, desc1, R1w, t1w), kf_of(kps2, desc2, R2w, t2w)
+    def points(kps, desc, shift, to_other, R, t):
+        n = len(kps)
+        z = 1.5 + rng.random(n) * 2.0
+        u = kps["x"].astype(np.float64) + shift + rng.normal(0, 2.0, n)
+        v = kps["y"].astype(np.float64) + shift + rng.normal(0, 2.0, n)
+        z[rng.random(n) < 0.03] *= -1.0
+        p_other = np.stack([(u - cx) * np.abs(z) / fx, (v - cy) * np.abs(z) / fy, z], 1)   # in the OTHER camera
+        p_own = to_other(p_other)                                                          # in this key frame's camera
+        pw = (p_own - t) @ R                                                               # world
+        d = np.linalg.norm(p_other, axis=1)
+        dmax = (d * sf[np.clip(kps["octave"], 0, len(sf) - 1)] * rng.uniform(0.7, 1.4, n)).astype(np.float32)
+        state = rng.choice(np.array([0, 1, 2], np.uint8), n, p=[0.15, 0.8, 0.05]).astype(np.uint8)
+        return dict(state=state, xyz=np.ascontiguousarray(pw.astype(np.float32)), normal=np.zeros((n, 3), np.float32),
+                    dist_range=np.ascontiguousarray(np.stack([dmax / sf[-1], dmax], 1).astype(np.float32)), desc=np.ascontiguousarray(desc))
+    mp1 = points(kps1, desc1, +3.0, lambda p2: s12 * (p2 @ R12.T) + t12, R1w, t1w)        # p1 = s12 R12 p2 + t12
+    mp2 = points(kps2, desc2, -3.0, lambda p1: ((p1 - t12) @ R12) / s12, R2w, t2w)        # p2 = R12^T (p1 - t12) / s12
+    n1 = len(kps1)
+    matched_in = np.full(n1, -1, np.int32)
+    cand = np.flatnonzero(mp2["state"] == 1)
+    pre = rng.choice(n1, n1 // 12, replace=False)
+    matched_in[pre] = rng.choice(cand, len(pre), replace=False)
+    return kf1, kf2, mp1, mp2, np.float32(s12), R12.astype(np.float32), t12.astype(np.float32), matched_in

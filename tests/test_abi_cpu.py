@@ -30,7 +30,7 @@ def test_struct_layouts():
     import plslam_b200 as pl
     assert pl.KP_DTYPE.itemsize == 28 and pl.KEYLINE_DTYPE.itemsize == 68
     assert C.sizeof(pl.KnnJob) == 32 and C.sizeof(pl.BowJob) == 144 and C.sizeof(pl.ProjJob) == 328 and C.sizeof(pl.TriJob) == 240
-    assert C.sizeof(pl.FuseJob) == 256 and C.sizeof(pl.KfProjJob) == 240 and C.sizeof(pl.FrustumJob) == 168 and C.sizeof(pl.FrontendIO) == 72 and C.sizeof(pl.LocalJob) == 160 and C.sizeof(pl.FrameCalib) == 40
+    assert C.sizeof(pl.FuseJob) == 304 and C.sizeof(pl.KfProjJob) == 240 and C.sizeof(pl.FrustumJob) == 168 and C.sizeof(pl.FrontendIO) == 72 and C.sizeof(pl.LocalJob) == 160 and C.sizeof(pl.FrameCalib) == 40
     assert [n for n in pl.KP_DTYPE.names] == ["x", "y", "size", "angle", "response", "octave", "class_id"]
 
 

@@ -141,6 +141,15 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
         for k in ("has", "nobs", "bad"):
             put(pfx + "kp_" + k, fkp[k])
         put(pfx + "par", [3.0 if pfx == "fu_" else 4.0, float(fkf["gwi"]), float(fkf["ghi"]), float(fkf["log_sf"]), float(fkf["mbf"])], np.float32)
+    # LoopClosing::ComputeSim3 (SearchBySim3)
+    from matchdata import sim3_case
+    skf1, skf2, smp1, smp2, ss12, sR12, st12, smi = sim3_case(ka, da, kb, db, sf, seed=21, s12=1.25)
+    for pfx, dd in (("s3_kf1_", skf1), ("s3_kf2_", skf2), ("s3_mp1_", smp1), ("s3_mp2_", smp2)):
+        for k, v in dd.items():
+            if k not in ("gwi", "ghi", "log_sf"):
+                put(pfx + k, v)
+    put("s3_R12", sR12, np.float32); put("s3_t12", st12, np.float32); put("s3_matched_in", smi, np.int32)
+    put("s3_par", [7.5, float(skf1["gwi"]), float(skf1["ghi"]), float(skf1["log_sf"]), float(ss12)], np.float32)
     # CreateNewMapPoints
     kps, desc = orc.extract(synth_frame(33))
     kf1, kf2, F12, pose, camt, sft, sg = triangulation_case(kps, desc, seed=33, stereo_fraction=0.5)
@@ -184,6 +193,9 @@ def test_matchers_through_the_reference_signatures(oracle, tmp_path):
     out = np.fromfile(d / "fs_out", np.int32)
     assert out[-1] == nf > 50 and np.array_equal(out[:-1], rep)
     assert np.array_equal(np.fromfile(d / "fs_log", np.int32).reshape(-1, 3), np.array(log, np.int32).reshape(-1, 3))
+    m, n = pl.search_by_sim3_host(skf1, skf2, smp1, smp2, ss12, sR12, st12, 7.5, smi)   # (pinned: test_golden_gpu.py, s3*)
+    out = np.fromfile(d / "s3_out", np.int32)
+    assert out[-1] == n > 50 and np.array_equal(out[:-1], m)
     ex, ey = pl.epipole(*pose, *camt)
     m12, n12, pairs = pl.search_for_triangulation_host(kf1, kf2, F12, ex, ey, sft, sg, False, True)
     out = np.fromfile(d / "tr_out", np.int32)

@@ -416,6 +416,36 @@ def test_fuse_sim3_equals_the_reference_matcher(oracle):
     assert total > 1000
 
 
+def _sim3_cases(g, extract, scale_factors):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from matchdata import sim3_case
+    from plslam_b200.synth import synth_pair
+    feats = {}
+    for k in range(int(g["s3_n"])):
+        seed, s12, th = g["s3%d_args" % k]
+        seed = int(seed)
+        if seed not in feats:
+            a, b = synth_pair(seed)
+            feats[seed] = (extract(a), extract(b))
+        (ka, da), (kb, db) = feats[seed]
+        yield (k,) + sim3_case(ka, da, kb, db, scale_factors, seed=seed, s12=float(s12)) + (float(th),)
+
+
+def test_search_by_sim3_equals_the_reference_matcher(oracle):
+    """ORBmatcher::SearchBySim3 (@0x838b0) executed from lib/libORB_SLAM2.so on two faked KeyFrames with their own faked map
+    points (three more matrix-expression shims: s * Mat, s * Mat.t(), -Mat): the mutually consistent matches it writes into
+    vpMatches12 and nFound (fixture s3*, scales 0.8 / 1 / 1.3)."""
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    o = oracle.OrbOracle()
+    total = 0
+    for k, kf1, kf2, mp1, mp2, s12, R12, t12, mi, th in _sim3_cases(g, o.extract, o.tables()["scale"]):
+        m, n = oracle.search_by_sim3(kf1, kf2, mp1, mp2, s12, R12, t12, th, mi)
+        assert n == int(g["s3%d_n" % k]) and np.array_equal(m, g["s3%d_match" % k]), k
+        total += n
+    assert total > 500
+
+
 def _frustum_cases(g):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

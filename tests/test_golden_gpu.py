@@ -257,6 +257,22 @@ def test_k_fuse_search_equals_the_reference_matcher():
     assert total > 1500
 
 
+def test_search_by_sim3_equals_the_reference_matcher():
+    """ORBmatcher::SearchBySim3 (@0x838b0) on the s3* fixtures: both directions on the device (k_fuse_search, sim3 mode), the
+    derived transforms from plslam_sim3_transforms, the agreement pass on the host."""
+    import plslam_b200 as pl
+    from oracle import bindings as ob
+    from test_golden_cpu import _sim3_cases
+    g = np.load(os.path.join(G, "reference_library2.npz"))
+    ex = pl.ORBextractor()
+    total = 0
+    for k, kf1, kf2, mp1, mp2, s12, R12, t12, mi, th in _sim3_cases(g, ex, _scale_factors()):
+        m, n = pl.search_by_sim3_host(kf1, kf2, mp1, mp2, s12, R12, t12, th, mi)
+        assert n == int(g["s3%d_n" % k]) and np.array_equal(m, g["s3%d_match" % k]), k
+        total += n
+    assert total > 500
+
+
 def test_k_is_in_frustum_equals_the_reference():
     """k_is_in_frustum (Frame::isInFrustum, @0xf5190) on the fz* fixtures: 3 x 3000 map points, every field the reference's
     function leaves in a MapPoint."""
