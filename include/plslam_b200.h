@@ -631,6 +631,33 @@ typedef struct plslam_frustum_job {
 int plslam_frame_is_in_frustum_batch_device(const plslam_frustum_job_t* d_jobs, int njobs, int max_m, void* stream);
 int plslam_frame_is_in_frustum_host(const plslam_frustum_job_t* job); /* HOST pointers inside *job */
 
+/* The line analogues of the Frame steps (reference include/Frame.h:267 UndistortKeyLines, :116 GetLinesInArea, :107
+ * isInFrustum(MapLine*, float)).  PARITY UNPINNED: the reference declares them and ships no definition in any form (no source;
+ * the prebuilt binary has no line code); the definitions follow the header contracts (include/MapLine.h:113-129) and the public
+ * PL-SLAM fork family, see oracle/frame_oracle.cc.  Host pointers, one frame per call. */
+/* both end points of n key lines through the pinned undistortPoints; xy4 / out_xy4: n x 4 (startX, startY, endX, endY) */
+int plslam_frame_undistort_keylines_host(const plslam_frame_calib_t* calib, const float* xy4, int n, float* out_xy4);
+/* nq window queries (x1, y1, x2, y2, r, minLevel, maxLevel as 7 floats each) over n key lines (pt.x, pt.y, angle, octave as 4
+ * floats each): out_start [nq + 1] offsets into out_items (capacity item_cap, indices ascending inside a query).  Returns
+ * PLSLAM_ERR_CAPACITY with out_start[nq] = the needed capacity when item_cap is too small. */
+int plslam_frame_lines_in_area_host(const float* queries7, int nq, const float* lines4, int n, int32_t* out_start,
+                                    int32_t* out_items, int item_cap);
+typedef struct plslam_line_frustum_job {
+  const float* ml_sp_ep;       /* M x 6 : MapLine::GetWorldPos() (start point, end point) */
+  const float* ml_normal;      /* M x 3 : GetNormal() */
+  const float* ml_dist_range;  /* M x 2 : mfMinDistance, mfMaxDistance */
+  uint8_t* in_view;            /* M : mbTrackInView */
+  float* proj;                 /* M x 6 : mTrackProjX1, Y1, X1R, X2, Y2, X2R */
+  int32_t* level;              /* M : mnTrackScaleLevel */
+  float* viewcos;              /* M : mTrackViewCos */
+  float cam[8];                /* fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY */
+  float tcw[12];               /* mRcw | mtcw */
+  float ow[3];                 /* mOw */
+  float mbf, log_scale_factor, viewing_cos_limit;
+  int32_t n_levels, m;
+} plslam_line_frustum_job_t;
+int plslam_frame_line_in_frustum_host(const plslam_line_frustum_job_t* job);
+
 /* ------------------------------------------------------------------------------------------------
  * On-disk formats either side of the path (host only, no device work).
  * ------------------------------------------------------------------------------------------------ */

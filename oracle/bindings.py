@@ -443,6 +443,44 @@ def fuse_replay(best_idx, mp, kf_points):
     return nf, log
 
 
+def undistort_keylines(calib10, xy4):
+    """Frame::UndistortKeyLines (UNPINNED definition, see frame_oracle.cc): n x 4 end points -> n x 4."""
+    xy4 = np.ascontiguousarray(xy4, np.float32)
+    out = np.empty_like(xy4)
+    c = np.ascontiguousarray(calib10, np.float32)
+    L = lib()
+    L.oracle_undistort_keylines.argtypes, L.oracle_undistort_keylines.restype = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], None
+    L.oracle_undistort_keylines(_p(c), _p(xy4), len(xy4), _p(out))
+    return out
+
+
+def get_lines_in_area(query7, lines4):
+    """Frame::GetLinesInArea (UNPINNED definition): query (x1, y1, x2, y2, r, minLevel, maxLevel) -> candidate indices."""
+    lines4 = np.ascontiguousarray(lines4, np.float32)
+    out = np.empty(max(len(lines4), 1), np.int32)
+    L = lib()
+    L.oracle_get_lines_in_area.argtypes = [C.c_float] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.oracle_get_lines_in_area.restype = C.c_int
+    q = [float(v) for v in query7]
+    n = L.oracle_get_lines_in_area(q[0], q[1], q[2], q[3], q[4], int(q[5]), int(q[6]), _p(lines4), len(lines4), _p(out), len(out))
+    return out[:n].copy()
+
+
+def line_in_frustum(sp_ep, normal, dist_range, cam8, tcw, ow, mbf, log_scale_factor, n_levels, cos_limit):
+    """Frame::isInFrustum(MapLine*, float) (UNPINNED definition) -> dict(in_view, proj [M,6], level, viewcos)."""
+    m = len(sp_ep)
+    a = [np.ascontiguousarray(sp_ep, np.float32), np.ascontiguousarray(normal, np.float32), np.ascontiguousarray(dist_range, np.float32),
+         np.ascontiguousarray(cam8, np.float32), np.ascontiguousarray(tcw, np.float32).reshape(12), np.ascontiguousarray(ow, np.float32).reshape(3)]
+    out = dict(in_view=np.zeros(max(m, 1), np.uint8), proj=np.zeros((max(m, 1), 6), np.float32), level=np.zeros(max(m, 1), np.int32),
+               viewcos=np.zeros(max(m, 1), np.float32))
+    L = lib()
+    L.oracle_line_in_frustum.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_int, C.c_float] + [C.c_void_p] * 4
+    L.oracle_line_in_frustum.restype = None
+    L.oracle_line_in_frustum(m, *[_p(x) for x in a], float(mbf), float(log_scale_factor), int(n_levels), float(cos_limit),
+                             _p(out["in_view"]), _p(out["proj"]), _p(out["level"]), _p(out["viewcos"]))
+    return {k: v[:m] for k, v in out.items()}
+
+
 def is_in_frustum(xyz, normal, dist_range, cam8, tcw, ow, mbf, log_scale_factor, n_levels, cos_limit):
     """Frame::isInFrustum over M map points -> dict(in_view, proj [M,3], level, viewcos)."""
     m = len(xyz)

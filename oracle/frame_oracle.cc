@@ -133,4 +133,94 @@ void oracle_frame_post(const float* calib10, const float* bounds4, const float* 
   grid_start[GC * GR] = off;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The line analogues of the Frame steps (reference include/Frame.h:107 isInFrustum(MapLine*, float), :116 GetLinesInArea, :267
+// UndistortKeyLines).  PARITY UNPINNED: the reference ships these as declarations only (no source, and lib/libORB_SLAM2.so is
+// stock ORB-SLAM2 without any line code).  The definitions below follow the header contracts (member names of
+// include/MapLine.h:113-129, the comments at Frame.h:106,115) and the public PL-SLAM fork family the reference derives from
+// (ORB-SLAM2_with_line: Frame.cc), restated from memory, with the point versions' arithmetic where they share a step.
+// ---------------------------------------------------------------------------------------------------------------------
+// Frame::UndistortKeyLines: both end points of every key line through cv::undistortPoints (the pinned primitive above); a zero
+// k1 copies.  xy: n x 4 (startPointX, startPointY, endPointX, endPointY).
+void oracle_undistort_keylines(const float* calib10, const float* xy4, int n, float* out_xy4) {
+  oracle_undistort_points(calib10, xy4, 2 * n, out_xy4);
+}
+// Frame::GetLinesInArea(x1, y1, x2, y2, r, minLevel, maxLevel): a key line is a candidate when the squared distance between
+// its mid point (KeyLine::pt) and the query's mid point is <= r * r, when (y1 - y2) / (x1 - x2) - keyline.angle <= r * 0.01
+// (the family's slope test, kept as written) and when its octave passes the level filter of GetFeaturesInArea.  lines: n x 4
+// (pt.x, pt.y, angle, octave as float).  Returns the number of candidates; out receives their indices in ascending order.
+int oracle_get_lines_in_area(float x1, float y1, float x2, float y2, float r, int minLevel, int maxLevel, const float* lines, int n,
+                             int* out, int cap) {
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel > 0);
+  const float mx = 0.5f * (x1 + x2), my = 0.5f * (y1 + y2);
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    const float px = lines[4 * i], py = lines[4 * i + 1], ang = lines[4 * i + 2];
+    const int oct = (int)lines[4 * i + 3];
+    const float dx = mx - px, dy = my - py;
+    const float distance = dx * dx + dy * dy;
+    if (distance > r * r) continue;
+    const float slope = (y1 - y2) / (x1 - x2) - ang;
+    if (slope > r * 0.01f) continue;
+    if (bCheckLevels) {
+      if (oct < minLevel) continue;
+      if (maxLevel >= 0 && oct > maxLevel) continue;
+    }
+    if (cnt < cap) out[cnt] = i;
+    ++cnt;
+  }
+  return cnt;
+}
+// Frame::isInFrustum(MapLine* pML, float viewingCosLimit): both end points in front of the camera and inside the image bounds,
+// the mid point inside the scale-invariance range and seen within the viewing-angle limit; fills mTrackProjX1/Y1/X1R, X2/Y2/X2R,
+// mnTrackScaleLevel, mTrackViewCos, mbTrackInView.  Arithmetic of the point version (oracle_is_in_frustum in match_oracle.cc):
+// gemm small path, float division, fused projections, norm and dot in double.  PredictScale(dist, logScaleFactor) =
+// ceil(log(mfMaxDistance / dist) / logScaleFactor) clamped to [0, nLevels - 1] with the restated logf.
+// sp_ep: M x 6 world end points; out_proj: M x 6 (u1, v1, u1r, u2, v2, u2r).
+extern "C" int oracle_predict_scale(float maxDistance, float dist, float logScaleFactor, int nLevels);
+void oracle_line_in_frustum(int M, const float* sp_ep, const float* normal, const float* distRange, const float* cam8,
+                            const float* Tcw, const float* Ow, float mbf, float logScaleFactor, int nLevels, float cosLimit,
+                            uint8_t* inView, float* proj6, int* level, float* viewCos) {
+  const float fx = cam8[0], fy = cam8[1], cx = cam8[2], cy = cam8[3], mnMinX = cam8[4], mnMaxX = cam8[5], mnMinY = cam8[6], mnMaxY = cam8[7];
+  for (int i = 0; i < M; ++i) {
+    inView[i] = 0;
+    for (int k = 0; k < 6; ++k) proj6[6 * i + k] = 0.f;
+    level[i] = 0;
+    viewCos[i] = 0.f;
+    float uv[2][3];
+    bool ok = true;
+    for (int e = 0; e < 2 && ok; ++e) {
+      const float* X = sp_ep + 6 * i + 3 * e;
+      float pc[3];
+      for (int r = 0; r < 3; ++r) {
+        const float p0 = Tcw[r * 4] * X[0], p1 = Tcw[r * 4 + 1] * X[1], p2 = Tcw[r * 4 + 2] * X[2];
+        pc[r] = (float)((double)((p0 + p1) + p2) + (double)Tcw[r * 4 + 3]);
+      }
+      if (pc[2] < 0.0f) { ok = false; break; }
+      const float invz = 1.0f / pc[2];
+      const float u = std::fmaf(pc[0] * fx, invz, cx), v = std::fmaf(pc[1] * fy, invz, cy);
+      if (u < mnMinX || u > mnMaxX || v < mnMinY || v > mnMaxY) { ok = false; break; }
+      uv[e][0] = u; uv[e][1] = v; uv[e][2] = std::fmaf(-invz, mbf, u);
+    }
+    if (!ok) continue;
+    float OM[3];
+    double n2 = 0;
+    for (int r = 0; r < 3; ++r) {
+      OM[r] = 0.5f * (sp_ep[6 * i + r] + sp_ep[6 * i + 3 + r]) - Ow[r];
+      n2 += (double)OM[r] * (double)OM[r];
+    }
+    const float dist = (float)std::sqrt(n2);
+    if (dist < 0.8f * distRange[2 * i] || dist > 1.2f * distRange[2 * i + 1]) continue;
+    double dot = 0;
+    for (int r = 0; r < 3; ++r) dot += (double)OM[r] * (double)normal[3 * i + r];
+    const float vc = (float)(dot / (double)dist);
+    if (vc < cosLimit) continue;
+    level[i] = oracle_predict_scale(distRange[2 * i + 1], dist, logScaleFactor, nLevels);
+    inView[i] = 1;
+    for (int e = 0; e < 2; ++e)
+      for (int k = 0; k < 3; ++k) proj6[6 * i + 3 * e + k] = uv[e][k];
+    viewCos[i] = vc;
+  }
+}
+
 }  // extern "C"

@@ -1,9 +1,11 @@
 // common.cuh — shared helpers for the sm_100a kernels and the C-ABI layer.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -127,8 +129,14 @@ struct StageTimer {
     }
   }
 };
-#define PL_STAGE_BEGIN(tm, name, st) do { if (tm) (tm)->begin(name, st); } while (0)
-#define PL_STAGE_END(tm, st) do { if (tm) (tm)->end(st); } while (0)
+// NVTX range per stage (tracing) when PLSLAM_NVTX=1: the ranges bracket the ENQUEUE of a stage's kernels on
+// the host thread (header-only nvtx3; a no-op unless a tool such as nsys is attached).
+inline bool nvtx_on() {
+  static const bool on = [] { const char* e = std::getenv("PLSLAM_NVTX"); return e && e[0] == '1'; }();
+  return on;
+}
+#define PL_STAGE_BEGIN(tm, name, st) do { if (::plslam::nvtx_on()) nvtxRangePushA(name); if (tm) (tm)->begin(name, st); } while (0)
+#define PL_STAGE_END(tm, st) do { if (tm) (tm)->end(st); if (::plslam::nvtx_on()) nvtxRangePop(); } while (0)
 
 #ifdef __CUDACC__
 // cvRound on float: round-half-even (x86 vcvtss2si in the reference binary)

@@ -11,6 +11,7 @@
 // (twin of oracle/frame_oracle.cc, which is pinned bit for bit against cv2 4.13's undistortPoints).
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 #include "common.cuh"
 #include "pl_math.cuh"
@@ -225,6 +226,111 @@ __global__ void __launch_bounds__(256) k_is_in_frustum(const plslam_frustum_job_
   J.viewcos[i] = vc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Line analogues of the Frame steps (Frame.h:267, :116, :107; parity unpinned, see the header and oracle/frame_oracle.cc).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_undistort_points(const __grid_constant__ plslam_frame_calib_t c, const float* __restrict__ xy,
+                                                          int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (c.k1 == 0.0f) {
+    out[2 * i] = xy[2 * i];
+    out[2 * i + 1] = xy[2 * i + 1];
+  } else {
+    undistort_point(c, xy[2 * i], xy[2 * i + 1], out + 2 * i, out + 2 * i + 1);
+  }
+}
+
+// GetLinesInArea: warp per query, lanes over the key lines 32 at a time, candidates appended in index order (ballot ranks).
+// Pass 0 counts (out_items == nullptr), pass 1 writes at out_start[q].
+__global__ void __launch_bounds__(256) k_lines_in_area(const float* __restrict__ queries7, int nq, const float* __restrict__ lines4, int n,
+                                                       int* __restrict__ counts, const int* __restrict__ out_start,
+                                                       int* __restrict__ out_items) {
+  const int lane = threadIdx.x & 31, q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const float* Q = queries7 + 7 * (size_t)q;
+  const float x1 = Q[0], y1 = Q[1], x2 = Q[2], y2 = Q[3], r = Q[4];
+  const int minLevel = (int)Q[5], maxLevel = (int)Q[6];
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel > 0);
+  const float mx = __fmul_rn(0.5f, __fadd_rn(x1, x2)), my = __fmul_rn(0.5f, __fadd_rn(y1, y2));
+  const float r2 = __fmul_rn(r, r), slopeMax = __fmul_rn(r, 0.01f);
+  const float slopeQ = __fdiv_rn(__fsub_rn(y1, y2), __fsub_rn(x1, x2));
+  int cnt = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int i = b + lane;
+    bool ok = false;
+    if (i < n) {
+      const float4 L = reinterpret_cast<const float4*>(lines4)[i];
+      const float dx = __fsub_rn(mx, L.x), dy = __fsub_rn(my, L.y);
+      const float distance = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      ok = !(distance > r2) && !(__fsub_rn(slopeQ, L.z) > slopeMax);
+      if (ok && bCheckLevels) {
+        const int oct = (int)L.w;
+        if (oct < minLevel || (maxLevel >= 0 && oct > maxLevel)) ok = false;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok && out_items) out_items[out_start[q] + cnt + __popc(m & ((1u << lane) - 1u))] = i;
+    cnt += __popc(m);
+  }
+  if (lane == 0 && counts) counts[q] = cnt;
+}
+
+__global__ void __launch_bounds__(256) k_line_in_frustum(const __grid_constant__ plslam_line_frustum_job_t J) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= J.m) return;
+  const float fx = J.cam[0], fy = J.cam[1], cx = J.cam[2], cy = J.cam[3];
+  const float mnMinX = J.cam[4], mnMaxX = J.cam[5], mnMinY = J.cam[6], mnMaxY = J.cam[7];
+  uint8_t inView = 0;
+  float pr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vc = 0.f;
+  int level = 0;
+  do {
+    float uv[6];
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float* X = J.ml_sp_ep + 6 * (size_t)i + 3 * e;
+      float pc[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float p0 = __fmul_rn(J.tcw[r * 4], X[0]), p1 = __fmul_rn(J.tcw[r * 4 + 1], X[1]), p2 = __fmul_rn(J.tcw[r * 4 + 2], X[2]);
+        pc[r] = (float)__dadd_rn((double)__fadd_rn(__fadd_rn(p0, p1), p2), (double)J.tcw[r * 4 + 3]);
+      }
+      if (pc[2] < 0.0f) { ok = false; break; }
+      const float invz = __fdiv_rn(1.0f, pc[2]);
+      const float u = __fmaf_rn(__fmul_rn(pc[0], fx), invz, cx), v = __fmaf_rn(__fmul_rn(pc[1], fy), invz, cy);
+      if (u < mnMinX || u > mnMaxX || v < mnMinY || v > mnMaxY) { ok = false; break; }
+      uv[3 * e] = u; uv[3 * e + 1] = v; uv[3 * e + 2] = __fmaf_rn(-invz, J.mbf, u);
+    }
+    if (!ok) break;
+    float OM[3];
+    double n2 = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      OM[r] = __fsub_rn(__fmul_rn(0.5f, __fadd_rn(J.ml_sp_ep[6 * (size_t)i + r], J.ml_sp_ep[6 * (size_t)i + 3 + r])), J.ow[r]);
+      n2 = __dadd_rn(n2, __dmul_rn((double)OM[r], (double)OM[r]));
+    }
+    const float dist = (float)sqrt(n2);
+    const float dMin = J.ml_dist_range[2 * (size_t)i], dMax = J.ml_dist_range[2 * (size_t)i + 1];
+    if (dist < __fmul_rn(0.8f, dMin) || dist > __fmul_rn(1.2f, dMax)) break;
+    double dot = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) dot = __dadd_rn(dot, __dmul_rn((double)OM[r], (double)J.ml_normal[3 * (size_t)i + r]));
+    const float c = (float)__ddiv_rn(dot, (double)dist);
+    if (c < J.viewing_cos_limit) break;
+    level = predict_scale_dev(dMax, dist, J.log_scale_factor, J.n_levels);
+    inView = 1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pr[k] = uv[k];
+    vc = c;
+  } while (false);
+  J.in_view[i] = inView;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) J.proj[6 * (size_t)i + k] = pr[k];
+  J.level[i] = level;
+  J.viewcos[i] = vc;
+}
+
 }  // namespace
 }  // namespace plslam
 
@@ -299,6 +405,86 @@ int plslam_frame_post_host(const plslam_frame_calib_t* calib, const float bounds
   }
   PL_CUDA(cudaMemcpy(grid_start, gs.p, (size_t)(NCELL + 1) * 4, cudaMemcpyDeviceToHost));
   if (n) PL_CUDA(cudaMemcpy(grid_items, gi.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return PLSLAM_OK;
+}
+
+int plslam_frame_undistort_keylines_host(const plslam_frame_calib_t* calib, const float* xy4, int n, float* out_xy4) {
+  PL_CHECK_ARG(calib && n >= 0);
+  if (n == 0) return PLSLAM_OK;
+  PL_CHECK_ARG(xy4 && out_xy4);
+  DevBuf in, out;
+  int rc;
+  if ((rc = in.ensure((size_t)n * 16)) || (rc = out.ensure((size_t)n * 16))) { in.release(); out.release(); return rc; }
+  cudaError_t e = cudaMemcpy(in.p, xy4, (size_t)n * 16, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_undistort_points<<<div_up(2 * n, 256), 256>>>(*calib, in.as<float>(), 2 * n, out.as<float>());
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_xy4, out.p, (size_t)n * 16, cudaMemcpyDeviceToHost);
+  in.release(); out.release();
+  if (e != cudaSuccess) { set_error("undistort_keylines: %s", cudaGetErrorString(e)); return PLSLAM_ERR_CUDA; }
+  return PLSLAM_OK;
+}
+
+int plslam_frame_lines_in_area_host(const float* queries7, int nq, const float* lines4, int n, int32_t* out_start,
+                                    int32_t* out_items, int item_cap) {
+  PL_CHECK_ARG(nq >= 0 && n >= 0 && out_start && item_cap >= 0);
+  out_start[0] = 0;
+  if (nq == 0) return PLSLAM_OK;
+  PL_CHECK_ARG(queries7 && (n == 0 || lines4) && (item_cap == 0 || out_items));
+  DevBuf dq, dl, dc, ds, di;
+  int rc = PLSLAM_OK;
+  cudaError_t e = cudaSuccess;
+  std::vector<int> cnt(nq, 0);
+  if ((rc = dq.ensure((size_t)nq * 28)) || (rc = dl.ensure((size_t)std::max(n, 1) * 16)) || (rc = dc.ensure((size_t)nq * 4)) ||
+      (rc = ds.ensure((size_t)(nq + 1) * 4))) goto done;
+  e = cudaMemcpy(dq.p, queries7, (size_t)nq * 28, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && n) e = cudaMemcpy(dl.p, lines4, (size_t)n * 16, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) goto done;
+  k_lines_in_area<<<div_up(nq, 8), 256>>>(dq.as<float>(), nq, dl.as<float>(), n, dc.as<int>(), nullptr, nullptr);
+  e = cudaMemcpy(cnt.data(), dc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) goto done;
+  for (int q = 0; q < nq; ++q) out_start[q + 1] = out_start[q] + cnt[q];
+  if (out_start[nq] > item_cap) { rc = PLSLAM_ERR_CAPACITY; set_error("lines_in_area: %d candidates, capacity %d", out_start[nq], item_cap); goto done; }
+  if (out_start[nq] > 0) {
+    if ((rc = di.ensure((size_t)out_start[nq] * 4))) goto done;
+    e = cudaMemcpy(ds.p, out_start, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) goto done;
+    k_lines_in_area<<<div_up(nq, 8), 256>>>(dq.as<float>(), nq, dl.as<float>(), n, nullptr, ds.as<int>(), di.as<int>());
+    e = cudaMemcpy(out_items, di.p, (size_t)out_start[nq] * 4, cudaMemcpyDeviceToHost);
+  }
+done:
+  dq.release(); dl.release(); dc.release(); ds.release(); di.release();
+  if (e != cudaSuccess) { set_error("lines_in_area: %s", cudaGetErrorString(e)); return PLSLAM_ERR_CUDA; }
+  return rc;
+}
+
+int plslam_frame_line_in_frustum_host(const plslam_line_frustum_job_t* job) {
+  PL_CHECK_ARG(job && job->m >= 0 && job->n_levels >= 1);
+  const int m = job->m;
+  if (m == 0) return PLSLAM_OK;
+  PL_CHECK_ARG(job->ml_sp_ep && job->ml_normal && job->ml_dist_range && job->in_view && job->proj && job->level && job->viewcos);
+  DevBuf in, out;
+  int rc;
+  if ((rc = in.ensure((size_t)m * 11 * 4)) || (rc = out.ensure((size_t)m * (24 + 4 + 4 + 1) + 64))) { in.release(); out.release(); return rc; }
+  float* dIn = in.as<float>();
+  plslam_line_frustum_job_t d = *job;
+  d.ml_sp_ep = dIn; d.ml_normal = dIn + 6 * (size_t)m; d.ml_dist_range = dIn + 9 * (size_t)m;
+  d.proj = out.as<float>(); d.viewcos = d.proj + 6 * (size_t)m;
+  d.level = reinterpret_cast<int32_t*>(d.viewcos + m); d.in_view = reinterpret_cast<uint8_t*>(d.level + m);
+  cudaError_t e = cudaMemcpy(dIn, job->ml_sp_ep, (size_t)m * 24, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dIn + 6 * (size_t)m, job->ml_normal, (size_t)m * 12, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dIn + 9 * (size_t)m, job->ml_dist_range, (size_t)m * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_line_in_frustum<<<div_up(m, 256), 256>>>(d);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(job->proj, d.proj, (size_t)m * 24, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(job->viewcos, d.viewcos, (size_t)m * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(job->level, d.level, (size_t)m * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(job->in_view, d.in_view, (size_t)m, cudaMemcpyDeviceToHost);
+  in.release(); out.release();
+  if (e != cudaSuccess) { set_error("line_in_frustum: %s", cudaGetErrorString(e)); return PLSLAM_ERR_CUDA; }
   return PLSLAM_OK;
 }
 

@@ -905,6 +905,47 @@ def is_in_frustum_host(xyz, normal, dist_range, cam8, tcw, ow, mbf, log_scale_fa
     return {k: v[:m] for k, v in out.items()}
 
 
+class LineFrustumJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ml_sp_ep", "ml_normal", "ml_dist_range", "in_view", "proj", "level", "viewcos")] + \
+               [("cam", C.c_float * 8), ("tcw", C.c_float * 12), ("ow", C.c_float * 3), ("mbf", C.c_float), ("log_scale_factor", C.c_float),
+                ("viewing_cos_limit", C.c_float), ("n_levels", C.c_int32), ("m", C.c_int32)]
+
+
+def undistort_keylines_host(calib, xy4):
+    """Frame::UndistortKeyLines (unpinned definition, include/plslam_b200.h): n x 4 end points -> n x 4."""
+    xy4 = np.ascontiguousarray(xy4, np.float32).reshape(-1, 4)
+    out = np.empty_like(xy4)
+    c = calib if isinstance(calib, FrameCalib) else FrameCalib.from_dict(calib)
+    _check(lib().plslam_frame_undistort_keylines_host(C.byref(c), _vp(xy4), len(xy4), _vp(out)))
+    return out
+
+
+def lines_in_area_host(queries7, lines4):
+    """Frame::GetLinesInArea for a batch of queries (unpinned definition) -> list of int32 index arrays."""
+    q = np.ascontiguousarray(queries7, np.float32).reshape(-1, 7)
+    l4 = np.ascontiguousarray(lines4, np.float32).reshape(-1, 4)
+    start = np.zeros(len(q) + 1, np.int32)
+    items = np.empty(max(len(q) * max(len(l4), 1), 1), np.int32)
+    _check(lib().plslam_frame_lines_in_area_host(_vp(q), len(q), _vp(l4), len(l4), _vp(start), _vp(items), len(items)))
+    return [items[start[i]:start[i + 1]].copy() for i in range(len(q))]
+
+
+def line_in_frustum_host(sp_ep, normal, dist_range, cam8, tcw, ow, mbf, log_scale_factor, n_levels, cos_limit):
+    """Frame::isInFrustum(MapLine*, float) over M map lines (unpinned definition) -> dict(in_view, proj [M,6], level, viewcos)."""
+    m = len(sp_ep)
+    x = np.ascontiguousarray(sp_ep, np.float32); nv = np.ascontiguousarray(normal, np.float32); dr = np.ascontiguousarray(dist_range, np.float32)
+    out = dict(in_view=np.zeros(max(m, 1), np.uint8), proj=np.zeros((max(m, 1), 6), np.float32), level=np.zeros(max(m, 1), np.int32),
+               viewcos=np.zeros(max(m, 1), np.float32))
+    j = LineFrustumJob(x.ctypes.data, nv.ctypes.data, dr.ctypes.data, out["in_view"].ctypes.data, out["proj"].ctypes.data,
+                       out["level"].ctypes.data, out["viewcos"].ctypes.data)
+    j.cam = (C.c_float * 8)(*np.asarray(cam8, np.float32))
+    j.tcw = (C.c_float * 12)(*np.asarray(tcw, np.float32).reshape(12))
+    j.ow = (C.c_float * 3)(*np.asarray(ow, np.float32).reshape(3))
+    j.mbf, j.log_scale_factor, j.viewing_cos_limit, j.n_levels, j.m = float(mbf), float(log_scale_factor), float(cos_limit), int(n_levels), m
+    _check(lib().plslam_frame_line_in_frustum_host(C.byref(j)))
+    return {k: v[:m] for k, v in out.items()}
+
+
 def predict_scale(max_distance, dist, log_scale_factor, n_levels):
     """MapPoint::PredictScale as the matcher kernels evaluate it."""
     f = lib().plslam_predict_scale
