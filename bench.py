@@ -371,12 +371,42 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def bind_host_threads(local, world):
+    """One rank per GPU on one node: keep the rank's submitting thread (and the pinned buffers it first touches) on the cores next
+    to its GPU.  NVML names the GPU's CPU affinity; when every GPU reports the same set (round 1: 0-31, NUMA 0 for all eight)
+    the set is split evenly over the local ranks so that they do not migrate over each other.  Returns what was done."""
+    info = {}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = sorted(c for c in range(ncpu) if (words[c // 64] >> (c % 64)) & 1)
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed] or allowed
+        nloc = max(1, min(world, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+        if nloc > 1 and len(cpus) >= 2 * nloc:
+            k = len(cpus) // nloc
+            cpus = cpus[(local % nloc) * k:(local % nloc + 1) * k]
+        os.sched_setaffinity(0, cpus)
+        info = {"cpus": "%d-%d (%d)" % (cpus[0], cpus[-1], len(cpus))}
+        try:
+            info["numa_node"] = int(open("/sys/bus/pci/devices/%s/numa_node" % pynvml.nvmlDeviceGetPciInfo(h).busId.lower()[4:]).read())
+        except Exception:
+            pass
+    except Exception as e:
+        info = {"unbound": str(e)[:80]}
+    return info
+
+
 def run_ours(a):
     import torch
     import plslam_b200 as pl
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    host_binding = bind_host_threads(local, world) if world > 1 else {}
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -590,6 +620,10 @@ def run_ours(a):
                            "steps_in_flight": depth, **voc_info,
                            "parallelism": "frames sharded over %d rank(s), no data-path collective" % world},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        # what one rank moved over PCIe while it was timed (its share of the wall clock of the e2e run): far below
+                        # the ~57 GB/s a B200 measured here sustains, i.e. the bus is not what the e2e figure waits for
+                        "per_rank_copy_gbs": {"h2d": h2d * a.steps / e2e_s / 1e9, "d2h": d2h * a.steps / e2e_s / 1e9},
+                        "host_binding": host_binding,
                         "by_api": {m: world * a.batch * a.steps / t for m, t in e2e_modes.items()},
                         "api": ("plslam_frontend_submit_host_wave (steps_in_flight steps per call) + plslam_frontend_wait_host" if e2e_mode == "wave"
                                 else "plslam_frontend_submit_host x K + plslam_frontend_wait_host") +
