@@ -63,8 +63,11 @@ def parse():
 
 
 WORKLOAD_PRESETS = {  # (width, height, nfeatures, batch, depth) of BASELINE.json's configs 3 and 5
-    "c3": (1280, 720, 2000, 128, 4),
-    "c5": (3840, 2160, 8000, 16, 2),
+    # batches in flight measured on B200 (profiles/r02_c35_sweep.log): C3 2.05 k frames/s at 4, 3.6 k at 12, 3.96 k at 24 (110 GB of
+    # workspace); C5 36.7 frames/s at 2, 79.8 at 6, 113 at 12, 90 at 20 (beyond ~300 frames in flight region growing switches to
+    # its one-warp-per-frame form, which needs far more frames than fit)
+    "c3": (1280, 720, 2000, 128, 24),
+    "c5": (3840, 2160, 8000, 16, 12),
 }
 
 
