@@ -835,7 +835,9 @@ __device__ __forceinline__ double rect_density(int n, const LsdRect& r) {
   return __ddiv_rn((double)n, __dmul_rn(sqrt(dist_sq_dev(r.x1, r.y1, r.x2, r.y2)), r.width));
 }
 
-// refine() + reduce_region_radius(); returns false when the region must be dropped. *n_io = region size.
+// refine() + reduce_region_radius() in their straight-line form (the CTA-per-frame kernel keeps it: its warps share one CTA's
+// instruction stream, and this is the form its inter-warp protocol was validated with); returns false when the region must be
+// dropped. *n_io = region size.
 template <int M>
 __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double prec, double p, LsdRect* rec,
                            double density_th, int variant) {
@@ -990,6 +992,171 @@ __device__ bool lsd_refine(const GrowCtx& C, int* n_io, double reg_angle, double
   return true;
 }
 
+// One seed of the LSD main loop: region_grow() -> region2rect() -> refine() (re-growing with the tolerance tau of the region's
+// first part) -> reduce_region_radius() (repeatedly), written as ONE loop around a single region-growing site and a single
+// rectangle-fitting site.  The straight-line form (grow; rect; refine{grow; rect; while{reduce; rect}}) inlines the growth twice and
+// the rectangle fit three times: 148 KB of code for k_lsd_grow, and with ~28 warps per SM at different places in it the warps
+// wait for instructions more than for anything else (ncu at saturation, 4096 frames per launch: stall_no_instruction 8.1 of 17
+// cycles per issued instruction, profiles/r02_kernels_ncu.md).  Same operations in the same order, hence the same result.
+// reg[0] must hold the seed pixel.  Returns whether the region yields a rectangle; *n_out = size of the region list left behind.
+template <int M>
+__device__ __forceinline__ bool lsd_seed_region(const GrowCtx& C, double prec, double p, double density_th, int min_reg_size,
+                                                int variant, LsdRect* rec, int* n_out) {
+  constexpr bool MW = M == GM_MW, BM = M == GM_BMS || M == GM_BMG;
+  const int lane = C.lane;
+  int phase = 0;          // 0 first growth, 1 re-grown by refine(), 2 inside reduce_region_radius()
+  double tol = prec;      // angular tolerance of the next growth
+  double reg_angle = 0, xc = 0, yc = 0, radSq = 0;
+  int n = 0;
+  while (true) {
+    if (BM && phase) __syncwarp();  // the bits refine() cleared are read by the growth that follows
+    n = (MW || (variant & 1)) ? lsd_region_grow_spec<M>(C, tol, &reg_angle) : lsd_region_grow<M>(C, tol, &reg_angle);
+    *n_out = n;
+    if (MW && C.mw_poisoned()) return false;
+    if (n < (phase ? 2 : min_reg_size)) return false;
+    while (true) {
+      lsd_region2rect(C, n, reg_angle, prec, p, rec);
+      const double density = rect_density(n, *rec);
+      if (density >= density_th) return true;
+      if (phase == 0) break;  // -> refine(): un-mark the region, estimate tau, grow again
+      if (phase == 1) {       // reduce_region_radius(): start from the farther end of the rectangle
+        const double radSq1 = dist_sq_dev(xc, yc, rec->x1, rec->y1), radSq2 = dist_sq_dev(xc, yc, rec->x2, rec->y2);
+        radSq = radSq1 > radSq2 ? radSq1 : radSq2;
+        phase = 2;
+      }
+      radSq = __dmul_rn(radSq, 0.75 * 0.75);
+      // The reference removes far points by swapping each with the current last element (that order defines the later
+      // sums).  Equivalent closed form (checked exhaustively against the sequential loop): with n' points kept, the far
+      // positions below n' in increasing order receive the kept points at or above n' in decreasing order.
+      if (n + (n >> 1) + 32 > (MW ? C.cap : C.P)) {  // no room for the scratch list behind the region (rare; kept for safety)
+        if (lane == 0) {
+          for (int i = 0; i < n; ++i) {
+            const unsigned pxy = C.reg_get(i);
+            const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+            if (dist_sq_dev(xc, yc, (double)px, (double)py) > radSq) {
+              if (MW) {
+                C.mw_release(py * C.sw + px);
+              } else if (BM) {
+                C.bm_clear<M>(py * C.sw + px);
+              } else {
+                unsigned* wp = C.wptr(py * C.sw + px);
+                *wp = *wp & ~USED_BIT;
+              }
+              C.reg_set(i, C.reg_get(n - 1));
+              C.reg_set(n - 1, pxy);
+              --n;
+              --i;
+            }
+          }
+        }
+        n = __shfl_sync(0xffffffffu, n, 0);
+      } else {
+        const unsigned FAR = 0x80000000u, FULL = 0xffffffffu, lt = (1u << lane) - 1u;  // row index < 2^15: bit 31 is free
+        int nfar = 0;
+        for (int c = 0; c < n; c += 32) {
+          const int i = c + lane;
+          bool far = false;
+          if (i < n) {
+            const unsigned pxy = C.reg_get(i);
+            const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+            far = dist_sq_dev(xc, yc, (double)px, (double)py) > radSq;
+            if (far) {
+              if (MW) {
+                C.mw_release(py * C.sw + px);
+              } else if (BM) {
+                C.bm_clear<M>(py * C.sw + px);
+              } else {
+                unsigned* wp = C.wptr(py * C.sw + px);
+                *wp = *wp & ~USED_BIT;
+              }
+              C.reg_set(i, pxy | FAR);
+            }
+          }
+          nfar += __popc(__ballot_sync(FULL, far));
+        }
+        __syncwarp();
+        const int nk = n - nfar;
+        // holes (far positions below nk, ascending) into scratch: the global list beyond n is free
+        unsigned* holes = C.regG + n;
+        int nh = 0;
+        for (int c = 0; c < nk; c += 32) {
+          const int i = c + lane;
+          const bool hole = i < nk && (C.reg_get(i) & FAR);
+          const unsigned b = __ballot_sync(FULL, hole);
+          if (hole) holes[nh + __popc(b & lt)] = (unsigned)i;
+          nh += __popc(b);
+        }
+        __syncwarp();
+        // fillers (kept positions at or above nk, descending): the k-th goes to the k-th hole
+        int nf = 0;
+        for (int c = n - 1; c >= nk; c -= 32) {
+          const int i = c - lane;
+          unsigned v = 0;
+          const bool fill = i >= nk && !((v = C.reg_get(i)) & FAR);
+          const unsigned b = __ballot_sync(FULL, fill);
+          if (fill) C.reg_set((int)holes[nf + __popc(b & lt)], v);
+          nf += __popc(b);
+        }
+        n = nk;
+      }
+      __syncwarp();
+      *n_out = n;
+      if (n < 2) return false;
+    }
+    // ---- refine(), first half: tau = 2 * standard deviation of the level-line angles near the seed
+    const unsigned seedxy = C.reg_get(0);
+    const int sy = (int)(seedxy >> 16), sx = (int)(seedxy & 0xffff);
+    xc = (double)sx;
+    yc = (double)sy;
+    const double ang_c = __dmul_rn((double)__uint_as_float(C.pix[sy * C.sw + sx].x), PL_DEG_TO_RADS);
+    double* sA = C.stage;
+    double* sF = C.stage + 32;
+    double* sV2 = C.stage + 64;
+    double acc = 0;
+    int cntN = 0;
+    for (int c = 0; c < n; c += 32) {
+      const int i = c + lane;
+      bool inside = false;
+      if (i < n) {
+        const unsigned pxy = C.reg_get(i);
+        const int py = (int)(pxy >> 16), px = (int)(pxy & 0xffff);
+        const int idx = py * C.sw + px;
+        const uint4 r = C.pix[idx];
+        if (MW) C.mw_release(idx);
+        else if (BM) C.bm_clear<M>(idx);
+        else *C.wptr(idx) = r.w & ~USED_BIT;
+        double flag = 0.0, v = 0.0;
+        if (sqrt(dist_sq_dev(xc, yc, (double)px, (double)py)) < rec->width) {
+          const double ang = __dmul_rn((double)__uint_as_float(r.x), PL_DEG_TO_RADS);
+          v = angle_diff_signed_dev(ang, ang_c);
+          flag = 1.0;
+        }
+        sA[lane] = v;
+        sF[lane] = flag;
+        sV2[lane] = __dmul_rn(v, v);
+        inside = flag != 0.0;
+      }
+      cntN += __popc(__ballot_sync(0xffffffffu, inside));
+      __syncwarp();
+      const int cnt = min(32, n - c);
+      // two ordered chains (sum of v, sum of v*v over the flagged points): lane 0 and lane 1 own one each
+      if (lane < 2) {
+        const double* row = lane == 0 ? sA : sV2;
+        for (int j = 0; j < cnt; ++j)
+          if (sF[j] != 0.0) acc = __dadd_rn(acc, row[j]);
+      }
+      __syncwarp();
+    }
+    const double sum = __shfl_sync(0xffffffffu, acc, 0), s_sum = __shfl_sync(0xffffffffu, acc, 1);
+    const double mean_angle = __ddiv_rn(sum, (double)cntN);
+    const double tau = __dmul_rn(
+        2.0, sqrt(__dadd_rn(__ddiv_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)), (double)cntN),
+                            __dmul_rn(mean_angle, mean_angle))));
+    tol = tau;
+    phase = 1;
+  }
+}
+
 constexpr int GROW_WARPS = 4;  // frames per CTA at most (one warp each): keeps the long-running kernel from holding every CTA slot of an SM
 // dynamic shared memory per frame: staging doubles, the head of the region list, and in GM_BMS the frame's bitmap
 __host__ __device__ inline size_t grow_smem_per_frame(int P, bool bitmap) {
@@ -1056,17 +1223,9 @@ __global__ void __launch_bounds__(32 * GROW_WARPS) k_lsd_grow(const __grid_const
       if (lane <= j) s = -1;
       if (lane == 0) C.reg_set(0, ((unsigned)(seed / L.sw) << 16) | (unsigned)(seed % L.sw));
       __syncwarp();
-      double reg_angle;
-      int n = (L.grow_variant & 1) ? lsd_region_grow_spec<M>(C, L.prec, &reg_angle) : lsd_region_grow<M>(C, L.prec, &reg_angle);
-      if (n < L.min_reg_size) continue;
       LsdRect rec;
-      GP_START();
-      lsd_region2rect(C, n, reg_angle, L.prec, L.p, &rec);
-      GP_ADD(2);
-      GP_START();
-      const bool keep = lsd_refine<M>(C, &n, reg_angle, L.prec, L.p, &rec, L.density_th, L.grow_variant);
-      GP_ADD(3);
-      if (!keep) continue;
+      int n = 0;
+      if (!lsd_seed_region<M>(C, L.prec, L.p, L.density_th, L.min_reg_size, L.grow_variant, &rec, &n)) continue;
       if (nrect < L.rect_cap) {
         if (lane == 0) rects[nrect] = rec;
       } else if (lane == 0) {
