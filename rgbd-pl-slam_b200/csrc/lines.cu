@@ -1010,7 +1010,9 @@ __device__ __forceinline__ bool lsd_seed_region(const GrowCtx& C, double prec, d
   int n = 0;
   while (true) {
     if (BM && phase) __syncwarp();  // the bits refine() cleared are read by the growth that follows
-    n = (MW || (variant & 1)) ? lsd_region_grow_spec<M>(C, tol, &reg_angle) : lsd_region_grow<M>(C, tol, &reg_angle);
+    (void)variant;  // (bit 0 once selected the one-accept-per-round scan, lsd_region_grow: dropped from this kernel, it doubled
+                    //  the growth code for an experiment switch; the function stays for reference)
+    n = lsd_region_grow_spec<M>(C, tol, &reg_angle);
     *n_out = n;
     if (MW && C.mw_poisoned()) return false;
     if (n < (phase ? 2 : min_reg_size)) return false;
