@@ -2327,6 +2327,9 @@ __global__ void __launch_bounds__(LBD_THREADS) k_lbd(const __grid_constant__ Lin
   // the tap indices (x - 1 -> 1 at x = 0, x + 1 -> W - 2 at x = W - 1), which stay inside the box.
   constexpr int LBD_CH = 32, LBD_TILE = 80, LBD_TROWS = 76;  // tile pitch 80: the box is widened to whole 4-byte words
   __shared__ __align__(16) uint8_t tile[LBD_TILE * LBD_TROWS];
+  // the chunk's positions, [step][row] (row-major over steps keeps a row's thread on its own bank column); in shared memory rather
+  // than registers so that the two loops over the chunk stay rolled: the unrolled form was 6.7 k instructions (107 KB of code)
+  __shared__ unsigned posS[LBD_CH][LBD_ROWS + 1];
   const bool wordLoads = ((reinterpret_cast<uintptr_t>(I) | (uintptr_t)pitch) & 3u) == 0;
   __shared__ int boxS[2][4];
   const bool rowThread = t < LBD_ROWS;
@@ -2358,22 +2361,19 @@ __global__ void __launch_bounds__(LBD_THREADS) k_lbd(const __grid_constant__ Lin
   const int xlo = W > 1 ? 1 : 0, xhi = W > 1 ? W - 2 : 0, ylo = H > 1 ? 1 : 0, yhi = H > 1 ? H - 2 : 0;
   for (int w0 = 0; w0 < lengthOfLSP; w0 += LBD_CH) {
     const int nst = min(LBD_CH, lengthOfLSP - w0);
-    unsigned pos[LBD_CH];  // (y << 16) | x of this row's steps
     int mnx = 0x7fff, mxx = 0, mny = 0x7fff, mxy = 0;
     if (rowThread) {
-#pragma unroll
-      for (int u = 0; u < LBD_CH; ++u) {
+#pragma unroll 1
+      for (int u = 0; u < nst; ++u) {
         short tc = (short)roundf(sCorX);
         const int x = (tc < 0) ? 0 : (tc > W - 1) ? W - 1 : tc;
         tc = (short)roundf(sCorY);
         const int y = (tc < 0) ? 0 : (tc > H - 1) ? H - 1 : tc;
-        pos[u] = ((unsigned)y << 16) | (unsigned)x;
-        if (u < nst) {
-          sCorX = __fadd_rn(sCorX, dL0);
-          sCorY = __fadd_rn(sCorY, dL1);
-          mnx = min(mnx, x); mxx = max(mxx, x);
-          mny = min(mny, y); mxy = max(mxy, y);
-        }
+        posS[u][hID] = ((unsigned)y << 16) | (unsigned)x;
+        sCorX = __fadd_rn(sCorX, dL0);
+        sCorY = __fadd_rn(sCorY, dL1);
+        mnx = min(mnx, x); mxx = max(mxx, x);
+        mny = min(mny, y); mxy = max(mxy, y);
       }
       if (hID == 0 || hID == LBD_ROWS - 1) {
         int* bs = boxS[hID ? 1 : 0];
@@ -2405,10 +2405,11 @@ __global__ void __launch_bounds__(LBD_THREADS) k_lbd(const __grid_constant__ Lin
     }
     __syncthreads();
     if (rowThread) {
-#pragma unroll
-      for (int u = 0; u < LBD_CH; ++u) {
-        if (u < nst) {
-          const int x = (int)(pos[u] & 0xffffu), y = (int)(pos[u] >> 16);
+#pragma unroll 2
+      for (int u = 0; u < nst; ++u) {
+        {
+          const unsigned pu = posS[u][hID];
+          const int x = (int)(pu & 0xffffu), y = (int)(pu >> 16);
           const int xm = x > 0 ? x - 1 : xlo, xp = x < W - 1 ? x + 1 : xhi;
           const int ym = y > 0 ? y - 1 : ylo, yp = y < H - 1 ? y + 1 : yhi;
           int dx, dy;
