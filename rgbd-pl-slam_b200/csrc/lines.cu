@@ -614,6 +614,8 @@ __device__ int lsd_region_grow_spec(const GrowCtx& C, double prec, double* reg_a
     const double arad = __dmul_rn((double)deg, PL_DEG_TO_RADS);
     const bool anyc = __any_sync(FULL, deg != NOTDEF_F);
     GP_ADD(0);
+    GP_CNT(6, m4);
+    GP_CNT(7, anyc ? 1 : 0);
     GP_START();
     if (anyc) {
       // lanes looking at the same pixel (MATCH.ANY costs a step per distinct value: only the candidate lanes take part)
@@ -1015,6 +1017,8 @@ __device__ __forceinline__ bool lsd_seed_region(const GrowCtx& C, double prec, d
     n = lsd_region_grow_spec<M>(C, tol, &reg_angle);
     *n_out = n;
     if (MW && C.mw_poisoned()) return false;
+    GP_CNT(15, (phase == 0 && n < min_reg_size) ? 1 : 0);
+    GP_CNT(5, (phase == 0 && n == 1) ? 1 : 0);
     if (n < (phase ? 2 : min_reg_size)) return false;
     while (true) {
       lsd_region2rect(C, n, reg_angle, prec, p, rec);
@@ -1936,40 +1940,54 @@ __device__ __forceinline__ double lsd_ntheta(double theta, float deg) {
   return n_theta;
 }
 
+// The part of a rectangle that rect_improve() changes and rect_nfa() reads, kept in registers (an LsdRect passed by
+// reference lives on the thread's stack: the round-1 form of this kernel moved 7x more local than global memory).
+struct NfaRect {
+  double x1, y1, x2, y2, width, p, prec;
+};
+
 // Row scan of rect_nfa(): counts the pixels of the rectangle (total) and, for up to 5 angular
 // tolerances at once, the aligned ones.  Warp-cooperative; results are warp-uniform.
 template <int NPREC>
-__device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* precs, const float* __restrict__ pix, int sw,
-                               int sh, int lane, int* total_out, int* alg_out) {
+__device__ __forceinline__ void rect_count_dev(const NfaRect& r, double theta, double rdx, double rdy, const double (&precs)[5],
+                                               const float* __restrict__ pix, int sw, int sh, int lane, int& total_out,
+                                               int (&alg_out)[5]) {
   const double hw = __dmul_rn(0.5, r.width);
-  const double dyhw = __dmul_rn(r.dy, hw), dxhw = __dmul_rn(r.dx, hw);
-  const double ux[4] = {__dsub_rn(r.x1, dyhw), __dsub_rn(r.x2, dyhw), __dadd_rn(r.x2, dyhw), __dadd_rn(r.x1, dyhw)};
-  const double uy[4] = {__dadd_rn(r.y1, dxhw), __dadd_rn(r.y2, dxhw), __dsub_rn(r.y2, dxhw), __dsub_rn(r.y1, dxhw)};
+  const double dyhw = __dmul_rn(rdy, hw), dxhw = __dmul_rn(rdx, hw);
+  double ux0 = __dsub_rn(r.x1, dyhw), ux1 = __dsub_rn(r.x2, dyhw), ux2 = __dadd_rn(r.x2, dyhw), ux3 = __dadd_rn(r.x1, dyhw);
+  double uy0 = __dadd_rn(r.y1, dxhw), uy1 = __dadd_rn(r.y2, dxhw), uy2 = __dsub_rn(r.y2, dxhw), uy3 = __dsub_rn(r.y1, dxhw);
+  // the corner that comes first in (y, x) order becomes corner 0; the rotation is done with selects so that the corners
+  // stay in registers (an array indexed by the offset would go to local memory)
   int off = 0;
-#pragma unroll
-  for (int i = 1; i < 4; ++i)
-    if (uy[i] < uy[off] || (uy[i] == uy[off] && ux[i] < ux[off])) off = i;
-  double vx[4], vy[4];
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    vx[n] = ux[(off + n) & 3];
-    vy[n] = uy[(off + n) & 3];
+  {
+    double by = uy0, bx = ux0;
+    if (uy1 < by || (uy1 == by && ux1 < bx)) { off = 1; by = uy1; bx = ux1; }
+    if (uy2 < by || (uy2 == by && ux2 < bx)) { off = 2; by = uy2; bx = ux2; }
+    if (uy3 < by || (uy3 == by && ux3 < bx)) { off = 3; }
   }
-  const int iy0 = (int)ceil(vy[0]), iy1 = (int)ceil(vy[1]), iy2 = (int)ceil(vy[2]), iy3 = (int)ceil(vy[3]);
-  const double s01 = (iy1 == iy0) ? 0.0 : __ddiv_rn(__dsub_rn(vx[1], vx[0]), __dsub_rn(vy[1], vy[0]));
-  const double s12 = (iy2 == iy1) ? 0.0 : __ddiv_rn(__dsub_rn(vx[2], vx[1]), __dsub_rn(vy[2], vy[1]));
-  const double s03 = (iy3 == iy0) ? 0.0 : __ddiv_rn(__dsub_rn(vx[3], vx[0]), __dsub_rn(vy[3], vy[0]));
-  const double s32 = (iy3 == iy2) ? 0.0 : __ddiv_rn(__dsub_rn(vx[2], vx[3]), __dsub_rn(vy[2], vy[3]));
+  if (off & 1) {
+    double t = ux0; ux0 = ux1; ux1 = ux2; ux2 = ux3; ux3 = t;
+    t = uy0; uy0 = uy1; uy1 = uy2; uy2 = uy3; uy3 = t;
+  }
+  if (off & 2) {
+    double t = ux0; ux0 = ux2; ux2 = t; t = ux1; ux1 = ux3; ux3 = t;
+    t = uy0; uy0 = uy2; uy2 = t; t = uy1; uy1 = uy3; uy3 = t;
+  }
+  const int iy0 = (int)ceil(uy0), iy1 = (int)ceil(uy1), iy2 = (int)ceil(uy2), iy3 = (int)ceil(uy3);
+  const double s01 = (iy1 == iy0) ? 0.0 : __ddiv_rn(__dsub_rn(ux1, ux0), __dsub_rn(uy1, uy0));
+  const double s12 = (iy2 == iy1) ? 0.0 : __ddiv_rn(__dsub_rn(ux2, ux1), __dsub_rn(uy2, uy1));
+  const double s03 = (iy3 == iy0) ? 0.0 : __ddiv_rn(__dsub_rn(ux3, ux0), __dsub_rn(uy3, uy0));
+  const double s32 = (iy3 == iy2) ? 0.0 : __ddiv_rn(__dsub_rn(ux2, ux3), __dsub_rn(uy2, uy3));
   int total = 0, alg[5] = {0, 0, 0, 0, 0};
   const int nrows = iy2 - iy0 + 1;
   const bool byRows = nrows >= 12;
   for (int yy = byRows ? iy0 + lane : iy0; yy <= iy2; yy += byRows ? 32 : 1) {
     if (yy < 0 || yy >= sh) continue;
     const double yd = (double)yy;
-    const double xa = (iy1 < yy) ? __dadd_rn(__dmul_rn(__dsub_rn(yd, vy[1]), s12), vx[1])
-                                 : __dadd_rn(__dmul_rn(__dsub_rn(yd, vy[0]), s01), vx[0]);
-    const double xb = (iy3 <= yy) ? __dadd_rn(__dmul_rn(__dsub_rn(yd, vy[3]), s32), vx[3])
-                                  : __dadd_rn(__dmul_rn(__dsub_rn(yd, vy[0]), s03), vx[0]);
+    const double xa = (iy1 < yy) ? __dadd_rn(__dmul_rn(__dsub_rn(yd, uy1), s12), ux1)
+                                 : __dadd_rn(__dmul_rn(__dsub_rn(yd, uy0), s01), ux0);
+    const double xb = (iy3 <= yy) ? __dadd_rn(__dmul_rn(__dsub_rn(yd, uy3), s32), ux3)
+                                  : __dadd_rn(__dmul_rn(__dsub_rn(yd, uy0), s03), ux0);
     int xs = (int)ceil(xa);
     int xe = (int)xb;
     if (xs < 0) xs = 0;
@@ -1977,7 +1995,7 @@ __device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* prec
     const float* row = pix + (size_t)yy * sw;
     for (int x = byRows ? xs : xs + lane; x <= xe; x += byRows ? 1 : 32) {
       ++total;
-      const double nt = lsd_ntheta(r.theta, __ldg(row + x));
+      const double nt = lsd_ntheta(theta, __ldg(row + x));
 #pragma unroll
       for (int j = 0; j < NPREC; ++j)
         if (nt <= precs[j]) ++alg[j];
@@ -1989,7 +2007,7 @@ __device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* prec
 #pragma unroll
     for (int j = 0; j < NPREC; ++j) alg[j] += __shfl_xor_sync(0xffffffffu, alg[j], d);
   }
-  *total_out = total;
+  total_out = total;
 #pragma unroll
   for (int j = 0; j < NPREC; ++j) alg_out[j] = alg[j];
 }
@@ -1997,88 +2015,90 @@ __device__ __noinline__ void rect_count_dev(const LsdRect& r, const double* prec
 // rect_improve(): within a stage the five candidate rectangles do not depend on which of them is
 // accepted, so their pixel counts are gathered first and the five nfa() evaluations (the expensive
 // part: log-gamma, a binomial tail) run on five lanes at once; the accept chain is then replayed in order.
-__device__ void lsd_nfa_rect(const LineParams& L, const float* __restrict__ pixAll, const LsdRect* __restrict__ rectsAll,
-                             LsdSegment* __restrict__ rectOut, uint8_t* __restrict__ rectValid, int f, int ri, int lane) {
+// Stage 0 is the rectangle as it arrives (one "variant", always accepted), so that the scan, nfa() and the replay have
+// ONE call site each and everything they touch stays in registers.
+__device__ __forceinline__ void lsd_nfa_rect(const LineParams& L, const float* __restrict__ pixAll,
+                                             const LsdRect* __restrict__ rectsAll, LsdSegment* __restrict__ rectOut,
+                                             uint8_t* __restrict__ rectValid, int f, int ri, int lane) {
   const float* pix = pixAll + (size_t)f * L.P;
-  LsdRect rec = rectsAll[(size_t)f * L.rect_cap + ri];
+  const LsdRect* rp = rectsAll + (size_t)f * L.rect_cap + ri;
+  NfaRect rec;
+  rec.x1 = rp->x1; rec.y1 = rp->y1; rec.x2 = rp->x2; rec.y2 = rp->y2; rec.width = rp->width; rec.p = rp->p; rec.prec = rp->prec;
+  const double theta = rp->theta, rdx = rp->dx, rdy = rp->dy;
   const double LOG_EPS = L.log_eps, LOG_NT = L.log_nt;
   const int sw = L.sw, sh = L.sh;
   const double delta = 0.5, delta_2 = delta / 2.0;
-  int total, alg[5];
-  double precs[5];
-  precs[0] = rec.prec;
-  rect_count_dev<1>(rec, precs, pix, sw, sh, lane, &total, alg);
-  double log_nfa = nfa_dev(total, alg[0], rec.p, LOG_NT);
-  for (int stage = 1; stage <= 5 && !(log_nfa > LOG_EPS); ++stage) {
-    const LsdRect rec0 = rec;  // the stage's variants derive from the rectangle it starts with
-    // variant n = the stage's step applied n+1 times (each step only if its width test holds, as in rect_improve)
-    auto variant = [&](int n, bool* ok) {
-      LsdRect r = rec0;
-      bool o = true;
-      for (int k = 0; k <= n; ++k) {
-        o = (stage == 1) || (__dsub_rn(r.width, delta) >= 0.5);
-        if (!o) break;
-        if (stage == 1 || stage == 5) {
-          r.p = __ddiv_rn(r.p, 2.0);
-          r.prec = __dmul_rn(r.p, PL_PI);
-        } else if (stage == 2) {
-          r.width = __dsub_rn(r.width, delta);
-        } else {
-          const double sx = __dmul_rn(-r.dy, delta_2), sy = __dmul_rn(r.dx, delta_2);
-          if (stage == 3) {
-            r.x1 = __dadd_rn(r.x1, sx); r.y1 = __dadd_rn(r.y1, sy);
-            r.x2 = __dadd_rn(r.x2, sx); r.y2 = __dadd_rn(r.y2, sy);
-          } else {
-            r.x1 = __dsub_rn(r.x1, sx); r.y1 = __dsub_rn(r.y1, sy);
-            r.x2 = __dsub_rn(r.x2, sx); r.y2 = __dsub_rn(r.y2, sy);
-          }
-          r.width = __dsub_rn(r.width, delta);
-        }
+  const double shx = __dmul_rn(-rdy, delta_2), shy = __dmul_rn(rdx, delta_2);  // the half-step of stages 3 and 4
+  // one step of a stage (the caller has checked the stage's width test)
+  auto step = [&](NfaRect& r, int stage) {
+    if (stage == 1 || stage == 5) {
+      r.p = __ddiv_rn(r.p, 2.0);
+      r.prec = __dmul_rn(r.p, PL_PI);
+    } else {
+      if (stage == 3) {
+        r.x1 = __dadd_rn(r.x1, shx); r.y1 = __dadd_rn(r.y1, shy);
+        r.x2 = __dadd_rn(r.x2, shx); r.y2 = __dadd_rn(r.y2, shy);
+      } else if (stage == 4) {
+        r.x1 = __dsub_rn(r.x1, shx); r.y1 = __dsub_rn(r.y1, shy);
+        r.x2 = __dsub_rn(r.x2, shx); r.y2 = __dsub_rn(r.y2, shy);
       }
-      *ok = o;
-      return r;
-    };
-    // pixel counts of the variants: lane n keeps (myTotal, myAlg, myP, myOk) of variant n
+      r.width = __dsub_rn(r.width, delta);
+    }
+  };
+  double log_nfa = 0.0;
+  for (int stage = 0; stage <= 5; ++stage) {
+    if (stage > 0 && log_nfa > LOG_EPS) break;
+    const NfaRect rec0 = rec;  // the stage's variants derive from the rectangle it starts with
+    // variant n = the stage's step applied n+1 times (each step only if its width test holds, as in rect_improve);
+    // lane n keeps (myTotal, myAlg, myP, myOk) of variant n
     int myTotal = 0, myAlg = 0;
     double myP = rec0.p;
     bool myOk = false;
     unsigned okMask = 0;
+    int total = 0, alg[5] = {0, 0, 0, 0, 0};
+    double precs[5] = {0, 0, 0, 0, 0};
     if (stage == 1 || stage == 5) {
-      bool ok0;
-      variant(0, &ok0);
-      if (ok0) {
+      if (stage == 1 || __dsub_rn(rec0.width, delta) >= 0.5) {  // the width does not change: one test for the five
         okMask = 0x1fu;
+        NfaRect r = rec0;
+#pragma unroll
         for (int n = 0; n < 5; ++n) {
-          bool o;
-          const LsdRect r = variant(n, &o);
+          step(r, 1);
           precs[n] = r.prec;
           if (lane == n) { myP = r.p; myOk = true; }
         }
-        rect_count_dev<5>(rec0, precs, pix, sw, sh, lane, &total, alg);
+        rect_count_dev<5>(rec0, theta, rdx, rdy, precs, pix, sw, sh, lane, total, alg);
         myTotal = total;
 #pragma unroll
         for (int n = 0; n < 5; ++n)
           if (lane == n) myAlg = alg[n];
       }
     } else {
-      for (int n = 0; n < 5; ++n) {
-        bool o;
-        const LsdRect r = variant(n, &o);
-        if (!o) break;
+      NfaRect r = rec0;
+      const int nv = stage == 0 ? 1 : 5;
+#pragma unroll 1
+      for (int n = 0; n < nv; ++n) {
+        if (stage > 0) {
+          if (!(__dsub_rn(r.width, delta) >= 0.5)) break;
+          step(r, stage);
+        }
         okMask |= 1u << n;
         precs[0] = r.prec;
-        rect_count_dev<1>(r, precs, pix, sw, sh, lane, &total, alg);
+        rect_count_dev<1>(r, theta, rdx, rdy, precs, pix, sw, sh, lane, total, alg);
         if (lane == n) { myTotal = total; myAlg = alg[0]; myP = r.p; myOk = true; }
       }
     }
     double myNfa = 0.0;
     if (myOk) myNfa = nfa_dev(myTotal, myAlg, myP, LOG_NT);
+    NfaRect r = rec0;
+#pragma unroll 1
     for (int n = 0; n < 5; ++n) {
+      if (!((okMask >> n) & 1u)) break;
+      if (stage > 0) step(r, stage);
       const double v = __shfl_sync(0xffffffffu, myNfa, n);
-      if (((okMask >> n) & 1u) && v > log_nfa) {
+      if (stage == 0 || v > log_nfa) {
         log_nfa = v;
-        bool o;
-        rec = variant(n, &o);
+        rec = r;
       }
     }
   }

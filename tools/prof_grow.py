@@ -19,7 +19,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); ls.extract_batch_device(imgs, out); e1.record(); torch.cuda.synchronize()
 L.plslam_debug_grow_prof(buf)
 v = [x / B for x in buf]
-names = ["load", "loop", "rect", "refine(incl regrow)", "kernel", "", "", "", "regions", "batches", "rounds", "mis-speculations", "points"]
+names = ["load", "loop", "rect", "refine(incl regrow)", "kernel", "single-pixel first growths", "frontier points over batches", "batches with a candidate", "regions", "batches", "rounds", "mis-speculations", "points", "", "", "first growths below min_reg_size"]
 print("lines pipeline %.2f ms/batch; per frame:" % e0.elapsed_time(e1))
 for n, x in zip(names, v):
     if n:
