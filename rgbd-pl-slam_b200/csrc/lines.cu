@@ -127,64 +127,88 @@ __global__ void __launch_bounds__(256) k_lsd_scale(const __grid_constant__ LineP
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double modgrad_of(int g2) { return sqrt(__dmul_rn((double)g2, 0.25)); }
 
+constexpr int GRAD_TW = 128, GRAD_TH = 8;  // pixels of a CTA's tile: warp = row, lane = 4 pixels 32 apart
 __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LineParams L, const uint8_t* __restrict__ scaled,
                                                   uint4* __restrict__ pix, float* __restrict__ degPlane,
                                                   int* __restrict__ maxg2, unsigned* __restrict__ bmAll) {
-  // Only ~1 pixel in 4 has a gradient above rho and needs the angle and its double-precision sin/cos.  The CTA's 32x8
-  // tile first writes the records of the undefined pixels and queues the defined ones in shared memory; the queue is
-  // then processed by full warps, so the double-precision pipe is not spent on mostly idle lanes.
-  __shared__ uint2 q[256];  // (pixel index in frame, gx & 0xffff | gy << 16)
-  __shared__ int qn;
+  // Only ~1 pixel in 4 has a gradient above rho and needs the angle and its double-precision sin/cos.  The CTA stages its
+  // 128x8 tile (+1 row, +1 column) in shared memory with word loads, writes the records of the undefined pixels and queues
+  // the defined ones (one shared-memory atomic per warp and 32 pixels); the queue is then processed by full warps, so the
+  // double-precision pipe is not spent on mostly idle lanes.  (Round-1 form: one pixel per thread, 196 k CTAs per batch with
+  // two barriers each and four byte loads per pixel - 0.90 ms per 256 frames, bound by barrier and shared-atomic latency.)
+  __shared__ uint32_t tile[GRAD_TH + 1][GRAD_TW / 4 + 1];
+  __shared__ uint2 q[GRAD_TW * GRAD_TH];  // (pixel index in frame, gx & 0xffff | gy << 16)
+  __shared__ int qn, cmax;
   const int f = blockIdx.z;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (threadIdx.x == 0) qn = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * GRAD_TW, y0 = blockIdx.y * GRAD_TH;
+  if (threadIdx.x == 0) { qn = 0; cmax = 0; }
+  {
+    const uint8_t* S = scaled + (size_t)f * L.spitch * L.sh;
+    for (int i = threadIdx.x; i < (GRAD_TH + 1) * (GRAD_TW / 4 + 1); i += 256) {
+      const int r = i / (GRAD_TW / 4 + 1), w = i - r * (GRAD_TW / 4 + 1);
+      const int yy = y0 + r, xb = x0 + 4 * w;
+      tile[r][w] = (yy < L.sh && xb < L.spitch) ? __ldg(reinterpret_cast<const uint32_t*>(S + (size_t)yy * L.spitch + xb)) : 0u;
+    }
+  }
   __syncthreads();
   uint4* P = pix + (size_t)f * L.P;
   float* DP = degPlane + (size_t)f * L.P;  // the angles alone, 4 B per pixel: what the rectangle scans of k_lsd_nfa read
-  int g2 = 0;
-  bool defined = false;
-  if (x < L.sw && y < L.sh) {
-    int gx = 0, gy = 0;
-    if (x < L.sw - 1 && y < L.sh - 1) {
-      const uint8_t* r0 = scaled + (size_t)f * L.spitch * L.sh + (size_t)y * L.spitch + x;
-      const uint8_t* r1 = r0 + L.spitch;
-      const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
+  const uint8_t* t0 = reinterpret_cast<const uint8_t*>(tile[warp]);
+  const uint8_t* t1 = reinterpret_cast<const uint8_t*>(tile[warp + 1]);
+  const int y = y0 + warp;
+  int m = 0;
+#pragma unroll
+  for (int j = 0; j < GRAD_TW / 32; ++j) {
+    const int xl = j * 32 + lane, x = x0 + xl;
+    int g2 = 0, gx = 0, gy = 0;
+    bool defined = false;
+    const bool inside = x < L.sw && y < L.sh;
+    if (inside && x < L.sw - 1 && y < L.sh - 1) {
+      const int DA = (int)t1[xl + 1] - (int)t0[xl], BC = (int)t0[xl + 1] - (int)t1[xl];
       gx = DA + BC;
       gy = DA - BC;
       g2 = gx * gx + gy * gy;
       defined = g2 >= L.g2_min;  // <=> sqrt(g2 / 4) > rho, threshold found on the host with the same double operations
     }
     const int idx = y * L.sw + x;
-    if (defined) q[atomicAdd(&qn, 1)] = make_uint2((unsigned)idx, ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16));
-    else {
+    const unsigned dm = __ballot_sync(0xffffffffu, defined);
+    int base = 0;
+    if (lane == 0 && dm) base = atomicAdd(&qn, __popc(dm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (defined) {
+      q[base + __popc(dm & ((1u << lane) - 1u))] = make_uint2((unsigned)idx, ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16));
+      m = max(m, g2);
+    } else if (inside) {
       P[idx] = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, (unsigned)g2);
       DP[idx] = NOTDEF_F;
     }
-  }
-  if (bmAll) {
-    // bitmap of the pixels that can never join a region (no defined angle): bit (idx & 31) of word (idx >> 5), zeroed by the
-    // caller.  A warp holds 32 consecutive pixels of one row = 32 consecutive bits, which straddle two words unless the row
-    // starts word-aligned.
-    const unsigned und = __ballot_sync(0xffffffffu, x < L.sw && y < L.sh && !defined);
-    if ((threadIdx.x & 31) == 0 && y < L.sh) {
-      const int bmWords = (L.P + 31) / 32;
-      unsigned* bm = bmAll + (size_t)f * ((bmWords + 3) / 4 * 4);
-      const int i0 = y * L.sw + blockIdx.x * 32, sft = i0 & 31;
-      if ((L.sw & 31) == 0) {
-        bm[i0 >> 5] = und;  // rows are whole words: this warp is the only writer (no memset needed)
-      } else if (und) {
-        atomicOr(bm + (i0 >> 5), und << sft);
-        if (sft && (und >> (32 - sft))) atomicOr(bm + (i0 >> 5) + 1, und >> (32 - sft));
+    if (bmAll) {
+      // bitmap of the pixels that can never join a region (no defined angle): bit (idx & 31) of word (idx >> 5), zeroed by the
+      // caller.  A warp holds 32 consecutive pixels of one row = 32 consecutive bits, which straddle two words unless the row
+      // starts word-aligned.
+      const unsigned und = __ballot_sync(0xffffffffu, inside && !defined);
+      if (lane == 0 && y < L.sh) {
+        const int bmWords = (L.P + 31) / 32;
+        unsigned* bm = bmAll + (size_t)f * ((bmWords + 3) / 4 * 4);
+        const int i0 = y * L.sw + x0 + j * 32, sft = i0 & 31;
+        if ((L.sw & 31) == 0) {
+          if (x0 + j * 32 < L.sw) bm[i0 >> 5] = und;  // rows are whole words: this warp is the only writer (no memset needed)
+        } else if (und) {
+          atomicOr(bm + (i0 >> 5), und << sft);
+          if (sft && (und >> (32 - sft))) atomicOr(bm + (i0 >> 5) + 1, und >> (32 - sft));
+        }
       }
     }
   }
-  int m = defined ? g2 : 0;
 #pragma unroll
   for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxg2 + f, m);
+  if (lane == 0 && m > 0) atomicMax(&cmax, m);
   __syncthreads();
-  if ((int)threadIdx.x < qn) {
-    const uint2 e = q[threadIdx.x];
+  if (threadIdx.x == 0 && cmax > 0) atomicMax(maxg2 + f, cmax);
+  const int n = qn;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const uint2 e = q[i];
     const int gx = (int)(short)(e.y & 0xffffu), gy = (int)e.y >> 16;
     const float deg = fast_atan2_dev((float)gx, (float)(-gy));
     const float af = (float)__dmul_rn((double)deg, PL_DEG_TO_RADS);
@@ -2728,7 +2752,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
     if ((rcb = ubm.ensure((size_t)std::max(batch, cfgB) * bmStride * sizeof(unsigned)))) return rcb;
     if (P.sw % 32) PL_CUDA(cudaMemsetAsync(ubm.p, 0, (size_t)batch * bmStride * sizeof(unsigned), st));
   }
-  k_lsd_grad<<<dim3(div_up(P.sw, 32), div_up(P.sh, 8), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(), degp.as<float>(),
+  k_lsd_grad<<<dim3(div_up(P.sw, GRAD_TW), div_up(P.sh, GRAD_TH), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(), degp.as<float>(),
                                                                              maxg2.as<int>(), usedMode != GM_REC ? ubm.as<unsigned>() : nullptr);
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_rowhist", st);
