@@ -130,7 +130,8 @@ __device__ __forceinline__ double modgrad_of(int g2) { return sqrt(__dmul_rn((do
 constexpr int GRAD_TW = 128, GRAD_TH = 8;  // pixels of a CTA's tile: warp = row, lane = 4 pixels 32 apart
 __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LineParams L, const uint8_t* __restrict__ scaled,
                                                   uint4* __restrict__ pix, float* __restrict__ degPlane,
-                                                  int* __restrict__ maxg2, unsigned* __restrict__ bmAll) {
+                                                  unsigned* __restrict__ g2Plane, int* __restrict__ maxg2,
+                                                  unsigned* __restrict__ bmAll) {
   // Only ~1 pixel in 4 has a gradient above rho and needs the angle and its double-precision sin/cos.  The CTA stages its
   // 128x8 tile (+1 row, +1 column) in shared memory with word loads, writes the records of the undefined pixels and queues
   // the defined ones (one shared-memory atomic per warp and 32 pixels); the queue is then processed by full warps, so the
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LinePa
   __syncthreads();
   uint4* P = pix + (size_t)f * L.P;
   float* DP = degPlane + (size_t)f * L.P;  // the angles alone, 4 B per pixel: what the rectangle scans of k_lsd_nfa read
+  unsigned* G2 = g2Plane + (size_t)f * L.P;  // gx^2 + gy^2 of the defined pixels, 0 elsewhere: what the seed sort reads
   const uint8_t* t0 = reinterpret_cast<const uint8_t*>(tile[warp]);
   const uint8_t* t1 = reinterpret_cast<const uint8_t*>(tile[warp + 1]);
   const int y = y0 + warp;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ LinePa
       defined = g2 >= L.g2_min;  // <=> sqrt(g2 / 4) > rho, threshold found on the host with the same double operations
     }
     const int idx = y * L.sw + x;
+    if (inside) G2[idx] = defined ? (unsigned)g2 : 0u;
     const unsigned dm = __ballot_sync(0xffffffffu, defined);
     int base = 0;
     if (lane == 0 && dm) base = atomicAdd(&qn, __popc(dm));
@@ -231,36 +234,41 @@ __device__ __forceinline__ int lsd_bin(int g2, int mg2) {
   return (int)__dmul_rn(modgrad_of(g2), bin_coef);
 }
 
-__global__ void __launch_bounds__(256) k_lsd_rowhist(const __grid_constant__ LineParams L, const uint4* __restrict__ pix,
-                                                     const int* __restrict__ maxg2, unsigned* __restrict__ rowhist) {
-  __shared__ unsigned hist[8][LSD_BINS];
+// The three kernels read the 4-byte g2 plane of k_lsd_grad (0 = no defined angle), not the 16-byte records, and the
+// histogram table has one row per GROUP of 8 image rows (the CTA of k_lsd_scatter rebuilds the split of a group's counts over
+// its 8 rows in shared memory): 0.85 GB of traffic per 256 frames of 640x480 instead of 3.0 GB with per-row tables.
+constexpr int SORT_ROWS = 8;  // image rows per CTA = per histogram row
+__global__ void __launch_bounds__(256) k_lsd_rowhist(const __grid_constant__ LineParams L, const unsigned* __restrict__ g2Plane,
+                                                     const int* __restrict__ maxg2, unsigned* __restrict__ grouphist) {
+  __shared__ unsigned hist[LSD_BINS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.y, y = blockIdx.x * 8 + warp;
-  if (y >= L.sh) return;
-  for (int i = lane; i < LSD_BINS; i += 32) hist[warp][i] = 0;
-  __syncwarp();
+  const int f = blockIdx.y, y = blockIdx.x * SORT_ROWS + warp;
+  for (int i = threadIdx.x; i < LSD_BINS; i += 256) hist[i] = 0;
+  __syncthreads();
   const int mg2 = maxg2[f];
-  const uint4* row = pix + (size_t)f * L.P + (size_t)y * L.sw;
-  if (mg2 > 0)
+  if (mg2 > 0 && y < L.sh) {
+    const unsigned* row = g2Plane + (size_t)f * L.P + (size_t)y * L.sw;
     for (int x = lane; x < L.sw; x += 32) {
-      const uint4 r = row[x];
-      if (__uint_as_float(r.x) != NOTDEF_F) atomicAdd(&hist[warp][lsd_bin((int)r.w, mg2)], 1u);
+      const unsigned g2 = row[x];
+      if (g2) atomicAdd(&hist[lsd_bin((int)g2, mg2)], 1u);
     }
-  __syncwarp();
-  unsigned* out = rowhist + ((size_t)f * L.sh + y) * LSD_BINS;
-  for (int i = lane; i < LSD_BINS; i += 32) out[i] = hist[warp][i];
+  }
+  __syncthreads();
+  unsigned* out = grouphist + ((size_t)f * gridDim.x + blockIdx.x) * LSD_BINS;
+  for (int i = threadIdx.x; i < LSD_BINS; i += 256) out[i] = hist[i];
 }
 
-__global__ void __launch_bounds__(LSD_BINS) k_lsd_colscan(const __grid_constant__ LineParams L, unsigned* __restrict__ rowhist,
-                                                          unsigned* __restrict__ binstart, int* __restrict__ nseeds) {
+__global__ void __launch_bounds__(LSD_BINS) k_lsd_colscan(const __grid_constant__ LineParams L, int ngroups,
+                                                          unsigned* __restrict__ grouphist, unsigned* __restrict__ binstart,
+                                                          int* __restrict__ nseeds) {
   __shared__ int tot[LSD_BINS];
   __shared__ int warpTmp[33];
   const int f = blockIdx.x, b = threadIdx.x;
-  unsigned* col = rowhist + (size_t)f * L.sh * LSD_BINS + b;
+  unsigned* col = grouphist + (size_t)f * ngroups * LSD_BINS + b;
   unsigned run = 0;
-  for (int y = 0; y < L.sh; ++y) {
-    const unsigned v = col[(size_t)y * LSD_BINS];
-    col[(size_t)y * LSD_BINS] = run;
+  for (int g = 0; g < ngroups; ++g) {
+    const unsigned v = col[(size_t)g * LSD_BINS];
+    col[(size_t)g * LSD_BINS] = run;
     run += v;
   }
   tot[LSD_BINS - 1 - b] = (int)run;  // descending bin order
@@ -270,37 +278,69 @@ __global__ void __launch_bounds__(LSD_BINS) k_lsd_colscan(const __grid_constant_
   if (b == 0) nseeds[f] = total;
 }
 
-__global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ LineParams L, const uint4* __restrict__ pix,
-                                                     const int* __restrict__ maxg2, const unsigned* __restrict__ rowhist,
+__global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ LineParams L, const unsigned* __restrict__ g2Plane,
+                                                     const int* __restrict__ maxg2, const unsigned* __restrict__ grouphist,
                                                      const unsigned* __restrict__ binstart, unsigned* __restrict__ seeds) {
-  __shared__ unsigned cnt[8][LSD_BINS];
+  __shared__ unsigned cnt[SORT_ROWS][LSD_BINS];
+  extern __shared__ unsigned sortList[];  // [SORT_ROWS][sw]: the seeds of each row in x order, x | bin << 16
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.y, y = blockIdx.x * 8 + warp;
-  if (y >= L.sh) return;
+  const unsigned lt = (1u << lane) - 1u;
+  const int f = blockIdx.y, y = blockIdx.x * SORT_ROWS + warp;
   const int mg2 = maxg2[f];
   if (mg2 <= 0) return;
   for (int i = lane; i < LSD_BINS; i += 32) cnt[warp][i] = 0;
   __syncwarp();
-  const uint4* row = pix + (size_t)f * L.P + (size_t)y * L.sw;
-  const unsigned* roff = rowhist + ((size_t)f * L.sh + y) * LSD_BINS;
-  const unsigned* bs = binstart + (size_t)f * LSD_BINS;
-  unsigned* out = seeds + (size_t)f * L.P;
-  for (int x0 = 0; x0 < L.sw; x0 += 32) {
-    const int x = x0 + lane;
-    bool def = false;
-    int bin = -1 - lane;  // unique non-matching key for undefined lanes
-    if (x < L.sw) {
-      const uint4 r = row[x];
-      if (__uint_as_float(r.x) != NOTDEF_F) {
-        def = true;
-        bin = lsd_bin((int)r.w, mg2);
+  const unsigned* row = g2Plane + (size_t)f * L.P + (size_t)y * L.sw;
+  unsigned* myList = sortList + (size_t)warp * L.sw;
+  // Pass 1: the row's seeds compacted in x order (~1 pixel in 4) with their bins (a double-precision square root each), and
+  // the row's count per bin; then, over the 8 warps, the offset of the row inside its group's share of each bin.
+  int nd = 0;
+  if (y < L.sh)
+    for (int x0 = 0; x0 < L.sw; x0 += 32) {
+      const int x = x0 + lane;
+      const unsigned g2 = x < L.sw ? row[x] : 0u;
+      const unsigned dm = __ballot_sync(0xffffffffu, g2 != 0u);
+      if (g2) {
+        const int bin = lsd_bin((int)g2, mg2);
+        atomicAdd(&cnt[warp][bin], 1u);
+        myList[nd + __popc(dm & lt)] = (unsigned)x | ((unsigned)bin << 16);
       }
+      nd += __popc(dm);
+    }
+  __syncthreads();
+  {
+    // cnt[w][b] becomes the position in the frame's seed list of the first seed of row w in bin b: start of the bin +
+    // the groups above + the rows of this group above
+    const unsigned* goff = grouphist + ((size_t)f * gridDim.x + blockIdx.x) * LSD_BINS;
+    const unsigned* bs = binstart + (size_t)f * LSD_BINS;
+    for (int b = threadIdx.x; b < LSD_BINS; b += 256) {
+      unsigned run = bs[b] + goff[b];
+#pragma unroll
+      for (int w = 0; w < SORT_ROWS; ++w) {
+        const unsigned v = cnt[w][b];
+        cnt[w][b] = run;
+        run += v;
+      }
+    }
+  }
+  __syncthreads();
+  if (y >= L.sh) return;
+  unsigned* out = seeds + (size_t)f * L.P;
+  // Pass 2: stable scatter, 32 seeds per step
+  for (int i0 = 0; i0 < nd; i0 += 32) {
+    const int i = i0 + lane;
+    const bool def = i < nd;
+    int bin = -1 - lane, x = 0;  // unique non-matching key for idle lanes
+    if (def) {
+      const unsigned e = myList[i];
+      bin = (int)(e >> 16);
+      x = (int)(e & 0xffffu);
     }
     const unsigned peers = __match_any_sync(0xffffffffu, bin);
     if (def) {
-      const int rank = __popc(peers & ((1u << lane) - 1));
+      const int rank = __popc(peers & lt);
       const unsigned base = cnt[warp][bin];
-      out[bs[bin] + roff[bin] + base + rank] = (unsigned)(y * L.sw + x);
+      out[base + rank] = (unsigned)(y * L.sw + x);
     }
     __syncwarp();
     if (def && (peers >> lane) == 1u) cnt[warp][bin] += __popc(peers);  // highest lane of each peer group
@@ -2570,7 +2610,7 @@ int debug_grow_prof(unsigned long long* out16) {
 LineExtractor::LineExtractor() {}
 
 LineExtractor::~LineExtractor() {
-  DevBuf* all[] = {&listpool, &rectstage, &recttmp, &owner, &degp, &scaled, &pix, &coef, &rowhist, &binstart, &maxg2, &seeds, &nseeds, &regbuf, &rects, &nrects,
+  DevBuf* all[] = {&listpool, &rectstage, &recttmp, &owner, &degp, &g2p, &ubm, &nfaq, &scaled, &pix, &coef, &rowhist, &binstart, &maxg2, &seeds, &nseeds, &regbuf, &rects, &nrects,
                    &rectout, &segs, &nsegs, &resp, &rowsum, &status, &stageIn, &stageKl, &stageDesc, &stageFuncs, &stageCnt};
   for (DevBuf* b : all) b->release();
   if (ownStream) cudaStreamDestroy(ownStream);
@@ -2681,7 +2721,8 @@ int LineExtractor::configure(int W, int H, int batch) {
   if ((rc = scaled.ensure(B * P.spitch * P.sh))) return rc;
   if ((rc = pix.ensure(B * P.P * sizeof(uint4)))) return rc;
   if ((rc = degp.ensure(B * P.P * sizeof(float)))) return rc;
-  if ((rc = rowhist.ensure(B * P.sh * LSD_BINS * sizeof(unsigned)))) return rc;
+  if ((rc = g2p.ensure(B * P.P * sizeof(unsigned)))) return rc;
+  if ((rc = rowhist.ensure(B * (size_t)div_up(P.sh, SORT_ROWS) * LSD_BINS * sizeof(unsigned)))) return rc;
   if ((rc = binstart.ensure(B * LSD_BINS * sizeof(unsigned)))) return rc;
   if ((rc = maxg2.ensure(B * sizeof(int)))) return rc;
   if ((rc = seeds.ensure(B * P.P * sizeof(unsigned)))) return rc;
@@ -2752,20 +2793,25 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
     if ((rcb = ubm.ensure((size_t)std::max(batch, cfgB) * bmStride * sizeof(unsigned)))) return rcb;
     if (P.sw % 32) PL_CUDA(cudaMemsetAsync(ubm.p, 0, (size_t)batch * bmStride * sizeof(unsigned), st));
   }
-  k_lsd_grad<<<dim3(div_up(P.sw, GRAD_TW), div_up(P.sh, GRAD_TH), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(), degp.as<float>(),
+  k_lsd_grad<<<dim3(div_up(P.sw, GRAD_TW), div_up(P.sh, GRAD_TH), batch), 256, 0, st>>>(P, scaled.as<uint8_t>(), pix.as<uint4>(), degp.as<float>(), g2p.as<unsigned>(),
                                                                              maxg2.as<int>(), usedMode != GM_REC ? ubm.as<unsigned>() : nullptr);
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_rowhist", st);
   PL_CARVEOUT(k_lsd_rowhist);
-  k_lsd_rowhist<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>());
+  k_lsd_rowhist<<<dim3(div_up(P.sh, SORT_ROWS), batch), 256, 0, st>>>(P, g2p.as<unsigned>(), maxg2.as<int>(), rowhist.as<unsigned>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_colscan", st);
   PL_CARVEOUT(k_lsd_colscan);
-  k_lsd_colscan<<<batch, LSD_BINS, 0, st>>>(P, rowhist.as<unsigned>(), binstart.as<unsigned>(), nseeds.as<int>());
+  k_lsd_colscan<<<batch, LSD_BINS, 0, st>>>(P, div_up(P.sh, SORT_ROWS), rowhist.as<unsigned>(), binstart.as<unsigned>(), nseeds.as<int>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_scatter", st);
   PL_CARVEOUT(k_lsd_scatter);
-  k_lsd_scatter<<<dim3(div_up(P.sh, 8), batch), 256, 0, st>>>(P, pix.as<uint4>(), maxg2.as<int>(), rowhist.as<unsigned>(),
+  {
+    static PerDeviceOnce attr;
+    if (attr.first()) PL_CUDA(cudaFuncSetAttribute(k_lsd_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  }
+  PL_CHECK_ARG((size_t)SORT_ROWS * P.sw * sizeof(unsigned) <= 160 * 1024);
+  k_lsd_scatter<<<dim3(div_up(P.sh, SORT_ROWS), batch), 256, (size_t)SORT_ROWS * P.sw * sizeof(unsigned), st>>>(P, g2p.as<unsigned>(), maxg2.as<int>(), rowhist.as<unsigned>(),
                                                               binstart.as<unsigned>(), seeds.as<unsigned>());
   PL_STAGE_END(timer, st);
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
@@ -2818,13 +2864,16 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
     const size_t perFrame = grow_smem_per_frame(P.P, usedMode == GM_BMS);
     int gw = gwEnv ? std::min(std::max(gwEnv, 1), GROW_WARPS) : GROW_WARPS;
     while (gw > 1 && perFrame * gw > 60 * 1024) gw >>= 1;
+    // experiment switch: extra dynamic shared memory per CTA, to cap how many region-growing CTAs an SM holds (its warps take
+    // 72 registers each: 7 CTAs of 4 frames fill the register file and leave no room for the other kernels of the pipeline)
+    static const size_t growPad = [] { const char* e = std::getenv("PLSLAM_GROW_PAD"); return e ? (size_t)std::atoi(e) : (size_t)0; }();
 #define PL_GROW_LAUNCH(MODE)                                                                                                  \
   do {                                                                                                                        \
     static PerDeviceOnce attr;                                                                                                \
     if (attr.first())                                                                                                         \
       PL_CUDA(cudaFuncSetAttribute(k_lsd_grow<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));               \
     PL_CARVEOUT(k_lsd_grow<MODE>);                                                                                            \
-    k_lsd_grow<MODE><<<div_up(batch, gw), 32 * gw, perFrame * gw, st>>>(P, pix.as<uint4>(), ubm.as<unsigned>(),               \
+    k_lsd_grow<MODE><<<div_up(batch, gw), 32 * gw, perFrame * gw + growPad, st>>>(P, pix.as<uint4>(), ubm.as<unsigned>(),               \
                                                                         seeds.as<unsigned>(), nseeds.as<int>(),               \
                                                                         regbuf.as<unsigned>(), rects.as<LsdRect>(),           \
                                                                         nrects.as<int>(), status.as<int>());                  \

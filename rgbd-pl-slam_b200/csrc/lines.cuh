@@ -66,7 +66,7 @@ class LineExtractor {
   int configure(int W, int H, int batch);
   int device = -1, numSMs = 148, cfgW = 0, cfgH = 0, cfgB = 0, last_batch = 0;
   LineParams P{};
-  DevBuf scaled, pix, degp, ubm, owner, recttmp, listpool, rectstage, coef, rowhist, binstart, maxg2, seeds, nseeds, regbuf, rects, nrects, nfaq, rectout, segs, nsegs, resp,
+  DevBuf scaled, pix, degp, g2p, ubm, owner, recttmp, listpool, rectstage, coef, rowhist, binstart, maxg2, seeds, nseeds, regbuf, rects, nrects, nfaq, rectout, segs, nsegs, resp,
       rowsum, status;
   DevBuf stageIn, stageKl, stageDesc, stageFuncs, stageCnt;
   cudaStream_t ownStream = nullptr;
