@@ -57,6 +57,10 @@ def parse():
                     help="BASELINE.json configs.  c2: 640x480 extract + kNN matching (headline); c3: 1280x720, nFeatures 2000, "
                          "128 frames (64 pairs) per step; c4: c2 plus ComputeBoW + SearchByBoW on every pair; c5: 3840x2160, "
                          "nFeatures 8000, 16 frames per step")
+    ap.add_argument("--wave", type=int, default=0,
+                    help="batches per plslam_frontend_submit_host_wave call of the e2e leg (0 = depth / 2: successive waves rotate "
+                         "over the slots, so only the first wave's upload is exposed; measured at 64 steps, 32 slots: 26.2 k "
+                         "frames/s with 32 per call, 27.1 k with 16, 22.7 k with 8, 25.0 k with 4 - profiles/r02_wave_sweep.log)")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency block")
     ap.add_argument("--voc-levels", type=int, default=6, help="depth L of the synthetic k=10 vocabulary (ORBvoc.txt: 6)")
     return ap.parse_args()
@@ -490,14 +494,18 @@ def run_ours(a):
     #   stream : plslam_frontend_submit_host per step (upload, kernels, download of a step chained in the slot's stream)
     #   wave   : plslam_frontend_submit_host_wave, `depth` steps per call (uploads one wave ahead on an upload stream, the
     #            slots of a wave start together, downloads on their own stream)
+    wave = a.wave if a.wave > 0 else max(1, depth // 2)
+    wave_sub = [0]  # batches submitted through the wave form so far: batch t goes to slot t % depth, buffer set (t // depth) & 1
+
     def host_steps(n, mode):
         if mode == "wave":
-            k = w = 0
+            k = 0
             while k < n:
-                m = min(depth, n - k)
-                fe.submit_host_wave([h_images] * m, h_outs2[w % 2][:m], True)
+                m = min(wave, n - k)
+                t0 = wave_sub[0]
+                fe.submit_host_wave([h_images] * m, [h_outs2[((t0 + i) // depth) & 1][(t0 + i) % depth] for i in range(m)], True)
+                wave_sub[0] += m
                 k += m
-                w += 1
         else:
             for k in range(n):
                 fe.submit_host(h_images, h_outs[k % depth], True)
@@ -628,7 +636,7 @@ def run_ours(a):
                         "per_rank_copy_gbs": {"h2d": h2d * a.steps / e2e_s / 1e9, "d2h": d2h * a.steps / e2e_s / 1e9},
                         "host_binding": host_binding,
                         "by_api": {m: world * a.batch * a.steps / t for m, t in e2e_modes.items()},
-                        "api": ("plslam_frontend_submit_host_wave (steps_in_flight steps per call) + plslam_frontend_wait_host" if e2e_mode == "wave"
+                        "api": ("plslam_frontend_submit_host_wave (%d steps per call, successive calls rotate over the slots) + plslam_frontend_wait_host" % wave if e2e_mode == "wave"
                                 else "plslam_frontend_submit_host x K + plslam_frontend_wait_host") +
                                " (pinned host buffers; H2D, kernels and D2H of every step inside the timed region, up to `steps_in_flight` steps overlapped)" +
                                ("; the C4 extras (ComputeBoW + SearchByBoW) are device-path only and not part of this e2e figure" if c4 else "")},

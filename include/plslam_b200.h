@@ -499,7 +499,9 @@ int plslam_frontend_submit_host_slot(plslam_frontend_t* h, int slot, const uint8
  * is not reading, every batch starts after the wave's last upload (the slots then run in phase, which is where the
  * pipeline is fastest), results leave on a download stream.  Returns once everything is enqueued; the uploads of a wave
  * overlap the kernels of the wave before it.  plslam_frontend_wait_host() returns when all results have landed.  The host
- * buffers of a wave must stay untouched until then. */
+ * buffers of a wave must stay untouched until then.  Successive waves rotate over the pipeline slots (a wave of n batches
+ * takes the next n slots), so waves smaller than `depth` keep the whole pipeline busy while only the first wave's upload is
+ * exposed: depth / 2 batches per call is what bench.py uses (profiles/r02_wave_sweep.log). */
 int plslam_frontend_submit_host_wave(plslam_frontend_t* h, const uint8_t* const* images, int n_batches, int batch, int width,
                                      int height, int pitch, size_t frame_stride, const plslam_frontend_io_t* ios, int match_pairs);
 /* Per-stage device times (ms, CUDA events on the launching streams) of the last process call made after

@@ -338,6 +338,7 @@ struct Slot {
   OutSet wOut[2];
   cudaEvent_t evRead[2] = {nullptr, nullptr}, evDl[2] = {nullptr, nullptr};
   bool wUsed[2] = {false, false};
+  unsigned wUse = 0;  // wave submissions this slot has taken: its parity selects the buffer set
   int wave_upload(int b, cudaStream_t sUpload, const uint8_t* images, int batch, int W, int H, int pitch, size_t stride,
                   int match_pairs) {
     int rc = init();
@@ -424,12 +425,15 @@ struct Frontend {
   int ensure_copy_stream() {
     if (!sCopy) PL_CUDA(cudaStreamCreateWithFlags(&sCopy, cudaStreamNonBlocking));
     if (!sDown) PL_CUDA(cudaStreamCreateWithFlags(&sDown, cudaStreamNonBlocking));
-    for (cudaEvent_t& e : evWave)
-      if (!e) PL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (evWave.empty()) {
+      evWave.assign(slots.size(), nullptr);  // one wave takes at least one slot: never more waves in flight than slots
+      for (cudaEvent_t& e : evWave) PL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     return PLSLAM_OK;
   }
-  cudaEvent_t evWave[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> evWave;
   unsigned waveIdx = 0;
+  int waveCursor = 0;  // first slot of the next wave: successive waves rotate over the slots
   int pump_all() {
     int rc = PLSLAM_OK;
     for (Slot* s : slots) {
@@ -579,14 +583,21 @@ int plslam_frontend_submit_host_wave(plslam_frontend_t* h, const uint8_t* const*
     PL_CHECK_ARG(io.keypoints && io.descriptors && io.kp_counts && io.keylines && io.line_descriptors && io.line_functions &&
                  io.line_counts && (!match_pairs || (io.orb_matches && io.line_matches)));
   }
-  const int b = (int)(F.waveIdx & 1u);
-  for (int i = 0; i < n_batches; ++i)
-    if ((rc = F.slots[i]->wave_upload(b, F.sCopy, images[i], batch, width, height, pitch, frame_stride, match_pairs))) return rc;
-  PL_CUDA(cudaEventRecord(F.evWave[b], F.sCopy));
-  for (int i = 0; i < n_batches; ++i)
-    if ((rc = F.slots[i]->wave_compute(b, F.evWave[b], F.sDown, batch, width, height, ios[i], match_pairs, F.timing))) return rc;
+  const int ns = (int)F.slots.size();
+  cudaEvent_t evUp = F.evWave[F.waveIdx % (unsigned)ns];
+  for (int i = 0; i < n_batches; ++i) {
+    Slot* s = F.slots[(F.waveCursor + i) % ns];
+    if ((rc = s->wave_upload((int)(s->wUse & 1u), F.sCopy, images[i], batch, width, height, pitch, frame_stride, match_pairs))) return rc;
+  }
+  PL_CUDA(cudaEventRecord(evUp, F.sCopy));
+  for (int i = 0; i < n_batches; ++i) {
+    Slot* s = F.slots[(F.waveCursor + i) % ns];
+    if ((rc = s->wave_compute((int)(s->wUse & 1u), evUp, F.sDown, batch, width, height, ios[i], match_pairs, F.timing))) return rc;
+    ++s->wUse;
+  }
   ++F.waveIdx;
-  F.lastSlot = n_batches - 1;
+  F.lastSlot = (F.waveCursor + n_batches - 1) % ns;
+  F.waveCursor = (F.waveCursor + n_batches) % ns;
   return PLSLAM_OK;
 }
 int plslam_frontend_wait_host(plslam_frontend_t* h) {
