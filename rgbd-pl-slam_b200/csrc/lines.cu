@@ -295,18 +295,29 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ Lin
   // Pass 1: the row's seeds compacted in x order (~1 pixel in 4) with their bins (a double-precision square root each), and
   // the row's count per bin; then, over the 8 warps, the offset of the row inside its group's share of each bin.
   int nd = 0;
-  if (y < L.sh)
-    for (int x0 = 0; x0 < L.sw; x0 += 32) {
-      const int x = x0 + lane;
-      const unsigned g2 = x < L.sw ? row[x] : 0u;
-      const unsigned dm = __ballot_sync(0xffffffffu, g2 != 0u);
-      if (g2) {
-        const int bin = lsd_bin((int)g2, mg2);
-        atomicAdd(&cnt[warp][bin], 1u);
-        myList[nd + __popc(dm & lt)] = (unsigned)x | ((unsigned)bin << 16);
+  if (y < L.sh) {
+    const double bin_coef = __ddiv_rn((double)(LSD_BINS - 1), modgrad_of(mg2));  // lsd_bin(), its frame constant hoisted
+    for (int xb = 0; xb < L.sw; xb += 8 * 32) {
+      unsigned g2v[8];  // eight loads in flight per lane
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int x = xb + k * 32 + lane;
+        g2v[k] = x < L.sw ? __ldg(row + x) : 0u;
       }
-      nd += __popc(dm);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int x = xb + k * 32 + lane;
+        const unsigned g2 = g2v[k];
+        const unsigned dm = __ballot_sync(0xffffffffu, g2 != 0u);
+        if (g2) {
+          const int bin = (int)__dmul_rn(modgrad_of((int)g2), bin_coef);
+          atomicAdd(&cnt[warp][bin], 1u);
+          myList[nd + __popc(dm & lt)] = (unsigned)x | ((unsigned)bin << 16);
+        }
+        nd += __popc(dm);
+      }
     }
+  }
   __syncthreads();
   {
     // cnt[w][b] becomes the position in the frame's seed list of the first seed of row w in bin b: start of the bin +
