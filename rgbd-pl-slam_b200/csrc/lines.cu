@@ -248,9 +248,17 @@ __global__ void __launch_bounds__(256) k_lsd_rowhist(const __grid_constant__ Lin
   const int mg2 = maxg2[f];
   if (mg2 > 0 && y < L.sh) {
     const unsigned* row = g2Plane + (size_t)f * L.P + (size_t)y * L.sw;
-    for (int x = lane; x < L.sw; x += 32) {
-      const unsigned g2 = row[x];
-      if (g2) atomicAdd(&hist[lsd_bin((int)g2, mg2)], 1u);
+    const double bin_coef = __ddiv_rn((double)(LSD_BINS - 1), modgrad_of(mg2));  // lsd_bin(), its frame constant hoisted
+    for (int xb = 0; xb < L.sw; xb += 8 * 32) {
+      unsigned g2v[8];  // eight loads in flight per lane
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int x = xb + k * 32 + lane;
+        g2v[k] = x < L.sw ? __ldg(row + x) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (g2v[k]) atomicAdd(&hist[(int)__dmul_rn(modgrad_of((int)g2v[k]), bin_coef)], 1u);
     }
   }
   __syncthreads();
