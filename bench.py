@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--max-lines", type=int, default=40)
     ap.add_argument("--depth", type=int, default=32,
                     help="batches (steps) in flight per GPU: pipeline slots of the front-end (measured on B200, 640x480, batch 256: "
-                         "16.2 k frames/s at 4 x 1024, 17.1-17.7 k at 16, 19.0 k at 32; ~3 GB of workspace per slot)")
+                         "16.9 k frames/s at 8, 23.1 k at 16, 23.2 k at 32 before the last kernel changes - profiles/r02h_depth_sweep.log; 28.7 k at 32 "
+                         "at the end of round 2; flat from 16 on: 16 batches are what the register file holds of k_lsd_grow; ~3 GB of workspace per slot)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
