@@ -62,6 +62,9 @@ def parse():
                     help="batches per plslam_frontend_submit_host_wave call of the e2e leg (0 = depth / 2: successive waves rotate "
                          "over the slots, so only the first wave's upload is exposed; measured at 64 steps, 32 slots: 26.2 k "
                          "frames/s with 32 per call, 27.1 k with 16, 22.7 k with 8, 25.0 k with 4 - profiles/r02_wave_sweep.log)")
+    ap.add_argument("--wave-ramp", default="auto",
+                    help="comma-separated sizes of the first waves of the e2e leg (then --wave); auto = depth/5 + the rest when the "
+                         "run passes over the slots only once (steps <= slots), none otherwise")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency block")
     ap.add_argument("--voc-levels", type=int, default=6, help="depth L of the synthetic k=10 vocabulary (ORBvoc.txt: 6)")
     return ap.parse_args()
@@ -446,7 +449,9 @@ def run_ours(a):
     d_images = torch.from_numpy(frames).cuda()
     outs = [fe.alloc(a.batch, device="cuda") for _ in range(depth)]
     out = outs[0]
-    streams = [torch.cuda.Stream() for _ in range(depth)]
+    # PLSLAM_STREAM_PRIO (experiment switch of the library, digits ORB / host+lines / copies): the device path runs the line
+    # branch on the caller's stream, so that stream carries the priority
+    streams = [torch.cuda.Stream(priority=-1 if os.environ.get("PLSLAM_STREAM_PRIO", "000")[1:2] == "1" else 0) for _ in range(depth)]
     h_images = torch.from_numpy(frames).pin_memory()
     h_outs = [fe.alloc(a.batch, pinned=True) for _ in range(depth)]
 
@@ -496,13 +501,23 @@ def run_ours(a):
     #   wave   : plslam_frontend_submit_host_wave, `depth` steps per call (uploads one wave ahead on an upload stream, the
     #            slots of a wave start together, downloads on their own stream)
     wave = a.wave if a.wave > 0 else max(1, depth // 2)
+    # Sizes of the first waves of a run (then `wave`).  A run that passes over the slots only once (steps <= slots: the driver's
+    # --steps 20) has no steady state whose phase could be kept, so it starts with a small wave (the GPU starts after 4 uploads
+    # instead of 10) and sends the rest as one: its staggered start also fills the tail of the first batches' region growing.
+    # Measured at 20 steps (profiles/r02_sched_sweeps.log): 21.4-21.6 k frames/s end to end with waves of 10 + 10, 24.4-26.8 k with
+    # 3-8 + rest; at 64 steps a ramp costs the phase (28.2 k -> 23.8-25.6 k), so longer runs keep equal waves.
+    if a.wave_ramp == "auto":
+        wave_ramp = [max(1, depth // 5), depth - max(1, depth // 5)] if a.steps <= depth and depth >= 4 else []
+    else:
+        wave_ramp = [int(v) for v in a.wave_ramp.split(",") if v]
     wave_sub = [0]  # batches submitted through the wave form so far: batch t goes to slot t % depth, buffer set (t // depth) & 1
 
     def host_steps(n, mode):
         if mode == "wave":
             k = 0
+            ramp = list(wave_ramp)
             while k < n:
-                m = min(wave, n - k)
+                m = min(ramp.pop(0) if ramp else wave, n - k, depth)
                 t0 = wave_sub[0]
                 fe.submit_host_wave([h_images] * m, [h_outs2[((t0 + i) // depth) & 1][(t0 + i) % depth] for i in range(m)], True)
                 wave_sub[0] += m
@@ -637,7 +652,7 @@ def run_ours(a):
                         "per_rank_copy_gbs": {"h2d": h2d * a.steps / e2e_s / 1e9, "d2h": d2h * a.steps / e2e_s / 1e9},
                         "host_binding": host_binding,
                         "by_api": {m: world * a.batch * a.steps / t for m, t in e2e_modes.items()},
-                        "api": ("plslam_frontend_submit_host_wave (%d steps per call, successive calls rotate over the slots) + plslam_frontend_wait_host" % wave if e2e_mode == "wave"
+                        "api": ("plslam_frontend_submit_host_wave (%s steps per call, successive calls rotate over the slots) + plslam_frontend_wait_host" % ("+".join(map(str, wave_ramp)) + " then %d" % wave if wave_ramp else str(wave)) if e2e_mode == "wave"
                                 else "plslam_frontend_submit_host x K + plslam_frontend_wait_host") +
                                " (pinned host buffers; H2D, kernels and D2H of every step inside the timed region, up to `steps_in_flight` steps overlapped)" +
                                ("; the C4 extras (ComputeBoW + SearchByBoW) are device-path only and not part of this e2e figure" if c4 else "")},

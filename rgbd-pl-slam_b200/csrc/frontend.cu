@@ -2,6 +2,7 @@
 // frames, i.e. the hot path Frame::Frame runs per RGB-D frame (reference include/Frame.h:60,67,70).
 // ORB and line stages are independent, so they run on two internal streams forked from the caller's
 // stream: the latency-bound line kernels (one warp per frame) overlap the throughput-bound ORB kernels.
+#include <string>
 #include <new>
 
 #include <chrono>
@@ -39,6 +40,13 @@ __global__ void k_make_pair_jobs(const uint8_t* desc, const int32_t* counts, int
 // One pipeline slot = one complete workspace (ORB + line extractors, streams, staging).  Independent
 // batches submitted on different slots overlap on the GPU: k_lsd_grow keeps one warp per frame busy for
 // tens of milliseconds at ~0.13 IPC, so several batches in flight are needed to fill the issue slots.
+// experiment switch PLSLAM_STREAM_PRIO = three digits "OHC": 1 = greatest stream priority for the ORB branch stream (O), the
+// host-path / line branch stream (H), the copy streams (C); default "000"
+static int stream_prio_digit(int i) {
+  static const std::string v = [] { const char* e = std::getenv("PLSLAM_STREAM_PRIO"); return std::string(e ? e : "000"); }();
+  return (int)v.size() > i && v[i] == '1';
+}
+
 struct Slot {
   OrbExtractor orb;
   LineExtractor lines;
@@ -75,8 +83,12 @@ struct Slot {
   }
   int init() {
     if (sOrb) return PLSLAM_OK;
-    PL_CUDA(cudaStreamCreateWithFlags(&sOrb, cudaStreamNonBlocking));
-    PL_CUDA(cudaStreamCreateWithFlags(&sHost, cudaStreamNonBlocking));
+    {
+      int least = 0, greatest = 0;
+      PL_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      PL_CUDA(cudaStreamCreateWithPriority(&sOrb, cudaStreamNonBlocking, stream_prio_digit(0) ? greatest : least));
+      PL_CUDA(cudaStreamCreateWithPriority(&sHost, cudaStreamNonBlocking, stream_prio_digit(1) ? greatest : least));
+    }
     PL_CUDA(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
     PL_CUDA(cudaEventCreateWithFlags(&evOrb, cudaEventDisableTiming));
     PL_CUDA(cudaEventCreateWithFlags(&evLines, cudaEventDisableTiming));
@@ -108,17 +120,36 @@ struct Slot {
     lines.timer = timing ? &tLines : nullptr;
     // the slot's previous batch (possibly submitted from another stream) must have drained: its workspace is reused
     if (used) PL_CUDA(cudaStreamWaitEvent(st, evDone, 0));
-    PL_CUDA(cudaEventRecord(evFork, st));
-    PL_CUDA(cudaStreamWaitEvent(sOrb, evFork, 0));
+    // experiment switch PLSLAM_ONE_STREAM: 1 = both branches in the caller's stream, lines first; 2 = ORB first (one hardware
+    // connection per slot instead of two: no aliasing of 2 x depth streams on the 32 connections, no concurrency inside a slot)
+    static const int oneStream = [] { const char* e = std::getenv("PLSLAM_ONE_STREAM"); return e ? std::atoi(e) : 0; }();
+    cudaStream_t sOrb = oneStream ? st : this->sOrb;
+    // experiment switch PLSLAM_ORB_AFTER: the ORB branch of a slot starts with the batch (0), once the line branch has reached
+    // its region-growing kernel (1: the kernels in front of it do not compete with ORB work), or after that kernel (2)
+    // Measured (profiles/r02_sched_sweeps.log): 29.4 k frames/s with 0, 29.7 k with 1 (three runs each), 26.5 k with 2: default 1.
+    static const int orbAfter = [] { const char* e = std::getenv("PLSLAM_ORB_AFTER"); return e ? std::atoi(e) : 1; }();
+    lines.mark_event = (!oneStream && orbAfter) ? evFork : nullptr;
+    lines.mark_where = orbAfter;
+    if (!oneStream && !orbAfter) {
+      PL_CUDA(cudaEventRecord(evFork, st));
+      PL_CUDA(cudaStreamWaitEvent(sOrb, evFork, 0));
+    }
     cudaStream_t sLines = st;  // every stream is a hardware connection: two per slot keep deep pipelines from aliasing queues
     // line branch first: its long sequential kernel should start as early as possible
     const auto tA = std::chrono::steady_clock::now();
+    if (oneStream == 2) {
+      rc = orb.extract_device(d_images, batch, W, H, pitch, stride, io.keypoints, io.descriptors, kpCap, io.kp_counts, sOrb);
+      if (rc) return rc;
+    }
     rc = lines.extract_device(d_images, batch, W, H, pitch, stride, io.keylines, io.line_descriptors, io.line_functions,
                               lnCap, io.line_counts, sLines);
     if (rc) return rc;
     const auto tB = std::chrono::steady_clock::now();
-    rc = orb.extract_device(d_images, batch, W, H, pitch, stride, io.keypoints, io.descriptors, kpCap, io.kp_counts, sOrb);
-    if (rc) return rc;
+    if (!oneStream && orbAfter) PL_CUDA(cudaStreamWaitEvent(sOrb, evFork, 0));
+    if (oneStream != 2) {
+      rc = orb.extract_device(d_images, batch, W, H, pitch, stride, io.keypoints, io.descriptors, kpCap, io.kp_counts, sOrb);
+      if (rc) return rc;
+    }
     const auto tC = std::chrono::steady_clock::now();
     if (trace_host()) {
       const double a = std::chrono::duration<double, std::milli>(tB - tA).count(), b = std::chrono::duration<double, std::milli>(tC - tB).count();
@@ -136,8 +167,10 @@ struct Slot {
       PL_STAGE_END(lines.timer, sLines);
       if (rc) return rc;
     }
-    PL_CUDA(cudaEventRecord(evOrb, sOrb));
-    PL_CUDA(cudaStreamWaitEvent(st, evOrb, 0));
+    if (!oneStream) {
+      PL_CUDA(cudaEventRecord(evOrb, sOrb));
+      PL_CUDA(cudaStreamWaitEvent(st, evOrb, 0));
+    }
     PL_CUDA(cudaEventRecord(evDone, st));
     used = true;
     return PLSLAM_OK;
@@ -423,8 +456,10 @@ struct Frontend {
   bool timing = false;
   cudaStream_t sCopy = nullptr, sDown = nullptr;  // upload / download streams of the host-scheduled path
   int ensure_copy_stream() {
-    if (!sCopy) PL_CUDA(cudaStreamCreateWithFlags(&sCopy, cudaStreamNonBlocking));
-    if (!sDown) PL_CUDA(cudaStreamCreateWithFlags(&sDown, cudaStreamNonBlocking));
+    int least = 0, greatest = 0;
+    PL_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    if (!sCopy) PL_CUDA(cudaStreamCreateWithPriority(&sCopy, cudaStreamNonBlocking, stream_prio_digit(2) ? greatest : least));
+    if (!sDown) PL_CUDA(cudaStreamCreateWithPriority(&sDown, cudaStreamNonBlocking, stream_prio_digit(2) ? greatest : least));
     if (evWave.empty()) {
       evWave.assign(slots.size(), nullptr);  // one wave takes at least one slot: never more waves in flight than slots
       for (cudaEvent_t& e : evWave) PL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

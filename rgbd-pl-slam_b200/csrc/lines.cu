@@ -2833,6 +2833,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
   k_lsd_scatter<<<dim3(div_up(P.sh, SORT_ROWS), batch), 256, (size_t)SORT_ROWS * P.sw * sizeof(unsigned), st>>>(P, g2p.as<unsigned>(), maxg2.as<int>(), rowhist.as<unsigned>(),
                                                               binstart.as<unsigned>(), seeds.as<unsigned>());
   PL_STAGE_END(timer, st);
+  if (mark_event && mark_where == 1) PL_CUDA(cudaEventRecord(mark_event, st));
   PL_STAGE_BEGIN(timer, "lsd_grow", st);
   P.batch = batch;
   // PLSLAM_GROW_MODE: 0 = one warp per frame (k_lsd_grow), 2 = speculative multi-warp growing with in-order retirement
@@ -2903,6 +2904,7 @@ int LineExtractor::extract_device(const uint8_t* d_images, int batch, int W, int
 #undef PL_GROW_LAUNCH
   }
   PL_STAGE_END(timer, st);
+  if (mark_event && mark_where == 2) PL_CUDA(cudaEventRecord(mark_event, st));
   static const bool grow_only = std::getenv("PLSLAM_DEBUG_STOP_AFTER_GROW") != nullptr;  // profiling aid (tools/)
   if (grow_only) return PLSLAM_OK;
   LsdSegment* rout = rectout.as<LsdSegment>();

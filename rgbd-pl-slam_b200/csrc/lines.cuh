@@ -58,6 +58,10 @@ class LineExtractor {
 
   StageTimer* timer = nullptr;
   const int* device_status() const { return status.as<int>(); }
+  // optional marker for the caller's scheduling: recorded on the extraction stream just before (1) or just after (2) the
+  // region-growing kernel is enqueued
+  cudaEvent_t mark_event = nullptr;
+  int mark_where = 0;
   int batches_in_flight = 1;  // how many batches like this one the caller keeps on the GPU at once (pipeline depth)
   int max_lines = 40;  // lsdNFeatures of the PL-SLAM fork family
   int rect_cap = 4096;
