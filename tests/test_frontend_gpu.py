@@ -93,6 +93,20 @@ def test_full_bench_batch_all_paths(oracle):
     fe.wait_host()
     for k in (0, 2, 4, 5, 7):
         _compare(oracle, pl, w_outs[k], ref, B, "wave submission %d" % k)
+    # waves smaller than the pipeline rotate over the slots (sizes 2, 1, 2, 3 over 3 slots: every slot alternates between
+    # its two buffer sets); alternate batches carry the frames in reversed order, so a stale staging buffer or a result set
+    # overwritten before it left for the host would show
+    h_rev = torch.from_numpy(np.ascontiguousarray(frames[::-1])).pin_memory()
+    ref_rev = ref[::-1]
+    r_outs = [fe.alloc(B, pinned=True) for _ in range(8)]
+    ins = [h_images if k % 2 == 0 else h_rev for k in range(8)]
+    k = 0
+    for m in (2, 1, 2, 3):
+        fe.submit_host_wave(ins[k:k + m], r_outs[k:k + m], True)
+        k += m
+    fe.wait_host()
+    for k in (0, 1, 2, 4, 5, 7):
+        _compare(oracle, pl, r_outs[k], ref if k % 2 == 0 else ref_rev, B, "rotating wave submission %d" % k)
     # synchronous host path from pageable memory
     out = fe.alloc(B)
     fe.process_host(frames, out, True)
