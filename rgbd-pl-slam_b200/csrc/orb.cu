@@ -39,6 +39,16 @@ __device__ __forceinline__ const uint8_t* level_ptr(const OrbParams& P, const Or
 // (ComputePyramid @0x70430, resize call @0x70b07; arithmetic SURVEY B.1).
 // One thread = 4 horizontally adjacent output pixels (one uchar4 store).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int resize_px(const uint8_t* S0, const uint8_t* S1, int sx, int xab, int b0, int b1) {
+  const int a0 = (short)(xab & 0xffff), a1 = xab >> 16;
+  int t0 = S0[sx] * a0, t1 = S1[sx] * a0;
+  if (a1) {
+    t0 += S0[sx + 1] * a1;
+    t1 += S1[sx + 1] * a1;
+  }
+  return (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+}
+
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ OrbParams P, OrbImages I, int l,
                                                 const int* __restrict__ coef) {
   const OrbLevel& D = P.lv[l];
@@ -49,31 +59,18 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ OrbParam
   int sp;
   const uint8_t* S = level_ptr(P, I, f, l - 1, sp);
   const int sh = P.lv[l - 1].h;
-  // tables: xofs[dw], xa[dw] (c0 | c1<<16), yofs[dh], ya[dh]
-  const int* xofs = coef + D.coefOff;
-  const int* xa = xofs + D.w;
-  const int* yofs = xa + D.w;
-  const int* ya = yofs + D.h;
-  const int sy = __ldg(yofs + y);
-  const int yab = __ldg(ya + y);
-  const int b0 = (short)(yab & 0xffff), b1 = yab >> 16;
+  // tables: int2 {source offset, c0 | c1 << 16} per destination column, then per destination row (padded to 4 entries)
+  const int2* xtab = reinterpret_cast<const int2*>(coef + D.coefOff);
+  const int2* ytab = xtab + ((D.w + 3) & ~3);
+  const int2 ye = __ldg(ytab + y);
+  const int sy = ye.x, b0 = (short)(ye.y & 0xffff), b1 = ye.y >> 16;
   const uint8_t* S0 = S + (size_t)sy * sp;
   const uint8_t* S1 = S + (size_t)min(sy + 1, sh - 1) * sp;
-  uint32_t out = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int x = min(x4 + i, D.w - 1);
-    const int sx = __ldg(xofs + x);
-    const int xab = __ldg(xa + x);
-    const int a0 = (short)(xab & 0xffff), a1 = xab >> 16;
-    int t0 = S0[sx] * a0, t1 = S1[sx] * a0;
-    if (a1) {
-      t0 += S0[sx + 1] * a1;
-      t1 += S1[sx + 1] * a1;
-    }
-    const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
-    out |= (uint32_t)(v & 0xff) << (8 * i);
-  }
+  const int4 e01 = __ldg(reinterpret_cast<const int4*>(xtab + x4)), e23 = __ldg(reinterpret_cast<const int4*>(xtab + x4) + 1);
+  const uint32_t out = (uint32_t)(resize_px(S0, S1, e01.x, e01.y, b0, b1) & 0xff) |
+                       ((uint32_t)(resize_px(S0, S1, e01.z, e01.w, b0, b1) & 0xff) << 8) |
+                       ((uint32_t)(resize_px(S0, S1, e23.x, e23.y, b0, b1) & 0xff) << 16) |
+                       ((uint32_t)(resize_px(S0, S1, e23.z, e23.w, b0, b1) & 0xff) << 24);
   uint8_t* Dp = I.pyr + (size_t)f * P.pyrFrameStride + D.off + (size_t)y * D.pitch + x4;
   *reinterpret_cast<uint32_t*>(Dp) = out;
 }
@@ -1074,8 +1071,11 @@ int OrbExtractor::configure(int W, int H, int batch) {
       // resize tables: xofs, xa, yofs, ya
       L.coefOff = coefOff;
       const OrbLevel& S = P.lv[l - 1];
+      // layout: per destination column an int2 {source offset, c0 | c1 << 16}, then the same per destination row; each table
+      // padded to a multiple of 4 entries so that four consecutive entries are two aligned 16-byte loads
       auto emit = [&](int ssize, int dsize) {
-        std::vector<int> ofs(dsize), ab(dsize);
+        const int dpad = (dsize + 3) & ~3;
+        std::vector<int> tab(2 * (size_t)dpad, 0);
         const double scale = 1.0 / ((double)dsize / ssize);
         for (int d = 0; d < dsize; ++d) {
           float fx = (float)((d + 0.5) * scale - 0.5);
@@ -1084,11 +1084,14 @@ int OrbExtractor::configure(int W, int H, int batch) {
           if (s < 0) { s = 0; fx = 0.f; }
           if (s >= ssize - 1) { s = ssize - 1; fx = 0.f; }
           const int c0 = cvRoundf_host((1.f - fx) * 2048.f), c1 = cvRoundf_host(fx * 2048.f);
-          ofs[d] = s;
-          ab[d] = (c0 & 0xffff) | (c1 << 16);
+          tab[2 * d] = s;
+          tab[2 * d + 1] = (c0 & 0xffff) | (c1 << 16);
         }
-        coefHost.insert(coefHost.end(), ofs.begin(), ofs.end());
-        coefHost.insert(coefHost.end(), ab.begin(), ab.end());
+        for (int d = dsize; d < dpad; ++d) {  // padding repeats the last entry (read by the lanes past the row end, never stored)
+          tab[2 * d] = tab[2 * (dsize - 1)];
+          tab[2 * d + 1] = tab[2 * (dsize - 1) + 1];
+        }
+        coefHost.insert(coefHost.end(), tab.begin(), tab.end());
       };
       emit(S.w, L.w);
       emit(S.h, L.h);
