@@ -657,6 +657,66 @@ struct BlurMaps {
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// K1, TMA form: the source patch of a 128x8 output tile (<= 176 x 12 bytes at level ratios up to 1.23) arrives by one
+// cp.async.bulk.tensor.3d from the [frame][row][byte] view of the source level; the 256 threads then take their taps from shared
+// memory.  Used for every level whose source view is TMA-legal (16-byte aligned base, pitch and frame stride) and whose ratio
+// fits the box; k_resize (plain loads) is the fallback.  The box starts at the tile's first source column rounded down to 16.
+constexpr int RS_TW = 128, RS_TH = 8, RS_BW = 176, RS_BH = 12;
+struct ResizeMaps {
+  CUtensorMap m[ORB_MAXL];  // m[l]: level l as the SOURCE of level l + 1, box RS_BW x RS_BH
+  unsigned tmaMask;         // bit l set: level l (destination) is built by k_resize_tma
+};
+
+struct AllMaps {
+  BlurMaps blur;
+  ResizeMaps rs;
+};
+
+__global__ void __launch_bounds__(256) k_resize_tma(const __grid_constant__ OrbParams P, const __grid_constant__ ResizeMaps Mp,
+                                                    OrbImages I, int l, const int* __restrict__ coef) {
+  __shared__ __align__(128) uint8_t patch[RS_BH][RS_BW];
+  __shared__ __align__(8) unsigned long long mbar;
+  const OrbLevel& D = P.lv[l];
+  const int f = blockIdx.z;
+  const int x0 = blockIdx.x * RS_TW, y0 = blockIdx.y * RS_TH;
+  const int2* xtab = reinterpret_cast<const int2*>(coef + D.coefOff);
+  const int2* ytab = xtab + ((D.w + 3) & ~3);
+  const int bx = __ldg(&xtab[x0].x) & ~15, by = __ldg(&ytab[y0].x);
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned bar = smem_u32(&mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(RS_BW * RS_BH) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(&patch[0][0])), "l"(reinterpret_cast<unsigned long long>(&Mp.m[l - 1])), "r"(bx), "r"(by), "r"(f), "r"(bar)
+        : "memory");
+    unsigned done = 0;  // one thread polls, the others park at the CTA barrier (as in k_blur)
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+  __syncthreads();
+  const int x4 = x0 + threadIdx.x * 4, y = y0 + threadIdx.y;
+  if (x4 >= D.w || y >= D.h) return;
+  const int sh = P.lv[l - 1].h;
+  const int2 ye = __ldg(ytab + y);
+  const int sy = ye.x, b0 = (short)(ye.y & 0xffff), b1 = ye.y >> 16;
+  const uint8_t* S0 = &patch[sy - by][0] - bx;
+  const uint8_t* S1 = &patch[min(sy + 1, sh - 1) - by][0] - bx;
+  const int4 e01 = __ldg(reinterpret_cast<const int4*>(xtab + x4)), e23 = __ldg(reinterpret_cast<const int4*>(xtab + x4) + 1);
+  const uint32_t out = (uint32_t)(resize_px(S0, S1, e01.x, e01.y, b0, b1) & 0xff) |
+                       ((uint32_t)(resize_px(S0, S1, e01.z, e01.w, b0, b1) & 0xff) << 8) |
+                       ((uint32_t)(resize_px(S0, S1, e23.x, e23.y, b0, b1) & 0xff) << 16) |
+                       ((uint32_t)(resize_px(S0, S1, e23.z, e23.w, b0, b1) & 0xff) << 24);
+  uint8_t* Dp = I.pyr + (size_t)f * P.pyrFrameStride + D.off + (size_t)y * D.pitch + x4;
+  *reinterpret_cast<uint32_t*>(Dp) = out;
+}
+
 // The tensor maps travel as a __grid_constant__ kernel parameter (12 x 128 B): no device copy of them exists, so a caller
 // that cycles through any number of input buffers never waits for a descriptor upload.
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbParams P, const __grid_constant__ BlurMaps Mp,
@@ -911,13 +971,14 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 // [frame][row][byte] view of one level of `batch` frames; false if the layout is not TMA-legal
-bool encode_level_map(CUtensorMap* m, const void* base, int w, int h, size_t pitch, size_t frameStride, int batch) {
+bool encode_level_map(CUtensorMap* m, const void* base, int w, int h, size_t pitch, size_t frameStride, int batch,
+                      int boxW = BOX_W, int boxH = BOX_H) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (frameStride & 15)) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
   const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
-  const cuuint32_t box[3] = {BOX_W, BOX_H, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1170,11 +1231,49 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
 
   PL_CUDA(cudaMemsetAsync(candCount.p, 0, (size_t)batch * ORB_MAXL * sizeof(int), st));
   // `status` is sticky: kernels only raise it, check_status() reads and re-arms it (several batches may be in flight)
+  // The TMA descriptors only depend on the buffers and the frame geometry: they are re-encoded (host only, ~1 us per
+  // level) when those change and passed to the kernel by value; four encoded sets are kept (input buffers the caller
+  // alternates between).
+  const uintptr_t key[6] = {(uintptr_t)d_images, (uintptr_t)pitch, (uintptr_t)frame_stride, (uintptr_t)batch,
+                            (uintptr_t)pyr.p, (uintptr_t)(W * 65536 + H)};
+  static_assert(sizeof(AllMaps) <= sizeof(mapsCache[0]), "mapsCache entry too small");
+  int slotIdx = -1;
+  for (int e = 0; e < 4; ++e)
+    if (std::memcmp(key, mapsKey[e], sizeof(key)) == 0) slotIdx = e;
+  if (slotIdx < 0) {
+    slotIdx = mapsNext;
+    mapsNext = (mapsNext + 1) & 3;
+    AllMaps A;
+    std::memset(&A, 0, sizeof(A));
+    BlurMaps& M = A.blur;
+    for (int l = 0; l < nlevels; ++l) {
+      const void* base = l ? (const void*)(pyr.as<uint8_t>() + P.lv[l].off) : (const void*)d_images;
+      const size_t lp = l ? (size_t)P.lv[l].pitch : (size_t)pitch, ls = l ? (size_t)P.pyrFrameStride : frame_stride;
+      if (encode_level_map(&M.m[l], base, P.lv[l].w, P.lv[l].h, lp, ls, batch)) M.tmaMask |= 1u << l;
+      // the same view with the box of k_resize_tma, when level l + 1 can be built from it: the source patch of a tile is
+      // at most ceil(127 r) + 2 + 15 columns (box origin rounded down to 16) and ceil(7 r) + 2 rows, r = size ratio
+      if (l + 1 < nlevels && (long long)(RS_TW - 1) * P.lv[l].w <= (long long)(RS_BW - 19) * P.lv[l + 1].w &&
+          (long long)2 * (RS_TH - 1) * P.lv[l].h <= (long long)(2 * RS_BH - 5) * P.lv[l + 1].h &&
+          encode_level_map(&A.rs.m[l], base, P.lv[l].w, P.lv[l].h, lp, ls, batch, RS_BW, RS_BH))
+        A.rs.tmaMask |= 1u << (l + 1);
+    }
+    std::memcpy(mapsCache[slotIdx], &A, sizeof(A));
+    std::memcpy(mapsKey[slotIdx], key, sizeof(key));
+  }
+  const AllMaps& allMaps = *reinterpret_cast<const AllMaps*>(mapsCache[slotIdx]);
   PL_STAGE_BEGIN(timer, "orb_pyramid(7 launches)", st);
   for (int l = 1; l < nlevels; ++l) {
     dim3 grid(div_up(P.lv[l].w, 128), div_up(P.lv[l].h, 8), batch);
-    PL_CARVEOUT(k_resize);
-    k_resize<<<grid, dim3(32, 8), 0, st>>>(P, I, l, coef.as<int>());
+    // PLSLAM_RESIZE_TMA=0 forces the plain-load form (measured: 55.6 us per launch against 62.5 us for the TMA form, 63.7 us
+    // for the round-1 kernel; 7 launches per 256 frames, i.e. 0.05 ms of an 8.6 ms step: the TMA form stays the default)
+    static const bool resizeTma = [] { const char* e = std::getenv("PLSLAM_RESIZE_TMA"); return !e || std::atoi(e) != 0; }();
+    if (resizeTma && ((allMaps.rs.tmaMask >> l) & 1u)) {
+      PL_CARVEOUT(k_resize_tma);
+      k_resize_tma<<<grid, dim3(32, 8), 0, st>>>(P, allMaps.rs, I, l, coef.as<int>());
+    } else {
+      PL_CARVEOUT(k_resize);
+      k_resize<<<grid, dim3(32, 8), 0, st>>>(P, I, l, coef.as<int>());
+    }
   }
   PL_STAGE_END(timer, st);
   {
@@ -1207,29 +1306,7 @@ int OrbExtractor::extract_device(const uint8_t* d_images, int batch, int W, int 
     bool k8 = true;
     for (int i = 0; i < 7; ++i) k8 = k8 && blurk[i] >= 0 && blurk[i] <= 255;
     PL_CHECK_ARG(k8);
-    // The TMA descriptors only depend on the buffers and the frame geometry: they are re-encoded (host only, ~1 us per
-    // level) when those change and passed to the kernel by value; four encoded sets are kept (input buffers the caller
-    // alternates between).
-    const uintptr_t key[6] = {(uintptr_t)d_images, (uintptr_t)pitch, (uintptr_t)frame_stride, (uintptr_t)batch,
-                              (uintptr_t)pyr.p, (uintptr_t)(W * 65536 + H)};
-    static_assert(sizeof(BlurMaps) <= sizeof(mapsCache[0]), "mapsCache entry too small");
-    int slotIdx = -1;
-    for (int e = 0; e < 4; ++e)
-      if (std::memcmp(key, mapsKey[e], sizeof(key)) == 0) slotIdx = e;
-    if (slotIdx < 0) {
-      slotIdx = mapsNext;
-      mapsNext = (mapsNext + 1) & 3;
-      BlurMaps M;
-      std::memset(&M, 0, sizeof(M));
-      for (int l = 0; l < nlevels; ++l) {
-        const void* base = l ? (const void*)(pyr.as<uint8_t>() + P.lv[l].off) : (const void*)d_images;
-        const size_t lp = l ? (size_t)P.lv[l].pitch : (size_t)pitch, ls = l ? (size_t)P.pyrFrameStride : frame_stride;
-        if (encode_level_map(&M.m[l], base, P.lv[l].w, P.lv[l].h, lp, ls, batch)) M.tmaMask |= 1u << l;
-      }
-      std::memcpy(mapsCache[slotIdx], &M, sizeof(M));
-      std::memcpy(mapsKey[slotIdx], key, sizeof(key));
-    }
-    const BlurMaps& dMaps = *reinterpret_cast<const BlurMaps*>(mapsCache[slotIdx]);
+    const BlurMaps& dMaps = allMaps.blur;
     PL_CARVEOUT(k_blur);
     k_blur<<<dim3(P.totalTiles, batch), 256, 0, st>>>(P, dMaps, I, lvlCnt.as<int>(), tileTab.as<unsigned>());
   }

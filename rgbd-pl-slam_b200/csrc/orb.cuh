@@ -88,8 +88,8 @@ class OrbExtractor {
   DevBuf stageIn, stageKps, stageDesc, stageCnt;
   cudaStream_t ownStream = nullptr;
   void* pinnedStatus = nullptr;
-  uintptr_t mapsKey[4][6] = {};  // what the cached TMA descriptor sets of k_blur were encoded for
-  alignas(64) unsigned char mapsCache[4][2048] = {};  // the encoded sets (host memory; passed to k_blur by value)
+  uintptr_t mapsKey[4][6] = {};  // what the cached TMA descriptor sets of k_blur and k_resize_tma were encoded for
+  alignas(64) unsigned char mapsCache[4][4096] = {};  // the encoded sets (host memory; passed to the kernels by value)
   int mapsNext = 0;
 };
 
