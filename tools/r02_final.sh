@@ -14,11 +14,13 @@ export PLSLAM_GROW_MODE=0
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 1 --depth 1 --no-cpu-baseline --no-latency > gpurun_out/${TAG}_ncu_bench.log 2>&1
 python tools/launch_summary.py gpurun_out/${TAG}_launches.csv | head -40
+if [ -z "$SKIP_FULL" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_lsd_grow|k_lsd_nfa$|k_lsd_grad|k_lbd|k_lsd_scatter|k_lsd_rowhist" -s 12 -c 6 -o gpurun_out/${TAG}_full \
   python bench.py --steps 2 --warmup 1 --depth 1 --no-cpu-baseline --no-latency > gpurun_out/${TAG}_full_ncu.log 2>&1
 tail -2 gpurun_out/${TAG}_full_ncu.log
+fi
 unset PLSLAM_GROW_MODE
-for w in c3 c5; do
+for w in c3 c4 c5; do
   timeout 400 python bench.py --workload $w --no-cpu-baseline --no-latency > gpurun_out/${TAG}_$w.json 2> gpurun_out/${TAG}_$w.err
   python tools/benchline.py ${TAG}_$w < gpurun_out/${TAG}_$w.json
 done
