@@ -198,3 +198,39 @@ def test_full_size_batch_properties():
         s, _ = torch.sort(d.long(), dim=1)
         assert torch.equal(s[:, 0], mm[:, 1]) and torch.equal(s[:, 1], mm[:, 3])
         assert torch.equal(d.argmin(1), mm[:, 0])  # ties -> lowest index
+
+
+def test_featureless_frames_in_a_batch(oracle):
+    """Empty and ragged results inside one batch: constant frames (no gradient at all: the seed sort, the region growing and
+    the rectangle queue see zero work), a frame of faint noise below every threshold, a single step edge (one line, no corner)
+    and two ordinary frames, through the extractors and the pipelined front-end with the pair matcher."""
+    import torch
+    import plslam_b200 as pl
+    from plslam_b200.synth import synth_frame
+    H, W = 480, 640
+    rng = np.random.default_rng(5)
+    frames = np.stack([
+        synth_frame(3, W, H),
+        np.zeros((H, W), np.uint8),
+        np.full((H, W), 255, np.uint8),
+        (128 + rng.integers(0, 3, (H, W))).astype(np.uint8),
+        np.concatenate([np.full((H, W // 2), 40, np.uint8), np.full((H, W - W // 2), 200, np.uint8)], axis=1),
+        synth_frame(4, W, H),
+    ])
+    B = len(frames)
+    ref = _oracle_batch(oracle, frames)
+    assert [len(r[0]) for r in ref][1:5] == [0, 0, 0, 0] and [len(r[2]) for r in ref][1:5] == [0, 0, 0, 1]
+    # extractors on their own
+    kl, desc, funcs, counts = pl.LineSegment().extract_batch_host(frames)
+    assert list(counts) == [len(r[2]) for r in ref]
+    # front-end: device path and host wave path, frame pairs (0,1) (2,3) (4,5) include empty-vs-empty and empty-vs-full matches
+    fe = pl.Frontend(depth=2)
+    out = fe.alloc(B, device="cuda")
+    fe.process_device(torch.from_numpy(frames).cuda(), out, True)
+    torch.cuda.synchronize()
+    fe.check_status()
+    _compare(oracle, pl, out, ref, B, "featureless frames, device path")
+    h_out = fe.alloc(B, pinned=True)
+    fe.submit_host_wave([torch.from_numpy(frames).pin_memory()], [h_out], True)
+    fe.wait_host()
+    _compare(oracle, pl, h_out, ref, B, "featureless frames, wave path")
