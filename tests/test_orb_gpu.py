@@ -95,3 +95,39 @@ def test_empty_image_is_silent():
     ex = _ext()
     k, d = ex(np.empty((0, 0), np.uint8))
     assert len(k) == 0 and d.shape == (0, 32)
+
+
+def test_device_batch_unaligned_view(oracle):
+    """Device-resident frames that are a misaligned VIEW of a larger buffer (odd base address, pitch and frame stride that are
+    no multiples of 16): level 0 is then not TMA-legal, so level 1 comes from the plain-load k_resize while the other levels
+    use k_resize_tma, k_blur reads level 0 with plain loads, and the word-staging paths of k_fast, k_lsd_scale and k_lbd see a
+    base that is not word aligned."""
+    import torch
+    import plslam_b200 as pl
+    from plslam_b200.synth import synth_frame
+    H, W, B = 250, 333, 3
+    imgs = np.stack([synth_frame(400 + i, W, H) for i in range(B)])
+    big = torch.zeros((B, H + 3, W + 9), dtype=torch.uint8, device="cuda")
+    view = big[:, 2:2 + H, 5:5 + W]
+    view.copy_(torch.from_numpy(imgs).cuda())
+    assert view.data_ptr() % 4 != 0 and view.stride(1) % 16 != 0
+    ex = _ext()
+    kps, desc, counts = ex.extract_batch_device(view)
+    ex.check_status()
+    ls = pl.LineSegment()
+    kl, ldesc, funcs, lcounts = ls.extract_batch_device(view)
+    ls.check_status()
+    torch.cuda.synchronize()
+    k = pl.kps_from_tensor(kps)
+    klines = pl.keylines_from_tensor(kl)
+    orc = oracle.OrbOracle()
+    for f in range(B):
+        o_kps, o_desc = orc.extract(imgs[f])
+        n = int(counts[f])
+        _compare_frame(o_kps, o_desc, k[f, :n], desc[f, :n].cpu().numpy(), "frame %d" % f)
+        okl, odesc, ofun, _ = oracle.extract_lines(imgs[f], 40)
+        m = int(lcounts[f])
+        assert m == len(okl), "frame %d line count" % f
+        for fld in okl.dtype.names:
+            assert np.array_equal(klines[f, :m][fld], okl[fld]), "frame %d keyline %s" % (f, fld)
+        assert np.array_equal(ldesc[f, :m].cpu().numpy(), odesc) and np.array_equal(funcs[f, :m].cpu().numpy(), ofun), "frame %d LBD" % f
