@@ -131,3 +131,19 @@ def test_device_batch_unaligned_view(oracle):
         for fld in okl.dtype.names:
             assert np.array_equal(klines[f, :m][fld], okl[fld]), "frame %d keyline %s" % (f, fld)
         assert np.array_equal(ldesc[f, :m].cpu().numpy(), odesc) and np.array_equal(funcs[f, :m].cpu().numpy(), ofun), "frame %d LBD" % f
+
+
+@pytest.mark.parametrize("cfg", [(300, 1.5, 4, 30, 10), (1500, 1.1, 8, 15, 5), (500, 1.2, 10, 20, 7), (50, 2.0, 3, 20, 7)])
+def test_other_extractor_settings(oracle, cfg):
+    """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) away from the ORB-SLAM2 defaults: level ratios the
+    TMA pyramid box does not hold (1.5, 2.0: plain-load k_resize), 10 levels, small quotas in the quad-tree."""
+    from plslam_b200.synth import synth_frame
+    nf, sf, nl, ini, mn = cfg
+    ex = _ext(nfeatures=nf, scaleFactor=sf, nlevels=nl, iniThFAST=ini, minThFAST=mn)
+    orc = oracle.OrbOracle(nf, sf, nl, ini, mn)
+    for seed in (7, 8):
+        img = synth_frame(seed)
+        o_kps, o_desc = orc.extract(img)
+        g_kps, g_desc = ex(img)
+        assert len(o_kps) > 0
+        _compare_frame(o_kps, o_desc, g_kps, g_desc, "cfg %s seed %d" % (cfg, seed))
