@@ -234,3 +234,27 @@ def test_featureless_frames_in_a_batch(oracle):
     fe.submit_host_wave([torch.from_numpy(frames).pin_memory()], [h_out], True)
     fe.wait_host()
     _compare(oracle, pl, h_out, ref, B, "featureless frames, wave path")
+
+
+def test_odd_batch_other_capacities(oracle):
+    """A batch of 5 frames (two pairs, the last frame unpaired) with nFeatures = 500 and the 15 strongest lines, 517x389 frames
+    (no dimension a multiple of a tile), three submissions over two slots."""
+    import torch
+    import plslam_b200 as pl
+    from plslam_b200.synth import synth_frame
+    H, W, B = 389, 517, 5
+    frames = np.stack([synth_frame(500 + i, W, H) for i in range(B)])
+    ref = _oracle_batch(oracle, frames, nfeatures=500, max_lines=15)
+    fe = pl.Frontend(nfeatures=500, max_lines=15, depth=2)
+    d_images = torch.from_numpy(frames).cuda()
+    outs = [fe.alloc(B, device="cuda") for _ in range(3)]
+    for o in outs:
+        fe.process_device(d_images, o, True)
+    torch.cuda.synchronize()
+    fe.check_status()
+    for k in (0, 2):
+        _compare(oracle, pl, outs[k], ref, B, "odd batch, submission %d" % k)
+    h_out = fe.alloc(B, pinned=True)
+    fe.submit_host(torch.from_numpy(frames).pin_memory(), h_out, True)
+    fe.wait_host()
+    _compare(oracle, pl, h_out, ref, B, "odd batch, host path")
