@@ -62,11 +62,25 @@ __global__ void __launch_bounds__(256) k_lsd_scale(const __grid_constant__ LineP
   const int nbx = bx1 - bx0 + 1, nby = by1 - by0 + 1;
   const uint8_t* S = img + (size_t)f * frame_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // raw patch (3-px halo, BORDER_REFLECT_101 at the image edges): warp = row, lanes along x
-  for (int r = warp; r < nby + 6; r += 8) {
-    const uint8_t* row = S + (size_t)reflect101_dev(by0 - 3 + r, L.H) * pitch;
-    for (int c = lane; c < RAW_P; c += 32)
-      raw[r][c] = c < nbx + 6 ? row[reflect101_dev(bx0 - 3 + c, L.W)] : (uint8_t)0;
+  // raw patch (3-px halo, BORDER_REFLECT_101 at the image edges): warp = row, lanes along x.  Tiles whose columns lie inside
+  // the image (6 of 8 per row at 640x480) take the rows as aligned words and realign them with a funnel shift; the others, and
+  // images whose rows are not word aligned, go byte by byte through the reflection.
+  const int cx0 = bx0 - 3;
+  if (cx0 >= 0 && cx0 + nbx + 6 <= L.W && ((pitch | (int)(frame_stride & 3) | (int)(reinterpret_cast<uintptr_t>(img) & 3)) & 3) == 0) {
+    const int xa = cx0 & ~3, sft = 8 * (cx0 - xa);
+    for (int r = warp; r < nby + 6; r += 8) {
+      const uint8_t* row = S + (size_t)reflect101_dev(by0 - 3 + r, L.H) * pitch;
+      // 25 source words cover the 24 words of the patch row at any shift; words past the pitch are never consumed
+      const uint32_t w0 = (lane <= RAW_P / 4 && xa + 4 * lane + 3 < pitch) ? __ldg(reinterpret_cast<const uint32_t*>(row + xa) + lane) : 0u;
+      const uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+      if (lane < RAW_P / 4) reinterpret_cast<uint32_t*>(raw[r])[lane] = __funnelshift_r(w0, w1, sft);
+    }
+  } else {
+    for (int r = warp; r < nby + 6; r += 8) {
+      const uint8_t* row = S + (size_t)reflect101_dev(by0 - 3 + r, L.H) * pitch;
+      for (int c = lane; c < RAW_P; c += 32)
+        raw[r][c] = c < nbx + 6 ? row[reflect101_dev(bx0 - 3 + c, L.W)] : (uint8_t)0;
+    }
   }
   __syncthreads();
   // horizontal 7-tap pass, 4 outputs per thread: aligned words, funnel shifts for the byte windows, dp4a for the taps
@@ -107,16 +121,33 @@ __global__ void __launch_bounds__(256) k_lsd_scale(const __grid_constant__ LineP
   }
   __syncthreads();
   uint8_t* D = scaled + (size_t)f * L.spitch * L.sh;
-  for (int i = threadIdx.x; i < ST_W * ST_H; i += 256) {
-    const int ty = i / ST_W, tx = i - ty * ST_W;
-    const int ox = ox0 + tx, oy = oy0 + ty;
-    if (ox >= L.sw || oy >= L.sh) continue;
-    const int sx = __ldg(xofs + ox), sy = __ldg(yofs + oy);
-    const int sx1 = min(sx + 1, L.W - 1), sy1 = min(sy + 1, L.H - 1);
-    const int a1 = __ldg(xc1 + ox), a0 = 256 - a1, b1 = __ldg(yc1 + oy), b0 = 256 - b1;
-    const int t0 = bl[sy - by0][sx - bx0] * a0 + bl[sy - by0][sx1 - bx0] * a1;
-    const int t1 = bl[sy1 - by0][sx - bx0] * a0 + bl[sy1 - by0][sx1 - bx0] * a1;
-    D[(size_t)oy * L.spitch + ox] = (uint8_t)((t0 * b0 + t1 * b1 + 32768) >> 16);
+  // thread = 4 consecutive output pixels of one row (16 rows x 16 quads = the CTA), one word store when the quad is complete
+  {
+    const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 4;
+    const int oy = oy0 + ty;
+    if (oy < L.sh && ox0 + tx < L.sw) {
+      const int sy = __ldg(yofs + oy), sy1 = min(sy + 1, L.H - 1);
+      const int b1 = __ldg(yc1 + oy), b0 = 256 - b1;
+      const uint8_t* r0 = bl[sy - by0];
+      const uint8_t* r1 = bl[sy1 - by0];
+      uint32_t out = 0;
+      const int nq = min(4, L.sw - (ox0 + tx));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ox = min(ox0 + tx + j, L.sw - 1);
+        const int sx = __ldg(xofs + ox), sx1 = min(sx + 1, L.W - 1);
+        const int a1 = __ldg(xc1 + ox), a0 = 256 - a1;
+        const int t0 = r0[sx - bx0] * a0 + r0[sx1 - bx0] * a1;
+        const int t1 = r1[sx - bx0] * a0 + r1[sx1 - bx0] * a1;
+        out |= (uint32_t)(uint8_t)((t0 * b0 + t1 * b1 + 32768) >> 16) << (8 * j);
+      }
+      uint8_t* dp = D + (size_t)oy * L.spitch + ox0 + tx;
+      if (nq == 4) {
+        *reinterpret_cast<uint32_t*>(dp) = out;  // spitch is a multiple of 32, ox0 + tx of 4
+      } else {
+        for (int j = 0; j < nq; ++j) dp[j] = (uint8_t)(out >> (8 * j));
+      }
+    }
   }
 }
 
