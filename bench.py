@@ -651,6 +651,11 @@ def run_ours(a):
                         # the ~57 GB/s a B200 measured here sustains, i.e. the bus is not what the e2e figure waits for
                         "per_rank_copy_gbs": {"h2d": h2d * a.steps / e2e_s / 1e9, "d2h": d2h * a.steps / e2e_s / 1e9},
                         "host_binding": host_binding,
+                        **({"note": "single pass over the slots (steps <= slots): the e2e leg starts with a small first wave (--wave-ramp), "
+                                    "so its batches run staggered - the first batches' latency-bound region growing overlaps the "
+                                    "throughput-bound kernels of the rest - while the device-resident loop starts all batches in phase and "
+                                    "ends with the tail of every batch's slowest frames; e2e can therefore exceed `value` in such a run "
+                                    "(DESIGN.md section 6, profiles/r02_sched_sweeps.log)"} if wave_ramp else {}),
                         "by_api": {m: world * a.batch * a.steps / t for m, t in e2e_modes.items()},
                         "api": ("plslam_frontend_submit_host_wave (%s steps per call, successive calls rotate over the slots) + plslam_frontend_wait_host" % ("+".join(map(str, wave_ramp)) + " then %d" % wave if wave_ramp else str(wave)) if e2e_mode == "wave"
                                 else "plslam_frontend_submit_host x K + plslam_frontend_wait_host") +
