@@ -382,6 +382,28 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def wave_ramp_sizes(spec, steps, depth):
+    """Sizes of the first waves of the e2e leg: `spec` = "auto" (depth/5 + the rest when the run passes over the slots only once,
+    none otherwise) or a comma-separated list."""
+    if spec == "auto":
+        first = max(1, depth // 5)
+        return [first, depth - first] if steps <= depth and depth >= 4 else []
+    return [int(v) for v in spec.split(",") if v]
+
+
+def wave_plan(n, depth, wave, ramp):
+    """Batches per plslam_frontend_submit_host_wave call for n steps: the ramp sizes first, then `wave`; never more than the
+    pipeline holds, never more than what is left."""
+    ramp = list(ramp)
+    out = []
+    k = 0
+    while k < n:
+        m = max(1, min(ramp.pop(0) if ramp else wave, n - k, depth))
+        out.append(m)
+        k += m
+    return out
+
+
 def bind_host_threads(local, world):
     """One rank per GPU on one node: keep the rank's submitting thread (and the pinned buffers it first touches) on the cores next
     to its GPU.  NVML names the GPU's CPU affinity; when every GPU reports the same set (round 1: 0-31, NUMA 0 for all eight)
@@ -506,18 +528,13 @@ def run_ours(a):
     # instead of 10) and sends the rest as one: its staggered start also fills the tail of the first batches' region growing.
     # Measured at 20 steps (profiles/r02_sched_sweeps.log): 21.4-21.6 k frames/s end to end with waves of 10 + 10, 24.4-26.8 k with
     # 3-8 + rest; at 64 steps a ramp costs the phase (28.2 k -> 23.8-25.6 k), so longer runs keep equal waves.
-    if a.wave_ramp == "auto":
-        wave_ramp = [max(1, depth // 5), depth - max(1, depth // 5)] if a.steps <= depth and depth >= 4 else []
-    else:
-        wave_ramp = [int(v) for v in a.wave_ramp.split(",") if v]
+    wave_ramp = wave_ramp_sizes(a.wave_ramp, a.steps, depth)
     wave_sub = [0]  # batches submitted through the wave form so far: batch t goes to slot t % depth, buffer set (t // depth) & 1
 
     def host_steps(n, mode):
         if mode == "wave":
             k = 0
-            ramp = list(wave_ramp)
-            while k < n:
-                m = min(ramp.pop(0) if ramp else wave, n - k, depth)
+            for m in wave_plan(n, depth, wave, wave_ramp):
                 t0 = wave_sub[0]
                 fe.submit_host_wave([h_images] * m, [h_outs2[((t0 + i) // depth) & 1][(t0 + i) % depth] for i in range(m)], True)
                 wave_sub[0] += m
